@@ -1,0 +1,100 @@
+// pack_kernels.cuh -- block-by-block packer kernels: one warp per 4x4 block.
+//
+// Replaces dxt_image::init_task + set_block_pixels (reference crnlib/crn_dxt_image.cpp:283-349,
+// :1427-1541): clamped 4x4 gather, per-element optimiser, selector bit packing into 8-byte elements.
+// Each kernel writes ONE 8-byte element of every block (element stride = bytes per block), so the
+// alpha and colour elements of DXT5 / the two halves of DXN are independent launches that can
+// overlap on the device.
+#pragma once
+#include "dxt5a_opt.cuh"
+#include "dxt1_opt.cuh"
+
+namespace crn {
+
+struct ImageView {
+    const uint8_t* rgba;   // device, RGBA8 row-major
+    uint32_t width, height, pitch;
+    uint32_t blocks_x, blocks_y;
+};
+
+// lanes 0..15 fetch pixel (x = lane&3, y = lane>>2) of block (bx,by) with edge clamping
+// (crn_dxt_image.cpp:334-344).  Other lanes return 0.
+__device__ __forceinline__ uint32_t fetch_block_pixel(const ImageView& img, uint32_t bx, uint32_t by)
+{
+    const unsigned lane = lane_id();
+    uint32_t px = 0;
+    if (lane < 16) {
+        uint32_t x = min(bx * 4 + (lane & 3), img.width - 1);
+        uint32_t y = min(by * 4 + (lane >> 2), img.height - 1);
+        px = *reinterpret_cast<const uint32_t*>(img.rgba + (size_t)y * img.pitch + (size_t)x * 4);
+    }
+    return px;
+}
+
+constexpr int kPackWarpsPerCta = 8;
+
+// DXT5A-type element (alpha of DXT5, DXT5A, both halves of DXN) ------------------------------------
+__global__ void __launch_bounds__(kPackWarpsPerCta * 32)
+pack_alpha_element_kernel(ImageView img, uint32_t comp, int quality, int both_types,
+                          uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs)
+{
+    __shared__ Dxt5aScratch scratch[kPackWarpsPerCta];
+    const unsigned warp = threadIdx.x >> 5;
+    Dxt5aScratch* sc = &scratch[warp];
+    const uint32_t total = img.blocks_x * img.blocks_y;
+    for (uint32_t b = blockIdx.x * kPackWarpsPerCta + warp; b < total; b += gridDim.x * kPackWarpsPerCta) {
+        const uint32_t bx = b % img.blocks_x, by = b / img.blocks_x;
+        const uint32_t px = fetch_block_pixel(img, bx, by);
+        const unsigned value = (px >> (8 * comp)) & 0xffu;
+        const unsigned long long elem = dxt5a_pack_block(sc, value, quality, both_types != 0);
+        if (lane_id() == 0)
+            *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = elem;
+    }
+}
+
+// DXT3 explicit 4-bit alpha element (crn_dxt_image.cpp:1524-1536, crn_dxt.h dxt3_block::set_alpha with
+// scaled=true: (v*15+128)/255 ... see dxt3_quantize) -- one thread per block, trivially bandwidth bound.
+__device__ __forceinline__ unsigned dxt3_quantize(unsigned v)
+{   // reference crnlib/crn_dxt.cpp dxt3_block::set_alpha scaled path: value = (value * 15U + 128U) / 255U
+    return (v * 15u + 128u) / 255u;
+}
+__global__ void pack_dxt3_alpha_kernel(ImageView img, uint32_t comp, uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs)
+{
+    const uint32_t total = img.blocks_x * img.blocks_y;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < total; b += gridDim.x * blockDim.x) {
+        const uint32_t bx = b % img.blocks_x, by = b / img.blocks_x;
+        unsigned long long bits = 0;
+        for (unsigned i = 0; i < 16; i++) {
+            uint32_t x = min(bx * 4 + (i & 3), img.width - 1);
+            uint32_t y = min(by * 4 + (i >> 2), img.height - 1);
+            unsigned v = img.rgba[(size_t)y * img.pitch + (size_t)x * 4 + comp];
+            bits |= (unsigned long long)dxt3_quantize(v) << (4 * i);
+        }
+        *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = bits;
+    }
+}
+
+// DXT1 colour element ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPackWarpsPerCta * 32)
+pack_color_element_kernel(ImageView img, Dxt1Params prm, int dxt1a,
+                          uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs)
+{
+    __shared__ Dxt1Scratch scratch[kPackWarpsPerCta];
+    const unsigned warp = threadIdx.x >> 5;
+    Dxt1Scratch* sc = &scratch[warp];
+    const uint32_t total = img.blocks_x * img.blocks_y;
+    for (uint32_t b = blockIdx.x * kPackWarpsPerCta + warp; b < total; b += gridDim.x * kPackWarpsPerCta) {
+        const uint32_t bx = b % img.blocks_x, by = b / img.blocks_x;
+        const uint32_t px = fetch_block_pixel(img, bx, by);
+        Dxt1Params p = prm;
+        if (dxt1a) {   // crn_dxt_image.cpp:1440-1451
+            const unsigned any = __ballot_sync(CRN_FULL_MASK, lane_id() < 16 && (px >> 24) < prm.alpha_threshold);
+            p.pixels_have_alpha = any != 0;
+        }
+        const unsigned long long elem = dxt1_pack_block(sc, px, p);
+        if (lane_id() == 0)
+            *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = elem;
+    }
+}
+
+}  // namespace crn

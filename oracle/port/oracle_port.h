@@ -1,0 +1,56 @@
+/* oracle/port/oracle_port.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, single-threaded restatement of the reference's hot path (crnlib 1.2.0), written from the
+ * algorithm, not copied: every function cites the reference file:line it follows.  Built into
+ * oracle/liboracle_port.so by oracle/Makefile and pinned against the unmodified reference
+ * (oracle/_ref/liboracle_ref.so) by tests/test_oracle_port.py and the committed fixtures in
+ * tests/golden/.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it;
+ * the product (crunch2_b200/, libcrn_b200.so) never does.
+ */
+#ifndef ORACLE_PORT_H
+#define ORACLE_PORT_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct op_dxt1_params {
+    uint32_t quality;              /* crn_dxt_quality 0..4 */
+    uint32_t perceptual;
+    uint32_t pixels_have_alpha;
+    uint32_t use_alpha_blocks;
+    uint32_t alpha_threshold;
+    uint32_t grayscale_sampling;
+    uint32_t transparent_for_black;
+    uint32_t force_alpha_blocks;
+} op_dxt1_params;
+
+typedef struct op_dxt1_result {
+    uint64_t error;
+    uint16_t low, high;
+    uint8_t alpha_block;
+} op_dxt1_result;
+
+/* crnlib::dxt1_endpoint_optimizer::compute with endpoint caching disabled (crn_dxt1.cpp:2234).
+ * pixels: num_pixels RGBA8 (r first).  selectors: num_pixels bytes out.  Returns 1 on success. */
+int op_dxt1_optimize(const uint8_t* pixels, uint32_t num_pixels, const op_dxt1_params* p,
+                     op_dxt1_result* r, uint8_t* selectors);
+
+/* crnlib::dxt5_endpoint_optimizer::compute (crn_dxt5a.cpp:40). */
+int op_dxt5_optimize(const uint8_t* pixels, uint32_t num_pixels, uint32_t comp_index, uint32_t quality,
+                     uint32_t use_both_block_types, uint8_t* first, uint8_t* second, uint8_t* selectors,
+                     uint64_t* error, uint8_t* block_type);
+
+/* dxt_image::init for the CRN compressor, endpoint caching disabled (crn_dxt_image.cpp:283-349,
+ * :1427-1541).  fmt is crnlib::dxt_format (0 DXT1, 1 DXT1A, 2 DXT3, 3 DXT5, 4 DXT5A, 5 DXN_XY, 6 DXN_YX).
+ * Returns bytes written. */
+uint32_t op_pack_image(int fmt, const uint8_t* rgba, uint32_t width, uint32_t height, uint32_t pitch,
+                       uint32_t quality, uint32_t perceptual, uint32_t use_both_block_types,
+                       uint32_t alpha_threshold, uint32_t transparent_for_black, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

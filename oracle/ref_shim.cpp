@@ -1,0 +1,288 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A thin extern "C" window onto the UNMODIFIED reference (crnlib 1.2.0), which
+// oracle/Makefile compiles from the sources where they lie under /root/reference
+// into oracle/_ref/liboracle_ref.so.  Only tests/, __graft_entry__.smoke() and
+// bench.py's CPU-baseline legs may load that library; the product never does.
+//
+// Every entry point below forwards to a reference class / function without
+// altering its arguments:
+//   ref_dxt1_optimize   -> crnlib::dxt1_endpoint_optimizer::compute   (crnlib/crn_dxt1.cpp:2234)
+//   ref_dxt5_optimize   -> crnlib::dxt5_endpoint_optimizer::compute   (crnlib/crn_dxt5a.cpp:40)
+//   ref_pack_image      -> crnlib::dxt_image::init                    (crnlib/crn_dxt_image.cpp:447)
+//   ref_compress        -> crn_compress                               (crnlib/crnlib.cpp:215)
+//   ref_transcode_*     -> crnd::crnd_unpack_begin/level/end          (inc/crn_decomp.h:4404-4460)
+//   ref_crn_to_dds      -> crn_decompress_crn_to_dds                  (crnlib/crnlib.cpp:269)
+#include "crn_core.h"
+#include "crn_dxt1.h"
+#include "crn_dxt5a.h"
+#include "crn_dxt_image.h"
+#include "crn_image.h"
+#include "crn_dxt_endpoint_refiner.h"
+#include "crn_dxt_fast.h"
+#include "crnlib.h"
+#include "crn_defs.h"   // declarations only (crnd:: API); the bodies live in crn_decomp.cpp
+#include <string.h>
+#include <time.h>
+
+using namespace crnlib;
+
+#define SHIM_API extern "C" __attribute__((visibility("default")))
+
+SHIM_API const char* ref_version(void) { return "crnlib-1.2.0-unmodified"; }
+
+// One N-pixel DXT1 endpoint optimisation.  pixels: RGBA8 (r first).  Returns 1 on success.
+SHIM_API int ref_dxt1_optimize(const uint8_t* pixels, uint32_t num_pixels, int quality, int perceptual,
+                               int pixels_have_alpha, int use_alpha_blocks, uint32_t alpha_threshold,
+                               int grayscale_sampling, int transparent_for_black, int force_alpha_blocks,
+                               uint16_t* low, uint16_t* high, uint8_t* selectors, uint64_t* error, uint8_t* alpha_block)
+{
+    dxt1_endpoint_optimizer opt;
+    dxt1_endpoint_optimizer::params p;
+    dxt1_endpoint_optimizer::results r;
+    p.m_pPixels = reinterpret_cast<const color_quad_u8*>(pixels);
+    p.m_num_pixels = num_pixels;
+    p.m_quality = (crn_dxt_quality)quality;
+    p.m_perceptual = perceptual != 0;
+    p.m_pixels_have_alpha = pixels_have_alpha != 0;
+    p.m_use_alpha_blocks = use_alpha_blocks != 0;
+    p.m_dxt1a_alpha_threshold = alpha_threshold;
+    p.m_grayscale_sampling = grayscale_sampling != 0;
+    p.m_use_transparent_indices_for_black = transparent_for_black != 0;
+    p.m_force_alpha_blocks = force_alpha_blocks != 0;
+    p.m_endpoint_caching = false;
+    r.m_pSelectors = selectors;
+    r.m_error = 0;
+    r.m_low_color = r.m_high_color = 0;
+    r.m_alpha_block = false;
+    if (!opt.compute(p, r))
+        return 0;
+    *low = r.m_low_color;
+    *high = r.m_high_color;
+    *error = r.m_error;
+    *alpha_block = r.m_alpha_block ? 1 : 0;
+    return 1;
+}
+
+// Batch form: n_blocks consecutive groups of pixels_per_block RGBA8 pixels, a fresh optimiser state per
+// group is NOT needed (caching disabled), so one optimiser instance is reused like the reference's block loop does.
+SHIM_API int ref_dxt1_optimize_batch(const uint8_t* pixels, uint32_t n_groups, uint32_t pixels_per_group, int quality, int perceptual,
+                                     int use_alpha_blocks, int dxt1a, uint32_t alpha_threshold, int transparent_for_black,
+                                     uint16_t* low, uint16_t* high, uint8_t* selectors, uint64_t* error, uint8_t* alpha_block)
+{
+    dxt1_endpoint_optimizer opt;
+    for (uint32_t g = 0; g < n_groups; g++)
+    {
+        const color_quad_u8* px = reinterpret_cast<const color_quad_u8*>(pixels) + (size_t)g * pixels_per_group;
+        dxt1_endpoint_optimizer::params p;
+        dxt1_endpoint_optimizer::results r;
+        bool have_alpha = false;
+        if (dxt1a)
+            for (uint32_t i = 0; i < pixels_per_group; i++)
+                if (px[i].a < alpha_threshold) { have_alpha = true; break; }
+        p.m_pPixels = px;
+        p.m_num_pixels = pixels_per_group;
+        p.m_quality = (crn_dxt_quality)quality;
+        p.m_perceptual = perceptual != 0;
+        p.m_pixels_have_alpha = have_alpha;
+        p.m_use_alpha_blocks = use_alpha_blocks != 0;
+        p.m_dxt1a_alpha_threshold = alpha_threshold;
+        p.m_use_transparent_indices_for_black = transparent_for_black != 0;
+        p.m_endpoint_caching = false;
+        r.m_pSelectors = selectors + (size_t)g * pixels_per_group;
+        r.m_error = 0;
+        if (!opt.compute(p, r))
+            return 0;
+        low[g] = r.m_low_color;
+        high[g] = r.m_high_color;
+        error[g] = r.m_error;
+        alpha_block[g] = r.m_alpha_block ? 1 : 0;
+    }
+    return 1;
+}
+
+SHIM_API int ref_dxt5_optimize_batch(const uint8_t* pixels, uint32_t n_groups, uint32_t pixels_per_group, uint32_t comp_index,
+                                     int quality, int use_both_block_types,
+                                     uint8_t* first, uint8_t* second, uint8_t* selectors, uint64_t* error, uint8_t* block_type)
+{
+    dxt5_endpoint_optimizer opt;
+    for (uint32_t g = 0; g < n_groups; g++)
+    {
+        dxt5_endpoint_optimizer::params p;
+        dxt5_endpoint_optimizer::results r;
+        p.m_pPixels = reinterpret_cast<const color_quad_u8*>(pixels) + (size_t)g * pixels_per_group;
+        p.m_num_pixels = pixels_per_group;
+        p.m_comp_index = comp_index;
+        p.m_quality = (crn_dxt_quality)quality;
+        p.m_use_both_block_types = use_both_block_types != 0;
+        r.m_pSelectors = selectors + (size_t)g * pixels_per_group;
+        if (!opt.compute(p, r))
+            return 0;
+        first[g] = r.m_first_endpoint;
+        second[g] = r.m_second_endpoint;
+        error[g] = r.m_error;
+        block_type[g] = r.m_block_type;
+    }
+    return 1;
+}
+
+// dxt_endpoint_refiner::refine (crnlib/crn_dxt_endpoint_refiner.cpp:36)
+SHIM_API int ref_refine_endpoints(const uint8_t* pixels, const uint8_t* selectors, uint32_t num_pixels, int dxt1_selectors,
+                                  int perceptual, uint32_t alpha_comp_index, uint64_t error_to_beat, int block_type,
+                                  uint32_t* low, uint32_t* high)
+{
+    dxt_endpoint_refiner refiner;
+    dxt_endpoint_refiner::params p;
+    dxt_endpoint_refiner::results r;
+    p.m_pPixels = reinterpret_cast<const color_quad_u8*>(pixels);
+    p.m_pSelectors = selectors;
+    p.m_num_pixels = num_pixels;
+    p.m_dxt1_selectors = dxt1_selectors != 0;
+    p.m_perceptual = perceptual != 0;
+    p.m_alpha_comp_index = alpha_comp_index;
+    p.m_error_to_beat = error_to_beat;
+    p.m_block_index = 0;
+    (void)block_type;
+    bool ok = refiner.refine(p, r);
+    *low = r.m_low_color;
+    *high = r.m_high_color;
+    return ok ? 1 : 0;
+}
+
+// Whole-image block-by-block packing through dxt_image::init with endpoint caching disabled
+// (the only thread-count independent configuration).  fmt is crnlib::dxt_format.
+// out must hold blocks_x*blocks_y*(8|16) bytes.  Returns bytes written or 0.
+SHIM_API uint32_t ref_pack_image(int fmt, const uint8_t* rgba, uint32_t width, uint32_t height, int quality, int perceptual,
+                                 int use_both_block_types, int transparent_for_black, uint32_t alpha_threshold,
+                                 int compressor, uint32_t helper_threads, uint8_t* out)
+{
+    image_u8 img;
+    img.alias(const_cast<color_quad_u8*>(reinterpret_cast<const color_quad_u8*>(rgba)), width, height);
+    dxt_image::pack_params pp;
+    pp.m_quality = (crn_dxt_quality)quality;
+    pp.m_perceptual = perceptual != 0;
+    pp.m_use_both_block_types = use_both_block_types != 0;
+    pp.m_use_transparent_indices_for_black = transparent_for_black != 0;
+    pp.m_dxt1a_alpha_threshold = alpha_threshold;
+    pp.m_compressor = (crn_dxt_compressor_type)compressor;
+    pp.m_num_helper_threads = helper_threads;
+    pp.m_endpoint_caching = false;
+    dxt_image d;
+    if (!d.init((dxt_format)fmt, img, pp))
+        return 0;
+    uint32_t n = d.get_size_in_bytes();
+    memcpy(out, d.get_element_ptr(), n);
+    return n;
+}
+
+// crn_compress through the public API.  images[f*levels+l] -> RGBA8 of level l (max(1,w>>l) x max(1,h>>l)).
+// Returns a malloc'd copy (free with ref_free) and its size; NULL on failure.
+SHIM_API void* ref_compress(int file_type, int format, uint32_t width, uint32_t height, uint32_t faces, uint32_t levels,
+                            const uint32_t* const* images, uint32_t flags, uint32_t quality_level, float target_bitrate,
+                            int dxt_quality, uint32_t helper_threads, uint32_t alpha_component,
+                            uint32_t* out_size, uint32_t* actual_quality, float* actual_bitrate, int want_bitrate)
+{
+    crn_comp_params cp;
+    cp.m_file_type = (crn_file_type)file_type;
+    cp.m_format = (crn_format)format;
+    cp.m_width = width;
+    cp.m_height = height;
+    cp.m_faces = faces;
+    cp.m_levels = levels;
+    cp.m_flags = flags;
+    cp.m_quality_level = quality_level;
+    cp.m_target_bitrate = target_bitrate;
+    cp.m_dxt_quality = (crn_dxt_quality)dxt_quality;
+    cp.m_num_helper_threads = helper_threads;
+    cp.m_alpha_component = alpha_component;
+    for (uint32_t f = 0; f < faces; f++)
+        for (uint32_t l = 0; l < levels; l++)
+            cp.m_pImages[f][l] = images[f * levels + l];
+    crn_uint32 size = 0, aq = 0;
+    float ab = 0.0f;
+    void* p = crn_compress(cp, size, &aq, want_bitrate ? &ab : NULL);
+    *out_size = 0;
+    if (!p)
+        return NULL;
+    void* q = malloc(size);
+    memcpy(q, p, size);
+    crn_free_block(p);
+    *out_size = size;
+    if (actual_quality) *actual_quality = aq;
+    if (actual_bitrate) *actual_bitrate = ab;
+    return q;
+}
+
+SHIM_API void ref_free(void* p) { free(p); }
+
+SHIM_API void* ref_crn_to_dds(const void* crn, uint32_t crn_size, uint32_t* dds_size)
+{
+    crn_uint32 sz = crn_size;
+    void* p = crn_decompress_crn_to_dds(crn, sz);
+    *dds_size = 0;
+    if (!p)
+        return NULL;
+    void* q = malloc(sz);
+    memcpy(q, p, sz);
+    crn_free_block(p);
+    *dds_size = sz;
+    return q;
+}
+
+// Texture info: out[0..7] = width,height,levels,faces,bytes_per_block,format,userdata0,userdata1
+SHIM_API int ref_crn_info(const void* crn, uint32_t crn_size, uint32_t* out)
+{
+    crnd::crn_texture_info ti;
+    if (!crnd::crnd_get_texture_info(crn, crn_size, &ti))
+        return 0;
+    out[0] = ti.m_width; out[1] = ti.m_height; out[2] = ti.m_levels; out[3] = ti.m_faces;
+    out[4] = ti.m_bytes_per_block; out[5] = (uint32_t)ti.m_format; out[6] = ti.m_userdata0; out[7] = ti.m_userdata1;
+    return 1;
+}
+
+SHIM_API void* ref_transcode_begin(const void* crn, uint32_t crn_size) { return crnd::crnd_unpack_begin(crn, crn_size); }
+SHIM_API int ref_transcode_level(void* ctx, void** face_ptrs, uint32_t dst_size, uint32_t row_pitch, uint32_t level)
+{
+    return crnd::crnd_unpack_level(ctx, face_ptrs, dst_size, row_pitch, level) ? 1 : 0;
+}
+SHIM_API void ref_transcode_end(void* ctx) { crnd::crnd_unpack_end(ctx); }
+
+// Timed whole-file transcode: unpacks every level `repeats` times into caller memory laid out
+// level-major / face-major, tightly pitched.  Returns seconds spent inside crnd_unpack_level only.
+SHIM_API double ref_transcode_all(const void* crn, uint32_t crn_size, uint8_t* out, uint64_t out_capacity, uint32_t repeats)
+{
+    crnd::crn_texture_info ti;
+    if (!crnd::crnd_get_texture_info(crn, crn_size, &ti))
+        return -1.0;
+    void* ctx = crnd::crnd_unpack_begin(crn, crn_size);
+    if (!ctx)
+        return -1.0;
+    double total = 0.0;
+    for (uint32_t rep = 0; rep < repeats; rep++)
+    {
+        uint64_t ofs = 0;
+        for (uint32_t l = 0; l < ti.m_levels; l++)
+        {
+            uint32_t w = ti.m_width >> l; if (!w) w = 1;
+            uint32_t h = ti.m_height >> l; if (!h) h = 1;
+            uint32_t bx = (w + 3) >> 2, by = (h + 3) >> 2;
+            uint32_t pitch = bx * ti.m_bytes_per_block;
+            uint32_t face_size = pitch * by;
+            void* faces[6];
+            for (uint32_t f = 0; f < ti.m_faces; f++)
+            {
+                if (ofs + face_size > out_capacity) { crnd::crnd_unpack_end(ctx); return -2.0; }
+                faces[f] = out + ofs;
+                ofs += face_size;
+            }
+            struct timespec t0, t1;
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            bool ok = crnd::crnd_unpack_level(ctx, faces, face_size, pitch, l);
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (!ok) { crnd::crnd_unpack_end(ctx); return -3.0; }
+            total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+        }
+    }
+    crnd::crnd_unpack_end(ctx);
+    return total;
+}
