@@ -1,0 +1,277 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the B200-native crnlib hot path ("Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  Workloads:
+  c1_dxt1_2048_mips   BASELINE.json configs[0]: block-by-block DXT1 (uber, perceptual, both block types,
+                      endpoint caching disabled) of a synthetic 2048x2048 RGB texture + full mip chain
+                      (12 levels, 349 527 blocks, 5 592 405 texels)
+  dxt5_2048           plain DXT5 of a 2048x2048 RGBA texture (alpha + colour kernels)
+Prints ONE JSON line (rank 0).  `value` is device time with inputs resident in HBM (CUDA events on the
+library's own stream, L2 flushed between timed steps); `e2e` is the same metric through the public host
+API (pinned host buffers, H2D + kernels + D2H inside the timed region).  N > 1: one process per GPU
+(torchrun), every rank packs its own texture (weak scaling, no data-path collective), max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "DXT1 block-by-block compress throughput (uber, perceptual)"
+UNIT = "Mtexel/s"
+
+
+def mip_chain(img):
+    """Synthetic mip chain by 2x2 box filter (input data only; the reference's Kaiser generator is out of
+    scope).  Both arms get the same pixels."""
+    levels = [img]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        a = levels[-1].astype(np.uint16)
+        h, w = a.shape[:2]
+        h2, w2 = max(1, h >> 1), max(1, w >> 1)
+        r0 = np.minimum(2 * np.arange(h2), h - 1); r1 = np.minimum(2 * np.arange(h2) + 1, h - 1)
+        c0 = np.minimum(2 * np.arange(w2), w - 1); c1 = np.minimum(2 * np.arange(w2) + 1, w - 1)
+        s4 = a[r0][:, c0] + a[r0][:, c1] + a[r1][:, c0] + a[r1][:, c1]
+        levels.append(((s4 + 2) // 4).astype(np.uint8))
+    return levels
+
+
+def make_workload(name, seed):
+    import blockgen
+    if name == "c1_dxt1_2048_mips":
+        img = blockgen.smooth_image(2048, 2048, seed, alpha=False)
+        return dict(fmt=0, levels=mip_chain(img))
+    if name == "dxt5_2048":
+        return dict(fmt=3, levels=[blockgen.smooth_image(2048, 2048, seed, alpha=True)])
+    raise SystemExit("unknown workload " + name)
+
+
+def texels(levels):
+    return int(sum(l.shape[0] * l.shape[1] for l in levels))
+
+
+def nblocks(levels):
+    return int(sum(((l.shape[0] + 3) // 4) * ((l.shape[1] + 3) // 4) for l in levels))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_threads():
+    return max(1, min(16, (os.cpu_count() or 1)))
+
+
+def run_cpu_baseline(wl, budget_s=12.0):
+    """The reference's own CPU implementation (oracle/_ref, dxt_image::init with its task pool, endpoint
+    caching disabled) on a bounded sample of the same workload: the largest level that fits the budget."""
+    import helpers
+    ref = helpers.load_ref()
+    kind = "reference"
+    threads = cpu_threads()
+    # pick a level by a quick calibration on a small one
+    lv = [l for l in wl["levels"] if l.shape[0] * l.shape[1] <= 128 * 128][0]
+    if ref is None:
+        kind = "port"
+        lib = helpers.load_port()
+        threads = 1
+        run = lambda im: helpers.port_pack(lib, wl["fmt"], im)  # noqa: E731
+    else:
+        run = lambda im: helpers.ref_pack(ref, wl["fmt"], im, threads=threads - 1)  # noqa: E731
+    t0 = time.perf_counter(); run(lv); dt = time.perf_counter() - t0
+    rate = lv.shape[0] * lv.shape[1] / max(dt, 1e-6)
+    cands = [l for l in wl["levels"] if l.shape[0] * l.shape[1] / rate <= budget_s]
+    sample = cands[0] if cands else lv
+    t0 = time.perf_counter(); run(sample); dt = time.perf_counter() - t0
+    return dict(value=sample.shape[0] * sample.shape[1] / dt / 1e6, unit=UNIT, cores=threads, kind=kind,
+                sample="level %dx%d of the workload (%d blocks), one pass, %.2f s" % (sample.shape[1], sample.shape[0], nblocks([sample]), dt)), sample, run
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1_dxt1_2048_mips")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": args.workload, "l2": "flushed between timed steps (256 MiB write)", "endpoint_caching": "disabled",
+              "dxt_quality": "uber", "flags": "perceptual|use_both_block_types"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = make_workload(args.workload, 2048)
+        base, sample, run = run_cpu_baseline(wl, budget_s=8.0)
+        for _ in range(min(args.warmup, 1)):
+            run(sample)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run(sample)
+        dt = time.perf_counter() - t0
+        v = sample.shape[0] * sample.shape[1] * args.steps / dt / 1e6
+        base["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config, "cpu_baseline": base,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    import torch
+    import crunch2_b200 as crn
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = crn.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    wl = make_workload(args.workload, 2048 + rank)
+    fmt, levels = wl["fmt"], wl["levels"]
+    bpb = crn.bytes_per_block(fmt)
+    params = crn.PackParams()
+    n_tex, n_blk = texels(levels), nblocks(levels)
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    d_in = [torch.from_numpy(l).to(dev) for l in levels]
+    d_out = [torch.empty(((l.shape[0] + 3) // 4) * ((l.shape[1] + 3) // 4) * bpb, dtype=torch.uint8, device=dev) for l in levels]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        for l, di, do in zip(levels, d_in, d_out):
+            ctx.pack_image_device(fmt, di, l.shape[1], l.shape[0], l.shape[1] * 4, do, params)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    ctx.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count
+    times = []
+    for _ in range(args.steps):
+        flush.fill_(1)                       # evict L2 (126 MB) between timed steps
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        step_device()
+        e1.record(ext)
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    barrier()
+    launches = ctx.launch_count - l0
+    total_ms = float(sum(times))
+
+    # dominant kernel: colour element kernel of the largest level, timed alone (same stream, events)
+    flush.fill_(2); torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(ext)
+    ctx.pack_image_device(fmt, d_in[0], levels[0].shape[1], levels[0].shape[0], levels[0].shape[1] * 4, d_out[0], params)
+    k1.record(ext); k1.synchronize()
+    top_ms = k0.elapsed_time(k1)
+    top_blocks = nblocks(levels[:1])
+
+    # ---- end-to-end arm: public host API, pinned buffers, copies inside the timed region -----------
+    pinned = [torch.from_numpy(l.copy()).pin_memory() for l in levels]
+    host_levels = [p.numpy() for p in pinned]
+    for _ in range(2):
+        for hl in host_levels:
+            ctx.pack_image(fmt, hl, params)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for hl in host_levels:
+            ctx.pack_image(fmt, hl, params)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop.set(); sampler.join(timeout=2)
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    value = n_tex * world * args.steps / (total_ms / 1e3) / 1e6
+    e2e_v = n_tex * world * args.steps / e2e_s / 1e6
+    algo_bytes = top_blocks * (64 + bpb)
+    achieved = algo_bytes / (top_ms / 1e3) / 1e9
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "int32", "data": "synthetic", "config": config,
+           "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(sum(l.nbytes for l in levels)), "d2h_bytes_per_step": int(n_blk * bpb)},
+           "gpu_launches": int(launches), "clocks": sampler.summary(),
+           "roofline": {"bound": "hbm", "kernel": "pack_color_element_kernel (level 0)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": achieved / peak_gbs, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                        "note": "issue-slot bound integer kernel: algorithmic HBM bytes are 72 B/block; see DESIGN.md and profiles/ for pipe utilisation",
+                        "blocks_per_s": top_blocks / (top_ms / 1e3), "ms": top_ms}}
+    if not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = run_cpu_baseline(wl)[0]
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

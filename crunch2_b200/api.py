@@ -1,0 +1,169 @@
+"""Host-side binding of the C-ABI library (include/crn_b200.h) -- the call a user makes.
+
+Mirrors the reference's interface for the path:
+  * `Context.pack_image`  <->  crnlib::dxt_image::init(fmt, image, pack_params)
+    (reference crnlib/crn_dxt_image.cpp:447-493), same formats, same knobs (`PackParams` mirrors
+    dxt_image::pack_params, crnlib/crn_dxt_image.h:166-228), same block layout, results equal to
+    the reference with endpoint caching disabled.
+Errors: the reference returns false/NULL; here a `CrnGpuError` carries the library's status and
+message.  The product path never touches oracle/ and refuses the g++ emulation build.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+FMT_DXT1, FMT_DXT1A, FMT_DXT3, FMT_DXT5, FMT_DXT5A, FMT_DXN_XY, FMT_DXN_YX = range(7)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class CrnGpuError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("crn_gpu status %d: %s" % (status, message))
+        self.status = status
+
+
+class _PackParams(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("dxt_quality", ctypes.c_uint32), ("perceptual", ctypes.c_uint32),
+                ("use_both_block_types", ctypes.c_uint32), ("dxt1a_alpha_threshold", ctypes.c_uint32),
+                ("use_transparent_indices_for_black", ctypes.c_uint32), ("grayscale_sampling", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32 * 5)]
+
+
+class PackParams:
+    """dxt_image::pack_params for the block-by-block path (defaults of crn_comp_params::clear())."""
+
+    def __init__(self, dxt_quality=4, perceptual=True, use_both_block_types=True, dxt1a_alpha_threshold=128,
+                 use_transparent_indices_for_black=False, grayscale_sampling=False):
+        self.dxt_quality = dxt_quality
+        self.perceptual = perceptual
+        self.use_both_block_types = use_both_block_types
+        self.dxt1a_alpha_threshold = dxt1a_alpha_threshold
+        self.use_transparent_indices_for_black = use_transparent_indices_for_black
+        self.grayscale_sampling = grayscale_sampling
+
+    def _c(self):
+        p = _PackParams()
+        p.struct_size = ctypes.sizeof(_PackParams)
+        p.dxt_quality = int(self.dxt_quality)
+        p.perceptual = int(bool(self.perceptual))
+        p.use_both_block_types = int(bool(self.use_both_block_types))
+        p.dxt1a_alpha_threshold = int(self.dxt1a_alpha_threshold)
+        p.use_transparent_indices_for_black = int(bool(self.use_transparent_indices_for_black))
+        p.grayscale_sampling = int(bool(self.grayscale_sampling))
+        return p
+
+
+def library_path():
+    return os.path.join(_HERE, "libcrn_b200.so")
+
+
+def _declare(lib):
+    vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
+    lib.crn_gpu_abi_version.restype = u32
+    lib.crn_gpu_is_native.restype = i32
+    lib.crn_gpu_device_count.restype = i32
+    lib.crn_gpu_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.crn_gpu_destroy.argtypes = [vp]
+    lib.crn_gpu_destroy.restype = None
+    lib.crn_gpu_last_error.argtypes = [vp]
+    lib.crn_gpu_last_error.restype = ctypes.c_char_p
+    lib.crn_gpu_stream.argtypes = [vp]
+    lib.crn_gpu_stream.restype = vp
+    lib.crn_gpu_synchronize.argtypes = [vp]
+    lib.crn_gpu_launch_count.argtypes = [vp]
+    lib.crn_gpu_launch_count.restype = ctypes.c_uint64
+    lib.crn_gpu_bytes_per_block.argtypes = [u32]
+    lib.crn_gpu_bytes_per_block.restype = u32
+    lib.crn_gpu_pack_image.argtypes = [vp, u32, ctypes.POINTER(_PackParams), vp, u32, u32, u32, vp]
+    lib.crn_gpu_pack_image_host.argtypes = [vp, u32, ctypes.POINTER(_PackParams), vp, u32, u32, u32, vp]
+    return lib
+
+
+def load_library(path=None):
+    """Loads the nvcc-built libcrn_b200.so.  Fails loudly: no emulation build, no CPU path."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or library_path()
+    if not os.path.exists(p):
+        raise CrnGpuError(-1, "%s is missing: build it with `make -C crunch2_b200/csrc` (nvcc, sm_100a); "
+                              "there is no CPU fallback" % p)
+    lib = _declare(ctypes.CDLL(p))
+    if not lib.crn_gpu_is_native():
+        raise CrnGpuError(-4, "%s is the g++ SIMT-emulation test build, not the product" % p)
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def bytes_per_block(fmt):
+    return 8 if fmt in (FMT_DXT1, FMT_DXT1A, FMT_DXT5A) else 16
+
+
+def _devptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One GPU + one stream (crn_gpu_ctx).  `lib` lets the tests drive the emulation build."""
+
+    def __init__(self, device=0, lib=None):
+        self._lib = lib if lib is not None else load_library()
+        self._ctx = ctypes.c_void_p()
+        rc = self._lib.crn_gpu_create(int(device), ctypes.byref(self._ctx))
+        if rc != 0:
+            self._ctx = None
+            raise CrnGpuError(rc, "crn_gpu_create(device=%d) failed (no CUDA device?)" % device)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.crn_gpu_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CrnGpuError(rc, (self._lib.crn_gpu_last_error(self._ctx) or b"").decode())
+
+    @property
+    def stream(self):
+        return self._lib.crn_gpu_stream(self._ctx)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.crn_gpu_launch_count(self._ctx))
+
+    def synchronize(self):
+        self._check(self._lib.crn_gpu_synchronize(self._ctx))
+
+    # --- block-by-block packing (dxt_image::init) -------------------------------------------------
+    def pack_image(self, fmt, rgba, params=None):
+        """rgba: (H, W, 4) uint8 numpy array (host; copies are part of the call).  Returns the packed
+        blocks as a uint8 numpy array of blocks_y*blocks_x*bytes_per_block bytes."""
+        params = params or PackParams()
+        a = np.ascontiguousarray(rgba, dtype=np.uint8)
+        if a.ndim != 3 or a.shape[2] != 4:
+            raise ValueError("expected an (H, W, 4) uint8 image")
+        h, w = a.shape[:2]
+        out = np.empty(((w + 3) // 4) * ((h + 3) // 4) * bytes_per_block(fmt), np.uint8)
+        cp = params._c()
+        self._check(self._lib.crn_gpu_pack_image_host(self._ctx, fmt, ctypes.byref(cp), a.ctypes.data_as(ctypes.c_void_p),
+                                                       w, h, w * 4, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def pack_image_device(self, fmt, d_rgba, width, height, pitch, d_out, params=None):
+        """Asynchronous, device pointers (ints or objects with data_ptr()) on this context's stream."""
+        params = params or PackParams()
+        cp = params._c()
+        src = _devptr(d_rgba) if hasattr(d_rgba, "data_ptr") else ctypes.c_void_p(int(d_rgba))
+        dst = _devptr(d_out) if hasattr(d_out, "data_ptr") else ctypes.c_void_p(int(d_out))
+        self._check(self._lib.crn_gpu_pack_image(self._ctx, fmt, ctypes.byref(cp), src, width, height, pitch, dst))

@@ -19,6 +19,12 @@ extern "C" {
 
 #define CRN_B200_ABI_VERSION 1
 
+#if defined(CRN_B200_BUILD) && defined(__GNUC__)
+#define CRN_API __attribute__((visibility("default")))
+#else
+#define CRN_API
+#endif
+
 typedef enum crn_gpu_status {
     CRN_GPU_OK = 0,
     CRN_GPU_ERR_NO_DEVICE = -1,
@@ -58,20 +64,20 @@ typedef struct crn_gpu_pack_params {
 typedef struct crn_gpu_ctx crn_gpu_ctx;
 
 /* Library / device ---------------------------------------------------------------------------- */
-uint32_t crn_gpu_abi_version(void);
+CRN_API uint32_t crn_gpu_abi_version(void);
 /* 1 when the library was compiled by nvcc for sm_100a, 0 for the g++ SIMT-emulation test build. */
-int crn_gpu_is_native(void);
-int crn_gpu_device_count(void);
-int crn_gpu_create(int device, crn_gpu_ctx** out_ctx);
-void crn_gpu_destroy(crn_gpu_ctx* ctx);
-const char* crn_gpu_last_error(const crn_gpu_ctx* ctx);
+CRN_API int crn_gpu_is_native(void);
+CRN_API int crn_gpu_device_count(void);
+CRN_API int crn_gpu_create(int device, crn_gpu_ctx** out_ctx);
+CRN_API void crn_gpu_destroy(crn_gpu_ctx* ctx);
+CRN_API const char* crn_gpu_last_error(const crn_gpu_ctx* ctx);
 /* The context's cudaStream_t (as void*), so a caller can order its own copies / events on it. */
-void* crn_gpu_stream(crn_gpu_ctx* ctx);
-int crn_gpu_synchronize(crn_gpu_ctx* ctx);
+CRN_API void* crn_gpu_stream(crn_gpu_ctx* ctx);
+CRN_API int crn_gpu_synchronize(crn_gpu_ctx* ctx);
 /* Kernels launched through this context since creation (bench.py reports it as gpu_launches). */
-uint64_t crn_gpu_launch_count(const crn_gpu_ctx* ctx);
-void crn_gpu_default_pack_params(crn_gpu_pack_params* p);
-uint32_t crn_gpu_bytes_per_block(uint32_t format);
+CRN_API uint64_t crn_gpu_launch_count(const crn_gpu_ctx* ctx);
+CRN_API void crn_gpu_default_pack_params(crn_gpu_pack_params* p);
+CRN_API uint32_t crn_gpu_bytes_per_block(uint32_t format);
 
 /* Block-by-block packing ------------------------------------------------
  * Replaces dxt_image::init / init_task / set_block_pixels for the CRN compressor
@@ -80,10 +86,10 @@ uint32_t crn_gpu_bytes_per_block(uint32_t format);
  * d_rgba: row-major RGBA8 (r first), `pitch_bytes` per row; blocks are gathered with edge clamping.
  * d_out: ((w+3)/4)*((h+3)/4) blocks of crn_gpu_bytes_per_block(format), row-major, alpha element first.
  * Asynchronous on the context's stream. */
-int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
+CRN_API int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                        const void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, void* d_out);
 /* Same through host buffers: H2D copy, kernels, D2H copy, synchronised on return. */
-int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
+CRN_API int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                             const void* h_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, void* h_out);
 
 #ifdef __cplusplus

@@ -140,8 +140,9 @@ inline bool try_complete_warp(Fiber* f)
         Fiber& g = c.fibers[t];
         if (g.state == DONE) die("collective mask names an exited lane");
         if (g.state != WAIT_WARP) return false;
-        if (g.mask != mask) die("lanes waiting with different member masks (divergent collective)");
-        if (g.op != f->op) die("lanes waiting on different collective operations");
+        // a member may still be parked at an EARLIER collective with a different mask / op (it will get
+        // here once that one completes); a genuine mismatch ends up in the deadlock detector.
+        if (g.mask != mask || g.op != f->op) return false;
     }
     c.collectives++;
     // all members present: compute results
