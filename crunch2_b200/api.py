@@ -87,7 +87,7 @@ def load_library(path=None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    p = path or library_path()
+    p = path or os.environ.get("CRN_B200_LIB") or library_path()   # CRN_B200_LIB: A/B builds of the same sources
     if not os.path.exists(p):
         raise CrnGpuError(-1, "%s is missing: build it with `make -C crunch2_b200/csrc` (nvcc, sm_100a); "
                               "there is no CPU fallback" % p)

@@ -19,6 +19,7 @@ struct crn_gpu_ctx {
     // reusable device staging for the *_host entry points
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
+    void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
 };
 
 namespace {
@@ -105,6 +106,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_state) cudaFree(ctx->d_state);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -173,6 +175,7 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
         CRN_LAUNCH(crn::pack_alpha_element_kernel, grid, threads, 0, ctx->stream, img, comp, q, both, out, bpb, ofs);
         ctx->launches++;
     };
+    int color_rc = CRN_GPU_OK;
     auto launch_color = [&](uint32_t ofs) {
         crn::Dxt1Params dp;
         dp.quality = q;
@@ -184,8 +187,22 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
         dp.grayscale_sampling = params->grayscale_sampling ? 1 : 0;
         dp.alpha_threshold = params->dxt1a_alpha_threshold;
         const int dxt1a = format == CRN_GPU_FMT_DXT1A;
-        CRN_LAUNCH(crn::pack_color_element_kernel, grid, threads, 0, ctx->stream, img, dp, dxt1a, out, bpb, ofs);
-        ctx->launches++;
+        // five phase kernels per chunk of blocks; the per-block state lives in ctx->d_state between them
+        const uint32_t chunk_cap = 1u << 18;
+        const uint32_t chunk = total < chunk_cap ? total : chunk_cap;
+        color_rc = ensure(ctx, &ctx->d_state, &ctx->d_state_cap, (size_t)chunk * sizeof(crn::Dxt1BlockState));
+        if (color_rc) return;
+        crn::Dxt1BlockState* st = static_cast<crn::Dxt1BlockState*>(ctx->d_state);
+        for (uint32_t first = 0; first < total; first += chunk) {
+            const uint32_t count = total - first < chunk ? total - first : chunk;
+            const int g = grid_for(ctx, count, crn::kPackWarpsPerCta, 8);
+            CRN_LAUNCH(crn::pack_color_phase_kernel<0>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
+            CRN_LAUNCH(crn::pack_color_phase_kernel<1>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
+            CRN_LAUNCH(crn::pack_color_phase_kernel<2>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
+            CRN_LAUNCH(crn::pack_color_phase_kernel<3>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
+            CRN_LAUNCH(crn::pack_color_phase_kernel<4>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
+            ctx->launches += 5;
+        }
     };
 
     switch (format) {
@@ -203,6 +220,7 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
     case CRN_GPU_FMT_DXN_YX: launch_alpha(1, 0); launch_alpha(0, 8); break;
     default: break;
     }
+    if (color_rc) return color_rc;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
 }

@@ -40,18 +40,32 @@ struct Dxt1Params {
     unsigned alpha_threshold;
 };
 
-struct Dxt1Scratch {           // per-warp shared memory
+struct Dxt1Best {              // warp-uniform
+    unsigned long long err;
+    unsigned lo, hi;
+    int alpha_block, alt_round, enforce, enforced_sel;
+};
+
+// Block state that travels between the phase kernels (global memory, 352 bytes per block).  The
+// optimiser is split into five kernels (set-up / LBG / sweep passes / post passes / finish) because one
+// fused kernel is ~11 K SASS instructions: with every warp of an SM in a different phase the
+// instruction caches thrash (ncu: 59 % of stall samples "no_instructions", profiles/r1c).  Each phase
+// kernel's hot code fits the 32 KB L1.5 instruction cache; the state round trip costs 0.7 KB of HBM
+// traffic per block and phase boundary, i.e. microseconds.
+struct Dxt1BlockState {
     int4 cw[16];               // unique colour i: r, g, b, weight (first-appearance order)
+    Dxt1Best best;             // running best solution (warp-uniform; written by lane 0)
+    float mean[3], axis[3], low[3], high[3];   // m_mean_norm_color, m_principle_axis, projected endpoints
+    int U, total_w, pixels_have_alpha, stage;  // stage: 0 optimise, 1 solved during set-up, 2 fully transparent
+};
+
+struct Dxt1Scratch : Dxt1BlockState {          // per-warp shared memory
+    int4 ce[16];               // unique colour i in evaluation form: 2wr*r, 2wg*g, 2wb*b, C2 (see eval_colour)
     uint16_t probe[2][32];     // sweep candidates for the low / high endpoint
     uint16_t packed[64];       // combinatorial-recovery endpoint list
     uint8_t sel[16];           // selectors of the current best per unique colour
 };
-
-struct Dxt1Best {              // warp-uniform
-    unsigned lo, hi;
-    unsigned long long err;
-    int alpha_block, alt_round, enforce, enforced_sel;
-};
+constexpr int kDxt1StateVec4 = (int)(sizeof(Dxt1BlockState) / 16);
 
 struct Dxt1Cfg {               // warp-uniform evaluation mode
     int U;
@@ -79,7 +93,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // static_cast<int>(double) as x86-64 cvttsd2si does it (out of range -> INT_MIN); CUDA would saturate.
 __device__ __forceinline__ int d2i_x86(double x) { return (x > -2147483649.0 && x < 2147483648.0) ? (int)x : (int)0x80000000; }
 
-__device__ __forceinline__ unsigned dxt1_dist(const Dxt1Cfg& cfg, int r, int g, int b, int pr, int pg, int pb)
+__device__ __forceinline__ unsigned dxt1_dist(const Dxt1Cfg cfg, int r, int g, int b, int pr, int pg, int pb)
 {
     if (cfg.gray) {   // crn_dxt1.cpp:1348-1363 with color::RGB_to_Y (crn_color.h:788-796)
         int y0 = (r * 19595 + g * 38470 + b * 7471 + 32768) >> 16;
@@ -91,63 +105,101 @@ __device__ __forceinline__ unsigned dxt1_dist(const Dxt1Cfg& cfg, int r, int g, 
     return (unsigned)(cfg.wr * dr * dr + cfg.wg * dg * dg + cfg.wb * db * db);
 }
 
+// Evaluation form of the colour distance.  color_distance (crn_color.h:720-745) is
+//   d(c,p) = wr*(cr-pr)^2 + wg*(cg-pg)^2 + wb*(cb-pb)^2 = C2(c) + P2(p) - (2wr*cr*pr + 2wg*cg*pg + 2wb*cb*pb)
+// (grayscale sampling, crn_dxt1.cpp:1348-1363: d = (Y(c)-Y(p))^2, the same shape in one dimension).
+// C2 does not depend on the palette entry, so min_k d(c,p_k) = C2 + min_k (P2_k - dot_k): three integer
+// multiply-adds per palette entry instead of eight, exactly the same integers.
+__device__ __forceinline__ int rgb_to_y(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 32768) >> 16; }
+__device__ __forceinline__ int4 eval_colour(const Dxt1Cfg cfg, int r, int g, int b)
+{   // (2wr*r, 2wg*g, 2wb*b, C2)
+    if (cfg.gray) { const int y = rgb_to_y(r, g, b); return make_int4(2 * y, 0, 0, y * y); }
+    return make_int4(2 * cfg.wr * r, 2 * cfg.wg * g, 2 * cfg.wb * b, cfg.wr * r * r + cfg.wg * g * g + cfg.wb * b * b);
+}
+__device__ __forceinline__ int4 eval_palette(const Dxt1Cfg cfg, int r, int g, int b)
+{   // (pr, pg, pb, P2)
+    if (cfg.gray) { const int y = rgb_to_y(r, g, b); return make_int4(y, 0, 0, y * y); }
+    return make_int4(r, g, b, cfg.wr * r * r + cfg.wg * g * g + cfg.wb * b * b);
+}
+__device__ __forceinline__ int eval_dprime(const int4 c, const int4 p) { return p.w - c.x * p.x - c.y * p.y - c.z * p.z; }
+
+template <bool DO4, bool DO3>
+__device__ __forceinline__ void dxt1_eval_loop(const Dxt1Scratch* sc, int U, const int4 p0, const int4 p1, const int4 p2, const int4 p3,
+                                               const int4 pm, unsigned long long& e4, unsigned long long& e3)
+{
+    e4 = 0; e3 = 0;
+#pragma unroll 2
+    for (int i = 0; i < U; i++) {
+        const int4 c = sc->ce[i];
+        const unsigned w = (unsigned)sc->cw[i].w;
+        const int d01 = min(eval_dprime(c, p0), eval_dprime(c, p1));
+        if (DO4) {
+            const int d = min(d01, min(eval_dprime(c, p2), eval_dprime(c, p3)));
+            e4 += (unsigned long long)(unsigned)(d + c.w) * w;
+        }
+        if (DO3) {
+            const int d = min(d01, eval_dprime(c, pm));
+            e3 += (unsigned long long)(unsigned)(d + c.w) * w;
+        }
+    }
+}
+
 // Lane-private evaluation of one candidate: evaluate_solution_uber / _hc_* without the bookkeeping
 // (crn_dxt1.cpp:1370-1561, :1759-1835).  err = min over allowed block types, alpha = 3-colour won.
-__device__ __forceinline__ void dxt1_eval(const Dxt1Scratch* sc, const Dxt1Cfg& cfg, unsigned lo, unsigned hi, int alt,
-                                          unsigned long long& err, int& alpha)
+__device__ __noinline__ void dxt1_eval(Dxt1Scratch* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
+                                       unsigned long long& err, int& alpha)
 {
     int r0, g0, b0, r1, g1, b1;
     unpack565(lo, true, r0, g0, b0);
     unpack565(hi, true, r1, g1, b1);
-    const int r2 = (r0 * 2 + r1 + alt) / 3, g2 = (g0 * 2 + g1 + alt) / 3, b2 = (b0 * 2 + b1 + alt) / 3;
-    const int r3 = (r1 * 2 + r0 + alt) / 3, g3 = (g1 * 2 + g0 + alt) / 3, b3 = (b1 * 2 + b0 + alt) / 3;
-    const int rm = (r0 + r1 + alt) >> 1, gm = (g0 + g1 + alt) >> 1, bm = (b0 + b1 + alt) >> 1;
-    unsigned long long e4 = 0, e3 = 0;
-    for (int i = 0; i < cfg.U; i++) {
-        const int4 c = sc->cw[i];
-        const unsigned d0 = dxt1_dist(cfg, c.x, c.y, c.z, r0, g0, b0);
-        const unsigned d1 = dxt1_dist(cfg, c.x, c.y, c.z, r1, g1, b1);
-        const unsigned d01 = min(d0, d1);
-        if (cfg.do4) {
-            const unsigned d2 = dxt1_dist(cfg, c.x, c.y, c.z, r2, g2, b2);
-            const unsigned d3 = dxt1_dist(cfg, c.x, c.y, c.z, r3, g3, b3);
-            e4 += (unsigned long long)min(d01, min(d2, d3)) * (unsigned)c.w;
-        }
-        if (cfg.do3) {
-            const unsigned dm = dxt1_dist(cfg, c.x, c.y, c.z, rm, gm, bm);
-            e3 += (unsigned long long)min(d01, dm) * (unsigned)c.w;
-        }
+    const int4 p0 = eval_palette(cfg, r0, g0, b0), p1 = eval_palette(cfg, r1, g1, b1);
+    const int4 p2 = eval_palette(cfg, (r0 * 2 + r1 + alt) / 3, (g0 * 2 + g1 + alt) / 3, (b0 * 2 + b1 + alt) / 3);
+    const int4 p3 = eval_palette(cfg, (r1 * 2 + r0 + alt) / 3, (g1 * 2 + g0 + alt) / 3, (b1 * 2 + b0 + alt) / 3);
+    const int4 pm = eval_palette(cfg, (r0 + r1 + alt) >> 1, (g0 + g1 + alt) >> 1, (b0 + b1 + alt) >> 1);
+    unsigned long long e4, e3;
+    if (cfg.do4 && cfg.do3) {
+        dxt1_eval_loop<true, true>(sc, cfg.U, p0, p1, p2, p3, pm, e4, e3);
+        alpha = e3 < e4; err = alpha ? e3 : e4;
+    } else if (cfg.do4) {
+        dxt1_eval_loop<true, false>(sc, cfg.U, p0, p1, p2, p3, pm, e4, e3);
+        alpha = 0; err = e4;
+    } else {
+        dxt1_eval_loop<false, true>(sc, cfg.U, p0, p1, p2, p3, pm, e4, e3);
+        alpha = 1; err = e3;
     }
-    if (cfg.do4 && cfg.do3) { alpha = e3 < e4; err = alpha ? e3 : e4; }
-    else if (cfg.do4) { alpha = 0; err = e4; }
-    else { alpha = 1; err = e3; }
 }
 
 // Commit candidate (lo, hi, alt) with error e / block type alpha as the new best, applying the
 // degenerate-endpoint fix-up of crn_dxt1.cpp:1563-1583 / :1781-1794.
-__device__ __forceinline__ void dxt1_accept(Dxt1Best& best, unsigned lo, unsigned hi, int alt, unsigned long long e, int alpha)
+__device__ __forceinline__ void dxt1_accept(Dxt1Scratch* sc, unsigned lo, unsigned hi, int alt, unsigned long long e, int alpha)
 {
-    best.lo = lo; best.hi = hi; best.err = e; best.alpha_block = alpha; best.alt_round = alt;
-    best.enforce = !alpha && lo == hi;
-    if (best.enforce) {
-        if ((best.lo & 31u) != 31u) { best.lo++; best.enforced_sel = 1; }
-        else { best.hi--; best.enforced_sel = 0; }
+    __syncwarp();                       // every lane has finished reading the previous best
+    if (lane_id() == 0) {
+        Dxt1Best nb;
+        nb.lo = lo; nb.hi = hi; nb.err = e; nb.alpha_block = alpha; nb.alt_round = alt; nb.enforced_sel = 0;
+        nb.enforce = !alpha && lo == hi;
+        if (nb.enforce) {
+            if ((nb.lo & 31u) != 31u) { nb.lo++; nb.enforced_sel = 1; }
+            else { nb.hi--; nb.enforced_sel = 0; }
+        }
+        sc->best = nb;
     }
+    __syncwarp();
 }
 
 // Static batch: every lane may hold one candidate (valid) whose sequence order is the lane index.
 // Returns true if the best improved.
-__device__ __forceinline__ bool dxt1_commit_static(const Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best,
+__device__ __noinline__ bool dxt1_commit_static(Dxt1Scratch* sc, const Dxt1Cfg cfg,
                                                    bool valid, unsigned lo, unsigned hi, int alt)
 {
     unsigned long long e = ~0ull; int alpha = 0;
     if (valid) dxt1_eval(sc, cfg, lo, hi, alt, e, alpha);
     unsigned long long key = e; unsigned idx = lane_id();
     warp_argmin_u64(key, idx);
-    if (key >= best.err) return false;
+    if (key >= sc->best.err) return false;
     const unsigned wlo = __shfl_sync(CRN_FULL_MASK, lo, idx), whi = __shfl_sync(CRN_FULL_MASK, hi, idx);
     const int walpha = __shfl_sync(CRN_FULL_MASK, alpha, idx);
-    dxt1_accept(best, wlo, whi, alt, key, walpha);
+    dxt1_accept(sc, wlo, whi, alt, key, walpha);
     return true;
 }
 
@@ -158,23 +210,23 @@ __device__ __forceinline__ void canon(unsigned& lo, unsigned& hi)
 
 // Selectors of the current best for every unique colour -> sc->sel (first minimum in palette order;
 // crn_dxt1.cpp:1407-1441 and :1845-1869 agree on ties).
-__device__ __forceinline__ void dxt1_best_selectors(Dxt1Scratch* sc, const Dxt1Cfg& cfg, const Dxt1Best& best)
+__device__ __noinline__ void dxt1_best_selectors(Dxt1Scratch* sc, const Dxt1Cfg cfg)
 {
     const unsigned lane = lane_id();
     if ((int)lane < cfg.U) {
         unsigned s;
-        if (best.enforce) s = (unsigned)best.enforced_sel;
+        if (sc->best.enforce) s = (unsigned)sc->best.enforced_sel;
         else {
             int r0, g0, b0, r1, g1, b1;
-            unpack565(best.lo, true, r0, g0, b0);
-            unpack565(best.hi, true, r1, g1, b1);
-            const int alt = best.alt_round;
+            unpack565(sc->best.lo, true, r0, g0, b0);
+            unpack565(sc->best.hi, true, r1, g1, b1);
+            const int alt = sc->best.alt_round;
             const int4 c = sc->cw[lane];
             unsigned be = dxt1_dist(cfg, c.x, c.y, c.z, r0, g0, b0);
             s = 0;
             unsigned e = dxt1_dist(cfg, c.x, c.y, c.z, r1, g1, b1);
             if (e < be) { be = e; s = 1; }
-            if (best.alpha_block) {
+            if (sc->best.alpha_block) {
                 e = dxt1_dist(cfg, c.x, c.y, c.z, (r0 + r1 + alt) >> 1, (g0 + g1 + alt) >> 1, (b0 + b1 + alt) >> 1);
                 if (e < be) { be = e; s = 2; }
             } else {
@@ -190,9 +242,9 @@ __device__ __forceinline__ void dxt1_best_selectors(Dxt1Scratch* sc, const Dxt1C
 }
 
 // refine_solution (crn_dxt1.cpp:525-698), levels 0 and 1.
-__device__ __forceinline__ bool dxt1_refine(Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best, int level)
+__device__ __noinline__ bool dxt1_refine(Dxt1Scratch* sc, const Dxt1Cfg cfg, int level)
 {
-    dxt1_best_selectors(sc, cfg, best);
+    dxt1_best_selectors(sc, cfg);
     double akku_0 = 0, akku_1 = 0, akku_2 = 0;
     double At1_r = 0, At1_g = 0, At1_b = 0, At2_r = 0, At2_g = 0, At2_b = 0;
     for (int i = 0; i < cfg.U; i++) {
@@ -225,7 +277,7 @@ __device__ __forceinline__ bool dxt1_refine(Dxt1Scratch* sc, const Dxt1Cfg& cfg,
         unsigned mx = (unsigned)((e0[0] << 11) | (e0[1] << 5) | e0[2]);
         unsigned mn = (unsigned)((e1[0] << 11) | (e1[1] << 5) | e1[2]);
         canon(mn, mx);
-        improved |= dxt1_commit_static(sc, cfg, best, lane_id() == 0, mn, mx, 0);
+        improved |= dxt1_commit_static(sc, cfg, lane_id() == 0, mn, mx, 0);
     } else {
         // 2 x 27 lattice neighbours, sequence = i*27 + (rr+1)*9 + (gr+1)*3 + (br+1)
 #pragma unroll 1
@@ -239,7 +291,7 @@ __device__ __forceinline__ bool dxt1_refine(Dxt1Scratch* sc, const Dxt1Cfg& cfg,
             else { c0[0] = clampi(c0[0] + rr, 0, 31); c0[1] = clampi(c0[1] + gr, 0, 63); c0[2] = clampi(c0[2] + br, 0, 31); }
             unsigned lo = pack565_unscaled(c0[0], c0[1], c0[2]), hi = pack565_unscaled(c1[0], c1[1], c1[2]);
             canon(lo, hi);
-            improved |= dxt1_commit_static(sc, cfg, best, valid, lo, hi, 0);
+            improved |= dxt1_commit_static(sc, cfg, valid, lo, hi, 0);
         }
     }
     return improved;
@@ -268,7 +320,7 @@ __device__ __forceinline__ float v3_sqdist(const V3& a, const V3& b)
     d = a.z - b.z; d2 += d * d;
     return d2;
 }
-__device__ __forceinline__ V3 norm_color(const Dxt1Scratch* sc, int i, const V3& mean)
+__device__ __forceinline__ V3 norm_color(Dxt1Scratch* sc, int i, const V3& mean)
 {   // m_norm_unique_colors[i] (crn_dxt1.cpp:168, :186)
     const int4 c = sc->cw[i];
     V3 v;
@@ -279,7 +331,7 @@ __device__ __forceinline__ V3 norm_color(const Dxt1Scratch* sc, int i, const V3&
 }
 
 // try_median4 (crn_dxt1.cpp:1181-1308)
-__device__ __forceinline__ bool dxt1_median4(Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best, int quality,
+__device__ __noinline__ bool dxt1_median4(Dxt1Scratch* sc, const Dxt1Cfg cfg, int quality,
                                              const V3& mean, const V3& low_color, const V3& high_color)
 {
     V3 means[4];
@@ -362,9 +414,9 @@ __device__ __forceinline__ bool dxt1_median4(Dxt1Scratch* sc, const Dxt1Cfg& cfg
         const int c0 = clampi((int)floorf(.5f + v1x * 31.0f), 0, 255), c1 = clampi((int)floorf(.5f + v1y * 63.0f), 0, 255), c2 = clampi((int)floorf(.5f + v1z * 31.0f), 0, 255);
         unsigned lo = pack565_unscaled(a0, a1, a2), hi = pack565_unscaled(c0, c1, c2);
         canon(lo, hi);
-        improved |= dxt1_commit_static(sc, cfg, best, lane < 6, lo, hi, 0);
+        improved |= dxt1_commit_static(sc, cfg, lane < 6, lo, hi, 0);
     }
-    improved |= dxt1_refine(sc, cfg, best, quality == 4 ? 1 : 0);
+    improved |= dxt1_refine(sc, cfg, quality == 4 ? 1 : 0);
     return improved;
 }
 
@@ -372,11 +424,11 @@ __device__ __forceinline__ bool dxt1_median4(Dxt1Scratch* sc, const Dxt1Cfg& cfg
 // (0 = low, 1 = high); the other endpoint is read from the live best (crn_dxt1.cpp:908-1015).
 // delta(idx, dr, dg, db) supplies candidate idx's offset.
 template <typename DeltaFn>
-__device__ __forceinline__ void dxt1_live_neighbours(const Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best, int which,
+__device__ __noinline__ void dxt1_live_neighbours(Dxt1Scratch* sc, const Dxt1Cfg cfg, int which,
                                                      int ncand, DeltaFn delta)
 {
     int cr, cg, cb;
-    unpack565(which ? best.hi : best.lo, false, cr, cg, cb);
+    unpack565(which ? sc->best.hi : sc->best.lo, false, cr, cg, cb);
     int pos = 0;
     while (pos < ncand) {
         const int idx = pos + (int)lane_id();
@@ -387,23 +439,23 @@ __device__ __forceinline__ void dxt1_live_neighbours(const Dxt1Scratch* sc, cons
         valid = valid && r >= 0 && r <= 31 && g >= 0 && g <= 63 && b >= 0 && b <= 31;
         unsigned lo, hi;
         const unsigned p = pack565_unscaled(max(r, 0), max(g, 0), max(b, 0));
-        if (which) { lo = best.lo; hi = p; } else { lo = p; hi = best.hi; }
+        if (which) { lo = sc->best.lo; hi = p; } else { lo = p; hi = sc->best.hi; }
         canon(lo, hi);
         unsigned long long e = ~0ull; int alpha = 0;
         if (valid) dxt1_eval(sc, cfg, lo, hi, 0, e, alpha);
-        const unsigned m = __ballot_sync(CRN_FULL_MASK, valid && e < best.err);
+        const unsigned m = __ballot_sync(CRN_FULL_MASK, valid && e < sc->best.err);
         if (!m) { pos += 32; continue; }
         const int t = __ffs((int)m) - 1;
         const unsigned long long we = __shfl_sync(CRN_FULL_MASK, e, t);
         const unsigned wlo = __shfl_sync(CRN_FULL_MASK, lo, t), whi = __shfl_sync(CRN_FULL_MASK, hi, t);
         const int wa = __shfl_sync(CRN_FULL_MASK, alpha, t);
-        dxt1_accept(best, wlo, whi, 0, we, wa);
+        dxt1_accept(sc, wlo, whi, 0, we, wa);
         pos = pos + t + 1;
     }
 }
 
 // try_average_block_as_solid (crn_dxt1.cpp:93-153)
-__device__ __forceinline__ bool dxt1_try_solid(const Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best, const Dxt1Params& prm)
+__device__ __noinline__ bool dxt1_try_solid(Dxt1Scratch* sc, const Dxt1Cfg cfg, const Dxt1Params& prm)
 {
     unsigned long long tot_r = 0, tot_g = 0, tot_b = 0;
     unsigned total_weight = 0;
@@ -437,7 +489,7 @@ __device__ __forceinline__ bool dxt1_try_solid(const Dxt1Scratch* sc, const Dxt1
             lo = ((unsigned)g_omatch5[2 * r] << 11) | ((unsigned)g_omatch6[2 * g] << 5) | g_omatch5[2 * b];
             hi = ((unsigned)g_omatch5[2 * r + 1] << 11) | ((unsigned)g_omatch6[2 * g + 1] << 5) | g_omatch5[2 * b + 1];
         }
-        improved |= dxt1_commit_static(sc, cfg, best, valid, lo, hi, 0);
+        improved |= dxt1_commit_static(sc, cfg, valid, lo, hi, 0);
     }
     return improved;
 }
@@ -451,7 +503,7 @@ __device__ __forceinline__ unsigned long long comp_err(const CompMoments& m, int
     return m.W[s] * p * p - m.WP2[s] * p + m.WPP[s];
 }
 __device__ __forceinline__ unsigned expand_comp(int comp, unsigned c) { return comp == 1 ? ((c << 2) | (c >> 4)) : ((c << 3) | (c >> 2)); }
-__device__ __forceinline__ void comp_moments(const Dxt1Scratch* sc, const Dxt1Cfg& cfg, int comp, CompMoments& m)
+__device__ __noinline__ void comp_moments(Dxt1Scratch* sc, const Dxt1Cfg cfg, int comp, CompMoments& m)
 {
 #pragma unroll
     for (int s = 0; s < 4; s++) m.W[s] = m.WP2[s] = m.WPP[s] = 0;
@@ -479,21 +531,21 @@ __device__ __forceinline__ void comp_moments(const Dxt1Scratch* sc, const Dxt1Cf
 }
 
 // optimize_endpoint_comps (crn_dxt1.cpp:415-486)
-__device__ __forceinline__ void dxt1_optimize_comps(Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best)
+__device__ __noinline__ void dxt1_optimize_comps(Dxt1Scratch* sc, const Dxt1Cfg cfg)
 {
-    dxt1_best_selectors(sc, cfg, best);
-    if (best.alpha_block || !best.err) return;
+    dxt1_best_selectors(sc, cfg);
+    if (sc->best.alpha_block || !sc->best.err) return;
     int sl[3], sh[3];
-    unpack565(best.lo, true, sl[0], sl[1], sl[2]);
-    unpack565(best.hi, true, sh[0], sh[1], sh[2]);
+    unpack565(sc->best.lo, true, sl[0], sl[1], sl[2]);
+    unpack565(sc->best.hi, true, sh[0], sh[1], sh[2]);
     const unsigned lane = lane_id();
 #pragma unroll 1
     for (int comp = 0; comp < 3; comp++) {
         unsigned p0 = (unsigned)(comp == 0 ? sl[0] : (comp == 1 ? sl[1] : sl[2]));
         unsigned p1 = (unsigned)(comp == 0 ? sh[0] : (comp == 1 ? sh[1] : sh[2]));
         int low[3], high[3];
-        unpack565(best.lo, false, low[0], low[1], low[2]);
-        unpack565(best.hi, false, high[0], high[1], high[2]);
+        unpack565(sc->best.lo, false, low[0], low[1], low[2]);
+        unpack565(sc->best.hi, false, high[0], high[1], high[2]);
         CompMoments m;
         comp_moments(sc, cfg, comp, m);
         const unsigned lowc = (unsigned)(comp == 0 ? low[0] : (comp == 1 ? low[1] : low[2]));
@@ -531,10 +583,10 @@ __device__ __forceinline__ void dxt1_optimize_comps(Dxt1Scratch* sc, const Dxt1C
                 unsigned long long ce; int ca;
                 const unsigned chi = pack565_unscaled(high[0], high[1], high[2]);
                 dxt1_eval(sc, cfg, packed_low, chi, 0, ce, ca);
-                if (ce >= best.err) continue;
-                dxt1_accept(best, packed_low, chi, 0, ce, ca);
-                if (!best.err) return;
-                dxt1_best_selectors(sc, cfg, best);
+                if (ce >= sc->best.err) continue;
+                dxt1_accept(sc, packed_low, chi, 0, ce, ca);
+                if (!sc->best.err) return;
+                dxt1_best_selectors(sc, cfg);
                 comp_moments(sc, cfg, comp, m);
                 best_error = comp_err(m, 0, expand_comp(comp, c0)) + comp_err(m, 1, expand_comp(comp, wc1)) +
                              comp_err(m, 2, (p0 * 2 + p1) / 3) + comp_err(m, 3, (p0 + p1 * 2) / 3);
@@ -556,7 +608,7 @@ __device__ __forceinline__ unsigned lerp_color_packed(const int4& a, const int4&
 }
 
 // try_combinatorial_encoding (crn_dxt1.cpp:1886-1997)
-__device__ __forceinline__ void dxt1_combinatorial(Dxt1Scratch* sc, const Dxt1Cfg& cfg, Dxt1Best& best)
+__device__ __noinline__ void dxt1_combinatorial(Dxt1Scratch* sc, const Dxt1Cfg cfg)
 {
     const int U = cfg.U;
     if (U < 2 || U > 4) return;
@@ -587,7 +639,7 @@ __device__ __forceinline__ void dxt1_combinatorial(Dxt1Scratch* sc, const Dxt1Cf
     const unsigned npairs = np * (np - 1) / 2;
 #pragma unroll 1
     for (int alt = 0; alt < 2; alt++) {
-        if (!best.err) break;
+        if (!sc->best.err) break;
         // per-lane running first-minimum over its pairs (sequence number k = i-major pair index)
         unsigned long long my_e = ~0ull; unsigned my_k = 0xffffffffu, my_lo = 0, my_hi = 0; int my_a = 0;
         unsigned i = 0, j = 1;
@@ -602,10 +654,10 @@ __device__ __forceinline__ void dxt1_combinatorial(Dxt1Scratch* sc, const Dxt1Cf
         unsigned long long key = my_e; unsigned idx = my_k;
         warp_argmin_u64(key, idx);
         // alt == 1: only a zero-error candidate is accepted (best error forced to 1, :1981-1996)
-        const unsigned long long bar = alt ? 1ull : best.err;
+        const unsigned long long bar = alt ? 1ull : sc->best.err;
         if (key < bar) {
             const unsigned src = idx & 31u;
-            dxt1_accept(best, __shfl_sync(CRN_FULL_MASK, my_lo, src), __shfl_sync(CRN_FULL_MASK, my_hi, src), alt, key,
+            dxt1_accept(sc, __shfl_sync(CRN_FULL_MASK, my_lo, src), __shfl_sync(CRN_FULL_MASK, my_hi, src), alt, key,
                         __shfl_sync(CRN_FULL_MASK, my_a, src));
         }
     }
@@ -624,22 +676,37 @@ __device__ __forceinline__ float pow275(float x)
     return (float)(d * d * s * q);
 }
 
-// 4x4 block: lanes 0..15 hold pixel 4y+x as RGBA8 (r in the low byte).  Returns the packed 8-byte DXT1
-// element (low565, high565, 16 x 2-bit selectors; crn_dxt.h:109-172) on every lane.
-__device__ __forceinline__ unsigned long long dxt1_pack_block(Dxt1Scratch* sc, uint32_t px, const Dxt1Params& prm)
+__device__ __forceinline__ Dxt1Cfg dxt1_make_cfg(const Dxt1Params& prm, int pixels_have_alpha, int U)
 {
-    const unsigned lane = lane_id();
     Dxt1Cfg cfg;
-    cfg.hc = prm.quality == 4 && !prm.pixels_have_alpha && !prm.force_alpha_blocks && !prm.use_alpha_blocks && !prm.grayscale_sampling;
+    cfg.U = U;
+    cfg.hc = prm.quality == 4 && !pixels_have_alpha && !prm.force_alpha_blocks && !prm.use_alpha_blocks && !prm.grayscale_sampling;
     const bool perceptual = prm.perceptual && !prm.grayscale_sampling;
     cfg.gray = !perceptual && prm.grayscale_sampling;
     cfg.wr = perceptual ? 8 : 1; cfg.wg = perceptual ? 25 : 1; cfg.wb = 1;
-    if (prm.pixels_have_alpha || prm.force_alpha_blocks) { cfg.do4 = false; cfg.do3 = true; }
+    if (pixels_have_alpha || prm.force_alpha_blocks) { cfg.do4 = false; cfg.do3 = true; }
     else if (!prm.use_alpha_blocks) { cfg.do4 = true; cfg.do3 = false; }
     else { cfg.do4 = true; cfg.do3 = true; }
+    return cfg;
+}
 
+// (re)build the evaluation form of the unique colours after a state load
+__device__ __forceinline__ void dxt1_build_eval_colours(Dxt1Scratch* sc, const Dxt1Cfg cfg)
+{
+    const unsigned lane = lane_id();
+    if ((int)lane < cfg.U) { const int4 c = sc->cw[lane]; sc->ce[lane] = eval_colour(cfg, c.x, c.y, c.z); }
+    __syncwarp();
+}
+
+// Phase 0 -- compute_internal up to the call of optimize_endpoints (crn_dxt1.cpp:2081-2232, :1069-1178).
+// lanes 0..15 hold pixel 4y+x as RGBA8 (r in the low byte).
+__device__ __forceinline__ void dxt1_phase_setup(Dxt1Scratch* sc, uint32_t px, const Dxt1Params& prm, int pixels_have_alpha)
+{
+    const unsigned lane = lane_id();
+    Dxt1Cfg cfg = dxt1_make_cfg(prm, pixels_have_alpha, 0);
+    const bool perceptual = prm.perceptual && !prm.grayscale_sampling;
     // ---- unique colours in first-appearance order (crn_dxt1.cpp:2113-2131)
-    const bool opaque = lane < 16 && (!prm.pixels_have_alpha || (px >> 24) >= prm.alpha_threshold);
+    const bool opaque = lane < 16 && (!pixels_have_alpha || (px >> 24) >= prm.alpha_threshold);
     const unsigned vmask = __ballot_sync(CRN_FULL_MASK, opaque);
     const unsigned key = px | 0xFF000000u;
     unsigned peers = 0;
@@ -649,25 +716,32 @@ __device__ __forceinline__ unsigned long long dxt1_pack_block(Dxt1Scratch* sc, u
     const int U = __popc(leaders);
     cfg.U = U;
     const unsigned my_u = __popc(leaders & lanemask_lt());
-    if (leader) sc->cw[my_u] = make_int4((int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff), __popc(peers));
-    const unsigned uidx = __shfl_sync(CRN_FULL_MASK, my_u, opaque ? __ffs((int)peers) - 1 : 0);
+    if (leader) {
+        const int r = (int)(px & 0xff), g = (int)((px >> 8) & 0xff), b = (int)((px >> 16) & 0xff);
+        sc->cw[my_u] = make_int4(r, g, b, __popc(peers));
+        sc->ce[my_u] = eval_colour(cfg, r, g, b);
+    }
     const unsigned total_w = (unsigned)__popc(vmask);
     const bool has_transparent = total_w != 16;
     __syncwarp();
 
-    Dxt1Best best;
-    best.lo = best.hi = 0; best.err = ~0ull; best.alpha_block = 0; best.alt_round = 0; best.enforce = 0; best.enforced_sel = 0;
-
-    if (U == 0) {   // :2205-2211
-        return 0xFFFFFFFF00000000ull;
+    if (lane == 0) {
+        sc->best.lo = sc->best.hi = 0; sc->best.err = ~0ull; sc->best.alpha_block = 0; sc->best.alt_round = 0; sc->best.enforce = 0; sc->best.enforced_sel = 0;
     }
+    __syncwarp();
+
+    if (lane == 0) { sc->U = U; sc->total_w = (int)total_w; sc->pixels_have_alpha = pixels_have_alpha; sc->stage = U == 0 ? 2 : 0; }
+    __syncwarp();
+    if (U == 0) return;   // :2205-2211
     if (U == 1 && !has_transparent) {   // :2212-2227
         const int4 c = sc->cw[0];
         const unsigned lo4 = ((unsigned)g_omatch5[2 * c.x] << 11) | ((unsigned)g_omatch6[2 * c.y] << 5) | g_omatch5[2 * c.z];
         const unsigned hi4 = ((unsigned)g_omatch5[2 * c.x + 1] << 11) | ((unsigned)g_omatch6[2 * c.y + 1] << 5) | g_omatch5[2 * c.z + 1];
         const unsigned lo3 = ((unsigned)g_omatch5_3[2 * c.x] << 11) | ((unsigned)g_omatch6_3[2 * c.y] << 5) | g_omatch5_3[2 * c.z];
         const unsigned hi3 = ((unsigned)g_omatch5_3[2 * c.x + 1] << 11) | ((unsigned)g_omatch6_3[2 * c.y + 1] << 5) | g_omatch5_3[2 * c.z + 1];
-        dxt1_commit_static(sc, cfg, best, lane < (prm.use_alpha_blocks ? 2u : 1u), lane ? lo3 : lo4, lane ? hi3 : hi4, 0);
+        dxt1_commit_static(sc, cfg, lane < (prm.use_alpha_blocks ? 2u : 1u), lane ? lo3 : lo4, lane ? hi3 : hi4, 0);
+        if (lane == 0) sc->stage = 1;
+        __syncwarp();
     } else {
         // ---- handle_multicolor_block (:1069-1178)
         int num_passes = 1;
@@ -814,6 +888,39 @@ __device__ __forceinline__ unsigned long long dxt1_pack_block(Dxt1Scratch* sc, u
             }
         }
 
+        if (lane == 0) {
+            sc->mean[0] = mean.x; sc->mean[1] = mean.y; sc->mean[2] = mean.z;
+            sc->axis[0] = axis.x; sc->axis[1] = axis.y; sc->axis[2] = axis.z;
+            sc->low[0] = low_color.x; sc->low[1] = low_color.y; sc->low[2] = low_color.z;
+            sc->high[0] = high_color.x; sc->high[1] = high_color.y; sc->high[2] = high_color.z;
+        }
+        __syncwarp();
+    }
+}
+
+// Phase 1 -- try_median4 (+ its least-squares refinement), first step of optimize_endpoints (:765-771).
+__device__ __forceinline__ void dxt1_phase_median4(Dxt1Scratch* sc, const Dxt1Params& prm)
+{
+    if (sc->stage != 0) return;
+    const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
+    V3 mean, low_color, high_color;
+    mean.x = sc->mean[0]; mean.y = sc->mean[1]; mean.z = sc->mean[2];
+    low_color.x = sc->low[0]; low_color.y = sc->low[1]; low_color.z = sc->low[2];
+    high_color.x = sc->high[0]; high_color.y = sc->high[1]; high_color.z = sc->high[2];
+    dxt1_median4(sc, cfg, prm.quality, mean, low_color, high_color);
+}
+
+// Phase 2 -- the probe-sweep / lattice-neighbour / refine passes of optimize_endpoints (:773-1028).
+__device__ __forceinline__ void dxt1_phase_passes(Dxt1Scratch* sc, const Dxt1Params& prm)
+{
+    if (sc->stage != 0) return;
+    const unsigned lane = lane_id();
+    const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
+    V3 axis, low_color, high_color;
+    axis.x = sc->axis[0]; axis.y = sc->axis[1]; axis.z = sc->axis[2];
+    low_color.x = sc->low[0]; low_color.y = sc->low[1]; low_color.z = sc->low[2];
+    high_color.x = sc->high[0]; high_color.y = sc->high[1]; high_color.z = sc->high[2];
+    {
         // ---- optimize_endpoints (:703-1067)
         const int quality = prm.quality;
         int num_passes_o, probe_range;
@@ -821,7 +928,6 @@ __device__ __forceinline__ unsigned long long dxt1_pack_block(Dxt1Scratch* sc, u
         // probe tables (:43-53) packed as bytes
         if (quality >= 4) { probe_range = 15; num_passes_o = 4; }
         else { probe_range = 10; num_passes_o = 2; }
-        dxt1_median4(sc, cfg, best, quality, mean, low_color, high_color);
 
         float sx = axis.x * dist_per_trial, sy = axis.y * dist_per_trial, sz = axis.z * dist_per_trial;
         sx *= 31.0f; sy *= 63.0f; sz *= 31.0f;
@@ -834,10 +940,10 @@ __device__ __forceinline__ unsigned long long dxt1_pack_block(Dxt1Scratch* sc, u
         for (int pass = 0; pass < num_passes_o; pass++) {
             if (pass) {
                 int r, g, b;
-                unpack565(best.lo, false, r, g, b); lcx = (float)r; lcy = (float)g; lcz = (float)b;
-                unpack565(best.hi, false, r, g, b); hcx = (float)r; hcy = (float)g; hcz = (float)b;
+                unpack565(sc->best.lo, false, r, g, b); lcx = (float)r; lcy = (float)g; lcz = (float)b;
+                unpack565(sc->best.hi, false, r, g, b); hcx = (float)r; hcy = (float)g; hcz = (float)b;
             }
-            const unsigned long long prev_best_error = best.err;
+            const unsigned long long prev_best_error = sc->best.err;
             if (!prev_best_error) break;
             // probe sweeps (:840-892): sequence index t: 0 -> (i=0,s=1); 2i-1 -> (i,s=0); 2i -> (i,s=1)
             int n_probe[2];
@@ -881,48 +987,73 @@ __device__ __forceinline__ unsigned long long dxt1_pack_block(Dxt1Scratch* sc, u
                 }
                 unsigned long long keyv = my_e; unsigned idx = my_k;
                 warp_argmin_u64(keyv, idx);
-                if (keyv < best.err) {
+                if (keyv < sc->best.err) {
                     const unsigned src = idx & 31u;
-                    dxt1_accept(best, __shfl_sync(CRN_FULL_MASK, my_lo, src), __shfl_sync(CRN_FULL_MASK, my_hi, src), 0, keyv,
+                    dxt1_accept(sc, __shfl_sync(CRN_FULL_MASK, my_lo, src), __shfl_sync(CRN_FULL_MASK, my_hi, src), 0, keyv,
                                 __shfl_sync(CRN_FULL_MASK, my_a, src));
                 }
             }
             // lattice neighbours (:905-1016); quality >= Normal always holds here
 #pragma unroll 1
             for (int which = 0; which < 2; which++) {
-                dxt1_live_neighbours(sc, cfg, best, which, 26, [](int idx, int& dr, int& dg, int& db) {
+                dxt1_live_neighbours(sc, cfg, which, 26, [](int idx, int& dr, int& dg, int& db) {
                     const int n = idx < 13 ? idx : idx + 1;   // g_adjacency (:489-522): x fastest, centre skipped
                     dr = n % 3 - 1; dg = (n / 3) % 3 - 1; db = n / 9 - 1;
                 });
                 if (quality == 4)
-                    dxt1_live_neighbours(sc, cfg, best, which, 6, [](int idx, int& dr, int& dg, int& db) {
+                    dxt1_live_neighbours(sc, cfg, which, 6, [](int idx, int& dr, int& dg, int& db) {
                         const int a = idx >> 1, s = (idx & 1) ? 2 : -2;
                         dr = a == 0 ? s : 0; dg = a == 1 ? s : 0; db = a == 2 ? s : 0;
                     });
             }
-            if (!best.err || (pass && best.err == prev_best_error)) break;
-            if (quality >= 4) dxt1_refine(sc, cfg, best, 1);
+            if (!sc->best.err || (pass && sc->best.err == prev_best_error)) break;
+            if (quality >= 4) dxt1_refine(sc, cfg, 1);
         }
-        // (:1030-1057)
-        if (best.err && !prm.pixels_have_alpha) {
-            bool choose_solid_block = false;
-            dxt1_best_selectors(sc, cfg, best);
-            bool all_equal = true;
-            for (int i = 1; i < U; i++) all_equal = all_equal && sc->sel[i] == sc->sel[0];
-            if (all_equal) choose_solid_block = dxt1_try_solid(sc, cfg, best, prm);
-            if (!choose_solid_block && quality == 4) dxt1_optimize_comps(sc, cfg, best);
-        }
-        if (quality == 4 && best.err) dxt1_combinatorial(sc, cfg, best);
     }
+}
 
+// Phase 3 -- solid-colour and per-component post passes (:1030-1046).
+__device__ __forceinline__ void dxt1_phase_post(Dxt1Scratch* sc, const Dxt1Params& prm)
+{
+    if (sc->stage != 0) return;
+    const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
+    const int quality = prm.quality;
+    const int U = sc->U;
+    if (sc->best.err && !sc->pixels_have_alpha) {
+        bool choose_solid_block = false;
+        dxt1_best_selectors(sc, cfg);
+        bool all_equal = true;
+        for (int i = 1; i < U; i++) all_equal = all_equal && sc->sel[i] == sc->sel[0];
+        if (all_equal) choose_solid_block = dxt1_try_solid(sc, cfg, prm);
+        if (!choose_solid_block && quality == 4) dxt1_optimize_comps(sc, cfg);
+    }
+}
+
+// Phase 4 -- combinatorial recovery (:1048-1056) and return_solution (:263-365).  Returns the packed 8-byte
+// DXT1 element (low565, high565, 16 x 2-bit selectors; crn_dxt.h:109-172) on every lane.
+__device__ __forceinline__ unsigned long long dxt1_phase_finish(Dxt1Scratch* sc, uint32_t px, const Dxt1Params& prm)
+{
+    const unsigned lane = lane_id();
+    if (sc->stage == 2) return 0xFFFFFFFF00000000ull;
+    const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
+    if (sc->stage == 0 && prm.quality == 4 && sc->best.err) dxt1_combinatorial(sc, cfg);
+    // pixel -> unique colour index, as in phase 0
+    const bool opaque = lane < 16 && (!sc->pixels_have_alpha || (px >> 24) >= prm.alpha_threshold);
+    const unsigned vmask = __ballot_sync(CRN_FULL_MASK, opaque);
+    unsigned peers = 0;
+    if (opaque) peers = __match_any_sync(vmask, px | 0xFF000000u);
+    const bool leader = opaque && (unsigned)(__ffs((int)peers) - 1) == lane;
+    const unsigned leaders = __ballot_sync(CRN_FULL_MASK, leader);
+    const unsigned my_u = __popc(leaders & lanemask_lt());
+    const unsigned uidx = __shfl_sync(CRN_FULL_MASK, my_u, opaque ? __ffs((int)peers) - 1 : 0);
     // ---- return_solution (:263-365)
-    dxt1_best_selectors(sc, cfg, best);
-    const bool invert = best.alpha_block ? (best.lo > best.hi) : (best.lo < best.hi);
-    const unsigned out_lo = invert ? best.hi : best.lo, out_hi = invert ? best.lo : best.hi;
+    dxt1_best_selectors(sc, cfg);
+    const bool invert = sc->best.alpha_block ? (sc->best.lo > sc->best.hi) : (sc->best.lo < sc->best.hi);
+    const unsigned out_lo = invert ? sc->best.hi : sc->best.lo, out_hi = invert ? sc->best.lo : sc->best.hi;
     unsigned s = 3;
     if (opaque) {
         s = sc->sel[uidx];
-        if (invert) s = best.alpha_block ? (s < 2 ? s ^ 1 : s) : (s ^ 1);   // g_invTableAlpha {1,0,2,3} / g_invTableColor {1,0,3,2}
+        if (invert) s = sc->best.alpha_block ? (s < 2 ? s ^ 1 : s) : (s ^ 1);   // g_invTableAlpha {1,0,2,3} / g_invTableColor {1,0,3,2}
     }
     unsigned bits = lane < 16 ? (s << (2 * lane)) : 0u;
 #pragma unroll

@@ -32,6 +32,9 @@ __device__ __forceinline__ uint32_t fetch_block_pixel(const ImageView& img, uint
 }
 
 constexpr int kPackWarpsPerCta = 8;
+#ifndef CRN_COLOR_MIN_CTAS
+#define CRN_COLOR_MIN_CTAS 2   // resident CTAs per SM the colour kernel is register-budgeted for
+#endif
 
 // DXT5A-type element (alpha of DXT5, DXT5A, both halves of DXN) ------------------------------------
 __global__ void __launch_bounds__(kPackWarpsPerCta * 32)
@@ -74,26 +77,55 @@ __global__ void pack_dxt3_alpha_kernel(ImageView img, uint32_t comp, uint8_t* __
     }
 }
 
-// DXT1 colour element ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPackWarpsPerCta * 32)
-pack_color_element_kernel(ImageView img, Dxt1Params prm, int dxt1a,
-                          uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs)
+// DXT1 colour element: five phase kernels over a chunk of blocks (see Dxt1BlockState) -----------------
+__device__ __forceinline__ void state_load(Dxt1Scratch* sc, const Dxt1BlockState* g)
 {
-    __shared__ Dxt1Scratch scratch[kPackWarpsPerCta];
+    const unsigned lane = lane_id();
+    if (lane < (unsigned)kDxt1StateVec4) reinterpret_cast<int4*>(sc)[lane] = reinterpret_cast<const int4*>(g)[lane];
+    __syncwarp();
+}
+__device__ __forceinline__ void state_store(Dxt1BlockState* g, const Dxt1Scratch* sc)
+{
+    const unsigned lane = lane_id();
+    __syncwarp();
+    if (lane < (unsigned)kDxt1StateVec4) reinterpret_cast<int4*>(g)[lane] = reinterpret_cast<const int4*>(sc)[lane];
+}
+
+// PHASE: 0 set-up, 1 LBG (try_median4), 2 sweep passes, 3 post passes, 4 finish (writes the element).
+// Blocks [first, first + count) of the image; states[i] belongs to block first + i.
+template <int PHASE>
+__global__ void __launch_bounds__(kPackWarpsPerCta * 32, CRN_COLOR_MIN_CTAS)
+pack_color_phase_kernel(ImageView img, Dxt1Params prm, int dxt1a, Dxt1BlockState* __restrict__ states, uint32_t first, uint32_t count,
+                        uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs)
+{
+    __shared__ __align__(16) Dxt1Scratch scratch[kPackWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5;
     Dxt1Scratch* sc = &scratch[warp];
-    const uint32_t total = img.blocks_x * img.blocks_y;
-    for (uint32_t b = blockIdx.x * kPackWarpsPerCta + warp; b < total; b += gridDim.x * kPackWarpsPerCta) {
-        const uint32_t bx = b % img.blocks_x, by = b / img.blocks_x;
-        const uint32_t px = fetch_block_pixel(img, bx, by);
-        Dxt1Params p = prm;
-        if (dxt1a) {   // crn_dxt_image.cpp:1440-1451
-            const unsigned any = __ballot_sync(CRN_FULL_MASK, lane_id() < 16 && (px >> 24) < prm.alpha_threshold);
-            p.pixels_have_alpha = any != 0;
+    for (uint32_t i = blockIdx.x * kPackWarpsPerCta + warp; i < count; i += gridDim.x * kPackWarpsPerCta) {
+        const uint32_t b = first + i;
+        uint32_t px = 0;
+        if (PHASE == 0 || PHASE == 4) px = fetch_block_pixel(img, b % img.blocks_x, b / img.blocks_x);
+        if (PHASE == 0) {
+            int pha = 0;
+            if (dxt1a)   // crn_dxt_image.cpp:1440-1451
+                pha = __ballot_sync(CRN_FULL_MASK, lane_id() < 16 && (px >> 24) < prm.alpha_threshold) != 0;
+            dxt1_phase_setup(sc, px, prm, pha);
+            state_store(&states[i], sc);
+        } else {
+            state_load(sc, &states[i]);
+            if (sc->stage == 0 || PHASE == 4) dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U));
+            if (PHASE == 1) dxt1_phase_median4(sc, prm);
+            if (PHASE == 2) dxt1_phase_passes(sc, prm);
+            if (PHASE == 3) dxt1_phase_post(sc, prm);
+            if (PHASE < 4) {
+                if (sc->stage == 0) state_store(&states[i], sc);
+            } else {
+                const unsigned long long elem = dxt1_phase_finish(sc, px, prm);
+                if (lane_id() == 0)
+                    *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = elem;
+            }
         }
-        const unsigned long long elem = dxt1_pack_block(sc, px, p);
-        if (lane_id() == 0)
-            *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = elem;
+        __syncwarp();
     }
 }
 
