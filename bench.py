@@ -125,6 +125,55 @@ def run_cpu_baseline(wl, budget_s=12.0):
                 sample="level %dx%d of the workload (%d blocks), one pass, %.2f s" % (sample.shape[1], sample.shape[0], nblocks([sample]), dt)), sample, run
 
 
+def run_transcode(ctx, ext, dev, flush, steps, peak_gbs, quick=False):
+    """CRN -> DXTn transcode of a synthetic 8192x8192 DXT5 .crn (BASELINE configs[3]; the reference's
+    compressor cannot write this size, so tests/crnsynth.py builds a valid stream).  Gtexel/s over all 14
+    levels excluding unpack_begin (reported separately), next to the reference decoder on one host core."""
+    import torch
+    import crnsynth
+    import helpers
+    size = 2048 if quick else 8192
+    data = crnsynth.synth_crn(size, size, "DXT5", seed=4, with_crc=False, n_color_ep=4096, n_color_sel=4096, n_alpha_ep=2048, n_alpha_sel=2048)
+    t0 = time.perf_counter(); tex = ctx.unpack_begin(data); begin_s = time.perf_counter() - t0
+    ntex = sum(max(1, size >> l) ** 2 for l in range(tex.info["levels"]))
+    d_out = torch.empty(tex.total_size, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        tex.unpack_all_device(d_out, tex.total_size)
+    ctx.synchronize()
+    times = []
+    for _ in range(steps):
+        flush.fill_(3); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext); tex.unpack_all_device(d_out, tex.total_size); e1.record(ext); e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    host_out = torch.empty(tex.total_size, dtype=torch.uint8).pin_memory().numpy()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t2 = ctx.unpack_begin(data)
+        ctx._check(ctx._lib.crn_gpu_crnd_unpack_all_levels_host(t2._tex, host_out.ctypes.data, host_out.size))
+        t2.close()
+    e2e_s = (time.perf_counter() - t0) / steps
+    out = {"workload": "crn_dxt5_%dx%d_14levels (synthetic stream, %.2f bpp)" % (size, size, len(data) * 8.0 / ntex), "value": ntex / (ms / 1e3) / 1e9,
+           "unit": "Gtexel/s", "ms": ms, "unpack_begin_ms": begin_s * 1e3,
+           "e2e": {"value": ntex / e2e_s / 1e9, "unit": "Gtexel/s", "h2d_bytes_per_step": len(data), "d2h_bytes_per_step": int(tex.total_size),
+                   "includes": "unpack_begin (host table parse + upload + palette kernel) + all levels + D2H"},
+           "roofline": {"bound": "hbm", "kernel": "transcode_levels_kernel", "achieved": (len(data) + tex.total_size) / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": (len(data) + tex.total_size) / (ms / 1e3) / 1e9 / peak_gbs, "traffic": None,
+                        "note": "one serial Huffman stream per mip level (SURVEY D5): latency-bound entropy decode, level 0 = 75% of the blocks"}}
+    ref = helpers.load_ref()
+    if ref is not None:
+        buf = np.frombuffer(data, np.uint8)
+        cpu_out = np.empty(tex.total_size, np.uint8)
+        secs = ref.ref_transcode_all(buf.ctypes.data_as(__import__("ctypes").c_void_p), len(data), cpu_out.ctypes.data_as(__import__("ctypes").c_void_p),
+                                     __import__("ctypes").c_uint64(cpu_out.size), 3)
+        out["cpu_baseline"] = {"value": ntex * 3 / secs / 1e9, "unit": "Gtexel/s", "cores": 1, "kind": "reference",
+                               "sample": "crnd_unpack_level over all levels, 3 repeats (the reference transcoder is single-threaded)"}
+        out["bit_exact_vs_reference"] = bool((d_out.cpu().numpy() == cpu_out).all())
+    tex.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -133,6 +182,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1_dxt1_2048_mips")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-transcode", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,6 +313,11 @@ def main():
                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                         "note": "issue-slot bound integer kernel: algorithmic HBM bytes are 72 B/block; see DESIGN.md and profiles/ for pipe utilisation",
                         "blocks_per_s": top_blocks / (top_ms / 1e3), "ms": top_ms}}
+    if not args.no_transcode:
+        try:
+            out["transcode"] = run_transcode(ctx, ext, dev, flush, max(2, min(args.steps, 5)), peak_gbs)
+        except Exception as e:
+            out["transcode"] = {"error": str(e)[:300]}
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = run_cpu_baseline(wl)[0]

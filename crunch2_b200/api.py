@@ -32,6 +32,11 @@ class _PackParams(ctypes.Structure):
                 ("reserved", ctypes.c_uint32 * 5)]
 
 
+class _TextureInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "width", "height", "levels", "faces", "bytes_per_block",
+                                                "userdata0", "userdata1", "format")]
+
+
 class PackParams:
     """dxt_image::pack_params for the block-by-block path (defaults of crn_comp_params::clear())."""
 
@@ -79,6 +84,18 @@ def _declare(lib):
     lib.crn_gpu_bytes_per_block.restype = u32
     lib.crn_gpu_pack_image.argtypes = [vp, u32, ctypes.POINTER(_PackParams), vp, u32, u32, u32, vp]
     lib.crn_gpu_pack_image_host.argtypes = [vp, u32, ctypes.POINTER(_PackParams), vp, u32, u32, u32, vp]
+    u64 = ctypes.c_uint64
+    lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
+    lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
+    lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
+    lib.crn_gpu_crnd_total_size.argtypes = [vp]
+    lib.crn_gpu_crnd_total_size.restype = u64
+    lib.crn_gpu_crnd_level_offset.argtypes = [vp, u32, u32]
+    lib.crn_gpu_crnd_level_offset.restype = u64
+    lib.crn_gpu_crnd_unpack_all_levels.argtypes = [vp, vp, u64]
+    lib.crn_gpu_crnd_unpack_all_levels_host.argtypes = [vp, vp, u64]
+    lib.crn_gpu_crnd_unpack_batch.argtypes = [vp, ctypes.POINTER(vp), u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
+    lib.crn_gpu_crnd_unpack_end.argtypes = [vp]
     return lib
 
 
@@ -167,3 +184,75 @@ class Context:
         src = _devptr(d_rgba) if hasattr(d_rgba, "data_ptr") else ctypes.c_void_p(int(d_rgba))
         dst = _devptr(d_out) if hasattr(d_out, "data_ptr") else ctypes.c_void_p(int(d_out))
         self._check(self._lib.crn_gpu_pack_image(self._ctx, fmt, ctypes.byref(cp), src, width, height, pitch, dst))
+
+    # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
+    def unpack_begin(self, crn_bytes):
+        """crnd_unpack_begin: returns a Texture bound to this context."""
+        return Texture(self, crn_bytes)
+
+    def unpack_batch(self, textures, d_dst_ptrs, capacities):
+        """All levels of several textures in ONE launch; d_dst_ptrs are device pointers (ints)."""
+        n = len(textures)
+        tp = (ctypes.c_void_p * n)(*[t._tex for t in textures])
+        dp = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p)) for p in d_dst_ptrs])
+        cp = (ctypes.c_uint64 * n)(*[int(c) for c in capacities])
+        self._check(self._lib.crn_gpu_crnd_unpack_batch(self._ctx, tp, n, dp, cp))
+
+
+def texture_info(crn_bytes, lib=None):
+    """crnd_get_texture_info: host-only header crack."""
+    lib = lib if lib is not None else load_library()
+    info = _TextureInfo()
+    info.struct_size = ctypes.sizeof(_TextureInfo)
+    buf = np.frombuffer(crn_bytes, np.uint8)
+    rc = lib.crn_gpu_crnd_get_texture_info(buf.ctypes.data_as(ctypes.c_void_p), len(crn_bytes), ctypes.byref(info))
+    if rc != 0:
+        raise CrnGpuError(rc, "not a CRN file")
+    return {k: getattr(info, k) for k, _ in _TextureInfo._fields_ if k != "struct_size"}
+
+
+class Texture:
+    """crnd_unpack_context: header + Huffman tables + palettes of one .crn, resident on the device."""
+
+    def __init__(self, ctx, crn_bytes):
+        self._c = ctx
+        self._lib = ctx._lib
+        self.info = texture_info(crn_bytes, self._lib)
+        buf = np.frombuffer(crn_bytes, np.uint8)
+        self._tex = ctypes.c_void_p()
+        ctx._check(self._lib.crn_gpu_crnd_unpack_begin(ctx._ctx, buf.ctypes.data_as(ctypes.c_void_p), len(crn_bytes), ctypes.byref(self._tex)))
+        self.total_size = int(self._lib.crn_gpu_crnd_total_size(self._tex))
+
+    def level_offset(self, level, face=0):
+        return int(self._lib.crn_gpu_crnd_level_offset(self._tex, level, face))
+
+    def level_blocks(self, level):
+        w, h = max(1, self.info["width"] >> level), max(1, self.info["height"] >> level)
+        return (w + 3) // 4, (h + 3) // 4
+
+    def unpack_all(self):
+        """Every level and face (tight, level-major / face-major) as one uint8 array on the host."""
+        out = np.empty(self.total_size, np.uint8)
+        self._c._check(self._lib.crn_gpu_crnd_unpack_all_levels_host(self._tex, out.ctypes.data_as(ctypes.c_void_p), out.size))
+        return out
+
+    def unpack_all_device(self, d_dst, capacity):
+        p = ctypes.c_void_p(d_dst.data_ptr()) if hasattr(d_dst, "data_ptr") else ctypes.c_void_p(int(d_dst))
+        self._c._check(self._lib.crn_gpu_crnd_unpack_all_levels(self._tex, p, int(capacity)))
+
+    def unpack_level_device(self, face_ptrs, dst_size, row_pitch, level):
+        """crnd_unpack_level with device destination pointers (ints), one per face."""
+        n = len(face_ptrs)
+        arr = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p)) for p in face_ptrs])
+        self._c._check(self._lib.crn_gpu_crnd_unpack_level(self._tex, arr, int(dst_size), int(row_pitch), int(level)))
+
+    def close(self):
+        if getattr(self, "_tex", None):
+            self._lib.crn_gpu_crnd_unpack_end(self._tex)
+            self._tex = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -5,6 +5,7 @@
 #include "../../include/crn_b200.h"
 #include "launch.h"
 #include "pack_kernels.cuh"
+#include "transcode_host.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -20,6 +21,8 @@ struct crn_gpu_ctx {
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
+    void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
+    int transcode_smem_set;
 };
 
 namespace {
@@ -107,6 +110,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_state) cudaFree(ctx->d_state);
+    if (ctx->d_files) cudaFree(ctx->d_files);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -244,6 +248,259 @@ int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pac
     if (rc) return rc;
     CRN_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CRN_GPU_OK;
+}
+
+
+/* ---- CRN -> DXTn transcoding --------------------------------------------------------------------- */
+
+struct crn_gpu_texture {
+    crn_gpu_ctx* ctx;
+    crn::CrnHeaderInfo hdr;
+    uint32_t bytes_per_block;
+    void* slab;                       // one device allocation holding everything below
+    crn::TranscodeFile host_file;     // host mirror; device copy at d_file
+    crn::TranscodeFile* d_file;
+    uint32_t rowbuf_ofs[16];
+    uint64_t level_ofs[16];           // tight layout offsets (face 0)
+    uint64_t level_face_size[16];
+    uint64_t total_size;
+};
+
+int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info)
+{
+    if (!info || info->struct_size != sizeof(crn_gpu_texture_info)) return CRN_GPU_ERR_BAD_PARAM;
+    crn::CrnHeaderInfo h;
+    if (!crn::crn_parse_header(static_cast<const uint8_t*>(h_crn), crn_size, h)) return CRN_GPU_ERR_BAD_DATA;
+    info->width = h.width; info->height = h.height; info->levels = h.levels; info->faces = h.faces;
+    info->bytes_per_block = (h.format == 0 || h.format == 9 || h.format == 10 || h.format == 11 || h.format == 13) ? 8 : 16;
+    info->userdata0 = h.userdata0; info->userdata1 = h.userdata1; info->format = h.format;
+    return CRN_GPU_OK;
+}
+
+static int transcode_launch(crn_gpu_ctx* ctx, const crn::TranscodeFile* d_files, uint32_t nfiles)
+{
+    const size_t smem = sizeof(crn::TranscodeSmem);
+#ifdef __CUDACC__
+    if (!ctx->transcode_smem_set) {
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->transcode_smem_set = 1;
+    }
+#endif
+    CRN_LAUNCH(crn::transcode_levels_kernel, nfiles, crn::kTranscodeWarps * 32, smem, ctx->stream, d_files);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, crn_gpu_texture** out_tex)
+{
+    if (!ctx || !out_tex) return CRN_GPU_ERR_BAD_PARAM;
+    *out_tex = nullptr;
+    const uint8_t* d = static_cast<const uint8_t*>(h_crn);
+    crn::CrnHeaderInfo h;
+    if (!crn::crn_parse_header(d, crn_size, h)) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crnd_unpack_begin: not a CRN file");
+    if (h.format > 9 || h.format == 1) return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crnd_unpack_begin: only DXT1/DXT5*/DXN/DXT5A .crn files are supported");
+    const bool has_color = h.format <= 6, has_alpha = h.format != 0;
+    if ((has_color && !h.pal_num[0]) || (has_alpha && !h.pal_num[2])) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crnd_unpack_begin: missing palette");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // Huffman models: init_tables (:3662-3692) then the model headers of each palette segment
+    crn::HostModel hm[crn::kNumModels];
+    {
+        crn::HostBits b = { d + h.tables_ofs, h.tables_size, 0 };
+        bool ok = hm[crn::kDmRef].receive(b);
+        if (ok && h.pal_num[0]) ok = hm[crn::kDmColorEp].receive(b) && hm[crn::kDmColorSel].receive(b);
+        if (ok && h.pal_num[2]) ok = hm[crn::kDmAlphaEp].receive(b) && hm[crn::kDmAlphaSel].receive(b);
+        if (!ok) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crnd_unpack_begin: corrupt Huffman tables");
+    }
+    uint32_t pal_data_ofs[4] = { 0, 0, 0, 0 }, pal_data_bit[4] = { 0, 0, 0, 0 };
+    for (int i = 0; i < 4; i++) {
+        if (!h.pal_num[i < 2 ? 0 : 2]) continue;
+        crn::HostBits b = { d + h.pal_ofs[i], h.pal_size[i], 0 };
+        bool ok = true;
+        if (i == 0) ok = hm[crn::kDmPalCe0].receive(b) && hm[crn::kDmPalCe1].receive(b);
+        else ok = hm[crn::kDmPalCs + (i - 1)].receive(b);
+        if (!ok) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crnd_unpack_begin: corrupt palette model");
+        pal_data_ofs[i] = h.pal_ofs[i] + (uint32_t)(b.pos >> 3);
+        pal_data_bit[i] = (uint32_t)(b.pos & 7);
+    }
+    std::vector<crn::HuffModelDev> dev_models(crn::kNumModels);
+    std::vector<uint16_t> pool;
+    for (int i = 0; i < crn::kNumModels; i++) hm[i].to_device(dev_models[i], pool);
+    if (pool.empty()) pool.push_back(0);
+
+    crn_gpu_texture* t = new (std::nothrow) crn_gpu_texture();
+    if (!t) return CRN_GPU_ERR_NO_MEMORY;
+    memset(static_cast<void*>(t), 0, sizeof(*t));
+    t->ctx = ctx; t->hdr = h;
+    t->bytes_per_block = (h.format == 0 || h.format == 9) ? 8 : 16;
+    uint32_t rowbuf_total = 0;
+    uint64_t ofs = 0;
+    for (uint32_t l = 0; l < h.levels; l++) {
+        const uint32_t w = h.width >> l ? h.width >> l : 1, hh = h.height >> l ? h.height >> l : 1;
+        const uint32_t bx = (w + 3) >> 2, by = (hh + 3) >> 2;
+        t->rowbuf_ofs[l] = rowbuf_total;
+        rowbuf_total += (bx + 1) & ~1u;
+        t->level_ofs[l] = ofs;
+        t->level_face_size[l] = (uint64_t)bx * by * t->bytes_per_block;
+        ofs += t->level_face_size[l] * h.faces;
+    }
+    t->total_size = ofs;
+
+    // carve one slab
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o_bytes = 0, o_models = align(o_bytes + crn_size + 16), o_pool = align(o_models + sizeof(crn::HuffModelDev) * crn::kNumModels);
+    size_t o_ce = align(o_pool + pool.size() * 2), o_cs = align(o_ce + 4 * (size_t)(h.pal_num[0] + 1)), o_ae = align(o_cs + 4 * (size_t)(h.pal_num[1] + 1));
+    size_t o_as = align(o_ae + 2 * (size_t)(h.pal_num[2] + 1)), o_row = align(o_as + 6 * (size_t)(h.pal_num[3] + 1));
+    size_t o_file = align(o_row + 8 * (size_t)rowbuf_total), total = align(o_file + sizeof(crn::TranscodeFile));
+    cudaError_t ce = cudaMalloc(&t->slab, total);
+    if (ce != cudaSuccess) { delete t; return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "cudaMalloc", ce); }
+    uint8_t* base = static_cast<uint8_t*>(t->slab);
+    crn::TranscodeFile& f = t->host_file;
+    f.bytes = base + o_bytes;
+    f.models = reinterpret_cast<const crn::HuffModelDev*>(base + o_models);
+    f.sorted_pool = reinterpret_cast<const uint16_t*>(base + o_pool);
+    f.color_endpoints = reinterpret_cast<uint32_t*>(base + o_ce);
+    f.color_selectors = reinterpret_cast<uint32_t*>(base + o_cs);
+    f.alpha_endpoints = reinterpret_cast<uint16_t*>(base + o_ae);
+    f.alpha_selectors = reinterpret_cast<uint16_t*>(base + o_as);
+    f.rowbuf_pool = reinterpret_cast<uint2*>(base + o_row);
+    f.num_color_endpoints = h.pal_num[0]; f.num_color_selectors = h.pal_num[1];
+    f.num_alpha_endpoints = h.pal_num[2]; f.num_alpha_selectors = h.pal_num[3];
+    for (int i = 0; i < 4; i++) { f.pal_data_ofs[i] = pal_data_ofs[i]; f.pal_data_bit[i] = pal_data_bit[i]; f.pal_size_end[i] = h.pal_ofs[i] + h.pal_size[i]; }
+    f.format = h.format; f.faces = h.faces;
+    t->d_file = reinterpret_cast<crn::TranscodeFile*>(base + o_file);
+
+    bool fail = false;
+    fail |= cudaMemsetAsync(base + o_bytes + crn_size, 0, 16, ctx->stream) != cudaSuccess;
+    fail |= cudaMemcpyAsync(base + o_bytes, d, crn_size, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess;
+    fail |= cudaMemcpyAsync(base + o_models, dev_models.data(), sizeof(crn::HuffModelDev) * crn::kNumModels, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess;
+    fail |= cudaMemcpyAsync(base + o_pool, pool.data(), pool.size() * 2, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess;
+    fail |= cudaMemcpyAsync(t->d_file, &f, sizeof(f), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess;
+    if (!fail) {
+        CRN_LAUNCH(crn::transcode_palettes_kernel, 1, 128, 0, ctx->stream, t->d_file);
+        ctx->launches++;
+        fail |= cudaGetLastError() != cudaSuccess;
+        // the host vectors above die at return: wait for the copies
+        fail |= cudaStreamSynchronize(ctx->stream) != cudaSuccess;
+    }
+    if (fail) { cudaFree(t->slab); delete t; return set_err(ctx, CRN_GPU_ERR_CUDA, "crnd_unpack_begin: upload / palette decode failed"); }
+    *out_tex = t;
+    return CRN_GPU_OK;
+}
+
+static void fill_level(crn_gpu_texture* t, uint32_t slot, uint32_t level, uint32_t row_pitch)
+{
+    const crn::CrnHeaderInfo& h = t->hdr;
+    crn::LevelStream& ls = t->host_file.levels[slot];
+    const uint32_t w = h.width >> level ? h.width >> level : 1, hh = h.height >> level ? h.height >> level : 1;
+    const uint32_t next = level + 1 < h.levels ? h.level_ofs[level + 1] : h.data_size;
+    ls.src_ofs = h.level_ofs[level];
+    ls.src_size = next > h.level_ofs[level] ? next - h.level_ofs[level] : 0;
+    ls.blocks_x = (w + 3) >> 2; ls.blocks_y = (hh + 3) >> 2;
+    ls.row_pitch = row_pitch ? row_pitch : ls.blocks_x * t->bytes_per_block;
+    ls.rowbuf_ofs = t->rowbuf_ofs[level];
+    ls.active = 1;
+}
+
+int crn_gpu_crnd_unpack_level(crn_gpu_texture* tex, void* const* d_dst_faces, uint32_t dst_size_in_bytes,
+                              uint32_t row_pitch_in_bytes, uint32_t level_index)
+{
+    if (!tex || !d_dst_faces) return CRN_GPU_ERR_BAD_PARAM;
+    crn_gpu_ctx* ctx = tex->ctx;
+    if (level_index >= tex->hdr.levels) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: level out of range");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 16; i++) tex->host_file.levels[i].active = 0;
+    fill_level(tex, 0, level_index, row_pitch_in_bytes);
+    crn::LevelStream& ls = tex->host_file.levels[0];
+    const uint32_t minpitch = ls.blocks_x * tex->bytes_per_block;     // crn_decomp.h:3569-3575
+    if (ls.row_pitch < minpitch || (ls.row_pitch & 3) || (uint64_t)dst_size_in_bytes < (uint64_t)ls.row_pitch * ls.blocks_y)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: bad pitch or destination size");
+    for (uint32_t f = 0; f < tex->hdr.faces; f++) {
+        if (!d_dst_faces[f]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: null face pointer");
+        ls.dst[f] = (unsigned long long)(uintptr_t)d_dst_faces[f];
+    }
+    CRN_CUDA(ctx, cudaMemcpyAsync(tex->d_file, &tex->host_file, sizeof(crn::TranscodeFile), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = transcode_launch(ctx, tex->d_file, 1);
+    if (rc) return rc;
+    // host_file is reused by the next call: make sure the async copy has read it
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CRN_GPU_OK;
+}
+
+uint64_t crn_gpu_crnd_total_size(const crn_gpu_texture* tex) { return tex ? tex->total_size : 0; }
+uint64_t crn_gpu_crnd_level_offset(const crn_gpu_texture* tex, uint32_t level_index, uint32_t face_index)
+{
+    if (!tex || level_index >= tex->hdr.levels || face_index >= tex->hdr.faces) return ~0ull;
+    return tex->level_ofs[level_index] + tex->level_face_size[level_index] * face_index;
+}
+
+static int prepare_all_levels(crn_gpu_texture* tex, void* d_dst, uint64_t dst_capacity)
+{
+    if (!d_dst || dst_capacity < tex->total_size) return set_err(tex->ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_all_levels: destination too small");
+    for (int i = 0; i < 16; i++) tex->host_file.levels[i].active = 0;
+    for (uint32_t l = 0; l < tex->hdr.levels; l++) {
+        fill_level(tex, l, l, 0);
+        for (uint32_t f = 0; f < tex->hdr.faces; f++)
+            tex->host_file.levels[l].dst[f] = (unsigned long long)(uintptr_t)(static_cast<uint8_t*>(d_dst) + tex->level_ofs[l] + tex->level_face_size[l] * f);
+    }
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_crnd_unpack_all_levels(crn_gpu_texture* tex, void* d_dst, uint64_t dst_capacity)
+{
+    if (!tex) return CRN_GPU_ERR_BAD_PARAM;
+    crn_gpu_ctx* ctx = tex->ctx;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = prepare_all_levels(tex, d_dst, dst_capacity);
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaMemcpyAsync(tex->d_file, &tex->host_file, sizeof(crn::TranscodeFile), cudaMemcpyHostToDevice, ctx->stream));
+    return transcode_launch(ctx, tex->d_file, 1);
+}
+
+int crn_gpu_crnd_unpack_all_levels_host(crn_gpu_texture* tex, void* h_dst, uint64_t dst_capacity)
+{
+    if (!tex || !h_dst) return CRN_GPU_ERR_BAD_PARAM;
+    crn_gpu_ctx* ctx = tex->ctx;
+    if (dst_capacity < tex->total_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_all_levels_host: destination too small");
+    int rc = ensure(ctx, &ctx->d_out, &ctx->d_out_cap, tex->total_size);
+    if (rc) return rc;
+    rc = crn_gpu_crnd_unpack_all_levels(tex, ctx->d_out, ctx->d_out_cap);
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaMemcpyAsync(h_dst, ctx->d_out, tex->total_size, cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_crnd_unpack_batch(crn_gpu_ctx* ctx, crn_gpu_texture* const* textures, uint32_t count, void* const* d_dst,
+                              const uint64_t* dst_capacity)
+{
+    if (!ctx || !textures || !d_dst || !dst_capacity || !count) return CRN_GPU_ERR_BAD_PARAM;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_files, &ctx->d_files_cap, sizeof(crn::TranscodeFile) * (size_t)count);
+    if (rc) return rc;
+    std::vector<crn::TranscodeFile> files(count);
+    for (uint32_t i = 0; i < count; i++) {
+        if (!textures[i] || textures[i]->ctx != ctx) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_batch: texture belongs to another context");
+        rc = prepare_all_levels(textures[i], d_dst[i], dst_capacity[i]);
+        if (rc) return rc;
+        files[i] = textures[i]->host_file;
+    }
+    CRN_CUDA(ctx, cudaMemcpyAsync(ctx->d_files, files.data(), sizeof(crn::TranscodeFile) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    rc = transcode_launch(ctx, static_cast<const crn::TranscodeFile*>(ctx->d_files), count);
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `files` dies at return
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_crnd_unpack_end(crn_gpu_texture* tex)
+{
+    if (!tex) return CRN_GPU_ERR_BAD_PARAM;
+    cudaSetDevice(tex->ctx->device);
+    cudaStreamSynchronize(tex->ctx->stream);
+    cudaFree(tex->slab);
+    delete tex;
     return CRN_GPU_OK;
 }
 

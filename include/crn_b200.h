@@ -92,6 +92,43 @@ CRN_API int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_
 CRN_API int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                             const void* h_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, void* h_out);
 
+/* CRN -> DXTn transcoding ---------------------------------------------------
+ * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
+ * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:
+ * the context borrows nothing after begin() returns (the file bytes are copied to the device);
+ * unpack_level writes blocks_y rows of blocks_x blocks per face, `row_pitch_in_bytes` apart (0 = tight,
+ * otherwise >= blocks_x * bytes_per_block and a multiple of 4), dst_size_in_bytes >= pitch * blocks_y,
+ * bit-for-bit what crnd_unpack_level produces.  Destination pointers are DEVICE memory. */
+typedef struct crn_gpu_texture_info {
+    uint32_t struct_size;          /* sizeof(crn_gpu_texture_info) */
+    uint32_t width, height, levels, faces;
+    uint32_t bytes_per_block;      /* 8 or 16 */
+    uint32_t userdata0, userdata1;
+    uint32_t format;               /* crn_format (inc/crnlib.h:72-112) */
+} crn_gpu_texture_info;
+
+typedef struct crn_gpu_texture crn_gpu_texture;
+
+/* Host-only header crack; no device needed. */
+CRN_API int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info);
+/* Parses header + Huffman models on the host, uploads the file, decodes the four palettes on the device. */
+CRN_API int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, crn_gpu_texture** out_tex);
+/* One level, caller-chosen destination per face (1 or 6 device pointers).  Asynchronous. */
+CRN_API int crn_gpu_crnd_unpack_level(crn_gpu_texture* tex, void* const* d_dst_faces, uint32_t dst_size_in_bytes,
+                                      uint32_t row_pitch_in_bytes, uint32_t level_index);
+/* All levels in ONE launch (levels decode concurrently, one warp each) into a tightly packed device
+ * buffer laid out level-major then face-major; crn_gpu_crnd_level_offset gives each face's offset. */
+CRN_API uint64_t crn_gpu_crnd_total_size(const crn_gpu_texture* tex);
+CRN_API uint64_t crn_gpu_crnd_level_offset(const crn_gpu_texture* tex, uint32_t level_index, uint32_t face_index);
+CRN_API int crn_gpu_crnd_unpack_all_levels(crn_gpu_texture* tex, void* d_dst, uint64_t dst_capacity);
+/* Same, then copies the result to host memory and synchronises. */
+CRN_API int crn_gpu_crnd_unpack_all_levels_host(crn_gpu_texture* tex, void* h_dst, uint64_t dst_capacity);
+/* Several textures of one context in ONE launch (one CTA per file): the batched form in which the
+ * per-level serial entropy decode is amortised.  d_dst[i] receives texture i, tight layout. */
+CRN_API int crn_gpu_crnd_unpack_batch(crn_gpu_ctx* ctx, crn_gpu_texture* const* textures, uint32_t count, void* const* d_dst,
+                                      const uint64_t* dst_capacity);
+CRN_API int crn_gpu_crnd_unpack_end(crn_gpu_texture* tex);
+
 #ifdef __cplusplus
 }
 #endif

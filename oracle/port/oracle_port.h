@@ -50,6 +50,14 @@ uint32_t op_pack_image(int fmt, const uint8_t* rgba, uint32_t width, uint32_t he
                        uint32_t quality, uint32_t perceptual, uint32_t use_both_block_types,
                        uint32_t alpha_threshold, uint32_t transparent_for_black, uint8_t* out);
 
+/* CRN -> DXTn transcoder (inc/crn_decomp.h): crnd_unpack_begin / crnd_get_texture_info / crnd_unpack_level /
+ * crnd_unpack_end.  info out[0..7] = width,height,levels,faces,bytes_per_block,format,userdata0,userdata1. */
+typedef struct op_crnd op_crnd;
+op_crnd* op_crnd_begin(const uint8_t* data, uint32_t size);
+int op_crnd_info(const uint8_t* data, uint32_t size, uint32_t* out);
+int op_crnd_unpack_level(op_crnd* c, void** dst_faces, uint32_t dst_size, uint32_t row_pitch, uint32_t level);
+void op_crnd_end(op_crnd* c);
+
 #ifdef __cplusplus
 }
 #endif

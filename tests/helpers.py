@@ -92,3 +92,68 @@ def mismatching_blocks(a, b, bpb):
     a = a.reshape(-1, bpb)
     b = b.reshape(-1, bpb)
     return np.nonzero((a != b).any(axis=1))[0]
+
+
+# ---- CRN files ------------------------------------------------------------------------------------
+CRN_FMT = dict(DXT1=0, DXT3=1, DXT5=2, DXT5_CCxY=3, DXT5_xGxR=4, DXT5_xGBR=5, DXT5_AGBR=6, DXN_XY=7, DXN_YX=8, DXT5A=9)
+
+
+def ref_compress(lib, images, fmt, file_type=0, quality=128, flags=1 | 2 | 8, bitrate=0.0, dxt_quality=4, threads=7, want_bitrate=False):
+    """crn_compress through the unmodified reference.  images[face][level] = (h, w, 4) uint8.
+    file_type 0 = CRN, 1 = DDS.  Returns (bytes, actual_quality, actual_bitrate)."""
+    faces, levels = len(images), len(images[0])
+    h, w = images[0][0].shape[:2]
+    flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]
+    arr = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
+    size = ctypes.c_uint32(); aq = ctypes.c_uint32(); ab = ctypes.c_float()
+    p = lib.ref_compress(file_type, fmt, w, h, faces, levels, arr, flags, quality, ctypes.c_float(bitrate), dxt_quality, threads, 3,
+                         ctypes.byref(size), ctypes.byref(aq), ctypes.byref(ab), int(want_bitrate))
+    if not p:
+        return None, 0, 0.0
+    data = ctypes.string_at(p, size.value)
+    lib.ref_free(ctypes.c_void_p(p))
+    return data, aq.value, ab.value
+
+
+def level_dims(w, h, level):
+    return max(1, w >> level), max(1, h >> level)
+
+
+def ref_unpack_all(lib, crn):
+    """Every level / face through crnd_unpack_level of the reference; returns list[level][face] -> bytes."""
+    buf = np.frombuffer(crn, np.uint8)
+    info = (ctypes.c_uint32 * 8)()
+    assert lib.ref_crn_info(P(buf), len(crn), info)
+    w, h, levels, faces, bpb = info[0], info[1], info[2], info[3], info[4]
+    ctx = lib.ref_transcode_begin(P(buf), len(crn))
+    assert ctx
+    out = []
+    for l in range(levels):
+        lw, lh = level_dims(w, h, l)
+        bx, by = (lw + 3) // 4, (lh + 3) // 4
+        faces_np = [np.zeros(bx * by * bpb, np.uint8) for _ in range(faces)]
+        ptrs = (ctypes.c_void_p * faces)(*[a.ctypes.data for a in faces_np])
+        assert lib.ref_transcode_level(ctypes.c_void_p(ctx), ptrs, bx * by * bpb, bx * bpb, l)
+        out.append([a.tobytes() for a in faces_np])
+    lib.ref_transcode_end(ctypes.c_void_p(ctx))
+    return out
+
+
+def port_unpack_all(lib, crn):
+    lib.op_crnd_begin.restype = ctypes.c_void_p
+    buf = np.frombuffer(crn, np.uint8)
+    info = (ctypes.c_uint32 * 8)()
+    assert lib.op_crnd_info(P(buf), len(crn), info)
+    w, h, levels, faces, bpb = info[0], info[1], info[2], info[3], info[4]
+    ctx = lib.op_crnd_begin(P(buf), len(crn))
+    assert ctx
+    out = []
+    for l in range(levels):
+        lw, lh = level_dims(w, h, l)
+        bx, by = (lw + 3) // 4, (lh + 3) // 4
+        faces_np = [np.zeros(bx * by * bpb, np.uint8) for _ in range(faces)]
+        ptrs = (ctypes.c_void_p * faces)(*[a.ctypes.data for a in faces_np])
+        assert lib.op_crnd_unpack_level(ctypes.c_void_p(ctx), ptrs, bx * by * bpb, bx * bpb, l)
+        out.append([a.tobytes() for a in faces_np])
+    lib.op_crnd_end(ctypes.c_void_p(ctx))
+    return out

@@ -1,0 +1,114 @@
+"""CPU tests of the CRN -> DXTn transcoder: oracle port against the golden .crn files written and decoded
+by the unmodified reference, the reference itself (when built), and the CUDA kernels under the SIMT
+emulator.  Synthetic .crn files (tests/crnsynth.py) cover what the reference's compressor cannot
+produce: 8192-entry palettes, long Huffman codes, ragged sizes."""
+import os
+
+import numpy as np
+import pytest
+
+import crnsynth
+import crunch2_b200 as crn
+import helpers
+
+GOLD = helpers.golden("crn_golden.json")["cases"]
+
+
+def load(case):
+    with open(os.path.join(helpers.ROOT, "tests", "golden", "crn", case["name"] + ".crn"), "rb") as f:
+        return f.read()
+
+
+def shas(levels):
+    return [[helpers.sha(np.frombuffer(fc, np.uint8)) for fc in lv] for lv in levels]
+
+
+def split_levels(tex, flat):
+    out = []
+    for l in range(tex.info["levels"]):
+        bx, by = tex.level_blocks(l)
+        n = bx * by * tex.info["bytes_per_block"]
+        out.append([flat[tex.level_offset(l, f):tex.level_offset(l, f) + n].tobytes() for f in range(tex.info["faces"])])
+    return out
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_port_matches_golden_crn(port, case):
+    assert shas(helpers.port_unpack_all(port, load(case))) == case["sha256"]
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_sim_matches_golden_crn(sim, case):
+    ctx = crn.Context(0, lib=sim)
+    data = load(case)
+    info = crn.texture_info(data, sim)
+    assert (info["width"], info["height"], info["faces"], info["levels"], info["format"]) == (case["width"], case["height"], case["faces"], case["levels"], case["format"])
+    tex = ctx.unpack_begin(data)
+    assert shas(split_levels(tex, tex.unpack_all())) == case["sha256"]
+    tex.close(); ctx.close()
+
+
+SYNTH = [("DXT1", 64, 64, 1, {}), ("DXT5", 100, 36, 1, {}), ("DXN_XY", 32, 48, 1, {}), ("DXT5A", 20, 12, 1, {}), ("DXT5", 32, 32, 6, {}),
+         ("DXT1", 256, 256, 1, dict(n_color_ep=8192, n_color_sel=8192)), ("DXT5", 8, 8, 1, dict(n_color_ep=9, n_color_sel=8, n_alpha_ep=8, n_alpha_sel=8)),
+         ("DXN_YX", 1, 1, 1, {}), ("DXT5", 260, 4, 1, dict(n_alpha_ep=8192, n_alpha_sel=8192))]
+
+
+@pytest.mark.parametrize("fmt,w,h,faces,kw", SYNTH)
+def test_synthetic_crn_port_ref_sim_agree(port, sim, fmt, w, h, faces, kw):
+    data = crnsynth.synth_crn(w, h, fmt, faces=faces, seed=5, **kw)
+    want = helpers.port_unpack_all(port, data)
+    ref = helpers.load_ref()
+    if ref is not None:
+        assert helpers.ref_unpack_all(ref, data) == want
+    ctx = crn.Context(0, lib=sim)
+    tex = ctx.unpack_begin(data)
+    assert split_levels(tex, tex.unpack_all()) == want
+    tex.close(); ctx.close()
+
+
+def test_unpack_level_contract(sim, port):
+    """crnd_unpack_level semantics: per-face destination pointers, explicit pitch, size / pitch validation
+    (inc/crn_decomp.h:3569-3575)."""
+    import ctypes
+    data = load([c for c in GOLD if c["name"] == "dxt1_cube_32_mips"][0])
+    want = helpers.port_unpack_all(port, data)
+    ctx = crn.Context(0, lib=sim)
+    tex = ctx.unpack_begin(data)
+    bx, by = tex.level_blocks(1)
+    pitch = bx * 8 + 16
+    bufs = [np.full(pitch * by, 0xEE, np.uint8) for _ in range(6)]
+    tex.unpack_level_device([b.ctypes.data for b in bufs], pitch * by, pitch, 1)
+    ctx.synchronize()
+    for f in range(6):
+        rows = bufs[f].reshape(by, pitch)
+        assert rows[:, :bx * 8].tobytes() == want[1][f]
+        assert (rows[:, bx * 8:] == 0xEE).all()          # padding untouched
+    with pytest.raises(crn.CrnGpuError):
+        tex.unpack_level_device([b.ctypes.data for b in bufs], 8, pitch, 1)          # destination too small
+    with pytest.raises(crn.CrnGpuError):
+        tex.unpack_level_device([b.ctypes.data for b in bufs], pitch * by, bx * 8 - 4, 1)   # pitch too small
+    with pytest.raises(crn.CrnGpuError):
+        tex.unpack_level_device([b.ctypes.data for b in bufs], pitch * by, pitch, 99)      # bad level
+    tex.close(); ctx.close()
+
+
+def test_bad_files_rejected(sim):
+    ctx = crn.Context(0, lib=sim)
+    with pytest.raises(crn.CrnGpuError):
+        ctx.unpack_begin(b"\0" * 200)
+    data = bytearray(load(GOLD[0]))
+    with pytest.raises(crn.CrnGpuError):
+        ctx.unpack_begin(bytes(data[:40]))
+    ctx.close()
+
+
+def test_batch_matches_single(sim, port):
+    ctx = crn.Context(0, lib=sim)
+    files = [load(c) for c in GOLD[:4]]
+    texs = [ctx.unpack_begin(d) for d in files]
+    outs = [np.zeros(t.total_size, np.uint8) for t in texs]
+    ctx.unpack_batch(texs, [o.ctypes.data for o in outs], [o.size for o in outs])
+    for t, o, d in zip(texs, outs, files):
+        assert split_levels(t, o) == helpers.port_unpack_all(port, d)
+        t.close()
+    ctx.close()
