@@ -353,7 +353,7 @@ int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_
     size_t o_bytes = 0, o_models = align(o_bytes + crn_size + 16), o_pool = align(o_models + sizeof(crn::HuffModelDev) * crn::kNumModels);
     size_t o_ce = align(o_pool + pool.size() * 2), o_cs = align(o_ce + 4 * (size_t)(h.pal_num[0] + 1)), o_ae = align(o_cs + 4 * (size_t)(h.pal_num[1] + 1));
     size_t o_as = align(o_ae + 2 * (size_t)(h.pal_num[2] + 1)), o_row = align(o_as + 6 * (size_t)(h.pal_num[3] + 1));
-    size_t o_file = align(o_row + 8 * (size_t)rowbuf_total), total = align(o_file + sizeof(crn::TranscodeFile));
+    size_t o_file = align(o_row + 9 * (size_t)rowbuf_total + 16), total = align(o_file + sizeof(crn::TranscodeFile));
     cudaError_t ce = cudaMalloc(&t->slab, total);
     if (ce != cudaSuccess) { delete t; return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "cudaMalloc", ce); }
     uint8_t* base = static_cast<uint8_t*>(t->slab);
@@ -366,6 +366,7 @@ int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_
     f.alpha_endpoints = reinterpret_cast<uint16_t*>(base + o_ae);
     f.alpha_selectors = reinterpret_cast<uint16_t*>(base + o_as);
     f.rowbuf_pool = reinterpret_cast<uint2*>(base + o_row);
+    f.rowbuf_total = rowbuf_total;
     f.num_color_endpoints = h.pal_num[0]; f.num_color_selectors = h.pal_num[1];
     f.num_alpha_endpoints = h.pal_num[2]; f.num_alpha_selectors = h.pal_num[3];
     for (int i = 0; i < 4; i++) { f.pal_data_ofs[i] = pal_data_ofs[i]; f.pal_data_bit[i] = pal_data_bit[i]; f.pal_size_end[i] = h.pal_ofs[i] + h.pal_size[i]; }

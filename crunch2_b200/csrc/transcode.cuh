@@ -56,35 +56,54 @@ struct TranscodeFile {                  // everything the kernels need for one .
     uint32_t* color_selectors;
     uint16_t* alpha_endpoints;          // lo | hi << 8
     uint16_t* alpha_selectors;          // 3 x uint16 per entry
-    uint2* rowbuf_pool;                 // per level: padded-width entries {ref | ce << 16, a0 | a1 << 16}
+    uint2* rowbuf_pool;                 // fallback row buffers for files too wide for shared memory: rowbuf_total uint2 values, then rowbuf_total reference bytes
+    uint32_t rowbuf_total, pad0;
     uint32_t num_color_endpoints, num_color_selectors, num_alpha_endpoints, num_alpha_selectors;
     uint32_t pal_data_ofs[4], pal_data_bit[4], pal_size_end[4];   // first symbol of each palette stream (byte, bit) and segment end
     uint32_t format, faces;
     LevelStream levels[16];
 };
 
-// MSB-first bit window: `buf` holds `cnt` valid bits left-justified.
+// MSB-first bit window: `buf` holds `cnt` valid bits left-justified.  Words are fetched as aligned 32-bit
+// loads (byte-swapped) and the NEXT word is always already in flight (`nextw`), so the refill never sits
+// on the symbol-to-symbol dependency chain.  Reads past `end` see zeros (crn_decomp.h:3168-3170); the
+// file image is padded so the aligned loads themselves never leave the allocation.
 struct BitWindow {
-    const uint8_t* p;
-    uint32_t pos, end;                  // next byte to fetch, one past the last valid byte
+    const uint32_t* words;              // 4-byte aligned base of the file image
+    uint32_t wi;                        // index of the word held in nextw
+    uint32_t end_byte;                  // one past the last valid byte of this stream
+    uint32_t nextw;                     // big-endian value of words[wi], masked to the stream end
     unsigned long long buf;
     int cnt;
 };
-__device__ __forceinline__ void bw_refill(BitWindow& w)
+__device__ __forceinline__ uint32_t bw_fetch(const BitWindow& w, uint32_t wi)
 {
-    while (w.cnt <= 56) {
-        const unsigned long long b = w.pos < w.end ? w.p[w.pos] : 0ull;   // zero padding past the end (crn_decomp.h:3168-3170)
-        w.pos++;
-        w.buf |= b << (56 - w.cnt);
-        w.cnt += 8;
+    uint32_t v = __byte_perm(w.words[wi], 0, 0x0123);
+    const uint32_t first = wi * 4;
+    if (first + 4 > w.end_byte) {       // zero the bytes that lie past the end of the stream
+        const uint32_t valid = first < w.end_byte ? w.end_byte - first : 0;
+        v = valid ? (v & (0xFFFFFFFFu << (32 - 8 * valid))) : 0u;
     }
+    return v;
+}
+__device__ __forceinline__ void bw_refill(BitWindow& w)
+{   // precondition: cnt <= 32
+    w.buf |= (unsigned long long)w.nextw << (32 - w.cnt);
+    w.cnt += 32;
+    w.wi++;
+    w.nextw = bw_fetch(w, w.wi);
 }
 __device__ __forceinline__ void bw_init(BitWindow& w, const uint8_t* p, uint32_t ofs, uint32_t end, uint32_t bit)
 {
-    w.p = p; w.pos = ofs; w.end = end; w.buf = 0; w.cnt = 0;
+    w.words = reinterpret_cast<const uint32_t*>(p);    // the file image is 256-byte aligned
+    w.end_byte = end;
+    w.wi = ofs >> 2;
+    w.nextw = bw_fetch(w, w.wi);
+    w.buf = 0; w.cnt = 0;
     bw_refill(w);
-    w.buf <<= bit; w.cnt -= (int)bit;
-    bw_refill(w);
+    const uint32_t skip = (ofs & 3) * 8 + bit;           // leading bits that belong to earlier data
+    w.buf <<= skip; w.cnt -= (int)skip;
+    if (w.cnt <= 32) bw_refill(w);
 }
 __device__ __forceinline__ uint32_t bw_decode(BitWindow& w, const uint32_t* lookup, const HuffModelDev* m, const uint16_t* pool)
 {
@@ -96,6 +115,31 @@ __device__ __forceinline__ uint32_t bw_decode(BitWindow& w, const uint32_t* look
         len = kHuffLookupBits + 1;
         while (len < 16 && k >= m->limit[len]) len++;
         sym = pool[m->sorted_ofs + m->first_idx[len] + ((k >> (16 - len)) - m->first_code[len])];
+    }
+    w.buf <<= len; w.cnt -= (int)len;
+    if (w.cnt <= 32) bw_refill(w);
+    return sym;
+}
+
+// Codes longer than the 11-bit lookup: the five left-justified limits of lengths 12..16 and the matching
+// symbol-pool bases, kept in shared memory per block model.  The LENGTH comes from register compares, so
+// the bit-parsing chain never waits for the symbol-pool load (only reference symbols feed back into
+// parsing, and their alphabet is 256 symbols).
+struct LongCodes {
+    uint32_t limit[5];                  // lengths 12..16
+    int32_t base[5];                    // sorted_ofs + first_idx[len] - first_code[len]
+    uint32_t pad[2];
+};
+__device__ __forceinline__ uint32_t bw_decode_fast(BitWindow& w, const uint32_t* lookup, const LongCodes* lc, const uint16_t* pool)
+{
+    const uint32_t t = lookup[(uint32_t)(w.buf >> (64 - kHuffLookupBits))];
+    uint32_t sym, len;
+    if (t != kHuffLong) { sym = t & 0xffffu; len = t >> 16; }
+    else {
+        const uint32_t k = (uint32_t)(w.buf >> 48);
+        const uint32_t i = (k >= lc->limit[0]) + (k >= lc->limit[1]) + (k >= lc->limit[2]) + (k >= lc->limit[3]);
+        len = 12 + i;
+        sym = pool[lc->base[i] + (int32_t)(k >> (4 - i))];
     }
     w.buf <<= len; w.cnt -= (int)len;
     if (w.cnt <= 32) bw_refill(w);
@@ -166,17 +210,129 @@ __global__ void __launch_bounds__(128) transcode_palettes_kernel(const Transcode
 }
 
 // ---- levels (unpack_level, crn_decomp.h:3552-3619, :3944-4223) ----------------------------------
-struct BlockBatch {                     // per-warp shared memory: 32 visible blocks awaiting expansion
-    uint32_t out_ofs[32];               // byte offset within the face
-    uint16_t ce[32], cs[32], a0[32], s0[32], a1[32], s1[32];
-    uint8_t face[32];
-    uint32_t n, done;
+// A single thread issues dependent instructions ~4-6 cycles apart, so what limits one level stream is
+// the NUMBER OF INSTRUCTIONS on lane 0's path, not memory.  Lane 0 therefore does only what is serial by
+// construction -- symbol lengths and the reference symbols that select the next code table -- and drops
+// raw symbols into a batch of up to 32 blocks of one block row.  Everything else is done by all lanes:
+// the running endpoint indices (":3983-3995": idx = (idx + delta) mod N, "left" keeps it, "top" reloads
+// it from the row above) are a segmented prefix sum over the batch, then palette gathers and stores.
+struct BlockBatch {                     // per-warp shared memory
+    uint16_t dce[32], da0[32], da1[32]; // endpoint index deltas (valid where ref == 0)
+    uint16_t cs[32], s0[32], s1[32];    // selector indices
+    uint8_t ref[32];                    // endpoint reference 0 new / 1 left / 2 top
+    uint32_t n, done, x0, y, face;
 };
+
+constexpr uint32_t kRowbufSmemEntries = 6144;      // every level of a <= 8192-wide texture (sum of padded widths < 2 * 2048 + 32)
 
 struct TranscodeSmem {
     uint32_t lookup[kNumBlockModels][kHuffLookupSize];
+    LongCodes longc[kNumBlockModels];
     BlockBatch batch[kTranscodeWarps];
+    uint2 rowval[kRowbufSmemEntries];   // per column: ce | a0 << 16, a1   (resolved indices of the row above)
+    uint8_t rowref[kRowbufSmemEntries]; // per column: reference of the odd row, delivered by the even row's group symbol
 };
+
+// segmented running-index scan over the batch for one component
+__device__ __forceinline__ uint32_t resolve_indices(uint32_t ref, uint32_t delta, uint32_t top, uint32_t carry, uint32_t n_pal, uint32_t n)
+{
+    const unsigned lane = lane_id();
+    uint32_t s = (ref == 0 && lane < n) ? delta : 0u;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+        const uint32_t v = __shfl_up_sync(CRN_FULL_MASK, s, ofs);
+        if ((int)lane >= ofs) s += v;
+    }
+    const unsigned resets = __ballot_sync(CRN_FULL_MASK, ref == 2 && lane < n);
+    const unsigned below = resets & (0xFFFFFFFFu >> (31 - lane));
+    const int h = below ? 31 - __clz((int)below) : 0;
+    const uint32_t top_h = __shfl_sync(CRN_FULL_MASK, top, h);
+    const uint32_t s_h = __shfl_sync(CRN_FULL_MASK, s, h);
+    const uint32_t v = below ? top_h + (s - s_h) : carry + s;
+    return v % n_pal;
+}
+
+template <bool HAS_COLOR, bool HAS_A0, bool IS_DXN>
+__device__ __forceinline__ void transcode_level(TranscodeSmem* sm, const TranscodeFile& f, const LevelStream& ls, BlockBatch* bb)
+{
+    const unsigned lane = lane_id();
+    const uint32_t faces = f.faces;
+    const uint32_t bs = ((HAS_COLOR && HAS_A0) || IS_DXN) ? 16u : 8u;   // DXT5 / DXN: two elements, DXT1 / DXT5A: one
+    const uint32_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
+    const uint32_t bxv = ls.blocks_x, byv = ls.blocks_y, pitch = ls.row_pitch;
+    const bool in_smem = ls.rowbuf_ofs + W <= kRowbufSmemEntries;
+    uint2* rowval = in_smem ? &sm->rowval[ls.rowbuf_ofs] : f.rowbuf_pool + ls.rowbuf_ofs;
+    uint8_t* rowref = in_smem ? &sm->rowref[ls.rowbuf_ofs] : reinterpret_cast<uint8_t*>(f.rowbuf_pool + f.rowbuf_total) + ls.rowbuf_ofs;
+    const uint16_t* pool = f.sorted_pool;
+    const uint32_t* ce_pal = f.color_endpoints; const uint32_t* cs_pal = f.color_selectors;
+    const uint16_t* ae_pal = f.alpha_endpoints; const uint16_t* as_pal = f.alpha_selectors;
+    const uint32_t nce = f.num_color_endpoints, nae = f.num_alpha_endpoints;
+    for (uint32_t i = lane; i < W; i += 32) { rowval[i] = make_uint2(0u, 0u); rowref[i] = 0; }
+    __syncwarp();
+
+    BitWindow w;
+    uint32_t group = 0, x = 0, y = 0, face = 0;
+    uint32_t ce = 0, a0 = 0, a1 = 0;                     // running indices (warp-uniform carry)
+    if (lane == 0) bw_init(w, f.bytes, ls.src_ofs, ls.src_ofs + ls.src_size, 0);
+    for (;;) {
+        if (lane == 0) {
+            const uint32_t n = min(32u, W - x);
+            bb->x0 = x; bb->y = y; bb->face = face; bb->n = n;
+            const bool odd = y & 1;
+            for (uint32_t i = 0; i < n; i++, x++) {
+                uint32_t r;
+                if (odd) r = rowref[x];
+                else {
+                    if (!(x & 1)) group = bw_decode_fast(w, sm->lookup[kDmRef], &sm->longc[kDmRef], pool);
+                    r = group & 3; rowref[x] = (uint8_t)((group >> 2) & 3); group >>= 4;
+                }
+                bb->ref[i] = (uint8_t)r;
+                if (!r) {
+                    if (HAS_COLOR) bb->dce[i] = (uint16_t)bw_decode_fast(w, sm->lookup[kDmColorEp], &sm->longc[kDmColorEp], pool);
+                    if (HAS_A0) bb->da0[i] = (uint16_t)bw_decode_fast(w, sm->lookup[kDmAlphaEp], &sm->longc[kDmAlphaEp], pool);
+                    if (IS_DXN) bb->da1[i] = (uint16_t)bw_decode_fast(w, sm->lookup[kDmAlphaEp], &sm->longc[kDmAlphaEp], pool);
+                }
+                if (HAS_COLOR) bb->cs[i] = (uint16_t)bw_decode_fast(w, sm->lookup[kDmColorSel], &sm->longc[kDmColorSel], pool);
+                if (HAS_A0) bb->s0[i] = (uint16_t)bw_decode_fast(w, sm->lookup[kDmAlphaSel], &sm->longc[kDmAlphaSel], pool);
+                if (IS_DXN) bb->s1[i] = (uint16_t)bw_decode_fast(w, sm->lookup[kDmAlphaSel], &sm->longc[kDmAlphaSel], pool);
+            }
+            if (x == W) { x = 0; if (++y == H) { y = 0; face++; } }
+            bb->done = face >= faces;
+        }
+        __syncwarp();
+        const uint32_t n = bb->n, done = bb->done, bx0 = bb->x0, by0 = bb->y, bf = bb->face;
+        {
+            const uint32_t col = bx0 + (lane < n ? lane : 0u);
+            const uint32_t ref = lane < n ? bb->ref[lane] : 1u;
+            const uint2 top = rowval[col];
+            uint32_t vce = 0, va0 = 0, va1 = 0;
+            if (HAS_COLOR) { vce = resolve_indices(ref, bb->dce[lane], top.x & 0xffffu, ce, nce, n); ce = __shfl_sync(CRN_FULL_MASK, vce, (int)n - 1); }
+            if (HAS_A0) { va0 = resolve_indices(ref, bb->da0[lane], top.x >> 16, a0, nae, n); a0 = __shfl_sync(CRN_FULL_MASK, va0, (int)n - 1); }
+            if (IS_DXN) { va1 = resolve_indices(ref, bb->da1[lane], top.y, a1, nae, n); a1 = __shfl_sync(CRN_FULL_MASK, va1, (int)n - 1); }
+            if (lane < n) {
+                rowval[col] = make_uint2(vce | (va0 << 16), va1);
+                if (by0 < byv && col < bxv) {
+                    uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ls.dst[bf]) + (size_t)by0 * pitch + (size_t)col * bs);
+                    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+                    if (HAS_A0) {
+                        const uint16_t* as0 = as_pal + 3u * bb->s0[lane];
+                        q0 = ae_pal[va0] | ((uint32_t)as0[0] << 16);
+                        q1 = as0[1] | ((uint32_t)as0[2] << 16);
+                        if (IS_DXN) {
+                            const uint16_t* as1 = as_pal + 3u * bb->s1[lane];
+                            q2 = ae_pal[va1] | ((uint32_t)as1[0] << 16);
+                            q3 = as1[1] | ((uint32_t)as1[2] << 16);
+                        } else if (HAS_COLOR) { q2 = ce_pal[vce]; q3 = cs_pal[bb->cs[lane]]; }
+                    } else { q0 = ce_pal[vce]; q1 = cs_pal[bb->cs[lane]]; }
+                    if (bs == 8) { o[0] = q0; o[1] = q1; }
+                    else { o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3; }
+                }
+            }
+        }
+        __syncwarp();
+        if (done) break;
+    }
+}
 
 __global__ void __launch_bounds__(kTranscodeWarps * 32) transcode_levels_kernel(const TranscodeFile* __restrict__ files)
 {
@@ -184,80 +340,22 @@ __global__ void __launch_bounds__(kTranscodeWarps * 32) transcode_levels_kernel(
     const TranscodeFile& f = files[blockIdx.x];
     for (uint32_t i = threadIdx.x; i < (uint32_t)(kNumBlockModels * kHuffLookupSize); i += blockDim.x)
         sm->lookup[i / kHuffLookupSize][i % kHuffLookupSize] = f.models[i / kHuffLookupSize].lookup[i % kHuffLookupSize];
+    if (threadIdx.x < kNumBlockModels * 5) {
+        const int m = threadIdx.x / 5, j = threadIdx.x % 5, len = 12 + j;
+        const HuffModelDev& hm = f.models[m];
+        sm->longc[m].limit[j] = hm.limit[len];
+        sm->longc[m].base[j] = (int32_t)(hm.sorted_ofs + hm.first_idx[len]) - (int32_t)hm.first_code[len];
+    }
     __syncthreads();
-    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    const LevelStream& ls = f.levels[warp];
+    const unsigned warp = threadIdx.x >> 5;
+    const LevelStream ls = f.levels[warp];              // by value: registers, not repeated global loads
     if (!ls.active) return;
     BlockBatch* bb = &sm->batch[warp];
     const uint32_t fmt = f.format;
-    const bool is_dxn = fmt == 7 || fmt == 8;
-    const bool has_color = fmt <= 6, has_a0 = fmt != 0;
-    const uint32_t bs = (fmt == 0 || fmt == 9) ? 8u : 16u;
-    const uint32_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
-    uint2* rowbuf = f.rowbuf_pool + ls.rowbuf_ofs;
-
-    // lane-0 decoder state
-    BitWindow w;
-    uint32_t ce = 0, a0 = 0, a1 = 0, group = 0, x = 0, y = 0, face = 0;
-    if (lane == 0) {
-        bw_init(w, f.bytes, ls.src_ofs, ls.src_ofs + ls.src_size, 0);
-        for (uint32_t i = 0; i < W; i++) rowbuf[i] = make_uint2(0u, 0u);
-    }
-    const uint32_t nce = f.num_color_endpoints, nae = f.num_alpha_endpoints;
-    const HuffModelDev* M = f.models;
-    for (;;) {
-        if (lane == 0) {
-            uint32_t n = 0;
-            while (face < f.faces && n < 32) {
-                const bool visible = y < ls.blocks_y && x < ls.blocks_x;
-                if (!(y & 1) && !(x & 1)) group = bw_decode(w, sm->lookup[kDmRef], &M[kDmRef], f.sorted_pool);
-                uint2 rb = rowbuf[x];
-                uint32_t r;
-                if (y & 1) r = rb.x & 0xffffu;
-                else { r = group & 3; group >>= 2; rb.x = (rb.x & 0xffff0000u) | (group & 3); group >>= 2; }
-                if (!r) {
-                    if (has_color) { ce += bw_decode(w, sm->lookup[kDmColorEp], &M[kDmColorEp], f.sorted_pool); if (ce >= nce) ce -= nce; }
-                    if (has_a0) { a0 += bw_decode(w, sm->lookup[kDmAlphaEp], &M[kDmAlphaEp], f.sorted_pool); if (a0 >= nae) a0 -= nae; }
-                    if (is_dxn) { a1 += bw_decode(w, sm->lookup[kDmAlphaEp], &M[kDmAlphaEp], f.sorted_pool); if (a1 >= nae) a1 -= nae; }
-                } else if (r == 2) { ce = rb.x >> 16; a0 = rb.y & 0xffffu; a1 = rb.y >> 16; }
-                // r == 0 and r == 1 both leave the running indices in the row buffer (:3986-3990)
-                rb.x = (rb.x & 0xffffu) | (ce << 16); rb.y = a0 | (a1 << 16);
-                rowbuf[x] = rb;
-                uint32_t cs = 0, s0 = 0, s1 = 0;
-                if (has_color) cs = bw_decode(w, sm->lookup[kDmColorSel], &M[kDmColorSel], f.sorted_pool);
-                if (has_a0) s0 = bw_decode(w, sm->lookup[kDmAlphaSel], &M[kDmAlphaSel], f.sorted_pool);
-                if (is_dxn) s1 = bw_decode(w, sm->lookup[kDmAlphaSel], &M[kDmAlphaSel], f.sorted_pool);
-                if (visible) {
-                    bb->out_ofs[n] = y * ls.row_pitch + x * bs;
-                    bb->ce[n] = (uint16_t)ce; bb->cs[n] = (uint16_t)cs; bb->a0[n] = (uint16_t)a0; bb->s0[n] = (uint16_t)s0;
-                    bb->a1[n] = (uint16_t)a1; bb->s1[n] = (uint16_t)s1; bb->face[n] = (uint8_t)face;
-                    n++;
-                }
-                if (++x == W) { x = 0; if (++y == H) { y = 0; face++; } }
-            }
-            bb->n = n; bb->done = face >= f.faces;
-        }
-        __syncwarp();
-        const uint32_t n = bb->n, done = bb->done;
-        if (lane < n) {
-            uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ls.dst[bb->face[lane]]) + bb->out_ofs[lane]);
-            uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-            if (has_a0) {
-                const uint16_t* as0 = f.alpha_selectors + 3u * bb->s0[lane];
-                q0 = f.alpha_endpoints[bb->a0[lane]] | ((uint32_t)as0[0] << 16);
-                q1 = as0[1] | ((uint32_t)as0[2] << 16);
-                if (is_dxn) {
-                    const uint16_t* as1 = f.alpha_selectors + 3u * bb->s1[lane];
-                    q2 = f.alpha_endpoints[bb->a1[lane]] | ((uint32_t)as1[0] << 16);
-                    q3 = as1[1] | ((uint32_t)as1[2] << 16);
-                } else if (has_color) { q2 = f.color_endpoints[bb->ce[lane]]; q3 = f.color_selectors[bb->cs[lane]]; }
-            } else { q0 = f.color_endpoints[bb->ce[lane]]; q1 = f.color_selectors[bb->cs[lane]]; }
-            if (bs == 8) { o[0] = q0; o[1] = q1; }
-            else { o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3; }
-        }
-        __syncwarp();
-        if (done) break;
-    }
+    if (fmt == 0) transcode_level<true, false, false>(sm, f, ls, bb);
+    else if (fmt == 9) transcode_level<false, true, false>(sm, f, ls, bb);
+    else if (fmt == 7 || fmt == 8) transcode_level<false, true, true>(sm, f, ls, bb);
+    else transcode_level<true, true, false>(sm, f, ls, bb);
 }
 
 }  // namespace crn

@@ -171,15 +171,17 @@ def _crc16_ref(data):
     return (~crc) & 0xFFFF
 
 
-def _skewed(rng, n, size):
-    """Indices with a long-tailed distribution so the Huffman codes have a spread of lengths."""
-    x = rng.geometric(min(0.5, 8.0 / max(n, 8)), size) - 1
+def _skewed(rng, n, size, p=None):
+    """Indices with a long-tailed distribution so the Huffman codes have a spread of lengths.  p is the
+    geometric parameter: the default 8/n gives a flat, high-entropy stream (many codes longer than the
+    decoder's first-level table), p ~ 0.05 gives bitrates like real .crn files (1-1.3 bits/texel)."""
+    x = rng.geometric(min(0.5, 8.0 / max(n, 8)) if p is None else p, size) - 1
     perm = rng.permutation(n)
     return perm[x % n]
 
 
 def synth_crn(width, height, fmt="DXT5", levels=None, faces=1, seed=1, n_color_ep=1024, n_color_sel=1024, n_alpha_ep=512, n_alpha_sel=512,
-              with_crc=True):
+              with_crc=True, skew=None):
     rng = np.random.default_rng(seed)
     f = FMT[fmt]
     has_color = f in (0, 2)
@@ -237,21 +239,25 @@ def synth_crn(width, height, fmt="DXT5", levels=None, faces=1, seed=1, n_color_e
         rows = faces * H
         # endpoint indices: row by row so that "left" (1) and "top" (2) references are consistent
         def resolve(npal):
+            """Endpoint index of every block.  New-endpoint blocks (ref 0) move the running index by a skewed
+            delta, "left" (1) keeps it, "top" (2) reloads the index of the block above: a segmented prefix
+            sum per row, carried across rows and faces exactly like the decoder's running index."""
             e = np.zeros((rows, W), np.int64)
-            fresh = _skewed(rng, npal, rows * W).reshape(rows, W)
-            last = 0
+            step = _skewed(rng, npal, rows * W, skew).reshape(rows, W)
+            carry = 0
+            ar = np.arange(W)
             for r in range(rows):
-                rr = ref[r].copy()
-                if r % H == 0:
-                    rr[rr == 2] = 0          # no row above inside this face for the writer to reference
+                rr = ref[r]
+                if r % H == 0 and (rr == 2).any():
+                    rr = rr.copy(); rr[rr == 2] = 0          # no row above inside this face for the writer to reference
                     ref[r] = rr
-                src = np.where(rr == 0, fresh[r], np.where(rr == 2, e[r - 1] if r else 0, -1))
-                # forward fill the "left" references from the previous block in scan order
-                idx = np.where(src >= 0, np.arange(W), -1)
-                idx = np.maximum.accumulate(idx)
-                row = np.where(idx >= 0, src[np.maximum(idx, 0)], last)
+                c = np.cumsum(np.where(rr == 0, step[r], 0))
+                h = np.maximum.accumulate(np.where(rr == 2, ar, -1))
+                top = e[r - 1] if r else e[0]
+                hh = np.maximum(h, 0)
+                row = np.where(h >= 0, top[hh] + c - c[hh], carry + c) % npal
                 e[r] = row
-                last = row[-1]
+                carry = int(row[-1])
             return e
         ce_idx = resolve(n_color_ep) if has_color else None
         a0_idx = resolve(n_alpha_ep) if has_a0 else None
@@ -271,13 +277,13 @@ def synth_crn(width, height, fmt="DXT5", levels=None, faces=1, seed=1, n_color_e
             return (flat - prev) % npal
         lvl = dict(W=W, H=H, n=n, ref=ref.ravel())
         if has_color:
-            lvl["ced"] = deltas(ce_idx, n_color_ep); lvl["cs"] = _skewed(rng, n_color_sel, n)
+            lvl["ced"] = deltas(ce_idx, n_color_ep); lvl["cs"] = _skewed(rng, n_color_sel, n, skew)
             all_ced.append(lvl["ced"][lvl["ref"] == 0]); all_cs.append(lvl["cs"])
         if has_a0:
-            lvl["a0d"] = deltas(a0_idx, n_alpha_ep); lvl["s0"] = _skewed(rng, n_alpha_sel, n)
+            lvl["a0d"] = deltas(a0_idx, n_alpha_ep); lvl["s0"] = _skewed(rng, n_alpha_sel, n, skew)
             all_aed.append(lvl["a0d"][lvl["ref"] == 0]); all_as.append(lvl["s0"])
         if has_a1:
-            lvl["a1d"] = deltas(a1_idx, n_alpha_ep); lvl["s1"] = _skewed(rng, n_alpha_sel, n)
+            lvl["a1d"] = deltas(a1_idx, n_alpha_ep); lvl["s1"] = _skewed(rng, n_alpha_sel, n, skew)
             all_aed.append(lvl["a1d"][lvl["ref"] == 0]); all_as.append(lvl["s1"])
         r2 = ref.reshape(faces, H, W)
         grp = (r2[:, 0::2, 0::2] | (r2[:, 1::2, 0::2] << 2) | (r2[:, 0::2, 1::2] << 4) | (r2[:, 1::2, 1::2] << 6))
