@@ -85,6 +85,8 @@ def _declare(lib):
     lib.crn_gpu_pack_image.argtypes = [vp, u32, ctypes.POINTER(_PackParams), vp, u32, u32, u32, vp]
     lib.crn_gpu_pack_image_host.argtypes = [vp, u32, ctypes.POINTER(_PackParams), vp, u32, u32, u32, vp]
     u64 = ctypes.c_uint64
+    lib.crn_gpu_dxt1_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), i32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
+    lib.crn_gpu_dxt5_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
     lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
@@ -184,6 +186,27 @@ class Context:
         src = _devptr(d_rgba) if hasattr(d_rgba, "data_ptr") else ctypes.c_void_p(int(d_rgba))
         dst = _devptr(d_out) if hasattr(d_out, "data_ptr") else ctypes.c_void_p(int(d_out))
         self._check(self._lib.crn_gpu_pack_image(self._ctx, fmt, ctypes.byref(cp), src, width, height, pitch, dst))
+
+    # --- cluster optimisers (qdxt1::pack_endpoints_task / qdxt5::pack_endpoints_task) -----------------
+    def optimize_clusters(self, kind, d_blocks, n_blocks, d_offsets, d_members, n_clusters, total_member_blocks, d_out, out_stride,
+                          out_offset, params=None, component=3, dxt1a=False, d_endpoints=None, d_error=None):
+        """kind = "color" or "alpha".  All pointers are device pointers (ints or objects with data_ptr())."""
+        params = params or PackParams()
+        cp = params._c()
+
+        def ptr(x):
+            if x is None:
+                return ctypes.c_void_p(0)
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        if kind == "color":
+            rc = self._lib.crn_gpu_dxt1_optimize_clusters(self._ctx, ctypes.byref(cp), int(bool(dxt1a)), ptr(d_blocks), n_blocks, ptr(d_offsets),
+                                                          ptr(d_members), n_clusters, total_member_blocks, ptr(d_out), out_stride, out_offset,
+                                                          ptr(d_endpoints), ptr(d_error))
+        else:
+            rc = self._lib.crn_gpu_dxt5_optimize_clusters(self._ctx, ctypes.byref(cp), component, ptr(d_blocks), n_blocks, ptr(d_offsets),
+                                                          ptr(d_members), n_clusters, total_member_blocks, ptr(d_out), out_stride, out_offset,
+                                                          ptr(d_endpoints), ptr(d_error))
+        self._check(rc)
 
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
     def unpack_begin(self, crn_bytes):

@@ -1,0 +1,240 @@
+// cluster_kernels.cuh -- N-pixel ("cluster") form of the endpoint optimisers and the selector re-vote
+// (SURVEY 8(a) rows a7, a9, a15/a20 core, a21): one warp per cluster, clusters given as CSR lists of
+// member blocks over a [n_blocks][16] RGBA8 block array.
+//
+// Replaces the bodies of qdxt1::pack_endpoints_task / qdxt5::pack_endpoints_task (reference
+// crnlib/crn_qdxt1.cpp:471-699, crnlib/crn_qdxt5.cpp:452-576: concatenate the member blocks' pixels,
+// run dxt1_/dxt5_endpoint_optimizer over all of them, write the shared endpoints and the per-pixel
+// selectors into every member block) and qdxt1::optimize_selectors_task (crn_qdxt1.cpp:714-865).
+// The optimiser code is the same as for 4x4 blocks (dxt1_opt.cuh / dxt5a_opt.cuh, templated on the scratch
+// type); what changes is where the unique colours live (global workspace instead of shared memory) and
+// how they are found: a hash table built with atomics, then ordered by first appearance so that every
+// order-sensitive float sum runs over the colours in exactly the reference's order.
+#pragma once
+#include "dxt1_opt.cuh"
+#include "dxt5a_opt.cuh"
+
+namespace crn {
+
+struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays live in the global workspace
+    int4* cw; int4* ce; uint8_t* sel;
+    Dxt1Best best;
+    float mean[3], axis[3], low[3], high[3];
+    int U, total_w, pixels_have_alpha, stage;
+    uint16_t probe[2][32];
+    uint16_t packed[64];
+};
+
+struct ClusterHashEntry { uint32_t key, first_inv, count, uidx; };   // first_inv = ~(index of first appearance)
+
+struct ClusterWorkspace {              // global scratch, all sized by the number of member pixels P
+    ClusterHashEntry* hash;            // 2 entries per pixel
+    uint32_t* mark;                    // 1 per pixel
+    int4* cw; int4* ce;                // 1 per pixel each
+    uint8_t* sel;                      // 1 per pixel
+};
+constexpr size_t kClusterWorkspaceBytesPerPixel = 2 * sizeof(ClusterHashEntry) + 4 + 16 + 16 + 1;
+
+constexpr int kClusterWarpsPerCta = 4;
+
+__device__ __forceinline__ uint32_t cluster_pixel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ members, uint32_t i)
+{
+    return blocks[(size_t)members[i >> 4] * 16 + (i & 15)];
+}
+
+__global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
+dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
+                              const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
+                              ClusterWorkspace ws, unsigned int* __restrict__ next_cluster,
+                              uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs,
+                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error)
+{
+    __shared__ Dxt1ClusterScratch scratch[kClusterWarpsPerCta];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    Dxt1ClusterScratch* sc = &scratch[warp];
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(next_cluster, 1u);
+        c = __shfl_sync(CRN_FULL_MASK, c, 0);
+        if (c >= n_clusters) break;
+        const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
+        const uint32_t* members = cluster_blocks + b0;
+        const uint32_t N = nb * 16, P = b0 * 16;
+        if (!nb) continue;
+        // ---- pixels_have_alpha as qdxt1 computes it (crn_qdxt1.cpp:625-656)
+        int pha = 0;
+        if (dxt1a) {
+            bool any = false;
+            for (uint32_t i = lane; i < N; i += 32) any = any || (cluster_pixel(blocks, members, i) >> 24) < prm.alpha_threshold;
+            pha = __any_sync(CRN_FULL_MASK, any);
+        }
+        // ---- unique colours + weights (crn_dxt1.cpp:2113-2131) via an atomics-built hash table
+        ClusterHashEntry* tab = ws.hash + 2 * (size_t)P;
+        const uint32_t cap = 2 * N;
+        uint32_t* mark = ws.mark + P;
+        unsigned opaque_cnt = 0;
+        for (uint32_t i = lane; i < N; i += 32) {
+            const uint32_t px = cluster_pixel(blocks, members, i);
+            if (pha && (px >> 24) < prm.alpha_threshold) continue;
+            opaque_cnt++;
+            const uint32_t key = px | 0xFF000000u;
+            uint32_t h = (key * 2654435761u) % cap;
+            for (;;) {
+                const uint32_t old = atomicCAS(&tab[h].key, 0u, key);
+                if (old == 0u || old == key) break;
+                h = h + 1 == cap ? 0 : h + 1;
+            }
+            atomicMax(&tab[h].first_inv, ~i);
+            atomicAdd(&tab[h].count, 1u);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) opaque_cnt += __shfl_xor_sync(CRN_FULL_MASK, opaque_cnt, ofs);
+        for (uint32_t s = lane; s < cap; s += 32)
+            if (tab[s].key) mark[~tab[s].first_inv] = s + 1;
+        __syncwarp();
+        if (lane == 0) { sc->cw = ws.cw + P; sc->ce = ws.ce + P; sc->sel = ws.sel + P; }
+        __syncwarp();
+        int U = 0;
+        for (uint32_t base = 0; base < N; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t v = i < N ? mark[i] : 0u;
+            const unsigned m = __ballot_sync(CRN_FULL_MASK, v != 0);
+            if (v) {
+                const int u = U + __popc(m & lanemask_lt());
+                ClusterHashEntry& e = tab[v - 1];
+                e.uidx = (uint32_t)u;
+                sc->cw[u] = make_int4((int)(e.key & 0xff), (int)((e.key >> 8) & 0xff), (int)((e.key >> 16) & 0xff), (int)e.count);
+            }
+            U += __popc(m);
+        }
+        __syncwarp();
+        // ---- the optimiser proper: same phases as the 4x4 block kernels, fused
+        dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, pha, U));
+        dxt1_setup_common(sc, prm, pha, U, opaque_cnt, opaque_cnt != N);
+        dxt1_phase_median4(sc, prm);
+        dxt1_phase_passes(sc, prm);
+        dxt1_phase_post(sc, prm);
+        // ---- finish: combinatorial recovery + return_solution (crn_dxt1.cpp:1048-1056, :263-365)
+        unsigned out_lo = 0, out_hi = 0;
+        bool invert = false;
+        int alpha_block = 1;
+        const int stage = sc->stage;
+        if (stage != 2) {
+            const Dxt1Cfg cfg = dxt1_make_cfg(prm, pha, U);
+            if (stage == 0 && prm.quality == 4 && sc->best.err) dxt1_combinatorial(sc, cfg);
+            dxt1_best_selectors(sc, cfg);
+            alpha_block = sc->best.alpha_block;
+            invert = alpha_block ? (sc->best.lo > sc->best.hi) : (sc->best.lo < sc->best.hi);
+            out_lo = invert ? sc->best.hi : sc->best.lo; out_hi = invert ? sc->best.lo : sc->best.hi;
+        }
+        if (lane == 0) {
+            if (out_endpoints) out_endpoints[c] = out_lo | (out_hi << 16);
+            if (out_error) out_error[c] = stage == 2 ? 0ull : sc->best.err;
+        }
+        // two member blocks per iteration: lanes 0-15 / 16-31
+        for (uint32_t base = 0; base < N; base += 32) {
+            const uint32_t i = base + lane;
+            unsigned s = 3;
+            if (i < N && stage != 2) {
+                const uint32_t px = cluster_pixel(blocks, members, i);
+                if (!(pha && (px >> 24) < prm.alpha_threshold)) {
+                    const uint32_t key = px | 0xFF000000u;
+                    uint32_t h = (key * 2654435761u) % cap;
+                    while (tab[h].key != key) h = h + 1 == cap ? 0 : h + 1;
+                    s = sc->sel[tab[h].uidx];
+                    if (invert) s = alpha_block ? (s < 2 ? s ^ 1 : s) : (s ^ 1);
+                }
+            }
+            unsigned bits = s << (2 * (lane & 15));
+#pragma unroll
+            for (int ofs = 8; ofs > 0; ofs >>= 1) bits |= __shfl_xor_sync(CRN_FULL_MASK, bits, ofs);
+            if ((lane & 15) == 0 && i < N) {
+                const unsigned long long elem = (unsigned long long)out_lo | ((unsigned long long)out_hi << 16) | ((unsigned long long)bits << 32);
+                *reinterpret_cast<unsigned long long*>(out + (size_t)members[i >> 4] * out_stride + out_ofs) = elem;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- DXT5A clusters (qdxt5::pack_endpoints_task, crn_qdxt5.cpp:452-576 -> dxt5_endpoint_optimizer) -----
+struct Dxt5aClusterScratch : Dxt5aScratch {
+    uint32_t first[256];               // ~index of first appearance per 8-bit value, 0 = absent
+    uint32_t count[256];
+    uint8_t uidx_of_value[256];
+};
+
+__global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
+dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
+                              const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, uint32_t comp, int quality, int both_types,
+                              unsigned int* __restrict__ next_cluster, uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs,
+                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error)
+{
+    __shared__ Dxt5aClusterScratch scratch[kClusterWarpsPerCta];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    Dxt5aClusterScratch* sc = &scratch[warp];
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(next_cluster, 1u);
+        c = __shfl_sync(CRN_FULL_MASK, c, 0);
+        if (c >= n_clusters) break;
+        const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
+        const uint32_t* members = cluster_blocks + b0;
+        const uint32_t N = nb * 16;
+        if (!nb) continue;
+        for (uint32_t v = lane; v < 256; v += 32) { sc->first[v] = 0; sc->count[v] = 0; }
+        __syncwarp();
+        for (uint32_t i = lane; i < N; i += 32) {
+            const uint32_t a = (cluster_pixel(blocks, members, i) >> (8 * comp)) & 0xffu;
+            atomicMax(&sc->first[a], ~i);
+            atomicAdd(&sc->count[a], 1u);
+        }
+        __syncwarp();
+        // unique values ordered by first appearance (crn_dxt5a.cpp:58-75): rank = number of present values seen earlier
+        int U = 0;
+        for (uint32_t v = lane; v < 256; v += 32) {
+            const uint32_t f = sc->first[v];
+            if (f) {
+                int rank = 0;
+                for (uint32_t o = 0; o < 256; o++) rank += sc->first[o] > f;     // larger ~index == earlier
+                sc->val[rank] = (uint8_t)v; sc->wgt[rank] = sc->count[v]; sc->uidx_of_value[v] = (uint8_t)rank;
+            }
+        }
+        __syncwarp();
+        for (uint32_t v = lane; v < 256; v += 32) U += sc->first[v] != 0;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) U += __shfl_xor_sync(CRN_FULL_MASK, U, ofs);
+        unsigned first, second;
+        unsigned long long err = 0;
+        if (U == 1) {
+            first = second = sc->val[0];
+            if (lane == 0) sc->sel[0] = 0;
+            __syncwarp();
+        } else {
+            const Dxt5aBest best = N > 33025u ? dxt5a_search<true>(sc, U, quality, both_types != 0) : dxt5a_search<false>(sc, U, quality, both_types != 0);
+            err = best.error;
+            dxt5a_finish(sc, U, best, first, second);
+        }
+        if (lane == 0) {
+            if (out_endpoints) out_endpoints[c] = first | (second << 8);
+            if (out_error) out_error[c] = err;
+        }
+        for (uint32_t base = 0; base < N; base += 32) {
+            const uint32_t i = base + lane;
+            unsigned long long bits = 0;
+            if (i < N) {
+                const uint32_t a = (cluster_pixel(blocks, members, i) >> (8 * comp)) & 0xffu;
+                bits = (unsigned long long)sc->sel[sc->uidx_of_value[a]] << (3 * (lane & 15));
+            }
+#pragma unroll
+            for (int ofs = 8; ofs > 0; ofs >>= 1) bits |= __shfl_xor_sync(CRN_FULL_MASK, bits, ofs);
+            if ((lane & 15) == 0 && i < N)
+                *reinterpret_cast<unsigned long long*>(out + (size_t)members[i >> 4] * out_stride + out_ofs) =
+                    (unsigned long long)first | ((unsigned long long)second << 8) | (bits << 16);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace crn

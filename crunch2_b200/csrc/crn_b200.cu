@@ -6,6 +6,7 @@
 #include "launch.h"
 #include "pack_kernels.cuh"
 #include "transcode_host.h"
+#include "cluster_kernels.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -21,6 +22,7 @@ struct crn_gpu_ctx {
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
+    void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
     int transcode_smem_set;
 };
@@ -111,6 +113,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_state) cudaFree(ctx->d_state);
     if (ctx->d_files) cudaFree(ctx->d_files);
+    if (ctx->d_cluster_ws) cudaFree(ctx->d_cluster_ws);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -251,6 +254,86 @@ int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pac
     return CRN_GPU_OK;
 }
 
+
+/* ---- cluster optimisers ---------------------------------------------------------------------------- */
+
+int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* params, int dxt1a,
+                                   const void* d_blocks_rgba, uint32_t n_blocks,
+                                   const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks,
+                                   uint32_t n_clusters, uint32_t total_member_blocks,
+                                   void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
+                                   uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!params || params->struct_size != sizeof(crn_gpu_pack_params) || !d_blocks_rgba || !n_blocks || !d_cluster_offsets ||
+        !d_cluster_blocks || !d_out || out_stride_bytes < 8 || (out_stride_bytes & 7) || (out_offset_bytes & 7))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_dxt1_optimize_clusters: bad argument");
+    if (params->dxt_quality < 3 || params->dxt_quality > 4)
+        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_dxt1_optimize_clusters: dxt_quality must be better (3) or uber (4)");
+    if (!n_clusters || !total_member_blocks) return CRN_GPU_OK;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t P = (size_t)total_member_blocks * 16;
+    const size_t need = P * crn::kClusterWorkspaceBytesPerPixel + 1024;
+    int rc = ensure(ctx, &ctx->d_cluster_ws, &ctx->d_cluster_ws_cap, need);
+    if (rc) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->d_cluster_ws);
+    crn::ClusterWorkspace ws;
+    size_t o = 256;                                     // first 256 bytes: the work-stealing counter
+    ws.hash = reinterpret_cast<crn::ClusterHashEntry*>(base + o); o += P * 2 * sizeof(crn::ClusterHashEntry);
+    ws.cw = reinterpret_cast<int4*>(base + o); o += P * 16;
+    ws.ce = reinterpret_cast<int4*>(base + o); o += P * 16;
+    ws.mark = reinterpret_cast<uint32_t*>(base + o); o += P * 4;
+    ws.sel = base + o;
+    // hash keys / first / count and the first-appearance marks must start at zero
+    CRN_CUDA(ctx, cudaMemsetAsync(base, 0, 256 + P * 2 * sizeof(crn::ClusterHashEntry), ctx->stream));
+    CRN_CUDA(ctx, cudaMemsetAsync(ws.mark, 0, P * 4, ctx->stream));
+    crn::Dxt1Params dp;
+    dp.quality = (int)params->dxt_quality;
+    dp.perceptual = params->perceptual ? 1 : 0;
+    dp.pixels_have_alpha = 0;
+    dp.use_alpha_blocks = params->use_both_block_types ? 1 : 0;
+    dp.force_alpha_blocks = 0;
+    dp.grayscale_sampling = params->grayscale_sampling ? 1 : 0;
+    // qdxt1::pack (crn_qdxt1.cpp:920-923): without 3-colour blocks the alpha threshold is forced to 0
+    dp.alpha_threshold = dp.use_alpha_blocks ? params->dxt1a_alpha_threshold : 0;
+    const int threads = crn::kClusterWarpsPerCta * 32;
+    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, 4);
+    CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
+               d_cluster_blocks, n_clusters, dp, (dxt1a && dp.use_alpha_blocks) ? 1 : 0, ws, reinterpret_cast<unsigned int*>(base),
+               static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes, d_cluster_endpoints,
+               reinterpret_cast<unsigned long long*>(d_cluster_error));
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* params, uint32_t component,
+                                   const void* d_blocks_rgba, uint32_t n_blocks,
+                                   const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks,
+                                   uint32_t n_clusters, uint32_t total_member_blocks,
+                                   void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
+                                   uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!params || params->struct_size != sizeof(crn_gpu_pack_params) || !d_blocks_rgba || !n_blocks || !d_cluster_offsets ||
+        !d_cluster_blocks || !d_out || component > 3 || out_stride_bytes < 8 || (out_stride_bytes & 7) || (out_offset_bytes & 7) ||
+        params->dxt_quality > 4)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_dxt5_optimize_clusters: bad argument");
+    if (!n_clusters || !total_member_blocks) return CRN_GPU_OK;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_cluster_ws, &ctx->d_cluster_ws_cap, 1024);
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaMemsetAsync(ctx->d_cluster_ws, 0, 256, ctx->stream));
+    const int threads = crn::kClusterWarpsPerCta * 32;
+    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, 4);
+    CRN_LAUNCH(crn::dxt5_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
+               d_cluster_blocks, n_clusters, component, (int)params->dxt_quality, params->use_both_block_types ? 1 : 0,
+               reinterpret_cast<unsigned int*>(ctx->d_cluster_ws), static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes,
+               d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error));
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
 
 /* ---- CRN -> DXTn transcoding --------------------------------------------------------------------- */
 

@@ -123,8 +123,8 @@ __device__ __forceinline__ int4 eval_palette(const Dxt1Cfg cfg, int r, int g, in
 }
 __device__ __forceinline__ int eval_dprime(const int4 c, const int4 p) { return p.w - c.x * p.x - c.y * p.y - c.z * p.z; }
 
-template <bool DO4, bool DO3>
-__device__ __forceinline__ void dxt1_eval_loop(const Dxt1Scratch* sc, int U, const int4 p0, const int4 p1, const int4 p2, const int4 p3,
+template <bool DO4, bool DO3, typename SC>
+__device__ __forceinline__ void dxt1_eval_loop(const SC* sc, int U, const int4 p0, const int4 p1, const int4 p2, const int4 p3,
                                                const int4 pm, unsigned long long& e4, unsigned long long& e3)
 {
     e4 = 0; e3 = 0;
@@ -146,7 +146,8 @@ __device__ __forceinline__ void dxt1_eval_loop(const Dxt1Scratch* sc, int U, con
 
 // Lane-private evaluation of one candidate: evaluate_solution_uber / _hc_* without the bookkeeping
 // (crn_dxt1.cpp:1370-1561, :1759-1835).  err = min over allowed block types, alpha = 3-colour won.
-__device__ __noinline__ void dxt1_eval(Dxt1Scratch* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
+template <typename SC>
+__device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
                                        unsigned long long& err, int& alpha)
 {
     int r0, g0, b0, r1, g1, b1;
@@ -171,7 +172,8 @@ __device__ __noinline__ void dxt1_eval(Dxt1Scratch* sc, const Dxt1Cfg cfg, unsig
 
 // Commit candidate (lo, hi, alt) with error e / block type alpha as the new best, applying the
 // degenerate-endpoint fix-up of crn_dxt1.cpp:1563-1583 / :1781-1794.
-__device__ __forceinline__ void dxt1_accept(Dxt1Scratch* sc, unsigned lo, unsigned hi, int alt, unsigned long long e, int alpha)
+template <typename SC>
+__device__ __forceinline__ void dxt1_accept(SC* sc, unsigned lo, unsigned hi, int alt, unsigned long long e, int alpha)
 {
     __syncwarp();                       // every lane has finished reading the previous best
     if (lane_id() == 0) {
@@ -189,7 +191,8 @@ __device__ __forceinline__ void dxt1_accept(Dxt1Scratch* sc, unsigned lo, unsign
 
 // Static batch: every lane may hold one candidate (valid) whose sequence order is the lane index.
 // Returns true if the best improved.
-__device__ __noinline__ bool dxt1_commit_static(Dxt1Scratch* sc, const Dxt1Cfg cfg,
+template <typename SC>
+__device__ __noinline__ bool dxt1_commit_static(SC* sc, const Dxt1Cfg cfg,
                                                    bool valid, unsigned lo, unsigned hi, int alt)
 {
     unsigned long long e = ~0ull; int alpha = 0;
@@ -210,10 +213,10 @@ __device__ __forceinline__ void canon(unsigned& lo, unsigned& hi)
 
 // Selectors of the current best for every unique colour -> sc->sel (first minimum in palette order;
 // crn_dxt1.cpp:1407-1441 and :1845-1869 agree on ties).
-__device__ __noinline__ void dxt1_best_selectors(Dxt1Scratch* sc, const Dxt1Cfg cfg)
+template <typename SC>
+__device__ __noinline__ void dxt1_best_selectors(SC* sc, const Dxt1Cfg cfg)
 {
-    const unsigned lane = lane_id();
-    if ((int)lane < cfg.U) {
+    for (int ci = (int)lane_id(); ci < cfg.U; ci += 32) {
         unsigned s;
         if (sc->best.enforce) s = (unsigned)sc->best.enforced_sel;
         else {
@@ -221,7 +224,7 @@ __device__ __noinline__ void dxt1_best_selectors(Dxt1Scratch* sc, const Dxt1Cfg 
             unpack565(sc->best.lo, true, r0, g0, b0);
             unpack565(sc->best.hi, true, r1, g1, b1);
             const int alt = sc->best.alt_round;
-            const int4 c = sc->cw[lane];
+            const int4 c = sc->cw[ci];
             unsigned be = dxt1_dist(cfg, c.x, c.y, c.z, r0, g0, b0);
             s = 0;
             unsigned e = dxt1_dist(cfg, c.x, c.y, c.z, r1, g1, b1);
@@ -236,13 +239,14 @@ __device__ __noinline__ void dxt1_best_selectors(Dxt1Scratch* sc, const Dxt1Cfg 
                 if (e < be) { be = e; s = 3; }
             }
         }
-        sc->sel[lane] = (uint8_t)s;
+        sc->sel[ci] = (uint8_t)s;
     }
     __syncwarp();
 }
 
 // refine_solution (crn_dxt1.cpp:525-698), levels 0 and 1.
-__device__ __noinline__ bool dxt1_refine(Dxt1Scratch* sc, const Dxt1Cfg cfg, int level)
+template <typename SC>
+__device__ __noinline__ bool dxt1_refine(SC* sc, const Dxt1Cfg cfg, int level)
 {
     dxt1_best_selectors(sc, cfg);
     double akku_0 = 0, akku_1 = 0, akku_2 = 0;
@@ -320,7 +324,8 @@ __device__ __forceinline__ float v3_sqdist(const V3& a, const V3& b)
     d = a.z - b.z; d2 += d * d;
     return d2;
 }
-__device__ __forceinline__ V3 norm_color(Dxt1Scratch* sc, int i, const V3& mean)
+template <typename SC>
+__device__ __forceinline__ V3 norm_color(SC* sc, int i, const V3& mean)
 {   // m_norm_unique_colors[i] (crn_dxt1.cpp:168, :186)
     const int4 c = sc->cw[i];
     V3 v;
@@ -331,7 +336,8 @@ __device__ __forceinline__ V3 norm_color(Dxt1Scratch* sc, int i, const V3& mean)
 }
 
 // try_median4 (crn_dxt1.cpp:1181-1308)
-__device__ __noinline__ bool dxt1_median4(Dxt1Scratch* sc, const Dxt1Cfg cfg, int quality,
+template <typename SC>
+__device__ __noinline__ bool dxt1_median4(SC* sc, const Dxt1Cfg cfg, int quality,
                                              const V3& mean, const V3& low_color, const V3& high_color)
 {
     V3 means[4];
@@ -423,8 +429,8 @@ __device__ __noinline__ bool dxt1_median4(Dxt1Scratch* sc, const Dxt1Cfg cfg, in
 // One "live" run over <= 32 lattice candidates around a fixed base colour of endpoint `which`
 // (0 = low, 1 = high); the other endpoint is read from the live best (crn_dxt1.cpp:908-1015).
 // delta(idx, dr, dg, db) supplies candidate idx's offset.
-template <typename DeltaFn>
-__device__ __noinline__ void dxt1_live_neighbours(Dxt1Scratch* sc, const Dxt1Cfg cfg, int which,
+template <typename SC, typename DeltaFn>
+__device__ __noinline__ void dxt1_live_neighbours(SC* sc, const Dxt1Cfg cfg, int which,
                                                      int ncand, DeltaFn delta)
 {
     int cr, cg, cb;
@@ -455,7 +461,8 @@ __device__ __noinline__ void dxt1_live_neighbours(Dxt1Scratch* sc, const Dxt1Cfg
 }
 
 // try_average_block_as_solid (crn_dxt1.cpp:93-153)
-__device__ __noinline__ bool dxt1_try_solid(Dxt1Scratch* sc, const Dxt1Cfg cfg, const Dxt1Params& prm)
+template <typename SC>
+__device__ __noinline__ bool dxt1_try_solid(SC* sc, const Dxt1Cfg cfg, const Dxt1Params& prm)
 {
     unsigned long long tot_r = 0, tot_g = 0, tot_b = 0;
     unsigned total_weight = 0;
@@ -503,7 +510,8 @@ __device__ __forceinline__ unsigned long long comp_err(const CompMoments& m, int
     return m.W[s] * p * p - m.WP2[s] * p + m.WPP[s];
 }
 __device__ __forceinline__ unsigned expand_comp(int comp, unsigned c) { return comp == 1 ? ((c << 2) | (c >> 4)) : ((c << 3) | (c >> 2)); }
-__device__ __noinline__ void comp_moments(Dxt1Scratch* sc, const Dxt1Cfg cfg, int comp, CompMoments& m)
+template <typename SC>
+__device__ __noinline__ void comp_moments(SC* sc, const Dxt1Cfg cfg, int comp, CompMoments& m)
 {
 #pragma unroll
     for (int s = 0; s < 4; s++) m.W[s] = m.WP2[s] = m.WPP[s] = 0;
@@ -531,7 +539,8 @@ __device__ __noinline__ void comp_moments(Dxt1Scratch* sc, const Dxt1Cfg cfg, in
 }
 
 // optimize_endpoint_comps (crn_dxt1.cpp:415-486)
-__device__ __noinline__ void dxt1_optimize_comps(Dxt1Scratch* sc, const Dxt1Cfg cfg)
+template <typename SC>
+__device__ __noinline__ void dxt1_optimize_comps(SC* sc, const Dxt1Cfg cfg)
 {
     dxt1_best_selectors(sc, cfg);
     if (sc->best.alpha_block || !sc->best.err) return;
@@ -608,7 +617,8 @@ __device__ __forceinline__ unsigned lerp_color_packed(const int4& a, const int4&
 }
 
 // try_combinatorial_encoding (crn_dxt1.cpp:1886-1997)
-__device__ __noinline__ void dxt1_combinatorial(Dxt1Scratch* sc, const Dxt1Cfg cfg)
+template <typename SC>
+__device__ __noinline__ void dxt1_combinatorial(SC* sc, const Dxt1Cfg cfg)
 {
     const int U = cfg.U;
     if (U < 2 || U > 4) return;
@@ -691,40 +701,22 @@ __device__ __forceinline__ Dxt1Cfg dxt1_make_cfg(const Dxt1Params& prm, int pixe
 }
 
 // (re)build the evaluation form of the unique colours after a state load
-__device__ __forceinline__ void dxt1_build_eval_colours(Dxt1Scratch* sc, const Dxt1Cfg cfg)
+template <typename SC>
+__device__ __forceinline__ void dxt1_build_eval_colours(SC* sc, const Dxt1Cfg cfg)
 {
-    const unsigned lane = lane_id();
-    if ((int)lane < cfg.U) { const int4 c = sc->cw[lane]; sc->ce[lane] = eval_colour(cfg, c.x, c.y, c.z); }
+    for (int ci = (int)lane_id(); ci < cfg.U; ci += 32) { const int4 c = sc->cw[ci]; sc->ce[ci] = eval_colour(cfg, c.x, c.y, c.z); }
     __syncwarp();
 }
 
-// Phase 0 -- compute_internal up to the call of optimize_endpoints (crn_dxt1.cpp:2081-2232, :1069-1178).
-// lanes 0..15 hold pixel 4y+x as RGBA8 (r in the low byte).
-__device__ __forceinline__ void dxt1_phase_setup(Dxt1Scratch* sc, uint32_t px, const Dxt1Params& prm, int pixels_have_alpha)
+// Phase 0, common part -- compute_internal after the unique colours exist (sc->cw / sc->ce filled,
+// first-appearance order) up to the call of optimize_endpoints (crn_dxt1.cpp:2131-2232, :1069-1178).
+template <typename SC>
+__device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm, int pixels_have_alpha, const int U, const unsigned total_w,
+                                                  const bool has_transparent)
 {
     const unsigned lane = lane_id();
-    Dxt1Cfg cfg = dxt1_make_cfg(prm, pixels_have_alpha, 0);
+    const Dxt1Cfg cfg = dxt1_make_cfg(prm, pixels_have_alpha, U);
     const bool perceptual = prm.perceptual && !prm.grayscale_sampling;
-    // ---- unique colours in first-appearance order (crn_dxt1.cpp:2113-2131)
-    const bool opaque = lane < 16 && (!pixels_have_alpha || (px >> 24) >= prm.alpha_threshold);
-    const unsigned vmask = __ballot_sync(CRN_FULL_MASK, opaque);
-    const unsigned key = px | 0xFF000000u;
-    unsigned peers = 0;
-    if (opaque) peers = __match_any_sync(vmask, key);
-    const bool leader = opaque && (unsigned)(__ffs((int)peers) - 1) == lane;
-    const unsigned leaders = __ballot_sync(CRN_FULL_MASK, leader);
-    const int U = __popc(leaders);
-    cfg.U = U;
-    const unsigned my_u = __popc(leaders & lanemask_lt());
-    if (leader) {
-        const int r = (int)(px & 0xff), g = (int)((px >> 8) & 0xff), b = (int)((px >> 16) & 0xff);
-        sc->cw[my_u] = make_int4(r, g, b, __popc(peers));
-        sc->ce[my_u] = eval_colour(cfg, r, g, b);
-    }
-    const unsigned total_w = (unsigned)__popc(vmask);
-    const bool has_transparent = total_w != 16;
-    __syncwarp();
-
     if (lane == 0) {
         sc->best.lo = sc->best.hi = 0; sc->best.err = ~0ull; sc->best.alpha_block = 0; sc->best.alt_round = 0; sc->best.enforce = 0; sc->best.enforced_sel = 0;
     }
@@ -898,8 +890,35 @@ __device__ __forceinline__ void dxt1_phase_setup(Dxt1Scratch* sc, uint32_t px, c
     }
 }
 
+// Phase 0 for a 4x4 block: lanes 0..15 hold pixel 4y+x as RGBA8 (r in the low byte).  Unique colours in
+// first-appearance order (crn_dxt1.cpp:2113-2131) come from one __match_any_sync.
+template <typename SC>
+__device__ __forceinline__ void dxt1_phase_setup(SC* sc, uint32_t px, const Dxt1Params& prm, int pixels_have_alpha)
+{
+    const unsigned lane = lane_id();
+    const Dxt1Cfg cfg = dxt1_make_cfg(prm, pixels_have_alpha, 0);
+    const bool opaque = lane < 16 && (!pixels_have_alpha || (px >> 24) >= prm.alpha_threshold);
+    const unsigned vmask = __ballot_sync(CRN_FULL_MASK, opaque);
+    const unsigned key = px | 0xFF000000u;
+    unsigned peers = 0;
+    if (opaque) peers = __match_any_sync(vmask, key);
+    const bool leader = opaque && (unsigned)(__ffs((int)peers) - 1) == lane;
+    const unsigned leaders = __ballot_sync(CRN_FULL_MASK, leader);
+    const int U = __popc(leaders);
+    const unsigned my_u = __popc(leaders & lanemask_lt());
+    if (leader) {
+        const int r = (int)(px & 0xff), g = (int)((px >> 8) & 0xff), b = (int)((px >> 16) & 0xff);
+        sc->cw[my_u] = make_int4(r, g, b, __popc(peers));
+        sc->ce[my_u] = eval_colour(cfg, r, g, b);
+    }
+    const unsigned total_w = (unsigned)__popc(vmask);
+    __syncwarp();
+    dxt1_setup_common(sc, prm, pixels_have_alpha, U, total_w, total_w != 16);
+}
+
 // Phase 1 -- try_median4 (+ its least-squares refinement), first step of optimize_endpoints (:765-771).
-__device__ __forceinline__ void dxt1_phase_median4(Dxt1Scratch* sc, const Dxt1Params& prm)
+template <typename SC>
+__device__ __forceinline__ void dxt1_phase_median4(SC* sc, const Dxt1Params& prm)
 {
     if (sc->stage != 0) return;
     const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
@@ -911,7 +930,8 @@ __device__ __forceinline__ void dxt1_phase_median4(Dxt1Scratch* sc, const Dxt1Pa
 }
 
 // Phase 2 -- the probe-sweep / lattice-neighbour / refine passes of optimize_endpoints (:773-1028).
-__device__ __forceinline__ void dxt1_phase_passes(Dxt1Scratch* sc, const Dxt1Params& prm)
+template <typename SC>
+__device__ __forceinline__ void dxt1_phase_passes(SC* sc, const Dxt1Params& prm)
 {
     if (sc->stage != 0) return;
     const unsigned lane = lane_id();
@@ -1013,7 +1033,8 @@ __device__ __forceinline__ void dxt1_phase_passes(Dxt1Scratch* sc, const Dxt1Par
 }
 
 // Phase 3 -- solid-colour and per-component post passes (:1030-1046).
-__device__ __forceinline__ void dxt1_phase_post(Dxt1Scratch* sc, const Dxt1Params& prm)
+template <typename SC>
+__device__ __forceinline__ void dxt1_phase_post(SC* sc, const Dxt1Params& prm)
 {
     if (sc->stage != 0) return;
     const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
@@ -1031,7 +1052,8 @@ __device__ __forceinline__ void dxt1_phase_post(Dxt1Scratch* sc, const Dxt1Param
 
 // Phase 4 -- combinatorial recovery (:1048-1056) and return_solution (:263-365).  Returns the packed 8-byte
 // DXT1 element (low565, high565, 16 x 2-bit selectors; crn_dxt.h:109-172) on every lane.
-__device__ __forceinline__ unsigned long long dxt1_phase_finish(Dxt1Scratch* sc, uint32_t px, const Dxt1Params& prm)
+template <typename SC>
+__device__ __forceinline__ unsigned long long dxt1_phase_finish(SC* sc, uint32_t px, const Dxt1Params& prm)
 {
     const unsigned lane = lane_id();
     if (sc->stage == 2) return 0xFFFFFFFF00000000ull;

@@ -92,6 +92,32 @@ CRN_API int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_
 CRN_API int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                             const void* h_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, void* h_out);
 
+/* Cluster ("N-pixel") endpoint optimisation -------------------------
+ * Replaces the bodies of qdxt1::pack_endpoints_task / qdxt5::pack_endpoints_task (reference
+ * crnlib/crn_qdxt1.cpp:471-699, crnlib/crn_qdxt5.cpp:452-576; the same per-cluster step is
+ * dxt_hc::determine_color/alpha_endpoint_codebook_task, crnlib/crn_dxt_hc.cpp:663-754, :1014-1130):
+ * for every cluster, the pixels of all member blocks are optimised as ONE N-pixel problem and the shared
+ * endpoints + per-pixel selectors are written into every member block's 8-byte element.
+ *   d_blocks_rgba    n_blocks x 16 RGBA8 pixels (dxt_pixel_block, pixel index 4y+x)
+ *   d_cluster_offsets n_clusters+1 CSR offsets into d_cluster_blocks; total_member_blocks = offsets[n_clusters]
+ *   d_out            element of block b is written at d_out + b*out_stride_bytes + out_offset_bytes
+ *   d_cluster_endpoints / d_cluster_error  optional (may be NULL): low|high<<16 (colour) or first|second<<8
+ *                    (alpha) and the optimiser's error per cluster
+ * Colour: params->use_both_block_types selects DXT1 semantics (3-colour blocks allowed); pass 0 for the
+ * colour element of DXT5.  dxt1a != 0 applies the alpha threshold as qdxt1 does.  Asynchronous. */
+CRN_API int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* params, int dxt1a,
+                                           const void* d_blocks_rgba, uint32_t n_blocks,
+                                           const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks,
+                                           uint32_t n_clusters, uint32_t total_member_blocks,
+                                           void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
+                                           uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error);
+CRN_API int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* params, uint32_t component,
+                                           const void* d_blocks_rgba, uint32_t n_blocks,
+                                           const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks,
+                                           uint32_t n_clusters, uint32_t total_member_blocks,
+                                           void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
+                                           uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

@@ -1,0 +1,106 @@
+"""Cluster (N-pixel) optimisers under the SIMT emulator vs the oracle port: for every cluster the shared
+endpoints, the optimiser's error and every member block's packed element must equal what
+dxt1_/dxt5_endpoint_optimizer produce on the concatenated pixels (qdxt1/qdxt5::pack_endpoints_task)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import blockgen
+import crunch2_b200 as crn
+import helpers
+
+P = helpers.P
+
+
+class Prm(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in "quality perceptual pixels_have_alpha use_alpha_blocks alpha_threshold grayscale transparent_for_black force_alpha_blocks".split()]
+
+
+class Res(ctypes.Structure):
+    _fields_ = [("error", ctypes.c_uint64), ("low", ctypes.c_uint16), ("high", ctypes.c_uint16), ("alpha_block", ctypes.c_uint8)]
+
+
+def make_clusters(n_blocks, sizes, seed):
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n_blocks)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    assert offs[-1] <= n_blocks
+    return offs, perm[:offs[-1]].astype(np.uint32)
+
+
+def port_color_cluster(port, px, q, perc, uab, pha):
+    n = len(px)
+    p = Prm(q, perc, pha, uab, 128 if uab else 0, 0, 0, 0); r = Res(); sel = np.zeros(n, np.uint8)
+    port.op_dxt1_optimize(P(px), n, ctypes.byref(p), ctypes.byref(r), P(sel))
+    return r.low, r.high, r.error, sel
+
+
+def run_color(ctx, port, blocks, offs, members, q=4, perc=1, uab=0, dxt1a=False):
+    n_blocks = len(blocks)
+    out = np.zeros((n_blocks, 8), np.uint8)
+    ep = np.zeros(len(offs) - 1, np.uint32); err = np.zeros(len(offs) - 1, np.uint64)
+    ctx.optimize_clusters("color", blocks.ctypes.data, n_blocks, offs.ctypes.data, members.ctypes.data, len(offs) - 1, int(offs[-1]),
+                          out.ctypes.data, 8, 0, crn.PackParams(dxt_quality=q, perceptual=perc, use_both_block_types=uab), dxt1a=dxt1a,
+                          d_endpoints=ep.ctypes.data, d_error=err.ctypes.data)
+    ctx.synchronize()
+    for c in range(len(offs) - 1):
+        m = members[offs[c]:offs[c + 1]]
+        px = np.ascontiguousarray(blocks[m].reshape(-1, 4))
+        pha = int(dxt1a and uab and (px[:, 3] < 128).any())
+        lo, hi, e, sel = port_color_cluster(port, px, q, perc, uab, pha)
+        assert (int(ep[c]) & 0xffff, int(ep[c]) >> 16) == (lo, hi), (c, len(m))
+        if not (pha and (px[:, 3] >= 128).sum() == 0):
+            assert int(err[c]) == e, (c, len(m))
+        for k, b in enumerate(m):
+            s = sel[16 * k:16 * k + 16]
+            bits = sum(int(s[i]) << (2 * i) for i in range(16))
+            want = np.frombuffer(int(lo | (hi << 16) | (bits << 32)).to_bytes(8, "little"), np.uint8)
+            assert (out[b] == want).all(), (c, k)
+
+
+@pytest.fixture(scope="module")
+def simctx(sim):
+    ctx = crn.Context(0, lib=sim)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("family", ["smooth", "noise", "four", "solid", "dark", "dxt_like"])
+def test_color_clusters_match_port(simctx, port, family):
+    blocks = blockgen.block_family(family, 120, 61)
+    offs, members = make_clusters(120, [1, 2, 3, 5, 8, 13, 40], 7)
+    run_color(simctx, port, blocks, offs, members, q=4, perc=1, uab=0)      # DXT5 colour element: hc evaluator
+    run_color(simctx, port, blocks, offs, members, q=4, perc=0, uab=1)      # DXT1: both block types
+    run_color(simctx, port, blocks, offs, members, q=3, perc=1, uab=0)
+
+
+def test_color_clusters_dxt1a(simctx, port):
+    blocks = blockgen.block_family("alpha_mix", 64, 5)
+    offs, members = make_clusters(64, [1, 4, 9, 20], 3)
+    run_color(simctx, port, blocks, offs, members, q=4, perc=1, uab=1, dxt1a=True)
+
+
+@pytest.mark.parametrize("family", ["smooth", "noise", "two", "gray"])
+def test_alpha_clusters_match_port(simctx, port, family):
+    blocks = blockgen.block_family(family, 200, 33)
+    offs, members = make_clusters(200, [1, 2, 7, 30, 100], 9)
+    n_blocks = len(blocks)
+    for comp, q, both in ((3, 4, 1), (0, 3, 0), (1, 2, 1)):
+        out = np.zeros((n_blocks, 16), np.uint8)
+        ep = np.zeros(len(offs) - 1, np.uint32); err = np.zeros(len(offs) - 1, np.uint64)
+        simctx.optimize_clusters("alpha", blocks.ctypes.data, n_blocks, offs.ctypes.data, members.ctypes.data, len(offs) - 1, int(offs[-1]),
+                                 out.ctypes.data, 16, 8, crn.PackParams(dxt_quality=q, use_both_block_types=both), component=comp,
+                                 d_endpoints=ep.ctypes.data, d_error=err.ctypes.data)
+        simctx.synchronize()
+        for c in range(len(offs) - 1):
+            m = members[offs[c]:offs[c + 1]]
+            px = np.ascontiguousarray(blocks[m].reshape(-1, 4)); n = len(px)
+            f = ctypes.c_uint8(); s = ctypes.c_uint8(); e = ctypes.c_uint64(); bt = ctypes.c_uint8(); sel = np.zeros(n, np.uint8)
+            port.op_dxt5_optimize(P(px), n, comp, q, both, ctypes.byref(f), ctypes.byref(s), P(sel), ctypes.byref(e), ctypes.byref(bt))
+            assert (int(ep[c]) & 0xff, int(ep[c]) >> 8) == (f.value, s.value), (family, comp, c)
+            assert int(err[c]) == e.value
+            for k, b in enumerate(m):
+                bits = sum(int(sel[16 * k + i]) << (3 * i) for i in range(16))
+                want = np.frombuffer(int(f.value | (s.value << 8) | (bits << 16)).to_bytes(8, "little"), np.uint8)
+                assert (out[b, 8:] == want).all() and (out[b, :8] == 0).all()

@@ -1,0 +1,55 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo processes partition the units of a batch without
+overlap, and the timing reduction is a max over ranks (the contract bench.py --gpus N relies on)."""
+import os
+import socket
+import subprocess
+import sys
+
+import helpers
+from crunch2_b200 import shard
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from crunch2_b200 import shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+dims = [(max(1, 2048 >> l), max(1, 2048 >> l)) for l in range(12)]
+costs = shard.unit_costs(dims, faces=6)
+mine = shard.partition_units(costs, world)[rank]
+t = shard.max_over_ranks(10.0 + rank)                 # slowest rank defines the step time
+total = shard.sum_over_ranks(sum(costs[i] for i in mine))
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+if rank == 0:
+    print(json.dumps(dict(t=t, total=total, units=gathered, ncosts=len(costs), sumcosts=sum(costs))))
+dist.destroy_process_group()
+'''
+
+
+def test_partition_is_balanced_and_complete():
+    costs = shard.unit_costs([(max(1, 4096 >> l), max(1, 1024 >> l)) for l in range(13)], faces=1) * 5
+    for world in (1, 2, 3, 8):
+        parts = shard.partition_units(costs, world)
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(len(costs)))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(costs)
+
+
+def test_gloo_world_size_2(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), helpers.ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["t"] == 11.0
+    assert d["total"] == d["sumcosts"]
+    flat = sorted(i for u in d["units"] for i in u)
+    assert flat == list(range(d["ncosts"]))
