@@ -87,6 +87,7 @@ def _declare(lib):
     u64 = ctypes.c_uint64
     lib.crn_gpu_dxt1_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), i32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
     lib.crn_gpu_dxt5_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
+    lib.crn_gpu_optimize_selectors.argtypes = [vp, u32, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, vp, u32, u32]
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
     lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
@@ -207,6 +208,16 @@ class Context:
                                                           ptr(d_members), n_clusters, total_member_blocks, ptr(d_out), out_stride, out_offset,
                                                           ptr(d_endpoints), ptr(d_error))
         self._check(rc)
+
+    def optimize_selectors(self, kind, d_blocks, n_blocks, d_offsets, d_members, n_clusters, d_elements, stride, offset, params=None, component=3):
+        """qdxt1/qdxt5::optimize_selectors_task: kind = "color" or "alpha"; d_elements is updated in place."""
+        params = params or PackParams()
+        cp = params._c()
+
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        self._check(self._lib.crn_gpu_optimize_selectors(self._ctx, 0 if kind == "color" else 1, ctypes.byref(cp), component, ptr(d_blocks), n_blocks,
+                                                         ptr(d_offsets), ptr(d_members), n_clusters, ptr(d_elements), stride, offset))
 
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
     def unpack_begin(self, crn_bytes):

@@ -237,4 +237,112 @@ dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
     }
 }
 
+// ---- selector re-vote (qdxt1::optimize_selectors_task, crn_qdxt1.cpp:714-865; qdxt5:: crn_qdxt5.cpp:578-687) --
+// One warp per selector cluster.  For each of the two block categories (colour: 4-colour / opaque 3-colour
+// blocks; alpha: 8-value / 6-value blocks) and each of the 16 pixel positions, the selector minimising the
+// error summed over the category's member blocks (each with ITS OWN endpoints) replaces the selectors of
+// every member.  Lane = pixel position (x16) x block parity (x2); sums are integers, so the order of
+// accumulation does not matter; ties keep the lowest selector like the reference's strict '<'.
+template <bool IS_ALPHA>
+__global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
+optimize_selectors_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
+                          const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, uint32_t comp, int perceptual,
+                          uint32_t alpha_threshold, uint8_t* __restrict__ elems, uint32_t stride, uint32_t ofs)
+{
+    constexpr int NS = IS_ALPHA ? 8 : 4;
+    const unsigned lane = lane_id(), pos = lane & 15, half = lane >> 4;
+    const uint32_t warps = gridDim.x * kClusterWarpsPerCta;
+    for (uint32_t c = blockIdx.x * kClusterWarpsPerCta + (threadIdx.x >> 5); c < n_clusters; c += warps) {
+        const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
+        if (nb <= 1) continue;
+        const uint32_t* members = cluster_blocks + b0;
+        unsigned long long err[2][NS];
+#pragma unroll
+        for (int k = 0; k < NS; k++) { err[0][k] = 0; err[1][k] = 0; }
+        unsigned cnt0 = 0, cnt1 = 0;
+        for (uint32_t j = half; j < nb; j += 2) {
+            const uint32_t b = members[j];
+            const unsigned long long e = *reinterpret_cast<const unsigned long long*>(elems + (size_t)b * stride + ofs);
+            const uint32_t px = blocks[(size_t)b * 16 + pos];
+            if (IS_ALPHA) {
+                const unsigned l = (unsigned)(e & 0xff), h = (unsigned)((e >> 8) & 0xff);
+                unsigned p[8];
+                const int cat = l <= h;                         // is_alpha6_block (crn_dxt.h:306-309)
+                if (cat) dxt5a_values6(l, h, p); else dxt5a_values8(l, h, p);
+                const int v = (int)((px >> (8 * comp)) & 0xffu);
+                if (cat) cnt1++; else cnt0++;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int d = v - (int)p[k]; if (cat) err[1][k] += (unsigned)(d * d); else err[0][k] += (unsigned)(d * d); }
+            } else {
+                const unsigned lo = (unsigned)(e & 0xffff), hi = (unsigned)((e >> 16) & 0xffff);
+                int cat = lo <= hi;                             // is_alpha_block
+                if (cat && alpha_threshold > 0) {               // 3-colour blocks with transparent pixels are left alone (:772-792)
+                    const unsigned any = __ballot_sync(0xffffu << (16 * half), (px >> 24) < alpha_threshold);
+                    if (any) cat = 2;
+                }
+                if (cat == 2) continue;
+                int r0, g0, b0c, r1, g1, b1;
+                unpack565(lo, true, r0, g0, b0c);
+                unpack565(hi, true, r1, g1, b1);
+                int pr[4], pg[4], pb[4];
+                pr[0] = r0; pg[0] = g0; pb[0] = b0c; pr[1] = r1; pg[1] = g1; pb[1] = b1;
+                if (!cat) {                                     // dxt1_block::get_block_colors4 (crn_dxt.cpp:246-260)
+                    pr[2] = (r0 * 2 + r1) / 3; pg[2] = (g0 * 2 + g1) / 3; pb[2] = (b0c * 2 + b1) / 3;
+                    pr[3] = (r1 * 2 + r0) / 3; pg[3] = (g1 * 2 + g0) / 3; pb[3] = (b1 * 2 + b0c) / 3;
+                } else {                                        // get_block_colors3 (:234-244)
+                    pr[2] = (r0 + r1) >> 1; pg[2] = (g0 + g1) >> 1; pb[2] = (b0c + b1) >> 1;
+                    pr[3] = 0; pg[3] = 0; pb[3] = 0;
+                }
+                const int r = (int)(px & 0xff), g = (int)((px >> 8) & 0xff), bl = (int)((px >> 16) & 0xff);
+                if (cat) cnt1++; else cnt0++;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int dr = r - pr[k], dg = g - pg[k], db = bl - pb[k];
+                    const unsigned d = perceptual ? (unsigned)(8 * dr * dr + 25 * dg * dg + db * db) : (unsigned)(dr * dr + dg * dg + db * db);
+                    if (cat) err[1][k] += d; else err[0][k] += d;
+                }
+            }
+        }
+        __syncwarp();
+        cnt0 += __shfl_xor_sync(CRN_FULL_MASK, cnt0, 16);
+        cnt1 += __shfl_xor_sync(CRN_FULL_MASK, cnt1, 16);
+        unsigned long long bits[2] = { 0, 0 };
+#pragma unroll
+        for (int cat = 0; cat < 2; cat++) {
+            unsigned best_s = 0;
+            unsigned long long best_e = 0xFFFFFFFFFFull;
+            const int max_s = IS_ALPHA ? 8 : (cat ? 3 : 4);
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                const unsigned long long t = err[cat][k] + __shfl_xor_sync(CRN_FULL_MASK, err[cat][k], 16);
+                if (k < max_s && t < best_e) { best_e = t; best_s = (unsigned)k; }
+            }
+            unsigned long long b = half == 0 ? (unsigned long long)best_s << ((IS_ALPHA ? 3 : 2) * pos) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b |= __shfl_xor_sync(CRN_FULL_MASK, b, o);
+            bits[cat] = b;
+        }
+        // write back: every member of a category with more than one block gets the voted selectors
+        for (uint32_t j = lane; j < nb; j += 32) {
+            const uint32_t b = members[j];
+            unsigned long long* pe = reinterpret_cast<unsigned long long*>(elems + (size_t)b * stride + ofs);
+            const unsigned long long e = *pe;
+            if (IS_ALPHA) {
+                const int cat = (unsigned)(e & 0xff) <= (unsigned)((e >> 8) & 0xff);
+                if ((cat ? cnt1 : cnt0) > 1) *pe = (e & 0xffffull) | (bits[cat] << 16);
+            } else {
+                const unsigned lo = (unsigned)(e & 0xffff), hi = (unsigned)((e >> 16) & 0xffff);
+                int cat = lo <= hi;
+                if (cat && alpha_threshold > 0) {
+                    bool any = false;
+                    for (int k = 0; k < 16; k++) any = any || (blocks[(size_t)b * 16 + k] >> 24) < alpha_threshold;
+                    if (any) cat = 2;
+                }
+                if (cat != 2 && (cat ? cnt1 : cnt0) > 1) *pe = (e & 0xffffffffull) | (bits[cat] << 32);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace crn

@@ -335,6 +335,34 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     return CRN_GPU_OK;
 }
 
+int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const crn_gpu_pack_params* params, uint32_t component,
+                               const void* d_blocks_rgba, uint32_t n_blocks,
+                               const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks, uint32_t n_clusters,
+                               void* d_elements, uint32_t stride_bytes, uint32_t offset_bytes)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (kind > 1 || !params || params->struct_size != sizeof(crn_gpu_pack_params) || component > 3 || !d_blocks_rgba || !n_blocks ||
+        !d_cluster_offsets || !d_cluster_blocks || !d_elements || stride_bytes < 8 || (stride_bytes & 7) || (offset_bytes & 7))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_optimize_selectors: bad argument");
+    if (!n_clusters) return CRN_GPU_OK;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int threads = crn::kClusterWarpsPerCta * 32;
+    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, 8);
+    const uint32_t* blocks = static_cast<const uint32_t*>(d_blocks_rgba);
+    uint8_t* el = static_cast<uint8_t*>(d_elements);
+    // qdxt1::pack (crn_qdxt1.cpp:920-923): without 3-colour blocks the alpha threshold is 0
+    const uint32_t thr = params->use_both_block_types ? params->dxt1a_alpha_threshold : 0;
+    if (kind == 0)
+        CRN_LAUNCH(crn::optimize_selectors_kernel<false>, grid, threads, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters,
+                   component, params->perceptual ? 1 : 0, thr, el, stride_bytes, offset_bytes);
+    else
+        CRN_LAUNCH(crn::optimize_selectors_kernel<true>, grid, threads, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters,
+                   component, 0, 0u, el, stride_bytes, offset_bytes);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
 /* ---- CRN -> DXTn transcoding --------------------------------------------------------------------- */
 
 struct crn_gpu_texture {

@@ -118,6 +118,18 @@ CRN_API int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_
                                            void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
                                            uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error);
 
+/* Selector re-vote per selector cluster -------------------------------------------
+ * Replaces qdxt1::optimize_selectors_task (crnlib/crn_qdxt1.cpp:714-865; kind 0) and
+ * qdxt5::optimize_selectors_task (crnlib/crn_qdxt5.cpp:578-687; kind 1): within each cluster and block
+ * category, every pixel position gets the selector minimising the error summed over the member blocks (each
+ * with its own endpoints), written into every member.  d_elements is updated in place.  For kind 0,
+ * params->perceptual selects the metric and dxt1a_alpha_threshold (0 = off) exempts 3-colour blocks that
+ * contain transparent pixels; for kind 1, `component` is the source channel. */
+CRN_API int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const crn_gpu_pack_params* params, uint32_t component,
+                                       const void* d_blocks_rgba, uint32_t n_blocks,
+                                       const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks, uint32_t n_clusters,
+                                       void* d_elements, uint32_t stride_bytes, uint32_t offset_bytes);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

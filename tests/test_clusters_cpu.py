@@ -104,3 +104,72 @@ def test_alpha_clusters_match_port(simctx, port, family):
                 bits = sum(int(sel[16 * k + i]) << (3 * i) for i in range(16))
                 want = np.frombuffer(int(f.value | (s.value << 8) | (bits << 16)).to_bytes(8, "little"), np.uint8)
                 assert (out[b, 8:] == want).all() and (out[b, :8] == 0).all()
+
+
+# ---- selector re-vote (qdxt1/qdxt5::optimize_selectors_task) ----------------------------------------
+def revote_reference(blocks, elems, offs, members, is_alpha, perceptual=1, comp=3, threshold=0):
+    """Straight numpy restatement of crn_qdxt1.cpp:714-865 / crn_qdxt5.cpp:578-687 for the test."""
+    out = elems.copy()
+    for c in range(len(offs) - 1):
+        m = members[offs[c]:offs[c + 1]]
+        if len(m) <= 1:
+            continue
+        cats = {0: [], 1: []}
+        for b in m:
+            e = int(elems[b])
+            if is_alpha:
+                cats[int((e & 0xff) <= ((e >> 8) & 0xff))].append(b)
+            else:
+                lo, hi = e & 0xffff, (e >> 16) & 0xffff
+                if lo > hi:
+                    cats[0].append(b)
+                elif not (threshold > 0 and (blocks[b][:, 3] < threshold).any()):
+                    cats[1].append(b)
+        for cat, bl in cats.items():
+            if len(bl) <= 1:
+                continue
+            ns = 8 if is_alpha else (3 if cat else 4)
+            tot = np.zeros((16, ns), np.int64)
+            for b in bl:
+                e = int(elems[b])
+                if is_alpha:
+                    l, h = e & 0xff, (e >> 8) & 0xff
+                    if l > h:
+                        vals = [l, h] + [(l * (7 - k) + h * k) // 7 for k in range(1, 7)]
+                    else:
+                        vals = [l, h] + [(l * (5 - k) + h * k) // 5 for k in range(1, 5)] + [0, 255]
+                    v = blocks[b][:, comp].astype(np.int64)
+                    tot += (v[:, None] - np.array(vals)[None, :]) ** 2
+                else:
+                    lo, hi = e & 0xffff, (e >> 16) & 0xffff
+                    def up(c):
+                        r, g, bb = (c >> 11) & 31, (c >> 5) & 63, c & 31
+                        return np.array([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (bb << 3) | (bb >> 2)])
+                    c0, c1 = up(lo), up(hi)
+                    pal = [c0, c1, (c0 * 2 + c1) // 3, (c1 * 2 + c0) // 3] if lo > hi else [c0, c1, (c0 + c1) >> 1]
+                    px = blocks[b][:, :3].astype(np.int64)
+                    w = np.array([8, 25, 1]) if perceptual else np.array([1, 1, 1])
+                    for k in range(ns):
+                        tot[:, k] += (((px - pal[k][None, :]) ** 2) * w).sum(1)
+            best = tot.argmin(1)
+            bits = sum(int(best[i]) << ((3 if is_alpha else 2) * i) for i in range(16))
+            for b in bl:
+                e = int(out[b])
+                out[b] = (e & 0xffff) | (bits << 16) if is_alpha else (e & 0xffffffff) | (bits << 32)
+    return out
+
+
+@pytest.mark.parametrize("is_alpha", [False, True])
+def test_selector_revote_matches_restatement(simctx, port, is_alpha):
+    blocks = blockgen.block_family("smooth", 300, 71)
+    img = helpers.blocks_to_image(blocks)
+    packed = helpers.port_pack(port, 4 if is_alpha else 0, img, 4, 1, 1)
+    elems = packed.view(np.uint64).copy()
+    offs, members = make_clusters(300, [1, 2, 3, 9, 30, 77, 150], 13)
+    want = revote_reference(blocks, elems, offs, members, is_alpha, threshold=128)   # default params: use_both_block_types keeps the 128 threshold
+    got = elems.copy()
+    simctx.optimize_selectors("alpha" if is_alpha else "color", blocks.ctypes.data, 300, offs.ctypes.data, members.ctypes.data, len(offs) - 1,
+                              got.ctypes.data, 8, 0, crn.PackParams(perceptual=True), component=3)
+    simctx.synchronize()
+    assert (got == want).all()
+    assert (got != elems).any()
