@@ -87,6 +87,7 @@ def _declare(lib):
     u64 = ctypes.c_uint64
     lib.crn_gpu_dxt1_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), i32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
     lib.crn_gpu_dxt5_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
+    lib.crn_gpu_qdxt_training.argtypes = [vp, u32, u32, vp, u32, vp, u32, vp, vp, vp]
     lib.crn_gpu_optimize_selectors.argtypes = [vp, u32, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, vp, u32, u32]
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]

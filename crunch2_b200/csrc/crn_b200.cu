@@ -7,6 +7,7 @@
 #include "pack_kernels.cuh"
 #include "transcode_host.h"
 #include "cluster_kernels.cuh"
+#include "qdxt_kernels.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -330,6 +331,41 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
                d_cluster_blocks, n_clusters, component, (int)params->dxt_quality, params->use_both_block_types ? 1 : 0,
                reinterpret_cast<unsigned int*>(ctx->d_cluster_ws), static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes,
                d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error));
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
+static bool build_mip_table(const crn_gpu_mip_desc* mips, uint32_t num_mips, uint32_t n_blocks, crn::QdxtMipTable& mt)
+{
+    if (!mips || !num_mips || num_mips > (uint32_t)crn::kQdxtMaxMips) return false;
+    uint32_t chunks = 0;
+    for (uint32_t i = 0; i < num_mips; i++) {
+        if (!mips[i].block_width || !mips[i].block_height ||
+            (uint64_t)mips[i].first_block + (uint64_t)mips[i].block_width * mips[i].block_height > n_blocks) return false;
+        mt.m[i].first_block = mips[i].first_block; mt.m[i].block_width = mips[i].block_width; mt.m[i].block_height = mips[i].block_height;
+        mt.m[i].first_chunk = chunks;
+        chunks += ((mips[i].block_width + 1) / 2) * ((mips[i].block_height + 1) / 2);
+    }
+    mt.num_mips = num_mips; mt.total_chunks = chunks;
+    return true;
+}
+
+int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, const void* d_blocks_rgba, uint32_t n_blocks,
+                          const crn_gpu_mip_desc* mips, uint32_t num_mips, void* d_vectors, uint32_t* d_weights, uint8_t* d_chunk_encoding)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    crn::QdxtMipTable mt;
+    if (kind > 1 || component > 3 || !d_blocks_rgba || !n_blocks || !d_vectors || !d_weights || !build_mip_table(mips, num_mips, n_blocks, mt))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_training: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int threads = crn::kQdxtWarpsPerCta * 32;
+    const int grid = grid_for(ctx, mt.total_chunks, crn::kQdxtWarpsPerCta, 8);
+    const uint32_t* blocks = static_cast<const uint32_t*>(d_blocks_rgba);
+    if (kind == 0)
+        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding);
+    else
+        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;

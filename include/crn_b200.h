@@ -118,6 +118,18 @@ CRN_API int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_
                                            void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
                                            uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error);
 
+/* Clustered-DDS quantiser, tile analysis -----------------------------------
+ * Replaces the training-vector half of qdxt1::init (kind 0; crnlib/crn_qdxt1.cpp:103-361) and qdxt5::init
+ * (kind 1, channel `component`; crnlib/crn_qdxt5.cpp:103-330) for the hierarchical (adaptive tile) mode:
+ * per 8x8 chunk the nine dxt_fast tile fits, the encoding choice, and one endpoint training vector +
+ * weight per block.  Blocks are laid out level after level as mipmapped_texture::qdxt_pack_init does;
+ * mips[i] = {first_block, block_width, block_height}.  d_vectors: 6 (kind 0: lo.rgb, hi.rgb) or 2 (kind 1)
+ * bytes per block; d_weights: uint32 per block; d_chunk_encoding: optional, one byte per chunk. */
+typedef struct crn_gpu_mip_desc { uint32_t first_block, block_width, block_height; } crn_gpu_mip_desc;
+CRN_API int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, const void* d_blocks_rgba, uint32_t n_blocks,
+                                  const crn_gpu_mip_desc* mips, uint32_t num_mips,
+                                  void* d_vectors, uint32_t* d_weights, uint8_t* d_chunk_encoding);
+
 /* Selector re-vote per selector cluster -------------------------------------------
  * Replaces qdxt1::optimize_selectors_task (crnlib/crn_qdxt1.cpp:714-865; kind 0) and
  * qdxt5::optimize_selectors_task (crnlib/crn_qdxt5.cpp:578-687; kind 1): within each cluster and block

@@ -50,6 +50,13 @@ uint32_t op_pack_image(int fmt, const uint8_t* rgba, uint32_t width, uint32_t he
                        uint32_t quality, uint32_t perceptual, uint32_t use_both_block_types,
                        uint32_t alpha_threshold, uint32_t transparent_for_black, uint8_t* out);
 
+/* dxt_fast primitives and the qdxt1/qdxt5 tile analysis (see dxt_fast_port.c). */
+void op_fast_color_block(uint32_t n, const uint8_t* px, uint32_t* low16, uint32_t* high16, uint8_t* sel);
+void op_fast_alpha_block(uint32_t n, const uint8_t* px, uint32_t comp, uint32_t* low8, uint32_t* high8, uint8_t* sel);
+void op_find_representative_colors(uint32_t n, const uint8_t* px, uint8_t* lo, uint8_t* hi);
+void op_qdxt_training(int kind, uint32_t comp, const uint8_t* blocks, uint32_t n_blocks, const uint32_t* mips, uint32_t num_mips,
+                      int hierarchical, uint8_t* out_vecs, uint32_t* out_weights, uint8_t* out_encoding);
+
 /* CRN -> DXTn transcoder (inc/crn_decomp.h): crnd_unpack_begin / crnd_get_texture_info / crnd_unpack_level /
  * crnd_unpack_end.  info out[0..7] = width,height,levels,faces,bytes_per_block,format,userdata0,userdata1. */
 typedef struct op_crnd op_crnd;

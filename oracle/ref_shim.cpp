@@ -286,3 +286,23 @@ SHIM_API double ref_transcode_all(const void* crn, uint32_t crn_size, uint8_t* o
     crnd::crnd_unpack_end(ctx);
     return total;
 }
+
+// dxt_fast primitives used by the clustered-DDS quantisers (crnlib/crn_dxt_fast.cpp:725, :788, :855)
+SHIM_API void ref_fast_color_block(uint32_t n, const uint8_t* pixels, uint32_t* low16, uint32_t* high16, uint8_t* selectors)
+{
+    uint lo, hi;
+    dxt_fast::compress_color_block(n, reinterpret_cast<const color_quad_u8*>(pixels), lo, hi, selectors);
+    *low16 = lo; *high16 = hi;
+}
+SHIM_API void ref_fast_alpha_block(uint32_t n, const uint8_t* pixels, uint32_t comp, uint32_t* low8, uint32_t* high8, uint8_t* selectors)
+{
+    uint lo, hi;
+    dxt_fast::compress_alpha_block(n, reinterpret_cast<const color_quad_u8*>(pixels), lo, hi, selectors, comp);
+    *low8 = lo; *high8 = hi;
+}
+SHIM_API void ref_find_representative_colors(uint32_t n, const uint8_t* pixels, uint8_t* lo, uint8_t* hi)
+{
+    color_quad_u8 l, h;
+    dxt_fast::find_representative_colors(n, reinterpret_cast<const color_quad_u8*>(pixels), l, h);
+    lo[0] = l.r; lo[1] = l.g; lo[2] = l.b; hi[0] = h.r; hi[1] = h.g; hi[2] = h.b;
+}
