@@ -1,0 +1,491 @@
+// vq_kernels.cuh -- top-down binary-split vector quantiser (SURVEY 8(a) row a19, and a13's split step)
+// for sm_100a: the clusterizer<VectorType> of the clustered-DDS path, frontier-batched.
+//
+// Replaces crnlib::clusterizer<V>::generate_codebook / split_node / compute_split_pca /
+// compute_split_estimate (reference crnlib/crn_clusterizer.h:65-167, :740-873, :487-600, :449-485) for
+// V = vec2F, vec6F, vec16F.  The reference pops the highest-variance leaf from a heap and splits it, one
+// node at a time.  A split only looks at the node's own vectors, so here EVERY splittable leaf of the
+// current frontier is split in the same round (one round = a fixed sequence of kernels over all vectors),
+// and the reference's split ORDER -- which decides where the codebook budget is spent and what
+// retrieve_clusters() prunes -- is replayed afterwards on the host from the recorded variances
+// (vq_host.h).  All vectors of the path have small integer components (endpoints 0..255, linear selectors
+// 0..7) and integer weights, so every sum is accumulated exactly in 64-bit integers with atomics:
+// the result does not depend on the order of accumulation and is reproducible run to run.  (The reference
+// accumulates the same sums in float, which rounds once a sum passes 2^24; cluster boundaries can
+// therefore differ in the last place -- this path is tolerance-class, see DESIGN.md.)
+#pragma once
+#include "warp_util.cuh"
+
+namespace crn {
+
+constexpr unsigned kVqNoSlot = 0xFFFFFFFFu;
+
+template <int D> struct VqSlot {              // split state of one frontier node
+    unsigned long long s2[D * (D + 1) / 2];   // sum w * v[x] * v[y], x <= y
+    unsigned long long s1[2][D];              // per side: sum w * v
+    unsigned long long wsum[2];
+    unsigned long long tt[2];                 // per side: sum w * (v . v)
+    unsigned long long far_key, opp_key;      // compute_split_estimate fallback: (float bits of dist << 32) | ~position
+    float axis[D];
+    float child[2][D];
+    float centroid[D];
+    float var[2];
+    float prev_total;
+    unsigned node, begin, count;
+    int state;                                // 0 iterating, 1 split done, 2 unsplittable
+    int loops;
+    int mode;                                 // 0 PCA, 1 two vectors, 2 estimate fallback pending
+    unsigned long long node_weight;
+};
+
+struct VqNodes {                              // SoA node table (capacity 2N + 1)
+    unsigned* begin; unsigned* count; int* left; unsigned* flags; float* variance; unsigned long long* weight; float* centroid;   // centroid: [node][D]
+};
+
+template <int D> __device__ __forceinline__ void vq_load(const uint8_t* __restrict__ vecs, unsigned id, float (&v)[D])
+{
+#pragma unroll
+    for (int d = 0; d < D; d++) v[d] = (float)vecs[(size_t)id * D + d];
+}
+
+// run-head segmented sum inside a warp; `take` bit k says lane + 2^k belongs to the same run
+__device__ __forceinline__ unsigned vq_take_mask(unsigned key)
+{
+    unsigned take = 0;
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const unsigned k2 = __shfl_down_sync(CRN_FULL_MASK, key, 1u << k);
+        if (lane + (1u << k) < 32 && k2 == key) take |= 1u << k;
+    }
+    return take;
+}
+__device__ __forceinline__ int vq_seg_sum(int val, unsigned take)
+{
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int v2 = __shfl_down_sync(CRN_FULL_MASK, val, 1u << k);
+        if (take >> k & 1) val += v2;
+    }
+    return val;
+}
+__device__ __forceinline__ bool vq_is_head(unsigned key)
+{
+    const unsigned kp = __shfl_up_sync(CRN_FULL_MASK, key, 1);
+    return key != kVqNoSlot && (lane_id() == 0 || kp != key);
+}
+__device__ __forceinline__ void vq_add(unsigned long long* p, int v) { if (v) atomicAdd(p, (unsigned long long)(long long)v); }
+
+// K1: second moments of every frontier node (PCA mode only)
+template <int D>
+__global__ void __launch_bounds__(256) vq_moments_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                         const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned slot = i < n ? pos_slot[i] : kVqNoSlot;
+    if (slot != kVqNoSlot && slots[slot].mode != 0) slot = kVqNoSlot;
+    const unsigned take = vq_take_mask(slot);
+    const bool head = vq_is_head(slot);
+    if (!__any_sync(CRN_FULL_MASK, slot != kVqNoSlot)) return;
+    int v[D]; int w = 0;
+    if (slot != kVqNoSlot) {
+        const unsigned id = perm[i];
+        w = (int)wts[id];
+#pragma unroll
+        for (int d = 0; d < D; d++) v[d] = vecs[(size_t)id * D + d];
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) v[d] = 0;
+    }
+    int k = 0;
+#pragma unroll
+    for (int x = 0; x < D; x++)
+#pragma unroll
+        for (int y = x; y < D; y++, k++) {
+            const int s = vq_seg_sum(w * v[x] * v[y], take);
+            if (head) vq_add(&slots[slot].s2[k], s);
+        }
+}
+
+// K2: covariance -> principal axis by power iteration (compute_split_pca, crn_clusterizer.h:487-575)
+template <int D>
+__global__ void vq_axis_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (sl.mode != 0) return;
+    float covar[D][D];
+    const double W = (double)sl.node_weight;
+    const float inv_w = 1.0f / (float)sl.node_weight;
+    int k = 0;
+    for (int x = 0; x < D; x++)
+        for (int y = x; y < D; y++, k++) {
+            // sum w (v-c)(v-c)^T = S2 - c_x S1_y - c_y S1_x + W c_x c_y with S1 = W c
+            const double c = (double)(long long)sl.s2[k] - W * (double)sl.centroid[x] * (double)sl.centroid[y];
+            covar[x][y] = (float)c * inv_w;
+            covar[y][x] = covar[x][y];
+        }
+    float axis[D], prev[D];
+    for (int i = 0; i < D; i++) {
+        axis[i] = D == 1 ? 1.0f : .75f + (1.25f - .75f) * ((float)i * (1.0f / (float)(D - 1 > 1 ? D - 1 : 1)));
+        prev[i] = axis[i];
+    }
+    for (int iter = 0; iter < 10; iter++) {
+        float x[D];
+        double max_sum = 0;
+        for (int i = 0; i < D; i++) {
+            double sum = 0;
+            for (int j = 0; j < D; j++) sum += (double)(axis[j] * covar[i][j]);
+            x[i] = (float)sum;
+            max_sum = max_sum > fabs(sum) ? max_sum : fabs(sum);
+        }
+        if (max_sum != 0.0) { const float m = (float)(1.0 / max_sum); for (int i = 0; i < D; i++) x[i] *= m; }
+        float nrm = 0;
+        for (int i = 0; i < D; i++) { const float dlt = prev[i] - x[i]; nrm += dlt * dlt; }
+        for (int i = 0; i < D; i++) { prev[i] = axis[i]; axis[i] = x[i]; }
+        if (nrm < .0025f) break;
+    }
+    {   // vec::normalize (crn_vec.h:674-689)
+        double nn = (double)(axis[0] * axis[0]);
+        for (int i = 1; i < D; i++) nn += (double)(axis[i] * axis[i]);
+        if (nn != 0) { const float sc = (float)(1.0 / sqrt(nn)); for (int i = 0; i < D; i++) axis[i] *= sc; }
+    }
+    for (int i = 0; i < D; i++) sl.axis[i] = axis[i];
+}
+
+// accumulate (w v, w, w v.v) of the vector at position i into side `side` of its slot
+template <int D>
+__device__ __forceinline__ void vq_accumulate_side(VqSlot<D>* __restrict__ slots, unsigned slot, unsigned take, bool head,
+                                                   const int (&v)[D], int w, int side, bool with_tt)
+{
+#pragma unroll
+    for (int sd = 0; sd < 2; sd++) {
+        const int m = (slot != kVqNoSlot && side == sd) ? w : 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const int s = vq_seg_sum(m * v[d], take);
+            if (head) vq_add(&slots[slot].s1[sd][d], s);
+        }
+        const int sw = vq_seg_sum(m, take);
+        if (head) vq_add(&slots[slot].wsum[sd], sw);
+        if (with_tt) {
+            int vv = 0;
+#pragma unroll
+            for (int d = 0; d < D; d++) vv += v[d] * v[d];
+            const int st = vq_seg_sum(m * vv, take);
+            if (head) vq_add(&slots[slot].tt[sd], st);
+        }
+    }
+}
+
+// K3: initial division by the sign of the projection onto the axis (crn_clusterizer.h:577-597)
+template <int D>
+__global__ void __launch_bounds__(256) vq_project_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                         const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned slot = i < n ? pos_slot[i] : kVqNoSlot;
+    if (slot != kVqNoSlot && slots[slot].mode != 0) slot = kVqNoSlot;
+    const unsigned take = vq_take_mask(slot);
+    const bool head = vq_is_head(slot);
+    if (!__any_sync(CRN_FULL_MASK, slot != kVqNoSlot)) return;
+    int v[D]; int w = 0, side = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) v[d] = 0;
+    if (slot != kVqNoSlot) {
+        const unsigned id = perm[i];
+        w = (int)wts[id];
+        const VqSlot<D>& sl = slots[slot];
+        float t = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            v[d] = vecs[(size_t)id * D + d];
+            const float df = (float)v[d] - sl.centroid[d];
+            if (d == 0) t = df * sl.axis[0]; else t += df * sl.axis[d];
+        }
+        side = ((double)t < 0.0) ? 0 : 1;
+    }
+    vq_accumulate_side<D>(slots, slot, take, head, v, w, side, false);
+}
+
+// K4: children estimates from the division, or flag the furthest/opposite fallback
+template <int D>
+__global__ void vq_children_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ perm, VqSlot<D>* __restrict__ slots, unsigned nslots)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (sl.mode == 1) {            // exactly two vectors (:489-494)
+        for (int d = 0; d < D; d++) { sl.child[0][d] = (float)vecs[(size_t)perm[sl.begin] * D + d]; sl.child[1][d] = (float)vecs[(size_t)perm[sl.begin + 1] * D + d]; }
+    } else if (sl.wsum[0] && sl.wsum[1]) {
+        const float il = (float)(1.0 / (double)sl.wsum[0]), ir = (float)(1.0 / (double)sl.wsum[1]);
+        for (int d = 0; d < D; d++) { sl.child[0][d] = (float)(long long)sl.s1[0][d] * il; sl.child[1][d] = (float)(long long)sl.s1[1][d] * ir; }
+    } else sl.mode = 2;
+    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; }
+    sl.wsum[0] = sl.wsum[1] = 0; sl.tt[0] = sl.tt[1] = 0;
+    sl.far_key = 0; sl.opp_key = 0;
+}
+
+// K4b/K4c: compute_split_estimate (:449-485): furthest vector from the centroid, then the vector furthest from it
+template <int D, int PASS>
+__global__ void __launch_bounds__(256) vq_estimate_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ perm,
+                                                          const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned slot = pos_slot[i];
+    if (slot == kVqNoSlot || slots[slot].mode != 2) return;
+    VqSlot<D>& sl = slots[slot];
+    float ref[D];
+    if (PASS == 0) { for (int d = 0; d < D; d++) ref[d] = sl.centroid[d]; }
+    else { const unsigned fp = ~(unsigned)(sl.far_key & 0xffffffffu); for (int d = 0; d < D; d++) ref[d] = (float)vecs[(size_t)perm[fp] * D + d]; }
+    float dist = 0;
+    for (int d = 0; d < D; d++) { const float df = (float)vecs[(size_t)perm[i] * D + d] - ref[d]; dist += df * df; }
+    const unsigned long long key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(~i);
+    atomicMax(PASS == 0 ? &sl.far_key : &sl.opp_key, key);
+}
+template <int D>
+__global__ void vq_estimate_finish_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ perm, VqSlot<D>* __restrict__ slots, unsigned nslots)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (sl.mode != 2) return;
+    const unsigned fp = ~(unsigned)(sl.far_key & 0xffffffffu), op = ~(unsigned)(sl.opp_key & 0xffffffffu);
+    for (int d = 0; d < D; d++) {
+        sl.child[0][d] = ((float)vecs[(size_t)perm[fp] * D + d] + sl.centroid[d]) * .5f;
+        sl.child[1][d] = ((float)vecs[(size_t)perm[op] * D + d] + sl.centroid[d]) * .5f;
+    }
+    sl.mode = 0;
+}
+
+// K5: one Lloyd iteration, assignment half (split_node loop body, :780-812)
+template <int D>
+__global__ void __launch_bounds__(256) vq_assign_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                        const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, uint8_t* __restrict__ side_out, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned slot = i < n ? pos_slot[i] : kVqNoSlot;
+    if (slot != kVqNoSlot && slots[slot].state != 0) slot = kVqNoSlot;
+    const unsigned take = vq_take_mask(slot);
+    const bool head = vq_is_head(slot);
+    if (!__any_sync(CRN_FULL_MASK, slot != kVqNoSlot)) return;
+    int v[D]; int w = 0, side = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) v[d] = 0;
+    if (slot != kVqNoSlot) {
+        const unsigned id = perm[i];
+        w = (int)wts[id];
+        const VqSlot<D>& sl = slots[slot];
+        float dl = 0, dr = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            v[d] = vecs[(size_t)id * D + d];
+            const float a = sl.child[0][d] - (float)v[d], b = sl.child[1][d] - (float)v[d];
+            dl += a * a; dr += b * b;
+        }
+        side = ((double)dl < (double)dr) ? 0 : 1;
+        side_out[i] = (uint8_t)side;
+    }
+    vq_accumulate_side<D>(slots, slot, take, head, v, w, side, true);
+}
+
+// K6: Lloyd iteration, update half + convergence tests (:814-846)
+template <int D>
+__global__ void vq_update_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots, unsigned* __restrict__ active_count)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (sl.state != 0) return;
+    if (!sl.wsum[0] || !sl.wsum[1]) { sl.state = 2; return; }       // unsplittable (:814-818)
+    float var[2];
+    for (int sd = 0; sd < 2; sd++) {
+        double dot = 0;
+        for (int d = 0; d < D; d++) { const double x = (double)(long long)sl.s1[sd][d]; dot += x * x; }
+        var[sd] = (float)((double)sl.tt[sd] - dot / (double)sl.wsum[sd]);
+        const float inv = 1.0f / (float)sl.wsum[sd];
+        for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
+    }
+    sl.var[0] = var[0]; sl.var[1] = var[1];
+    sl.node_weight = sl.wsum[0];             // keeps W_left; W_right = total - left is recomputed at finalize from wsum[1]
+    const float total = var[0] + var[1];
+    sl.loops++;
+    bool done = false;
+    if (total < .00001f) done = true;
+    else if (((sl.prev_total - total) / total) < .00125f) done = true;
+    else if (sl.loops >= 8) done = true;
+    sl.prev_total = total;
+    if (done) { sl.state = 1; return; }
+    // another iteration: clear the accumulators (child weights are re-accumulated)
+    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; }
+    sl.wsum[0] = sl.wsum[1] = 0; sl.tt[0] = sl.tt[1] = 0;
+    atomicAdd(active_count, 1u);
+}
+
+// K7: flags for the stable partition: 1 where the element moves to the LEFT child of a node that was split
+__global__ void __launch_bounds__(256) vq_left_flags_kernel(const unsigned* __restrict__ pos_slot, const int* __restrict__ slot_state, const uint8_t* __restrict__ side,
+                                                            unsigned* __restrict__ flags, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned slot = pos_slot[i];
+    flags[i] = (slot != kVqNoSlot && slot_state[slot] == 1 && side[i] == 0) ? 1u : 0u;
+}
+
+// exclusive scan of 32-bit values: per-block (1024 elements) totals, scan of totals, final pass
+__global__ void __launch_bounds__(256) vq_scan_block_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ out, unsigned* __restrict__ block_sums, unsigned n)
+{
+    __shared__ unsigned warp_tot[8];
+    const unsigned base = blockIdx.x * 1024u + threadIdx.x * 4u;
+    unsigned v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < n ? in[base + k] : 0u; s += v[k]; }
+    unsigned incl = s;
+#pragma unroll
+    for (int ofs = 1; ofs < 32; ofs <<= 1) { const unsigned t = __shfl_up_sync(CRN_FULL_MASK, incl, ofs); if ((int)lane_id() >= ofs) incl += t; }
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned woff = 0;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); w++) woff += warp_tot[w];
+    unsigned run = woff + incl - s;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + incl;
+}
+__global__ void vq_scan_sums_kernel(unsigned* __restrict__ block_sums, unsigned nblocks)
+{   // single thread block, serial over <= a few thousand entries per thread chunk
+    __shared__ unsigned part[256];
+    const unsigned per = (nblocks + 255) / 256, b = threadIdx.x * per, e = min(b + per, nblocks);
+    unsigned s = 0;
+    for (unsigned i = b; i < e; i++) s += block_sums[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    unsigned off = 0;
+    for (unsigned t = 0; t < threadIdx.x; t++) off += part[t];
+    for (unsigned i = b; i < e; i++) { const unsigned v = block_sums[i]; block_sums[i] = off; off += v; }
+}
+__global__ void __launch_bounds__(256) vq_scan_add_kernel(unsigned* __restrict__ out, const unsigned* __restrict__ block_sums, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += block_sums[i >> 10];
+}
+
+// K8: create the two children of every split slot
+template <int D>
+__global__ void vq_finalize_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots, const unsigned* __restrict__ left_scan, unsigned n, VqNodes nodes,
+                                   unsigned* __restrict__ node_counter)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (sl.state == 2) { nodes.flags[sl.node] |= 1u; return; }
+    if (sl.state != 1) return;
+    const unsigned b = sl.begin, c = sl.count;
+    const unsigned l_end = b + c < n ? left_scan[b + c] : left_scan[n];     // left_scan has n + 1 entries
+    const unsigned nleft = l_end - left_scan[b];
+    const unsigned child = atomicAdd(node_counter, 2u);
+    nodes.left[sl.node] = (int)child;
+    for (int sd = 0; sd < 2; sd++) {
+        const unsigned id = child + sd;
+        nodes.begin[id] = sd ? b + nleft : b;
+        nodes.count[id] = sd ? c - nleft : nleft;
+        nodes.left[id] = -1;
+        nodes.flags[id] = 0;
+        nodes.variance[id] = sl.var[sd];
+        nodes.weight[id] = sl.wsum[sd];
+        for (int d = 0; d < D; d++) nodes.centroid[(size_t)id * D + d] = sl.child[sd][d];
+    }
+}
+
+// K9: scatter into the partitioned order; elements of nodes that were not split keep their place
+template <int D>
+__global__ void __launch_bounds__(256) vq_scatter_kernel(const unsigned* __restrict__ perm, unsigned* __restrict__ perm_out, const unsigned* __restrict__ pos_slot,
+                                                         const VqSlot<D>* __restrict__ slots, const uint8_t* __restrict__ side, const unsigned* __restrict__ left_scan, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned slot = pos_slot[i];
+    unsigned dst = i;
+    if (slot != kVqNoSlot && slots[slot].state == 1) {
+        const unsigned b = slots[slot].begin, c = slots[slot].count;
+        const unsigned lb = left_scan[b], li = left_scan[i];
+        const unsigned nleft = left_scan[b + c] - lb;
+        dst = side[i] == 0 ? b + (li - lb) : b + nleft + ((i - b) - (li - lb));
+    }
+    perm_out[dst] = perm[i];
+}
+
+// K10: next frontier = nodes created in [first_new, node_end) with more than one vector and positive variance.
+// head[i] = node id + 1 at the node's first position; the compaction (scan over head != 0) orders the slots by position.
+__global__ void __launch_bounds__(256) vq_mark_heads_kernel(VqNodes nodes, unsigned first_new, unsigned node_end, unsigned* __restrict__ head)
+{
+    const unsigned id = first_new + blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= node_end) return;
+    if (nodes.count[id] > 1 && nodes.variance[id] > 0.0f) head[nodes.begin[id]] = id + 1;
+}
+__global__ void __launch_bounds__(256) vq_head_flags_kernel(const unsigned* __restrict__ head, unsigned* __restrict__ flags, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = head[i] ? 1u : 0u;
+}
+template <int D>
+__global__ void __launch_bounds__(256) vq_make_slots_kernel(const unsigned* __restrict__ head, const unsigned* __restrict__ head_scan, VqNodes nodes,
+                                                            VqSlot<D>* __restrict__ slots, unsigned* __restrict__ pos_slot_starts, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    const unsigned id = head[i] - 1, s = head_scan[i];
+    VqSlot<D>& sl = slots[s];
+    for (int k = 0; k < D * (D + 1) / 2; k++) sl.s2[k] = 0;
+    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; sl.centroid[d] = nodes.centroid[(size_t)id * D + d]; sl.axis[d] = 0; }
+    sl.wsum[0] = sl.wsum[1] = 0; sl.tt[0] = sl.tt[1] = 0; sl.far_key = 0; sl.opp_key = 0;
+    sl.var[0] = sl.var[1] = 0; sl.prev_total = 1e+10f;
+    sl.node = id; sl.begin = nodes.begin[id]; sl.count = nodes.count[id];
+    sl.state = 0; sl.loops = 0; sl.mode = nodes.count[id] == 2 ? 1 : 0;
+    sl.node_weight = nodes.weight[id];
+    pos_slot_starts[s] = i;
+}
+// every position learns its slot: binary search over the slots' first positions
+template <int D>
+__global__ void __launch_bounds__(256) vq_pos_slot_kernel(const unsigned* __restrict__ slot_starts, const VqSlot<D>* __restrict__ slots, unsigned nslots,
+                                                          unsigned* __restrict__ pos_slot, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned lo = 0, hi = nslots;           // last slot with start <= i
+    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (slot_starts[mid] <= i) lo = mid + 1; else hi = mid; }
+    unsigned res = kVqNoSlot;
+    if (lo > 0) { const unsigned s = lo - 1; if (i < slots[s].begin + slots[s].count) res = s; }
+    pos_slot[i] = res;
+}
+template <int D>
+__global__ void vq_slot_states_kernel(const VqSlot<D>* __restrict__ slots, unsigned nslots, int* __restrict__ states)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslots) states[s] = slots[s].state;
+}
+
+// root statistics: sum w v, sum w, sum w v.v over all vectors (generate_codebook, :77-92)
+template <int D>
+__global__ void __launch_bounds__(256) vq_root_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ ids, unsigned n,
+                                                      unsigned long long* __restrict__ acc /* D + 2 */)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v[D]; int w = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) v[d] = 0;
+    if (i < n) { const unsigned id = ids[i]; w = (int)wts[id]; for (int d = 0; d < D; d++) v[d] = vecs[(size_t)id * D + d]; }
+    int vv = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        vv += v[d] * v[d];
+        const int s = __reduce_add_sync(CRN_FULL_MASK, w * v[d]);
+        if (lane_id() == 0) vq_add(&acc[d], s);
+    }
+    const int sw = __reduce_add_sync(CRN_FULL_MASK, w), st = __reduce_add_sync(CRN_FULL_MASK, w * vv);
+    if (lane_id() == 0) { vq_add(&acc[D], sw); vq_add(&acc[D + 1], st); }
+}
+
+}  // namespace crn

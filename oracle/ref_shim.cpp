@@ -306,3 +306,56 @@ SHIM_API void ref_find_representative_colors(uint32_t n, const uint8_t* pixels, 
     dxt_fast::find_representative_colors(n, reinterpret_cast<const color_quad_u8*>(pixels), l, h);
     lo[0] = l.r; lo[1] = l.g; lo[2] = l.b; hi[0] = h.r; hi[1] = h.g; hi[2] = h.b;
 }
+
+// clusterizer<vecNF>::generate_codebook + retrieve_clusters (crnlib/crn_clusterizer.h:65, :301) and
+// threaded_clusterizer<shim_vec16F>::create_clusters (crnlib/crn_threaded_clusterizer.h:70).
+#include "crn_clusterizer.h"
+#include "crn_threaded_clusterizer.h"
+typedef vec<6, float> shim_vec6F;
+typedef vec<16, float> shim_vec16F;
+template <typename V>
+static int run_clusterizer(uint32_t n, const float* vecs, const uint32_t* weights, uint32_t max_size, uint32_t retrieve,
+                           uint32_t* cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
+{
+    clusterizer<V> c;
+    c.reserve_training_vecs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        V v;
+        for (uint32_t d = 0; d < V::num_elements; d++) v[d] = vecs[(size_t)i * V::num_elements + d];
+        c.add_training_vec(v, weights[i]);
+    }
+    if (!c.generate_codebook(max_size)) return 0;
+    *codebook_size = c.get_codebook_size();
+    crnlib::vector<crnlib::vector<uint> > clusters;
+    c.retrieve_clusters(retrieve ? retrieve : c.get_codebook_size(), clusters);
+    *num_clusters = clusters.size();
+    for (uint32_t k = 0; k < clusters.size(); k++)
+        for (uint32_t j = 0; j < clusters[k].size(); j++) cluster_of[clusters[k][j]] = k;
+    return 1;
+}
+SHIM_API int ref_clusterizer(uint32_t dims, uint32_t n, const float* vecs, const uint32_t* weights, uint32_t max_size, uint32_t retrieve,
+                             uint32_t* cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
+{
+    if (dims == 2) return run_clusterizer<vec2F>(n, vecs, weights, max_size, retrieve, cluster_of, num_clusters, codebook_size);
+    if (dims == 6) return run_clusterizer<shim_vec6F>(n, vecs, weights, max_size, retrieve, cluster_of, num_clusters, codebook_size);
+    if (dims == 16) return run_clusterizer<shim_vec16F>(n, vecs, weights, max_size, retrieve, cluster_of, num_clusters, codebook_size);
+    return 0;
+}
+SHIM_API int ref_threaded_clusterizer16(uint32_t n, const float* vecs, const uint32_t* weights, uint32_t max_clusters, uint32_t threads,
+                                        uint32_t* cluster_of, uint32_t* num_clusters)
+{
+    task_pool pool;
+    if (!pool.init(threads)) return 0;
+    threaded_clusterizer<shim_vec16F> tc(pool);
+    threaded_clusterizer<shim_vec16F>::weighted_vec_array wv(n);
+    for (uint32_t i = 0; i < n; i++) {
+        for (uint32_t d = 0; d < 16; d++) wv[i].m_vec[d] = vecs[(size_t)i * 16 + d];
+        wv[i].m_weight = weights[i];
+    }
+    crnlib::vector<crnlib::vector<uint> > clusters;
+    if (!tc.create_clusters(wv, max_clusters, clusters, NULL, NULL)) return 0;
+    *num_clusters = clusters.size();
+    for (uint32_t k = 0; k < clusters.size(); k++)
+        for (uint32_t j = 0; j < clusters[k].size(); j++) cluster_of[clusters[k][j]] = k;
+    return 1;
+}
