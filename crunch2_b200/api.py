@@ -220,6 +220,17 @@ class Context:
         self._check(self._lib.crn_gpu_optimize_selectors(self._ctx, 0 if kind == "color" else 1, ctypes.byref(cp), component, ptr(d_blocks), n_blocks,
                                                          ptr(d_offsets), ptr(d_members), n_clusters, ptr(d_elements), stride, offset))
 
+    def vq_clusterize(self, d_vectors, d_weights, n, dims, max_codebook_size=65535, retrieve_max_clusters=0, threaded=False):
+        """clusterizer<V>::generate_codebook + retrieve_clusters (threaded: threaded_clusterizer<V>::create_clusters).
+        d_vectors: u8[n][dims], d_weights: u32[n] on the device.  Returns (cluster_of[n] numpy, num_clusters, codebook_size)."""
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        cluster_of = np.zeros(n, np.uint32)
+        k, cb = ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self._lib.crn_gpu_vq_clusterize(self._ctx, dims, ptr(d_vectors), ptr(d_weights), n, max_codebook_size, retrieve_max_clusters,
+                                                    1 if threaded else 0, cluster_of.ctypes.data_as(ctypes.c_void_p), ctypes.byref(k), ctypes.byref(cb)))
+        return cluster_of, k.value, cb.value
+
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
     def unpack_begin(self, crn_bytes):
         """crnd_unpack_begin: returns a Texture bound to this context."""

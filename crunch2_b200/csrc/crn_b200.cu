@@ -8,6 +8,7 @@
 #include "transcode_host.h"
 #include "cluster_kernels.cuh"
 #include "qdxt_kernels.cuh"
+#include "vq_host.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -64,6 +65,22 @@ int grid_for(const crn_gpu_ctx* ctx, uint32_t total_blocks, int warps_per_cta, i
     return (int)(g ? g : 1);
 }
 
+}  // namespace
+
+namespace {
+template <int D>
+int vq_clusterize(crn_gpu_ctx* ctx, const uint8_t* d_vecs, const uint32_t* d_wts, uint32_t n, uint32_t max_size, uint32_t retrieve, int threaded,
+                  uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
+{
+    crn::VqBuilder<D> builder(ctx->stream, &ctx->launches);
+    crn::VqResult res;
+    const cudaError_t ce = builder.build(d_vecs, d_wts, n, max_size, threaded != 0, res);
+    if (ce != cudaSuccess) return set_err(ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "crn_gpu_vq_clusterize", ce);
+    if (codebook_size) *codebook_size = res.codebook_size();
+    const uint32_t k = res.retrieve(retrieve, h_cluster_of);
+    if (num_clusters) *num_clusters = k;
+    return CRN_GPU_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -397,6 +414,24 @@ int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const crn_gpu_pa
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
+}
+
+/* ---- vector quantiser ----------------------------------------------------------------------------- */
+
+int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d_vectors, const uint32_t* d_weights, uint32_t n,
+                          uint32_t max_codebook_size, uint32_t retrieve_max_clusters, int threaded,
+                          uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if ((dims != 2 && dims != 6 && dims != 16) || !d_vectors || !d_weights || !n || !max_codebook_size || !h_cluster_of)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_vq_clusterize: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint8_t* v = static_cast<const uint8_t*>(d_vectors);
+    switch (dims) {
+    case 2: return vq_clusterize<2>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
+    case 6: return vq_clusterize<6>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
+    default: return vq_clusterize<16>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
+    }
 }
 
 /* ---- CRN -> DXTn transcoding --------------------------------------------------------------------- */

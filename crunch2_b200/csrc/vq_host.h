@@ -1,0 +1,354 @@
+// vq_host.h -- host driver of the frontier-batched vector quantiser (vq_kernels.cuh).
+//
+// The device splits whole frontiers; this file decides WHICH leaves are worth splitting and replays the
+// reference's split order.  crnlib::clusterizer<V>::generate_codebook (crnlib/crn_clusterizer.h:100-139)
+// keeps the leaves in a binary max-heap keyed by variance, pops the worst one, splits it, counts
+// total_leaves up (even when the node turned out unsplittable) and stops at max_size.  VqTreeSim below is
+// that loop, fed with the split results the device produced one round earlier; it stalls when the heap top
+// has not been split on the device yet, which is what triggers the next round.  A leaf outside the
+// `max_size - total_leaves` highest variances of the heap can never be popped, so it is not sent to the
+// device.  retrieve_clusters() (:301-332) is the pruning walk over the recorded split ranks.
+#pragma once
+#include <algorithm>
+#include <vector>
+#include "vq_kernels.cuh"
+
+namespace crn {
+
+struct VqHostNode {
+    uint32_t begin = 0, count = 0;
+    int32_t left = -1;               // device child id (right = left + 1), -1 while not split on the device
+    float variance = 0;
+    int32_t split_rank = -1;         // m_codebook_index of an interior node: order in which the reference split it
+    uint8_t processed = 0, unsplittable = 0;
+};
+
+struct VqTreeSim {                   // one clusterizer<V> instance
+    uint32_t root = 0, max_size = 0, total_leaves = 1, split_index = 0;
+    std::vector<uint32_t> heap;      // 1-based, as the reference's
+    uint32_t heap_size = 0;
+
+    void insert(const std::vector<VqHostNode>& nodes, uint32_t id)
+    {   // insert_heap (:384-414): sift up while the parent is not strictly greater
+        const float v = nodes[id].variance;
+        uint32_t pos = ++heap_size;
+        if (heap_size >= heap.size()) heap.resize(heap_size + 1);
+        for (;;) {
+            const uint32_t parent = pos >> 1;
+            if (!parent || nodes[heap[parent]].variance > v) break;
+            heap[pos] = heap[parent];
+            pos = parent;
+        }
+        heap[pos] = id;
+    }
+    uint32_t pop(const std::vector<VqHostNode>& nodes)
+    {   // generate_codebook :114-121 + down_heap (:416-444)
+        const uint32_t top = heap[1];
+        heap[1] = heap[heap_size--];
+        if (heap_size) {
+            uint32_t pos = 1, child;
+            const uint32_t orig = heap[1];
+            const float ov = nodes[orig].variance;
+            while ((child = pos << 1) <= heap_size) {
+                if (child < heap_size && nodes[heap[child]].variance < nodes[heap[child + 1]].variance) child++;
+                if (ov > nodes[heap[child]].variance) break;
+                heap[pos] = heap[child];
+                pos = child;
+            }
+            heap[pos] = orig;
+        }
+        return top;
+    }
+    bool finished() const { return !(total_leaves < max_size && heap_size); }
+    // advance as far as the device results allow
+    void run(std::vector<VqHostNode>& nodes)
+    {
+        while (!finished()) {
+            VqHostNode& nd = nodes[heap[1]];
+            if (nd.count != 1 && !nd.processed) return;
+            const uint32_t id = pop(nodes);
+            VqHostNode& node = nodes[id];
+            if (node.count != 1 && !node.unsplittable) {          // split_node (:740-873)
+                node.split_rank = (int32_t)split_index++;
+                for (uint32_t c = 0; c < 2; c++) {
+                    const uint32_t ch = (uint32_t)node.left + c;
+                    if (nodes[ch].count > 1 && nodes[ch].variance > 0.0f) insert(nodes, ch);
+                }
+            }
+            total_leaves++;
+        }
+    }
+    // leaves of the heap that can still be popped and have not been split on the device
+    void wanted(const std::vector<VqHostNode>& nodes, std::vector<uint32_t>& out) const
+    {
+        if (finished()) return;
+        const uint32_t budget = max_size - total_leaves;
+        float thresh = -1.0f;
+        if (heap_size > budget) {
+            std::vector<float> v(heap_size);
+            for (uint32_t i = 0; i < heap_size; i++) v[i] = nodes[heap[1 + i]].variance;
+            std::nth_element(v.begin(), v.begin() + (budget - 1), v.end(), [](float a, float b) { return a > b; });
+            thresh = v[budget - 1];
+        }
+        for (uint32_t i = 1; i <= heap_size; i++) {
+            const VqHostNode& nd = nodes[heap[i]];
+            if (!nd.processed && nd.variance >= thresh) out.push_back(heap[i]);
+        }
+    }
+};
+
+struct VqResult {                    // host-side outcome of one build
+    std::vector<VqHostNode> nodes;
+    std::vector<VqTreeSim> trees;
+    std::vector<uint32_t> perm;      // vector indices, grouped by node range
+    uint32_t rounds = 0, device_splits = 0;
+
+    uint32_t codebook_size() const
+    {
+        uint32_t s = 0;
+        for (const VqTreeSim& t : trees) s += 1 + t.split_index;
+        return s;
+    }
+    // retrieve_clusters(max_clusters) over every tree, in the reference's order; cluster_of[vector] = cluster index.
+    // max_clusters == 0 keeps every leaf.  Members of a cluster are, as in the reference, in ascending vector order
+    // when they are listed by scanning cluster_of.
+    uint32_t retrieve(uint32_t max_clusters, uint32_t* cluster_of) const
+    {
+        uint32_t nclusters = 0;
+        std::vector<uint32_t> stack;
+        for (const VqTreeSim& t : trees) {
+            stack.clear();
+            uint32_t cur = t.root;
+            for (;;) {
+                const VqHostNode& nd = nodes[cur];
+                const bool leaf = nd.split_rank < 0;
+                if (leaf || (max_clusters && (uint32_t)nd.split_rank + 2 > max_clusters)) {
+                    for (uint32_t i = nd.begin; i < nd.begin + nd.count; i++) cluster_of[perm[i]] = nclusters;
+                    nclusters++;
+                    if (stack.empty()) break;
+                    cur = stack.back();
+                    stack.pop_back();
+                    continue;
+                }
+                stack.push_back((uint32_t)nd.left + 1);
+                cur = (uint32_t)nd.left;
+            }
+        }
+        return nclusters;
+    }
+};
+
+template <int D> class VqBuilder {
+public:
+    explicit VqBuilder(cudaStream_t stream, uint64_t* launch_counter) : stream_(stream), launches_(launch_counter) {}
+    ~VqBuilder() { release(); }
+
+    // d_vecs: u8[n][D], d_wts: u32[n] (device).  threaded: crnlib::threaded_clusterizer<V>::create_clusters
+    // (crn_threaded_clusterizer.h:70-174): three PCA divisions into <= 4 partitions, each its own clusterizer.
+    cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, uint32_t n, uint32_t max_size, bool threaded, VqResult& res)
+    {
+        res = VqResult();
+        if (!n) return cudaSuccess;
+        cudaError_t ce = allocate(n, max_size);
+        if (ce != cudaSuccess) return ce;
+        n_ = n; vecs_ = d_vecs; wts_ = d_wts;
+        std::vector<VqHostNode>& nodes = res.nodes;
+
+        // root: identity order + statistics
+        launch_fill_identity(n);
+        cudaMemsetAsync(d_acc_, 0, sizeof(unsigned long long) * (D + 2), stream_);
+        CRN_LAUNCH(vq_root_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, d_perm_[0], n, d_acc_); count();
+        CRN_LAUNCH(vq_root_finish_kernel<D>, 1, 32, 0, stream_, d_acc_, nodes_, n); count();
+        const unsigned first_free_node = 1;
+        cudaMemcpyAsync(d_node_counter_, &first_free_node, sizeof(unsigned), cudaMemcpyHostToDevice, stream_);
+        float root_var = 0;
+        cudaMemcpyAsync(&root_var, nodes_.variance, sizeof(float), cudaMemcpyDeviceToHost, stream_);
+        ce = cudaStreamSynchronize(stream_);
+        if (ce != cudaSuccess) return ce;
+        nodes.resize(1);
+        nodes[0].begin = 0; nodes[0].count = n; nodes[0].variance = root_var;
+
+        std::vector<uint32_t> frontier;
+        if (threaded && max_size >= 128) {
+            // compute_split x3 (:93-95)
+            frontier.assign(1, 0u);
+            ce = round(frontier, nodes, true);
+            if (ce != cudaSuccess) return ce;
+            frontier.clear();
+            const uint32_t a = (uint32_t)nodes[0].left;
+            for (uint32_t c = 0; c < 2; c++) if (nodes[a + c].count) frontier.push_back(a + c);
+            ce = round(frontier, nodes, true);
+            if (ce != cudaSuccess) return ce;
+            std::vector<uint32_t> parts;
+            for (uint32_t c = 0; c < 2; c++) {
+                if (!nodes[a + c].count) continue;
+                const uint32_t b = (uint32_t)nodes[a + c].left;
+                for (uint32_t k = 0; k < 2; k++) if (nodes[b + k].count) parts.push_back(b + k);
+            }
+            const uint32_t total = (uint32_t)parts.size();
+            for (uint32_t p : parts) {
+                VqTreeSim t;
+                t.root = p; t.max_size = (max_size + total / 2) / total;
+                res.trees.push_back(t);
+            }
+            for (VqHostNode& nd : nodes) nd.processed = 0;      // presplit results are not clusterizer splits
+            for (uint32_t p : parts) nodes[p].left = -1;
+        } else {
+            VqTreeSim t;
+            t.root = 0; t.max_size = max_size;
+            res.trees.push_back(t);
+        }
+        for (VqTreeSim& t : res.trees) {
+            t.heap.assign(t.max_size + 2, 0u);
+            t.heap[1] = t.root; t.heap_size = 1;              // the root enters the heap unconditionally (:100-102)
+        }
+
+        for (;;) {
+            frontier.clear();
+            for (VqTreeSim& t : res.trees) { t.run(nodes); t.wanted(nodes, frontier); }
+            if (frontier.empty()) break;
+            std::sort(frontier.begin(), frontier.end(), [&](uint32_t x, uint32_t y) { return nodes[x].begin < nodes[y].begin; });
+            ce = round(frontier, nodes, false);
+            if (ce != cudaSuccess) return ce;
+            res.rounds++;
+            res.device_splits += (uint32_t)frontier.size();
+        }
+        res.perm.resize(n);
+        cudaMemcpyAsync(res.perm.data(), d_perm_[cur_], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream_);
+        return cudaStreamSynchronize(stream_);
+    }
+
+    const uint32_t* device_perm() const { return d_perm_[cur_]; }
+
+private:
+    cudaStream_t stream_;
+    uint64_t* launches_;
+    uint32_t n_ = 0, cap_n_ = 0, cap_slots_ = 0;
+    const uint8_t* vecs_ = nullptr;
+    const uint32_t* wts_ = nullptr;
+    int cur_ = 0;
+    unsigned* d_perm_[2] = {nullptr, nullptr};
+    unsigned *d_pos_slot_ = nullptr, *d_flags_ = nullptr, *d_scan_ = nullptr, *d_block_sums_ = nullptr, *d_slot_node_ = nullptr, *d_slot_starts_ = nullptr;
+    unsigned *d_node_counter_ = nullptr, *d_active_ = nullptr;
+    int* d_slot_states_ = nullptr;
+    uint8_t* d_side_ = nullptr;
+    unsigned long long* d_acc_ = nullptr;
+    VqSlot<D>* d_slots_ = nullptr;
+    VqSlotResult* d_results_ = nullptr;
+    VqNodes nodes_ = {};
+    std::vector<VqSlotResult> h_results_;
+
+    static unsigned grid(unsigned n) { return (n + 255) / 256; }
+    void count() { if (launches_) ++*launches_; }
+
+    template <typename T> cudaError_t dev_alloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+    void release()
+    {
+        void* ptrs[] = {d_perm_[0], d_perm_[1], d_pos_slot_, d_flags_, d_scan_, d_block_sums_, d_slot_node_, d_slot_starts_, d_node_counter_, d_active_, d_slot_states_,
+                        d_side_, d_acc_, d_slots_, d_results_, nodes_.begin, nodes_.count, nodes_.left, nodes_.flags, nodes_.variance, nodes_.weight, nodes_.centroid};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        d_perm_[0] = d_perm_[1] = nullptr; d_pos_slot_ = d_flags_ = d_scan_ = d_block_sums_ = d_slot_node_ = d_slot_starts_ = d_node_counter_ = d_active_ = nullptr;
+        d_slot_states_ = nullptr; d_side_ = nullptr; d_acc_ = nullptr; d_slots_ = nullptr; d_results_ = nullptr; nodes_ = VqNodes();
+        cap_n_ = cap_slots_ = 0;
+    }
+    cudaError_t allocate(uint32_t n, uint32_t max_size)
+    {
+        const uint32_t slots = std::max<uint32_t>(4u, std::min<uint32_t>(n / 2 + 4, max_size + 4));
+        if (n <= cap_n_ && slots <= cap_slots_) return cudaSuccess;
+        release();
+        const size_t node_cap = (size_t)2 * n + 16;
+        cudaError_t ce;
+#define VQ_ALLOC(p, cnt) if ((ce = dev_alloc(&(p), (cnt))) != cudaSuccess) return ce
+        VQ_ALLOC(d_perm_[0], n); VQ_ALLOC(d_perm_[1], n); VQ_ALLOC(d_pos_slot_, n); VQ_ALLOC(d_flags_, (size_t)n + 1); VQ_ALLOC(d_scan_, (size_t)n + 1);
+        VQ_ALLOC(d_block_sums_, (size_t)n / 1024 + 2); VQ_ALLOC(d_slot_node_, slots); VQ_ALLOC(d_slot_starts_, slots); VQ_ALLOC(d_node_counter_, 1); VQ_ALLOC(d_active_, 1);
+        VQ_ALLOC(d_slot_states_, slots); VQ_ALLOC(d_side_, n); VQ_ALLOC(d_acc_, D + 2); VQ_ALLOC(d_slots_, slots); VQ_ALLOC(d_results_, slots);
+        VQ_ALLOC(nodes_.begin, node_cap); VQ_ALLOC(nodes_.count, node_cap); VQ_ALLOC(nodes_.left, node_cap); VQ_ALLOC(nodes_.flags, node_cap);
+        VQ_ALLOC(nodes_.variance, node_cap); VQ_ALLOC(nodes_.weight, node_cap); VQ_ALLOC(nodes_.centroid, node_cap * D);
+#undef VQ_ALLOC
+        cap_n_ = n; cap_slots_ = slots;
+        return cudaSuccess;
+    }
+    void launch_fill_identity(uint32_t n);
+
+    // exclusive scan of d_flags_[0..m) into d_scan_
+    void scan(uint32_t m)
+    {
+        const unsigned nb = (m + 1023) / 1024;
+        CRN_LAUNCH(vq_scan_block_kernel, nb, 256, 0, stream_, d_flags_, d_scan_, d_block_sums_, m); count();
+        if (nb > 1) {
+            CRN_LAUNCH(vq_scan_sums_kernel, 1, 256, 0, stream_, d_block_sums_, nb); count();
+            CRN_LAUNCH(vq_scan_add_kernel, grid(m), 256, 0, stream_, d_scan_, d_block_sums_, m); count();
+        }
+    }
+
+    // split every node of `frontier` (sorted by first position) on the device and record the results
+    cudaError_t round(const std::vector<uint32_t>& frontier, std::vector<VqHostNode>& nodes, bool presplit)
+    {
+        const unsigned F = (unsigned)frontier.size(), n = n_;
+        if (!F) return cudaSuccess;
+        if (F > cap_slots_) return cudaErrorInvalidValue;
+        const unsigned gs = (F + 127) / 128;
+        cudaMemcpyAsync(d_slot_node_, frontier.data(), sizeof(unsigned) * F, cudaMemcpyHostToDevice, stream_);
+        unsigned* perm = d_perm_[cur_];
+        unsigned* perm_out = d_perm_[cur_ ^ 1];
+        CRN_LAUNCH(vq_init_slots_kernel<D>, gs, 128, 0, stream_, d_slot_node_, nodes_, d_slots_, d_slot_starts_, F, presplit ? 1 : 0); count();
+        CRN_LAUNCH(vq_pos_slot_kernel<D>, grid(n), 256, 0, stream_, d_slot_starts_, d_slots_, F, d_pos_slot_, n); count();
+        CRN_LAUNCH(vq_moments_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, n); count();
+        CRN_LAUNCH(vq_axis_kernel<D>, gs, 128, 0, stream_, d_slots_, F); count();
+        CRN_LAUNCH(vq_project_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n, presplit ? 1 : 0); count();
+        if (presplit) {
+            CRN_LAUNCH(vq_presplit_children_kernel<D>, gs, 128, 0, stream_, d_slots_, F); count();
+        } else {
+            CRN_LAUNCH(vq_children_kernel<D>, gs, 128, 0, stream_, vecs_, perm, d_slots_, F); count();
+            CRN_LAUNCH((vq_estimate_kernel<D, 0>), grid(n), 256, 0, stream_, vecs_, perm, d_pos_slot_, d_slots_, n); count();
+            CRN_LAUNCH((vq_estimate_kernel<D, 1>), grid(n), 256, 0, stream_, vecs_, perm, d_pos_slot_, d_slots_, n); count();
+            CRN_LAUNCH(vq_estimate_finish_kernel<D>, gs, 128, 0, stream_, vecs_, perm, d_slots_, F); count();
+            for (int it = 0; it < 8; it++) {
+                CRN_LAUNCH(vq_assign_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n); count();
+                CRN_LAUNCH(vq_update_kernel<D>, gs, 128, 0, stream_, d_slots_, F, d_active_); count();
+            }
+        }
+        CRN_LAUNCH(vq_slot_states_kernel<D>, gs, 128, 0, stream_, d_slots_, F, d_slot_states_); count();
+        cudaMemsetAsync(d_flags_ + n, 0, sizeof(unsigned), stream_);
+        CRN_LAUNCH(vq_left_flags_kernel, grid(n), 256, 0, stream_, d_pos_slot_, d_slot_states_, d_side_, d_flags_, n); count();
+        scan(n + 1);
+        CRN_LAUNCH(vq_finalize_kernel<D>, gs, 128, 0, stream_, d_slots_, F, d_scan_, n, nodes_, d_node_counter_); count();
+        CRN_LAUNCH(vq_scatter_kernel<D>, grid(n), 256, 0, stream_, perm, perm_out, d_pos_slot_, d_slots_, d_side_, d_scan_, n); count();
+        CRN_LAUNCH(vq_export_kernel<D>, gs, 128, 0, stream_, d_slots_, F, nodes_, d_results_); count();
+        cur_ ^= 1;
+        h_results_.resize(F);
+        cudaMemcpyAsync(h_results_.data(), d_results_, sizeof(VqSlotResult) * F, cudaMemcpyDeviceToHost, stream_);
+        cudaError_t ce = cudaStreamSynchronize(stream_);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return ce;
+        for (unsigned s = 0; s < F; s++) {
+            const VqSlotResult& r = h_results_[s];
+            VqHostNode& nd = nodes[frontier[s]];
+            nd.processed = 1;
+            if (r.state != 1) { nd.unsplittable = 1; continue; }
+            if (nodes.size() < (size_t)r.child + 2) nodes.resize((size_t)r.child + 2);
+            VqHostNode& par = nodes[frontier[s]];
+            par.left = (int32_t)r.child;
+            VqHostNode& l = nodes[r.child];
+            VqHostNode& rr = nodes[r.child + 1];
+            l = VqHostNode(); rr = VqHostNode();
+            l.begin = par.begin; l.count = r.left_count; l.variance = r.var_left;
+            rr.begin = par.begin + r.left_count; rr.count = r.right_count; rr.variance = r.var_right;
+        }
+        return cudaSuccess;
+    }
+};
+
+__global__ void __launch_bounds__(256) vq_identity_kernel(unsigned* __restrict__ perm, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = i;
+}
+template <int D> void VqBuilder<D>::launch_fill_identity(uint32_t n)
+{
+    cur_ = 0;
+    CRN_LAUNCH(vq_identity_kernel, grid(n), 256, 0, stream_, d_perm_[0], n); count();
+}
+
+}  // namespace crn

@@ -182,7 +182,8 @@ __device__ __forceinline__ void vq_accumulate_side(VqSlot<D>* __restrict__ slots
 // K3: initial division by the sign of the projection onto the axis (crn_clusterizer.h:577-597)
 template <int D>
 __global__ void __launch_bounds__(256) vq_project_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
-                                                         const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, unsigned n)
+                                                         const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, uint8_t* __restrict__ side_out,
+                                                         unsigned n, int presplit)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned slot = i < n ? pos_slot[i] : kVqNoSlot;
@@ -205,8 +206,28 @@ __global__ void __launch_bounds__(256) vq_project_kernel(const uint8_t* __restri
             if (d == 0) t = df * sl.axis[0]; else t += df * sl.axis[d];
         }
         side = ((double)t < 0.0) ? 0 : 1;
+        if (presplit) side_out[i] = (uint8_t)side;
     }
-    vq_accumulate_side<D>(slots, slot, take, head, v, w, side, false);
+    vq_accumulate_side<D>(slots, slot, take, head, v, w, side, presplit != 0);
+}
+
+// threaded_clusterizer::compute_split (crn_threaded_clusterizer.h:335-369): the division itself is the split, no
+// Lloyd iterations; the two sides become roots, with the statistics generate_codebook() gives a root (:77-93)
+template <int D>
+__global__ void vq_presplit_children_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    for (int sd = 0; sd < 2; sd++) {
+        if (!sl.wsum[sd]) { sl.var[sd] = 0; for (int d = 0; d < D; d++) sl.child[sd][d] = 0; continue; }
+        double dot = 0;
+        for (int d = 0; d < D; d++) { const double x = (double)(long long)sl.s1[sd][d]; dot += x * x; }
+        sl.var[sd] = (float)((double)sl.tt[sd] - dot / (double)sl.wsum[sd]);
+        const float inv = 1.0f / (float)sl.wsum[sd];
+        for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
+    }
+    sl.state = 1;
 }
 
 // K4: children estimates from the division, or flag the furthest/opposite fallback
@@ -309,7 +330,6 @@ __global__ void vq_update_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots,
         for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
     }
     sl.var[0] = var[0]; sl.var[1] = var[1];
-    sl.node_weight = sl.wsum[0];             // keeps W_left; W_right = total - left is recomputed at finalize from wsum[1]
     const float total = var[0] + var[1];
     sl.loops++;
     bool done = false;
@@ -357,7 +377,7 @@ __global__ void __launch_bounds__(256) vq_scan_block_kernel(const unsigned* __re
 __global__ void vq_scan_sums_kernel(unsigned* __restrict__ block_sums, unsigned nblocks)
 {   // single thread block, serial over <= a few thousand entries per thread chunk
     __shared__ unsigned part[256];
-    const unsigned per = (nblocks + 255) / 256, b = threadIdx.x * per, e = min(b + per, nblocks);
+    const unsigned per = (nblocks + 255) / 256, b = threadIdx.x * per, e = umin(b + per, nblocks);
     unsigned s = 0;
     for (unsigned i = b; i < e; i++) s += block_sums[i];
     part[threadIdx.x] = s;
@@ -383,8 +403,7 @@ __global__ void vq_finalize_kernel(VqSlot<D>* __restrict__ slots, unsigned nslot
     if (sl.state == 2) { nodes.flags[sl.node] |= 1u; return; }
     if (sl.state != 1) return;
     const unsigned b = sl.begin, c = sl.count;
-    const unsigned l_end = b + c < n ? left_scan[b + c] : left_scan[n];     // left_scan has n + 1 entries
-    const unsigned nleft = l_end - left_scan[b];
+    const unsigned nleft = left_scan[b + c] - left_scan[b];                 // left_scan has n + 1 entries
     const unsigned child = atomicAdd(node_counter, 2u);
     nodes.left[sl.node] = (int)child;
     for (int sd = 0; sd < 2; sd++) {
@@ -417,35 +436,23 @@ __global__ void __launch_bounds__(256) vq_scatter_kernel(const unsigned* __restr
     perm_out[dst] = perm[i];
 }
 
-// K10: next frontier = nodes created in [first_new, node_end) with more than one vector and positive variance.
-// head[i] = node id + 1 at the node's first position; the compaction (scan over head != 0) orders the slots by position.
-__global__ void __launch_bounds__(256) vq_mark_heads_kernel(VqNodes nodes, unsigned first_new, unsigned node_end, unsigned* __restrict__ head)
-{
-    const unsigned id = first_new + blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= node_end) return;
-    if (nodes.count[id] > 1 && nodes.variance[id] > 0.0f) head[nodes.begin[id]] = id + 1;
-}
-__global__ void __launch_bounds__(256) vq_head_flags_kernel(const unsigned* __restrict__ head, unsigned* __restrict__ flags, unsigned n)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = head[i] ? 1u : 0u;
-}
+// K0: split state of the frontier nodes the host selected (slot order = ascending first position)
 template <int D>
-__global__ void __launch_bounds__(256) vq_make_slots_kernel(const unsigned* __restrict__ head, const unsigned* __restrict__ head_scan, VqNodes nodes,
-                                                            VqSlot<D>* __restrict__ slots, unsigned* __restrict__ pos_slot_starts, unsigned n)
+__global__ void vq_init_slots_kernel(const unsigned* __restrict__ slot_node, VqNodes nodes, VqSlot<D>* __restrict__ slots, unsigned* __restrict__ slot_starts,
+                                     unsigned nslots, int presplit)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !head[i]) return;
-    const unsigned id = head[i] - 1, s = head_scan[i];
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const unsigned id = slot_node[s];
     VqSlot<D>& sl = slots[s];
     for (int k = 0; k < D * (D + 1) / 2; k++) sl.s2[k] = 0;
-    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; sl.centroid[d] = nodes.centroid[(size_t)id * D + d]; sl.axis[d] = 0; }
+    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; sl.centroid[d] = nodes.centroid[(size_t)id * D + d]; sl.axis[d] = 0; sl.child[0][d] = 0; sl.child[1][d] = 0; }
     sl.wsum[0] = sl.wsum[1] = 0; sl.tt[0] = sl.tt[1] = 0; sl.far_key = 0; sl.opp_key = 0;
     sl.var[0] = sl.var[1] = 0; sl.prev_total = 1e+10f;
     sl.node = id; sl.begin = nodes.begin[id]; sl.count = nodes.count[id];
-    sl.state = 0; sl.loops = 0; sl.mode = nodes.count[id] == 2 ? 1 : 0;
+    sl.state = 0; sl.loops = 0; sl.mode = (!presplit && nodes.count[id] == 2) ? 1 : 0;
     sl.node_weight = nodes.weight[id];
-    pos_slot_starts[s] = i;
+    slot_starts[s] = sl.begin;
 }
 // every position learns its slot: binary search over the slots' first positions
 template <int D>
@@ -465,6 +472,36 @@ __global__ void vq_slot_states_kernel(const VqSlot<D>* __restrict__ slots, unsig
 {
     const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < nslots) states[s] = slots[s].state;
+}
+
+struct VqSlotResult { int state; unsigned child; unsigned left_count, right_count; float var_left, var_right; };
+template <int D>
+__global__ void vq_export_kernel(const VqSlot<D>* __restrict__ slots, unsigned nslots, VqNodes nodes, VqSlotResult* __restrict__ out)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    const VqSlot<D>& sl = slots[s];
+    VqSlotResult r = {sl.state, 0u, 0u, 0u, 0.0f, 0.0f};
+    if (sl.state == 1) {
+        r.child = (unsigned)nodes.left[sl.node];
+        r.left_count = nodes.count[r.child]; r.right_count = nodes.count[r.child + 1];
+        r.var_left = sl.var[0]; r.var_right = sl.var[1];
+    }
+    out[s] = r;
+}
+
+// the root node: centroid, weight and variance from the sums of vq_root_kernel (generate_codebook, :77-93)
+template <int D>
+__global__ void vq_root_finish_kernel(const unsigned long long* __restrict__ acc, VqNodes nodes, unsigned n)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const unsigned long long W = acc[D];
+    double dot = 0;
+    for (int d = 0; d < D; d++) { const double x = (double)(long long)acc[d]; dot += x * x; }
+    nodes.begin[0] = 0; nodes.count[0] = n; nodes.left[0] = -1; nodes.flags[0] = 0; nodes.weight[0] = W;
+    nodes.variance[0] = W ? (float)((double)acc[D + 1] - dot / (double)W) : 0.0f;
+    const float inv = W ? 1.0f / (float)W : 0.0f;
+    for (int d = 0; d < D; d++) nodes.centroid[d] = (float)(long long)acc[d] * inv;
 }
 
 // root statistics: sum w v, sum w, sum w v.v over all vectors (generate_codebook, :77-92)

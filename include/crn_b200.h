@@ -142,6 +142,21 @@ CRN_API int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const cr
                                        const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks, uint32_t n_clusters,
                                        void* d_elements, uint32_t stride_bytes, uint32_t offset_bytes);
 
+/* Top-down binary-split vector quantiser ------------------------------------------
+ * Replaces crnlib::clusterizer<V>::generate_codebook + retrieve_clusters (crnlib/crn_clusterizer.h:65-167,
+ * :301-332) and, with threaded != 0, crnlib::threaded_clusterizer<V>::create_clusters
+ * (crnlib/crn_threaded_clusterizer.h:70-174), for V = vec2F / vec6F / vec16F with integer components
+ * 0..255 (dims = 2, 6, 16).  d_vectors: dims bytes per vector; d_weights: uint32 per vector (both device).
+ * max_codebook_size is generate_codebook's max_size (the per-call budget of create_clusters when threaded);
+ * retrieve_max_clusters is retrieve_clusters' argument (0 = every leaf, which is what create_clusters does).
+ * h_cluster_of (HOST, n entries) receives each vector's cluster index; clusters are numbered in the
+ * reference's retrieval order and listing the members of a cluster by ascending vector index reproduces the
+ * reference's member order.  Float sums are accumulated exactly (64-bit integers), so cluster boundaries can
+ * differ from the reference's float accumulation in the last place: tolerance class, see DESIGN.md. */
+CRN_API int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d_vectors, const uint32_t* d_weights, uint32_t n,
+                                  uint32_t max_codebook_size, uint32_t retrieve_max_clusters, int threaded,
+                                  uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

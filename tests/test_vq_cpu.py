@@ -1,0 +1,105 @@
+"""Frontier-batched vector quantiser (vq_kernels.cuh / vq_host.h) under the SIMT emulator vs the reference's
+clusterizer<V> / threaded_clusterizer<V> (oracle/_ref).  Sums are exact integers on the device and floats in the
+reference, so large inputs may differ in a handful of boundary vectors: small cases must match exactly, larger
+ones must agree on >= 99.5 % of the vectors' co-membership."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import crunch2_b200 as crn
+import helpers
+
+P = helpers.P
+
+
+def make_vectors(dims, n, seed, kind="clumpy"):
+    rng = np.random.default_rng(seed)
+    if dims == 16:      # linear selector vectors 0..7
+        if kind == "clumpy":
+            base = rng.integers(0, 8, (max(n // 20, 1), 16))
+            vecs = np.clip(base[rng.integers(0, len(base), n)] + rng.integers(-1, 2, (n, 16)), 0, 7)
+        else:
+            vecs = rng.integers(0, 8, (n, 16))
+    else:               # endpoint vectors 0..255
+        centers = rng.integers(0, 256, (max(n // 30, 1), dims))
+        vecs = np.clip(centers[rng.integers(0, len(centers), n)] + rng.normal(0, 6, (n, dims)), 0, 255)
+    return np.ascontiguousarray(vecs.astype(np.uint8)), rng.integers(1, 9, n).astype(np.uint32)
+
+
+def ref_clusterize(ref, vecs, w, max_size, retrieve, threaded):
+    n, dims = vecs.shape
+    fv = np.ascontiguousarray(vecs.astype(np.float32))
+    co = np.zeros(n, np.uint32); k = ctypes.c_uint32(); cb = ctypes.c_uint32()
+    if threaded:
+        assert ref.ref_threaded_clusterizer16(n, P(fv), P(w), max_size, 1, P(co), ctypes.byref(k)) == 1
+        return co, k.value, None
+    assert ref.ref_clusterizer(dims, n, P(fv), P(w), max_size, retrieve, P(co), ctypes.byref(k), ctypes.byref(cb)) == 1
+    return co, k.value, cb.value
+
+
+def agreement(a, b):
+    """fraction of vectors whose cluster has exactly the same member set in both partitions"""
+    n = len(a)
+    def sig(c):
+        order = np.argsort(c, kind="stable")
+        bounds = np.flatnonzero(np.diff(c[order])) + 1
+        out = np.zeros(n, np.uint64)
+        for grp in np.split(order, bounds):
+            out[grp] = (np.uint64(len(grp)) << np.uint64(40)) ^ np.uint64(int(grp.min()) * 2654435761 % (1 << 40)) ^ np.uint64(int(grp.sum()) % (1 << 40))
+        return out
+    return float(np.mean(sig(a) == sig(b)))
+
+
+@pytest.fixture(scope="module")
+def simctx(sim):
+    ctx = crn.Context(0, lib=sim)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("dims,n,max_size,retrieve,threaded,seed", [
+    (6, 300, 65535, 40, False, 1),
+    (6, 2000, 65535, 200, False, 2),
+    (2, 1500, 65535, 100, False, 3),
+    (16, 1000, 65535, 100, False, 4),
+    (6, 2000, 100, 0, False, 5),        # budget-limited codebook, every leaf retrieved
+    (16, 2000, 300, 0, True, 6),        # threaded_clusterizer: 3 PCA divisions + 4 clusterizers
+    (16, 500, 100, 0, True, 7),         # below 128 clusters: single clusterizer
+    (6, 1, 65535, 10, False, 8),        # single vector
+    (2, 64, 65535, 1000, False, 9),     # more clusters asked for than vectors
+])
+def test_matches_reference_exactly(simctx, ref, dims, n, max_size, retrieve, threaded, seed):
+    vecs, w = make_vectors(dims, n, seed)
+    co_r, k_r, cb_r = ref_clusterize(ref, vecs, w, max_size, retrieve, threaded)
+    co_g, k_g, cb_g = simctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, n, dims, max_size, retrieve, threaded)
+    assert k_g == k_r
+    if cb_r is not None:
+        assert cb_g == cb_r
+    assert np.array_equal(co_g, co_r)
+
+
+def test_duplicates_and_constant_input(simctx, ref):
+    # all vectors equal: the root has zero variance and is never split; duplicates make unsplittable nodes
+    vecs = np.full((200, 6), 77, np.uint8); w = np.ones(200, np.uint32)
+    co_g, k_g, cb_g = simctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, 200, 6, 65535, 16, False)
+    co_r, k_r, cb_r = ref_clusterize(ref, vecs, w, 65535, 16, False)
+    assert (k_g, cb_g) == (k_r, cb_r) and np.array_equal(co_g, co_r)
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, (7, 6)).astype(np.uint8)
+    vecs = np.ascontiguousarray(base[rng.integers(0, 7, 500)]); w = rng.integers(1, 4, 500).astype(np.uint32)
+    co_g, k_g, cb_g = simctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, 500, 6, 65535, 64, False)
+    co_r, k_r, cb_r = ref_clusterize(ref, vecs, w, 65535, 64, False)
+    assert (k_g, cb_g) == (k_r, cb_r) and np.array_equal(co_g, co_r)
+
+
+@pytest.mark.parametrize("dims,n,max_size,retrieve,threaded,seed", [
+    (6, 5000, 65535, 5000, False, 15),
+    (16, 6000, 3000, 0, True, 14),
+])
+def test_large_agrees_within_float_noise(simctx, ref, dims, n, max_size, retrieve, threaded, seed):
+    vecs, w = make_vectors(dims, n, seed, "uniform" if dims == 16 else "clumpy")
+    co_r, k_r, _ = ref_clusterize(ref, vecs, w, max_size, retrieve, threaded)
+    co_g, k_g, _ = simctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, n, dims, max_size, retrieve, threaded)
+    assert k_g == k_r
+    assert agreement(co_g, co_r) >= 0.995
