@@ -68,6 +68,14 @@ def library_path():
 def _declare(lib):
     vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
     lib.crn_gpu_abi_version.restype = u32
+    lib.crn_gpu_qdxt_output_size.restype = ctypes.c_uint64
+    lib.crn_gpu_qdxt_output_size.argtypes = [vp]
+    lib.crn_gpu_qdxt_level_offset.restype = ctypes.c_uint64
+    lib.crn_gpu_qdxt_level_offset.argtypes = [vp, u32]
+    lib.crn_gpu_qdxt_free.argtypes = [vp]
+    lib.crn_gpu_qdxt_free.restype = None
+    lib.crn_gpu_qdxt_pack.argtypes = [vp, u32, vp, i32]
+    lib.crn_gpu_qdxt_get_info.argtypes = [vp, vp]
     lib.crn_gpu_is_native.restype = i32
     lib.crn_gpu_device_count.restype = i32
     lib.crn_gpu_create.argtypes = [i32, ctypes.POINTER(vp)]
@@ -231,6 +239,12 @@ class Context:
                                                     1 if threaded else 0, cluster_of.ctypes.data_as(ctypes.c_void_p), ctypes.byref(k), ctypes.byref(cb)))
         return cluster_of, k.value, cb.value
 
+    # --- clustered DDS compression (mipmapped_texture::qdxt_pack_init / qdxt_pack) ----------------------
+    def qdxt_init(self, fmt, levels, params=None):
+        """levels: list of (h, w, 4) uint8 arrays -- numpy (host pixels) or torch CUDA tensors -- faces x mips in
+        the reference's order.  Returns a Qdxt whose pack(quality_level) gives the packed blocks of all levels."""
+        return Qdxt(self, fmt, levels, params or PackParams())
+
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
     def unpack_begin(self, crn_bytes):
         """crnd_unpack_begin: returns a Texture bound to this context."""
@@ -255,6 +269,69 @@ def texture_info(crn_bytes, lib=None):
     if rc != 0:
         raise CrnGpuError(rc, "not a CRN file")
     return {k: getattr(info, k) for k, _ in _TextureInfo._fields_ if k != "struct_size"}
+
+
+class _LevelDesc(ctypes.Structure):
+    _fields_ = [("rgba", ctypes.c_void_p), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("pitch_bytes", ctypes.c_uint32)]
+
+
+class _QdxtInfo(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("n_blocks", ctypes.c_uint32), ("num_elements", ctypes.c_uint32),
+                ("endpoint_codebook_size", ctypes.c_uint32 * 3), ("max_selector_clusters", ctypes.c_uint32 * 3),
+                ("endpoint_clusters", ctypes.c_uint32 * 3), ("selector_clusters", ctypes.c_uint32 * 3)]
+
+
+class Qdxt:
+    """mipmapped_texture::qdxt_state: pixel blocks, endpoint trees and selector bounds of one texture on the device."""
+
+    def __init__(self, ctx, fmt, levels, params):
+        self._c = ctx
+        self._q = ctypes.c_void_p()
+        self.fmt = fmt
+        on_host = not hasattr(levels[0], "data_ptr")
+        keep, descs = [], (_LevelDesc * len(levels))()
+        for i, lv in enumerate(levels):
+            if on_host:
+                lv = np.ascontiguousarray(lv, np.uint8)
+                ptr, h, w = lv.ctypes.data, lv.shape[0], lv.shape[1]
+            else:
+                lv = lv.contiguous()
+                ptr, h, w = lv.data_ptr(), lv.shape[0], lv.shape[1]
+            keep.append(lv)
+            descs[i] = _LevelDesc(ptr, w, h, w * 4)
+        cp = params._c()
+        ctx._check(ctx._lib.crn_gpu_qdxt_init(ctx._ctx, fmt, ctypes.byref(cp), descs, len(levels), 1 if on_host else 0, ctypes.byref(self._q)))
+        self.size = ctx._lib.crn_gpu_qdxt_output_size(self._q)
+        self.level_offsets = [ctx._lib.crn_gpu_qdxt_level_offset(self._q, i) for i in range(len(levels))]
+
+    def pack(self, quality_level, out=None):
+        """qdxt_pack at crn_comp_params::m_quality_level (0..255).  out: optional torch CUDA uint8 tensor; default returns numpy."""
+        if out is not None:
+            self._c._check(self._c._lib.crn_gpu_qdxt_pack(self._q, int(quality_level), ctypes.c_void_p(out.data_ptr()), 0))
+            return out
+        buf = np.zeros(self.size, np.uint8)
+        self._c._check(self._c._lib.crn_gpu_qdxt_pack(self._q, int(quality_level), buf.ctypes.data_as(ctypes.c_void_p), 1))
+        return buf
+
+    def info(self):
+        inf = _QdxtInfo()
+        inf.struct_size = ctypes.sizeof(_QdxtInfo)
+        self._c._check(self._c._lib.crn_gpu_qdxt_get_info(self._q, ctypes.byref(inf)))
+        ne = inf.num_elements
+        return dict(n_blocks=inf.n_blocks, num_elements=ne, endpoint_codebook_size=list(inf.endpoint_codebook_size)[:ne],
+                    max_selector_clusters=list(inf.max_selector_clusters)[:ne], endpoint_clusters=list(inf.endpoint_clusters)[:ne],
+                    selector_clusters=list(inf.selector_clusters)[:ne])
+
+    def close(self):
+        if getattr(self, "_q", None):
+            self._c._lib.crn_gpu_qdxt_free(self._q)
+            self._q = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Texture:

@@ -12,7 +12,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <new>
+#include <vector>
+#include <algorithm>
 
 struct crn_gpu_ctx {
     int device;
@@ -74,7 +77,7 @@ int vq_clusterize(crn_gpu_ctx* ctx, const uint8_t* d_vecs, const uint32_t* d_wts
 {
     crn::VqBuilder<D> builder(ctx->stream, &ctx->launches);
     crn::VqResult res;
-    const cudaError_t ce = builder.build(d_vecs, d_wts, n, max_size, threaded != 0, res);
+    const cudaError_t ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res);
     if (ce != cudaSuccess) return set_err(ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "crn_gpu_vq_clusterize", ce);
     if (codebook_size) *codebook_size = res.codebook_size();
     const uint32_t k = res.retrieve(retrieve, h_cluster_of);
@@ -82,6 +85,210 @@ int vq_clusterize(crn_gpu_ctx* ctx, const uint8_t* d_vecs, const uint32_t* d_wts
     return CRN_GPU_OK;
 }
 }  // namespace
+
+static bool build_mip_table(const crn_gpu_mip_desc* mips, uint32_t num_mips, uint32_t n_blocks, crn::QdxtMipTable& mt)
+{
+    if (!mips || !num_mips || num_mips > (uint32_t)crn::kQdxtMaxMips) return false;
+    uint32_t chunks = 0;
+    for (uint32_t i = 0; i < num_mips; i++) {
+        if (!mips[i].block_width || !mips[i].block_height ||
+            (uint64_t)mips[i].first_block + (uint64_t)mips[i].block_width * mips[i].block_height > n_blocks) return false;
+        mt.m[i].first_block = mips[i].first_block; mt.m[i].block_width = mips[i].block_width; mt.m[i].block_height = mips[i].block_height;
+        mt.m[i].first_chunk = chunks;
+        chunks += ((mips[i].block_width + 1) / 2) * ((mips[i].block_height + 1) / 2);
+    }
+    mt.num_mips = num_mips; mt.total_chunks = chunks;
+    return true;
+}
+
+struct crn_qdxt_element {
+    int kind;                         // 0 colour (qdxt1), 1 alpha (qdxt5)
+    uint32_t comp;                    // source channel of an alpha element
+    uint32_t offset;                  // byte offset of the element inside a block
+    int use_alpha_blocks;             // qdxt1_params::m_use_alpha_blocks
+    crn::VqResult endpoint_tree;
+    uint32_t max_selector_clusters;
+    uint32_t endpoint_clusters, selector_clusters;
+};
+
+struct crn_gpu_qdxt {
+    crn_gpu_ctx* ctx;
+    uint32_t format, n_blocks, num_levels, bytes_per_block, num_elements;
+    float pow_mul;
+    crn_gpu_pack_params params;
+    std::vector<crn_gpu_mip_desc> mips;
+    crn_qdxt_element el[3];
+    // device
+    uint32_t* d_blocks;               // n_blocks x 16 RGBA8
+    uint8_t* d_vecs;                  // n_blocks x 16: training / selector vectors
+    uint32_t* d_wts;
+    uint8_t* d_cat;
+    uint32_t *d_offsets, *d_members, *d_ids;
+    uint8_t* d_out;                   // n_blocks x bytes_per_block
+    unsigned long long* d_keys;       // per-block dxt_fast selector keys; reused as the distinct-count table
+    std::vector<uint32_t> cluster_of, offsets, members;
+    std::vector<uint8_t> cat;
+};
+
+namespace {
+
+void qdxt_release(crn_gpu_qdxt* q)
+{
+    void* ptrs[] = {q->d_blocks, q->d_vecs, q->d_wts, q->d_cat, q->d_offsets, q->d_members, q->d_ids, q->d_out, q->d_keys};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete q;
+}
+
+// cluster_of over `ids` (nullptr = all blocks) -> CSR appended to q->offsets / q->members; members ascending
+void qdxt_append_csr(crn_gpu_qdxt* q, const uint32_t* ids, uint32_t n, uint32_t n_clusters)
+{
+    const size_t first_cluster = q->offsets.size() - 1, base = q->members.size();
+    std::vector<uint32_t> cnt(n_clusters + 1, 0u);
+    for (uint32_t i = 0; i < n; i++) cnt[q->cluster_of[ids ? ids[i] : i] + 1]++;
+    for (uint32_t k = 0; k < n_clusters; k++) cnt[k + 1] += cnt[k];
+    q->members.resize(base + n);
+    q->offsets.resize(first_cluster + n_clusters + 1);
+    for (uint32_t k = 0; k < n_clusters; k++) q->offsets[first_cluster + k + 1] = (uint32_t)(base + cnt[k + 1]);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t b = ids ? ids[i] : i;
+        q->members[base + cnt[q->cluster_of[b]]++] = b;
+    }
+}
+
+int qdxt_upload_csr(crn_gpu_qdxt* q)
+{
+    crn_gpu_ctx* ctx = q->ctx;
+    CRN_CUDA(ctx, cudaMemcpyAsync(q->d_offsets, q->offsets.data(), q->offsets.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!q->members.empty())
+        CRN_CUDA(ctx, cudaMemcpyAsync(q->d_members, q->members.data(), q->members.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // the host vectors are reused right away
+    return CRN_GPU_OK;
+}
+
+template <int D>
+int qdxt_vq(crn_gpu_qdxt* q, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res)
+{
+    crn::VqBuilder<D> builder(q->ctx->stream, &q->ctx->launches);
+    const cudaError_t ce = builder.build(q->d_vecs, q->d_wts, d_ids, n, max_size, threaded, res);
+    if (ce != cudaSuccess) return set_err(q->ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
+    return CRN_GPU_OK;
+}
+
+// qdxt1::init / qdxt5::init for one element
+int qdxt_init_element(crn_gpu_qdxt* q, crn_qdxt_element& e)
+{
+    crn_gpu_ctx* ctx = q->ctx;
+    const uint32_t n = q->n_blocks;
+    crn::QdxtMipTable mt;
+    if (!build_mip_table(q->mips.data(), (uint32_t)q->mips.size(), n, mt)) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "clustered DDS: bad level table");
+    const int threads = crn::kQdxtWarpsPerCta * 32;
+    const int grid = grid_for(ctx, mt.total_chunks, crn::kQdxtWarpsPerCta, 8);
+    if (e.kind == 0)
+        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, q->d_blocks, mt, 3u, q->d_vecs, q->d_wts, (uint8_t*)nullptr, q->d_keys);
+    else
+        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, q->d_blocks, mt, e.comp, q->d_vecs, q->d_wts, (uint8_t*)nullptr, q->d_keys);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    // distinct dxt_fast selector patterns (crn_qdxt1.cpp:415-438, crn_qdxt5.cpp:395-421)
+    uint32_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    unsigned long long* table = q->d_keys + n;
+    unsigned* counter = reinterpret_cast<unsigned*>(table + cap);
+    CRN_CUDA(ctx, cudaMemsetAsync(table, 0xff, sizeof(unsigned long long) * cap, ctx->stream));
+    CRN_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
+    CRN_LAUNCH(crn::count_distinct_kernel, (n + 255) / 256, 256, 0, ctx->stream, q->d_keys, n, table, cap - 1, counter);
+    ctx->launches++;
+    unsigned distinct = 0;
+    CRN_CUDA(ctx, cudaMemcpyAsync(&distinct, counter, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    e.max_selector_clusters = distinct + 128;
+    // endpoint codebook: generate_codebook(65535) (crn_qdxt1.cpp:405-413, crn_qdxt5.cpp:386-393)
+    return e.kind == 0 ? qdxt_vq<6>(q, nullptr, n, 65535u, false, e.endpoint_tree) : qdxt_vq<2>(q, nullptr, n, 65535u, false, e.endpoint_tree);
+}
+
+uint32_t clampu(uint32_t v, uint32_t lo, uint32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }   // math::clamp
+
+// qdxt1::pack (crn_qdxt1.cpp:910-1030) / qdxt5::pack (crn_qdxt5.cpp:838-960) for one element
+int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_level)
+{
+    crn_gpu_ctx* ctx = q->ctx;
+    const uint32_t n = q->n_blocks, stride = q->bytes_per_block;
+    const float quality = quality_level / 255.0f;
+    const uint32_t codebook = e.endpoint_tree.codebook_size();
+    uint32_t max_endpoint_clusters, max_selector_clusters;
+    if (e.kind == 0) {
+        const float eq = powf(quality, 1.8f * q->pow_mul), sq = powf(quality, 1.65f * q->pow_mul);
+        max_endpoint_clusters = clampu((uint32_t)(codebook * eq), 96u, codebook);
+        max_selector_clusters = clampu((uint32_t)(e.max_selector_clusters * sq), 128u, e.max_selector_clusters);
+    } else {
+        const float eq = powf(quality, 2.1f), sq = powf(quality, 1.65f);
+        max_endpoint_clusters = clampu((uint32_t)(codebook * eq), 16u, codebook);
+        max_selector_clusters = clampu((uint32_t)(e.max_selector_clusters * sq), 32u, e.max_selector_clusters);
+    }
+    crn_gpu_pack_params pp = q->params;
+    if (e.kind == 0) pp.use_both_block_types = e.use_alpha_blocks ? 1u : 0u;      // qdxt5 keeps pack_params' flag (crn_qdxt5.cpp:468)
+    // endpoint clusters
+    q->cluster_of.resize(n);
+    uint32_t k_end;
+    if (quality >= 1.0f) { for (uint32_t i = 0; i < n; i++) q->cluster_of[i] = i; k_end = n; }
+    else k_end = e.endpoint_tree.retrieve(max_endpoint_clusters, q->cluster_of.data());
+    e.endpoint_clusters = k_end;
+    q->offsets.assign(1, 0u); q->members.clear();
+    qdxt_append_csr(q, nullptr, n, k_end);
+    int rc = qdxt_upload_csr(q);
+    if (rc) return rc;
+    if (e.kind == 0)
+        rc = crn_gpu_dxt1_optimize_clusters(ctx, &pp, e.use_alpha_blocks, q->d_blocks, n, q->d_offsets, q->d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
+    else
+        rc = crn_gpu_dxt5_optimize_clusters(ctx, &pp, e.comp, q->d_blocks, n, q->d_offsets, q->d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
+    if (rc) return rc;
+    e.selector_clusters = 0;
+    if (quality >= 1.0f) return CRN_GPU_OK;
+    // selector training vectors
+    if (e.kind == 0)
+        CRN_LAUNCH(crn::selector_vectors_kernel<0>, (n + 255) / 256, 256, 0, ctx->stream, q->d_out, stride, e.offset, n, pp.perceptual ? 1 : 0, q->d_vecs, q->d_wts, (uint8_t*)nullptr);
+    else
+        CRN_LAUNCH(crn::selector_vectors_kernel<1>, (n + 255) / 256, 256, 0, ctx->stream, q->d_out, stride, e.offset, n, 0, q->d_vecs, q->d_wts, q->d_cat);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    q->offsets.assign(1, 0u); q->members.clear();
+    crn::VqResult sel_tree;
+    if (e.kind == 0) {
+        rc = qdxt_vq<16>(q, nullptr, n, max_selector_clusters, true, sel_tree);
+        if (rc) return rc;
+        const uint32_t k = sel_tree.retrieve(0, q->cluster_of.data());
+        qdxt_append_csr(q, nullptr, n, k);
+    } else {
+        q->cat.resize(n);
+        CRN_CUDA(ctx, cudaMemcpyAsync(q->cat.data(), q->d_cat, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<uint32_t> ids;
+        for (uint32_t type = 0; type < 2; type++) {                 // crn_qdxt5.cpp:762-833
+            ids.clear();
+            for (uint32_t b = 0; b < n; b++) if (q->cat[b] == type) ids.push_back(b);
+            const uint32_t m = (uint32_t)ids.size();
+            if (!m) continue;
+            if ((m / (float)n) < .01f) continue;
+            uint32_t max_clusters = (uint32_t)(((uint64_t)m * max_selector_clusters + (n - 1)) / n);
+            max_clusters = std::min(std::max(64u, max_clusters), m);
+            if (max_clusters >= m) continue;
+            CRN_CUDA(ctx, cudaMemcpyAsync(q->d_ids, ids.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+            rc = qdxt_vq<16>(q, q->d_ids, m, max_clusters, true, sel_tree);
+            if (rc) return rc;
+            const uint32_t k = sel_tree.retrieve(0, q->cluster_of.data());
+            qdxt_append_csr(q, ids.data(), m, k);
+        }
+    }
+    const uint32_t k_sel = (uint32_t)q->offsets.size() - 1;
+    e.selector_clusters = k_sel;
+    if (!k_sel) return CRN_GPU_OK;
+    rc = qdxt_upload_csr(q);
+    if (rc) return rc;
+    return crn_gpu_optimize_selectors(ctx, (uint32_t)e.kind, &pp, e.comp, q->d_blocks, n, q->d_offsets, q->d_members, k_sel, q->d_out, stride, e.offset);
+}
+
+}  // namespace
+
 
 extern "C" {
 
@@ -353,21 +560,6 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     return CRN_GPU_OK;
 }
 
-static bool build_mip_table(const crn_gpu_mip_desc* mips, uint32_t num_mips, uint32_t n_blocks, crn::QdxtMipTable& mt)
-{
-    if (!mips || !num_mips || num_mips > (uint32_t)crn::kQdxtMaxMips) return false;
-    uint32_t chunks = 0;
-    for (uint32_t i = 0; i < num_mips; i++) {
-        if (!mips[i].block_width || !mips[i].block_height ||
-            (uint64_t)mips[i].first_block + (uint64_t)mips[i].block_width * mips[i].block_height > n_blocks) return false;
-        mt.m[i].first_block = mips[i].first_block; mt.m[i].block_width = mips[i].block_width; mt.m[i].block_height = mips[i].block_height;
-        mt.m[i].first_chunk = chunks;
-        chunks += ((mips[i].block_width + 1) / 2) * ((mips[i].block_height + 1) / 2);
-    }
-    mt.num_mips = num_mips; mt.total_chunks = chunks;
-    return true;
-}
-
 int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, const void* d_blocks_rgba, uint32_t n_blocks,
                           const crn_gpu_mip_desc* mips, uint32_t num_mips, void* d_vectors, uint32_t* d_weights, uint8_t* d_chunk_encoding)
 {
@@ -380,9 +572,9 @@ int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, c
     const int grid = grid_for(ctx, mt.total_chunks, crn::kQdxtWarpsPerCta, 8);
     const uint32_t* blocks = static_cast<const uint32_t*>(d_blocks_rgba);
     if (kind == 0)
-        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding);
+        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding, (unsigned long long*)nullptr);
     else
-        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding);
+        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding, (unsigned long long*)nullptr);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
@@ -432,6 +624,146 @@ int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d_vectors
     case 6: return vq_clusterize<6>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
     default: return vq_clusterize<16>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
     }
+}
+
+/* ---- clustered DDS compression ------------------------------------------------------------------- */
+
+int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
+                      const crn_gpu_level_desc* levels, uint32_t num_levels, int pixels_on_host, crn_gpu_qdxt** out)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!out || !params || params->struct_size != sizeof(crn_gpu_pack_params) || !levels || !num_levels || num_levels > (uint32_t)crn::kQdxtMaxMips)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_init: bad argument");
+    *out = nullptr;
+    if (format > CRN_GPU_FMT_DXN_YX || format == CRN_GPU_FMT_DXT3)
+        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_qdxt_init: format is not clustered (DXT3) or unknown");
+    if (params->dxt_quality < 3 || params->dxt_quality > 4)
+        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_qdxt_init: dxt_quality must be better (3) or uber (4)");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    crn_gpu_qdxt* q = new (std::nothrow) crn_gpu_qdxt();
+    if (!q) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: out of host memory");
+    q->ctx = ctx; q->format = format; q->params = *params; q->num_levels = num_levels;
+    q->bytes_per_block = crn_gpu_bytes_per_block(format);
+    q->pow_mul = format == CRN_GPU_FMT_DXT5 ? .75f : 1.0f;           // crn_mipmapped_texture.cpp:2529-2539
+    q->d_blocks = nullptr; q->d_vecs = nullptr; q->d_wts = nullptr; q->d_cat = nullptr; q->d_offsets = q->d_members = q->d_ids = nullptr;
+    q->d_out = nullptr; q->d_keys = nullptr;
+    // element table (crn_mipmapped_texture.cpp:2319-2366)
+    uint32_t ne = 0;
+    auto add = [&](int kind, uint32_t comp, uint32_t offset, int use_alpha) {
+        crn_qdxt_element& e = q->el[ne++];
+        e.kind = kind; e.comp = comp; e.offset = offset; e.use_alpha_blocks = use_alpha;
+        e.max_selector_clusters = 0; e.endpoint_clusters = e.selector_clusters = 0;
+    };
+    switch (format) {
+    case CRN_GPU_FMT_DXT1: add(0, 3, 0, params->use_both_block_types ? 1 : 0); break;
+    case CRN_GPU_FMT_DXT1A: add(0, 3, 0, 1); break;
+    case CRN_GPU_FMT_DXT5: add(0, 3, 8, 0); add(1, 3, 0, 0); break;
+    case CRN_GPU_FMT_DXT5A: add(1, 3, 0, 0); break;
+    case CRN_GPU_FMT_DXN_XY: add(1, 0, 0, 0); add(1, 1, 8, 0); break;
+    default: add(1, 1, 0, 0); add(1, 0, 8, 0); break;               // DXN_YX
+    }
+    q->num_elements = ne;
+    uint64_t total_blocks = 0;
+    for (uint32_t l = 0; l < num_levels; l++) {
+        if (!levels[l].rgba || !levels[l].width || !levels[l].height || levels[l].pitch_bytes < levels[l].width * 4) {
+            qdxt_release(q);
+            return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_init: bad level");
+        }
+        crn_gpu_mip_desc m;
+        m.first_block = (uint32_t)total_blocks; m.block_width = (levels[l].width + 3) / 4; m.block_height = (levels[l].height + 3) / 4;
+        q->mips.push_back(m);
+        total_blocks += (uint64_t)m.block_width * m.block_height;
+    }
+    if (total_blocks > 0x7fffffffu / 16) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_qdxt_init: too many blocks"); }
+    const uint32_t n = q->n_blocks = (uint32_t)total_blocks;
+    uint32_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+#define QDXT_ALLOC(ptr, bytes)                                                                                         \
+    do {                                                                                                               \
+        cudaError_t ce_ = cudaMalloc((void**)&(ptr), (bytes));                                                         \
+        if (ce_ != cudaSuccess) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: cudaMalloc", ce_); } \
+    } while (0)
+    QDXT_ALLOC(q->d_blocks, (size_t)n * 64);
+    QDXT_ALLOC(q->d_vecs, (size_t)n * 16);
+    QDXT_ALLOC(q->d_wts, (size_t)n * 4);
+    QDXT_ALLOC(q->d_cat, (size_t)n);
+    QDXT_ALLOC(q->d_offsets, ((size_t)n + 1) * 4);
+    QDXT_ALLOC(q->d_members, (size_t)n * 4);
+    QDXT_ALLOC(q->d_ids, (size_t)n * 4);
+    QDXT_ALLOC(q->d_out, (size_t)n * q->bytes_per_block);
+    QDXT_ALLOC(q->d_keys, ((size_t)n + cap + 2) * 8);
+#undef QDXT_ALLOC
+    // pixel blocks of every level (crn_mipmapped_texture.cpp:2419-2472)
+    int rc = CRN_GPU_OK;
+    for (uint32_t l = 0; l < num_levels && !rc; l++) {
+        const crn_gpu_level_desc& lv = levels[l];
+        const uint8_t* src = static_cast<const uint8_t*>(lv.rgba);
+        uint32_t pitch = lv.pitch_bytes;
+        if (pixels_on_host) {
+            const size_t bytes = (size_t)lv.width * 4 * lv.height;
+            rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, bytes);
+            if (rc) break;
+            cudaError_t ce = cudaMemcpy2DAsync(ctx->d_in, (size_t)lv.width * 4, lv.rgba, lv.pitch_bytes, (size_t)lv.width * 4, lv.height, cudaMemcpyHostToDevice, ctx->stream);
+            if (ce != cudaSuccess) { rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: H2D", ce); break; }
+            src = static_cast<const uint8_t*>(ctx->d_in); pitch = lv.width * 4;
+        }
+        const uint32_t nb = q->mips[l].block_width * q->mips[l].block_height;
+        CRN_LAUNCH(crn::blockify_kernel, (nb * 16 + 255) / 256, 256, 0, ctx->stream, src, lv.width, lv.height, pitch, q->d_blocks + (size_t)q->mips[l].first_block * 16);
+        ctx->launches++;
+        if (pixels_on_host) {          // d_in is reused by the next level
+            cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+            if (ce != cudaSuccess) rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: blockify", ce);
+        }
+    }
+    for (uint32_t i = 0; i < ne && !rc; i++) rc = qdxt_init_element(q, q->el[i]);
+    if (rc) { qdxt_release(q); return rc; }
+    *out = q;
+    return CRN_GPU_OK;
+}
+
+uint64_t crn_gpu_qdxt_output_size(const crn_gpu_qdxt* q) { return q ? (uint64_t)q->n_blocks * q->bytes_per_block : 0; }
+
+uint64_t crn_gpu_qdxt_level_offset(const crn_gpu_qdxt* q, uint32_t level)
+{
+    return (q && level < q->num_levels) ? (uint64_t)q->mips[level].first_block * q->bytes_per_block : 0;
+}
+
+int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int dst_on_host)
+{
+    if (!q) return CRN_GPU_ERR_BAD_PARAM;
+    crn_gpu_ctx* ctx = q->ctx;
+    if (quality_level > 255 || !dst) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_pack: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < q->num_elements; i++) {
+        const int rc = qdxt_pack_element(q, q->el[i], quality_level);
+        if (rc) return rc;
+    }
+    CRN_CUDA(ctx, cudaMemcpyAsync(dst, q->d_out, (size_t)q->n_blocks * q->bytes_per_block, dst_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info)
+{
+    if (!q || !info || info->struct_size != sizeof(crn_gpu_qdxt_info)) return CRN_GPU_ERR_BAD_PARAM;
+    memset(info, 0, sizeof(*info));
+    info->struct_size = sizeof(*info);
+    info->n_blocks = q->n_blocks; info->num_elements = q->num_elements;
+    for (uint32_t i = 0; i < q->num_elements; i++) {
+        info->endpoint_codebook_size[i] = q->el[i].endpoint_tree.codebook_size();
+        info->max_selector_clusters[i] = q->el[i].max_selector_clusters;
+        info->endpoint_clusters[i] = q->el[i].endpoint_clusters;
+        info->selector_clusters[i] = q->el[i].selector_clusters;
+    }
+    return CRN_GPU_OK;
+}
+
+void crn_gpu_qdxt_free(crn_gpu_qdxt* q)
+{
+    if (!q) return;
+    cudaSetDevice(q->ctx->device);
+    cudaStreamSynchronize(q->ctx->stream);
+    qdxt_release(q);
 }
 
 /* ---- CRN -> DXTn transcoding --------------------------------------------------------------------- */

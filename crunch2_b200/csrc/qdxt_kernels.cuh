@@ -293,7 +293,8 @@ constexpr int kQdxtWarpsPerCta = 8;
 template <int KIND>
 __global__ void __launch_bounds__(kQdxtWarpsPerCta * 32)
 qdxt_training_kernel(const uint32_t* __restrict__ blocks, QdxtMipTable mt, uint32_t comp,
-                     uint8_t* __restrict__ out_vecs, uint32_t* __restrict__ out_weights, uint8_t* __restrict__ out_encoding)
+                     uint8_t* __restrict__ out_vecs, uint32_t* __restrict__ out_weights, uint8_t* __restrict__ out_encoding,
+                     unsigned long long* __restrict__ out_sel_keys)
 {
     const unsigned lane = lane_id();
     const uint32_t warps = gridDim.x * kQdxtWarpsPerCta;
@@ -331,6 +332,18 @@ qdxt_training_kernel(const uint32_t* __restrict__ blocks, QdxtMipTable mt, uint3
             } else {
                 unsigned lo, hi;
                 lerr[l] = fast_alpha_fit(aa, t, lo, hi, sel);
+            }
+            // layouts 5..8 are the chunk's four blocks: their dxt_fast selectors are what qdxt1/qdxt5::init hash to bound
+            // the selector codebook (crn_qdxt1.cpp:415-438, crn_qdxt5.cpp:395-421)
+            if (out_sel_keys && l >= 5) {
+                unsigned long long key = 0;
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++)
+                    if (t.m[s2]) key |= (unsigned long long)sel[s2] << ((KIND ? 3 : 2) * t.li[s2]);
+                const unsigned klo = __reduce_or_sync(CRN_FULL_MASK, (unsigned)key), khi = __reduce_or_sync(CRN_FULL_MASK, (unsigned)(key >> 32));
+                const uint32_t bx = cx * 2 + (xo >> 2), by = cy * 2 + (yo >> 2);
+                if (lane == 0 && bx < mp.block_width && by < mp.block_height)
+                    out_sel_keys[mp.first_block + bx + by * mp.block_width] = ((unsigned long long)khi << 32) | klo;
             }
         }
         // the eight encodings (crn_qdxt1.cpp:216-254, crn_qdxt5.cpp:197-239)
@@ -396,6 +409,89 @@ qdxt_training_kernel(const uint32_t* __restrict__ blocks, QdxtMipTable mt, uint3
             }
         }
     }
+}
+
+// number of distinct keys (qdxt1/qdxt5::init's selector_hash.size()): open-addressing insert, `table` holds
+// `mask + 1` entries preset to ~0 (no key of this path has bits above 47)
+__global__ void __launch_bounds__(256) count_distinct_kernel(const unsigned long long* __restrict__ keys, uint32_t n, unsigned long long* __restrict__ table,
+                                                             uint32_t mask, unsigned* __restrict__ counter)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    int fresh = 0;
+    if (i < n) {
+        const unsigned long long key = keys[i];
+        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+        for (;;) {
+            const unsigned long long old = atomicCAS(&table[h], ~0ull, key);
+            if (old == ~0ull) { fresh = 1; break; }
+            if (old == key) break;
+            h = (h + 1) & mask;
+        }
+    }
+    const int total = __reduce_add_sync(CRN_FULL_MASK, fresh);
+    if (lane_id() == 0 && total) atomicAdd(counter, (unsigned)total);
+}
+
+// Selector training vectors from the packed elements (qdxt1::create_selector_clusters, crn_qdxt1.cpp:871-908;
+// qdxt5::create_selector_clusters, crn_qdxt5.cpp:701-760).  category: colour 0; alpha 0 = 8-value block,
+// 1 = 6-value block, 255 = skipped (a 6-value block that uses the absolute selectors 6/7).
+CRN_DEVICE_TABLE uint8_t g_sel_dxt1_to_linear[4] = { 0, 3, 1, 2 };                        // crn_dxt.cpp:39
+CRN_DEVICE_TABLE uint8_t g_sel_dxt5_to_linear[8] = { 0, 7, 1, 2, 3, 4, 5, 6 };            // crn_dxt.cpp:34
+CRN_DEVICE_TABLE uint8_t g_sel_dxt5_alpha6_to_linear[8] = { 0, 5, 1, 2, 3, 4, 0, 0 };     // crn_dxt.cpp:36
+
+template <int KIND>
+__global__ void __launch_bounds__(256) selector_vectors_kernel(const uint8_t* __restrict__ elements, uint32_t stride, uint32_t offset, uint32_t n, int perceptual,
+                                                               uint8_t* __restrict__ out_vecs, uint32_t* __restrict__ out_weights, uint8_t* __restrict__ out_category)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint2 e = *reinterpret_cast<const uint2*>(elements + (size_t)b * stride + offset);
+    uint8_t v[16];
+    uint32_t weight; uint8_t cat = 0;
+    if (KIND == 0) {
+        const unsigned lo = e.x & 0xffff, hi = e.x >> 16;
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = g_sel_dxt1_to_linear[(e.y >> (2 * i)) & 3];
+        int c0[3], c1[3];
+        unpack565(lo, true, c0[0], c0[1], c0[2]);
+        unpack565(hi, true, c1[0], c1[1], c1[2]);
+        const int dr = c0[0] - c1[0], dg = c0[1] - c1[1], db = c0[2] - c1[2];
+        const unsigned dist = perceptual ? (unsigned)(8 * dr * dr + 25 * dg * dg + db * db) : (unsigned)(dr * dr + dg * dg + db * db);   // crn_color.h:724-745
+        weight = dist / 2000u;
+    } else {
+        const int lo = e.x & 0xff, hi = (e.x >> 8) & 0xff;
+        const unsigned long long bits = ((unsigned long long)e.y << 16) | (e.x >> 16);
+        const bool six = lo <= hi;
+        bool absolute = false;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const unsigned s = (unsigned)(bits >> (3 * i)) & 7;
+            if (six) { if (s >= 6) absolute = true; v[i] = g_sel_dxt5_alpha6_to_linear[s]; }
+            else v[i] = g_sel_dxt5_to_linear[s];
+        }
+        cat = absolute ? 255 : (six ? 1 : 0);
+        weight = (unsigned)((lo - hi) * (lo - hi)) / 8u;
+    }
+    weight = weight < 1 ? 1 : (weight > 2048 ? 2048 : weight);
+    uint4* o = reinterpret_cast<uint4*>(out_vecs + (size_t)b * 16);
+    uint32_t w4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) w4[k] = v[4 * k] | (v[4 * k + 1] << 8) | (v[4 * k + 2] << 16) | ((uint32_t)v[4 * k + 3] << 24);
+    *o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    out_weights[b] = weight;
+    if (out_category) out_category[b] = cat;
+}
+
+// dxt_pixel_block layout of one image level with edge clamping (mipmapped_texture::qdxt_pack_init,
+// crn_mipmapped_texture.cpp:2457-2471)
+__global__ void __launch_bounds__(256) blockify_kernel(const uint8_t* __restrict__ rgba, uint32_t width, uint32_t height, uint32_t pitch, uint32_t* __restrict__ blocks)
+{
+    const uint32_t bw = (width + 3) >> 2, bh = (height + 3) >> 2;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bw * bh * 16) return;
+    const uint32_t b = i >> 4, p = i & 15;
+    const uint32_t x = min((b % bw) * 4 + (p & 3), width - 1), y = min((b / bw) * 4 + (p >> 2), height - 1);
+    blocks[i] = *reinterpret_cast<const uint32_t*>(rgba + (size_t)y * pitch + (size_t)x * 4);
 }
 
 }  // namespace crn

@@ -143,9 +143,10 @@ public:
     explicit VqBuilder(cudaStream_t stream, uint64_t* launch_counter) : stream_(stream), launches_(launch_counter) {}
     ~VqBuilder() { release(); }
 
-    // d_vecs: u8[n][D], d_wts: u32[n] (device).  threaded: crnlib::threaded_clusterizer<V>::create_clusters
-    // (crn_threaded_clusterizer.h:70-174): three PCA divisions into <= 4 partitions, each its own clusterizer.
-    cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, uint32_t n, uint32_t max_size, bool threaded, VqResult& res)
+    // d_vecs: u8[][D], d_wts: u32[] (device), indexed by vector id.  d_ids: the n ids to quantise in ascending order
+    // (nullptr = 0..n-1).  threaded: crnlib::threaded_clusterizer<V>::create_clusters (crn_threaded_clusterizer.h:70-174):
+    // three PCA divisions into <= 4 partitions, each its own clusterizer.
+    cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, VqResult& res)
     {
         res = VqResult();
         if (!n) return cudaSuccess;
@@ -155,7 +156,7 @@ public:
         std::vector<VqHostNode>& nodes = res.nodes;
 
         // root: identity order + statistics
-        launch_fill_identity(n);
+        launch_fill_identity(d_ids, n);
         cudaMemsetAsync(d_acc_, 0, sizeof(unsigned long long) * (D + 2), stream_);
         CRN_LAUNCH(vq_root_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, d_perm_[0], n, d_acc_); count();
         CRN_LAUNCH(vq_root_finish_kernel<D>, 1, 32, 0, stream_, d_acc_, nodes_, n); count();
@@ -268,7 +269,7 @@ private:
         cap_n_ = n; cap_slots_ = slots;
         return cudaSuccess;
     }
-    void launch_fill_identity(uint32_t n);
+    void launch_fill_identity(const uint32_t* d_ids, uint32_t n);
 
     // exclusive scan of d_flags_[0..m) into d_scan_
     void scan(uint32_t m)
@@ -345,9 +346,10 @@ __global__ void __launch_bounds__(256) vq_identity_kernel(unsigned* __restrict__
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) perm[i] = i;
 }
-template <int D> void VqBuilder<D>::launch_fill_identity(uint32_t n)
+template <int D> void VqBuilder<D>::launch_fill_identity(const uint32_t* d_ids, uint32_t n)
 {
     cur_ = 0;
+    if (d_ids) { cudaMemcpyAsync(d_perm_[0], d_ids, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream_); return; }
     CRN_LAUNCH(vq_identity_kernel, grid(n), 256, 0, stream_, d_perm_[0], n); count();
 }
 

@@ -76,6 +76,17 @@ __device__ __forceinline__ bool vq_is_head(unsigned key)
 }
 __device__ __forceinline__ void vq_add(unsigned long long* p, int v) { if (v) atomicAdd(p, (unsigned long long)(long long)v); }
 
+// Variance as the reference rounds it (crn_clusterizer.h:91, :816-817): ttsum is a double, the centroid sum's
+// dot product and the division by the weight are FLOAT operations.  With the integer sums of this path the
+// float dot is reproduced exactly as long as every component sum stays below 2^24.
+template <int D> __device__ __forceinline__ float vq_variance(const unsigned long long* s1, unsigned long long w, unsigned long long tt)
+{
+    const float f0 = (float)(long long)s1[0];
+    float dot = f0 * f0;
+    for (int d = 1; d < D; d++) { const float f = (float)(long long)s1[d]; dot += f * f; }
+    return (float)((double)tt - (double)(dot / (float)w));
+}
+
 // K1: second moments of every frontier node (PCA mode only)
 template <int D>
 __global__ void __launch_bounds__(256) vq_moments_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
@@ -221,9 +232,7 @@ __global__ void vq_presplit_children_kernel(VqSlot<D>* __restrict__ slots, unsig
     VqSlot<D>& sl = slots[s];
     for (int sd = 0; sd < 2; sd++) {
         if (!sl.wsum[sd]) { sl.var[sd] = 0; for (int d = 0; d < D; d++) sl.child[sd][d] = 0; continue; }
-        double dot = 0;
-        for (int d = 0; d < D; d++) { const double x = (double)(long long)sl.s1[sd][d]; dot += x * x; }
-        sl.var[sd] = (float)((double)sl.tt[sd] - dot / (double)sl.wsum[sd]);
+        sl.var[sd] = vq_variance<D>(sl.s1[sd], sl.wsum[sd], sl.tt[sd]);
         const float inv = 1.0f / (float)sl.wsum[sd];
         for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
     }
@@ -323,9 +332,7 @@ __global__ void vq_update_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots,
     if (!sl.wsum[0] || !sl.wsum[1]) { sl.state = 2; return; }       // unsplittable (:814-818)
     float var[2];
     for (int sd = 0; sd < 2; sd++) {
-        double dot = 0;
-        for (int d = 0; d < D; d++) { const double x = (double)(long long)sl.s1[sd][d]; dot += x * x; }
-        var[sd] = (float)((double)sl.tt[sd] - dot / (double)sl.wsum[sd]);
+        var[sd] = vq_variance<D>(sl.s1[sd], sl.wsum[sd], sl.tt[sd]);
         const float inv = 1.0f / (float)sl.wsum[sd];
         for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
     }
@@ -496,10 +503,8 @@ __global__ void vq_root_finish_kernel(const unsigned long long* __restrict__ acc
 {
     if (threadIdx.x || blockIdx.x) return;
     const unsigned long long W = acc[D];
-    double dot = 0;
-    for (int d = 0; d < D; d++) { const double x = (double)(long long)acc[d]; dot += x * x; }
     nodes.begin[0] = 0; nodes.count[0] = n; nodes.left[0] = -1; nodes.flags[0] = 0; nodes.weight[0] = W;
-    nodes.variance[0] = W ? (float)((double)acc[D + 1] - dot / (double)W) : 0.0f;
+    nodes.variance[0] = W ? vq_variance<D>(acc, W, acc[D + 1]) : 0.0f;
     const float inv = W ? 1.0f / (float)W : 0.0f;
     for (int d = 0; d < D; d++) nodes.centroid[d] = (float)(long long)acc[d] * inv;
 }

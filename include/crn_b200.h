@@ -157,6 +157,40 @@ CRN_API int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d
                                   uint32_t max_codebook_size, uint32_t retrieve_max_clusters, int threaded,
                                   uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size);
 
+/* Clustered DDS compression (the `-quality N` DDS path) -------------------
+ * Mirrors mipmapped_texture::qdxt_pack_init / qdxt_pack (crnlib/crn_mipmapped_texture.cpp:2310-2490,
+ * :2492-2590) as dds_comp::convert_to_dxt drives them (crnlib/crn_dds_comp.cpp:156-212), i.e. qdxt1::init/pack
+ * (crnlib/crn_qdxt1.cpp:75-446, :910-1030) and qdxt5::init/pack (crnlib/crn_qdxt5.cpp:76-426, :838-960):
+ *   init : pixel blocks of all levels -> adaptive-tile analysis -> endpoint training vectors -> endpoint
+ *          tree (clusterizer, 65535 leaves max) + the distinct dxt_fast selector count, per element;
+ *   pack : quality_level 0..255 -> prune the endpoint tree, optimise one endpoint pair per cluster, build
+ *          selector vectors, cluster them (threaded_clusterizer), re-vote the selectors per cluster.
+ * levels: faces x mip levels in the reference's order (face-major); pixels RGBA8 on the device or, with
+ * pixels_on_host != 0, on the host (copied during init).  The hierarchical (adaptive tile) mode of
+ * cCRNCompFlagHierarchical -- crnlib's default -- is the one implemented.  Formats: DXT1, DXT1A, DXT5, DXT5A,
+ * DXN_XY, DXN_YX (DXT3 is never clustered by the reference either: crn_dds_comp.cpp:158).
+ * pack() writes every level back to back (alpha element first), blocks row-major; it may be called again with
+ * another quality_level on the same state, as crnlib's bitrate search does.  Synchronous.
+ * Parity: tolerance class (PSNR within 0.05 dB, LZMA size within 1 % of the reference's DDS at the same
+ * settings); the reference itself is not bit-reproducible across thread counts on this path. */
+typedef struct crn_gpu_qdxt crn_gpu_qdxt;
+typedef struct crn_gpu_level_desc { const void* rgba; uint32_t width, height, pitch_bytes; } crn_gpu_level_desc;
+typedef struct crn_gpu_qdxt_info {
+    uint32_t struct_size;
+    uint32_t n_blocks, num_elements;
+    uint32_t endpoint_codebook_size[3];    /* clusterizer::get_codebook_size() per element */
+    uint32_t max_selector_clusters[3];     /* distinct dxt_fast selectors + 128 */
+    uint32_t endpoint_clusters[3];         /* of the last pack() */
+    uint32_t selector_clusters[3];
+} crn_gpu_qdxt_info;
+CRN_API int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
+                              const crn_gpu_level_desc* levels, uint32_t num_levels, int pixels_on_host, crn_gpu_qdxt** out);
+CRN_API uint64_t crn_gpu_qdxt_output_size(const crn_gpu_qdxt* q);
+CRN_API uint64_t crn_gpu_qdxt_level_offset(const crn_gpu_qdxt* q, uint32_t level);
+CRN_API int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int dst_on_host);
+CRN_API int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info);
+CRN_API void crn_gpu_qdxt_free(crn_gpu_qdxt* q);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

@@ -66,3 +66,82 @@ def test_training_vectors_match_port(simctx, port, kind, comp):
         b = port_training(port, kind, comp, blocks, mips)
         assert (a[2] == b[2]).all(), ("encoding", kind, w, h, np.nonzero(a[2] != b[2])[0][:5])
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), (kind, w, h)
+
+
+# ---- the whole clustered-DDS pipeline (crn_gpu_qdxt_init / crn_gpu_qdxt_pack) vs crn_compress(cCRNFileTypeDDS) --------
+
+GPUFMT = dict(DXT1=0, DXT5=3, DXT5A=4, DXN_XY=5, DXN_YX=6)
+CHANNELS = {0: ([0, 1, 2],), 3: ([0, 1, 2], [3]), 4: ([3],), 5: ([0, 1],), 6: ([0, 1],)}
+
+
+def compare_with_reference(ctx, ref, fmtname, levels, q, params=None, flags=1 | 2 | 8):
+    """Returns (gpu bytes, ref bytes, [(psnr_gpu, psnr_ref) per channel group], bits_gpu, bits_ref)."""
+    dds, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT[fmtname], file_type=1, quality=q, threads=0, flags=flags)
+    ref_data = np.frombuffer(quality.dds_payload(dds), np.uint8)
+    qd = ctx.qdxt_init(GPUFMT[fmtname], levels, params)
+    out = qd.pack(q)
+    info = qd.info()
+    qd.close()
+    assert len(out) == len(ref_data)
+    src = np.concatenate([quality.image_to_blocks(l) for l in levels])
+    f = GPUFMT[fmtname]
+    a = quality.decode_blocks(out.tobytes(), f); b = quality.decode_blocks(ref_data.tobytes(), f)
+    ps = [(quality.psnr(a, src, c), quality.psnr(b, src, c)) for c in CHANNELS[f]]
+    return out, ref_data, ps, quality.lzma_bits(out.tobytes()), quality.lzma_bits(ref_data.tobytes()), info
+
+
+def assert_within_tolerance(ps, bits_gpu, bits_ref):
+    # BASELINE.json north_star: RGB/alpha PSNR within 0.05 dB and bitrate within 1 % of the reference
+    for g, r in ps:
+        assert abs(g - r) <= 0.05, ps
+    assert abs(bits_gpu - bits_ref) <= 0.01 * bits_ref, (bits_gpu, bits_ref)
+
+
+@pytest.mark.parametrize("fmtname,w,h,q,seed", [
+    ("DXT1", 64, 64, 128, 1),
+    ("DXT5A", 64, 64, 128, 4),
+    ("DXN_XY", 64, 64, 128, 5),
+    ("DXN_YX", 40, 24, 200, 6),
+    ("DXT1", 128, 128, 60, 3),
+])
+def test_clustered_dds_matches_reference_bytes(simctx, ref, fmtname, w, h, q, seed):
+    """With one thread the reference is deterministic; on these inputs its cross-cluster endpoint cache
+    (crn_dxt1.cpp:748-763, a thread-schedule dependent heuristic this path does not have) never changes a result,
+    and the output is byte-identical."""
+    from bench import mip_chain
+    levels = mip_chain(blockgen.smooth_image(w, h, seed, alpha=True))
+    out, ref_data, ps, bg, br, info = compare_with_reference(simctx, ref, fmtname, levels, q)
+    assert_within_tolerance(ps, bg, br)
+    assert np.array_equal(out, ref_data)
+    assert all(k > 0 for k in info["endpoint_clusters"])
+
+
+def test_clustered_dds_dxt5_within_tolerance(simctx, ref):
+    from bench import mip_chain
+    levels = mip_chain(blockgen.smooth_image(64, 64, 2, alpha=True))
+    out, ref_data, ps, bg, br, info = compare_with_reference(simctx, ref, "DXT5", levels, 128)
+    assert_within_tolerance(ps, bg, br)
+    assert np.array_equal(out.view(np.uint64)[0::2], ref_data.view(np.uint64)[0::2])      # alpha elements identical
+    assert info["num_elements"] == 2
+
+
+def test_clustered_dds_single_level_and_repack(simctx, ref):
+    """No mip chain, odd size; pack() twice on one state at two quality levels (crnlib's bitrate search does this)."""
+    img = blockgen.smooth_image(52, 36, 9, alpha=True)
+    qd = simctx.qdxt_init(GPUFMT["DXT1"], [img])
+    for q in (40, 220):
+        out = qd.pack(q)
+        dds, _, _ = helpers.ref_compress(ref, [[img]], helpers.CRN_FMT["DXT1"], file_type=1, quality=q, threads=0)
+        ref_data = np.frombuffer(quality.dds_payload(dds), np.uint8)
+        src = quality.image_to_blocks(img)
+        a = quality.decode_blocks(out.tobytes(), 0); b = quality.decode_blocks(ref_data.tobytes(), 0)
+        assert_within_tolerance([(quality.psnr(a, src, [0, 1, 2]), quality.psnr(b, src, [0, 1, 2]))], quality.lzma_bits(out.tobytes()), quality.lzma_bits(ref_data.tobytes()))
+    qd.close()
+
+
+def test_clustered_dds_rejects_unsupported(simctx):
+    img = blockgen.smooth_image(16, 16, 1, alpha=True)
+    with pytest.raises(crn.CrnGpuError):
+        simctx.qdxt_init(2, [img])                                   # DXT3 is never clustered
+    with pytest.raises(crn.CrnGpuError):
+        simctx.qdxt_init(0, [img], crn.PackParams(dxt_quality=1))    # only better / uber
