@@ -159,7 +159,7 @@ public:
         launch_fill_identity(d_ids, n);
         cudaMemsetAsync(d_acc_, 0, sizeof(unsigned long long) * (D + 2), stream_);
         CRN_LAUNCH(vq_root_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, d_perm_[0], n, d_acc_); count();
-        CRN_LAUNCH(vq_root_finish_kernel<D>, 1, 32, 0, stream_, d_acc_, nodes_, n); count();
+        CRN_LAUNCH(vq_root_finish_kernel<D>, 1, 32, 0, stream_, vecs_, wts_, d_perm_[0], d_acc_, nodes_, n, (threaded && max_size >= 128) ? 1 : 0); count();
         const unsigned first_free_node = 1;
         cudaMemcpyAsync(d_node_counter_, &first_free_node, sizeof(unsigned), cudaMemcpyHostToDevice, stream_);
         float root_var = 0;
@@ -173,12 +173,12 @@ public:
         if (threaded && max_size >= 128) {
             // compute_split x3 (:93-95)
             frontier.assign(1, 0u);
-            ce = round(frontier, nodes, true);
+            ce = round(frontier, nodes, 1);
             if (ce != cudaSuccess) return ce;
             frontier.clear();
             const uint32_t a = (uint32_t)nodes[0].left;
             for (uint32_t c = 0; c < 2; c++) if (nodes[a + c].count) frontier.push_back(a + c);
-            ce = round(frontier, nodes, true);
+            ce = round(frontier, nodes, 2);
             if (ce != cudaSuccess) return ce;
             std::vector<uint32_t> parts;
             for (uint32_t c = 0; c < 2; c++) {
@@ -209,7 +209,7 @@ public:
             for (VqTreeSim& t : res.trees) { t.run(nodes); t.wanted(nodes, frontier); }
             if (frontier.empty()) break;
             std::sort(frontier.begin(), frontier.end(), [&](uint32_t x, uint32_t y) { return nodes[x].begin < nodes[y].begin; });
-            ce = round(frontier, nodes, false);
+            ce = round(frontier, nodes, 0);
             if (ce != cudaSuccess) return ce;
             res.rounds++;
             res.device_splits += (uint32_t)frontier.size();
@@ -283,7 +283,8 @@ private:
     }
 
     // split every node of `frontier` (sorted by first position) on the device and record the results
-    cudaError_t round(const std::vector<uint32_t>& frontier, std::vector<VqHostNode>& nodes, bool presplit)
+    // presplit: 0 = clusterizer split; 1 / 2 = first / second level of threaded_clusterizer's PCA divisions
+    cudaError_t round(const std::vector<uint32_t>& frontier, std::vector<VqHostNode>& nodes, int presplit)
     {
         const unsigned F = (unsigned)frontier.size(), n = n_;
         if (!F) return cudaSuccess;
@@ -294,11 +295,13 @@ private:
         unsigned* perm_out = d_perm_[cur_ ^ 1];
         CRN_LAUNCH(vq_init_slots_kernel<D>, gs, 128, 0, stream_, d_slot_node_, nodes_, d_slots_, d_slot_starts_, F, presplit ? 1 : 0); count();
         CRN_LAUNCH(vq_pos_slot_kernel<D>, grid(n), 256, 0, stream_, d_slot_starts_, d_slots_, F, d_pos_slot_, n); count();
-        CRN_LAUNCH(vq_moments_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, n); count();
-        CRN_LAUNCH(vq_axis_kernel<D>, gs, 128, 0, stream_, d_slots_, F); count();
+        const unsigned gw = (F + kVqSeqWarps - 1) / kVqSeqWarps;
+        CRN_LAUNCH(vq_covariance_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_slots_, F); count();
+        CRN_LAUNCH(vq_axis_kernel<D>, gs, 128, 0, stream_, d_slots_, F, presplit ? 1 : 0); count();
         CRN_LAUNCH(vq_project_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n, presplit ? 1 : 0); count();
+        CRN_LAUNCH(vq_float_sums_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, F, 0); count();
         if (presplit) {
-            CRN_LAUNCH(vq_presplit_children_kernel<D>, gs, 128, 0, stream_, d_slots_, F); count();
+            CRN_LAUNCH(vq_presplit_children_kernel<D>, gs, 128, 0, stream_, d_slots_, F, presplit == 1 ? 1 : 0); count();
         } else {
             CRN_LAUNCH(vq_children_kernel<D>, gs, 128, 0, stream_, vecs_, perm, d_slots_, F); count();
             CRN_LAUNCH((vq_estimate_kernel<D, 0>), grid(n), 256, 0, stream_, vecs_, perm, d_pos_slot_, d_slots_, n); count();
@@ -306,6 +309,7 @@ private:
             CRN_LAUNCH(vq_estimate_finish_kernel<D>, gs, 128, 0, stream_, vecs_, perm, d_slots_, F); count();
             for (int it = 0; it < 8; it++) {
                 CRN_LAUNCH(vq_assign_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n); count();
+                CRN_LAUNCH(vq_float_sums_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, F, 1); count();
                 CRN_LAUNCH(vq_update_kernel<D>, gs, 128, 0, stream_, d_slots_, F, d_active_); count();
             }
         }

@@ -8,11 +8,18 @@
 // current frontier is split in the same round (one round = a fixed sequence of kernels over all vectors),
 // and the reference's split ORDER -- which decides where the codebook budget is spent and what
 // retrieve_clusters() prunes -- is replayed afterwards on the host from the recorded variances
-// (vq_host.h).  All vectors of the path have small integer components (endpoints 0..255, linear selectors
-// 0..7) and integer weights, so every sum is accumulated exactly in 64-bit integers with atomics:
-// the result does not depend on the order of accumulation and is reproducible run to run.  (The reference
-// accumulates the same sums in float, which rounds once a sum passes 2^24; cluster boundaries can
-// therefore differ in the last place -- this path is tolerance-class, see DESIGN.md.)
+// (vq_host.h).
+//
+// Arithmetic.  The reference accumulates its per-node sums in FLOAT, in member order, and every decision
+// (split side, heap order) hangs on those roundings, so they are reproduced, not approximated:
+//  * all vectors of the path have small integer components (endpoints 0..255, linear selectors 0..7) and
+//    integer weights.  Sums of w*v are accumulated exactly in 64-bit integers with atomics (order free,
+//    reproducible); while such a sum stays below 2^24 the reference's float accumulation is exact too and the
+//    two agree bit for bit.  The few nodes (the top of the tree) whose sums pass 2^24 are re-accumulated
+//    in float, sequentially in member order, one lane per accumulator (vq_float_sums_kernel);
+//  * the covariance sums have fractional terms and always round: one warp per node accumulates them in
+//    float in member order, one lane per matrix entry (vq_covariance_kernel);
+//  * ttsum / weights are doubles / integers in the reference and exact here.
 #pragma once
 #include "warp_util.cuh"
 
@@ -21,8 +28,9 @@ namespace crn {
 constexpr unsigned kVqNoSlot = 0xFFFFFFFFu;
 
 template <int D> struct VqSlot {              // split state of one frontier node
-    unsigned long long s2[D * (D + 1) / 2];   // sum w * v[x] * v[y], x <= y
-    unsigned long long s1[2][D];              // per side: sum w * v
+    float covar[D * (D + 1) / 2];             // sum (v - c)[x] * ((v - c)[y] * w), x <= y, float in member order
+    float fs1[2][D];                          // per side: sum w * v as the reference's float accumulation gives it
+    unsigned long long s1[2][D];              // per side: sum w * v, exact
     unsigned long long wsum[2];
     unsigned long long tt[2];                 // per side: sum w * (v . v)
     unsigned long long far_key, opp_key;      // compute_split_estimate fallback: (float bits of dist << 32) | ~position
@@ -78,63 +86,127 @@ __device__ __forceinline__ void vq_add(unsigned long long* p, int v) { if (v) at
 
 // Variance as the reference rounds it (crn_clusterizer.h:91, :816-817): ttsum is a double, the centroid sum's
 // dot product and the division by the weight are FLOAT operations.  With the integer sums of this path the
-// float dot is reproduced exactly as long as every component sum stays below 2^24.
-template <int D> __device__ __forceinline__ float vq_variance(const unsigned long long* s1, unsigned long long w, unsigned long long tt)
+// fs1 is the float-accumulated centroid sum (see vq_float_sums_kernel).
+template <int D> __device__ __forceinline__ float vq_variance(const float* fs1, unsigned long long w, unsigned long long tt)
 {
-    const float f0 = (float)(long long)s1[0];
-    float dot = f0 * f0;
-    for (int d = 1; d < D; d++) { const float f = (float)(long long)s1[d]; dot += f * f; }
+    float dot = fs1[0] * fs1[0];
+    for (int d = 1; d < D; d++) dot += fs1[d] * fs1[d];
     return (float)((double)tt - (double)(dot / (float)w));
 }
 
-// K1: second moments of every frontier node (PCA mode only)
+constexpr int kVqSeqWarps = 4;                // warps per CTA of the sequential (member order) kernels
+
+// Sequential float accumulation of sum w*v over members [begin, begin+count) in order, one lane per (side, component):
+// lane = side * D + d.  `side` may be nullptr (everything on side 0).  tile_p / tile_s are this warp's staging rows.
 template <int D>
-__global__ void __launch_bounds__(256) vq_moments_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
-                                                         const unsigned* __restrict__ pos_slot, VqSlot<D>* __restrict__ slots, unsigned n)
+__device__ __forceinline__ float vq_seq_side_sum(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                 const uint8_t* __restrict__ side, unsigned begin, unsigned count, float (*tile_p)[D], uint8_t* tile_s)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned slot = i < n ? pos_slot[i] : kVqNoSlot;
-    if (slot != kVqNoSlot && slots[slot].mode != 0) slot = kVqNoSlot;
-    const unsigned take = vq_take_mask(slot);
-    const bool head = vq_is_head(slot);
-    if (!__any_sync(CRN_FULL_MASK, slot != kVqNoSlot)) return;
-    int v[D]; int w = 0;
-    if (slot != kVqNoSlot) {
-        const unsigned id = perm[i];
-        w = (int)wts[id];
+    const unsigned lane = lane_id();
+    const unsigned my_side = lane / D, my_d = lane % D;
+    float acc = 0.0f;
+    for (unsigned base = 0; base < count; base += 32) {
+        const unsigned m = base + lane;
+        if (m < count) {
+            const unsigned id = perm[begin + m];
+            const float w = (float)wts[id];
+            tile_s[lane] = side ? side[begin + m] : (uint8_t)0;
 #pragma unroll
-        for (int d = 0; d < D; d++) v[d] = vecs[(size_t)id * D + d];
-    } else {
-#pragma unroll
-        for (int d = 0; d < D; d++) v[d] = 0;
-    }
-    int k = 0;
-#pragma unroll
-    for (int x = 0; x < D; x++)
-#pragma unroll
-        for (int y = x; y < D; y++, k++) {
-            const int s = vq_seg_sum(w * v[x] * v[y], take);
-            if (head) vq_add(&slots[slot].s2[k], s);
+            for (int d = 0; d < D; d++) tile_p[lane][d] = (float)vecs[(size_t)id * D + d] * w;
         }
+        __syncwarp();
+        const unsigned cnt = count - base < 32u ? count - base : 32u;
+        if (lane < 2 * D)
+            for (unsigned j = 0; j < cnt; j++)
+                if (tile_s[j] == my_side) acc += tile_p[j][my_d];
+        __syncwarp();
+    }
+    return acc;
 }
 
-// K2: covariance -> principal axis by power iteration (compute_split_pca, crn_clusterizer.h:487-575)
+// K1: covariance sums in the reference's order and precision (compute_split_pca, crn_clusterizer.h:496-508;
+// threaded_clusterizer::compute_pca, crn_threaded_clusterizer.h:252-266).  One warp per slot.
 template <int D>
-__global__ void vq_axis_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots)
+__global__ void __launch_bounds__(kVqSeqWarps * 32) vq_covariance_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                                        VqSlot<D>* __restrict__ slots, unsigned nslots)
+{
+    constexpr int P = D * (D + 1) / 2, PER = (P + 31) / 32;
+    __shared__ float dv[kVqSeqWarps][32][D], dw[kVqSeqWarps][32][D];
+    const unsigned wi = threadIdx.x >> 5, lane = lane_id();
+    const unsigned s = blockIdx.x * kVqSeqWarps + wi;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (sl.mode != 0) return;
+    int xa[PER], ya[PER];
+    float acc[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int a = (int)lane + 32 * k, x = 0;
+        xa[k] = 0; ya[k] = 0; acc[k] = 0.0f;
+        if (a < P) { int rem = a; while (rem >= D - x) { rem -= D - x; x++; } xa[k] = x; ya[k] = x + rem; }
+    }
+    float c[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) c[d] = sl.centroid[d];
+    const unsigned begin = sl.begin, count = sl.count;
+    for (unsigned base = 0; base < count; base += 32) {
+        const unsigned m = base + lane;
+        if (m < count) {
+            const unsigned id = perm[begin + m];
+            const float w = (float)wts[id];
+#pragma unroll
+            for (int d = 0; d < D; d++) { const float v = (float)vecs[(size_t)id * D + d] - c[d]; dv[wi][lane][d] = v; dw[wi][lane][d] = v * w; }
+        }
+        __syncwarp();
+        const unsigned cnt = count - base < 32u ? count - base : 32u;
+        for (unsigned j = 0; j < cnt; j++) {
+#pragma unroll
+            for (int k = 0; k < PER; k++) acc[k] = acc[k] + dv[wi][j][xa[k]] * dw[wi][j][ya[k]];
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k++) if ((int)lane + 32 * k < P) sl.covar[lane + 32 * k] = acc[k];
+}
+
+// Float centroid sums of every slot that is being split: (float) of the exact integer sum while that is below 2^24
+// (the reference's running float sum is exact there), else re-accumulated in member order.  One warp per slot.
+// phase 0: after the projection (mode 0 slots), phase 1: after a Lloyd assignment (state 0 slots).
+template <int D>
+__global__ void __launch_bounds__(kVqSeqWarps * 32) vq_float_sums_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                                        const uint8_t* __restrict__ side, VqSlot<D>* __restrict__ slots, unsigned nslots, int phase)
+{
+    __shared__ float tile_p[kVqSeqWarps][32][D];
+    __shared__ uint8_t tile_s[kVqSeqWarps][32];
+    const unsigned wi = threadIdx.x >> 5, lane = lane_id();
+    const unsigned s = blockIdx.x * kVqSeqWarps + wi;
+    if (s >= nslots) return;
+    VqSlot<D>& sl = slots[s];
+    if (phase == 0 ? sl.mode != 0 : sl.state != 0) return;
+    const bool mine = lane < 2 * D;
+    const unsigned long long exact = mine ? sl.s1[lane / D][lane % D] : 0ull;
+    const bool big = __any_sync(CRN_FULL_MASK, exact >= (1ull << 24));
+    float f = (float)(long long)exact;
+    if (big) f = vq_seq_side_sum<D>(vecs, wts, perm, side, sl.begin, sl.count, tile_p[wi], tile_s[wi]);
+    if (mine) sl.fs1[lane / D][lane % D] = f;
+}
+
+// K2: covariance -> principal axis by power iteration (compute_split_pca, crn_clusterizer.h:510-579; presplit:
+// threaded_clusterizer::compute_pca, crn_threaded_clusterizer.h:268-329, which scales by a double reciprocal)
+template <int D>
+__global__ void vq_axis_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots, int presplit)
 {
     const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     VqSlot<D>& sl = slots[s];
     if (sl.mode != 0) return;
     float covar[D][D];
-    const double W = (double)sl.node_weight;
     const float inv_w = 1.0f / (float)sl.node_weight;
+    const double inv_wd = 1.0 / (double)sl.node_weight;
     int k = 0;
     for (int x = 0; x < D; x++)
         for (int y = x; y < D; y++, k++) {
-            // sum w (v-c)(v-c)^T = S2 - c_x S1_y - c_y S1_x + W c_x c_y with S1 = W c
-            const double c = (double)(long long)sl.s2[k] - W * (double)sl.centroid[x] * (double)sl.centroid[y];
-            covar[x][y] = (float)c * inv_w;
+            covar[x][y] = presplit ? (float)((double)sl.covar[k] * inv_wd) : sl.covar[k] * inv_w;
             covar[y][x] = covar[x][y];
         }
     float axis[D], prev[D];
@@ -217,7 +289,7 @@ __global__ void __launch_bounds__(256) vq_project_kernel(const uint8_t* __restri
             if (d == 0) t = df * sl.axis[0]; else t += df * sl.axis[d];
         }
         side = ((double)t < 0.0) ? 0 : 1;
-        if (presplit) side_out[i] = (uint8_t)side;
+        side_out[i] = (uint8_t)side;
     }
     vq_accumulate_side<D>(slots, slot, take, head, v, w, side, presplit != 0);
 }
@@ -225,16 +297,22 @@ __global__ void __launch_bounds__(256) vq_project_kernel(const uint8_t* __restri
 // threaded_clusterizer::compute_split (crn_threaded_clusterizer.h:335-369): the division itself is the split, no
 // Lloyd iterations; the two sides become roots, with the statistics generate_codebook() gives a root (:77-93)
 template <int D>
-__global__ void vq_presplit_children_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots)
+__global__ void vq_presplit_children_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots, int children_are_pca_nodes)
 {
     const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     VqSlot<D>& sl = slots[s];
     for (int sd = 0; sd < 2; sd++) {
-        if (!sl.wsum[sd]) { sl.var[sd] = 0; for (int d = 0; d < D; d++) sl.child[sd][d] = 0; continue; }
-        sl.var[sd] = vq_variance<D>(sl.s1[sd], sl.wsum[sd], sl.tt[sd]);
-        const float inv = 1.0f / (float)sl.wsum[sd];
-        for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
+        sl.var[sd] = 0;
+        if (!sl.wsum[sd]) { for (int d = 0; d < D; d++) sl.child[sd][d] = 0; continue; }
+        if (children_are_pca_nodes) {      // compute_pca's centroid (crn_threaded_clusterizer.h:243-247)
+            const double inv = 1.0 / (double)sl.wsum[sd];
+            for (int d = 0; d < D; d++) sl.child[sd][d] = (float)((double)sl.fs1[sd][d] * inv);
+        } else {                           // a clusterizer root (crn_clusterizer.h:91-93)
+            sl.var[sd] = vq_variance<D>(sl.fs1[sd], sl.wsum[sd], sl.tt[sd]);
+            const float inv = 1.0f / (float)sl.wsum[sd];
+            for (int d = 0; d < D; d++) sl.child[sd][d] = sl.fs1[sd][d] * inv;
+        }
     }
     sl.state = 1;
 }
@@ -250,7 +328,7 @@ __global__ void vq_children_kernel(const uint8_t* __restrict__ vecs, const unsig
         for (int d = 0; d < D; d++) { sl.child[0][d] = (float)vecs[(size_t)perm[sl.begin] * D + d]; sl.child[1][d] = (float)vecs[(size_t)perm[sl.begin + 1] * D + d]; }
     } else if (sl.wsum[0] && sl.wsum[1]) {
         const float il = (float)(1.0 / (double)sl.wsum[0]), ir = (float)(1.0 / (double)sl.wsum[1]);
-        for (int d = 0; d < D; d++) { sl.child[0][d] = (float)(long long)sl.s1[0][d] * il; sl.child[1][d] = (float)(long long)sl.s1[1][d] * ir; }
+        for (int d = 0; d < D; d++) { sl.child[0][d] = sl.fs1[0][d] * il; sl.child[1][d] = sl.fs1[1][d] * ir; }
     } else sl.mode = 2;
     for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; }
     sl.wsum[0] = sl.wsum[1] = 0; sl.tt[0] = sl.tt[1] = 0;
@@ -332,9 +410,9 @@ __global__ void vq_update_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots,
     if (!sl.wsum[0] || !sl.wsum[1]) { sl.state = 2; return; }       // unsplittable (:814-818)
     float var[2];
     for (int sd = 0; sd < 2; sd++) {
-        var[sd] = vq_variance<D>(sl.s1[sd], sl.wsum[sd], sl.tt[sd]);
+        var[sd] = vq_variance<D>(sl.fs1[sd], sl.wsum[sd], sl.tt[sd]);
         const float inv = 1.0f / (float)sl.wsum[sd];
-        for (int d = 0; d < D; d++) sl.child[sd][d] = (float)(long long)sl.s1[sd][d] * inv;
+        for (int d = 0; d < D; d++) sl.child[sd][d] = sl.fs1[sd][d] * inv;
     }
     sl.var[0] = var[0]; sl.var[1] = var[1];
     const float total = var[0] + var[1];
@@ -452,8 +530,8 @@ __global__ void vq_init_slots_kernel(const unsigned* __restrict__ slot_node, VqN
     if (s >= nslots) return;
     const unsigned id = slot_node[s];
     VqSlot<D>& sl = slots[s];
-    for (int k = 0; k < D * (D + 1) / 2; k++) sl.s2[k] = 0;
-    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; sl.centroid[d] = nodes.centroid[(size_t)id * D + d]; sl.axis[d] = 0; sl.child[0][d] = 0; sl.child[1][d] = 0; }
+    for (int k = 0; k < D * (D + 1) / 2; k++) sl.covar[k] = 0;
+    for (int d = 0; d < D; d++) { sl.s1[0][d] = 0; sl.s1[1][d] = 0; sl.fs1[0][d] = 0; sl.fs1[1][d] = 0; sl.centroid[d] = nodes.centroid[(size_t)id * D + d]; sl.axis[d] = 0; sl.child[0][d] = 0; sl.child[1][d] = 0; }
     sl.wsum[0] = sl.wsum[1] = 0; sl.tt[0] = sl.tt[1] = 0; sl.far_key = 0; sl.opp_key = 0;
     sl.var[0] = sl.var[1] = 0; sl.prev_total = 1e+10f;
     sl.node = id; sl.begin = nodes.begin[id]; sl.count = nodes.count[id];
@@ -497,16 +575,29 @@ __global__ void vq_export_kernel(const VqSlot<D>* __restrict__ slots, unsigned n
     out[s] = r;
 }
 
-// the root node: centroid, weight and variance from the sums of vq_root_kernel (generate_codebook, :77-93)
+// the root node: centroid, weight and variance from the sums of vq_root_kernel (generate_codebook, :77-93; with
+// presplit the root is threaded_clusterizer::compute_pca's node, whose centroid is scaled by a double reciprocal).
+// One warp; re-accumulates in float when a sum passed 2^24.
 template <int D>
-__global__ void vq_root_finish_kernel(const unsigned long long* __restrict__ acc, VqNodes nodes, unsigned n)
+__global__ void __launch_bounds__(32) vq_root_finish_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                           const unsigned long long* __restrict__ acc, VqNodes nodes, unsigned n, int presplit)
 {
-    if (threadIdx.x || blockIdx.x) return;
+    __shared__ float tile_p[32][D];
+    __shared__ uint8_t tile_s[32];
+    __shared__ float fs[D];
+    const unsigned lane = lane_id();
+    const unsigned long long exact = lane < D ? acc[lane] : 0ull;
+    const bool big = __any_sync(CRN_FULL_MASK, exact >= (1ull << 24));
+    float f = (float)(long long)exact;
+    if (big) f = vq_seq_side_sum<D>(vecs, wts, perm, nullptr, 0u, n, tile_p, tile_s);
+    if (lane < D) fs[lane] = f;
+    __syncwarp();
+    if (lane) return;
     const unsigned long long W = acc[D];
     nodes.begin[0] = 0; nodes.count[0] = n; nodes.left[0] = -1; nodes.flags[0] = 0; nodes.weight[0] = W;
-    nodes.variance[0] = W ? vq_variance<D>(acc, W, acc[D + 1]) : 0.0f;
-    const float inv = W ? 1.0f / (float)W : 0.0f;
-    for (int d = 0; d < D; d++) nodes.centroid[d] = (float)(long long)acc[d] * inv;
+    nodes.variance[0] = W ? vq_variance<D>(fs, W, acc[D + 1]) : 0.0f;
+    if (presplit) { const double inv = W ? 1.0 / (double)W : 0.0; for (int d = 0; d < D; d++) nodes.centroid[d] = (float)((double)fs[d] * inv); }
+    else { const float inv = W ? 1.0f / (float)W : 0.0f; for (int d = 0; d < D; d++) nodes.centroid[d] = fs[d] * inv; }
 }
 
 // root statistics: sum w v, sum w, sum w v.v over all vectors (generate_codebook, :77-92)
