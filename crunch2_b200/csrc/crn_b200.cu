@@ -29,6 +29,7 @@ struct crn_gpu_ctx {
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
     void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
+    crn::VqWorkspace vq_ws;              // slab of the vector quantiser
     int transcode_smem_set;
 };
 
@@ -75,7 +76,7 @@ template <int D>
 int vq_clusterize(crn_gpu_ctx* ctx, const uint8_t* d_vecs, const uint32_t* d_wts, uint32_t n, uint32_t max_size, uint32_t retrieve, int threaded,
                   uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
 {
-    crn::VqBuilder<D> builder(ctx->stream, &ctx->launches);
+    crn::VqBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws);
     crn::VqResult res;
     const cudaError_t ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res);
     if (ce != cudaSuccess) return set_err(ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "crn_gpu_vq_clusterize", ce);
@@ -168,7 +169,7 @@ int qdxt_upload_csr(crn_gpu_qdxt* q)
 template <int D>
 int qdxt_vq(crn_gpu_qdxt* q, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res)
 {
-    crn::VqBuilder<D> builder(q->ctx->stream, &q->ctx->launches);
+    crn::VqBuilder<D> builder(q->ctx->stream, &q->ctx->launches, &q->ctx->vq_ws);
     const cudaError_t ce = builder.build(q->d_vecs, q->d_wts, d_ids, n, max_size, threaded, res);
     if (ce != cudaSuccess) return set_err(q->ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
     return CRN_GPU_OK;
@@ -338,6 +339,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_state) cudaFree(ctx->d_state);
     if (ctx->d_files) cudaFree(ctx->d_files);
+    if (ctx->vq_ws.base) cudaFree(ctx->vq_ws.base);
     if (ctx->d_cluster_ws) cudaFree(ctx->d_cluster_ws);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

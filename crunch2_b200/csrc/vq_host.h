@@ -10,6 +10,7 @@
 // device.  retrieve_clusters() (:301-332) is the pruning walk over the recorded split ranks.
 #pragma once
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 #include "vq_kernels.cuh"
 
@@ -138,10 +139,11 @@ struct VqResult {                    // host-side outcome of one build
     }
 };
 
+struct VqWorkspace { void* base = nullptr; size_t cap = 0; };     // device slab reused across builds
+
 template <int D> class VqBuilder {
 public:
-    explicit VqBuilder(cudaStream_t stream, uint64_t* launch_counter) : stream_(stream), launches_(launch_counter) {}
-    ~VqBuilder() { release(); }
+    VqBuilder(cudaStream_t stream, uint64_t* launch_counter, VqWorkspace* ws) : stream_(stream), launches_(launch_counter), ws_(ws) {}
 
     // d_vecs: u8[][D], d_wts: u32[] (device), indexed by vector id.  d_ids: the n ids to quantise in ascending order
     // (nullptr = 0..n-1).  threaded: crnlib::threaded_clusterizer<V>::create_clusters (crn_threaded_clusterizer.h:70-174):
@@ -159,7 +161,11 @@ public:
         launch_fill_identity(d_ids, n);
         cudaMemsetAsync(d_acc_, 0, sizeof(unsigned long long) * (D + 2), stream_);
         CRN_LAUNCH(vq_root_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, d_perm_[0], n, d_acc_); count();
-        CRN_LAUNCH(vq_root_finish_kernel<D>, 1, 32, 0, stream_, vecs_, wts_, d_perm_[0], d_acc_, nodes_, n, (threaded && max_size >= 128) ? 1 : 0); count();
+        CRN_LAUNCH(vq_root_prepare_kernel<D>, 1, 32, 0, stream_, d_acc_, d_slots_, n); count();
+        cudaMemsetAsync(d_side_, 0, n, stream_);
+        cudaMemsetAsync(d_big_count_, 0, sizeof(unsigned) * kBigLists, stream_);
+        float_sums(d_perm_[0], 1, 2, 0);
+        CRN_LAUNCH(vq_root_finish_kernel<D>, 1, 32, 0, stream_, d_acc_, d_slots_, nodes_, n, (threaded && max_size >= 128) ? 1 : 0); count();
         const unsigned first_free_node = 1;
         cudaMemcpyAsync(d_node_counter_, &first_free_node, sizeof(unsigned), cudaMemcpyHostToDevice, stream_);
         float root_var = 0;
@@ -224,13 +230,15 @@ public:
 private:
     cudaStream_t stream_;
     uint64_t* launches_;
+    VqWorkspace* ws_;
     uint32_t n_ = 0, cap_n_ = 0, cap_slots_ = 0;
     const uint8_t* vecs_ = nullptr;
     const uint32_t* wts_ = nullptr;
     int cur_ = 0;
     unsigned* d_perm_[2] = {nullptr, nullptr};
     unsigned *d_pos_slot_ = nullptr, *d_flags_ = nullptr, *d_scan_ = nullptr, *d_block_sums_ = nullptr, *d_slot_node_ = nullptr, *d_slot_starts_ = nullptr;
-    unsigned *d_node_counter_ = nullptr, *d_active_ = nullptr;
+    unsigned *d_node_counter_ = nullptr, *d_active_ = nullptr, *d_big_count_ = nullptr, *d_big_list_ = nullptr;
+    static constexpr int kBigLists = 10;     // one per pass of a round: 8 Lloyd iterations, the projection, the covariance
     int* d_slot_states_ = nullptr;
     uint8_t* d_side_ = nullptr;
     unsigned long long* d_acc_ = nullptr;
@@ -242,34 +250,47 @@ private:
     static unsigned grid(unsigned n) { return (n + 255) / 256; }
     void count() { if (launches_) ++*launches_; }
 
-    template <typename T> cudaError_t dev_alloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
-    void release()
-    {
-        void* ptrs[] = {d_perm_[0], d_perm_[1], d_pos_slot_, d_flags_, d_scan_, d_block_sums_, d_slot_node_, d_slot_starts_, d_node_counter_, d_active_, d_slot_states_,
-                        d_side_, d_acc_, d_slots_, d_results_, nodes_.begin, nodes_.count, nodes_.left, nodes_.flags, nodes_.variance, nodes_.weight, nodes_.centroid};
-        for (void* p : ptrs) if (p) cudaFree(p);
-        d_perm_[0] = d_perm_[1] = nullptr; d_pos_slot_ = d_flags_ = d_scan_ = d_block_sums_ = d_slot_node_ = d_slot_starts_ = d_node_counter_ = d_active_ = nullptr;
-        d_slot_states_ = nullptr; d_side_ = nullptr; d_acc_ = nullptr; d_slots_ = nullptr; d_results_ = nullptr; nodes_ = VqNodes();
-        cap_n_ = cap_slots_ = 0;
-    }
+    // every device array is carved from one slab the caller keeps between builds (no cudaMalloc / cudaFree per build)
     cudaError_t allocate(uint32_t n, uint32_t max_size)
     {
         const uint32_t slots = std::max<uint32_t>(4u, std::min<uint32_t>(n / 2 + 4, max_size + 4));
-        if (n <= cap_n_ && slots <= cap_slots_) return cudaSuccess;
-        release();
         const size_t node_cap = (size_t)2 * n + 16;
-        cudaError_t ce;
-#define VQ_ALLOC(p, cnt) if ((ce = dev_alloc(&(p), (cnt))) != cudaSuccess) return ce
-        VQ_ALLOC(d_perm_[0], n); VQ_ALLOC(d_perm_[1], n); VQ_ALLOC(d_pos_slot_, n); VQ_ALLOC(d_flags_, (size_t)n + 1); VQ_ALLOC(d_scan_, (size_t)n + 1);
-        VQ_ALLOC(d_block_sums_, (size_t)n / 1024 + 2); VQ_ALLOC(d_slot_node_, slots); VQ_ALLOC(d_slot_starts_, slots); VQ_ALLOC(d_node_counter_, 1); VQ_ALLOC(d_active_, 1);
-        VQ_ALLOC(d_slot_states_, slots); VQ_ALLOC(d_side_, n); VQ_ALLOC(d_acc_, D + 2); VQ_ALLOC(d_slots_, slots); VQ_ALLOC(d_results_, slots);
-        VQ_ALLOC(nodes_.begin, node_cap); VQ_ALLOC(nodes_.count, node_cap); VQ_ALLOC(nodes_.left, node_cap); VQ_ALLOC(nodes_.flags, node_cap);
-        VQ_ALLOC(nodes_.variance, node_cap); VQ_ALLOC(nodes_.weight, node_cap); VQ_ALLOC(nodes_.centroid, node_cap * D);
-#undef VQ_ALLOC
+        for (int pass = 0; pass < 2; pass++) {
+            size_t off = 0;
+            uint8_t* base = pass ? static_cast<uint8_t*>(ws_->base) : nullptr;
+            auto carve = [&](auto*& p, size_t cnt) {
+                using T = std::remove_pointer_t<std::remove_reference_t<decltype(p)>>;
+                if (pass) p = reinterpret_cast<T*>(base + off);
+                off += (cnt * sizeof(T) + 255) & ~(size_t)255;
+            };
+            carve(d_perm_[0], n); carve(d_perm_[1], n); carve(d_pos_slot_, n); carve(d_flags_, (size_t)n + 1); carve(d_scan_, (size_t)n + 1);
+            carve(d_block_sums_, (size_t)n / 1024 + 2); carve(d_slot_node_, slots); carve(d_slot_starts_, slots); carve(d_node_counter_, 1); carve(d_active_, 1);
+            carve(d_big_count_, kBigLists); carve(d_big_list_, (size_t)kBigLists * slots);
+            carve(d_slot_states_, slots); carve(d_side_, n); carve(d_acc_, D + 2); carve(d_slots_, slots); carve(d_results_, slots);
+            carve(nodes_.begin, node_cap); carve(nodes_.count, node_cap); carve(nodes_.left, node_cap); carve(nodes_.flags, node_cap);
+            carve(nodes_.variance, node_cap); carve(nodes_.weight, node_cap); carve(nodes_.centroid, node_cap * D);
+            if (!pass && off > ws_->cap) {
+                if (ws_->base) cudaFree(ws_->base);
+                ws_->base = nullptr; ws_->cap = 0;
+                const cudaError_t ce = cudaMalloc(&ws_->base, off);
+                if (ce != cudaSuccess) return ce;
+                ws_->cap = off;
+            }
+        }
         cap_n_ = n; cap_slots_ = slots;
         return cudaSuccess;
     }
     void launch_fill_identity(const uint32_t* d_ids, uint32_t n);
+
+    // float centroid sums of the slots of one pass (see vq_float_sums_kernel); `list` selects this pass's big-slot list
+    void float_sums(const unsigned* perm, unsigned F, int phase, int list)
+    {
+        unsigned* cnt = d_big_count_ + list;
+        unsigned* lst = d_big_list_ + (size_t)list * cap_slots_;
+        CRN_LAUNCH(vq_float_sums_kernel<D>, (F + 255) / 256, 256, 0, stream_, d_slots_, F, phase, cnt, lst); count();
+        CRN_LAUNCH((vq_stream_kernel<D, 0>), stream_grid(F), kVqStreamThreads, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, cnt, lst); count();
+    }
+    static unsigned stream_grid(unsigned F) { return F < 128u ? F : 128u; }
 
     // exclusive scan of d_flags_[0..m) into d_scan_
     void scan(uint32_t m)
@@ -296,10 +317,12 @@ private:
         CRN_LAUNCH(vq_init_slots_kernel<D>, gs, 128, 0, stream_, d_slot_node_, nodes_, d_slots_, d_slot_starts_, F, presplit ? 1 : 0); count();
         CRN_LAUNCH(vq_pos_slot_kernel<D>, grid(n), 256, 0, stream_, d_slot_starts_, d_slots_, F, d_pos_slot_, n); count();
         const unsigned gw = (F + kVqSeqWarps - 1) / kVqSeqWarps;
-        CRN_LAUNCH(vq_covariance_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_slots_, F); count();
+        cudaMemsetAsync(d_big_count_, 0, sizeof(unsigned) * kBigLists, stream_);
+        CRN_LAUNCH(vq_covariance_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_slots_, F, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
+        CRN_LAUNCH((vq_stream_kernel<D, 1>), stream_grid(F), kVqStreamThreads, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
         CRN_LAUNCH(vq_axis_kernel<D>, gs, 128, 0, stream_, d_slots_, F, presplit ? 1 : 0); count();
         CRN_LAUNCH(vq_project_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n, presplit ? 1 : 0); count();
-        CRN_LAUNCH(vq_float_sums_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, F, 0); count();
+        float_sums(perm, F, 0, 8);
         if (presplit) {
             CRN_LAUNCH(vq_presplit_children_kernel<D>, gs, 128, 0, stream_, d_slots_, F, presplit == 1 ? 1 : 0); count();
         } else {
@@ -309,7 +332,7 @@ private:
             CRN_LAUNCH(vq_estimate_finish_kernel<D>, gs, 128, 0, stream_, vecs_, perm, d_slots_, F); count();
             for (int it = 0; it < 8; it++) {
                 CRN_LAUNCH(vq_assign_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n); count();
-                CRN_LAUNCH(vq_float_sums_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, F, 1); count();
+                float_sums(perm, F, 1, it);
                 CRN_LAUNCH(vq_update_kernel<D>, gs, 128, 0, stream_, d_slots_, F, d_active_); count();
             }
         }

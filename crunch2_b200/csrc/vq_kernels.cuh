@@ -94,49 +94,32 @@ template <int D> __device__ __forceinline__ float vq_variance(const float* fs1, 
     return (float)((double)tt - (double)(dot / (float)w));
 }
 
-constexpr int kVqSeqWarps = 4;                // warps per CTA of the sequential (member order) kernels
+constexpr int kVqSeqWarps = 4;                // warps per CTA of the warp-per-slot kernels
+constexpr unsigned kVqCovBig = 256;           // slots with more members stream through vq_stream_kernel
+constexpr int kVqStreamThreads = 256;         // = members per tile
 
-// Sequential float accumulation of sum w*v over members [begin, begin+count) in order, one lane per (side, component):
-// lane = side * D + d.  `side` may be nullptr (everything on side 0).  tile_p / tile_s are this warp's staging rows.
-template <int D>
-__device__ __forceinline__ float vq_seq_side_sum(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
-                                                 const uint8_t* __restrict__ side, unsigned begin, unsigned count, float (*tile_p)[D], uint8_t* tile_s)
+__device__ __forceinline__ void vq_big_append(unsigned* __restrict__ big_count, unsigned* __restrict__ big_list, unsigned slot)
 {
-    const unsigned lane = lane_id();
-    const unsigned my_side = lane / D, my_d = lane % D;
-    float acc = 0.0f;
-    for (unsigned base = 0; base < count; base += 32) {
-        const unsigned m = base + lane;
-        if (m < count) {
-            const unsigned id = perm[begin + m];
-            const float w = (float)wts[id];
-            tile_s[lane] = side ? side[begin + m] : (uint8_t)0;
-#pragma unroll
-            for (int d = 0; d < D; d++) tile_p[lane][d] = (float)vecs[(size_t)id * D + d] * w;
-        }
-        __syncwarp();
-        const unsigned cnt = count - base < 32u ? count - base : 32u;
-        if (lane < 2 * D)
-            for (unsigned j = 0; j < cnt; j++)
-                if (tile_s[j] == my_side) acc += tile_p[j][my_d];
-        __syncwarp();
-    }
-    return acc;
+    big_list[atomicAdd(big_count, 1u)] = slot;
 }
 
 // K1: covariance sums in the reference's order and precision (compute_split_pca, crn_clusterizer.h:496-508;
-// threaded_clusterizer::compute_pca, crn_threaded_clusterizer.h:252-266).  One warp per slot.
+// threaded_clusterizer::compute_pca, crn_threaded_clusterizer.h:252-266).  One warp per slot, one lane per matrix
+// entry (several for D = 16); slots with more than kVqCovBig members are handed to vq_stream_kernel<D, 1>.
 template <int D>
 __global__ void __launch_bounds__(kVqSeqWarps * 32) vq_covariance_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
-                                                                        VqSlot<D>* __restrict__ slots, unsigned nslots)
+                                                                        VqSlot<D>* __restrict__ slots, unsigned nslots,
+                                                                        unsigned* __restrict__ big_count, unsigned* __restrict__ big_list)
 {
     constexpr int P = D * (D + 1) / 2, PER = (P + 31) / 32;
-    __shared__ float dv[kVqSeqWarps][32][D], dw[kVqSeqWarps][32][D];
+    __shared__ float dv[kVqSeqWarps][32][D + 1], dw[kVqSeqWarps][32][D + 1];
     const unsigned wi = threadIdx.x >> 5, lane = lane_id();
     const unsigned s = blockIdx.x * kVqSeqWarps + wi;
     if (s >= nslots) return;
     VqSlot<D>& sl = slots[s];
     if (sl.mode != 0) return;
+    const unsigned begin = sl.begin, count = sl.count;
+    if (count > kVqCovBig) { if (lane == 0) vq_big_append(big_count, big_list, s); return; }
     int xa[PER], ya[PER];
     float acc[PER];
 #pragma unroll
@@ -148,7 +131,6 @@ __global__ void __launch_bounds__(kVqSeqWarps * 32) vq_covariance_kernel(const u
     float c[D];
 #pragma unroll
     for (int d = 0; d < D; d++) c[d] = sl.centroid[d];
-    const unsigned begin = sl.begin, count = sl.count;
     for (unsigned base = 0; base < count; base += 32) {
         const unsigned m = base + lane;
         if (m < count) {
@@ -170,25 +152,96 @@ __global__ void __launch_bounds__(kVqSeqWarps * 32) vq_covariance_kernel(const u
 }
 
 // Float centroid sums of every slot that is being split: (float) of the exact integer sum while that is below 2^24
-// (the reference's running float sum is exact there), else re-accumulated in member order.  One warp per slot.
-// phase 0: after the projection (mode 0 slots), phase 1: after a Lloyd assignment (state 0 slots).
+// (the reference's running float sum is exact there); slots beyond that are handed to vq_stream_kernel<D, 0>.
+// phase 0: after the projection (mode 0 slots), phase 1: after a Lloyd assignment (state 0 slots), 2: every slot.
 template <int D>
-__global__ void __launch_bounds__(kVqSeqWarps * 32) vq_float_sums_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
-                                                                        const uint8_t* __restrict__ side, VqSlot<D>* __restrict__ slots, unsigned nslots, int phase)
+__global__ void __launch_bounds__(256) vq_float_sums_kernel(VqSlot<D>* __restrict__ slots, unsigned nslots, int phase,
+                                                           unsigned* __restrict__ big_count, unsigned* __restrict__ big_list)
 {
-    __shared__ float tile_p[kVqSeqWarps][32][D];
-    __shared__ uint8_t tile_s[kVqSeqWarps][32];
-    const unsigned wi = threadIdx.x >> 5, lane = lane_id();
-    const unsigned s = blockIdx.x * kVqSeqWarps + wi;
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     VqSlot<D>& sl = slots[s];
-    if (phase == 0 ? sl.mode != 0 : sl.state != 0) return;
-    const bool mine = lane < 2 * D;
-    const unsigned long long exact = mine ? sl.s1[lane / D][lane % D] : 0ull;
-    const bool big = __any_sync(CRN_FULL_MASK, exact >= (1ull << 24));
-    float f = (float)(long long)exact;
-    if (big) f = vq_seq_side_sum<D>(vecs, wts, perm, side, sl.begin, sl.count, tile_p[wi], tile_s[wi]);
-    if (mine) sl.fs1[lane / D][lane % D] = f;
+    if (phase == 0 ? sl.mode != 0 : (phase == 1 ? sl.state != 0 : false)) return;
+    bool big = false;
+    for (int sd = 0; sd < 2; sd++)
+        for (int d = 0; d < D; d++) {
+            const unsigned long long e = sl.s1[sd][d];
+            big |= e >= (1ull << 24);
+            sl.fs1[sd][d] = (float)(long long)e;
+        }
+    if (big) vq_big_append(big_count, big_list, s);
+}
+
+// Member-order float accumulation for the few large slots: one CTA per slot streams the members through shared
+// memory (tile t+1 gathered while tile t is consumed) and one thread per accumulator adds them up in order.
+// MODE 0: fs1[side][d] += w * v[d]           (2D accumulators; the product is an exact small integer)
+// MODE 1: covar[x][y] += (v-c)[x] * ((v-c)[y] * w)
+template <int D, int MODE>
+__global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                                    const uint8_t* __restrict__ side, VqSlot<D>* __restrict__ slots,
+                                                                    const unsigned* __restrict__ big_count, const unsigned* __restrict__ big_list)
+{
+    constexpr int T = kVqStreamThreads, R = D + 1, P = D * (D + 1) / 2;
+    constexpr int NACC = MODE == 0 ? 2 * D : P;
+    __shared__ float rec[2][T][R];
+    const unsigned tid = threadIdx.x;
+    const unsigned nbig = *big_count;
+    for (unsigned e = blockIdx.x; e < nbig; e += gridDim.x) {
+        VqSlot<D>& sl = slots[big_list[e]];
+        const unsigned begin = sl.begin, count = sl.count, tiles = (count + T - 1) / T;
+        float c[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) c[d] = MODE == 1 ? sl.centroid[d] : 0.0f;
+        int xa = 0, ya = 0;
+        if (MODE == 1 && tid < (unsigned)P) { int rem = (int)tid, x = 0; while (rem >= D - x) { rem -= D - x; x++; } xa = x; ya = x + rem; }
+        const unsigned my_side = tid / D, my_d = tid % D;
+        float acc = 0.0f;
+        // software pipeline: id of tile t+2, data of tile t+1
+        unsigned id1 = 0, id2 = 0;
+        uint8_t vb[D]; unsigned wv = 0, sv = 0;
+        auto load_id = [&](unsigned t) -> unsigned { const unsigned m = t * T + tid; return m < count ? perm[begin + m] : 0u; };
+        auto load_data = [&](unsigned t, unsigned id) {
+            const unsigned m = t * T + tid;
+            if (m < count) {
+                wv = wts[id];
+                sv = (MODE == 0 && side) ? side[begin + m] : 0u;
+#pragma unroll
+                for (int d = 0; d < D; d++) vb[d] = vecs[(size_t)id * D + d];
+            }
+        };
+        auto store_data = [&](unsigned buf) {
+            const float w = (float)wv;
+#pragma unroll
+            for (int d = 0; d < D; d++) rec[buf][tid][d] = MODE == 0 ? (float)vb[d] * w : (float)vb[d] - c[d];
+            rec[buf][tid][D] = MODE == 0 ? __uint_as_float(sv) : w;
+        };
+        load_data(0, load_id(0));
+        store_data(0);
+        if (tiles > 1) id1 = load_id(1);
+        __syncthreads();
+        for (unsigned t = 0; t < tiles; t++) {
+            if (t + 1 < tiles) load_data(t + 1, id1);
+            if (t + 2 < tiles) id2 = load_id(t + 2);
+            const unsigned cnt = count - t * T < (unsigned)T ? count - t * T : (unsigned)T;
+            const float (*rb)[R] = rec[t & 1];
+            if (tid < (unsigned)NACC) {
+                if (MODE == 0) {
+#pragma unroll 8
+                    for (unsigned j = 0; j < cnt; j++)
+                        if (__float_as_uint(rb[j][D]) == my_side) acc += rb[j][my_d];
+                } else {
+#pragma unroll 8
+                    for (unsigned j = 0; j < cnt; j++) acc = acc + rb[j][xa] * (rb[j][ya] * rb[j][D]);
+                }
+            }
+            if (t + 1 < tiles) store_data((t + 1) & 1);
+            __syncthreads();
+            id1 = id2;
+        }
+        if (tid < (unsigned)NACC) {
+            if (MODE == 0) sl.fs1[my_side][my_d] = acc; else sl.covar[tid] = acc;
+        }
+    }
 }
 
 // K2: covariance -> principal axis by power iteration (compute_split_pca, crn_clusterizer.h:510-579; presplit:
@@ -575,24 +628,22 @@ __global__ void vq_export_kernel(const VqSlot<D>* __restrict__ slots, unsigned n
     out[s] = r;
 }
 
-// the root node: centroid, weight and variance from the sums of vq_root_kernel (generate_codebook, :77-93; with
-// presplit the root is threaded_clusterizer::compute_pca's node, whose centroid is scaled by a double reciprocal).
-// One warp; re-accumulates in float when a sum passed 2^24.
+// The root goes through the same float-sum machinery as a one-sided pseudo slot (slot 0, every member on side 0).
 template <int D>
-__global__ void __launch_bounds__(32) vq_root_finish_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
-                                                           const unsigned long long* __restrict__ acc, VqNodes nodes, unsigned n, int presplit)
+__global__ void vq_root_prepare_kernel(const unsigned long long* __restrict__ acc, VqSlot<D>* __restrict__ slots, unsigned n)
 {
-    __shared__ float tile_p[32][D];
-    __shared__ uint8_t tile_s[32];
-    __shared__ float fs[D];
-    const unsigned lane = lane_id();
-    const unsigned long long exact = lane < D ? acc[lane] : 0ull;
-    const bool big = __any_sync(CRN_FULL_MASK, exact >= (1ull << 24));
-    float f = (float)(long long)exact;
-    if (big) f = vq_seq_side_sum<D>(vecs, wts, perm, nullptr, 0u, n, tile_p, tile_s);
-    if (lane < D) fs[lane] = f;
-    __syncwarp();
-    if (lane) return;
+    if (threadIdx.x || blockIdx.x) return;
+    VqSlot<D>& sl = slots[0];
+    for (int d = 0; d < D; d++) { sl.s1[0][d] = acc[d]; sl.s1[1][d] = 0; sl.fs1[0][d] = 0; sl.fs1[1][d] = 0; }
+    sl.begin = 0; sl.count = n; sl.mode = 0; sl.state = 0; sl.node = 0;
+}
+// the root node: centroid, weight and variance (generate_codebook, :77-93; with presplit the root is
+// threaded_clusterizer::compute_pca's node, whose centroid is scaled by a double reciprocal)
+template <int D>
+__global__ void vq_root_finish_kernel(const unsigned long long* __restrict__ acc, const VqSlot<D>* __restrict__ slots, VqNodes nodes, unsigned n, int presplit)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const float* fs = slots[0].fs1[0];
     const unsigned long long W = acc[D];
     nodes.begin[0] = 0; nodes.count[0] = n; nodes.left[0] = -1; nodes.flags[0] = 0; nodes.weight[0] = W;
     nodes.variance[0] = W ? vq_variance<D>(fs, W, acc[D + 1]) : 0.0f;
