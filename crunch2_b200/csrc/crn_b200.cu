@@ -13,9 +13,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include <new>
 #include <vector>
 #include <algorithm>
+#ifdef __CUDACC__
+#include <thread>
+#endif
 
 struct crn_gpu_ctx {
     int device;
@@ -110,6 +114,17 @@ struct crn_qdxt_element {
     crn::VqResult endpoint_tree;
     uint32_t max_selector_clusters;
     uint32_t endpoint_clusters, selector_clusters;
+    // every element is an independent chain of short, latency-bound kernels with host decisions in between, so each
+    // one gets its own stream + scratch (a private crn_gpu_ctx) and its own host thread
+    crn_gpu_ctx* ctx;
+    uint8_t* d_vecs;                  // n_blocks x 16: training / selector vectors
+    uint32_t* d_wts;
+    uint8_t* d_cat;
+    uint32_t *d_offsets, *d_members, *d_ids;
+    unsigned long long* d_keys;       // per-block dxt_fast selector keys + the distinct-count table
+    std::vector<uint32_t> cluster_of, offsets, members;
+    std::vector<uint8_t> cat;
+    int rc;
 };
 
 struct crn_gpu_qdxt {
@@ -119,92 +134,132 @@ struct crn_gpu_qdxt {
     crn_gpu_pack_params params;
     std::vector<crn_gpu_mip_desc> mips;
     crn_qdxt_element el[3];
-    // device
     uint32_t* d_blocks;               // n_blocks x 16 RGBA8
-    uint8_t* d_vecs;                  // n_blocks x 16: training / selector vectors
-    uint32_t* d_wts;
-    uint8_t* d_cat;
-    uint32_t *d_offsets, *d_members, *d_ids;
     uint8_t* d_out;                   // n_blocks x bytes_per_block
-    unsigned long long* d_keys;       // per-block dxt_fast selector keys; reused as the distinct-count table
-    std::vector<uint32_t> cluster_of, offsets, members;
-    std::vector<uint8_t> cat;
 };
 
 namespace {
 
 void qdxt_release(crn_gpu_qdxt* q)
 {
-    void* ptrs[] = {q->d_blocks, q->d_vecs, q->d_wts, q->d_cat, q->d_offsets, q->d_members, q->d_ids, q->d_out, q->d_keys};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (uint32_t i = 0; i < q->num_elements; i++) {
+        crn_qdxt_element& e = q->el[i];
+        void* ptrs[] = {e.d_vecs, e.d_wts, e.d_cat, e.d_offsets, e.d_members, e.d_ids, e.d_keys};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        if (e.ctx) crn_gpu_destroy(e.ctx);
+    }
+    if (q->d_blocks) cudaFree(q->d_blocks);
+    if (q->d_out) cudaFree(q->d_out);
     delete q;
 }
 
-// cluster_of over `ids` (nullptr = all blocks) -> CSR appended to q->offsets / q->members; members ascending
-void qdxt_append_csr(crn_gpu_qdxt* q, const uint32_t* ids, uint32_t n, uint32_t n_clusters)
+// cluster_of over `ids` (nullptr = all blocks) -> CSR appended to e.offsets / e.members; members ascending
+void qdxt_append_csr(crn_qdxt_element& e, const uint32_t* ids, uint32_t n, uint32_t n_clusters)
 {
-    const size_t first_cluster = q->offsets.size() - 1, base = q->members.size();
+    const size_t first_cluster = e.offsets.size() - 1, base = e.members.size();
     std::vector<uint32_t> cnt(n_clusters + 1, 0u);
-    for (uint32_t i = 0; i < n; i++) cnt[q->cluster_of[ids ? ids[i] : i] + 1]++;
+    for (uint32_t i = 0; i < n; i++) cnt[e.cluster_of[ids ? ids[i] : i] + 1]++;
     for (uint32_t k = 0; k < n_clusters; k++) cnt[k + 1] += cnt[k];
-    q->members.resize(base + n);
-    q->offsets.resize(first_cluster + n_clusters + 1);
-    for (uint32_t k = 0; k < n_clusters; k++) q->offsets[first_cluster + k + 1] = (uint32_t)(base + cnt[k + 1]);
+    e.members.resize(base + n);
+    e.offsets.resize(first_cluster + n_clusters + 1);
+    for (uint32_t k = 0; k < n_clusters; k++) e.offsets[first_cluster + k + 1] = (uint32_t)(base + cnt[k + 1]);
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t b = ids ? ids[i] : i;
-        q->members[base + cnt[q->cluster_of[b]]++] = b;
+        e.members[base + cnt[e.cluster_of[b]]++] = b;
     }
 }
 
-int qdxt_upload_csr(crn_gpu_qdxt* q)
+int qdxt_upload_csr(crn_qdxt_element& e)
 {
-    crn_gpu_ctx* ctx = q->ctx;
-    CRN_CUDA(ctx, cudaMemcpyAsync(q->d_offsets, q->offsets.data(), q->offsets.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (!q->members.empty())
-        CRN_CUDA(ctx, cudaMemcpyAsync(q->d_members, q->members.data(), q->members.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    crn_gpu_ctx* ctx = e.ctx;
+    CRN_CUDA(ctx, cudaMemcpyAsync(e.d_offsets, e.offsets.data(), e.offsets.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!e.members.empty())
+        CRN_CUDA(ctx, cudaMemcpyAsync(e.d_members, e.members.data(), e.members.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // the host vectors are reused right away
     return CRN_GPU_OK;
 }
 
 template <int D>
-int qdxt_vq(crn_gpu_qdxt* q, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res)
+int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res)
 {
-    crn::VqBuilder<D> builder(q->ctx->stream, &q->ctx->launches, &q->ctx->vq_ws);
-    const cudaError_t ce = builder.build(q->d_vecs, q->d_wts, d_ids, n, max_size, threaded, res);
-    if (ce != cudaSuccess) return set_err(q->ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
+    crn::VqBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws);
+    const cudaError_t ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res);
+    if (ce != cudaSuccess) return set_err(e.ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
     return CRN_GPU_OK;
 }
+
+// runs fn(element) for every element, one host thread each (the SIMT-emulation test build is single threaded)
+template <typename F>
+int qdxt_for_each_element(crn_gpu_qdxt* q, F fn)
+{
+#ifdef __CUDACC__
+    std::vector<std::thread> threads;
+    for (uint32_t i = 1; i < q->num_elements; i++)
+        threads.emplace_back([q, i, &fn]() { cudaSetDevice(q->ctx->device); q->el[i].rc = fn(q->el[i]); });
+    q->el[0].rc = fn(q->el[0]);
+    for (std::thread& t : threads) t.join();
+#else
+    for (uint32_t i = 0; i < q->num_elements; i++) q->el[i].rc = fn(q->el[i]);
+#endif
+    for (uint32_t i = 0; i < q->num_elements; i++) {
+        crn_qdxt_element& e = q->el[i];
+        q->ctx->launches += e.ctx->launches; e.ctx->launches = 0;
+        if (e.rc) { snprintf(q->ctx->err, sizeof(q->ctx->err), "%s", e.ctx->err); return e.rc; }
+    }
+    return CRN_GPU_OK;
+}
+
+// CRN_B200_TRACE=1: wall-clock per phase (synchronising), for tuning only
+struct QdxtTrace {
+    bool on; crn_gpu_ctx* ctx; double t0;
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit QdxtTrace(crn_gpu_ctx* c) : on(getenv("CRN_B200_TRACE") != nullptr), ctx(c), t0(0) { if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); } }
+    void mark(const char* what, int el)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double t = now();
+        fprintf(stderr, "[crn_b200] element %d %-28s %8.2f ms  (launches so far %llu)\n", el, what, t - t0, (unsigned long long)ctx->launches);
+        t0 = t;
+    }
+};
 
 // qdxt1::init / qdxt5::init for one element
 int qdxt_init_element(crn_gpu_qdxt* q, crn_qdxt_element& e)
 {
-    crn_gpu_ctx* ctx = q->ctx;
+    crn_gpu_ctx* ctx = e.ctx;
     const uint32_t n = q->n_blocks;
     crn::QdxtMipTable mt;
     if (!build_mip_table(q->mips.data(), (uint32_t)q->mips.size(), n, mt)) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "clustered DDS: bad level table");
+    QdxtTrace tr(ctx);
+    const int eli = (int)(&e - q->el);
     const int threads = crn::kQdxtWarpsPerCta * 32;
     const int grid = grid_for(ctx, mt.total_chunks, crn::kQdxtWarpsPerCta, 8);
     if (e.kind == 0)
-        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, q->d_blocks, mt, 3u, q->d_vecs, q->d_wts, (uint8_t*)nullptr, q->d_keys);
+        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, q->d_blocks, mt, 3u, e.d_vecs, e.d_wts, (uint8_t*)nullptr, e.d_keys);
     else
-        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, q->d_blocks, mt, e.comp, q->d_vecs, q->d_wts, (uint8_t*)nullptr, q->d_keys);
+        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, q->d_blocks, mt, e.comp, e.d_vecs, e.d_wts, (uint8_t*)nullptr, e.d_keys);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     // distinct dxt_fast selector patterns (crn_qdxt1.cpp:415-438, crn_qdxt5.cpp:395-421)
     uint32_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
-    unsigned long long* table = q->d_keys + n;
+    unsigned long long* table = e.d_keys + n;
     unsigned* counter = reinterpret_cast<unsigned*>(table + cap);
     CRN_CUDA(ctx, cudaMemsetAsync(table, 0xff, sizeof(unsigned long long) * cap, ctx->stream));
     CRN_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
-    CRN_LAUNCH(crn::count_distinct_kernel, (n + 255) / 256, 256, 0, ctx->stream, q->d_keys, n, table, cap - 1, counter);
+    CRN_LAUNCH(crn::count_distinct_kernel, (n + 255) / 256, 256, 0, ctx->stream, e.d_keys, n, table, cap - 1, counter);
     ctx->launches++;
     unsigned distinct = 0;
     CRN_CUDA(ctx, cudaMemcpyAsync(&distinct, counter, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     e.max_selector_clusters = distinct + 128;
+    tr.mark("init: tile analysis + distinct", eli);
     // endpoint codebook: generate_codebook(65535) (crn_qdxt1.cpp:405-413, crn_qdxt5.cpp:386-393)
-    return e.kind == 0 ? qdxt_vq<6>(q, nullptr, n, 65535u, false, e.endpoint_tree) : qdxt_vq<2>(q, nullptr, n, 65535u, false, e.endpoint_tree);
+    const int rc = e.kind == 0 ? qdxt_vq<6>(e, nullptr, n, 65535u, false, e.endpoint_tree) : qdxt_vq<2>(e, nullptr, n, 65535u, false, e.endpoint_tree);
+    if (tr.on) fprintf(stderr, "[crn_b200] endpoint tree: %u rounds, %u device splits\n", e.endpoint_tree.rounds, e.endpoint_tree.device_splits);
+    tr.mark("init: endpoint tree", eli);
+    return rc;
 }
 
 uint32_t clampu(uint32_t v, uint32_t lo, uint32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }   // math::clamp
@@ -212,7 +267,7 @@ uint32_t clampu(uint32_t v, uint32_t lo, uint32_t hi) { return v < lo ? lo : (v 
 // qdxt1::pack (crn_qdxt1.cpp:910-1030) / qdxt5::pack (crn_qdxt5.cpp:838-960) for one element
 int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_level)
 {
-    crn_gpu_ctx* ctx = q->ctx;
+    crn_gpu_ctx* ctx = e.ctx;
     const uint32_t n = q->n_blocks, stride = q->bytes_per_block;
     const float quality = quality_level / 255.0f;
     const uint32_t codebook = e.endpoint_tree.codebook_size();
@@ -226,66 +281,73 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
         max_endpoint_clusters = clampu((uint32_t)(codebook * eq), 16u, codebook);
         max_selector_clusters = clampu((uint32_t)(e.max_selector_clusters * sq), 32u, e.max_selector_clusters);
     }
+    QdxtTrace tr(ctx);
+    const int eli = (int)(&e - q->el);
     crn_gpu_pack_params pp = q->params;
     if (e.kind == 0) pp.use_both_block_types = e.use_alpha_blocks ? 1u : 0u;      // qdxt5 keeps pack_params' flag (crn_qdxt5.cpp:468)
     // endpoint clusters
-    q->cluster_of.resize(n);
+    e.cluster_of.resize(n);
     uint32_t k_end;
-    if (quality >= 1.0f) { for (uint32_t i = 0; i < n; i++) q->cluster_of[i] = i; k_end = n; }
-    else k_end = e.endpoint_tree.retrieve(max_endpoint_clusters, q->cluster_of.data());
+    if (quality >= 1.0f) { for (uint32_t i = 0; i < n; i++) e.cluster_of[i] = i; k_end = n; }
+    else k_end = e.endpoint_tree.retrieve(max_endpoint_clusters, e.cluster_of.data());
     e.endpoint_clusters = k_end;
-    q->offsets.assign(1, 0u); q->members.clear();
-    qdxt_append_csr(q, nullptr, n, k_end);
-    int rc = qdxt_upload_csr(q);
+    e.offsets.assign(1, 0u); e.members.clear();
+    qdxt_append_csr(e, nullptr, n, k_end);
+    int rc = qdxt_upload_csr(e);
     if (rc) return rc;
+    tr.mark("pack: retrieve + CSR", eli);
     if (e.kind == 0)
-        rc = crn_gpu_dxt1_optimize_clusters(ctx, &pp, e.use_alpha_blocks, q->d_blocks, n, q->d_offsets, q->d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
+        rc = crn_gpu_dxt1_optimize_clusters(ctx, &pp, e.use_alpha_blocks, q->d_blocks, n, e.d_offsets, e.d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
     else
-        rc = crn_gpu_dxt5_optimize_clusters(ctx, &pp, e.comp, q->d_blocks, n, q->d_offsets, q->d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
+        rc = crn_gpu_dxt5_optimize_clusters(ctx, &pp, e.comp, q->d_blocks, n, e.d_offsets, e.d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
     if (rc) return rc;
+    tr.mark("pack: endpoint optimisation", eli);
     e.selector_clusters = 0;
     if (quality >= 1.0f) return CRN_GPU_OK;
     // selector training vectors
     if (e.kind == 0)
-        CRN_LAUNCH(crn::selector_vectors_kernel<0>, (n + 255) / 256, 256, 0, ctx->stream, q->d_out, stride, e.offset, n, pp.perceptual ? 1 : 0, q->d_vecs, q->d_wts, (uint8_t*)nullptr);
+        CRN_LAUNCH(crn::selector_vectors_kernel<0>, (n + 255) / 256, 256, 0, ctx->stream, q->d_out, stride, e.offset, n, pp.perceptual ? 1 : 0, e.d_vecs, e.d_wts, (uint8_t*)nullptr);
     else
-        CRN_LAUNCH(crn::selector_vectors_kernel<1>, (n + 255) / 256, 256, 0, ctx->stream, q->d_out, stride, e.offset, n, 0, q->d_vecs, q->d_wts, q->d_cat);
+        CRN_LAUNCH(crn::selector_vectors_kernel<1>, (n + 255) / 256, 256, 0, ctx->stream, q->d_out, stride, e.offset, n, 0, e.d_vecs, e.d_wts, e.d_cat);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
-    q->offsets.assign(1, 0u); q->members.clear();
+    e.offsets.assign(1, 0u); e.members.clear();
     crn::VqResult sel_tree;
     if (e.kind == 0) {
-        rc = qdxt_vq<16>(q, nullptr, n, max_selector_clusters, true, sel_tree);
+        rc = qdxt_vq<16>(e, nullptr, n, max_selector_clusters, true, sel_tree);
         if (rc) return rc;
-        const uint32_t k = sel_tree.retrieve(0, q->cluster_of.data());
-        qdxt_append_csr(q, nullptr, n, k);
+        const uint32_t k = sel_tree.retrieve(0, e.cluster_of.data());
+        qdxt_append_csr(e, nullptr, n, k);
     } else {
-        q->cat.resize(n);
-        CRN_CUDA(ctx, cudaMemcpyAsync(q->cat.data(), q->d_cat, n, cudaMemcpyDeviceToHost, ctx->stream));
+        e.cat.resize(n);
+        CRN_CUDA(ctx, cudaMemcpyAsync(e.cat.data(), e.d_cat, n, cudaMemcpyDeviceToHost, ctx->stream));
         CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::vector<uint32_t> ids;
         for (uint32_t type = 0; type < 2; type++) {                 // crn_qdxt5.cpp:762-833
             ids.clear();
-            for (uint32_t b = 0; b < n; b++) if (q->cat[b] == type) ids.push_back(b);
+            for (uint32_t b = 0; b < n; b++) if (e.cat[b] == type) ids.push_back(b);
             const uint32_t m = (uint32_t)ids.size();
             if (!m) continue;
             if ((m / (float)n) < .01f) continue;
             uint32_t max_clusters = (uint32_t)(((uint64_t)m * max_selector_clusters + (n - 1)) / n);
             max_clusters = std::min(std::max(64u, max_clusters), m);
             if (max_clusters >= m) continue;
-            CRN_CUDA(ctx, cudaMemcpyAsync(q->d_ids, ids.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-            rc = qdxt_vq<16>(q, q->d_ids, m, max_clusters, true, sel_tree);
+            CRN_CUDA(ctx, cudaMemcpyAsync(e.d_ids, ids.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+            rc = qdxt_vq<16>(e, e.d_ids, m, max_clusters, true, sel_tree);
             if (rc) return rc;
-            const uint32_t k = sel_tree.retrieve(0, q->cluster_of.data());
-            qdxt_append_csr(q, ids.data(), m, k);
+            const uint32_t k = sel_tree.retrieve(0, e.cluster_of.data());
+            qdxt_append_csr(e, ids.data(), m, k);
         }
     }
-    const uint32_t k_sel = (uint32_t)q->offsets.size() - 1;
+    const uint32_t k_sel = (uint32_t)e.offsets.size() - 1;
     e.selector_clusters = k_sel;
+    tr.mark("pack: selector VQ", eli);
     if (!k_sel) return CRN_GPU_OK;
-    rc = qdxt_upload_csr(q);
+    rc = qdxt_upload_csr(e);
     if (rc) return rc;
-    return crn_gpu_optimize_selectors(ctx, (uint32_t)e.kind, &pp, e.comp, q->d_blocks, n, q->d_offsets, q->d_members, k_sel, q->d_out, stride, e.offset);
+    rc = crn_gpu_optimize_selectors(ctx, (uint32_t)e.kind, &pp, e.comp, q->d_blocks, n, e.d_offsets, e.d_members, k_sel, q->d_out, stride, e.offset);
+    tr.mark("pack: selector re-vote", eli);
+    return rc;
 }
 
 }  // namespace
@@ -319,7 +381,7 @@ int crn_gpu_create(int device, crn_gpu_ctx** out_ctx)
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return CRN_GPU_ERR_NO_DEVICE;
     crn_gpu_ctx* ctx = new (std::nothrow) crn_gpu_ctx();
     if (!ctx) return CRN_GPU_ERR_NO_MEMORY;
-    memset(ctx, 0, sizeof(*ctx));
+    memset(static_cast<void*>(ctx), 0, sizeof(*ctx));
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CRN_GPU_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
@@ -647,14 +709,15 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     q->ctx = ctx; q->format = format; q->params = *params; q->num_levels = num_levels;
     q->bytes_per_block = crn_gpu_bytes_per_block(format);
     q->pow_mul = format == CRN_GPU_FMT_DXT5 ? .75f : 1.0f;           // crn_mipmapped_texture.cpp:2529-2539
-    q->d_blocks = nullptr; q->d_vecs = nullptr; q->d_wts = nullptr; q->d_cat = nullptr; q->d_offsets = q->d_members = q->d_ids = nullptr;
-    q->d_out = nullptr; q->d_keys = nullptr;
+    q->d_blocks = nullptr; q->d_out = nullptr; q->num_elements = 0;
     // element table (crn_mipmapped_texture.cpp:2319-2366)
     uint32_t ne = 0;
     auto add = [&](int kind, uint32_t comp, uint32_t offset, int use_alpha) {
         crn_qdxt_element& e = q->el[ne++];
         e.kind = kind; e.comp = comp; e.offset = offset; e.use_alpha_blocks = use_alpha;
         e.max_selector_clusters = 0; e.endpoint_clusters = e.selector_clusters = 0;
+        e.ctx = nullptr; e.d_vecs = nullptr; e.d_wts = nullptr; e.d_cat = nullptr; e.d_offsets = e.d_members = e.d_ids = nullptr; e.d_keys = nullptr; e.rc = 0;
+        q->num_elements = ne;
     };
     switch (format) {
     case CRN_GPU_FMT_DXT1: add(0, 3, 0, params->use_both_block_types ? 1 : 0); break;
@@ -686,14 +749,18 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
         if (ce_ != cudaSuccess) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: cudaMalloc", ce_); } \
     } while (0)
     QDXT_ALLOC(q->d_blocks, (size_t)n * 64);
-    QDXT_ALLOC(q->d_vecs, (size_t)n * 16);
-    QDXT_ALLOC(q->d_wts, (size_t)n * 4);
-    QDXT_ALLOC(q->d_cat, (size_t)n);
-    QDXT_ALLOC(q->d_offsets, ((size_t)n + 1) * 4);
-    QDXT_ALLOC(q->d_members, (size_t)n * 4);
-    QDXT_ALLOC(q->d_ids, (size_t)n * 4);
     QDXT_ALLOC(q->d_out, (size_t)n * q->bytes_per_block);
-    QDXT_ALLOC(q->d_keys, ((size_t)n + cap + 2) * 8);
+    for (uint32_t i = 0; i < ne; i++) {
+        crn_qdxt_element& e = q->el[i];
+        if (crn_gpu_create(ctx->device, &e.ctx) != CRN_GPU_OK) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: element stream"); }
+        QDXT_ALLOC(e.d_vecs, (size_t)n * 16);
+        QDXT_ALLOC(e.d_wts, (size_t)n * 4);
+        QDXT_ALLOC(e.d_cat, (size_t)n);
+        QDXT_ALLOC(e.d_offsets, ((size_t)n + 1) * 4);
+        QDXT_ALLOC(e.d_members, (size_t)n * 4);
+        QDXT_ALLOC(e.d_ids, (size_t)n * 4);
+        QDXT_ALLOC(e.d_keys, ((size_t)n + cap + 2) * 8);
+    }
 #undef QDXT_ALLOC
     // pixel blocks of every level (crn_mipmapped_texture.cpp:2419-2472)
     int rc = CRN_GPU_OK;
@@ -717,7 +784,8 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
             if (ce != cudaSuccess) rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: blockify", ce);
         }
     }
-    for (uint32_t i = 0; i < ne && !rc; i++) rc = qdxt_init_element(q, q->el[i]);
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: blockify");
+    if (!rc) rc = qdxt_for_each_element(q, [q](crn_qdxt_element& e) { return qdxt_init_element(q, e); });
     if (rc) { qdxt_release(q); return rc; }
     *out = q;
     return CRN_GPU_OK;
@@ -736,10 +804,12 @@ int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int ds
     crn_gpu_ctx* ctx = q->ctx;
     if (quality_level > 255 || !dst) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_pack: bad argument");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (uint32_t i = 0; i < q->num_elements; i++) {
-        const int rc = qdxt_pack_element(q, q->el[i], quality_level);
-        if (rc) return rc;
-    }
+    const int rc = qdxt_for_each_element(q, [q, quality_level](crn_qdxt_element& e) {
+        const int r = qdxt_pack_element(q, e, quality_level);
+        if (!r && cudaStreamSynchronize(e.ctx->stream) != cudaSuccess) return set_err(e.ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_pack: element stream");
+        return r;
+    });
+    if (rc) return rc;
     CRN_CUDA(ctx, cudaMemcpyAsync(dst, q->d_out, (size_t)q->n_blocks * q->bytes_per_block, dst_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;

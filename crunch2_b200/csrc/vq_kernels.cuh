@@ -225,13 +225,49 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
             const unsigned cnt = count - t * T < (unsigned)T ? count - t * T : (unsigned)T;
             const float (*rb)[R] = rec[t & 1];
             if (tid < (unsigned)NACC) {
+                // batches of 8 members: all shared-memory reads first, then the products, then the ordered adds, so
+                // that only the 4-cycle FADD chain is serial (ptxas does not software-pipeline this loop by itself)
+                unsigned j = 0;
                 if (MODE == 0) {
-#pragma unroll 8
-                    for (unsigned j = 0; j < cnt; j++)
-                        if (__float_as_uint(rb[j][D]) == my_side) acc += rb[j][my_d];
+                    float v[8]; unsigned sd[8];
+                    if (cnt >= 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { sd[u] = __float_as_uint(rb[u][D]); v[u] = rb[u][my_d]; }
+#pragma unroll 2
+                        for (; j + 16 <= cnt; j += 8) {
+                            float v2[8]; unsigned sd2[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { sd2[u] = __float_as_uint(rb[j + 8 + u][D]); v2[u] = rb[j + 8 + u][my_d]; }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) acc += sd[u] == my_side ? v[u] : 0.0f;      // x + 0.0f == x
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { sd[u] = sd2[u]; v[u] = v2[u]; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc += sd[u] == my_side ? v[u] : 0.0f;
+                        j += 8;
+                    }
+                    for (; j < cnt; j++) acc += __float_as_uint(rb[j][D]) == my_side ? rb[j][my_d] : 0.0f;
                 } else {
-#pragma unroll 8
-                    for (unsigned j = 0; j < cnt; j++) acc = acc + rb[j][xa] * (rb[j][ya] * rb[j][D]);
+                    float a[8];
+                    if (cnt >= 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) a[u] = rb[u][xa] * (rb[u][ya] * rb[u][D]);
+#pragma unroll 2
+                        for (; j + 16 <= cnt; j += 8) {
+                            float a2[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) a2[u] = rb[j + 8 + u][xa] * (rb[j + 8 + u][ya] * rb[j + 8 + u][D]);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) acc = acc + a[u];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) a[u] = a2[u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc = acc + a[u];
+                        j += 8;
+                    }
+                    for (; j < cnt; j++) acc = acc + rb[j][xa] * (rb[j][ya] * rb[j][D]);
                 }
             }
             if (t + 1 < tiles) store_data((t + 1) & 1);
