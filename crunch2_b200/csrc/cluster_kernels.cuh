@@ -33,7 +33,8 @@ struct ClusterWorkspace {              // global scratch, all sized by the numbe
     int4* cw; int4* ce;                // 1 per pixel each
     uint8_t* sel;                      // 1 per pixel
 };
-constexpr size_t kClusterWorkspaceBytesPerPixel = 2 * sizeof(ClusterHashEntry) + 4 + 16 + 16 + 1;
+// + first-appearance flags and their scan (4 + 4 per pixel)
+constexpr size_t kClusterWorkspaceBytesPerPixel = 2 * sizeof(ClusterHashEntry) + 4 + 16 + 16 + 1 + 8;
 
 constexpr int kClusterWarpsPerCta = 4;
 
@@ -42,11 +43,80 @@ __device__ __forceinline__ uint32_t cluster_pixel(const uint32_t* __restrict__ b
     return blocks[(size_t)members[i >> 4] * 16 + (i & 15)];
 }
 
+// cluster that owns member position m: last c with offsets[c] <= m
+__device__ __forceinline__ uint32_t cluster_of_member(const uint32_t* __restrict__ offsets, uint32_t n_clusters, uint32_t m)
+{
+    uint32_t lo = 0, hi = n_clusters;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= m) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// The unique-colour extraction (crn_dxt1.cpp:2113-2131) is data parallel over ALL member pixels of ALL clusters:
+//   insert  (thread per pixel)      hash table of the pixel's cluster: key, earliest index, count
+//   mark    (thread per table slot) mark[first index] = slot + 1
+//   scan    (vq_scan_* kernels)     rank of every first appearance
+//   compact (thread per pixel)      unique colour u of the cluster = colour whose first appearance has rank u
+// so that the per-cluster warp below only runs the optimiser over the U unique colours.
+__global__ void __launch_bounds__(256)
+cluster_hash_insert_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets, const uint32_t* __restrict__ cluster_blocks,
+                           uint32_t n_clusters, uint32_t total_pixels, int dxt1a, uint32_t alpha_threshold, ClusterWorkspace ws, uint32_t* __restrict__ transparent)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_pixels) return;
+    const uint32_t m = g >> 4, c = cluster_of_member(cluster_offsets, n_clusters, m);
+    const uint32_t P = cluster_offsets[c] * 16, N = (cluster_offsets[c + 1] - cluster_offsets[c]) * 16, i = g - P;
+    const uint32_t px = blocks[(size_t)cluster_blocks[m] * 16 + (g & 15)];
+    if (dxt1a && (px >> 24) < alpha_threshold) { atomicAdd(&transparent[c], 1u); return; }     // crn_qdxt1.cpp:625-656
+    ClusterHashEntry* tab = ws.hash + 2 * (size_t)P;
+    const uint32_t cap = 2 * N, key = px | 0xFF000000u;
+    uint32_t h = (key * 2654435761u) % cap;
+    for (;;) {
+        const uint32_t old = atomicCAS(&tab[h].key, 0u, key);
+        if (old == 0u || old == key) break;
+        h = h + 1 == cap ? 0 : h + 1;
+    }
+    atomicMax(&tab[h].first_inv, ~i);
+    atomicAdd(&tab[h].count, 1u);
+}
+
+__global__ void __launch_bounds__(256)
+cluster_mark_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, uint32_t total_pixels, ClusterWorkspace ws)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= 2 * total_pixels) return;
+    const ClusterHashEntry e = ws.hash[s];
+    if (!e.key) return;
+    const uint32_t c = cluster_of_member(cluster_offsets, n_clusters, s >> 5), P = cluster_offsets[c] * 16;
+    ws.mark[P + ~e.first_inv] = s - 2 * P + 1;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_first_flags_kernel(const uint32_t* __restrict__ mark, uint32_t* __restrict__ flags, uint32_t total_pixels)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= total_pixels) flags[g] = (g < total_pixels && mark[g]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_compact_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, uint32_t total_pixels, ClusterWorkspace ws, const uint32_t* __restrict__ rank)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_pixels) return;
+    const uint32_t v = ws.mark[g];
+    if (!v) return;
+    const uint32_t c = cluster_of_member(cluster_offsets, n_clusters, g >> 4), P = cluster_offsets[c] * 16;
+    const uint32_t u = rank[g] - rank[P];
+    ClusterHashEntry& e = ws.hash[2 * (size_t)P + v - 1];
+    e.uidx = u;
+    ws.cw[P + u] = make_int4((int)(e.key & 0xff), (int)((e.key >> 8) & 0xff), (int)((e.key >> 16) & 0xff), (int)e.count);
+}
+
+struct ClusterResult { uint32_t endpoints; uint32_t flags; };      // flags: bit 0 invert, bit 1 alpha_block, bits 2-3 stage
+
 __global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
-dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
-                              const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
-                              ClusterWorkspace ws, unsigned int* __restrict__ next_cluster,
-                              uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs,
+dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
+                              ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
+                              unsigned int* __restrict__ next_cluster, ClusterResult* __restrict__ results,
                               uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error)
 {
     __shared__ Dxt1ClusterScratch scratch[kClusterWarpsPerCta];
@@ -58,56 +128,13 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
         c = __shfl_sync(CRN_FULL_MASK, c, 0);
         if (c >= n_clusters) break;
         const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
-        const uint32_t* members = cluster_blocks + b0;
         const uint32_t N = nb * 16, P = b0 * 16;
         if (!nb) continue;
-        // ---- pixels_have_alpha as qdxt1 computes it (crn_qdxt1.cpp:625-656)
-        int pha = 0;
-        if (dxt1a) {
-            bool any = false;
-            for (uint32_t i = lane; i < N; i += 32) any = any || (cluster_pixel(blocks, members, i) >> 24) < prm.alpha_threshold;
-            pha = __any_sync(CRN_FULL_MASK, any);
-        }
-        // ---- unique colours + weights (crn_dxt1.cpp:2113-2131) via an atomics-built hash table
-        ClusterHashEntry* tab = ws.hash + 2 * (size_t)P;
-        const uint32_t cap = 2 * N;
-        uint32_t* mark = ws.mark + P;
-        unsigned opaque_cnt = 0;
-        for (uint32_t i = lane; i < N; i += 32) {
-            const uint32_t px = cluster_pixel(blocks, members, i);
-            if (pha && (px >> 24) < prm.alpha_threshold) continue;
-            opaque_cnt++;
-            const uint32_t key = px | 0xFF000000u;
-            uint32_t h = (key * 2654435761u) % cap;
-            for (;;) {
-                const uint32_t old = atomicCAS(&tab[h].key, 0u, key);
-                if (old == 0u || old == key) break;
-                h = h + 1 == cap ? 0 : h + 1;
-            }
-            atomicMax(&tab[h].first_inv, ~i);
-            atomicAdd(&tab[h].count, 1u);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) opaque_cnt += __shfl_xor_sync(CRN_FULL_MASK, opaque_cnt, ofs);
-        for (uint32_t s = lane; s < cap; s += 32)
-            if (tab[s].key) mark[~tab[s].first_inv] = s + 1;
-        __syncwarp();
+        const uint32_t ntransp = dxt1a ? transparent[c] : 0u;
+        const int pha = ntransp != 0;                       // pixels_have_alpha as qdxt1 computes it
+        const unsigned opaque_cnt = N - ntransp;
+        const int U = (int)(rank[P + N] - rank[P]);
         if (lane == 0) { sc->cw = ws.cw + P; sc->ce = ws.ce + P; sc->sel = ws.sel + P; }
-        __syncwarp();
-        int U = 0;
-        for (uint32_t base = 0; base < N; base += 32) {
-            const uint32_t i = base + lane;
-            const uint32_t v = i < N ? mark[i] : 0u;
-            const unsigned m = __ballot_sync(CRN_FULL_MASK, v != 0);
-            if (v) {
-                const int u = U + __popc(m & lanemask_lt());
-                ClusterHashEntry& e = tab[v - 1];
-                e.uidx = (uint32_t)u;
-                sc->cw[u] = make_int4((int)(e.key & 0xff), (int)((e.key >> 8) & 0xff), (int)((e.key >> 16) & 0xff), (int)e.count);
-            }
-            U += __popc(m);
-        }
         __syncwarp();
         // ---- the optimiser proper: same phases as the 4x4 block kernels, fused
         dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, pha, U));
@@ -129,33 +156,49 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
             out_lo = invert ? sc->best.hi : sc->best.lo; out_hi = invert ? sc->best.lo : sc->best.hi;
         }
         if (lane == 0) {
+            results[c].endpoints = out_lo | (out_hi << 16);
+            results[c].flags = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2);
             if (out_endpoints) out_endpoints[c] = out_lo | (out_hi << 16);
             if (out_error) out_error[c] = stage == 2 ? 0ull : sc->best.err;
         }
-        // two member blocks per iteration: lanes 0-15 / 16-31
-        for (uint32_t base = 0; base < N; base += 32) {
-            const uint32_t i = base + lane;
-            unsigned s = 3;
-            if (i < N && stage != 2) {
-                const uint32_t px = cluster_pixel(blocks, members, i);
-                if (!(pha && (px >> 24) < prm.alpha_threshold)) {
-                    const uint32_t key = px | 0xFF000000u;
-                    uint32_t h = (key * 2654435761u) % cap;
-                    while (tab[h].key != key) h = h + 1 == cap ? 0 : h + 1;
-                    s = sc->sel[tab[h].uidx];
-                    if (invert) s = alpha_block ? (s < 2 ? s ^ 1 : s) : (s ^ 1);
-                }
-            }
-            unsigned bits = s << (2 * (lane & 15));
-#pragma unroll
-            for (int ofs = 8; ofs > 0; ofs >>= 1) bits |= __shfl_xor_sync(CRN_FULL_MASK, bits, ofs);
-            if ((lane & 15) == 0 && i < N) {
-                const unsigned long long elem = (unsigned long long)out_lo | ((unsigned long long)out_hi << 16) | ((unsigned long long)bits << 32);
-                *reinterpret_cast<unsigned long long*>(out + (size_t)members[i >> 4] * out_stride + out_ofs) = elem;
-            }
-        }
         __syncwarp();
     }
+}
+
+// selectors of every member pixel from its unique colour's selector; 16 lanes per member block
+__global__ void __launch_bounds__(256)
+cluster_write_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets, const uint32_t* __restrict__ cluster_blocks,
+                     uint32_t n_clusters, uint32_t total_pixels, int dxt1a, uint32_t alpha_threshold, ClusterWorkspace ws, const uint32_t* __restrict__ transparent,
+                     const ClusterResult* __restrict__ results, uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = lane_id();
+    unsigned s = 3;
+    uint32_t endpoints = 0, block = 0;
+    if (g < total_pixels) {
+        const uint32_t m = g >> 4, c = cluster_of_member(cluster_offsets, n_clusters, m);
+        const uint32_t P = cluster_offsets[c] * 16, N = (cluster_offsets[c + 1] - cluster_offsets[c]) * 16;
+        const ClusterResult r = results[c];
+        const int stage = (int)(r.flags >> 2), invert = r.flags & 1, alpha_block = (r.flags >> 1) & 1;
+        const int pha = dxt1a && transparent[c] != 0;
+        endpoints = r.endpoints; block = cluster_blocks[m];
+        if (stage != 2) {
+            const uint32_t px = blocks[(size_t)block * 16 + (g & 15)];
+            if (!(pha && (px >> 24) < alpha_threshold)) {
+                const ClusterHashEntry* tab = ws.hash + 2 * (size_t)P;
+                const uint32_t cap = 2 * N, key = px | 0xFF000000u;
+                uint32_t h = (key * 2654435761u) % cap;
+                while (tab[h].key != key) h = h + 1 == cap ? 0 : h + 1;
+                s = ws.sel[P + tab[h].uidx];
+                if (invert) s = alpha_block ? (s < 2 ? s ^ 1 : s) : (s ^ 1);
+            }
+        }
+    }
+    unsigned bits = s << (2 * (lane & 15));
+#pragma unroll
+    for (int ofs = 8; ofs > 0; ofs >>= 1) bits |= __shfl_xor_sync(CRN_FULL_MASK, bits, ofs);
+    if ((lane & 15) == 0 && g < total_pixels)
+        *reinterpret_cast<unsigned long long*>(out + (size_t)block * out_stride + out_ofs) = (unsigned long long)endpoints | ((unsigned long long)bits << 32);
 }
 
 // ---- DXT5A clusters (qdxt5::pack_endpoints_task, crn_qdxt5.cpp:452-576 -> dxt5_endpoint_optimizer) -----

@@ -562,7 +562,8 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     if (!n_clusters || !total_member_blocks) return CRN_GPU_OK;
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t P = (size_t)total_member_blocks * 16;
-    const size_t need = P * crn::kClusterWorkspaceBytesPerPixel + 1024;
+    const size_t nb_scan = (P + 1 + 1023) / 1024;
+    const size_t need = P * crn::kClusterWorkspaceBytesPerPixel + (size_t)n_clusters * 12 + nb_scan * 4 + 4096;
     int rc = ensure(ctx, &ctx->d_cluster_ws, &ctx->d_cluster_ws_cap, need);
     if (rc) return rc;
     uint8_t* base = static_cast<uint8_t*>(ctx->d_cluster_ws);
@@ -572,10 +573,16 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     ws.cw = reinterpret_cast<int4*>(base + o); o += P * 16;
     ws.ce = reinterpret_cast<int4*>(base + o); o += P * 16;
     ws.mark = reinterpret_cast<uint32_t*>(base + o); o += P * 4;
+    uint32_t* flags = reinterpret_cast<uint32_t*>(base + o); o += (P + 2) * 4;
+    uint32_t* rank = reinterpret_cast<uint32_t*>(base + o); o += (P + 2) * 4;
+    uint32_t* block_sums = reinterpret_cast<uint32_t*>(base + o); o += (nb_scan + 2) * 4;
+    uint32_t* transparent = reinterpret_cast<uint32_t*>(base + o); o += (size_t)n_clusters * 4;
+    crn::ClusterResult* results = reinterpret_cast<crn::ClusterResult*>(base + o); o += (size_t)n_clusters * 8;
     ws.sel = base + o;
     // hash keys / first / count and the first-appearance marks must start at zero
     CRN_CUDA(ctx, cudaMemsetAsync(base, 0, 256 + P * 2 * sizeof(crn::ClusterHashEntry), ctx->stream));
     CRN_CUDA(ctx, cudaMemsetAsync(ws.mark, 0, P * 4, ctx->stream));
+    CRN_CUDA(ctx, cudaMemsetAsync(transparent, 0, (size_t)n_clusters * 4, ctx->stream));
     crn::Dxt1Params dp;
     dp.quality = (int)params->dxt_quality;
     dp.perceptual = params->perceptual ? 1 : 0;
@@ -585,13 +592,31 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     dp.grayscale_sampling = params->grayscale_sampling ? 1 : 0;
     // qdxt1::pack (crn_qdxt1.cpp:920-923): without 3-colour blocks the alpha threshold is forced to 0
     dp.alpha_threshold = dp.use_alpha_blocks ? params->dxt1a_alpha_threshold : 0;
+    const int scan_alpha = (dxt1a && dp.use_alpha_blocks) ? 1 : 0;
+    const uint32_t* blocks = static_cast<const uint32_t*>(d_blocks_rgba);
+    const uint32_t TP = (uint32_t)P;
+    const unsigned gp = (TP + 255) / 256;
+    CRN_LAUNCH(crn::cluster_hash_insert_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent);
+    CRN_LAUNCH(crn::cluster_mark_kernel, (2 * TP + 255) / 256, 256, 0, ctx->stream, d_cluster_offsets, n_clusters, TP, ws);
+    CRN_LAUNCH(crn::cluster_first_flags_kernel, (TP + 1 + 255) / 256, 256, 0, ctx->stream, ws.mark, flags, TP);
+    {   // exclusive scan of the TP + 1 flags
+        const uint32_t m = TP + 1, nb = (m + 1023) / 1024;
+        CRN_LAUNCH(crn::vq_scan_block_kernel, nb, 256, 0, ctx->stream, flags, rank, block_sums, m);
+        ctx->launches++;
+        if (nb > 1) {
+            CRN_LAUNCH(crn::vq_scan_sums_kernel, 1, 256, 0, ctx->stream, block_sums, nb);
+            CRN_LAUNCH(crn::vq_scan_add_kernel, (m + 255) / 256, 256, 0, ctx->stream, rank, block_sums, m);
+            ctx->launches += 2;
+        }
+    }
+    CRN_LAUNCH(crn::cluster_compact_kernel, gp, 256, 0, ctx->stream, d_cluster_offsets, n_clusters, TP, ws, rank);
     const int threads = crn::kClusterWarpsPerCta * 32;
     const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, 4);
-    CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
-               d_cluster_blocks, n_clusters, dp, (dxt1a && dp.use_alpha_blocks) ? 1 : 0, ws, reinterpret_cast<unsigned int*>(base),
-               static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes, d_cluster_endpoints,
-               reinterpret_cast<unsigned long long*>(d_cluster_error));
-    ctx->launches++;
+    CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, d_cluster_offsets, n_clusters, dp, scan_alpha, ws, rank, transparent,
+               reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error));
+    CRN_LAUNCH(crn::cluster_write_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent,
+               results, static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes);
+    ctx->launches += 6;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
 }

@@ -155,6 +155,7 @@ public:
         cudaError_t ce = allocate(n, max_size);
         if (ce != cudaSuccess) return ce;
         n_ = n; vecs_ = d_vecs; wts_ = d_wts;
+        if (kSmemCov > 48 * 1024) cudaFuncSetAttribute(vq_stream_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov);
         std::vector<VqHostNode>& nodes = res.nodes;
 
         // root: identity order + statistics
@@ -238,6 +239,7 @@ private:
     unsigned* d_perm_[2] = {nullptr, nullptr};
     unsigned *d_pos_slot_ = nullptr, *d_flags_ = nullptr, *d_scan_ = nullptr, *d_block_sums_ = nullptr, *d_slot_node_ = nullptr, *d_slot_starts_ = nullptr;
     unsigned *d_node_counter_ = nullptr, *d_active_ = nullptr, *d_big_count_ = nullptr, *d_big_list_ = nullptr;
+    static constexpr size_t kSmemSum = VqStreamCfg<D, 0>::smem_bytes, kSmemCov = VqStreamCfg<D, 1>::smem_bytes;
     static constexpr int kBigLists = 10;     // one per pass of a round: 8 Lloyd iterations, the projection, the covariance
     int* d_slot_states_ = nullptr;
     uint8_t* d_side_ = nullptr;
@@ -288,7 +290,7 @@ private:
         unsigned* cnt = d_big_count_ + list;
         unsigned* lst = d_big_list_ + (size_t)list * cap_slots_;
         CRN_LAUNCH(vq_float_sums_kernel<D>, (F + 255) / 256, 256, 0, stream_, d_slots_, F, phase, cnt, lst); count();
-        CRN_LAUNCH((vq_stream_kernel<D, 0>), stream_grid(F), kVqStreamThreads, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, cnt, lst); count();
+        CRN_LAUNCH((vq_stream_kernel<D, 0>), stream_grid(F), kVqStreamThreads, kSmemSum, stream_, vecs_, wts_, perm, d_side_, d_slots_, cnt, lst); count();
     }
     static unsigned stream_grid(unsigned F) { return F < 128u ? F : 128u; }
 
@@ -319,7 +321,7 @@ private:
         const unsigned gw = (F + kVqSeqWarps - 1) / kVqSeqWarps;
         cudaMemsetAsync(d_big_count_, 0, sizeof(unsigned) * kBigLists, stream_);
         CRN_LAUNCH(vq_covariance_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_slots_, F, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
-        CRN_LAUNCH((vq_stream_kernel<D, 1>), stream_grid(F), kVqStreamThreads, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
+        CRN_LAUNCH((vq_stream_kernel<D, 1>), stream_grid(F), kVqStreamThreads, kSmemCov, stream_, vecs_, wts_, perm, d_side_, d_slots_, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
         CRN_LAUNCH(vq_axis_kernel<D>, gs, 128, 0, stream_, d_slots_, F, presplit ? 1 : 0); count();
         CRN_LAUNCH(vq_project_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n, presplit ? 1 : 0); count();
         float_sums(perm, F, 0, 8);

@@ -173,17 +173,29 @@ __global__ void __launch_bounds__(256) vq_float_sums_kernel(VqSlot<D>* __restric
 }
 
 // Member-order float accumulation for the few large slots: one CTA per slot streams the members through shared
-// memory (tile t+1 gathered while tile t is consumed) and one thread per accumulator adds them up in order.
-// MODE 0: fs1[side][d] += w * v[d]           (2D accumulators; the product is an exact small integer)
+// memory in tiles.  Per tile: (1) one thread per member stages its vector, (2) all threads expand the staged
+// members into one addend per (member, accumulator), (3) one thread per accumulator adds its column up in member
+// order -- the only serial part, a bare LDS + FADD chain.  The next tile's gathers are in flight meanwhile.
+// MODE 0: fs1[side][d] += w * v[d]           (2D accumulators; the addend is an exact small integer, or 0 for the other side)
 // MODE 1: covar[x][y] += (v-c)[x] * ((v-c)[y] * w)
+template <int D, int MODE> struct VqStreamCfg {
+    static constexpr int P = D * (D + 1) / 2;
+    static constexpr int NACC = MODE == 0 ? 2 * D : P;
+    static constexpr int T = D == 16 ? 128 : 256;            // members per tile
+    static constexpr int R = D + 1;                          // staged record: D floats + (side | weight)
+    static constexpr size_t smem_bytes = sizeof(float) * ((size_t)T * R + (size_t)T * NACC);
+};
+
 template <int D, int MODE>
 __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
                                                                     const uint8_t* __restrict__ side, VqSlot<D>* __restrict__ slots,
                                                                     const unsigned* __restrict__ big_count, const unsigned* __restrict__ big_list)
 {
-    constexpr int T = kVqStreamThreads, R = D + 1, P = D * (D + 1) / 2;
-    constexpr int NACC = MODE == 0 ? 2 * D : P;
-    __shared__ float rec[2][T][R];
+    using Cfg = VqStreamCfg<D, MODE>;
+    constexpr int T = Cfg::T, R = Cfg::R, P = Cfg::P, NACC = Cfg::NACC, NT = kVqStreamThreads;
+    CRN_DYN_SMEM(float, smem);
+    float (*st)[R] = reinterpret_cast<float (*)[R]>(smem);
+    float (*add)[NACC] = reinterpret_cast<float (*)[NACC]>(smem + T * R);
     const unsigned tid = threadIdx.x;
     const unsigned nbig = *big_count;
     for (unsigned e = blockIdx.x; e < nbig; e += gridDim.x) {
@@ -192,90 +204,73 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
         float c[D];
 #pragma unroll
         for (int d = 0; d < D; d++) c[d] = MODE == 1 ? sl.centroid[d] : 0.0f;
-        int xa = 0, ya = 0;
-        if (MODE == 1 && tid < (unsigned)P) { int rem = (int)tid, x = 0; while (rem >= D - x) { rem -= D - x; x++; } xa = x; ya = x + rem; }
-        const unsigned my_side = tid / D, my_d = tid % D;
         float acc = 0.0f;
-        // software pipeline: id of tile t+2, data of tile t+1
+        // software pipeline: id of tile t+2, data of tile t+1 in registers
         unsigned id1 = 0, id2 = 0;
         uint8_t vb[D]; unsigned wv = 0, sv = 0;
-        auto load_id = [&](unsigned t) -> unsigned { const unsigned m = t * T + tid; return m < count ? perm[begin + m] : 0u; };
+        auto load_id = [&](unsigned t) -> unsigned { const unsigned m = t * T + tid; return (tid < (unsigned)T && m < count) ? perm[begin + m] : 0u; };
         auto load_data = [&](unsigned t, unsigned id) {
             const unsigned m = t * T + tid;
-            if (m < count) {
+            if (tid < (unsigned)T && m < count) {
                 wv = wts[id];
                 sv = (MODE == 0 && side) ? side[begin + m] : 0u;
 #pragma unroll
                 for (int d = 0; d < D; d++) vb[d] = vecs[(size_t)id * D + d];
             }
         };
-        auto store_data = [&](unsigned buf) {
-            const float w = (float)wv;
-#pragma unroll
-            for (int d = 0; d < D; d++) rec[buf][tid][d] = MODE == 0 ? (float)vb[d] * w : (float)vb[d] - c[d];
-            rec[buf][tid][D] = MODE == 0 ? __uint_as_float(sv) : w;
-        };
         load_data(0, load_id(0));
-        store_data(0);
         if (tiles > 1) id1 = load_id(1);
-        __syncthreads();
         for (unsigned t = 0; t < tiles; t++) {
+            if (tid < (unsigned)T) {
+                const float w = (float)wv;
+#pragma unroll
+                for (int d = 0; d < D; d++) st[tid][d] = MODE == 0 ? (float)vb[d] * w : (float)vb[d] - c[d];
+                st[tid][D] = MODE == 0 ? __uint_as_float(sv) : w;
+            }
             if (t + 1 < tiles) load_data(t + 1, id1);
             if (t + 2 < tiles) id2 = load_id(t + 2);
+            __syncthreads();
             const unsigned cnt = count - t * T < (unsigned)T ? count - t * T : (unsigned)T;
-            const float (*rb)[R] = rec[t & 1];
-            if (tid < (unsigned)NACC) {
-                // batches of 8 members: all shared-memory reads first, then the products, then the ordered adds, so
-                // that only the 4-cycle FADD chain is serial (ptxas does not software-pipeline this loop by itself)
-                unsigned j = 0;
-                if (MODE == 0) {
-                    float v[8]; unsigned sd[8];
-                    if (cnt >= 8) {
-#pragma unroll
-                        for (int u = 0; u < 8; u++) { sd[u] = __float_as_uint(rb[u][D]); v[u] = rb[u][my_d]; }
-#pragma unroll 2
-                        for (; j + 16 <= cnt; j += 8) {
-                            float v2[8]; unsigned sd2[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) { sd2[u] = __float_as_uint(rb[j + 8 + u][D]); v2[u] = rb[j + 8 + u][my_d]; }
-#pragma unroll
-                            for (int u = 0; u < 8; u++) acc += sd[u] == my_side ? v[u] : 0.0f;      // x + 0.0f == x
-#pragma unroll
-                            for (int u = 0; u < 8; u++) { sd[u] = sd2[u]; v[u] = v2[u]; }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) acc += sd[u] == my_side ? v[u] : 0.0f;
-                        j += 8;
-                    }
-                    for (; j < cnt; j++) acc += __float_as_uint(rb[j][D]) == my_side ? rb[j][my_d] : 0.0f;
-                } else {
-                    float a[8];
-                    if (cnt >= 8) {
-#pragma unroll
-                        for (int u = 0; u < 8; u++) a[u] = rb[u][xa] * (rb[u][ya] * rb[u][D]);
-#pragma unroll 2
-                        for (; j + 16 <= cnt; j += 8) {
-                            float a2[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) a2[u] = rb[j + 8 + u][xa] * (rb[j + 8 + u][ya] * rb[j + 8 + u][D]);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) acc = acc + a[u];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) a[u] = a2[u];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) acc = acc + a[u];
-                        j += 8;
-                    }
-                    for (; j < cnt; j++) acc = acc + rb[j][xa] * (rb[j][ya] * rb[j][D]);
+            for (unsigned item = tid; item < cnt * NACC; item += NT) {
+                const unsigned j = item / NACC, a = item % NACC;
+                float v;
+                if (MODE == 0) v = __float_as_uint(st[j][D]) == a / D ? st[j][a % D] : 0.0f;
+                else {
+                    int rem = (int)a, x = 0;
+                    while (rem >= D - x) { rem -= D - x; x++; }
+                    v = st[j][x] * (st[j][x + rem] * st[j][D]);
                 }
+                add[j][a] = v;
             }
-            if (t + 1 < tiles) store_data((t + 1) & 1);
+            __syncthreads();
+            if (tid < (unsigned)NACC) {
+                // batches of 8: the loads of the next batch are issued before the ordered adds of this one
+                unsigned j = 0;
+                float a0[8];
+                if (cnt >= 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) a0[u] = add[u][tid];
+#pragma unroll 2
+                    for (; j + 16 <= cnt; j += 8) {
+                        float a1[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) a1[u] = add[j + 8 + u][tid];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc = acc + a0[u];         // x + 0.0f == x (MODE 0, other side)
+#pragma unroll
+                        for (int u = 0; u < 8; u++) a0[u] = a1[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc = acc + a0[u];
+                    j += 8;
+                }
+                for (; j < cnt; j++) acc = acc + add[j][tid];
+            }
             __syncthreads();
             id1 = id2;
         }
         if (tid < (unsigned)NACC) {
-            if (MODE == 0) sl.fs1[my_side][my_d] = acc; else sl.covar[tid] = acc;
+            if (MODE == 0) sl.fs1[tid / D][tid % D] = acc; else sl.covar[tid] = acc;
         }
     }
 }
