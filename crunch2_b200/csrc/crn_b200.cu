@@ -295,6 +295,14 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
     qdxt_append_csr(e, nullptr, n, k_end);
     int rc = qdxt_upload_csr(e);
     if (rc) return rc;
+    if (tr.on) {
+        std::vector<uint32_t> sz(k_end);
+        for (uint32_t k = 0; k < k_end; k++) sz[k] = e.offsets[k + 1] - e.offsets[k];
+        std::sort(sz.begin(), sz.end(), [](uint32_t a, uint32_t b) { return a > b; });
+        fprintf(stderr, "[crn_b200] element %d endpoint clusters %u, largest (blocks):", eli, k_end);
+        for (uint32_t k = 0; k < 8 && k < k_end; k++) fprintf(stderr, " %u", sz[k]);
+        fprintf(stderr, "  median %u\n", sz[k_end / 2]);
+    }
     tr.mark("pack: retrieve + CSR", eli);
     if (e.kind == 0)
         rc = crn_gpu_dxt1_optimize_clusters(ctx, &pp, e.use_alpha_blocks, q->d_blocks, n, e.d_offsets, e.d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);

@@ -239,6 +239,8 @@ private:
     unsigned* d_perm_[2] = {nullptr, nullptr};
     unsigned *d_pos_slot_ = nullptr, *d_flags_ = nullptr, *d_scan_ = nullptr, *d_block_sums_ = nullptr, *d_slot_node_ = nullptr, *d_slot_starts_ = nullptr;
     unsigned *d_node_counter_ = nullptr, *d_active_ = nullptr, *d_big_count_ = nullptr, *d_big_list_ = nullptr;
+    unsigned *d_chunk_start_ = nullptr, *d_overflow_count_ = nullptr, *d_overflow_list_ = nullptr, *d_table_ = nullptr, max_chunks_ = 0;
+    VqBigDir* d_dir_ = nullptr;
     static constexpr size_t kSmemSum = VqStreamCfg<D, 0>::smem_bytes, kSmemCov = VqStreamCfg<D, 1>::smem_bytes;
     static constexpr int kBigLists = 10;     // one per pass of a round: 8 Lloyd iterations, the projection, the covariance
     int* d_slot_states_ = nullptr;
@@ -268,6 +270,9 @@ private:
             carve(d_perm_[0], n); carve(d_perm_[1], n); carve(d_pos_slot_, n); carve(d_flags_, (size_t)n + 1); carve(d_scan_, (size_t)n + 1);
             carve(d_block_sums_, (size_t)n / 1024 + 2); carve(d_slot_node_, slots); carve(d_slot_starts_, slots); carve(d_node_counter_, 1); carve(d_active_, 1);
             carve(d_big_count_, kBigLists); carve(d_big_list_, (size_t)kBigLists * slots);
+            max_chunks_ = n / kVqChunk + kVqMaxBig;
+            carve(d_chunk_start_, kVqMaxBig + 1); carve(d_overflow_count_, kBigLists); carve(d_overflow_list_, slots); carve(d_dir_, kBigLists);
+            carve(d_table_, (size_t)max_chunks_ * (2 * D) * (kVqEMax + 1) * 2);
             carve(d_slot_states_, slots); carve(d_side_, n); carve(d_acc_, D + 2); carve(d_slots_, slots); carve(d_results_, slots);
             carve(nodes_.begin, node_cap); carve(nodes_.count, node_cap); carve(nodes_.left, node_cap); carve(nodes_.flags, node_cap);
             carve(nodes_.variance, node_cap); carve(nodes_.weight, node_cap); carve(nodes_.centroid, node_cap * D);
@@ -290,7 +295,13 @@ private:
         unsigned* cnt = d_big_count_ + list;
         unsigned* lst = d_big_list_ + (size_t)list * cap_slots_;
         CRN_LAUNCH(vq_float_sums_kernel<D>, (F + 255) / 256, 256, 0, stream_, d_slots_, F, phase, cnt, lst); count();
-        CRN_LAUNCH((vq_stream_kernel<D, 0>), stream_grid(F), kVqStreamThreads, kSmemSum, stream_, vecs_, wts_, perm, d_side_, d_slots_, cnt, lst); count();
+        // slots whose sums passed 2^24: chunk tables + ordered walk (a few slots that do not fit stream instead)
+        VqBigDir* dir = d_dir_ + list;
+        unsigned* ovc = d_overflow_count_ + list;
+        CRN_LAUNCH(vq_big_dir_kernel<D>, 1, 32, 0, stream_, cnt, lst, d_slots_, d_chunk_start_, dir, ovc, d_overflow_list_, max_chunks_); count();
+        CRN_LAUNCH(vq_chunk_sim_kernel<D>, (max_chunks_ + kVqSeqWarps - 1) / kVqSeqWarps, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, lst, d_chunk_start_, dir, d_table_); count();
+        CRN_LAUNCH(vq_chunk_apply_kernel<D>, (std::min<unsigned>(F, kVqMaxBig) + kVqSeqWarps - 1) / kVqSeqWarps, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_side_, d_slots_, lst, d_chunk_start_, dir, d_table_); count();
+        CRN_LAUNCH((vq_stream_kernel<D, 0>), stream_grid(F), kVqStreamThreads, kSmemSum, stream_, vecs_, wts_, perm, d_side_, d_slots_, ovc, d_overflow_list_); count();
     }
     static unsigned stream_grid(unsigned F) { return F < 128u ? F : 128u; }
 

@@ -182,8 +182,8 @@ template <int D, int MODE> struct VqStreamCfg {
     static constexpr int P = D * (D + 1) / 2;
     static constexpr int NACC = MODE == 0 ? 2 * D : P;
     static constexpr int T = D == 16 ? 128 : 256;            // members per tile
-    static constexpr int R = D + 1;                          // staged record: D floats + (side | weight)
-    static constexpr size_t smem_bytes = sizeof(float) * ((size_t)T * R + (size_t)T * NACC);
+    static constexpr int ROW = NACC | 1;                     // odd row length: conflict-free column writes
+    static constexpr size_t smem_bytes = sizeof(float) * (size_t)T * ROW;
 };
 
 template <int D, int MODE>
@@ -192,10 +192,9 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
                                                                     const unsigned* __restrict__ big_count, const unsigned* __restrict__ big_list)
 {
     using Cfg = VqStreamCfg<D, MODE>;
-    constexpr int T = Cfg::T, R = Cfg::R, P = Cfg::P, NACC = Cfg::NACC, NT = kVqStreamThreads;
+    constexpr int T = Cfg::T, ROW = Cfg::ROW, NACC = Cfg::NACC;
     CRN_DYN_SMEM(float, smem);
-    float (*st)[R] = reinterpret_cast<float (*)[R]>(smem);
-    float (*add)[NACC] = reinterpret_cast<float (*)[NACC]>(smem + T * R);
+    float (*add)[ROW] = reinterpret_cast<float (*)[ROW]>(smem);
     const unsigned tid = threadIdx.x;
     const unsigned nbig = *big_count;
     for (unsigned e = blockIdx.x; e < nbig; e += gridDim.x) {
@@ -208,6 +207,8 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
         // software pipeline: id of tile t+2, data of tile t+1 in registers
         unsigned id1 = 0, id2 = 0;
         uint8_t vb[D]; unsigned wv = 0, sv = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) vb[d] = 0;
         auto load_id = [&](unsigned t) -> unsigned { const unsigned m = t * T + tid; return (tid < (unsigned)T && m < count) ? perm[begin + m] : 0u; };
         auto load_data = [&](unsigned t, unsigned id) {
             const unsigned m = t * T + tid;
@@ -221,28 +222,31 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
         load_data(0, load_id(0));
         if (tiles > 1) id1 = load_id(1);
         for (unsigned t = 0; t < tiles; t++) {
+            // expand this thread's member into its row of addends (indices are compile-time constants)
             if (tid < (unsigned)T) {
                 const float w = (float)wv;
+                if (MODE == 0) {
 #pragma unroll
-                for (int d = 0; d < D; d++) st[tid][d] = MODE == 0 ? (float)vb[d] * w : (float)vb[d] - c[d];
-                st[tid][D] = MODE == 0 ? __uint_as_float(sv) : w;
+                    for (int d = 0; d < D; d++) {
+                        const float p = (float)vb[d] * w;
+                        add[tid][d] = sv == 0 ? p : 0.0f;
+                        add[tid][D + d] = sv == 1 ? p : 0.0f;
+                    }
+                } else {
+                    float dv[D];
+#pragma unroll
+                    for (int d = 0; d < D; d++) dv[d] = (float)vb[d] - c[d];
+                    int a = 0;
+#pragma unroll
+                    for (int x = 0; x < D; x++)
+#pragma unroll
+                        for (int y = x; y < D; y++, a++) add[tid][a] = dv[x] * (dv[y] * w);
+                }
             }
             if (t + 1 < tiles) load_data(t + 1, id1);
             if (t + 2 < tiles) id2 = load_id(t + 2);
             __syncthreads();
             const unsigned cnt = count - t * T < (unsigned)T ? count - t * T : (unsigned)T;
-            for (unsigned item = tid; item < cnt * NACC; item += NT) {
-                const unsigned j = item / NACC, a = item % NACC;
-                float v;
-                if (MODE == 0) v = __float_as_uint(st[j][D]) == a / D ? st[j][a % D] : 0.0f;
-                else {
-                    int rem = (int)a, x = 0;
-                    while (rem >= D - x) { rem -= D - x; x++; }
-                    v = st[j][x] * (st[j][x + rem] * st[j][D]);
-                }
-                add[j][a] = v;
-            }
-            __syncthreads();
             if (tid < (unsigned)NACC) {
                 // batches of 8: the loads of the next batch are issued before the ordered adds of this one
                 unsigned j = 0;
@@ -273,6 +277,209 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
             if (MODE == 0) sl.fs1[tid / D][tid % D] = acc; else sl.covar[tid] = acc;
         }
     }
+}
+
+// ---- exact parallel evaluation of a member-order FLOAT sum of non-negative integers ---------------------
+// acc <- RN(acc + x_i) for i = 0, 1, ... is sequential, but inside one binade [2^(23+e), 2^(24+e)) the running
+// value is a multiple of ulp = 2^e and a step only depends on the PARITY of acc / ulp (ties round to even):
+//     x = q * ulp + r;   acc/ulp <- acc/ulp + q + [r > ulp/2] + [r == ulp/2 and (acc/ulp + q) odd].
+// So for a chunk of 256 members the map acc -> acc' is "add delta[e][parity] * 2^e" as long as the chunk stays
+// inside binade e.  vq_chunk_sim_kernel tabulates delta for every plausible e and both parities, all chunks in
+// parallel; vq_chunk_apply_kernel then walks the chunks in order (one table lookup per chunk instead of 256 adds)
+// and re-runs the few chunks that cross a binade boundary step by step.  Everything is integer arithmetic, and
+// the result is bit-identical to the sequential float accumulation.
+constexpr int kVqChunk = 256;                 // members per chunk
+constexpr int kVqEMax = 16;                   // exponents 0..16: sums below 2^40
+constexpr unsigned kVqMaxBig = 1024;          // big slots per pass handled this way (the rest streams)
+
+struct VqBigDir {                             // written by vq_big_dir_kernel
+    unsigned nbig;                            // slots handled by the chunk kernels
+    unsigned nchunks;
+    unsigned noverflow;                       // slots left to vq_stream_kernel<D, 0>
+    unsigned pad;
+};
+
+__device__ __forceinline__ int vq_binade(unsigned long long y) { return y < (1ull << 24) ? 0 : 40 - __clzll((long long)y); }
+
+// RN(acc + x) for a float-representable integer acc
+__device__ __forceinline__ unsigned long long vq_fl_add(unsigned long long acc, unsigned x)
+{
+    const unsigned long long y = acc + x;
+    if (y < (1ull << 24)) return y;
+    const int e = 40 - __clzll((long long)y);
+    const unsigned long long ulp = 1ull << e, r = y & (ulp - 1), half = ulp >> 1;
+    unsigned long long y0 = y - r;
+    if (r > half || (r == half && ((y0 >> e) & 1))) y0 += ulp;
+    return y0;
+}
+
+// chunk directory: chunk_start[i] = first chunk of big slot i; slots beyond kVqMaxBig / max_chunks overflow
+template <int D>
+__global__ void vq_big_dir_kernel(const unsigned* __restrict__ big_count, unsigned* __restrict__ big_list, const VqSlot<D>* __restrict__ slots,
+                                  unsigned* __restrict__ chunk_start, VqBigDir* __restrict__ dir, unsigned* __restrict__ overflow_count,
+                                  unsigned* __restrict__ overflow_list, unsigned max_chunks)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const unsigned n = *big_count;
+    unsigned nb = 0, nc = 0, nov = 0;
+    for (unsigned i = 0; i < n; i++) {
+        const unsigned s = big_list[i];
+        const unsigned c = (slots[s].count + kVqChunk - 1) / kVqChunk;
+        if (nb < kVqMaxBig && nc + c <= max_chunks) { big_list[nb] = s; chunk_start[nb] = nc; nb++; nc += c; }
+        else overflow_list[nov++] = s;
+    }
+    chunk_start[nb] = nc;
+    dir->nbig = nb; dir->nchunks = nc; dir->noverflow = nov;
+    *overflow_count = nov;
+}
+
+// addends of 32 members: tile_x[j][d] = w * v[d] (exact), tile_s[j] = side
+template <int D>
+__device__ __forceinline__ void vq_load_subtile(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                const uint8_t* __restrict__ side, unsigned pos, unsigned end, unsigned (*tile_x)[D + 1], uint8_t* tile_s)
+{
+    const unsigned lane = lane_id(), m = pos + lane;
+    if (m < end) {
+        const unsigned id = perm[m], w = wts[id];
+        tile_s[lane] = side ? side[m] : (uint8_t)0;
+#pragma unroll
+        for (int d = 0; d < D; d++) tile_x[lane][d] = (unsigned)vecs[(size_t)id * D + d] * w;
+    }
+}
+
+// table layout: [chunk][accumulator 0..2D-1][e 0..kVqEMax][parity]
+template <int D> __device__ __forceinline__ size_t vq_tab_index(unsigned chunk, unsigned a, int e, unsigned p)
+{
+    return (((size_t)chunk * (2 * D) + a) * (kVqEMax + 1) + (unsigned)e) * 2 + p;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kVqSeqWarps * 32) vq_chunk_sim_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                                       const uint8_t* __restrict__ side, const VqSlot<D>* __restrict__ slots,
+                                                                       const unsigned* __restrict__ big_list, const unsigned* __restrict__ chunk_start,
+                                                                       const VqBigDir* __restrict__ dir, unsigned* __restrict__ table)
+{
+    __shared__ unsigned tile_x[kVqSeqWarps][32][D + 1];
+    __shared__ uint8_t tile_s[kVqSeqWarps][32];
+    const unsigned wi = threadIdx.x >> 5, lane = lane_id();
+    const unsigned chunk = blockIdx.x * kVqSeqWarps + wi;
+    if (chunk >= dir->nchunks) return;
+    unsigned lo = 0, hi = dir->nbig;                     // big slot that owns the chunk
+    while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (chunk_start[mid] <= chunk) lo = mid; else hi = mid; }
+    const VqSlot<D>& sl = slots[big_list[lo]];
+    const unsigned k = chunk - chunk_start[lo];
+    const unsigned pos0 = sl.begin + k * kVqChunk, end = sl.begin + sl.count;
+    const unsigned stop = pos0 + kVqChunk < end ? pos0 + kVqChunk : end;
+    const bool mine = lane < 2 * D;
+    const unsigned my_side = lane / D, my_d = lane % D;
+    // exponents worth tabulating: up to one past the binade of the slot's largest exact sum
+    unsigned long long mx = mine ? sl.s1[my_side][my_d] : 0ull;
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) { const unsigned long long o = __shfl_xor_sync(CRN_FULL_MASK, mx, ofs); mx = o > mx ? o : mx; }
+    int emax = vq_binade(mx) + 1;
+    emax = emax > kVqEMax ? kVqEMax : emax;
+    unsigned A[kVqEMax + 1][2];
+#pragma unroll
+    for (int e = 0; e <= kVqEMax; e++) { A[e][0] = 0; A[e][1] = 1; }
+    unsigned sum = 0;
+    for (unsigned pos = pos0; pos < stop; pos += 32) {
+        vq_load_subtile<D>(vecs, wts, perm, side, pos, stop, tile_x[wi], tile_s[wi]);
+        __syncwarp();
+        const unsigned cnt = stop - pos < 32u ? stop - pos : 32u;
+        if (mine)
+            for (unsigned j = 0; j < cnt; j++) {
+                if (tile_s[wi][j] != my_side) continue;
+                const unsigned x = tile_x[wi][j][my_d];
+                sum += x;
+#pragma unroll
+                for (int e = 1; e <= kVqEMax; e++) {
+                    if (e <= emax) {
+                        const unsigned q = x >> e, r = x & ((1u << e) - 1), half = 1u << (e - 1);
+#pragma unroll
+                        for (int p = 0; p < 2; p++) {
+                            const unsigned t = A[e][p] + q;
+                            A[e][p] = t + ((r > half) | ((r == half) & (t & 1u)));
+                        }
+                    }
+                }
+            }
+        __syncwarp();
+    }
+    if (mine) {
+        table[vq_tab_index<D>(chunk, lane, 0, 0)] = sum;
+        table[vq_tab_index<D>(chunk, lane, 0, 1)] = sum;
+#pragma unroll
+        for (int e = 1; e <= kVqEMax; e++)
+            if (e <= emax) { table[vq_tab_index<D>(chunk, lane, e, 0)] = A[e][0]; table[vq_tab_index<D>(chunk, lane, e, 1)] = A[e][1] - 1u; }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kVqSeqWarps * 32) vq_chunk_apply_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                                         const uint8_t* __restrict__ side, VqSlot<D>* __restrict__ slots,
+                                                                         const unsigned* __restrict__ big_list, const unsigned* __restrict__ chunk_start,
+                                                                         const VqBigDir* __restrict__ dir, const unsigned* __restrict__ table)
+{
+    __shared__ unsigned tile_x[kVqSeqWarps][32][D + 1];
+    __shared__ uint8_t tile_s[kVqSeqWarps][32];
+    const unsigned wi = threadIdx.x >> 5, lane = lane_id();
+    const unsigned b = blockIdx.x * kVqSeqWarps + wi;
+    if (b >= dir->nbig) return;
+    VqSlot<D>& sl = slots[big_list[b]];
+    const unsigned c0 = chunk_start[b], nchunks = chunk_start[b + 1] - c0;
+    const unsigned end = sl.begin + sl.count;
+    const bool mine = lane < 2 * D;
+    const unsigned my_side = lane / D, my_d = lane % D;
+    unsigned long long mx = mine ? sl.s1[my_side][my_d] : 0ull;
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) { const unsigned long long o = __shfl_xor_sync(CRN_FULL_MASK, mx, ofs); mx = o > mx ? o : mx; }
+    int emax = vq_binade(mx) + 1;
+    emax = emax > kVqEMax ? kVqEMax : emax;
+    unsigned long long acc = 0;
+    for (unsigned k0 = 0; k0 < nchunks; k0 += 8) {
+        // both parities of up to 8 chunks at the current binade, fetched before they are needed
+        const int e0 = vq_binade(acc);
+        unsigned d0[8], d1[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            d0[u] = d1[u] = 0;
+            if (mine && k0 + u < nchunks && e0 <= emax) {
+                const uint2 v = *reinterpret_cast<const uint2*>(&table[vq_tab_index<D>(c0 + k0 + u, lane, e0, 0)]);
+                d0[u] = v.x; d1[u] = v.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (k0 + u >= nchunks) break;                       // warp-uniform
+            bool ok = true;
+            unsigned long long next = acc;
+            if (mine) {
+                const int e = vq_binade(acc);
+                ok = e <= emax;
+                if (ok) {
+                    unsigned lo = d0[u], hi = d1[u];
+                    if (e != e0) { const uint2 v = *reinterpret_cast<const uint2*>(&table[vq_tab_index<D>(c0 + k0 + u, lane, e, 0)]); lo = v.x; hi = v.y; }
+                    const unsigned dlt = ((acc >> e) & 1ull) ? hi : lo;
+                    next = acc + ((unsigned long long)dlt << e);
+                    ok = next < (1ull << (24 + e));               // the whole chunk stayed inside the binade
+                }
+            }
+            if (__all_sync(CRN_FULL_MASK, ok)) { acc = next; continue; }
+            // some accumulator crosses a binade boundary inside this chunk: every lane replays it step by step
+            const unsigned pos0 = sl.begin + (k0 + u) * kVqChunk;
+            const unsigned stop = pos0 + kVqChunk < end ? pos0 + kVqChunk : end;
+            for (unsigned pos = pos0; pos < stop; pos += 32) {
+                vq_load_subtile<D>(vecs, wts, perm, side, pos, stop, tile_x[wi], tile_s[wi]);
+                __syncwarp();
+                const unsigned cnt = stop - pos < 32u ? stop - pos : 32u;
+                if (mine)
+                    for (unsigned j = 0; j < cnt; j++)
+                        if (tile_s[wi][j] == my_side) acc = vq_fl_add(acc, tile_x[wi][j][my_d]);
+                __syncwarp();
+            }
+        }
+    }
+    if (mine) sl.fs1[my_side][my_d] = (float)(long long)acc;       // exactly representable
 }
 
 // K2: covariance -> principal axis by power iteration (compute_split_pca, crn_clusterizer.h:510-579; presplit:

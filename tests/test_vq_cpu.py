@@ -96,8 +96,9 @@ def test_duplicates_and_constant_input(simctx, ref):
 @pytest.mark.parametrize("dims,n,max_size,retrieve,threaded,seed,max_weight", [
     (6, 5000, 65535, 5000, False, 15, 8),
     (16, 6000, 3000, 0, True, 14, 8),
-    (6, 12000, 65535, 1500, False, 16, 8),       # root sums 12000 * 255 * 8 > 2^24: float re-accumulation path
-    (16, 3000, 500, 0, True, 17, 2048),          # selector weights up to 2048: sums pass 2^24 as well
+    (6, 24000, 65535, 1500, False, 16, 64),      # centroid sums ~2^27: several binade crossings in the float accumulation
+    (2, 20000, 65535, 300, False, 18, 8),        # sums just above 2^24
+    (16, 8000, 500, 0, True, 17, 2048),          # selector weights up to 2048: sums pass 2^24 as well
 ])
 def test_large_matches_reference_exactly(simctx, ref, dims, n, max_size, retrieve, threaded, seed, max_weight):
     vecs, w = make_vectors(dims, n, seed, "uniform" if dims == 16 else "clumpy", max_weight)
