@@ -123,24 +123,31 @@ __device__ __forceinline__ int4 eval_palette(const Dxt1Cfg cfg, int r, int g, in
 }
 __device__ __forceinline__ int eval_dprime(const int4 c, const int4 p) { return p.w - c.x * p.x - c.y * p.y - c.z * p.z; }
 
+// `bound` = error of the current best: a candidate whose partial sum has reached it can only be rejected (every
+// acceptance test is a strict '<' against the best), so the lane stops there -- the reference's own early out
+// (crn_dxt1.cpp:1436, :1475, :1512, :1544 against the trial solution, :1773, :1812 against the best).  Lanes leave independently; the warp moves on when the last one is done.
 template <bool DO4, bool DO3, typename SC>
 __device__ __forceinline__ void dxt1_eval_loop(const SC* sc, int U, const int4 p0, const int4 p1, const int4 p2, const int4 p3,
-                                               const int4 pm, unsigned long long& e4, unsigned long long& e3)
+                                               const int4 pm, unsigned long long bound, unsigned long long& e4, unsigned long long& e3)
 {
     e4 = 0; e3 = 0;
+    for (int i = 0; i < U;) {
+        const int stop = min(U, i + 8);
 #pragma unroll 2
-    for (int i = 0; i < U; i++) {
-        const int4 c = sc->ce[i];
-        const unsigned w = (unsigned)sc->cw[i].w;
-        const int d01 = min(eval_dprime(c, p0), eval_dprime(c, p1));
-        if (DO4) {
-            const int d = min(d01, min(eval_dprime(c, p2), eval_dprime(c, p3)));
-            e4 += (unsigned long long)(unsigned)(d + c.w) * w;
+        for (; i < stop; i++) {
+            const int4 c = sc->ce[i];
+            const unsigned w = (unsigned)sc->cw[i].w;
+            const int d01 = min(eval_dprime(c, p0), eval_dprime(c, p1));
+            if (DO4) {
+                const int d = min(d01, min(eval_dprime(c, p2), eval_dprime(c, p3)));
+                e4 += (unsigned long long)(unsigned)(d + c.w) * w;
+            }
+            if (DO3) {
+                const int d = min(d01, eval_dprime(c, pm));
+                e3 += (unsigned long long)(unsigned)(d + c.w) * w;
+            }
         }
-        if (DO3) {
-            const int d = min(d01, eval_dprime(c, pm));
-            e3 += (unsigned long long)(unsigned)(d + c.w) * w;
-        }
+        if ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound)) break;
     }
 }
 
@@ -158,14 +165,15 @@ __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, u
     const int4 p3 = eval_palette(cfg, (r1 * 2 + r0 + alt) / 3, (g1 * 2 + g0 + alt) / 3, (b1 * 2 + b0 + alt) / 3);
     const int4 pm = eval_palette(cfg, (r0 + r1 + alt) >> 1, (g0 + g1 + alt) >> 1, (b0 + b1 + alt) >> 1);
     unsigned long long e4, e3;
+    const unsigned long long bound = sc->best.err;
     if (cfg.do4 && cfg.do3) {
-        dxt1_eval_loop<true, true>(sc, cfg.U, p0, p1, p2, p3, pm, e4, e3);
+        dxt1_eval_loop<true, true>(sc, cfg.U, p0, p1, p2, p3, pm, bound, e4, e3);
         alpha = e3 < e4; err = alpha ? e3 : e4;
     } else if (cfg.do4) {
-        dxt1_eval_loop<true, false>(sc, cfg.U, p0, p1, p2, p3, pm, e4, e3);
+        dxt1_eval_loop<true, false>(sc, cfg.U, p0, p1, p2, p3, pm, bound, e4, e3);
         alpha = 0; err = e4;
     } else {
-        dxt1_eval_loop<false, true>(sc, cfg.U, p0, p1, p2, p3, pm, e4, e3);
+        dxt1_eval_loop<false, true>(sc, cfg.U, p0, p1, p2, p3, pm, bound, e4, e3);
         alpha = 1; err = e3;
     }
 }

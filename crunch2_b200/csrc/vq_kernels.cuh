@@ -468,15 +468,17 @@ __global__ void __launch_bounds__(kVqSeqWarps * 32) vq_chunk_apply_kernel(const 
             // some accumulator crosses a binade boundary inside this chunk: every lane replays it step by step
             const unsigned pos0 = sl.begin + (k0 + u) * kVqChunk;
             const unsigned stop = pos0 + kVqChunk < end ? pos0 + kVqChunk : end;
+            // (the float unit does the rounding here: acc is a float-representable integer < 2^63, the addends are < 2^24)
+            float accf = (float)(long long)acc;
             for (unsigned pos = pos0; pos < stop; pos += 32) {
                 vq_load_subtile<D>(vecs, wts, perm, side, pos, stop, tile_x[wi], tile_s[wi]);
                 __syncwarp();
                 const unsigned cnt = stop - pos < 32u ? stop - pos : 32u;
                 if (mine)
-                    for (unsigned j = 0; j < cnt; j++)
-                        if (tile_s[wi][j] == my_side) acc = vq_fl_add(acc, tile_x[wi][j][my_d]);
+                    for (unsigned j = 0; j < cnt; j++) accf += tile_s[wi][j] == my_side ? (float)tile_x[wi][j][my_d] : 0.0f;
                 __syncwarp();
             }
+            acc = (unsigned long long)accf;
         }
     }
     if (mine) sl.fs1[my_side][my_d] = (float)(long long)acc;       // exactly representable
