@@ -4,14 +4,19 @@
     python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload NAME]
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Workloads:
+  c2_dxt5_q128_4096_mips  (default) BASELINE.json configs[1]: clustered .DDS DXT5 at -quality 128 of a synthetic
+                      4096x4096 RGBA texture + full mip chain (13 levels, 1 398 103 blocks, 22 369 621 texels):
+                      tile analysis -> endpoint clusterizer -> per-cluster endpoint optimisation -> selector
+                      clusterizer -> selector re-vote, both elements (crn_gpu_qdxt_init + crn_gpu_qdxt_pack)
   c1_dxt1_2048_mips   BASELINE.json configs[0]: block-by-block DXT1 (uber, perceptual, both block types,
                       endpoint caching disabled) of a synthetic 2048x2048 RGB texture + full mip chain
                       (12 levels, 349 527 blocks, 5 592 405 texels)
   dxt5_2048           plain DXT5 of a 2048x2048 RGBA texture (alpha + colour kernels)
 Prints ONE JSON line (rank 0).  `value` is device time with inputs resident in HBM (CUDA events on the
 library's own stream, L2 flushed between timed steps); `e2e` is the same metric through the public host
-API (pinned host buffers, H2D + kernels + D2H inside the timed region).  N > 1: one process per GPU
-(torchrun), every rank packs its own texture (weak scaling, no data-path collective), max over ranks.
+API (host buffers, H2D + kernels + D2H inside the timed region).  N > 1: one process per GPU (torchrun),
+every rank compresses its own texture (weak scaling, no data-path collective), max over ranks.  The default
+run also reports configs[0] (`block_pack`) and configs[3] (`transcode`) as extra objects of the same line.
 """
 import argparse
 import json
@@ -27,8 +32,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "DXT1 block-by-block compress throughput (uber, perceptual)"
+METRICS = {"c2_dxt5_q128_4096_mips": "clustered DXT5 .DDS compress throughput (-quality 128, uber, perceptual)",
+           "c1_dxt1_2048_mips": "DXT1 block-by-block compress throughput (uber, perceptual)",
+           "dxt5_2048": "DXT5 block-by-block compress throughput (uber, perceptual)"}
 UNIT = "Mtexel/s"
+CLUSTERED = ("c2_dxt5_q128_4096_mips",)
+CRN_FMT_OF = {0: 0, 3: 2}            # dxt_format -> crn_format for the reference's crn_compress
 
 
 def mip_chain(img):
@@ -48,6 +57,8 @@ def mip_chain(img):
 
 def make_workload(name, seed):
     import blockgen
+    if name == "c2_dxt5_q128_4096_mips":
+        return dict(fmt=3, levels=mip_chain(blockgen.smooth_image(4096, 4096, seed, alpha=True)), quality=128)
     if name == "c1_dxt1_2048_mips":
         img = blockgen.smooth_image(2048, 2048, seed, alpha=False)
         return dict(fmt=0, levels=mip_chain(img))
@@ -96,6 +107,19 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
 
 
+class quiet_stdout:
+    """The reference prints progress to fd 1 from C; keep the bench's stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_threads():
     return max(1, min(16, (os.cpu_count() or 1)))
 
@@ -107,6 +131,22 @@ def run_cpu_baseline(wl, budget_s=12.0):
     ref = helpers.load_ref()
     kind = "reference"
     threads = cpu_threads()
+    if "quality" in wl:
+        # clustered DDS: crn_compress(cCRNFileTypeDDS) of the unmodified reference on all host threads.  The cost per
+        # texel depends on the texture size (codebook budgets), so the sample is a whole mip chain: the full
+        # workload when the budget allows (~13 s on 16 threads), else the chain below its 2048x2048 level.
+        if ref is None:
+            raise RuntimeError("oracle/_ref is not built: the clustered path has no CPU port to time")
+        full = budget_s >= 10.0 and threads >= 12
+        sample_levels = wl["levels"] if full else wl["levels"][1:]
+
+        def run(lv):
+            with quiet_stdout():
+                return helpers.ref_compress(ref, [lv], CRN_FMT_OF[wl["fmt"]], file_type=1, quality=wl["quality"], threads=threads - 1)
+        t0 = time.perf_counter(); run(sample_levels); dt = time.perf_counter() - t0
+        return dict(value=texels(sample_levels) / dt / 1e6, unit=UNIT, cores=threads, kind=kind,
+                    sample="%s mip chain from %dx%d (%d blocks), crn_compress to DDS at quality %d, one pass, %.2f s" % (
+                        "the whole workload:" if full else "bounded:", sample_levels[0].shape[1], sample_levels[0].shape[0], nblocks(sample_levels), wl["quality"], dt)), sample_levels, run
     # pick a level by a quick calibration on a small one
     lv = [l for l in wl["levels"] if l.shape[0] * l.shape[1] <= 128 * 128][0]
     if ref is None:
@@ -198,36 +238,173 @@ def run_transcode(ctx, ext, dev, flush, steps, peak_gbs, quick=False):
     return out
 
 
+def run_clustered(args, ctx, ext, dev, wl, barrier, world):
+    """BASELINE configs[1]: clustered DDS (qdxt init + pack) of one texture per rank.  The path is a chain of
+    kernels with host decisions in between (frontier-batched VQ, cluster retrieval), on one stream + host thread per
+    element; crn_gpu_qdxt_pack returns with every stream drained, so the CUDA events recorded on the library's main
+    stream before init and after pack bracket exactly the device work of the step."""
+    import torch
+    import crunch2_b200 as crn
+    fmt, levels, q = wl["fmt"], wl["levels"], wl["quality"]
+    params = crn.PackParams()
+    d_in = [torch.from_numpy(np.ascontiguousarray(l)).to(dev) for l in levels]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nblocks(levels) * crn.bytes_per_block(fmt), dtype=torch.uint8, device=dev)
+    info = {}
+
+    def step_device():
+        qd = ctx.qdxt_init(fmt, d_in, params)
+        qd.pack(q, out=d_out)
+        info.update(qd.info())
+        qd.close()
+
+    for _ in range(args.warmup if os.environ.get("CRN_BENCH_PROFILING") else max(args.warmup, 3)):   # profiling passes (ncu) may warm up less; never a bench value
+        step_device()
+    ctx.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count
+    times, opt_ms = [], []
+    for _ in range(args.steps):
+        flush.fill_(1)                       # evict L2 (126 MB) between timed steps
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        step_device()
+        e1.record(ext)
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+        opt_ms.append(list(info["endpoint_opt_ms"]))
+    barrier()
+    launches = ctx.launch_count - l0
+    # end to end: pixels in pinned host memory, compressed blocks back in host memory
+    pinned = [torch.from_numpy(np.ascontiguousarray(l)).pin_memory() for l in levels]
+    host_levels = [p.numpy() for p in pinned]
+
+    def step_host():
+        qd = ctx.qdxt_init(fmt, host_levels, params)
+        out = qd.pack(q)
+        qd.close()
+        return out
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_out = step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop.set(); sampler.join(timeout=2)
+    # dominant kernel family: the per-cluster endpoint optimisation of the colour element (dxt1_optimize_clusters_*),
+    # bracketed by events on the element's own stream inside the library (crn_gpu_qdxt_info::endpoint_opt_ms)
+    col_ms = float(np.mean([o[0] for o in opt_ms]))               # element 0 of DXT1 / DXT5 is the colour element
+    top = {"kernel": "dxt1_optimize_clusters_* (colour element, %d endpoint clusters)" % info["endpoint_clusters"][0],
+           "ms": col_ms, "blocks": nblocks(levels), "bytes_per_block": 64 + 8,
+           "all_elements_ms": [float(x) for x in np.mean(np.array(opt_ms), axis=0)],
+           "note": "issue-slot bound integer search (SURVEY 8(d)): algorithmic HBM bytes are 64 B pixels in + 8 B element out per block; "
+                   "see DESIGN.md section 6 and profiles/ for the pipe utilisation that actually bounds it"}
+    extra = {"qdxt": {k: v for k, v in info.items() if k != "endpoint_opt_ms"}, "out_md5": __import__("hashlib").md5(host_out.tobytes()).hexdigest()}
+    return float(sum(times)), e2e_s, launches, sampler, top, flush, extra
+
+
+def run_block_pack(args, ctx, ext, dev, wl, barrier, world):
+    """BASELINE configs[0]: block-by-block packing (dxt_image::init), one texture + mip chain per rank."""
+    import torch
+    import crunch2_b200 as crn
+    fmt, levels = wl["fmt"], wl["levels"]
+    bpb = crn.bytes_per_block(fmt)
+    params = crn.PackParams()
+    d_in = [torch.from_numpy(l).to(dev) for l in levels]
+    d_out = [torch.empty(((l.shape[0] + 3) // 4) * ((l.shape[1] + 3) // 4) * bpb, dtype=torch.uint8, device=dev) for l in levels]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        for l, di, do in zip(levels, d_in, d_out):
+            ctx.pack_image_device(fmt, di, l.shape[1], l.shape[0], l.shape[1] * 4, do, params)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    ctx.synchronize()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count
+    times = []
+    for _ in range(args.steps):
+        flush.fill_(1)                       # evict L2 (126 MB) between timed steps
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        step_device()
+        e1.record(ext)
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    barrier()
+    launches = ctx.launch_count - l0
+    # dominant kernel family: colour element kernels of the largest level, timed alone (same stream, events)
+    flush.fill_(2); torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(ext)
+    ctx.pack_image_device(fmt, d_in[0], levels[0].shape[1], levels[0].shape[0], levels[0].shape[1] * 4, d_out[0], params)
+    k1.record(ext); k1.synchronize()
+    top = {"kernel": "pack_color_phase_kernel<0..4> (level 0)", "ms": k0.elapsed_time(k1), "blocks": nblocks(levels[:1]), "bytes_per_block": 64 + bpb,
+           "note": "issue-slot bound integer kernel: algorithmic HBM bytes are 64 B in + the block out; see DESIGN.md and profiles/ for pipe utilisation"}
+    # end-to-end arm: public host API, pinned buffers, copies inside the timed region
+    pinned = [torch.from_numpy(l.copy()).pin_memory() for l in levels]
+    host_levels = [p.numpy() for p in pinned]
+    for _ in range(2):
+        for hl in host_levels:
+            ctx.pack_image(fmt, hl, params)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for hl in host_levels:
+            ctx.pack_image(fmt, hl, params)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop.set(); sampler.join(timeout=2)
+    return float(sum(times)), e2e_s, launches, sampler, top, flush, {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1_dxt1_2048_mips")
+    ap.add_argument("--workload", default="c2_dxt5_q128_4096_mips", choices=sorted(METRICS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-transcode", action="store_true")
+    ap.add_argument("--no-block-pack", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": args.workload, "l2": "flushed between timed steps (256 MiB write)", "endpoint_caching": "disabled",
-              "dxt_quality": "uber", "flags": "perceptual|use_both_block_types"}
+    clustered = args.workload in CLUSTERED
+    metric = METRICS[args.workload]
+    config = {"workload": args.workload, "l2": "flushed between timed steps (256 MiB write)", "dxt_quality": "uber",
+              "flags": "perceptual|use_both_block_types"}
+    if clustered:
+        config.update({"quality_level": 128, "file_type": "DDS", "levels": 13, "partitioning": "one texture per GPU"})
+    else:
+        config["endpoint_caching"] = "disabled"
 
     if args.impl == "reference":
         if rank != 0:
             return
         wl = make_workload(args.workload, 2048)
-        base, sample, run = run_cpu_baseline(wl, budget_s=8.0)
-        for _ in range(min(args.warmup, 1)):
+        base, sample, run = run_cpu_baseline(wl, budget_s=12.0 if clustered else 8.0)
+        ntex = texels(sample) if isinstance(sample, list) else sample.shape[0] * sample.shape[1]
+        for _ in range(0 if clustered else min(args.warmup, 1)):      # the calibration pass above already warmed the clustered path
             run(sample)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             run(sample)
         dt = time.perf_counter() - t0
-        v = sample.shape[0] * sample.shape[1] * args.steps / dt / 1e6
+        v = ntex * args.steps / dt / 1e6
         base["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config, "cpu_baseline": base,
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
@@ -245,18 +422,7 @@ def main():
     wl = make_workload(args.workload, 2048 + rank)
     fmt, levels = wl["fmt"], wl["levels"]
     bpb = crn.bytes_per_block(fmt)
-    params = crn.PackParams()
     n_tex, n_blk = texels(levels), nblocks(levels)
-
-    # ---- device-resident arm -------------------------------------------------------------------
-    d_in = [torch.from_numpy(l).to(dev) for l in levels]
-    d_out = [torch.empty(((l.shape[0] + 3) // 4) * ((l.shape[1] + 3) // 4) * bpb, dtype=torch.uint8, device=dev) for l in levels]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    torch.cuda.synchronize()
-
-    def step_device():
-        for l, di, do in zip(levels, d_in, d_out):
-            ctx.pack_image_device(fmt, di, l.shape[1], l.shape[0], l.shape[1] * 4, do, params)
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,50 +430,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    ctx.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    l0 = ctx.launch_count
-    times = []
-    for _ in range(args.steps):
-        flush.fill_(1)                       # evict L2 (126 MB) between timed steps
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext)
-        step_device()
-        e1.record(ext)
-        e1.synchronize()
-        times.append(e0.elapsed_time(e1))
-    barrier()
-    launches = ctx.launch_count - l0
-    total_ms = float(sum(times))
-
-    # dominant kernel: colour element kernel of the largest level, timed alone (same stream, events)
-    flush.fill_(2); torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(ext)
-    ctx.pack_image_device(fmt, d_in[0], levels[0].shape[1], levels[0].shape[0], levels[0].shape[1] * 4, d_out[0], params)
-    k1.record(ext); k1.synchronize()
-    top_ms = k0.elapsed_time(k1)
-    top_blocks = nblocks(levels[:1])
-
-    # ---- end-to-end arm: public host API, pinned buffers, copies inside the timed region -----------
-    pinned = [torch.from_numpy(l.copy()).pin_memory() for l in levels]
-    host_levels = [p.numpy() for p in pinned]
-    for _ in range(2):
-        for hl in host_levels:
-            ctx.pack_image(fmt, hl, params)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for hl in host_levels:
-            ctx.pack_image(fmt, hl, params)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    sampler.stop.set(); sampler.join(timeout=2)
+    runner = run_clustered if clustered else run_block_pack
+    total_ms, e2e_s, launches, sampler, top, flush, extra = runner(args, ctx, ext, dev, wl, barrier, world)
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -326,18 +450,30 @@ def main():
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     value = n_tex * world * args.steps / (total_ms / 1e3) / 1e6
     e2e_v = n_tex * world * args.steps / e2e_s / 1e6
-    algo_bytes = top_blocks * (64 + bpb)
-    achieved = algo_bytes / (top_ms / 1e3) / 1e9
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    achieved = top["blocks"] * top["bytes_per_block"] / (top["ms"] / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650", "note": top["note"],
+            "blocks_per_s": top["blocks"] / (top["ms"] / 1e3), "ms": top["ms"]}
+    if "all_elements_ms" in top:
+        roof["all_elements_ms"] = top["all_elements_ms"]
+    out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "int32", "data": "synthetic", "config": config,
            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(sum(l.nbytes for l in levels)), "d2h_bytes_per_step": int(n_blk * bpb)},
-           "gpu_launches": int(launches), "clocks": sampler.summary(),
-           "roofline": {"bound": "hbm", "kernel": "pack_color_element_kernel (level 0)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                        "frac": achieved / peak_gbs, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                        "note": "issue-slot bound integer kernel: algorithmic HBM bytes are 72 B/block; see DESIGN.md and profiles/ for pipe utilisation",
-                        "blocks_per_s": top_blocks / (top_ms / 1e3), "ms": top_ms}}
-    if not args.no_transcode:
+           "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+    out.update(extra)
+    if clustered and not args.no_block_pack and world == 1:
+        try:                                  # configs[0] next to the headline, same contract, fewer steps
+            wl1 = make_workload("c1_dxt1_2048_mips", 2048)
+            a2 = argparse.Namespace(**vars(args)); a2.steps = min(args.steps, 3); a2.warmup = 3
+            ms1, e2e1, ln1, _, top1, _, _ = run_block_pack(a2, ctx, ext, dev, wl1, barrier, world)
+            t1 = texels(wl1["levels"])
+            out["block_pack"] = {"workload": "c1_dxt1_2048_mips", "value": t1 * a2.steps / (ms1 / 1e3) / 1e6, "unit": UNIT,
+                                 "e2e": t1 * a2.steps / e2e1 / 1e6, "gpu_launches": int(ln1), "level0_ms": top1["ms"],
+                                 "level0_blocks_per_s": top1["blocks"] / (top1["ms"] / 1e3)}
+        except Exception as e:
+            out["block_pack"] = {"error": str(e)[:300]}
+    if not args.no_transcode and world == 1:
         try:
             out["transcode"] = run_transcode(ctx, ext, dev, flush, max(2, min(args.steps, 5)), peak_gbs)
         except Exception as e:

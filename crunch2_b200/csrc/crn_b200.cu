@@ -124,6 +124,8 @@ struct crn_qdxt_element {
     unsigned long long* d_keys;       // per-block dxt_fast selector keys + the distinct-count table
     std::vector<uint32_t> cluster_of, offsets, members;
     std::vector<uint8_t> cat;
+    cudaEvent_t ev_opt[2];            // brackets the endpoint optimisation of the last pack()
+    float endpoint_opt_ms;
     int rc;
 };
 
@@ -146,6 +148,7 @@ void qdxt_release(crn_gpu_qdxt* q)
         crn_qdxt_element& e = q->el[i];
         void* ptrs[] = {e.d_vecs, e.d_wts, e.d_cat, e.d_offsets, e.d_members, e.d_ids, e.d_keys};
         for (void* p : ptrs) if (p) cudaFree(p);
+        for (cudaEvent_t ev : e.ev_opt) if (ev) cudaEventDestroy(ev);
         if (e.ctx) crn_gpu_destroy(e.ctx);
     }
     if (q->d_blocks) cudaFree(q->d_blocks);
@@ -304,10 +307,12 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
         fprintf(stderr, "  median %u\n", sz[k_end / 2]);
     }
     tr.mark("pack: retrieve + CSR", eli);
+    cudaEventRecord(e.ev_opt[0], ctx->stream);
     if (e.kind == 0)
         rc = crn_gpu_dxt1_optimize_clusters(ctx, &pp, e.use_alpha_blocks, q->d_blocks, n, e.d_offsets, e.d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
     else
         rc = crn_gpu_dxt5_optimize_clusters(ctx, &pp, e.comp, q->d_blocks, n, e.d_offsets, e.d_members, k_end, n, q->d_out, stride, e.offset, nullptr, nullptr);
+    cudaEventRecord(e.ev_opt[1], ctx->stream);
     if (rc) return rc;
     tr.mark("pack: endpoint optimisation", eli);
     e.selector_clusters = 0;
@@ -749,7 +754,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
         crn_qdxt_element& e = q->el[ne++];
         e.kind = kind; e.comp = comp; e.offset = offset; e.use_alpha_blocks = use_alpha;
         e.max_selector_clusters = 0; e.endpoint_clusters = e.selector_clusters = 0;
-        e.ctx = nullptr; e.d_vecs = nullptr; e.d_wts = nullptr; e.d_cat = nullptr; e.d_offsets = e.d_members = e.d_ids = nullptr; e.d_keys = nullptr; e.rc = 0;
+        e.ctx = nullptr; e.d_vecs = nullptr; e.d_wts = nullptr; e.d_cat = nullptr; e.d_offsets = e.d_members = e.d_ids = nullptr; e.d_keys = nullptr; e.rc = 0; e.ev_opt[0] = e.ev_opt[1] = nullptr; e.endpoint_opt_ms = 0;
         q->num_elements = ne;
     };
     switch (format) {
@@ -786,6 +791,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     for (uint32_t i = 0; i < ne; i++) {
         crn_qdxt_element& e = q->el[i];
         if (crn_gpu_create(ctx->device, &e.ctx) != CRN_GPU_OK) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: element stream"); }
+        if (cudaEventCreate(&e.ev_opt[0]) != cudaSuccess || cudaEventCreate(&e.ev_opt[1]) != cudaSuccess) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: events"); }
         QDXT_ALLOC(e.d_vecs, (size_t)n * 16);
         QDXT_ALLOC(e.d_wts, (size_t)n * 4);
         QDXT_ALLOC(e.d_cat, (size_t)n);
@@ -840,6 +846,7 @@ int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int ds
     const int rc = qdxt_for_each_element(q, [q, quality_level](crn_qdxt_element& e) {
         const int r = qdxt_pack_element(q, e, quality_level);
         if (!r && cudaStreamSynchronize(e.ctx->stream) != cudaSuccess) return set_err(e.ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_pack: element stream");
+        if (!r) cudaEventElapsedTime(&e.endpoint_opt_ms, e.ev_opt[0], e.ev_opt[1]);
         return r;
     });
     if (rc) return rc;
@@ -859,6 +866,7 @@ int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info)
         info->max_selector_clusters[i] = q->el[i].max_selector_clusters;
         info->endpoint_clusters[i] = q->el[i].endpoint_clusters;
         info->selector_clusters[i] = q->el[i].selector_clusters;
+        info->endpoint_opt_ms[i] = q->el[i].endpoint_opt_ms;
     }
     return CRN_GPU_OK;
 }

@@ -182,6 +182,7 @@ typedef struct crn_gpu_qdxt_info {
     uint32_t max_selector_clusters[3];     /* distinct dxt_fast selectors + 128 */
     uint32_t endpoint_clusters[3];         /* of the last pack() */
     uint32_t selector_clusters[3];
+    float endpoint_opt_ms[3];              /* device time of the per-cluster endpoint optimisation kernels of the last pack() */
 } crn_gpu_qdxt_info;
 CRN_API int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                               const crn_gpu_level_desc* levels, uint32_t num_levels, int pixels_on_host, crn_gpu_qdxt** out);
