@@ -76,35 +76,52 @@ def nblocks(levels):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (profiling recipe's clocks line), through NVML
+    in-process (nvidia_ml_py): spawning nvidia-smi five times a second takes driver locks and slows a launch-heavy
+    path down measurably.  Falls back to nvidia-smi when NVML cannot be loaded."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.25):
         super().__init__(daemon=True)
-        self.index = index
+        self.index, self.period = index, period
         self.stop = threading.Event()
-        self.rows = []
+        self.sm, self.max_sm, self.reasons = [], None, set()
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop.is_set():
+                self.sm.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.reasons.update(n for n, b in bits.items() if r & b)
+                self.stop.wait(self.period)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [x.strip() for x in out.split(",")]
+                if len(c) >= 6 and c[0].isdigit():
+                    self.sm.append(int(c[0])); self.max_sm = int(c[1])
+                    self.reasons.update(n for i, n in enumerate(names) if c[2 + i].lower().startswith("active"))
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(1.0)
 
     def summary(self):
-        if not self.rows:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 class quiet_stdout:
@@ -303,7 +320,7 @@ def run_clustered(args, ctx, ext, dev, wl, barrier, world):
            "all_elements_ms": [float(x) for x in np.mean(np.array(opt_ms), axis=0)],
            "note": "issue-slot bound integer search (SURVEY 8(d)): algorithmic HBM bytes are 64 B pixels in + 8 B element out per block; "
                    "see DESIGN.md section 6 and profiles/ for the pipe utilisation that actually bounds it"}
-    extra = {"qdxt": {k: v for k, v in info.items() if k != "endpoint_opt_ms"}, "out_md5": __import__("hashlib").md5(host_out.tobytes()).hexdigest()}
+    extra = {"step_ms": [round(t, 2) for t in times], "qdxt": {k: v for k, v in info.items() if k != "endpoint_opt_ms"}, "out_md5": __import__("hashlib").md5(host_out.tobytes()).hexdigest()}
     return float(sum(times)), e2e_s, launches, sampler, top, flush, extra
 
 

@@ -35,6 +35,11 @@ struct crn_gpu_ctx {
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
     crn::VqWorkspace vq_ws;              // slab of the vector quantiser
     int transcode_smem_set;
+    // clustered path: per-element child contexts (own stream + scratch) and a cache of released device buffers, both
+    // kept for the life of this context so that compressing texture after texture does not pay cudaMalloc / cudaFree
+    crn_gpu_ctx* child[3];
+    struct PoolBlock { void* p; size_t cap; };
+    std::vector<PoolBlock>* pool;
 };
 
 namespace {
@@ -63,6 +68,41 @@ int ensure(crn_gpu_ctx* ctx, void** p, size_t* cap, size_t need)
     if (ce != cudaSuccess) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "cudaMalloc", ce);
     *cap = need;
     return CRN_GPU_OK;
+}
+
+// device buffers of the clustered path: best fit from the context's cache (at most 2x oversize), else cudaMalloc
+cudaError_t pool_alloc(crn_gpu_ctx* ctx, void** out, size_t bytes, size_t* cap_out)
+{
+    if (!bytes) bytes = 256;
+    if (ctx->pool) {
+        int best = -1;
+        for (size_t i = 0; i < ctx->pool->size(); i++) {
+            const size_t c = (*ctx->pool)[i].cap;
+            if (c >= bytes && c <= 2 * bytes + (1u << 20) && (best < 0 || c < (*ctx->pool)[best].cap)) best = (int)i;
+        }
+        if (best >= 0) {
+            *out = (*ctx->pool)[best].p; *cap_out = (*ctx->pool)[best].cap;
+            ctx->pool->erase(ctx->pool->begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t ce = cudaMalloc(out, bytes);
+    if (ce != cudaSuccess && ctx->pool && !ctx->pool->empty()) {       // give the cache back and retry once
+        for (auto& b : *ctx->pool) cudaFree(b.p);
+        ctx->pool->clear();
+        (void)cudaGetLastError();
+        ce = cudaMalloc(out, bytes);
+    }
+    *cap_out = bytes;
+    return ce;
+}
+
+void pool_free(crn_gpu_ctx* ctx, void* p, size_t cap)
+{
+    if (!p) return;
+    if (!ctx->pool) ctx->pool = new (std::nothrow) std::vector<crn_gpu_ctx::PoolBlock>();
+    if (!ctx->pool || ctx->pool->size() >= 64) { cudaFree(p); return; }
+    ctx->pool->push_back({p, cap});
 }
 
 int grid_for(const crn_gpu_ctx* ctx, uint32_t total_blocks, int warps_per_cta, int ctas_per_sm)
@@ -122,6 +162,7 @@ struct crn_qdxt_element {
     uint8_t* d_cat;
     uint32_t *d_offsets, *d_members, *d_ids;
     unsigned long long* d_keys;       // per-block dxt_fast selector keys + the distinct-count table
+    size_t caps[7];                   // pool capacities of d_vecs, d_wts, d_cat, d_offsets, d_members, d_ids, d_keys
     std::vector<uint32_t> cluster_of, offsets, members;
     std::vector<uint8_t> cat;
     cudaEvent_t ev_opt[2];            // brackets the endpoint optimisation of the last pack()
@@ -138,6 +179,7 @@ struct crn_gpu_qdxt {
     crn_qdxt_element el[3];
     uint32_t* d_blocks;               // n_blocks x 16 RGBA8
     uint8_t* d_out;                   // n_blocks x bytes_per_block
+    size_t d_blocks_cap, d_out_cap;
 };
 
 namespace {
@@ -147,12 +189,12 @@ void qdxt_release(crn_gpu_qdxt* q)
     for (uint32_t i = 0; i < q->num_elements; i++) {
         crn_qdxt_element& e = q->el[i];
         void* ptrs[] = {e.d_vecs, e.d_wts, e.d_cat, e.d_offsets, e.d_members, e.d_ids, e.d_keys};
-        for (void* p : ptrs) if (p) cudaFree(p);
+        for (int k = 0; k < 7; k++) pool_free(q->ctx, ptrs[k], e.caps[k]);
         for (cudaEvent_t ev : e.ev_opt) if (ev) cudaEventDestroy(ev);
-        if (e.ctx) crn_gpu_destroy(e.ctx);
+        // e.ctx is q->ctx->child[i]: it stays with the parent context
     }
-    if (q->d_blocks) cudaFree(q->d_blocks);
-    if (q->d_out) cudaFree(q->d_out);
+    pool_free(q->ctx, q->d_blocks, q->d_blocks_cap);
+    pool_free(q->ctx, q->d_out, q->d_out_cap);
     delete q;
 }
 
@@ -416,6 +458,11 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_files) cudaFree(ctx->d_files);
     if (ctx->vq_ws.base) cudaFree(ctx->vq_ws.base);
     if (ctx->d_cluster_ws) cudaFree(ctx->d_cluster_ws);
+    for (crn_gpu_ctx* c : ctx->child) if (c) crn_gpu_destroy(c);
+    if (ctx->pool) {
+        for (auto& b : *ctx->pool) cudaFree(b.p);
+        delete ctx->pool;
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -747,7 +794,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     q->ctx = ctx; q->format = format; q->params = *params; q->num_levels = num_levels;
     q->bytes_per_block = crn_gpu_bytes_per_block(format);
     q->pow_mul = format == CRN_GPU_FMT_DXT5 ? .75f : 1.0f;           // crn_mipmapped_texture.cpp:2529-2539
-    q->d_blocks = nullptr; q->d_out = nullptr; q->num_elements = 0;
+    q->d_blocks = nullptr; q->d_out = nullptr; q->num_elements = 0; q->d_blocks_cap = q->d_out_cap = 0;
     // element table (crn_mipmapped_texture.cpp:2319-2366)
     uint32_t ne = 0;
     auto add = [&](int kind, uint32_t comp, uint32_t offset, int use_alpha) {
@@ -755,6 +802,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
         e.kind = kind; e.comp = comp; e.offset = offset; e.use_alpha_blocks = use_alpha;
         e.max_selector_clusters = 0; e.endpoint_clusters = e.selector_clusters = 0;
         e.ctx = nullptr; e.d_vecs = nullptr; e.d_wts = nullptr; e.d_cat = nullptr; e.d_offsets = e.d_members = e.d_ids = nullptr; e.d_keys = nullptr; e.rc = 0; e.ev_opt[0] = e.ev_opt[1] = nullptr; e.endpoint_opt_ms = 0;
+        memset(e.caps, 0, sizeof(e.caps));
         q->num_elements = ne;
     };
     switch (format) {
@@ -781,47 +829,50 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     const uint32_t n = q->n_blocks = (uint32_t)total_blocks;
     uint32_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
-#define QDXT_ALLOC(ptr, bytes)                                                                                         \
+#define QDXT_ALLOC(ptr, bytes, cap)                                                                                    \
     do {                                                                                                               \
-        cudaError_t ce_ = cudaMalloc((void**)&(ptr), (bytes));                                                         \
-        if (ce_ != cudaSuccess) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: cudaMalloc", ce_); } \
+        cudaError_t ce_ = pool_alloc(ctx, (void**)&(ptr), (bytes), &(cap));                                            \
+        if (ce_ != cudaSuccess) { (ptr) = nullptr; qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: cudaMalloc", ce_); } \
     } while (0)
-    QDXT_ALLOC(q->d_blocks, (size_t)n * 64);
-    QDXT_ALLOC(q->d_out, (size_t)n * q->bytes_per_block);
+    QDXT_ALLOC(q->d_blocks, (size_t)n * 64, q->d_blocks_cap);
+    QDXT_ALLOC(q->d_out, (size_t)n * q->bytes_per_block, q->d_out_cap);
     for (uint32_t i = 0; i < ne; i++) {
         crn_qdxt_element& e = q->el[i];
-        if (crn_gpu_create(ctx->device, &e.ctx) != CRN_GPU_OK) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: element stream"); }
+        if (!ctx->child[i] && crn_gpu_create(ctx->device, &ctx->child[i]) != CRN_GPU_OK) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: element stream"); }
+        e.ctx = ctx->child[i];
+        e.ctx->launches = 0;
         if (cudaEventCreate(&e.ev_opt[0]) != cudaSuccess || cudaEventCreate(&e.ev_opt[1]) != cudaSuccess) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: events"); }
-        QDXT_ALLOC(e.d_vecs, (size_t)n * 16);
-        QDXT_ALLOC(e.d_wts, (size_t)n * 4);
-        QDXT_ALLOC(e.d_cat, (size_t)n);
-        QDXT_ALLOC(e.d_offsets, ((size_t)n + 1) * 4);
-        QDXT_ALLOC(e.d_members, (size_t)n * 4);
-        QDXT_ALLOC(e.d_ids, (size_t)n * 4);
-        QDXT_ALLOC(e.d_keys, ((size_t)n + cap + 2) * 8);
+        QDXT_ALLOC(e.d_vecs, (size_t)n * 16, e.caps[0]);
+        QDXT_ALLOC(e.d_wts, (size_t)n * 4, e.caps[1]);
+        QDXT_ALLOC(e.d_cat, (size_t)n, e.caps[2]);
+        QDXT_ALLOC(e.d_offsets, ((size_t)n + 1) * 4, e.caps[3]);
+        QDXT_ALLOC(e.d_members, (size_t)n * 4, e.caps[4]);
+        QDXT_ALLOC(e.d_ids, (size_t)n * 4, e.caps[5]);
+        QDXT_ALLOC(e.d_keys, ((size_t)n + cap + 2) * 8, e.caps[6]);
     }
 #undef QDXT_ALLOC
     // pixel blocks of every level (crn_mipmapped_texture.cpp:2419-2472)
     int rc = CRN_GPU_OK;
+    if (pixels_on_host) {              // one staging buffer for the whole chain: copies and gathers queue back to back
+        size_t total = 0;
+        for (uint32_t l = 0; l < num_levels; l++) total += (((size_t)levels[l].width * 4 * levels[l].height) + 255) & ~(size_t)255;
+        rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, total);
+    }
+    size_t stage = 0;
     for (uint32_t l = 0; l < num_levels && !rc; l++) {
         const crn_gpu_level_desc& lv = levels[l];
         const uint8_t* src = static_cast<const uint8_t*>(lv.rgba);
         uint32_t pitch = lv.pitch_bytes;
         if (pixels_on_host) {
-            const size_t bytes = (size_t)lv.width * 4 * lv.height;
-            rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, bytes);
-            if (rc) break;
-            cudaError_t ce = cudaMemcpy2DAsync(ctx->d_in, (size_t)lv.width * 4, lv.rgba, lv.pitch_bytes, (size_t)lv.width * 4, lv.height, cudaMemcpyHostToDevice, ctx->stream);
+            uint8_t* d = static_cast<uint8_t*>(ctx->d_in) + stage;
+            stage += (((size_t)lv.width * 4 * lv.height) + 255) & ~(size_t)255;
+            cudaError_t ce = cudaMemcpy2DAsync(d, (size_t)lv.width * 4, lv.rgba, lv.pitch_bytes, (size_t)lv.width * 4, lv.height, cudaMemcpyHostToDevice, ctx->stream);
             if (ce != cudaSuccess) { rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: H2D", ce); break; }
-            src = static_cast<const uint8_t*>(ctx->d_in); pitch = lv.width * 4;
+            src = d; pitch = lv.width * 4;
         }
         const uint32_t nb = q->mips[l].block_width * q->mips[l].block_height;
         CRN_LAUNCH(crn::blockify_kernel, (nb * 16 + 255) / 256, 256, 0, ctx->stream, src, lv.width, lv.height, pitch, q->d_blocks + (size_t)q->mips[l].first_block * 16);
         ctx->launches++;
-        if (pixels_on_host) {          // d_in is reused by the next level
-            cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-            if (ce != cudaSuccess) rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: blockify", ce);
-        }
     }
     if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: blockify");
     if (!rc) rc = qdxt_for_each_element(q, [q](crn_qdxt_element& e) { return qdxt_init_element(q, e); });

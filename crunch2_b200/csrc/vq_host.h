@@ -9,7 +9,14 @@
 // `max_size - total_leaves` highest variances of the heap can never be popped, so it is not sent to the
 // device.  retrieve_clusters() (:301-332) is the pruning walk over the recorded split ranks.
 #pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
 #include <algorithm>
+#ifdef __CUDACC__
+#include <thread>
+#endif
 #include <type_traits>
 #include <vector>
 #include "vq_kernels.cuh"
@@ -24,11 +31,28 @@ struct VqHostNode {
     uint8_t processed = 0, unsplittable = 0;
 };
 
+struct VqHeapEntry { float variance; uint32_t id; };   // the key travels with the id: sift loops stay inside one array
+
 struct VqTreeSim {                   // one clusterizer<V> instance
     uint32_t root = 0, max_size = 0, total_leaves = 1, split_index = 0;
-    std::vector<uint32_t> heap;      // 1-based, as the reference's
+    std::vector<VqHeapEntry> heap;   // 1-based, as the reference's
     uint32_t heap_size = 0;
+    // Bookkeeping for wanted(): a histogram of the keys in the heap (8192 bins over the float's exponent + 4 mantissa
+    // bits; variances are >= 0 so the bit pattern is monotonic) and the heap members not yet sent to the device.
+    static constexpr uint32_t kBins = 8192;
+    std::vector<uint32_t> hist;
+    std::vector<VqHeapEntry> pending;
+    static uint32_t bin_of(float v) { uint32_t b; memcpy(&b, &v, 4); return (b >> 19) & (kBins - 1); }
+    static float bin_floor(uint32_t bin) { const uint32_t b = bin << 19; float v; memcpy(&v, &b, 4); return v; }
 
+    void reset(const std::vector<VqHostNode>& nodes)
+    {
+        heap.assign((size_t)max_size + 2, VqHeapEntry{0.0f, 0u});
+        hist.assign(kBins, 0u);
+        pending.clear();
+        heap_size = 0;
+        insert(nodes, root);                                   // the root enters the heap unconditionally (:100-102)
+    }
     void insert(const std::vector<VqHostNode>& nodes, uint32_t id)
     {   // insert_heap (:384-414): sift up while the parent is not strictly greater
         const float v = nodes[id].variance;
@@ -36,23 +60,25 @@ struct VqTreeSim {                   // one clusterizer<V> instance
         if (heap_size >= heap.size()) heap.resize(heap_size + 1);
         for (;;) {
             const uint32_t parent = pos >> 1;
-            if (!parent || nodes[heap[parent]].variance > v) break;
+            if (!parent || heap[parent].variance > v) break;
             heap[pos] = heap[parent];
             pos = parent;
         }
-        heap[pos] = id;
+        heap[pos] = VqHeapEntry{v, id};
+        hist[bin_of(v)]++;
+        pending.push_back(VqHeapEntry{v, id});
     }
-    uint32_t pop(const std::vector<VqHostNode>& nodes)
+    uint32_t pop()
     {   // generate_codebook :114-121 + down_heap (:416-444)
-        const uint32_t top = heap[1];
+        const uint32_t top = heap[1].id;
+        hist[bin_of(heap[1].variance)]--;
         heap[1] = heap[heap_size--];
         if (heap_size) {
             uint32_t pos = 1, child;
-            const uint32_t orig = heap[1];
-            const float ov = nodes[orig].variance;
+            const VqHeapEntry orig = heap[1];
             while ((child = pos << 1) <= heap_size) {
-                if (child < heap_size && nodes[heap[child]].variance < nodes[heap[child + 1]].variance) child++;
-                if (ov > nodes[heap[child]].variance) break;
+                if (child < heap_size && heap[child].variance < heap[child + 1].variance) child++;
+                if (orig.variance > heap[child].variance) break;
                 heap[pos] = heap[child];
                 pos = child;
             }
@@ -65,9 +91,9 @@ struct VqTreeSim {                   // one clusterizer<V> instance
     void run(std::vector<VqHostNode>& nodes)
     {
         while (!finished()) {
-            VqHostNode& nd = nodes[heap[1]];
+            VqHostNode& nd = nodes[heap[1].id];
             if (nd.count != 1 && !nd.processed) return;
-            const uint32_t id = pop(nodes);
+            const uint32_t id = pop();
             VqHostNode& node = nodes[id];
             if (node.count != 1 && !node.unsplittable) {          // split_node (:740-873)
                 node.split_rank = (int32_t)split_index++;
@@ -79,22 +105,26 @@ struct VqTreeSim {                   // one clusterizer<V> instance
             total_leaves++;
         }
     }
-    // leaves of the heap that can still be popped and have not been split on the device
-    void wanted(const std::vector<VqHostNode>& nodes, std::vector<uint32_t>& out) const
+    // Leaves of the heap that can still be popped and have not been split on the device: at most `budget` more pops
+    // can happen, so a key below the budget-th largest of the heap is out of reach.  The cut is taken at the lower
+    // edge of the histogram bin holding that key -- a few more nodes than strictly needed go to the device, never fewer.
+    // Every node returned is split by the round that follows (VqBuilder::round is synchronous), so it leaves `pending`.
+    void wanted(std::vector<uint32_t>& out)
     {
-        if (finished()) return;
+        if (finished()) { pending.clear(); return; }
         const uint32_t budget = max_size - total_leaves;
         float thresh = -1.0f;
         if (heap_size > budget) {
-            std::vector<float> v(heap_size);
-            for (uint32_t i = 0; i < heap_size; i++) v[i] = nodes[heap[1 + i]].variance;
-            std::nth_element(v.begin(), v.begin() + (budget - 1), v.end(), [](float a, float b) { return a > b; });
-            thresh = v[budget - 1];
+            uint32_t seen = 0, bin = kBins;
+            while (bin > 0 && seen < budget) seen += hist[--bin];
+            thresh = bin_floor(bin);
         }
-        for (uint32_t i = 1; i <= heap_size; i++) {
-            const VqHostNode& nd = nodes[heap[i]];
-            if (!nd.processed && nd.variance >= thresh) out.push_back(heap[i]);
+        size_t keep = 0;
+        for (size_t i = 0; i < pending.size(); i++) {
+            if (pending[i].variance >= thresh) out.push_back(pending[i].id);
+            else pending[keep++] = pending[i];
         }
+        pending.resize(keep);
     }
 };
 
@@ -173,6 +203,7 @@ public:
         cudaMemcpyAsync(&root_var, nodes_.variance, sizeof(float), cudaMemcpyDeviceToHost, stream_);
         ce = cudaStreamSynchronize(stream_);
         if (ce != cudaSuccess) return ce;
+        nodes.reserve(std::min<size_t>((size_t)2 * n + 16, (size_t)4 * max_size + 64));
         nodes.resize(1);
         nodes[0].begin = 0; nodes[0].count = n; nodes[0].variance = root_var;
 
@@ -206,16 +237,15 @@ public:
             t.root = 0; t.max_size = max_size;
             res.trees.push_back(t);
         }
-        for (VqTreeSim& t : res.trees) {
-            t.heap.assign(t.max_size + 2, 0u);
-            t.heap[1] = t.root; t.heap_size = 1;              // the root enters the heap unconditionally (:100-102)
-        }
+        for (VqTreeSim& t : res.trees) t.reset(nodes);
 
         for (;;) {
+            const double th = now_ms();
             frontier.clear();
-            for (VqTreeSim& t : res.trees) { t.run(nodes); t.wanted(nodes, frontier); }
+            advance_trees(res.trees, nodes, frontier);
             if (frontier.empty()) break;
             std::sort(frontier.begin(), frontier.end(), [&](uint32_t x, uint32_t y) { return nodes[x].begin < nodes[y].begin; });
+            t_heap_ += now_ms() - th;
             ce = round(frontier, nodes, 0);
             if (ce != cudaSuccess) return ce;
             res.rounds++;
@@ -223,7 +253,11 @@ public:
         }
         res.perm.resize(n);
         cudaMemcpyAsync(res.perm.data(), d_perm_[cur_], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream_);
-        return cudaStreamSynchronize(stream_);
+        ce = cudaStreamSynchronize(stream_);
+        if (getenv("CRN_B200_TRACE"))
+            fprintf(stderr, "[crn_b200] vq<%d> n=%u max=%u: %u rounds, host enqueue %.1f ms, sync wait %.1f ms, host results %.1f ms, host heap %.1f ms\n", D, n, max_size,
+                    res.rounds, t_enqueue_, t_sync_, t_results_, t_heap_);
+        return ce;
     }
 
     const uint32_t* device_perm() const { return d_perm_[cur_]; }
@@ -250,9 +284,32 @@ private:
     VqSlotResult* d_results_ = nullptr;
     VqNodes nodes_ = {};
     std::vector<VqSlotResult> h_results_;
+    double t_enqueue_ = 0, t_sync_ = 0, t_results_ = 0, t_heap_ = 0;      // CRN_B200_TRACE attribution of the host loop
+    static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
     static unsigned grid(unsigned n) { return (n + 255) / 256; }
     void count() { if (launches_) ++*launches_; }
+
+    // Replays the reference's heap loop for every tree and collects the next frontier.  threaded_clusterizer's partitions
+    // are independent clusterizers over disjoint node sets, and with hundreds of thousands of leaves the replay is bound
+    // by cache misses, so each tree gets its own host thread once the heaps are large (product build only).
+    static void advance_trees(std::vector<VqTreeSim>& trees, std::vector<VqHostNode>& nodes, std::vector<uint32_t>& frontier)
+    {
+#ifdef __CUDACC__
+        size_t live = 0;
+        for (const VqTreeSim& t : trees) live += t.pending.size();
+        if (trees.size() > 1 && live > 4096) {
+            std::vector<std::vector<uint32_t>> parts(trees.size());
+            std::vector<std::thread> th;
+            for (size_t i = 1; i < trees.size(); i++) th.emplace_back([&, i]() { trees[i].run(nodes); trees[i].wanted(parts[i]); });
+            trees[0].run(nodes); trees[0].wanted(parts[0]);
+            for (std::thread& t : th) t.join();
+            for (const std::vector<uint32_t>& p : parts) frontier.insert(frontier.end(), p.begin(), p.end());
+            return;
+        }
+#endif
+        for (VqTreeSim& t : trees) { t.run(nodes); t.wanted(frontier); }
+    }
 
     // every device array is carved from one slab the caller keeps between builds (no cudaMalloc / cudaFree per build)
     cudaError_t allocate(uint32_t n, uint32_t max_size)
@@ -324,6 +381,7 @@ private:
         if (!F) return cudaSuccess;
         if (F > cap_slots_) return cudaErrorInvalidValue;
         const unsigned gs = (F + 127) / 128;
+        const double t0 = now_ms();
         cudaMemcpyAsync(d_slot_node_, frontier.data(), sizeof(unsigned) * F, cudaMemcpyHostToDevice, stream_);
         unsigned* perm = d_perm_[cur_];
         unsigned* perm_out = d_perm_[cur_ ^ 1];
@@ -332,7 +390,7 @@ private:
         const unsigned gw = (F + kVqSeqWarps - 1) / kVqSeqWarps;
         cudaMemsetAsync(d_big_count_, 0, sizeof(unsigned) * kBigLists, stream_);
         CRN_LAUNCH(vq_covariance_kernel<D>, gw, kVqSeqWarps * 32, 0, stream_, vecs_, wts_, perm, d_slots_, F, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
-        CRN_LAUNCH((vq_stream_kernel<D, 1>), stream_grid(F), kVqStreamThreads, kSmemCov, stream_, vecs_, wts_, perm, d_side_, d_slots_, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
+        CRN_LAUNCH(vq_stream_cov_kernel<D>, std::min<unsigned>(F * VqCovCfg<D>::S, 592u), VqCovCfg<D>::THREADS, 0, stream_, vecs_, wts_, perm, d_slots_, d_big_count_ + 9, d_big_list_ + (size_t)9 * cap_slots_); count();
         CRN_LAUNCH(vq_axis_kernel<D>, gs, 128, 0, stream_, d_slots_, F, presplit ? 1 : 0); count();
         CRN_LAUNCH(vq_project_kernel<D>, grid(n), 256, 0, stream_, vecs_, wts_, perm, d_pos_slot_, d_slots_, d_side_, n, presplit ? 1 : 0); count();
         float_sums(perm, F, 0, 8);
@@ -359,7 +417,11 @@ private:
         cur_ ^= 1;
         h_results_.resize(F);
         cudaMemcpyAsync(h_results_.data(), d_results_, sizeof(VqSlotResult) * F, cudaMemcpyDeviceToHost, stream_);
+        const double t1 = now_ms();
         cudaError_t ce = cudaStreamSynchronize(stream_);
+        const double t2 = now_ms();
+        t_enqueue_ += t1 - t0; t_sync_ += t2 - t1;
+        if (getenv("CRN_B200_TRACE_ROUNDS")) fprintf(stderr, "[crn_b200]   vq<%d> round F=%u enqueue %.2f ms wait %.2f ms\n", D, F, t1 - t0, t2 - t1);
         if (ce != cudaSuccess) return ce;
         ce = cudaGetLastError();
         if (ce != cudaSuccess) return ce;
@@ -377,6 +439,7 @@ private:
             l.begin = par.begin; l.count = r.left_count; l.variance = r.var_left;
             rr.begin = par.begin + r.left_count; rr.count = r.right_count; rr.variance = r.var_right;
         }
+        t_results_ += now_ms() - t2;
         return cudaSuccess;
     }
 };

@@ -279,6 +279,138 @@ __global__ void __launch_bounds__(kVqStreamThreads) vq_stream_kernel(const uint8
     }
 }
 
+// Covariance of the large slots, second generation (replaces vq_stream_kernel<D, 1> on the hot path).  The float
+// accumulation of one matrix entry is a serial chain by definition of the reference (compute_split_pca adds in member
+// order, crn_clusterizer.h:496-508), so the only things to win are (a) keeping that chain at the FADD latency and
+// (b) running the independent chains side by side:
+//   * warp-specialised CTA: 128 producer threads gather one member each and expand it into addends in shared memory,
+//     ADD_WARPS warps own one accumulator per thread and add their column up in member order.  Two tile buffers: the
+//     producers fill tile t while the adders consume tile t-1, one barrier per tile.
+//   * for D = 16 the 136 chains of a slot are split over S = 4 CTAs (34 each); each computes only its own products.
+template <int D> struct VqCovCfg {
+    static constexpr int P = D * (D + 1) / 2;
+    static constexpr int S = D == 16 ? 4 : 1;
+    static constexpr int CP = (P + S - 1) / S;
+    static constexpr int T = 128;
+    static constexpr int ROW = CP | 1;                       // odd row length: conflict-free column reads and row writes
+    static constexpr int ADD_WARPS = (CP + 31) / 32;
+    static constexpr int THREADS = T + 32 * ADD_WARPS;
+};
+
+template <int D> struct VqPacked { unsigned w[(D + 3) / 4]; };
+template <int D> __device__ __forceinline__ VqPacked<D> vq_load_packed(const uint8_t* __restrict__ vecs, unsigned id)
+{
+    VqPacked<D> r;
+    if (D == 16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(vecs + (size_t)id * 16);
+        r.w[0] = q.x; r.w[1] = q.y; r.w[2 % ((D + 3) / 4)] = q.z; r.w[3 % ((D + 3) / 4)] = q.w;
+    } else {
+        const unsigned short* h = reinterpret_cast<const unsigned short*>(vecs + (size_t)id * D);      // D even: 2-byte aligned
+#pragma unroll
+        for (int k = 0; k < (D + 3) / 4; k++) {
+            unsigned v = h[2 * k];
+            if (4 * k + 2 < D) v |= (unsigned)h[2 * k + 1] << 16;
+            r.w[k] = v;
+        }
+    }
+    return r;
+}
+template <int D> __device__ __forceinline__ float vq_packed_get(const VqPacked<D>& p, int d) { return (float)((p.w[d >> 2] >> (8 * (d & 3))) & 0xffu); }
+
+template <int D, int PART>
+__device__ __forceinline__ void vq_cov_expand(const VqPacked<D>& pk, float w, const float (&c)[D], float* __restrict__ row)
+{
+    constexpr int LO = PART * VqCovCfg<D>::CP, HI = LO + VqCovCfg<D>::CP;
+    float dv[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) dv[d] = vq_packed_get<D>(pk, d) - c[d];
+    int a = 0;
+#pragma unroll
+    for (int x = 0; x < D; x++)
+#pragma unroll
+        for (int y = x; y < D; y++, a++)
+            if (a >= LO && a < HI) row[a - LO] = dv[x] * (dv[y] * w);
+}
+
+template <int D>
+__global__ void __launch_bounds__(VqCovCfg<D>::THREADS) vq_stream_cov_kernel(const uint8_t* __restrict__ vecs, const unsigned* __restrict__ wts, const unsigned* __restrict__ perm,
+                                                                           VqSlot<D>* __restrict__ slots, const unsigned* __restrict__ big_count, const unsigned* __restrict__ big_list)
+{
+    using Cfg = VqCovCfg<D>;
+    constexpr int T = Cfg::T, ROW = Cfg::ROW, S = Cfg::S, CP = Cfg::CP, P = Cfg::P;
+    __shared__ float add[2][T][ROW];
+    const unsigned tid = threadIdx.x;
+    const bool producer = tid < (unsigned)T;
+    const unsigned total = *big_count * (unsigned)S;
+    for (unsigned e = blockIdx.x; e < total; e += gridDim.x) {
+        const unsigned part = e % S;
+        VqSlot<D>& sl = slots[big_list[e / S]];
+        const unsigned begin = sl.begin, count = sl.count, tiles = (count + T - 1) / T;
+        float c[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) c[d] = sl.centroid[d];
+        // producer pipeline (two dependent gathers per member): member data two tiles ahead, ids four tiles ahead
+        unsigned id_c = 0xffffffffu, id_d = 0xffffffffu;
+        VqPacked<D> v0 = {}, v1 = {};
+        unsigned w0 = 0, w1 = 0;
+        auto load_id = [&](unsigned t) -> unsigned { const unsigned m = t * T + tid; return (t < tiles && m < count) ? perm[begin + m] : 0xffffffffu; };
+        if (producer) {
+            const unsigned id_a = load_id(0), id_b = load_id(1);
+            id_c = load_id(2); id_d = load_id(3);
+            if (id_a != 0xffffffffu) { v0 = vq_load_packed<D>(vecs, id_a); w0 = wts[id_a]; }
+            if (id_b != 0xffffffffu) { v1 = vq_load_packed<D>(vecs, id_b); w1 = wts[id_b]; }
+        }
+        const unsigned a_local = tid - (unsigned)T;                       // adders: accumulator within this part
+        const bool adds = !producer && a_local < (unsigned)CP && part * CP + a_local < (unsigned)P;
+        float acc = 0.0f;
+        for (unsigned t = 0; t <= tiles; t++) {
+            if (producer) {
+                if (t < tiles) {
+                    float* row = add[t & 1][tid];
+                    const float w = (float)w0;
+                    if (t * T + tid < count) {
+                        switch (part) {
+                        case 0: vq_cov_expand<D, 0>(v0, w, c, row); break;
+                        case 1: if (S > 1) vq_cov_expand<D, (S > 1 ? 1 : 0)>(v0, w, c, row); break;
+                        case 2: if (S > 2) vq_cov_expand<D, (S > 2 ? 2 : 0)>(v0, w, c, row); break;
+                        default: if (S > 3) vq_cov_expand<D, (S > 3 ? 3 : 0)>(v0, w, c, row); break;
+                        }
+                    }
+                    v0 = v1; w0 = w1;
+                    if (id_c != 0xffffffffu) { v1 = vq_load_packed<D>(vecs, id_c); w1 = wts[id_c]; }
+                    id_c = id_d;
+                    id_d = load_id(t + 4);
+                }
+            } else if (adds && t > 0) {
+                const unsigned tt = t - 1;
+                const unsigned cnt = count - tt * T < (unsigned)T ? count - tt * T : (unsigned)T;
+                const float (*buf)[ROW] = add[tt & 1];
+                unsigned j = 0;
+                if (cnt >= 16) {
+                    float a0[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) a0[u] = buf[u][a_local];
+                    for (; j + 32 <= cnt; j += 16) {
+                        float a1[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) a1[u] = buf[j + 16 + u][a_local];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) acc = acc + a0[u];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) a0[u] = a1[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; u++) acc = acc + a0[u];
+                    j += 16;
+                }
+                for (; j < cnt; j++) acc = acc + buf[j][a_local];
+            }
+            __syncthreads();
+        }
+        if (adds) sl.covar[part * CP + a_local] = acc;
+    }
+}
+
 // ---- exact parallel evaluation of a member-order FLOAT sum of non-negative integers ---------------------
 // acc <- RN(acc + x_i) for i = 0, 1, ... is sequential, but inside one binade [2^(23+e), 2^(24+e)) the running
 // value is a multiple of ulp = 2^e and a step only depends on the PARITY of acc / ulp (ties round to even):
