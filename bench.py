@@ -205,19 +205,23 @@ def run_transcode(ctx, ext, dev, flush, steps, peak_gbs, quick=False):
         times.append(e0.elapsed_time(e1))
     ms = sum(times) / len(times)
     host_out = torch.empty(tex.total_size, dtype=torch.uint8).pin_memory().numpy()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+
+    def e2e_step():
         t2 = ctx.unpack_begin(data)
         ctx._check(ctx._lib.crn_gpu_crnd_unpack_all_levels_host(t2._tex, host_out.ctypes.data, host_out.size))
         t2.close()
+    e2e_step()                               # staging buffers of the host entry point are allocated once per context
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
     e2e_s = (time.perf_counter() - t0) / steps
     out = {"workload": "crn_dxt5_%dx%d_14levels (synthetic stream, %.2f bpp)" % (size, size, len(data) * 8.0 / ntex), "value": ntex / (ms / 1e3) / 1e9,
            "unit": "Gtexel/s", "ms": ms, "unpack_begin_ms": begin_s * 1e3,
            "e2e": {"value": ntex / e2e_s / 1e9, "unit": "Gtexel/s", "h2d_bytes_per_step": len(data), "d2h_bytes_per_step": int(tex.total_size),
                    "includes": "unpack_begin (host table parse + upload + palette kernel) + all levels + D2H"},
-           "roofline": {"bound": "hbm", "kernel": "transcode_levels_kernel", "achieved": (len(data) + tex.total_size) / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+           "roofline": {"bound": "hbm", "kernel": "transcode_walk_resolve_kernel (+ transcode_tables_kernel)", "achieved": (len(data) + tex.total_size) / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                         "frac": (len(data) + tex.total_size) / (ms / 1e3) / 1e9 / peak_gbs, "traffic": None,
-                        "note": "one serial Huffman stream per mip level (SURVEY D5): latency-bound entropy decode, level 0 = 75% of the blocks"}}
+                        "note": "one serial Huffman stream per mip level (SURVEY D5): the walk over per-bit-offset transition tables is a single-thread dependency chain (one shared-memory lookup per 2-4 blocks), level 0 = 75% of the blocks; table build and value decode are parallel"}}
     ref = helpers.load_ref()
     if ref is not None:
         buf = np.frombuffer(data, np.uint8)

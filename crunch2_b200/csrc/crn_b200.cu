@@ -6,6 +6,7 @@
 #include "launch.h"
 #include "pack_kernels.cuh"
 #include "transcode_host.h"
+#include "transcode_wide.cuh"
 #include "cluster_kernels.cuh"
 #include "qdxt_kernels.cuh"
 #include "vq_host.h"
@@ -33,6 +34,8 @@ struct crn_gpu_ctx {
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
     void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
+    void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
+    int wide_smem_set;
     crn::VqWorkspace vq_ws;              // slab of the vector quantiser
     int transcode_smem_set;
     // clustered path: per-element child contexts (own stream + scratch) and a cache of released device buffers, both
@@ -456,6 +459,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_state) cudaFree(ctx->d_state);
     if (ctx->d_files) cudaFree(ctx->d_files);
+    if (ctx->d_wide) cudaFree(ctx->d_wide);
     if (ctx->vq_ws.base) cudaFree(ctx->vq_ws.base);
     if (ctx->d_cluster_ws) cudaFree(ctx->d_cluster_ws);
     for (crn_gpu_ctx* c : ctx->child) if (c) crn_gpu_destroy(c);
@@ -971,6 +975,86 @@ static int transcode_launch(crn_gpu_ctx* ctx, const crn::TranscodeFile* d_files,
     return CRN_GPU_OK;
 }
 
+// Levels of at least this many blocks take the table / walk / resolve kernels of transcode_wide.cuh
+// (CRN_B200_WIDE_MIN_BLOCKS overrides the default; the CPU tests lower it to cover the path on small files).
+static uint32_t wide_min_blocks()
+{
+    const char* e = getenv("CRN_B200_WIDE_MIN_BLOCKS");
+    if (e && *e) return (uint32_t)strtoul(e, nullptr, 10);
+    return 4096u;
+}
+
+// Uploads the texture's level table and launches the transcoder for every active level: large levels through the wide
+// path, the rest through the warp-per-level kernel.
+static int transcode_texture(crn_gpu_texture* tex)
+{
+    crn_gpu_ctx* ctx = tex->ctx;
+    crn::TranscodeFile& hf = tex->host_file;
+    const uint32_t min_blocks = wide_min_blocks();
+    std::vector<crn::WideLevel> wide;
+    size_t bytes = 256 * 17;                                         // descriptors first
+    uint32_t next_cta = 0, small_levels = 0;
+    for (uint32_t slot = 0; slot < 16; slot++) {
+        crn::LevelStream& ls = hf.levels[slot];
+        if (!ls.active) continue;
+        const uint32_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
+        const uint64_t blocks = (uint64_t)W * H * hf.faces;
+        if (blocks < min_blocks || W > crn::kWideMaxW || ls.src_size >= (1u << 27) || blocks >= (1ull << 31)) { small_levels++; continue; }
+        crn::WideLevel wl;
+        memset(&wl, 0, sizeof(wl));
+        wl.file = tex->d_file; wl.slot = slot; wl.nbits = ls.src_size * 8; wl.W = W; wl.H = H;
+        wl.nrows = H * hf.faces; wl.npairs = wl.nrows * (W / 2);
+        wl.ntiles = (wl.nbits + crn::kWideT - 1) / crn::kWideT;
+        if (!wl.ntiles) wl.ntiles = 1;
+        wl.stride = (uint32_t)((((size_t)wl.ntiles * crn::kWideT + 4 * crn::kWideWB + crn::kWideMW) + 255) & ~(size_t)255);
+        wl.first_cta = next_cta; wl.num_ctas = (wl.ntiles + crn::kWideTilesPerCta - 1) / crn::kWideTilesPerCta;
+        next_cta += wl.num_ctas;
+        crn::wide_format_slots(hf.format, wl.ne, wl.ns, wl.e_model, wl.s_model);
+        wl.tab = reinterpret_cast<uint8_t*>(bytes);                  // offsets for now, rebased below
+        bytes += (size_t)crn::kWideTabBytes * wl.stride;
+        wl.pair_ofs = reinterpret_cast<uint32_t*>(bytes);
+        bytes += ((size_t)wl.npairs * 4 + 255) & ~(size_t)255;
+        ls.active = 0;                                               // the warp-per-level kernel skips it
+        wide.push_back(wl);
+    }
+    CRN_CUDA(ctx, cudaMemcpyAsync(tex->d_file, &hf, sizeof(crn::TranscodeFile), cudaMemcpyHostToDevice, ctx->stream));
+    if (small_levels) {
+        const int rc = transcode_launch(ctx, tex->d_file, 1);
+        if (rc) return rc;
+    }
+    if (wide.empty()) return CRN_GPU_OK;
+    if (wide.size() > 16) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "transcode: too many levels");
+    int rc = ensure(ctx, &ctx->d_wide, &ctx->d_wide_cap, bytes);
+    if (rc) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->d_wide);
+    static_assert(sizeof(crn::WideLevel) * 16 <= 256 * 16, "descriptor area");
+    CRN_CUDA(ctx, cudaMemsetAsync(base + 256 * 16, 0, 256, ctx->stream));        // row counters, one per level
+    uint32_t li = 0;
+    for (crn::WideLevel& wl : wide) {
+        wl.progress = reinterpret_cast<uint32_t*>(base + 256 * 16) + (li++) * 4;
+        wl.tab = base + reinterpret_cast<size_t>(wl.tab);
+        wl.pair_ofs = reinterpret_cast<uint32_t*>(base + reinterpret_cast<size_t>(wl.pair_ofs));
+        const size_t built = (size_t)wl.ntiles * crn::kWideT;        // entries the table kernel writes; the windows read a little further
+        for (int a = 0; a < 6; a++) CRN_CUDA(ctx, cudaMemsetAsync(wl.tab + (size_t)a * wl.stride + built, 0, wl.stride - built, ctx->stream));
+        for (int a = 0; a < 2; a++) CRN_CUDA(ctx, cudaMemsetAsync(wl.tab + (size_t)(6 + 2 * a) * wl.stride + 2 * built, 0, 2 * (wl.stride - built), ctx->stream));
+    }
+    // pageable source: the call returns once the descriptors are staged, so the vector may die with this frame
+    CRN_CUDA(ctx, cudaMemcpyAsync(base, wide.data(), sizeof(crn::WideLevel) * wide.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const crn::WideLevel* d_levels = reinterpret_cast<const crn::WideLevel*>(base);
+    const uint32_t nl = (uint32_t)wide.size();
+#ifdef __CUDACC__
+    if (!ctx->wide_smem_set) {
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_walk_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::WideSmemBC)));
+        ctx->wide_smem_set = 1;
+    }
+#endif
+    CRN_LAUNCH(crn::transcode_tables_kernel, next_cta, crn::kWideThreadsA, 0, ctx->stream, d_levels, nl);
+    CRN_LAUNCH(crn::transcode_walk_resolve_kernel, 2 * nl, crn::kWideThreadsC, sizeof(crn::WideSmemBC), ctx->stream, d_levels, getenv("CRN_B200_WIDE_NOPIPE") ? 0 : 1);
+    ctx->launches += 2;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
 int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, crn_gpu_texture** out_tex)
 {
     if (!ctx || !out_tex) return CRN_GPU_ERR_BAD_PARAM;
@@ -1100,8 +1184,7 @@ int crn_gpu_crnd_unpack_level(crn_gpu_texture* tex, void* const* d_dst_faces, ui
         if (!d_dst_faces[f]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: null face pointer");
         ls.dst[f] = (unsigned long long)(uintptr_t)d_dst_faces[f];
     }
-    CRN_CUDA(ctx, cudaMemcpyAsync(tex->d_file, &tex->host_file, sizeof(crn::TranscodeFile), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = transcode_launch(ctx, tex->d_file, 1);
+    int rc = transcode_texture(tex);
     if (rc) return rc;
     // host_file is reused by the next call: make sure the async copy has read it
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1134,8 +1217,7 @@ int crn_gpu_crnd_unpack_all_levels(crn_gpu_texture* tex, void* d_dst, uint64_t d
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = prepare_all_levels(tex, d_dst, dst_capacity);
     if (rc) return rc;
-    CRN_CUDA(ctx, cudaMemcpyAsync(tex->d_file, &tex->host_file, sizeof(crn::TranscodeFile), cudaMemcpyHostToDevice, ctx->stream));
-    return transcode_launch(ctx, tex->d_file, 1);
+    return transcode_texture(tex);
 }
 
 int crn_gpu_crnd_unpack_all_levels_host(crn_gpu_texture* tex, void* h_dst, uint64_t dst_capacity)

@@ -75,3 +75,25 @@ def test_gpu_batch(gpu_ctx, port):
     for t, o, d in zip(texs, outs, files):
         assert split_levels(t, o.cpu().numpy()) == helpers.port_unpack_all(port, d)
         t.close()
+
+
+@pytest.mark.parametrize("min_blocks", ["1", "4096"])
+@pytest.mark.parametrize("fmt,w,h,faces", [("DXT1", 2048, 1024, 1), ("DXT5", 1024, 1024, 1), ("DXN_XY", 512, 512, 6), ("DXT5A", 4096, 256, 1), ("DXT5", 260, 100, 1)])
+def test_gpu_wide_path(gpu_ctx, port, monkeypatch, fmt, w, h, faces, min_blocks):
+    """Levels through transcode_wide.cuh (all of them with the threshold at 1; the default threshold otherwise),
+    bit-exact against the oracle, and the same bytes as the warp-per-level kernel gives."""
+    data = crnsynth.synth_crn(w, h, fmt, faces=faces, seed=31, skew=0.1)
+    want = helpers.port_unpack_all(port, data)
+    monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", min_blocks)
+    tex = gpu_ctx.unpack_begin(data)
+    l0 = gpu_ctx.launch_count
+    got = tex.unpack_all()
+    wide_launches = gpu_ctx.launch_count - l0
+    assert split_levels(tex, got) == want
+    monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", "4000000000")
+    l0 = gpu_ctx.launch_count
+    narrow = tex.unpack_all()
+    bx, by = tex.level_blocks(0)
+    assert gpu_ctx.launch_count - l0 == 1 and (wide_launches >= 2 or (((bx + 1) & ~1) * ((by + 1) & ~1) * faces < int(min_blocks)))
+    assert np.array_equal(got, narrow)
+    tex.close()

@@ -112,3 +112,44 @@ def test_batch_matches_single(sim, port):
         assert split_levels(t, o) == helpers.port_unpack_all(port, d)
         t.close()
     ctx.close()
+
+
+WIDE = [("DXT1", 256, 256, 1, {}), ("DXT5", 260, 100, 1, {}), ("DXN_XY", 128, 64, 1, {}), ("DXT5A", 260, 36, 1, {}), ("DXT5", 64, 64, 6, {}),
+        ("DXT1", 512, 64, 1, dict(n_color_ep=8192, n_color_sel=8192)), ("DXT5", 1024, 16, 1, dict(n_alpha_ep=8192, n_alpha_sel=8192, skew=0.1))]
+
+
+@pytest.mark.parametrize("min_blocks", ["1", "64"])
+@pytest.mark.parametrize("fmt,w,h,faces,kw", WIDE)
+def test_wide_path_matches_port(port, sim, monkeypatch, fmt, w, h, faces, kw, min_blocks):
+    """transcode_wide.cuh (transition tables -> walk -> resolve) on files small enough for the emulator: every level
+    ("1") or only the large ones ("64", the rest through the warp-per-level kernel), bit-exact against the oracle."""
+    monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", min_blocks)
+    data = crnsynth.synth_crn(w, h, fmt, faces=faces, seed=11, **kw)
+    want = helpers.port_unpack_all(port, data)
+    ctx = crn.Context(0, lib=sim)
+    tex = ctx.unpack_begin(data)
+    l0 = ctx.launch_count
+    got = split_levels(tex, tex.unpack_all())
+    assert ctx.launch_count - l0 == (2 if min_blocks == "1" else 3)
+    assert got == want
+    # one level at a time with a pitch, as crnd_unpack_level is called
+    bx, by = tex.level_blocks(0)
+    bpb = tex.info["bytes_per_block"]
+    pitch = bx * bpb + 8
+    bufs = [np.full(pitch * by, 0xEE, np.uint8) for _ in range(faces)]
+    tex.unpack_level_device([b.ctypes.data for b in bufs], pitch * by, pitch, 0)
+    ctx.synchronize()
+    for f in range(faces):
+        rows = bufs[f].reshape(by, pitch)
+        assert rows[:, :bx * bpb].tobytes() == want[0][f]
+        assert (rows[:, bx * bpb:] == 0xEE).all()
+    tex.close(); ctx.close()
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_wide_path_matches_golden_crn(sim, monkeypatch, case):
+    monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", "1")
+    ctx = crn.Context(0, lib=sim)
+    tex = ctx.unpack_begin(load(case))
+    assert shas(split_levels(tex, tex.unpack_all())) == case["sha256"]
+    tex.close(); ctx.close()
