@@ -113,7 +113,7 @@ cluster_compact_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_
 
 struct ClusterResult { uint32_t endpoints; uint32_t flags; };      // flags: bit 0 invert, bit 1 alpha_block, bits 2-3 stage
 
-__global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
+__global__ void __launch_bounds__(kClusterWarpsPerCta * 32, 5)
 dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
                               ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
                               unsigned int* __restrict__ next_cluster, ClusterResult* __restrict__ results,

@@ -228,10 +228,10 @@ int qdxt_upload_csr(crn_qdxt_element& e)
 }
 
 template <int D>
-int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res)
+int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res, uint32_t* d_perm_out = nullptr)
 {
     crn::VqBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws);
-    const cudaError_t ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res);
+    const cudaError_t ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out);
     if (ce != cudaSuccess) return set_err(e.ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
     return CRN_GPU_OK;
 }
@@ -371,11 +371,14 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
     CRN_CUDA(ctx, cudaGetLastError());
     e.offsets.assign(1, 0u); e.members.clear();
     crn::VqResult sel_tree;
+    // selector clusters keep every leaf, so the CSR lists are the leaves' position ranges over the final permutation,
+    // which goes device-to-device into d_members (see vq_leaf_offsets); only the offsets travel
+    uint32_t sel_members = 0;
     if (e.kind == 0) {
-        rc = qdxt_vq<16>(e, nullptr, n, max_selector_clusters, true, sel_tree);
+        rc = qdxt_vq<16>(e, nullptr, n, max_selector_clusters, true, sel_tree, e.d_members);
         if (rc) return rc;
-        const uint32_t k = sel_tree.retrieve(0, e.cluster_of.data());
-        qdxt_append_csr(e, nullptr, n, k);
+        crn::vq_leaf_offsets(sel_tree, 0u, e.offsets);
+        sel_members = n;
     } else {
         e.cat.resize(n);
         CRN_CUDA(ctx, cudaMemcpyAsync(e.cat.data(), e.d_cat, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -391,10 +394,10 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
             max_clusters = std::min(std::max(64u, max_clusters), m);
             if (max_clusters >= m) continue;
             CRN_CUDA(ctx, cudaMemcpyAsync(e.d_ids, ids.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-            rc = qdxt_vq<16>(e, e.d_ids, m, max_clusters, true, sel_tree);
+            rc = qdxt_vq<16>(e, e.d_ids, m, max_clusters, true, sel_tree, e.d_members + sel_members);
             if (rc) return rc;
-            const uint32_t k = sel_tree.retrieve(0, e.cluster_of.data());
-            qdxt_append_csr(e, ids.data(), m, k);
+            crn::vq_leaf_offsets(sel_tree, sel_members, e.offsets);
+            sel_members += m;
         }
     }
     const uint32_t k_sel = (uint32_t)e.offsets.size() - 1;
@@ -675,7 +678,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     }
     CRN_LAUNCH(crn::cluster_compact_kernel, gp, 256, 0, ctx->stream, d_cluster_offsets, n_clusters, TP, ws, rank);
     const int threads = crn::kClusterWarpsPerCta * 32;
-    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, 4);
+    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, getenv("CRN_B200_CLUSTER_CTAS") ? atoi(getenv("CRN_B200_CLUSTER_CTAS")) : 5);
     CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, d_cluster_offsets, n_clusters, dp, scan_alpha, ws, rank, transparent,
                reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error));
     CRN_LAUNCH(crn::cluster_write_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent,
@@ -703,7 +706,7 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     if (rc) return rc;
     CRN_CUDA(ctx, cudaMemsetAsync(ctx->d_cluster_ws, 0, 256, ctx->stream));
     const int threads = crn::kClusterWarpsPerCta * 32;
-    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, 4);
+    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, getenv("CRN_B200_CLUSTER_CTAS") ? atoi(getenv("CRN_B200_CLUSTER_CTAS")) : 5);
     CRN_LAUNCH(crn::dxt5_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
                d_cluster_blocks, n_clusters, component, (int)params->dxt_quality, params->use_both_block_types ? 1 : 0,
                reinterpret_cast<unsigned int*>(ctx->d_cluster_ws), static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes,
@@ -984,76 +987,92 @@ static uint32_t wide_min_blocks()
     return 4096u;
 }
 
-// Uploads the texture's level table and launches the transcoder for every active level: large levels through the wide
-// path, the rest through the warp-per-level kernel.
-static int transcode_texture(crn_gpu_texture* tex)
+// Launches the transcoder for every active level of `count` textures whose level tables (host_file) are filled in:
+// large levels through the wide path (transcode_wide.cuh), the rest through the warp-per-level kernel.  d_files: device
+// array the level tables are uploaded to (the texture's own d_file for a single texture).
+static int transcode_textures(crn_gpu_ctx* ctx, crn_gpu_texture* const* texs, uint32_t count, crn::TranscodeFile* d_files)
 {
-    crn_gpu_ctx* ctx = tex->ctx;
-    crn::TranscodeFile& hf = tex->host_file;
     const uint32_t min_blocks = wide_min_blocks();
     std::vector<crn::WideLevel> wide;
-    size_t bytes = 256 * 17;                                         // descriptors first
+    std::vector<crn::TranscodeFile> files(count);
+    size_t bytes = 0;
     uint32_t next_cta = 0, small_levels = 0;
-    for (uint32_t slot = 0; slot < 16; slot++) {
-        crn::LevelStream& ls = hf.levels[slot];
-        if (!ls.active) continue;
-        const uint32_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
-        const uint64_t blocks = (uint64_t)W * H * hf.faces;
-        if (blocks < min_blocks || W > crn::kWideMaxW || ls.src_size >= (1u << 27) || blocks >= (1ull << 31)) { small_levels++; continue; }
-        crn::WideLevel wl;
-        memset(&wl, 0, sizeof(wl));
-        wl.file = tex->d_file; wl.slot = slot; wl.nbits = ls.src_size * 8; wl.W = W; wl.H = H;
-        wl.nrows = H * hf.faces; wl.npairs = wl.nrows * (W / 2);
-        wl.ntiles = (wl.nbits + crn::kWideT - 1) / crn::kWideT;
-        if (!wl.ntiles) wl.ntiles = 1;
-        wl.stride = (uint32_t)((((size_t)wl.ntiles * crn::kWideT + 4 * crn::kWideWB + crn::kWideMW) + 255) & ~(size_t)255);
-        wl.first_cta = next_cta; wl.num_ctas = (wl.ntiles + crn::kWideTilesPerCta - 1) / crn::kWideTilesPerCta;
-        next_cta += wl.num_ctas;
-        crn::wide_format_slots(hf.format, wl.ne, wl.ns, wl.e_model, wl.s_model);
-        wl.tab = reinterpret_cast<uint8_t*>(bytes);                  // offsets for now, rebased below
-        bytes += (size_t)crn::kWideTabBytes * wl.stride;
-        wl.pair_ofs = reinterpret_cast<uint32_t*>(bytes);
-        bytes += ((size_t)wl.npairs * 4 + 255) & ~(size_t)255;
-        ls.active = 0;                                               // the warp-per-level kernel skips it
-        wide.push_back(wl);
+    for (uint32_t t = 0; t < count; t++) {
+        crn::TranscodeFile& hf = texs[t]->host_file;
+        for (uint32_t slot = 0; slot < 16; slot++) {
+            crn::LevelStream& ls = hf.levels[slot];
+            if (!ls.active) continue;
+            const uint32_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
+            const uint64_t blocks = (uint64_t)W * H * hf.faces;
+            if (blocks < min_blocks || W > crn::kWideMaxW || ls.src_size >= (1u << 27) || blocks >= (1ull << 31)) { small_levels++; continue; }
+            crn::WideLevel wl;
+            memset(&wl, 0, sizeof(wl));
+            wl.file = d_files + t; wl.slot = slot; wl.nbits = ls.src_size * 8; wl.W = W; wl.H = H;
+            wl.nrows = H * hf.faces; wl.npairs = wl.nrows * (W / 2);
+            wl.ntiles = (wl.nbits + crn::kWideT - 1) / crn::kWideT;
+            if (!wl.ntiles) wl.ntiles = 1;
+            wl.stride = (uint32_t)((((size_t)wl.ntiles * crn::kWideT + 4 * crn::kWideWB + crn::kWideMW) + 255) & ~(size_t)255);
+            wl.first_cta = next_cta; wl.num_ctas = (wl.ntiles + crn::kWideTilesPerCta - 1) / crn::kWideTilesPerCta;
+            next_cta += wl.num_ctas;
+            crn::wide_format_slots(hf.format, wl.ne, wl.ns, wl.e_model, wl.s_model);
+            wl.tab = reinterpret_cast<uint8_t*>(bytes);                  // offsets for now, rebased below
+            bytes += (size_t)crn::kWideTabBytes * wl.stride;
+            wl.pair_ofs = reinterpret_cast<uint32_t*>(bytes);
+            bytes += ((size_t)wl.npairs * 4 + 255) & ~(size_t)255;
+            ls.active = 0;                                               // the warp-per-level kernel skips it
+            wide.push_back(wl);
+        }
+        files[t] = hf;
     }
-    CRN_CUDA(ctx, cudaMemcpyAsync(tex->d_file, &hf, sizeof(crn::TranscodeFile), cudaMemcpyHostToDevice, ctx->stream));
+    // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may die with this frame
+    CRN_CUDA(ctx, cudaMemcpyAsync(d_files, files.data(), sizeof(crn::TranscodeFile) * count, cudaMemcpyHostToDevice, ctx->stream));
     if (small_levels) {
-        const int rc = transcode_launch(ctx, tex->d_file, 1);
+        const int rc = transcode_launch(ctx, d_files, count);
         if (rc) return rc;
     }
     if (wide.empty()) return CRN_GPU_OK;
-    if (wide.size() > 16) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "transcode: too many levels");
-    int rc = ensure(ctx, &ctx->d_wide, &ctx->d_wide_cap, bytes);
+    const uint32_t nl = (uint32_t)wide.size();
+    const size_t o_progress = (sizeof(crn::WideLevel) * nl + 255) & ~(size_t)255, o_data = (o_progress + 4 * (size_t)nl + 255) & ~(size_t)255;
+    int rc = ensure(ctx, &ctx->d_wide, &ctx->d_wide_cap, o_data + bytes);
     if (rc) return rc;
     uint8_t* base = static_cast<uint8_t*>(ctx->d_wide);
-    static_assert(sizeof(crn::WideLevel) * 16 <= 256 * 16, "descriptor area");
-    CRN_CUDA(ctx, cudaMemsetAsync(base + 256 * 16, 0, 256, ctx->stream));        // row counters, one per level
-    uint32_t li = 0;
-    for (crn::WideLevel& wl : wide) {
-        wl.progress = reinterpret_cast<uint32_t*>(base + 256 * 16) + (li++) * 4;
-        wl.tab = base + reinterpret_cast<size_t>(wl.tab);
-        wl.pair_ofs = reinterpret_cast<uint32_t*>(base + reinterpret_cast<size_t>(wl.pair_ofs));
-        const size_t built = (size_t)wl.ntiles * crn::kWideT;        // entries the table kernel writes; the windows read a little further
-        for (int a = 0; a < 6; a++) CRN_CUDA(ctx, cudaMemsetAsync(wl.tab + (size_t)a * wl.stride + built, 0, wl.stride - built, ctx->stream));
-        for (int a = 0; a < 2; a++) CRN_CUDA(ctx, cudaMemsetAsync(wl.tab + (size_t)(6 + 2 * a) * wl.stride + 2 * built, 0, 2 * (wl.stride - built), ctx->stream));
+    CRN_CUDA(ctx, cudaMemsetAsync(base + o_progress, 0, 4 * (size_t)nl, ctx->stream));        // row counters, one per level
+    for (uint32_t i = 0; i < nl; i++) {
+        crn::WideLevel& wl = wide[i];
+        wl.progress = reinterpret_cast<uint32_t*>(base + o_progress) + i;
+        wl.tab = base + o_data + reinterpret_cast<size_t>(wl.tab);
+        wl.pair_ofs = reinterpret_cast<uint32_t*>(base + o_data + reinterpret_cast<size_t>(wl.pair_ofs));
     }
-    // pageable source: the call returns once the descriptors are staged, so the vector may die with this frame
-    CRN_CUDA(ctx, cudaMemcpyAsync(base, wide.data(), sizeof(crn::WideLevel) * wide.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CRN_CUDA(ctx, cudaMemcpyAsync(base, wide.data(), sizeof(crn::WideLevel) * nl, cudaMemcpyHostToDevice, ctx->stream));
     const crn::WideLevel* d_levels = reinterpret_cast<const crn::WideLevel*>(base);
-    const uint32_t nl = (uint32_t)wide.size();
+    const size_t smem = sizeof(crn::WideSmemBC);
 #ifdef __CUDACC__
     if (!ctx->wide_smem_set) {
-        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_walk_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::WideSmemBC)));
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_walk_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->wide_smem_set = 1;
     }
 #endif
+    const int pipe = getenv("CRN_B200_WIDE_NOPIPE") ? 0 : 1;
     CRN_LAUNCH(crn::transcode_tables_kernel, next_cta, crn::kWideThreadsA, 0, ctx->stream, d_levels, nl);
-    CRN_LAUNCH(crn::transcode_walk_resolve_kernel, 2 * nl, crn::kWideThreadsC, sizeof(crn::WideSmemBC), ctx->stream, d_levels, getenv("CRN_B200_WIDE_NOPIPE") ? 0 : 1);
-    ctx->launches += 2;
+    // CRN_B200_WIDE_SPLIT: 1 forces the two-launch form, 0 the fused one (tests; the emulator runs CTAs one after another)
+    const char* split_env = getenv("CRN_B200_WIDE_SPLIT");
+    const bool fused = split_env ? split_env[0] == '0' : 2 * nl <= (uint32_t)ctx->sm_count;
+    if (fused) {
+        // one CTA per SM at this shared-memory size: every walker / resolver pair is resident, the resolver trails the walker
+        CRN_LAUNCH(crn::transcode_walk_resolve_kernel, 2 * nl, crn::kWideThreadsC, smem, ctx->stream, d_levels, pipe);
+        ctx->launches += 2;
+    } else {
+        CRN_LAUNCH(crn::transcode_walk_kernel, nl, crn::kWideThreadsC, smem, ctx->stream, d_levels, pipe);
+        CRN_LAUNCH(crn::transcode_resolve_kernel, nl, crn::kWideThreadsC, smem, ctx->stream, d_levels);
+        ctx->launches += 3;
+    }
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
 }
+
+static int transcode_texture(crn_gpu_texture* tex) { return transcode_textures(tex->ctx, &tex, 1, tex->d_file); }
 
 int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, crn_gpu_texture** out_tex)
 {
@@ -1241,17 +1260,14 @@ int crn_gpu_crnd_unpack_batch(crn_gpu_ctx* ctx, crn_gpu_texture* const* textures
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure(ctx, &ctx->d_files, &ctx->d_files_cap, sizeof(crn::TranscodeFile) * (size_t)count);
     if (rc) return rc;
-    std::vector<crn::TranscodeFile> files(count);
     for (uint32_t i = 0; i < count; i++) {
         if (!textures[i] || textures[i]->ctx != ctx) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_batch: texture belongs to another context");
         rc = prepare_all_levels(textures[i], d_dst[i], dst_capacity[i]);
         if (rc) return rc;
-        files[i] = textures[i]->host_file;
     }
-    CRN_CUDA(ctx, cudaMemcpyAsync(ctx->d_files, files.data(), sizeof(crn::TranscodeFile) * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-    rc = transcode_launch(ctx, static_cast<const crn::TranscodeFile*>(ctx->d_files), count);
+    rc = transcode_textures(ctx, textures, count, static_cast<crn::TranscodeFile*>(ctx->d_files));
     if (rc) return rc;
-    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `files` dies at return
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
 }
 

@@ -88,9 +88,9 @@ __device__ __forceinline__ uint32_t wide_peek16(const uint8_t* bytes, uint32_t i
 __global__ void __launch_bounds__(kWideThreadsA) transcode_tables_kernel(const WideLevel* __restrict__ levels, uint32_t nlevels)
 {
     __shared__ WideSmemA sm;
-    uint32_t li = 0;
-    while (li + 1 < nlevels && blockIdx.x >= levels[li + 1].first_cta) li++;
-    const WideLevel& wl = levels[li];
+    uint32_t lo = 0, hi = nlevels;                                   // last level whose first_cta <= blockIdx.x
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (levels[mid].first_cta <= blockIdx.x) lo = mid; else hi = mid; }
+    const WideLevel& wl = levels[lo];
     const TranscodeFile& f = *wl.file;
     const LevelStream& ls = f.levels[wl.slot];
     const unsigned tid = threadIdx.x;
@@ -179,6 +179,18 @@ __global__ void __launch_bounds__(kWideThreadsA) transcode_tables_kernel(const W
             const uint32_t* src = reinterpret_cast<const uint32_t*>(a ? sm.Gt2 : sm.Gd2);
             uint32_t* dst = reinterpret_cast<uint32_t*>(wl.tab + (size_t)(6 + 2 * a) * wl.stride + (size_t)base_bit * 2);
             for (uint32_t i = tid; i < (uint32_t)kWideT / 2; i += blockDim.x) dst[i] = src[i];
+        }
+    }
+    // the walker's windows read a little past the last tile: the level's last CTA zeroes that tail of every array
+    if (tile0 + kWideTilesPerCta >= wl.ntiles) {
+        const uint32_t built = wl.ntiles * kWideT, tail = wl.stride - built;          // both multiples of 4
+        for (int a = 0; a < 6; a++) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(wl.tab + (size_t)a * wl.stride + built);
+            for (uint32_t i = tid; i < tail / 4; i += blockDim.x) dst[i] = 0u;
+        }
+        for (int a = 0; a < 2; a++) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(wl.tab + (size_t)(6 + 2 * a) * wl.stride + (size_t)built * 2);
+            for (uint32_t i = tid; i < tail / 2; i += blockDim.x) dst[i] = 0u;
         }
     }
 }
@@ -600,12 +612,8 @@ __device__ __forceinline__ void wide_resolve_level(WideSmemC* sm, const WideLeve
 // 32 CTAs, all resident, so the consumer can poll the producer's row counter).
 union WideSmemBC { WideSmemB b; WideSmemC c; };
 
-__global__ void __launch_bounds__(kWideThreadsC) transcode_walk_resolve_kernel(const WideLevel* __restrict__ levels, int pipe)
+__device__ __forceinline__ void wide_resolve(WideSmemC* sm, const WideLevel& wl)
 {
-    CRN_DYN_SMEM(WideSmemBC, smu);
-    const WideLevel& wl = levels[blockIdx.x >> 1];
-    if (!(blockIdx.x & 1)) { wide_walk(&smu->b, wl, pipe); return; }
-    WideSmemC* sm = &smu->c;
     const TranscodeFile& f = *wl.file;
     for (uint32_t i = threadIdx.x; i < (uint32_t)(kNumBlockModels * kHuffLookupSize); i += blockDim.x)
         sm->lookup[i / kHuffLookupSize][i % kHuffLookupSize] = f.models[i / kHuffLookupSize].lookup[i % kHuffLookupSize];
@@ -622,6 +630,27 @@ __global__ void __launch_bounds__(kWideThreadsC) transcode_walk_resolve_kernel(c
     else if (fmt == 9) wide_resolve_level<false, true, false>(sm, wl, f, ls);
     else if (fmt == 7 || fmt == 8) wide_resolve_level<false, true, true>(sm, wl, f, ls);
     else wide_resolve_level<true, true, false>(sm, wl, f, ls);
+}
+
+__global__ void __launch_bounds__(kWideThreadsC) transcode_walk_resolve_kernel(const WideLevel* __restrict__ levels, int pipe)
+{
+    CRN_DYN_SMEM(WideSmemBC, smu);
+    const WideLevel& wl = levels[blockIdx.x >> 1];
+    if (!(blockIdx.x & 1)) wide_walk(&smu->b, wl, pipe);
+    else wide_resolve(&smu->c, wl);
+}
+
+// Batches with more levels than SM pairs: the same two roles as two launches (no co-residency needed; the resolver
+// finds every row counter already at its final value).
+__global__ void __launch_bounds__(kWideThreadsC) transcode_walk_kernel(const WideLevel* __restrict__ levels, int pipe)
+{
+    CRN_DYN_SMEM(WideSmemBC, smu);
+    wide_walk(&smu->b, levels[blockIdx.x], pipe);
+}
+__global__ void __launch_bounds__(kWideThreadsC) transcode_resolve_kernel(const WideLevel* __restrict__ levels)
+{
+    CRN_DYN_SMEM(WideSmemBC, smu);
+    wide_resolve(&smu->c, levels[blockIdx.x]);
 }
 
 }  // namespace crn

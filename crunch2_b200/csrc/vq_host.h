@@ -15,6 +15,11 @@
 #include <time.h>
 #include <algorithm>
 #ifdef __CUDACC__
+#include <atomic>
+#include <memory>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #endif
 #include <type_traits>
@@ -29,6 +34,10 @@ struct VqHostNode {
     float variance = 0;
     int32_t split_rank = -1;         // m_codebook_index of an interior node: order in which the reference split it
     uint8_t processed = 0, unsplittable = 0;
+    // copies of the children's count / variance: the heap replay decides about both children from the parent's record
+    // alone (one cache line per pop instead of three; the node table of a large build is tens of MB)
+    uint32_t child_count[2] = {0, 0};
+    float child_var[2] = {0, 0};
 };
 
 struct VqHeapEntry { float variance; uint32_t id; };   // the key travels with the id: sift loops stay inside one array
@@ -40,6 +49,10 @@ struct VqTreeSim {                   // one clusterizer<V> instance
     // Bookkeeping for wanted(): a histogram of the keys in the heap (8192 bins over the float's exponent + 4 mantissa
     // bits; variances are >= 0 so the bit pattern is monotonic) and the heap members not yet sent to the device.
     static constexpr uint32_t kBins = 8192;
+    // Nodes split by the replay, in split order (rank = index).  Written to VqHostNode::split_rank once the build is over:
+    // the node table is shared by the trees' threads and its records are interleaved, so writing ranks during the replay
+    // would bounce cache lines between cores.
+    std::vector<uint32_t> split_log;
     std::vector<uint32_t> hist;
     std::vector<VqHeapEntry> pending;
     static uint32_t bin_of(float v) { uint32_t b; memcpy(&b, &v, 4); return (b >> 19) & (kBins - 1); }
@@ -51,11 +64,10 @@ struct VqTreeSim {                   // one clusterizer<V> instance
         hist.assign(kBins, 0u);
         pending.clear();
         heap_size = 0;
-        insert(nodes, root);                                   // the root enters the heap unconditionally (:100-102)
+        insert(root, nodes[root].variance);                    // the root enters the heap unconditionally (:100-102)
     }
-    void insert(const std::vector<VqHostNode>& nodes, uint32_t id)
+    void insert(uint32_t id, float v)
     {   // insert_heap (:384-414): sift up while the parent is not strictly greater
-        const float v = nodes[id].variance;
         uint32_t pos = ++heap_size;
         if (heap_size >= heap.size()) heap.resize(heap_size + 1);
         for (;;) {
@@ -93,14 +105,15 @@ struct VqTreeSim {                   // one clusterizer<V> instance
         while (!finished()) {
             VqHostNode& nd = nodes[heap[1].id];
             if (nd.count != 1 && !nd.processed) return;
+            // the next top is one of the root's children: have their records on the way
+            if (heap_size >= 3) { __builtin_prefetch(&nodes[heap[2].id]); __builtin_prefetch(&nodes[heap[3].id]); }
             const uint32_t id = pop();
-            VqHostNode& node = nodes[id];
+            const VqHostNode& node = nodes[id];
             if (node.count != 1 && !node.unsplittable) {          // split_node (:740-873)
-                node.split_rank = (int32_t)split_index++;
-                for (uint32_t c = 0; c < 2; c++) {
-                    const uint32_t ch = (uint32_t)node.left + c;
-                    if (nodes[ch].count > 1 && nodes[ch].variance > 0.0f) insert(nodes, ch);
-                }
+                split_log.push_back(id);
+                split_index++;
+                for (uint32_t c = 0; c < 2; c++)
+                    if (node.child_count[c] > 1 && node.child_var[c] > 0.0f) insert((uint32_t)node.left + c, node.child_var[c]);
             }
             total_leaves++;
         }
@@ -169,7 +182,95 @@ struct VqResult {                    // host-side outcome of one build
     }
 };
 
+// Every node covers a contiguous range of the final permutation and the splits are stable partitions of an ascending id
+// list, so with every leaf kept (retrieve_clusters(0)) cluster k is simply the k-th leaf in position order and its members
+// are perm[begin .. begin + count) -- already ascending, already on the device.  Appends the leaves' first positions
+// (+ base) to `offsets` (which ends with the running total) in the reference's retrieval order; returns the leaf count.
+inline uint32_t vq_leaf_offsets(const VqResult& res, uint32_t base, std::vector<uint32_t>& offsets)
+{
+    uint32_t leaves = 0, total = 0;
+    std::vector<uint32_t> stack;
+    offsets.pop_back();                                            // the running total comes back at the end
+    for (const VqTreeSim& t : res.trees) {
+        stack.clear();
+        uint32_t cur = t.root;
+        for (;;) {
+            const VqHostNode& nd = res.nodes[cur];
+            if (nd.split_rank < 0) {
+                offsets.push_back(base + nd.begin);
+                total = nd.begin + nd.count;
+                leaves++;
+                if (stack.empty()) break;
+                cur = stack.back();
+                stack.pop_back();
+                continue;
+            }
+            stack.push_back((uint32_t)nd.left + 1);
+            cur = (uint32_t)nd.left;
+        }
+    }
+    offsets.push_back(base + total);
+    return leaves;
+}
+
 struct VqWorkspace { void* base = nullptr; size_t cap = 0; };     // device slab reused across builds
+
+#ifdef __CUDACC__
+// Three helper threads that live as long as one build: the host replay and the result scatter of a round are split four
+// ways (spawning threads per round cost more than the work they did).
+class VqPool {
+public:
+    VqPool() { for (int i = 0; i < 3; i++) workers_[i] = std::thread([this, i]() { loop(i + 1); }); }
+    ~VqPool()
+    {
+        stop_.store(true);
+        gen_.fetch_add(1);
+        { std::lock_guard<std::mutex> l(m_); }
+        cv_.notify_all();
+        for (std::thread& t : workers_) t.join();
+    }
+    // fn(part) for part = 0..3, part 0 on the calling thread; returns when all four are done
+    void run4(const std::function<void(int)>& fn)
+    {
+        fn_ = &fn;
+        pending_.store(3);
+        gen_.fetch_add(1);
+        { std::lock_guard<std::mutex> l(m_); }
+        cv_.notify_all();
+        fn(0);
+        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+private:
+    // Rounds follow each other within a millisecond or two, and a sleeping thread takes about that long to get going
+    // again, so a worker first spins on the generation counter and only then parks on the condition variable.
+    void loop(int part)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            const double t0 = now();
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                if (now() - t0 > 4.0) {
+                    std::unique_lock<std::mutex> l(m_);
+                    cv_.wait(l, [&]() { return gen_.load() != seen; });
+                    break;
+                }
+            }
+            seen = gen_.load();
+            if (stop_.load()) return;
+            (*fn_)(part);
+            pending_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    std::thread workers_[3];
+    std::mutex m_;
+    std::condition_variable cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> pending_{0};
+    std::atomic<bool> stop_{false};
+};
+#endif
 
 template <int D> class VqBuilder {
 public:
@@ -178,7 +279,9 @@ public:
     // d_vecs: u8[][D], d_wts: u32[] (device), indexed by vector id.  d_ids: the n ids to quantise in ascending order
     // (nullptr = 0..n-1).  threaded: crnlib::threaded_clusterizer<V>::create_clusters (crn_threaded_clusterizer.h:70-174):
     // three PCA divisions into <= 4 partitions, each its own clusterizer.
-    cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, VqResult& res)
+    // d_perm_out (optional, device, n entries): receives the final permutation; the host copy res.perm is then skipped.
+    cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, VqResult& res,
+                      uint32_t* d_perm_out = nullptr)
     {
         res = VqResult();
         if (!n) return cudaSuccess;
@@ -244,19 +347,27 @@ public:
             frontier.clear();
             advance_trees(res.trees, nodes, frontier);
             if (frontier.empty()) break;
-            std::sort(frontier.begin(), frontier.end(), [&](uint32_t x, uint32_t y) { return nodes[x].begin < nodes[y].begin; });
             t_heap_ += now_ms() - th;
             ce = round(frontier, nodes, 0);
             if (ce != cudaSuccess) return ce;
             res.rounds++;
             res.device_splits += (uint32_t)frontier.size();
         }
-        res.perm.resize(n);
-        cudaMemcpyAsync(res.perm.data(), d_perm_[cur_], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream_);
+        for (VqTreeSim& t : res.trees) {                          // m_codebook_index of the interior nodes
+            for (size_t k = 0; k < t.split_log.size(); k++) nodes[t.split_log[k]].split_rank = (int32_t)k;
+            std::vector<uint32_t>().swap(t.split_log);
+        }
+        if (d_perm_out) cudaMemcpyAsync(d_perm_out, d_perm_[cur_], sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream_);
+        else {
+            res.perm.resize(n);
+            cudaMemcpyAsync(res.perm.data(), d_perm_[cur_], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream_);
+        }
         ce = cudaStreamSynchronize(stream_);
         if (getenv("CRN_B200_TRACE"))
             fprintf(stderr, "[crn_b200] vq<%d> n=%u max=%u: %u rounds, host enqueue %.1f ms, sync wait %.1f ms, host results %.1f ms, host heap %.1f ms\n", D, n, max_size,
                     res.rounds, t_enqueue_, t_sync_, t_results_, t_heap_);
+        if (getenv("CRN_B200_TRACE"))
+            for (int i = 0; i < 4; i++) fprintf(stderr, "[crn_b200]   tree %d: run %.1f ms, wanted %.1f ms, sort %.1f ms\n", i, tm_[i][0], tm_[i][1], tm_[i][2]);
         return ce;
     }
 
@@ -293,22 +404,42 @@ private:
     // Replays the reference's heap loop for every tree and collects the next frontier.  threaded_clusterizer's partitions
     // are independent clusterizers over disjoint node sets, and with hundreds of thousands of leaves the replay is bound
     // by cache misses, so each tree gets its own host thread once the heaps are large (product build only).
-    static void advance_trees(std::vector<VqTreeSim>& trees, std::vector<VqHostNode>& nodes, std::vector<uint32_t>& frontier)
+    // one tree: replay, collect, and order its part of the frontier by first position (what the device kernels expect);
+    // the keys are gathered first so that the sort itself runs on a contiguous array
+    static void advance_tree(VqTreeSim& t, std::vector<VqHostNode>& nodes, std::vector<uint32_t>& part, double* tm)
     {
+        const double a = now_ms();
+        t.run(nodes);
+        const double b = now_ms();
+        t.wanted(part);
+        const double c = now_ms();
+        tm[0] += b - a; tm[1] += c - b;
+        if (part.size() < 2) return;
+        std::vector<unsigned long long> keyed(part.size());
+        for (size_t i = 0; i < part.size(); i++) keyed[i] = ((unsigned long long)nodes[part[i]].begin << 32) | part[i];
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t i = 0; i < part.size(); i++) part[i] = (uint32_t)keyed[i];
+        tm[2] += now_ms() - c;
+    }
+    double tm_[4][4] = {};           // CRN_B200_TRACE: per tree, ms in run / wanted / sort
+#ifdef __CUDACC__
+    std::unique_ptr<VqPool> pool_;
+#endif
+    void advance_trees(std::vector<VqTreeSim>& trees, std::vector<VqHostNode>& nodes, std::vector<uint32_t>& frontier)
+    {
+        // threaded_clusterizer's partitions cover ascending, disjoint position ranges, so the per-tree parts concatenate
+        // into a sorted frontier
+        std::vector<std::vector<uint32_t>> parts(trees.size());
 #ifdef __CUDACC__
         size_t live = 0;
         for (const VqTreeSim& t : trees) live += t.pending.size();
-        if (trees.size() > 1 && live > 4096) {
-            std::vector<std::vector<uint32_t>> parts(trees.size());
-            std::vector<std::thread> th;
-            for (size_t i = 1; i < trees.size(); i++) th.emplace_back([&, i]() { trees[i].run(nodes); trees[i].wanted(parts[i]); });
-            trees[0].run(nodes); trees[0].wanted(parts[0]);
-            for (std::thread& t : th) t.join();
-            for (const std::vector<uint32_t>& p : parts) frontier.insert(frontier.end(), p.begin(), p.end());
-            return;
-        }
+        if (trees.size() > 1 && trees.size() <= 4 && live > 4096) {
+            if (!pool_) pool_.reset(new VqPool());
+            pool_->run4([&](int i) { if ((size_t)i < trees.size()) advance_tree(trees[i], nodes, parts[i], tm_[i]); });
+        } else
 #endif
-        for (VqTreeSim& t : trees) { t.run(nodes); t.wanted(frontier); }
+        for (size_t i = 0; i < trees.size(); i++) advance_tree(trees[i], nodes, parts[i], tm_[i & 3]);
+        for (const std::vector<uint32_t>& p : parts) frontier.insert(frontier.end(), p.begin(), p.end());
     }
 
     // every device array is carved from one slab the caller keeps between builds (no cudaMalloc / cudaFree per build)
@@ -425,20 +556,34 @@ private:
         if (ce != cudaSuccess) return ce;
         ce = cudaGetLastError();
         if (ce != cudaSuccess) return ce;
-        for (unsigned s = 0; s < F; s++) {
-            const VqSlotResult& r = h_results_[s];
-            VqHostNode& nd = nodes[frontier[s]];
-            nd.processed = 1;
-            if (r.state != 1) { nd.unsplittable = 1; continue; }
-            if (nodes.size() < (size_t)r.child + 2) nodes.resize((size_t)r.child + 2);
-            VqHostNode& par = nodes[frontier[s]];
-            par.left = (int32_t)r.child;
-            VqHostNode& l = nodes[r.child];
-            VqHostNode& rr = nodes[r.child + 1];
-            l = VqHostNode(); rr = VqHostNode();
-            l.begin = par.begin; l.count = r.left_count; l.variance = r.var_left;
-            rr.begin = par.begin + r.left_count; rr.count = r.right_count; rr.variance = r.var_right;
-        }
+        // children ids are handed out by a device counter: size the node table once, then scatter the results (disjoint
+        // parents and children, so the four quarters of the frontier can go in parallel)
+        size_t need = nodes.size();
+        for (unsigned s = 0; s < F; s++) if (h_results_[s].state == 1) need = std::max(need, (size_t)h_results_[s].child + 2);
+        if (nodes.size() < need) nodes.resize(need);
+        auto scatter = [&](unsigned s0, unsigned s1) {
+            for (unsigned s = s0; s < s1; s++) {
+                const VqSlotResult& r = h_results_[s];
+                VqHostNode& par = nodes[frontier[s]];
+                par.processed = 1;
+                if (r.state != 1) { par.unsplittable = 1; continue; }
+                par.left = (int32_t)r.child;
+                VqHostNode& l = nodes[r.child];
+                VqHostNode& rr = nodes[r.child + 1];
+                l = VqHostNode(); rr = VqHostNode();
+                l.begin = par.begin; l.count = r.left_count; l.variance = r.var_left;
+                rr.begin = par.begin + r.left_count; rr.count = r.right_count; rr.variance = r.var_right;
+                par.child_count[0] = r.left_count; par.child_count[1] = r.right_count;
+                par.child_var[0] = r.var_left; par.child_var[1] = r.var_right;
+            }
+        };
+#ifdef __CUDACC__
+        if (F > 8192) {
+            if (!pool_) pool_.reset(new VqPool());
+            pool_->run4([&](int i) { scatter((unsigned)((size_t)F * i / 4), (unsigned)((size_t)F * (i + 1) / 4)); });
+        } else
+#endif
+        scatter(0, F);
         t_results_ += now_ms() - t2;
         return cudaSuccess;
     }

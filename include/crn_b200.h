@@ -151,8 +151,8 @@ CRN_API int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const cr
  * retrieve_max_clusters is retrieve_clusters' argument (0 = every leaf, which is what create_clusters does).
  * h_cluster_of (HOST, n entries) receives each vector's cluster index; clusters are numbered in the
  * reference's retrieval order and listing the members of a cluster by ascending vector index reproduces the
- * reference's member order.  Float sums are accumulated exactly (64-bit integers), so cluster boundaries can
- * differ from the reference's float accumulation in the last place: tolerance class, see DESIGN.md. */
+ * reference's member order.  The reference's member-order float accumulations (centroids, covariances) are
+ * reproduced bit for bit, so the cluster assignment equals the reference's. */
 CRN_API int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d_vectors, const uint32_t* d_weights, uint32_t n,
                                   uint32_t max_codebook_size, uint32_t retrieve_max_clusters, int threaded,
                                   uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size);

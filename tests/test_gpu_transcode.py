@@ -97,3 +97,15 @@ def test_gpu_wide_path(gpu_ctx, port, monkeypatch, fmt, w, h, faces, min_blocks)
     assert gpu_ctx.launch_count - l0 == 1 and (wide_launches >= 2 or (((bx + 1) & ~1) * ((by + 1) & ~1) * faces < int(min_blocks)))
     assert np.array_equal(got, narrow)
     tex.close()
+
+
+def test_gpu_wide_batch(gpu_ctx, port):
+    """Batch of files whose large levels take the wide path (more levels than SM pairs: walk and resolve as two launches)."""
+    fmts = ["DXT1", "DXT5", "DXN_XY", "DXT5A"]
+    files = [crnsynth.synth_crn(512, 512, fmts[i % 4], seed=60 + i, skew=0.1) for i in range(48)]
+    texs = [gpu_ctx.unpack_begin(d) for d in files]
+    outs = [device_buffer(t.total_size) for t in texs]
+    gpu_ctx.unpack_batch(texs, [o.data_ptr() for o in outs], [t.total_size for t in texs])
+    for t, o, d in zip(texs, outs, files):
+        assert split_levels(t, o.cpu().numpy()) == helpers.port_unpack_all(port, d)
+        t.close()

@@ -118,19 +118,21 @@ WIDE = [("DXT1", 256, 256, 1, {}), ("DXT5", 260, 100, 1, {}), ("DXN_XY", 128, 64
         ("DXT1", 512, 64, 1, dict(n_color_ep=8192, n_color_sel=8192)), ("DXT5", 1024, 16, 1, dict(n_alpha_ep=8192, n_alpha_sel=8192, skew=0.1))]
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
 @pytest.mark.parametrize("min_blocks", ["1", "64"])
 @pytest.mark.parametrize("fmt,w,h,faces,kw", WIDE)
-def test_wide_path_matches_port(port, sim, monkeypatch, fmt, w, h, faces, kw, min_blocks):
+def test_wide_path_matches_port(port, sim, monkeypatch, fmt, w, h, faces, kw, min_blocks, split):
     """transcode_wide.cuh (transition tables -> walk -> resolve) on files small enough for the emulator: every level
     ("1") or only the large ones ("64", the rest through the warp-per-level kernel), bit-exact against the oracle."""
     monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", min_blocks)
+    monkeypatch.setenv("CRN_B200_WIDE_SPLIT", split)          # walker + resolver in one launch / in two
     data = crnsynth.synth_crn(w, h, fmt, faces=faces, seed=11, **kw)
     want = helpers.port_unpack_all(port, data)
     ctx = crn.Context(0, lib=sim)
     tex = ctx.unpack_begin(data)
     l0 = ctx.launch_count
     got = split_levels(tex, tex.unpack_all())
-    assert ctx.launch_count - l0 == (2 if min_blocks == "1" else 3)
+    assert ctx.launch_count - l0 == (2 if min_blocks == "1" else 3) + int(split)
     assert got == want
     # one level at a time with a pitch, as crnd_unpack_level is called
     bx, by = tex.level_blocks(0)
@@ -149,7 +151,24 @@ def test_wide_path_matches_port(port, sim, monkeypatch, fmt, w, h, faces, kw, mi
 @pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
 def test_wide_path_matches_golden_crn(sim, monkeypatch, case):
     monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", "1")
+    monkeypatch.setenv("CRN_B200_WIDE_SPLIT", "0")
     ctx = crn.Context(0, lib=sim)
     tex = ctx.unpack_begin(load(case))
     assert shas(split_levels(tex, tex.unpack_all())) == case["sha256"]
     tex.close(); ctx.close()
+
+
+def test_wide_batch_matches_single(sim, port, monkeypatch):
+    """crnd_unpack_batch with the large levels of every file on the wide path (one table / walk / resolve launch for all)."""
+    monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", "64")
+    ctx = crn.Context(0, lib=sim)
+    files = [crnsynth.synth_crn(w, h, f, seed=40 + i) for i, (f, w, h) in enumerate([("DXT1", 128, 64), ("DXT5", 64, 64), ("DXN_XY", 36, 260), ("DXT5A", 64, 32), ("DXT5", 8, 8)])]
+    texs = [ctx.unpack_begin(d) for d in files]
+    outs = [np.zeros(t.total_size, np.uint8) for t in texs]
+    l0 = ctx.launch_count
+    ctx.unpack_batch(texs, [o.ctypes.data for o in outs], [o.size for o in outs])
+    assert ctx.launch_count - l0 == 4                      # warp-per-level kernel + tables + walk + resolve
+    for t, o, d in zip(texs, outs, files):
+        assert split_levels(t, o) == helpers.port_unpack_all(port, d)
+        t.close()
+    ctx.close()
