@@ -97,6 +97,8 @@ def _declare(lib):
     lib.crn_gpu_dxt5_optimize_clusters.argtypes = [vp, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, u32, vp, u32, u32, vp, vp]
     lib.crn_gpu_qdxt_training.argtypes = [vp, u32, u32, vp, u32, vp, u32, vp, vp, vp]
     lib.crn_gpu_optimize_selectors.argtypes = [vp, u32, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, vp, u32, u32]
+    lib.crn_gpu_refine_endpoints.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp, vp, vp, u32, vp, vp, vp, vp]
+    lib.crn_gpu_nearest_codebook.argtypes = [vp, u32, vp, u32, vp, u32, vp]
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
     lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
@@ -238,6 +240,21 @@ class Context:
         self._check(self._lib.crn_gpu_vq_clusterize(self._ctx, dims, ptr(d_vectors), ptr(d_weights), n, max_codebook_size, retrieve_max_clusters,
                                                     1 if threaded else 0, cluster_of.ctypes.data_as(ctypes.c_void_p), ctypes.byref(k), ctypes.byref(cb)))
         return cluster_of, k.value, cb.value
+
+    # --- dxt_hc building blocks ---------------------------------------------------------------------------
+    def refine_endpoints(self, dxt1_selectors, d_pixels, d_selectors, d_offsets, n_clusters, d_endpoints, d_error, d_ok,
+                         perceptual=True, component=0, d_error_to_beat=None):
+        """dxt_endpoint_refiner::refine per CSR cluster of pixels; outputs low | high << 16, error, ok (device arrays)."""
+        def ptr(x):
+            return None if x is None else (ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x)))
+        self._check(self._lib.crn_gpu_refine_endpoints(self._ctx, 1 if dxt1_selectors else 0, 1 if perceptual else 0, component, ptr(d_pixels), ptr(d_selectors),
+                                                       ptr(d_offsets), n_clusters, ptr(d_error_to_beat), ptr(d_endpoints), ptr(d_error), ptr(d_ok)))
+
+    def nearest_codebook(self, dims, d_vectors, n, d_codebook, k, d_out):
+        """dxt_hc::determine_color/alpha_endpoint_clusters_task: first nearest codebook entry per float vector."""
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        self._check(self._lib.crn_gpu_nearest_codebook(self._ctx, dims, ptr(d_vectors), n, ptr(d_codebook), k, ptr(d_out)))
 
     # --- clustered DDS compression (mipmapped_texture::qdxt_pack_init / qdxt_pack) ----------------------
     def qdxt_init(self, fmt, levels, params=None):

@@ -10,6 +10,7 @@
 #include "cluster_kernels.cuh"
 #include "qdxt_kernels.cuh"
 #include "vq_host.h"
+#include "refiner_kernels.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -951,6 +952,39 @@ struct crn_gpu_texture {
     uint64_t level_face_size[16];
     uint64_t total_size;
 };
+
+int crn_gpu_refine_endpoints(crn_gpu_ctx* ctx, int dxt1_selectors, int perceptual, uint32_t component,
+                             const void* d_pixels_rgba, const uint8_t* d_selectors, const uint32_t* d_offsets, uint32_t n_clusters,
+                             const uint64_t* d_error_to_beat, uint32_t* d_endpoints, uint64_t* d_error, uint8_t* d_ok)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!d_pixels_rgba || !d_selectors || !d_offsets || !d_endpoints || !d_error || !d_ok || component > 3)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_refine_endpoints: bad argument");
+    if (!n_clusters) return CRN_GPU_OK;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int grid = grid_for(ctx, n_clusters, crn::kRefineWarpsPerCta, 8);
+    CRN_LAUNCH(crn::refine_endpoints_kernel, grid, crn::kRefineWarpsPerCta * 32, 0, ctx->stream, static_cast<const uint32_t*>(d_pixels_rgba), d_selectors, d_offsets,
+               n_clusters, dxt1_selectors ? 1 : 0, perceptual ? 1 : 0, component, reinterpret_cast<const unsigned long long*>(d_error_to_beat),
+               d_endpoints, reinterpret_cast<unsigned long long*>(d_error), d_ok);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_nearest_codebook(crn_gpu_ctx* ctx, uint32_t dims, const float* d_vectors, uint32_t n, const float* d_codebook, uint32_t codebook_size, uint32_t* d_out)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if ((dims != 2 && dims != 6) || !d_vectors || !d_codebook || !d_out || !codebook_size)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_nearest_codebook: bad argument");
+    if (!n) return CRN_GPU_OK;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned grid = (n + crn::kNearestThreads - 1) / crn::kNearestThreads;
+    if (dims == 6) CRN_LAUNCH(crn::nearest_codebook_kernel<6>, grid, crn::kNearestThreads, 0, ctx->stream, d_vectors, n, d_codebook, codebook_size, d_out);
+    else CRN_LAUNCH(crn::nearest_codebook_kernel<2>, grid, crn::kNearestThreads, 0, ctx->stream, d_vectors, n, d_codebook, codebook_size, d_out);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
 
 int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info)
 {

@@ -192,6 +192,22 @@ CRN_API int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst
 CRN_API int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info);
 CRN_API void crn_gpu_qdxt_free(crn_gpu_qdxt* q);
 
+/* dxt_hc building blocks -- stand-alone; the dxt_hc pipeline itself is not built yet ----
+ * crn_gpu_refine_endpoints replaces crnlib::dxt_endpoint_refiner::refine (crnlib/crn_dxt_endpoint_refiner.cpp:36-301)
+ * as dxt_hc::determine_color/alpha_endpoint_codebook_task call it per endpoint cluster (crnlib/crn_dxt_hc.cpp:739-753,
+ * :1102-1129).  Clusters are CSR ranges over a pixel array: d_pixels_rgba (RGBA8) and d_selectors (one byte per pixel:
+ * DXT1 selectors when dxt1_selectors != 0, else DXT5 alpha selectors of channel `component`), d_offsets[n_clusters+1].
+ * d_error_to_beat: optional per-cluster params::m_error_to_beat (NULL = UINT64_MAX).  Outputs per cluster:
+ * d_endpoints = m_low_color | m_high_color << 16, d_error = m_error, d_ok = refine()'s return value.  Bit-exact. */
+CRN_API int crn_gpu_refine_endpoints(crn_gpu_ctx* ctx, int dxt1_selectors, int perceptual, uint32_t component,
+                                     const void* d_pixels_rgba, const uint8_t* d_selectors, const uint32_t* d_offsets, uint32_t n_clusters,
+                                     const uint64_t* d_error_to_beat, uint32_t* d_endpoints, uint64_t* d_error, uint8_t* d_ok);
+/* crn_gpu_nearest_codebook replaces dxt_hc::determine_color_endpoint_clusters_task (dims 6, crnlib/crn_dxt_hc.cpp:836-886)
+ * and determine_alpha_endpoint_clusters_task (dims 2, :1132-1163): for each of n float vectors the index of the first
+ * codebook entry at minimum squared distance (float, summed in component order). */
+CRN_API int crn_gpu_nearest_codebook(crn_gpu_ctx* ctx, uint32_t dims, const float* d_vectors, uint32_t n,
+                                     const float* d_codebook, uint32_t codebook_size, uint32_t* d_out);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

@@ -57,6 +57,13 @@ void op_find_representative_colors(uint32_t n, const uint8_t* px, uint8_t* lo, u
 void op_qdxt_training(int kind, uint32_t comp, const uint8_t* blocks, uint32_t n_blocks, const uint32_t* mips, uint32_t num_mips,
                       int hierarchical, uint8_t* out_vecs, uint32_t* out_weights, uint8_t* out_encoding);
 
+/* crnlib::dxt_endpoint_refiner::refine (crn_dxt_endpoint_refiner.cpp:36-301).  px: n RGBA8, sel: n selectors (DXT1 or
+ * DXT5 block order).  Returns r.m_error < error_to_beat; low / high / error are always written. */
+int op_refine(int dxt1_selectors, int perceptual, uint32_t comp, const uint8_t* px, uint32_t n, const uint8_t* sel,
+              uint64_t error_to_beat, uint32_t* low, uint32_t* high, uint64_t* error);
+/* nearest codebook entry, first minimum (crn_dxt_hc.cpp:836-886, :1132-1163) */
+void op_nearest_codebook(uint32_t dims, const float* vecs, uint32_t n, const float* codebook, uint32_t k, uint32_t* out);
+
 /* CRN -> DXTn transcoder (inc/crn_decomp.h): crnd_unpack_begin / crnd_get_texture_info / crnd_unpack_level /
  * crnd_unpack_end.  info out[0..7] = width,height,levels,faces,bytes_per_block,format,userdata0,userdata1. */
 typedef struct op_crnd op_crnd;

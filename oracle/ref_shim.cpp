@@ -359,3 +359,27 @@ SHIM_API int ref_threaded_clusterizer16(uint32_t n, const float* vecs, const uin
         for (uint32_t j = 0; j < clusters[k].size(); j++) cluster_of[clusters[k][j]] = k;
     return 1;
 }
+
+// ref_refine -> crnlib::dxt_endpoint_refiner::refine (crnlib/crn_dxt_endpoint_refiner.cpp:36), one call per cluster.
+// offsets: n_clusters + 1 CSR offsets into pixels / selectors.  ok[c] = refine()'s return value.
+SHIM_API void ref_refine(int dxt1_selectors, int perceptual, uint32_t comp, const uint8_t* pixels, const uint8_t* selectors,
+                         const uint32_t* offsets, uint32_t n_clusters, const uint64_t* error_to_beat,
+                         uint32_t* low, uint32_t* high, uint64_t* error, uint8_t* ok)
+{
+    dxt_endpoint_refiner refiner;
+    for (uint32_t c = 0; c < n_clusters; c++)
+    {
+        dxt_endpoint_refiner::params p;
+        dxt_endpoint_refiner::results r;
+        p.m_pPixels = reinterpret_cast<const color_quad_u8*>(pixels) + offsets[c];
+        p.m_num_pixels = offsets[c + 1] - offsets[c];
+        p.m_pSelectors = selectors + offsets[c];
+        p.m_alpha_comp_index = comp;
+        p.m_error_to_beat = error_to_beat ? error_to_beat[c] : cUINT64_MAX;
+        p.m_dxt1_selectors = dxt1_selectors != 0;
+        p.m_perceptual = perceptual != 0;
+        r.m_low_color = 0; r.m_high_color = 0; r.m_error = cUINT64_MAX;
+        ok[c] = refiner.refine(p, r) ? 1 : 0;
+        low[c] = r.m_low_color; high[c] = r.m_high_color; error[c] = r.m_error;
+    }
+}
