@@ -99,6 +99,7 @@ def _declare(lib):
     lib.crn_gpu_optimize_selectors.argtypes = [vp, u32, ctypes.POINTER(_PackParams), u32, vp, u32, vp, vp, u32, vp, u32, u32]
     lib.crn_gpu_refine_endpoints.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp, vp, vp, u32, vp, vp, vp, vp]
     lib.crn_gpu_nearest_codebook.argtypes = [vp, u32, vp, u32, vp, u32, vp]
+    lib.crn_gpu_assign_selectors.argtypes = [vp, u32, ctypes.c_int, u32, vp, u32, vp, vp, vp, u32, vp, vp, vp]
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
     lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
@@ -255,6 +256,13 @@ class Context:
         def ptr(x):
             return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
         self._check(self._lib.crn_gpu_nearest_codebook(self._ctx, dims, ptr(d_vectors), n, ptr(d_codebook), k, ptr(d_out)))
+
+    def assign_selectors(self, kind, d_blocks, n_blocks, d_values, d_codebook, k, d_best_index, d_refined, d_used, perceptual=True, component=0, d_values_accum=None):
+        """dxt_hc::create_color/alpha_selector_codebook_task + re-vote: kind = "color" or "alpha" (device arrays)."""
+        def ptr(x):
+            return None if x is None else (ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x)))
+        self._check(self._lib.crn_gpu_assign_selectors(self._ctx, 0 if kind == "color" else 1, 1 if perceptual else 0, component, ptr(d_blocks), n_blocks, ptr(d_values),
+                                                       ptr(d_values_accum), ptr(d_codebook), k, ptr(d_best_index), ptr(d_refined), ptr(d_used)))
 
     # --- clustered DDS compression (mipmapped_texture::qdxt_pack_init / qdxt_pack) ----------------------
     def qdxt_init(self, fmt, levels, params=None):

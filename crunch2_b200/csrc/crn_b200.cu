@@ -986,6 +986,40 @@ int crn_gpu_nearest_codebook(crn_gpu_ctx* ctx, uint32_t dims, const float* d_vec
     return CRN_GPU_OK;
 }
 
+int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int perceptual, uint32_t component,
+                             const void* d_blocks_rgba, uint32_t n_blocks, const void* d_block_values, const void* d_block_values_accum,
+                             const uint64_t* d_codebook, uint32_t codebook_size,
+                             uint32_t* d_best_index, uint64_t* d_refined_codebook, uint8_t* d_used)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (kind > 1 || component > 3 || !d_blocks_rgba || !d_block_values || !d_codebook || !codebook_size || !d_best_index || !d_refined_codebook || !d_used)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_assign_selectors: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t tab_bytes = (size_t)codebook_size * 16 * (kind ? 8 : 4) * sizeof(uint32_t);
+    int rc = ensure(ctx, &ctx->d_cluster_ws, &ctx->d_cluster_ws_cap, tab_bytes);
+    if (rc) return rc;
+    uint32_t* tot = static_cast<uint32_t*>(ctx->d_cluster_ws);
+    CRN_CUDA(ctx, cudaMemsetAsync(tot, 0, tab_bytes, ctx->stream));
+    CRN_CUDA(ctx, cudaMemsetAsync(d_used, 0, codebook_size, ctx->stream));
+    const unsigned long long* cb = reinterpret_cast<const unsigned long long*>(d_codebook);
+    unsigned long long* refined = reinterpret_cast<unsigned long long*>(d_refined_codebook);
+    if (n_blocks) {
+        const int grid = grid_for(ctx, n_blocks, crn::kAssignWarpsPerCta, 8);
+        if (kind == 0)
+            CRN_LAUNCH(crn::assign_selectors_kernel<0>, grid, crn::kAssignWarpsPerCta * 32, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), n_blocks,
+                       static_cast<const uint8_t*>(d_block_values), static_cast<const uint8_t*>(nullptr), cb, codebook_size, perceptual ? 1 : 0, component, d_best_index, tot, d_used);
+        else
+            CRN_LAUNCH(crn::assign_selectors_kernel<1>, grid, crn::kAssignWarpsPerCta * 32, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), n_blocks,
+                       static_cast<const uint8_t*>(d_block_values), static_cast<const uint8_t*>(d_block_values_accum), cb, codebook_size, 0, component, d_best_index, tot, d_used);
+        ctx->launches++;
+    }
+    if (kind == 0) CRN_LAUNCH(crn::revote_selectors_kernel<0>, (codebook_size + 255) / 256, 256, 0, ctx->stream, tot, codebook_size, refined);
+    else CRN_LAUNCH(crn::revote_selectors_kernel<1>, (codebook_size + 255) / 256, 256, 0, ctx->stream, tot, codebook_size, refined);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
 int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info)
 {
     if (!info || info->struct_size != sizeof(crn_gpu_texture_info)) return CRN_GPU_ERR_BAD_PARAM;

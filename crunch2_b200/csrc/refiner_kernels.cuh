@@ -246,3 +246,128 @@ nearest_codebook_kernel(const float* __restrict__ vecs, uint32_t n, const float*
 }
 
 }  // namespace crn
+
+// ---- selector codebook assignment + re-vote -----------------------------------------------------
+// assign_selectors_kernel replaces dxt_hc::create_color_selector_codebook_task (KIND 0, crnlib/crn_dxt_hc.cpp:1306-1360)
+// and create_alpha_selector_codebook_task (KIND 1, :1516-1586): for every block, the codebook entry (16 selectors of 2 or
+// 3 bits) with the smallest summed error against the block's palette values -- an exhaustive blocks x codebook search.
+// As in the reference the 16-term sum is folded into table lookups (colour: E2[16][4] -> E4[8][16] -> E8[4][256], four
+// lookups per entry; alpha: E3[16][8] -> E6[8][64], eight lookups), here with the tables of one block in shared memory,
+// one warp per block and one lane per codebook entry; the first minimum wins (strict < in entry order).  The block's
+// per-pixel error table is then added into the winner's table (uint32 wrap-around sums, so the order does not matter).
+// revote_selectors_kernel is the tail of create_color/alpha_selector_codebook (:1488-1503, :1702-1720): every entry's
+// selectors are replaced by the per-pixel arg-min of its accumulated table, with the reference's pairwise tie order.
+namespace crn {
+
+constexpr int kAssignWarpsPerCta = 4;
+
+template <int KIND> struct AssignSmem {
+    static constexpr int V = KIND == 0 ? 4 : 8;
+    uint32_t E1[16][V];                               // E2 (colour) / E3 (alpha)
+    uint32_t Emid[KIND == 0 ? 8 * 16 : 1];            // E4 (colour only)
+    uint32_t Ebig[KIND == 0 ? 4 * 256 : 8 * 64];      // E8 / E6
+};
+
+template <int KIND>
+__device__ __forceinline__ void assign_fill_e1(AssignSmem<KIND>& sm, const uint32_t* __restrict__ block, const uint8_t* __restrict__ values, int perceptual, uint32_t comp)
+{
+    constexpr int V = AssignSmem<KIND>::V;
+    const unsigned lane = lane_id();
+    for (unsigned t = lane; t < 16u * V; t += 32) {
+        const unsigned p = t / V, s = t % V;
+        const uint32_t px = block[p];
+        if (KIND == 0) {
+            const uint32_t c = reinterpret_cast<const uint32_t*>(values)[s];
+            const int dr = (int)(px & 0xffu) - (int)(c & 0xffu), dg = (int)((px >> 8) & 0xffu) - (int)((c >> 8) & 0xffu), db = (int)((px >> 16) & 0xffu) - (int)((c >> 16) & 0xffu);
+            sm.E1[p][s] = perceptual ? (uint32_t)(8 * dr * dr) + (uint32_t)(25 * dg * dg) + (uint32_t)(db * db) : (uint32_t)(dr * dr + dg * dg + db * db);
+        } else {
+            const int d = (int)((px >> (8 * comp)) & 0xffu) - (int)values[s];
+            sm.E1[p][s] = (uint32_t)(d * d);
+        }
+    }
+}
+
+// blocks: n x 16 RGBA8.  values: per block 4 RGBA8 colours (KIND 0, 16 bytes) or 8 alpha values (KIND 1, 8 bytes);
+// values_accum (KIND 1, optional): the values whose error table is accumulated (the cluster's refined alpha values).
+template <int KIND>
+__global__ void __launch_bounds__(kAssignWarpsPerCta * 32)
+assign_selectors_kernel(const uint32_t* __restrict__ blocks, uint32_t n_blocks, const uint8_t* __restrict__ values, const uint8_t* __restrict__ values_accum,
+                        const unsigned long long* __restrict__ codebook, uint32_t K, int perceptual, uint32_t comp,
+                        uint32_t* __restrict__ best_index, uint32_t* __restrict__ total_errors, uint8_t* __restrict__ used)
+{
+    constexpr int V = AssignSmem<KIND>::V, VB = KIND == 0 ? 16 : 8;
+    __shared__ AssignSmem<KIND> smem[kAssignWarpsPerCta];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    AssignSmem<KIND>& sm = smem[warp];
+    const uint32_t warps = gridDim.x * kAssignWarpsPerCta;
+    for (uint32_t b = blockIdx.x * kAssignWarpsPerCta + warp; b < n_blocks; b += warps) {
+        assign_fill_e1<KIND>(sm, blocks + (size_t)b * 16, values + (size_t)b * VB, perceptual, comp);
+        __syncwarp();
+        if (KIND == 0) {
+            for (unsigned t = lane; t < 8u * 16u; t += 32) { const unsigned p = t >> 4, s = t & 15u; sm.Emid[t] = sm.E1[p << 1][s & 3u] + sm.E1[p << 1 | 1][s >> 2]; }
+            __syncwarp();
+            for (unsigned t = lane; t < 4u * 256u; t += 32) { const unsigned p = t >> 8, s = t & 255u; sm.Ebig[t] = sm.Emid[(p << 1) * 16 + (s & 15u)] + sm.Emid[(p << 1 | 1) * 16 + (s >> 4)]; }
+        } else {
+            for (unsigned t = lane; t < 8u * 64u; t += 32) { const unsigned p = t >> 6, s = t & 63u; sm.Ebig[t] = sm.E1[p << 1][s & 7u] + sm.E1[p << 1 | 1][s >> 3]; }
+        }
+        __syncwarp();
+        uint32_t e_best = 0xffffffffu, i_best = 0xffffffffu;
+        for (uint32_t s = lane; s < K; s += 32) {
+            const unsigned long long sel = codebook[s];
+            uint32_t e;
+            if (KIND == 0) {
+                const uint32_t q = (uint32_t)sel;
+                e = sm.Ebig[q & 255u] + sm.Ebig[256 + ((q >> 8) & 255u)] + sm.Ebig[512 + ((q >> 16) & 255u)] + sm.Ebig[768 + (q >> 24)];
+            } else {
+                e = sm.Ebig[sel & 63u];
+#pragma unroll
+                for (int k = 1; k < 8; k++) e += sm.Ebig[64 * k + ((sel >> (6 * k)) & 63u)];
+            }
+            if (e < e_best) { e_best = e; i_best = s; }           // s ascending per lane: the first minimum is kept
+        }
+        // (error, index) lexicographic minimum; best_error starts at UINT32_MAX in the reference, so an entry whose error is
+        // exactly UINT32_MAX never wins and index 0 stays
+#pragma unroll
+        for (int ofs = 16; ofs; ofs >>= 1) {
+            const uint32_t e2 = __shfl_xor_sync(CRN_FULL_MASK, e_best, ofs), i2 = __shfl_xor_sync(CRN_FULL_MASK, i_best, ofs);
+            if (e2 < e_best || (e2 == e_best && i2 < i_best)) { e_best = e2; i_best = i2; }
+        }
+        const uint32_t best = e_best == 0xffffffffu ? 0u : i_best;
+        if (KIND == 1 && values_accum) {
+            __syncwarp();
+            assign_fill_e1<KIND>(sm, blocks + (size_t)b * 16, values_accum + (size_t)b * VB, perceptual, comp);
+            __syncwarp();
+        }
+        uint32_t* tot = total_errors + (size_t)best * 16 * V;
+        for (unsigned t = lane; t < 16u * V; t += 32) atomicAdd(&tot[t], sm.E1[t / V][t % V]);
+        if (lane == 0) { used[best] = 1; best_index[b] = best; }
+        __syncwarp();
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+revote_selectors_kernel(const uint32_t* __restrict__ total_errors, uint32_t K, unsigned long long* __restrict__ refined)
+{
+    constexpr int V = KIND == 0 ? 4 : 8;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const uint32_t* tab = total_errors + (size_t)i * 16 * V;
+    unsigned long long out = 0;
+    for (unsigned p = 0; p < 16; p++) {
+        const uint32_t* e = tab + p * V;
+        unsigned s;
+        if (KIND == 0) {
+            const unsigned s03 = e[3] < e[0] ? 3 : 0, s12 = e[2] < e[1] ? 2 : 1;
+            s = e[s12] < e[s03] ? s12 : s03;
+        } else {
+            const unsigned s07 = e[7] < e[0] ? 7 : 0, s12 = e[2] < e[1] ? 2 : 1, s34 = e[4] < e[3] ? 4 : 3, s56 = e[6] < e[5] ? 6 : 5;
+            const unsigned s02 = e[s12] < e[s07] ? s12 : s07, s36 = e[s56] < e[s34] ? s56 : s34;
+            s = e[s36] < e[s02] ? s36 : s02;
+        }
+        out |= (unsigned long long)s << (p * (KIND == 0 ? 2 : 3));
+    }
+    refined[i] = out;
+}
+
+}  // namespace crn

@@ -208,6 +208,22 @@ CRN_API int crn_gpu_refine_endpoints(crn_gpu_ctx* ctx, int dxt1_selectors, int p
 CRN_API int crn_gpu_nearest_codebook(crn_gpu_ctx* ctx, uint32_t dims, const float* d_vectors, uint32_t n,
                                      const float* d_codebook, uint32_t codebook_size, uint32_t* d_out);
 
+/* crn_gpu_assign_selectors replaces dxt_hc::create_color_selector_codebook_task (kind 0,
+ * crnlib/crn_dxt_hc.cpp:1306-1360) / create_alpha_selector_codebook_task (kind 1, :1516-1586) and the re-vote tail of
+ * create_color/alpha_selector_codebook (:1488-1503, :1702-1720): the exhaustive blocks x codebook search (first entry at
+ * minimum summed error), the per-entry error tables, and the refined selectors.
+ *   d_blocks_rgba   n_blocks x 16 RGBA8
+ *   d_block_values  per block the palette it is matched against: kind 0: 4 RGBA8 colours (color_cluster::color_values,
+ *                   16 bytes); kind 1: 8 alpha values (alpha_cluster::alpha_values as bytes, 8 bytes), channel `component`
+ *   d_block_values_accum  kind 1, optional: the values whose error is accumulated (refined_alpha_values); NULL = same
+ *   d_codebook      codebook_size selectors, uint64 each: 16 x 2 bits (kind 0, low 32 bits) or 16 x 3 bits (kind 1),
+ *                   pixel p at bit 2p / 3p
+ * Outputs: d_best_index[n_blocks], d_refined_codebook[codebook_size] (uint64), d_used[codebook_size].  Bit-exact. */
+CRN_API int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int perceptual, uint32_t component,
+                                     const void* d_blocks_rgba, uint32_t n_blocks, const void* d_block_values, const void* d_block_values_accum,
+                                     const uint64_t* d_codebook, uint32_t codebook_size,
+                                     uint32_t* d_best_index, uint64_t* d_refined_codebook, uint8_t* d_used);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

@@ -64,6 +64,10 @@ int op_refine(int dxt1_selectors, int perceptual, uint32_t comp, const uint8_t* 
 /* nearest codebook entry, first minimum (crn_dxt_hc.cpp:836-886, :1132-1163) */
 void op_nearest_codebook(uint32_t dims, const float* vecs, uint32_t n, const float* codebook, uint32_t k, uint32_t* out);
 
+/* selector codebook assignment + re-vote (crn_dxt_hc.cpp:1306-1360, :1488-1503; alpha :1516-1586, :1702-1720) */
+void op_assign_selectors(int kind, int perceptual, uint32_t comp, const uint8_t* blocks, uint32_t n, const uint8_t* values, const uint8_t* values_accum,
+                         const uint64_t* codebook, uint32_t K, uint32_t* best_index, uint64_t* refined, uint8_t* used);
+
 /* CRN -> DXTn transcoder (inc/crn_decomp.h): crnd_unpack_begin / crnd_get_texture_info / crnd_unpack_level /
  * crnd_unpack_end.  info out[0..7] = width,height,levels,faces,bytes_per_block,format,userdata0,userdata1. */
 typedef struct op_crnd op_crnd;

@@ -143,8 +143,8 @@ int op_refine(int dxt1_selectors, int perceptual, uint32_t comp, const uint8_t* 
  * determine_alpha_endpoint_clusters_task (:1132-1163; dims 2): index of the first codebook entry at minimum float
  * squared distance, the sum taken in component order.  The reference skips entries whose partial sum already exceeds
  * the distance to the tree-search leaf; such an entry cannot be the minimum, so the result is the plain first arg-min.
- * (This function has no stand-alone counterpart to call in the reference -- it is a private task of dxt_hc -- so it is
- * checked against a direct restatement only: parity unpinned for this one function.) */
+ * Pinned against the reference's own task, run on a tree_clusterizer codebook (ref_hc_nearest_codebook in oracle/ref_shim.cpp,
+ * tests/test_refiner_cpu.py). */
 void op_nearest_codebook(uint32_t dims, const float* vecs, uint32_t n, const float* codebook, uint32_t k, uint32_t* out)
 {
     for (uint32_t i = 0; i < n; i++) {
@@ -159,4 +159,58 @@ void op_nearest_codebook(uint32_t dims, const float* vecs, uint32_t n, const flo
         }
         out[i] = bi;
     }
+}
+
+/* dxt_hc::create_color_selector_codebook_task (kind 0, crn_dxt_hc.cpp:1306-1360) / create_alpha_selector_codebook_task
+ * (kind 1, :1516-1586) over all blocks, then the re-vote tail of create_color/alpha_selector_codebook (:1488-1503,
+ * :1702-1720).  values: per block 4 RGBA8 colours (kind 0) or 8 alpha values (kind 1); values_accum: optional (kind 1). */
+void op_assign_selectors(int kind, int perceptual, uint32_t comp, const uint8_t* blocks, uint32_t n, const uint8_t* values, const uint8_t* values_accum,
+                         const uint64_t* codebook, uint32_t K, uint32_t* best_index, uint64_t* refined, uint8_t* used)
+{
+    const uint32_t V = kind ? 8 : 4;
+    uint32_t* tot = (uint32_t*)calloc((size_t)K * 16 * V, 4);
+    memset(used, 0, K);
+    for (uint32_t b = 0; b < n; b++) {
+        uint32_t E[16][8];
+        const uint8_t* px = blocks + (size_t)b * 64;
+        for (int pass = 0; pass < 2; pass++) {
+            const uint8_t* vals = (pass && kind && values_accum ? values_accum : values) + (size_t)b * (kind ? 8 : 16);
+            for (uint32_t p = 0; p < 16; p++)
+                for (uint32_t s = 0; s < V; s++) {
+                    if (!kind) {
+                        const int dr = (int)px[4 * p] - vals[4 * s], dg = (int)px[4 * p + 1] - vals[4 * s + 1], db = (int)px[4 * p + 2] - vals[4 * s + 2];
+                        E[p][s] = perceptual ? (uint32_t)(8 * dr * dr) + (uint32_t)(25 * dg * dg) + (uint32_t)(db * db) : (uint32_t)(dr * dr + dg * dg + db * db);
+                    } else { const int d = (int)px[4 * p + comp] - vals[s]; E[p][s] = (uint32_t)(d * d); }
+                }
+            if (pass) break;
+            uint32_t best = 0, best_err = UINT32_MAX;
+            for (uint32_t s = 0; s < K; s++) {
+                uint64_t sel = codebook[s];
+                uint32_t e = 0;
+                for (uint32_t p = 0; p < 16; p++, sel >>= (kind ? 3 : 2)) e += E[p][sel & (V - 1)];
+                if (e < best_err) { best_err = e; best = s; }
+            }
+            best_index[b] = best;
+            if (!(kind && values_accum)) break;
+        }
+        uint32_t* t = tot + (size_t)best_index[b] * 16 * V;
+        for (uint32_t p = 0; p < 16; p++) for (uint32_t s = 0; s < V; s++) t[p * V + s] += E[p][s];
+        used[best_index[b]] = 1;
+    }
+    for (uint32_t i = 0; i < K; i++) {
+        uint64_t out = 0;
+        for (uint32_t p = 0; p < 16; p++) {
+            const uint32_t* e = tot + ((size_t)i * 16 + p) * V;
+            uint32_t s;
+            if (!kind) { const uint32_t s03 = e[3] < e[0] ? 3 : 0, s12 = e[2] < e[1] ? 2 : 1; s = e[s12] < e[s03] ? s12 : s03; }
+            else {
+                const uint32_t s07 = e[7] < e[0] ? 7 : 0, s12 = e[2] < e[1] ? 2 : 1, s34 = e[4] < e[3] ? 4 : 3, s56 = e[6] < e[5] ? 6 : 5;
+                const uint32_t s02 = e[s12] < e[s07] ? s12 : s07, s36 = e[s56] < e[s34] ? s56 : s34;
+                s = e[s36] < e[s02] ? s36 : s02;
+            }
+            out |= (uint64_t)s << (p * (kind ? 3 : 2));
+        }
+        refined[i] = out;
+    }
+    free(tot);
 }

@@ -383,3 +383,121 @@ SHIM_API void ref_refine(int dxt1_selectors, int perceptual, uint32_t comp, cons
         low[c] = r.m_low_color; high[c] = r.m_high_color; error[c] = r.m_error;
     }
 }
+
+// ---- dxt_hc private tasks, for pinning the oracle port (tests only) ---------------------------------------------------
+// The functions below call UNMODIFIED private member tasks of crnlib::dxt_hc on a hand-filled object.  Access control is
+// lifted for this translation unit only (the class layout does not depend on it); every header dxt_hc.h pulls in is
+// included normally first so that nothing but dxt_hc itself is affected.
+#include "crn_tree_clusterizer.h"
+#include "crn_threading.h"
+#include "crn_dxt_hc_common.h"
+#include "crn_dxt_endpoint_refiner.h"
+#include <queue>
+#define private public
+#include "crn_dxt_hc.h"
+#undef private
+
+namespace {
+struct shim_color_selector_details { shim_color_selector_details() { memset(this, 0, sizeof(*this)); } uint error[16][4]; bool used; };   // layout of crn_dxt_hc.cpp:1296-1304
+struct shim_alpha_selector_details { shim_alpha_selector_details() { memset(this, 0, sizeof(*this)); } uint error[16][8]; bool used; };   // crn_dxt_hc.cpp:1506-1514
+}
+
+// ref_hc_assign_selectors -> dxt_hc::create_color_selector_codebook_task (kind 0, crn_dxt_hc.cpp:1306) /
+// create_alpha_selector_codebook_task (kind 1, :1516) over all blocks with one task.  Block b is matched against its own
+// palette: values = 4 RGBA8 colours (kind 0) or 8 alpha values (kind 1); values_accum optional (kind 1: refined values).
+// n <= 65535 (cluster indices are uint16).  errors: K x 16 x (4|8) uint32 out.
+SHIM_API int ref_hc_assign_selectors(int kind, int perceptual, uint32_t comp, const uint8_t* blocks, uint32_t n, const uint8_t* values, const uint8_t* values_accum,
+                                     const uint64_t* codebook, uint32_t K, uint32_t* best_index, uint32_t* errors, uint8_t* used)
+{
+    if (n > 65535) return 0;
+    task_pool tp;
+    if (!tp.init(0)) return 0;
+    dxt_hc hc;
+    hc.m_pTask_pool = &tp;
+    hc.m_num_blocks = n;
+    hc.m_has_subblocks = false;
+    hc.m_blocks = (color_quad_u8(*)[16])blocks;
+    hc.m_params.m_perceptual = perceptual != 0;
+    hc.m_endpoint_indices.resize(n);
+    hc.m_selector_indices.resize(n);
+    if (!kind)
+    {
+        hc.m_color_clusters.resize(n);
+        for (uint32_t b = 0; b < n; b++)
+        {
+            hc.m_endpoint_indices[b].color = (uint16)b;
+            for (uint s = 0; s < 4; s++)
+                hc.m_color_clusters[b].color_values[s] = color_quad_u8(values[b * 16 + s * 4], values[b * 16 + s * 4 + 1], values[b * 16 + s * 4 + 2], values[b * 16 + s * 4 + 3]);
+        }
+        hc.m_color_selectors.resize(K);
+        for (uint32_t i = 0; i < K; i++) hc.m_color_selectors[i] = (uint32)codebook[i];
+        crnlib::vector<shim_color_selector_details> details(K);
+        hc.create_color_selector_codebook_task(0, &details);
+        for (uint32_t i = 0; i < K; i++) { memcpy(errors + (size_t)i * 64, details[i].error, 256); used[i] = details[i].used; }
+        for (uint32_t b = 0; b < n; b++) best_index[b] = hc.m_selector_indices[b].color;
+    }
+    else
+    {
+        hc.m_num_alpha_blocks = 1;
+        hc.m_params.m_alpha_component_indices[0] = comp;
+        hc.m_alpha_clusters.resize(n);
+        for (uint32_t b = 0; b < n; b++)
+        {
+            hc.m_endpoint_indices[b].component[1] = (uint16)b;
+            hc.m_alpha_clusters[b].refined_alpha = values_accum != NULL;
+            for (uint s = 0; s < 8; s++)
+            {
+                hc.m_alpha_clusters[b].alpha_values[s] = values[b * 8 + s];
+                hc.m_alpha_clusters[b].refined_alpha_values[s] = values_accum ? values_accum[b * 8 + s] : 0;
+            }
+        }
+        hc.m_alpha_selectors.resize(K);
+        for (uint32_t i = 0; i < K; i++) hc.m_alpha_selectors[i] = codebook[i];
+        crnlib::vector<shim_alpha_selector_details> details(K);
+        hc.create_alpha_selector_codebook_task(0, &details);
+        for (uint32_t i = 0; i < K; i++) { memcpy(errors + (size_t)i * 128, details[i].error, 512); used[i] = details[i].used; }
+        for (uint32_t b = 0; b < n; b++) best_index[b] = hc.m_selector_indices[b].component[1];
+    }
+    hc.m_pTask_pool = NULL;
+    return 1;
+}
+
+// ref_hc_nearest_codebook -> tree_clusterizer<vec6F / vec2F>::generate_codebook over the n training vectors (weights 1..),
+// then dxt_hc::determine_color_endpoint_clusters_task (dims 6, crn_dxt_hc.cpp:836) / determine_alpha_endpoint_clusters_task
+// (dims 2, :1132) with one tile per vector.  Returns the codebook size; codebook_out: up to max_size x dims floats.
+SHIM_API uint32_t ref_hc_nearest_codebook(uint32_t dims, const float* vecs, const uint32_t* weights, uint32_t n, uint32_t max_size, float* codebook_out, uint32_t* index_out)
+{
+    task_pool tp;
+    if (!tp.init(0)) return 0;
+    dxt_hc hc;
+    hc.m_pTask_pool = &tp;
+    hc.m_tiles.resize(n);
+    crnlib::vector<uint> w(n);
+    for (uint32_t i = 0; i < n; i++) { w[i] = weights[i]; hc.m_tiles[i].pixels.resize(1); }
+    uint32_t k = 0;
+    if (dims == 6)
+    {
+        typedef vec<6, float> vec6F; crnlib::vector<vec6F> v(n);
+        for (uint32_t i = 0; i < n; i++) { for (uint d = 0; d < 6; d++) v[i][d] = vecs[i * 6 + d]; hc.m_tiles[i].color_endpoint = v[i]; }
+        tree_clusterizer<vec6F> vq;
+        vq.generate_codebook(v.get_ptr(), w.get_ptr(), n, max_size, true, &tp);
+        k = vq.get_codebook_size();
+        for (uint32_t i = 0; i < k; i++) for (uint d = 0; d < 6; d++) codebook_out[i * 6 + d] = vq.get_codebook_entry(i)[d];
+        hc.determine_color_endpoint_clusters_task(0, &vq);
+        for (uint32_t i = 0; i < n; i++) index_out[i] = hc.m_tiles[i].cluster_indices[0];
+    }
+    else
+    {
+        hc.m_num_alpha_blocks = 1;
+        typedef vec<2, float> vec2F; crnlib::vector<vec2F> v(n);
+        for (uint32_t i = 0; i < n; i++) { for (uint d = 0; d < 2; d++) v[i][d] = vecs[i * 2 + d]; hc.m_tiles[i].alpha_endpoints[0] = v[i]; }
+        tree_clusterizer<vec2F> vq;
+        vq.generate_codebook(v.get_ptr(), w.get_ptr(), n, max_size, false, &tp);
+        k = vq.get_codebook_size();
+        for (uint32_t i = 0; i < k; i++) for (uint d = 0; d < 2; d++) codebook_out[i * 2 + d] = vq.get_codebook_entry(i)[d];
+        hc.determine_alpha_endpoint_clusters_task(0, &vq);
+        for (uint32_t i = 0; i < n; i++) index_out[i] = hc.m_tiles[i].cluster_indices[1];
+    }
+    hc.m_pTask_pool = NULL;
+    return k;
+}

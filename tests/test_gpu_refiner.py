@@ -28,3 +28,20 @@ def test_gpu_nearest_codebook(gpu_ctx, port, dims, n, k):
     gpu_ctx.nearest_codebook(dims, dv, n, dc, k, out)
     gpu_ctx.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("kind,perc,comp,with_accum,n,k", [(0, 1, 0, False, 60000, 2700), (0, 0, 0, False, 5000, 8192), (1, 0, 3, False, 60000, 2700), (1, 0, 1, True, 5000, 8192)])
+def test_gpu_assign_selectors(gpu_ctx, port, kind, perc, comp, with_accum, n, k):
+    from test_refiner_cpu import make_assign_case, port_assign
+    blocks, values, accum, codebook = make_assign_case(31 + kind, kind, n, k)
+    accum = accum if with_accum else None
+    want = port_assign(port, kind, perc, comp, blocks, values, accum, codebook)
+    dev = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).cuda()
+    d_blocks, d_values, d_cb = dev(blocks), dev(values), dev(codebook)
+    d_accum = dev(accum) if accum is not None else None
+    best = torch.zeros(n, dtype=torch.int32, device="cuda"); refined = torch.zeros(k, dtype=torch.int64, device="cuda"); used = torch.zeros(k, dtype=torch.uint8, device="cuda")
+    gpu_ctx.assign_selectors("alpha" if kind else "color", d_blocks, n, d_values, d_cb, k, best, refined, used, perceptual=bool(perc), component=comp, d_values_accum=d_accum)
+    gpu_ctx.synchronize()
+    assert np.array_equal(best.cpu().numpy().view(np.uint32), want[0])
+    assert np.array_equal(refined.cpu().numpy().view(np.uint64), want[1])
+    assert np.array_equal(used.cpu().numpy(), want[2])
