@@ -220,7 +220,9 @@ def run_transcode(ctx, ext, dev, flush, steps, peak_gbs, quick=False):
            "e2e": {"value": ntex / e2e_s / 1e9, "unit": "Gtexel/s", "h2d_bytes_per_step": len(data), "d2h_bytes_per_step": int(tex.total_size),
                    "includes": "unpack_begin (host table parse + upload + palette kernel) + all levels + D2H"},
            "roofline": {"bound": "hbm", "kernel": "transcode_walk_resolve_kernel (+ transcode_tables_kernel)", "achieved": (len(data) + tex.total_size) / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                        "frac": (len(data) + tex.total_size) / (ms / 1e3) / 1e9 / peak_gbs, "traffic": None,
+                        "frac": (len(data) + tex.total_size) / (ms / 1e3) / 1e9 / peak_gbs,
+                        "traffic": (1071789000 + 96898304 + 13745000 + 999730688) if not quick else None,
+                        "traffic_unit": "bytes per step: ncu dram read + write of transcode_walk_resolve_kernel and transcode_tables_kernel (profiles/r1y_ncu_full_summaries.txt); the tables are 10 B per bit of the stream",
                         "note": "one serial Huffman stream per mip level (SURVEY D5): the walk over per-bit-offset transition tables is a single-thread dependency chain (one shared-memory lookup per 2-4 blocks), level 0 = 75% of the blocks; table build and value decode are parallel"}}
     ref = helpers.load_ref()
     if ref is not None:
@@ -321,6 +323,9 @@ def run_clustered(args, ctx, ext, dev, wl, barrier, world):
     col_ms = float(np.mean([o[0] for o in opt_ms]))               # element 0 of DXT1 / DXT5 is the colour element
     top = {"kernel": "dxt1_optimize_clusters_* (colour element, %d endpoint clusters)" % info["endpoint_clusters"][0],
            "ms": col_ms, "blocks": nblocks(levels), "bytes_per_block": 64 + 8,
+           # dram__bytes_read.sum + dram__bytes_write.sum of dxt1_optimize_clusters_kernel on this exact workload, one launch
+           # (profiles/r1y_ncu_full_summaries.txt): the 61 B/pixel cluster workspace (hash table, unique colours) on top of the 72 B/block
+           "traffic": 748257280 + 621472000,
            "all_elements_ms": [float(x) for x in np.mean(np.array(opt_ms), axis=0)],
            "note": "issue-slot bound integer search (SURVEY 8(d)): algorithmic HBM bytes are 64 B pixels in + 8 B element out per block; "
                    "see DESIGN.md section 6 and profiles/ for the pipe utilisation that actually bounds it"}
@@ -472,7 +477,8 @@ def main():
     value = n_tex * world * args.steps / (total_ms / 1e3) / 1e6
     e2e_v = n_tex * world * args.steps / e2e_s / 1e6
     achieved = top["blocks"] * top["bytes_per_block"] / (top["ms"] / 1e3) / 1e9
-    roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+    roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": top.get("traffic"),
+            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650", "note": top["note"],
             "blocks_per_s": top["blocks"] / (top["ms"] / 1e3), "ms": top["ms"]}
     if "all_elements_ms" in top:
