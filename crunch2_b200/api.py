@@ -37,6 +37,24 @@ class _TextureInfo(ctypes.Structure):
                                                 "userdata0", "userdata1", "format")]
 
 
+class _HcLevel(ctypes.Structure):
+    _fields_ = [("first_block", ctypes.c_uint32), ("num_blocks", ctypes.c_uint32), ("block_width", ctypes.c_uint32), ("weight", ctypes.c_float)]
+
+
+class _HcParams(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("format", ctypes.c_uint32), ("num_blocks", ctypes.c_uint32), ("num_levels", ctypes.c_uint32),
+                ("num_faces", ctypes.c_uint32), ("levels", _HcLevel * 16), ("perceptual", ctypes.c_uint32),
+                ("color_endpoint_codebook_size", ctypes.c_uint32), ("color_selector_codebook_size", ctypes.c_uint32),
+                ("alpha_endpoint_codebook_size", ctypes.c_uint32), ("alpha_selector_codebook_size", ctypes.c_uint32),
+                ("adaptive_tile_color_psnr_derating", ctypes.c_float), ("adaptive_tile_alpha_psnr_derating", ctypes.c_float),
+                ("adaptive_tile_color_alpha_weighting_ratio", ctypes.c_float), ("alpha_component_indices", ctypes.c_uint32 * 2)]
+
+
+class _HcInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "num_blocks", "num_tiles", "n_color_endpoints", "n_alpha_endpoints",
+                                                "n_color_selectors", "n_alpha_selectors")] + [("vq_rounds", ctypes.c_uint32 * 4), ("unique_vectors", ctypes.c_uint32 * 4)]
+
+
 class PackParams:
     """dxt_image::pack_params for the block-by-block path (defaults of crn_comp_params::clear())."""
 
@@ -100,6 +118,16 @@ def _declare(lib):
     lib.crn_gpu_refine_endpoints.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp, vp, vp, u32, vp, vp, vp, vp]
     lib.crn_gpu_nearest_codebook.argtypes = [vp, u32, vp, u32, vp, u32, vp]
     lib.crn_gpu_assign_selectors.argtypes = [vp, u32, ctypes.c_int, u32, vp, u32, vp, vp, vp, u32, vp, vp, vp]
+    lib.crn_gpu_default_hc_params.argtypes = [ctypes.POINTER(_HcParams)]
+    lib.crn_gpu_default_hc_params.restype = None
+    lib.crn_gpu_hc_compress.argtypes = [vp, ctypes.POINTER(_HcParams), vp, i32, ctypes.POINTER(vp)]
+    lib.crn_gpu_hc_get_info.argtypes = [vp, ctypes.POINTER(_HcInfo)]
+    for name in ("endpoint_indices", "selector_indices", "color_endpoints", "alpha_endpoints", "color_selectors", "alpha_selectors", "block_encodings", "tile_indices"):
+        f = getattr(lib, "crn_gpu_hc_" + name)
+        f.argtypes = [vp]
+        f.restype = vp
+    lib.crn_gpu_hc_free.argtypes = [vp]
+    lib.crn_gpu_hc_free.restype = None
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
     lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
@@ -263,6 +291,57 @@ class Context:
             return None if x is None else (ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x)))
         self._check(self._lib.crn_gpu_assign_selectors(self._ctx, 0 if kind == "color" else 1, 1 if perceptual else 0, component, ptr(d_blocks), n_blocks, ptr(d_values),
                                                        ptr(d_values_accum), ptr(d_codebook), k, ptr(d_best_index), ptr(d_refined), ptr(d_used)))
+
+    # --- dxt_hc::compress (crnlib/crn_dxt_hc.cpp:98-312): blocks of all levels -> palettes + per-block indices ---------
+    def hc_compress(self, fmt, blocks, levels, num_faces=1, perceptual=True, codebook_sizes=(3072, 3072, 3072, 3072),
+                    deratings=(2.0, 2.0, 3.0), alpha_components=(3, 0)):
+        """blocks: (n, 16, 4) uint8 numpy array (host) or a torch CUDA tensor of the same shape; levels: list of
+        (first_block, num_blocks, block_width, weight) as crn_comp::quantize_images lays them out (crnlib/crn_comp.cpp:706-741);
+        codebook_sizes: colour endpoints, colour selectors, alpha endpoints, alpha selectors.  Returns a dict of numpy arrays
+        named as dxt_hc::compress's outputs plus 'info'."""
+        p = _HcParams()
+        self._lib.crn_gpu_default_hc_params(ctypes.byref(p))
+        on_host = not hasattr(blocks, "data_ptr")
+        if on_host:
+            blocks = np.ascontiguousarray(blocks, np.uint8)
+            n = blocks.shape[0]
+            ptr = blocks.ctypes.data_as(ctypes.c_void_p)
+        else:
+            n = int(blocks.shape[0])
+            ptr = ctypes.c_void_p(blocks.data_ptr())
+        p.format = int(fmt); p.num_blocks = n; p.num_levels = len(levels); p.num_faces = int(num_faces)
+        for i, (first, nb, bw, weight) in enumerate(levels):
+            p.levels[i].first_block = int(first); p.levels[i].num_blocks = int(nb); p.levels[i].block_width = int(bw); p.levels[i].weight = float(weight)
+        p.perceptual = int(bool(perceptual))
+        (p.color_endpoint_codebook_size, p.color_selector_codebook_size, p.alpha_endpoint_codebook_size, p.alpha_selector_codebook_size) = [int(x) for x in codebook_sizes]
+        (p.adaptive_tile_color_psnr_derating, p.adaptive_tile_alpha_psnr_derating, p.adaptive_tile_color_alpha_weighting_ratio) = [float(x) for x in deratings]
+        p.alpha_component_indices[0], p.alpha_component_indices[1] = int(alpha_components[0]), int(alpha_components[1])
+        h = ctypes.c_void_p()
+        self._check(self._lib.crn_gpu_hc_compress(self._ctx, ctypes.byref(p), ptr, 1 if on_host else 0, ctypes.byref(h)))
+        try:
+            info = _HcInfo()
+            info.struct_size = ctypes.sizeof(_HcInfo)
+            self._check(self._lib.crn_gpu_hc_get_info(h, ctypes.byref(info)))
+
+            def arr(name, count, dtype):
+                if not count:
+                    return np.zeros(0, dtype)
+                addr = getattr(self._lib, "crn_gpu_hc_" + name)(h)
+                return np.ctypeslib.as_array(ctypes.cast(addr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (count,)).copy()
+            out = {
+                "endpoint_indices": arr("endpoint_indices", n * 4, np.uint16).reshape(n, 4),
+                "selector_indices": arr("selector_indices", n * 4, np.uint16).reshape(n, 4),
+                "color_endpoints": arr("color_endpoints", info.n_color_endpoints, np.uint32),
+                "alpha_endpoints": arr("alpha_endpoints", info.n_alpha_endpoints, np.uint32),
+                "color_selectors": arr("color_selectors", info.n_color_selectors, np.uint32),
+                "alpha_selectors": arr("alpha_selectors", info.n_alpha_selectors, np.uint64),
+                "block_encodings": arr("block_encodings", n, np.uint8),
+                "tile_indices": arr("tile_indices", n, np.uint32),
+                "info": {"num_tiles": info.num_tiles, "vq_rounds": list(info.vq_rounds), "unique_vectors": list(info.unique_vectors)},
+            }
+        finally:
+            self._lib.crn_gpu_hc_free(h)
+        return out
 
     # --- clustered DDS compression (mipmapped_texture::qdxt_pack_init / qdxt_pack) ----------------------
     def qdxt_init(self, fmt, levels, params=None):

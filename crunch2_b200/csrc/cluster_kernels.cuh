@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kClusterWarpsPerCta * 32, 5)
 dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
                               ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
                               unsigned int* __restrict__ next_cluster, ClusterResult* __restrict__ results,
-                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error)
+                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags)
 {
     __shared__ Dxt1ClusterScratch scratch[kClusterWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -160,6 +160,8 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
             results[c].flags = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2);
             if (out_endpoints) out_endpoints[c] = out_lo | (out_hi << 16);
             if (out_error) out_error[c] = stage == 2 ? 0ull : sc->best.err;
+            // dxt_hc wants results::m_reordered (bit 0) and m_alternate_rounding (bit 4) (crn_dxt1.cpp:279-282)
+            if (out_flags) out_flags[c] = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2) | ((stage != 2 && sc->best.alt_round) ? 16u : 0u);
         }
         __syncwarp();
     }
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
 dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
                               const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, uint32_t comp, int quality, int both_types,
                               unsigned int* __restrict__ next_cluster, uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs,
-                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error)
+                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags)
 {
     __shared__ Dxt5aClusterScratch scratch[kClusterWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -250,6 +252,7 @@ dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
         for (int ofs = 16; ofs > 0; ofs >>= 1) U += __shfl_xor_sync(CRN_FULL_MASK, U, ofs);
         unsigned first, second;
         unsigned long long err = 0;
+        unsigned reordered = 0;                              // results::m_reordered (crn_dxt5a.cpp:150-182)
         if (U == 1) {
             first = second = sc->val[0];
             if (lane == 0) sc->sel[0] = 0;
@@ -258,10 +261,12 @@ dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
             const Dxt5aBest best = N > 33025u ? dxt5a_search<true>(sc, U, quality, both_types != 0) : dxt5a_search<false>(sc, U, quality, both_types != 0);
             err = best.error;
             dxt5a_finish(sc, U, best, first, second);
+            reordered = (best.first != best.second && first != best.first) ? 1u : 0u;
         }
         if (lane == 0) {
             if (out_endpoints) out_endpoints[c] = first | (second << 8);
             if (out_error) out_error[c] = err;
+            if (out_flags) out_flags[c] = reordered;
         }
         for (uint32_t base = 0; base < N; base += 32) {
             const uint32_t i = base + lane;

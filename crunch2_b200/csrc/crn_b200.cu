@@ -11,6 +11,7 @@
 #include "qdxt_kernels.cuh"
 #include "vq_host.h"
 #include "refiner_kernels.cuh"
+#include "hc_kernels.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,6 +35,7 @@ struct crn_gpu_ctx {
     void* d_out; size_t d_out_cap;
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
     void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
+    uint32_t* d_cluster_flags;           // set by the dxt_hc pipeline around a cluster-optimiser call: per-cluster m_reordered / m_alternate_rounding out
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
     void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
     int wide_smem_set;
@@ -415,6 +417,8 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
 }  // namespace
 
 
+#include "hc_host.h"
+
 extern "C" {
 
 uint32_t crn_gpu_abi_version(void) { return CRN_B200_ABI_VERSION; }
@@ -681,7 +685,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     const int threads = crn::kClusterWarpsPerCta * 32;
     const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, getenv("CRN_B200_CLUSTER_CTAS") ? atoi(getenv("CRN_B200_CLUSTER_CTAS")) : 5);
     CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, d_cluster_offsets, n_clusters, dp, scan_alpha, ws, rank, transparent,
-               reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error));
+               reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags);
     CRN_LAUNCH(crn::cluster_write_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent,
                results, static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes);
     ctx->launches += 6;
@@ -711,7 +715,7 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     CRN_LAUNCH(crn::dxt5_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
                d_cluster_blocks, n_clusters, component, (int)params->dxt_quality, params->use_both_block_types ? 1 : 0,
                reinterpret_cast<unsigned int*>(ctx->d_cluster_ws), static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes,
-               d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error));
+               d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
@@ -1019,6 +1023,56 @@ int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int perceptual, ui
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
 }
+
+void crn_gpu_default_hc_params(crn_gpu_hc_params* p)
+{   // dxt_hc::params::params() (crnlib/crn_dxt_hc.h:105-131)
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->format = CRN_GPU_FMT_DXT1; p->num_faces = 1; p->perceptual = 1;
+    p->color_endpoint_codebook_size = p->color_selector_codebook_size = p->alpha_endpoint_codebook_size = p->alpha_selector_codebook_size = 3072;
+    p->adaptive_tile_color_psnr_derating = 2.0f; p->adaptive_tile_alpha_psnr_derating = 2.0f; p->adaptive_tile_color_alpha_weighting_ratio = 3.0f;
+    p->alpha_component_indices[0] = 3; p->alpha_component_indices[1] = 0;
+}
+
+int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (out) *out = nullptr;
+    if (!params || params->struct_size != sizeof(crn_gpu_hc_params) || !blocks_rgba || !out || !params->num_blocks || !params->num_levels ||
+        params->num_levels > 16 || !params->num_faces || params->alpha_component_indices[0] > 3 || params->alpha_component_indices[1] > 3 ||
+        !params->color_endpoint_codebook_size || !params->color_selector_codebook_size || !params->alpha_endpoint_codebook_size || !params->alpha_selector_codebook_size ||
+        params->color_endpoint_codebook_size > 65535 || params->color_selector_codebook_size > 65535 || params->alpha_endpoint_codebook_size > 65535 ||
+        params->alpha_selector_codebook_size > 65535)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_hc_compress: bad argument");
+    crn_gpu_hc* H = new (std::nothrow) crn_gpu_hc();
+    if (!H) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory");
+    memset(&H->info, 0, sizeof(H->info));
+    H->info.struct_size = sizeof(H->info);
+    int rc;
+    try { rc = hc_compress_impl(ctx, params, blocks_rgba, blocks_on_host, H); }
+    catch (const std::bad_alloc&) { rc = set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
+    ctx->d_cluster_flags = nullptr;
+    if (rc) { delete H; return rc; }
+    *out = H;
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_hc_get_info(const crn_gpu_hc* hc, crn_gpu_hc_info* info)
+{
+    if (!hc || !info || info->struct_size != sizeof(crn_gpu_hc_info)) return CRN_GPU_ERR_BAD_PARAM;
+    *info = hc->info;
+    return CRN_GPU_OK;
+}
+const uint16_t* crn_gpu_hc_endpoint_indices(const crn_gpu_hc* hc) { return hc ? hc->endpoint_indices.data() : nullptr; }
+const uint16_t* crn_gpu_hc_selector_indices(const crn_gpu_hc* hc) { return hc ? hc->selector_indices.data() : nullptr; }
+const uint32_t* crn_gpu_hc_color_endpoints(const crn_gpu_hc* hc) { return hc ? hc->color_endpoints.data() : nullptr; }
+const uint32_t* crn_gpu_hc_alpha_endpoints(const crn_gpu_hc* hc) { return hc ? hc->alpha_endpoints.data() : nullptr; }
+const uint32_t* crn_gpu_hc_color_selectors(const crn_gpu_hc* hc) { return hc ? hc->color_selectors.data() : nullptr; }
+const uint64_t* crn_gpu_hc_alpha_selectors(const crn_gpu_hc* hc) { return hc ? hc->alpha_selectors.data() : nullptr; }
+const uint8_t* crn_gpu_hc_block_encodings(const crn_gpu_hc* hc) { return hc ? hc->block_encodings.data() : nullptr; }
+const uint32_t* crn_gpu_hc_tile_indices(const crn_gpu_hc* hc) { return hc ? hc->tile_indices.data() : nullptr; }
+void crn_gpu_hc_free(crn_gpu_hc* hc) { delete hc; }
 
 int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info)
 {

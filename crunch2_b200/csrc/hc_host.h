@@ -1,0 +1,524 @@
+// hc_host.h -- host driver of the dxt_hc pipeline (included by crn_b200.cu after its helpers).
+//
+// Replaces crnlib::dxt_hc::compress (reference crnlib/crn_dxt_hc.cpp:98-312) for the DXT formats: tile determination
+// (a12) -> endpoint tree quantisers (a13) -> nearest-codebook assignment (a14) -> per-cluster endpoint codebooks (a15:
+// cluster optimiser + per-block selectors + refiner) -> selector codebooks (a16: tree quantiser + exhaustive search +
+// re-vote) -> palette dedup / index remap / reference flags (a17).  Everything per-pixel, per-block, per-cluster or
+// per-tree-node runs on the device; the host keeps what is inherently a small serial structure: the tree quantiser's
+// priority queue (HcTreeVq, replaying crn_tree_clusterizer.h:89-171 on split results the device produced a frontier
+// at a time), the sort + dedup of training vectors, the CSR build, and the final remap.
+#pragma once
+#include <queue>
+
+namespace {
+
+struct HcBuf {                                   // pooled device buffer
+    crn_gpu_ctx* ctx = nullptr; void* p = nullptr; size_t cap = 0;
+    ~HcBuf() { if (p) pool_free(ctx, p, cap); }
+    cudaError_t alloc(crn_gpu_ctx* c, size_t bytes) { ctx = c; return pool_alloc(c, &p, bytes, &cap); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+#define HC_ALLOC(buf, bytes)                                                                         \
+    do {                                                                                             \
+        cudaError_t ce_ = (buf).alloc(ctx, (bytes));                                                 \
+        if (ce_ != cudaSuccess) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "dxt_hc: cudaMalloc", ce_); \
+    } while (0)
+#define HC_RC(call) do { int rc_ = (call); if (rc_) return rc_; } while (0)
+
+// ---- tree_clusterizer<V>::generate_codebook (crn_tree_clusterizer.h:89-171), single-task semantics ------------------
+template <int D>
+struct HcTreeVq {
+    struct Node {
+        float centroid[D]; unsigned long long total_weight; float variance; uint32_t begin, end; int left, right;
+        bool have_result; crn::HcTreeSlot<D> res;
+    };
+    struct HeapEntry {                            // NodeInfo (:46-59): larger variance first, then lower index
+        uint32_t index; float variance;
+        bool operator<(const HeapEntry& o) const { return index < o.index ? variance < o.variance : o.variance >= variance; }
+    };
+    std::vector<float> codebook;                  // K x D
+    uint32_t rounds = 0, device_splits = 0;
+
+    int build(crn_gpu_ctx* ctx, const float* h_vecs, const uint32_t* h_wts, uint32_t n, uint32_t max_splits)
+    {
+        codebook.clear();
+        if (!n || !max_splits) return CRN_GPU_OK;
+        HcBuf d_vecs, d_wts, d_perm, d_tmp, d_slots, d_list, d_root;
+        HC_ALLOC(d_vecs, (size_t)n * D * 4); HC_ALLOC(d_wts, (size_t)n * 4); HC_ALLOC(d_perm, (size_t)n * 4); HC_ALLOC(d_tmp, (size_t)n * 4);
+        HC_ALLOC(d_root, (D + 2) * 8);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_vecs.p, h_vecs, (size_t)n * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_wts.p, h_wts, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CRN_LAUNCH(crn::hc_tree_root_kernel<D>, 1, 512, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), n, d_perm.as<uint32_t>(), d_root.as<double>());
+        ctx->launches++;
+        double h_root[D + 2];
+        CRN_CUDA(ctx, cudaMemcpyAsync(h_root, d_root.p, sizeof(h_root), cudaMemcpyDeviceToHost, ctx->stream));
+        CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<Node> nodes;
+        nodes.reserve((size_t)max_splits * 2 + 2);
+        {
+            Node r; memset(&r, 0, sizeof(r));
+            r.begin = 0; r.end = n; r.left = r.right = -1; r.have_result = false;
+            r.total_weight = (unsigned long long)h_root[D + 1];
+            float dot = 0;
+            for (int d = 0; d < D; d++) { r.centroid[d] = (float)h_root[d]; dot = d ? dot + r.centroid[d] * r.centroid[d] : r.centroid[d] * r.centroid[d]; }
+            r.variance = (float)(h_root[D] - (double)(dot / (float)r.total_weight));
+            const float inv = 1.0f / (float)r.total_weight;
+            for (int d = 0; d < D; d++) r.centroid[d] *= inv;
+            nodes.push_back(r);
+        }
+        std::vector<HeapEntry> heap;               // std::priority_queue semantics via push_heap / pop_heap, iterable
+        heap.push_back({ 0u, nodes[0].variance });
+        uint32_t splits = 1;
+        std::vector<crn::HcTreeSlot<D>> h_slots;
+        std::vector<uint32_t> round_nodes, small_list, large_list;
+        size_t slot_cap = 0, list_cap = 0;
+        bool done = false;
+        while (!done) {
+            // ---- replay the reference's loop as far as the device results reach
+            bool need_round = false;
+            while (splits < max_splits) {
+                if (heap.empty()) { done = true; break; }
+                const uint32_t ni = heap.front().index;
+                if (nodes[ni].variance <= 0.0f || nodes[ni].begin + 1 == nodes[ni].end) { done = true; break; }
+                if (!nodes[ni].have_result) { need_round = true; break; }
+                std::pop_heap(heap.begin(), heap.end()); heap.pop_back();
+                const crn::HcTreeSlot<D> r = nodes[ni].res;
+                if (r.state == 1) {
+                    Node l, rt; memset(&l, 0, sizeof(l)); memset(&rt, 0, sizeof(rt));
+                    l.left = l.right = rt.left = rt.right = -1;
+                    l.begin = nodes[ni].begin; l.end = rt.begin = nodes[ni].begin + r.n_left; rt.end = nodes[ni].end;
+                    for (int d = 0; d < D; d++) { l.centroid[d] = r.lc[d]; rt.centroid[d] = r.rc[d]; }
+                    l.total_weight = r.lw; rt.total_weight = r.rw; l.variance = r.lvar; rt.variance = r.rvar;
+                    nodes[ni].left = (int)nodes.size(); nodes.push_back(l);
+                    nodes[ni].right = (int)nodes.size(); nodes.push_back(rt);
+                    heap.push_back({ (uint32_t)nodes[ni].left, l.variance }); std::push_heap(heap.begin(), heap.end());
+                    heap.push_back({ (uint32_t)nodes[ni].right, rt.variance }); std::push_heap(heap.begin(), heap.end());
+                }
+                splits++;
+            }
+            if (splits >= max_splits) done = true;
+            if (done || !need_round) break;
+            // ---- one device round: every leaf the queue could still reach
+            round_nodes.clear();
+            for (const HeapEntry& e : heap) {
+                const Node& nd = nodes[e.index];
+                if (!nd.have_result && nd.variance > 0.0f && nd.begin + 1 != nd.end) round_nodes.push_back(e.index);
+            }
+            const uint32_t budget = max_splits - splits;
+            if (round_nodes.size() > budget) {
+                std::partial_sort(round_nodes.begin(), round_nodes.begin() + budget, round_nodes.end(), [&](uint32_t a, uint32_t b) {
+                    return HeapEntry{ b, nodes[b].variance } < HeapEntry{ a, nodes[a].variance };
+                });
+                round_nodes.resize(budget);
+            }
+            const uint32_t nr = (uint32_t)round_nodes.size();
+            h_slots.resize(nr);
+            small_list.clear(); large_list.clear();
+            for (uint32_t i = 0; i < nr; i++) {
+                const Node& nd = nodes[round_nodes[i]];
+                crn::HcTreeSlot<D>& s = h_slots[i];
+                memset(&s, 0, sizeof(s));
+                s.begin = nd.begin; s.end = nd.end; s.total_weight = nd.total_weight;
+                for (int d = 0; d < D; d++) s.centroid[d] = nd.centroid[d];
+                (nd.end - nd.begin >= 2048 ? large_list : small_list).push_back(i);
+            }
+            if (nr > slot_cap) {
+                if (d_slots.p) { pool_free(ctx, d_slots.p, d_slots.cap); d_slots.p = nullptr; }
+                if (d_list.p) { pool_free(ctx, d_list.p, d_list.cap); d_list.p = nullptr; }
+                slot_cap = (size_t)nr * 2 + 64; list_cap = slot_cap;
+                HC_ALLOC(d_slots, slot_cap * sizeof(crn::HcTreeSlot<D>)); HC_ALLOC(d_list, list_cap * 4);
+            }
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_slots.p, h_slots.data(), (size_t)nr * sizeof(crn::HcTreeSlot<D>), cudaMemcpyHostToDevice, ctx->stream));
+            uint32_t* dl = d_list.as<uint32_t>();
+            if (!large_list.empty()) {
+                CRN_CUDA(ctx, cudaMemcpyAsync(dl, large_list.data(), large_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CRN_LAUNCH((crn::hc_tree_split_kernel<D, 256>), (unsigned)large_list.size(), 256, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), d_perm.as<uint32_t>(),
+                           d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), dl, (uint32_t)large_list.size());
+                ctx->launches++;
+            }
+            if (!small_list.empty()) {
+                uint32_t* dsm = dl + large_list.size();
+                CRN_CUDA(ctx, cudaMemcpyAsync(dsm, small_list.data(), small_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                const unsigned grid = (unsigned)std::min<size_t>(small_list.size(), (size_t)ctx->sm_count * 32);
+                CRN_LAUNCH((crn::hc_tree_split_kernel<D, 32>), grid, 32, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), d_perm.as<uint32_t>(),
+                           d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), dsm, (uint32_t)small_list.size());
+                ctx->launches++;
+            }
+            CRN_CUDA(ctx, cudaGetLastError());
+            CRN_CUDA(ctx, cudaMemcpyAsync(h_slots.data(), d_slots.p, (size_t)nr * sizeof(crn::HcTreeSlot<D>), cudaMemcpyDeviceToHost, ctx->stream));
+            CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint32_t i = 0; i < nr; i++) { nodes[round_nodes[i]].res = h_slots[i]; nodes[round_nodes[i]].have_result = true; }
+            rounds++; device_splits += nr;
+        }
+        for (size_t i = 0; i < nodes.size(); i++)
+            if (nodes[i].left == -1) codebook.insert(codebook.end(), nodes[i].centroid, nodes[i].centroid + D);
+        return CRN_GPU_OK;
+    }
+    uint32_t size() const { return (uint32_t)(codebook.size() / D); }
+};
+
+template <int D> struct HcVecKey {
+    float v[D]; uint32_t w;
+    bool operator<(const HcVecKey& o) const {      // std::pair<vec, uint> ordering (crn_vec.h:279-294, then the weight)
+        for (int d = 0; d < D; d++) { if (v[d] < o.v[d]) return true; if (v[d] != o.v[d]) return false; }
+        return w < o.w;
+    }
+    bool same_vec(const HcVecKey& o) const { for (int d = 0; d < D; d++) if (v[d] != o.v[d]) return false; return true; }
+};
+
+// sort + merge of equal vectors with saturating weights (determine_color_endpoints, crn_dxt_hc.cpp:888-968)
+template <int D>
+void hc_sort_dedup(std::vector<HcVecKey<D>>& keys, std::vector<float>& vecs, std::vector<uint32_t>& wts)
+{
+    std::sort(keys.begin(), keys.end());
+    vecs.clear(); wts.clear();
+    for (size_t i = 0; i < keys.size(); i++) {
+        if (wts.empty() || !keys[i].same_vec(keys[i - 1])) { vecs.insert(vecs.end(), keys[i].v, keys[i].v + D); wts.push_back(keys[i].w); }
+        else if (wts.back() > 0xffffffffu - keys[i].w) wts.back() = 0xffffffffu;
+        else wts.back() += keys[i].w;
+    }
+}
+
+}  // namespace
+
+struct crn_gpu_hc {
+    crn_gpu_hc_info info;
+    std::vector<uint16_t> endpoint_indices, selector_indices;     // n x 4
+    std::vector<uint32_t> color_endpoints, alpha_endpoints, color_selectors;
+    std::vector<uint64_t> alpha_selectors;
+    std::vector<uint8_t> block_encodings;
+    std::vector<uint32_t> tile_indices;
+};
+
+namespace {
+
+// one endpoint element of the pipeline (colour, or the alpha channels together): clusters, per-block selectors, refined endpoints
+struct HcElementOut {
+    std::vector<uint32_t> tile_cluster;            // per used tile (per component for alpha)
+    std::vector<uint32_t> cluster_endpoints;       // final packed endpoints per cluster (low | high << 16)
+    std::vector<uint8_t> cluster_used;
+    uint32_t K = 0;
+};
+
+int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void* blocks_rgba, int on_host, crn_gpu_hc* H)
+{
+    const uint32_t n = prm->num_blocks;
+    const uint32_t fmt = prm->format;
+    const bool has_color = fmt == CRN_GPU_FMT_DXT1 || fmt == CRN_GPU_FMT_DXT5;
+    const int na = fmt == CRN_GPU_FMT_DXT5 || fmt == CRN_GPU_FMT_DXT5A ? 1 : ((fmt == CRN_GPU_FMT_DXN_XY || fmt == CRN_GPU_FMT_DXN_YX) ? 2 : 0);
+    if (!has_color && !na) return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_hc_compress: format must be DXT1, DXT5, DXT5A or DXN");
+    const uint32_t comp0 = prm->alpha_component_indices[0], comp1 = prm->alpha_component_indices[1];
+    const int perceptual = prm->perceptual ? 1 : 0;
+    // ---- parameters of the tile pass (crn_dxt_hc.cpp:126-146)
+    crn::HcTileParams TP; memset(&TP, 0, sizeof(TP));
+    TP.num_levels = prm->num_levels; TP.num_faces = prm->num_faces; TP.has_color = has_color; TP.num_alpha = na;
+    TP.alpha_comp[0] = comp0; TP.alpha_comp[1] = comp1; TP.color_alpha_ratio = prm->adaptive_tile_color_alpha_weighting_ratio;
+    static const unsigned tile_derating[8] = { 0, 1, 1, 2, 2, 2, 2, 3 };
+    uint32_t chunks = 0, expect = 0;
+    for (uint32_t l = 0; l < prm->num_levels; l++) {
+        const crn_gpu_hc_level& L = prm->levels[l];
+        if (!L.block_width || (L.block_width & 1) || L.first_block != expect || !L.num_blocks || L.num_blocks % (2 * L.block_width * prm->num_faces))
+            return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_hc_compress: levels must be contiguous, with even block widths and an even number of block rows per face");
+        TP.levels[l].first_block = L.first_block; TP.levels[l].num_blocks = L.num_blocks; TP.levels[l].block_width = L.block_width;
+        TP.levels[l].weight = L.weight; TP.levels[l].first_chunk = chunks;
+        chunks += L.num_blocks / 4; expect += L.num_blocks;
+        float der = prm->adaptive_tile_color_psnr_derating;
+        if (l && der > .25f) { const float d = der / powf(3.0f, (float)l); der = d > .25f ? d : .25f; }
+        for (int e = 0; e < 8; e++) TP.color_derating[l][e] = 0.0f + (der - 0.0f) * ((float)tile_derating[e] / 3.0f);
+    }
+    if (expect != n) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_hc_compress: levels do not cover num_blocks");
+    for (int e = 0; e < 8; e++) TP.alpha_derating[e] = 0.0f + (prm->adaptive_tile_alpha_psnr_derating - 0.0f) * ((float)tile_derating[e] / 3.0f);
+    TP.total_chunks = chunks;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    // ---- a12: tiles
+    HcBuf d_blocks_own, d_enc, d_tile, d_npix, d_pixofs, d_vpix, d_cvec, d_avec;
+    const uint32_t* d_blocks = static_cast<const uint32_t*>(blocks_rgba);
+    if (on_host) {
+        HC_ALLOC(d_blocks_own, (size_t)n * 64);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_blocks_own.p, blocks_rgba, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+        d_blocks = d_blocks_own.as<uint32_t>();
+    }
+    HC_ALLOC(d_enc, n); HC_ALLOC(d_tile, (size_t)n * 4); HC_ALLOC(d_npix, n); HC_ALLOC(d_pixofs, n); HC_ALLOC(d_vpix, (size_t)n * 64);
+    if (has_color) HC_ALLOC(d_cvec, (size_t)n * 24);
+    if (na) HC_ALLOC(d_avec, (size_t)na * n * 8);
+    CRN_LAUNCH(crn::hc_tiles_kernel, grid_for(ctx, chunks, crn::kHcTileWarps, 8), crn::kHcTileWarps * 32, 0, st, d_blocks, TP, d_enc.as<uint8_t>(), d_tile.as<uint32_t>(),
+               d_npix.as<uint8_t>(), d_pixofs.as<uint8_t>(), d_vpix.as<uint32_t>());
+    const int ncomp = (has_color ? 1 : 0) + na;
+    CRN_LAUNCH(crn::hc_palettize_kernel, (n * ncomp + 127) / 128, 128, 0, st, d_vpix.as<uint32_t>(), d_npix.as<uint8_t>(), d_pixofs.as<uint8_t>(), n, (int)has_color, na, comp0, comp1,
+               perceptual, d_cvec.as<float>(), d_avec.as<float>());
+    ctx->launches += 2;
+    CRN_CUDA(ctx, cudaGetLastError());
+    std::vector<uint8_t> h_npix(n), h_pixofs(n);
+    H->block_encodings.resize(n); H->tile_indices.resize(n);
+    std::vector<float> h_cvec(has_color ? (size_t)n * 6 : 0), h_avec((size_t)na * n * 2);
+    CRN_CUDA(ctx, cudaMemcpyAsync(h_npix.data(), d_npix.p, n, cudaMemcpyDeviceToHost, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(h_pixofs.data(), d_pixofs.p, n, cudaMemcpyDeviceToHost, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(H->block_encodings.data(), d_enc.p, n, cudaMemcpyDeviceToHost, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(H->tile_indices.data(), d_tile.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (has_color) CRN_CUDA(ctx, cudaMemcpyAsync(h_cvec.data(), d_cvec.p, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    if (na) CRN_CUDA(ctx, cudaMemcpyAsync(h_avec.data(), d_avec.p, (size_t)na * n * 8, cudaMemcpyDeviceToHost, st));
+    CRN_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<uint32_t> used_slots;               // tile slots in order (m_tiles[t].pixels.size() != 0)
+    std::vector<float> slot_weight(n);
+    for (uint32_t l = 0; l < prm->num_levels; l++)
+        for (uint32_t b = prm->levels[l].first_block, e = b + prm->levels[l].num_blocks; b < e; b++) slot_weight[b] = prm->levels[l].weight;
+    for (uint32_t s = 0; s < n; s++) if (h_npix[s]) used_slots.push_back(s);
+    const uint32_t num_tiles = (uint32_t)used_slots.size();
+    std::vector<uint32_t> slot_rank(n, 0xffffffffu);
+    for (uint32_t i = 0; i < num_tiles; i++) slot_rank[used_slots[i]] = i;
+    H->info.num_tiles = num_tiles;
+    H->endpoint_indices.assign((size_t)n * 4, 0); H->selector_indices.assign((size_t)n * 4, 0);
+    std::vector<uint16_t> raw_endpoint((size_t)n * 3, 0), raw_selector((size_t)n * 3, 0);
+    std::vector<uint32_t> color_cluster_ep, alpha_cluster_ep;
+    std::vector<uint8_t> color_cluster_used, alpha_cluster_used;
+    std::vector<uint32_t> color_sel_cb; std::vector<uint64_t> alpha_sel_cb; std::vector<uint8_t> color_sel_used, alpha_sel_used;
+
+    crn_gpu_pack_params pp; crn_gpu_default_pack_params(&pp);
+    pp.dxt_quality = 4; pp.perceptual = (uint32_t)perceptual; pp.use_both_block_types = 0;
+
+    // ---- one pass per endpoint kind: 0 colour, 1 alpha (all alpha channels share one codebook)
+    for (int kind = 0; kind < 2; kind++) {
+        if (kind == 0 && !has_color) continue;
+        if (kind == 1 && !na) continue;
+        const int ncp = kind ? na : 1;                                   // components handled together
+        const uint32_t NV = (uint32_t)ncp * n;                           // virtual blocks (= member blocks in the CSR)
+        // a13: training vectors -> sorted unique weighted vectors -> tree quantiser
+        std::vector<float> codebook; uint32_t K = 0;
+        std::vector<float> tile_vecs;                                    // compact, [component][tile][dims]
+        if (kind == 0) {
+            std::vector<HcVecKey<6>> keys(num_tiles);
+            tile_vecs.resize((size_t)num_tiles * 6);
+            for (uint32_t i = 0; i < num_tiles; i++) {
+                const uint32_t s = used_slots[i];
+                memcpy(keys[i].v, &h_cvec[(size_t)s * 6], 24); memcpy(&tile_vecs[(size_t)i * 6], &h_cvec[(size_t)s * 6], 24);
+                keys[i].w = (uint32_t)((float)h_npix[s] * slot_weight[s]);
+            }
+            std::vector<float> uv; std::vector<uint32_t> uw;
+            hc_sort_dedup<6>(keys, uv, uw);
+            HcTreeVq<6> vq;
+            HC_RC(vq.build(ctx, uv.data(), uw.data(), (uint32_t)uw.size(), std::min(num_tiles, prm->color_endpoint_codebook_size)));
+            codebook.swap(vq.codebook); K = (uint32_t)(codebook.size() / 6);
+            H->info.vq_rounds[0] = vq.rounds; H->info.unique_vectors[0] = (uint32_t)uw.size();
+        } else {
+            std::vector<HcVecKey<2>> keys((size_t)na * num_tiles);
+            tile_vecs.resize((size_t)na * num_tiles * 2);
+            for (int a = 0; a < na; a++)
+                for (uint32_t i = 0; i < num_tiles; i++) {
+                    const uint32_t s = used_slots[i];
+                    const float* v = &h_avec[((size_t)a * n + s) * 2];
+                    HcVecKey<2>& k = keys[(size_t)a * num_tiles + i];
+                    k.v[0] = v[0]; k.v[1] = v[1]; k.w = h_npix[s];
+                    tile_vecs[((size_t)a * num_tiles + i) * 2] = v[0]; tile_vecs[((size_t)a * num_tiles + i) * 2 + 1] = v[1];
+                }
+            std::vector<float> uv; std::vector<uint32_t> uw;
+            hc_sort_dedup<2>(keys, uv, uw);
+            HcTreeVq<2> vq;
+            HC_RC(vq.build(ctx, uv.data(), uw.data(), (uint32_t)uw.size(), std::min(num_tiles, prm->alpha_endpoint_codebook_size)));
+            codebook.swap(vq.codebook); K = (uint32_t)(codebook.size() / 2);
+            H->info.vq_rounds[1] = vq.rounds; H->info.unique_vectors[1] = (uint32_t)uw.size();
+        }
+        if (!K) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: empty endpoint codebook");
+        // a14: nearest codebook entry per tile (per component)
+        const uint32_t dims = kind ? 2 : 6, NT = (uint32_t)ncp * num_tiles;
+        HcBuf d_tvec, d_cb, d_tcl;
+        HC_ALLOC(d_tvec, (size_t)NT * dims * 4); HC_ALLOC(d_cb, (size_t)K * dims * 4); HC_ALLOC(d_tcl, (size_t)NT * 4);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_tvec.p, tile_vecs.data(), (size_t)NT * dims * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_cb.p, codebook.data(), (size_t)K * dims * 4, cudaMemcpyHostToDevice, st));
+        HC_RC(crn_gpu_nearest_codebook(ctx, dims, d_tvec.as<float>(), NT, d_cb.as<float>(), K, d_tcl.as<uint32_t>()));
+        std::vector<uint32_t> tcl(NT);
+        CRN_CUDA(ctx, cudaMemcpyAsync(tcl.data(), d_tcl.p, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        // cluster member lists: the tiles' 16-pixel virtual blocks, component-major then tile-slot order (:970-977, :1246-1260)
+        std::vector<uint32_t> offs(K + 1, 0), members(NV), block_cluster(NV);
+        for (int a = 0; a < ncp; a++)
+            for (uint32_t i = 0; i < num_tiles; i++) offs[tcl[(size_t)a * num_tiles + i] + 1] += h_npix[used_slots[i]] / 16;
+        for (uint32_t c = 0; c < K; c++) offs[c + 1] += offs[c];
+        {
+            std::vector<uint32_t> cur(offs.begin(), offs.end() - 1);
+            for (int a = 0; a < ncp; a++)
+                for (uint32_t i = 0; i < num_tiles; i++) {
+                    const uint32_t s = used_slots[i], c = tcl[(size_t)a * num_tiles + i];
+                    const uint32_t vb0 = (uint32_t)a * n + (s & ~3u) + h_pixofs[s] / 16;
+                    for (uint32_t k = 0; k < h_npix[s] / 16u; k++) members[cur[c]++] = vb0 + k;
+                }
+        }
+        for (int a = 0; a < ncp; a++)
+            for (uint32_t b = 0; b < n; b++) {
+                const uint32_t c = tcl[(size_t)a * num_tiles + slot_rank[H->tile_indices[b]]];
+                block_cluster[(size_t)a * n + b] = c;
+                raw_endpoint[(size_t)b * 3 + (kind ? 1 + a : 0)] = (uint16_t)c;
+            }
+        std::vector<uint32_t> poffs(K + 1);
+        for (uint32_t c = 0; c <= K; c++) poffs[c] = offs[c] * 16;
+        // a15: per-cluster optimiser over the virtual blocks
+        HcBuf d_vsrc, d_offs, d_mem, d_elem, d_ep, d_err, d_flags, d_bcl, d_bsel, d_bval, d_cpix, d_csel, d_poffs, d_rep, d_rerr, d_rok, d_bw, d_bacc, d_grey;
+        const uint32_t* d_vblocks = d_vpix.as<uint32_t>();
+        if (kind == 1) {                                                 // grey copies of the tile-ordered pixels, one plane per channel
+            HC_ALLOC(d_vsrc, (size_t)NV * 64);
+            for (int a = 0; a < na; a++)
+                CRN_LAUNCH(crn::hc_grey_kernel, (unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st, d_vpix.as<uint32_t>(), (size_t)n * 16, a ? comp1 : comp0, d_vsrc.as<uint32_t>() + (size_t)a * n * 16);
+            ctx->launches += na;
+            d_vblocks = d_vsrc.as<uint32_t>();
+        }
+        HC_ALLOC(d_offs, (size_t)(K + 1) * 4); HC_ALLOC(d_poffs, (size_t)(K + 1) * 4); HC_ALLOC(d_mem, (size_t)NV * 4); HC_ALLOC(d_elem, (size_t)NV * 8);
+        HC_ALLOC(d_ep, (size_t)K * 4); HC_ALLOC(d_err, (size_t)K * 8); HC_ALLOC(d_flags, (size_t)K * 4); HC_ALLOC(d_bcl, (size_t)NV * 4);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_offs.p, offs.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_poffs.p, poffs.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_mem.p, members.data(), (size_t)NV * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_bcl.p, block_cluster.data(), (size_t)NV * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemsetAsync(d_ep.p, 0, (size_t)K * 4, st));
+        CRN_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, (size_t)K * 8, st));
+        CRN_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, (size_t)K * 4, st));
+        ctx->d_cluster_flags = d_flags.as<uint32_t>();
+        int rc = kind == 0 ? crn_gpu_dxt1_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>())
+                           : crn_gpu_dxt5_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>());
+        ctx->d_cluster_flags = nullptr;
+        if (rc) return rc;
+        // per-block selectors + weights against the cluster palette
+        HC_ALLOC(d_bsel, (size_t)NV * 8); HC_ALLOC(d_bval, (size_t)NV * (kind ? 8 : 16));
+        if (kind == 0) {
+            HC_ALLOC(d_bw, (size_t)n * 4);
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_bw.p, slot_weight.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            CRN_LAUNCH(crn::hc_color_blocks_kernel, (n + 255) / 256, 256, 0, st, d_blocks, n, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(), d_bw.as<float>(),
+                       d_enc.as<uint8_t>(), perceptual, d_bsel.as<unsigned long long>(), d_bval.as<uint32_t>());
+        } else {
+            CRN_LAUNCH(crn::hc_alpha_blocks_kernel, (NV + 255) / 256, 256, 0, st, d_blocks, n, na, comp0, comp1, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(),
+                       d_enc.as<uint8_t>(), d_bsel.as<unsigned long long>(), d_bval.as<uint8_t>());
+        }
+        // refiner over the cluster pixel lists with the optimiser's selectors (a10)
+        HC_ALLOC(d_cpix, (size_t)NV * 64); HC_ALLOC(d_csel, (size_t)NV * 16); HC_ALLOC(d_rep, (size_t)K * 4); HC_ALLOC(d_rerr, (size_t)K * 8); HC_ALLOC(d_rok, K);
+        CRN_LAUNCH(crn::hc_gather_cluster_pixels_kernel, (unsigned)(((size_t)NV * 16 + 255) / 256), 256, 0, st, d_vblocks, d_mem.as<uint32_t>(), NV * 16, kind,
+                   d_elem.as<unsigned long long>(), d_cpix.as<uint32_t>(), d_csel.as<uint8_t>());
+        ctx->launches += 2;
+        HC_RC(crn_gpu_refine_endpoints(ctx, kind == 0 ? 1 : 0, perceptual, 0, d_cpix.p, d_csel.as<uint8_t>(), d_poffs.as<uint32_t>(), K, d_err.as<uint64_t>(),
+                                       d_rep.as<uint32_t>(), d_rerr.as<uint64_t>(), d_rok.as<uint8_t>()));
+        std::vector<uint32_t> ep(K), rep(K); std::vector<uint8_t> rok(K);
+        CRN_CUDA(ctx, cudaMemcpyAsync(ep.data(), d_ep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(rep.data(), d_rep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(rok.data(), d_rok.p, K, cudaMemcpyDeviceToHost, st));
+        // a16: selector codebook.  Training set = the distinct block selectors with summed weights (:1379-1444, :1588-1660)
+        std::vector<unsigned long long> bsel(NV);
+        CRN_CUDA(ctx, cudaMemcpyAsync(bsel.data(), d_bsel.p, (size_t)NV * 8, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<uint32_t>& cl_ep = kind ? alpha_cluster_ep : color_cluster_ep;
+        std::vector<uint8_t>& cl_used = kind ? alpha_cluster_used : color_cluster_used;
+        cl_ep.resize(K); cl_used.resize(K);
+        for (uint32_t c = 0; c < K; c++) {
+            cl_used[c] = offs[c + 1] != offs[c];
+            if (kind == 0) cl_ep[c] = rok[c] ? rep[c] : ep[c];                                           // dxt1_block::pack_endpoints(first, second) = low | high << 16
+            else cl_ep[c] = rok[c] ? ((rep[c] & 0xffff) | ((rep[c] >> 16) << 8)) : (ep[c] & 0xffff);     // dxt5_block::pack_endpoints = first | second << 8
+        }
+        std::sort(bsel.begin(), bsel.end());
+        std::vector<float> sv; std::vector<uint32_t> sw;
+        {
+            const int bits = kind ? 3 : 2, wshift = kind ? 16 : 32;
+            unsigned long long prev = 0;
+            float lut[8];
+            for (int s = 0; s < 8; s++) lut[s] = kind ? ((float)s + 0.5f) * 0.125f : ((float)s + 0.5f) * 0.25f;
+            for (size_t i = 0; i < bsel.size(); i++) {
+                const uint32_t weight = kind ? (uint32_t)(bsel[i] & 0xffff) : (uint32_t)bsel[i];
+                unsigned long long sel = bsel[i] >> wshift;
+                if (sw.empty() || sel != prev) {
+                    prev = sel;
+                    float v[16];
+                    for (int p = 0; p < 16; p++, sel >>= bits) v[15 - p] = lut[sel & ((1u << bits) - 1)];
+                    sv.insert(sv.end(), v, v + 16); sw.push_back(weight);
+                } else if (sw.back() > 0xffffffffu - weight) sw.back() = 0xffffffffu;
+                else sw.back() += weight;
+            }
+        }
+        HcTreeVq<16> svq;
+        HC_RC(svq.build(ctx, sv.data(), sw.data(), (uint32_t)sw.size(), kind ? prm->alpha_selector_codebook_size : prm->color_selector_codebook_size));
+        const uint32_t KS = svq.size();
+        H->info.vq_rounds[2 + kind] = svq.rounds; H->info.unique_vectors[2 + kind] = (uint32_t)sw.size();
+        if (!KS) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: empty selector codebook");
+        std::vector<uint64_t> scb(KS);
+        for (uint32_t i = 0; i < KS; i++) {
+            uint64_t s = 0;
+            for (int j = 0; j < 16; j++) s |= (uint64_t)(uint32_t)(svq.codebook[(size_t)i * 16 + j] * (kind ? 8.0f : 4.0f)) << ((kind ? 3 : 2) * j);
+            scb[i] = kind ? s : (uint64_t)(uint32_t)s;
+        }
+        // exhaustive search + re-vote
+        HcBuf d_scb, d_best, d_refined, d_used;
+        HC_ALLOC(d_scb, (size_t)KS * 8); HC_ALLOC(d_best, (size_t)NV * 4); HC_ALLOC(d_refined, (size_t)KS * 8); HC_ALLOC(d_used, KS);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_scb.p, scb.data(), (size_t)KS * 8, cudaMemcpyHostToDevice, st));
+        const void* search_blocks = d_blocks;
+        const void* accum = nullptr;
+        if (kind == 1) {
+            HC_ALLOC(d_grey, (size_t)NV * 64); HC_ALLOC(d_bacc, (size_t)NV * 8);
+            for (int a = 0; a < na; a++)
+                CRN_LAUNCH(crn::hc_grey_kernel, (unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, st, d_blocks, (size_t)n * 16, a ? comp1 : comp0, d_grey.as<uint32_t>() + (size_t)a * n * 16);
+            CRN_LAUNCH(crn::hc_alpha_refined_values_kernel, (NV + 255) / 256, 256, 0, st, NV, d_bcl.as<uint32_t>(), d_rep.as<uint32_t>(), d_rok.as<uint8_t>(), d_bval.as<uint8_t>(), d_bacc.as<uint8_t>());
+            ctx->launches += na + 1;
+            search_blocks = d_grey.p; accum = d_bacc.p;
+        }
+        HC_RC(crn_gpu_assign_selectors(ctx, (uint32_t)kind, perceptual, 0, search_blocks, NV, d_bval.p, accum, d_scb.as<uint64_t>(), KS, d_best.as<uint32_t>(), d_refined.as<uint64_t>(), d_used.as<uint8_t>()));
+        std::vector<uint32_t> best(NV); std::vector<uint64_t> refined(KS); std::vector<uint8_t> used(KS);
+        CRN_CUDA(ctx, cudaMemcpyAsync(best.data(), d_best.p, (size_t)NV * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(refined.data(), d_refined.p, (size_t)KS * 8, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(used.data(), d_used.p, KS, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int a = 0; a < ncp; a++)
+            for (uint32_t b = 0; b < n; b++) raw_selector[(size_t)b * 3 + (kind ? 1 + a : 0)] = (uint16_t)best[(size_t)a * n + b];
+        if (kind == 0) { color_sel_cb.resize(KS); for (uint32_t i = 0; i < KS; i++) color_sel_cb[i] = (uint32_t)refined[i]; color_sel_used = used; }
+        else { alpha_sel_cb = refined; alpha_sel_used = used; }
+    }
+
+    // ---- a17: palette dedup, index remap, reference flags (crn_dxt_hc.cpp:200-310)
+    auto dedup32 = [](const std::vector<uint32_t>& in, const std::vector<uint8_t>& used, std::vector<uint32_t>& out, std::vector<uint16_t>& remap) {
+        remap.assign(in.size(), 0);
+        std::vector<int64_t> table(1u << 17, -1);
+        for (size_t i = 0; i < in.size(); i++) {
+            if (!used[i]) continue;
+            uint32_t h = (in[i] * 2654435761u) >> 15;
+            for (;;) {
+                if (table[h] < 0) { table[h] = (int64_t)out.size(); remap[i] = (uint16_t)out.size(); out.push_back(in[i]); break; }
+                if (out[(size_t)table[h]] == in[i]) { remap[i] = (uint16_t)table[h]; break; }
+                h = (h + 1) & ((1u << 17) - 1);
+            }
+        }
+    };
+    auto dedup64 = [](const std::vector<uint64_t>& in, const std::vector<uint8_t>& used, std::vector<uint64_t>& out, std::vector<uint16_t>& remap) {
+        remap.assign(in.size(), 0);
+        std::vector<int64_t> table(1u << 17, -1);
+        for (size_t i = 0; i < in.size(); i++) {
+            if (!used[i]) continue;
+            uint32_t h = (uint32_t)((in[i] * 0x9E3779B97F4A7C15ull) >> 47);
+            for (;;) {
+                if (table[h] < 0) { table[h] = (int64_t)out.size(); remap[i] = (uint16_t)out.size(); out.push_back(in[i]); break; }
+                if (out[(size_t)table[h]] == in[i]) { remap[i] = (uint16_t)table[h]; break; }
+                h = (h + 1) & ((1u << 17) - 1);
+            }
+        }
+    };
+    std::vector<uint16_t> ce_remap, ae_remap, cs_remap, as_remap;
+    dedup32(color_cluster_ep, color_cluster_used, H->color_endpoints, ce_remap);
+    dedup32(alpha_cluster_ep, alpha_cluster_used, H->alpha_endpoints, ae_remap);
+    dedup32(color_sel_cb, color_sel_used, H->color_selectors, cs_remap);
+    dedup64(alpha_sel_cb, alpha_sel_used, H->alpha_selectors, as_remap);
+    for (uint32_t l = 0; l < prm->num_levels; l++) {
+        const uint32_t first = prm->levels[l].first_block, end = first + prm->levels[l].num_blocks, bw = prm->levels[l].block_width;
+        uint32_t b = first;
+        for (uint32_t by = 0; b < end; by++)
+            for (uint32_t bx = 0; bx < bw; bx++, b++) {
+                bool top = by != 0, left = top || bx;
+                for (int c = has_color ? 0 : 1; c < 1 + na; c++) {
+                    const uint16_t e = (c ? ae_remap : ce_remap)[raw_endpoint[(size_t)b * 3 + c]];
+                    left = left && e == H->endpoint_indices[(size_t)(b - 1) * 4 + c];
+                    top = top && e == H->endpoint_indices[(size_t)(b - bw) * 4 + c];
+                    H->endpoint_indices[(size_t)b * 4 + c] = e;
+                    H->selector_indices[(size_t)b * 4 + c] = (c ? as_remap : cs_remap)[raw_selector[(size_t)b * 3 + c]];
+                }
+                H->endpoint_indices[(size_t)b * 4 + 3] = left ? 1 : (top ? 2 : 0);
+            }
+    }
+    H->info.num_blocks = n;
+    H->info.n_color_endpoints = (uint32_t)H->color_endpoints.size(); H->info.n_alpha_endpoints = (uint32_t)H->alpha_endpoints.size();
+    H->info.n_color_selectors = (uint32_t)H->color_selectors.size(); H->info.n_alpha_selectors = (uint32_t)H->alpha_selectors.size();
+    return CRN_GPU_OK;
+}
+
+}  // namespace

@@ -224,6 +224,54 @@ CRN_API int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int percep
                                      const uint64_t* d_codebook, uint32_t codebook_size,
                                      uint32_t* d_best_index, uint64_t* d_refined_codebook, uint8_t* d_used);
 
+/* dxt_hc pipeline --------------------------------------------------------------
+ * crn_gpu_hc_compress replaces crnlib::dxt_hc::compress (reference crnlib/crn_dxt_hc.cpp:98-312; params mirror
+ * dxt_hc::params, crnlib/crn_dxt_hc.h:103-172) as crn_comp::quantize_images calls it (crnlib/crn_comp.cpp:717-766) for
+ * the DXT formats: from the [block][16] RGBA8 array of all levels and faces to the four palettes and the per-block
+ * endpoint / selector indices + reference flags that the CRN writer codes.  Tile determination, tile palettizing, the
+ * three tree quantisers, nearest-codebook assignment, the per-cluster optimiser + refiner, the per-block selector
+ * assignment and the selector search / re-vote run on the device.  Tolerance-class, like the reference itself (its
+ * output depends on the helper-thread count): same algorithm, float sums in a different (fixed, deterministic) order.
+ *   levels[i]       first_block / num_blocks / block_width / weight as crn_comp sets them; block widths and the number
+ *                   of block rows per face must be even (crn_comp pads levels to multiples of 8 pixels)
+ *   blocks_rgba     num_blocks x 16 RGBA8, host (blocks_on_host != 0) or device memory
+ * Results are host arrays owned by the returned object (release with crn_gpu_hc_free):
+ *   endpoint_indices  num_blocks x 4 uint16: color, alpha0, alpha1, reference (0 none, 1 left, 2 top)
+ *   selector_indices  num_blocks x 4 uint16: color, alpha0, alpha1, 0
+ *   color_endpoints   uint32 low565 | high565 << 16;  alpha_endpoints uint32 first | second << 8
+ *   color_selectors   uint32, pixel p at bits 2p (linear selector order);  alpha_selectors uint64, pixel p at bits 3p */
+typedef struct crn_gpu_hc_level { uint32_t first_block, num_blocks, block_width; float weight; } crn_gpu_hc_level;
+typedef struct crn_gpu_hc_params {
+    uint32_t struct_size;               /* sizeof(crn_gpu_hc_params) */
+    uint32_t format;                    /* CRN_GPU_FMT_DXT1, DXT5, DXT5A, DXN_XY or DXN_YX */
+    uint32_t num_blocks, num_levels, num_faces;
+    crn_gpu_hc_level levels[16];
+    uint32_t perceptual;
+    uint32_t color_endpoint_codebook_size, color_selector_codebook_size, alpha_endpoint_codebook_size, alpha_selector_codebook_size;
+    float adaptive_tile_color_psnr_derating, adaptive_tile_alpha_psnr_derating, adaptive_tile_color_alpha_weighting_ratio;
+    uint32_t alpha_component_indices[2];
+} crn_gpu_hc_params;
+typedef struct crn_gpu_hc_info {
+    uint32_t struct_size;               /* sizeof(crn_gpu_hc_info) */
+    uint32_t num_blocks, num_tiles;
+    uint32_t n_color_endpoints, n_alpha_endpoints, n_color_selectors, n_alpha_selectors;
+    uint32_t vq_rounds[4];              /* device rounds of the four tree quantisers: colour / alpha endpoints, colour / alpha selectors */
+    uint32_t unique_vectors[4];         /* their training-set sizes */
+} crn_gpu_hc_info;
+typedef struct crn_gpu_hc crn_gpu_hc;
+CRN_API void crn_gpu_default_hc_params(crn_gpu_hc_params* p);
+CRN_API int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out);
+CRN_API int crn_gpu_hc_get_info(const crn_gpu_hc* hc, crn_gpu_hc_info* info);
+CRN_API const uint16_t* crn_gpu_hc_endpoint_indices(const crn_gpu_hc* hc);
+CRN_API const uint16_t* crn_gpu_hc_selector_indices(const crn_gpu_hc* hc);
+CRN_API const uint32_t* crn_gpu_hc_color_endpoints(const crn_gpu_hc* hc);
+CRN_API const uint32_t* crn_gpu_hc_alpha_endpoints(const crn_gpu_hc* hc);
+CRN_API const uint32_t* crn_gpu_hc_color_selectors(const crn_gpu_hc* hc);
+CRN_API const uint64_t* crn_gpu_hc_alpha_selectors(const crn_gpu_hc* hc);
+CRN_API const uint8_t* crn_gpu_hc_block_encodings(const crn_gpu_hc* hc);      /* m_block_encodings, one byte per block */
+CRN_API const uint32_t* crn_gpu_hc_tile_indices(const crn_gpu_hc* hc);        /* m_tile_indices */
+CRN_API void crn_gpu_hc_free(crn_gpu_hc* hc);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:

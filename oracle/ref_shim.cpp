@@ -501,3 +501,54 @@ SHIM_API uint32_t ref_hc_nearest_codebook(uint32_t dims, const float* vecs, cons
     hc.m_pTask_pool = NULL;
     return k;
 }
+
+// ref_hc_compress -> dxt_hc::compress (crn_dxt_hc.cpp:98-312) with `threads` helper threads (0 = the single-task tree
+// quantiser: no "alternative" sub-trees, the deterministic configuration the device pipeline is compared against).
+// levels: num_levels x {first_block, num_blocks, block_width, weight-as-float-bits}.  Outputs mirror crn_gpu_hc_*:
+// endpoint_indices / selector_indices n x 4 uint16 (color, alpha0, alpha1, reference | 0); palettes up to 65536
+// entries each; sizes[4] = color endpoints, alpha endpoints, color selectors, alpha selectors.  encodings / tile_indices
+// (n each) optional.  blocks are copied (dxt_hc only reads them for the DXT formats).
+SHIM_API int ref_hc_compress(int format, uint32_t n, uint32_t num_levels, uint32_t num_faces, const uint32_t* levels, int perceptual,
+                             const uint32_t* codebook_sizes, const float* deratings, const uint32_t* alpha_comps, uint32_t threads,
+                             const uint8_t* blocks, uint16_t* endpoint_indices, uint16_t* selector_indices,
+                             uint32_t* color_endpoints, uint32_t* alpha_endpoints, uint32_t* color_selectors, uint64_t* alpha_selectors,
+                             uint32_t* sizes, uint8_t* encodings, uint32_t* tile_indices)
+{
+    task_pool tp;
+    if (!tp.init(threads)) return 0;
+    dxt_hc::params p;
+    p.m_num_blocks = n; p.m_num_levels = num_levels; p.m_num_faces = num_faces;
+    for (uint32_t l = 0; l < num_levels; l++)
+    {
+        p.m_levels[l].m_first_block = levels[l * 4]; p.m_levels[l].m_num_blocks = levels[l * 4 + 1]; p.m_levels[l].m_block_width = levels[l * 4 + 2];
+        memcpy(&p.m_levels[l].m_weight, &levels[l * 4 + 3], 4);
+    }
+    p.m_format = (dxt_format)format;
+    p.m_perceptual = perceptual != 0;
+    p.m_hierarchical = true;
+    p.m_color_endpoint_codebook_size = codebook_sizes[0]; p.m_color_selector_codebook_size = codebook_sizes[1];
+    p.m_alpha_endpoint_codebook_size = codebook_sizes[2]; p.m_alpha_selector_codebook_size = codebook_sizes[3];
+    p.m_adaptive_tile_color_psnr_derating = deratings[0]; p.m_adaptive_tile_alpha_psnr_derating = deratings[1];
+    p.m_adaptive_tile_color_alpha_weighting_ratio = deratings[2];
+    p.m_alpha_component_indices[0] = alpha_comps[0]; p.m_alpha_component_indices[1] = alpha_comps[1];
+    p.m_pTask_pool = &tp;
+    crnlib::vector<color_quad_u8> copy(n * 16);
+    memcpy(copy.get_ptr(), blocks, (size_t)n * 64);
+    crnlib::vector<dxt_hc::endpoint_indices_details> ei;
+    crnlib::vector<dxt_hc::selector_indices_details> si;
+    crnlib::vector<uint32> ce, ae, cs;
+    crnlib::vector<uint64> as;
+    dxt_hc hc;
+    if (!hc.compress((color_quad_u8(*)[16])copy.get_ptr(), ei, si, ce, ae, cs, as, p)) return 0;
+    for (uint32_t b = 0; b < n; b++)
+    {
+        for (uint c = 0; c < 3; c++) { endpoint_indices[b * 4 + c] = ei[b].component[c]; selector_indices[b * 4 + c] = si[b].component[c]; }
+        endpoint_indices[b * 4 + 3] = ei[b].reference; selector_indices[b * 4 + 3] = 0;
+        if (encodings) encodings[b] = hc.m_block_encodings[b];
+        if (tile_indices) tile_indices[b] = hc.m_tile_indices[b];
+    }
+    sizes[0] = ce.size(); sizes[1] = ae.size(); sizes[2] = cs.size(); sizes[3] = as.size();
+    memcpy(color_endpoints, ce.get_ptr(), ce.size() * 4); memcpy(alpha_endpoints, ae.get_ptr(), ae.size() * 4);
+    memcpy(color_selectors, cs.get_ptr(), cs.size() * 4); memcpy(alpha_selectors, as.get_ptr(), as.size() * 8);
+    return 1;
+}
