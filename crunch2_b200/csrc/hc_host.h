@@ -38,6 +38,8 @@ struct HcTreeVq {
         bool operator<(const HeapEntry& o) const { return index < o.index ? variance < o.variance : o.variance >= variance; }
     };
     std::vector<float> codebook;                  // K x D
+    static constexpr int kClusterCtas = 8, kClusterThreads = 512;
+    static constexpr uint32_t kHugeNode = 8192;
     uint32_t rounds = 0, device_splits = 0;
 
     int build(crn_gpu_ctx* ctx, const float* h_vecs, const uint32_t* h_wts, uint32_t n, uint32_t max_splits)
@@ -71,7 +73,7 @@ struct HcTreeVq {
         heap.push_back({ 0u, nodes[0].variance });
         uint32_t splits = 1;
         std::vector<crn::HcTreeSlot<D>> h_slots;
-        std::vector<uint32_t> round_nodes, small_list, large_list;
+        std::vector<uint32_t> round_nodes, small_list, large_list, huge_list;
         size_t slot_cap = 0, list_cap = 0;
         bool done = false;
         while (!done) {
@@ -114,14 +116,19 @@ struct HcTreeVq {
             }
             const uint32_t nr = (uint32_t)round_nodes.size();
             h_slots.resize(nr);
-            small_list.clear(); large_list.clear();
+            small_list.clear(); large_list.clear(); huge_list.clear();
             for (uint32_t i = 0; i < nr; i++) {
                 const Node& nd = nodes[round_nodes[i]];
                 crn::HcTreeSlot<D>& s = h_slots[i];
                 memset(&s, 0, sizeof(s));
                 s.begin = nd.begin; s.end = nd.end; s.total_weight = nd.total_weight;
                 for (int d = 0; d < D; d++) s.centroid[d] = nd.centroid[d];
-                (nd.end - nd.begin >= 2048 ? large_list : small_list).push_back(i);
+                const uint32_t sz = nd.end - nd.begin;
+#ifdef __CUDACC__
+                (sz >= kHugeNode ? huge_list : (sz >= 1024 ? large_list : small_list)).push_back(i);
+#else
+                (sz >= 1024 ? large_list : small_list).push_back(i);      // the emulator has no thread-block clusters
+#endif
             }
             if (nr > slot_cap) {
                 if (d_slots.p) { pool_free(ctx, d_slots.p, d_slots.cap); d_slots.p = nullptr; }
@@ -131,18 +138,33 @@ struct HcTreeVq {
             }
             CRN_CUDA(ctx, cudaMemcpyAsync(d_slots.p, h_slots.data(), (size_t)nr * sizeof(crn::HcTreeSlot<D>), cudaMemcpyHostToDevice, ctx->stream));
             uint32_t* dl = d_list.as<uint32_t>();
+#ifdef __CUDACC__
+            if (!huge_list.empty()) {          // a cluster of kClusterCtas CTAs per node, partial sums exchanged through distributed shared memory
+                CRN_CUDA(ctx, cudaMemcpyAsync(dl, huge_list.data(), huge_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+                const unsigned nclusters = (unsigned)std::min<size_t>(huge_list.size(), (size_t)std::max(1, ctx->sm_count / kClusterCtas) * 2);
+                cfg.gridDim = dim3(nclusters * kClusterCtas); cfg.blockDim = dim3(kClusterThreads); cfg.stream = ctx->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                CRN_CUDA(ctx, cudaLaunchKernelEx(&cfg, crn::hc_tree_split_kernel<D, kClusterThreads, kClusterCtas>, (const float*)d_vecs.as<float>(), (const uint32_t*)d_wts.as<uint32_t>(),
+                                                 d_perm.as<uint32_t>(), d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), (const uint32_t*)dl, (uint32_t)huge_list.size()));
+                ctx->launches++;
+                dl += huge_list.size();
+            }
+#endif
             if (!large_list.empty()) {
                 CRN_CUDA(ctx, cudaMemcpyAsync(dl, large_list.data(), large_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-                CRN_LAUNCH((crn::hc_tree_split_kernel<D, 256>), (unsigned)large_list.size(), 256, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), d_perm.as<uint32_t>(),
+                CRN_LAUNCH((crn::hc_tree_split_kernel<D, 256, 1>), (unsigned)large_list.size(), 256, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), d_perm.as<uint32_t>(),
                            d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), dl, (uint32_t)large_list.size());
                 ctx->launches++;
+                dl += large_list.size();
             }
             if (!small_list.empty()) {
-                uint32_t* dsm = dl + large_list.size();
-                CRN_CUDA(ctx, cudaMemcpyAsync(dsm, small_list.data(), small_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CRN_CUDA(ctx, cudaMemcpyAsync(dl, small_list.data(), small_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
                 const unsigned grid = (unsigned)std::min<size_t>(small_list.size(), (size_t)ctx->sm_count * 32);
-                CRN_LAUNCH((crn::hc_tree_split_kernel<D, 32>), grid, 32, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), d_perm.as<uint32_t>(),
-                           d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), dsm, (uint32_t)small_list.size());
+                CRN_LAUNCH((crn::hc_tree_split_kernel<D, 32, 1>), grid, 32, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), d_perm.as<uint32_t>(),
+                           d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), dl, (uint32_t)small_list.size());
                 ctx->launches++;
             }
             CRN_CUDA(ctx, cudaGetLastError());
@@ -233,6 +255,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
+    QdxtTrace tr(ctx);
     // ---- a12: tiles
     HcBuf d_blocks_own, d_enc, d_tile, d_npix, d_pixofs, d_vpix, d_cvec, d_avec;
     const uint32_t* d_blocks = static_cast<const uint32_t*>(blocks_rgba);
@@ -261,6 +284,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     if (has_color) CRN_CUDA(ctx, cudaMemcpyAsync(h_cvec.data(), d_cvec.p, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
     if (na) CRN_CUDA(ctx, cudaMemcpyAsync(h_avec.data(), d_avec.p, (size_t)na * n * 8, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaStreamSynchronize(st));
+    tr.mark("hc tiles + palettize + D2H", 0);
     std::vector<uint32_t> used_slots;               // tile slots in order (m_tiles[t].pixels.size() != 0)
     std::vector<float> slot_weight(n);
     for (uint32_t l = 0; l < prm->num_levels; l++)
@@ -320,6 +344,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             codebook.swap(vq.codebook); K = (uint32_t)(codebook.size() / 2);
             H->info.vq_rounds[1] = vq.rounds; H->info.unique_vectors[1] = (uint32_t)uw.size();
         }
+        tr.mark("hc endpoint sort + tree VQ", kind);
         if (!K) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: empty endpoint codebook");
         // a14: nearest codebook entry per tile (per component)
         const uint32_t dims = kind ? 2 : 6, NT = (uint32_t)ncp * num_tiles;
@@ -331,6 +356,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         std::vector<uint32_t> tcl(NT);
         CRN_CUDA(ctx, cudaMemcpyAsync(tcl.data(), d_tcl.p, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        tr.mark("hc nearest codebook", kind);
         // cluster member lists: the tiles' 16-pixel virtual blocks, component-major then tile-slot order (:970-977, :1246-1260)
         std::vector<uint32_t> offs(K + 1, 0), members(NV), block_cluster(NV);
         for (int a = 0; a < ncp; a++)
@@ -353,6 +379,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             }
         std::vector<uint32_t> poffs(K + 1);
         for (uint32_t c = 0; c <= K; c++) poffs[c] = offs[c] * 16;
+        tr.mark("hc CSR build (host)", kind);
         // a15: per-cluster optimiser over the virtual blocks
         HcBuf d_vsrc, d_offs, d_mem, d_elem, d_ep, d_err, d_flags, d_bcl, d_bsel, d_bval, d_cpix, d_csel, d_poffs, d_rep, d_rerr, d_rok, d_bw, d_bacc, d_grey;
         const uint32_t* d_vblocks = d_vpix.as<uint32_t>();
@@ -377,6 +404,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                            : crn_gpu_dxt5_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>());
         ctx->d_cluster_flags = nullptr;
         if (rc) return rc;
+        tr.mark("hc cluster optimiser", kind);
         // per-block selectors + weights against the cluster palette
         HC_ALLOC(d_bsel, (size_t)NV * 8); HC_ALLOC(d_bval, (size_t)NV * (kind ? 8 : 16));
         if (kind == 0) {
@@ -403,6 +431,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         std::vector<unsigned long long> bsel(NV);
         CRN_CUDA(ctx, cudaMemcpyAsync(bsel.data(), d_bsel.p, (size_t)NV * 8, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        tr.mark("hc block selectors + refiner + D2H", kind);
         std::vector<uint32_t>& cl_ep = kind ? alpha_cluster_ep : color_cluster_ep;
         std::vector<uint8_t>& cl_used = kind ? alpha_cluster_used : color_cluster_used;
         cl_ep.resize(K); cl_used.resize(K);
@@ -430,10 +459,12 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                 else sw.back() += weight;
             }
         }
+        tr.mark("hc selector sort + dedup (host)", kind);
         HcTreeVq<16> svq;
         HC_RC(svq.build(ctx, sv.data(), sw.data(), (uint32_t)sw.size(), kind ? prm->alpha_selector_codebook_size : prm->color_selector_codebook_size));
         const uint32_t KS = svq.size();
         H->info.vq_rounds[2 + kind] = svq.rounds; H->info.unique_vectors[2 + kind] = (uint32_t)sw.size();
+        tr.mark("hc selector tree VQ", kind);
         if (!KS) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: empty selector codebook");
         std::vector<uint64_t> scb(KS);
         for (uint32_t i = 0; i < KS; i++) {
@@ -461,6 +492,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         CRN_CUDA(ctx, cudaMemcpyAsync(refined.data(), d_refined.p, (size_t)KS * 8, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaMemcpyAsync(used.data(), d_used.p, KS, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        tr.mark("hc selector search + re-vote", kind);
         for (int a = 0; a < ncp; a++)
             for (uint32_t b = 0; b < n; b++) raw_selector[(size_t)b * 3 + (kind ? 1 + a : 0)] = (uint16_t)best[(size_t)a * n + b];
         if (kind == 0) { color_sel_cb.resize(KS); for (uint32_t i = 0; i < KS; i++) color_sel_cb[i] = (uint32_t)refined[i]; color_sel_used = used; }
@@ -515,6 +547,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                 H->endpoint_indices[(size_t)b * 4 + 3] = left ? 1 : (top ? 2 : 0);
             }
     }
+    tr.mark("hc tail (host)", 0);
     H->info.num_blocks = n;
     H->info.n_color_endpoints = (uint32_t)H->color_endpoints.size(); H->info.n_alpha_endpoints = (uint32_t)H->alpha_endpoints.size();
     H->info.n_color_selectors = (uint32_t)H->color_selectors.size(); H->info.n_alpha_selectors = (uint32_t)H->alpha_selectors.size();

@@ -371,47 +371,88 @@ template <int D> struct HcTreeSlot {
     float lvar, rvar;
 };
 
-template <int T> struct HcRed { double d[T / 32]; unsigned long long u[T / 32]; };
+// Reductions over the threads that work on one node: one CTA of T threads (G == 1) or a thread-block cluster of G CTAs
+// (G > 1, nvcc build only) whose per-CTA partials are exchanged through distributed shared memory.  The summation order is
+// fixed (lanes by shuffle tree, warps in order, CTAs in rank order), so results are deterministic and identical in every CTA.
+template <int T, int K> struct HcRed {
+    double part_d[T / 32][K];
+    unsigned long long part_u[T / 32][4];
+    double cta_d[2][K];                       // double-buffered by call parity: one cluster barrier per reduction
+    unsigned long long cta_u[2][4];
+    double tot_d[K];
+    unsigned long long tot_u[4], pre_u[4];
+};
 
-template <int T> __device__ __forceinline__ double hc_block_sum(double v, double* red)
+#ifdef __CUDACC__
+}  // namespace crn
+#include <cooperative_groups.h>
+namespace crn {
+namespace cg = cooperative_groups;
+#endif
+
+template <int G> __device__ __forceinline__ unsigned hc_cta_rank()
 {
-#pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(CRN_FULL_MASK, v, ofs);
-    if (T == 32) return v;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0;
-#pragma unroll
-    for (int w = 0; w < T / 32; w++) s += red[w];
-    return s;
+#ifdef __CUDACC__
+    if (G > 1) return cg::this_cluster().block_rank();
+#endif
+    return 0;
 }
-template <int T> __device__ __forceinline__ unsigned long long hc_block_sum_u64(unsigned long long v, unsigned long long* red)
+template <int G> __device__ __forceinline__ void hc_group_sync()
 {
-#pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(CRN_FULL_MASK, v, ofs);
-    if (T == 32) return v;
+#ifdef __CUDACC__
+    if (G > 1) { cg::this_cluster().sync(); return; }
+#endif
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    unsigned long long s = 0;
-#pragma unroll
-    for (int w = 0; w < T / 32; w++) s += red[w];
-    return s;
 }
-// maximum key over the CTA (key = float distance bits << 32 | ~position: largest distance, then lowest position)
-template <int T> __device__ __forceinline__ unsigned long long hc_block_max_u64(unsigned long long v, unsigned long long* red)
+
+// sums nd doubles (v) and nu <= 4 uint64 (u) over the group; u_prefix receives the sum over the CTAs of lower rank.
+// SUM_U false: the uint64 entries are reduced with max instead (u_prefix unused).
+template <int T, int G, int K, bool SUM_U>
+__device__ __forceinline__ void hc_group_reduce(HcRed<T, K>& R, unsigned& parity, double* v, int nd, unsigned long long* u, int nu, unsigned long long* u_prefix)
 {
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int k = 0; k < nd; k++) {
+        double x = v[k];
 #pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1) { const unsigned long long o = __shfl_xor_sync(CRN_FULL_MASK, v, ofs); v = o > v ? o : v; }
-    if (T == 32) return v;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    unsigned long long s = 0;
+        for (int ofs = 16; ofs > 0; ofs >>= 1) x += __shfl_xor_sync(CRN_FULL_MASK, x, ofs);
+        if (lane == 0) R.part_d[warp][k] = x;
+    }
+    for (int k = 0; k < nu; k++) {
+        unsigned long long x = u[k];
 #pragma unroll
-    for (int w = 0; w < T / 32; w++) s = red[w] > s ? red[w] : s;
-    return s;
+        for (int ofs = 16; ofs > 0; ofs >>= 1) { const unsigned long long o = __shfl_xor_sync(CRN_FULL_MASK, x, ofs); x = SUM_U ? x + o : (o > x ? o : x); }
+        if (lane == 0) R.part_u[warp][k] = x;
+    }
+    __syncthreads();
+    const unsigned pb = parity & 1; parity++;
+    if ((int)tid < nd) { double s = 0; for (int w = 0; w < T / 32; w++) s += R.part_d[w][tid]; R.cta_d[pb][tid] = s; if (G == 1) R.tot_d[tid] = s; }
+    if ((int)tid >= nd && (int)tid < nd + nu) {
+        const int k = tid - nd; unsigned long long s = 0;
+        for (int w = 0; w < T / 32; w++) s = SUM_U ? s + R.part_u[w][k] : (R.part_u[w][k] > s ? R.part_u[w][k] : s);
+        R.cta_u[pb][k] = s; if (G == 1) { R.tot_u[k] = s; R.pre_u[k] = 0; }
+    }
+    if (T == 32) __syncwarp();
+#ifdef __CUDACC__
+    if (G > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();
+        const unsigned me = cl.block_rank();
+        if ((int)tid < nd) { double s = 0; for (unsigned r = 0; r < (unsigned)G; r++) s += cl.map_shared_rank(&R.cta_d[pb][0], r)[tid]; R.tot_d[tid] = s; }
+        if ((int)tid >= nd && (int)tid < nd + nu) {
+            const int k = tid - nd; unsigned long long s = 0, pre = 0;
+            for (unsigned r = 0; r < (unsigned)G; r++) {
+                const unsigned long long x = cl.map_shared_rank(&R.cta_u[pb][0], r)[k];
+                if (r == me) pre = s;
+                s = SUM_U ? s + x : (x > s ? x : s);
+            }
+            R.tot_u[k] = s; R.pre_u[k] = pre;
+        }
+    }
+#endif
+    __syncthreads();
+    for (int k = 0; k < nd; k++) v[k] = R.tot_d[k];
+    for (int k = 0; k < nu; k++) { u[k] = R.tot_u[k]; if (u_prefix) u_prefix[k] = R.pre_u[k]; }
+    __syncthreads();                             // tot_* may be rewritten by the next call
 }
 
 template <int D> __device__ __forceinline__ void hc_load_vec(const float* __restrict__ vecs, uint32_t id, float (&v)[D])
@@ -440,10 +481,11 @@ __global__ void __launch_bounds__(512)
 hc_tree_root_kernel(const float* __restrict__ vecs, const uint32_t* __restrict__ wts, uint32_t n, uint32_t* __restrict__ perm, double* __restrict__ out)
 {
     constexpr int T = 512;
-    __shared__ HcRed<T> red;
-    double s[D], tt = 0; unsigned long long tw = 0;
+    __shared__ HcRed<T, D + 1> red;
+    unsigned parity = 0;
+    double s[D + 1]; unsigned long long tw = 0;
 #pragma unroll
-    for (int d = 0; d < D; d++) s[d] = 0;
+    for (int d = 0; d <= D; d++) s[d] = 0;
     for (uint32_t i = threadIdx.x; i < n; i += T) {
         float v[D]; hc_load_vec<D>(vecs, i, v);
         const unsigned w = wts[i];
@@ -452,30 +494,34 @@ hc_tree_root_kernel(const float* __restrict__ vecs, const uint32_t* __restrict__
         for (int d = 1; d < D; d++) dot += v[d] * v[d];
 #pragma unroll
         for (int d = 0; d < D; d++) s[d] += (double)(v[d] * (float)w);
-        tt += (double)(dot * (float)w); tw += w;
+        s[D] += (double)(dot * (float)w); tw += w;
         perm[i] = i;
     }
-#pragma unroll
-    for (int d = 0; d < D; d++) { const double r = hc_block_sum<T>(s[d], red.d); if (threadIdx.x == 0) out[d] = r; }
-    const double rt = hc_block_sum<T>(tt, red.d);
-    const unsigned long long rw = hc_block_sum_u64<T>(tw, red.u);
-    if (threadIdx.x == 0) { out[D] = rt; out[D + 1] = (double)rw; }
+    hc_group_reduce<T, 1, D + 1, true>(red, parity, s, D + 1, &tw, 1, nullptr);
+    if (threadIdx.x == 0) { for (int d = 0; d <= D; d++) out[d] = s[d]; out[D + 1] = (double)tw; }
 }
 
-template <int D, int T>
+// One node per group (CTA, or cluster of G CTAs).  CTA r of the group owns the contiguous member segment r.
+template <int D, int T, int G>
 __global__ void __launch_bounds__(T)
 hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict__ wts, uint32_t* __restrict__ perm, uint32_t* __restrict__ perm_tmp,
                      HcTreeSlot<D>* __restrict__ slots, const uint32_t* __restrict__ slot_list, uint32_t nslots)
 {
-    __shared__ HcRed<T> red;
+    constexpr int K = D == 16 ? 18 : D * (D + 1) / 2 + D + 2;       // widest batch: Lloyd sums (D + 1) / totals (D + 1) / D <= 6 covariance
     constexpr int COVN = D == 16 ? T * 16 : D * D;
+    __shared__ HcRed<T, K> red;
     __shared__ float s_cov[COVN];
+    __shared__ double s_cpart[D == 16 ? 256 : 1];
     __shared__ float s_axis[D];
     __shared__ uint32_t s_warp_cnt[T / 32 + 1];
     const unsigned tid = threadIdx.x;
-    for (uint32_t si = blockIdx.x; si < nslots; si += gridDim.x) {
+    const unsigned rank = hc_cta_rank<G>();
+    unsigned parity = 0;
+    for (uint32_t si = blockIdx.x / G; si < nslots; si += gridDim.x / G) {
         HcTreeSlot<D>& S = slots[slot_list[si]];
         const uint32_t begin = S.begin, end = S.end;
+        const uint32_t seg = (end - begin + G - 1) / G;
+        const uint32_t sb = min(end, begin + rank * seg), se = min(end, sb + seg);          // this CTA's members
         float centroid[D];
 #pragma unroll
         for (int d = 0; d < D; d++) centroid[d] = S.centroid[d];
@@ -485,26 +531,25 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             unsigned long long key = 0;
-            for (uint32_t i = begin + tid; i < end; i += T) {
+            for (uint32_t i = sb + tid; i < se; i += T) {
                 float v[D]; hc_load_vec<D>(vecs, perm[i], v);
                 const float d2 = pass ? hc_sqdist<D>(v, seed[0]) : hc_sqdist<D>(v, centroid);
                 const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(~i);
                 key = k > key ? k : key;
             }
-            key = hc_block_max_u64<T>(key, red.u);
+            hc_group_reduce<T, G, K, false>(red, parity, nullptr, 0, &key, 1, nullptr);
             const uint32_t pos = ~(unsigned)key;
             hc_load_vec<D>(vecs, perm[pos], seed[pass]);
         }
         float left[D], right[D];
 #pragma unroll
         for (int d = 0; d < D; d++) { left[d] = (seed[0][d] + centroid[d]) * .5f; right[d] = (seed[1][d] + centroid[d]) * .5f; }
-        // node totals (needed for right = total - left)
-        double tot[D], tot_tt;
+        // node totals (right sums = total - left sums)
+        double tot[D + 1];
         {
-            double s[D], tt = 0;
 #pragma unroll
-            for (int d = 0; d < D; d++) s[d] = 0;
-            for (uint32_t i = begin + tid; i < end; i += T) {
+            for (int d = 0; d <= D; d++) tot[d] = 0;
+            for (uint32_t i = sb + tid; i < se; i += T) {
                 const uint32_t id = perm[i];
                 float v[D]; hc_load_vec<D>(vecs, id, v);
                 const float w = (float)wts[id];
@@ -512,12 +557,10 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
 #pragma unroll
                 for (int d = 1; d < D; d++) dot += v[d] * v[d];
 #pragma unroll
-                for (int d = 0; d < D; d++) s[d] += (double)(v[d] * w);
-                tt += (double)(dot * w);
+                for (int d = 0; d < D; d++) tot[d] += (double)(v[d] * w);
+                tot[D] += (double)(dot * w);
             }
-#pragma unroll
-            for (int d = 0; d < D; d++) tot[d] = hc_block_sum<T>(s[d], red.d);
-            tot_tt = hc_block_sum<T>(tt, red.d);
+            hc_group_reduce<T, G, K, true>(red, parity, tot, D + 1, nullptr, 0, nullptr);
         }
         if (begin + 2 < end) {
             // covariance (:335-357)
@@ -527,7 +570,7 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
                 float acc[16];
 #pragma unroll
                 for (int y = 0; y < 16; y++) acc[y] = 0.0f;
-                for (uint32_t i = begin + ml; i < end; i += LANES) {
+                for (uint32_t i = sb + ml; i < se; i += LANES) {
                     const uint32_t id = perm[i];
                     float v[D]; hc_load_vec<D>(vecs, id, v);
                     const float w = (float)wts[id];
@@ -541,42 +584,46 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
 #pragma unroll
                 for (int y = 0; y < 16; y++) s_cov[tid * 16 + y] = acc[y];
                 __syncthreads();
-                float mine[(256 + T - 1) / T];
-#pragma unroll
-                for (int k = 0; k < (256 + T - 1) / T; k++) {
-                    const int e = tid + k * T;
+                for (int e = tid; e < 256; e += T) {
+                    const int ex = e >> 4, ey = e & 15;
                     double s = 0;
-                    if (e < 256) { const int ex = e >> 4, ey = e & 15; for (int l = 0; l < LANES; l++) s += (double)s_cov[(l * 16 + ex) * 16 + ey]; }
-                    mine[k] = (float)s / (float)total_weight;
+                    for (int l = 0; l < LANES; l++) s += (double)s_cov[(l * 16 + ex) * 16 + ey];
+                    s_cpart[e % (D == 16 ? 256 : 1)] = s;
                 }
-                __syncthreads();
-#pragma unroll
-                for (int k = 0; k < (256 + T - 1) / T; k++) { const int e = tid + k * T; if (e < 256) s_cov[e] = mine[k]; }
-                __syncthreads();
+                hc_group_sync<G>();
+                for (int e = tid; e < 256; e += T) {
+                    double s = s_cpart[e % (D == 16 ? 256 : 1)];
+#ifdef __CUDACC__
+                    if (G > 1) { s = 0; for (unsigned r = 0; r < (unsigned)G; r++) s += cg::this_cluster().map_shared_rank(&s_cpart[0], r)[e % (D == 16 ? 256 : 1)]; }
+#endif
+                    s_cov[e] = (float)s / (float)total_weight;
+                }
+                hc_group_sync<G>();
             } else {
-                float acc[D][D];
+                constexpr int NC = D * (D + 1) / 2;
+                float acc[NC];
 #pragma unroll
-                for (int x = 0; x < D; x++)
-#pragma unroll
-                    for (int y = 0; y < D; y++) acc[x][y] = 0.0f;
-                for (uint32_t i = begin + tid; i < end; i += T) {
+                for (int k = 0; k < NC; k++) acc[k] = 0.0f;
+                for (uint32_t i = sb + tid; i < se; i += T) {
                     const uint32_t id = perm[i];
                     float v[D]; hc_load_vec<D>(vecs, id, v);
                     const float w = (float)wts[id];
 #pragma unroll
                     for (int d = 0; d < D; d++) v[d] -= centroid[d];
+                    int k = 0;
 #pragma unroll
                     for (int x = 0; x < D; x++)
 #pragma unroll
-                        for (int y = x; y < D; y++) acc[x][y] += v[x] * (v[y] * w);
+                        for (int y = x; y < D; y++) acc[k++] += v[x] * (v[y] * w);
                 }
+                double dacc[NC];
 #pragma unroll
-                for (int x = 0; x < D; x++)
-#pragma unroll
-                    for (int y = x; y < D; y++) {
-                        const double r = hc_block_sum<T>((double)acc[x][y], red.d);
-                        if (tid == 0) { const float c = (float)r / (float)total_weight; s_cov[x * D + y] = c; s_cov[y * D + x] = c; }
-                    }
+                for (int k = 0; k < NC; k++) dacc[k] = (double)acc[k];
+                hc_group_reduce<T, G, K, true>(red, parity, dacc, NC, nullptr, 0, nullptr);
+                if (tid == 0) {
+                    int k = 0;
+                    for (int x = 0; x < D; x++) for (int y = x; y < D; y++) { const float c = (float)dacc[k++] / (float)total_weight; s_cov[(x * D + y) % COVN] = c; s_cov[(y * D + x) % COVN] = c; }
+                }
                 __syncthreads();
             }
             // 10 power iterations from (1, ..., 1) with max-normalisation, then normalise (:358-386)
@@ -609,27 +656,25 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
 #pragma unroll
             for (int d = 0; d < D; d++) axis[d] = s_axis[d];
             // split by the sign of the projection (:387-412)
-            double sl[D], lw = 0, tw = 0;
+            double sl[D + 2];
 #pragma unroll
-            for (int d = 0; d < D; d++) sl[d] = 0;
-            for (uint32_t i = begin + tid; i < end; i += T) {
+            for (int d = 0; d < D + 2; d++) sl[d] = 0;
+            for (uint32_t i = sb + tid; i < se; i += T) {
                 const uint32_t id = perm[i];
                 float v[D]; hc_load_vec<D>(vecs, id, v);
                 const float w = (float)wts[id];
                 float t = (v[0] - centroid[0]) * axis[0];
 #pragma unroll
                 for (int d = 1; d < D; d++) t += (v[d] - centroid[d]) * axis[d];
-                tw += (double)w;
+                sl[D + 1] += (double)w;
                 if (t < 0.0f) {
 #pragma unroll
                     for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
-                    lw += (double)w;
+                    sl[D] += (double)w;
                 }
             }
-            lw = hc_block_sum<T>(lw, red.d); tw = hc_block_sum<T>(tw, red.d);
-#pragma unroll
-            for (int d = 0; d < D; d++) sl[d] = hc_block_sum<T>(sl[d], red.d);
-            const double rw = tw - lw;
+            hc_group_reduce<T, G, K, true>(red, parity, sl, D + 2, nullptr, 0, nullptr);
+            const double lw = sl[D], rw = sl[D + 1] - sl[D];
             if (lw > 0.0 && rw > 0.0) {
                 const float fl = (float)(1.0 / lw), fr = (float)(1.0 / rw);
 #pragma unroll
@@ -639,15 +684,17 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
         // Lloyd iterations until the variance stops improving (:413-519)
         float prev_total_variance = 1e+10f, lvar = 0, rvar = 0;
         unsigned long long lw = 0, rw = 0;
-        uint32_t n_left = 0;
+        uint32_t n_left = 0, left_before = 0;
         bool unsplittable = false;
         float used_left[D], used_right[D];
 #pragma unroll 1
         for (unsigned loops = 0; loops < 1024; loops++) {
-            double sl[D], lt = 0; unsigned long long w_l = 0, cnt = 0;
+            double sl[D + 1]; unsigned long long uu[2] = { 0, 0 }, upre[2];
 #pragma unroll
-            for (int d = 0; d < D; d++) { sl[d] = 0; used_left[d] = left[d]; used_right[d] = right[d]; }
-            for (uint32_t i = begin + tid; i < end; i += T) {
+            for (int d = 0; d <= D; d++) sl[d] = 0;
+#pragma unroll
+            for (int d = 0; d < D; d++) { used_left[d] = left[d]; used_right[d] = right[d]; }
+            for (uint32_t i = sb + tid; i < se; i += T) {
                 const uint32_t id = perm[i];
                 float v[D]; hc_load_vec<D>(vecs, id, v);
                 if (hc_sqdist<D>(left, v) < hc_sqdist<D>(right, v)) {
@@ -657,21 +704,20 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
                     for (int d = 1; d < D; d++) dot += v[d] * v[d];
 #pragma unroll
                     for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
-                    lt += (double)(dot * w); w_l += wi; cnt++;
+                    sl[D] += (double)(dot * w); uu[0] += wi; uu[1]++;
                 }
             }
-            lw = hc_block_sum_u64<T>(w_l, red.u);
-            n_left = (uint32_t)hc_block_sum_u64<T>(cnt, red.u);
+            hc_group_reduce<T, G, K, true>(red, parity, sl, D + 1, uu, 2, upre);
+            lw = uu[0]; n_left = (uint32_t)uu[1]; left_before = (uint32_t)upre[1];
             rw = total_weight - lw;
             if (!lw || !rw) { unsplittable = true; break; }
-            lt = hc_block_sum<T>(lt, red.d);
             float nl[D], nr[D];
 #pragma unroll
-            for (int d = 0; d < D; d++) { const double r = hc_block_sum<T>(sl[d], red.d); nl[d] = (float)r; nr[d] = (float)(tot[d] - r); }
+            for (int d = 0; d < D; d++) { nl[d] = (float)sl[d]; nr[d] = (float)(tot[d] - sl[d]); }
             float ldot = nl[0] * nl[0], rdot = nr[0] * nr[0];
 #pragma unroll
             for (int d = 1; d < D; d++) { ldot += nl[d] * nl[d]; rdot += nr[d] * nr[d]; }
-            lvar = (float)(lt - (double)(ldot / (float)lw)); rvar = (float)((tot_tt - lt) - (double)(rdot / (float)rw));
+            lvar = (float)(sl[D] - (double)(ldot / (float)lw)); rvar = (float)((tot[D] - sl[D]) - (double)(rdot / (float)rw));
             const float fl = 1.0f / (float)lw, fr = 1.0f / (float)rw;
 #pragma unroll
             for (int d = 0; d < D; d++) { left[d] = nl[d] * fl; right[d] = nr[d] * fr; }
@@ -681,11 +727,11 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
             prev_total_variance = total_variance;
         }
         if (!unsplittable) {
-            // stable partition by the last assignment (:521-535)
-            uint32_t base_l = begin, base_r = begin + n_left;
-            for (uint32_t i0 = begin; i0 < end; i0 += T) {
+            // stable partition by the last assignment (:521-535): lefts of lower-ranked CTAs come first
+            uint32_t base_l = begin + left_before, base_r = begin + n_left + ((sb - begin) - left_before);
+            for (uint32_t i0 = sb; i0 < se; i0 += T) {
                 const uint32_t i = i0 + tid;
-                uint32_t id = 0; bool valid = i < end, is_left = false;
+                uint32_t id = 0; bool valid = i < se, is_left = false;
                 if (valid) {
                     id = perm[i];
                     float v[D]; hc_load_vec<D>(vecs, id, v);
@@ -711,17 +757,17 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
                 }
                 base_l += tot_l; base_r += tot_r;
             }
-            __syncthreads();
-            for (uint32_t i = begin + tid; i < end; i += T) perm[i] = perm_tmp[i];
+            hc_group_sync<G>();
+            for (uint32_t i = sb + tid; i < se; i += T) perm[i] = perm_tmp[i];
         }
-        if (tid == 0) {
+        if (tid == 0 && rank == 0) {
             S.state = unsplittable ? 2 : 1;
             S.n_left = n_left;
 #pragma unroll
             for (int d = 0; d < D; d++) { S.lc[d] = left[d]; S.rc[d] = right[d]; }
             S.lw = lw; S.rw = rw; S.lvar = lvar; S.rvar = rvar;
         }
-        __syncthreads();
+        hc_group_sync<G>();
     }
 }
 

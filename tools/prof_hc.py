@@ -12,7 +12,8 @@ import numpy as np  # noqa: E402
 import crunch2_b200 as crn  # noqa: E402
 import hc_util  # noqa: E402
 import quality  # noqa: E402
-from bench import mip_chain, synth_texture  # noqa: E402
+import blockgen  # noqa: E402
+from bench import mip_chain  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("size", type=int)
@@ -24,7 +25,7 @@ ap.add_argument("--threads", type=int, default=15)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 fmt = {"DXT1": 0, "DXT5": 3, "DXT5A": 4, "DXN": 5}[a.fmt]
-faces = [mip_chain(synth_texture(a.size, a.size, 3000 + f, alpha=True)) for f in range(a.faces)]
+faces = [mip_chain(blockgen.smooth_image(a.size, a.size, 3000 + f, alpha=True)) for f in range(a.faces)]
 blocks, levels = hc_util.hc_layout(faces)
 ac = (0, 1) if fmt == 5 else (3, 0)
 cbs = (a.cb,) * 4
