@@ -261,6 +261,56 @@ def run_transcode(ctx, ext, dev, flush, steps, peak_gbs, quick=False):
     return out
 
 
+def run_dxt_hc(ctx, dev, steps, with_reference=True):
+    """BASELINE configs[2]'s quantiser: dxt_hc::compress of a 6-face 2048^2 DXT1 cubemap with full mip chains (2 097 216
+    blocks after crn_comp's 8-pixel padding) at 4096-entry codebooks -- palettes + indices, i.e. everything of CRN
+    compression up to the (host, out-of-scope) Huffman writer.  Device-resident blocks, then host blocks; the reference's
+    dxt_hc::compress on the host cores beside it."""
+    import torch
+    import blockgen
+    import hc_util
+    import quality
+    faces = [mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False)) for f in range(6)]
+    blocks, levels = hc_util.hc_layout(faces)
+    n = len(blocks)
+    ntex = n * 16
+    cbs = (4096, 4096, 4096, 4096)
+    d_blocks = torch.from_numpy(blocks).to(dev)
+    g = None
+    for _ in range(2):
+        g = ctx.hc_compress(0, d_blocks, levels, num_faces=6, codebook_sizes=cbs)
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        g = ctx.hc_compress(0, d_blocks, levels, num_faces=6, codebook_sizes=cbs)
+    dt = (time.perf_counter() - t0) / steps
+    launches = (ctx.launch_count - l0) // steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.hc_compress(0, blocks, levels, num_faces=6, codebook_sizes=cbs)
+    dth = (time.perf_counter() - t0) / steps
+    pg = hc_util.hc_decode(0, g)
+    out = {"workload": "c3_quantiser_dxt1_cubemap_6x2048_mips (dxt_hc::compress, 4096-entry codebooks)", "blocks": n,
+           "value": ntex / dt / 1e6, "unit": UNIT, "ms": dt * 1e3, "timing": "host wall clock around the synchronous C-ABI call",
+           "e2e": {"value": ntex / dth / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(blocks.nbytes), "d2h_bytes_per_step": int(n * 16 + 4 * 4096 * 8)},
+           "gpu_launches": int(launches), "psnr_rgb": quality.psnr(pg, blocks, [0, 1, 2]), "index_entropy_bits": hc_util.index_entropy_bits(g, 0),
+           "palettes": [len(g[k]) for k in ("color_endpoints", "color_selectors")], "info": g["info"]}
+    if with_reference:
+        import helpers
+        ref = helpers.load_ref()
+        if ref is not None:
+            th = cpu_threads()
+            t0 = time.perf_counter()
+            r = hc_util.ref_hc_compress(ref, 0, blocks, levels, num_faces=6, codebook_sizes=cbs, threads=th - 1)
+            dtr = time.perf_counter() - t0
+            pr = hc_util.hc_decode(0, r)
+            out["reference"] = {"value": ntex / dtr / 1e6, "unit": UNIT, "ms": dtr * 1e3, "cores": th, "kind": "reference", "psnr_rgb": quality.psnr(pr, blocks, [0, 1, 2]),
+                                "index_entropy_bits": hc_util.index_entropy_bits(r, 0), "palettes": [len(r[k]) for k in ("color_endpoints", "color_selectors")],
+                                "tiles_equal": bool(np.array_equal(g["tile_indices"], r["tile_indices"]))}
+    return out
+
+
 def run_clustered(args, ctx, ext, dev, wl, barrier, world):
     """BASELINE configs[1]: clustered DDS (qdxt init + pack) of one texture per rank.  The path is a chain of
     kernels with host decisions in between (frontier-batched VQ, cluster retrieval), on one stream + host thread per
@@ -403,6 +453,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-transcode", action="store_true")
     ap.add_argument("--no-block-pack", action="store_true")
+    ap.add_argument("--no-hc", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -505,6 +556,11 @@ def main():
             out["transcode"] = run_transcode(ctx, ext, dev, flush, max(2, min(args.steps, 5)), peak_gbs)
         except Exception as e:
             out["transcode"] = {"error": str(e)[:300]}
+    if not args.no_hc and world == 1:
+        try:
+            out["dxt_hc"] = run_dxt_hc(ctx, dev, 2, with_reference=not args.no_cpu_baseline)
+        except Exception as e:
+            out["dxt_hc"] = {"error": str(e)[:300]}
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = run_cpu_baseline(wl)[0]

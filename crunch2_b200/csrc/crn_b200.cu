@@ -22,6 +22,7 @@
 #include <algorithm>
 #ifdef __CUDACC__
 #include <thread>
+#include <cub/device/device_radix_sort.cuh>
 #endif
 
 struct crn_gpu_ctx {

@@ -42,15 +42,22 @@ struct HcTreeVq {
     static constexpr uint32_t kHugeNode = 8192;
     uint32_t rounds = 0, device_splits = 0;
 
-    int build(crn_gpu_ctx* ctx, const float* h_vecs, const uint32_t* h_wts, uint32_t n, uint32_t max_splits)
+    // vecs / wts: host arrays (on_device == false, uploaded here) or device arrays that stay valid during the call
+    int build(crn_gpu_ctx* ctx, const float* vecs, const uint32_t* wts_in, uint32_t n, uint32_t max_splits, bool on_device = false)
     {
         codebook.clear();
         if (!n || !max_splits) return CRN_GPU_OK;
         HcBuf d_vecs, d_wts, d_perm, d_tmp, d_slots, d_list, d_root;
-        HC_ALLOC(d_vecs, (size_t)n * D * 4); HC_ALLOC(d_wts, (size_t)n * 4); HC_ALLOC(d_perm, (size_t)n * 4); HC_ALLOC(d_tmp, (size_t)n * 4);
+        HC_ALLOC(d_perm, (size_t)n * 4); HC_ALLOC(d_tmp, (size_t)n * 4);
         HC_ALLOC(d_root, (D + 2) * 8);
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_vecs.p, h_vecs, (size_t)n * D * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_wts.p, h_wts, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (on_device) {                           // borrowed: never returned to the pool by this object
+            d_vecs.p = const_cast<float*>(vecs); d_wts.p = const_cast<uint32_t*>(wts_in);
+        } else {
+            HC_ALLOC(d_vecs, (size_t)n * D * 4); HC_ALLOC(d_wts, (size_t)n * 4);
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_vecs.p, vecs, (size_t)n * D * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_wts.p, wts_in, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        struct Borrow { HcBuf& a; HcBuf& b; bool on; ~Borrow() { if (on) { a.p = nullptr; b.p = nullptr; } } } borrow{ d_vecs, d_wts, on_device };
         CRN_LAUNCH(crn::hc_tree_root_kernel<D>, 1, 512, 0, ctx->stream, d_vecs.as<float>(), d_wts.as<uint32_t>(), n, d_perm.as<uint32_t>(), d_root.as<double>());
         ctx->launches++;
         double h_root[D + 2];
@@ -428,21 +435,56 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         CRN_CUDA(ctx, cudaMemcpyAsync(rep.data(), d_rep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaMemcpyAsync(rok.data(), d_rok.p, K, cudaMemcpyDeviceToHost, st));
         // a16: selector codebook.  Training set = the distinct block selectors with summed weights (:1379-1444, :1588-1660)
-        std::vector<unsigned long long> bsel(NV);
-        CRN_CUDA(ctx, cudaMemcpyAsync(bsel.data(), d_bsel.p, (size_t)NV * 8, cudaMemcpyDeviceToHost, st));
-        CRN_CUDA(ctx, cudaStreamSynchronize(st));
-        tr.mark("hc block selectors + refiner + D2H", kind);
         std::vector<uint32_t>& cl_ep = kind ? alpha_cluster_ep : color_cluster_ep;
         std::vector<uint8_t>& cl_used = kind ? alpha_cluster_used : color_cluster_used;
         cl_ep.resize(K); cl_used.resize(K);
-        for (uint32_t c = 0; c < K; c++) {
-            cl_used[c] = offs[c + 1] != offs[c];
-            if (kind == 0) cl_ep[c] = rok[c] ? rep[c] : ep[c];                                           // dxt1_block::pack_endpoints(first, second) = low | high << 16
-            else cl_ep[c] = rok[c] ? ((rep[c] & 0xffff) | ((rep[c] >> 16) << 8)) : (ep[c] & 0xffff);     // dxt5_block::pack_endpoints = first | second << 8
+        HcTreeVq<16> svq;
+        const uint32_t max_sel = kind ? prm->alpha_selector_codebook_size : prm->color_selector_codebook_size;
+        uint32_t n_unique_sel = 0;
+#ifdef __CUDACC__
+        {   // sort, run heads, ranks, vectors + summed weights: all on the device
+            HcBuf d_sorted, d_temp, d_head, d_rank, d_bsums, d_sv, d_sw;
+            const int wshift = kind ? 16 : 32;
+            HC_ALLOC(d_sorted, (size_t)NV * 8);
+            size_t temp_bytes = 0;
+            CRN_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, d_bsel.as<unsigned long long>(), d_sorted.as<unsigned long long>(), (int)NV, 0, 64, st));
+            HC_ALLOC(d_temp, temp_bytes);
+            CRN_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_temp.p, temp_bytes, d_bsel.as<unsigned long long>(), d_sorted.as<unsigned long long>(), (int)NV, 0, 64, st));
+            const uint32_t m = NV + 1, nb = (m + 1023) / 1024;
+            HC_ALLOC(d_head, (size_t)m * 4); HC_ALLOC(d_rank, (size_t)m * 4); HC_ALLOC(d_bsums, (size_t)(nb + 2) * 4);
+            CRN_LAUNCH(crn::hc_sel_heads_kernel, (m + 255) / 256, 256, 0, st, d_sorted.as<unsigned long long>(), NV, wshift, d_head.as<uint32_t>());
+            CRN_LAUNCH(crn::vq_scan_block_kernel, nb, 256, 0, st, d_head.as<uint32_t>(), d_rank.as<uint32_t>(), d_bsums.as<uint32_t>(), m);
+            if (nb > 1) {
+                CRN_LAUNCH(crn::vq_scan_sums_kernel, 1, 256, 0, st, d_bsums.as<uint32_t>(), nb);
+                CRN_LAUNCH(crn::vq_scan_add_kernel, (m + 255) / 256, 256, 0, st, d_rank.as<uint32_t>(), d_bsums.as<uint32_t>(), m);
+            }
+            ctx->launches += 5;
+            CRN_CUDA(ctx, cudaMemcpyAsync(&n_unique_sel, d_rank.as<uint32_t>() + NV, 4, cudaMemcpyDeviceToHost, st));
+            CRN_CUDA(ctx, cudaStreamSynchronize(st));
+            for (uint32_t c = 0; c < K; c++) {
+                cl_used[c] = offs[c + 1] != offs[c];
+                if (kind == 0) cl_ep[c] = rok[c] ? rep[c] : ep[c];                                           // dxt1_block::pack_endpoints(first, second) = low | high << 16
+                else cl_ep[c] = rok[c] ? ((rep[c] & 0xffff) | ((rep[c] >> 16) << 8)) : (ep[c] & 0xffff);     // dxt5_block::pack_endpoints = first | second << 8
+            }
+            HC_ALLOC(d_sv, (size_t)n_unique_sel * 64); HC_ALLOC(d_sw, (size_t)n_unique_sel * 4);
+            CRN_LAUNCH(crn::hc_sel_vectors_kernel, (NV + 255) / 256, 256, 0, st, d_sorted.as<unsigned long long>(), d_head.as<uint32_t>(), d_rank.as<uint32_t>(), NV, kind,
+                       d_sv.as<float>(), d_sw.as<uint32_t>());
+            ctx->launches++;
+            tr.mark("hc selector sort + dedup (device)", kind);
+            HC_RC(svq.build(ctx, d_sv.as<float>(), d_sw.as<uint32_t>(), n_unique_sel, max_sel, true));
         }
-        std::sort(bsel.begin(), bsel.end());
-        std::vector<float> sv; std::vector<uint32_t> sw;
-        {
+#else
+        {   // emulation build (no cub): the same steps on the host
+            std::vector<unsigned long long> bsel(NV);
+            CRN_CUDA(ctx, cudaMemcpyAsync(bsel.data(), d_bsel.p, (size_t)NV * 8, cudaMemcpyDeviceToHost, st));
+            CRN_CUDA(ctx, cudaStreamSynchronize(st));
+            for (uint32_t c = 0; c < K; c++) {
+                cl_used[c] = offs[c + 1] != offs[c];
+                if (kind == 0) cl_ep[c] = rok[c] ? rep[c] : ep[c];
+                else cl_ep[c] = rok[c] ? ((rep[c] & 0xffff) | ((rep[c] >> 16) << 8)) : (ep[c] & 0xffff);
+            }
+            std::sort(bsel.begin(), bsel.end());
+            std::vector<float> sv; std::vector<uint32_t> sw;
             const int bits = kind ? 3 : 2, wshift = kind ? 16 : 32;
             unsigned long long prev = 0;
             float lut[8];
@@ -458,12 +500,13 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                 } else if (sw.back() > 0xffffffffu - weight) sw.back() = 0xffffffffu;
                 else sw.back() += weight;
             }
+            n_unique_sel = (uint32_t)sw.size();
+            tr.mark("hc selector sort + dedup (host)", kind);
+            HC_RC(svq.build(ctx, sv.data(), sw.data(), n_unique_sel, max_sel));
         }
-        tr.mark("hc selector sort + dedup (host)", kind);
-        HcTreeVq<16> svq;
-        HC_RC(svq.build(ctx, sv.data(), sw.data(), (uint32_t)sw.size(), kind ? prm->alpha_selector_codebook_size : prm->color_selector_codebook_size));
+#endif
         const uint32_t KS = svq.size();
-        H->info.vq_rounds[2 + kind] = svq.rounds; H->info.unique_vectors[2 + kind] = (uint32_t)sw.size();
+        H->info.vq_rounds[2 + kind] = svq.rounds; H->info.unique_vectors[2 + kind] = n_unique_sel;
         tr.mark("hc selector tree VQ", kind);
         if (!KS) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: empty selector codebook");
         std::vector<uint64_t> scb(KS);

@@ -913,4 +913,39 @@ hc_grey_kernel(const uint32_t* __restrict__ pixels, size_t n_pixels, uint32_t co
     if (g < n_pixels) out[g] = ((pixels[g] >> (8 * comp)) & 0xff) * 0x01010101u;
 }
 
+// ---- selector training set on the device (create_*_selector_codebook, crn_dxt_hc.cpp:1379-1444, :1588-1660) ---------
+// keys = m_block_selectors sorted ascending (selector << wshift | weight).  head[i] = 1 where a new selector starts.
+__global__ void __launch_bounds__(256)
+hc_sel_heads_kernel(const unsigned long long* __restrict__ keys, uint32_t n, int wshift, uint32_t* __restrict__ head)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    head[i] = (i < n && (i == 0 || (keys[i] >> wshift) != (keys[i - 1] >> wshift))) ? 1u : 0u;
+}
+// one thread per run: the 16-D vector of the selector (pixel p of the packed selector is vector component p) and the
+// saturating sum of the run's weights
+__global__ void __launch_bounds__(256)
+hc_sel_vectors_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ head, const uint32_t* __restrict__ rank, uint32_t n, int kind,
+                      float* __restrict__ vecs, uint32_t* __restrict__ wts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    const int bits = kind ? 3 : 2, wshift = kind ? 16 : 32;
+    const unsigned long long wmask = kind ? 0xffffull : 0xffffffffull;
+    unsigned long long sel = keys[i] >> wshift;
+    unsigned long long w = keys[i] & wmask;
+    for (uint32_t j = i + 1; j < n && !head[j]; j++) { w += keys[j] & wmask; if (w > 0xffffffffull) w = 0xffffffffull; }
+    const uint32_t o = rank[i];
+    wts[o] = (uint32_t)w;
+    float v[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++, sel >>= bits) {
+        const unsigned sv = (unsigned)(sel & ((1u << bits) - 1));
+        v[15 - p] = kind ? ((float)sv + 0.5f) * 0.125f : ((float)sv + 0.5f) * 0.25f;
+    }
+    float4* dst = reinterpret_cast<float4*>(vecs + (size_t)o * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
 }  // namespace crn
