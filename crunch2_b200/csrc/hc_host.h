@@ -230,6 +230,73 @@ struct HcElementOut {
     uint32_t K = 0;
 };
 
+// a13 front half: the (component, tile) training vectors, compacted on the device into d_tvec (what the nearest-codebook
+// search reads afterwards), sorted, merged and quantised.  nvcc build: six / two stable LSD radix passes over the float bit
+// patterns (cub) + run heads + scan, never leaving the device; emulation build: the same on the host.
+template <int D>
+int hc_endpoint_codebook(crn_gpu_ctx* ctx, int kind, const float* d_src, const uint32_t* d_used, const std::vector<uint32_t>& used_slots, const uint8_t* d_npix,
+                         const std::vector<uint8_t>& h_npix, const std::vector<float>& slot_weight, uint32_t n, int ncp, const crn::HcLevelWeights& LW,
+                         uint32_t max_size, HcBuf& d_tvec, std::vector<float>& codebook, uint32_t& rounds, uint32_t& n_unique)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t num_tiles = (uint32_t)used_slots.size(), NT = (uint32_t)ncp * num_tiles;
+    HcBuf d_w;
+    HC_ALLOC(d_tvec, (size_t)NT * D * 4); HC_ALLOC(d_w, (size_t)NT * 4);
+    CRN_LAUNCH(crn::hc_compact_tiles_kernel<D>, (NT + 255) / 256, 256, 0, st, d_src, d_used, d_npix, n, num_tiles, NT, kind, LW, d_tvec.as<float>(), d_w.as<uint32_t>());
+    ctx->launches++;
+    HcTreeVq<D> vq;
+#ifdef __CUDACC__
+    {
+        HcBuf d_perm[2], d_keys[2], d_temp, d_head, d_rank, d_bsums, d_uv, d_uw;
+        for (int k = 0; k < 2; k++) { HC_ALLOC(d_perm[k], (size_t)NT * 4); HC_ALLOC(d_keys[k], (size_t)NT * 4); }
+        size_t temp_bytes = 0;
+        CRN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys[0].as<uint32_t>(), d_keys[1].as<uint32_t>(), d_perm[0].as<uint32_t>(), d_perm[1].as<uint32_t>(), (int)NT, 0, 32, st));
+        HC_ALLOC(d_temp, temp_bytes);
+        CRN_LAUNCH(crn::hc_iota_kernel, (NT + 255) / 256, 256, 0, st, d_perm[0].as<uint32_t>(), NT);
+        int cur = 0;
+        for (int comp = D - 1; comp >= 0; comp--) {       // least significant component first; every pass is stable
+            CRN_LAUNCH(crn::hc_gather_key_kernel, (NT + 255) / 256, 256, 0, st, d_tvec.as<float>(), d_perm[cur].as<uint32_t>(), D, comp, NT, d_keys[0].as<uint32_t>());
+            CRN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_temp.p, temp_bytes, d_keys[0].as<uint32_t>(), d_keys[1].as<uint32_t>(), d_perm[cur].as<uint32_t>(), d_perm[cur ^ 1].as<uint32_t>(),
+                                                          (int)NT, 0, 32, st));
+            cur ^= 1;
+            ctx->launches += 3;
+        }
+        const uint32_t m = NT + 1, nb = (m + 1023) / 1024;
+        HC_ALLOC(d_head, (size_t)m * 4); HC_ALLOC(d_rank, (size_t)m * 4); HC_ALLOC(d_bsums, (size_t)(nb + 2) * 4);
+        CRN_LAUNCH(crn::hc_vec_heads_kernel<D>, (m + 255) / 256, 256, 0, st, d_tvec.as<float>(), d_perm[cur].as<uint32_t>(), NT, d_head.as<uint32_t>());
+        CRN_LAUNCH(crn::vq_scan_block_kernel, nb, 256, 0, st, d_head.as<uint32_t>(), d_rank.as<uint32_t>(), d_bsums.as<uint32_t>(), m);
+        if (nb > 1) {
+            CRN_LAUNCH(crn::vq_scan_sums_kernel, 1, 256, 0, st, d_bsums.as<uint32_t>(), nb);
+            CRN_LAUNCH(crn::vq_scan_add_kernel, (m + 255) / 256, 256, 0, st, d_rank.as<uint32_t>(), d_bsums.as<uint32_t>(), m);
+        }
+        ctx->launches += 5;
+        CRN_CUDA(ctx, cudaMemcpyAsync(&n_unique, d_rank.as<uint32_t>() + NT, 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        HC_ALLOC(d_uv, (size_t)n_unique * D * 4); HC_ALLOC(d_uw, (size_t)n_unique * 4);
+        CRN_LAUNCH(crn::hc_vec_unique_kernel<D>, (NT + 255) / 256, 256, 0, st, d_tvec.as<float>(), d_w.as<uint32_t>(), d_perm[cur].as<uint32_t>(), d_head.as<uint32_t>(),
+                   d_rank.as<uint32_t>(), NT, d_uv.as<float>(), d_uw.as<uint32_t>());
+        ctx->launches++;
+        HC_RC(vq.build(ctx, d_uv.as<float>(), d_uw.as<uint32_t>(), n_unique, max_size, true));
+    }
+#else
+    {
+        std::vector<HcVecKey<D>> keys(NT);
+        std::vector<float> tv((size_t)NT * D); std::vector<uint32_t> tw(NT);
+        CRN_CUDA(ctx, cudaMemcpyAsync(tv.data(), d_tvec.p, (size_t)NT * D * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(tw.data(), d_w.p, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < NT; i++) { memcpy(keys[i].v, &tv[(size_t)i * D], D * 4); keys[i].w = tw[i]; }
+        std::vector<float> uv; std::vector<uint32_t> uw;
+        hc_sort_dedup<D>(keys, uv, uw);
+        n_unique = (uint32_t)uw.size();
+        HC_RC(vq.build(ctx, uv.data(), uw.data(), n_unique, max_size));
+    }
+#endif
+    codebook.swap(vq.codebook);
+    rounds = vq.rounds;
+    return CRN_GPU_OK;
+}
+
 int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void* blocks_rgba, int on_host, crn_gpu_hc* H)
 {
     const uint32_t n = prm->num_blocks;
@@ -283,13 +350,10 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     CRN_CUDA(ctx, cudaGetLastError());
     std::vector<uint8_t> h_npix(n), h_pixofs(n);
     H->block_encodings.resize(n); H->tile_indices.resize(n);
-    std::vector<float> h_cvec(has_color ? (size_t)n * 6 : 0), h_avec((size_t)na * n * 2);
     CRN_CUDA(ctx, cudaMemcpyAsync(h_npix.data(), d_npix.p, n, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaMemcpyAsync(h_pixofs.data(), d_pixofs.p, n, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaMemcpyAsync(H->block_encodings.data(), d_enc.p, n, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaMemcpyAsync(H->tile_indices.data(), d_tile.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (has_color) CRN_CUDA(ctx, cudaMemcpyAsync(h_cvec.data(), d_cvec.p, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
-    if (na) CRN_CUDA(ctx, cudaMemcpyAsync(h_avec.data(), d_avec.p, (size_t)na * n * 8, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaStreamSynchronize(st));
     tr.mark("hc tiles + palettize + D2H", 0);
     std::vector<uint32_t> used_slots;               // tile slots in order (m_tiles[t].pixels.size() != 0)
@@ -301,6 +365,14 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     std::vector<uint32_t> slot_rank(n, 0xffffffffu);
     for (uint32_t i = 0; i < num_tiles; i++) slot_rank[used_slots[i]] = i;
     H->info.num_tiles = num_tiles;
+    if (!num_tiles) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: no tiles");
+    HcBuf d_used;
+    HC_ALLOC(d_used, (size_t)num_tiles * 4);
+    CRN_CUDA(ctx, cudaMemcpyAsync(d_used.p, used_slots.data(), (size_t)num_tiles * 4, cudaMemcpyHostToDevice, st));
+    crn::HcLevelWeights LW; memset(&LW, 0, sizeof(LW));
+    LW.num_levels = prm->num_levels;
+    for (uint32_t l = 0; l < prm->num_levels; l++) { LW.first_block[l] = prm->levels[l].first_block; LW.weight[l] = prm->levels[l].weight; }
+    LW.first_block[prm->num_levels] = n;
     H->endpoint_indices.assign((size_t)n * 4, 0); H->selector_indices.assign((size_t)n * 4, 0);
     std::vector<uint16_t> raw_endpoint((size_t)n * 3, 0), raw_selector((size_t)n * 3, 0);
     std::vector<uint32_t> color_cluster_ep, alpha_cluster_ep;
@@ -318,46 +390,22 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         const uint32_t NV = (uint32_t)ncp * n;                           // virtual blocks (= member blocks in the CSR)
         // a13: training vectors -> sorted unique weighted vectors -> tree quantiser
         std::vector<float> codebook; uint32_t K = 0;
-        std::vector<float> tile_vecs;                                    // compact, [component][tile][dims]
+        HcBuf d_tvec;
         if (kind == 0) {
-            std::vector<HcVecKey<6>> keys(num_tiles);
-            tile_vecs.resize((size_t)num_tiles * 6);
-            for (uint32_t i = 0; i < num_tiles; i++) {
-                const uint32_t s = used_slots[i];
-                memcpy(keys[i].v, &h_cvec[(size_t)s * 6], 24); memcpy(&tile_vecs[(size_t)i * 6], &h_cvec[(size_t)s * 6], 24);
-                keys[i].w = (uint32_t)((float)h_npix[s] * slot_weight[s]);
-            }
-            std::vector<float> uv; std::vector<uint32_t> uw;
-            hc_sort_dedup<6>(keys, uv, uw);
-            HcTreeVq<6> vq;
-            HC_RC(vq.build(ctx, uv.data(), uw.data(), (uint32_t)uw.size(), std::min(num_tiles, prm->color_endpoint_codebook_size)));
-            codebook.swap(vq.codebook); K = (uint32_t)(codebook.size() / 6);
-            H->info.vq_rounds[0] = vq.rounds; H->info.unique_vectors[0] = (uint32_t)uw.size();
+            HC_RC(hc_endpoint_codebook<6>(ctx, 0, d_cvec.as<float>(), d_used.as<uint32_t>(), used_slots, d_npix.as<uint8_t>(), h_npix, slot_weight, n, 1, LW,
+                                          std::min(num_tiles, prm->color_endpoint_codebook_size), d_tvec, codebook, H->info.vq_rounds[0], H->info.unique_vectors[0]));
+            K = (uint32_t)(codebook.size() / 6);
         } else {
-            std::vector<HcVecKey<2>> keys((size_t)na * num_tiles);
-            tile_vecs.resize((size_t)na * num_tiles * 2);
-            for (int a = 0; a < na; a++)
-                for (uint32_t i = 0; i < num_tiles; i++) {
-                    const uint32_t s = used_slots[i];
-                    const float* v = &h_avec[((size_t)a * n + s) * 2];
-                    HcVecKey<2>& k = keys[(size_t)a * num_tiles + i];
-                    k.v[0] = v[0]; k.v[1] = v[1]; k.w = h_npix[s];
-                    tile_vecs[((size_t)a * num_tiles + i) * 2] = v[0]; tile_vecs[((size_t)a * num_tiles + i) * 2 + 1] = v[1];
-                }
-            std::vector<float> uv; std::vector<uint32_t> uw;
-            hc_sort_dedup<2>(keys, uv, uw);
-            HcTreeVq<2> vq;
-            HC_RC(vq.build(ctx, uv.data(), uw.data(), (uint32_t)uw.size(), std::min(num_tiles, prm->alpha_endpoint_codebook_size)));
-            codebook.swap(vq.codebook); K = (uint32_t)(codebook.size() / 2);
-            H->info.vq_rounds[1] = vq.rounds; H->info.unique_vectors[1] = (uint32_t)uw.size();
+            HC_RC(hc_endpoint_codebook<2>(ctx, 1, d_avec.as<float>(), d_used.as<uint32_t>(), used_slots, d_npix.as<uint8_t>(), h_npix, slot_weight, n, na, LW,
+                                          std::min(num_tiles, prm->alpha_endpoint_codebook_size), d_tvec, codebook, H->info.vq_rounds[1], H->info.unique_vectors[1]));
+            K = (uint32_t)(codebook.size() / 2);
         }
         tr.mark("hc endpoint sort + tree VQ", kind);
         if (!K) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: empty endpoint codebook");
         // a14: nearest codebook entry per tile (per component)
         const uint32_t dims = kind ? 2 : 6, NT = (uint32_t)ncp * num_tiles;
-        HcBuf d_tvec, d_cb, d_tcl;
-        HC_ALLOC(d_tvec, (size_t)NT * dims * 4); HC_ALLOC(d_cb, (size_t)K * dims * 4); HC_ALLOC(d_tcl, (size_t)NT * 4);
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_tvec.p, tile_vecs.data(), (size_t)NT * dims * 4, cudaMemcpyHostToDevice, st));
+        HcBuf d_cb, d_tcl;
+        HC_ALLOC(d_cb, (size_t)K * dims * 4); HC_ALLOC(d_tcl, (size_t)NT * 4);
         CRN_CUDA(ctx, cudaMemcpyAsync(d_cb.p, codebook.data(), (size_t)K * dims * 4, cudaMemcpyHostToDevice, st));
         HC_RC(crn_gpu_nearest_codebook(ctx, dims, d_tvec.as<float>(), NT, d_cb.as<float>(), K, d_tcl.as<uint32_t>()));
         std::vector<uint32_t> tcl(NT);

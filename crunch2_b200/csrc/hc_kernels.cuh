@@ -948,4 +948,73 @@ hc_sel_vectors_kernel(const unsigned long long* __restrict__ keys, const uint32_
     for (int q = 0; q < 4; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// ---- endpoint training set on the device (determine_color/alpha_endpoints, crn_dxt_hc.cpp:888-968, :1165-1244) --------
+struct HcLevelWeights { uint32_t first_block[kHcMaxLevels + 1]; float weight[kHcMaxLevels]; uint32_t num_levels; };
+
+// compact (component, tile) list: entry i = a * num_tiles + t takes the vector of tile slot used[t] of plane a and the
+// weight the reference gives it: (uint)(pixels * level weight) for colour, pixels for alpha
+template <int D>
+__global__ void __launch_bounds__(256)
+hc_compact_tiles_kernel(const float* __restrict__ src, const uint32_t* __restrict__ used, const uint8_t* __restrict__ tile_npix, uint32_t n_slots, uint32_t num_tiles,
+                        uint32_t total, int kind, HcLevelWeights LW, float* __restrict__ out_vecs, uint32_t* __restrict__ out_wts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t a = i / num_tiles, slot = used[i % num_tiles];
+    const float* v = src + ((size_t)a * n_slots + slot) * D;
+#pragma unroll
+    for (int d = 0; d < D; d++) out_vecs[(size_t)i * D + d] = v[d];
+    const unsigned np = tile_npix[slot];
+    if (kind) out_wts[i] = np;
+    else {
+        uint32_t l = 0;
+        while (l + 1 < LW.num_levels && slot >= LW.first_block[l + 1]) l++;
+        out_wts[i] = (uint32_t)((float)np * LW.weight[l]);
+    }
+}
+__global__ void __launch_bounds__(256) hc_iota_kernel(uint32_t* __restrict__ p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+// sort key of one LSD pass: component `comp` of the vectors in the current order (non-negative floats order like their bits)
+__global__ void __launch_bounds__(256)
+hc_gather_key_kernel(const float* __restrict__ vecs, const uint32_t* __restrict__ perm, int D, int comp, uint32_t n, uint32_t* __restrict__ keys)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = __float_as_uint(vecs[(size_t)perm[i] * D + comp]);
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+hc_vec_heads_kernel(const float* __restrict__ vecs, const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ head)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    unsigned h = 0;
+    if (i < n) {
+        h = i == 0;
+        if (i) {
+            const float* a = vecs + (size_t)perm[i] * D; const float* b = vecs + (size_t)perm[i - 1] * D;
+#pragma unroll
+            for (int d = 0; d < D; d++) h |= a[d] != b[d];
+        }
+    }
+    head[i] = h;
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+hc_vec_unique_kernel(const float* __restrict__ vecs, const uint32_t* __restrict__ wts, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ head,
+                     const uint32_t* __restrict__ rank, uint32_t n, float* __restrict__ out_vecs, uint32_t* __restrict__ out_wts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    unsigned long long w = wts[perm[i]];
+    for (uint32_t j = i + 1; j < n && !head[j]; j++) { w += wts[perm[j]]; if (w > 0xffffffffull) w = 0xffffffffull; }
+    const uint32_t o = rank[i];
+    out_wts[o] = (uint32_t)w;
+    const float* v = vecs + (size_t)perm[i] * D;
+#pragma unroll
+    for (int d = 0; d < D; d++) out_vecs[(size_t)o * D + d] = v[d];
+}
+
 }  // namespace crn
