@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kClusterWarpsPerCta * 32, 5)
 dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
                               ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
                               unsigned int* __restrict__ next_cluster, ClusterResult* __restrict__ results,
-                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags)
+                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags,
+                              const uint32_t* __restrict__ order)
 {
     __shared__ Dxt1ClusterScratch scratch[kClusterWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -127,6 +128,7 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
         if (lane == 0) c = atomicAdd(next_cluster, 1u);
         c = __shfl_sync(CRN_FULL_MASK, c, 0);
         if (c >= n_clusters) break;
+        if (order) c = order[c];                             // largest clusters first: the work-stealing tail is one small cluster, not one huge one
         const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
         const uint32_t N = nb * 16, P = b0 * 16;
         if (!nb) continue;
@@ -214,7 +216,8 @@ __global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
 dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
                               const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, uint32_t comp, int quality, int both_types,
                               unsigned int* __restrict__ next_cluster, uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs,
-                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags)
+                              uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags,
+                              const uint32_t* __restrict__ order)
 {
     __shared__ Dxt5aClusterScratch scratch[kClusterWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -224,6 +227,7 @@ dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
         if (lane == 0) c = atomicAdd(next_cluster, 1u);
         c = __shfl_sync(CRN_FULL_MASK, c, 0);
         if (c >= n_clusters) break;
+        if (order) c = order[c];
         const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
         const uint32_t* members = cluster_blocks + b0;
         const uint32_t N = nb * 16;

@@ -36,6 +36,7 @@ struct crn_gpu_ctx {
     void* d_out; size_t d_out_cap;
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
     void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
+    const uint32_t* d_cluster_order;     // set by the dxt_hc pipeline: clusters in descending size, the order the work-stealing loop takes them
     uint32_t* d_cluster_flags;           // set by the dxt_hc pipeline around a cluster-optimiser call: per-cluster m_reordered / m_alternate_rounding out
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
     void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
@@ -686,7 +687,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     const int threads = crn::kClusterWarpsPerCta * 32;
     const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, getenv("CRN_B200_CLUSTER_CTAS") ? atoi(getenv("CRN_B200_CLUSTER_CTAS")) : 5);
     CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, d_cluster_offsets, n_clusters, dp, scan_alpha, ws, rank, transparent,
-               reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags);
+               reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags, ctx->d_cluster_order);
     CRN_LAUNCH(crn::cluster_write_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent,
                results, static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes);
     ctx->launches += 6;
@@ -716,7 +717,7 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     CRN_LAUNCH(crn::dxt5_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
                d_cluster_blocks, n_clusters, component, (int)params->dxt_quality, params->use_both_block_types ? 1 : 0,
                reinterpret_cast<unsigned int*>(ctx->d_cluster_ws), static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes,
-               d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags);
+               d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags, ctx->d_cluster_order);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
@@ -1053,7 +1054,7 @@ int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const
     int rc;
     try { rc = hc_compress_impl(ctx, params, blocks_rgba, blocks_on_host, H); }
     catch (const std::bad_alloc&) { rc = set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
-    ctx->d_cluster_flags = nullptr;
+    ctx->d_cluster_flags = nullptr; ctx->d_cluster_order = nullptr;
     if (rc) { delete H; return rc; }
     *out = H;
     return CRN_GPU_OK;

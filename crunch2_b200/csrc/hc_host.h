@@ -454,10 +454,17 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         CRN_CUDA(ctx, cudaMemsetAsync(d_ep.p, 0, (size_t)K * 4, st));
         CRN_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, (size_t)K * 8, st));
         CRN_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, (size_t)K * 4, st));
-        ctx->d_cluster_flags = d_flags.as<uint32_t>();
+        std::vector<uint32_t> order(K);
+        for (uint32_t c = 0; c < K; c++) order[c] = c;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return offs[a + 1] - offs[a] > offs[b + 1] - offs[b]; });
+        if (tr.on) fprintf(stderr, "[crn_b200] kind %d: %u clusters, %u member blocks, largest %u, median %u\n", kind, K, NV, offs[order[0] + 1] - offs[order[0]], offs[order[K / 2] + 1] - offs[order[K / 2]]);
+        HcBuf d_order;
+        HC_ALLOC(d_order, (size_t)K * 4);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_order.p, order.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+        ctx->d_cluster_flags = d_flags.as<uint32_t>(); ctx->d_cluster_order = d_order.as<uint32_t>();
         int rc = kind == 0 ? crn_gpu_dxt1_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>())
                            : crn_gpu_dxt5_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>());
-        ctx->d_cluster_flags = nullptr;
+        ctx->d_cluster_flags = nullptr; ctx->d_cluster_order = nullptr;
         if (rc) return rc;
         tr.mark("hc cluster optimiser", kind);
         // per-block selectors + weights against the cluster palette
