@@ -261,6 +261,47 @@ def run_transcode(ctx, ext, dev, flush, steps, peak_gbs, quick=False):
     return out
 
 
+def run_unpack(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
+    """DXT5 blocks of an 8192 x 8192 texture -> RGBA8 (dxt_image::unpack): the bandwidth-bound kernel of the path.
+    Algorithmic bytes: 16 B in + 64 B out per block; input + output (335 MB) exceed L2 and L2 is flushed between steps."""
+    import torch
+    w = h = 8192
+    n = (w // 4) * (h // 4)
+    g = torch.Generator(device="cpu"); g.manual_seed(5)
+    blocks = torch.randint(0, 256, (n * 16,), dtype=torch.uint8, generator=g)
+    d_blocks = blocks.to(dev)
+    d_rgba = torch.empty(h * w * 4, dtype=torch.uint8, device=dev)
+    ctx.unpack_image_device(3, d_blocks, w, h, d_rgba, w * 4); torch.cuda.synchronize()
+    ts = []
+    for _ in range(max(3, steps)):
+        flush.fill_(6); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext); ctx.unpack_image_device(3, d_blocks, w, h, d_rgba, w * 4); e1.record(ext); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    gbs = n * 80 / (ms / 1e3) / 1e9
+    out = {"workload": "dxt5_8192x8192 blocks -> RGBA8 (dxt_image::unpack)", "value": w * h / (ms / 1e3) / 1e9, "unit": "Gtexel/s", "ms": ms,
+           "roofline": {"bound": "hbm", "kernel": "unpack_blocks_kernel", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                        "bytes_per_block": 80, "blocks": n}}
+    if with_reference:
+        import helpers
+        ref = helpers.load_ref()
+        if ref is not None:
+            sw = sh = 2048                                        # bounded sample: the reference unpacks one block at a time on one thread
+            hb = np.ascontiguousarray(blocks.numpy()[: (sw // 4) * (sh // 4) * 16])
+            o = np.zeros((sh, sw, 4), np.uint8)
+            t0 = time.perf_counter()
+            ref.ref_unpack_image(3, hb.ctypes.data, sw, sh, o.ctypes.data)
+            dt = time.perf_counter() - t0
+            got = np.empty((sh, sw, 4), np.uint8)
+            d_small = torch.empty(sh * sw * 4, dtype=torch.uint8, device=dev)
+            ctx.unpack_image_device(3, d_blocks, sw, sh, d_small, sw * 4); torch.cuda.synchronize()
+            got = d_small.cpu().numpy().reshape(sh, sw, 4)
+            out["reference"] = {"value": sw * sh / dt / 1e9, "unit": "Gtexel/s", "cores": 1, "kind": "reference", "sample": "2048x2048 of the same blocks, dxt_image::unpack",
+                                "bit_exact": bool(np.array_equal(got, o))}
+    return out
+
+
 def run_dxt_hc(ctx, dev, steps, with_reference=True):
     """BASELINE configs[2]'s quantiser: dxt_hc::compress of a 6-face 2048^2 DXT1 cubemap with full mip chains (2 097 216
     blocks after crn_comp's 8-pixel padding) at 4096-entry codebooks -- palettes + indices, i.e. everything of CRN
@@ -556,6 +597,11 @@ def main():
             out["transcode"] = run_transcode(ctx, ext, dev, flush, max(2, min(args.steps, 5)), peak_gbs)
         except Exception as e:
             out["transcode"] = {"error": str(e)[:300]}
+    if not args.no_transcode and world == 1:
+        try:
+            out["unpack"] = run_unpack(ctx, ext, dev, flush, max(3, min(args.steps, 5)), peak_gbs, with_reference=not args.no_cpu_baseline)
+        except Exception as e:
+            out["unpack"] = {"error": str(e)[:300]}
     if not args.no_hc and world == 1:
         try:
             out["dxt_hc"] = run_dxt_hc(ctx, dev, 2, with_reference=not args.no_cpu_baseline)

@@ -118,6 +118,8 @@ def _declare(lib):
     lib.crn_gpu_refine_endpoints.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp, vp, vp, u32, vp, vp, vp, vp]
     lib.crn_gpu_nearest_codebook.argtypes = [vp, u32, vp, u32, vp, u32, vp]
     lib.crn_gpu_assign_selectors.argtypes = [vp, u32, ctypes.c_int, u32, vp, u32, vp, vp, vp, u32, vp, vp, vp]
+    lib.crn_gpu_unpack_image.argtypes = [vp, u32, vp, u32, u32, vp, u32]
+    lib.crn_gpu_unpack_image_host.argtypes = [vp, u32, vp, u32, u32, vp, u32]
     lib.crn_gpu_default_hc_params.argtypes = [ctypes.POINTER(_HcParams)]
     lib.crn_gpu_default_hc_params.restype = None
     lib.crn_gpu_hc_compress.argtypes = [vp, ctypes.POINTER(_HcParams), vp, i32, ctypes.POINTER(vp)]
@@ -291,6 +293,23 @@ class Context:
             return None if x is None else (ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x)))
         self._check(self._lib.crn_gpu_assign_selectors(self._ctx, 0 if kind == "color" else 1, 1 if perceptual else 0, component, ptr(d_blocks), n_blocks, ptr(d_values),
                                                        ptr(d_values_accum), ptr(d_codebook), k, ptr(d_best_index), ptr(d_refined), ptr(d_used)))
+
+    # --- dxt_image::unpack (crnlib/crn_dxt_image.cpp:495-567): blocks -> RGBA8 pixels ------------------------------
+    def unpack_image(self, fmt, blocks, width, height):
+        """blocks: bytes / uint8 array as pack_image returns -> (height, width, 4) uint8."""
+        b = np.ascontiguousarray(np.frombuffer(blocks, np.uint8) if not isinstance(blocks, np.ndarray) else blocks.view(np.uint8).ravel())
+        need = ((width + 3) // 4) * ((height + 3) // 4) * bytes_per_block(fmt)
+        if b.size < need:
+            raise ValueError("block buffer too small")
+        out = np.empty((height, width, 4), np.uint8)
+        self._check(self._lib.crn_gpu_unpack_image_host(self._ctx, int(fmt), b.ctypes.data_as(ctypes.c_void_p), width, height,
+                                                        out.ctypes.data_as(ctypes.c_void_p), width * 4))
+        return out
+
+    def unpack_image_device(self, fmt, d_blocks, width, height, d_rgba, pitch):
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        self._check(self._lib.crn_gpu_unpack_image(self._ctx, int(fmt), ptr(d_blocks), width, height, ptr(d_rgba), pitch))
 
     # --- dxt_hc::compress (crnlib/crn_dxt_hc.cpp:98-312): blocks of all levels -> palettes + per-block indices ---------
     def hc_compress(self, fmt, blocks, levels, num_faces=1, perceptual=True, codebook_sizes=(3072, 3072, 3072, 3072),

@@ -12,6 +12,7 @@
 #include "vq_host.h"
 #include "refiner_kernels.cuh"
 #include "hc_kernels.cuh"
+#include "unpack_kernels.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1023,6 +1024,40 @@ int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int perceptual, ui
     else CRN_LAUNCH(crn::revote_selectors_kernel<1>, (codebook_size + 255) / 256, 256, 0, ctx->stream, tot, codebook_size, refined);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_unpack_image(crn_gpu_ctx* ctx, uint32_t format, const void* d_blocks, uint32_t width, uint32_t height, void* d_rgba, uint32_t pitch_bytes)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!d_blocks || !d_rgba || !width || !height || pitch_bytes < width * 4u || (pitch_bytes & 3u) || !crn_gpu_bytes_per_block(format))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_unpack_image: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t bxn = (width + 3) >> 2, byn = (height + 3) >> 2, total = bxn * byn;
+    CRN_LAUNCH(crn::unpack_blocks_kernel, (total + 255) / 256, 256, 0, ctx->stream, static_cast<const unsigned long long*>(d_blocks), format, width, height, bxn, total,
+               static_cast<uint8_t*>(d_rgba), pitch_bytes);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_unpack_image_host(crn_gpu_ctx* ctx, uint32_t format, const void* h_blocks, uint32_t width, uint32_t height, void* h_rgba, uint32_t pitch_bytes)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    const uint32_t bpb = crn_gpu_bytes_per_block(format);
+    if (!h_blocks || !h_rgba || !width || !height || pitch_bytes < width * 4u || (pitch_bytes & 3u) || !bpb)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_unpack_image_host: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t in_bytes = (size_t)((width + 3) >> 2) * ((height + 3) >> 2) * bpb, out_bytes = (size_t)pitch_bytes * height;
+    int rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes);
+    if (rc) return rc;
+    rc = ensure(ctx, &ctx->d_out, &ctx->d_out_cap, out_bytes);
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, h_blocks, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = crn_gpu_unpack_image(ctx, format, ctx->d_in, width, height, ctx->d_out, pitch_bytes);
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaMemcpyAsync(h_rgba, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
 }
 

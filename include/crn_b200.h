@@ -224,6 +224,15 @@ CRN_API int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int percep
                                      const uint64_t* d_codebook, uint32_t codebook_size,
                                      uint32_t* d_best_index, uint64_t* d_refined_codebook, uint8_t* d_used);
 
+/* DXTn blocks -> RGBA8 pixels ------------------------------------------------------------
+ * Replaces crnlib::dxt_image::unpack (reference crnlib/crn_dxt_image.cpp:495-567 with get_block_pixels, :1094-1190), the
+ * decode half of crn_decompress_dds_to_images (crnlib/crnlib.cpp:293-333) and of crn_decompress_block (:451-498).
+ * d_blocks: ((w+3)/4)*((h+3)/4) blocks as crn_gpu_pack_image writes them; d_rgba: height rows of pitch_bytes.  Channels
+ * the format does not carry are 0, alpha 255, like the reference's scratch block.  Bit-exact.  Asynchronous; the _host
+ * variant copies in and out and synchronises. */
+CRN_API int crn_gpu_unpack_image(crn_gpu_ctx* ctx, uint32_t format, const void* d_blocks, uint32_t width, uint32_t height, void* d_rgba, uint32_t pitch_bytes);
+CRN_API int crn_gpu_unpack_image_host(crn_gpu_ctx* ctx, uint32_t format, const void* h_blocks, uint32_t width, uint32_t height, void* h_rgba, uint32_t pitch_bytes);
+
 /* dxt_hc pipeline --------------------------------------------------------------
  * crn_gpu_hc_compress replaces crnlib::dxt_hc::compress (reference crnlib/crn_dxt_hc.cpp:98-312; params mirror
  * dxt_hc::params, crnlib/crn_dxt_hc.h:103-172) as crn_comp::quantize_images calls it (crnlib/crn_comp.cpp:717-766) for

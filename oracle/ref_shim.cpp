@@ -552,3 +552,15 @@ SHIM_API int ref_hc_compress(int format, uint32_t n, uint32_t num_levels, uint32
     memcpy(color_selectors, cs.get_ptr(), cs.size() * 4); memcpy(alpha_selectors, as.get_ptr(), as.size() * 8);
     return 1;
 }
+
+// ref_unpack_image -> dxt_image::init(fmt, w, h) + the caller's elements + dxt_image::unpack (crn_dxt_image.cpp:495-567).
+SHIM_API int ref_unpack_image(int fmt, const uint8_t* blocks, uint32_t width, uint32_t height, uint8_t* rgba_out)
+{
+    dxt_image di;
+    if (!di.init((dxt_format)fmt, width, height, false)) return 0;
+    memcpy(di.get_element_ptr(), blocks, (size_t)di.get_total_elements() * sizeof(dxt_image::element));
+    image_u8 img;
+    if (!di.unpack(img)) return 0;
+    for (uint32_t y = 0; y < height; y++) memcpy(rgba_out + (size_t)y * width * 4, img.get_scanline(y), (size_t)width * 4);
+    return 1;
+}
