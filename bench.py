@@ -291,7 +291,7 @@ def run_unpack(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
             hb = np.ascontiguousarray(blocks.numpy()[: (sw // 4) * (sh // 4) * 16])
             o = np.zeros((sh, sw, 4), np.uint8)
             t0 = time.perf_counter()
-            ref.ref_unpack_image(3, hb.ctypes.data, sw, sh, o.ctypes.data)
+            ref.ref_unpack_image(3, helpers.P(hb), sw, sh, helpers.P(o))
             dt = time.perf_counter() - t0
             got = np.empty((sh, sw, 4), np.uint8)
             d_small = torch.empty(sh * sw * 4, dtype=torch.uint8, device=dev)

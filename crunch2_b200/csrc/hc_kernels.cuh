@@ -192,8 +192,8 @@ hc_tiles_kernel(const uint32_t* __restrict__ blocks, HcTileParams P, uint8_t* __
 template <int D>
 __device__ void hc_split_vectors(const float (*vec)[D], const unsigned* wts, unsigned size, float (&res0)[D], float (&res1)[D])
 {
-    float wv[64][D];
-    double wdp[64];
+    // weightedVectors[i] = v * (float)weight and weightedDotProducts[i] = v.dot(v) * weight are recomputed where used: the same
+    // operands give the same floats, and the per-thread local-memory footprint halves
     float centroid[D];
     for (int d = 0; d < D; d++) centroid[d] = 0.0f;
     unsigned long long total_weight = 0;
@@ -202,10 +202,9 @@ __device__ void hc_split_vectors(const float (*vec)[D], const unsigned* wts, uns
         const unsigned weight = wts[i];
         float dot = vec[i][0] * vec[i][0];
         for (int d = 1; d < D; d++) dot += vec[i][d] * vec[i][d];
-        for (int d = 0; d < D; d++) { wv[i][d] = vec[i][d] * (float)weight; centroid[d] += wv[i][d]; }
+        for (int d = 0; d < D; d++) centroid[d] += vec[i][d] * (float)weight;
         total_weight += weight;
-        wdp[i] = (double)(dot * (float)weight);
-        ttsum += wdp[i];
+        ttsum += (double)(dot * (float)weight);
     }
     float cdot = centroid[0] * centroid[0];
     for (int d = 1; d < D; d++) cdot += centroid[d] * centroid[d];
@@ -264,8 +263,8 @@ __device__ void hc_split_vectors(const float (*vec)[D], const unsigned* wts, uns
         for (unsigned i = 0; i < size; i++) {
             float t = (vec[i][0] - centroid[0]) * axis[0];
             for (int d = 1; d < D; d++) t += (vec[i][d] - centroid[d]) * axis[d];
-            if ((double)t < 0.0) { for (int d = 0; d < D; d++) nl[d] += wv[i][d]; lw += (double)(float)wts[i]; }
-            else { for (int d = 0; d < D; d++) nr[d] += wv[i][d]; rw += (double)(float)wts[i]; }
+            if ((double)t < 0.0) { for (int d = 0; d < D; d++) nl[d] += vec[i][d] * (float)wts[i]; lw += (double)(float)wts[i]; }
+            else { for (int d = 0; d < D; d++) nr[d] += vec[i][d] * (float)wts[i]; rw += (double)(float)wts[i]; }
         }
         if (lw > 0.0 && rw > 0.0) {
             const float sl = (float)(1.0 / lw), sr = (float)(1.0 / rw);
@@ -282,8 +281,11 @@ __device__ void hc_split_vectors(const float (*vec)[D], const unsigned* wts, uns
             float dl = 0, dr = 0;
             for (int d = 0; d < D; d++) { const float x = left[d] - vec[i][d]; dl += x * x; }
             for (int d = 0; d < D; d++) { const float x = right[d] - vec[i][d]; dr += x * x; }
-            if ((double)dl < (double)dr) { for (int d = 0; d < D; d++) nl[d] += wv[i][d]; lt += wdp[i]; lw += wts[i]; }
-            else { for (int d = 0; d < D; d++) nr[d] += wv[i][d]; rt += wdp[i]; rw += wts[i]; }
+            float dot = vec[i][0] * vec[i][0];
+            for (int d = 1; d < D; d++) dot += vec[i][d] * vec[i][d];
+            const double wdp = (double)(dot * (float)wts[i]);
+            if ((double)dl < (double)dr) { for (int d = 0; d < D; d++) nl[d] += vec[i][d] * (float)wts[i]; lt += wdp; lw += wts[i]; }
+            else { for (int d = 0; d < D; d++) nr[d] += vec[i][d] * (float)wts[i]; rt += wdp; rw += wts[i]; }
         }
         if (!lw || !rw) return;
         float ldot = nl[0] * nl[0], rdot = nr[0] * nr[0];

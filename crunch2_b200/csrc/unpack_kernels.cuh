@@ -42,14 +42,14 @@ __device__ __forceinline__ void unpack_alpha_element(unsigned long long e, unsig
     const unsigned l = (unsigned)(e & 0xff), h = (unsigned)((e >> 8) & 0xff);
     unsigned v[8];
     if (l > h) dxt5a_values8(l, h, v); else dxt5a_values6(l, h, v);
+    // the eight values as bytes of two registers: one PRMT per pixel picks value[selector]
+    const unsigned lo4 = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24), hi4 = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
     const unsigned long long sel = e >> 16;
     const unsigned sh = 8 * comp, mask = ~(0xffu << sh);
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const unsigned s = (unsigned)(sel >> (3 * i)) & 7u;
-        unsigned a = v[0];
-#pragma unroll
-        for (int k = 1; k < 8; k++) if (s == (unsigned)k) a = v[k];
+        const unsigned a = __byte_perm(lo4, hi4, s) & 0xffu;
         px[i] = (px[i] & mask) | (a << sh);
     }
 }
