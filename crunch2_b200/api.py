@@ -55,6 +55,14 @@ class _HcInfo(ctypes.Structure):
                                                 "n_color_selectors", "n_alpha_selectors")] + [("vq_rounds", ctypes.c_uint32 * 4), ("unique_vectors", ctypes.c_uint32 * 4)]
 
 
+class _ResampleParams(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("filter", ctypes.c_uint32), ("filter_scale", ctypes.c_float), ("srgb", ctypes.c_uint32),
+                ("source_gamma", ctypes.c_float), ("wrapping", ctypes.c_uint32), ("num_comps", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 3)]
+
+
+MIP_FILTERS = {"box": 0, "tent": 1, "lanczos4": 2, "mitchell": 3, "kaiser": 4}
+
+
 class PackParams:
     """dxt_image::pack_params for the block-by-block path (defaults of crn_comp_params::clear())."""
 
@@ -118,6 +126,13 @@ def _declare(lib):
     lib.crn_gpu_refine_endpoints.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, vp, vp, vp, u32, vp, vp, vp, vp]
     lib.crn_gpu_nearest_codebook.argtypes = [vp, u32, vp, u32, vp, u32, vp]
     lib.crn_gpu_assign_selectors.argtypes = [vp, u32, ctypes.c_int, u32, vp, u32, vp, vp, vp, u32, vp, vp, vp]
+    lib.crn_gpu_default_resample_params.argtypes = [ctypes.POINTER(_ResampleParams)]
+    lib.crn_gpu_default_resample_params.restype = None
+    lib.crn_gpu_resample.argtypes = [vp, ctypes.POINTER(_ResampleParams), vp, u32, u32, u32, vp, u32, u32, u32]
+    lib.crn_gpu_mip_level_count.argtypes = [u32, u32, u32, u32]
+    lib.crn_gpu_mip_level_count.restype = u32
+    lib.crn_gpu_generate_mipmaps.argtypes = [vp, ctypes.POINTER(_ResampleParams), vp, u32, u32, u32, u32, u32, vp, u64, ctypes.POINTER(u32)]
+    lib.crn_gpu_generate_mipmaps_host.argtypes = [vp, ctypes.POINTER(_ResampleParams), vp, u32, u32, u32, u32, u32, vp, u64, ctypes.POINTER(u32)]
     lib.crn_gpu_unpack_image.argtypes = [vp, u32, vp, u32, u32, vp, u32]
     lib.crn_gpu_unpack_image_host.argtypes = [vp, u32, vp, u32, u32, vp, u32]
     lib.crn_gpu_default_hc_params.argtypes = [ctypes.POINTER(_HcParams)]
@@ -293,6 +308,47 @@ class Context:
             return None if x is None else (ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x)))
         self._check(self._lib.crn_gpu_assign_selectors(self._ctx, 0 if kind == "color" else 1, 1 if perceptual else 0, component, ptr(d_blocks), n_blocks, ptr(d_values),
                                                        ptr(d_values_accum), ptr(d_codebook), k, ptr(d_best_index), ptr(d_refined), ptr(d_used)))
+
+    # --- mip chain (mipmapped_texture::generate_mipmaps, crnlib/crn_mipmapped_texture.cpp:2140-2220) ---------------
+    def _resample_params(self, filter, filter_scale, srgb, source_gamma, wrapping, num_comps):
+        p = _ResampleParams()
+        self._lib.crn_gpu_default_resample_params(ctypes.byref(p))
+        p.filter = MIP_FILTERS[filter] if isinstance(filter, str) else int(filter)
+        p.filter_scale = float(filter_scale); p.srgb = int(bool(srgb)); p.source_gamma = float(source_gamma)
+        p.wrapping = int(bool(wrapping)); p.num_comps = int(num_comps)
+        return p
+
+    def generate_mipmaps(self, rgba, filter="kaiser", filter_scale=0.9, srgb=True, source_gamma=2.2, wrapping=False, num_comps=4,
+                         min_mip_size=1, max_levels=16):
+        """rgba: (h, w, 4) uint8 -> list of levels [level0, level1, ...] (numpy), level l = max(1, w >> l) x max(1, h >> l)."""
+        img = np.ascontiguousarray(rgba, np.uint8)
+        h, w = img.shape[:2]
+        p = self._resample_params(filter, filter_scale, srgb, source_gamma, wrapping, num_comps)
+        n = self._lib.crn_gpu_mip_level_count(w, h, min_mip_size, max_levels)
+        sizes = [(max(1, h >> l), max(1, w >> l)) for l in range(1, n)]
+        out = np.empty(sum(a * b * 4 for a, b in sizes) or 1, np.uint8)
+        nl = ctypes.c_uint32(0)
+        self._check(self._lib.crn_gpu_generate_mipmaps_host(self._ctx, ctypes.byref(p), img.ctypes.data_as(ctypes.c_void_p), w, h, w * 4, min_mip_size, max_levels,
+                                                            out.ctypes.data_as(ctypes.c_void_p), out.size, ctypes.byref(nl)))
+        levels, o = [img], 0
+        for a, b in sizes:
+            levels.append(out[o:o + a * b * 4].reshape(a, b, 4).copy()); o += a * b * 4
+        return levels
+
+    def resample_device(self, d_src, sw, sh, spitch, d_dst, dw, dh, dpitch, filter="kaiser", filter_scale=1.0, srgb=True, source_gamma=2.2, wrapping=False, num_comps=4):
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        p = self._resample_params(filter, filter_scale, srgb, source_gamma, wrapping, num_comps)
+        self._check(self._lib.crn_gpu_resample(self._ctx, ctypes.byref(p), ptr(d_src), sw, sh, spitch, ptr(d_dst), dw, dh, dpitch))
+
+    def generate_mipmaps_device(self, d_level0, w, h, pitch, d_mips, capacity, filter="kaiser", filter_scale=0.9, srgb=True, source_gamma=2.2, wrapping=False,
+                                num_comps=4, min_mip_size=1, max_levels=16):
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        p = self._resample_params(filter, filter_scale, srgb, source_gamma, wrapping, num_comps)
+        nl = ctypes.c_uint32(0)
+        self._check(self._lib.crn_gpu_generate_mipmaps(self._ctx, ctypes.byref(p), ptr(d_level0), w, h, pitch, min_mip_size, max_levels, ptr(d_mips), capacity, ctypes.byref(nl)))
+        return nl.value
 
     # --- dxt_image::unpack (crnlib/crn_dxt_image.cpp:495-567): blocks -> RGBA8 pixels ------------------------------
     def unpack_image(self, fmt, blocks, width, height):

@@ -13,6 +13,8 @@
 #include "refiner_kernels.cuh"
 #include "hc_kernels.cuh"
 #include "unpack_kernels.cuh"
+#include "mip_kernels.cuh"
+#include "mip_host.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1057,6 +1059,132 @@ int crn_gpu_unpack_image_host(crn_gpu_ctx* ctx, uint32_t format, const void* h_b
     rc = crn_gpu_unpack_image(ctx, format, ctx->d_in, width, height, ctx->d_out, pitch_bytes);
     if (rc) return rc;
     CRN_CUDA(ctx, cudaMemcpyAsync(h_rgba, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CRN_GPU_OK;
+}
+
+void crn_gpu_default_resample_params(crn_gpu_resample_params* p)
+{   // what crn_mipmap_params (inc/crnlib.h:471-574) + create_texture_mipmaps (crnlib/crn_texture_comp.cpp:552-566) hand to generate_mipmaps
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->filter = 4; p->filter_scale = 0.9f; p->srgb = 1; p->source_gamma = 2.2f; p->wrapping = 0; p->num_comps = 4;
+}
+
+namespace {
+struct MipPlan {                 // device copies of both contributor lists and the gamma tables for one (src, dst) size pair
+    HcBuf off_x, pix_x, wgt_x, off_y, pix_y, wgt_y, to_linear, to_srgb, tmp;
+};
+int mip_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* prm, const void* d_src, uint32_t sw, uint32_t sh, uint32_t spitch,
+                 void* d_dst, uint32_t dw, uint32_t dh, uint32_t dpitch)
+{
+    cudaStream_t st = ctx->stream;
+    if (sw == dw && sh == dh) {   // dst = src (crn_image_utils.cpp:693-697)
+        CRN_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dpitch, d_src, spitch, (size_t)sw * 4, sh, cudaMemcpyDeviceToDevice, st));
+        return CRN_GPU_OK;
+    }
+    const MipFilter& F = g_mip_filters[prm->filter];
+    MipContribs cx, cy;
+    if (!mip_make_clist((int)sw, (int)dw, prm->wrapping != 0, F, prm->filter_scale, cx) || !mip_make_clist((int)sh, (int)dh, prm->wrapping != 0, F, prm->filter_scale, cy))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_resample: could not build the contributor lists");
+    MipPlan P;
+    HC_ALLOC(P.off_x, cx.off.size() * 4); HC_ALLOC(P.pix_x, cx.pix.size() * 4); HC_ALLOC(P.wgt_x, cx.wgt.size() * 4);
+    HC_ALLOC(P.off_y, cy.off.size() * 4); HC_ALLOC(P.pix_y, cy.pix.size() * 4); HC_ALLOC(P.wgt_y, cy.wgt.size() * 4);
+    HC_ALLOC(P.to_linear, 256 * 4); HC_ALLOC(P.to_srgb, 8192); HC_ALLOC(P.tmp, (size_t)sh * dw * 16);
+    float to_linear[256]; uint8_t to_srgb[8192];
+    if (prm->srgb) {   // crn_image_utils.cpp:686-712
+        const float source_gamma = prm->source_gamma;
+        for (int i = 0; i < 256; ++i) to_linear[i] = (float)pow(i * 1.0f / 255.0f, source_gamma);
+        const float inv_size = 1.0f / 8192, inv_gamma = 1.0f / source_gamma;
+        for (int i = 0; i < 8192; ++i) {
+            int k = (int)(255.0f * pow(i * inv_size, inv_gamma) + .5f);
+            to_srgb[i] = (uint8_t)(k < 0 ? 0 : (k > 255 ? 255 : k));
+        }
+        CRN_CUDA(ctx, cudaMemcpyAsync(P.to_linear.p, to_linear, sizeof(to_linear), cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(P.to_srgb.p, to_srgb, sizeof(to_srgb), cudaMemcpyHostToDevice, st));
+    }
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.off_x.p, cx.off.data(), cx.off.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.pix_x.p, cx.pix.data(), cx.pix.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.wgt_x.p, cx.wgt.data(), cx.wgt.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.off_y.p, cy.off.data(), cy.off.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.pix_y.p, cy.pix.data(), cy.pix.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.wgt_y.p, cy.wgt.data(), cy.wgt.size() * 4, cudaMemcpyHostToDevice, st));
+    const int nc = (int)prm->num_comps, srgb = prm->srgb ? 1 : 0;
+    const unsigned tx = dw >= 256 ? 256 : (dw >= 64 ? 64 : 32);
+    CRN_LAUNCH(crn::mip_resample_x_kernel, dim3((dw + tx - 1) / tx, sh), tx, 0, st, static_cast<const uint8_t*>(d_src), spitch, sh, dw, nc, srgb,
+               P.off_x.as<uint32_t>(), P.pix_x.as<uint32_t>(), P.wgt_x.as<float>(), P.to_linear.as<float>(), P.tmp.as<float4>());
+    CRN_LAUNCH(crn::mip_resample_y_kernel, dim3((dw + tx - 1) / tx, dh), tx, 0, st, P.tmp.as<float4>(), dw, dh, nc, srgb,
+               P.off_y.as<uint32_t>(), P.pix_y.as<uint32_t>(), P.wgt_y.as<float>(), P.to_srgb.as<uint8_t>(), static_cast<uint8_t*>(d_dst), dpitch);
+    ctx->launches += 2;
+    CRN_CUDA(ctx, cudaGetLastError());
+    // the host vectors and pooled buffers die here: make sure the copies and kernels that read them are done
+    CRN_CUDA(ctx, cudaStreamSynchronize(st));
+    return CRN_GPU_OK;
+}
+bool mip_params_ok(const crn_gpu_resample_params* p)
+{
+    return p && p->struct_size == sizeof(crn_gpu_resample_params) && p->filter < 5 && p->filter_scale > 0.0f && (p->num_comps == 3 || p->num_comps == 4) &&
+           (!p->srgb || p->source_gamma > 0.0f);
+}
+}  // namespace
+
+int crn_gpu_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_src, uint32_t src_width, uint32_t src_height, uint32_t src_pitch_bytes,
+                     void* d_dst, uint32_t dst_width, uint32_t dst_height, uint32_t dst_pitch_bytes)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!mip_params_ok(params) || !d_src || !d_dst || !src_width || !src_height || !dst_width || !dst_height || src_width > 16384 || src_height > 16384 ||
+        dst_width > 16384 || dst_height > 16384 || src_pitch_bytes < src_width * 4u || dst_pitch_bytes < dst_width * 4u || (src_pitch_bytes & 3u) || (dst_pitch_bytes & 3u))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_resample: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    return mip_resample(ctx, params, d_src, src_width, src_height, src_pitch_bytes, d_dst, dst_width, dst_height, dst_pitch_bytes);
+}
+
+uint32_t crn_gpu_mip_level_count(uint32_t width, uint32_t height, uint32_t min_mip_size, uint32_t max_levels)
+{   // mipmapped_texture::generate_mipmaps, crn_mipmapped_texture.cpp:2145-2157
+    uint32_t n = 1;
+    while (width > min_mip_size || height > min_mip_size) { width >>= 1; height >>= 1; n++; }
+    if (max_levels > 0 && n > max_levels) n = max_levels;
+    return n;
+}
+
+int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
+                             uint32_t min_mip_size, uint32_t max_levels, void* d_mips, uint64_t capacity, uint32_t* num_levels)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!mip_params_ok(params) || !d_level0 || !width || !height || width > 16384 || height > 16384 || pitch_bytes < width * 4u || (pitch_bytes & 3u) || !min_mip_size)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps: bad argument");
+    const uint32_t n = crn_gpu_mip_level_count(width, height, min_mip_size, max_levels);
+    uint64_t need = 0;
+    for (uint32_t l = 1; l < n; l++) need += (uint64_t)std::max(1u, width >> l) * std::max(1u, height >> l) * 4;
+    if (num_levels) *num_levels = n;
+    if (need && (!d_mips || capacity < need)) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps: output buffer too small");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t* out = static_cast<uint8_t*>(d_mips);
+    for (uint32_t l = 1; l < n; l++) {        // every level is resampled from level 0 (:2171-2196)
+        const uint32_t mw = std::max(1u, width >> l), mh = std::max(1u, height >> l);
+        int rc = mip_resample(ctx, params, d_level0, width, height, pitch_bytes, out, mw, mh, mw * 4);
+        if (rc) return rc;
+        out += (size_t)mw * mh * 4;
+    }
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_generate_mipmaps_host(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* h_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
+                                  uint32_t min_mip_size, uint32_t max_levels, void* h_mips, uint64_t capacity, uint32_t* num_levels)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!h_level0 || !width || !height || pitch_bytes < width * 4u || !min_mip_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps_host: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n = crn_gpu_mip_level_count(width, height, min_mip_size, max_levels);
+    uint64_t need = 0;
+    for (uint32_t l = 1; l < n; l++) need += (uint64_t)std::max(1u, width >> l) * std::max(1u, height >> l) * 4;
+    if (need && (!h_mips || capacity < need)) { if (num_levels) *num_levels = n; return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps_host: output buffer too small"); }
+    HcBuf d_in, d_out;
+    HC_ALLOC(d_in, (size_t)pitch_bytes * height); HC_ALLOC(d_out, need ? need : 256);
+    CRN_CUDA(ctx, cudaMemcpyAsync(d_in.p, h_level0, (size_t)pitch_bytes * height, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = crn_gpu_generate_mipmaps(ctx, params, d_in.p, width, height, pitch_bytes, min_mip_size, max_levels, d_out.p, need, num_levels);
+    if (rc) return rc;
+    if (need) CRN_CUDA(ctx, cudaMemcpyAsync(h_mips, d_out.p, need, cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
 }

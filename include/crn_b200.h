@@ -233,6 +233,35 @@ CRN_API int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int percep
 CRN_API int crn_gpu_unpack_image(crn_gpu_ctx* ctx, uint32_t format, const void* d_blocks, uint32_t width, uint32_t height, void* d_rgba, uint32_t pitch_bytes);
 CRN_API int crn_gpu_unpack_image_host(crn_gpu_ctx* ctx, uint32_t format, const void* h_blocks, uint32_t width, uint32_t height, void* h_rgba, uint32_t pitch_bytes);
 
+/* Resampling and mip-chain generation ---------------------------------------------------------
+ * crn_gpu_resample replaces image_utils::resample in the form the public API runs it (params.m_multithreaded, i.e.
+ * threaded_resampler: reference crnlib/crn_image_utils.cpp:668-875, crnlib/crn_threaded_resampler.cpp:64-350, contributor
+ * lists from Resampler::make_clist, crnlib/crn_resampler.cpp:119-420); crn_gpu_generate_mipmaps replaces
+ * mipmapped_texture::generate_mipmaps (crnlib/crn_mipmapped_texture.cpp:2140-2220): level l = max(1, w >> l) x max(1, h >> l),
+ * every level resampled from level 0.  RGBA8 in and out, first_comp = 0.  Bit-exact (the contributor weights and gamma
+ * tables are computed on the host with the reference's arithmetic and the same libm; the kernels keep its float order).
+ *   filter        crn_mip_filter (inc/crnlib.h:438-446): 0 box, 1 tent, 2 lanczos4, 3 mitchell, 4 kaiser (crnlib/crn_resample_filters.cpp)
+ *   num_comps     4: filter alpha too; 3: alpha of the output is 255 (the reference passes 4 when the image has valid alpha)
+ *   d_mips        levels 1 .. n-1, tight (pitch = width * 4), one after the other; *num_levels = n including level 0 */
+typedef struct crn_gpu_resample_params {
+    uint32_t struct_size;               /* sizeof(crn_gpu_resample_params) */
+    uint32_t filter;
+    float filter_scale;                 /* crn_mipmap_params::m_blurriness (mips) / 1.0 (plain resize) */
+    uint32_t srgb;                      /* m_gamma_filtering */
+    float source_gamma;                 /* 2.2 */
+    uint32_t wrapping;                  /* m_tiled */
+    uint32_t num_comps;
+    uint32_t reserved[3];
+} crn_gpu_resample_params;
+CRN_API void crn_gpu_default_resample_params(crn_gpu_resample_params* p);
+CRN_API int crn_gpu_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_src, uint32_t src_width, uint32_t src_height, uint32_t src_pitch_bytes,
+                             void* d_dst, uint32_t dst_width, uint32_t dst_height, uint32_t dst_pitch_bytes);
+CRN_API uint32_t crn_gpu_mip_level_count(uint32_t width, uint32_t height, uint32_t min_mip_size, uint32_t max_levels);
+CRN_API int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
+                                     uint32_t min_mip_size, uint32_t max_levels, void* d_mips, uint64_t capacity, uint32_t* num_levels);
+CRN_API int crn_gpu_generate_mipmaps_host(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* h_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
+                                          uint32_t min_mip_size, uint32_t max_levels, void* h_mips, uint64_t capacity, uint32_t* num_levels);
+
 /* dxt_hc pipeline --------------------------------------------------------------
  * crn_gpu_hc_compress replaces crnlib::dxt_hc::compress (reference crnlib/crn_dxt_hc.cpp:98-312; params mirror
  * dxt_hc::params, crnlib/crn_dxt_hc.h:103-172) as crn_comp::quantize_images calls it (crnlib/crn_comp.cpp:717-766) for

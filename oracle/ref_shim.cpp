@@ -564,3 +564,19 @@ SHIM_API int ref_unpack_image(int fmt, const uint8_t* blocks, uint32_t width, ui
     for (uint32_t y = 0; y < height; y++) memcpy(rgba_out + (size_t)y * width * 4, img.get_scanline(y), (size_t)width * 4);
     return 1;
 }
+
+// ref_resample -> image_utils::resample (crn_image_utils.cpp:876-886): multithreaded != 0 takes the task-pool form
+// (threaded_resampler), 0 the single-thread Resampler.  RGBA8 in and out.
+#include "crn_image_utils.h"
+SHIM_API int ref_resample(const uint8_t* src, uint32_t sw, uint32_t sh, uint8_t* dst, uint32_t dw, uint32_t dh, const char* filter, float filter_scale,
+                          int srgb, float gamma, int wrapping, uint32_t num_comps, int multithreaded)
+{
+    image_u8 s(sw, sh), d;
+    for (uint32_t y = 0; y < sh; y++) memcpy(s.get_scanline(y), src + (size_t)y * sw * 4, (size_t)sw * 4);
+    image_utils::resample_params rp;
+    rp.m_dst_width = dw; rp.m_dst_height = dh; rp.m_pFilter = filter; rp.m_filter_scale = filter_scale; rp.m_srgb = srgb != 0;
+    rp.m_wrapping = wrapping != 0; rp.m_first_comp = 0; rp.m_num_comps = num_comps; rp.m_source_gamma = gamma; rp.m_multithreaded = multithreaded != 0;
+    if (!image_utils::resample(s, d, rp)) return 0;
+    for (uint32_t y = 0; y < dh; y++) memcpy(dst + (size_t)y * dw * 4, d.get_scanline(y), (size_t)dw * 4);
+    return 1;
+}
