@@ -302,6 +302,49 @@ def run_unpack(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
     return out
 
 
+def run_mipgen(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
+    """Mip chain of a 4096 x 4096 RGBA texture (Kaiser, sRGB, blurriness 0.9: crn_mipmap_params defaults), every level from
+    level 0 as mipmapped_texture::generate_mipmaps does.  Algorithmic bytes: per level one read of level 0 + one write of the
+    level.  The reference (image_utils::resample on all host threads) runs beside it on a 2048^2 sample."""
+    import torch
+    import blockgen
+    w = h = 4096
+    img = blockgen.smooth_image(w, h, 77, alpha=True)
+    d_img = torch.from_numpy(img).to(dev)
+    n = 13
+    out_bytes = sum(max(1, w >> l) * max(1, h >> l) * 4 for l in range(1, n))
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+    ctx.generate_mipmaps_device(d_img, w, h, w * 4, d_out, out_bytes); torch.cuda.synchronize()
+    ts = []
+    l0 = ctx.launch_count
+    for _ in range(max(2, steps)):
+        flush.fill_(7); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext); ctx.generate_mipmaps_device(d_img, w, h, w * 4, d_out, out_bytes); e1.record(ext); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    launches = (ctx.launch_count - l0) // len(ts)
+    ms = sum(ts) / len(ts)
+    alg = (n - 1) * w * h * 4 + out_bytes
+    out = {"workload": "mip chain of 4096x4096 RGBA, 13 levels (kaiser, sRGB, blurriness 0.9), each level from level 0", "value": w * h / (ms / 1e3) / 1e6,
+           "unit": "Mtexel/s of level 0", "ms": ms, "gpu_launches": int(launches), "includes": "host contributor lists + table uploads per level",
+           "roofline": {"bound": "hbm", "kernel": "mip_resample_x_kernel + mip_resample_y_kernel", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": alg / (ms / 1e3) / 1e9 / peak_gbs, "algorithmic_bytes": alg}}
+    if with_reference:
+        import helpers
+        ref = helpers.load_ref()
+        if ref is not None:
+            from test_mip_cpu import ref_mips
+            small = np.ascontiguousarray(img[:2048, :2048])
+            t0 = time.perf_counter()
+            want = ref_mips(ref, small)
+            dt = time.perf_counter() - t0
+            got = ctx.generate_mipmaps(small)
+            out["reference"] = {"value": 2048 * 2048 / dt / 1e6, "unit": "Mtexel/s of level 0", "ms": dt * 1e3, "cores": os.cpu_count(), "kind": "reference",
+                                "sample": "2048x2048 crop, 12 levels, image_utils::resample (threaded_resampler, all host threads)",
+                                "bit_exact": bool(all(np.array_equal(a, b) for a, b in zip(got, want)))}
+    return out
+
+
 def run_dxt_hc(ctx, dev, steps, with_reference=True):
     """BASELINE configs[2]'s quantiser: dxt_hc::compress of a 6-face 2048^2 DXT1 cubemap with full mip chains (2 097 216
     blocks after crn_comp's 8-pixel padding) at 4096-entry codebooks -- palettes + indices, i.e. everything of CRN
@@ -602,6 +645,11 @@ def main():
             out["unpack"] = run_unpack(ctx, ext, dev, flush, max(3, min(args.steps, 5)), peak_gbs, with_reference=not args.no_cpu_baseline)
         except Exception as e:
             out["unpack"] = {"error": str(e)[:300]}
+    if not args.no_transcode and world == 1:
+        try:
+            out["mipgen"] = run_mipgen(ctx, ext, dev, flush, max(2, min(args.steps, 3)), peak_gbs, with_reference=not args.no_cpu_baseline)
+        except Exception as e:
+            out["mipgen"] = {"error": str(e)[:300]}
     if not args.no_hc and world == 1:
         try:
             out["dxt_hc"] = run_dxt_hc(ctx, dev, 2, with_reference=not args.no_cpu_baseline)

@@ -1072,27 +1072,25 @@ void crn_gpu_default_resample_params(crn_gpu_resample_params* p)
 }
 
 namespace {
-struct MipPlan {                 // device copies of both contributor lists and the gamma tables for one (src, dst) size pair
-    HcBuf off_x, pix_x, wgt_x, off_y, pix_y, wgt_y, to_linear, to_srgb, tmp;
-};
-int mip_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* prm, const void* d_src, uint32_t sw, uint32_t sh, uint32_t spitch,
-                 void* d_dst, uint32_t dw, uint32_t dh, uint32_t dpitch)
-{
-    cudaStream_t st = ctx->stream;
-    if (sw == dw && sh == dh) {   // dst = src (crn_image_utils.cpp:693-697)
-        CRN_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dpitch, d_src, spitch, (size_t)sw * 4, sh, cudaMemcpyDeviceToDevice, st));
-        return CRN_GPU_OK;
-    }
-    const MipFilter& F = g_mip_filters[prm->filter];
+struct MipPlan {                 // one (src, dst) size pair: host contributor lists, then their device copies + the intermediate image
+    uint32_t dw = 0, dh = 0;
+    bool ok = false, same_xy = false;
     MipContribs cx, cy;
-    if (!mip_make_clist((int)sw, (int)dw, prm->wrapping != 0, F, prm->filter_scale, cx) || !mip_make_clist((int)sh, (int)dh, prm->wrapping != 0, F, prm->filter_scale, cy))
-        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_resample: could not build the contributor lists");
-    MipPlan P;
-    HC_ALLOC(P.off_x, cx.off.size() * 4); HC_ALLOC(P.pix_x, cx.pix.size() * 4); HC_ALLOC(P.wgt_x, cx.wgt.size() * 4);
-    HC_ALLOC(P.off_y, cy.off.size() * 4); HC_ALLOC(P.pix_y, cy.pix.size() * 4); HC_ALLOC(P.wgt_y, cy.wgt.size() * 4);
-    HC_ALLOC(P.to_linear, 256 * 4); HC_ALLOC(P.to_srgb, 8192); HC_ALLOC(P.tmp, (size_t)sh * dw * 16);
-    float to_linear[256]; uint8_t to_srgb[8192];
+    HcBuf off_x, pix_x, wgt_x, off_y, pix_y, wgt_y, tmp;
+};
+void mip_plan_build(MipPlan* P, const crn_gpu_resample_params* prm, uint32_t sw, uint32_t sh)
+{
+    const MipFilter& F = g_mip_filters[prm->filter];
+    P->same_xy = sw == sh && P->dw == P->dh;                // square level of a square image: one list serves both axes
+    P->ok = mip_make_clist((int)sw, (int)P->dw, prm->wrapping != 0, F, prm->filter_scale, P->cx) &&
+            (P->same_xy || mip_make_clist((int)sh, (int)P->dh, prm->wrapping != 0, F, prm->filter_scale, P->cy));
+}
+struct MipTablesDev { HcBuf to_linear, to_srgb; };
+int mip_tables_upload(crn_gpu_ctx* ctx, const crn_gpu_resample_params* prm, MipTablesDev& T)
+{
+    HC_ALLOC(T.to_linear, 256 * 4); HC_ALLOC(T.to_srgb, 8192);
     if (prm->srgb) {   // crn_image_utils.cpp:686-712
+        float to_linear[256]; uint8_t to_srgb[8192];
         const float source_gamma = prm->source_gamma;
         for (int i = 0; i < 256; ++i) to_linear[i] = (float)pow(i * 1.0f / 255.0f, source_gamma);
         const float inv_size = 1.0f / 8192, inv_gamma = 1.0f / source_gamma;
@@ -1100,25 +1098,56 @@ int mip_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* prm, const voi
             int k = (int)(255.0f * pow(i * inv_size, inv_gamma) + .5f);
             to_srgb[i] = (uint8_t)(k < 0 ? 0 : (k > 255 ? 255 : k));
         }
-        CRN_CUDA(ctx, cudaMemcpyAsync(P.to_linear.p, to_linear, sizeof(to_linear), cudaMemcpyHostToDevice, st));
-        CRN_CUDA(ctx, cudaMemcpyAsync(P.to_srgb.p, to_srgb, sizeof(to_srgb), cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(T.to_linear.p, to_linear, sizeof(to_linear), cudaMemcpyHostToDevice, ctx->stream));
+        CRN_CUDA(ctx, cudaMemcpyAsync(T.to_srgb.p, to_srgb, sizeof(to_srgb), cudaMemcpyHostToDevice, ctx->stream));
+        CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the tables live on this stack frame
     }
-    CRN_CUDA(ctx, cudaMemcpyAsync(P.off_x.p, cx.off.data(), cx.off.size() * 4, cudaMemcpyHostToDevice, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(P.pix_x.p, cx.pix.data(), cx.pix.size() * 4, cudaMemcpyHostToDevice, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(P.wgt_x.p, cx.wgt.data(), cx.wgt.size() * 4, cudaMemcpyHostToDevice, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(P.off_y.p, cy.off.data(), cy.off.size() * 4, cudaMemcpyHostToDevice, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(P.pix_y.p, cy.pix.data(), cy.pix.size() * 4, cudaMemcpyHostToDevice, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(P.wgt_y.p, cy.wgt.data(), cy.wgt.size() * 4, cudaMemcpyHostToDevice, st));
+    return CRN_GPU_OK;
+}
+// uploads the plan and enqueues the two passes; the caller keeps the plan alive until the stream is drained
+int mip_plan_launch(crn_gpu_ctx* ctx, const crn_gpu_resample_params* prm, MipPlan& P, const MipTablesDev& T, const void* d_src, uint32_t sw, uint32_t sh, uint32_t spitch,
+                    void* d_dst, uint32_t dpitch)
+{
+    cudaStream_t st = ctx->stream;
+    if (!P.ok) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_resample: could not build the contributor lists");
+    const uint32_t dw = P.dw, dh = P.dh;
+    const MipContribs& cy = P.same_xy ? P.cx : P.cy;
+    HC_ALLOC(P.off_x, P.cx.off.size() * 4); HC_ALLOC(P.pix_x, P.cx.pix.size() * 4); HC_ALLOC(P.wgt_x, P.cx.wgt.size() * 4);
+    HC_ALLOC(P.tmp, (size_t)sh * dw * 16);
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.off_x.p, P.cx.off.data(), P.cx.off.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.pix_x.p, P.cx.pix.data(), P.cx.pix.size() * 4, cudaMemcpyHostToDevice, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(P.wgt_x.p, P.cx.wgt.data(), P.cx.wgt.size() * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t* d_off_y = P.off_x.as<uint32_t>(); const uint32_t* d_pix_y = P.pix_x.as<uint32_t>(); const float* d_wgt_y = P.wgt_x.as<float>();
+    if (!P.same_xy) {
+        HC_ALLOC(P.off_y, cy.off.size() * 4); HC_ALLOC(P.pix_y, cy.pix.size() * 4); HC_ALLOC(P.wgt_y, cy.wgt.size() * 4);
+        CRN_CUDA(ctx, cudaMemcpyAsync(P.off_y.p, cy.off.data(), cy.off.size() * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(P.pix_y.p, cy.pix.data(), cy.pix.size() * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(P.wgt_y.p, cy.wgt.data(), cy.wgt.size() * 4, cudaMemcpyHostToDevice, st));
+        d_off_y = P.off_y.as<uint32_t>(); d_pix_y = P.pix_y.as<uint32_t>(); d_wgt_y = P.wgt_y.as<float>();
+    }
     const int nc = (int)prm->num_comps, srgb = prm->srgb ? 1 : 0;
-    const unsigned tx = dw >= 256 ? 256 : (dw >= 64 ? 64 : 32);
-    CRN_LAUNCH(crn::mip_resample_x_kernel, dim3((dw + tx - 1) / tx, sh), tx, 0, st, static_cast<const uint8_t*>(d_src), spitch, sh, dw, nc, srgb,
-               P.off_x.as<uint32_t>(), P.pix_x.as<uint32_t>(), P.wgt_x.as<float>(), P.to_linear.as<float>(), P.tmp.as<float4>());
-    CRN_LAUNCH(crn::mip_resample_y_kernel, dim3((dw + tx - 1) / tx, dh), tx, 0, st, P.tmp.as<float4>(), dw, dh, nc, srgb,
-               P.off_y.as<uint32_t>(), P.pix_y.as<uint32_t>(), P.wgt_y.as<float>(), P.to_srgb.as<uint8_t>(), static_cast<uint8_t*>(d_dst), dpitch);
+    const size_t tot_x = (size_t)sh * dw * 4, tot_y = (size_t)dh * dw * 4;
+    CRN_LAUNCH(crn::mip_resample_x_kernel, (unsigned)((tot_x + 255) / 256), 256, 0, st, static_cast<const uint8_t*>(d_src), spitch, sh, dw, nc, srgb,
+               P.off_x.as<uint32_t>(), P.pix_x.as<uint32_t>(), P.wgt_x.as<float>(), T.to_linear.as<float>(), P.tmp.as<float>());
+    CRN_LAUNCH(crn::mip_resample_y_kernel, (unsigned)((tot_y + 255) / 256), 256, 0, st, P.tmp.as<float>(), dw, dh, nc, srgb,
+               d_off_y, d_pix_y, d_wgt_y, T.to_srgb.as<uint8_t>(), static_cast<uint8_t*>(d_dst), dpitch);
     ctx->launches += 2;
     CRN_CUDA(ctx, cudaGetLastError());
-    // the host vectors and pooled buffers die here: make sure the copies and kernels that read them are done
-    CRN_CUDA(ctx, cudaStreamSynchronize(st));
+    return CRN_GPU_OK;
+}
+int mip_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* prm, const void* d_src, uint32_t sw, uint32_t sh, uint32_t spitch,
+                 void* d_dst, uint32_t dw, uint32_t dh, uint32_t dpitch)
+{
+    if (sw == dw && sh == dh) {   // dst = src (crn_image_utils.cpp:693-697)
+        CRN_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dpitch, d_src, spitch, (size_t)sw * 4, sh, cudaMemcpyDeviceToDevice, ctx->stream));
+        return CRN_GPU_OK;
+    }
+    MipPlan P; P.dw = dw; P.dh = dh;
+    mip_plan_build(&P, prm, sw, sh);
+    MipTablesDev T;
+    HC_RC(mip_tables_upload(ctx, prm, T));
+    HC_RC(mip_plan_launch(ctx, prm, P, T, d_src, sw, sh, spitch, d_dst, dpitch));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));         // the plan's host vectors and pooled buffers die here
     return CRN_GPU_OK;
 }
 bool mip_params_ok(const crn_gpu_resample_params* p)
@@ -1159,13 +1188,28 @@ int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_params* pa
     if (num_levels) *num_levels = n;
     if (need && (!d_mips || capacity < need)) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps: output buffer too small");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
-    uint8_t* out = static_cast<uint8_t*>(d_mips);
-    for (uint32_t l = 1; l < n; l++) {        // every level is resampled from level 0 (:2171-2196)
-        const uint32_t mw = std::max(1u, width >> l), mh = std::max(1u, height >> l);
-        int rc = mip_resample(ctx, params, d_level0, width, height, pitch_bytes, out, mw, mh, mw * 4);
-        if (rc) return rc;
-        out += (size_t)mw * mh * 4;
+    // every level is resampled from level 0 (:2171-2196).  The contributor lists of all levels are built concurrently on host
+    // threads (a few hundred thousand libm calls each), then the levels are enqueued back to back and the stream drained once.
+    std::vector<MipPlan> plans(n > 1 ? n - 1 : 0);
+    for (uint32_t l = 1; l < n; l++) { plans[l - 1].dw = std::max(1u, width >> l); plans[l - 1].dh = std::max(1u, height >> l); }
+#ifdef __CUDACC__
+    {
+        std::vector<std::thread> th;
+        for (uint32_t l = 1; l < n; l++) th.emplace_back(mip_plan_build, &plans[l - 1], params, width, height);
+        for (auto& t : th) t.join();
     }
+#else
+    for (uint32_t l = 1; l < n; l++) mip_plan_build(&plans[l - 1], params, width, height);
+#endif
+    MipTablesDev T;
+    HC_RC(mip_tables_upload(ctx, params, T));
+    uint8_t* out = static_cast<uint8_t*>(d_mips);
+    for (uint32_t l = 1; l < n; l++) {
+        MipPlan& P = plans[l - 1];
+        HC_RC(mip_plan_launch(ctx, params, P, T, d_level0, width, height, pitch_bytes, out, P.dw * 4));
+        out += (size_t)P.dw * P.dh * 4;
+    }
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
 }
 

@@ -70,20 +70,26 @@ bool mip_make_clist(int src_x, int dst_x, bool wrap, const MipFilter& F, float f
     const float xscale = dst_x / (float)src_x;
     const bool down = xscale < 1.0f;
     const float half_width = down ? (F.support / xscale) * filter_scale : F.support * filter_scale;
+    std::vector<float> fv;
     for (int i = 0; i < dst_x; i++) {
         float center = ((float)i + NUDGE) / xscale;
         center -= NUDGE;
         center += 0.0f;
         const int left = (int)(float)floor(center - half_width), right = (int)(float)ceil(center + half_width);
+        // the reference evaluates the filter twice per tap (once to normalise, once to weight); the value is the same both
+        // times, so it is computed once and kept
+        fv.resize((size_t)(right - left + 1));
         float total_weight = 0;
-        for (int j = left; j <= right; j++)
-            total_weight += down ? F.func((center - (float)j) * xscale * oo_filter_scale) : F.func((center - (float)j) * oo_filter_scale);
+        for (int j = left; j <= right; j++) {
+            fv[(size_t)(j - left)] = down ? F.func((center - (float)j) * xscale * oo_filter_scale) : F.func((center - (float)j) * oo_filter_scale);
+            total_weight += fv[(size_t)(j - left)];
+        }
         const float norm = static_cast<float>(1.0f / total_weight);
         total_weight = 0;
         int max_k = -1; float max_w = -1e+20f;
         const size_t first = out.pix.size();
         for (int j = left; j <= right; j++) {
-            const float weight = (down ? F.func((center - (float)j) * xscale * oo_filter_scale) : F.func((center - (float)j) * oo_filter_scale)) * norm;
+            const float weight = fv[(size_t)(j - left)] * norm;
             if (weight == 0.0f) continue;
             const int n = mip_reflect(j, src_x, wrap);
             const int k = (int)(out.pix.size() - first);
