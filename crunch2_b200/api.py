@@ -135,6 +135,7 @@ def _declare(lib):
     lib.crn_gpu_generate_mipmaps_host.argtypes = [vp, ctypes.POINTER(_ResampleParams), vp, u32, u32, u32, u32, u32, vp, u64, ctypes.POINTER(u32)]
     lib.crn_gpu_unpack_image.argtypes = [vp, u32, vp, u32, u32, vp, u32]
     lib.crn_gpu_unpack_image_host.argtypes = [vp, u32, vp, u32, u32, vp, u32]
+    lib.crn_gpu_blockify.argtypes = [vp, vp, u32, u32, u32, u32, vp, ctypes.POINTER(u32), ctypes.POINTER(u32)]
     lib.crn_gpu_default_hc_params.argtypes = [ctypes.POINTER(_HcParams)]
     lib.crn_gpu_default_hc_params.restype = None
     lib.crn_gpu_hc_compress.argtypes = [vp, ctypes.POINTER(_HcParams), vp, i32, ctypes.POINTER(vp)]
@@ -366,6 +367,14 @@ class Context:
         def ptr(x):
             return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
         self._check(self._lib.crn_gpu_unpack_image(self._ctx, int(fmt), ptr(d_blocks), width, height, ptr(d_rgba), pitch))
+
+    def blockify(self, d_rgba, width, height, pitch, d_blocks, pad_pixels=8):
+        """crn_comp::quantize_images' gather on the device (d_rgba / d_blocks: torch CUDA tensors or device pointers); returns (blocks_x, blocks_y)."""
+        def ptr(x):
+            return ctypes.c_void_p(x.data_ptr()) if hasattr(x, "data_ptr") else ctypes.c_void_p(int(x))
+        bx, by = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self._check(self._lib.crn_gpu_blockify(self._ctx, ptr(d_rgba), width, height, pitch, pad_pixels, ptr(d_blocks), ctypes.byref(bx), ctypes.byref(by)))
+        return bx.value, by.value
 
     # --- dxt_hc::compress (crnlib/crn_dxt_hc.cpp:98-312): blocks of all levels -> palettes + per-block indices ---------
     def hc_compress(self, fmt, blocks, levels, num_faces=1, perceptual=True, codebook_sizes=(3072, 3072, 3072, 3072),

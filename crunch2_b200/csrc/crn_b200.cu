@@ -1233,6 +1233,24 @@ int crn_gpu_generate_mipmaps_host(crn_gpu_ctx* ctx, const crn_gpu_resample_param
     return CRN_GPU_OK;
 }
 
+int crn_gpu_blockify(crn_gpu_ctx* ctx, const void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t pad_pixels, void* d_blocks,
+                     uint32_t* blocks_x, uint32_t* blocks_y)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!d_rgba || !d_blocks || !width || !height || pitch_bytes < width * 4u || (pitch_bytes & 3u) || (pad_pixels != 4 && pad_pixels != 8))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_blockify: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t bw = ((width + pad_pixels - 1) / pad_pixels * pad_pixels) >> 2, bh = ((height + pad_pixels - 1) / pad_pixels * pad_pixels) >> 2;
+    if (blocks_x) *blocks_x = bw;
+    if (blocks_y) *blocks_y = bh;
+    const size_t total = (size_t)bw * bh * 16;
+    CRN_LAUNCH(crn::blockify_padded_kernel, (unsigned)((total + 255) / 256), 256, 0, ctx->stream, static_cast<const uint8_t*>(d_rgba), width, height, pitch_bytes, pad_pixels,
+               static_cast<uint32_t*>(d_blocks));
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}
+
 void crn_gpu_default_hc_params(crn_gpu_hc_params* p)
 {   // dxt_hc::params::params() (crnlib/crn_dxt_hc.h:105-131)
     if (!p) return;

@@ -51,6 +51,8 @@ mip_resample_x_kernel(const uint8_t* __restrict__ src, uint32_t src_pitch, uint3
         const uint32_t* row = reinterpret_cast<const uint32_t*>(src + (size_t)y * src_pitch);
         const float* l = lut[c == 3 ? 1 : 0];
         const unsigned sh = 8 * c;
+        // the loads of the next taps do not depend on the running sum: unrolled so they are in flight while the adds retire in order
+#pragma unroll 8
         for (uint32_t k = c_off[x], e = c_off[x + 1]; k < e; k++) s += l[(row[c_pix[k]] >> sh) & 0xff] * c_wgt[k];
     }
     tmp[id] = s;
@@ -74,6 +76,7 @@ mip_resample_y_kernel(const float* __restrict__ tmp, uint32_t dst_w, uint32_t ds
         if (k1 - k0 == 1) s = tmp[(size_t)c_pix[k0] * stride + col];
         else {
             s = tmp[(size_t)c_pix[k0] * stride + col] * c_wgt[k0];
+#pragma unroll 8
             for (uint32_t k = k0 + 1; k < k1; k++) s += tmp[(size_t)c_pix[k] * stride + col] * c_wgt[k];
         }
         out = mip_to_u8(mip_clamp01(s), (srgb && c != 3) ? 1 : 0, to_srgb);

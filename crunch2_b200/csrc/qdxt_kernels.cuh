@@ -494,4 +494,17 @@ __global__ void __launch_bounds__(256) blockify_kernel(const uint8_t* __restrict
     blocks[i] = *reinterpret_cast<const uint32_t*>(rgba + (size_t)y * pitch + (size_t)x * 4);
 }
 
+
+// same gather with the level padded to a multiple of `pad` pixels (8 for crn_comp::quantize_images, crn_comp.cpp:717-741)
+__global__ void __launch_bounds__(256) blockify_padded_kernel(const uint8_t* __restrict__ rgba, uint32_t width, uint32_t height, uint32_t pitch, uint32_t pad,
+                                                              uint32_t* __restrict__ blocks)
+{
+    const uint32_t bw = ((width + pad - 1) / pad * pad) >> 2, bh = ((height + pad - 1) / pad * pad) >> 2;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bw * bh * 16) return;
+    const uint32_t b = i >> 4, p = i & 15;
+    const uint32_t x = min((b % bw) * 4 + (p & 3), width - 1), y = min((b / bw) * 4 + (p >> 2), height - 1);
+    blocks[i] = *reinterpret_cast<const uint32_t*>(rgba + (size_t)y * pitch + (size_t)x * 4);
+}
+
 }  // namespace crn

@@ -262,6 +262,12 @@ CRN_API int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_pa
 CRN_API int crn_gpu_generate_mipmaps_host(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* h_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
                                           uint32_t min_mip_size, uint32_t max_levels, void* h_mips, uint64_t capacity, uint32_t* num_levels);
 
+/* Block gather: image -> contiguous [block][16] RGBA8 with edge clamp, the level padded to a multiple of
+ * pad_pixels: 8 for crn_comp::quantize_images (reference crnlib/crn_comp.cpp:717-741, feeds crn_gpu_hc_compress), 4 for
+ * mipmapped_texture::qdxt_pack_init (crnlib/crn_mipmapped_texture.cpp:2418-2472).  d_blocks: blocks_x * blocks_y * 64 bytes. */
+CRN_API int crn_gpu_blockify(crn_gpu_ctx* ctx, const void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t pad_pixels, void* d_blocks,
+                             uint32_t* blocks_x, uint32_t* blocks_y);
+
 /* dxt_hc pipeline --------------------------------------------------------------
  * crn_gpu_hc_compress replaces crnlib::dxt_hc::compress (reference crnlib/crn_dxt_hc.cpp:98-312; params mirror
  * dxt_hc::params, crnlib/crn_dxt_hc.h:103-172) as crn_comp::quantize_images calls it (crnlib/crn_comp.cpp:717-766) for

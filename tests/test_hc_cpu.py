@@ -87,3 +87,15 @@ def test_hc_rejects_bad_params(simctx):
         simctx.hc_compress(0, blocks, [(0, 6, 3, 1.0)])          # odd block width
     with pytest.raises(crn.CrnGpuError):
         simctx.hc_compress(2, np.zeros((4, 16, 4), np.uint8), [(0, 4, 2, 1.0)])   # DXT3 is not a dxt_hc format
+
+
+def test_blockify_matches_crn_comp_layout(simctx):
+    """a24 for the CRN path: crn_comp::quantize_images' gather (levels padded to 8 pixels, edge clamp) == hc_layout."""
+    for (w, h) in ((20, 12), (8, 8), (3, 5)):
+        img = blockgen.smooth_image(w, h, 3 * w + h, alpha=True)
+        want, levels = hc_util.hc_layout([[img]])
+        got = np.zeros_like(want)
+        bx, by = simctx.blockify(img.ctypes.data, w, h, w * 4, got.ctypes.data, 8)
+        simctx.synchronize()
+        assert (bx, by) == (((w + 7) & ~7) >> 2, ((h + 7) & ~7) >> 2) and bx == levels[0][2]
+        assert np.array_equal(got, want)
