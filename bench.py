@@ -345,6 +345,44 @@ def run_mipgen(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
     return out
 
 
+def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
+    """BASELINE configs[4] (bounded): a batch of 1024 x 1024 textures, formats cycling DXT1 / DXT5 / DXN_XY (i mod 3), each
+    clustered-compressed at quality 128 to DDS blocks through the public binding (host pixels in, host blocks out).  Textures
+    are partitioned over the ranks by crunch2_b200.shard.partition_units (no data-path collective); every rank times its own
+    share and the job's rate is all textures over the slowest rank."""
+    import blockgen
+    from crunch2_b200 import shard
+    fmts = [(0, "DXT1"), (3, "DXT5"), (5, "DXN_XY")]
+    mine = shard.partition_units([65536] * n_textures, world)[rank]
+    imgs = {i: blockgen.smooth_image(1024, 1024, 50000 + i, alpha=True) for i in mine}
+    if mine:                                                     # warm the context's buffer pool
+        q = ctx.qdxt_init(fmts[mine[0] % 3][0], [imgs[mine[0]]]); q.pack(128); q.close()
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for i in mine:
+        q = ctx.qdxt_init(fmts[i % 3][0], [imgs[i]]); q.pack(128); q.close()
+    dt = time.perf_counter() - t0
+    dt_all = shard.max_over_ranks(dt, dev)
+    out = {"workload": "c5_batch: %d x 1024x1024 (DXT1/DXT5/DXN_XY mix), clustered DDS q128, one level each" % n_textures, "n_textures": n_textures,
+           "value": n_textures * 1024 * 1024 / dt_all / 1e6, "unit": UNIT, "ms_per_texture": dt_all * 1e3 / max(1, len(mine)), "timing": "host wall clock, host pixels in / host blocks out",
+           "gpu_launches_per_texture": int((ctx.launch_count - l0) // max(1, len(mine))), "partitioning": "texture -> rank (LPT), %d rank(s)" % world}
+    if with_reference and rank == 0:
+        import helpers
+        ref = helpers.load_ref()
+        if ref is not None:
+            th = cpu_threads()
+            sample = list(range(min(3, n_textures)))
+            t0 = time.perf_counter()
+            with quiet_stdout():
+                for i in sample:
+                    img = imgs[i] if i in imgs else blockgen.smooth_image(1024, 1024, 50000 + i, alpha=True)
+                    helpers.ref_compress(ref, [[img]], helpers.CRN_FMT[fmts[i % 3][1]], file_type=1, quality=128, threads=th - 1)
+            dtr = time.perf_counter() - t0
+            out["reference"] = {"value": len(sample) * 1024 * 1024 / dtr / 1e6, "unit": UNIT, "cores": th, "kind": "reference",
+                                "sample": "the first %d textures of the batch (one of each format), crn_compress to DDS" % len(sample)}
+    return out
+
+
 def run_dxt_hc(ctx, dev, steps, with_reference=True):
     """BASELINE configs[2]'s quantiser: dxt_hc::compress of a 6-face 2048^2 DXT1 cubemap with full mip chains (2 097 216
     blocks after crn_comp's 8-pixel padding) at 4096-entry codebooks -- palettes + indices, i.e. everything of CRN
@@ -594,6 +632,12 @@ def main():
     runner = run_clustered if clustered else run_block_pack
     total_ms, e2e_s, launches, sampler, top, flush, extra = runner(args, ctx, ext, dev, wl, barrier, world)
 
+    batch_c5 = None
+    if clustered and not args.no_block_pack:
+        try:
+            batch_c5 = run_batch_c5(ctx, dev, rank, world, 6 * world, with_reference=not args.no_cpu_baseline)
+        except Exception as e:
+            batch_c5 = {"error": str(e)[:300]}
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -624,6 +668,8 @@ def main():
            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(sum(l.nbytes for l in levels)), "d2h_bytes_per_step": int(n_blk * bpb)},
            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
     out.update(extra)
+    if batch_c5 is not None:
+        out["batch_c5"] = batch_c5
     if clustered and not args.no_block_pack and world == 1:
         try:                                  # configs[0] next to the headline, same contract, fewer steps
             wl1 = make_workload("c1_dxt1_2048_mips", 2048)
