@@ -222,24 +222,16 @@ struct crn_gpu_hc {
 
 namespace {
 
-// one endpoint element of the pipeline (colour, or the alpha channels together): clusters, per-block selectors, refined endpoints
-struct HcElementOut {
-    std::vector<uint32_t> tile_cluster;            // per used tile (per component for alpha)
-    std::vector<uint32_t> cluster_endpoints;       // final packed endpoints per cluster (low | high << 16)
-    std::vector<uint8_t> cluster_used;
-    uint32_t K = 0;
-};
-
 // a13 front half: the (component, tile) training vectors, compacted on the device into d_tvec (what the nearest-codebook
 // search reads afterwards), sorted, merged and quantised.  nvcc build: six / two stable LSD radix passes over the float bit
 // patterns (cub) + run heads + scan, never leaving the device; emulation build: the same on the host.
 template <int D>
-int hc_endpoint_codebook(crn_gpu_ctx* ctx, int kind, const float* d_src, const uint32_t* d_used, const std::vector<uint32_t>& used_slots, const uint8_t* d_npix,
-                         const std::vector<uint8_t>& h_npix, const std::vector<float>& slot_weight, uint32_t n, int ncp, const crn::HcLevelWeights& LW,
+int hc_endpoint_codebook(crn_gpu_ctx* ctx, int kind, const float* d_src, const uint32_t* d_used, uint32_t num_tiles, const uint8_t* d_npix,
+                         uint32_t n, int ncp, const crn::HcLevelWeights& LW,
                          uint32_t max_size, HcBuf& d_tvec, std::vector<float>& codebook, uint32_t& rounds, uint32_t& n_unique)
 {
     cudaStream_t st = ctx->stream;
-    const uint32_t num_tiles = (uint32_t)used_slots.size(), NT = (uint32_t)ncp * num_tiles;
+    const uint32_t NT = (uint32_t)ncp * num_tiles;
     HcBuf d_w;
     HC_ALLOC(d_tvec, (size_t)NT * D * 4); HC_ALLOC(d_w, (size_t)NT * 4);
     CRN_LAUNCH(crn::hc_compact_tiles_kernel<D>, (NT + 255) / 256, 256, 0, st, d_src, d_used, d_npix, n, num_tiles, NT, kind, LW, d_tvec.as<float>(), d_w.as<uint32_t>());
@@ -392,11 +384,11 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         std::vector<float> codebook; uint32_t K = 0;
         HcBuf d_tvec;
         if (kind == 0) {
-            HC_RC(hc_endpoint_codebook<6>(ctx, 0, d_cvec.as<float>(), d_used.as<uint32_t>(), used_slots, d_npix.as<uint8_t>(), h_npix, slot_weight, n, 1, LW,
+            HC_RC(hc_endpoint_codebook<6>(ctx, 0, d_cvec.as<float>(), d_used.as<uint32_t>(), num_tiles, d_npix.as<uint8_t>(), n, 1, LW,
                                           std::min(num_tiles, prm->color_endpoint_codebook_size), d_tvec, codebook, H->info.vq_rounds[0], H->info.unique_vectors[0]));
             K = (uint32_t)(codebook.size() / 6);
         } else {
-            HC_RC(hc_endpoint_codebook<2>(ctx, 1, d_avec.as<float>(), d_used.as<uint32_t>(), used_slots, d_npix.as<uint8_t>(), h_npix, slot_weight, n, na, LW,
+            HC_RC(hc_endpoint_codebook<2>(ctx, 1, d_avec.as<float>(), d_used.as<uint32_t>(), num_tiles, d_npix.as<uint8_t>(), n, na, LW,
                                           std::min(num_tiles, prm->alpha_endpoint_codebook_size), d_tvec, codebook, H->info.vq_rounds[1], H->info.unique_vectors[1]));
             K = (uint32_t)(codebook.size() / 2);
         }

@@ -47,3 +47,16 @@ def test_gpu_hc_device_input(gpu_ctx, ref):
     b = gpu_ctx.hc_compress(3, torch.from_numpy(blocks).cuda(), levels, codebook_sizes=(64, 64, 32, 64))
     for k in ("endpoint_indices", "selector_indices", "color_endpoints", "alpha_selectors"):
         assert np.array_equal(a[k], b[k]), k      # deterministic, host and device input alike
+
+
+def test_gpu_hc_large_codebooks_uniform(gpu_ctx, ref):
+    """8192-entry selector codebooks (the reference's maximum), uniform colour metric, thread-block-cluster tree kernels
+    (training sets above 8192 vectors)."""
+    from bench import mip_chain
+    img = blockgen.smooth_image(512, 512, 55, alpha=True)
+    blocks, levels = hc_util.hc_layout([mip_chain(img)])
+    g = gpu_ctx.hc_compress(3, blocks, levels, perceptual=False, codebook_sizes=(4096, 8192, 2048, 8192))
+    r = hc_util.ref_hc_compress(ref, 3, blocks, levels, perceptual=False, codebook_sizes=(4096, 8192, 2048, 8192))
+    assert np.array_equal(g["tile_indices"], r["tile_indices"])
+    assert_tolerance(3, blocks, g, r, (3, 0))
+    assert g["info"]["unique_vectors"][2] > 8192
