@@ -38,7 +38,24 @@ struct HcTreeVq {
         bool operator<(const HeapEntry& o) const { return index < o.index ? variance < o.variance : o.variance >= variance; }
     };
     std::vector<float> codebook;                  // K x D
-    static constexpr int kClusterCtas = 8, kClusterThreads = 512;
+    static constexpr int kClusterCtas = 8, kWideClusterCtas = 16, kClusterThreads = 512;
+    bool wide_ok = true;
+#ifdef __CUDACC__
+    template <int G>
+    static bool launch_cluster(crn_gpu_ctx* ctx, const HcBuf& d_vecs, const HcBuf& d_wts, const HcBuf& d_perm, const HcBuf& d_tmp, const HcBuf& d_slots, const uint32_t* dl, uint32_t count)
+    {
+        auto kernel = crn::hc_tree_split_kernel<D, kClusterThreads, G>;
+        if (G > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return false;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        const unsigned nclusters = (unsigned)std::min<size_t>(count, (size_t)std::max(1, ctx->sm_count / G) * 2);
+        cfg.gridDim = dim3(nclusters * G); cfg.blockDim = dim3(kClusterThreads); cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, (const float*)d_vecs.as<float>(), (const uint32_t*)d_wts.as<uint32_t>(), d_perm.as<uint32_t>(), d_tmp.as<uint32_t>(),
+                                  d_slots.as<crn::HcTreeSlot<D>>(), dl, count) == cudaSuccess;
+    }
+#endif
     static constexpr uint32_t kHugeNode = 8192;
     uint32_t rounds = 0, device_splits = 0;
 
@@ -146,16 +163,17 @@ struct HcTreeVq {
             CRN_CUDA(ctx, cudaMemcpyAsync(d_slots.p, h_slots.data(), (size_t)nr * sizeof(crn::HcTreeSlot<D>), cudaMemcpyHostToDevice, ctx->stream));
             uint32_t* dl = d_list.as<uint32_t>();
 #ifdef __CUDACC__
-            if (!huge_list.empty()) {          // a cluster of kClusterCtas CTAs per node, partial sums exchanged through distributed shared memory
+            if (!huge_list.empty()) {          // a thread-block cluster per node, partial sums exchanged through distributed shared memory
                 CRN_CUDA(ctx, cudaMemcpyAsync(dl, huge_list.data(), huge_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-                cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-                const unsigned nclusters = (unsigned)std::min<size_t>(huge_list.size(), (size_t)std::max(1, ctx->sm_count / kClusterCtas) * 2);
-                cfg.gridDim = dim3(nclusters * kClusterCtas); cfg.blockDim = dim3(kClusterThreads); cfg.stream = ctx->stream;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.attrs = at; cfg.numAttrs = 1;
-                CRN_CUDA(ctx, cudaLaunchKernelEx(&cfg, crn::hc_tree_split_kernel<D, kClusterThreads, kClusterCtas>, (const float*)d_vecs.as<float>(), (const uint32_t*)d_wts.as<uint32_t>(),
-                                                 d_perm.as<uint32_t>(), d_tmp.as<uint32_t>(), d_slots.as<crn::HcTreeSlot<D>>(), (const uint32_t*)dl, (uint32_t)huge_list.size()));
+                // the first rounds have a handful of very large nodes: 16-CTA clusters (non-portable size, one per GPC) put twice
+                // the SMs on each of them; from 9 nodes on, 8-CTA clusters fill the machine anyway
+                bool launched = false;
+                if (huge_list.size() <= 8 && wide_ok) {
+                    launched = launch_cluster<kWideClusterCtas>(ctx, d_vecs, d_wts, d_perm, d_tmp, d_slots, dl, (uint32_t)huge_list.size());
+                    if (!launched) { wide_ok = false; (void)cudaGetLastError(); }
+                }
+                if (!launched && !launch_cluster<kClusterCtas>(ctx, d_vecs, d_wts, d_perm, d_tmp, d_slots, dl, (uint32_t)huge_list.size()))
+                    return set_err(ctx, CRN_GPU_ERR_CUDA, "dxt_hc: cluster launch of hc_tree_split_kernel failed", cudaGetLastError());
                 ctx->launches++;
                 dl += huge_list.size();
             }

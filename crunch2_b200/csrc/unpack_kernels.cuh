@@ -12,28 +12,32 @@
 
 namespace crn {
 
+// The kernel is issue-bound (86 % issue-active, profiles/r1z_ncu_unpack_mip_summaries.txt), so the per-pixel work is kept to a
+// handful of instructions: selectors are peeled off 32-bit words, the alpha value is picked by one PRMT and merged into the
+// pixel by a second one.
 __device__ __forceinline__ void unpack_color_element(unsigned long long e, bool keep_alpha, unsigned (&px)[16])
 {
     const unsigned c0 = (unsigned)(e & 0xffff), c1 = (unsigned)((e >> 16) & 0xffff);
     unsigned r0 = (c0 >> 11) & 31, g0 = (c0 >> 5) & 63, b0 = c0 & 31, r1 = (c1 >> 11) & 31, g1 = (c1 >> 5) & 63, b1 = c1 & 31;
     r0 = (r0 << 3) | (r0 >> 2); g0 = (g0 << 2) | (g0 >> 4); b0 = (b0 << 3) | (b0 >> 2);
     r1 = (r1 << 3) | (r1 >> 2); g1 = (g1 << 2) | (g1 >> 4); b1 = (b1 << 3) | (b1 >> 2);
-    unsigned pal[4];
-    pal[0] = r0 | (g0 << 8) | (b0 << 16) | 0xff000000u;
-    pal[1] = r1 | (g1 << 8) | (b1 << 16) | 0xff000000u;
+    unsigned p0, p1, p2, p3;
+    p0 = r0 | (g0 << 8) | (b0 << 16) | 0xff000000u;
+    p1 = r1 | (g1 << 8) | (b1 << 16) | 0xff000000u;
     if (c0 > c1) {
-        pal[2] = ((r0 * 2 + r1) / 3) | (((g0 * 2 + g1) / 3) << 8) | (((b0 * 2 + b1) / 3) << 16) | 0xff000000u;
-        pal[3] = ((r1 * 2 + r0) / 3) | (((g1 * 2 + g0) / 3) << 8) | (((b1 * 2 + b0) / 3) << 16) | 0xff000000u;
+        p2 = ((r0 * 2 + r1) / 3) | (((g0 * 2 + g1) / 3) << 8) | (((b0 * 2 + b1) / 3) << 16) | 0xff000000u;
+        p3 = ((r1 * 2 + r0) / 3) | (((g1 * 2 + g0) / 3) << 8) | (((b1 * 2 + b0) / 3) << 16) | 0xff000000u;
     } else {
-        pal[2] = ((r0 + r1) >> 1) | (((g0 + g1) >> 1) << 8) | (((b0 + b1) >> 1) << 16) | 0xff000000u;
-        pal[3] = 0;
+        p2 = ((r0 + r1) >> 1) | (((g0 + g1) >> 1) << 8) | (((b0 + b1) >> 1) << 16) | 0xff000000u;
+        p3 = 0;
     }
     const unsigned sel = (unsigned)(e >> 32);
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const unsigned s = (sel >> (2 * i)) & 3u;
-        const unsigned v = s == 0 ? pal[0] : (s == 1 ? pal[1] : (s == 2 ? pal[2] : pal[3]));
-        px[i] = keep_alpha ? v : ((px[i] & 0xff000000u) | (v & 0x00ffffffu));
+        const unsigned lo = (sel >> (2 * i)) & 1u, hi = (sel >> (2 * i + 1)) & 1u;
+        const unsigned a = lo ? p1 : p0, b = lo ? p3 : p2;
+        const unsigned v = hi ? b : a;
+        px[i] = keep_alpha ? v : __byte_perm(v, px[i], 0x7210);          // colour bytes from v, alpha byte kept
     }
 }
 
@@ -42,15 +46,15 @@ __device__ __forceinline__ void unpack_alpha_element(unsigned long long e, unsig
     const unsigned l = (unsigned)(e & 0xff), h = (unsigned)((e >> 8) & 0xff);
     unsigned v[8];
     if (l > h) dxt5a_values8(l, h, v); else dxt5a_values6(l, h, v);
-    // the eight values as bytes of two registers: one PRMT per pixel picks value[selector]
+    // the eight values as bytes of two registers: one PRMT per pixel picks value[selector], a second one drops it into channel `comp`
     const unsigned lo4 = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24), hi4 = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
-    const unsigned long long sel = e >> 16;
-    const unsigned sh = 8 * comp, mask = ~(0xffu << sh);
+    const unsigned s_lo = (unsigned)(e >> 16) & 0xffffffu, s_hi = (unsigned)(e >> 40);       // pixels 0-7 / 8-15, 3 bits each
+    const unsigned merge = comp == 0 ? 0x3214u : (comp == 1 ? 0x3240u : (comp == 2 ? 0x3410u : 0x4210u));
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const unsigned s = (unsigned)(sel >> (3 * i)) & 7u;
-        const unsigned a = __byte_perm(lo4, hi4, s) & 0xffu;
-        px[i] = (px[i] & mask) | (a << sh);
+        const unsigned s = ((i < 8 ? s_lo : s_hi) >> (3 * (i & 7))) & 7u;
+        const unsigned a = __byte_perm(lo4, hi4, s);                                          // byte 0 = value[s]
+        px[i] = __byte_perm(px[i], a, merge);
     }
 }
 
