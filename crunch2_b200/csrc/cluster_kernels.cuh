@@ -23,6 +23,7 @@ struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays 
     int U, total_w, pixels_have_alpha, stage;
     uint16_t probe[2][32];
     uint16_t packed[64];
+    uint32_t hist[64], cursor[64];     // eval-colour ordering: counts / write cursors per magnitude class
 };
 
 struct ClusterHashEntry { uint32_t key, first_inv, count, uidx; };   // first_inv = ~(index of first appearance)
@@ -31,10 +32,11 @@ struct ClusterWorkspace {              // global scratch, all sized by the numbe
     ClusterHashEntry* hash;            // 2 entries per pixel
     uint32_t* mark;                    // 1 per pixel
     int4* cw; int4* ce;                // 1 per pixel each
+    int4* ce2;                         // 1 per pixel: the evaluation colours again, heaviest contributors first
     uint8_t* sel;                      // 1 per pixel
 };
 // + first-appearance flags and their scan (4 + 4 per pixel)
-constexpr size_t kClusterWorkspaceBytesPerPixel = 2 * sizeof(ClusterHashEntry) + 4 + 16 + 16 + 1 + 8;
+constexpr size_t kClusterWorkspaceBytesPerPixel = 2 * sizeof(ClusterHashEntry) + 4 + 16 + 16 + 16 + 1 + 8;
 
 constexpr int kClusterWarpsPerCta = 4;
 
@@ -111,6 +113,45 @@ cluster_compact_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_
     ws.cw[P + u] = make_int4((int)(e.key & 0xff), (int)((e.key >> 8) & 0xff), (int)((e.key >> 16) & 0xff), (int)e.count);
 }
 
+// Evaluation order of the unique colours.  A candidate's error is an integer sum over the colours, so the order does not
+// change any result; what it changes is how soon a poor candidate's partial sum passes the best error and the lane stops
+// (dxt1_eval_loop).  The reference sorts m_evaluated_colors by weighted projection for the same reason
+// (crn_dxt1.cpp:798-816).  Here: one counting pass over 64 magnitude classes of weight * squared distance to the cluster's
+// mean colour, heaviest class first -- O(U), against the ~10^4 evaluations that follow.
+__device__ __forceinline__ void cluster_order_eval_colours(Dxt1ClusterScratch* sc, const Dxt1Cfg cfg, int4* __restrict__ dst)
+{
+    const unsigned lane = lane_id();
+    const int U = cfg.U;
+    if (U <= 64) return;
+    long long sw = 0, sr = 0, sg = 0, sb = 0;
+    for (int i = (int)lane; i < U; i += 32) { const int4 c = sc->cw[i]; sw += c.w; sr += (long long)c.x * c.w; sg += (long long)c.y * c.w; sb += (long long)c.z * c.w; }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        sw += __shfl_xor_sync(CRN_FULL_MASK, sw, ofs); sr += __shfl_xor_sync(CRN_FULL_MASK, sr, ofs);
+        sg += __shfl_xor_sync(CRN_FULL_MASK, sg, ofs); sb += __shfl_xor_sync(CRN_FULL_MASK, sb, ofs);
+    }
+    const int mr = (int)(sr / sw), mg = (int)(sg / sw), mb = (int)(sb / sw);
+    const int wr = cfg.gray ? 1 : cfg.wr, wg = cfg.gray ? 1 : cfg.wg, wb = cfg.gray ? 1 : cfg.wb;
+    for (unsigned k = lane; k < 64; k += 32) { sc->hist[k] = 0; sc->cursor[k] = 0; }
+    __syncwarp();
+    auto cls_of = [&](const int4 c) -> unsigned {
+        const int dr = c.x - mr, dg = c.y - mg, db = c.z - mb;
+        const unsigned long long key = (unsigned long long)(unsigned)(wr * dr * dr + wg * dg * dg + wb * db * db) * (unsigned)c.w;
+        return key ? 63u - (unsigned)__clzll((long long)key) : 0u;
+    };
+    for (int i = (int)lane; i < U; i += 32) atomicAdd(&sc->hist[cls_of(sc->cw[i])], 1u);
+    __syncwarp();
+    if (lane == 0) { unsigned run = 0; for (int k = 63; k >= 0; k--) { const unsigned h = sc->hist[k]; sc->hist[k] = run; run += h; } }   // hist -> start of class, heaviest first
+    __syncwarp();
+    for (int i = (int)lane; i < U; i += 32) {
+        const unsigned k = cls_of(sc->cw[i]);
+        dst[sc->hist[k] + atomicAdd(&sc->cursor[k], 1u)] = sc->ce[i];
+    }
+    __syncwarp();
+    if (lane == 0) sc->ce = dst;
+    __syncwarp();
+}
+
 struct ClusterResult { uint32_t endpoints; uint32_t flags; };      // flags: bit 0 invert, bit 1 alpha_block, bits 2-3 stage
 
 __global__ void __launch_bounds__(kClusterWarpsPerCta * 32, 5)
@@ -140,6 +181,7 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
         __syncwarp();
         // ---- the optimiser proper: same phases as the 4x4 block kernels, fused
         dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, pha, U));
+        cluster_order_eval_colours(sc, dxt1_make_cfg(prm, pha, U), ws.ce2 + P);
         dxt1_setup_common(sc, prm, pha, U, opaque_cnt, opaque_cnt != N);
         dxt1_phase_median4(sc, prm);
         dxt1_phase_passes(sc, prm);

@@ -649,6 +649,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     ws.hash = reinterpret_cast<crn::ClusterHashEntry*>(base + o); o += P * 2 * sizeof(crn::ClusterHashEntry);
     ws.cw = reinterpret_cast<int4*>(base + o); o += P * 16;
     ws.ce = reinterpret_cast<int4*>(base + o); o += P * 16;
+    ws.ce2 = reinterpret_cast<int4*>(base + o); o += P * 16;
     ws.mark = reinterpret_cast<uint32_t*>(base + o); o += P * 4;
     uint32_t* flags = reinterpret_cast<uint32_t*>(base + o); o += (P + 2) * 4;
     uint32_t* rank = reinterpret_cast<uint32_t*>(base + o); o += (P + 2) * 4;

@@ -60,7 +60,7 @@ struct Dxt1BlockState {
 };
 
 struct Dxt1Scratch : Dxt1BlockState {          // per-warp shared memory
-    int4 ce[16];               // unique colour i in evaluation form: 2wr*r, 2wg*g, 2wb*b, C2 (see eval_colour)
+    int4 ce[16];               // unique colour i in evaluation form: 2wr*r | 2wg*g << 16, 2wb*b, C2, weight (see eval_colour)
     uint16_t probe[2][32];     // sweep candidates for the low / high endpoint
     uint16_t packed[64];       // combinatorial-recovery endpoint list
     uint8_t sel[16];           // selectors of the current best per unique colour
@@ -111,17 +111,18 @@ __device__ __forceinline__ unsigned dxt1_dist(const Dxt1Cfg cfg, int r, int g, i
 // C2 does not depend on the palette entry, so min_k d(c,p_k) = C2 + min_k (P2_k - dot_k): three integer
 // multiply-adds per palette entry instead of eight, exactly the same integers.
 __device__ __forceinline__ int rgb_to_y(int r, int g, int b) { return (r * 19595 + g * 38470 + b * 7471 + 32768) >> 16; }
-__device__ __forceinline__ int4 eval_colour(const Dxt1Cfg cfg, int r, int g, int b)
-{   // (2wr*r, 2wg*g, 2wb*b, C2)
-    if (cfg.gray) { const int y = rgb_to_y(r, g, b); return make_int4(2 * y, 0, 0, y * y); }
-    return make_int4(2 * cfg.wr * r, 2 * cfg.wg * g, 2 * cfg.wb * b, cfg.wr * r * r + cfg.wg * g * g + cfg.wb * b * b);
+__device__ __forceinline__ int4 eval_colour(const Dxt1Cfg cfg, int r, int g, int b, int weight)
+{   // (2wr*r | 2wg*g << 16, 2wb*b, C2, weight): everything the evaluator needs about one unique colour in ONE 16-byte load
+    // (2wg*g <= 12750, so the two halves of .x never touch)
+    if (cfg.gray) { const int y = rgb_to_y(r, g, b); return make_int4(2 * y, 0, y * y, weight); }
+    return make_int4((2 * cfg.wr * r) | ((2 * cfg.wg * g) << 16), 2 * cfg.wb * b, cfg.wr * r * r + cfg.wg * g * g + cfg.wb * b * b, weight);
 }
 __device__ __forceinline__ int4 eval_palette(const Dxt1Cfg cfg, int r, int g, int b)
 {   // (pr, pg, pb, P2)
     if (cfg.gray) { const int y = rgb_to_y(r, g, b); return make_int4(y, 0, 0, y * y); }
     return make_int4(r, g, b, cfg.wr * r * r + cfg.wg * g * g + cfg.wb * b * b);
 }
-__device__ __forceinline__ int eval_dprime(const int4 c, const int4 p) { return p.w - c.x * p.x - c.y * p.y - c.z * p.z; }
+__device__ __forceinline__ int eval_dprime(const int cx, const int cy, const int cz, const int4 p) { return p.w - cx * p.x - cy * p.y - cz * p.z; }
 
 // `bound` = error of the current best: a candidate whose partial sum has reached it can only be rejected (every
 // acceptance test is a strict '<' against the best), so the lane stops there -- the reference's own early out
@@ -136,15 +137,16 @@ __device__ __forceinline__ void dxt1_eval_loop(const SC* sc, int U, const int4 p
 #pragma unroll 2
         for (; i < stop; i++) {
             const int4 c = sc->ce[i];
-            const unsigned w = (unsigned)sc->cw[i].w;
-            const int d01 = min(eval_dprime(c, p0), eval_dprime(c, p1));
+            const unsigned w = (unsigned)c.w;
+            const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
+            const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
             if (DO4) {
-                const int d = min(d01, min(eval_dprime(c, p2), eval_dprime(c, p3)));
-                e4 += (unsigned long long)(unsigned)(d + c.w) * w;
+                const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
+                e4 += (unsigned long long)(unsigned)(d + c.z) * w;
             }
             if (DO3) {
-                const int d = min(d01, eval_dprime(c, pm));
-                e3 += (unsigned long long)(unsigned)(d + c.w) * w;
+                const int d = min(d01, eval_dprime(cx, cy, cz, pm));
+                e3 += (unsigned long long)(unsigned)(d + c.z) * w;
             }
         }
         if ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound)) break;
@@ -712,7 +714,7 @@ __device__ __forceinline__ Dxt1Cfg dxt1_make_cfg(const Dxt1Params& prm, int pixe
 template <typename SC>
 __device__ __forceinline__ void dxt1_build_eval_colours(SC* sc, const Dxt1Cfg cfg)
 {
-    for (int ci = (int)lane_id(); ci < cfg.U; ci += 32) { const int4 c = sc->cw[ci]; sc->ce[ci] = eval_colour(cfg, c.x, c.y, c.z); }
+    for (int ci = (int)lane_id(); ci < cfg.U; ci += 32) { const int4 c = sc->cw[ci]; sc->ce[ci] = eval_colour(cfg, c.x, c.y, c.z, c.w); }
     __syncwarp();
 }
 
@@ -917,7 +919,7 @@ __device__ __forceinline__ void dxt1_phase_setup(SC* sc, uint32_t px, const Dxt1
     if (leader) {
         const int r = (int)(px & 0xff), g = (int)((px >> 8) & 0xff), b = (int)((px >> 16) & 0xff);
         sc->cw[my_u] = make_int4(r, g, b, __popc(peers));
-        sc->ce[my_u] = eval_colour(cfg, r, g, b);
+        sc->ce[my_u] = eval_colour(cfg, r, g, b, __popc(peers));
     }
     const unsigned total_w = (unsigned)__popc(vmask);
     __syncwarp();
