@@ -173,3 +173,13 @@ def test_selector_revote_matches_restatement(simctx, port, is_alpha):
     simctx.synchronize()
     assert (got == want).all()
     assert (got != elems).any()
+
+
+def test_color_clusters_many_unique_colours(simctx, port):
+    """Clusters with hundreds to ~1600 unique colours: the evaluation colours are re-ordered heaviest-first and candidates are
+    endpoints, error and every selector must still equal the port's."""
+    blocks = np.concatenate([blockgen.block_family("noise", 70, 11), blockgen.block_family("smooth", 70, 12)])
+    offs, members = make_clusters(140, [100, 25, 14], 9)
+    run_color(simctx, port, blocks, offs, members, q=4, perc=1, uab=0)      # hc evaluator
+    run_color(simctx, port, blocks, offs, members, q=4, perc=0, uab=1)      # both block types
+    run_color(simctx, port, blocks, offs, members, q=3, perc=1, uab=1)
