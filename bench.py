@@ -282,7 +282,8 @@ def run_unpack(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
     gbs = n * 80 / (ms / 1e3) / 1e9
     out = {"workload": "dxt5_8192x8192 blocks -> RGBA8 (dxt_image::unpack)", "value": w * h / (ms / 1e3) / 1e9, "unit": "Gtexel/s", "ms": ms,
            "roofline": {"bound": "hbm", "kernel": "unpack_blocks_kernel", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
-                        "bytes_per_block": 80, "blocks": n}}
+                        "bytes_per_block": 80, "blocks": n, "traffic": 67138816 + 210419968,
+                        "traffic_unit": "bytes per launch: ncu dram read + write (profiles/r1z_ncu_unpack_mip_summaries.txt); part of the output is still in L2 when the launch ends"}}
     if with_reference:
         import helpers
         ref = helpers.load_ref()
