@@ -392,10 +392,14 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     crn_gpu_pack_params pp; crn_gpu_default_pack_params(&pp);
     pp.dxt_quality = 4; pp.perceptual = (uint32_t)perceptual; pp.use_both_block_types = 0;
 
-    // ---- one pass per endpoint kind: 0 colour, 1 alpha (all alpha channels share one codebook)
-    for (int kind = 0; kind < 2; kind++) {
-        if (kind == 0 && !has_color) continue;
-        if (kind == 1 && !na) continue;
+    // ---- one pass per endpoint kind: 0 colour, 1 alpha (all alpha channels share one codebook).  The two passes are
+    // independent; for DXT5 they run concurrently, the alpha pass on a child context (own stream, scratch and buffer pool).
+    CRN_CUDA(ctx, cudaStreamSynchronize(st));                          // d_used and everything the tile pass produced is complete
+    crn_gpu_ctx* const parent = ctx;
+    auto run_kind = [&](crn_gpu_ctx* ctx, int kind) -> int {
+        cudaStream_t st = ctx->stream;
+        QdxtTrace tr(ctx);
+        (void)parent;
         const int ncp = kind ? na : 1;                                   // components handled together
         const uint32_t NV = (uint32_t)ncp * n;                           // virtual blocks (= member blocks in the CSR)
         // a13: training vectors -> sorted unique weighted vectors -> tree quantiser
@@ -605,7 +609,25 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             for (uint32_t b = 0; b < n; b++) raw_selector[(size_t)b * 3 + (kind ? 1 + a : 0)] = (uint16_t)best[(size_t)a * n + b];
         if (kind == 0) { color_sel_cb.resize(KS); for (uint32_t i = 0; i < KS; i++) color_sel_cb[i] = (uint32_t)refined[i]; color_sel_used = used; }
         else { alpha_sel_cb = refined; alpha_sel_used = used; }
-    }
+        return CRN_GPU_OK;
+    };
+    if (has_color && na) {
+#ifdef __CUDACC__
+        if (!ctx->child[0] && crn_gpu_create(ctx->device, &ctx->child[0]) != CRN_GPU_OK) return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_hc_compress: element stream");
+        crn_gpu_ctx* child = ctx->child[0];
+        const uint64_t l0 = child->launches;
+        int rc1 = CRN_GPU_OK;
+        std::thread alpha_thread([&] { cudaSetDevice(child->device); rc1 = run_kind(child, 1); child->d_cluster_flags = nullptr; child->d_cluster_order = nullptr; });
+        const int rc0 = run_kind(ctx, 0);
+        alpha_thread.join();
+        ctx->launches += child->launches - l0;
+        if (rc0) return rc0;
+        if (rc1) return set_err(ctx, rc1, child->err);
+#else
+        HC_RC(run_kind(ctx, 0));                                        // the emulator is single-threaded
+        HC_RC(run_kind(ctx, 1));
+#endif
+    } else HC_RC(run_kind(ctx, has_color ? 0 : 1));
 
     // ---- a17: palette dedup, index remap, reference flags (crn_dxt_hc.cpp:200-310)
     auto dedup32 = [](const std::vector<uint32_t>& in, const std::vector<uint8_t>& used, std::vector<uint32_t>& out, std::vector<uint16_t>& remap) {
