@@ -412,9 +412,11 @@ def run_dxt_hc(ctx, dev, steps, with_reference=True):
     dt = sorted(td)[len(td) // 2]                       # median: the call has ~70 host round trips and the box's host side is shared
     launches = (ctx.launch_count - l0) // steps
     th_ = []
+    pinned = torch.from_numpy(blocks).pin_memory()      # e2e: inputs start in pinned host memory, results end in host arrays
+    blocks_pinned = pinned.numpy()
     for _ in range(steps):
         t0 = time.perf_counter()
-        ctx.hc_compress(0, blocks, levels, num_faces=6, codebook_sizes=cbs)
+        ctx.hc_compress(0, blocks_pinned, levels, num_faces=6, codebook_sizes=cbs)
         th_.append(time.perf_counter() - t0)
     dth = sorted(th_)[len(th_) // 2]
     pg = hc_util.hc_decode(0, g)
