@@ -367,9 +367,6 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     CRN_CUDA(ctx, cudaStreamSynchronize(st));
     tr.mark("hc tiles + palettize + D2H", 0);
     std::vector<uint32_t> used_slots;               // tile slots in order (m_tiles[t].pixels.size() != 0)
-    std::vector<float> slot_weight(n);
-    for (uint32_t l = 0; l < prm->num_levels; l++)
-        for (uint32_t b = prm->levels[l].first_block, e = b + prm->levels[l].num_blocks; b < e; b++) slot_weight[b] = prm->levels[l].weight;
     for (uint32_t s = 0; s < n; s++) if (h_npix[s]) used_slots.push_back(s);
     const uint32_t num_tiles = (uint32_t)used_slots.size();
     std::vector<uint32_t> slot_rank(n, 0xffffffffu);
@@ -450,7 +447,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         for (uint32_t c = 0; c <= K; c++) poffs[c] = offs[c] * 16;
         tr.mark("hc CSR build (host)", kind);
         // a15: per-cluster optimiser over the virtual blocks
-        HcBuf d_vsrc, d_offs, d_mem, d_elem, d_ep, d_err, d_flags, d_bcl, d_bsel, d_bval, d_cpix, d_csel, d_poffs, d_rep, d_rerr, d_rok, d_bw, d_bacc, d_grey;
+        HcBuf d_vsrc, d_offs, d_mem, d_elem, d_ep, d_err, d_flags, d_bcl, d_bsel, d_bval, d_cpix, d_csel, d_poffs, d_rep, d_rerr, d_rok, d_bacc, d_grey;
         const uint32_t* d_vblocks = d_vpix.as<uint32_t>();
         if (kind == 1) {                                                 // grey copies of the tile-ordered pixels, one plane per channel
             HC_ALLOC(d_vsrc, (size_t)NV * 64);
@@ -484,9 +481,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         // per-block selectors + weights against the cluster palette
         HC_ALLOC(d_bsel, (size_t)NV * 8); HC_ALLOC(d_bval, (size_t)NV * (kind ? 8 : 16));
         if (kind == 0) {
-            HC_ALLOC(d_bw, (size_t)n * 4);
-            CRN_CUDA(ctx, cudaMemcpyAsync(d_bw.p, slot_weight.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-            CRN_LAUNCH(crn::hc_color_blocks_kernel, (n + 255) / 256, 256, 0, st, d_blocks, n, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(), d_bw.as<float>(),
+            CRN_LAUNCH(crn::hc_color_blocks_kernel, (n + 255) / 256, 256, 0, st, d_blocks, n, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(), LW,
                        d_enc.as<uint8_t>(), perceptual, d_bsel.as<unsigned long long>(), d_bval.as<uint32_t>());
         } else {
             CRN_LAUNCH(crn::hc_alpha_blocks_kernel, (NV + 255) / 256, 256, 0, st, d_blocks, n, na, comp0, comp1, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(),

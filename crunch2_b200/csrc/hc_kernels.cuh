@@ -27,6 +27,15 @@ struct HcTileParams {
     uint32_t alpha_comp[2];
 };
 
+// level weights by block index (dxt_hc::params::m_levels[].m_weight): blocks and tile slots of a level share its index range
+struct HcLevelWeights { uint32_t first_block[kHcMaxLevels + 1]; float weight[kHcMaxLevels]; uint32_t num_levels; };
+__device__ __forceinline__ float hc_level_weight(const HcLevelWeights& LW, uint32_t block)
+{
+    uint32_t l = 0;
+    while (l + 1 < LW.num_levels && block >= LW.first_block[l + 1]) l++;
+    return LW.weight[l];
+}
+
 // tile t of determine_tiles_task as a rectangle of the 8x8 chunk (x, y, w, h): 0-3 the four blocks in the order
 // b, b+width, b+1, b+width+1; 4/5 left / right column; 6/7 top / bottom row; 8 the whole chunk (:389-390, :433-440).
 // The reference's pixel order inside every tile is row-major over that rectangle.
@@ -779,7 +788,7 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
 // of the block's cluster in linear order (color_cluster::color_values, without the alternate rounding) for the selector search.
 __global__ void __launch_bounds__(256)
 hc_color_blocks_kernel(const uint32_t* __restrict__ blocks, uint32_t n_blocks, const uint32_t* __restrict__ block_cluster, const uint32_t* __restrict__ cluster_endpoints,
-                       const uint32_t* __restrict__ cluster_flags, const float* __restrict__ block_weight, const uint8_t* __restrict__ block_encoding, int perceptual,
+                       const uint32_t* __restrict__ cluster_flags, HcLevelWeights LW, const uint8_t* __restrict__ block_encoding, int perceptual,
                        unsigned long long* __restrict__ block_selectors, uint32_t* __restrict__ block_values)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -800,7 +809,7 @@ hc_color_blocks_kernel(const uint32_t* __restrict__ blocks, uint32_t n_blocks, c
     const int d0r = cs[0][0] - cs[3][0], d0g = cs[0][1] - cs[3][1], d0b = cs[0][2] - cs[3][2];
     const unsigned endpoint_weight = (unsigned)(wr * d0r * d0r + wg * d0g * d0g + wb * d0b * d0b) / 2000u;
     const float ew = 1.15f + (1.0f - 1.15f) * ((float)block_encoding[b] / 7.0f);                // math::lerp(1.15f, 1.0f, i / 7.0f)
-    float wf = (float)endpoint_weight * block_weight[b];                                        // uint * float
+    float wf = (float)endpoint_weight * hc_level_weight(LW, b);                                // uint * float (m_block_weights[b])
     // math::clamp<uint>(float, 1, 2048): the float converts to uint first (x86 cvttss2si semantics for in-range values)
     unsigned wu = (unsigned)wf; wu = wu < 1 ? 1 : (wu > 2048 ? 2048 : wu);
     const unsigned weight = (unsigned)((float)wu * ew);
@@ -951,7 +960,6 @@ hc_sel_vectors_kernel(const unsigned long long* __restrict__ keys, const uint32_
 }
 
 // ---- endpoint training set on the device (determine_color/alpha_endpoints, crn_dxt_hc.cpp:888-968, :1165-1244) --------
-struct HcLevelWeights { uint32_t first_block[kHcMaxLevels + 1]; float weight[kHcMaxLevels]; uint32_t num_levels; };
 
 // compact (component, tile) list: entry i = a * num_tiles + t takes the vector of tile slot used[t] of plane a and the
 // weight the reference gives it: (uint)(pixels * level weight) for colour, pixels for alpha
@@ -968,11 +976,7 @@ hc_compact_tiles_kernel(const float* __restrict__ src, const uint32_t* __restric
     for (int d = 0; d < D; d++) out_vecs[(size_t)i * D + d] = v[d];
     const unsigned np = tile_npix[slot];
     if (kind) out_wts[i] = np;
-    else {
-        uint32_t l = 0;
-        while (l + 1 < LW.num_levels && slot >= LW.first_block[l + 1]) l++;
-        out_wts[i] = (uint32_t)((float)np * LW.weight[l]);
-    }
+    else out_wts[i] = (uint32_t)((float)np * hc_level_weight(LW, slot));
 }
 __global__ void __launch_bounds__(256) hc_iota_kernel(uint32_t* __restrict__ p, uint32_t n)
 {
