@@ -51,6 +51,7 @@ struct crn_gpu_ctx {
     crn_gpu_ctx* child[3];
     struct PoolBlock { void* p; size_t cap; };
     std::vector<PoolBlock>* pool;
+    std::vector<PoolBlock>* pin_pool;    // pinned host staging blocks of the dxt_hc pipeline, cached like the device pool
 };
 
 namespace {
@@ -106,6 +107,36 @@ cudaError_t pool_alloc(crn_gpu_ctx* ctx, void** out, size_t bytes, size_t* cap_o
     }
     *cap_out = bytes;
     return ce;
+}
+
+// pinned host memory for the transfers of the dxt_hc pipeline: DMA at link speed instead of the driver's pageable bounce
+// copies, and no dependence on how busy the host's memory system is.  Cached per context; nullptr when pinning fails.
+void* pin_alloc(crn_gpu_ctx* ctx, size_t bytes, size_t* cap_out)
+{
+    if (!bytes) bytes = 256;
+    if (ctx->pin_pool) {
+        int best = -1;
+        for (size_t i = 0; i < ctx->pin_pool->size(); i++) {
+            const size_t c = (*ctx->pin_pool)[i].cap;
+            if (c >= bytes && c <= 2 * bytes + (1u << 20) && (best < 0 || c < (*ctx->pin_pool)[best].cap)) best = (int)i;
+        }
+        if (best >= 0) {
+            void* p = (*ctx->pin_pool)[best].p; *cap_out = (*ctx->pin_pool)[best].cap;
+            ctx->pin_pool->erase(ctx->pin_pool->begin() + best);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    *cap_out = bytes;
+    return p;
+}
+void pin_free(crn_gpu_ctx* ctx, void* p, size_t cap)
+{
+    if (!p) return;
+    if (!ctx->pin_pool) ctx->pin_pool = new (std::nothrow) std::vector<crn_gpu_ctx::PoolBlock>();
+    if (!ctx->pin_pool || ctx->pin_pool->size() >= 32) { cudaFreeHost(p); return; }
+    ctx->pin_pool->push_back({p, cap});
 }
 
 void pool_free(crn_gpu_ctx* ctx, void* p, size_t cap)
@@ -479,6 +510,10 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->pool) {
         for (auto& b : *ctx->pool) cudaFree(b.p);
         delete ctx->pool;
+    }
+    if (ctx->pin_pool) {
+        for (auto& b : *ctx->pin_pool) cudaFreeHost(b.p);
+        delete ctx->pin_pool;
     }
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -19,6 +19,26 @@ struct HcBuf {                                   // pooled device buffer
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
+template <typename T>
+struct HcHost {                                  // host array for a transfer: pinned when possible, plain heap otherwise
+    crn_gpu_ctx* ctx = nullptr; T* p = nullptr; size_t cap = 0, count = 0; bool pinned = false;
+    HcHost(crn_gpu_ctx* c, size_t n) : ctx(c), count(n)
+    {
+        p = static_cast<T*>(pin_alloc(c, n * sizeof(T), &cap));
+        pinned = p != nullptr;
+        if (!p) p = static_cast<T*>(malloc(n ? n * sizeof(T) : 1));
+        if (!p) throw std::bad_alloc();
+    }
+    ~HcHost() { if (pinned) pin_free(ctx, p, cap); else free(p); }
+    HcHost(const HcHost&) = delete;
+    HcHost& operator=(const HcHost&) = delete;
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return count; }
+};
+
 #define HC_ALLOC(buf, bytes)                                                                         \
     do {                                                                                             \
         cudaError_t ce_ = (buf).alloc(ctx, (bytes));                                                 \
@@ -358,17 +378,21 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                perceptual, d_cvec.as<float>(), d_avec.as<float>());
     ctx->launches += 2;
     CRN_CUDA(ctx, cudaGetLastError());
-    std::vector<uint8_t> h_npix(n), h_pixofs(n);
+    HcHost<uint8_t> h_npix(ctx, n), h_pixofs(ctx, n), h_enc(ctx, n);
+    HcHost<uint32_t> h_tile(ctx, n);
     H->block_encodings.resize(n); H->tile_indices.resize(n);
     CRN_CUDA(ctx, cudaMemcpyAsync(h_npix.data(), d_npix.p, n, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaMemcpyAsync(h_pixofs.data(), d_pixofs.p, n, cudaMemcpyDeviceToHost, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(H->block_encodings.data(), d_enc.p, n, cudaMemcpyDeviceToHost, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(H->tile_indices.data(), d_tile.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(h_enc.data(), d_enc.p, n, cudaMemcpyDeviceToHost, st));
+    CRN_CUDA(ctx, cudaMemcpyAsync(h_tile.data(), d_tile.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CRN_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(H->block_encodings.data(), h_enc.data(), n);
+    memcpy(H->tile_indices.data(), h_tile.data(), (size_t)n * 4);
     tr.mark("hc tiles + palettize + D2H", 0);
-    std::vector<uint32_t> used_slots;               // tile slots in order (m_tiles[t].pixels.size() != 0)
-    for (uint32_t s = 0; s < n; s++) if (h_npix[s]) used_slots.push_back(s);
-    const uint32_t num_tiles = (uint32_t)used_slots.size();
+    uint32_t num_tiles = 0;
+    for (uint32_t s = 0; s < n; s++) num_tiles += h_npix[s] != 0;
+    HcHost<uint32_t> used_slots(ctx, num_tiles);     // tile slots in order (m_tiles[t].pixels.size() != 0)
+    for (uint32_t s = 0, i = 0; s < n; s++) if (h_npix[s]) used_slots[i++] = s;
     std::vector<uint32_t> slot_rank(n, 0xffffffffu);
     for (uint32_t i = 0; i < num_tiles; i++) slot_rank[used_slots[i]] = i;
     H->info.num_tiles = num_tiles;
@@ -419,12 +443,13 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         HC_ALLOC(d_cb, (size_t)K * dims * 4); HC_ALLOC(d_tcl, (size_t)NT * 4);
         CRN_CUDA(ctx, cudaMemcpyAsync(d_cb.p, codebook.data(), (size_t)K * dims * 4, cudaMemcpyHostToDevice, st));
         HC_RC(crn_gpu_nearest_codebook(ctx, dims, d_tvec.as<float>(), NT, d_cb.as<float>(), K, d_tcl.as<uint32_t>()));
-        std::vector<uint32_t> tcl(NT);
+        HcHost<uint32_t> tcl(ctx, NT);
         CRN_CUDA(ctx, cudaMemcpyAsync(tcl.data(), d_tcl.p, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaStreamSynchronize(st));
         tr.mark("hc nearest codebook", kind);
         // cluster member lists: the tiles' 16-pixel virtual blocks, component-major then tile-slot order (:970-977, :1246-1260)
-        std::vector<uint32_t> offs(K + 1, 0), members(NV), block_cluster(NV);
+        std::vector<uint32_t> offs(K + 1, 0);
+        HcHost<uint32_t> members(ctx, NV), block_cluster(ctx, NV);
         for (int a = 0; a < ncp; a++)
             for (uint32_t i = 0; i < num_tiles; i++) offs[tcl[(size_t)a * num_tiles + i] + 1] += h_npix[used_slots[i]] / 16;
         for (uint32_t c = 0; c < K; c++) offs[c + 1] += offs[c];
@@ -594,7 +619,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             search_blocks = d_grey.p; accum = d_bacc.p;
         }
         HC_RC(crn_gpu_assign_selectors(ctx, (uint32_t)kind, perceptual, 0, search_blocks, NV, d_bval.p, accum, d_scb.as<uint64_t>(), KS, d_best.as<uint32_t>(), d_refined.as<uint64_t>(), d_used.as<uint8_t>()));
-        std::vector<uint32_t> best(NV); std::vector<uint64_t> refined(KS); std::vector<uint8_t> used(KS);
+        HcHost<uint32_t> best(ctx, NV); std::vector<uint64_t> refined(KS); std::vector<uint8_t> used(KS);
         CRN_CUDA(ctx, cudaMemcpyAsync(best.data(), d_best.p, (size_t)NV * 4, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaMemcpyAsync(refined.data(), d_refined.p, (size_t)KS * 8, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaMemcpyAsync(used.data(), d_used.p, KS, cudaMemcpyDeviceToHost, st));
@@ -623,6 +648,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         HC_RC(run_kind(ctx, 1));
 #endif
     } else HC_RC(run_kind(ctx, has_color ? 0 : 1));
+    tr.mark("hc endpoint + selector passes (total)", 0);
 
     // ---- a17: palette dedup, index remap, reference flags (crn_dxt_hc.cpp:200-310)
     auto dedup32 = [](const std::vector<uint32_t>& in, const std::vector<uint8_t>& used, std::vector<uint32_t>& out, std::vector<uint16_t>& remap) {
