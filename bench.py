@@ -384,6 +384,39 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
     return out
 
 
+def run_dxt_hc_sharded(ctx, dev, rank, world, steps):
+    """ONE texture on all ranks (strong scaling): the configs[2] quantiser workload of run_dxt_hc with the per-cluster endpoint
+    optimisation + refinement dealt to the ranks by cluster and the 16-byte-per-cluster results all-gathered over NCCL
+    (crn_gpu_hc_params::shard_*).  Every rank ends with the full, identical result; time = slowest rank."""
+    import torch
+    import blockgen
+    import hc_util
+    from crunch2_b200 import shard
+    faces = [mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False)) for f in range(6)]
+    blocks, levels = hc_util.hc_layout(faces)
+    n = len(blocks)
+    cbs = (4096, 4096, 4096, 4096)
+    d_blocks = torch.from_numpy(blocks).to(dev)
+    gather = lambda buf, per: shard.allgather_inplace(buf, per, dev)  # noqa: E731
+    g = None
+    for _ in range(2):
+        g = ctx.hc_compress(0, d_blocks, levels, num_faces=6, codebook_sizes=cbs, shard=(rank, world, gather))
+    td = []
+    for _ in range(steps):
+        torch.cuda.synchronize(); torch.distributed.barrier()
+        t0 = time.perf_counter()
+        g = ctx.hc_compress(0, d_blocks, levels, num_faces=6, codebook_sizes=cbs, shard=(rank, world, gather))
+        td.append(shard.max_over_ranks(time.perf_counter() - t0, dev))
+    dt = sorted(td)[len(td) // 2]
+    import hashlib
+    digest = hashlib.sha256(g["endpoint_indices"].tobytes() + g["selector_indices"].tobytes() + g["color_endpoints"].tobytes()).hexdigest()
+    digests = [None] * world
+    torch.distributed.all_gather_object(digests, digest)
+    return {"workload": "c3_quantiser_dxt1_cubemap_6x2048_mips, ONE texture sharded over %d GPUs by endpoint cluster" % world, "scaling": "strong",
+            "value": n * 16 / dt / 1e6, "unit": UNIT, "ms": dt * 1e3, "step_ms": [round(x * 1e3, 1) for x in td], "collective": "NCCL all-gather of 16 B per cluster, twice per call",
+            "identical_on_all_ranks": bool(all(d == digests[0] for d in digests)), "sha256": digest[:16]}
+
+
 def run_dxt_hc(ctx, dev, steps, with_reference=True):
     """BASELINE configs[2]'s quantiser: dxt_hc::compress of a 6-face 2048^2 DXT1 cubemap with full mip chains (2 097 216
     blocks after crn_comp's 8-pixel padding) at 4096-entry codebooks -- palettes + indices, i.e. everything of CRN
@@ -647,6 +680,12 @@ def main():
             batch_c5 = run_batch_c5(ctx, dev, rank, world, 6 * world, with_reference=not args.no_cpu_baseline)
         except Exception as e:
             batch_c5 = {"error": str(e)[:300]}
+    hc_sharded = None
+    if world > 1 and clustered and not args.no_hc:
+        try:
+            hc_sharded = run_dxt_hc_sharded(ctx, dev, rank, world, 3)
+        except Exception as e:
+            hc_sharded = {"error": str(e)[:300]}
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -679,6 +718,8 @@ def main():
     out.update(extra)
     if batch_c5 is not None:
         out["batch_c5"] = batch_c5
+    if hc_sharded is not None:
+        out["dxt_hc_sharded"] = hc_sharded
     if clustered and not args.no_block_pack and world == 1:
         try:                                  # configs[0] next to the headline, same contract, fewer steps
             wl1 = make_workload("c1_dxt1_2048_mips", 2048)

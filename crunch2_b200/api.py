@@ -47,7 +47,11 @@ class _HcParams(ctypes.Structure):
                 ("color_endpoint_codebook_size", ctypes.c_uint32), ("color_selector_codebook_size", ctypes.c_uint32),
                 ("alpha_endpoint_codebook_size", ctypes.c_uint32), ("alpha_selector_codebook_size", ctypes.c_uint32),
                 ("adaptive_tile_color_psnr_derating", ctypes.c_float), ("adaptive_tile_alpha_psnr_derating", ctypes.c_float),
-                ("adaptive_tile_color_alpha_weighting_ratio", ctypes.c_float), ("alpha_component_indices", ctypes.c_uint32 * 2)]
+                ("adaptive_tile_color_alpha_weighting_ratio", ctypes.c_float), ("alpha_component_indices", ctypes.c_uint32 * 2),
+                ("shard_rank", ctypes.c_uint32), ("shard_count", ctypes.c_uint32), ("exchange", ctypes.c_void_p), ("exchange_user", ctypes.c_void_p)]
+
+
+EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32)
 
 
 class _HcInfo(ctypes.Structure):
@@ -378,11 +382,14 @@ class Context:
 
     # --- dxt_hc::compress (crnlib/crn_dxt_hc.cpp:98-312): blocks of all levels -> palettes + per-block indices ---------
     def hc_compress(self, fmt, blocks, levels, num_faces=1, perceptual=True, codebook_sizes=(3072, 3072, 3072, 3072),
-                    deratings=(2.0, 2.0, 3.0), alpha_components=(3, 0)):
+                    deratings=(2.0, 2.0, 3.0), alpha_components=(3, 0), shard=None):
         """blocks: (n, 16, 4) uint8 numpy array (host) or a torch CUDA tensor of the same shape; levels: list of
         (first_block, num_blocks, block_width, weight) as crn_comp::quantize_images lays them out (crnlib/crn_comp.cpp:706-741);
-        codebook_sizes: colour endpoints, colour selectors, alpha endpoints, alpha selectors.  Returns a dict of numpy arrays
-        named as dxt_hc::compress's outputs plus 'info'."""
+        codebook_sizes: colour endpoints, colour selectors, alpha endpoints, alpha selectors.  shard = (rank, world,
+        allgather) spreads the per-cluster optimisation of this ONE texture over `world` ranks that all make the same call;
+        allgather(buf_u8, bytes_per_rank) fills every rank's slice of the numpy buffer in place (crunch2_b200.shard.
+        allgather_inplace does it over torch.distributed).  Returns a dict of numpy arrays named as dxt_hc::compress's
+        outputs plus 'info'."""
         p = _HcParams()
         self._lib.crn_gpu_default_hc_params(ctypes.byref(p))
         on_host = not hasattr(blocks, "data_ptr")
@@ -400,6 +407,22 @@ class Context:
         (p.color_endpoint_codebook_size, p.color_selector_codebook_size, p.alpha_endpoint_codebook_size, p.alpha_selector_codebook_size) = [int(x) for x in codebook_sizes]
         (p.adaptive_tile_color_psnr_derating, p.adaptive_tile_alpha_psnr_derating, p.adaptive_tile_color_alpha_weighting_ratio) = [float(x) for x in deratings]
         p.alpha_component_indices[0], p.alpha_component_indices[1] = int(alpha_components[0]), int(alpha_components[1])
+        cb = None
+        if shard is not None and int(shard[1]) > 1:
+            rank, world, gather = shard
+            failure = []
+
+            def _exchange(user, buf, bytes_per_rank, nranks):
+                try:
+                    arr = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), (int(bytes_per_rank) * int(nranks),))
+                    gather(arr, int(bytes_per_rank))
+                    return 0
+                except Exception as e:  # never let an exception cross the C boundary
+                    failure.append(e)
+                    return 1
+            cb = EXCHANGE_FN(_exchange)
+            p.shard_rank, p.shard_count = int(rank), int(world)
+            p.exchange = ctypes.cast(cb, ctypes.c_void_p)
         h = ctypes.c_void_p()
         self._check(self._lib.crn_gpu_hc_compress(self._ctx, ctypes.byref(p), ptr, 1 if on_host else 0, ctypes.byref(h)))
         try:

@@ -1296,6 +1296,7 @@ void crn_gpu_default_hc_params(crn_gpu_hc_params* p)
     p->color_endpoint_codebook_size = p->color_selector_codebook_size = p->alpha_endpoint_codebook_size = p->alpha_selector_codebook_size = 3072;
     p->adaptive_tile_color_psnr_derating = 2.0f; p->adaptive_tile_alpha_psnr_derating = 2.0f; p->adaptive_tile_color_alpha_weighting_ratio = 3.0f;
     p->alpha_component_indices[0] = 3; p->alpha_component_indices[1] = 0;
+    p->shard_rank = 0; p->shard_count = 1; p->exchange = nullptr; p->exchange_user = nullptr;
 }
 
 int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out)
@@ -1306,7 +1307,8 @@ int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const
         params->num_levels > 16 || !params->num_faces || params->alpha_component_indices[0] > 3 || params->alpha_component_indices[1] > 3 ||
         !params->color_endpoint_codebook_size || !params->color_selector_codebook_size || !params->alpha_endpoint_codebook_size || !params->alpha_selector_codebook_size ||
         params->color_endpoint_codebook_size > 65535 || params->color_selector_codebook_size > 65535 || params->alpha_endpoint_codebook_size > 65535 ||
-        params->alpha_selector_codebook_size > 65535)
+        params->alpha_selector_codebook_size > 65535 || !params->shard_count || params->shard_rank >= params->shard_count ||
+        (params->shard_count > 1 && !params->exchange))
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_hc_compress: bad argument");
     crn_gpu_hc* H = new (std::nothrow) crn_gpu_hc();
     if (!H) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory");

@@ -481,29 +481,84 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             ctx->launches += na;
             d_vblocks = d_vsrc.as<uint32_t>();
         }
-        HC_ALLOC(d_offs, (size_t)(K + 1) * 4); HC_ALLOC(d_poffs, (size_t)(K + 1) * 4); HC_ALLOC(d_mem, (size_t)NV * 4); HC_ALLOC(d_elem, (size_t)NV * 8);
-        HC_ALLOC(d_ep, (size_t)K * 4); HC_ALLOC(d_err, (size_t)K * 8); HC_ALLOC(d_flags, (size_t)K * 4); HC_ALLOC(d_bcl, (size_t)NV * 4);
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_offs.p, offs.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_poffs.p, poffs.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, st));
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_mem.p, members.data(), (size_t)NV * 4, cudaMemcpyHostToDevice, st));
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_bcl.p, block_cluster.data(), (size_t)NV * 4, cudaMemcpyHostToDevice, st));
-        CRN_CUDA(ctx, cudaMemsetAsync(d_ep.p, 0, (size_t)K * 4, st));
-        CRN_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, (size_t)K * 8, st));
-        CRN_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, (size_t)K * 4, st));
         std::vector<uint32_t> order(K);
         for (uint32_t c = 0; c < K; c++) order[c] = c;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return offs[a + 1] - offs[a] > offs[b + 1] - offs[b]; });
         if (tr.on) fprintf(stderr, "[crn_b200] kind %d: %u clusters, %u member blocks, largest %u, median %u\n", kind, K, NV, offs[order[0] + 1] - offs[order[0]], offs[order[K / 2] + 1] - offs[order[K / 2]]);
+        // The clusters this rank optimises: all of them, or every shard_count-th of the size-ordered list (crn_gpu_hc_params).
+        const uint32_t SC = prm->shard_count, SR = prm->shard_rank;
+        const uint32_t Kopt = SC > 1 ? (K > SR ? (K - SR + SC - 1) / SC : 0) : K;
+        std::vector<uint32_t> opt_offs(Kopt + 1, 0), opt_poffs(Kopt + 1, 0), opt_order(Kopt);
+        uint32_t NVopt = NV;
+        if (SC > 1) {
+            for (uint32_t j = 0; j < Kopt; j++) { const uint32_t c = order[SR + j * SC]; opt_offs[j + 1] = opt_offs[j] + (offs[c + 1] - offs[c]); }
+            NVopt = opt_offs[Kopt];
+        } else opt_offs = offs;
+        HcHost<uint32_t> opt_members(ctx, SC > 1 ? NVopt : 0);
+        if (SC > 1)
+            for (uint32_t j = 0; j < Kopt; j++) { const uint32_t c = order[SR + j * SC]; memcpy(opt_members.data() + opt_offs[j], members.data() + offs[c], (size_t)(offs[c + 1] - offs[c]) * 4); }
+        for (uint32_t j = 0; j <= Kopt; j++) opt_poffs[j] = opt_offs[j] * 16;
+        for (uint32_t j = 0; j < Kopt; j++) opt_order[j] = SC > 1 ? j : order[j];               // a rank's own list is already largest-first
+        const uint32_t* h_opt_members = SC > 1 ? opt_members.data() : members.data();
+        HC_ALLOC(d_offs, (size_t)(Kopt + 1) * 4); HC_ALLOC(d_poffs, (size_t)(Kopt + 1) * 4); HC_ALLOC(d_mem, (size_t)NVopt * 4 + 4); HC_ALLOC(d_elem, (size_t)NV * 8);
+        HC_ALLOC(d_ep, (size_t)K * 4); HC_ALLOC(d_err, (size_t)K * 8); HC_ALLOC(d_flags, (size_t)K * 4); HC_ALLOC(d_bcl, (size_t)NV * 4);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_offs.p, opt_offs.data(), (size_t)(Kopt + 1) * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_poffs.p, opt_poffs.data(), (size_t)(Kopt + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (NVopt) CRN_CUDA(ctx, cudaMemcpyAsync(d_mem.p, h_opt_members, (size_t)NVopt * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_bcl.p, block_cluster.data(), (size_t)NV * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaMemsetAsync(d_ep.p, 0, (size_t)K * 4, st));
+        CRN_CUDA(ctx, cudaMemsetAsync(d_err.p, 0, (size_t)K * 8, st));
+        CRN_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, (size_t)K * 4, st));
         HcBuf d_order;
-        HC_ALLOC(d_order, (size_t)K * 4);
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_order.p, order.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+        HC_ALLOC(d_order, (size_t)Kopt * 4 + 4);
+        if (Kopt) CRN_CUDA(ctx, cudaMemcpyAsync(d_order.p, opt_order.data(), (size_t)Kopt * 4, cudaMemcpyHostToDevice, st));
         ctx->d_cluster_flags = d_flags.as<uint32_t>(); ctx->d_cluster_order = d_order.as<uint32_t>();
-        int rc = kind == 0 ? crn_gpu_dxt1_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>())
-                           : crn_gpu_dxt5_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), K, NV, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>());
+        int rc = kind == 0 ? crn_gpu_dxt1_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), Kopt, NVopt, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>())
+                           : crn_gpu_dxt5_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), Kopt, NVopt, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>());
         ctx->d_cluster_flags = nullptr; ctx->d_cluster_order = nullptr;
         if (rc) return rc;
         tr.mark("hc cluster optimiser", kind);
-        // per-block selectors + weights against the cluster palette
+        // refiner over the cluster pixel lists with the optimiser's selectors (a10)
+        HC_ALLOC(d_cpix, (size_t)NVopt * 64 + 64); HC_ALLOC(d_csel, (size_t)NVopt * 16 + 16); HC_ALLOC(d_rep, (size_t)K * 4); HC_ALLOC(d_rerr, (size_t)K * 8); HC_ALLOC(d_rok, K);
+        if (NVopt) {
+            CRN_LAUNCH(crn::hc_gather_cluster_pixels_kernel, (unsigned)(((size_t)NVopt * 16 + 255) / 256), 256, 0, st, d_vblocks, d_mem.as<uint32_t>(), NVopt * 16, kind,
+                       d_elem.as<unsigned long long>(), d_cpix.as<uint32_t>(), d_csel.as<uint8_t>());
+            ctx->launches++;
+        }
+        HC_RC(crn_gpu_refine_endpoints(ctx, kind == 0 ? 1 : 0, perceptual, 0, d_cpix.p, d_csel.as<uint8_t>(), d_poffs.as<uint32_t>(), Kopt, d_err.as<uint64_t>(),
+                                       d_rep.as<uint32_t>(), d_rerr.as<uint64_t>(), d_rok.as<uint8_t>()));
+        std::vector<uint32_t> ep(K, 0), rep(K, 0); std::vector<uint8_t> rok(K, 0);
+        if (SC > 1) {
+            // this rank's results -> all ranks: one 16-byte record per cluster through the caller's all-gather
+            std::vector<uint32_t> s_ep(Kopt), s_fl(Kopt), s_rep(Kopt); std::vector<uint8_t> s_rok(Kopt);
+            if (Kopt) {
+                CRN_CUDA(ctx, cudaMemcpyAsync(s_ep.data(), d_ep.p, (size_t)Kopt * 4, cudaMemcpyDeviceToHost, st));
+                CRN_CUDA(ctx, cudaMemcpyAsync(s_fl.data(), d_flags.p, (size_t)Kopt * 4, cudaMemcpyDeviceToHost, st));
+                CRN_CUDA(ctx, cudaMemcpyAsync(s_rep.data(), d_rep.p, (size_t)Kopt * 4, cudaMemcpyDeviceToHost, st));
+                CRN_CUDA(ctx, cudaMemcpyAsync(s_rok.data(), d_rok.p, Kopt, cudaMemcpyDeviceToHost, st));
+            }
+            CRN_CUDA(ctx, cudaStreamSynchronize(st));
+            const uint32_t per = (K + SC - 1) / SC;
+            std::vector<uint32_t> xbuf((size_t)SC * per * 4, 0);
+            for (uint32_t j = 0; j < Kopt; j++) { uint32_t* r = &xbuf[((size_t)SR * per + j) * 4]; r[0] = s_ep[j]; r[1] = s_fl[j]; r[2] = s_rep[j]; r[3] = s_rok[j]; }
+            if (prm->exchange(prm->exchange_user, xbuf.data(), (uint64_t)per * 16, SC) != 0) return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_hc_compress: the exchange callback failed");
+            std::vector<uint32_t> fl(K, 0);
+            for (uint32_t r = 0; r < SC; r++)
+                for (uint32_t j = 0; r + j * SC < K; j++) {
+                    const uint32_t c = order[r + j * SC]; const uint32_t* q = &xbuf[((size_t)r * per + j) * 4];
+                    ep[c] = q[0]; fl[c] = q[1]; rep[c] = q[2]; rok[c] = (uint8_t)q[3];
+                }
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_ep.p, ep.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_flags.p, fl.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_rep.p, rep.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_rok.p, rok.data(), K, cudaMemcpyHostToDevice, st));
+            CRN_CUDA(ctx, cudaStreamSynchronize(st));              // fl lives on this frame
+        } else {
+            CRN_CUDA(ctx, cudaMemcpyAsync(ep.data(), d_ep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+            CRN_CUDA(ctx, cudaMemcpyAsync(rep.data(), d_rep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
+            CRN_CUDA(ctx, cudaMemcpyAsync(rok.data(), d_rok.p, K, cudaMemcpyDeviceToHost, st));
+        }
+        // per-block selectors + weights against the cluster palette (all clusters, every rank)
         HC_ALLOC(d_bsel, (size_t)NV * 8); HC_ALLOC(d_bval, (size_t)NV * (kind ? 8 : 16));
         if (kind == 0) {
             CRN_LAUNCH(crn::hc_color_blocks_kernel, (n + 255) / 256, 256, 0, st, d_blocks, n, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(), LW,
@@ -512,17 +567,7 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             CRN_LAUNCH(crn::hc_alpha_blocks_kernel, (NV + 255) / 256, 256, 0, st, d_blocks, n, na, comp0, comp1, d_bcl.as<uint32_t>(), d_ep.as<uint32_t>(), d_flags.as<uint32_t>(),
                        d_enc.as<uint8_t>(), d_bsel.as<unsigned long long>(), d_bval.as<uint8_t>());
         }
-        // refiner over the cluster pixel lists with the optimiser's selectors (a10)
-        HC_ALLOC(d_cpix, (size_t)NV * 64); HC_ALLOC(d_csel, (size_t)NV * 16); HC_ALLOC(d_rep, (size_t)K * 4); HC_ALLOC(d_rerr, (size_t)K * 8); HC_ALLOC(d_rok, K);
-        CRN_LAUNCH(crn::hc_gather_cluster_pixels_kernel, (unsigned)(((size_t)NV * 16 + 255) / 256), 256, 0, st, d_vblocks, d_mem.as<uint32_t>(), NV * 16, kind,
-                   d_elem.as<unsigned long long>(), d_cpix.as<uint32_t>(), d_csel.as<uint8_t>());
-        ctx->launches += 2;
-        HC_RC(crn_gpu_refine_endpoints(ctx, kind == 0 ? 1 : 0, perceptual, 0, d_cpix.p, d_csel.as<uint8_t>(), d_poffs.as<uint32_t>(), K, d_err.as<uint64_t>(),
-                                       d_rep.as<uint32_t>(), d_rerr.as<uint64_t>(), d_rok.as<uint8_t>()));
-        std::vector<uint32_t> ep(K), rep(K); std::vector<uint8_t> rok(K);
-        CRN_CUDA(ctx, cudaMemcpyAsync(ep.data(), d_ep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
-        CRN_CUDA(ctx, cudaMemcpyAsync(rep.data(), d_rep.p, (size_t)K * 4, cudaMemcpyDeviceToHost, st));
-        CRN_CUDA(ctx, cudaMemcpyAsync(rok.data(), d_rok.p, K, cudaMemcpyDeviceToHost, st));
+        ctx->launches++;
         // a16: selector codebook.  Training set = the distinct block selectors with summed weights (:1379-1444, :1588-1660)
         std::vector<uint32_t>& cl_ep = kind ? alpha_cluster_ep : color_cluster_ep;
         std::vector<uint8_t>& cl_used = kind ? alpha_cluster_used : color_cluster_used;

@@ -44,3 +44,22 @@ def sum_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t[0])
+
+
+def allgather_inplace(buf_u8, bytes_per_rank, device=None):
+    """In-place all-gather of a numpy uint8 buffer of world * bytes_per_rank bytes whose own slice is filled (the exchange
+    crn_gpu_hc_compress asks for when one texture is sharded over the ranks).  gloo gathers the host tensor directly; NCCL
+    needs device tensors, so the (small: 16 bytes per cluster) buffer is staged through `device`."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    full = torch.from_numpy(buf_u8).view(world, bytes_per_rank)
+    if dist.get_backend() == "nccl":
+        d = full.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        dist.all_gather_into_tensor(d.view(-1), d[rank].clone())
+        full.copy_(d.cpu())
+    else:
+        out = [torch.empty(bytes_per_rank, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(out, full[rank].clone())
+        for r in range(world):
+            full[r].copy_(out[r])

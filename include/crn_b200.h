@@ -284,6 +284,9 @@ CRN_API int crn_gpu_blockify(crn_gpu_ctx* ctx, const void* d_rgba, uint32_t widt
  *   selector_indices  num_blocks x 4 uint16: color, alpha0, alpha1, 0
  *   color_endpoints   uint32 low565 | high565 << 16;  alpha_endpoints uint32 first | second << 8
  *   color_selectors   uint32, pixel p at bits 2p (linear selector order);  alpha_selectors uint64, pixel p at bits 3p */
+/* In-place all-gather over the ranks sharing one dxt_hc call: h_buf (host memory) holds nranks slices of bytes_per_rank
+ * bytes, the caller's own slice is filled; on return (0 = success) every slice must be. */
+typedef int (*crn_gpu_exchange_fn)(void* user, void* h_buf, uint64_t bytes_per_rank, uint32_t nranks);
 typedef struct crn_gpu_hc_level { uint32_t first_block, num_blocks, block_width; float weight; } crn_gpu_hc_level;
 typedef struct crn_gpu_hc_params {
     uint32_t struct_size;               /* sizeof(crn_gpu_hc_params) */
@@ -294,6 +297,13 @@ typedef struct crn_gpu_hc_params {
     uint32_t color_endpoint_codebook_size, color_selector_codebook_size, alpha_endpoint_codebook_size, alpha_selector_codebook_size;
     float adaptive_tile_color_psnr_derating, adaptive_tile_alpha_psnr_derating, adaptive_tile_color_alpha_weighting_ratio;
     uint32_t alpha_component_indices[2];
+    /* One texture on several GPUs: the per-cluster endpoint optimisation + refinement (more than half of the call) is dealt
+     * to shard_count ranks by cluster, largest first; every rank runs the rest of the pipeline itself and the per-cluster
+     * results (16 bytes per cluster) are all-gathered through `exchange` -- NCCL / gloo on the caller's side.  Every rank
+     * must make the same call on the same blocks; the result is identical on all ranks and identical to shard_count = 1. */
+    uint32_t shard_rank, shard_count;   /* default 0, 1 */
+    crn_gpu_exchange_fn exchange;       /* required when shard_count > 1 */
+    void* exchange_user;
 } crn_gpu_hc_params;
 typedef struct crn_gpu_hc_info {
     uint32_t struct_size;               /* sizeof(crn_gpu_hc_info) */

@@ -53,3 +53,49 @@ def test_gloo_world_size_2(tmp_path):
     assert d["total"] == d["sumcosts"]
     flat = sorted(i for u in d["units"] for i in u)
     assert flat == list(range(d["ncosts"]))
+
+
+HC_WORKER = r'''
+import os, sys, json, hashlib
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np
+import torch, torch.distributed as dist
+import blockgen, helpers, hc_util
+import crunch2_b200 as crn
+from crunch2_b200 import shard
+from bench import mip_chain
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ctx = crn.Context(0, lib=helpers.load_sim())          # the real kernels under the SIMT emulator
+out = {}
+for fmt in (0, 3):
+    img = blockgen.smooth_image(64, 48, 11, alpha=True)
+    blocks, levels = hc_util.hc_layout([mip_chain(img)[:3]])
+    whole = ctx.hc_compress(fmt, blocks, levels, codebook_sizes=(48, 48, 24, 48))
+    part = ctx.hc_compress(fmt, blocks, levels, codebook_sizes=(48, 48, 24, 48), shard=(rank, world, shard.allgather_inplace))
+    same = all(np.array_equal(whole[k], part[k]) for k in ("endpoint_indices", "selector_indices", "color_endpoints", "alpha_endpoints", "color_selectors", "alpha_selectors"))
+    out[str(fmt)] = dict(same=bool(same), sha=hashlib.sha256(part["endpoint_indices"].tobytes() + part["selector_indices"].tobytes()).hexdigest())
+gathered = [None] * world
+dist.all_gather_object(gathered, out)
+if rank == 0:
+    print(json.dumps(gathered))
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_sharded_dxt_hc(tmp_path, sim):
+    """One texture on two ranks: the per-cluster optimisation is dealt to the ranks, results all-gathered (gloo here, NCCL on
+    the GPUs); every rank must end with exactly the unsharded result."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "hc_worker.py"
+    script.write_text(HC_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), helpers.ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    ranks = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    assert len(ranks) == 2
+    for fmt in ("0", "3"):
+        assert ranks[0][fmt]["same"] and ranks[1][fmt]["same"]
+        assert ranks[0][fmt]["sha"] == ranks[1][fmt]["sha"]
