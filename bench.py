@@ -653,8 +653,6 @@ def main():
     import crunch2_b200 as crn
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"              # keeps NCCL's version banner off stdout: rank 0 prints exactly one line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
