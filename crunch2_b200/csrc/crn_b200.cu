@@ -143,7 +143,7 @@ void pool_free(crn_gpu_ctx* ctx, void* p, size_t cap)
 {
     if (!p) return;
     if (!ctx->pool) ctx->pool = new (std::nothrow) std::vector<crn_gpu_ctx::PoolBlock>();
-    if (!ctx->pool || ctx->pool->size() >= 64) { cudaFree(p); return; }
+    if (!ctx->pool || ctx->pool->size() >= 160) { cudaFree(p); return; }   // one dxt_hc call holds ~70 buffers
     ctx->pool->push_back({p, cap});
 }
 
