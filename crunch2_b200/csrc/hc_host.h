@@ -676,15 +676,26 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         else { alpha_sel_cb = refined; alpha_sel_used = used; }
         return CRN_GPU_OK;
     };
-    if (has_color && na) {
+    // (sharded calls stay sequential: the two passes' exchanges must reach every rank in the same order)
+    if (has_color && na && prm->shard_count > 1) {
+        HC_RC(run_kind(ctx, 0));
+        HC_RC(run_kind(ctx, 1));
+    } else if (has_color && na) {
 #ifdef __CUDACC__
         if (!ctx->child[0] && crn_gpu_create(ctx->device, &ctx->child[0]) != CRN_GPU_OK) return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_hc_compress: element stream");
         crn_gpu_ctx* child = ctx->child[0];
         const uint64_t l0 = child->launches;
         int rc1 = CRN_GPU_OK;
-        std::thread alpha_thread([&] { cudaSetDevice(child->device); rc1 = run_kind(child, 1); child->d_cluster_flags = nullptr; child->d_cluster_order = nullptr; });
-        const int rc0 = run_kind(ctx, 0);
-        alpha_thread.join();
+        std::thread alpha_thread([&] {
+            cudaSetDevice(child->device);
+            try { rc1 = run_kind(child, 1); }
+            catch (const std::bad_alloc&) { rc1 = set_err(child, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
+            child->d_cluster_flags = nullptr; child->d_cluster_order = nullptr;
+        });
+        int rc0;
+        try { rc0 = run_kind(ctx, 0); }
+        catch (const std::bad_alloc&) { rc0 = set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
+        alpha_thread.join();                                        // never leave the frame with the thread running
         ctx->launches += child->launches - l0;
         if (rc0) return rc0;
         if (rc1) return set_err(ctx, rc1, child->err);
