@@ -7,8 +7,8 @@ compute call raises unless the nvcc-built library is present and a CUDA device i
 """
 from .api import (  # noqa: F401
     CrnGpuError, Context, PackParams, FMT_DXT1, FMT_DXT1A, FMT_DXT3, FMT_DXT5, FMT_DXT5A, FMT_DXN_XY, FMT_DXN_YX,
-    bytes_per_block, library_path, load_library, Texture, texture_info,
+    bytes_per_block, library_path, load_library, Texture, texture_info, crn_params, crn_hc_params, crn_write,
 )
 
-__all__ = ["CrnGpuError", "Context", "PackParams", "Texture", "texture_info", "bytes_per_block", "library_path", "load_library",
+__all__ = ["CrnGpuError", "Context", "PackParams", "Texture", "texture_info", "bytes_per_block", "library_path", "load_library", "crn_params", "crn_hc_params", "crn_write",
            "FMT_DXT1", "FMT_DXT1A", "FMT_DXT3", "FMT_DXT5", "FMT_DXT5A", "FMT_DXN_XY", "FMT_DXN_YX"]

@@ -51,6 +51,12 @@ class _HcParams(ctypes.Structure):
                 ("shard_rank", ctypes.c_uint32), ("shard_count", ctypes.c_uint32), ("exchange", ctypes.c_void_p), ("exchange_user", ctypes.c_void_p)]
 
 
+class _CrnParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "crn_format", "width", "height", "levels", "faces", "quality_level", "perceptual",
+                                                "alpha_component", "userdata0", "userdata1")] + [("palette_sizes", ctypes.c_uint32 * 4),
+                ("adaptive_tile_color_psnr_derating", ctypes.c_float), ("adaptive_tile_alpha_psnr_derating", ctypes.c_float)]
+
+
 EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32)
 
 
@@ -150,6 +156,13 @@ def _declare(lib):
         f.restype = vp
     lib.crn_gpu_hc_free.argtypes = [vp]
     lib.crn_gpu_hc_free.restype = None
+    lib.crn_gpu_default_crn_params.argtypes = [ctypes.POINTER(_CrnParams)]
+    lib.crn_gpu_default_crn_params.restype = None
+    lib.crn_gpu_crn_hc_params.argtypes = [ctypes.POINTER(_CrnParams), ctypes.POINTER(_HcParams)]
+    lib.crn_gpu_crn_write.argtypes = [ctypes.POINTER(_CrnParams), ctypes.POINTER(_HcParams), vp, vp, vp, u32, vp, u32, vp, u32, vp, u32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
+    lib.crn_gpu_compress_crn.argtypes = [vp, ctypes.POINTER(_CrnParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float)]
+    lib.crn_gpu_free_file.argtypes = [vp]
+    lib.crn_gpu_free_file.restype = None
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
     lib.crn_gpu_crnd_unpack_begin.argtypes = [vp, vp, u32, ctypes.POINTER(vp)]
     lib.crn_gpu_crnd_unpack_level.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
@@ -450,6 +463,25 @@ class Context:
             self._lib.crn_gpu_hc_free(h)
         return out
 
+    def compress_crn(self, images, crn_format, quality_level=128, perceptual=True, alpha_component=3, palette_sizes=None, userdata=(0, 0)):
+        """crn_compress to a .CRN at one quality level (crn_comp::compress_pass, crnlib/crn_comp.cpp:1613): images[face][level]
+        = (h, w, 4) uint8 host arrays, level l being max(1, w >> l) x max(1, h >> l).  Returns (file bytes, bits per texel)."""
+        faces, levels = len(images), len(images[0])
+        h, w = images[0][0].shape[:2]
+        p = crn_params(crn_format, w, h, levels, faces, quality_level, perceptual, alpha_component, palette_sizes, userdata, lib=self._lib)
+        flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]
+        for i, a in enumerate(flat):
+            lw, lh = max(1, w >> (i % levels)), max(1, h >> (i % levels))
+            if a.shape != (lh, lw, 4):
+                raise ValueError("image %d has shape %s, expected %s" % (i, a.shape, (lh, lw, 4)))
+        ptrs = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
+        out = ctypes.c_void_p(); size = ctypes.c_uint32(); rate = ctypes.c_float()
+        self._check(self._lib.crn_gpu_compress_crn(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size), ctypes.byref(rate)))
+        try:
+            return ctypes.string_at(out, size.value), rate.value
+        finally:
+            self._lib.crn_gpu_free_file(out)
+
     # --- clustered DDS compression (mipmapped_texture::qdxt_pack_init / qdxt_pack) ----------------------
     def qdxt_init(self, fmt, levels, params=None):
         """levels: list of (h, w, 4) uint8 arrays -- numpy (host pixels) or torch CUDA tensors -- faces x mips in
@@ -468,6 +500,51 @@ class Context:
         dp = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p)) for p in d_dst_ptrs])
         cp = (ctypes.c_uint64 * n)(*[int(c) for c in capacities])
         self._check(self._lib.crn_gpu_crnd_unpack_batch(self._ctx, tp, n, dp, cp))
+
+
+def crn_params(crn_format, width, height, levels=1, faces=1, quality_level=128, perceptual=True, alpha_component=3, palette_sizes=None, userdata=(0, 0), lib=None):
+    lib = lib if lib is not None else load_library()
+    p = _CrnParams()
+    lib.crn_gpu_default_crn_params(ctypes.byref(p))
+    p.crn_format, p.width, p.height, p.levels, p.faces = int(crn_format), int(width), int(height), int(levels), int(faces)
+    p.quality_level, p.perceptual, p.alpha_component = int(quality_level), int(bool(perceptual)), int(alpha_component)
+    p.userdata0, p.userdata1 = int(userdata[0]), int(userdata[1])
+    if palette_sizes is not None:
+        for i in range(4):
+            p.palette_sizes[i] = int(palette_sizes[i])
+    return p
+
+
+def crn_hc_params(params, lib=None):
+    """crn_comp's level table and dxt_hc parameters for a .CRN of these crn_params (host only)."""
+    lib = lib if lib is not None else load_library()
+    hp = _HcParams()
+    rc = lib.crn_gpu_crn_hc_params(ctypes.byref(params), ctypes.byref(hp))
+    if rc != 0:
+        raise CrnGpuError(rc, "crn_gpu_crn_hc_params failed (%d)" % rc)
+    return hp
+
+
+def crn_write(params, hc_params, out, lib=None):
+    """Palettes + indices (dict named as Context.hc_compress's result) -> .crn bytes; the writer back-end of crn_comp
+    (crnlib/crn_comp.cpp:767-1496).  Host only."""
+    lib = lib if lib is not None else load_library()
+    keep = {k: np.ascontiguousarray(out[k], dt) for k, dt in (("endpoint_indices", np.uint16), ("selector_indices", np.uint16), ("color_endpoints", np.uint32),
+                                                              ("alpha_endpoints", np.uint32), ("color_selectors", np.uint32), ("alpha_selectors", np.uint64))}
+
+    def ptr(k):
+        return keep[k].ctypes.data_as(ctypes.c_void_p) if keep[k].size else None
+    f = ctypes.c_void_p(); size = ctypes.c_uint32()
+    rc = lib.crn_gpu_crn_write(ctypes.byref(params), ctypes.byref(hc_params), ptr("endpoint_indices"), ptr("selector_indices"),
+                               ptr("color_endpoints"), keep["color_endpoints"].size, ptr("alpha_endpoints"), keep["alpha_endpoints"].size,
+                               ptr("color_selectors"), keep["color_selectors"].size, ptr("alpha_selectors"), keep["alpha_selectors"].size,
+                               ctypes.byref(f), ctypes.byref(size))
+    if rc != 0:
+        raise CrnGpuError(rc, "crn_gpu_crn_write failed (%d)" % rc)
+    try:
+        return ctypes.string_at(f, size.value)
+    finally:
+        lib.crn_gpu_free_file(f)
 
 
 def texture_info(crn_bytes, lib=None):

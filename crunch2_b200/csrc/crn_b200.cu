@@ -454,6 +454,7 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
 
 
 #include "hc_host.h"
+#include "crn_writer.h"
 
 extern "C" {
 
@@ -1338,6 +1339,168 @@ const uint64_t* crn_gpu_hc_alpha_selectors(const crn_gpu_hc* hc) { return hc ? h
 const uint8_t* crn_gpu_hc_block_encodings(const crn_gpu_hc* hc) { return hc ? hc->block_encodings.data() : nullptr; }
 const uint32_t* crn_gpu_hc_tile_indices(const crn_gpu_hc* hc) { return hc ? hc->tile_indices.data() : nullptr; }
 void crn_gpu_hc_free(crn_gpu_hc* hc) { delete hc; }
+
+/* ---- .CRN writer back-end (crn_writer.h) ------------------------------------------------------------------- */
+
+void crn_gpu_default_crn_params(crn_gpu_crn_params* p)
+{   // crn_comp_params::clear() (inc/crnlib.h:241-285)
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->crn_format = 0; p->levels = 1; p->faces = 1;
+    p->quality_level = 255; p->perceptual = 1; p->alpha_component = 3;
+    p->adaptive_tile_color_psnr_derating = 2.0f; p->adaptive_tile_alpha_psnr_derating = 2.0f;
+}
+
+static bool crn_params_ok(const crn_gpu_crn_params* p)
+{
+    return p && p->struct_size == sizeof(crn_gpu_crn_params) && p->width >= 1 && p->height >= 1 && p->width <= 4096 && p->height <= 4096 &&   // cCRNMaxLevelResolution
+           p->levels >= 1 && p->levels <= 16 && (p->faces == 1 || p->faces == 6) && p->quality_level <= 255 && p->alpha_component <= 3;
+}
+
+int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
+{
+    if (!crn_params_ok(p) || !hp) return CRN_GPU_ERR_BAD_PARAM;
+    crn_gpu_default_hc_params(hp);
+    hp->perceptual = p->perceptual ? 1 : 0;
+    hp->adaptive_tile_color_psnr_derating = p->adaptive_tile_color_psnr_derating;
+    hp->adaptive_tile_alpha_psnr_derating = p->adaptive_tile_alpha_psnr_derating;
+    float color_mul = 1.0f;
+    const float alpha_mul = 1.0f;
+    switch (p->crn_format) {                                     // crn_comp.cpp:594-660
+    case 0: hp->format = CRN_GPU_FMT_DXT1; break;
+    case 2: hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = p->alpha_component; color_mul = .75f; break;
+    case 7: hp->format = CRN_GPU_FMT_DXN_XY; hp->alpha_component_indices[0] = 0; hp->alpha_component_indices[1] = 1; hp->perceptual = 0; break;
+    case 8: hp->format = CRN_GPU_FMT_DXN_YX; hp->alpha_component_indices[0] = 1; hp->alpha_component_indices[1] = 0; hp->perceptual = 0; break;
+    case 9: hp->format = CRN_GPU_FMT_DXT5A; hp->alpha_component_indices[0] = p->alpha_component; hp->perceptual = 0; break;
+    default: return CRN_GPU_ERR_UNSUPPORTED;                     // DXT3 is refused by the reference too; swizzled DXT5 variants and ETC are not built
+    }
+    auto clampu = [](uint32_t v, uint32_t lo, uint32_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    const uint32_t kMin = 8, kMax = 8192;                        // cCRNMinPaletteSize / cCRNMaxPaletteSize
+    if (p->palette_sizes[0] && p->palette_sizes[1] && p->palette_sizes[2] && p->palette_sizes[3]) {
+        hp->color_endpoint_codebook_size = clampu(p->palette_sizes[0], kMin, kMax); hp->color_selector_codebook_size = clampu(p->palette_sizes[1], kMin, kMax);
+        hp->alpha_endpoint_codebook_size = clampu(p->palette_sizes[2], kMin, kMax); hp->alpha_selector_codebook_size = clampu(p->palette_sizes[3], kMin, kMax);
+    } else {                                                     // crn_comp.cpp:539-575
+        const uint32_t max_entries = clampu(((p->width + 3) / 4) * ((p->height + 3) / 4), kMin, kMax);
+        float quality = (float)p->quality_level / 255;
+        quality = quality < 0.0f ? 0.0f : (quality > 1.0f ? 1.0f : quality);
+        auto size_for = [&](float floor_entries, float power) {
+            const float q = powf(quality, power);
+            const float a = floor_entries > (float)kMin ? floor_entries : (float)kMin;
+            const float v = .5f + (a + ((float)max_entries - a) * q);
+            return clampu((uint32_t)v, kMin, kMax);
+        };
+        hp->color_endpoint_codebook_size = size_for(64, 1.8f * color_mul);
+        hp->color_selector_codebook_size = size_for(96, 1.65f * color_mul);
+        hp->alpha_endpoint_codebook_size = size_for(24, 2.1f * alpha_mul);
+        hp->alpha_selector_codebook_size = size_for(48, 1.65f * alpha_mul);
+    }
+    hp->num_levels = p->levels; hp->num_faces = p->faces;
+    uint32_t total = 0;
+    for (uint32_t l = 0; l < p->levels; l++) {                   // crn_comp.cpp:458-466, :706-712
+        const uint32_t w = std::max(1u, p->width >> l), h = std::max(1u, p->height >> l);
+        hp->levels[l].block_width = ((w + 7) & ~7u) >> 2;
+        hp->levels[l].first_block = total;
+        hp->levels[l].num_blocks = p->faces * hp->levels[l].block_width * (((h + 7) & ~7u) >> 2);
+        hp->levels[l].weight = std::min(12.0f, powf(1.3f, (float)l));
+        total += hp->levels[l].num_blocks;
+    }
+    hp->num_blocks = total;
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, const uint16_t* endpoint_indices, const uint16_t* selector_indices,
+                      const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
+                      const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
+                      void** out_file, uint32_t* out_size)
+{
+    if (out_file) *out_file = nullptr;
+    if (out_size) *out_size = 0;
+    if (!crn_params_ok(p) || !hp || hp->struct_size != sizeof(crn_gpu_hc_params) || !endpoint_indices || !selector_indices || !out_file || !out_size ||
+        hp->num_levels != p->levels || hp->num_faces != p->faces || !hp->num_blocks)
+        return CRN_GPU_ERR_BAD_PARAM;
+    crnw::Input in;
+    memset(&in, 0, sizeof(in));
+    in.crn_format = p->crn_format; in.width = p->width; in.height = p->height; in.num_levels = p->levels; in.num_faces = p->faces;
+    in.userdata0 = p->userdata0; in.userdata1 = p->userdata1;
+    switch (hp->format) {
+    case CRN_GPU_FMT_DXT1: in.has_color = true; break;
+    case CRN_GPU_FMT_DXT5: in.has_color = true; in.has_alpha0 = true; break;
+    case CRN_GPU_FMT_DXT5A: in.has_alpha0 = true; break;
+    case CRN_GPU_FMT_DXN_XY: case CRN_GPU_FMT_DXN_YX: in.has_alpha0 = in.has_alpha1 = true; break;
+    default: return CRN_GPU_ERR_UNSUPPORTED;
+    }
+    if ((in.has_color && (!color_endpoints || !color_selectors || !n_color_endpoints || !n_color_selectors || n_color_endpoints > 8192 || n_color_selectors > 8192)) ||
+        (in.has_alpha0 && (!alpha_endpoints || !alpha_selectors || !n_alpha_endpoints || !n_alpha_selectors || n_alpha_endpoints > 8192 || n_alpha_selectors > 8192)))
+        return CRN_GPU_ERR_BAD_PARAM;
+    crnw::Level lv[16];
+    for (uint32_t l = 0; l < hp->num_levels; l++) lv[l] = { hp->levels[l].first_block, hp->levels[l].num_blocks, hp->levels[l].block_width };
+    in.levels = lv; in.num_blocks = hp->num_blocks;
+    in.endpoint_indices = endpoint_indices; in.selector_indices = selector_indices;
+    in.color_endpoints = color_endpoints; in.n_color_endpoints = in.has_color ? n_color_endpoints : 0;
+    in.color_selectors = color_selectors; in.n_color_selectors = in.has_color ? n_color_selectors : 0;
+    in.alpha_endpoints = alpha_endpoints; in.n_alpha_endpoints = in.has_alpha0 ? n_alpha_endpoints : 0;
+    in.alpha_selectors = alpha_selectors; in.n_alpha_selectors = in.has_alpha0 ? n_alpha_selectors : 0;
+    // every index must address its palette: a bad one would otherwise be read out of bounds
+    for (uint32_t b = 0; b < in.num_blocks; b++) {
+        const uint16_t* e = endpoint_indices + (size_t)b * 4; const uint16_t* s = selector_indices + (size_t)b * 4;
+        if (e[3] > 2 || (in.has_color && (e[0] >= n_color_endpoints || s[0] >= n_color_selectors)) ||
+            (in.has_alpha0 && (e[1] >= n_alpha_endpoints || s[1] >= n_alpha_selectors)) || (in.has_alpha1 && (e[2] >= n_alpha_endpoints || s[2] >= n_alpha_selectors)))
+            return CRN_GPU_ERR_BAD_DATA;
+    }
+    try {
+        crnw::Writer w(in);
+        std::vector<uint8_t> file;
+        if (!w.write(file)) return CRN_GPU_ERR_BAD_DATA;
+        void* m = malloc(file.size());
+        if (!m) return CRN_GPU_ERR_NO_MEMORY;
+        memcpy(m, file.data(), file.size());
+        *out_file = m; *out_size = (uint32_t)file.size();
+    } catch (const std::bad_alloc&) { return CRN_GPU_ERR_NO_MEMORY; }
+    return CRN_GPU_OK;
+}
+
+void crn_gpu_free_file(void* file) { free(file); }
+
+int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate)
+{
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (out_file) *out_file = nullptr;
+    if (out_size) *out_size = 0;
+    if (out_bitrate) *out_bitrate = 0.0f;
+    if (!crn_params_ok(p) || !h_images || !out_file || !out_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: bad argument");
+    for (uint32_t i = 0; i < p->faces * p->levels; i++)
+        if (!h_images[i]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: missing image");      // alias_images, crn_comp.cpp:432-435
+    crn_gpu_hc_params hp;
+    int rc = crn_gpu_crn_hc_params(p, &hp);
+    if (rc) return set_err(ctx, rc, "crn_gpu_compress_crn: unsupported format");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the [block][16] array of all levels and faces (crn_comp.cpp:717-741), gathered on the device from one staging image
+    HcBuf d_blocks, d_img;
+    if (d_blocks.alloc(ctx, (size_t)hp.num_blocks * 64) != cudaSuccess || d_img.alloc(ctx, (size_t)p->width * p->height * 4) != cudaSuccess)
+        return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_crn: out of device memory");
+    uint64_t texels = 0;
+    for (uint32_t l = 0; l < p->levels; l++) {
+        const uint32_t w = std::max(1u, p->width >> l), h = std::max(1u, p->height >> l);
+        const uint32_t per_face = hp.levels[l].num_blocks / p->faces;
+        for (uint32_t f = 0; f < p->faces; f++) {
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_img.p, h_images[f * p->levels + l], (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+            rc = crn_gpu_blockify(ctx, d_img.p, w, h, w * 4, 8, d_blocks.as<uint8_t>() + ((size_t)hp.levels[l].first_block + (size_t)f * per_face) * 64, nullptr, nullptr);
+            if (rc) return rc;
+            texels += (uint64_t)w * h;
+        }
+    }
+    crn_gpu_hc* H = nullptr;
+    rc = crn_gpu_hc_compress(ctx, &hp, d_blocks.p, 0, &H);
+    if (rc) return rc;
+    rc = crn_gpu_crn_write(p, &hp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),
+                           H->alpha_endpoints.data(), (uint32_t)H->alpha_endpoints.size(), H->color_selectors.data(), (uint32_t)H->color_selectors.size(),
+                           H->alpha_selectors.data(), (uint32_t)H->alpha_selectors.size(), out_file, out_size);
+    crn_gpu_hc_free(H);
+    if (rc) return set_err(ctx, rc, "crn_gpu_compress_crn: the writer rejected the quantiser's output");
+    if (out_bitrate) *out_bitrate = (*out_size * 8.0f) / (float)texels;                                          // crn_comp.cpp:1640-1653
+    return CRN_GPU_OK;
+}
 
 int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info)
 {

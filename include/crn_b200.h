@@ -326,6 +326,42 @@ CRN_API const uint8_t* crn_gpu_hc_block_encodings(const crn_gpu_hc* hc);      /*
 CRN_API const uint32_t* crn_gpu_hc_tile_indices(const crn_gpu_hc* hc);        /* m_tile_indices */
 CRN_API void crn_gpu_hc_free(crn_gpu_hc* hc);
 
+/* .CRN writer back-end ---------------------------------------------------------------
+ * Replaces what crn_comp does after quantize_images (reference crnlib/crn_comp.cpp): optimize_color / optimize_alpha
+ * (:990-1058, :1285-1354: palette orderings, four endpoint trials costed by their coded size), pack_* (:43-293),
+ * the two pack_blocks passes of compress_internal (:295-422, :1515-1611), pack_data_models and create_comp_data
+ * (:1356-1496).  Host C++ (no device work, usable without a GPU): the orderings follow the reference step for step;
+ * a file decodes (crnd_unpack_level) to exactly the blocks the reference's own writer would produce from the same
+ * palettes and indices, and on every test vector it is byte-identical to the reference's file (tests/test_crn_writer_cpu.py).
+ * crn_gpu_crn_params mirrors the crn_comp_params fields crn_comp reads for a .CRN (inc/crnlib.h:231-414). */
+typedef struct crn_gpu_crn_params {
+    uint32_t struct_size;               /* sizeof(crn_gpu_crn_params) */
+    uint32_t crn_format;                /* crn_format: 0 DXT1, 2 DXT5, 7 DXN_XY, 8 DXN_YX, 9 DXT5A (others: CRN_GPU_ERR_UNSUPPORTED) */
+    uint32_t width, height, levels, faces;
+    uint32_t quality_level;             /* m_quality_level, 0..255 */
+    uint32_t perceptual;                /* cCRNCompFlagPerceptual */
+    uint32_t alpha_component;           /* m_alpha_component */
+    uint32_t userdata0, userdata1;
+    uint32_t palette_sizes[4];          /* colour endpoints, colour selectors, alpha endpoints, alpha selectors; any 0 = derive all
+                                           from quality_level (otherwise cCRNCompFlagManualPaletteSizes) */
+    float adaptive_tile_color_psnr_derating, adaptive_tile_alpha_psnr_derating;
+} crn_gpu_crn_params;
+CRN_API void crn_gpu_default_crn_params(crn_gpu_crn_params* p);
+/* crn_comp::alias_images' level table + quantize_images' parameter derivation (crn_comp.cpp:458-466, :525-716): fills
+ * every field of *hp (format, blocks, levels with weights min(12, 1.3^level), codebook sizes from the quality level). */
+CRN_API int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp);
+/* Palettes + indices (the arrays of crn_gpu_hc_*, or any source with that layout) -> .crn bytes.  *out_file is
+ * malloc'ed by the library; release it with crn_gpu_free_file. */
+CRN_API int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, const uint16_t* endpoint_indices, const uint16_t* selector_indices,
+                              const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
+                              const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
+                              void** out_file, uint32_t* out_size);
+/* crn_comp::compress_pass (crn_comp.cpp:1613-1656) for one quality level: h_images[face * levels + level] are host RGBA8
+ * images of max(1, width >> level) x max(1, height >> level), tight pitch (crn_comp_params::m_pImages).  Gathers the
+ * padded blocks on the device, runs crn_gpu_hc_compress and the writer.  out_bitrate (optional) = file bits / texels. */
+CRN_API int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate);
+CRN_API void crn_gpu_free_file(void* file);
+
 /* CRN -> DXTn transcoding ---------------------------------------------------
  * Mirrors the crnd_* API of inc/crn_defs.h:139-221 (bodies in inc/crn_decomp.h): crnd_get_texture_info
  * (:2737), crnd_unpack_begin (:4404), crnd_unpack_level (:4441), crnd_unpack_end (:4478).  Same contract:
