@@ -473,6 +473,44 @@ def run_dxt_hc(ctx, dev, steps, with_reference=True):
     return out
 
 
+def run_crn_compress(ctx, dev, with_reference=True):
+    """BASELINE configs[2] end to end: crn_compress of a 6-face 2048^2 DXT1 cubemap with full mip chains to a .CRN at a target
+    bitrate of 1.25 bpp -- host pixels in, file bytes out (crn_gpu_compress_crn: block gather, one dxt_hc pass + host writer per
+    trial of the reference's quality search, blocks resident in HBM across trials).  Also one fixed-quality pass (q128), beside
+    the reference's crn_compress of the same pass on the host cores (its whole search would take minutes)."""
+    import blockgen
+    faces = [mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False)) for f in range(6)]
+    ntex = sum(l.shape[0] * l.shape[1] for f in faces for l in f)
+    ctx.compress_crn(faces, 0, quality_level=128)                              # warm-up: buffer pool, pinned staging
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    data, rate, q = ctx.compress_crn(faces, 0, quality_level=128)
+    dt_pass = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    t0 = time.perf_counter()
+    sdata, srate, sq = ctx.compress_crn(faces, 0, target_bitrate=1.25)
+    dt_search = time.perf_counter() - t0
+    tex = ctx.unpack_begin(sdata)                                               # the file goes back through our own transcoder
+    nbytes = int(tex.unpack_all().nbytes)
+    tex.close()
+    out = {"workload": "c3_crn_dxt1_cubemap_6x2048_mips", "texels": ntex, "timing": "host wall clock, host pixels in / file bytes out",
+           "pass_q128": {"value": ntex / dt_pass / 1e6, "unit": UNIT, "ms": dt_pass * 1e3, "file_bytes": len(data), "bpp": rate, "gpu_launches": int(launches)},
+           "target_1.25bpp": {"value": ntex / dt_search / 1e6, "unit": UNIT, "ms": dt_search * 1e3, "file_bytes": len(sdata), "bpp": srate, "quality_level": int(sq),
+                              "transcoded_bytes": nbytes},
+           "e2e": {"value": ntex / dt_pass / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(ntex * 4), "d2h_bytes_per_step": int(len(data))}}
+    if with_reference:
+        import helpers
+        ref = helpers.load_ref()
+        if ref is not None:
+            th = cpu_threads()
+            t0 = time.perf_counter()
+            rdata, _, _ = helpers.ref_compress(ref, faces, 0, file_type=0, quality=128, threads=th - 1)
+            dtr = time.perf_counter() - t0
+            out["reference"] = {"value": ntex / dtr / 1e6, "unit": UNIT, "ms": dtr * 1e3, "cores": th, "kind": "reference", "sample": "one crn_compress pass at quality 128 (no bitrate search)",
+                                "file_bytes": len(rdata), "bpp": len(rdata) * 8.0 / ntex}
+    return out
+
+
 def run_clustered(args, ctx, ext, dev, wl, barrier, world):
     """BASELINE configs[1]: clustered DDS (qdxt init + pack) of one texture per rank.  The path is a chain of
     kernels with host decisions in between (frontier-batched VQ, cluster retrieval), on one stream + host thread per
@@ -749,6 +787,11 @@ def main():
             out["dxt_hc"] = run_dxt_hc(ctx, dev, 3, with_reference=not args.no_cpu_baseline)
         except Exception as e:
             out["dxt_hc"] = {"error": str(e)[:300]}
+    if not args.no_hc and world == 1:
+        try:
+            out["crn_compress"] = run_crn_compress(ctx, dev, with_reference=not args.no_cpu_baseline)
+        except Exception as e:
+            out["crn_compress"] = {"error": str(e)[:300]}
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = run_cpu_baseline(wl)[0]

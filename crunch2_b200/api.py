@@ -54,7 +54,8 @@ class _HcParams(ctypes.Structure):
 class _CrnParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "crn_format", "width", "height", "levels", "faces", "quality_level", "perceptual",
                                                 "alpha_component", "userdata0", "userdata1")] + [("palette_sizes", ctypes.c_uint32 * 4),
-                ("adaptive_tile_color_psnr_derating", ctypes.c_float), ("adaptive_tile_alpha_psnr_derating", ctypes.c_float)]
+                ("adaptive_tile_color_psnr_derating", ctypes.c_float), ("adaptive_tile_alpha_psnr_derating", ctypes.c_float),
+                ("target_bitrate", ctypes.c_float)]
 
 
 EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32)
@@ -160,7 +161,7 @@ def _declare(lib):
     lib.crn_gpu_default_crn_params.restype = None
     lib.crn_gpu_crn_hc_params.argtypes = [ctypes.POINTER(_CrnParams), ctypes.POINTER(_HcParams)]
     lib.crn_gpu_crn_write.argtypes = [ctypes.POINTER(_CrnParams), ctypes.POINTER(_HcParams), vp, vp, vp, u32, vp, u32, vp, u32, vp, u32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
-    lib.crn_gpu_compress_crn.argtypes = [vp, ctypes.POINTER(_CrnParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float)]
+    lib.crn_gpu_compress_crn.argtypes = [vp, ctypes.POINTER(_CrnParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u32)]
     lib.crn_gpu_free_file.argtypes = [vp]
     lib.crn_gpu_free_file.restype = None
     lib.crn_gpu_crnd_get_texture_info.argtypes = [vp, u32, ctypes.POINTER(_TextureInfo)]
@@ -463,22 +464,24 @@ class Context:
             self._lib.crn_gpu_hc_free(h)
         return out
 
-    def compress_crn(self, images, crn_format, quality_level=128, perceptual=True, alpha_component=3, palette_sizes=None, userdata=(0, 0)):
-        """crn_compress to a .CRN at one quality level (crn_comp::compress_pass, crnlib/crn_comp.cpp:1613): images[face][level]
-        = (h, w, 4) uint8 host arrays, level l being max(1, w >> l) x max(1, h >> l).  Returns (file bytes, bits per texel)."""
+    def compress_crn(self, images, crn_format, quality_level=128, perceptual=True, alpha_component=3, palette_sizes=None, userdata=(0, 0), target_bitrate=0.0):
+        """crn_compress to a .CRN (crn_comp::compress_pass, crnlib/crn_comp.cpp:1613; with target_bitrate > 0 the quality search
+        of crnlib/crn_texture_comp.cpp:120-262): images[face][level] = (h, w, 4) uint8 host arrays, level l being
+        max(1, w >> l) x max(1, h >> l).  Returns (file bytes, bits per texel, quality level)."""
         faces, levels = len(images), len(images[0])
         h, w = images[0][0].shape[:2]
         p = crn_params(crn_format, w, h, levels, faces, quality_level, perceptual, alpha_component, palette_sizes, userdata, lib=self._lib)
+        p.target_bitrate = float(target_bitrate)
         flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]
         for i, a in enumerate(flat):
             lw, lh = max(1, w >> (i % levels)), max(1, h >> (i % levels))
             if a.shape != (lh, lw, 4):
                 raise ValueError("image %d has shape %s, expected %s" % (i, a.shape, (lh, lw, 4)))
         ptrs = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
-        out = ctypes.c_void_p(); size = ctypes.c_uint32(); rate = ctypes.c_float()
-        self._check(self._lib.crn_gpu_compress_crn(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size), ctypes.byref(rate)))
+        out = ctypes.c_void_p(); size = ctypes.c_uint32(); rate = ctypes.c_float(); q = ctypes.c_uint32()
+        self._check(self._lib.crn_gpu_compress_crn(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size), ctypes.byref(rate), ctypes.byref(q)))
         try:
-            return ctypes.string_at(out, size.value), rate.value
+            return ctypes.string_at(out, size.value), rate.value, q.value
         finally:
             self._lib.crn_gpu_free_file(out)
 

@@ -1462,12 +1462,14 @@ int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, 
 
 void crn_gpu_free_file(void* file) { free(file); }
 
-int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate)
+int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate,
+                         uint32_t* out_quality)
 {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
     if (out_bitrate) *out_bitrate = 0.0f;
+    if (out_quality) *out_quality = 0;
     if (!crn_params_ok(p) || !h_images || !out_file || !out_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: bad argument");
     for (uint32_t i = 0; i < p->faces * p->levels; i++)
         if (!h_images[i]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: missing image");      // alias_images, crn_comp.cpp:432-435
@@ -1475,7 +1477,8 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
     int rc = crn_gpu_crn_hc_params(p, &hp);
     if (rc) return set_err(ctx, rc, "crn_gpu_compress_crn: unsupported format");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
-    // the [block][16] array of all levels and faces (crn_comp.cpp:717-741), gathered on the device from one staging image
+    // the [block][16] array of all levels and faces (crn_comp.cpp:717-741), gathered on the device from one staging image;
+    // it stays in HBM for every trial of the bitrate search (the reference restarts from the pixels on each pass)
     HcBuf d_blocks, d_img;
     if (d_blocks.alloc(ctx, (size_t)hp.num_blocks * 64) != cudaSuccess || d_img.alloc(ctx, (size_t)p->width * p->height * 4) != cudaSuccess)
         return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_crn: out of device memory");
@@ -1490,15 +1493,82 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
             texels += (uint64_t)w * h;
         }
     }
-    crn_gpu_hc* H = nullptr;
-    rc = crn_gpu_hc_compress(ctx, &hp, d_blocks.p, 0, &H);
-    if (rc) return rc;
-    rc = crn_gpu_crn_write(p, &hp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),
-                           H->alpha_endpoints.data(), (uint32_t)H->alpha_endpoints.size(), H->color_selectors.data(), (uint32_t)H->color_selectors.size(),
-                           H->alpha_selectors.data(), (uint32_t)H->alpha_selectors.size(), out_file, out_size);
-    crn_gpu_hc_free(H);
-    if (rc) return set_err(ctx, rc, "crn_gpu_compress_crn: the writer rejected the quantiser's output");
-    if (out_bitrate) *out_bitrate = (*out_size * 8.0f) / (float)texels;                                          // crn_comp.cpp:1640-1653
+    // one crn_comp::compress_pass at a quality level: quantise, write, report bits per texel
+    auto pass = [&](uint32_t quality, void** file, uint32_t* size, float* bitrate) -> int {
+        crn_gpu_crn_params q = *p;
+        q.quality_level = quality;
+        crn_gpu_hc_params qhp;
+        int r = crn_gpu_crn_hc_params(&q, &qhp);
+        if (r) return r;
+        crn_gpu_hc* H = nullptr;
+        r = crn_gpu_hc_compress(ctx, &qhp, d_blocks.p, 0, &H);
+        if (r) return r;
+        r = crn_gpu_crn_write(&q, &qhp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),
+                              H->alpha_endpoints.data(), (uint32_t)H->alpha_endpoints.size(), H->color_selectors.data(), (uint32_t)H->color_selectors.size(),
+                              H->alpha_selectors.data(), (uint32_t)H->alpha_selectors.size(), file, size);
+        crn_gpu_hc_free(H);
+        if (r) return set_err(ctx, r, "crn_gpu_compress_crn: the writer rejected the quantiser's output");
+        *bitrate = (*size * 8.0f) / (float)texels;                                                                // crn_comp.cpp:1640-1653
+        return CRN_GPU_OK;
+    };
+    const bool manual = p->palette_sizes[0] && p->palette_sizes[1] && p->palette_sizes[2] && p->palette_sizes[3];
+    if (!(p->target_bitrate > 0.0f) || manual) {
+        float rate = 0.0f;
+        rc = pass(p->quality_level, out_file, out_size, &rate);
+        if (rc) return rc;
+        if (out_bitrate) *out_bitrate = rate;
+        if (out_quality) *out_quality = p->quality_level;
+        return CRN_GPU_OK;
+    }
+    // Interpolative search for the quality level closest to the target bitrate (create_compressed_texture,
+    // crnlib/crn_texture_comp.cpp:120-262): same bracket updates, interpolation, acceptance rule and stop test.
+    const float target = p->target_bitrate;
+    float best_bitrate = 1e+10f, cached[256];
+    int best_quality = -1, low = 0, high = 255;
+    for (int i = 0; i < 256; i++) cached[i] = -1.0f;
+    void* best_file = nullptr; uint32_t best_size = 0;
+    uint32_t iter = 0;
+    bool binary = false;
+    while (low <= high) {
+        int trial = (low + high) / 2;
+        if (iter && !binary) {
+            int blo = trial;
+            while (cached[blo] < 0 && blo > 0) blo--;
+            if (cached[blo] < 0) trial = (int)((float)low + ((float)high - (float)low) * .33f);
+            else {
+                int bhi = trial + 1;
+                if (bhi <= 255) {
+                    while (cached[bhi] < 0 && bhi < 255) bhi++;
+                    if (cached[bhi] >= 0) {
+                        const float rlo = cached[blo], rhi = cached[bhi];
+                        if (rlo < rhi && rlo < target && rhi >= target) {
+                            const int q = low + (int)(((target - rlo) * (high - low)) / (rhi - rlo));
+                            if (q >= low && q <= high) trial = q;
+                        }
+                    }
+                }
+            }
+        }
+        void* file = nullptr; uint32_t size = 0; float rate = 0.0f;
+        rc = pass((uint32_t)trial, &file, &size, &rate);
+        if (rc) { free(best_file); return rc; }
+        cached[trial] = rate;
+        if (best_quality < 0 || (rate <= target && best_bitrate > target) ||
+            ((rate <= target || best_bitrate > target) && fabsf(rate - target) < fabsf(best_bitrate - target))) {
+            best_bitrate = rate; best_quality = trial;
+            free(best_file); best_file = file; best_size = size; file = nullptr;
+            if (best_bitrate <= target && fabsf(best_bitrate - target) < .005f) break;
+        }
+        free(file);
+        if (rate > target) high = trial - 1; else low = trial + 1;
+        if (++iter > 8) binary = true;
+    }
+    // (the reference retries without adaptive block sizes when even quality 255 stays under the target; dxt_hc's
+    //  non-hierarchical mode is not built, so the best hierarchical result stands)
+    if (best_quality < 0) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_crn: bitrate search found nothing");
+    *out_file = best_file; *out_size = best_size;
+    if (out_bitrate) *out_bitrate = best_bitrate;
+    if (out_quality) *out_quality = (uint32_t)best_quality;
     return CRN_GPU_OK;
 }
 

@@ -345,6 +345,7 @@ typedef struct crn_gpu_crn_params {
     uint32_t palette_sizes[4];          /* colour endpoints, colour selectors, alpha endpoints, alpha selectors; any 0 = derive all
                                            from quality_level (otherwise cCRNCompFlagManualPaletteSizes) */
     float adaptive_tile_color_psnr_derating, adaptive_tile_alpha_psnr_derating;
+    float target_bitrate;               /* m_target_bitrate in bits per texel; 0 = use quality_level (crn_gpu_compress_crn only) */
 } crn_gpu_crn_params;
 CRN_API void crn_gpu_default_crn_params(crn_gpu_crn_params* p);
 /* crn_comp::alias_images' level table + quantize_images' parameter derivation (crn_comp.cpp:458-466, :525-716): fills
@@ -356,10 +357,14 @@ CRN_API int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_para
                               const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
                               const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
                               void** out_file, uint32_t* out_size);
-/* crn_comp::compress_pass (crn_comp.cpp:1613-1656) for one quality level: h_images[face * levels + level] are host RGBA8
- * images of max(1, width >> level) x max(1, height >> level), tight pitch (crn_comp_params::m_pImages).  Gathers the
- * padded blocks on the device, runs crn_gpu_hc_compress and the writer.  out_bitrate (optional) = file bits / texels. */
-CRN_API int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate);
+/* crn_compress to a .CRN (create_compressed_texture, crnlib/crn_texture_comp.cpp:60-275, over crn_comp::compress_pass,
+ * crn_comp.cpp:1613-1656): h_images[face * levels + level] are host RGBA8 images of max(1, width >> level) x
+ * max(1, height >> level), tight pitch (crn_comp_params::m_pImages).  Gathers the padded blocks on the device once, then per
+ * pass runs crn_gpu_hc_compress and the writer.  target_bitrate > 0 runs the reference's interpolative quality search
+ * (same bracket / interpolation / acceptance rules) over blocks that stay resident in HBM.  out_bitrate (optional) = file
+ * bits / texels, out_quality (optional) = the quality level of the returned file. */
+CRN_API int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate,
+                                 uint32_t* out_quality);
 CRN_API void crn_gpu_free_file(void* file);
 
 /* CRN -> DXTn transcoding ---------------------------------------------------

@@ -1,0 +1,54 @@
+"""crn_compress to .CRN on the device (crn_gpu_compress_crn through the C-ABI: block gather kernel, dxt_hc pipeline, host
+writer) against the reference's crn_compress, plus the round trip through our own transcoder.  Tolerance class: PSNR within
+0.05 dB, file size (= CRN bitrate) within 1 % of the reference (north_star)."""
+import numpy as np
+import pytest
+
+import blockgen
+import crunch2_b200 as crn
+import helpers
+from test_crn_compress_cpu import check
+
+pytestmark = pytest.mark.gpu
+
+
+def chain(w, h, seed, n=None):
+    from bench import mip_chain
+    c = mip_chain(blockgen.smooth_image(w, h, seed, alpha=True))
+    return c if n is None else c[:n]
+
+
+@pytest.mark.parametrize("name,w,h,q", [("DXT1", 256, 256, 128), ("DXT5", 256, 128, 128), ("DXN_XY", 128, 128, 200), ("DXT5A", 128, 128, 90)])
+def test_crn_quality_level_matches_reference(gpu_ctx, ref, name, w, h, q):
+    face_levels = [chain(w, h, 40 + w)]
+    want, _, _ = helpers.ref_compress(ref, face_levels, helpers.CRN_FMT[name], file_type=0, quality=q, threads=0)
+    l0 = gpu_ctx.launch_count
+    got, rate, used_q = gpu_ctx.compress_crn(face_levels, helpers.CRN_FMT[name], quality_level=q)
+    assert gpu_ctx.launch_count > l0 and used_q == q
+    check(ref, name, face_levels, got, want)
+    # our transcoder and the reference's decoder agree on our file, level by level
+    tex = gpu_ctx.unpack_begin(got)
+    mine = tex.unpack_all().tobytes()
+    tex.close()
+    assert mine == b"".join(b"".join(lv) for lv in helpers.ref_unpack_all(ref, got))
+
+
+def test_crn_target_bitrate_matches_reference(gpu_ctx, ref):
+    face_levels = [chain(256, 256, 77)]
+    target = 1.25
+    want, ref_q, ref_rate = helpers.ref_compress(ref, face_levels, helpers.CRN_FMT["DXT1"], file_type=0, bitrate=target, threads=0, want_bitrate=True)
+    got, rate, q = gpu_ctx.compress_crn(face_levels, helpers.CRN_FMT["DXT1"], target_bitrate=target)
+    assert abs(rate - target) <= abs(ref_rate - target) + 0.01, (rate, ref_rate, q, ref_q)
+    assert abs(int(q) - int(ref_q)) <= 4, (q, ref_q)
+    check(ref, "DXT1", face_levels, got, want, psnr_tol=0.1, size_tol=0.01)
+
+
+def test_crn_cubemap(gpu_ctx, ref):
+    faces = [chain(128, 128, 500 + f) for f in range(6)]
+    want, _, _ = helpers.ref_compress(ref, faces, helpers.CRN_FMT["DXT1"], file_type=0, quality=128, threads=0)
+    got, _, _ = gpu_ctx.compress_crn(faces, helpers.CRN_FMT["DXT1"], quality_level=128)
+    check(ref, "DXT1", faces, got, want)
+    tex = gpu_ctx.unpack_begin(got)
+    mine = tex.unpack_all().tobytes()
+    tex.close()
+    assert mine == b"".join(b"".join(lv) for lv in helpers.ref_unpack_all(ref, got))
