@@ -175,6 +175,8 @@ def _declare(lib):
     lib.crn_gpu_crnd_unpack_all_levels_host.argtypes = [vp, vp, u64]
     lib.crn_gpu_crnd_unpack_batch.argtypes = [vp, ctypes.POINTER(vp), u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     lib.crn_gpu_crnd_unpack_end.argtypes = [vp]
+    lib.crn_gpu_dds_header.argtypes = [u32, u32, u32, u32, u32, vp]
+    lib.crn_gpu_crn_to_dds.argtypes = [vp, vp, u32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
     return lib
 
 
@@ -492,6 +494,16 @@ class Context:
         return Qdxt(self, fmt, levels, params or PackParams())
 
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
+    def crn_to_dds(self, crn_bytes):
+        """crn_decompress_crn_to_dds (inc/crnlib.h:620): .crn bytes -> .dds bytes, transcoded on the device."""
+        buf = np.frombuffer(crn_bytes, np.uint8)
+        out = ctypes.c_void_p(); size = ctypes.c_uint32()
+        self._check(self._lib.crn_gpu_crn_to_dds(self._ctx, buf.ctypes.data_as(ctypes.c_void_p), len(crn_bytes), ctypes.byref(out), ctypes.byref(size)))
+        try:
+            return ctypes.string_at(out, size.value)
+        finally:
+            self._lib.crn_gpu_free_file(out)
+
     def unpack_begin(self, crn_bytes):
         """crnd_unpack_begin: returns a Texture bound to this context."""
         return Texture(self, crn_bytes)

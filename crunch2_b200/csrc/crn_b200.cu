@@ -1901,4 +1901,76 @@ int crn_gpu_crnd_unpack_end(crn_gpu_texture* tex)
     return CRN_GPU_OK;
 }
 
+/* ---- DDS container edge ------------------------------------------------------------------- */
+
+int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uint32_t levels, uint32_t faces, void* out_128_bytes)
+{   // "DDS " + DDSURFACEDESC2 as mipmapped_texture::write_dds fills it for the block formats (crnlib/crn_mipmapped_texture.cpp:921-1084)
+    if (!out_128_bytes || !width || !height || !levels || levels > 16 || (faces != 1 && faces != 6)) return CRN_GPU_ERR_BAD_PARAM;
+    auto fourcc = [](char a, char b, char c, char d) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24); };
+    uint32_t cc, bitcount = 0, bits_per_texel = 8;
+    switch (crn_format) {                                        // crn_format -> pixel_format (crn_mipmapped_texture.cpp:2700-2745), then write_dds' switch
+    case 0: cc = fourcc('D', 'X', 'T', '1'); bits_per_texel = 4; break;
+    case 2: cc = fourcc('D', 'X', 'T', '5'); break;
+    case 3: cc = fourcc('D', 'X', 'T', '5'); bitcount = fourcc('C', 'C', 'x', 'Y'); break;
+    case 4: cc = fourcc('D', 'X', 'T', '5'); bitcount = fourcc('x', 'G', 'x', 'R'); break;
+    case 5: cc = fourcc('D', 'X', 'T', '5'); bitcount = fourcc('x', 'G', 'B', 'R'); break;
+    case 6: cc = fourcc('D', 'X', 'T', '5'); bitcount = fourcc('A', 'G', 'B', 'R'); break;
+    case 7: cc = fourcc('A', 'T', 'I', '2'); bitcount = fourcc('A', '2', 'X', 'Y'); break;
+    case 8: cc = fourcc('A', 'T', 'I', '2'); break;
+    case 9: cc = fourcc('A', 'T', 'I', '1'); bits_per_texel = 4; break;
+    default: return CRN_GPU_ERR_UNSUPPORTED;
+    }
+    uint32_t h[32];
+    memset(h, 0, sizeof(h));
+    h[0] = fourcc('D', 'D', 'S', ' ');
+    h[1] = 124;
+    h[2] = 0x1u | 0x2u | 0x4u | 0x1000u | 0x80000u;              // CAPS | HEIGHT | WIDTH | PIXELFORMAT | LINEARSIZE
+    h[3] = height; h[4] = width;
+    h[5] = (((width + 3) & ~3u) * ((height + 3) & ~3u) * bits_per_texel) >> 3;
+    h[27] = 0x1000u;                                             // DDSCAPS_TEXTURE
+    if (levels > 1) { h[7] = levels; h[2] |= 0x20000u; h[27] |= 0x400000u | 0x8u; }     // MIPMAPCOUNT; MIPMAP | COMPLEX
+    if (faces > 1) { h[27] |= 0x8u; h[28] = 0x200u | 0xFC00u; }                          // CUBEMAP + the six face bits
+    h[19] = 32; h[20] = 0x4u; h[21] = cc; h[22] = bitcount;      // DDPF_FOURCC
+    memcpy(out_128_bytes, h, 128);
+    return CRN_GPU_OK;
+}
+
+int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, void** out_file, uint32_t* out_size)
+{   // crn_decompress_crn_to_dds (crnlib/crnlib.cpp:269-291): transcode every level on the device, lay the faces out DDS-style
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (out_file) *out_file = nullptr;
+    if (out_size) *out_size = 0;
+    if (!h_crn || !out_file || !out_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_crn_to_dds: bad argument");
+    crn_gpu_texture_info ti; ti.struct_size = sizeof(ti);
+    int rc = crn_gpu_crnd_get_texture_info(h_crn, crn_size, &ti);
+    if (rc) return set_err(ctx, rc, "crn_gpu_crn_to_dds: not a CRN file");
+    uint8_t header[128];
+    rc = crn_gpu_dds_header(ti.format, ti.width, ti.height, ti.levels, ti.faces, header);
+    if (rc) return set_err(ctx, rc, "crn_gpu_crn_to_dds: format has no DDS form here");
+    crn_gpu_texture* tex = nullptr;
+    rc = crn_gpu_crnd_unpack_begin(ctx, h_crn, crn_size, &tex);
+    if (rc) return rc;
+    const uint64_t total = crn_gpu_crnd_total_size(tex);
+    uint8_t* file = static_cast<uint8_t*>(malloc(128 + total));
+    uint8_t* tmp = static_cast<uint8_t*>(malloc(total ? total : 1));
+    if (!file || !tmp) { free(file); free(tmp); crn_gpu_crnd_unpack_end(tex); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_crn_to_dds: out of host memory"); }
+    rc = crn_gpu_crnd_unpack_all_levels_host(tex, tmp, total);
+    if (rc == CRN_GPU_OK) {
+        memcpy(file, header, 128);
+        uint8_t* dst = file + 128;
+        for (uint32_t f = 0; f < ti.faces; f++)                  // write_dds: faces outermost (crn_mipmapped_texture.cpp:1093-1094)
+            for (uint32_t l = 0; l < ti.levels; l++) {
+                const uint32_t w = std::max(1u, ti.width >> l), h = std::max(1u, ti.height >> l);
+                const size_t bytes = (size_t)((w + 3) >> 2) * ((h + 3) >> 2) * ti.bytes_per_block;
+                memcpy(dst, tmp + crn_gpu_crnd_level_offset(tex, l, f), bytes);
+                dst += bytes;
+            }
+        *out_file = file; *out_size = (uint32_t)(128 + total);
+        file = nullptr;
+    }
+    free(file); free(tmp);
+    crn_gpu_crnd_unpack_end(tex);
+    return rc;
+}
+
 }  // extern "C"

@@ -404,6 +404,15 @@ CRN_API int crn_gpu_crnd_unpack_batch(crn_gpu_ctx* ctx, crn_gpu_texture* const* 
                                       const uint64_t* dst_capacity);
 CRN_API int crn_gpu_crnd_unpack_end(crn_gpu_texture* tex);
 
+/* DDS container edge --------------------------------------------------------------------
+ * crn_gpu_dds_header: the 128 bytes ("DDS " + DDSURFACEDESC2) mipmapped_texture::write_dds writes for a block-compressed
+ * texture (crnlib/crn_mipmapped_texture.cpp:921-1084), from the crn_format of a .crn header; host only.
+ * crn_gpu_crn_to_dds: crn_decompress_crn_to_dds (inc/crnlib.h:620, crnlib/crnlib.cpp:269-291) -- all levels transcoded on the
+ * device, payload laid out faces outermost; byte-identical to the reference's file.  *out_file is malloc'ed by the library;
+ * release it with crn_gpu_free_file. */
+CRN_API int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uint32_t levels, uint32_t faces, void* out_128_bytes);
+CRN_API int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, void** out_file, uint32_t* out_size);
+
 #ifdef __cplusplus
 }
 #endif

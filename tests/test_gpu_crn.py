@@ -52,3 +52,15 @@ def test_crn_cubemap(gpu_ctx, ref):
     mine = tex.unpack_all().tobytes()
     tex.close()
     assert mine == b"".join(b"".join(lv) for lv in helpers.ref_unpack_all(ref, got))
+
+
+@pytest.mark.parametrize("fmt,w,h,faces", [("DXT5", 512, 256, 1), ("DXT1", 64, 64, 6), ("DXN_XY", 100, 60, 1)])
+def test_crn_to_dds_matches_reference(gpu_ctx, ref, fmt, w, h, faces):
+    """crn_decompress_crn_to_dds: byte-identical .dds (header + every level of every face)."""
+    import crnsynth
+    from test_dds_cpu import ref_to_dds
+    data = crnsynth.synth_crn(w, h, fmt, faces=faces, seed=w)
+    l0 = gpu_ctx.launch_count
+    got = gpu_ctx.crn_to_dds(data)
+    assert gpu_ctx.launch_count > l0
+    assert got == ref_to_dds(ref, data)
