@@ -58,6 +58,10 @@ class _CrnParams(ctypes.Structure):
                 ("target_bitrate", ctypes.c_float)]
 
 
+class _DdsParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "crn_format", "width", "height", "levels", "faces", "quality_level", "dxt1a_for_transparency")] + [("pack", _PackParams)]
+
+
 EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32)
 
 
@@ -176,6 +180,9 @@ def _declare(lib):
     lib.crn_gpu_crnd_unpack_batch.argtypes = [vp, ctypes.POINTER(vp), u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     lib.crn_gpu_crnd_unpack_end.argtypes = [vp]
     lib.crn_gpu_dds_header.argtypes = [u32, u32, u32, u32, u32, vp]
+    lib.crn_gpu_default_dds_params.argtypes = [ctypes.POINTER(_DdsParams)]
+    lib.crn_gpu_default_dds_params.restype = None
+    lib.crn_gpu_compress_dds.argtypes = [vp, ctypes.POINTER(_DdsParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32)]
     lib.crn_gpu_crn_to_dds.argtypes = [vp, vp, u32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
     return lib
 
@@ -494,6 +501,26 @@ class Context:
         return Qdxt(self, fmt, levels, params or PackParams())
 
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
+    def compress_dds(self, images, crn_format, quality_level=255, params=None, dxt1a_for_transparency=False):
+        """crn_compress to a .DDS (dds_comp, crnlib/crn_dds_comp.cpp:148-289): images[face][level] = (h, w, 4) uint8 host arrays.
+        quality_level 255 packs block by block, lower values take the clustered path.  Returns the file bytes."""
+        faces, levels = len(images), len(images[0])
+        h, w = images[0][0].shape[:2]
+        p = _DdsParams()
+        self._lib.crn_gpu_default_dds_params(ctypes.byref(p))
+        p.crn_format, p.width, p.height, p.levels, p.faces = int(crn_format), int(w), int(h), int(levels), int(faces)
+        p.quality_level, p.dxt1a_for_transparency = int(quality_level), int(bool(dxt1a_for_transparency))
+        if params is not None:
+            p.pack = params._c()
+        flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]
+        ptrs = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
+        out = ctypes.c_void_p(); size = ctypes.c_uint32()
+        self._check(self._lib.crn_gpu_compress_dds(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size)))
+        try:
+            return ctypes.string_at(out, size.value)
+        finally:
+            self._lib.crn_gpu_free_file(out)
+
     def crn_to_dds(self, crn_bytes):
         """crn_decompress_crn_to_dds (inc/crnlib.h:620): .crn bytes -> .dds bytes, transcoded on the device."""
         buf = np.frombuffer(crn_bytes, np.uint8)

@@ -1910,6 +1910,7 @@ int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uin
     uint32_t cc, bitcount = 0, bits_per_texel = 8;
     switch (crn_format) {                                        // crn_format -> pixel_format (crn_mipmapped_texture.cpp:2700-2745), then write_dds' switch
     case 0: cc = fourcc('D', 'X', 'T', '1'); bits_per_texel = 4; break;
+    case 1: cc = fourcc('D', 'X', 'T', '3'); break;
     case 2: cc = fourcc('D', 'X', 'T', '5'); break;
     case 3: cc = fourcc('D', 'X', 'T', '5'); bitcount = fourcc('C', 'C', 'x', 'Y'); break;
     case 4: cc = fourcc('D', 'X', 'T', '5'); bitcount = fourcc('x', 'G', 'x', 'R'); break;
@@ -1932,6 +1933,77 @@ int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uin
     if (faces > 1) { h[27] |= 0x8u; h[28] = 0x200u | 0xFC00u; }                          // CUBEMAP + the six face bits
     h[19] = 32; h[20] = 0x4u; h[21] = cc; h[22] = bitcount;      // DDPF_FOURCC
     memcpy(out_128_bytes, h, 128);
+    return CRN_GPU_OK;
+}
+
+void crn_gpu_default_dds_params(crn_gpu_dds_params* p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->levels = 1; p->faces = 1; p->quality_level = 255;
+    crn_gpu_default_pack_params(&p->pack);
+}
+
+int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size)
+{   // dds_comp::compress_init + convert_to_dxt + compress_pass (crnlib/crn_dds_comp.cpp:148-289)
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (out_file) *out_file = nullptr;
+    if (out_size) *out_size = 0;
+    if (!p || p->struct_size != sizeof(crn_gpu_dds_params) || !h_images || !out_file || !out_size || p->width < 1 || p->height < 1 || p->width > 4096 || p->height > 4096 ||
+        p->levels < 1 || p->levels > 16 || (p->faces != 1 && p->faces != 6) || p->quality_level > 255 || p->pack.struct_size != sizeof(crn_gpu_pack_params))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_dds: bad argument");
+    const uint32_t count = p->faces * p->levels;
+    for (uint32_t i = 0; i < count; i++)
+        if (!h_images[i]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_dds: missing image");     // create_dds_tex, crn_dds_comp.cpp:71-74
+    uint32_t fmt;
+    switch (p->crn_format) {                                     // pixel_format_helpers::convert_crn_format_to_pixel_format
+    case 0: fmt = CRN_GPU_FMT_DXT1; break;
+    case 1: fmt = CRN_GPU_FMT_DXT3; break;
+    case 2: fmt = CRN_GPU_FMT_DXT5; break;
+    case 7: fmt = CRN_GPU_FMT_DXN_XY; break;
+    case 8: fmt = CRN_GPU_FMT_DXN_YX; break;
+    case 9: fmt = CRN_GPU_FMT_DXT5A; break;
+    default: return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: swizzled DXT5 variants and ETC are not built");
+    }
+    std::vector<crn_gpu_level_desc> lv(count);                   // face-major: the order write_dds emits and qdxt_pack_init walks
+    bool has_alpha = false;
+    for (uint32_t f = 0; f < p->faces; f++)
+        for (uint32_t l = 0; l < p->levels; l++) {
+            const uint32_t w = std::max(1u, p->width >> l), h = std::max(1u, p->height >> l);
+            lv[f * p->levels + l] = { h_images[f * p->levels + l], w, h, w * 4 };
+            if (!has_alpha && fmt == CRN_GPU_FMT_DXT1 && p->dxt1a_for_transparency) {                             // image_utils::has_alpha
+                const uint8_t* px = static_cast<const uint8_t*>(h_images[f * p->levels + l]);
+                for (size_t i = 0, n = (size_t)w * h; i < n; i++) if (px[i * 4 + 3] < 255) { has_alpha = true; break; }
+            }
+        }
+    if (fmt == CRN_GPU_FMT_DXT1 && has_alpha && p->pack.use_both_block_types && p->dxt1a_for_transparency) fmt = CRN_GPU_FMT_DXT1A;   // crn_dds_comp.cpp:243-246
+    const uint32_t bpb = crn_gpu_bytes_per_block(fmt);
+    uint64_t payload = 0;
+    for (const crn_gpu_level_desc& d : lv) payload += (uint64_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
+    uint8_t* file = static_cast<uint8_t*>(malloc(128 + payload));
+    if (!file) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_dds: out of host memory");
+    int rc = crn_gpu_dds_header(p->crn_format, p->width, p->height, p->levels, p->faces, file);
+    if (rc == CRN_GPU_OK) {
+        if (p->quality_level == 255 || fmt == CRN_GPU_FMT_DXT3) {                                                // crn_dds_comp.cpp:150-157: block by block
+            uint8_t* dst = file + 128;
+            for (const crn_gpu_level_desc& d : lv) {
+                rc = crn_gpu_pack_image_host(ctx, fmt, &p->pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
+                if (rc) break;
+                dst += (size_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
+            }
+        } else {                                                                                                 // clustered: qdxt_pack_init + qdxt_pack
+            crn_gpu_qdxt* q = nullptr;
+            rc = crn_gpu_qdxt_init(ctx, fmt, &p->pack, lv.data(), count, 1, &q);
+            if (rc == CRN_GPU_OK) {
+                if (crn_gpu_qdxt_output_size(q) != payload) rc = set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_dds: payload size mismatch");
+                else rc = crn_gpu_qdxt_pack(q, p->quality_level, file + 128, 1);
+                crn_gpu_qdxt_free(q);
+            }
+        }
+    }
+    if (rc) { free(file); return rc; }
+    *out_file = file; *out_size = (uint32_t)(128 + payload);
     return CRN_GPU_OK;
 }
 

@@ -412,6 +412,22 @@ CRN_API int crn_gpu_crnd_unpack_end(crn_gpu_texture* tex);
  * release it with crn_gpu_free_file. */
 CRN_API int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uint32_t levels, uint32_t faces, void* out_128_bytes);
 CRN_API int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, void** out_file, uint32_t* out_size);
+/* crn_compress(cCRNFileTypeDDS) (inc/crnlib.h:609; dds_comp::compress_init / convert_to_dxt / compress_pass,
+ * crnlib/crn_dds_comp.cpp:148-289): quality_level 255 (or DXT3) packs block by block (crn_gpu_pack_image), anything lower runs
+ * the clustered path (crn_gpu_qdxt_init + crn_gpu_qdxt_pack); the result is a complete .dds file (header + faces outermost).
+ * h_images[face * levels + level]: host RGBA8, tight pitch.  DXT1 becomes DXT1A under the reference's rule (any alpha < 255,
+ * both block types, dxt1a_for_transparency).  The target-bitrate search over LZMA-compressed size is not built (LZMA is out
+ * of scope): call again with another quality_level. */
+typedef struct crn_gpu_dds_params {
+    uint32_t struct_size;               /* sizeof(crn_gpu_dds_params) */
+    uint32_t crn_format;                /* 0 DXT1, 1 DXT3, 2 DXT5, 7 DXN_XY, 8 DXN_YX, 9 DXT5A */
+    uint32_t width, height, levels, faces;
+    uint32_t quality_level;             /* m_quality_level */
+    uint32_t dxt1a_for_transparency;    /* cCRNCompFlagDXT1AForTransparency */
+    crn_gpu_pack_params pack;           /* dxt_image::pack_params::init(crn_comp_params) (crnlib/crn_dxt_image.h:192-203) */
+} crn_gpu_dds_params;
+CRN_API void crn_gpu_default_dds_params(crn_gpu_dds_params* p);
+CRN_API int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size);
 
 #ifdef __cplusplus
 }

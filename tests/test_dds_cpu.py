@@ -43,7 +43,7 @@ def test_header_arguments(sim):
     out = (ctypes.c_uint8 * 128)()
     assert sim.crn_gpu_dds_header(0, 64, 64, 7, 1, out) == 0
     assert bytes(out[:4]) == b"DDS "
-    assert sim.crn_gpu_dds_header(1, 64, 64, 7, 1, out) != 0      # DXT3 never comes out of a .crn
+    assert sim.crn_gpu_dds_header(10, 64, 64, 7, 1, out) != 0     # ETC1: not a format of this path
     assert sim.crn_gpu_dds_header(0, 0, 64, 7, 1, out) != 0
     assert sim.crn_gpu_dds_header(0, 64, 64, 1, 2, out) != 0
 
@@ -51,3 +51,40 @@ def test_header_arguments(sim):
 def test_crn_to_dds_rejects_garbage(simctx):
     with pytest.raises(crn.CrnGpuError):
         simctx.crn_to_dds(b"not a crn file at all, just some bytes to get past any minimum size check........................")
+
+
+# ---- crn_compress(cCRNFileTypeDDS): whole files against the reference's ------------------------------------------
+FLAGS_EXACT = 1 | 2 | 8 | 32      # perceptual | hierarchical | both block types | endpoint caching off (the thread-independent mode)
+
+
+def chain(w, h, seed, n=None):
+    import blockgen
+    from bench import mip_chain
+    c = mip_chain(blockgen.smooth_image(w, h, seed, alpha=True))
+    return c if n is None else c[:n]
+
+
+@pytest.mark.parametrize("fmt,w,h,n", [("DXT1", 32, 16, None), ("DXT5", 16, 16, 2), ("DXT3", 16, 8, 1), ("DXN_XY", 12, 20, 2), ("DXT5A", 16, 16, 3)])
+def test_compress_dds_block_by_block_matches_reference_file(simctx, ref, fmt, w, h, n):
+    levels = chain(w, h, 60 + w, n)
+    want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT[fmt], file_type=1, quality=255, threads=0, flags=FLAGS_EXACT)
+    got = simctx.compress_dds([levels], helpers.CRN_FMT[fmt], quality_level=255)
+    assert got[:128] == want[:128]
+    assert got == want
+
+
+def test_compress_dds_cubemap_and_dxt1a(simctx, ref):
+    faces = [chain(8, 8, 700 + f, 2) for f in range(6)]
+    for f in faces:
+        f[0][0:4, 0:4, 3] = 0                  # transparent texels: DXT1 becomes DXT1A under cCRNCompFlagDXT1AForTransparency (128)
+    want, _, _ = helpers.ref_compress(ref, faces, helpers.CRN_FMT["DXT1"], file_type=1, quality=255, threads=0, flags=FLAGS_EXACT | 128)
+    got = simctx.compress_dds(faces, helpers.CRN_FMT["DXT1"], quality_level=255, dxt1a_for_transparency=True)
+    assert got == want
+
+
+def test_compress_dds_clustered_matches_reference_file(simctx, ref):
+    """Clustered path: on this input the single-thread reference is reproduced byte for byte (as in test_qdxt_cpu)."""
+    levels = chain(64, 64, 1)
+    want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT["DXT1"], file_type=1, quality=128, threads=0, flags=1 | 2 | 8)
+    got = simctx.compress_dds([levels], helpers.CRN_FMT["DXT1"], quality_level=128)
+    assert got == want

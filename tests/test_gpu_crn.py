@@ -64,3 +64,25 @@ def test_crn_to_dds_matches_reference(gpu_ctx, ref, fmt, w, h, faces):
     got = gpu_ctx.crn_to_dds(data)
     assert gpu_ctx.launch_count > l0
     assert got == ref_to_dds(ref, data)
+
+
+@pytest.mark.parametrize("fmt,w,h", [("DXT1", 256, 256), ("DXT5", 128, 64), ("DXN_YX", 64, 64)])
+def test_compress_dds_block_by_block_is_the_reference_file(gpu_ctx, ref, fmt, w, h):
+    """crn_compress(cCRNFileTypeDDS) at quality 255, endpoint caching off: the whole .dds, header included, byte for byte."""
+    levels = chain(w, h, 9 + w)
+    want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT[fmt], file_type=1, quality=255, threads=0, flags=1 | 2 | 8 | 32)
+    got = gpu_ctx.compress_dds([levels], helpers.CRN_FMT[fmt], quality_level=255)
+    assert got == want
+
+
+def test_compress_dds_clustered_within_tolerance(gpu_ctx, ref):
+    import quality
+    from test_qdxt_cpu import assert_within_tolerance
+    levels = chain(256, 256, 31)
+    want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT["DXT5"], file_type=1, quality=128, threads=0, flags=1 | 2 | 8)
+    got = gpu_ctx.compress_dds([levels], helpers.CRN_FMT["DXT5"], quality_level=128)
+    assert len(got) == len(want) and got[:128] == want[:128]
+    src = np.concatenate([quality.image_to_blocks(l) for l in levels])
+    a, b = quality.decode_blocks(got[128:], 3), quality.decode_blocks(want[128:], 3)
+    ps = [(quality.psnr(a, src, c), quality.psnr(b, src, c)) for c in ([0, 1, 2], [3])]
+    assert_within_tolerance(ps, quality.lzma_bits(got[128:]), quality.lzma_bits(want[128:]))
