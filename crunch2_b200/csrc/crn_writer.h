@@ -20,7 +20,11 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -54,6 +58,20 @@ struct BitWriter {
         acc = (acc << nbits) | (v & ((nbits >= 32) ? 0xFFFFFFFFu : ((1u << nbits) - 1u)));
         nacc += (int)nbits;
         while (nacc >= 8) { bytes.push_back((uint8_t)(acc >> (nacc - 8))); nacc -= 8; }
+    }
+    void append(const BitWriter& o)       // o's bits (unfinished: whole bytes + its pending bits) after ours
+    {
+        if (nacc == 0) { bytes.insert(bytes.end(), o.bytes.begin(), o.bytes.end()); total += 8ull * o.bytes.size(); }
+        else {
+            const int sft = nacc;
+            uint32_t carry = (uint32_t)(acc & ((1u << sft) - 1u));
+            const size_t at = bytes.size();
+            bytes.resize(at + o.bytes.size());
+            uint8_t* dst = bytes.data() + at;
+            for (size_t k = 0; k < o.bytes.size(); k++) { const uint32_t v = (carry << 8) | o.bytes[k]; dst[k] = (uint8_t)(v >> sft); carry = v & ((1u << sft) - 1u); }
+            acc = carry; total += 8ull * o.bytes.size();
+        }
+        if (o.nacc) put((uint32_t)(o.acc & ((1u << o.nacc) - 1u)), (uint32_t)o.nacc);
     }
     void finish() { if (!simulate) { uint64_t t = total; put(0, 7); total = t; nacc = 0; acc = 0; } }
 };
@@ -322,18 +340,25 @@ struct Transitions {
     std::vector<uint32_t> row_start;     // n + 1
     std::vector<uint32_t> col, cnt;
     std::vector<uint32_t> sum;
-    void build(uint32_t n, std::vector<uint64_t>& pairs)    // pairs: (i << 32 | j), both directions present
-    {
-        std::sort(pairs.begin(), pairs.end());
+    // for_each(f) must call f(i, j) once per directed transition, and enumerate the same sequence each time it is called
+    template <typename Enum>
+    void build(uint32_t n, Enum&& for_each)
+    {   // bucket by row, then count each row's columns in a dense scratch table: linear in the number of transitions
+        std::vector<uint32_t> start(n + 1, 0);
+        for_each([&](uint32_t i, uint32_t) { start[i + 1]++; });
+        for (uint32_t i = 0; i < n; i++) start[i + 1] += start[i];
+        std::vector<uint32_t> cols(start[n]), fill(start.begin(), start.end() - 1);
+        for_each([&](uint32_t i, uint32_t j) { cols[fill[i]++] = j; });
         row_start.assign(n + 1, 0); col.clear(); cnt.clear(); sum.assign(n, 0);
-        for (size_t k = 0; k < pairs.size();) {
-            size_t e = k;
-            while (e < pairs.size() && pairs[e] == pairs[k]) e++;
-            const uint32_t i = (uint32_t)(pairs[k] >> 32), j = (uint32_t)pairs[k];
-            col.push_back(j); cnt.push_back((uint32_t)(e - k)); row_start[i + 1]++; sum[i] += (uint32_t)(e - k);
-            k = e;
+        std::vector<uint32_t> seen(n, 0), touched;
+        for (uint32_t i = 0; i < n; i++) {
+            touched.clear();
+            for (uint32_t k = start[i]; k < start[i + 1]; k++) if (!seen[cols[k]]++) touched.push_back(cols[k]);
+            std::sort(touched.begin(), touched.end());
+            for (uint32_t j : touched) { col.push_back(j); cnt.push_back(seen[j]); seen[j] = 0; }
+            sum[i] = start[i + 1] - start[i];
+            row_start[i + 1] = (uint32_t)col.size();
         }
-        for (uint32_t i = 0; i < n; i++) row_start[i + 1] += row_start[i];
     }
     uint16_t busiest() const
     {
@@ -478,14 +503,17 @@ struct Writer {
     bool order_color()
     {
         const uint32_t n = in.n_color_endpoints;
-        std::vector<uint64_t> pairs;
-        uint32_t prev = 0;
-        for (uint32_t b = 0; b < in.num_blocks; b++) {
-            const uint32_t i = in.endpoint_indices[(size_t)b * 4];
-            if (coded(b) && i != prev) { pairs.push_back(((uint64_t)i << 32) | prev); pairs.push_back(((uint64_t)prev << 32) | i); }
-            prev = i;
-        }
-        Transitions T; T.build(n, pairs);
+        const auto tb0 = std::chrono::steady_clock::now();
+        Transitions T;
+        T.build(n, [&](auto&& emit) {
+            uint32_t prev = 0;
+            for (uint32_t b = 0; b < in.num_blocks; b++) {
+                const uint32_t i = in.endpoint_indices[(size_t)b * 4];
+                if (coded(b) && i != prev) { emit(i, prev); emit(prev, i); }
+                prev = i;
+            }
+        });
+        if (getenv("CRN_B200_TRACE")) fprintf(stderr, "[crn_writer] colour transitions: %zu distinct, build %.1f ms\n", T.col.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
         const uint16_t selected = T.busiest();
         std::vector<ColorEp> eps(n);
         for (uint32_t i = 0; i < n; i++) { unpack565(in.color_endpoints[i] & 0xFFFFu, true, eps[i].lo); unpack565(in.color_endpoints[i] >> 16, true, eps[i].hi); }
@@ -493,16 +521,19 @@ struct Writer {
         std::vector<uint16_t> remap[4]; std::vector<uint8_t> packed[4]; uint64_t bits[4]; bool ok[4] = {false, false, false, false};
         bool sel_ok = true;
         std::vector<std::thread> pool;
+        pool.emplace_back([&]() { sel_ok = order_color_selectors(); });          // independent of the endpoint order
         for (int t = 0; t < 4; t++)
             pool.emplace_back([&, t]() {
+                const auto tt0 = std::chrono::steady_clock::now();
                 if (t) remap_color_endpoints(eps.data(), T, n, selected, weights[t], remap[t]);
                 else {
                     ColorEp zero; memset(&zero, 0, sizeof(zero));
                     greedy_chain(eps.data(), n, zero, [](const ColorEp& a, const ColorEp& b) { return ep_dist(a, b); }, remap[0]);
-                    sel_ok = order_color_selectors();
                 }
+                const auto tt1 = std::chrono::steady_clock::now();
                 ok[t] = pack_color_endpoints(in, remap[t], packed[t]);
                 if (ok[t]) bits[t] = trial_bits(0, remap[t], packed[t]);
+                if (getenv("CRN_B200_TRACE")) fprintf(stderr, "[crn_writer] colour trial %d: order %.1f ms, cost %.1f ms\n", t, std::chrono::duration<double, std::milli>(tt1 - tt0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt1).count());
             });
         for (auto& th : pool) th.join();
         uint64_t best = 0xFFFFFFFFull;
@@ -550,17 +581,18 @@ struct Writer {
     bool order_alpha()
     {
         const uint32_t n = in.n_alpha_endpoints;
-        std::vector<uint64_t> pairs;
-        uint32_t prev[2] = {0, 0};
-        for (uint32_t b = 0; b < in.num_blocks; b++) {
-            const uint32_t i0 = in.endpoint_indices[(size_t)b * 4 + 1], i1 = in.endpoint_indices[(size_t)b * 4 + 2];
-            if (coded(b)) {
-                if (in.has_alpha0 && i0 != prev[0]) { pairs.push_back(((uint64_t)i0 << 32) | prev[0]); pairs.push_back(((uint64_t)prev[0] << 32) | i0); }
-                if (in.has_alpha1 && i1 != prev[1]) { pairs.push_back(((uint64_t)i1 << 32) | prev[1]); pairs.push_back(((uint64_t)prev[1] << 32) | i1); }
+        Transitions T;
+        T.build(n, [&](auto&& emit) {
+            uint32_t prev[2] = {0, 0};
+            for (uint32_t b = 0; b < in.num_blocks; b++) {
+                const uint32_t i0 = in.endpoint_indices[(size_t)b * 4 + 1], i1 = in.endpoint_indices[(size_t)b * 4 + 2];
+                if (coded(b)) {
+                    if (in.has_alpha0 && i0 != prev[0]) { emit(i0, prev[0]); emit(prev[0], i0); }
+                    if (in.has_alpha1 && i1 != prev[1]) { emit(i1, prev[1]); emit(prev[1], i1); }
+                }
+                prev[0] = i0; prev[1] = i1;
             }
-            prev[0] = i0; prev[1] = i1;
-        }
-        Transitions T; T.build(n, pairs);
+        });
         const uint16_t selected = T.busiest();
         std::vector<AlphaEp> eps(n);
         for (uint32_t i = 0; i < n; i++) { eps[i].lo = (uint8_t)(in.alpha_endpoints[i] & 0xFF); eps[i].hi = (uint8_t)((in.alpha_endpoints[i] >> 8) & 0xFF); }
@@ -568,13 +600,13 @@ struct Writer {
         std::vector<uint16_t> remap[4]; std::vector<uint8_t> packed[4]; uint64_t bits[4]; bool ok[4] = {false, false, false, false};
         bool sel_ok = true;
         std::vector<std::thread> pool;
+        pool.emplace_back([&]() { sel_ok = order_alpha_selectors(); });
         for (int t = 0; t < 4; t++)
             pool.emplace_back([&, t]() {
                 if (t) remap_alpha_endpoints(eps.data(), T, n, selected, weights[t], remap[t]);
                 else {
                     AlphaEp zero = {0, 0};
                     greedy_chain(eps.data(), n, zero, [](const AlphaEp& a, const AlphaEp& b) { return alpha_dist(a, b); }, remap[0]);
-                    sel_ok = order_alpha_selectors();
                 }
                 ok[t] = pack_alpha_endpoints(in, remap[t], packed[t]);
                 if (ok[t]) bits[t] = trial_bits(1, remap[t], packed[t]);
@@ -591,15 +623,19 @@ struct Writer {
     // One walk over a level in stream order (crn_comp.cpp:349-420): with models == nullptr it fills the histograms.
     struct Stats { std::vector<uint32_t> ref, ep[2], sel[2]; };
     struct Models { Model ref, ep[2], sel[2]; };
-    void walk_level(uint32_t l, Stats* st, const Models* md, BitWriter* bw) const
+    // Rows [by0, by1) of a level (by0 even).  The running endpoint index a block is coded against is simply the previous
+    // block's index (crn_comp.cpp:392-408 updates it on every block), so row ranges are independent of each other.
+    void walk_rows(uint32_t l, uint32_t by0, uint32_t by1, Stats* st, const Models* md, BitWriter* bw) const
     {
         const Level& lv = in.levels[l];
         const bool has[3] = {in.has_color, in.has_alpha0, in.has_alpha1};
         uint32_t run[3] = {0, 0, 0};
         const uint32_t W = lv.block_width;
         const uint16_t* E = in.endpoint_indices;
-        uint32_t b = lv.first_block;
-        for (uint32_t by = 0, e = b + lv.num_blocks; b < e; by++)
+        uint32_t b = lv.first_block + by0 * W;
+        if (by0)
+            for (int c = 0; c < 3; c++) if (has[c]) run[c] = ep_remap[c ? 1 : 0][E[(size_t)(b - 1) * 4 + c]];
+        for (uint32_t by = by0, e = lv.first_block + by1 * W; b < e; by++)
             for (uint32_t bx = 0; bx < W; bx++, b++) {
                 if (!(by & 1) && !(bx & 1)) {
                     const uint32_t g = (E[(size_t)b * 4 + 3] & 3u) | ((E[(size_t)(b + W) * 4 + 3] & 3u) << 2) | ((E[(size_t)(b + 1) * 4 + 3] & 3u) << 4) |
@@ -636,6 +672,10 @@ struct Writer {
             const Level& lv = in.levels[l];
             if (!lv.block_width || (lv.block_width & 1) || lv.num_blocks % (2 * lv.block_width) || (uint64_t)lv.first_block + lv.num_blocks > in.num_blocks) return false;
         }
+        const bool trace = getenv("CRN_B200_TRACE") != nullptr;
+        auto now = []() { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        const auto t0 = now();
         // colour and alpha orderings are independent: run them side by side
         bool ok_c = true, ok_a = true;
         std::thread ta;
@@ -644,11 +684,33 @@ struct Writer {
         if (has_alpha) ta.join();
         if (!ok_c || !ok_a) return false;
 
+        const auto t1 = now();
         Stats st;
         st.ref.assign(256, 0);
         if (in.has_color) { st.ep[0].assign(in.n_color_endpoints, 0); st.sel[0].assign(in.n_color_selectors, 0); }
         if (has_alpha) { st.ep[1].assign(in.n_alpha_endpoints, 0); st.sel[1].assign(in.n_alpha_selectors, 0); }
-        for (uint32_t l = 0; l < in.num_levels; l++) walk_level(l, &st, nullptr, nullptr);
+        // both passes over the blocks run as row-range tasks on host threads (per-thread histograms, per-task bit buffers)
+        struct Task { uint32_t level, by0, by1; };
+        std::vector<Task> tasks;
+        for (uint32_t l = 0; l < in.num_levels; l++) {
+            const uint32_t W = in.levels[l].block_width, rows = in.levels[l].num_blocks / W;
+            const uint32_t step = std::max(2u, (65536u / W) & ~1u);
+            for (uint32_t y = 0; y < rows; y += step) tasks.push_back({l, y, std::min(rows, y + step)});
+        }
+        const uint32_t nthreads = std::max(1u, std::min<uint32_t>({(uint32_t)tasks.size(), std::max(1u, std::thread::hardware_concurrency()), 16u}));
+        auto run_tasks = [&](auto&& body) {
+            std::atomic<uint32_t> next{0};
+            std::vector<std::thread> pool;
+            for (uint32_t t = 0; t < nthreads; t++)
+                pool.emplace_back([&, t]() { for (uint32_t i; (i = next.fetch_add(1)) < tasks.size();) body(t, i); });
+            for (auto& th : pool) th.join();
+        };
+        {
+            std::vector<Stats> part(nthreads, st);
+            run_tasks([&](uint32_t t, uint32_t i) { walk_rows(tasks[i].level, tasks[i].by0, tasks[i].by1, &part[t], nullptr, nullptr); });
+            auto merge = [](std::vector<uint32_t>& a, const std::vector<uint32_t>& b) { for (size_t k = 0; k < a.size(); k++) a[k] += b[k]; };
+            for (const Stats& ps : part) { merge(st.ref, ps.ref); for (int k = 0; k < 2; k++) { merge(st.ep[k], ps.ep[k]); merge(st.sel[k], ps.sel[k]); } }
+        }
         Models md;
         if (!build_model(st.ref.data(), 256, 16, md.ref)) return false;
         for (int k = 0; k < 2; k++) {
@@ -656,12 +718,22 @@ struct Writer {
             if (!st.sel[k].empty() && !build_model(st.sel[k].data(), (uint32_t)st.sel[k].size(), 16, md.sel[k])) return false;
         }
         for (int k = 0; k < 2; k++) if (!st.ep[k].empty() && md.ep[k].len.empty()) { md.ep[k].len.assign(st.ep[k].size(), 0); md.ep[k].code.assign(st.ep[k].size(), 0); }
+        const auto t2 = now();
         packed_levels.resize(in.num_levels);
         {
-            std::vector<std::thread> pool;
-            for (uint32_t l = 0; l < in.num_levels; l++)
-                pool.emplace_back([&, l]() { BitWriter bw; bw.bytes.reserve(in.levels[l].num_blocks); walk_level(l, nullptr, &md, &bw); bw.finish(); packed_levels[l].swap(bw.bytes); });
-            for (auto& th : pool) th.join();
+            std::vector<BitWriter> piece(tasks.size());
+            run_tasks([&](uint32_t, uint32_t i) {
+                piece[i].bytes.reserve((size_t)(tasks[i].by1 - tasks[i].by0) * in.levels[tasks[i].level].block_width);
+                walk_rows(tasks[i].level, tasks[i].by0, tasks[i].by1, nullptr, &md, &piece[i]);
+            });
+            size_t i = 0;
+            for (uint32_t l = 0; l < in.num_levels; l++) {
+                BitWriter bw;
+                bw.bytes.swap(piece[i].bytes); bw.acc = piece[i].acc; bw.nacc = piece[i].nacc; bw.total = piece[i].total;
+                for (i++; i < tasks.size() && tasks[i].level == l; i++) bw.append(piece[i]);
+                bw.finish();
+                packed_levels[l].swap(bw.bytes);
+            }
         }
         {
             BitWriter bw;
@@ -673,6 +745,8 @@ struct Writer {
             bw.finish();
             packed_models.swap(bw.bytes);
         }
+        const auto t3 = now();
+        if (trace) fprintf(stderr, "[crn_writer] orderings %.1f ms, histogram pass %.1f ms, coding pass %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
         // file assembly (crn_comp.cpp:1414-1496; header of inc/crn_defs.h:286-341, big-endian fields)
         const uint32_t header_size = 70 + 4 * in.num_levels;
         file.assign(header_size, 0);
