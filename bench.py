@@ -19,6 +19,8 @@ every rank compresses its own texture (weak scaling, no data-path collective), m
 run also reports configs[0] (`block_pack`) and configs[3] (`transcode`) as extra objects of the same line.
 """
 import argparse
+import contextlib
+import ctypes
 import json
 import os
 import subprocess
@@ -473,6 +475,23 @@ def run_dxt_hc(ctx, dev, steps, with_reference=True):
     return out
 
 
+@contextlib.contextmanager
+def c_stdout_to_stderr():
+    """The reference's console prints progress lines ("Compressing using quality level N") with printf on stdout; this
+    process's stdout carries exactly one JSON line, so C-level stdout goes to stderr while the reference runs."""
+    libc = ctypes.CDLL(None)
+    sys.stdout.flush()
+    libc.fflush(None)
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        libc.fflush(None)
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_crn_compress(ctx, dev, with_reference=True):
     """BASELINE configs[2] end to end: crn_compress of a 6-face 2048^2 DXT1 cubemap with full mip chains to a .CRN at a target
     bitrate of 1.25 bpp -- host pixels in, file bytes out (crn_gpu_compress_crn: block gather, one dxt_hc pass + host writer per
@@ -504,7 +523,8 @@ def run_crn_compress(ctx, dev, with_reference=True):
         if ref is not None:
             th = cpu_threads()
             t0 = time.perf_counter()
-            rdata, _, _ = helpers.ref_compress(ref, faces, 0, file_type=0, quality=128, threads=th - 1)
+            with c_stdout_to_stderr():
+                rdata, _, _ = helpers.ref_compress(ref, faces, 0, file_type=0, quality=128, threads=th - 1)
             dtr = time.perf_counter() - t0
             out["reference"] = {"value": ntex / dtr / 1e6, "unit": UNIT, "ms": dtr * 1e3, "cores": th, "kind": "reference", "sample": "one crn_compress pass at quality 128 (no bitrate search)",
                                 "file_bytes": len(rdata), "bpp": len(rdata) * 8.0 / ntex}
