@@ -180,6 +180,7 @@ def _declare(lib):
     lib.crn_gpu_crnd_unpack_batch.argtypes = [vp, ctypes.POINTER(vp), u32, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     lib.crn_gpu_crnd_unpack_end.argtypes = [vp]
     lib.crn_gpu_dds_header.argtypes = [u32, u32, u32, u32, u32, vp]
+    lib.crn_gpu_compress_mip_chain.argtypes = [vp, u32, ctypes.POINTER(_CrnParams), ctypes.POINTER(_DdsParams), vp, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32)]
     lib.crn_gpu_default_dds_params.argtypes = [ctypes.POINTER(_DdsParams)]
     lib.crn_gpu_default_dds_params.restype = None
     lib.crn_gpu_compress_dds.argtypes = [vp, ctypes.POINTER(_DdsParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32)]
@@ -516,6 +517,29 @@ class Context:
         ptrs = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
         out = ctypes.c_void_p(); size = ctypes.c_uint32()
         self._check(self._lib.crn_gpu_compress_dds(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size)))
+        try:
+            return ctypes.string_at(out, size.value)
+        finally:
+            self._lib.crn_gpu_free_file(out)
+
+    def compress_mip_chain(self, faces_level0, crn_format, file_type="dds", quality_level=255, params=None, perceptual=True):
+        """crn_compress with default crn_mipmap_params (inc/crnlib.h:614): faces_level0 = list of (h, w, 4) uint8 level-0 images;
+        the mip chain is generated on the device, then compressed to a .dds (file_type "dds") or .crn ("crn").  Returns bytes."""
+        imgs = [np.ascontiguousarray(a, np.uint8) for a in faces_level0]
+        h, w = imgs[0].shape[:2]
+        ptrs = (ctypes.c_void_p * len(imgs))(*[a.ctypes.data for a in imgs])
+        out = ctypes.c_void_p(); size = ctypes.c_uint32()
+        if file_type == "crn":
+            cp = crn_params(crn_format, w, h, 1, len(imgs), quality_level, perceptual, lib=self._lib)
+            rc = self._lib.crn_gpu_compress_mip_chain(self._ctx, 0, ctypes.byref(cp), None, None, 0, 0, ptrs, ctypes.byref(out), ctypes.byref(size))
+        else:
+            dp = _DdsParams()
+            self._lib.crn_gpu_default_dds_params(ctypes.byref(dp))
+            dp.crn_format, dp.width, dp.height, dp.levels, dp.faces, dp.quality_level = int(crn_format), int(w), int(h), 1, len(imgs), int(quality_level)
+            if params is not None:
+                dp.pack = params._c()
+            rc = self._lib.crn_gpu_compress_mip_chain(self._ctx, 1, None, ctypes.byref(dp), None, 0, 0, ptrs, ctypes.byref(out), ctypes.byref(size))
+        self._check(rc)
         try:
             return ctypes.string_at(out, size.value)
         finally:

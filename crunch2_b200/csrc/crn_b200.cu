@@ -2007,6 +2007,52 @@ int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const vo
     return CRN_GPU_OK;
 }
 
+int crn_gpu_compress_mip_chain(crn_gpu_ctx* ctx, uint32_t file_type, const crn_gpu_crn_params* cp, const crn_gpu_dds_params* dp, const crn_gpu_resample_params* mip,
+                               uint32_t min_mip_size, uint32_t max_levels, const void* const* h_level0_faces, void** out_file, uint32_t* out_size)
+{   // crn_compress(const crn_comp_params&, const crn_mipmap_params&, ...) (inc/crnlib.h:614): create_texture_mipmaps in generate mode
+    // (crnlib/crn_texture_comp.cpp:352-575) -> generate_mipmaps -> the compressor of the file type
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (out_file) *out_file = nullptr;
+    if (out_size) *out_size = 0;
+    const bool crn = file_type == 0;
+    if (file_type > 1 || (crn ? !crn_params_ok(cp) : (!dp || dp->struct_size != sizeof(crn_gpu_dds_params))) || !h_level0_faces || !out_file || !out_size ||
+        (mip && mip->struct_size != sizeof(crn_gpu_resample_params)))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_mip_chain: bad argument");
+    const uint32_t width = crn ? cp->width : dp->width, height = crn ? cp->height : dp->height, faces = crn ? cp->faces : dp->faces;
+    if (!width || !height || width > 4096 || height > 4096 || (faces != 1 && faces != 6)) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_mip_chain: bad size");
+    for (uint32_t f = 0; f < faces; f++) if (!h_level0_faces[f]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_mip_chain: missing image");
+    crn_gpu_resample_params rp;
+    if (mip) rp = *mip;
+    else { crn_gpu_default_resample_params(&rp); rp.filter = 4; rp.filter_scale = .9f; rp.srgb = 1; rp.source_gamma = 2.2f; rp.wrapping = 0; rp.num_comps = 0; }   // crn_mipmap_params::clear()
+    if (!rp.num_comps) {                                         // alpha is filtered only when the source has any (is_component_valid(3))
+        bool has_alpha = false;
+        for (uint32_t f = 0; f < faces && !has_alpha; f++) {
+            const uint8_t* px = static_cast<const uint8_t*>(h_level0_faces[f]);
+            for (size_t i = 0, n = (size_t)width * height; i < n; i++) if (px[i * 4 + 3] < 255) { has_alpha = true; break; }
+        }
+        rp.num_comps = has_alpha ? 4 : 3;
+    }
+    const uint32_t levels = crn_gpu_mip_level_count(width, height, min_mip_size ? min_mip_size : 1, max_levels ? std::min(max_levels, 16u) : 16u);
+    size_t mip_bytes = 0;
+    for (uint32_t l = 1; l < levels; l++) mip_bytes += (size_t)std::max(1u, width >> l) * std::max(1u, height >> l) * 4;
+    std::vector<std::vector<uint8_t>> chains(faces);
+    std::vector<const void*> images((size_t)faces * levels);
+    for (uint32_t f = 0; f < faces; f++) {
+        chains[f].resize(mip_bytes ? mip_bytes : 1);
+        uint32_t n = 0;
+        int rc = crn_gpu_generate_mipmaps_host(ctx, &rp, h_level0_faces[f], width, height, width * 4, min_mip_size ? min_mip_size : 1, max_levels ? std::min(max_levels, 16u) : 16u,
+                                               chains[f].data(), chains[f].size(), &n);
+        if (rc) return rc;
+        if (n != levels) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_mip_chain: level count mismatch");
+        images[(size_t)f * levels] = h_level0_faces[f];
+        size_t at = 0;
+        for (uint32_t l = 1; l < levels; l++) { images[(size_t)f * levels + l] = chains[f].data() + at; at += (size_t)std::max(1u, width >> l) * std::max(1u, height >> l) * 4; }
+    }
+    if (crn) { crn_gpu_crn_params q = *cp; q.levels = levels; return crn_gpu_compress_crn(ctx, &q, images.data(), out_file, out_size, nullptr, nullptr); }
+    crn_gpu_dds_params q = *dp; q.levels = levels;
+    return crn_gpu_compress_dds(ctx, &q, images.data(), out_file, out_size);
+}
+
 int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, void** out_file, uint32_t* out_size)
 {   // crn_decompress_crn_to_dds (crnlib/crnlib.cpp:269-291): transcode every level on the device, lay the faces out DDS-style
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;

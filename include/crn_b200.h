@@ -429,6 +429,15 @@ typedef struct crn_gpu_dds_params {
 CRN_API void crn_gpu_default_dds_params(crn_gpu_dds_params* p);
 CRN_API int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size);
 
+/* crn_compress with a crn_mipmap_params (inc/crnlib.h:614; create_texture_mipmaps in its generate mode,
+ * crnlib/crn_texture_comp.cpp:352-575): level 0 of each face in, the chain from crn_gpu_generate_mipmaps, then
+ * crn_gpu_compress_crn (file_type 0, `cp`) or crn_gpu_compress_dds (file_type 1, `dp`); the params' `levels` is replaced by the
+ * generated count.  mip = NULL takes crn_mipmap_params' defaults (kaiser, gamma filtering 2.2, blurriness 0.9); num_comps 0 =
+ * decide like the reference (4 when any source texel has alpha < 255, else 3).  min_mip_size / max_levels 0 = 1 / 16.
+ * Cropping, clamping and rescaling of the source (crn_mipmap_params::m_window_*, m_clamp_*, m_scale_mode) are not built. */
+CRN_API int crn_gpu_compress_mip_chain(crn_gpu_ctx* ctx, uint32_t file_type, const crn_gpu_crn_params* cp, const crn_gpu_dds_params* dp, const crn_gpu_resample_params* mip,
+                                       uint32_t min_mip_size, uint32_t max_levels, const void* const* h_level0_faces, void** out_file, uint32_t* out_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,6 +213,32 @@ SHIM_API void* ref_compress(int file_type, int format, uint32_t width, uint32_t 
     return q;
 }
 
+// crn_compress with a crn_mipmap_params (inc/crnlib.h:614): level 0 in, the reference generates the chain (defaults of
+// crn_mipmap_params::clear(): kaiser, gamma filtering 2.2, blurriness 0.9, down to 1x1) and compresses it.
+SHIM_API void* ref_compress_mip_chain(int file_type, int format, uint32_t width, uint32_t height, const uint32_t* level0, uint32_t flags,
+                                      uint32_t quality_level, int dxt_quality, uint32_t helper_threads, uint32_t* out_size)
+{
+    crn_comp_params cp;
+    cp.m_file_type = (crn_file_type)file_type;
+    cp.m_format = (crn_format)format;
+    cp.m_width = width; cp.m_height = height; cp.m_faces = 1; cp.m_levels = 1;
+    cp.m_flags = flags;
+    cp.m_quality_level = quality_level;
+    cp.m_dxt_quality = (crn_dxt_quality)dxt_quality;
+    cp.m_num_helper_threads = helper_threads;
+    cp.m_pImages[0][0] = level0;
+    crn_mipmap_params mp;
+    crn_uint32 size = 0;
+    void* p = crn_compress(cp, mp, size, NULL, NULL);
+    *out_size = 0;
+    if (!p) return NULL;
+    void* q = malloc(size);
+    memcpy(q, p, size);
+    crn_free_block(p);
+    *out_size = size;
+    return q;
+}
+
 SHIM_API void ref_free(void* p) { free(p); }
 
 SHIM_API void* ref_crn_to_dds(const void* crn, uint32_t crn_size, uint32_t* dds_size)

@@ -88,3 +88,40 @@ def test_compress_dds_clustered_matches_reference_file(simctx, ref):
     want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT["DXT1"], file_type=1, quality=128, threads=0, flags=1 | 2 | 8)
     got = simctx.compress_dds([levels], helpers.CRN_FMT["DXT1"], quality_level=128)
     assert got == want
+
+
+# ---- crn_compress with a crn_mipmap_params: level 0 in, generated chain, whole file out ----------------------------
+def ref_compress_mip_chain(ref, img, fmt, file_type, quality, flags):
+    ref.ref_compress_mip_chain.restype = ctypes.c_void_p
+    h, w = img.shape[:2]
+    size = ctypes.c_uint32()
+    img = np.ascontiguousarray(img)
+    p = ref.ref_compress_mip_chain(file_type, helpers.CRN_FMT[fmt], w, h, img.ctypes.data_as(ctypes.c_void_p), flags, quality, 4, 0, ctypes.byref(size))
+    assert p
+    d = ctypes.string_at(p, size.value)
+    ref.ref_free(ctypes.c_void_p(p))
+    return d
+
+
+@pytest.mark.parametrize("fmt,w,h,alpha", [("DXT1", 32, 16, False), ("DXT5", 24, 24, True), ("DXT5", 16, 16, False), ("DXT5A", 20, 12, True)])
+def test_compress_mip_chain_dds_matches_reference_file(simctx, ref, fmt, w, h, alpha):
+    """crn_compress(comp_params, mipmap_params) with the default crn_mipmap_params: generated chain + packer, byte for byte."""
+    import blockgen
+    img = blockgen.smooth_image(w, h, 90 + w, alpha=True)
+    if not alpha:
+        img[..., 3] = 255                     # no alpha anywhere: the reference filters three components and writes 255
+    want = ref_compress_mip_chain(ref, img, fmt, 1, 255, FLAGS_EXACT)
+    got = simctx.compress_mip_chain([img], helpers.CRN_FMT[fmt], "dds", quality_level=255)
+    assert got[:128] == want[:128]
+    assert got == want
+
+
+def test_compress_mip_chain_crn_within_tolerance(simctx, ref):
+    import blockgen
+    from test_crn_compress_cpu import check
+    img = blockgen.smooth_image(64, 64, 8, alpha=True)
+    want = ref_compress_mip_chain(ref, img, "DXT1", 0, 128, 1 | 2 | 8)
+    got = simctx.compress_mip_chain([img], helpers.CRN_FMT["DXT1"], "crn", quality_level=128)
+    levels = simctx.generate_mipmaps(img)
+    check(ref, "DXT1", [levels], got, want)
+    assert crn.texture_info(got, lib=simctx._lib)["levels"] == 7

@@ -86,3 +86,12 @@ def test_compress_dds_clustered_within_tolerance(gpu_ctx, ref):
     a, b = quality.decode_blocks(got[128:], 3), quality.decode_blocks(want[128:], 3)
     ps = [(quality.psnr(a, src, c), quality.psnr(b, src, c)) for c in ([0, 1, 2], [3])]
     assert_within_tolerance(ps, quality.lzma_bits(got[128:]), quality.lzma_bits(want[128:]))
+
+
+def test_compress_mip_chain_is_the_reference_file(gpu_ctx, ref):
+    """crn_compress(comp_params, mipmap_params): level 0 in, chain generated on the device, packed, .dds byte for byte."""
+    from test_dds_cpu import ref_compress_mip_chain
+    img = blockgen.smooth_image(256, 128, 3, alpha=True)
+    want = ref_compress_mip_chain(ref, img, "DXT5", 1, 255, 1 | 2 | 8 | 32)
+    got = gpu_ctx.compress_mip_chain([img], helpers.CRN_FMT["DXT5"], "dds", quality_level=255)
+    assert got == want
