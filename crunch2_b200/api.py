@@ -55,7 +55,8 @@ class _CrnParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "crn_format", "width", "height", "levels", "faces", "quality_level", "perceptual",
                                                 "alpha_component", "userdata0", "userdata1")] + [("palette_sizes", ctypes.c_uint32 * 4),
                 ("adaptive_tile_color_psnr_derating", ctypes.c_float), ("adaptive_tile_alpha_psnr_derating", ctypes.c_float),
-                ("target_bitrate", ctypes.c_float)]
+                ("target_bitrate", ctypes.c_float), ("shard_rank", ctypes.c_uint32), ("shard_count", ctypes.c_uint32),
+                ("exchange", ctypes.c_void_p), ("exchange_user", ctypes.c_void_p)]
 
 
 class _DdsParams(ctypes.Structure):
@@ -474,7 +475,8 @@ class Context:
             self._lib.crn_gpu_hc_free(h)
         return out
 
-    def compress_crn(self, images, crn_format, quality_level=128, perceptual=True, alpha_component=3, palette_sizes=None, userdata=(0, 0), target_bitrate=0.0):
+    def compress_crn(self, images, crn_format, quality_level=128, perceptual=True, alpha_component=3, palette_sizes=None, userdata=(0, 0), target_bitrate=0.0,
+                     shard=None):
         """crn_compress to a .CRN (crn_comp::compress_pass, crnlib/crn_comp.cpp:1613; with target_bitrate > 0 the quality search
         of crnlib/crn_texture_comp.cpp:120-262): images[face][level] = (h, w, 4) uint8 host arrays, level l being
         max(1, w >> l) x max(1, h >> l).  Returns (file bytes, bits per texel, quality level)."""
@@ -482,6 +484,20 @@ class Context:
         h, w = images[0][0].shape[:2]
         p = crn_params(crn_format, w, h, levels, faces, quality_level, perceptual, alpha_component, palette_sizes, userdata, lib=self._lib)
         p.target_bitrate = float(target_bitrate)
+        cb = None
+        if shard is not None and int(shard[1]) > 1:          # (rank, world, allgather): as in hc_compress, every rank makes this same call
+            rank, world, gather = shard
+
+            def _exchange(user, buf, bytes_per_rank, nranks):
+                try:
+                    arr = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), (int(bytes_per_rank) * int(nranks),))
+                    gather(arr, int(bytes_per_rank))
+                    return 0
+                except Exception:  # never let an exception cross the C boundary
+                    return 1
+            cb = EXCHANGE_FN(_exchange)
+            p.shard_rank, p.shard_count = int(rank), int(world)
+            p.exchange = ctypes.cast(cb, ctypes.c_void_p)
         flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]
         for i, a in enumerate(flat):
             lw, lh = max(1, w >> (i % levels)), max(1, h >> (i % levels))

@@ -1470,7 +1470,8 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
     if (out_size) *out_size = 0;
     if (out_bitrate) *out_bitrate = 0.0f;
     if (out_quality) *out_quality = 0;
-    if (!crn_params_ok(p) || !h_images || !out_file || !out_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: bad argument");
+    if (!crn_params_ok(p) || !h_images || !out_file || !out_size || (p->shard_count > 1 && (!p->exchange || p->shard_rank >= p->shard_count)))
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: bad argument");
     for (uint32_t i = 0; i < p->faces * p->levels; i++)
         if (!h_images[i]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_crn: missing image");      // alias_images, crn_comp.cpp:432-435
     crn_gpu_hc_params hp;
@@ -1500,6 +1501,7 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         crn_gpu_hc_params qhp;
         int r = crn_gpu_crn_hc_params(&q, &qhp);
         if (r) return r;
+        if (p->shard_count > 1) { qhp.shard_rank = p->shard_rank; qhp.shard_count = p->shard_count; qhp.exchange = p->exchange; qhp.exchange_user = p->exchange_user; }
         crn_gpu_hc* H = nullptr;
         r = crn_gpu_hc_compress(ctx, &qhp, d_blocks.p, 0, &H);
         if (r) return r;

@@ -346,6 +346,11 @@ typedef struct crn_gpu_crn_params {
                                            from quality_level (otherwise cCRNCompFlagManualPaletteSizes) */
     float adaptive_tile_color_psnr_derating, adaptive_tile_alpha_psnr_derating;
     float target_bitrate;               /* m_target_bitrate in bits per texel; 0 = use quality_level (crn_gpu_compress_crn only) */
+    /* One texture on several GPUs (crn_gpu_compress_crn only): passed to every crn_gpu_hc_compress of the call, see
+     * crn_gpu_hc_params.  Every rank makes the same call on the same images and returns the same file. */
+    uint32_t shard_rank, shard_count;   /* default 0, 1 (0 is read as 1) */
+    crn_gpu_exchange_fn exchange;       /* required when shard_count > 1 */
+    void* exchange_user;
 } crn_gpu_crn_params;
 CRN_API void crn_gpu_default_crn_params(crn_gpu_crn_params* p);
 /* crn_comp::alias_images' level table + quantize_images' parameter derivation (crn_comp.cpp:458-466, :525-716): fills

@@ -99,3 +99,42 @@ def test_gloo_sharded_dxt_hc(tmp_path, sim):
     for fmt in ("0", "3"):
         assert ranks[0][fmt]["same"] and ranks[1][fmt]["same"]
         assert ranks[0][fmt]["sha"] == ranks[1][fmt]["sha"]
+
+
+CRN_WORKER = r'''
+import os, sys, json, hashlib
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch, torch.distributed as dist
+import blockgen, helpers
+import crunch2_b200 as crn
+from crunch2_b200 import shard
+from bench import mip_chain
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ctx = crn.Context(0, lib=helpers.load_sim())
+faces = [mip_chain(blockgen.smooth_image(64, 48, 11, alpha=True))[:3]]
+whole, _, _ = ctx.compress_crn(faces, 2, quality_level=128)
+part, rate, q = ctx.compress_crn(faces, 2, quality_level=128, shard=(rank, world, shard.allgather_inplace))
+out = dict(same=bool(whole == part), sha=hashlib.sha256(part).hexdigest(), size=len(part))
+gathered = [None] * world
+dist.all_gather_object(gathered, out)
+if rank == 0:
+    print(json.dumps(gathered))
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_sharded_crn_compress(tmp_path, sim):
+    """crn_compress to .CRN of one texture on two ranks (quantiser sharded by cluster, writer replicated): both ranks return the
+    unsharded file, byte for byte."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "crn_worker.py"
+    script.write_text(CRN_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), helpers.ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    ranks = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    assert len(ranks) == 2 and ranks[0]["same"] and ranks[1]["same"]
+    assert ranks[0]["sha"] == ranks[1]["sha"] and ranks[0]["size"] > 100
