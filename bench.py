@@ -414,9 +414,26 @@ def run_dxt_hc_sharded(ctx, dev, rank, world, steps):
     digest = hashlib.sha256(g["endpoint_indices"].tobytes() + g["selector_indices"].tobytes() + g["color_endpoints"].tobytes()).hexdigest()
     digests = [None] * world
     torch.distributed.all_gather_object(digests, digest)
-    return {"workload": "c3_quantiser_dxt1_cubemap_6x2048_mips, ONE texture sharded over %d GPUs by endpoint cluster" % world, "scaling": "strong",
-            "value": n * 16 / dt / 1e6, "unit": UNIT, "ms": dt * 1e3, "step_ms": [round(x * 1e3, 1) for x in td], "collective": "NCCL all-gather of 16 B per cluster, twice per call",
-            "identical_on_all_ranks": bool(all(d == digests[0] for d in digests)), "sha256": digest[:16]}
+    out = {"workload": "c3_quantiser_dxt1_cubemap_6x2048_mips, ONE texture sharded over %d GPUs by endpoint cluster" % world, "scaling": "strong",
+           "value": n * 16 / dt / 1e6, "unit": UNIT, "ms": dt * 1e3, "step_ms": [round(x * 1e3, 1) for x in td], "collective": "NCCL all-gather of 16 B per cluster, twice per call",
+           "identical_on_all_ranks": bool(all(d == digests[0] for d in digests)), "sha256": digest[:16]}
+    # the same texture through the whole call: host pixels -> .crn at quality 128, quantiser sharded, writer replicated on every rank
+    try:
+        ntex = sum(l.shape[0] * l.shape[1] for f in faces for l in f)
+        data = ctx.compress_crn(faces, 0, quality_level=128, shard=(rank, world, gather))[0]
+        tc = []
+        for _ in range(2):
+            torch.cuda.synchronize(); torch.distributed.barrier()
+            t0 = time.perf_counter()
+            data = ctx.compress_crn(faces, 0, quality_level=128, shard=(rank, world, gather))[0]
+            tc.append(shard.max_over_ranks(time.perf_counter() - t0, dev))
+        files = [None] * world
+        torch.distributed.all_gather_object(files, hashlib.sha256(data).hexdigest())
+        out["crn_compress_q128"] = {"value": ntex / min(tc) / 1e6, "unit": UNIT, "ms": min(tc) * 1e3, "file_bytes": len(data),
+                                    "identical_on_all_ranks": bool(all(f == files[0] for f in files)), "timing": "host wall clock, max over ranks, host pixels in / file bytes out"}
+    except Exception as e:
+        out["crn_compress_q128"] = {"error": str(e)[:300]}
+    return out
 
 
 def run_dxt_hc(ctx, dev, steps, with_reference=True):
