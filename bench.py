@@ -126,6 +126,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keeps the process's real stdout for the ONE JSON line: fd 1 is pointed at stderr for everything else that writes to it
+    from C (NCCL's version banner under NCCL_DEBUG=VERSION, the reference's console), whatever the environment sets."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        ctypes.CDLL(None).fflush(None)
+        os.write(_JSON_FD, line)
+
+
 class quiet_stdout:
     """The reference prints progress to fd 1 from C; keep the bench's stdout to the one JSON line."""
 
@@ -692,6 +715,7 @@ def main():
     ap.add_argument("--no-block-pack", action="store_true")
     ap.add_argument("--no-hc", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -718,7 +742,7 @@ def main():
         dt = time.perf_counter() - t0
         v = ntex * args.steps / dt / 1e6
         base["value"] = v
-        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        emit(({"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config, "cpu_baseline": base,
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
@@ -834,7 +858,7 @@ def main():
             out["cpu_baseline"] = run_cpu_baseline(wl)[0]
         except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
