@@ -1477,6 +1477,8 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
     crn_gpu_hc_params hp;
     int rc = crn_gpu_crn_hc_params(p, &hp);
     if (rc) return set_err(ctx, rc, "crn_gpu_compress_crn: unsupported format");
+    timespec ts_begin; clock_gettime(CLOCK_MONOTONIC, &ts_begin);
+    const double t_begin = ts_begin.tv_sec * 1e3 + ts_begin.tv_nsec * 1e-6;
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     // the [block][16] array of all levels and faces (crn_comp.cpp:717-741), gathered on the device from one staging image;
     // it stays in HBM for every trial of the bitrate search (the reference restarts from the pixels on each pass)
@@ -1494,8 +1496,12 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
             texels += (uint64_t)w * h;
         }
     }
+    const bool trace = getenv("CRN_B200_TRACE") != nullptr;
+    auto wall_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    if (trace) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[crn_b200] compress_crn: upload + block gather %.1f ms\n", wall_ms() - t_begin); }
     // one crn_comp::compress_pass at a quality level: quantise, write, report bits per texel
     auto pass = [&](uint32_t quality, void** file, uint32_t* size, float* bitrate) -> int {
+        const double tp0 = wall_ms();
         crn_gpu_crn_params q = *p;
         q.quality_level = quality;
         crn_gpu_hc_params qhp;
@@ -1505,12 +1511,14 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         crn_gpu_hc* H = nullptr;
         r = crn_gpu_hc_compress(ctx, &qhp, d_blocks.p, 0, &H);
         if (r) return r;
+        const double tp1 = wall_ms();
         r = crn_gpu_crn_write(&q, &qhp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),
                               H->alpha_endpoints.data(), (uint32_t)H->alpha_endpoints.size(), H->color_selectors.data(), (uint32_t)H->color_selectors.size(),
                               H->alpha_selectors.data(), (uint32_t)H->alpha_selectors.size(), file, size);
         crn_gpu_hc_free(H);
         if (r) return set_err(ctx, r, "crn_gpu_compress_crn: the writer rejected the quantiser's output");
         *bitrate = (*size * 8.0f) / (float)texels;                                                                // crn_comp.cpp:1640-1653
+        if (trace) fprintf(stderr, "[crn_b200] compress_crn pass q%u: quantiser %.1f ms, writer %.1f ms, %u bytes\n", quality, tp1 - tp0, wall_ms() - tp1, *size);
         return CRN_GPU_OK;
     };
     const bool manual = p->palette_sizes[0] && p->palette_sizes[1] && p->palette_sizes[2] && p->palette_sizes[3];
