@@ -443,6 +443,7 @@ def run_dxt_hc_sharded(ctx, dev, rank, world, steps):
     # the same texture through the whole call: host pixels -> .crn at quality 128, quantiser sharded, writer replicated on every rank
     try:
         ntex = sum(l.shape[0] * l.shape[1] for f in faces for l in f)
+        faces = [[np.ascontiguousarray(l) for l in f] for f in faces]           # tight-pitch host images (crn_comp_params::m_pImages)
         data = ctx.compress_crn(faces, 0, quality_level=128, shard=(rank, world, gather))[0]
         tc = []
         for _ in range(2):
@@ -538,7 +539,8 @@ def run_crn_compress(ctx, dev, with_reference=True):
     trial of the reference's quality search, blocks resident in HBM across trials).  Also one fixed-quality pass (q128), beside
     the reference's crn_compress of the same pass on the host cores (its whole search would take minutes)."""
     import blockgen
-    faces = [mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False)) for f in range(6)]
+    # tight-pitch host images, as crn_comp_params::m_pImages requires (mip_chain's levels are strided views)
+    faces = [[np.ascontiguousarray(l) for l in mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False))] for f in range(6)]
     ntex = sum(l.shape[0] * l.shape[1] for f in faces for l in f)
     ctx.compress_crn(faces, 0, quality_level=128)                              # warm-up: buffer pool, pinned staging
     l0 = ctx.launch_count

@@ -12,7 +12,8 @@ from bench import mip_chain  # noqa: E402
 
 q = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 ctx = crn.Context(0)
-faces = [mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False)) for f in range(6)]
+import numpy as np  # noqa: E402
+faces = [[np.ascontiguousarray(l) for l in mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False))] for f in range(6)]
 ctx.compress_crn(faces, 0, quality_level=q)
 for _ in range(2):
     t0 = time.perf_counter()
