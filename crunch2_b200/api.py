@@ -449,7 +449,10 @@ class Context:
             p.shard_rank, p.shard_count = int(rank), int(world)
             p.exchange = ctypes.cast(cb, ctypes.c_void_p)
         h = ctypes.c_void_p()
-        self._check(self._lib.crn_gpu_hc_compress(self._ctx, ctypes.byref(p), ptr, 1 if on_host else 0, ctypes.byref(h)))
+        rc = self._lib.crn_gpu_hc_compress(self._ctx, ctypes.byref(p), ptr, 1 if on_host else 0, ctypes.byref(h))
+        if rc and cb is not None and failure:
+            raise failure[0]                                  # the collective's own exception, not "the exchange callback failed"
+        self._check(rc)
         try:
             info = _HcInfo()
             info.struct_size = ctypes.sizeof(_HcInfo)
@@ -487,13 +490,15 @@ class Context:
         cb = None
         if shard is not None and int(shard[1]) > 1:          # (rank, world, allgather): as in hc_compress, every rank makes this same call
             rank, world, gather = shard
+            failure = []
 
             def _exchange(user, buf, bytes_per_rank, nranks):
                 try:
                     arr = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), (int(bytes_per_rank) * int(nranks),))
                     gather(arr, int(bytes_per_rank))
                     return 0
-                except Exception:  # never let an exception cross the C boundary
+                except Exception as e:  # never let an exception cross the C boundary
+                    failure.append(e)
                     return 1
             cb = EXCHANGE_FN(_exchange)
             p.shard_rank, p.shard_count = int(rank), int(world)
@@ -505,7 +510,10 @@ class Context:
                 raise ValueError("image %d has shape %s, expected %s" % (i, a.shape, (lh, lw, 4)))
         ptrs = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
         out = ctypes.c_void_p(); size = ctypes.c_uint32(); rate = ctypes.c_float(); q = ctypes.c_uint32()
-        self._check(self._lib.crn_gpu_compress_crn(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size), ctypes.byref(rate), ctypes.byref(q)))
+        rc = self._lib.crn_gpu_compress_crn(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size), ctypes.byref(rate), ctypes.byref(q))
+        if rc and cb is not None and failure:
+            raise failure[0]
+        self._check(rc)
         try:
             return ctypes.string_at(out, size.value), rate.value, q.value
         finally:

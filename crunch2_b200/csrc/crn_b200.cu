@@ -7,6 +7,7 @@
 #include "pack_kernels.cuh"
 #include "transcode_host.h"
 #include "transcode_wide.cuh"
+#include "transcode_streams.cuh"
 #include "cluster_kernels.cuh"
 #include "qdxt_kernels.cuh"
 #include "vq_host.h"
@@ -34,6 +35,7 @@ struct crn_gpu_ctx {
     int sm_count;
     uint64_t launches;
     char err[256];
+    crn_gpu_progress_fn progress; void* progress_user;   // crn_gpu_set_progress
     // reusable device staging for the *_host entry points
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
@@ -43,7 +45,7 @@ struct crn_gpu_ctx {
     uint32_t* d_cluster_flags;           // set by the dxt_hc pipeline around a cluster-optimiser call: per-cluster m_reordered / m_alternate_rounding out
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
     void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
-    int wide_smem_set;
+    int wide_smem_set, streams_smem_set;
     crn::VqWorkspace vq_ws;              // slab of the vector quantiser
     int transcode_smem_set;
     // clustered path: per-element child contexts (own stream + scratch) and a cache of released device buffers, both
@@ -63,6 +65,23 @@ int set_err(crn_gpu_ctx* ctx, int code, const char* what, cudaError_t ce = cudaS
         else snprintf(ctx->err, sizeof(ctx->err), "%s", what);
     }
     return code;
+}
+
+// crn_progress_callback_func semantics: called on the calling thread between phases; 0 from the callback cancels the call.
+int progress_tick(crn_gpu_ctx* ctx, uint32_t phase, uint32_t total, uint32_t sub, uint32_t subtotal)
+{
+    if (!ctx || !ctx->progress) return CRN_GPU_OK;
+    return ctx->progress(phase, total, sub, subtotal, ctx->progress_user) ? CRN_GPU_OK : set_err(ctx, CRN_GPU_ERR_CANCELLED, "cancelled by the progress callback");
+}
+
+// Every extern "C" body runs inside this: nothing may unwind across the C boundary (include/crn_b200.h: "never throws").
+template <typename F>
+int crn_guard(crn_gpu_ctx* ctx, F&& body) noexcept
+{
+    try { return body(); }
+    catch (const std::bad_alloc&) { return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "out of host memory"); }
+    catch (const std::exception& e) { return set_err(ctx, CRN_GPU_ERR_BAD_DATA, e.what()); }
+    catch (...) { return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "unexpected exception"); }
 }
 
 #define CRN_CUDA(ctx, call)                                                          \
@@ -461,23 +480,23 @@ extern "C" {
 uint32_t crn_gpu_abi_version(void) { return CRN_B200_ABI_VERSION; }
 
 int crn_gpu_is_native(void)
-{
+{ return crn_guard(nullptr, [&]() -> int {
 #ifdef __CUDACC__
     return 1;
 #else
     return 0;
 #endif
-}
+}); }
 
 int crn_gpu_device_count(void)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
-}
+}); }
 
 int crn_gpu_create(int device, crn_gpu_ctx** out_ctx)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!out_ctx) return CRN_GPU_ERR_BAD_PARAM;
     *out_ctx = nullptr;
     int n = 0;
@@ -493,7 +512,7 @@ int crn_gpu_create(int device, crn_gpu_ctx** out_ctx)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CRN_GPU_ERR_CUDA; }
     *out_ctx = ctx;
     return CRN_GPU_OK;
-}
+}); }
 
 void crn_gpu_destroy(crn_gpu_ctx* ctx)
 {
@@ -525,10 +544,15 @@ void* crn_gpu_stream(crn_gpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullp
 uint64_t crn_gpu_launch_count(const crn_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int crn_gpu_synchronize(crn_gpu_ctx* ctx)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
+}); }
+
+void crn_gpu_set_progress(crn_gpu_ctx* ctx, crn_gpu_progress_fn fn, void* user)
+{
+    if (ctx) { ctx->progress = fn; ctx->progress_user = user; }
 }
 
 void crn_gpu_default_pack_params(crn_gpu_pack_params* p)
@@ -553,7 +577,7 @@ uint32_t crn_gpu_bytes_per_block(uint32_t format)
 
 int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                        const void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, void* d_out)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!params || params->struct_size != sizeof(crn_gpu_pack_params) || !d_rgba || !d_out || !width || !height ||
         pitch_bytes < width * 4u || (pitch_bytes & 3u))
@@ -632,11 +656,11 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
     if (color_rc) return color_rc;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                             const void* h_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, void* h_out)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!h_rgba || !h_out || !width || !height) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_pack_image_host: bad argument");
     const uint32_t bpb = crn_gpu_bytes_per_block(format);
@@ -654,7 +678,7 @@ int crn_gpu_pack_image_host(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pac
     CRN_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 
 /* ---- cluster optimisers ---------------------------------------------------------------------------- */
@@ -665,7 +689,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
                                    uint32_t n_clusters, uint32_t total_member_blocks,
                                    void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
                                    uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!params || params->struct_size != sizeof(crn_gpu_pack_params) || !d_blocks_rgba || !n_blocks || !d_cluster_offsets ||
         !d_cluster_blocks || !d_out || out_stride_bytes < 8 || (out_stride_bytes & 7) || (out_offset_bytes & 7))
@@ -733,7 +757,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     ctx->launches += 6;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* params, uint32_t component,
                                    const void* d_blocks_rgba, uint32_t n_blocks,
@@ -741,7 +765,7 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
                                    uint32_t n_clusters, uint32_t total_member_blocks,
                                    void* d_out, uint32_t out_stride_bytes, uint32_t out_offset_bytes,
                                    uint32_t* d_cluster_endpoints, uint64_t* d_cluster_error)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!params || params->struct_size != sizeof(crn_gpu_pack_params) || !d_blocks_rgba || !n_blocks || !d_cluster_offsets ||
         !d_cluster_blocks || !d_out || component > 3 || out_stride_bytes < 8 || (out_stride_bytes & 7) || (out_offset_bytes & 7) ||
@@ -761,11 +785,11 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, const void* d_blocks_rgba, uint32_t n_blocks,
                           const crn_gpu_mip_desc* mips, uint32_t num_mips, void* d_vectors, uint32_t* d_weights, uint8_t* d_chunk_encoding)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     crn::QdxtMipTable mt;
     if (kind > 1 || component > 3 || !d_blocks_rgba || !n_blocks || !d_vectors || !d_weights || !build_mip_table(mips, num_mips, n_blocks, mt))
@@ -781,13 +805,13 @@ int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, c
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const crn_gpu_pack_params* params, uint32_t component,
                                const void* d_blocks_rgba, uint32_t n_blocks,
                                const uint32_t* d_cluster_offsets, const uint32_t* d_cluster_blocks, uint32_t n_clusters,
                                void* d_elements, uint32_t stride_bytes, uint32_t offset_bytes)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (kind > 1 || !params || params->struct_size != sizeof(crn_gpu_pack_params) || component > 3 || !d_blocks_rgba || !n_blocks ||
         !d_cluster_offsets || !d_cluster_blocks || !d_elements || stride_bytes < 8 || (stride_bytes & 7) || (offset_bytes & 7))
@@ -809,14 +833,14 @@ int crn_gpu_optimize_selectors(crn_gpu_ctx* ctx, uint32_t kind, const crn_gpu_pa
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 /* ---- vector quantiser ----------------------------------------------------------------------------- */
 
 int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d_vectors, const uint32_t* d_weights, uint32_t n,
                           uint32_t max_codebook_size, uint32_t retrieve_max_clusters, int threaded,
                           uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if ((dims != 2 && dims != 6 && dims != 16) || !d_vectors || !d_weights || !n || !max_codebook_size || !h_cluster_of)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_vq_clusterize: bad argument");
@@ -827,13 +851,13 @@ int crn_gpu_vq_clusterize(crn_gpu_ctx* ctx, uint32_t dims, const void* d_vectors
     case 6: return vq_clusterize<6>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
     default: return vq_clusterize<16>(ctx, v, d_weights, n, max_codebook_size, retrieve_max_clusters, threaded, h_cluster_of, num_clusters, codebook_size);
     }
-}
+}); }
 
 /* ---- clustered DDS compression ------------------------------------------------------------------- */
 
 int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                       const crn_gpu_level_desc* levels, uint32_t num_levels, int pixels_on_host, crn_gpu_qdxt** out)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!out || !params || params->struct_size != sizeof(crn_gpu_pack_params) || !levels || !num_levels || num_levels > (uint32_t)crn::kQdxtMaxMips)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_init: bad argument");
@@ -933,7 +957,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     if (rc) { qdxt_release(q); return rc; }
     *out = q;
     return CRN_GPU_OK;
-}
+}); }
 
 uint64_t crn_gpu_qdxt_output_size(const crn_gpu_qdxt* q) { return q ? (uint64_t)q->n_blocks * q->bytes_per_block : 0; }
 
@@ -943,7 +967,7 @@ uint64_t crn_gpu_qdxt_level_offset(const crn_gpu_qdxt* q, uint32_t level)
 }
 
 int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int dst_on_host)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!q) return CRN_GPU_ERR_BAD_PARAM;
     crn_gpu_ctx* ctx = q->ctx;
     if (quality_level > 255 || !dst) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_pack: bad argument");
@@ -958,10 +982,10 @@ int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int ds
     CRN_CUDA(ctx, cudaMemcpyAsync(dst, q->d_out, (size_t)q->n_blocks * q->bytes_per_block, dst_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!q || !info || info->struct_size != sizeof(crn_gpu_qdxt_info)) return CRN_GPU_ERR_BAD_PARAM;
     memset(info, 0, sizeof(*info));
     info->struct_size = sizeof(*info);
@@ -974,7 +998,7 @@ int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info)
         info->endpoint_opt_ms[i] = q->el[i].endpoint_opt_ms;
     }
     return CRN_GPU_OK;
-}
+}); }
 
 void crn_gpu_qdxt_free(crn_gpu_qdxt* q)
 {
@@ -1002,7 +1026,7 @@ struct crn_gpu_texture {
 int crn_gpu_refine_endpoints(crn_gpu_ctx* ctx, int dxt1_selectors, int perceptual, uint32_t component,
                              const void* d_pixels_rgba, const uint8_t* d_selectors, const uint32_t* d_offsets, uint32_t n_clusters,
                              const uint64_t* d_error_to_beat, uint32_t* d_endpoints, uint64_t* d_error, uint8_t* d_ok)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!d_pixels_rgba || !d_selectors || !d_offsets || !d_endpoints || !d_error || !d_ok || component > 3)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_refine_endpoints: bad argument");
@@ -1015,10 +1039,10 @@ int crn_gpu_refine_endpoints(crn_gpu_ctx* ctx, int dxt1_selectors, int perceptua
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_nearest_codebook(crn_gpu_ctx* ctx, uint32_t dims, const float* d_vectors, uint32_t n, const float* d_codebook, uint32_t codebook_size, uint32_t* d_out)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if ((dims != 2 && dims != 6) || !d_vectors || !d_codebook || !d_out || !codebook_size)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_nearest_codebook: bad argument");
@@ -1030,13 +1054,13 @@ int crn_gpu_nearest_codebook(crn_gpu_ctx* ctx, uint32_t dims, const float* d_vec
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int perceptual, uint32_t component,
                              const void* d_blocks_rgba, uint32_t n_blocks, const void* d_block_values, const void* d_block_values_accum,
                              const uint64_t* d_codebook, uint32_t codebook_size,
                              uint32_t* d_best_index, uint64_t* d_refined_codebook, uint8_t* d_used)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (kind > 1 || component > 3 || !d_blocks_rgba || !d_block_values || !d_codebook || !codebook_size || !d_best_index || !d_refined_codebook || !d_used)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_assign_selectors: bad argument");
@@ -1064,10 +1088,10 @@ int crn_gpu_assign_selectors(crn_gpu_ctx* ctx, uint32_t kind, int perceptual, ui
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_unpack_image(crn_gpu_ctx* ctx, uint32_t format, const void* d_blocks, uint32_t width, uint32_t height, void* d_rgba, uint32_t pitch_bytes)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!d_blocks || !d_rgba || !width || !height || pitch_bytes < width * 4u || (pitch_bytes & 3u) || !crn_gpu_bytes_per_block(format))
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_unpack_image: bad argument");
@@ -1078,10 +1102,10 @@ int crn_gpu_unpack_image(crn_gpu_ctx* ctx, uint32_t format, const void* d_blocks
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_unpack_image_host(crn_gpu_ctx* ctx, uint32_t format, const void* h_blocks, uint32_t width, uint32_t height, void* h_rgba, uint32_t pitch_bytes)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     const uint32_t bpb = crn_gpu_bytes_per_block(format);
     if (!h_blocks || !h_rgba || !width || !height || pitch_bytes < width * 4u || (pitch_bytes & 3u) || !bpb)
@@ -1098,7 +1122,7 @@ int crn_gpu_unpack_image_host(crn_gpu_ctx* ctx, uint32_t format, const void* h_b
     CRN_CUDA(ctx, cudaMemcpyAsync(h_rgba, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 void crn_gpu_default_resample_params(crn_gpu_resample_params* p)
 {   // what crn_mipmap_params (inc/crnlib.h:471-574) + create_texture_mipmaps (crnlib/crn_texture_comp.cpp:552-566) hand to generate_mipmaps
@@ -1196,14 +1220,14 @@ bool mip_params_ok(const crn_gpu_resample_params* p)
 
 int crn_gpu_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_src, uint32_t src_width, uint32_t src_height, uint32_t src_pitch_bytes,
                      void* d_dst, uint32_t dst_width, uint32_t dst_height, uint32_t dst_pitch_bytes)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!mip_params_ok(params) || !d_src || !d_dst || !src_width || !src_height || !dst_width || !dst_height || src_width > 16384 || src_height > 16384 ||
         dst_width > 16384 || dst_height > 16384 || src_pitch_bytes < src_width * 4u || dst_pitch_bytes < dst_width * 4u || (src_pitch_bytes & 3u) || (dst_pitch_bytes & 3u))
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_resample: bad argument");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     return mip_resample(ctx, params, d_src, src_width, src_height, src_pitch_bytes, d_dst, dst_width, dst_height, dst_pitch_bytes);
-}
+}); }
 
 uint32_t crn_gpu_mip_level_count(uint32_t width, uint32_t height, uint32_t min_mip_size, uint32_t max_levels)
 {   // mipmapped_texture::generate_mipmaps, crn_mipmapped_texture.cpp:2145-2157
@@ -1215,7 +1239,7 @@ uint32_t crn_gpu_mip_level_count(uint32_t width, uint32_t height, uint32_t min_m
 
 int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
                              uint32_t min_mip_size, uint32_t max_levels, void* d_mips, uint64_t capacity, uint32_t* num_levels)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!mip_params_ok(params) || !d_level0 || !width || !height || width > 16384 || height > 16384 || pitch_bytes < width * 4u || (pitch_bytes & 3u) || !min_mip_size)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps: bad argument");
@@ -1248,11 +1272,11 @@ int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_params* pa
     }
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_generate_mipmaps_host(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* h_level0, uint32_t width, uint32_t height, uint32_t pitch_bytes,
                                   uint32_t min_mip_size, uint32_t max_levels, void* h_mips, uint64_t capacity, uint32_t* num_levels)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!h_level0 || !width || !height || pitch_bytes < width * 4u || !min_mip_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_generate_mipmaps_host: bad argument");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1268,11 +1292,11 @@ int crn_gpu_generate_mipmaps_host(crn_gpu_ctx* ctx, const crn_gpu_resample_param
     if (need) CRN_CUDA(ctx, cudaMemcpyAsync(h_mips, d_out.p, need, cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_blockify(crn_gpu_ctx* ctx, const void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t pad_pixels, void* d_blocks,
                      uint32_t* blocks_x, uint32_t* blocks_y)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (!d_rgba || !d_blocks || !width || !height || pitch_bytes < width * 4u || (pitch_bytes & 3u) || (pad_pixels != 4 && pad_pixels != 8))
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_blockify: bad argument");
@@ -1286,7 +1310,7 @@ int crn_gpu_blockify(crn_gpu_ctx* ctx, const void* d_rgba, uint32_t width, uint3
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
-}
+}); }
 
 void crn_gpu_default_hc_params(crn_gpu_hc_params* p)
 {   // dxt_hc::params::params() (crnlib/crn_dxt_hc.h:105-131)
@@ -1301,7 +1325,7 @@ void crn_gpu_default_hc_params(crn_gpu_hc_params* p)
 }
 
 int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out) *out = nullptr;
     if (!params || params->struct_size != sizeof(crn_gpu_hc_params) || !blocks_rgba || !out || !params->num_blocks || !params->num_levels ||
@@ -1322,14 +1346,14 @@ int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const
     if (rc) { delete H; return rc; }
     *out = H;
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_hc_get_info(const crn_gpu_hc* hc, crn_gpu_hc_info* info)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!hc || !info || info->struct_size != sizeof(crn_gpu_hc_info)) return CRN_GPU_ERR_BAD_PARAM;
     *info = hc->info;
     return CRN_GPU_OK;
-}
+}); }
 const uint16_t* crn_gpu_hc_endpoint_indices(const crn_gpu_hc* hc) { return hc ? hc->endpoint_indices.data() : nullptr; }
 const uint16_t* crn_gpu_hc_selector_indices(const crn_gpu_hc* hc) { return hc ? hc->selector_indices.data() : nullptr; }
 const uint32_t* crn_gpu_hc_color_endpoints(const crn_gpu_hc* hc) { return hc ? hc->color_endpoints.data() : nullptr; }
@@ -1359,7 +1383,7 @@ static bool crn_params_ok(const crn_gpu_crn_params* p)
 }
 
 int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!crn_params_ok(p) || !hp) return CRN_GPU_ERR_BAD_PARAM;
     crn_gpu_default_hc_params(hp);
     hp->perceptual = p->perceptual ? 1 : 0;
@@ -1407,13 +1431,13 @@ int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
     }
     hp->num_blocks = total;
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, const uint16_t* endpoint_indices, const uint16_t* selector_indices,
                       const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
                       const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
                       void** out_file, uint32_t* out_size)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
     if (!crn_params_ok(p) || !hp || hp->struct_size != sizeof(crn_gpu_hc_params) || !endpoint_indices || !selector_indices || !out_file || !out_size ||
@@ -1458,13 +1482,13 @@ int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, 
         *out_file = m; *out_size = (uint32_t)file.size();
     } catch (const std::bad_alloc&) { return CRN_GPU_ERR_NO_MEMORY; }
     return CRN_GPU_OK;
-}
+}); }
 
 void crn_gpu_free_file(void* file) { free(file); }
 
 int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate,
                          uint32_t* out_quality)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
@@ -1518,6 +1542,7 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         crn_gpu_hc_free(H);
         if (r) return set_err(ctx, r, "crn_gpu_compress_crn: the writer rejected the quantiser's output");
         *bitrate = (*size * 8.0f) / (float)texels;                                                                // crn_comp.cpp:1640-1653
+        if ((r = progress_tick(ctx, 24, 25, 1, 1)) != CRN_GPU_OK) { free(*file); *file = nullptr; *size = 0; return r; }   // crn_comp.cpp:1600
         if (trace) fprintf(stderr, "[crn_b200] compress_crn pass q%u: quantiser %.1f ms, writer %.1f ms, %u bytes\n", quality, tp1 - tp0, wall_ms() - tp1, *size);
         return CRN_GPU_OK;
     };
@@ -1580,10 +1605,10 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
     if (out_bitrate) *out_bitrate = best_bitrate;
     if (out_quality) *out_quality = (uint32_t)best_quality;
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_texture_info* info)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!info || info->struct_size != sizeof(crn_gpu_texture_info)) return CRN_GPU_ERR_BAD_PARAM;
     crn::CrnHeaderInfo h;
     if (!crn::crn_parse_header(static_cast<const uint8_t*>(h_crn), crn_size, h)) return CRN_GPU_ERR_BAD_DATA;
@@ -1591,7 +1616,7 @@ int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_
     info->bytes_per_block = (h.format == 0 || h.format == 9 || h.format == 10 || h.format == 11 || h.format == 13) ? 8 : 16;
     info->userdata0 = h.userdata0; info->userdata1 = h.userdata1; info->format = h.format;
     return CRN_GPU_OK;
-}
+}); }
 
 static int transcode_launch(crn_gpu_ctx* ctx, const crn::TranscodeFile* d_files, uint32_t nfiles)
 {
@@ -1620,9 +1645,71 @@ static uint32_t wide_min_blocks()
 // Launches the transcoder for every active level of `count` textures whose level tables (host_file) are filled in:
 // large levels through the wide path (transcode_wide.cuh), the rest through the warp-per-level kernel.  d_files: device
 // array the level tables are uploaded to (the texture's own d_file for a single texture).
+// The lane-per-stream kernel (transcode_streams.cuh) is OFF unless CRN_B200_STREAMS_MIN names a stream count from which to
+// use it: measured on the B200 (profiles/r2a_transcode_lane_per_stream.jsonl) it reaches 6-16 Gtexel/s on 1 K - 16 K file
+// batches against 33 Gtexel/s for the CTA-per-file kernels -- with every file of the batch in flight at once the per-file
+// tables and palettes (~100-200 KB each) fall out of L2 and every symbol value costs a DRAM round trip.
+static uint32_t streams_min()
+{
+    const char* e = getenv("CRN_B200_STREAMS_MIN");
+    if (e && *e) return (uint32_t)strtoul(e, nullptr, 10);
+    return 0xFFFFFFFFu;
+}
+
+static int transcode_streams(crn_gpu_ctx* ctx, crn_gpu_texture* const* texs, uint32_t count, crn::TranscodeFile* d_files, uint32_t nstreams)
+{
+    struct Key { uint64_t blocks; uint32_t fmt_class, file, slot; };
+    std::vector<Key> keys;
+    keys.reserve(nstreams);
+    std::vector<crn::TranscodeFile> files(count);
+    for (uint32_t t = 0; t < count; t++) {
+        const crn::TranscodeFile& hf = texs[t]->host_file;
+        files[t] = hf;
+        const uint32_t fc = (hf.format == 0) ? 0u : (hf.format == 9 ? 1u : ((hf.format == 7 || hf.format == 8) ? 2u : 3u));
+        for (uint32_t slot = 0; slot < 16; slot++) {
+            const crn::LevelStream& ls = hf.levels[slot];
+            if (!ls.active) continue;
+            const uint64_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
+            keys.push_back(Key{ W * H * hf.faces, fc, t, slot });
+        }
+    }
+    // lanes of a warp run in lock step: neighbours should be the same format and the same length
+    std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+        if (a.blocks != b.blocks) return a.blocks > b.blocks;
+        if (a.fmt_class != b.fmt_class) return a.fmt_class < b.fmt_class;
+        return a.file != b.file ? a.file < b.file : a.slot < b.slot;
+    });
+    std::vector<crn::StreamDesc> sd(keys.size());
+    for (size_t i = 0; i < keys.size(); i++) { sd[i].file = d_files + keys[i].file; sd[i].slot = keys[i].slot; sd[i].pad = 0; }
+    int rc = ensure(ctx, &ctx->d_wide, &ctx->d_wide_cap, sizeof(crn::StreamDesc) * sd.size());
+    if (rc) return rc;
+    CRN_CUDA(ctx, cudaMemcpyAsync(d_files, files.data(), sizeof(crn::TranscodeFile) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CRN_CUDA(ctx, cudaMemcpyAsync(ctx->d_wide, sd.data(), sizeof(crn::StreamDesc) * sd.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t smem = sizeof(crn::StreamSmem);
+#ifdef __CUDACC__
+    if (!ctx->streams_smem_set) {
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->streams_smem_set = 1;
+    }
+#endif
+    const uint32_t n = (uint32_t)sd.size();
+    CRN_LAUNCH(crn::transcode_streams_kernel, (n + crn::kStreamThreads - 1) / crn::kStreamThreads, crn::kStreamThreads, smem, ctx->stream,
+               static_cast<const crn::StreamDesc*>(ctx->d_wide), n);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    // the host vectors above are pageable sources of async copies: staged before cudaMemcpyAsync returns
+    return CRN_GPU_OK;
+}
+
 static int transcode_textures(crn_gpu_ctx* ctx, crn_gpu_texture* const* texs, uint32_t count, crn::TranscodeFile* d_files)
 {
     const uint32_t min_blocks = wide_min_blocks();
+    {
+        uint32_t nstreams = 0;
+        for (uint32_t t = 0; t < count; t++)
+            for (uint32_t slot = 0; slot < 16; slot++) nstreams += texs[t]->host_file.levels[slot].active ? 1u : 0u;
+        if (nstreams >= streams_min()) return transcode_streams(ctx, texs, count, d_files, nstreams);
+    }
     std::vector<crn::WideLevel> wide;
     std::vector<crn::TranscodeFile> files(count);
     size_t bytes = 0;
@@ -1705,7 +1792,7 @@ static int transcode_textures(crn_gpu_ctx* ctx, crn_gpu_texture* const* texs, ui
 static int transcode_texture(crn_gpu_texture* tex) { return transcode_textures(tex->ctx, &tex, 1, tex->d_file); }
 
 int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, crn_gpu_texture** out_tex)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx || !out_tex) return CRN_GPU_ERR_BAD_PARAM;
     *out_tex = nullptr;
     const uint8_t* d = static_cast<const uint8_t*>(h_crn);
@@ -1724,6 +1811,13 @@ int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_
         if (ok && h.pal_num[0]) ok = hm[crn::kDmColorEp].receive(b) && hm[crn::kDmColorSel].receive(b);
         if (ok && h.pal_num[2]) ok = hm[crn::kDmAlphaEp].receive(b) && hm[crn::kDmAlphaSel].receive(b);
         if (!ok) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crnd_unpack_begin: corrupt Huffman tables");
+        // Decoded symbols index the palettes directly (selectors) or step through them (endpoint deltas): a model the format needs must
+        // exist, and may not name more entries than its palette holds (the reference trusts the file here; we do not).
+        auto fits = [&](int m, uint32_t pal) { const size_t n = hm[m].len.size(); return n >= 1 && n <= pal && !hm[m].sorted.empty(); };
+        ok = !hm[crn::kDmRef].sorted.empty() && hm[crn::kDmRef].len.size() <= 256;
+        if (ok && has_color) ok = fits(crn::kDmColorEp, h.pal_num[0]) && fits(crn::kDmColorSel, h.pal_num[1]);
+        if (ok && has_alpha) ok = fits(crn::kDmAlphaEp, h.pal_num[2]) && fits(crn::kDmAlphaSel, h.pal_num[3]);
+        if (!ok) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crnd_unpack_begin: Huffman models do not match the palettes");
     }
     uint32_t pal_data_ofs[4] = { 0, 0, 0, 0 }, pal_data_bit[4] = { 0, 0, 0, 0 };
     for (int i = 0; i < 4; i++) {
@@ -1800,7 +1894,7 @@ int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_
     if (fail) { cudaFree(t->slab); delete t; return set_err(ctx, CRN_GPU_ERR_CUDA, "crnd_unpack_begin: upload / palette decode failed"); }
     *out_tex = t;
     return CRN_GPU_OK;
-}
+}); }
 
 static void fill_level(crn_gpu_texture* t, uint32_t slot, uint32_t level, uint32_t row_pitch)
 {
@@ -1818,7 +1912,7 @@ static void fill_level(crn_gpu_texture* t, uint32_t slot, uint32_t level, uint32
 
 int crn_gpu_crnd_unpack_level(crn_gpu_texture* tex, void* const* d_dst_faces, uint32_t dst_size_in_bytes,
                               uint32_t row_pitch_in_bytes, uint32_t level_index)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!tex || !d_dst_faces) return CRN_GPU_ERR_BAD_PARAM;
     crn_gpu_ctx* ctx = tex->ctx;
     if (level_index >= tex->hdr.levels) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: level out of range");
@@ -1838,7 +1932,33 @@ int crn_gpu_crnd_unpack_level(crn_gpu_texture* tex, void* const* d_dst_faces, ui
     // host_file is reused by the next call: make sure the async copy has read it
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
+
+int crn_gpu_crnd_unpack_level_host(crn_gpu_texture* tex, void* const* h_dst_faces, uint32_t dst_size_in_bytes,
+                                   uint32_t row_pitch_in_bytes, uint32_t level_index)
+{ return crn_guard(tex ? tex->ctx : nullptr, [&]() -> int {
+    if (!tex || !h_dst_faces) return CRN_GPU_ERR_BAD_PARAM;
+    crn_gpu_ctx* ctx = tex->ctx;
+    if (level_index >= tex->hdr.levels) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: level out of range");
+    const uint32_t w = tex->hdr.width >> level_index ? tex->hdr.width >> level_index : 1, hh = tex->hdr.height >> level_index ? tex->hdr.height >> level_index : 1;
+    const uint32_t bx = (w + 3) >> 2, by = (hh + 3) >> 2, tight = bx * tex->bytes_per_block;
+    const uint32_t pitch = row_pitch_in_bytes ? row_pitch_in_bytes : tight;                                      // crn_decomp.h:3569-3575
+    if (pitch < tight || (pitch & 3) || (uint64_t)dst_size_in_bytes < (uint64_t)pitch * by)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: bad pitch or destination size");
+    const uint32_t faces = tex->hdr.faces;
+    for (uint32_t f = 0; f < faces; f++) if (!h_dst_faces[f]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_level: null face pointer");
+    const size_t face_bytes = (size_t)tight * by;
+    int rc = ensure(ctx, &ctx->d_out, &ctx->d_out_cap, face_bytes * faces);
+    if (rc) return rc;
+    void* d_faces[6];
+    for (uint32_t f = 0; f < faces; f++) d_faces[f] = static_cast<uint8_t*>(ctx->d_out) + face_bytes * f;
+    rc = crn_gpu_crnd_unpack_level(tex, d_faces, (uint32_t)face_bytes, tight, level_index);
+    if (rc) return rc;
+    for (uint32_t f = 0; f < faces; f++)
+        CRN_CUDA(ctx, cudaMemcpy2DAsync(h_dst_faces[f], pitch, d_faces[f], tight, tight, by, cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CRN_GPU_OK;
+}); }
 
 uint64_t crn_gpu_crnd_total_size(const crn_gpu_texture* tex) { return tex ? tex->total_size : 0; }
 uint64_t crn_gpu_crnd_level_offset(const crn_gpu_texture* tex, uint32_t level_index, uint32_t face_index)
@@ -1860,17 +1980,17 @@ static int prepare_all_levels(crn_gpu_texture* tex, void* d_dst, uint64_t dst_ca
 }
 
 int crn_gpu_crnd_unpack_all_levels(crn_gpu_texture* tex, void* d_dst, uint64_t dst_capacity)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!tex) return CRN_GPU_ERR_BAD_PARAM;
     crn_gpu_ctx* ctx = tex->ctx;
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = prepare_all_levels(tex, d_dst, dst_capacity);
     if (rc) return rc;
     return transcode_texture(tex);
-}
+}); }
 
 int crn_gpu_crnd_unpack_all_levels_host(crn_gpu_texture* tex, void* h_dst, uint64_t dst_capacity)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!tex || !h_dst) return CRN_GPU_ERR_BAD_PARAM;
     crn_gpu_ctx* ctx = tex->ctx;
     if (dst_capacity < tex->total_size) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crnd_unpack_all_levels_host: destination too small");
@@ -1881,11 +2001,11 @@ int crn_gpu_crnd_unpack_all_levels_host(crn_gpu_texture* tex, void* h_dst, uint6
     CRN_CUDA(ctx, cudaMemcpyAsync(h_dst, ctx->d_out, tex->total_size, cudaMemcpyDeviceToHost, ctx->stream));
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_crnd_unpack_batch(crn_gpu_ctx* ctx, crn_gpu_texture* const* textures, uint32_t count, void* const* d_dst,
                               const uint64_t* dst_capacity)
-{
+{ return crn_guard(ctx, [&]() -> int {
     if (!ctx || !textures || !d_dst || !dst_capacity || !count) return CRN_GPU_ERR_BAD_PARAM;
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = ensure(ctx, &ctx->d_files, &ctx->d_files_cap, sizeof(crn::TranscodeFile) * (size_t)count);
@@ -1899,22 +2019,22 @@ int crn_gpu_crnd_unpack_batch(crn_gpu_ctx* ctx, crn_gpu_texture* const* textures
     if (rc) return rc;
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_crnd_unpack_end(crn_gpu_texture* tex)
-{
+{ return crn_guard(nullptr, [&]() -> int {
     if (!tex) return CRN_GPU_ERR_BAD_PARAM;
     cudaSetDevice(tex->ctx->device);
     cudaStreamSynchronize(tex->ctx->stream);
     cudaFree(tex->slab);
     delete tex;
     return CRN_GPU_OK;
-}
+}); }
 
 /* ---- DDS container edge ------------------------------------------------------------------- */
 
 int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uint32_t levels, uint32_t faces, void* out_128_bytes)
-{   // "DDS " + DDSURFACEDESC2 as mipmapped_texture::write_dds fills it for the block formats (crnlib/crn_mipmapped_texture.cpp:921-1084)
+{ return crn_guard(nullptr, [&]() -> int {   // "DDS " + DDSURFACEDESC2 as mipmapped_texture::write_dds fills it for the block formats (crnlib/crn_mipmapped_texture.cpp:921-1084)
     if (!out_128_bytes || !width || !height || !levels || levels > 16 || (faces != 1 && faces != 6)) return CRN_GPU_ERR_BAD_PARAM;
     auto fourcc = [](char a, char b, char c, char d) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24); };
     uint32_t cc, bitcount = 0, bits_per_texel = 8;
@@ -1944,7 +2064,7 @@ int crn_gpu_dds_header(uint32_t crn_format, uint32_t width, uint32_t height, uin
     h[19] = 32; h[20] = 0x4u; h[21] = cc; h[22] = bitcount;      // DDPF_FOURCC
     memcpy(out_128_bytes, h, 128);
     return CRN_GPU_OK;
-}
+}); }
 
 void crn_gpu_default_dds_params(crn_gpu_dds_params* p)
 {
@@ -1956,7 +2076,7 @@ void crn_gpu_default_dds_params(crn_gpu_dds_params* p)
 }
 
 int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size)
-{   // dds_comp::compress_init + convert_to_dxt + compress_pass (crnlib/crn_dds_comp.cpp:148-289)
+{ return crn_guard(ctx, [&]() -> int {   // dds_comp::compress_init + convert_to_dxt + compress_pass (crnlib/crn_dds_comp.cpp:148-289)
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
@@ -1991,35 +2111,43 @@ int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const vo
     const uint32_t bpb = crn_gpu_bytes_per_block(fmt);
     uint64_t payload = 0;
     for (const crn_gpu_level_desc& d : lv) payload += (uint64_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
+    if (128 + payload > 0xFFFFFFFFull) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_dds: file would exceed 4 GiB (crn_uint32 size)");
     uint8_t* file = static_cast<uint8_t*>(malloc(128 + payload));
     if (!file) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_dds: out of host memory");
     int rc = crn_gpu_dds_header(p->crn_format, p->width, p->height, p->levels, p->faces, file);
     if (rc == CRN_GPU_OK) {
         if (p->quality_level == 255 || fmt == CRN_GPU_FMT_DXT3) {                                                // crn_dds_comp.cpp:150-157: block by block
             uint8_t* dst = file + 128;
+            uint64_t done = 0;
             for (const crn_gpu_level_desc& d : lv) {
-                rc = crn_gpu_pack_image_host(ctx, fmt, &p->pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
+                rc = progress_tick(ctx, 0, 1, (uint32_t)(payload ? done * 100 / payload : 0), 100);             // crn_dds_comp.cpp:130-134, :233-236
+                if (rc == CRN_GPU_OK) rc = crn_gpu_pack_image_host(ctx, fmt, &p->pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
                 if (rc) break;
-                dst += (size_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
+                const size_t sz = (size_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
+                dst += sz; done += sz;
             }
+            if (rc == CRN_GPU_OK) rc = progress_tick(ctx, 0, 1, 100, 100);
         } else {                                                                                                 // clustered: qdxt_pack_init + qdxt_pack
             crn_gpu_qdxt* q = nullptr;
-            rc = crn_gpu_qdxt_init(ctx, fmt, &p->pack, lv.data(), count, 1, &q);
+            rc = progress_tick(ctx, 0, 2, 0, 100);                                                               // crn_dds_comp.cpp:136-146, :172-188
+            if (rc == CRN_GPU_OK) rc = crn_gpu_qdxt_init(ctx, fmt, &p->pack, lv.data(), count, 1, &q);
             if (rc == CRN_GPU_OK) {
                 if (crn_gpu_qdxt_output_size(q) != payload) rc = set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_dds: payload size mismatch");
-                else rc = crn_gpu_qdxt_pack(q, p->quality_level, file + 128, 1);
+                else rc = progress_tick(ctx, 1, 2, 0, 100);
+                if (rc == CRN_GPU_OK) rc = crn_gpu_qdxt_pack(q, p->quality_level, file + 128, 1);
                 crn_gpu_qdxt_free(q);
+                if (rc == CRN_GPU_OK) rc = progress_tick(ctx, 1, 2, 100, 100);
             }
         }
     }
     if (rc) { free(file); return rc; }
     *out_file = file; *out_size = (uint32_t)(128 + payload);
     return CRN_GPU_OK;
-}
+}); }
 
 int crn_gpu_compress_mip_chain(crn_gpu_ctx* ctx, uint32_t file_type, const crn_gpu_crn_params* cp, const crn_gpu_dds_params* dp, const crn_gpu_resample_params* mip,
                                uint32_t min_mip_size, uint32_t max_levels, const void* const* h_level0_faces, void** out_file, uint32_t* out_size)
-{   // crn_compress(const crn_comp_params&, const crn_mipmap_params&, ...) (inc/crnlib.h:614): create_texture_mipmaps in generate mode
+{ return crn_guard(ctx, [&]() -> int {   // crn_compress(const crn_comp_params&, const crn_mipmap_params&, ...) (inc/crnlib.h:614): create_texture_mipmaps in generate mode
     // (crnlib/crn_texture_comp.cpp:352-575) -> generate_mipmaps -> the compressor of the file type
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out_file) *out_file = nullptr;
@@ -2061,10 +2189,10 @@ int crn_gpu_compress_mip_chain(crn_gpu_ctx* ctx, uint32_t file_type, const crn_g
     if (crn) { crn_gpu_crn_params q = *cp; q.levels = levels; return crn_gpu_compress_crn(ctx, &q, images.data(), out_file, out_size, nullptr, nullptr); }
     crn_gpu_dds_params q = *dp; q.levels = levels;
     return crn_gpu_compress_dds(ctx, &q, images.data(), out_file, out_size);
-}
+}); }
 
 int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, void** out_file, uint32_t* out_size)
-{   // crn_decompress_crn_to_dds (crnlib/crnlib.cpp:269-291): transcode every level on the device, lay the faces out DDS-style
+{ return crn_guard(ctx, [&]() -> int {   // crn_decompress_crn_to_dds (crnlib/crnlib.cpp:269-291): transcode every level on the device, lay the faces out DDS-style
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
@@ -2079,6 +2207,7 @@ int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, v
     rc = crn_gpu_crnd_unpack_begin(ctx, h_crn, crn_size, &tex);
     if (rc) return rc;
     const uint64_t total = crn_gpu_crnd_total_size(tex);
+    if (128 + total > 0xFFFFFFFFull) { crn_gpu_crnd_unpack_end(tex); return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_crn_to_dds: file would exceed 4 GiB (crn_uint32 size)"); }
     uint8_t* file = static_cast<uint8_t*>(malloc(128 + total));
     uint8_t* tmp = static_cast<uint8_t*>(malloc(total ? total : 1));
     if (!file || !tmp) { free(file); free(tmp); crn_gpu_crnd_unpack_end(tex); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_crn_to_dds: out of host memory"); }
@@ -2099,6 +2228,6 @@ int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn_size, v
     free(file); free(tmp);
     crn_gpu_crnd_unpack_end(tex);
     return rc;
-}
+}); }
 
 }  // extern "C"

@@ -690,11 +690,13 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
             cudaSetDevice(child->device);
             try { rc1 = run_kind(child, 1); }
             catch (const std::bad_alloc&) { rc1 = set_err(child, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
+            catch (...) { rc1 = set_err(child, CRN_GPU_ERR_BAD_DATA, "crn_gpu_hc_compress: exception in the alpha pass"); }   // nothing escapes a thread
             child->d_cluster_flags = nullptr; child->d_cluster_order = nullptr;
         });
         int rc0;
         try { rc0 = run_kind(ctx, 0); }
         catch (const std::bad_alloc&) { rc0 = set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
+        catch (...) { rc0 = set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_hc_compress: exception in the colour pass"); }
         alpha_thread.join();                                        // never leave the frame with the thread running
         ctx->launches += child->launches - l0;
         if (rc0) return rc0;

@@ -32,7 +32,8 @@ struct HuffModelDev {
     uint32_t first_idx[17];
     uint32_t sorted_ofs;                // into the file's uint16 sorted-symbol pool
     uint32_t nsyms;
-    uint32_t pad[2];
+    uint32_t nsorted;                   // symbols with a code (entries of this model in the pool)
+    uint32_t pad;
 };
 
 enum { kDmRef = 0, kDmColorEp = 1, kDmColorSel = 2, kDmAlphaEp = 3, kDmAlphaSel = 4, kNumBlockModels = 5,
@@ -78,12 +79,10 @@ struct BitWindow {
 };
 __device__ __forceinline__ uint32_t bw_fetch(const BitWindow& w, uint32_t wi)
 {
-    uint32_t v = __byte_perm(w.words[wi], 0, 0x0123);
     const uint32_t first = wi * 4;
-    if (first + 4 > w.end_byte) {       // zero the bytes that lie past the end of the stream
-        const uint32_t valid = first < w.end_byte ? w.end_byte - first : 0;
-        v = valid ? (v & (0xFFFFFFFFu << (32 - 8 * valid))) : 0u;
-    }
+    if (first >= w.end_byte) return 0u; // past the end: zeros, and NO load (a truncated / corrupt stream keeps "decoding" here)
+    uint32_t v = __byte_perm(w.words[wi], 0, 0x0123);
+    if (first + 4 > w.end_byte) v &= 0xFFFFFFFFu << (32 - 8 * (w.end_byte - first));   // zero the bytes past the end
     return v;
 }
 __device__ __forceinline__ void bw_refill(BitWindow& w)
@@ -114,7 +113,9 @@ __device__ __forceinline__ uint32_t bw_decode(BitWindow& w, const uint32_t* look
         const uint32_t k = (uint32_t)(w.buf >> 48);
         len = kHuffLookupBits + 1;
         while (len < 16 && k >= m->limit[len]) len++;
-        sym = pool[m->sorted_ofs + m->first_idx[len] + ((k >> (16 - len)) - m->first_code[len])];
+        // incomplete codes (corrupt files) can index past the model's symbols: clamp (the reference returns symbol 0, crn_decomp.h:3239)
+        const uint32_t idx = m->first_idx[len] + ((k >> (16 - len)) - m->first_code[len]);
+        sym = idx < m->nsorted ? pool[m->sorted_ofs + idx] : 0u;
     }
     w.buf <<= len; w.cnt -= (int)len;
     if (w.cnt <= 32) bw_refill(w);
@@ -128,8 +129,15 @@ __device__ __forceinline__ uint32_t bw_decode(BitWindow& w, const uint32_t* look
 struct LongCodes {
     uint32_t limit[5];                  // lengths 12..16
     int32_t base[5];                    // sorted_ofs + first_idx[len] - first_code[len]
-    uint32_t pad[2];
+    int32_t pool_lo, pool_hi;           // this model's slice of the pool [lo, hi): indices outside it (corrupt files) read as symbol 0
 };
+__device__ __forceinline__ void longcodes_fill(LongCodes& lc, const HuffModelDev& hm, int j)
+{   // one thread per (model, j = 0..4)
+    const int len = 12 + j;
+    lc.limit[j] = hm.limit[len];
+    lc.base[j] = (int32_t)(hm.sorted_ofs + hm.first_idx[len]) - (int32_t)hm.first_code[len];
+    if (j == 0) { lc.pool_lo = (int32_t)hm.sorted_ofs; lc.pool_hi = (int32_t)(hm.sorted_ofs + hm.nsorted); }
+}
 __device__ __forceinline__ uint32_t bw_decode_fast(BitWindow& w, const uint32_t* lookup, const LongCodes* lc, const uint16_t* pool)
 {
     const uint32_t t = lookup[(uint32_t)(w.buf >> (64 - kHuffLookupBits))];
@@ -139,7 +147,8 @@ __device__ __forceinline__ uint32_t bw_decode_fast(BitWindow& w, const uint32_t*
         const uint32_t k = (uint32_t)(w.buf >> 48);
         const uint32_t i = (k >= lc->limit[0]) + (k >= lc->limit[1]) + (k >= lc->limit[2]) + (k >= lc->limit[3]);
         len = 12 + i;
-        sym = pool[lc->base[i] + (int32_t)(k >> (4 - i))];
+        const int32_t idx = lc->base[i] + (int32_t)(k >> (4 - i));
+        sym = (idx >= lc->pool_lo && idx < lc->pool_hi) ? pool[idx] : 0u;
     }
     w.buf <<= len; w.cnt -= (int)len;
     if (w.cnt <= 32) bw_refill(w);
@@ -340,12 +349,7 @@ __global__ void __launch_bounds__(kTranscodeWarps * 32) transcode_levels_kernel(
     const TranscodeFile& f = files[blockIdx.x];
     for (uint32_t i = threadIdx.x; i < (uint32_t)(kNumBlockModels * kHuffLookupSize); i += blockDim.x)
         sm->lookup[i / kHuffLookupSize][i % kHuffLookupSize] = f.models[i / kHuffLookupSize].lookup[i % kHuffLookupSize];
-    if (threadIdx.x < kNumBlockModels * 5) {
-        const int m = threadIdx.x / 5, j = threadIdx.x % 5, len = 12 + j;
-        const HuffModelDev& hm = f.models[m];
-        sm->longc[m].limit[j] = hm.limit[len];
-        sm->longc[m].base[j] = (int32_t)(hm.sorted_ofs + hm.first_idx[len]) - (int32_t)hm.first_code[len];
-    }
+    if (threadIdx.x < kNumBlockModels * 5) longcodes_fill(sm->longc[threadIdx.x / 5], f.models[threadIdx.x / 5], threadIdx.x % 5);
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5;
     const LevelStream ls = f.levels[warp];              // by value: registers, not repeated global loads

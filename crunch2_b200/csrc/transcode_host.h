@@ -91,6 +91,7 @@ struct HostModel {
         for (int i = 0; i < kHuffLookupSize; i++) d.lookup[i] = kHuffLong;
         d.sorted_ofs = (uint32_t)pool.size();
         d.nsyms = (uint32_t)len.size();
+        d.nsorted = (uint32_t)sorted.size();
         pool.insert(pool.end(), sorted.begin(), sorted.end());
         for (int l = 1; l <= 16; l++) {
             d.first_code[l] = first_code[l]; d.first_idx[l] = first_idx[l];
@@ -119,7 +120,7 @@ inline bool crn_parse_header(const uint8_t* d, uint32_t size, CrnHeaderInfo& h)
 {
     if (!d || size < 74) return false;
     if (be_n(d, 2) != (('H' << 8) | 'x')) return false;
-    if (be_n(d + 2, 2) < 74 || size < be_n(d + 6, 4)) return false;
+    if (be_n(d + 2, 2) < 74 || size < be_n(d + 2, 2) || size < be_n(d + 6, 4)) return false;   // header_size and data_size lie within the buffer
     h.data_size = be_n(d + 6, 4);
     h.width = be_n(d + 12, 2); h.height = be_n(d + 14, 2); h.levels = d[16]; h.faces = d[17]; h.format = d[18];
     h.userdata0 = be_n(d + 25, 4); h.userdata1 = be_n(d + 29, 4);

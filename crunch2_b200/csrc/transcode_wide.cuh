@@ -70,6 +70,7 @@ struct WideSmemA {
     uint16_t ref11[kHuffLookupSize];         // reference model: sym | len << 8, 0xffff = longer than 11
     uint32_t limit[5][4];                    // left-justified limits of lengths 12..15 per model slot (E0 E1 S0 S1 R)
     int32_t ref_base[5];                     // symbol-pool bases of the reference model's long codes
+    int32_t ref_lo, ref_hi;                  // the reference model's slice of the pool (indices outside: symbol 0)
     uint8_t bytes[(kWideT + kWideML) / 8 + 8];
     uint8_t L[4][kWideT + kWideML];
     uint8_t B[2][kWideT + kWideMB];          // [0] selectors only, [1] endpoints + selectors
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(kWideThreadsA) transcode_tables_kernel(const W
     }
     if (tid < 20) sm.limit[tid / 4][tid % 4] = f.models[models[tid / 4]].limit[12 + tid % 4];
     if (tid < 5) { const HuffModelDev& hm = f.models[kDmRef]; sm.ref_base[tid] = (int32_t)(hm.sorted_ofs + hm.first_idx[12 + tid]) - (int32_t)hm.first_code[12 + tid]; }
+    if (tid == 5) { const HuffModelDev& hm = f.models[kDmRef]; sm.ref_lo = (int32_t)hm.sorted_ofs; sm.ref_hi = (int32_t)(hm.sorted_ofs + hm.nsorted); }
     const uint32_t ne = wl.ne, ns = wl.ns;
     const uint32_t tile0 = (blockIdx.x - wl.first_cta) * kWideTilesPerCta;
     for (uint32_t tile = tile0; tile < tile0 + kWideTilesPerCta && tile < wl.ntiles; tile++) {
@@ -155,7 +157,8 @@ __global__ void __launch_bounds__(kWideThreadsA) transcode_tables_kernel(const W
             else {
                 const uint32_t i = (k >= sm.limit[4][0]) + (k >= sm.limit[4][1]) + (k >= sm.limit[4][2]) + (k >= sm.limit[4][3]);
                 len = 12 + i;
-                g = f.sorted_pool[sm.ref_base[i] + (int32_t)(k >> (4 - i))] & 0xffu;
+                const int32_t pi = sm.ref_base[i] + (int32_t)(k >> (4 - i));
+                g = (pi >= sm.ref_lo && pi < sm.ref_hi) ? (f.sorted_pool[pi] & 0xffu) : 0u;
             }
             const uint32_t t0 = (g & 3u) == 0u, t1 = ((g >> 4) & 3u) == 0u;
             sm.Gd[idx] = (uint8_t)(len + sm.PP[t0 + 2 * t1][idx + len]);
@@ -617,12 +620,7 @@ __device__ __forceinline__ void wide_resolve(WideSmemC* sm, const WideLevel& wl)
     const TranscodeFile& f = *wl.file;
     for (uint32_t i = threadIdx.x; i < (uint32_t)(kNumBlockModels * kHuffLookupSize); i += blockDim.x)
         sm->lookup[i / kHuffLookupSize][i % kHuffLookupSize] = f.models[i / kHuffLookupSize].lookup[i % kHuffLookupSize];
-    if (threadIdx.x < kNumBlockModels * 5) {
-        const int m = threadIdx.x / 5, j = threadIdx.x % 5, len = 12 + j;
-        const HuffModelDev& hm = f.models[m];
-        sm->longc[m].limit[j] = hm.limit[len];
-        sm->longc[m].base[j] = (int32_t)(hm.sorted_ofs + hm.first_idx[len]) - (int32_t)hm.first_code[len];
-    }
+    if (threadIdx.x < kNumBlockModels * 5) longcodes_fill(sm->longc[threadIdx.x / 5], f.models[threadIdx.x / 5], threadIdx.x % 5);
     __syncthreads();
     const LevelStream& ls = f.levels[wl.slot];
     const uint32_t fmt = f.format;

@@ -32,7 +32,8 @@ typedef enum crn_gpu_status {
     CRN_GPU_ERR_CUDA = -3,
     CRN_GPU_ERR_UNSUPPORTED = -4,
     CRN_GPU_ERR_NO_MEMORY = -5,
-    CRN_GPU_ERR_BAD_DATA = -6
+    CRN_GPU_ERR_BAD_DATA = -6,
+    CRN_GPU_ERR_CANCELLED = -7          /* the progress callback returned 0 */
 } crn_gpu_status;
 
 /* Block formats.  Numbering follows crnlib::dxt_format (reference crnlib/crn_dxt.h:56-76) so the
@@ -76,6 +77,13 @@ CRN_API void* crn_gpu_stream(crn_gpu_ctx* ctx);
 CRN_API int crn_gpu_synchronize(crn_gpu_ctx* ctx);
 /* Kernels launched through this context since creation (bench.py reports it as gpu_launches). */
 CRN_API uint64_t crn_gpu_launch_count(const crn_gpu_ctx* ctx);
+/* Progress / cancel hook, the C form of crn_progress_callback_func (reference inc/crnlib.h:224-228).  The whole-call entry
+ * points (crn_gpu_compress_dds / _crn / _mip_chain) invoke it on the CALLING thread between device phases with the
+ * reference's phase numbering where it has one -- .CRN: (24, 25, 1, 1) at the end of each pass (crn_comp.cpp:1600);
+ * .DDS: (0, 1, percent, 100) block-by-block (crn_dds_comp.cpp:130-134, :233-236), (0, 2, ..) init and (1, 2, ..) pack for the
+ * clustered path (:136-146, :172-188).  Returning 0 abandons the call with CRN_GPU_ERR_CANCELLED.  fn = NULL removes it. */
+typedef int (*crn_gpu_progress_fn)(uint32_t phase_index, uint32_t total_phases, uint32_t subphase_index, uint32_t total_subphases, void* user);
+CRN_API void crn_gpu_set_progress(crn_gpu_ctx* ctx, crn_gpu_progress_fn fn, void* user);
 CRN_API void crn_gpu_default_pack_params(crn_gpu_pack_params* p);
 CRN_API uint32_t crn_gpu_bytes_per_block(uint32_t format);
 
@@ -396,6 +404,11 @@ CRN_API int crn_gpu_crnd_unpack_begin(crn_gpu_ctx* ctx, const void* h_crn, uint3
 /* One level, caller-chosen destination per face (1 or 6 device pointers).  Asynchronous. */
 CRN_API int crn_gpu_crnd_unpack_level(crn_gpu_texture* tex, void* const* d_dst_faces, uint32_t dst_size_in_bytes,
                                       uint32_t row_pitch_in_bytes, uint32_t level_index);
+/* Same with HOST destination pointers -- crnd_unpack_level's own contract (inc/crn_decomp.h:4441-4476: "cached or write
+ * combined memory"): the level is transcoded into device scratch and each face copied out row by row at the caller's pitch.
+ * Synchronous. */
+CRN_API int crn_gpu_crnd_unpack_level_host(crn_gpu_texture* tex, void* const* h_dst_faces, uint32_t dst_size_in_bytes,
+                                           uint32_t row_pitch_in_bytes, uint32_t level_index);
 /* All levels in ONE launch (levels decode concurrently, one warp each) into a tightly packed device
  * buffer laid out level-major then face-major; crn_gpu_crnd_level_offset gives each face's offset. */
 CRN_API uint64_t crn_gpu_crnd_total_size(const crn_gpu_texture* tex);

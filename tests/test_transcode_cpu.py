@@ -172,3 +172,74 @@ def test_wide_batch_matches_single(sim, port, monkeypatch):
         assert split_levels(t, o) == helpers.port_unpack_all(port, d)
         t.close()
     ctx.close()
+
+
+def _level_ofs(data, level):
+    return int.from_bytes(data[70 + 4 * level:74 + 4 * level], "big")
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+def test_truncated_and_corrupt_files_are_safe(sim, wide, monkeypatch):
+    """ADVICE r1 (high): a truncated level stream must read as zeros past its end (crn_decomp.h:3168-3170), never past the file image;
+    corrupt headers / models are rejected at unpack_begin.  The emulator build runs under the host's memory protection, so an
+    out-of-bounds walk of hundreds of KB would fault here."""
+    if wide:
+        monkeypatch.setenv("CRN_B200_WIDE_MIN_BLOCKS", "64")
+    ctx = crn.Context(0, lib=sim)
+    data = bytearray(crnsynth.synth_crn(256, 128, "DXT5", seed=11))
+    # 1. level 0's stream cut to 40 bytes: declared size stays 256x128, the decoder keeps "decoding" zeros
+    cut = bytes(data[:_level_ofs(data, 0) + 40])
+    hdr = bytearray(cut)
+    hdr[6:10] = len(cut).to_bytes(4, "big")          # data_size must fit the buffer
+    try:
+        tex = ctx.unpack_begin(bytes(hdr))
+    except crn.CrnGpuError:
+        tex = None                                   # rejecting is fine too (level offsets of the mips now lie past the end)
+    if tex is not None:
+        out = tex.unpack_all()
+        assert out.size == tex.total_size
+        tex.close()
+    # 2. a 74-byte buffer that claims 16 levels: header_size > size
+    tiny = bytearray(data[:74]); tiny[16] = 16; tiny[2:4] = (70 + 64).to_bytes(2, "big"); tiny[6:10] = (74).to_bytes(4, "big")
+    with pytest.raises(crn.CrnGpuError):
+        ctx.unpack_begin(bytes(tiny))
+    # 3. selector palette count zeroed while the format needs it
+    bad = bytearray(data); bad[33 + 8 + 6:33 + 8 + 8] = (0).to_bytes(2, "big")
+    with pytest.raises(crn.CrnGpuError):
+        ctx.unpack_begin(bytes(bad))
+    # 4. random garbage after the header: either rejected or decoded without leaving the file image
+    rng = np.random.default_rng(3)
+    junk = bytearray(data); first = _level_ofs(data, 0)
+    junk[first:] = rng.integers(0, 256, len(junk) - first, dtype=np.uint8).tobytes()
+    try:
+        tex = ctx.unpack_begin(bytes(junk))
+        assert tex.unpack_all().size == tex.total_size
+        tex.close()
+    except crn.CrnGpuError:
+        pass
+    ctx.close()
+
+
+def test_lane_per_stream_kernel_matches_port(sim, port, monkeypatch):
+    """transcode_streams_kernel (one lane per level stream, the large-batch path): forced on with CRN_B200_STREAMS_MIN=1.
+    Single files of every format (golden .crn from the reference + synthetic ones with 8192-entry palettes and long codes),
+    then one mixed-format batch through crn_gpu_crnd_unpack_batch."""
+    monkeypatch.setenv("CRN_B200_STREAMS_MIN", "1")
+    ctx = crn.Context(0, lib=sim)
+    l0 = ctx.launch_count
+    datas = [load(c) for c in GOLD]
+    datas += [crnsynth.synth_crn(w, h, fmt, faces=faces, seed=7, **kw) for fmt, w, h, faces, kw in SYNTH]
+    wants = [helpers.port_unpack_all(port, d) for d in datas]
+    for d, want in zip(datas, wants):
+        tex = ctx.unpack_begin(d)
+        assert split_levels(tex, tex.unpack_all()) == want
+        tex.close()
+    texs = [ctx.unpack_begin(d) for d in datas]
+    bufs = [np.full(t.total_size + 16, 0xEE, np.uint8) for t in texs]
+    ctx.unpack_batch(texs, [b.ctypes.data for b in bufs], [t.total_size for t in texs])
+    for t, b, want in zip(texs, bufs, wants):
+        assert split_levels(t, b[:t.total_size]) == want
+        assert (b[t.total_size:] == 0xEE).all()
+        t.close()
+    assert ctx.launch_count - l0 >= len(datas) + 1
+    ctx.close()
