@@ -60,10 +60,15 @@ class _CrnParams(ctypes.Structure):
 
 
 class _DdsParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "crn_format", "width", "height", "levels", "faces", "quality_level", "dxt1a_for_transparency")] + [("pack", _PackParams)]
+    _fields_ = ([(n, ctypes.c_uint32) for n in ("struct_size", "crn_format", "width", "height", "levels", "faces", "quality_level", "dxt1a_for_transparency")] + [("pack", _PackParams)]
+                + [("target_bitrate", ctypes.c_float), ("hierarchical", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 2)])
 
 
 EXCHANGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32)
+
+
+class _DdsDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("struct_size", "width", "height", "levels", "faces", "pixel_format", "file_format", "block_format")]
 
 
 class _HcInfo(ctypes.Structure):
@@ -185,6 +190,15 @@ def _declare(lib):
     lib.crn_gpu_default_dds_params.argtypes = [ctypes.POINTER(_DdsParams)]
     lib.crn_gpu_default_dds_params.restype = None
     lib.crn_gpu_compress_dds.argtypes = [vp, ctypes.POINTER(_DdsParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32)]
+    lib.crn_gpu_compress_dds_ex.argtypes = [vp, ctypes.POINTER(_DdsParams), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u32)]
+    lib.crn_gpu_lzma_size.argtypes = [vp, u64]
+    lib.crn_gpu_lzma_size.restype = u64
+    lib.crn_gpu_crnd_unpack_level_host.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32]
+    lib.crn_gpu_dds_get_desc.argtypes = [vp, u32, ctypes.POINTER(_DdsDesc)]
+    lib.crn_gpu_dds_to_images.argtypes = [vp, vp, u32, ctypes.POINTER(vp), u32, ctypes.POINTER(_DdsDesc)]
+    lib.crn_gpu_convert_pixels.argtypes = [vp, vp, u32, u32, u32, u32]
+    lib.crn_gpu_set_progress.argtypes = [vp, vp, vp]
+    lib.crn_gpu_set_progress.restype = None
     lib.crn_gpu_crn_to_dds.argtypes = [vp, vp, u32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
     return lib
 
@@ -526,7 +540,7 @@ class Context:
         return Qdxt(self, fmt, levels, params or PackParams())
 
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
-    def compress_dds(self, images, crn_format, quality_level=255, params=None, dxt1a_for_transparency=False):
+    def compress_dds(self, images, crn_format, quality_level=255, params=None, dxt1a_for_transparency=False, target_bitrate=0.0, with_rate=False):
         """crn_compress to a .DDS (dds_comp, crnlib/crn_dds_comp.cpp:148-289): images[face][level] = (h, w, 4) uint8 host arrays.
         quality_level 255 packs block by block, lower values take the clustered path.  Returns the file bytes."""
         faces, levels = len(images), len(images[0])
@@ -540,9 +554,18 @@ class Context:
         flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]
         ptrs = (ctypes.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
         out = ctypes.c_void_p(); size = ctypes.c_uint32()
-        self._check(self._lib.crn_gpu_compress_dds(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size)))
+        if not with_rate and not target_bitrate:
+            self._check(self._lib.crn_gpu_compress_dds(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size)))
+            try:
+                return ctypes.string_at(out, size.value)
+            finally:
+                self._lib.crn_gpu_free_file(out)
+        # crn_compress's optional outputs: (file, LZMA bits per texel, quality level); target_bitrate runs the reference's search
+        p.target_bitrate = float(target_bitrate)
+        rate = ctypes.c_float(); q = ctypes.c_uint32()
+        self._check(self._lib.crn_gpu_compress_dds_ex(self._ctx, ctypes.byref(p), ptrs, ctypes.byref(out), ctypes.byref(size), ctypes.byref(rate), ctypes.byref(q)))
         try:
-            return ctypes.string_at(out, size.value)
+            return ctypes.string_at(out, size.value), rate.value, q.value
         finally:
             self._lib.crn_gpu_free_file(out)
 
@@ -568,6 +591,27 @@ class Context:
             return ctypes.string_at(out, size.value)
         finally:
             self._lib.crn_gpu_free_file(out)
+
+    def dds_to_images(self, dds_bytes):
+        """crn_decompress_dds_to_images (inc/crnlib.h:634): .dds bytes -> (list of (h, w, 4) uint8 images indexed level + levels * face, desc dict).
+        Block formats are decoded and uncooked on the device; the reference's uncompressed layouts go through the mask-extraction kernel."""
+        buf = np.frombuffer(dds_bytes, np.uint8)
+        d = _DdsDesc(); d.struct_size = ctypes.sizeof(_DdsDesc)
+        rc = self._lib.crn_gpu_dds_get_desc(buf.ctypes.data_as(ctypes.c_void_p), len(dds_bytes), ctypes.byref(d))
+        if rc:
+            raise CrnGpuError(rc, "not a .dds file this path reads")
+        imgs = []
+        for f in range(d.faces):
+            for l in range(d.levels):
+                imgs.append(np.empty((max(1, d.height >> l), max(1, d.width >> l), 4), np.uint8))
+        # index level + levels * face
+        ptrs = (ctypes.c_void_p * len(imgs))(*[a.ctypes.data for a in imgs])
+        self._check(self._lib.crn_gpu_dds_to_images(self._ctx, buf.ctypes.data_as(ctypes.c_void_p), len(dds_bytes), ptrs, len(imgs), ctypes.byref(d)))
+        return imgs, {n: getattr(d, n) for n in ("width", "height", "levels", "faces", "pixel_format", "file_format", "block_format")}
+
+    def convert_pixels_device(self, d_rgba, width, height, pitch, conversion):
+        """image_utils::convert_image on a device image in place (1 To_CCxY ... 9 XY_to_XYZ, include/crn_b200.h)."""
+        self._check(self._lib.crn_gpu_convert_pixels(self._ctx, ctypes.c_void_p(int(d_rgba)), int(width), int(height), int(pitch), int(conversion)))
 
     def crn_to_dds(self, crn_bytes):
         """crn_decompress_crn_to_dds (inc/crnlib.h:620): .crn bytes -> .dds bytes, transcoded on the device."""

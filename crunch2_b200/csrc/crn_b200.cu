@@ -14,6 +14,7 @@
 #include "refiner_kernels.cuh"
 #include "hc_kernels.cuh"
 #include "unpack_kernels.cuh"
+#include "dds_kernels.cuh"
 #include "mip_kernels.cuh"
 #include "mip_host.h"
 #include <stdio.h>
@@ -21,6 +22,7 @@
 #include <string.h>
 #include <math.h>
 #include <time.h>
+#include <dlfcn.h>
 #include <new>
 #include <vector>
 #include <algorithm>
@@ -1486,6 +1488,63 @@ int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, 
 
 void crn_gpu_free_file(void* file) { free(file); }
 
+// Interpolative search for the quality level closest to a target bitrate (create_compressed_texture,
+// crnlib/crn_texture_comp.cpp:120-262): same bracket updates, interpolation, acceptance rule and stop test.
+// pass(quality, &file, &size, &rate) produces a malloc'ed file; the best one is returned.
+}  // extern "C" (templates need C++ linkage)
+template <typename Pass>
+static int bitrate_search(crn_gpu_ctx* ctx, float target, Pass pass, void** out_file, uint32_t* out_size, float* out_bitrate, int* out_quality, float* out_highest)
+{
+    float best_bitrate = 1e+10f, cached[256], highest = 0.0f;
+    int best_quality = -1, low = 0, high = 255;
+    for (int i = 0; i < 256; i++) cached[i] = -1.0f;
+    void* best_file = nullptr; uint32_t best_size = 0;
+    uint32_t iter = 0;
+    bool binary = false;
+    while (low <= high) {
+        int trial = (low + high) / 2;
+        if (iter && !binary) {
+            int blo = trial;
+            while (cached[blo] < 0 && blo > 0) blo--;
+            if (cached[blo] < 0) trial = (int)((float)low + ((float)high - (float)low) * .33f);
+            else {
+                int bhi = trial + 1;
+                if (bhi <= 255) {
+                    while (cached[bhi] < 0 && bhi < 255) bhi++;
+                    if (cached[bhi] >= 0) {
+                        const float rlo = cached[blo], rhi = cached[bhi];
+                        if (rlo < rhi && rlo < target && rhi >= target) {
+                            const int q = low + (int)(((target - rlo) * (high - low)) / (rhi - rlo));
+                            if (q >= low && q <= high) trial = q;
+                        }
+                    }
+                }
+            }
+        }
+        void* file = nullptr; uint32_t size = 0; float rate = 0.0f;
+        const int rc = pass((uint32_t)trial, &file, &size, &rate);
+        if (rc) { free(best_file); return rc; }
+        cached[trial] = rate;
+        if (rate > highest) highest = rate;
+        if (best_quality < 0 || (rate <= target && best_bitrate > target) ||
+            ((rate <= target || best_bitrate > target) && fabsf(rate - target) < fabsf(best_bitrate - target))) {
+            best_bitrate = rate; best_quality = trial;
+            free(best_file); best_file = file; best_size = size; file = nullptr;
+            if (best_bitrate <= target && fabsf(best_bitrate - target) < .005f) break;
+        }
+        free(file);
+        if (rate > target) high = trial - 1; else low = trial + 1;
+        if (++iter > 8) binary = true;
+    }
+    if (best_quality < 0) { free(best_file); return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "bitrate search found nothing"); }
+    *out_file = best_file; *out_size = best_size;
+    if (out_bitrate) *out_bitrate = best_bitrate;
+    if (out_quality) *out_quality = best_quality;
+    if (out_highest) *out_highest = highest;
+    return CRN_GPU_OK;
+}
+extern "C" {
+
 int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate,
                          uint32_t* out_quality)
 { return crn_guard(ctx, [&]() -> int {
@@ -1555,53 +1614,11 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         if (out_quality) *out_quality = p->quality_level;
         return CRN_GPU_OK;
     }
-    // Interpolative search for the quality level closest to the target bitrate (create_compressed_texture,
-    // crnlib/crn_texture_comp.cpp:120-262): same bracket updates, interpolation, acceptance rule and stop test.
-    const float target = p->target_bitrate;
-    float best_bitrate = 1e+10f, cached[256];
-    int best_quality = -1, low = 0, high = 255;
-    for (int i = 0; i < 256; i++) cached[i] = -1.0f;
-    void* best_file = nullptr; uint32_t best_size = 0;
-    uint32_t iter = 0;
-    bool binary = false;
-    while (low <= high) {
-        int trial = (low + high) / 2;
-        if (iter && !binary) {
-            int blo = trial;
-            while (cached[blo] < 0 && blo > 0) blo--;
-            if (cached[blo] < 0) trial = (int)((float)low + ((float)high - (float)low) * .33f);
-            else {
-                int bhi = trial + 1;
-                if (bhi <= 255) {
-                    while (cached[bhi] < 0 && bhi < 255) bhi++;
-                    if (cached[bhi] >= 0) {
-                        const float rlo = cached[blo], rhi = cached[bhi];
-                        if (rlo < rhi && rlo < target && rhi >= target) {
-                            const int q = low + (int)(((target - rlo) * (high - low)) / (rhi - rlo));
-                            if (q >= low && q <= high) trial = q;
-                        }
-                    }
-                }
-            }
-        }
-        void* file = nullptr; uint32_t size = 0; float rate = 0.0f;
-        rc = pass((uint32_t)trial, &file, &size, &rate);
-        if (rc) { free(best_file); return rc; }
-        cached[trial] = rate;
-        if (best_quality < 0 || (rate <= target && best_bitrate > target) ||
-            ((rate <= target || best_bitrate > target) && fabsf(rate - target) < fabsf(best_bitrate - target))) {
-            best_bitrate = rate; best_quality = trial;
-            free(best_file); best_file = file; best_size = size; file = nullptr;
-            if (best_bitrate <= target && fabsf(best_bitrate - target) < .005f) break;
-        }
-        free(file);
-        if (rate > target) high = trial - 1; else low = trial + 1;
-        if (++iter > 8) binary = true;
-    }
     // (the reference retries without adaptive block sizes when even quality 255 stays under the target; dxt_hc's
     //  non-hierarchical mode is not built, so the best hierarchical result stands)
-    if (best_quality < 0) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_crn: bitrate search found nothing");
-    *out_file = best_file; *out_size = best_size;
+    int best_quality = -1; float best_bitrate = 0.0f;
+    rc = bitrate_search(ctx, p->target_bitrate, pass, out_file, out_size, &best_bitrate, &best_quality, nullptr);
+    if (rc) return rc;
     if (out_bitrate) *out_bitrate = best_bitrate;
     if (out_quality) *out_quality = (uint32_t)best_quality;
     return CRN_GPU_OK;
@@ -1618,16 +1635,18 @@ int crn_gpu_crnd_get_texture_info(const void* h_crn, uint32_t crn_size, crn_gpu_
     return CRN_GPU_OK;
 }); }
 
-static int transcode_launch(crn_gpu_ctx* ctx, const crn::TranscodeFile* d_files, uint32_t nfiles)
+static int transcode_launch(crn_gpu_ctx* ctx, const crn::TranscodeFile* d_files, uint32_t nfiles, uint32_t row_entries)
 {
-    const size_t smem = sizeof(crn::TranscodeSmem);
+    // shared-memory row buffers sized by the widest file of the launch: a batch of 1024^2 textures then runs 4 CTAs per SM, not 2
+    if (row_entries > crn::kRowbufSmemEntries) row_entries = crn::kRowbufSmemEntries;
+    const size_t smem = crn::transcode_smem_bytes(row_entries);
 #ifdef __CUDACC__
     if (!ctx->transcode_smem_set) {
-        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRN_CUDA(ctx, cudaFuncSetAttribute(crn::transcode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)crn::transcode_smem_bytes(crn::kRowbufSmemEntries)));
         ctx->transcode_smem_set = 1;
     }
 #endif
-    CRN_LAUNCH(crn::transcode_levels_kernel, nfiles, crn::kTranscodeWarps * 32, smem, ctx->stream, d_files);
+    CRN_LAUNCH(crn::transcode_levels_kernel, nfiles, crn::kTranscodeWarps * 32, smem, ctx->stream, d_files, row_entries);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
@@ -1744,7 +1763,9 @@ static int transcode_textures(crn_gpu_ctx* ctx, crn_gpu_texture* const* texs, ui
     // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may die with this frame
     CRN_CUDA(ctx, cudaMemcpyAsync(d_files, files.data(), sizeof(crn::TranscodeFile) * count, cudaMemcpyHostToDevice, ctx->stream));
     if (small_levels) {
-        const int rc = transcode_launch(ctx, d_files, count);
+        uint32_t row_entries = 0;
+        for (uint32_t t = 0; t < count; t++) row_entries = std::max(row_entries, texs[t]->host_file.rowbuf_total);
+        const int rc = transcode_launch(ctx, d_files, count, row_entries);
         if (rc) return rc;
     }
     if (wide.empty()) return CRN_GPU_OK;
@@ -2072,14 +2093,56 @@ void crn_gpu_default_dds_params(crn_gpu_dds_params* p)
     memset(p, 0, sizeof(*p));
     p->struct_size = sizeof(*p);
     p->levels = 1; p->faces = 1; p->quality_level = 255;
+    p->hierarchical = 1;
     crn_gpu_default_pack_params(&p->pack);
 }
 
+// LZMA-compressed size of a buffer, the DDS path's bitrate measure (dds_comp::compress_pass, crnlib/crn_dds_comp.cpp:291-303 ->
+// lzma_codec::pack, crnlib/crn_lzma_codec.cpp:45-112: LZMA SDK level 5 = 16 MiB dictionary, lc 3, lp 0, pb 2, fb 32, bt4, plus a 20-byte
+// header).  The reference vendors the LZMA SDK; LZMA is out of this path's scope, so the system's liblzma is loaded at
+// run time with the same coder parameters (the two encoders' sizes agree to a fraction of a percent).  0 = liblzma not available.
+static uint64_t lzma_packed_size(const void* data, size_t n)
+{
+    struct Filter { uint64_t id; void* options; };
+    typedef int (*preset_fn)(void*, uint32_t);
+    typedef int (*encode_fn)(const Filter*, const void*, const uint8_t*, size_t, uint8_t*, size_t*, size_t);
+    static preset_fn preset = nullptr; static encode_fn encode = nullptr; static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        void* h = dlopen("liblzma.so.5", RTLD_NOW | RTLD_LOCAL);
+        if (h) { preset = (preset_fn)dlsym(h, "lzma_lzma_preset"); encode = (encode_fn)dlsym(h, "lzma_raw_buffer_encode"); }
+    }
+    if (!preset || !encode || !n) return 0;
+    alignas(16) uint8_t opt[512];                                  // lzma_options_lzma (first member: uint32_t dict_size), generously sized
+    memset(opt, 0, sizeof(opt));
+    if (preset(opt, 5)) return 0;                                  // preset 5: normal mode, bt4, nice_len 32, lc 3 / lp 0 / pb 2
+    const uint32_t dict = 1u << 24;
+    memcpy(opt, &dict, 4);
+    const Filter filters[2] = { { 0x4000000000000001ull, opt }, { ~0ull, nullptr } };   // LZMA_FILTER_LZMA1, LZMA_VLI_UNKNOWN
+    const size_t cap = n + (n >> 2) + 4096;
+    uint8_t* out = static_cast<uint8_t*>(malloc(cap));
+    if (!out) return 0;
+    size_t pos = 0;
+    const int rc = encode(filters, nullptr, static_cast<const uint8_t*>(data), n, out, &pos, cap);
+    free(out);
+    return rc == 0 ? (uint64_t)pos + 20 : 0;                       // + sizeof(lzma_codec::header) (crnlib/crn_lzma_codec.h:72-88)
+}
+
+uint64_t crn_gpu_lzma_size(const void* data, uint64_t size) { return lzma_packed_size(data, (size_t)size); }
+
 int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size)
+{
+    return crn_gpu_compress_dds_ex(ctx, p, h_images, out_file, out_size, nullptr, nullptr);
+}
+
+int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size, float* out_bitrate,
+                            uint32_t* out_quality)
 { return crn_guard(ctx, [&]() -> int {   // dds_comp::compress_init + convert_to_dxt + compress_pass (crnlib/crn_dds_comp.cpp:148-289)
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
+    if (out_bitrate) *out_bitrate = 0.0f;
+    if (out_quality) *out_quality = 0;
     if (!p || p->struct_size != sizeof(crn_gpu_dds_params) || !h_images || !out_file || !out_size || p->width < 1 || p->height < 1 || p->width > 4096 || p->height > 4096 ||
         p->levels < 1 || p->levels > 16 || (p->faces != 1 && p->faces != 6) || p->quality_level > 255 || p->pack.struct_size != sizeof(crn_gpu_pack_params))
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_dds: bad argument");
@@ -2112,36 +2175,245 @@ int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const vo
     uint64_t payload = 0;
     for (const crn_gpu_level_desc& d : lv) payload += (uint64_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
     if (128 + payload > 0xFFFFFFFFull) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_compress_dds: file would exceed 4 GiB (crn_uint32 size)");
-    uint8_t* file = static_cast<uint8_t*>(malloc(128 + payload));
-    if (!file) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_dds: out of host memory");
-    int rc = crn_gpu_dds_header(p->crn_format, p->width, p->height, p->levels, p->faces, file);
-    if (rc == CRN_GPU_OK) {
-        if (p->quality_level == 255 || fmt == CRN_GPU_FMT_DXT3) {                                                // crn_dds_comp.cpp:150-157: block by block
+    uint64_t total_texels = 0;                                                                                   // get_total_pixels_in_all_faces_and_mips
+    for (const crn_gpu_level_desc& d : lv) total_texels += (uint64_t)d.width * d.height;
+    uint8_t header[128];
+    int rc = crn_gpu_dds_header(p->crn_format, p->width, p->height, p->levels, p->faces, header);
+    if (rc) return set_err(ctx, rc, "crn_gpu_compress_dds: format has no DDS form");
+    if (p->hierarchical == 0 && p->quality_level < 255 && fmt != CRN_GPU_FMT_DXT3)
+        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: the non-hierarchical clustered mode is not built");
+    crn_gpu_qdxt* q = nullptr;                                                                                   // kept across the passes of a search (m_pQDXT_state)
+    // one compress_pass: convert_to_dxt + write_dds (+ the LZMA measurement when a rate is wanted)
+    auto pass = [&](uint32_t quality, void** file_out, uint32_t* size_out, float* rate) -> int {
+        uint8_t* file = static_cast<uint8_t*>(malloc(128 + payload));
+        if (!file) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_dds: out of host memory");
+        memcpy(file, header, 128);
+        int r = CRN_GPU_OK;
+        if (quality == 255 || fmt == CRN_GPU_FMT_DXT3) {                                                         // crn_dds_comp.cpp:150-157: block by block
             uint8_t* dst = file + 128;
             uint64_t done = 0;
             for (const crn_gpu_level_desc& d : lv) {
-                rc = progress_tick(ctx, 0, 1, (uint32_t)(payload ? done * 100 / payload : 0), 100);             // crn_dds_comp.cpp:130-134, :233-236
-                if (rc == CRN_GPU_OK) rc = crn_gpu_pack_image_host(ctx, fmt, &p->pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
-                if (rc) break;
+                r = progress_tick(ctx, 0, 1, (uint32_t)(payload ? done * 100 / payload : 0), 100);               // crn_dds_comp.cpp:130-134, :233-236
+                if (r == CRN_GPU_OK) r = crn_gpu_pack_image_host(ctx, fmt, &p->pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
+                if (r) break;
                 const size_t sz = (size_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
                 dst += sz; done += sz;
             }
-            if (rc == CRN_GPU_OK) rc = progress_tick(ctx, 0, 1, 100, 100);
-        } else {                                                                                                 // clustered: qdxt_pack_init + qdxt_pack
-            crn_gpu_qdxt* q = nullptr;
-            rc = progress_tick(ctx, 0, 2, 0, 100);                                                               // crn_dds_comp.cpp:136-146, :172-188
-            if (rc == CRN_GPU_OK) rc = crn_gpu_qdxt_init(ctx, fmt, &p->pack, lv.data(), count, 1, &q);
-            if (rc == CRN_GPU_OK) {
-                if (crn_gpu_qdxt_output_size(q) != payload) rc = set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_dds: payload size mismatch");
-                else rc = progress_tick(ctx, 1, 2, 0, 100);
-                if (rc == CRN_GPU_OK) rc = crn_gpu_qdxt_pack(q, p->quality_level, file + 128, 1);
-                crn_gpu_qdxt_free(q);
-                if (rc == CRN_GPU_OK) rc = progress_tick(ctx, 1, 2, 100, 100);
+            if (r == CRN_GPU_OK) r = progress_tick(ctx, 0, 1, 100, 100);
+        } else {                                                                                                 // clustered: qdxt_pack_init once, qdxt_pack per pass
+            const bool first = q == nullptr;
+            if (first) {
+                r = progress_tick(ctx, 0, 2, 0, 100);                                                            // crn_dds_comp.cpp:136-146, :172-188
+                if (r == CRN_GPU_OK) r = crn_gpu_qdxt_init(ctx, fmt, &p->pack, lv.data(), count, 1, &q);
+                if (r == CRN_GPU_OK && crn_gpu_qdxt_output_size(q) != payload) r = set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_dds: payload size mismatch");
             }
+            if (r == CRN_GPU_OK) r = first ? progress_tick(ctx, 1, 2, 0, 100) : progress_tick(ctx, 0, 1, 0, 100);
+            if (r == CRN_GPU_OK) r = crn_gpu_qdxt_pack(q, quality, file + 128, 1);
+            if (r == CRN_GPU_OK) r = first ? progress_tick(ctx, 1, 2, 100, 100) : progress_tick(ctx, 0, 1, 100, 100);
+        }
+        if (r) { free(file); return r; }
+        if (rate) {
+            const uint64_t packed = lzma_packed_size(file, (size_t)(128 + payload));
+            *rate = (packed && total_texels) ? (packed * 8.0f) / (float)total_texels : 0.0f;
+        }
+        *file_out = file; *size_out = (uint32_t)(128 + payload);
+        return CRN_GPU_OK;
+    };
+    // create_compressed_texture (crnlib/crn_texture_comp.cpp:86-118): one pass unless a bitrate target applies
+    if (!(p->target_bitrate > 0.0f) || fmt == CRN_GPU_FMT_DXT3) {
+        float rate = 0.0f;
+        rc = pass(p->quality_level, out_file, out_size, out_bitrate ? &rate : nullptr);
+        if (q) crn_gpu_qdxt_free(q);
+        if (rc) return rc;
+        if (out_bitrate) *out_bitrate = rate;
+        if (out_quality) *out_quality = p->quality_level;
+        return CRN_GPU_OK;
+    }
+    if (!lzma_packed_size("crn", 3)) { if (q) crn_gpu_qdxt_free(q); return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: a target bitrate needs liblzma.so.5 for the size measurement"); }
+    int best_quality = -1; float best_bitrate = 0.0f;
+    rc = bitrate_search(ctx, p->target_bitrate, pass, out_file, out_size, &best_bitrate, &best_quality, nullptr);
+    if (q) crn_gpu_qdxt_free(q);
+    // (the reference's retry without adaptive block sizes, crn_texture_comp.cpp:232-250, needs the non-hierarchical mode: not built)
+    if (rc) return rc;
+    if (out_bitrate) *out_bitrate = best_bitrate;
+    if (out_quality) *out_quality = (uint32_t)best_quality;
+    return CRN_GPU_OK;
+}); }
+
+/* ---- .dds in: read_dds + unpack_from_dxt ------------------------------------------------------------ */
+namespace {
+struct DdsParsed {
+    crn_gpu_dds_desc d;
+    bool fourcc;
+    uint32_t pitch;                      // of level 0 (bytes per surface for block formats, per line otherwise)
+    uint32_t uncook;                     // crn::PixelConversion applied after the unpack, 0 = none
+    crn::DdsRawFormat raw;
+};
+constexpr uint32_t dds_cc(char a, char b, char c, char d) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24); }
+uint32_t popcount32(uint32_t m) { uint32_t n = 0; while (m) { m &= m - 1; n++; } return n; }          // math::bitmask_size
+uint32_t ctz32(uint32_t m) { uint32_t n = 0; if (!m) return 0; while (!(m & 1)) { m >>= 1; n++; } return n; }   // math::bitmask_ofs
+
+// mipmapped_texture::read_dds_internal up to the payload (crnlib/crn_mipmapped_texture.cpp:489-725)
+int dds_parse(const void* h_dds, uint32_t size, DdsParsed& P)
+{
+    memset(&P, 0, sizeof(P));
+    P.d.struct_size = sizeof(crn_gpu_dds_desc);
+    if (!h_dds || size < 128) return CRN_GPU_ERR_BAD_DATA;
+    uint32_t h[32];
+    memcpy(h, h_dds, 128);
+    if (h[0] != dds_cc('D', 'D', 'S', ' ') || h[1] != 124) return CRN_GPU_ERR_BAD_DATA;
+    const uint32_t flags = h[2], height = h[3], width = h[4], caps = h[27], caps2 = h[28];
+    const uint32_t pf_flags = h[20], cc = h[21], bitcount = h[22];
+    if (!height || !width || height > 8192 || width > 8192) return CRN_GPU_ERR_BAD_DATA;
+    uint32_t levels = 1;
+    if ((flags & 0x20000u) && (caps & 0x400000u) && h[7]) {
+        levels = h[7];
+        uint32_t maxm = 1;
+        for (uint32_t w = width, hh = height; w > 1 || hh > 1; w >>= 1, hh >>= 1) maxm++;               // utils::compute_max_mips
+        if (levels > maxm) return CRN_GPU_ERR_BAD_DATA;
+    }
+    uint32_t faces = 1;
+    if (caps & 0x8u) {
+        if (caps2 & 0x200u) { if ((caps2 & 0xFC00u) != 0xFC00u) return CRN_GPU_ERR_UNSUPPORTED; faces = 6; }
+        else if (caps2 & 0x200000u) return CRN_GPU_ERR_UNSUPPORTED;                                    // volume textures
+    }
+    if (pf_flags & 0x20u) return CRN_GPU_ERR_UNSUPPORTED;                                              // palettized
+    const uint32_t RGBx = dds_cc('R', 'G', 'B', 'x'), RGBA = dds_cc('R', 'G', 'B', 'A'), Lx = dds_cc('L', 'x', 'x', 'x'), LA = dds_cc('L', 'x', 'x', 'A'), xA = dds_cc('x', 'x', 'x', 'A');
+    P.d.width = width; P.d.height = height; P.d.levels = levels; P.d.faces = faces;
+    P.d.block_format = 0xFFFFFFFFu;
+    P.fourcc = (pf_flags & 0x4u) != 0;
+    uint32_t bits_per_pixel = bitcount;
+    if (P.fourcc) {
+        uint32_t ff = cc, bf, out = RGBA, bpp = 8;
+        if (cc == dds_cc('D', 'X', 'T', '1')) { bf = CRN_GPU_FMT_DXT1; out = RGBx; bpp = 4; }
+        else if (cc == dds_cc('D', 'X', 'T', '2') || cc == dds_cc('D', 'X', 'T', '3')) { bf = CRN_GPU_FMT_DXT3; ff = dds_cc('D', 'X', 'T', '3'); }
+        else if (cc == dds_cc('D', 'X', 'T', '4') || cc == dds_cc('D', 'X', 'T', '5')) {
+            bf = CRN_GPU_FMT_DXT5; ff = dds_cc('D', 'X', 'T', '5');
+            if (bitcount == dds_cc('C', 'C', 'x', 'Y')) { ff = bitcount; P.uncook = crn::kConvFromCCxY; out = RGBx; }
+            else if (bitcount == dds_cc('x', 'G', 'x', 'R')) { ff = bitcount; P.uncook = crn::kConvFromxGxR; out = RGBx; }
+            else if (bitcount == dds_cc('x', 'G', 'B', 'R')) { ff = bitcount; P.uncook = crn::kConvFromxGBR; out = RGBx; }
+            else if (bitcount == dds_cc('A', 'G', 'B', 'R')) { ff = bitcount; P.uncook = crn::kConvFromAGBR; out = RGBA; }
+        } else if (cc == dds_cc('A', 'T', 'I', '2')) {
+            if (bitcount == dds_cc('A', '2', 'X', 'Y')) { bf = CRN_GPU_FMT_DXN_XY; ff = dds_cc('A', '2', 'X', 'Y'); } else bf = CRN_GPU_FMT_DXN_YX;
+            P.uncook = crn::kConvXYtoXYZ; out = RGBx;
+        } else if (cc == dds_cc('A', 'T', 'I', '1')) { bf = CRN_GPU_FMT_DXT5A; bpp = 4; }
+        else return CRN_GPU_ERR_UNSUPPORTED;                                                           // ETC family, unknown FOURCCs
+        P.d.block_format = bf; P.d.file_format = ff; P.d.pixel_format = out;
+        bits_per_pixel = bpp;
+    } else if (bitcount < 8 || bitcount > 32 || (bitcount & 7)) return CRN_GPU_ERR_UNSUPPORTED;
+    else if (pf_flags & 0x40u) P.d.file_format = (pf_flags & 0x20000u) ? ((pf_flags & 1u) ? LA : Lx) : ((pf_flags & 1u) ? RGBA : RGBx);
+    else if (pf_flags & 1u) P.d.file_format = (pf_flags & 0x20000u) ? LA : xA;
+    else if (pf_flags & 0x20000u) P.d.file_format = Lx;
+    else if (pf_flags & 2u) P.d.file_format = xA;
+    else return CRN_GPU_ERR_UNSUPPORTED;
+    if (!P.fourcc) P.d.pixel_format = P.d.file_format;
+    const uint32_t default_pitch = P.fourcc ? ((((width + 3) & ~3u) * ((height + 3) & ~3u) * bits_per_pixel) >> 3) : ((width * bits_per_pixel) >> 3);
+    uint32_t pitch = 0;
+    if ((flags & 0x8u) && !(flags & 0x80000u)) pitch = h[5];
+    if (!pitch) pitch = default_pitch;
+    else if (pitch > default_pitch * 8) return CRN_GPU_ERR_BAD_DATA;
+    P.pitch = pitch;
+    if (!P.fourcc) {
+        P.raw.bytes_per_pixel = bitcount >> 3;
+        for (int i = 0; i < 4; i++) { P.raw.mask_size[i] = popcount32(h[23 + i]); P.raw.mask_ofs[i] = ctz32(h[23 + i]); }
+        P.raw.luminance = (pf_flags & 0x20000u) ? 1u : 0u;
+        if (P.raw.luminance && !P.raw.mask_size[0]) { P.raw.mask_size[0] = bitcount >> 3; if (pf_flags & 1u) P.raw.mask_size[0] /= 2; }   // :720-724 (sic: bytes, not bits)
+    }
+    return CRN_GPU_OK;
+}
+}  // namespace
+
+int crn_gpu_dds_get_desc(const void* h_dds, uint32_t dds_size, crn_gpu_dds_desc* desc)
+{ return crn_guard(nullptr, [&]() -> int {
+    if (!desc || desc->struct_size != sizeof(crn_gpu_dds_desc)) return CRN_GPU_ERR_BAD_PARAM;
+    DdsParsed P;
+    const int rc = dds_parse(h_dds, dds_size, P);
+    if (rc) return rc;
+    *desc = P.d;
+    return CRN_GPU_OK;
+}); }
+
+int crn_gpu_convert_pixels(crn_gpu_ctx* ctx, void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t conversion)
+{ return crn_guard(ctx, [&]() -> int {
+    if (!ctx || !d_rgba || !width || !height || pitch_bytes < width * 4 || (pitch_bytes & 3) || conversion < 1 || conversion > 9) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_convert_pixels: bad argument");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = (uint64_t)width * height;
+    CRN_LAUNCH(crn::pixel_convert_kernel, (uint32_t)((n + 255) / 256), 256, 0, ctx->stream, static_cast<uint8_t*>(d_rgba), width, height, pitch_bytes, conversion);
+    ctx->launches++;
+    CRN_CUDA(ctx, cudaGetLastError());
+    return CRN_GPU_OK;
+}); }
+
+int crn_gpu_dds_to_images(crn_gpu_ctx* ctx, const void* h_dds, uint32_t dds_size, void* const* h_images, uint32_t num_images, crn_gpu_dds_desc* desc)
+{ return crn_guard(ctx, [&]() -> int {
+    if (!ctx || !h_images || (desc && desc->struct_size != sizeof(crn_gpu_dds_desc))) return CRN_GPU_ERR_BAD_PARAM;
+    DdsParsed P;
+    int rc = dds_parse(h_dds, dds_size, P);
+    if (rc) return set_err(ctx, rc, "crn_gpu_dds_to_images: not a .dds file this path reads");
+    const uint32_t faces = P.d.faces, levels = P.d.levels;
+    if (num_images < faces * levels) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_dds_to_images: too few image pointers");
+    for (uint32_t i = 0; i < faces * levels; i++) if (!h_images[i]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_dds_to_images: null image pointer");
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    // payload layout: faces outermost, level 0 of each face padded to `pitch` (:741-776, :787-800)
+    const uint32_t bpb = P.fourcc ? crn_gpu_bytes_per_block(P.d.block_format) : 0;
+    struct Surf { uint64_t src_ofs, src_bytes, dst_ofs; uint32_t w, h, line_pitch; };
+    std::vector<Surf> surfs(faces * levels);
+    uint64_t ofs = 128, dst_total = 0;
+    for (uint32_t f = 0; f < faces; f++)
+        for (uint32_t l = 0; l < levels; l++) {
+            Surf& s = surfs[l + levels * f];
+            s.w = std::max(1u, P.d.width >> l); s.h = std::max(1u, P.d.height >> l);
+            uint64_t actual, stored;
+            if (P.fourcc) { actual = (uint64_t)((s.w + 3) >> 2) * ((s.h + 3) >> 2) * bpb; stored = l ? actual : std::max<uint64_t>(actual, P.pitch); s.line_pitch = 0; }
+            else { const uint32_t line = s.w * P.raw.bytes_per_pixel; s.line_pitch = l ? line : P.pitch; actual = stored = (uint64_t)s.line_pitch * s.h; if (s.line_pitch < line) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_dds_to_images: pitch below the line size"); }
+            s.src_ofs = ofs; s.src_bytes = actual; ofs += stored;
+            if (s.src_ofs + actual > dds_size) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_dds_to_images: truncated file");
+            s.dst_ofs = dst_total; dst_total += ((uint64_t)s.w * s.h * 4 + 255) & ~255ull;
+        }
+    const uint64_t payload = ofs > dds_size ? (uint64_t)dds_size - 128 : ofs - 128;
+    rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)payload + 272);
+    if (rc) return rc;
+    rc = ensure(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)dst_total + 256);
+    if (rc) return rc;
+    uint8_t* d_src = static_cast<uint8_t*>(ctx->d_in);
+    uint8_t* d_dst = static_cast<uint8_t*>(ctx->d_out);
+    uint32_t* d_flag = reinterpret_cast<uint32_t*>(d_src + (((size_t)payload + 15) & ~(size_t)15));
+    CRN_CUDA(ctx, cudaMemcpyAsync(d_src, static_cast<const uint8_t*>(h_dds) + 128, (size_t)payload, cudaMemcpyHostToDevice, ctx->stream));
+    CRN_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+    for (const Surf& s : surfs) {
+        const uint8_t* src = d_src + (s.src_ofs - 128);
+        uint8_t* dst = d_dst + s.dst_ofs;
+        const uint64_t n = (uint64_t)s.w * s.h;
+        if (P.fourcc) {
+            if ((s.src_ofs - 128) & 7) return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_dds_to_images: surface not 8-byte aligned in the file");
+            const uint32_t bx = (s.w + 3) >> 2, by = (s.h + 3) >> 2, nb = bx * by;
+            // 16-byte formats are read as ulonglong2: d_in is 256-byte aligned and every surface size is a multiple of the block size
+            if (bpb == 16 && ((s.src_ofs - 128) & 15)) return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_dds_to_images: surface not 16-byte aligned in the file");
+            if (P.d.block_format == CRN_GPU_FMT_DXT1) {
+                CRN_LAUNCH(crn::dxt1_has_alpha_kernel, (nb + 255) / 256, 256, 0, ctx->stream, reinterpret_cast<const unsigned long long*>(src), nb, d_flag);
+                ctx->launches++;
+            }
+            CRN_LAUNCH(crn::unpack_blocks_kernel, (nb + 255) / 256, 256, 0, ctx->stream, reinterpret_cast<const unsigned long long*>(src), P.d.block_format, s.w, s.h, bx, nb, dst, s.w * 4);
+            ctx->launches++;
+            if (P.uncook) {
+                CRN_LAUNCH(crn::pixel_convert_kernel, (uint32_t)((n + 255) / 256), 256, 0, ctx->stream, dst, s.w, s.h, s.w * 4, P.uncook);
+                ctx->launches++;
+            }
+        } else {
+            CRN_LAUNCH(crn::dds_raw_pixels_kernel, (uint32_t)((n + 255) / 256), 256, 0, ctx->stream, src, s.line_pitch, s.w, s.h, P.raw, reinterpret_cast<uint32_t*>(dst));
+            ctx->launches++;
         }
     }
-    if (rc) { free(file); return rc; }
-    *out_file = file; *out_size = (uint32_t)(128 + payload);
+    CRN_CUDA(ctx, cudaGetLastError());
+    uint32_t flag = 0;
+    for (size_t i = 0; i < surfs.size(); i++)
+        CRN_CUDA(ctx, cudaMemcpyAsync(h_images[i], d_dst + surfs[i].dst_ofs, (size_t)surfs[i].w * surfs[i].h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (P.d.block_format == CRN_GPU_FMT_DXT1 && flag) {                                                // change_dxt1_to_dxt1a (:866-882)
+        P.d.block_format = CRN_GPU_FMT_DXT1A; P.d.file_format = dds_cc('D', 'X', '1', 'A'); P.d.pixel_format = dds_cc('R', 'G', 'B', 'A');
+    }
+    if (desc) *desc = P.d;
     return CRN_GPU_OK;
 }); }
 

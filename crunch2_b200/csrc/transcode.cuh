@@ -238,9 +238,13 @@ struct TranscodeSmem {
     uint32_t lookup[kNumBlockModels][kHuffLookupSize];
     LongCodes longc[kNumBlockModels];
     BlockBatch batch[kTranscodeWarps];
-    uint2 rowval[kRowbufSmemEntries];   // per column: ce | a0 << 16, a1   (resolved indices of the row above)
-    uint8_t rowref[kRowbufSmemEntries]; // per column: reference of the odd row, delivered by the even row's group symbol
+    uint32_t row_entries;               // columns the launch reserved behind this struct (<= kRowbufSmemEntries; sized by the widest file of the
+                                        // batch, so that a batch of small textures fits more CTAs per SM)
+    uint32_t pad[3];
+    uint2 rowval[1];                    // row_entries x { ce | a0 << 16, a1 } (resolved indices of the row above), then row_entries reference
+                                        // bytes (the odd row's references, delivered by the even row's group symbol)
 };
+__host__ __device__ inline size_t transcode_smem_bytes(uint32_t row_entries) { return sizeof(TranscodeSmem) + (size_t)row_entries * 9 + 16; }
 
 // segmented running-index scan over the batch for one component
 __device__ __forceinline__ uint32_t resolve_indices(uint32_t ref, uint32_t delta, uint32_t top, uint32_t carry, uint32_t n_pal, uint32_t n)
@@ -269,9 +273,9 @@ __device__ __forceinline__ void transcode_level(TranscodeSmem* sm, const Transco
     const uint32_t bs = ((HAS_COLOR && HAS_A0) || IS_DXN) ? 16u : 8u;   // DXT5 / DXN: two elements, DXT1 / DXT5A: one
     const uint32_t W = (ls.blocks_x + 1) & ~1u, H = (ls.blocks_y + 1) & ~1u;
     const uint32_t bxv = ls.blocks_x, byv = ls.blocks_y, pitch = ls.row_pitch;
-    const bool in_smem = ls.rowbuf_ofs + W <= kRowbufSmemEntries;
+    const bool in_smem = ls.rowbuf_ofs + W <= sm->row_entries;
     uint2* rowval = in_smem ? &sm->rowval[ls.rowbuf_ofs] : f.rowbuf_pool + ls.rowbuf_ofs;
-    uint8_t* rowref = in_smem ? &sm->rowref[ls.rowbuf_ofs] : reinterpret_cast<uint8_t*>(f.rowbuf_pool + f.rowbuf_total) + ls.rowbuf_ofs;
+    uint8_t* rowref = in_smem ? reinterpret_cast<uint8_t*>(&sm->rowval[sm->row_entries]) + ls.rowbuf_ofs : reinterpret_cast<uint8_t*>(f.rowbuf_pool + f.rowbuf_total) + ls.rowbuf_ofs;
     const uint16_t* pool = f.sorted_pool;
     const uint32_t* ce_pal = f.color_endpoints; const uint32_t* cs_pal = f.color_selectors;
     const uint16_t* ae_pal = f.alpha_endpoints; const uint16_t* as_pal = f.alpha_selectors;
@@ -343,10 +347,11 @@ __device__ __forceinline__ void transcode_level(TranscodeSmem* sm, const Transco
     }
 }
 
-__global__ void __launch_bounds__(kTranscodeWarps * 32) transcode_levels_kernel(const TranscodeFile* __restrict__ files)
+__global__ void __launch_bounds__(kTranscodeWarps * 32) transcode_levels_kernel(const TranscodeFile* __restrict__ files, uint32_t row_entries)
 {
     CRN_DYN_SMEM(TranscodeSmem, sm);
     const TranscodeFile& f = files[blockIdx.x];
+    if (threadIdx.x == 0) sm->row_entries = row_entries;
     for (uint32_t i = threadIdx.x; i < (uint32_t)(kNumBlockModels * kHuffLookupSize); i += blockDim.x)
         sm->lookup[i / kHuffLookupSize][i % kHuffLookupSize] = f.models[i / kHuffLookupSize].lookup[i % kHuffLookupSize];
     if (threadIdx.x < kNumBlockModels * 5) longcodes_fill(sm->longc[threadIdx.x / 5], f.models[threadIdx.x / 5], threadIdx.x % 5);

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define CRN_B200_ABI_VERSION 1
+#define CRN_B200_ABI_VERSION 2
 
 #if defined(CRN_B200_BUILD) && defined(__GNUC__)
 #define CRN_API __attribute__((visibility("default")))
@@ -434,8 +434,7 @@ CRN_API int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn
  * crnlib/crn_dds_comp.cpp:148-289): quality_level 255 (or DXT3) packs block by block (crn_gpu_pack_image), anything lower runs
  * the clustered path (crn_gpu_qdxt_init + crn_gpu_qdxt_pack); the result is a complete .dds file (header + faces outermost).
  * h_images[face * levels + level]: host RGBA8, tight pitch.  DXT1 becomes DXT1A under the reference's rule (any alpha < 255,
- * both block types, dxt1a_for_transparency).  The target-bitrate search over LZMA-compressed size is not built (LZMA is out
- * of scope): call again with another quality_level. */
+ * both block types, dxt1a_for_transparency). */
 typedef struct crn_gpu_dds_params {
     uint32_t struct_size;               /* sizeof(crn_gpu_dds_params) */
     uint32_t crn_format;                /* 0 DXT1, 1 DXT3, 2 DXT5, 7 DXN_XY, 8 DXN_YX, 9 DXT5A */
@@ -443,9 +442,44 @@ typedef struct crn_gpu_dds_params {
     uint32_t quality_level;             /* m_quality_level */
     uint32_t dxt1a_for_transparency;    /* cCRNCompFlagDXT1AForTransparency */
     crn_gpu_pack_params pack;           /* dxt_image::pack_params::init(crn_comp_params) (crnlib/crn_dxt_image.h:192-203) */
+    float target_bitrate;               /* m_target_bitrate: LZMA-compressed bits per texel; 0 = use quality_level (crn_gpu_compress_dds_ex only) */
+    uint32_t hierarchical;              /* cCRNCompFlagHierarchical (default 1; 0 is CRN_GPU_ERR_UNSUPPORTED below quality 255) */
+    uint32_t reserved[2];
 } crn_gpu_dds_params;
 CRN_API void crn_gpu_default_dds_params(crn_gpu_dds_params* p);
 CRN_API int crn_gpu_compress_dds(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size);
+/* Same with crn_compress's two optional outputs (inc/crnlib.h:609) and the target-bitrate search of create_compressed_texture
+ * (crnlib/crn_texture_comp.cpp:120-262) over dds_comp::compress_pass (crnlib/crn_dds_comp.cpp:254-306): the clustered state is built once
+ * (qdxt_pack_init) and every trial is one qdxt_pack at that quality level, as in the reference.  out_bitrate = LZMA-compressed file bits /
+ * texels of all faces and levels; the size comes from the system's liblzma (dlopen, same coder parameters as the reference's vendored LZMA
+ * SDK at its default level) -- 0.0 when liblzma is absent, and a target bitrate is then CRN_GPU_ERR_UNSUPPORTED.  out_quality = the level
+ * of the returned file.  Either output may be NULL. */
+CRN_API int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const void* const* h_images, void** out_file, uint32_t* out_size,
+                                    float* out_bitrate, uint32_t* out_quality);
+/* The size measurement alone (bytes, 0 = liblzma unavailable); host only. */
+CRN_API uint64_t crn_gpu_lzma_size(const void* data, uint64_t size);
+
+/* .dds in: crn_decompress_dds_to_images (inc/crnlib.h:634, crnlib/crnlib.cpp:293-333) = mipmapped_texture::read_dds
+ * (crnlib/crn_mipmapped_texture.cpp:489-862) + unpack_from_dxt(uncook = true) (:2013-2031, mip_level::get_unpacked_image :358-371).
+ * Block formats (DXT1 / DXT1A by the reference's scan for transparent texels, DXT3, DXT5 and its four swizzled variants, DXN_XY / ATI2,
+ * DXT5A) are decoded on the device (unpack_blocks_kernel) and "uncooked" (swizzles undone, DXN z regenerated); the uncompressed layouts
+ * the reference reads (8-32 bit RGB / luminance / alpha with channel bit masks) go through a mask-extraction kernel.  Bit-exact.
+ * crn_gpu_dds_get_desc is host-only and reports the geometry plus `pixel_format` = the crnlib::pixel_format (inc/dds_defs.h:33-69) the
+ * DECODED images carry (what crn_texture_desc::m_fmt_fourcc receives) -- for a DXT1 file under the assumption that no block is transparent;
+ * crn_gpu_dds_to_images rewrites *desc (may be NULL) with the final answer.  h_images[level + levels * face] (crnlib.cpp:327): caller
+ * memory of max(1, width >> level) * max(1, height >> level) * 4 bytes each, RGBA8 (r first). */
+typedef struct crn_gpu_dds_desc {
+    uint32_t struct_size;               /* sizeof(crn_gpu_dds_desc) */
+    uint32_t width, height, levels, faces;
+    uint32_t pixel_format;              /* of the decoded images: 'RGBx', 'RGBA', 'Lxxx', 'LxxA' or 'xxxA' */
+    uint32_t file_format;               /* crnlib::pixel_format of the file (DXT1 ... or one of the above) */
+    uint32_t block_format;              /* crn_gpu_format of the payload, 0xFFFFFFFF for an uncompressed file */
+} crn_gpu_dds_desc;
+CRN_API int crn_gpu_dds_get_desc(const void* h_dds, uint32_t dds_size, crn_gpu_dds_desc* desc);
+CRN_API int crn_gpu_dds_to_images(crn_gpu_ctx* ctx, const void* h_dds, uint32_t dds_size, void* const* h_images, uint32_t num_images, crn_gpu_dds_desc* desc);
+/* image_utils::convert_image (crnlib/crn_image_utils.cpp:1181-1380) on a device image, in place: conversion 1 To_CCxY, 2 From_CCxY,
+ * 3 To_xGxR, 4 From_xGxR, 5 To_xGBR, 6 From_xGBR, 7 To_AGBR, 8 From_AGBR, 9 XY_to_XYZ.  Asynchronous. */
+CRN_API int crn_gpu_convert_pixels(crn_gpu_ctx* ctx, void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t conversion);
 
 /* crn_compress with a crn_mipmap_params (inc/crnlib.h:614; create_texture_mipmaps in its generate mode,
  * crnlib/crn_texture_comp.cpp:352-575): level 0 of each face in, the chain from crn_gpu_generate_mipmaps, then

@@ -606,3 +606,46 @@ SHIM_API int ref_resample(const uint8_t* src, uint32_t sw, uint32_t sh, uint8_t*
     for (uint32_t y = 0; y < dh; y++) memcpy(dst + (size_t)y * dw * 4, d.get_scanline(y), (size_t)dw * 4);
     return 1;
 }
+
+// ref_dds_to_images -> what crn_decompress_dds_to_images (crnlib/crnlib.cpp:293-333) does in a build with asserts enabled: read_dds, then
+// per level mip_level::get_unpacked_image(tmp, cUnpackFlagUncook) -- the call mip_level::unpack_from_dxt makes INSIDE CRNLIB_ASSERT
+// (crn_mipmapped_texture.cpp:188-197), which a release (NDEBUG) build such as this one compiles out, so the public function itself returns
+// NULL images here.  out: tight RGBA8 images, index level + levels * face, one after the other; desc: faces, width, height, levels, fourcc.
+#include "crn_mipmapped_texture.h"
+#include "crn_buffer_stream.h"
+SHIM_API int ref_dds_to_images(const uint8_t* dds, uint32_t dds_size, uint8_t* out, uint64_t out_capacity, uint32_t* desc)
+{
+    mipmapped_texture tex;
+    buffer_stream in_stream(dds, dds_size);
+    data_stream_serializer in_serializer(in_stream);
+    if (!tex.read_dds(in_serializer)) return 0;
+    uint64_t ofs = 0;
+    pixel_format fmt = tex.get_format();
+    for (uint f = 0; f < tex.get_num_faces(); f++)
+        for (uint l = 0; l < tex.get_num_levels(); l++) {
+            mip_level* pLevel = tex.get_level(f, l);
+            image_u8 tmp;
+            image_u8* pImg = pLevel->get_unpacked_image(tmp, cUnpackFlagUncook);
+            if (!pImg) return 0;
+            const uint64_t bytes = (uint64_t)pImg->get_width() * pImg->get_height() * 4;
+            if (ofs + bytes > out_capacity) return 0;
+            for (uint y = 0; y < pImg->get_height(); y++) memcpy(out + ofs + (size_t)y * pImg->get_width() * 4, pImg->get_scanline(y), (size_t)pImg->get_width() * 4);
+            ofs += bytes;
+            if (!f && !l && tex.is_packed()) {                                  // mip_level::assign(image, PIXEL_FMT_INVALID) (:99-120)
+                if (pImg->is_grayscale()) fmt = pImg->is_component_valid(3) ? PIXEL_FMT_A8L8 : PIXEL_FMT_L8;
+                else fmt = pImg->is_component_valid(3) ? PIXEL_FMT_A8R8G8B8 : PIXEL_FMT_R8G8B8;
+            }
+        }
+    desc[0] = tex.get_num_faces(); desc[1] = tex.get_width(); desc[2] = tex.get_height(); desc[3] = tex.get_num_levels(); desc[4] = (uint32_t)fmt;
+    return 1;
+}
+
+// ref_convert_image -> image_utils::convert_image (crn_image_utils.cpp:1181-1380), conversion_type as the enum's integer value.
+SHIM_API int ref_convert_image(uint8_t* rgba, uint32_t w, uint32_t h, int conv_type)
+{
+    image_u8 img(w, h);
+    for (uint32_t y = 0; y < h; y++) memcpy(img.get_scanline(y), rgba + (size_t)y * w * 4, (size_t)w * 4);
+    image_utils::convert_image(img, (image_utils::conversion_type)conv_type);
+    for (uint32_t y = 0; y < h; y++) memcpy(rgba + (size_t)y * w * 4, img.get_scanline(y), (size_t)w * 4);
+    return 1;
+}

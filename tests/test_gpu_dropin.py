@@ -1,0 +1,12 @@
+"""-m gpu: the drop-in (libcrnlib_b200.so over the CUDA library) against the unmodified reference through the same test program, at 256 x 256
+(see tests/test_dropin_cpu.py).  The binaries are prebuilt by __graft_entry__.build() where the reference's headers exist."""
+import pytest
+
+from test_dropin_cpu import compare_demo, run_demo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("size", [64, 256])
+def test_gpu_dropin_matches_reference(size):
+    compare_demo(run_demo("demo_b200", size), run_demo("demo_ref", size))
