@@ -11,6 +11,7 @@
 #include "cluster_kernels.cuh"
 #include "qdxt_kernels.cuh"
 #include "vq_host.h"
+#include "vq_fast_host.h"
 #include "refiner_kernels.cuh"
 #include "hc_kernels.cuh"
 #include "unpack_kernels.cuh"
@@ -49,6 +50,7 @@ struct crn_gpu_ctx {
     void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
     int wide_smem_set, streams_smem_set;
     crn::VqWorkspace vq_ws;              // slab of the vector quantiser
+    int vq_exact;                        // crn_gpu_set_vq_mode: 1 = member-order float emulation (vq_kernels.cuh), 0 = single-launch frontier splits (vq_fast.cuh)
     int transcode_smem_set;
     // clustered path: per-element child contexts (own stream + scratch) and a cache of released device buffers, both
     // kept for the life of this context so that compressing texture after texture does not pay cudaMalloc / cudaFree
@@ -183,9 +185,10 @@ template <int D>
 int vq_clusterize(crn_gpu_ctx* ctx, const uint8_t* d_vecs, const uint32_t* d_wts, uint32_t n, uint32_t max_size, uint32_t retrieve, int threaded,
                   uint32_t* h_cluster_of, uint32_t* num_clusters, uint32_t* codebook_size)
 {
-    crn::VqBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws);
     crn::VqResult res;
-    const cudaError_t ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res);
+    cudaError_t ce;
+    if (ctx->vq_exact) { crn::VqBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws); ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res); }
+    else { crn::VqFastBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws, ctx->sm_count); ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res); }
     if (ce != cudaSuccess) return set_err(ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "crn_gpu_vq_clusterize", ce);
     if (codebook_size) *codebook_size = res.codebook_size();
     const uint32_t k = res.retrieve(retrieve, h_cluster_of);
@@ -230,6 +233,7 @@ struct crn_qdxt_element {
     std::vector<uint8_t> cat;
     cudaEvent_t ev_opt[2];            // brackets the endpoint optimisation of the last pack()
     float endpoint_opt_ms;
+    int vq_exact;                     // copied from the parent context at init
     int rc;
 };
 
@@ -290,8 +294,9 @@ int qdxt_upload_csr(crn_qdxt_element& e)
 template <int D>
 int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res, uint32_t* d_perm_out = nullptr)
 {
-    crn::VqBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws);
-    const cudaError_t ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out);
+    cudaError_t ce;
+    if (e.vq_exact) { crn::VqBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws); ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out); }
+    else { crn::VqFastBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws, e.ctx->sm_count); ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out); }
     if (ce != cudaSuccess) return set_err(e.ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
     return CRN_GPU_OK;
 }
@@ -511,6 +516,7 @@ int crn_gpu_create(int device, crn_gpu_ctx** out_ctx)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return CRN_GPU_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
+    { const char* e = getenv("CRN_B200_VQ_EXACT"); ctx->vq_exact = (e && *e && *e != '0') ? 1 : 0; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CRN_GPU_ERR_CUDA; }
     *out_ctx = ctx;
     return CRN_GPU_OK;
@@ -527,6 +533,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_files) cudaFree(ctx->d_files);
     if (ctx->d_wide) cudaFree(ctx->d_wide);
     if (ctx->vq_ws.base) cudaFree(ctx->vq_ws.base);
+    if (ctx->vq_ws.nodes) cudaFree(ctx->vq_ws.nodes);
     if (ctx->d_cluster_ws) cudaFree(ctx->d_cluster_ws);
     for (crn_gpu_ctx* c : ctx->child) if (c) crn_gpu_destroy(c);
     if (ctx->pool) {
@@ -551,6 +558,11 @@ int crn_gpu_synchronize(crn_gpu_ctx* ctx)
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
 }); }
+
+void crn_gpu_set_vq_mode(crn_gpu_ctx* ctx, int exact_member_order)
+{
+    if (ctx) ctx->vq_exact = exact_member_order ? 1 : 0;
+}
 
 void crn_gpu_set_progress(crn_gpu_ctx* ctx, crn_gpu_progress_fn fn, void* user)
 {
@@ -920,6 +932,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
         crn_qdxt_element& e = q->el[i];
         if (!ctx->child[i] && crn_gpu_create(ctx->device, &ctx->child[i]) != CRN_GPU_OK) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: element stream"); }
         e.ctx = ctx->child[i];
+        e.vq_exact = ctx->vq_exact;
         e.ctx->launches = 0;
         if (cudaEventCreate(&e.ev_opt[0]) != cudaSuccess || cudaEventCreate(&e.ev_opt[1]) != cudaSuccess) { qdxt_release(q); return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_init: events"); }
         QDXT_ALLOC(e.d_vecs, (size_t)n * 16, e.caps[0]);

@@ -1,0 +1,398 @@
+// vq_fast.cuh -- crnlib::clusterizer<V>::split_node as ONE launch per frontier (tolerance-class form).
+//
+// Replaces clusterizer<V>::split_node + compute_split_pca (+ compute_split_estimate) (reference crnlib/crn_clusterizer.h:740-873, :478-616,
+// :446-476) and threaded_clusterizer<V>::compute_split (crnlib/crn_threaded_clusterizer.h:222-366) for V = vec2F / vec6F / vec16F with
+// byte components, as the clustered-DDS quantiser uses them (qdxt1 / qdxt5: endpoint trees in init, selector clustering in pack).
+//
+// vq_kernels.cuh reproduces the reference's member-order FLOAT accumulations bit for bit (so the cluster assignment is the reference's own),
+// at the price of ~60 launches per round and serial accumulation chains.  The contract for the clustered path is a tolerance (BASELINE.json:
+// PSNR within 0.05 dB, bitrate within 1 %), and the reference's own result already moves with its helper-thread count, so this file does the
+// same algorithm with sums in a fixed PARALLEL order (per-thread partial sums in double, shuffle tree, warps in order, CTAs in rank order):
+// deterministic, not bit-identical.  One group of threads owns one node for the whole of split_node, as in hc_tree_split_kernel:
+// a warp below 1024 members, a 256-thread CTA below 8192, a thread-block cluster of 8 / 16 CTAs x 512 threads above (partials through DSMEM).
+// Everything of one split -- covariance, power iteration (start vector lerp(.75, 1.25), early exit on |delta| < .0025), projection split,
+// <= 8 Lloyd rounds (stop at relative gain < .00125), stable partition -- happens inside that one launch.
+#pragma once
+#include "hc_kernels.cuh"
+
+namespace crn {
+
+// The node table lives in HBM for the whole build: a split reads its node's range / centroid / weight there and writes the two children's
+// records (the host hands out the child ids before the launch), so a round moves 8 bytes per node to the device and 16 bytes back.
+struct VqFastNodes {
+    uint32_t* begin; uint32_t* end;      // member range of the node in `perm`
+    float* centroid;                     // D floats per node
+    unsigned long long* weight;
+};
+struct VqFastResult { int state; uint32_t n_left; float lvar, rvar; };      // state: 1 split, 2 unsplittable
+
+template <int D> __device__ __forceinline__ void vqf_load(const uint8_t* __restrict__ vecs, uint32_t id, float (&v)[D])
+{
+    if (D == 16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(vecs + (size_t)id * 16);
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k % D] = (float)((w[k >> 2] >> (8 * (k & 3))) & 255u);
+    } else if (D == 2) {
+        const uint16_t q = *reinterpret_cast<const uint16_t*>(vecs + (size_t)id * 2);
+        v[0] = (float)(q & 255u); v[1 % D] = (float)(q >> 8);
+    } else {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(vecs + (size_t)id * D);      // D = 6: 2-byte aligned
+#pragma unroll
+        for (int k = 0; k < D / 2; k++) { const uint32_t q = p[k]; v[2 * k] = (float)(q & 255u); v[(2 * k + 1) % D] = (float)(q >> 8); }
+    }
+}
+
+// mode: 0 = clusterizer<V>::split_node; 1 = threaded_clusterizer<V>::compute_split (own centroid, PCA division only; the children come back
+// with the root statistics generate_codebook would compute for them, crn_clusterizer.h:76-93)
+template <int D, int T, int G>
+__global__ void __launch_bounds__(T)
+vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restrict__ wts, uint32_t* __restrict__ perm, uint32_t* __restrict__ perm_tmp,
+                     VqFastNodes N, const uint2* __restrict__ slots, const uint32_t* __restrict__ slot_list, uint32_t nslots, VqFastResult* __restrict__ results, int mode)
+{
+    constexpr int NC = D * (D + 1) / 2;
+    constexpr int K = D == 16 ? 18 : NC + D + 2;
+    constexpr int COVN = D == 16 ? T * 16 : D * D;
+    __shared__ HcRed<T, K> red;
+    __shared__ float s_cov[COVN];
+    __shared__ double s_cpart[D == 16 ? 256 : 1];
+    __shared__ float s_axis[D];
+    __shared__ uint32_t s_warp_cnt[T / 32 + 1];
+    const unsigned tid = threadIdx.x;
+    const unsigned rank = hc_cta_rank<G>();
+    unsigned parity = 0;
+    for (uint32_t si = blockIdx.x / G; si < nslots; si += gridDim.x / G) {
+        const uint32_t slot = slot_list[si], node = slots[slot].x, child = slots[slot].y;      // children: child, child + 1
+        const uint32_t begin = N.begin[node], end = N.end[node];
+        const uint32_t seg = (end - begin + G - 1) / G;
+        const uint32_t sb = min(end, begin + rank * seg), se = min(end, sb + seg);          // this CTA's members
+        // node totals: sum of weighted vectors, sum of weighted dot products, total weight (right-hand sums = total - left-hand sums)
+        double tot[D + 2];
+        {
+#pragma unroll
+            for (int d = 0; d < D + 2; d++) tot[d] = 0;
+            for (uint32_t i = sb + tid; i < se; i += T) {
+                const uint32_t id = perm[i];
+                float v[D]; vqf_load<D>(vecs, id, v);
+                const float w = (float)wts[id];
+                float dot = v[0] * v[0];
+#pragma unroll
+                for (int d = 1; d < D; d++) dot += v[d] * v[d];
+#pragma unroll
+                for (int d = 0; d < D; d++) tot[d] += (double)(v[d] * w);
+                tot[D] += (double)(dot * w); tot[D + 1] += (double)w;
+            }
+            hc_group_reduce<T, G, K, true>(red, parity, tot, D + 2, nullptr, 0, nullptr);
+        }
+        float centroid[D];
+        unsigned long long total_weight;
+        if (mode == 1) {                         // compute_pca's own centroid (crn_threaded_clusterizer.h:226-245)
+            total_weight = (unsigned long long)tot[D + 1];
+            const double inv = tot[D + 1] != 0.0 ? 1.0 / tot[D + 1] : 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) centroid[d] = (float)((double)(float)tot[d] * inv);
+        } else {
+            total_weight = N.weight[node];
+#pragma unroll
+            for (int d = 0; d < D; d++) centroid[d] = N.centroid[(size_t)node * D + d];
+        }
+        float left[D], right[D];
+        bool have_split = false;
+        if (mode == 0 && end - begin == 2) {     // compute_split_pca :480-485
+            vqf_load<D>(vecs, perm[begin], left); vqf_load<D>(vecs, perm[begin + 1], right);
+            have_split = true;
+        } else {
+            // covariance of the centred members (:489-521)
+            if (D == 16) {
+                constexpr int LANES = T / 16;
+                const int x = tid & 15, ml = tid >> 4;
+                float acc[16];
+#pragma unroll
+                for (int y = 0; y < 16; y++) acc[y] = 0.0f;
+                for (uint32_t i = sb + ml; i < se; i += LANES) {
+                    const uint32_t id = perm[i];
+                    float v[D]; vqf_load<D>(vecs, id, v);
+                    const float w = (float)wts[id];
+                    float vx = 0;
+#pragma unroll
+                    for (int d = 0; d < D; d++) { v[d] -= centroid[d]; if (d == x) vx = v[d]; }
+#pragma unroll
+                    for (int y = 0; y < 16; y++) acc[y % D] += vx * (v[y % D] * w);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int y = 0; y < 16; y++) s_cov[(tid * 16 + y) % COVN] = acc[y];
+                __syncthreads();
+                for (int e = tid; e < 256; e += T) {
+                    const int ex = e >> 4, ey = e & 15;
+                    double s = 0;
+                    for (int l = 0; l < LANES; l++) s += (double)s_cov[((l * 16 + ex) * 16 + ey) % COVN];
+                    s_cpart[e % (D == 16 ? 256 : 1)] = s;
+                }
+                hc_group_sync<G>();
+                for (int e = tid; e < 256; e += T) {
+                    double s = s_cpart[e % (D == 16 ? 256 : 1)];
+#ifdef __CUDACC__
+                    if (G > 1) { s = 0; for (unsigned r = 0; r < (unsigned)G; r++) s += cg::this_cluster().map_shared_rank(&s_cpart[0], r)[e % (D == 16 ? 256 : 1)]; }
+#endif
+                    s_cov[e % COVN] = (float)s * (1.0f / (float)total_weight);
+                }
+                hc_group_sync<G>();
+            } else {
+                float acc[NC];
+#pragma unroll
+                for (int k = 0; k < NC; k++) acc[k] = 0.0f;
+                for (uint32_t i = sb + tid; i < se; i += T) {
+                    const uint32_t id = perm[i];
+                    float v[D]; vqf_load<D>(vecs, id, v);
+                    const float w = (float)wts[id];
+#pragma unroll
+                    for (int d = 0; d < D; d++) v[d] -= centroid[d];
+                    int k = 0;
+#pragma unroll
+                    for (int x = 0; x < D; x++)
+#pragma unroll
+                        for (int y = x; y < D; y++) acc[k++] += v[x] * (v[y] * w);
+                }
+                double dacc[NC];
+#pragma unroll
+                for (int k = 0; k < NC; k++) dacc[k] = (double)acc[k];
+                hc_group_reduce<T, G, K, true>(red, parity, dacc, NC, nullptr, 0, nullptr);
+                if (tid == 0) {
+                    int k = 0;
+                    for (int x = 0; x < D; x++) for (int y = x; y < D; y++) { const float c = (float)dacc[k++] * (1.0f / (float)total_weight); s_cov[(x * D + y) % COVN] = c; s_cov[(y * D + x) % COVN] = c; }
+                }
+                __syncthreads();
+            }
+            // power iteration (:523-571): start lerp(.75, 1.25, i / (N - 1)), max-normalised, stops when |axis[k - 1] - axis[k + 1]| < .0025
+            if (tid == 0) {
+                float axis[D], prev[D];
+#pragma unroll
+                for (int d = 0; d < D; d++) { axis[d] = .75f + (1.25f - .75f) * ((float)d * (1.0f / (float)(D - 1))); prev[d] = axis[d]; }
+                for (int iter = 0; iter < 10; iter++) {
+                    float xv[D];
+                    double max_sum = 0;
+                    for (int i = 0; i < D; i++) {
+                        double sum = 0;
+                        for (int j = 0; j < D; j++) {
+                            const float c = i <= j ? s_cov[(i * D + j) % COVN] : s_cov[(j * D + i) % COVN];
+                            sum += (double)(axis[j] * c);
+                        }
+                        xv[i] = (float)sum;
+                        const double a = sum < 0 ? -sum : sum;
+                        max_sum = max_sum > a ? max_sum : a;
+                    }
+                    if (max_sum != 0.0) { const float sc = (float)(1.0f / max_sum); for (int i = 0; i < D; i++) xv[i] *= sc; }
+                    float dn = 0;
+                    for (int i = 0; i < D; i++) { const float dd = prev[i] - xv[i]; dn += dd * dd; prev[i] = axis[i]; axis[i] = xv[i]; }
+                    if (sqrtf(dn) < .0025f) break;
+                }
+                double n = (double)(axis[0] * axis[0]);
+                for (int i = 1; i < D; i++) n += (double)(axis[i] * axis[i]);
+                if (n != 0) { const float sc = (float)(1.0f / sqrt(n)); for (int i = 0; i < D; i++) axis[i] *= sc; }
+                for (int i = 0; i < D; i++) s_axis[i] = axis[i];
+            }
+            __syncthreads();
+            float axis[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) axis[d] = s_axis[d];
+            if (mode == 1) {
+                // compute_division (:335-358): members with a negative projection go left.  Then the root statistics of both sides.
+#pragma unroll
+                for (int d = 0; d < D; d++) { left[d] = axis[d]; right[d] = centroid[d]; }      // carried to the partition below as (axis, centroid)
+            } else {
+                // projection split (:573-606): means of the two sides, or compute_split_estimate when one side is empty
+                double sl[D + 1];
+#pragma unroll
+                for (int d = 0; d <= D; d++) sl[d] = 0;
+                for (uint32_t i = sb + tid; i < se; i += T) {
+                    const uint32_t id = perm[i];
+                    float v[D]; vqf_load<D>(vecs, id, v);
+                    const float w = (float)wts[id];
+                    float t = (v[0] - centroid[0]) * axis[0];
+#pragma unroll
+                    for (int d = 1; d < D; d++) t += (v[d] - centroid[d]) * axis[d];
+                    if (t < 0.0f) {
+#pragma unroll
+                        for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
+                        sl[D] += (double)w;
+                    }
+                }
+                hc_group_reduce<T, G, K, true>(red, parity, sl, D + 1, nullptr, 0, nullptr);
+                const double lwt = sl[D], rwt = tot[D + 1] - sl[D];
+                if (lwt > 0.0 && rwt > 0.0) {
+                    const float fl = (float)(1.0f / lwt), fr = (float)(1.0f / rwt);
+#pragma unroll
+                    for (int d = 0; d < D; d++) { left[d] = (float)sl[d] * fl; right[d] = (float)(tot[d] - sl[d]) * fr; }
+                    have_split = true;
+                }
+            }
+        }
+        if (mode == 0 && !have_split) {
+            // compute_split_estimate (:446-476): furthest from the centroid, then furthest from that one (first maximum in member order)
+            float seed[2][D];
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                unsigned long long key = 0;
+                for (uint32_t i = sb + tid; i < se; i += T) {
+                    float v[D]; vqf_load<D>(vecs, perm[i], v);
+                    const float d2 = pass ? hc_sqdist<D>(v, seed[0]) : hc_sqdist<D>(v, centroid);
+                    const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(~i);
+                    key = k > key ? k : key;
+                }
+                hc_group_reduce<T, G, K, false>(red, parity, nullptr, 0, &key, 1, nullptr);
+                const uint32_t pos = ~(unsigned)key;
+                vqf_load<D>(vecs, perm[pos], seed[pass]);
+            }
+#pragma unroll
+            for (int d = 0; d < D; d++) { left[d] = (seed[0][d] + centroid[d]) * .5f; right[d] = (seed[1][d] + centroid[d]) * .5f; }
+        }
+        // Lloyd rounds (:761-836), at most 8; a presplit runs the loop body once with the projection as the assignment
+        float prev_total_variance = 1e+10f, lvar = 0, rvar = 0;
+        unsigned long long lw = 0, rw = 0;
+        uint32_t n_left = 0, left_before = 0;
+        bool unsplittable = false;
+        float used_left[D], used_right[D];
+        const unsigned max_loops = mode == 1 ? 1u : 8u;
+#pragma unroll 1
+        for (unsigned loops = 0; loops < max_loops; loops++) {
+            double sl[D + 1]; unsigned long long uu[2] = { 0, 0 }, upre[2];
+#pragma unroll
+            for (int d = 0; d <= D; d++) sl[d] = 0;
+#pragma unroll
+            for (int d = 0; d < D; d++) { used_left[d] = left[d]; used_right[d] = right[d]; }
+            for (uint32_t i = sb + tid; i < se; i += T) {
+                const uint32_t id = perm[i];
+                float v[D]; vqf_load<D>(vecs, id, v);
+                bool is_left;
+                if (mode == 1) {
+                    float t = (v[0] - right[0]) * left[0];
+#pragma unroll
+                    for (int d = 1; d < D; d++) t += (v[d] - right[d]) * left[d];
+                    is_left = t < 0.0f;
+                } else is_left = hc_sqdist<D>(left, v) < hc_sqdist<D>(right, v);
+                if (is_left) {
+                    const unsigned wi = wts[id]; const float w = (float)wi;
+                    float dot = v[0] * v[0];
+#pragma unroll
+                    for (int d = 1; d < D; d++) dot += v[d] * v[d];
+#pragma unroll
+                    for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
+                    sl[D] += (double)(dot * w); uu[0] += wi; uu[1]++;
+                }
+            }
+            hc_group_reduce<T, G, K, true>(red, parity, sl, D + 1, uu, 2, upre);
+            lw = uu[0]; n_left = (uint32_t)uu[1]; left_before = (uint32_t)upre[1];
+            rw = (unsigned long long)tot[D + 1] - lw;
+            if (mode == 1) {
+                // the children of a division may be empty (their partition is then skipped, crn_threaded_clusterizer.h:101-118)
+                float nl[D], nr[D];
+#pragma unroll
+                for (int d = 0; d < D; d++) { nl[d] = (float)sl[d]; nr[d] = (float)(tot[d] - sl[d]); }
+                float ldot = nl[0] * nl[0], rdot = nr[0] * nr[0];
+#pragma unroll
+                for (int d = 1; d < D; d++) { ldot += nl[d] * nl[d]; rdot += nr[d] * nr[d]; }
+                lvar = lw ? (float)(sl[D] - (double)(ldot / (float)lw)) : 0.0f;
+                rvar = rw ? (float)((tot[D] - sl[D]) - (double)(rdot / (float)rw)) : 0.0f;
+                const float fl = lw ? 1.0f / (float)lw : 0.0f, fr = rw ? 1.0f / (float)rw : 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; d++) { left[d] = nl[d] * fl; right[d] = nr[d] * fr; }
+                break;
+            }
+            if (!lw || !rw) { unsplittable = true; break; }
+            float nl[D], nr[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) { nl[d] = (float)sl[d]; nr[d] = (float)(tot[d] - sl[d]); }
+            float ldot = nl[0] * nl[0], rdot = nr[0] * nr[0];
+#pragma unroll
+            for (int d = 1; d < D; d++) { ldot += nl[d] * nl[d]; rdot += nr[d] * nr[d]; }
+            lvar = (float)(sl[D] - (double)(ldot / (float)lw)); rvar = (float)((tot[D] - sl[D]) - (double)(rdot / (float)rw));
+            const float fl = 1.0f / (float)lw, fr = 1.0f / (float)rw;
+#pragma unroll
+            for (int d = 0; d < D; d++) { left[d] = nl[d] * fl; right[d] = nr[d] * fr; }
+            const float total_variance = lvar + rvar;
+            if (total_variance < .00001f) break;
+            if (((prev_total_variance - total_variance) / total_variance) < .00125f) break;
+            prev_total_variance = total_variance;
+        }
+        if (!unsplittable) {
+            // stable partition by the last assignment (:838-871): lefts of lower-ranked CTAs come first
+            uint32_t base_l = begin + left_before, base_r = begin + n_left + ((sb - begin) - left_before);
+            for (uint32_t i0 = sb; i0 < se; i0 += T) {
+                const uint32_t i = i0 + tid;
+                uint32_t id = 0; bool valid = i < se, is_left = false;
+                if (valid) {
+                    id = perm[i];
+                    float v[D]; vqf_load<D>(vecs, id, v);
+                    if (mode == 1) {
+                        float t = (v[0] - used_right[0]) * used_left[0];
+#pragma unroll
+                        for (int d = 1; d < D; d++) t += (v[d] - used_right[d]) * used_left[d];
+                        is_left = t < 0.0f;
+                    } else is_left = hc_sqdist<D>(used_left, v) < hc_sqdist<D>(used_right, v);
+                }
+                const unsigned bl = __ballot_sync(CRN_FULL_MASK, valid && is_left), br = __ballot_sync(CRN_FULL_MASK, valid && !is_left);
+                uint32_t pre_l = 0, pre_r = 0, tot_l = __popc(bl), tot_r = __popc(br);
+                if (T > 32) {
+                    __syncthreads();
+                    if ((tid & 31) == 0) { s_warp_cnt[tid >> 5] = (uint32_t)__popc(bl) | ((uint32_t)__popc(br) << 16); }
+                    __syncthreads();
+                    tot_l = tot_r = 0;
+                    for (unsigned w = 0; w < T / 32; w++) {
+                        const uint32_t c = s_warp_cnt[w];
+                        if (w < (tid >> 5)) { pre_l += c & 0xffff; pre_r += c >> 16; }
+                        tot_l += c & 0xffff; tot_r += c >> 16;
+                    }
+                }
+                if (valid) {
+                    const unsigned lt_mask = (1u << (tid & 31)) - 1u;
+                    if (is_left) perm_tmp[base_l + pre_l + __popc(bl & lt_mask)] = id;
+                    else perm_tmp[base_r + pre_r + __popc(br & lt_mask)] = id;
+                }
+                base_l += tot_l; base_r += tot_r;
+            }
+            hc_group_sync<G>();
+            for (uint32_t i = sb + tid; i < se; i += T) perm[i] = perm_tmp[i];
+        }
+        if (tid == 0 && rank == 0) {
+            VqFastResult r; r.state = unsplittable ? 2 : 1; r.n_left = n_left; r.lvar = lvar; r.rvar = rvar;
+            results[slot] = r;
+            if (!unsplittable) {
+                N.begin[child] = begin; N.end[child] = begin + n_left; N.begin[child + 1] = begin + n_left; N.end[child + 1] = end;
+                N.weight[child] = lw; N.weight[child + 1] = rw;
+#pragma unroll
+                for (int d = 0; d < D; d++) { N.centroid[(size_t)child * D + d] = left[d]; N.centroid[(size_t)(child + 1) * D + d] = right[d]; }
+            }
+        }
+        hc_group_sync<G>();
+    }
+}
+
+// root of a clusterizer (generate_codebook :76-93): statistics of the whole training set.  out: D weighted sums, the weighted dot-product sum, the weight
+template <int D>
+__global__ void __launch_bounds__(512)
+vq_fast_root_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restrict__ wts, const uint32_t* __restrict__ ids, uint32_t n, uint32_t* __restrict__ perm, double* __restrict__ out)
+{
+    constexpr int T = 512;
+    __shared__ HcRed<T, D + 2> red;
+    unsigned parity = 0;
+    double s[D + 2];
+#pragma unroll
+    for (int d = 0; d < D + 2; d++) s[d] = 0;
+    for (uint32_t i = blockIdx.x * T + threadIdx.x; i < n; i += gridDim.x * T) {
+        const uint32_t id = ids ? ids[i] : i;
+        float v[D]; vqf_load<D>(vecs, id, v);
+        const float w = (float)wts[id];
+        float dot = v[0] * v[0];
+#pragma unroll
+        for (int d = 1; d < D; d++) dot += v[d] * v[d];
+#pragma unroll
+        for (int d = 0; d < D; d++) s[d] += (double)(v[d] * w);
+        s[D] += (double)(dot * w); s[D + 1] += (double)w;
+        perm[i] = id;
+    }
+    hc_group_reduce<T, 1, D + 2, true>(red, parity, s, D + 2, nullptr, 0, nullptr);
+    if (threadIdx.x == 0) for (int d = 0; d < D + 2; d++) out[(size_t)blockIdx.x * (D + 2) + d] = s[d];
+}
+
+}  // namespace crn

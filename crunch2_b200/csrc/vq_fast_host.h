@@ -1,0 +1,296 @@
+// vq_fast_host.h -- host driver of the single-launch-per-frontier vector quantiser (vq_fast.cuh), tolerance-class twin of VqBuilder.
+//
+// Same division of labour as vq_host.h: the device splits whole frontiers, VqTreeSim replays crnlib::clusterizer<V>::generate_codebook's
+// heap loop (crnlib/crn_clusterizer.h:100-139) on the results to recover the split order and the stop point, and VqResult carries the tree
+// for retrieve_clusters().  What changed is the device round: one launch per node-size class (warp / CTA / thread-block cluster per node)
+// instead of ~60 launches, a node table that stays in HBM (8 bytes per node up, 16 bytes back per round), no member-order emulation.
+#pragma once
+#include "vq_fast.cuh"
+#include "vq_host.h"
+
+namespace crn {
+
+template <int D> class VqFastBuilder {
+public:
+    VqFastBuilder(cudaStream_t stream, uint64_t* launch_counter, VqWorkspace* ws, int sm_count) : stream_(stream), launches_(launch_counter), ws_(ws), sm_count_(sm_count) {}
+
+    // Same contract as VqBuilder<D>::build (vq_host.h): d_vecs u8[][D], d_wts u32[], d_ids ascending ids (nullptr = 0..n-1);
+    // threaded = threaded_clusterizer<V>::create_clusters (three PCA divisions, then one clusterizer per non-empty partition).
+    cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, VqResult& res,
+                      uint32_t* d_perm_out = nullptr)
+    {
+        res = VqResult();
+        if (!n) return cudaSuccess;
+        n_ = n; vecs_ = d_vecs; wts_ = d_wts;
+        cudaError_t ce = allocate(n, max_size);
+        if (ce != cudaSuccess) return ce;
+        std::vector<VqHostNode>& nodes = res.nodes;
+        // root statistics (generate_codebook :76-93)
+        const unsigned rg = std::max(1u, std::min<unsigned>((n + 8191) / 8192, 64u));
+        CRN_LAUNCH(vq_fast_root_kernel<D>, rg, 512, 0, stream_, vecs_, wts_, d_ids, n, d_perm_, d_root_); count();
+        std::vector<double> part((size_t)rg * (D + 2));
+        cudaMemcpyAsync(part.data(), d_root_, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, stream_);
+        ce = cudaStreamSynchronize(stream_);
+        if (ce != cudaSuccess) return ce;
+        double tot[D + 2];
+        for (int d = 0; d < D + 2; d++) { tot[d] = 0; for (unsigned g = 0; g < rg; g++) tot[d] += part[(size_t)g * (D + 2) + d]; }
+        nodes.reserve(std::min<size_t>((size_t)2 * n + 16, (size_t)4 * max_size + 64));
+        nodes.resize(1);
+        nodes[0].begin = 0; nodes[0].count = n;
+        {
+            float c[D], dot = 0;
+            for (int d = 0; d < D; d++) { c[d] = (float)tot[d]; dot = d ? dot + c[d] * c[d] : c[d] * c[d]; }
+            const unsigned long long tw = (unsigned long long)tot[D + 1];
+            nodes[0].variance = (float)(tot[D] - (double)(dot / (float)tw));
+            const float inv = 1.0f / (float)tw;
+            for (int d = 0; d < D; d++) c[d] *= inv;
+            const uint32_t be[2] = { 0u, n };
+            cudaMemcpyAsync(nodes_.begin, &be[0], 4, cudaMemcpyHostToDevice, stream_);
+            cudaMemcpyAsync(nodes_.end, &be[1], 4, cudaMemcpyHostToDevice, stream_);
+            cudaMemcpyAsync(nodes_.centroid, c, sizeof(c), cudaMemcpyHostToDevice, stream_);
+            cudaMemcpyAsync(nodes_.weight, &tw, 8, cudaMemcpyHostToDevice, stream_);
+            ce = cudaStreamSynchronize(stream_);                      // the sources are locals
+            if (ce != cudaSuccess) return ce;
+        }
+        std::vector<uint32_t> frontier;
+        if (threaded && max_size >= 128) {
+            // compute_split x3 (crn_threaded_clusterizer.h:93-95)
+            frontier.assign(1, 0u);
+            ce = round(frontier, nodes, 1);
+            if (ce != cudaSuccess) return ce;
+            frontier.clear();
+            const uint32_t a = (uint32_t)nodes[0].left;
+            for (uint32_t c = 0; c < 2; c++) if (nodes[a + c].count) frontier.push_back(a + c);
+            ce = round(frontier, nodes, 1);
+            if (ce != cudaSuccess) return ce;
+            std::vector<uint32_t> parts;
+            for (uint32_t c = 0; c < 2; c++) {
+                if (!nodes[a + c].count) continue;
+                const uint32_t b = (uint32_t)nodes[a + c].left;
+                for (uint32_t k = 0; k < 2; k++) if (nodes[b + k].count) parts.push_back(b + k);
+            }
+            const uint32_t total = (uint32_t)parts.size();
+            for (uint32_t p : parts) {
+                VqTreeSim t;
+                t.root = p; t.max_size = (max_size + total / 2) / total;
+                res.trees.push_back(t);
+            }
+            for (VqHostNode& nd : nodes) nd.processed = 0;           // the divisions are not clusterizer splits
+            for (uint32_t p : parts) nodes[p].left = -1;
+        } else {
+            VqTreeSim t;
+            t.root = 0; t.max_size = max_size;
+            res.trees.push_back(t);
+        }
+        for (VqTreeSim& t : res.trees) t.reset(nodes);
+        for (;;) {
+            frontier.clear();
+            for (VqTreeSim& t : res.trees) { t.run(nodes); t.wanted(frontier); }
+            if (frontier.empty()) break;
+            ce = round(frontier, nodes, 0);
+            if (ce != cudaSuccess) return ce;
+            res.rounds++;
+            res.device_splits += (uint32_t)frontier.size();
+        }
+        for (VqTreeSim& t : res.trees) {                              // m_codebook_index of the interior nodes
+            for (size_t k = 0; k < t.split_log.size(); k++) nodes[t.split_log[k]].split_rank = (int32_t)k;
+            std::vector<uint32_t>().swap(t.split_log);
+        }
+        if (d_perm_out) cudaMemcpyAsync(d_perm_out, d_perm_, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream_);
+        else {
+            res.perm.resize(n);
+            cudaMemcpyAsync(res.perm.data(), d_perm_, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream_);
+        }
+        ce = cudaStreamSynchronize(stream_);
+        if (getenv("CRN_B200_TRACE"))
+            fprintf(stderr, "[crn_b200] vq_fast<%d> n=%u max=%u: %u rounds, %u device splits, enqueue %.1f ms, wait %.1f ms, host %.1f ms\n", D, n, max_size, res.rounds, res.device_splits,
+                    t_enqueue_, t_sync_, t_host_);
+        return ce;
+    }
+
+    const uint32_t* device_perm() const { return d_perm_; }
+
+private:
+    cudaStream_t stream_;
+    uint64_t* launches_;
+    VqWorkspace* ws_;
+    int sm_count_;
+    uint32_t n_ = 0, node_cap_ = 0, slot_cap_ = 0;
+    const uint8_t* vecs_ = nullptr;
+    const uint32_t* wts_ = nullptr;
+    uint32_t *d_perm_ = nullptr, *d_tmp_ = nullptr, *d_list_ = nullptr;
+    uint2* d_slots_ = nullptr;
+    VqFastResult* d_results_ = nullptr;
+    double* d_root_ = nullptr;
+    VqFastNodes nodes_ = {};
+    bool wide_ok_ = true;
+    std::vector<uint2> h_slots_;
+    std::vector<VqFastResult> h_results_;
+    std::vector<uint32_t> lists_[3];
+    double t_enqueue_ = 0, t_sync_ = 0, t_host_ = 0;
+    static constexpr uint32_t kHugeNode = 8192, kLargeNode = 1024;
+    static constexpr int kClusterCtas = 8, kWideClusterCtas = 16, kClusterThreads = 512;
+    static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    void count() { if (launches_) ++*launches_; }
+
+    // The node table: two children per device split.  A frontier may hold nodes the replay never pops, so the number of device splits of a
+    // build is not known in advance: the table starts at 4 x max_size nodes and doubles when a round would overflow it (contents copied).
+    static constexpr size_t node_bytes() { return 4 + 4 + 4 * (size_t)D + 8 + 1; }   // + slack for the 256-byte alignment of the four arrays at small capacities
+    cudaError_t ensure_nodes(size_t need, size_t live)
+    {
+        if (need <= node_cap_) return cudaSuccess;
+        size_t cap = std::max<size_t>(node_cap_, 1024);
+        while (cap < need) cap *= 2;
+        const size_t bytes = cap * node_bytes() + 1024;
+        void* buf = ws_->nodes;
+        const bool fresh = live || !ws_->nodes || ws_->nodes_cap < bytes;
+        if (fresh) {
+            const cudaError_t ce = cudaMalloc(&buf, bytes);
+            if (ce != cudaSuccess) return ce;
+        }
+        VqFastNodes nn;
+        uint8_t* b = static_cast<uint8_t*>(buf);
+        nn.weight = reinterpret_cast<unsigned long long*>(b); b += (cap * 8 + 255) & ~(size_t)255;
+        nn.begin = reinterpret_cast<uint32_t*>(b); b += (cap * 4 + 255) & ~(size_t)255;
+        nn.end = reinterpret_cast<uint32_t*>(b); b += (cap * 4 + 255) & ~(size_t)255;
+        nn.centroid = reinterpret_cast<float*>(b);
+        if (live) {
+            cudaMemcpyAsync(nn.weight, nodes_.weight, live * 8, cudaMemcpyDeviceToDevice, stream_);
+            cudaMemcpyAsync(nn.begin, nodes_.begin, live * 4, cudaMemcpyDeviceToDevice, stream_);
+            cudaMemcpyAsync(nn.end, nodes_.end, live * 4, cudaMemcpyDeviceToDevice, stream_);
+            cudaMemcpyAsync(nn.centroid, nodes_.centroid, live * 4 * D, cudaMemcpyDeviceToDevice, stream_);
+            const cudaError_t ce = cudaStreamSynchronize(stream_);
+            if (ce != cudaSuccess) { cudaFree(buf); return ce; }
+        }
+        if (fresh) { if (ws_->nodes) cudaFree(ws_->nodes); ws_->nodes = buf; ws_->nodes_cap = bytes; }
+        nodes_ = nn; node_cap_ = (uint32_t)cap;
+        return cudaSuccess;
+    }
+
+    // one slab the caller keeps between builds
+    cudaError_t allocate(uint32_t n, uint32_t max_size)
+    {
+        const size_t slots = std::max<size_t>(8, std::min<size_t>((size_t)n / 2 + 8, (size_t)max_size + 8));
+        node_cap_ = 0;
+        cudaError_t ne = ensure_nodes(std::min<size_t>((size_t)2 * n + 16, (size_t)4 * max_size + 64), 0);
+        if (ne != cudaSuccess) return ne;
+        for (int pass = 0; pass < 2; pass++) {
+            size_t off = 0;
+            uint8_t* base = pass ? static_cast<uint8_t*>(ws_->base) : nullptr;
+            auto carve = [&](auto*& p, size_t cnt) {
+                using T = std::remove_pointer_t<std::remove_reference_t<decltype(p)>>;
+                if (pass) p = reinterpret_cast<T*>(base + off);
+                off += (cnt * sizeof(T) + 255) & ~(size_t)255;
+            };
+            carve(d_perm_, n); carve(d_tmp_, n); carve(d_list_, slots); carve(d_slots_, slots); carve(d_results_, slots); carve(d_root_, (size_t)64 * (D + 2));
+            if (!pass && off > ws_->cap) {
+                if (ws_->base) cudaFree(ws_->base);
+                ws_->base = nullptr; ws_->cap = 0;
+                const cudaError_t ce = cudaMalloc(&ws_->base, off);
+                if (ce != cudaSuccess) return ce;
+                ws_->cap = off;
+            }
+        }
+        slot_cap_ = (uint32_t)slots;
+        return cudaSuccess;
+    }
+
+#ifdef __CUDACC__
+    template <int G> bool launch_cluster(const uint32_t* dl, uint32_t cnt, int mode)
+    {
+        auto kernel = vq_fast_split_kernel<D, kClusterThreads, G>;
+        if (G > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return false;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        const unsigned nclusters = (unsigned)std::min<size_t>(cnt, (size_t)std::max(1, sm_count_ / G) * 2);
+        cfg.gridDim = dim3(nclusters * G); cfg.blockDim = dim3(kClusterThreads); cfg.stream = stream_;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode) == cudaSuccess;
+    }
+#endif
+
+    // split every node of `frontier` on the device and record the results; mode 1 = threaded_clusterizer's PCA division
+    cudaError_t round(const std::vector<uint32_t>& frontier, std::vector<VqHostNode>& nodes, int mode)
+    {
+        const double t0 = now_ms();
+        h_slots_.clear();
+        for (int k = 0; k < 3; k++) lists_[k].clear();
+        std::vector<uint32_t> slot_node;
+        uint32_t next_child = (uint32_t)nodes.size();
+        for (uint32_t id : frontier) {
+            VqHostNode& nd = nodes[id];
+            if (nd.count < 2 && mode == 0) { nd.processed = 1; nd.unsplittable = 1; continue; }
+            const uint32_t s = (uint32_t)h_slots_.size();
+            h_slots_.push_back(make_uint2(id, next_child));
+            slot_node.push_back(id);
+            next_child += 2;
+#ifdef __CUDACC__
+            lists_[nd.count >= kHugeNode ? 0 : (nd.count >= kLargeNode ? 1 : 2)].push_back(s);
+#else
+            lists_[nd.count >= kLargeNode ? 1 : 2].push_back(s);      // the emulator has no thread-block clusters
+#endif
+        }
+        const uint32_t F = (uint32_t)h_slots_.size();
+        if (!F) return cudaSuccess;
+        if (F > slot_cap_) return cudaErrorMemoryAllocation;
+        if (next_child > node_cap_) { const cudaError_t ge = ensure_nodes(next_child, nodes.size()); if (ge != cudaSuccess) return ge; }
+        cudaMemcpyAsync(d_slots_, h_slots_.data(), sizeof(uint2) * F, cudaMemcpyHostToDevice, stream_);
+        std::vector<uint32_t> all;
+        all.reserve(F);
+        for (int k = 0; k < 3; k++) all.insert(all.end(), lists_[k].begin(), lists_[k].end());
+        cudaMemcpyAsync(d_list_, all.data(), sizeof(uint32_t) * F, cudaMemcpyHostToDevice, stream_);
+        const uint32_t* dl = d_list_;
+#ifdef __CUDACC__
+        if (!lists_[0].empty()) {
+            const uint32_t cnt = (uint32_t)lists_[0].size();
+            bool launched = false;
+            if (cnt <= 8 && wide_ok_) {
+                launched = launch_cluster<kWideClusterCtas>(dl, cnt, mode);
+                if (!launched) { wide_ok_ = false; (void)cudaGetLastError(); }
+            }
+            if (!launched && !launch_cluster<kClusterCtas>(dl, cnt, mode)) return cudaGetLastError();
+            count();
+            dl += cnt;
+        }
+#endif
+        if (!lists_[1].empty()) {
+            const uint32_t cnt = (uint32_t)lists_[1].size();
+            CRN_LAUNCH((vq_fast_split_kernel<D, 256, 1>), cnt, 256, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
+            dl += cnt;
+        }
+        if (!lists_[2].empty()) {
+            const uint32_t cnt = (uint32_t)lists_[2].size();
+            const unsigned grid = (unsigned)std::min<size_t>(cnt, (size_t)sm_count_ * 32);
+            CRN_LAUNCH((vq_fast_split_kernel<D, 32, 1>), grid, 32, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
+        }
+        h_results_.resize(F);
+        cudaMemcpyAsync(h_results_.data(), d_results_, sizeof(VqFastResult) * F, cudaMemcpyDeviceToHost, stream_);
+        const double t1 = now_ms();
+        cudaError_t ce = cudaStreamSynchronize(stream_);
+        const double t2 = now_ms();
+        if (ce != cudaSuccess) return ce;
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return ce;
+        nodes.resize(next_child);
+        for (uint32_t s = 0; s < F; s++) {
+            const VqFastResult& r = h_results_[s];
+            VqHostNode& par = nodes[slot_node[s]];
+            par.processed = 1;
+            if (r.state != 1) { par.unsplittable = 1; continue; }
+            const uint32_t child = h_slots_[s].y;
+            par.left = (int32_t)child;
+            VqHostNode& l = nodes[child];
+            VqHostNode& rr = nodes[child + 1];
+            l = VqHostNode(); rr = VqHostNode();
+            l.begin = par.begin; l.count = r.n_left; l.variance = r.lvar;
+            rr.begin = par.begin + r.n_left; rr.count = par.count - r.n_left; rr.variance = r.rvar;
+            par.child_count[0] = l.count; par.child_count[1] = rr.count;
+            par.child_var[0] = r.lvar; par.child_var[1] = r.rvar;
+        }
+        t_enqueue_ += t1 - t0; t_sync_ += t2 - t1; t_host_ += now_ms() - t2;
+        return cudaSuccess;
+    }
+};
+
+}  // namespace crn

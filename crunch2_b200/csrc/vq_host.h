@@ -213,7 +213,10 @@ inline uint32_t vq_leaf_offsets(const VqResult& res, uint32_t base, std::vector<
     return leaves;
 }
 
-struct VqWorkspace { void* base = nullptr; size_t cap = 0; };     // device slab reused across builds
+struct VqWorkspace {                 // device slab reused across builds (+ the growable node table of the single-launch builder, vq_fast_host.h)
+    void* base = nullptr; size_t cap = 0;
+    void* nodes = nullptr; size_t nodes_cap = 0;
+};
 
 #ifdef __CUDACC__
 // Three helper threads that live as long as one build: the host replay and the result scatter of a round are split four

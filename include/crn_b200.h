@@ -84,6 +84,12 @@ CRN_API uint64_t crn_gpu_launch_count(const crn_gpu_ctx* ctx);
  * clustered path (:136-146, :172-188).  Returning 0 abandons the call with CRN_GPU_ERR_CANCELLED.  fn = NULL removes it. */
 typedef int (*crn_gpu_progress_fn)(uint32_t phase_index, uint32_t total_phases, uint32_t subphase_index, uint32_t total_subphases, void* user);
 CRN_API void crn_gpu_set_progress(crn_gpu_ctx* ctx, crn_gpu_progress_fn fn, void* user);
+/* Vector-quantiser flavour of the clustered-DDS path (crn_gpu_vq_clusterize, crn_gpu_qdxt_init / _pack and everything above them).
+ * 0 (default): crnlib::clusterizer<V>'s algorithm with sums in a fixed parallel order, one launch per frontier (csrc/vq_fast.cuh) -- the
+ *    tolerance class BASELINE.json states for clustered output (PSNR within 0.05 dB, bitrate within 1 %).
+ * 1: the reference's member-order float accumulations reproduced bit for bit (csrc/vq_kernels.cuh), so that the cluster assignment EQUALS
+ *    the reference's -- several times slower; kept for verification.  The environment variable CRN_B200_VQ_EXACT=1 sets it at context creation. */
+CRN_API void crn_gpu_set_vq_mode(crn_gpu_ctx* ctx, int exact_member_order);
 CRN_API void crn_gpu_default_pack_params(crn_gpu_pack_params* p);
 CRN_API uint32_t crn_gpu_bytes_per_block(uint32_t format);
 

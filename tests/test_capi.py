@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(which, sim):
         lib = sim
     for s in declared_symbols():
         assert hasattr(lib, s), s
-    assert lib.crn_gpu_abi_version() == 1
+    assert lib.crn_gpu_abi_version() == 2
 
 
 def test_native_library_is_the_nvcc_build():

@@ -10,9 +10,12 @@ import crunch2_b200 as crn
 import helpers
 
 
-@pytest.fixture(scope="module")
-def simctx(sim):
+@pytest.fixture(scope="module", params=["fast", "exact"])
+def simctx(sim, request):
+    """Both vector-quantiser flavours (crn_gpu_set_vq_mode): "exact" reproduces the reference's member-order float sums, so the clustered
+    output can be compared byte for byte; "fast" (the default) is held to the tolerance only."""
     ctx = crn.Context(0, lib=sim)
+    ctx.set_vq_mode(request.param == "exact")
     yield ctx
     ctx.close()
 
@@ -87,7 +90,9 @@ def test_compress_dds_clustered_matches_reference_file(simctx, ref):
     levels = chain(64, 64, 1)
     want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT["DXT1"], file_type=1, quality=128, threads=0, flags=1 | 2 | 8)
     got = simctx.compress_dds([levels], helpers.CRN_FMT["DXT1"], quality_level=128)
-    assert got == want
+    assert len(got) == len(want) and got[:128] == want[:128]
+    if simctx.vq_exact:
+        assert got == want
 
 
 # ---- crn_compress with a crn_mipmap_params: level 0 in, generated chain, whole file out ----------------------------

@@ -23,11 +23,14 @@ SYMBOLS = ["crn_compress(crn_comp_params const&, unsigned int&, unsigned int*, f
            "crnd::crnd_get_level_data(void const*, unsigned int, unsigned int, unsigned int*)", "crnd::crnd_create_segmented_file(", "crnd::crnd_set_memory_callbacks("]
 
 
-def run_demo(name, size):
+def run_demo(name, size, exact_vq=False):
     exe = os.path.join(BUILD, name)
     if not os.path.exists(exe):
         pytest.skip("%s not built (tests/dropin/build.sh needs /root/reference)" % exe)
-    r = subprocess.run([exe, str(size)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+    # exact_vq: the member-order vector quantiser (crn_gpu_set_vq_mode), so that 64 x 64 inputs -- where a few dozen clusters make the
+    # tolerance figures noisy -- can be compared at the contract's bound; 256 x 256 and up run the default quantiser
+    env = dict(os.environ, CRN_B200_VQ_EXACT="1" if exact_vq else "0")
+    r = subprocess.run([exe, str(size)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     out = {}
     for line in r.stdout.splitlines():                  # the reference prints console chatter on stdout as well: keep the tagged lines
@@ -78,4 +81,4 @@ def test_dropin_exports_the_reference_symbols():
 
 
 def test_dropin_matches_reference_under_emulator(built):
-    compare_demo(run_demo("demo_sim", 64), run_demo("demo_ref", 64))
+    compare_demo(run_demo("demo_sim", 64, exact_vq=True), run_demo("demo_ref", 64))

@@ -7,6 +7,6 @@ from test_dropin_cpu import compare_demo, run_demo
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("size", [64, 256])
-def test_gpu_dropin_matches_reference(size):
-    compare_demo(run_demo("demo_b200", size), run_demo("demo_ref", size))
+@pytest.mark.parametrize("size,exact_vq", [(64, True), (256, False), (512, False)])
+def test_gpu_dropin_matches_reference(size, exact_vq):
+    compare_demo(run_demo("demo_b200", size, exact_vq), run_demo("demo_ref", size))

@@ -54,8 +54,25 @@ def agreement(a, b):
 @pytest.fixture(scope="module")
 def simctx(sim):
     ctx = crn.Context(0, lib=sim)
+    ctx.set_vq_mode(True)            # the exact member-order builder (vq_kernels.cuh); the default single-launch builder is tested at the end
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="module")
+def fastctx(sim):
+    ctx = crn.Context(0, lib=sim)    # default mode: single-launch frontier splits (vq_fast.cuh), tolerance class
+    yield ctx
+    ctx.close()
+
+
+def distortion(vecs, w, co):
+    """weighted squared error of every vector against its cluster's weighted centroid: what the quantiser minimises"""
+    v = vecs.astype(np.float64); ww = w.astype(np.float64)
+    k = int(co.max()) + 1
+    sw = np.bincount(co, ww, k)
+    cen = np.stack([np.bincount(co, ww * v[:, d], k) / sw for d in range(v.shape[1])], 1)
+    return float((ww * ((v - cen[co]) ** 2).sum(1)).sum())
 
 
 @pytest.mark.parametrize("dims,n,max_size,retrieve,threaded,seed", [
@@ -106,3 +123,37 @@ def test_large_matches_reference_exactly(simctx, ref, dims, n, max_size, retriev
     co_g, k_g, _ = simctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, n, dims, max_size, retrieve, threaded)
     assert k_g == k_r
     assert np.array_equal(co_g, co_r)
+
+
+@pytest.mark.parametrize("dims,n,max_size,retrieve,threaded,seed,max_weight", [
+    (6, 300, 65535, 40, False, 1, 8), (6, 2000, 65535, 200, False, 2, 8), (2, 1500, 65535, 100, False, 3, 8), (16, 1000, 65535, 100, False, 4, 8),
+    (6, 2000, 100, 0, False, 5, 8), (16, 2000, 300, 0, True, 6, 8), (16, 500, 100, 0, True, 7, 8), (6, 1, 65535, 10, False, 8, 8), (2, 64, 65535, 1000, False, 9, 8),
+    (6, 5000, 65535, 5000, False, 15, 8), (16, 6000, 3000, 0, True, 14, 8), (6, 24000, 65535, 1500, False, 16, 64), (2, 20000, 65535, 300, False, 18, 8), (16, 8000, 500, 0, True, 17, 2048),
+])
+def test_fast_builder_within_tolerance_of_reference(fastctx, ref, dims, n, max_size, retrieve, threaded, seed, max_weight):
+    """The default builder runs the same algorithm with sums in a parallel order: the tree may differ where two candidates are within a
+    rounding of each other, so it is held to what the clustered path's contract needs -- the same number of clusters (+- 1 %) and a
+    quantisation error within 1 % of the reference's (the reference moves by as much with its own thread count)."""
+    vecs, w = make_vectors(dims, n, seed, "uniform" if (dims == 16 and n > 2000) else "clumpy", max_weight)
+    co_r, k_r, _ = ref_clusterize(ref, vecs, w, max_size, retrieve, threaded)
+    co_g, k_g, _ = fastctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, n, dims, max_size, retrieve, threaded)
+    assert abs(k_g - k_r) <= max(1, k_r // 100)
+    assert co_g.max() == k_g - 1 and len(np.unique(co_g)) == k_g
+    if k_r > 1 and n > 1:
+        d_r, d_g = distortion(vecs, w, co_r), distortion(vecs, w, co_g)
+        assert d_g <= d_r * 1.01 + 1e-6, (d_g, d_r)
+        # most vectors sit in clusters with exactly the reference's member set
+        assert agreement(co_g, co_r) > 0.5
+
+
+def test_fast_builder_degenerate_inputs(fastctx, ref):
+    vecs = np.full((200, 6), 77, np.uint8); w = np.ones(200, np.uint32)
+    co_g, k_g, cb_g = fastctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, 200, 6, 65535, 16, False)
+    co_r, k_r, cb_r = ref_clusterize(ref, vecs, w, 65535, 16, False)
+    assert (k_g, cb_g) == (k_r, cb_r) and np.array_equal(co_g, co_r)
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, (7, 6)).astype(np.uint8)
+    vecs = np.ascontiguousarray(base[rng.integers(0, 7, 500)]); w = rng.integers(1, 4, 500).astype(np.uint32)
+    co_g, k_g, cb_g = fastctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, 500, 6, 65535, 64, False)
+    co_r, k_r, cb_r = ref_clusterize(ref, vecs, w, 65535, 64, False)
+    assert k_g == k_r and distortion(vecs, w, co_g) <= distortion(vecs, w, co_r) + 1e-6
