@@ -50,6 +50,7 @@ struct crn_gpu_ctx {
     void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
     int wide_smem_set, streams_smem_set;
     crn::VqWorkspace vq_ws;              // slab of the vector quantiser
+    crn::VqFastScratch* vq_scratch;      // host arrays of the single-launch builder, kept between builds
     int vq_exact;                        // crn_gpu_set_vq_mode: 1 = member-order float emulation (vq_kernels.cuh), 0 = single-launch frontier splits (vq_fast.cuh)
     int transcode_smem_set;
     // clustered path: per-element child contexts (own stream + scratch) and a cache of released device buffers, both
@@ -188,7 +189,11 @@ int vq_clusterize(crn_gpu_ctx* ctx, const uint8_t* d_vecs, const uint32_t* d_wts
     crn::VqResult res;
     cudaError_t ce;
     if (ctx->vq_exact) { crn::VqBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws); ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res); }
-    else { crn::VqFastBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws, ctx->sm_count); ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res); }
+    else {
+        if (!ctx->vq_scratch) ctx->vq_scratch = new crn::VqFastScratch();
+        crn::VqFastBuilder<D> builder(ctx->stream, &ctx->launches, &ctx->vq_ws, ctx->sm_count, ctx->vq_scratch);
+        ce = builder.build(d_vecs, d_wts, nullptr, n, max_size, threaded != 0, res);
+    }
     if (ce != cudaSuccess) return set_err(ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "crn_gpu_vq_clusterize", ce);
     if (codebook_size) *codebook_size = res.codebook_size();
     const uint32_t k = res.retrieve(retrieve, h_cluster_of);
@@ -218,6 +223,7 @@ struct crn_qdxt_element {
     uint32_t offset;                  // byte offset of the element inside a block
     int use_alpha_blocks;             // qdxt1_params::m_use_alpha_blocks
     crn::VqResult endpoint_tree;
+    crn::VqResult sel_tree;           // selector tree of the last pack(): kept so that its host arrays are reused by the next one
     uint32_t max_selector_clusters;
     uint32_t endpoint_clusters, selector_clusters;
     // every element is an independent chain of short, latency-bound kernels with host decisions in between, so each
@@ -296,7 +302,11 @@ int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max
 {
     cudaError_t ce;
     if (e.vq_exact) { crn::VqBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws); ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out); }
-    else { crn::VqFastBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws, e.ctx->sm_count); ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out); }
+    else {
+        if (!e.ctx->vq_scratch) e.ctx->vq_scratch = new crn::VqFastScratch();
+        crn::VqFastBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws, e.ctx->sm_count, e.ctx->vq_scratch);
+        ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out);
+    }
     if (ce != cudaSuccess) return set_err(e.ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
     return CRN_GPU_OK;
 }
@@ -435,7 +445,7 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     e.offsets.assign(1, 0u); e.members.clear();
-    crn::VqResult sel_tree;
+    crn::VqResult& sel_tree = e.sel_tree;
     // selector clusters keep every leaf, so the CSR lists are the leaves' position ranges over the final permutation,
     // which goes device-to-device into d_members (see vq_leaf_offsets); only the offsets travel
     uint32_t sel_members = 0;
@@ -534,6 +544,7 @@ void crn_gpu_destroy(crn_gpu_ctx* ctx)
     if (ctx->d_wide) cudaFree(ctx->d_wide);
     if (ctx->vq_ws.base) cudaFree(ctx->vq_ws.base);
     if (ctx->vq_ws.nodes) cudaFree(ctx->vq_ws.nodes);
+    delete ctx->vq_scratch;
     if (ctx->d_cluster_ws) cudaFree(ctx->d_cluster_ws);
     for (crn_gpu_ctx* c : ctx->child) if (c) crn_gpu_destroy(c);
     if (ctx->pool) {

@@ -368,6 +368,150 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
     }
 }
 
+// Tiny nodes, one THREAD per node.  A 600 K-leaf selector tree ends in hundreds of thousands of nodes with two or three members; a warp (let
+// alone its shuffle reductions and barriers) per such node costs ~100 us, a thread walking the members serially a few microseconds.  The
+// thread follows split_node literally (member-order sums, as the reference); only the power iteration is applied matrix-free
+// (covar * axis = sum_m w_m ((v_m - c) . axis)(v_m - c) / W) instead of through the N x N matrix, to stay in registers.
+constexpr uint32_t kVqTinyNode = 12;
+template <int D>
+__global__ void __launch_bounds__(128)
+vq_fast_tiny_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restrict__ wts, uint32_t* __restrict__ perm, VqFastNodes N, const uint2* __restrict__ slots,
+                    const uint32_t* __restrict__ slot_list, uint32_t nslots, VqFastResult* __restrict__ results)
+{
+    const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= nslots) return;
+    const uint32_t slot = slot_list[si], node = slots[slot].x, child = slots[slot].y;
+    const uint32_t begin = N.begin[node], end = N.end[node], cnt = end - begin;
+    uint32_t ids[kVqTinyNode];
+#pragma unroll
+    for (uint32_t i = 0; i < kVqTinyNode; i++) ids[i] = i < cnt ? perm[begin + i] : 0u;
+    float centroid[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) centroid[d] = N.centroid[(size_t)node * D + d];
+    const unsigned long long total_weight = N.weight[node];
+    float left[D], right[D];
+    bool have = false;
+    if (cnt == 2) { vqf_load<D>(vecs, ids[0], left); vqf_load<D>(vecs, ids[1], right); have = true; }
+    else {
+        float axis[D], prev[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) { axis[d] = .75f + (1.25f - .75f) * ((float)d * (1.0f / (float)(D - 1))); prev[d] = axis[d]; }
+        const float inv_w = 1.0f / (float)total_weight;
+        for (int iter = 0; iter < 10; iter++) {
+            float xv[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) xv[d] = 0.0f;
+            for (uint32_t i = 0; i < cnt; i++) {
+                float v[D]; vqf_load<D>(vecs, ids[i], v);
+                float t = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; d++) { v[d] -= centroid[d]; t += v[d] * axis[d]; }
+                t *= (float)wts[ids[i]] * inv_w;
+#pragma unroll
+                for (int d = 0; d < D; d++) xv[d] += t * v[d];
+            }
+            float max_sum = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; d++) max_sum = fmaxf(max_sum, fabsf(xv[d]));
+            if (max_sum != 0.0f) { const float sc = 1.0f / max_sum;
+#pragma unroll
+                for (int d = 0; d < D; d++) xv[d] *= sc; }
+            float dn = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; d++) { const float dd = prev[d] - xv[d]; dn += dd * dd; prev[d] = axis[d]; axis[d] = xv[d]; }
+            if (sqrtf(dn) < .0025f) break;
+        }
+        {
+            double n2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) n2 += (double)(axis[d] * axis[d]);
+            if (n2 != 0.0) { const float sc = (float)(1.0f / sqrt(n2));
+#pragma unroll
+                for (int d = 0; d < D; d++) axis[d] *= sc; }
+        }
+        float ls[D], rs[D]; double lw = 0.0, rw = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) { ls[d] = 0.0f; rs[d] = 0.0f; }
+        for (uint32_t i = 0; i < cnt; i++) {
+            float v[D]; vqf_load<D>(vecs, ids[i], v);
+            const float w = (float)wts[ids[i]];
+            float t = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; d++) t += (v[d] - centroid[d]) * axis[d];
+            if (t < 0.0f) { lw += (double)w;
+#pragma unroll
+                for (int d = 0; d < D; d++) ls[d] += v[d] * w; }
+            else { rw += (double)w;
+#pragma unroll
+                for (int d = 0; d < D; d++) rs[d] += v[d] * w; }
+        }
+        if (lw > 0.0 && rw > 0.0) {
+            const float fl = (float)(1.0f / lw), fr = (float)(1.0f / rw);
+#pragma unroll
+            for (int d = 0; d < D; d++) { left[d] = ls[d] * fl; right[d] = rs[d] * fr; }
+            have = true;
+        }
+    }
+    if (!have) {                                 // compute_split_estimate (:446-476)
+        float far_[D], opp[D]; float best = -1.0f;
+        for (uint32_t i = 0; i < cnt; i++) { float v[D]; vqf_load<D>(vecs, ids[i], v); const float d2 = hc_sqdist<D>(v, centroid); if (d2 > best) { best = d2;
+#pragma unroll
+            for (int d = 0; d < D; d++) far_[d] = v[d]; } }
+        best = -1.0f;
+        for (uint32_t i = 0; i < cnt; i++) { float v[D]; vqf_load<D>(vecs, ids[i], v); const float d2 = hc_sqdist<D>(v, far_); if (d2 > best) { best = d2;
+#pragma unroll
+            for (int d = 0; d < D; d++) opp[d] = v[d]; } }
+#pragma unroll
+        for (int d = 0; d < D; d++) { left[d] = (far_[d] + centroid[d]) * .5f; right[d] = (opp[d] + centroid[d]) * .5f; }
+    }
+    // Lloyd rounds (:761-836)
+    float prev_total_variance = 1e+10f, lvar = 0.0f, rvar = 0.0f;
+    unsigned long long lwt = 0, rwt = 0;
+    uint32_t side = 0, n_left = 0;
+    bool unsplittable = false;
+    for (unsigned loops = 0; loops < 8; loops++) {
+        float nl[D], nr[D]; double ltt = 0.0, rtt = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) { nl[d] = 0.0f; nr[d] = 0.0f; }
+        lwt = 0; rwt = 0; side = 0; n_left = 0;
+        for (uint32_t i = 0; i < cnt; i++) {
+            float v[D]; vqf_load<D>(vecs, ids[i], v);
+            const unsigned wi = wts[ids[i]]; const float w = (float)wi;
+            float dot = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; d++) dot += v[d] * v[d];
+            if (hc_sqdist<D>(left, v) < hc_sqdist<D>(right, v)) { side |= 1u << i; n_left++; lwt += wi; ltt += (double)(dot * w);
+#pragma unroll
+                for (int d = 0; d < D; d++) nl[d] += v[d] * w; }
+            else { rwt += wi; rtt += (double)(dot * w);
+#pragma unroll
+                for (int d = 0; d < D; d++) nr[d] += v[d] * w; }
+        }
+        if (!lwt || !rwt) { unsplittable = true; break; }
+        float ldot = 0.0f, rdot = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; d++) { ldot += nl[d] * nl[d]; rdot += nr[d] * nr[d]; }
+        lvar = (float)(ltt - (double)(ldot / (float)lwt)); rvar = (float)(rtt - (double)(rdot / (float)rwt));
+        const float fl = 1.0f / (float)lwt, fr = 1.0f / (float)rwt;
+#pragma unroll
+        for (int d = 0; d < D; d++) { left[d] = nl[d] * fl; right[d] = nr[d] * fr; }
+        const float total_variance = lvar + rvar;
+        if (total_variance < .00001f) break;
+        if (((prev_total_variance - total_variance) / total_variance) < .00125f) break;
+        prev_total_variance = total_variance;
+    }
+    VqFastResult r; r.state = unsplittable ? 2 : 1; r.n_left = n_left; r.lvar = lvar; r.rvar = rvar;
+    results[slot] = r;
+    if (unsplittable) return;
+    uint32_t pl = begin, pr = begin + n_left;                                 // stable partition
+#pragma unroll
+    for (uint32_t i = 0; i < kVqTinyNode; i++) if (i < cnt) { if ((side >> i) & 1u) perm[pl++] = ids[i]; else perm[pr++] = ids[i]; }
+    N.begin[child] = begin; N.end[child] = begin + n_left; N.begin[child + 1] = begin + n_left; N.end[child + 1] = end;
+    N.weight[child] = lwt; N.weight[child + 1] = rwt;
+#pragma unroll
+    for (int d = 0; d < D; d++) { N.centroid[(size_t)child * D + d] = left[d]; N.centroid[(size_t)(child + 1) * D + d] = right[d]; }
+}
+
 // root of a clusterizer (generate_codebook :76-93): statistics of the whole training set.  out: D weighted sums, the weighted dot-product sum, the weight
 template <int D>
 __global__ void __launch_bounds__(512)

@@ -10,16 +10,97 @@
 
 namespace crn {
 
+// The reference pops the leaf of largest variance, splits it, and counts one leaf more (even when the split fails) until max_size leaves
+// exist (generate_codebook, crn_clusterizer.h:100-139).  A node's variance here is its within-node squared error, and a split never increases
+// the total, so a child's key is <= its parent's: the pops are then simply ALL candidate nodes in descending key order, parents before
+// children, and the popped set is the (max_size - 1) largest keys of the tree.  That turns the reference's heap loop into a threshold:
+// VqOrderSim keeps a histogram of the keys of every candidate seen so far (a candidate = a node with more than one member and a positive
+// variance), sends to the device every unsplit candidate whose key could still be among the (max_size - 1) largest, and at the end ranks the
+// winners by (key descending, node id ascending).  A child's key is clamped to its parent's (float rounding can put it a hair above), so the
+// order stays parent-first.  O(1) per node and no pointer chasing, against ~20 dependent cache misses per pop for the heap replay of
+// VqTreeSim -- which matters when a selector tree has 600 K leaves.  (Ties between equal keys may be popped in a different order than the
+// reference's heap would: tolerance class, like the rest of this builder.)
+struct VqOrderSim {
+    uint32_t root = 0, max_size = 0;
+    static constexpr uint32_t kBins = 1u << 16;
+    std::vector<uint32_t> hist;                         // keys of all candidates, by the top 16 bits of the float (monotonic for keys >= 0)
+    struct Cand { float key; uint32_t id; };
+    std::vector<Cand> pending;                          // candidates not yet split on the device
+    std::vector<Cand> done;                             // candidates the device has processed (split or found unsplittable)
+    uint32_t total = 0;
+    static uint32_t bin_of(float v) { uint32_t b; memcpy(&b, &v, 4); return b >> 16; }
+    static float bin_floor(uint32_t bin) { const uint32_t b = bin << 16; float v; memcpy(&v, &b, 4); return v; }
+    void reset(const std::vector<VqHostNode>& nodes)
+    {
+        hist.assign(kBins, 0u); pending.clear(); done.clear(); total = 0;
+        add(root, nodes[root].variance, nodes[root].count, 3.0e38f, true);
+    }
+    void add(uint32_t id, float var, uint32_t count, float parent_key, bool is_root = false)
+    {
+        // the root enters unconditionally (:100-102); children only with more than one member and a positive variance (:857-871)
+        if (!is_root && !(count > 1 && var > 0.0f)) return;
+        const float key = var < parent_key ? var : parent_key;
+        hist[bin_of(key < 0.0f ? 0.0f : key)]++;
+        pending.push_back(Cand{ key, id });
+        total++;
+    }
+    uint32_t budget() const { return max_size ? max_size - 1 : 0; }
+    // candidates that may still be among the budget() largest keys and have no device result yet; they leave `pending`
+    void wanted(std::vector<uint32_t>& out)
+    {
+        const uint32_t b = budget();
+        float thresh = -1.0f;
+        if (total > b) {
+            uint32_t seen = 0, bin = kBins;
+            while (bin > 0 && seen < b) seen += hist[--bin];
+            thresh = b ? bin_floor(bin) : 3.4e38f;
+        }
+        size_t keep = 0;
+        for (size_t i = 0; i < pending.size(); i++) {
+            if (pending[i].key >= thresh) { out.push_back(pending[i].id); done.push_back(pending[i]); }
+            else pending[keep++] = pending[i];
+        }
+        pending.resize(keep);
+    }
+    // after the last round: ranks of the budget() winners (the nodes the reference would have popped), in pop order
+    void finish(std::vector<VqHostNode>& nodes, uint32_t& split_index)
+    {
+        const uint32_t b = budget();
+        auto before = [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key > y.key : x.id < y.id; };
+        if (done.size() > b) { std::nth_element(done.begin(), done.begin() + b, done.end(), before); done.resize(b); }
+        std::sort(done.begin(), done.end(), before);
+        uint32_t rank = 0;
+        for (const Cand& c : done) {
+            VqHostNode& nd = nodes[c.id];
+            if (nd.count != 1 && !nd.unsplittable && nd.left >= 0) nd.split_rank = (int32_t)rank++;      // a failed split still used up its pop
+        }
+        split_index = rank;
+    }
+};
+
+// Host-side arrays of a build, kept by the caller between builds: a 600 K-leaf tree needs ~100 MB of them, and fresh allocations of that size
+// come back from the OS page by page (first-touch faults cost more than the work done on the data).
+struct VqFastScratch {
+    std::vector<uint2> slots;
+    std::vector<VqFastResult> results;
+    std::vector<uint32_t> lists[4];                     // node-size classes: thread-block cluster, CTA, warp, single thread
+    std::vector<uint32_t> slot_node, all, node_sim;     // node_sim: which sim (partition) a node belongs to
+    std::vector<VqOrderSim> sims;
+    std::vector<uint32_t> parts[4];
+};
+
 template <int D> class VqFastBuilder {
 public:
-    VqFastBuilder(cudaStream_t stream, uint64_t* launch_counter, VqWorkspace* ws, int sm_count) : stream_(stream), launches_(launch_counter), ws_(ws), sm_count_(sm_count) {}
+    VqFastBuilder(cudaStream_t stream, uint64_t* launch_counter, VqWorkspace* ws, int sm_count, VqFastScratch* scratch)
+        : stream_(stream), launches_(launch_counter), ws_(ws), sm_count_(sm_count), sc_(*scratch), h_slots_(scratch->slots), h_results_(scratch->results), lists_(scratch->lists),
+          sims_(scratch->sims), node_sim_(scratch->node_sim) {}
 
     // Same contract as VqBuilder<D>::build (vq_host.h): d_vecs u8[][D], d_wts u32[], d_ids ascending ids (nullptr = 0..n-1);
     // threaded = threaded_clusterizer<V>::create_clusters (three PCA divisions, then one clusterizer per non-empty partition).
     cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, VqResult& res,
                       uint32_t* d_perm_out = nullptr)
     {
-        res = VqResult();
+        res.nodes.clear(); res.trees.clear(); res.perm.clear(); res.rounds = 0; res.device_splits = 0;      // capacity kept (see VqFastScratch)
         if (!n) return cudaSuccess;
         n_ = n; vecs_ = d_vecs; wts_ = d_wts;
         cudaError_t ce = allocate(n, max_size);
@@ -82,19 +163,38 @@ public:
             t.root = 0; t.max_size = max_size;
             res.trees.push_back(t);
         }
-        for (VqTreeSim& t : res.trees) t.reset(nodes);
+        sims_.resize(res.trees.size());
+        for (size_t i = 0; i < sims_.size(); i++) { sims_[i].root = res.trees[i].root; sims_[i].max_size = res.trees[i].max_size; sims_[i].reset(nodes); }
+        node_sim_.assign(nodes.size(), 0u);
+        for (size_t i = 0; i < sims_.size(); i++) node_sim_[sims_[i].root] = (uint32_t)i;
         for (;;) {
+            const double th = now_ms();
             frontier.clear();
-            for (VqTreeSim& t : res.trees) { t.run(nodes); t.wanted(frontier); }
+            bool par_wanted = false;
+#ifdef __CUDACC__
+            size_t live = 0;
+            for (const VqOrderSim& t : sims_) live += t.pending.size();
+            if (sims_.size() > 1 && sims_.size() <= 4 && live > 32768) {
+                std::vector<uint32_t> (&parts)[4] = sc_.parts;
+                for (int i = 0; i < 4; i++) parts[i].clear();
+                if (!pool_) pool_.reset(new VqPool());
+                pool_->run4([&](int i) { if ((size_t)i < sims_.size()) sims_[i].wanted(parts[i]); });
+                for (size_t i = 0; i < sims_.size(); i++) frontier.insert(frontier.end(), parts[i].begin(), parts[i].end());
+                par_wanted = true;
+            }
+#endif
+            if (!par_wanted) for (VqOrderSim& t : sims_) t.wanted(frontier);
+            t_host_ += now_ms() - th;
             if (frontier.empty()) break;
             ce = round(frontier, nodes, 0);
             if (ce != cudaSuccess) return ce;
             res.rounds++;
             res.device_splits += (uint32_t)frontier.size();
         }
-        for (VqTreeSim& t : res.trees) {                              // m_codebook_index of the interior nodes
-            for (size_t k = 0; k < t.split_log.size(); k++) nodes[t.split_log[k]].split_rank = (int32_t)k;
-            std::vector<uint32_t>().swap(t.split_log);
+        {
+            const double th = now_ms();
+            for (size_t i = 0; i < sims_.size(); i++) sims_[i].finish(nodes, res.trees[i].split_index);      // m_codebook_index of the interior nodes
+            t_host_ += now_ms() - th;
         }
         if (d_perm_out) cudaMemcpyAsync(d_perm_out, d_perm_, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream_);
         else {
@@ -124,9 +224,15 @@ private:
     double* d_root_ = nullptr;
     VqFastNodes nodes_ = {};
     bool wide_ok_ = true;
-    std::vector<uint2> h_slots_;
-    std::vector<VqFastResult> h_results_;
-    std::vector<uint32_t> lists_[3];
+    VqFastScratch& sc_;
+    std::vector<uint2>& h_slots_;
+    std::vector<VqFastResult>& h_results_;
+    std::vector<uint32_t> (&lists_)[4];
+#ifdef __CUDACC__
+    std::unique_ptr<VqPool> pool_;
+#endif
+    std::vector<VqOrderSim>& sims_;
+    std::vector<uint32_t>& node_sim_;
     double t_enqueue_ = 0, t_sync_ = 0, t_host_ = 0;
     static constexpr uint32_t kHugeNode = 8192, kLargeNode = 1024;
     static constexpr int kClusterCtas = 8, kWideClusterCtas = 16, kClusterThreads = 512;
@@ -215,8 +321,9 @@ private:
     {
         const double t0 = now_ms();
         h_slots_.clear();
-        for (int k = 0; k < 3; k++) lists_[k].clear();
-        std::vector<uint32_t> slot_node;
+        for (int k = 0; k < 4; k++) lists_[k].clear();
+        std::vector<uint32_t>& slot_node = sc_.slot_node;
+        slot_node.clear();
         uint32_t next_child = (uint32_t)nodes.size();
         for (uint32_t id : frontier) {
             VqHostNode& nd = nodes[id];
@@ -225,10 +332,11 @@ private:
             h_slots_.push_back(make_uint2(id, next_child));
             slot_node.push_back(id);
             next_child += 2;
+            const bool tiny = mode == 0 && nd.count <= kVqTinyNode;
 #ifdef __CUDACC__
-            lists_[nd.count >= kHugeNode ? 0 : (nd.count >= kLargeNode ? 1 : 2)].push_back(s);
+            lists_[tiny ? 3 : (nd.count >= kHugeNode ? 0 : (nd.count >= kLargeNode ? 1 : 2))].push_back(s);
 #else
-            lists_[nd.count >= kLargeNode ? 1 : 2].push_back(s);      // the emulator has no thread-block clusters
+            lists_[tiny ? 3 : (nd.count >= kLargeNode ? 1 : 2)].push_back(s);      // the emulator has no thread-block clusters
 #endif
         }
         const uint32_t F = (uint32_t)h_slots_.size();
@@ -236,9 +344,9 @@ private:
         if (F > slot_cap_) return cudaErrorMemoryAllocation;
         if (next_child > node_cap_) { const cudaError_t ge = ensure_nodes(next_child, nodes.size()); if (ge != cudaSuccess) return ge; }
         cudaMemcpyAsync(d_slots_, h_slots_.data(), sizeof(uint2) * F, cudaMemcpyHostToDevice, stream_);
-        std::vector<uint32_t> all;
-        all.reserve(F);
-        for (int k = 0; k < 3; k++) all.insert(all.end(), lists_[k].begin(), lists_[k].end());
+        std::vector<uint32_t>& all = sc_.all;
+        all.clear();
+        for (int k = 0; k < 4; k++) all.insert(all.end(), lists_[k].begin(), lists_[k].end());
         cudaMemcpyAsync(d_list_, all.data(), sizeof(uint32_t) * F, cudaMemcpyHostToDevice, stream_);
         const uint32_t* dl = d_list_;
 #ifdef __CUDACC__
@@ -263,6 +371,11 @@ private:
             const uint32_t cnt = (uint32_t)lists_[2].size();
             const unsigned grid = (unsigned)std::min<size_t>(cnt, (size_t)sm_count_ * 32);
             CRN_LAUNCH((vq_fast_split_kernel<D, 32, 1>), grid, 32, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
+            dl += cnt;
+        }
+        if (!lists_[3].empty()) {
+            const uint32_t cnt = (uint32_t)lists_[3].size();
+            CRN_LAUNCH(vq_fast_tiny_kernel<D>, (cnt + 127) / 128, 128, 0, stream_, vecs_, wts_, d_perm_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_); count();
         }
         h_results_.resize(F);
         cudaMemcpyAsync(h_results_.data(), d_results_, sizeof(VqFastResult) * F, cudaMemcpyDeviceToHost, stream_);
@@ -273,22 +386,51 @@ private:
         ce = cudaGetLastError();
         if (ce != cudaSuccess) return ce;
         nodes.resize(next_child);
-        for (uint32_t s = 0; s < F; s++) {
-            const VqFastResult& r = h_results_[s];
-            VqHostNode& par = nodes[slot_node[s]];
-            par.processed = 1;
-            if (r.state != 1) { par.unsplittable = 1; continue; }
-            const uint32_t child = h_slots_[s].y;
-            par.left = (int32_t)child;
-            VqHostNode& l = nodes[child];
-            VqHostNode& rr = nodes[child + 1];
-            l = VqHostNode(); rr = VqHostNode();
-            l.begin = par.begin; l.count = r.n_left; l.variance = r.lvar;
-            rr.begin = par.begin + r.n_left; rr.count = par.count - r.n_left; rr.variance = r.rvar;
-            par.child_count[0] = l.count; par.child_count[1] = rr.count;
-            par.child_var[0] = r.lvar; par.child_var[1] = r.rvar;
+        if (mode == 0) node_sim_.resize(next_child, 0u);
+        auto scatter = [&](uint32_t s0, uint32_t s1) {
+            for (uint32_t s = s0; s < s1; s++) {
+                const VqFastResult& r = h_results_[s];
+                VqHostNode& par = nodes[slot_node[s]];
+                par.processed = 1;
+                if (r.state != 1) { par.unsplittable = 1; continue; }
+                const uint32_t child = h_slots_[s].y;
+                par.left = (int32_t)child;
+                VqHostNode& l = nodes[child];
+                VqHostNode& rr = nodes[child + 1];
+                l.begin = par.begin; l.count = r.n_left; l.variance = r.lvar;
+                rr.begin = par.begin + r.n_left; rr.count = par.count - r.n_left; rr.variance = r.rvar;
+                par.child_count[0] = l.count; par.child_count[1] = rr.count;
+                par.child_var[0] = r.lvar; par.child_var[1] = r.rvar;
+                if (mode == 0) {
+                    const uint32_t si = node_sim_[slot_node[s]];
+                    node_sim_[child] = si; node_sim_[child + 1] = si;
+                    const float pk = par.variance;
+                    l.variance = r.lvar < pk ? r.lvar : pk; rr.variance = r.rvar < pk ? r.rvar : pk;      // keys never exceed the parent's (see VqOrderSim)
+                    sims_[si].add(child, l.variance, l.count, pk);
+                    sims_[si].add(child + 1, rr.variance, rr.count, pk);
+                }
+            }
+        };
+        // threaded_clusterizer's partitions are independent: their slots are contiguous in the frontier (wanted() is called sim by sim),
+        // every record written belongs to one partition only, so each partition's share goes to its own host thread
+        bool done_parallel = false;
+#ifdef __CUDACC__
+        if (mode == 0 && sims_.size() > 1 && sims_.size() <= 4 && F > 16384) {
+            uint32_t bounds[5] = { 0, F, F, F, F };
+            uint32_t nb = 1;
+            for (uint32_t s = 1; s < F && nb < 4; s++) if (node_sim_[slot_node[s]] != node_sim_[slot_node[s - 1]]) bounds[nb++] = s;
+            for (uint32_t k = nb; k <= 4; k++) bounds[k] = F;
+            if (!pool_) pool_.reset(new VqPool());
+            pool_->run4([&](int i) { if (bounds[i] < bounds[i + 1]) scatter(bounds[i], bounds[i + 1]); });
+            done_parallel = true;
         }
-        t_enqueue_ += t1 - t0; t_sync_ += t2 - t1; t_host_ += now_ms() - t2;
+#endif
+        if (!done_parallel) scatter(0, F);
+        const double t3 = now_ms();
+        t_enqueue_ += t1 - t0; t_sync_ += t2 - t1; t_host_ += t3 - t2;
+        if (getenv("CRN_B200_TRACE_ROUNDS"))
+            fprintf(stderr, "[crn_b200]   vq_fast<%d> round F=%u (cluster %zu, cta %zu, warp %zu, thread %zu): device %.2f ms, host %.2f ms\n", D, F, lists_[0].size(), lists_[1].size(), lists_[2].size(), lists_[3].size(),
+                    t2 - t0, t3 - t2);
         return cudaSuccess;
     }
 };
