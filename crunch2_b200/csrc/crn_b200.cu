@@ -298,14 +298,14 @@ int qdxt_upload_csr(crn_qdxt_element& e)
 }
 
 template <int D>
-int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res, uint32_t* d_perm_out = nullptr)
+int qdxt_vq(crn_qdxt_element& e, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, crn::VqResult& res, uint32_t* d_perm_out = nullptr, bool need_ranks = true)
 {
     cudaError_t ce;
     if (e.vq_exact) { crn::VqBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws); ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out); }
     else {
         if (!e.ctx->vq_scratch) e.ctx->vq_scratch = new crn::VqFastScratch();
         crn::VqFastBuilder<D> builder(e.ctx->stream, &e.ctx->launches, &e.ctx->vq_ws, e.ctx->sm_count, e.ctx->vq_scratch);
-        ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out);
+        ce = builder.build(e.d_vecs, e.d_wts, d_ids, n, max_size, threaded, res, d_perm_out, need_ranks);
     }
     if (ce != cudaSuccess) return set_err(e.ctx, ce == cudaErrorMemoryAllocation ? CRN_GPU_ERR_NO_MEMORY : CRN_GPU_ERR_CUDA, "clustered DDS: vector quantiser", ce);
     return CRN_GPU_OK;
@@ -450,7 +450,7 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
     // which goes device-to-device into d_members (see vq_leaf_offsets); only the offsets travel
     uint32_t sel_members = 0;
     if (e.kind == 0) {
-        rc = qdxt_vq<16>(e, nullptr, n, max_selector_clusters, true, sel_tree, e.d_members);
+        rc = qdxt_vq<16>(e, nullptr, n, max_selector_clusters, true, sel_tree, e.d_members, false);
         if (rc) return rc;
         crn::vq_leaf_offsets(sel_tree, 0u, e.offsets);
         sel_members = n;
@@ -469,7 +469,7 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
             max_clusters = std::min(std::max(64u, max_clusters), m);
             if (max_clusters >= m) continue;
             CRN_CUDA(ctx, cudaMemcpyAsync(e.d_ids, ids.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-            rc = qdxt_vq<16>(e, e.d_ids, m, max_clusters, true, sel_tree, e.d_members + sel_members);
+            rc = qdxt_vq<16>(e, e.d_ids, m, max_clusters, true, sel_tree, e.d_members + sel_members, false);
             if (rc) return rc;
             crn::vq_leaf_offsets(sel_tree, sel_members, e.offsets);
             sel_members += m;

@@ -62,13 +62,30 @@ struct VqOrderSim {
         }
         pending.resize(keep);
     }
-    // after the last round: ranks of the budget() winners (the nodes the reference would have popped), in pop order
-    void finish(std::vector<VqHostNode>& nodes, uint32_t& split_index)
+    // after the last round: the budget() winners (the nodes the reference would have popped).  Everything above the histogram bin that holds
+    // the budget-th key wins outright; only that bin's entries need a selection.  need_ranks: also order them as the reference pops them
+    // (m_codebook_index, what retrieve_clusters(max) prunes by); a caller that keeps every leaf only needs to know WHICH nodes were split.
+    void finish(std::vector<VqHostNode>& nodes, uint32_t& split_index, bool need_ranks)
     {
         const uint32_t b = budget();
         auto before = [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key > y.key : x.id < y.id; };
-        if (done.size() > b) { std::nth_element(done.begin(), done.begin() + b, done.end(), before); done.resize(b); }
-        std::sort(done.begin(), done.end(), before);
+        if (done.size() > b) {
+            uint32_t seen = 0, bin = kBins;
+            while (bin > 0 && seen < b) seen += hist[--bin];          // keys in bins above `bin` all win; `bin` is split
+            const uint32_t above = seen - hist[bin];
+            size_t keep = 0;
+            std::vector<Cand> edge;
+            for (const Cand& c : done) {
+                const uint32_t cb = bin_of(c.key < 0.0f ? 0.0f : c.key);
+                if (cb > bin) done[keep++] = c;
+                else if (cb == bin) edge.push_back(c);
+            }
+            done.resize(keep);
+            const size_t want = b > above ? b - above : 0;
+            if (edge.size() > want) { std::nth_element(edge.begin(), edge.begin() + want, edge.end(), before); edge.resize(want); }
+            done.insert(done.end(), edge.begin(), edge.end());
+        }
+        if (need_ranks) std::sort(done.begin(), done.end(), before);
         uint32_t rank = 0;
         for (const Cand& c : done) {
             VqHostNode& nd = nodes[c.id];
@@ -97,8 +114,9 @@ public:
 
     // Same contract as VqBuilder<D>::build (vq_host.h): d_vecs u8[][D], d_wts u32[], d_ids ascending ids (nullptr = 0..n-1);
     // threaded = threaded_clusterizer<V>::create_clusters (three PCA divisions, then one clusterizer per non-empty partition).
+    // need_ranks = false: the caller keeps every leaf (retrieve_clusters(0) / vq_leaf_offsets) and does not need the split order.
     cudaError_t build(const uint8_t* d_vecs, const uint32_t* d_wts, const uint32_t* d_ids, uint32_t n, uint32_t max_size, bool threaded, VqResult& res,
-                      uint32_t* d_perm_out = nullptr)
+                      uint32_t* d_perm_out = nullptr, bool need_ranks = true)
     {
         res.nodes.clear(); res.trees.clear(); res.perm.clear(); res.rounds = 0; res.device_splits = 0;      // capacity kept (see VqFastScratch)
         if (!n) return cudaSuccess;
@@ -184,7 +202,7 @@ public:
             }
 #endif
             if (!par_wanted) for (VqOrderSim& t : sims_) t.wanted(frontier);
-            t_host_ += now_ms() - th;
+            t_wanted_ += now_ms() - th;
             if (frontier.empty()) break;
             ce = round(frontier, nodes, 0);
             if (ce != cudaSuccess) return ce;
@@ -193,8 +211,16 @@ public:
         }
         {
             const double th = now_ms();
-            for (size_t i = 0; i < sims_.size(); i++) sims_[i].finish(nodes, res.trees[i].split_index);      // m_codebook_index of the interior nodes
-            t_host_ += now_ms() - th;
+            bool par = false;
+#ifdef __CUDACC__
+            if (sims_.size() > 1 && sims_.size() <= 4 && nodes.size() > 65536) {
+                if (!pool_) pool_.reset(new VqPool());
+                pool_->run4([&](int i) { if ((size_t)i < sims_.size()) sims_[i].finish(nodes, res.trees[i].split_index, need_ranks); });
+                par = true;
+            }
+#endif
+            if (!par) for (size_t i = 0; i < sims_.size(); i++) sims_[i].finish(nodes, res.trees[i].split_index, need_ranks);      // m_codebook_index of the interior nodes
+            t_finish_ += now_ms() - th;
         }
         if (d_perm_out) cudaMemcpyAsync(d_perm_out, d_perm_, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream_);
         else {
@@ -203,8 +229,8 @@ public:
         }
         ce = cudaStreamSynchronize(stream_);
         if (getenv("CRN_B200_TRACE"))
-            fprintf(stderr, "[crn_b200] vq_fast<%d> n=%u max=%u: %u rounds, %u device splits, enqueue %.1f ms, wait %.1f ms, host %.1f ms\n", D, n, max_size, res.rounds, res.device_splits,
-                    t_enqueue_, t_sync_, t_host_);
+            fprintf(stderr, "[crn_b200] vq_fast<%d> n=%u max=%u: %u rounds, %u device splits, device+copies %.1f ms (of which slot prep %.1f), scatter %.1f ms, wanted %.1f ms, finish %.1f ms\n", D, n,
+                    max_size, res.rounds, res.device_splits, t_enqueue_ + t_sync_, t_prep_, t_host_, t_wanted_, t_finish_);
         return ce;
     }
 
@@ -233,7 +259,7 @@ private:
 #endif
     std::vector<VqOrderSim>& sims_;
     std::vector<uint32_t>& node_sim_;
-    double t_enqueue_ = 0, t_sync_ = 0, t_host_ = 0;
+    double t_enqueue_ = 0, t_sync_ = 0, t_host_ = 0, t_wanted_ = 0, t_finish_ = 0, t_prep_ = 0;
     static constexpr uint32_t kHugeNode = 8192, kLargeNode = 1024;
     static constexpr int kClusterCtas = 8, kWideClusterCtas = 16, kClusterThreads = 512;
     static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
@@ -321,6 +347,7 @@ private:
     {
         const double t0 = now_ms();
         h_slots_.clear();
+        double t_prep = 0;
         for (int k = 0; k < 4; k++) lists_[k].clear();
         std::vector<uint32_t>& slot_node = sc_.slot_node;
         slot_node.clear();
@@ -341,6 +368,7 @@ private:
         }
         const uint32_t F = (uint32_t)h_slots_.size();
         if (!F) return cudaSuccess;
+        t_prep = now_ms() - t0; t_prep_ += t_prep;
         if (F > slot_cap_) return cudaErrorMemoryAllocation;
         if (next_child > node_cap_) { const cudaError_t ge = ensure_nodes(next_child, nodes.size()); if (ge != cudaSuccess) return ge; }
         cudaMemcpyAsync(d_slots_, h_slots_.data(), sizeof(uint2) * F, cudaMemcpyHostToDevice, stream_);

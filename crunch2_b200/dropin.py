@@ -18,7 +18,9 @@ PROGRESS_FN = ctypes.CFUNCTYPE(ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32
 
 class CrnCompParams(ctypes.Structure):      # crn_comp_params, inc/crnlib.h:231-414
     _fields_ = [("m_size_of_obj", ctypes.c_uint32), ("m_file_type", ctypes.c_uint32), ("m_faces", ctypes.c_uint32), ("m_width", ctypes.c_uint32),
-                ("m_height", ctypes.c_uint32), ("m_levels", ctypes.c_uint32), ("m_format", ctypes.c_uint32), ("m_flags", ctypes.c_uint32),
+                ("m_height", ctypes.c_uint32), ("m_levels", ctypes.c_uint32),
+                # enum crn_format holds both -1 (cCRNFmtInvalid) and 0xFFFFFFFF (cCRNFmtForceDWORD): its underlying type is 64 bits wide
+                ("m_format", ctypes.c_int64), ("m_flags", ctypes.c_uint32),
                 ("m_pImages", (ctypes.c_void_p * MAX_LEVELS) * MAX_FACES), ("m_target_bitrate", ctypes.c_float), ("m_quality_level", ctypes.c_uint32),
                 ("m_dxt1a_alpha_threshold", ctypes.c_uint32), ("m_dxt_quality", ctypes.c_uint32), ("m_dxt_compressor_type", ctypes.c_uint32),
                 ("m_alpha_component", ctypes.c_uint32), ("m_crn_adaptive_tile_color_psnr_derating", ctypes.c_float),

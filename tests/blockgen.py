@@ -9,16 +9,19 @@ import numpy as np
 
 
 def smooth_image(w, h, seed, alpha=False):
+    """Three low-frequency sin / cos fields per channel + N(0, 10) noise.  The fields are separable in x, y and x + y, so
+    they are evaluated on 1-D axes and broadcast / gathered -- bit-identical to evaluating them on the full grid, and several times faster."""
     rng = np.random.default_rng(seed)
-    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    xs = np.arange(w, dtype=np.float64); ys = np.arange(h, dtype=np.float64); ss = np.arange(w + h - 1, dtype=np.float64)
+    xy = (np.arange(h)[:, None] + np.arange(w)[None, :])
     chans = []
     for c in range(3):
         p1, p2, p3 = rng.uniform(43, 177, 3)
-        f = np.sin(x / p1 + c) + np.cos(y / p2 - c) + np.sin((x + y) / p3)
+        f = (np.sin(xs / p1 + c)[None, :] + np.cos(ys / p2 - c)[:, None]) + np.sin(ss / p3)[xy]
         f = (f - f.min()) / max(f.max() - f.min(), 1e-9)
         chans.append(27 + 200 * f + rng.normal(0, 10, (h, w)))
     if alpha:
-        a = 128 + 64 * np.sin(x / 17.0) + rng.normal(0, 8, (h, w))
+        a = (128 + 64 * np.sin(xs / 17.0))[None, :] + rng.normal(0, 8, (h, w))
     else:
         a = np.full((h, w), 255.0)
     img = np.stack(chans + [a], axis=-1)
