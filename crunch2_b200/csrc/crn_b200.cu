@@ -612,10 +612,7 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
     if (params->dxt_quality > 4 || params->dxt1a_alpha_threshold > 255)
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_pack_image: parameter out of range");
     const bool has_color = format == CRN_GPU_FMT_DXT1 || format == CRN_GPU_FMT_DXT1A || format == CRN_GPU_FMT_DXT3 || format == CRN_GPU_FMT_DXT5;
-    if (has_color && params->dxt_quality < 3)
-        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_pack_image: colour blocks need dxt_quality better (3) or uber (4)");
-    if (has_color && params->use_transparent_indices_for_black)
-        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_pack_image: use_transparent_indices_for_black is not implemented");
+    (void)has_color;
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
 
     crn::ImageView img;
@@ -648,18 +645,24 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
         // five phase kernels per chunk of blocks; the per-block state lives in ctx->d_state between them
         const uint32_t chunk_cap = 1u << 18;
         const uint32_t chunk = total < chunk_cap ? total : chunk_cap;
-        color_rc = ensure(ctx, &ctx->d_state, &ctx->d_state_cap, (size_t)chunk * sizeof(crn::Dxt1BlockState));
+        // try_alpha_as_black_optimization (crn_dxt1.cpp:2241-2244): only where 3-colour blocks are allowed at all
+        const bool black = params->use_transparent_indices_for_black && dp.use_alpha_blocks;
+        const size_t state_bytes = (((size_t)chunk * sizeof(crn::Dxt1BlockState)) + 255) & ~(size_t)255;
+        color_rc = ensure(ctx, &ctx->d_state, &ctx->d_state_cap, state_bytes + (black ? (size_t)chunk * 8 : 0));
         if (color_rc) return;
         crn::Dxt1BlockState* st = static_cast<crn::Dxt1BlockState*>(ctx->d_state);
+        unsigned long long* errs = black ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_state) + state_bytes) : nullptr;
         for (uint32_t first = 0; first < total; first += chunk) {
             const uint32_t count = total - first < chunk ? total - first : chunk;
             const int g = grid_for(ctx, count, crn::kPackWarpsPerCta, 8);
-            CRN_LAUNCH(crn::pack_color_phase_kernel<0>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
-            CRN_LAUNCH(crn::pack_color_phase_kernel<1>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
-            CRN_LAUNCH(crn::pack_color_phase_kernel<2>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
-            CRN_LAUNCH(crn::pack_color_phase_kernel<3>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
-            CRN_LAUNCH(crn::pack_color_phase_kernel<4>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs);
-            ctx->launches += 5;
+            for (int run = black ? 1 : 0; run <= (black ? 2 : 0); run++) {
+                CRN_LAUNCH(crn::pack_color_phase_kernel<0>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs, run, errs);
+                CRN_LAUNCH(crn::pack_color_phase_kernel<1>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs, run, errs);
+                CRN_LAUNCH(crn::pack_color_phase_kernel<2>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs, run, errs);
+                CRN_LAUNCH(crn::pack_color_phase_kernel<3>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs, run, errs);
+                CRN_LAUNCH(crn::pack_color_phase_kernel<4>, g, threads, 0, ctx->stream, img, dp, dxt1a, st, first, count, out, bpb, ofs, run, errs);
+                ctx->launches += 5;
+            }
         }
     };
 
@@ -719,8 +722,8 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     if (!params || params->struct_size != sizeof(crn_gpu_pack_params) || !d_blocks_rgba || !n_blocks || !d_cluster_offsets ||
         !d_cluster_blocks || !d_out || out_stride_bytes < 8 || (out_stride_bytes & 7) || (out_offset_bytes & 7))
         return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_dxt1_optimize_clusters: bad argument");
-    if (params->dxt_quality < 3 || params->dxt_quality > 4)
-        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_dxt1_optimize_clusters: dxt_quality must be better (3) or uber (4)");
+    if (params->dxt_quality > 4)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_dxt1_optimize_clusters: dxt_quality out of range");
     if (!n_clusters || !total_member_blocks) return CRN_GPU_OK;
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t P = (size_t)total_member_blocks * 16;
@@ -889,8 +892,8 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     *out = nullptr;
     if (format > CRN_GPU_FMT_DXN_YX || format == CRN_GPU_FMT_DXT3)
         return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_qdxt_init: format is not clustered (DXT3) or unknown");
-    if (params->dxt_quality < 3 || params->dxt_quality > 4)
-        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_qdxt_init: dxt_quality must be better (3) or uber (4)");
+    if (params->dxt_quality > 4)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_qdxt_init: dxt_quality out of range");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     crn_gpu_qdxt* q = new (std::nothrow) crn_gpu_qdxt();
     if (!q) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: out of host memory");

@@ -29,9 +29,11 @@ namespace crn {
 // probe tables (crn_dxt1.cpp:43-53)
 CRN_DEVICE_TABLE uint8_t g_uber_probe[15] = { 0, 1, 2, 3, 5, 7, 9, 10, 13, 15, 19, 27, 43, 59, 91 };
 CRN_DEVICE_TABLE uint8_t g_better_probe[10] = { 0, 1, 2, 3, 5, 9, 15, 19, 27, 43 };
+CRN_DEVICE_TABLE uint8_t g_normal_probe[5] = { 0, 1, 3, 5, 7 };
+CRN_DEVICE_TABLE uint8_t g_fast_probe[4] = { 0, 1, 2, 3 };
 
 struct Dxt1Params {
-    int quality;               // crn_dxt_quality, 3 (better) and 4 (uber) are implemented on device
+    int quality;               // crn_dxt_quality 0 superfast .. 4 uber (below better: evaluate_solution_fast, fewer probes / passes)
     int perceptual;
     int pixels_have_alpha;
     int use_alpha_blocks;
@@ -73,6 +75,8 @@ struct Dxt1Cfg {               // warp-uniform evaluation mode
     int wr, wg, wb;            // channel weights of color_distance (crn_color.h:720-745)
     bool gray;
     bool hc;                   // m_evaluate_hc (:2085)
+    bool fast;                 // quality < better: evaluate_solution_fast (:1594-1757) instead of _uber
+    bool perc;                 // m_perceptual (perceptual && !grayscale_sampling): scales the fast evaluator's axis by 8 / 24
 };
 
 __device__ __forceinline__ void unpack565(unsigned c, bool scaled, int& r, int& g, int& b)
@@ -153,12 +157,77 @@ __device__ __forceinline__ void dxt1_eval_loop(const SC* sc, int U, const int4 p
     }
 }
 
+// evaluate_solution_fast (crn_dxt1.cpp:1594-1757), lane-private: the selector of a colour comes from the position of its projection on the
+// endpoint axis between the palette entries' projections (NOT from the nearest entry), the error from color_distance to that entry.
+// which entry a colour takes: 4-colour block 0 / 2 / 3 / 1 along the axis, 3-colour block 0 / 2 / 1
+struct Dxt1FastAxis { int dirr, dirg, dirb, c0Point, halfPoint, c3Point, c02Point, c21Point; int c[4][3], m[3]; };
+__device__ __forceinline__ Dxt1FastAxis dxt1_fast_axis(const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt)
+{
+    Dxt1FastAxis A;
+    unpack565(lo, true, A.c[0][0], A.c[0][1], A.c[0][2]);
+    unpack565(hi, true, A.c[1][0], A.c[1][1], A.c[1][2]);
+    int vr = A.c[1][0] - A.c[0][0], vg = A.c[1][1] - A.c[0][1], vb = A.c[1][2] - A.c[0][2];
+    if (cfg.perc) { vr *= 8; vg *= 24; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        A.c[2][k] = (A.c[0][k] * 2 + A.c[1][k] + alt) / 3; A.c[3][k] = (A.c[1][k] * 2 + A.c[0][k] + alt) / 3;
+        A.m[k] = (A.c[0][k] + A.c[1][k] + alt) >> 1;
+    }
+    const int s0 = A.c[0][0] * vr + A.c[0][1] * vg + A.c[0][2] * vb, s1 = A.c[1][0] * vr + A.c[1][1] * vg + A.c[1][2] * vb;
+    const int s2 = A.c[2][0] * vr + A.c[2][1] * vg + A.c[2][2] * vb, s3 = A.c[3][0] * vr + A.c[3][1] * vg + A.c[3][2] * vb;
+    const int sm = A.m[0] * vr + A.m[1] * vg + A.m[2] * vb;
+    A.dirr = vr * 2; A.dirg = vg * 2; A.dirb = vb * 2;
+    A.c0Point = s1 + s3; A.halfPoint = s3 + s2; A.c3Point = s2 + s0;
+    A.c02Point = s0 + sm; A.c21Point = sm + s1;
+    return A;
+}
+__device__ __forceinline__ unsigned dxt1_fast_sel4(const Dxt1FastAxis& A, int r, int g, int b)
+{
+    const int dot = r * A.dirr + g * A.dirg + b * A.dirb;
+    return dot >= A.halfPoint ? (dot < A.c0Point ? 3u : 1u) : (dot < A.c3Point ? 0u : 2u);
+}
+__device__ __forceinline__ unsigned dxt1_fast_sel3(const Dxt1FastAxis& A, int r, int g, int b)
+{
+    const int dot = r * A.dirr + g * A.dirg + b * A.dirb;
+    return dot < A.c02Point ? 0u : (dot < A.c21Point ? 2u : 1u);
+}
+template <typename SC>
+__device__ __noinline__ void dxt1_eval_fast(SC* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt, unsigned long long& err, int& alpha)
+{
+    const Dxt1FastAxis A = dxt1_fast_axis(cfg, lo, hi, alt);
+    unsigned long long best = sc->best.err;              // m_trial_solution.m_error starts at the best's (:1598)
+    alpha = 0;
+    if (cfg.do4) {
+        unsigned long long te = 0;
+        for (int i = cfg.U - 1; i >= 0; i--) {
+            const int4 c = sc->cw[i];
+            const unsigned bi = dxt1_fast_sel4(A, c.x, c.y, c.z);
+            te += (unsigned long long)dxt1_dist(cfg, c.x, c.y, c.z, A.c[bi][0], A.c[bi][1], A.c[bi][2]) * (unsigned)c.w;
+            if (te >= best) break;
+        }
+        if (te < best) { best = te; alpha = 0; }
+    }
+    if (cfg.do3) {
+        unsigned long long te = 0;
+        for (int i = cfg.U - 1; i >= 0; i--) {
+            const int4 c = sc->cw[i];
+            const unsigned bi = dxt1_fast_sel3(A, c.x, c.y, c.z);
+            const int* p = bi == 2 ? A.m : A.c[bi];
+            te += (unsigned long long)dxt1_dist(cfg, c.x, c.y, c.z, p[0], p[1], p[2]) * (unsigned)c.w;
+            if (te >= best) break;
+        }
+        if (te < best) { best = te; alpha = 1; }
+    }
+    err = best;                                          // == the running best's error when neither block type improved: never accepted
+}
+
 // Lane-private evaluation of one candidate: evaluate_solution_uber / _hc_* without the bookkeeping
 // (crn_dxt1.cpp:1370-1561, :1759-1835).  err = min over allowed block types, alpha = 3-colour won.
 template <typename SC>
 __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
                                        unsigned long long& err, int& alpha)
 {
+    if (cfg.fast) { dxt1_eval_fast(sc, cfg, lo, hi, alt, err, alpha); return; }
     int r0, g0, b0, r1, g1, b1;
     unpack565(lo, true, r0, g0, b0);
     unpack565(hi, true, r1, g1, b1);
@@ -229,7 +298,11 @@ __device__ __noinline__ void dxt1_best_selectors(SC* sc, const Dxt1Cfg cfg)
     for (int ci = (int)lane_id(); ci < cfg.U; ci += 32) {
         unsigned s;
         if (sc->best.enforce) s = (unsigned)sc->best.enforced_sel;
-        else {
+        else if (cfg.fast) {           // the selectors evaluate_solution_fast recorded for the winner (:1656, :1694)
+            const Dxt1FastAxis A = dxt1_fast_axis(cfg, sc->best.lo, sc->best.hi, sc->best.alt_round);
+            const int4 c = sc->cw[ci];
+            s = sc->best.alpha_block ? dxt1_fast_sel3(A, c.x, c.y, c.z) : dxt1_fast_sel4(A, c.x, c.y, c.z);
+        } else {
             int r0, g0, b0, r1, g1, b1;
             unpack565(sc->best.lo, true, r0, g0, b0);
             unpack565(sc->best.hi, true, r1, g1, b1);
@@ -704,6 +777,7 @@ __device__ __forceinline__ Dxt1Cfg dxt1_make_cfg(const Dxt1Params& prm, int pixe
     const bool perceptual = prm.perceptual && !prm.grayscale_sampling;
     cfg.gray = !perceptual && prm.grayscale_sampling;
     cfg.wr = perceptual ? 8 : 1; cfg.wg = perceptual ? 25 : 1; cfg.wb = 1;
+    cfg.fast = prm.quality < 3; cfg.perc = perceptual;
     if (pixels_have_alpha || prm.force_alpha_blocks) { cfg.do4 = false; cfg.do3 = true; }
     else if (!prm.use_alpha_blocks) { cfg.do4 = true; cfg.do3 = false; }
     else { cfg.do4 = true; cfg.do3 = true; }
@@ -930,7 +1004,7 @@ __device__ __forceinline__ void dxt1_phase_setup(SC* sc, uint32_t px, const Dxt1
 template <typename SC>
 __device__ __forceinline__ void dxt1_phase_median4(SC* sc, const Dxt1Params& prm)
 {
-    if (sc->stage != 0) return;
+    if (sc->stage != 0 || prm.quality < 3) return;      // try_median4 only from better up (:765-771)
     const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
     V3 mean, low_color, high_color;
     mean.x = sc->mean[0]; mean.y = sc->mean[1]; mean.z = sc->mean[2];
@@ -956,8 +1030,11 @@ __device__ __forceinline__ void dxt1_phase_passes(SC* sc, const Dxt1Params& prm)
         int num_passes_o, probe_range;
         float dist_per_trial = .015625f;
         // probe tables (:43-53) packed as bytes
-        if (quality >= 4) { probe_range = 15; num_passes_o = 4; }
-        else { probe_range = 10; num_passes_o = 2; }
+        const uint8_t* probe_tab;
+        if (quality >= 4) { probe_tab = g_uber_probe; probe_range = 15; num_passes_o = 4; }
+        else if (quality == 3) { probe_tab = g_better_probe; probe_range = 10; num_passes_o = 2; }
+        else if (quality == 2) { probe_tab = g_normal_probe; probe_range = 5; num_passes_o = 2; dist_per_trial = .027063293f; }
+        else { probe_tab = g_fast_probe; probe_range = 4; num_passes_o = quality == 1 ? 2 : 1; dist_per_trial = .027063293f; }
 
         float sx = axis.x * dist_per_trial, sy = axis.y * dist_per_trial, sz = axis.z * dist_per_trial;
         sx *= 31.0f; sy *= 63.0f; sz *= 31.0f;
@@ -985,14 +1062,14 @@ __device__ __forceinline__ void dxt1_phase_passes(SC* sc, const Dxt1Params& prm)
                 const int i = (t + 1) >> 1, s = (t == 0) ? 1 : ((t & 1) ? 0 : 1);
                 int packed = -1, prev = -1;
                 if (t < nseq) {
-                    const int x = quality >= 4 ? g_uber_probe[min(i, 14)] : g_better_probe[min(i, 9)];
+                    const int x = probe_tab[min(i, probe_range - 1)];
                     const float fx = (float)x;
                     const float ax = s ? sx : -sx, ay = s ? sy : -sy, az = s ? sz : -sz;
                     const float px_ = ix + ax * fx, py_ = iy + ay * fx, pz_ = iz + az * fx;
                     packed = clampi((int)floorf(pz_), 0, 31) | (clampi((int)floorf(py_), 0, 63) << 5) | (clampi((int)floorf(px_), 0, 31) << 11);
                     const bool has_prev = s ? (i >= 1) : (i >= 2);
                     if (has_prev) {
-                        const int xp = quality >= 4 ? g_uber_probe[i - 1] : g_better_probe[i - 1];
+                        const int xp = probe_tab[i - 1];
                         const float fp = (float)xp;
                         const float qx = ix + ax * fp, qy = iy + ay * fp, qz = iz + az * fp;
                         prev = clampi((int)floorf(qz), 0, 31) | (clampi((int)floorf(qy), 0, 63) << 5) | (clampi((int)floorf(qx), 0, 31) << 11);
@@ -1023,9 +1100,9 @@ __device__ __forceinline__ void dxt1_phase_passes(SC* sc, const Dxt1Params& prm)
                                 __shfl_sync(CRN_FULL_MASK, my_a, src));
                 }
             }
-            // lattice neighbours (:905-1016); quality >= Normal always holds here
+            // lattice neighbours (:905-1016), from normal quality up
 #pragma unroll 1
-            for (int which = 0; which < 2; which++) {
+            for (int which = 0; which < 2 && quality >= 2; which++) {
                 dxt1_live_neighbours(sc, cfg, which, 26, [](int idx, int& dr, int& dg, int& db) {
                     const int n = idx < 13 ? idx : idx + 1;   // g_adjacency (:489-522): x fastest, centre skipped
                     dr = n % 3 - 1; dg = (n / 3) % 3 - 1; db = n / 9 - 1;
@@ -1050,7 +1127,7 @@ __device__ __forceinline__ void dxt1_phase_post(SC* sc, const Dxt1Params& prm)
     const Dxt1Cfg cfg = dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U);
     const int quality = prm.quality;
     const int U = sc->U;
-    if (sc->best.err && !sc->pixels_have_alpha) {
+    if (quality >= 2 && sc->best.err && !sc->pixels_have_alpha) {      // :1030
         bool choose_solid_block = false;
         dxt1_best_selectors(sc, cfg);
         bool all_equal = true;

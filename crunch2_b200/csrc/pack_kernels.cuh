@@ -93,10 +93,14 @@ __device__ __forceinline__ void state_store(Dxt1BlockState* g, const Dxt1Scratch
 
 // PHASE: 0 set-up, 1 LBG (try_median4), 2 sweep passes, 3 post passes, 4 finish (writes the element).
 // Blocks [first, first + count) of the image; states[i] belongs to block first + i.
+// black: try_alpha_as_black_optimization (crn_dxt1.cpp:2001-2079, :2241-2244; cCRNCompFlagUseTransparentIndicesForBlack) as a second run of
+// the five phases.  1 = the normal run, which also records its error per block in err_buf; 2 = the run with every near-black pixel
+// (r, g, b <= 4) made transparent, for the blocks the reference retries (no transparent pixel of their own, some but not all unique colours
+// near black): its element replaces the first one when its error over ALL 16 pixels -- black standing for the transparent index -- is lower.
 template <int PHASE>
 __global__ void __launch_bounds__(kPackWarpsPerCta * 32, CRN_COLOR_MIN_CTAS)
 pack_color_phase_kernel(ImageView img, Dxt1Params prm, int dxt1a, Dxt1BlockState* __restrict__ states, uint32_t first, uint32_t count,
-                        uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs)
+                        uint8_t* __restrict__ out, uint32_t bytes_per_block, uint32_t elem_ofs, int black, unsigned long long* __restrict__ err_buf)
 {
     __shared__ __align__(16) Dxt1Scratch scratch[kPackWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5;
@@ -104,24 +108,57 @@ pack_color_phase_kernel(ImageView img, Dxt1Params prm, int dxt1a, Dxt1BlockState
     for (uint32_t i = blockIdx.x * kPackWarpsPerCta + warp; i < count; i += gridDim.x * kPackWarpsPerCta) {
         const uint32_t b = first + i;
         uint32_t px = 0;
-        if (PHASE == 0 || PHASE == 4) px = fetch_block_pixel(img, b % img.blocks_x, b / img.blocks_x);
+        if (PHASE == 0 || PHASE == 4) px = fetch_block_pixel(img, b % img.blocks_x, b / img.blocks_x);      // lanes 0..15: pixel 4y + x (edge clamped)
+        const bool is_dark = (px & 0xffu) <= 4u && ((px >> 8) & 0xffu) <= 4u && ((px >> 16) & 0xffu) <= 4u;
         if (PHASE == 0) {
             int pha = 0;
             if (dxt1a)   // crn_dxt_image.cpp:1440-1451
                 pha = __ballot_sync(CRN_FULL_MASK, lane_id() < 16 && (px >> 24) < prm.alpha_threshold) != 0;
-            dxt1_phase_setup(sc, px, prm, pha);
+            if (black == 2) {
+                // unique colours of the block and how many of them are near black (:2003-2016)
+                const unsigned lanes16 = 0xffffu;
+                unsigned peers = 0;
+                if (lane_id() < 16) peers = __match_any_sync(lanes16, px | 0xFF000000u);
+                const bool leader = lane_id() < 16 && (unsigned)(__ffs((int)peers) - 1) == lane_id();
+                const unsigned uniq = __popc(__ballot_sync(CRN_FULL_MASK, leader)), uniq_dark = __popc(__ballot_sync(CRN_FULL_MASK, leader && is_dark));
+                if (pha || !uniq_dark || uniq_dark == uniq) {
+                    if (lane_id() == 0) sc->stage = 3;                   // not retried: the later phases and the comparison skip this block
+                    __syncwarp();
+                } else dxt1_phase_setup(sc, is_dark ? (px & 0x00ffffffu) : px, prm, 1);
+            } else dxt1_phase_setup(sc, px, prm, pha);
             state_store(&states[i], sc);
         } else {
             state_load(sc, &states[i]);
+            if (sc->stage == 3) { __syncwarp(); continue; }
             if (sc->stage == 0 || PHASE == 4) dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, sc->pixels_have_alpha, sc->U));
             if (PHASE == 1) dxt1_phase_median4(sc, prm);
             if (PHASE == 2) dxt1_phase_passes(sc, prm);
             if (PHASE == 3) dxt1_phase_post(sc, prm);
             if (PHASE < 4) {
                 if (sc->stage == 0) state_store(&states[i], sc);
-            } else {
+            } else if (black != 2) {
                 const unsigned long long elem = dxt1_phase_finish(sc, px, prm);
-                if (lane_id() == 0)
+                if (lane_id() == 0) {
+                    *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = elem;
+                    if (black == 1) err_buf[i] = sc->stage == 2 ? 0ull : sc->best.err;
+                }
+            } else if (sc->stage != 3) {
+                const unsigned long long elem = dxt1_phase_finish(sc, is_dark ? (px & 0x00ffffffu) : px, prm);
+                // error of the retried block over all 16 pixels against its 3-colour palette, index 3 = black (:2046-2068; get_block_colors3)
+                const Dxt1Cfg cfg = dxt1_make_cfg(prm, 1, sc->U);
+                int r0, g0, b0, r1, g1, b1;
+                unpack565((unsigned)(elem & 0xffff), true, r0, g0, b0);
+                unpack565((unsigned)((elem >> 16) & 0xffff), true, r1, g1, b1);
+                unsigned long long te = 0;
+                if (lane_id() < 16) {
+                    const unsigned sel = (unsigned)(elem >> (32 + 2 * lane_id())) & 3u;
+                    const int pr = sel == 0 ? r0 : (sel == 1 ? r1 : (sel == 2 ? (r0 + r1) >> 1 : 0));
+                    const int pg = sel == 0 ? g0 : (sel == 1 ? g1 : (sel == 2 ? (g0 + g1) >> 1 : 0));
+                    const int pb = sel == 0 ? b0 : (sel == 1 ? b1 : (sel == 2 ? (b0 + b1) >> 1 : 0));
+                    te = dxt1_dist(cfg, (int)(px & 0xffu), (int)((px >> 8) & 0xffu), (int)((px >> 16) & 0xffu), pr, pg, pb);
+                }
+                te = warp_sum_u64(te);
+                if (lane_id() == 0 && te < err_buf[i])
                     *reinterpret_cast<unsigned long long*>(out + (size_t)b * bytes_per_block + elem_ofs) = elem;
             }
         }

@@ -183,3 +183,12 @@ def test_color_clusters_many_unique_colours(simctx, port):
     run_color(simctx, port, blocks, offs, members, q=4, perc=1, uab=0)      # hc evaluator
     run_color(simctx, port, blocks, offs, members, q=4, perc=0, uab=1)      # both block types
     run_color(simctx, port, blocks, offs, members, q=3, perc=1, uab=1)
+
+
+@pytest.mark.parametrize("q", [0, 1, 2, 3])
+def test_color_clusters_lower_quality_levels_match_port(simctx, port, q):
+    """the N-pixel optimiser below uber quality: evaluate_solution_fast for 0-2 (crn_dxt1.cpp:1594-1757), fewer probes / passes (:715-771)"""
+    blocks = blockgen.block_family("smooth", 60, 31 + q)
+    offs, members = make_clusters(60, [1, 2, 3, 5, 8, 13], 40 + q)
+    run_color(simctx, port, blocks, offs, members, q=q, perc=1, uab=0)
+    run_color(simctx, port, blocks, offs, members, q=q, perc=0, uab=1)

@@ -92,3 +92,19 @@ def test_gpu_full_size_properties(gpu_ctx, port):
     selv = sel[..., 0] | (sel[..., 1] << 1)
     three = lo <= hi
     assert not (selv[three] == 3).any()      # opaque input: index 3 of a 3-colour block is never selected
+
+
+@pytest.mark.parametrize("q", [0, 1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 3])
+def test_gpu_low_quality_levels(gpu_ctx, port, q, fmt):
+    """row a6 on the device: evaluate_solution_fast and the superfast / fast / normal flows, bit-exact vs the port and the reference"""
+    from test_sim_kernels import check_low_quality
+    check_low_quality(gpu_ctx, port, q, fmt)
+
+
+@pytest.mark.parametrize("q", [1, 3, 4])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_gpu_transparent_indices_for_black(gpu_ctx, port, q, fmt):
+    """row a8 on the device: try_alpha_as_black_optimization"""
+    from test_sim_kernels import check_transparent_for_black
+    check_transparent_for_black(gpu_ctx, port, q, fmt)

@@ -164,4 +164,21 @@ def test_clustered_dds_rejects_unsupported(simctx):
     with pytest.raises(crn.CrnGpuError):
         simctx.qdxt_init(2, [img])                                   # DXT3 is never clustered
     with pytest.raises(crn.CrnGpuError):
-        simctx.qdxt_init(0, [img], crn.PackParams(dxt_quality=1))    # only better / uber
+        simctx.qdxt_init(0, [img], crn.PackParams(dxt_quality=7))    # crn_dxt_quality is 0 .. 4
+
+
+@pytest.mark.parametrize("dxt_quality", [0, 2])
+def test_clustered_dds_lower_dxt_quality(sim, ref, dxt_quality):
+    """m_dxt_quality below better reaches the per-cluster optimiser through qdxt1_params (crn_qdxt1.cpp:556-575): evaluate_solution_fast"""
+    ctx = crn.Context(0, lib=sim)
+    ctx.set_vq_mode(True)
+    img = blockgen.smooth_image(96, 96, 21, alpha=False)
+    qd = ctx.qdxt_init(GPUFMT["DXT1"], [img], crn.PackParams(dxt_quality=dxt_quality))
+    out = qd.pack(128)
+    qd.close()
+    dds, _, _ = helpers.ref_compress(ref, [[img]], helpers.CRN_FMT["DXT1"], file_type=1, quality=128, threads=0, dxt_quality=dxt_quality)
+    ref_data = np.frombuffer(quality.dds_payload(dds), np.uint8)
+    src = quality.image_to_blocks(img)
+    a = quality.decode_blocks(out.tobytes(), 0); b = quality.decode_blocks(ref_data.tobytes(), 0)
+    assert_within_tolerance([(quality.psnr(a, src, [0, 1, 2]), quality.psnr(b, src, [0, 1, 2]))], quality.lzma_bits(out.tobytes()), quality.lzma_bits(ref_data.tobytes()), 96 * 96)
+    ctx.close()
