@@ -744,9 +744,11 @@ def run_clustered(args, ctx, ext, dev, wl, barrier, world):
            # (profiles/r1y_ncu_full_summaries.txt): the 61 B/pixel cluster workspace (hash table, unique colours) on top of the 72 B/block
            "traffic": 748257280 + 621472000,
            "all_elements_ms": [float(x) for x in np.mean(np.array(opt_ms), axis=0)],
+           "issue": {"candidates": int(info["opt_candidates"][0]), "colour_evals": int(info["opt_colour_evals"][0]), "palette_entries": int(info["opt_palette_entries"][0]),
+                     "clusters": int(info["endpoint_clusters"][0])},
            "note": "issue-slot bound integer search (SURVEY 8(d)): algorithmic HBM bytes are 64 B pixels in + 8 B element out per block; "
                    "see DESIGN.md section 6 and profiles/ for the pipe utilisation that actually bounds it"}
-    extra = {"step_ms": [round(t, 2) for t in times], "qdxt": {k: v for k, v in info.items() if k != "endpoint_opt_ms"}, "out_md5": __import__("hashlib").md5(host_out.tobytes()).hexdigest(),
+    extra = {"step_ms": [round(t, 2) for t in times], "qdxt": {k: v for k, v in info.items() if k != "endpoint_opt_ms" and not k.startswith("opt_")}, "out_md5": __import__("hashlib").md5(host_out.tobytes()).hexdigest(),
              "e2e_api": "crn_compress(const crn_comp_params&, crn_uint32&, crn_uint32*, float*) exported by crunch2_b200/libcrnlib_b200.so (cCRNFileTypeDDS, host pixels in, .dds bytes out)",
              "_ours_payload": host_out}
     return float(sum(times)), e2e_s, launches, sampler, top, flush, extra
@@ -916,6 +918,20 @@ def main():
             "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650", "note": top["note"],
             "blocks_per_s": top["blocks"] / (top["ms"] / 1e3), "ms": top["ms"]}
+    if top.get("issue"):
+        # The bound that applies: integer issue rate.  One candidate evaluation over U unique colours and P palette entries is
+        # U * (11 P + 1) integer operations; the kernel counts its own evaluations (crn_gpu_qdxt_info::opt_*), the peak is SMs x 128 lanes x clock.
+        iss = top["issue"]
+        sm_mhz = float(sampler.summary().get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        sms = int(torch.cuda.get_device_properties(dev).multi_processor_count)
+        peak_ops = sms * 128 * sm_mhz * 1e6
+        ops = iss["colour_evals"] * (11 * iss["palette_entries"] + 1)
+        roof["issue"] = {"bound": "issue", "candidates": iss["candidates"], "candidates_per_cluster": iss["candidates"] / max(1, iss["clusters"]),
+                         "candidates_per_block": iss["candidates"] / max(1, top["blocks"]), "colour_evals": iss["colour_evals"], "palette_entries": iss["palette_entries"],
+                         "int_ops": ops, "achieved": ops / (top["ms"] / 1e3) / 1e12, "peak": peak_ops / 1e12, "unit": "Tint-op/s", "frac": ops / (top["ms"] / 1e3) / peak_ops,
+                         "peak_source": "%d SMs x 128 lanes x %.0f MHz (median SM clock sampled during the timed region)" % (sms, sm_mhz),
+                         "note": "algorithmic count U*(11P+1) per evaluation, full U for every candidate: the kernel's lane-private early-out skips part of it, "
+                                 "so frac can exceed the executed-instruction utilisation ncu reports (profiles/)"}
     if "all_elements_ms" in top:
         roof["all_elements_ms"] = top["all_elements_ms"]
     out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -707,7 +707,8 @@ class _LevelDesc(ctypes.Structure):
 class _QdxtInfo(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("n_blocks", ctypes.c_uint32), ("num_elements", ctypes.c_uint32),
                 ("endpoint_codebook_size", ctypes.c_uint32 * 3), ("max_selector_clusters", ctypes.c_uint32 * 3),
-                ("endpoint_clusters", ctypes.c_uint32 * 3), ("selector_clusters", ctypes.c_uint32 * 3), ("endpoint_opt_ms", ctypes.c_float * 3)]
+                ("endpoint_clusters", ctypes.c_uint32 * 3), ("selector_clusters", ctypes.c_uint32 * 3), ("endpoint_opt_ms", ctypes.c_float * 3),
+                ("opt_candidates", ctypes.c_uint64 * 3), ("opt_colour_evals", ctypes.c_uint64 * 3), ("opt_palette_entries", ctypes.c_uint32 * 3), ("reserved", ctypes.c_uint32)]
 
 
 class Qdxt:
@@ -749,7 +750,8 @@ class Qdxt:
         ne = inf.num_elements
         return dict(n_blocks=inf.n_blocks, num_elements=ne, endpoint_codebook_size=list(inf.endpoint_codebook_size)[:ne],
                     max_selector_clusters=list(inf.max_selector_clusters)[:ne], endpoint_clusters=list(inf.endpoint_clusters)[:ne],
-                    selector_clusters=list(inf.selector_clusters)[:ne], endpoint_opt_ms=list(inf.endpoint_opt_ms)[:ne])
+                    selector_clusters=list(inf.selector_clusters)[:ne], endpoint_opt_ms=list(inf.endpoint_opt_ms)[:ne],
+                    opt_candidates=list(inf.opt_candidates)[:ne], opt_colour_evals=list(inf.opt_colour_evals)[:ne], opt_palette_entries=list(inf.opt_palette_entries)[:ne])
 
     def close(self):
         if getattr(self, "_q", None):

@@ -24,7 +24,11 @@ struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays 
     uint16_t probe[2][32];
     uint16_t packed[64];
     uint32_t hist[64], cursor[64];     // eval-colour ordering: counts / write cursors per magnitude class
+    uint32_t n_eval[32];               // per lane: candidates evaluated (dxt1_eval calls) and unique colours they range over (sum of U):
+    unsigned long long n_cu[32];       // the algorithmic work of SURVEY 8(d), U * (11 P + 1) integer ops per evaluation
 };
+// found by dxt1_eval through argument-dependent lookup; the 4x4-block scratch type has no counters (generic no-op in dxt1_opt.cuh)
+__device__ __forceinline__ void dxt1_count_eval(Dxt1ClusterScratch* sc, int U) { sc->n_eval[lane_id()]++; sc->n_cu[lane_id()] += (unsigned)U; }
 
 struct ClusterHashEntry { uint32_t key, first_inv, count, uidx; };   // first_inv = ~(index of first appearance)
 
@@ -164,11 +168,22 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
     __shared__ Dxt1ClusterScratch scratch[kClusterWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     Dxt1ClusterScratch* sc = &scratch[warp];
+    sc->n_eval[lane] = 0; sc->n_cu[lane] = 0;
+    __syncwarp();
     for (;;) {
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(next_cluster, 1u);
         c = __shfl_sync(CRN_FULL_MASK, c, 0);
-        if (c >= n_clusters) break;
+        if (c >= n_clusters) {
+            // work counters of this warp -> the two 64-bit words behind the work-stealing counter (next_cluster + 16 / + 18)
+            unsigned long long ne = sc->n_eval[lane], nc = sc->n_cu[lane];
+            ne = warp_sum_u64(ne); nc = warp_sum_u64(nc);
+            if (lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 16), ne);
+                atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 18), nc);
+            }
+            break;
+        }
         if (order) c = order[c];                             // largest clusters first: the work-stealing tail is one small cluster, not one huge one
         const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
         const uint32_t N = nb * 16, P = b0 * 16;

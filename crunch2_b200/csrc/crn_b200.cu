@@ -239,6 +239,7 @@ struct crn_qdxt_element {
     std::vector<uint8_t> cat;
     cudaEvent_t ev_opt[2];            // brackets the endpoint optimisation of the last pack()
     float endpoint_opt_ms;
+    uint64_t opt_stats[3];            // of the last pack(): candidates evaluated, unique colours they ranged over (sum of U), palette entries per evaluation
     int vq_exact;                     // copied from the parent context at init
     int rc;
 };
@@ -1005,6 +1006,14 @@ int crn_gpu_qdxt_pack(crn_gpu_qdxt* q, uint32_t quality_level, void* dst, int ds
         const int r = qdxt_pack_element(q, e, quality_level);
         if (!r && cudaStreamSynchronize(e.ctx->stream) != cudaSuccess) return set_err(e.ctx, CRN_GPU_ERR_CUDA, "crn_gpu_qdxt_pack: element stream");
         if (!r) cudaEventElapsedTime(&e.endpoint_opt_ms, e.ev_opt[0], e.ev_opt[1]);
+        e.opt_stats[0] = e.opt_stats[1] = e.opt_stats[2] = 0;
+        if (!r && e.kind == 0 && e.ctx->d_cluster_ws) {      // work counters the colour optimiser left behind its work-stealing counter
+            uint64_t st[2] = { 0, 0 };
+            if (cudaMemcpy(st, static_cast<uint8_t*>(e.ctx->d_cluster_ws) + 64, 16, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                e.opt_stats[0] = st[0]; e.opt_stats[1] = st[1];
+                e.opt_stats[2] = e.use_alpha_blocks ? 7 : 4;     // 4-colour palette, plus the 3-colour one where both block types are tried
+            }
+        }
         return r;
     });
     if (rc) return rc;
@@ -1025,6 +1034,7 @@ int crn_gpu_qdxt_get_info(const crn_gpu_qdxt* q, crn_gpu_qdxt_info* info)
         info->endpoint_clusters[i] = q->el[i].endpoint_clusters;
         info->selector_clusters[i] = q->el[i].selector_clusters;
         info->endpoint_opt_ms[i] = q->el[i].endpoint_opt_ms;
+        info->opt_candidates[i] = q->el[i].opt_stats[0]; info->opt_colour_evals[i] = q->el[i].opt_stats[1]; info->opt_palette_entries[i] = (uint32_t)q->el[i].opt_stats[2];
     }
     return CRN_GPU_OK;
 }); }

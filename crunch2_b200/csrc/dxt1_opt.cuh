@@ -221,12 +221,15 @@ __device__ __noinline__ void dxt1_eval_fast(SC* sc, const Dxt1Cfg cfg, unsigned 
     err = best;                                          // == the running best's error when neither block type improved: never accepted
 }
 
+template <typename SC> __device__ __forceinline__ void dxt1_count_eval(SC*, int) {}      // work counters: only the cluster scratch has them
+
 // Lane-private evaluation of one candidate: evaluate_solution_uber / _hc_* without the bookkeeping
 // (crn_dxt1.cpp:1370-1561, :1759-1835).  err = min over allowed block types, alpha = 3-colour won.
 template <typename SC>
 __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
                                        unsigned long long& err, int& alpha)
 {
+    dxt1_count_eval(sc, cfg.U);
     if (cfg.fast) { dxt1_eval_fast(sc, cfg, lo, hi, alt, err, alpha); return; }
     int r0, g0, b0, r1, g1, b1;
     unpack565(lo, true, r0, g0, b0);

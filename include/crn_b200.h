@@ -197,6 +197,11 @@ typedef struct crn_gpu_qdxt_info {
     uint32_t endpoint_clusters[3];         /* of the last pack() */
     uint32_t selector_clusters[3];
     float endpoint_opt_ms[3];              /* device time of the per-cluster endpoint optimisation kernels of the last pack() */
+    /* algorithmic work of the colour element's optimiser in the last pack(): candidate endpoint pairs evaluated, the unique
+     * colours they ranged over (sum of U over the evaluations) and the palette entries P per evaluation: integer ops = colour_evals * (11 P + 1) */
+    uint64_t opt_candidates[3], opt_colour_evals[3];
+    uint32_t opt_palette_entries[3];
+    uint32_t reserved;
 } crn_gpu_qdxt_info;
 CRN_API int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_params* params,
                               const crn_gpu_level_desc* levels, uint32_t num_levels, int pixels_on_host, crn_gpu_qdxt** out);

@@ -60,9 +60,7 @@ def test_bad_arguments_are_rejected(sim):
     with pytest.raises(crn.CrnGpuError) as e:
         ctx.pack_image(99, img)
     assert e.value.status == -2
-    with pytest.raises(crn.CrnGpuError) as e:
-        ctx.pack_image(crn.FMT_DXT1, img, crn.PackParams(dxt_quality=1))
-    assert e.value.status == -4
+    assert ctx.pack_image(crn.FMT_DXT1, img, crn.PackParams(dxt_quality=1)).size == 8 * ((img.shape[0] + 3) // 4) * ((img.shape[1] + 3) // 4)   # every crn_dxt_quality is implemented
     with pytest.raises(crn.CrnGpuError) as e:
         ctx.pack_image(crn.FMT_DXT1, img, crn.PackParams(dxt_quality=9))
     assert e.value.status == -2
