@@ -197,6 +197,8 @@ def _declare(lib):
     lib.crn_gpu_dds_get_desc.argtypes = [vp, u32, ctypes.POINTER(_DdsDesc)]
     lib.crn_gpu_dds_to_images.argtypes = [vp, vp, u32, ctypes.POINTER(vp), u32, ctypes.POINTER(_DdsDesc)]
     lib.crn_gpu_convert_pixels.argtypes = [vp, vp, u32, u32, u32, u32]
+    lib.crn_gpu_pool_mallocs.argtypes = [vp]
+    lib.crn_gpu_pool_mallocs.restype = u64
     lib.crn_gpu_set_vq_mode.argtypes = [vp, ctypes.c_int]
     lib.crn_gpu_set_vq_mode.restype = None
     lib.crn_gpu_set_progress.argtypes = [vp, vp, vp]
@@ -264,6 +266,11 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.crn_gpu_launch_count(self._ctx))
+
+    @property
+    def pool_mallocs(self):
+        """cudaMalloc calls of the context's buffer pool so far (stands still in steady state)"""
+        return int(self._lib.crn_gpu_pool_mallocs(self._ctx))
 
     def set_vq_mode(self, exact_member_order):
         """crn_gpu_set_vq_mode: True = the reference's member-order float sums bit for bit (slow, verification); False = single-launch frontier splits."""

@@ -59,6 +59,7 @@ struct crn_gpu_ctx {
     struct PoolBlock { void* p; size_t cap; };
     std::vector<PoolBlock>* pool;
     std::vector<PoolBlock>* pin_pool;    // pinned host staging blocks of the dxt_hc pipeline, cached like the device pool
+    uint64_t pool_mallocs;               // cudaMalloc calls made by pool_alloc since creation (crn_gpu_pool_mallocs): 0 growth in steady state
 };
 
 namespace {
@@ -107,9 +108,21 @@ int ensure(crn_gpu_ctx* ctx, void** p, size_t* cap, size_t need)
 }
 
 // device buffers of the clustered path: best fit from the context's cache (at most 2x oversize), else cudaMalloc
+// Requests are rounded up to size classes (eight per power of two above 64 KiB, i.e. at most 12.5 % slack): the trials of a bitrate search ask
+// for slightly different sizes every time (codebook sizes change with the quality level), and exact-size blocks would never be reused.
+size_t pool_size_class(size_t bytes)
+{
+    if (bytes <= (64u << 10)) return (bytes + 4095) & ~(size_t)4095;
+    size_t p2 = 64u << 10;
+    while (p2 * 2 <= bytes) p2 *= 2;
+    const size_t step = p2 / 8;
+    return ((bytes + step - 1) / step) * step;
+}
+
 cudaError_t pool_alloc(crn_gpu_ctx* ctx, void** out, size_t bytes, size_t* cap_out)
 {
     if (!bytes) bytes = 256;
+    bytes = pool_size_class(bytes);
     if (ctx->pool) {
         int best = -1;
         for (size_t i = 0; i < ctx->pool->size(); i++) {
@@ -122,6 +135,7 @@ cudaError_t pool_alloc(crn_gpu_ctx* ctx, void** out, size_t bytes, size_t* cap_o
             return cudaSuccess;
         }
     }
+    ctx->pool_mallocs++;
     cudaError_t ce = cudaMalloc(out, bytes);
     if (ce != cudaSuccess && ctx->pool && !ctx->pool->empty()) {       // give the cache back and retry once
         for (auto& b : *ctx->pool) cudaFree(b.p);
@@ -138,6 +152,7 @@ cudaError_t pool_alloc(crn_gpu_ctx* ctx, void** out, size_t bytes, size_t* cap_o
 void* pin_alloc(crn_gpu_ctx* ctx, size_t bytes, size_t* cap_out)
 {
     if (!bytes) bytes = 256;
+    bytes = pool_size_class(bytes);
     if (ctx->pin_pool) {
         int best = -1;
         for (size_t i = 0; i < ctx->pin_pool->size(); i++) {
@@ -570,6 +585,14 @@ int crn_gpu_synchronize(crn_gpu_ctx* ctx)
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CRN_GPU_OK;
 }); }
+
+uint64_t crn_gpu_pool_mallocs(const crn_gpu_ctx* ctx)
+{
+    if (!ctx) return 0;
+    uint64_t n = ctx->pool_mallocs;
+    for (int i = 0; i < 3; i++) if (ctx->child[i]) n += ctx->child[i]->pool_mallocs;
+    return n;
+}
 
 void crn_gpu_set_vq_mode(crn_gpu_ctx* ctx, int exact_member_order)
 {
@@ -1363,7 +1386,9 @@ void crn_gpu_default_hc_params(crn_gpu_hc_params* p)
     p->shard_rank = 0; p->shard_count = 1; p->exchange = nullptr; p->exchange_user = nullptr;
 }
 
-int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out)
+}  // extern "C"
+// crn_gpu_hc_compress with the quality-independent state (tile pass, training sets) kept in *prep across calls on the same blocks
+static int hc_compress_prepared(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out, HcPrepared* prep)
 { return crn_guard(ctx, [&]() -> int {
     if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
     if (out) *out = nullptr;
@@ -1379,13 +1404,19 @@ int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const
     memset(&H->info, 0, sizeof(H->info));
     H->info.struct_size = sizeof(H->info);
     int rc;
-    try { rc = hc_compress_impl(ctx, params, blocks_rgba, blocks_on_host, H); }
+    try { rc = hc_compress_impl(ctx, params, blocks_rgba, blocks_on_host, H, prep); }
     catch (const std::bad_alloc&) { rc = set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_hc_compress: out of host memory"); }
     ctx->d_cluster_flags = nullptr; ctx->d_cluster_order = nullptr;
     if (rc) { delete H; return rc; }
     *out = H;
     return CRN_GPU_OK;
 }); }
+
+extern "C" {
+int crn_gpu_hc_compress(crn_gpu_ctx* ctx, const crn_gpu_hc_params* params, const void* blocks_rgba, int blocks_on_host, crn_gpu_hc** out)
+{
+    return hc_compress_prepared(ctx, params, blocks_rgba, blocks_on_host, out, nullptr);
+}
 
 int crn_gpu_hc_get_info(const crn_gpu_hc* hc, crn_gpu_hc_info* info)
 { return crn_guard(nullptr, [&]() -> int {
@@ -1619,7 +1650,9 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
     const bool trace = getenv("CRN_B200_TRACE") != nullptr;
     auto wall_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     if (trace) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[crn_b200] compress_crn: upload + block gather %.1f ms\n", wall_ms() - t_begin); }
-    // one crn_comp::compress_pass at a quality level: quantise, write, report bits per texel
+    // one crn_comp::compress_pass at a quality level: quantise, write, report bits per texel.  The tile pass and the sorted training sets do
+    // not depend on the quality level: computed by the first pass, kept in `prepared` for the other trials of a search.
+    HcPrepared prepared;
     auto pass = [&](uint32_t quality, void** file, uint32_t* size, float* bitrate) -> int {
         const double tp0 = wall_ms();
         crn_gpu_crn_params q = *p;
@@ -1629,7 +1662,7 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         if (r) return r;
         if (p->shard_count > 1) { qhp.shard_rank = p->shard_rank; qhp.shard_count = p->shard_count; qhp.exchange = p->exchange; qhp.exchange_user = p->exchange_user; }
         crn_gpu_hc* H = nullptr;
-        r = crn_gpu_hc_compress(ctx, &qhp, d_blocks.p, 0, &H);
+        r = hc_compress_prepared(ctx, &qhp, d_blocks.p, 0, &H, &prepared);
         if (r) return r;
         const double tp1 = wall_ms();
         r = crn_gpu_crn_write(&q, &qhp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),

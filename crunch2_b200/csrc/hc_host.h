@@ -260,24 +260,47 @@ struct crn_gpu_hc {
 
 namespace {
 
-// a13 front half: the (component, tile) training vectors, compacted on the device into d_tvec (what the nearest-codebook
-// search reads afterwards), sorted, merged and quantised.  nvcc build: six / two stable LSD radix passes over the float bit
-// patterns (cub) + run heads + scan, never leaving the device; emulation build: the same on the host.
+// Quality-independent products of one dxt_hc call: the tile pass (a12) and, per endpoint kind, the sorted unique weighted training vectors
+// (a13 front half).  crn_comp restarts from pixels on every trial of a bitrate search (crn_texture_comp.cpp:120-262 -> crn_comp::compress_pass);
+// none of this depends on the quality level, so crn_gpu_compress_crn keeps one HcPrepared across the trials.
+template <int D> struct HcTrainingSet {
+    bool valid = false;
+    HcBuf d_tvec, d_uv, d_uw;                 // tile vectors (what the nearest-codebook search reads), unique vectors + weights
+    uint32_t n_unique = 0;
+    std::vector<float> uv; std::vector<uint32_t> uw;     // emulation build: the unique set on the host
+};
+struct HcPrepared {
+    bool valid = false;
+    uint32_t n = 0, num_tiles = 0;
+    HcBuf d_enc, d_tile, d_npix, d_pixofs, d_vpix, d_cvec, d_avec, d_used;
+    std::vector<uint8_t> h_npix, h_pixofs, h_enc;
+    std::vector<uint32_t> h_tile, used_slots, slot_rank;
+    HcTrainingSet<6> ts6;
+    HcTrainingSet<2> ts2;
+};
+
+// a13 front half: the (component, tile) training vectors, compacted on the device into ts.d_tvec (what the nearest-codebook
+// search reads afterwards), sorted and merged (once per HcPrepared); then the tree quantiser at this call's codebook size.  nvcc build:
+// six / two stable LSD radix passes over the float bit patterns (cub) + run heads + scan, never leaving the device; emulation build: the
+// same on the host.
 template <int D>
 int hc_endpoint_codebook(crn_gpu_ctx* ctx, int kind, const float* d_src, const uint32_t* d_used, uint32_t num_tiles, const uint8_t* d_npix,
                          uint32_t n, int ncp, const crn::HcLevelWeights& LW,
-                         uint32_t max_size, HcBuf& d_tvec, std::vector<float>& codebook, uint32_t& rounds, uint32_t& n_unique)
+                         uint32_t max_size, HcTrainingSet<D>& ts, std::vector<float>& codebook, uint32_t& rounds, uint32_t& n_unique)
 {
     cudaStream_t st = ctx->stream;
     const uint32_t NT = (uint32_t)ncp * num_tiles;
+    HcTreeVq<D> vq;
+    if (!ts.valid) {
+    HcBuf& d_tvec = ts.d_tvec;
     HcBuf d_w;
     HC_ALLOC(d_tvec, (size_t)NT * D * 4); HC_ALLOC(d_w, (size_t)NT * 4);
     CRN_LAUNCH(crn::hc_compact_tiles_kernel<D>, (NT + 255) / 256, 256, 0, st, d_src, d_used, d_npix, n, num_tiles, NT, kind, LW, d_tvec.as<float>(), d_w.as<uint32_t>());
     ctx->launches++;
-    HcTreeVq<D> vq;
 #ifdef __CUDACC__
     {
-        HcBuf d_perm[2], d_keys[2], d_temp, d_head, d_rank, d_bsums, d_uv, d_uw;
+        HcBuf d_perm[2], d_keys[2], d_temp, d_head, d_rank, d_bsums;
+        HcBuf& d_uv = ts.d_uv; HcBuf& d_uw = ts.d_uw;
         for (int k = 0; k < 2; k++) { HC_ALLOC(d_perm[k], (size_t)NT * 4); HC_ALLOC(d_keys[k], (size_t)NT * 4); }
         size_t temp_bytes = 0;
         CRN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_keys[0].as<uint32_t>(), d_keys[1].as<uint32_t>(), d_perm[0].as<uint32_t>(), d_perm[1].as<uint32_t>(), (int)NT, 0, 32, st));
@@ -300,13 +323,12 @@ int hc_endpoint_codebook(crn_gpu_ctx* ctx, int kind, const float* d_src, const u
             CRN_LAUNCH(crn::vq_scan_add_kernel, (m + 255) / 256, 256, 0, st, d_rank.as<uint32_t>(), d_bsums.as<uint32_t>(), m);
         }
         ctx->launches += 5;
-        CRN_CUDA(ctx, cudaMemcpyAsync(&n_unique, d_rank.as<uint32_t>() + NT, 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(&ts.n_unique, d_rank.as<uint32_t>() + NT, 4, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaStreamSynchronize(st));
-        HC_ALLOC(d_uv, (size_t)n_unique * D * 4); HC_ALLOC(d_uw, (size_t)n_unique * 4);
+        HC_ALLOC(d_uv, (size_t)ts.n_unique * D * 4); HC_ALLOC(d_uw, (size_t)ts.n_unique * 4);
         CRN_LAUNCH(crn::hc_vec_unique_kernel<D>, (NT + 255) / 256, 256, 0, st, d_tvec.as<float>(), d_w.as<uint32_t>(), d_perm[cur].as<uint32_t>(), d_head.as<uint32_t>(),
                    d_rank.as<uint32_t>(), NT, d_uv.as<float>(), d_uw.as<uint32_t>());
         ctx->launches++;
-        HC_RC(vq.build(ctx, d_uv.as<float>(), d_uw.as<uint32_t>(), n_unique, max_size, true));
     }
 #else
     {
@@ -316,18 +338,24 @@ int hc_endpoint_codebook(crn_gpu_ctx* ctx, int kind, const float* d_src, const u
         CRN_CUDA(ctx, cudaMemcpyAsync(tw.data(), d_w.p, (size_t)NT * 4, cudaMemcpyDeviceToHost, st));
         CRN_CUDA(ctx, cudaStreamSynchronize(st));
         for (uint32_t i = 0; i < NT; i++) { memcpy(keys[i].v, &tv[(size_t)i * D], D * 4); keys[i].w = tw[i]; }
-        std::vector<float> uv; std::vector<uint32_t> uw;
-        hc_sort_dedup<D>(keys, uv, uw);
-        n_unique = (uint32_t)uw.size();
-        HC_RC(vq.build(ctx, uv.data(), uw.data(), n_unique, max_size));
+        hc_sort_dedup<D>(keys, ts.uv, ts.uw);
+        ts.n_unique = (uint32_t)ts.uw.size();
     }
+#endif
+    ts.valid = true;
+    }
+    n_unique = ts.n_unique;
+#ifdef __CUDACC__
+    HC_RC(vq.build(ctx, ts.d_uv.template as<float>(), ts.d_uw.template as<uint32_t>(), ts.n_unique, max_size, true));
+#else
+    HC_RC(vq.build(ctx, ts.uv.data(), ts.uw.data(), ts.n_unique, max_size));
 #endif
     codebook.swap(vq.codebook);
     rounds = vq.rounds;
     return CRN_GPU_OK;
 }
 
-int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void* blocks_rgba, int on_host, crn_gpu_hc* H)
+int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void* blocks_rgba, int on_host, crn_gpu_hc* H, HcPrepared* prep = nullptr)
 {
     const uint32_t n = prm->num_blocks;
     const uint32_t fmt = prm->format;
@@ -360,46 +388,57 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     cudaStream_t st = ctx->stream;
 
     QdxtTrace tr(ctx);
-    // ---- a12: tiles
-    HcBuf d_blocks_own, d_enc, d_tile, d_npix, d_pixofs, d_vpix, d_cvec, d_avec;
+    // ---- a12: tiles (once per HcPrepared: the tile pass does not depend on the codebook sizes)
+    HcPrepared local_prep;
+    HcPrepared& PR = prep ? *prep : local_prep;
+    if (PR.valid && PR.n != n) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_hc_compress: prepared state belongs to another block array");
+    HcBuf d_blocks_own;
+    HcBuf &d_enc = PR.d_enc, &d_tile = PR.d_tile, &d_npix = PR.d_npix, &d_pixofs = PR.d_pixofs, &d_vpix = PR.d_vpix, &d_cvec = PR.d_cvec, &d_avec = PR.d_avec, &d_used = PR.d_used;
+    std::vector<uint8_t>& h_npix = PR.h_npix; std::vector<uint8_t>& h_pixofs = PR.h_pixofs;
+    std::vector<uint32_t>& used_slots = PR.used_slots; std::vector<uint32_t>& slot_rank = PR.slot_rank;
     const uint32_t* d_blocks = static_cast<const uint32_t*>(blocks_rgba);
-    if (on_host) {
-        HC_ALLOC(d_blocks_own, (size_t)n * 64);
-        CRN_CUDA(ctx, cudaMemcpyAsync(d_blocks_own.p, blocks_rgba, (size_t)n * 64, cudaMemcpyHostToDevice, st));
-        d_blocks = d_blocks_own.as<uint32_t>();
+    if (!PR.valid) {
+        if (on_host) {
+            HC_ALLOC(d_blocks_own, (size_t)n * 64);
+            CRN_CUDA(ctx, cudaMemcpyAsync(d_blocks_own.p, blocks_rgba, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+            d_blocks = d_blocks_own.as<uint32_t>();
+        }
+        HC_ALLOC(d_enc, n); HC_ALLOC(d_tile, (size_t)n * 4); HC_ALLOC(d_npix, n); HC_ALLOC(d_pixofs, n); HC_ALLOC(d_vpix, (size_t)n * 64);
+        if (has_color) HC_ALLOC(d_cvec, (size_t)n * 24);
+        if (na) HC_ALLOC(d_avec, (size_t)na * n * 8);
+        CRN_LAUNCH(crn::hc_tiles_kernel, grid_for(ctx, chunks, crn::kHcTileWarps, 8), crn::kHcTileWarps * 32, 0, st, d_blocks, TP, d_enc.as<uint8_t>(), d_tile.as<uint32_t>(),
+                   d_npix.as<uint8_t>(), d_pixofs.as<uint8_t>(), d_vpix.as<uint32_t>());
+        const int ncomp = (has_color ? 1 : 0) + na;
+        CRN_LAUNCH(crn::hc_palettize_kernel, (n * ncomp + 127) / 128, 128, 0, st, d_vpix.as<uint32_t>(), d_npix.as<uint8_t>(), d_pixofs.as<uint8_t>(), n, (int)has_color, na, comp0, comp1,
+                   perceptual, d_cvec.as<float>(), d_avec.as<float>());
+        ctx->launches += 2;
+        CRN_CUDA(ctx, cudaGetLastError());
+        HcHost<uint8_t> s_npix(ctx, n), s_pixofs(ctx, n), s_enc(ctx, n);
+        HcHost<uint32_t> s_tile(ctx, n);
+        CRN_CUDA(ctx, cudaMemcpyAsync(s_npix.data(), d_npix.p, n, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(s_pixofs.data(), d_pixofs.p, n, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(s_enc.data(), d_enc.p, n, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaMemcpyAsync(s_tile.data(), d_tile.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        h_npix.assign(s_npix.data(), s_npix.data() + n); h_pixofs.assign(s_pixofs.data(), s_pixofs.data() + n);
+        PR.h_enc.assign(s_enc.data(), s_enc.data() + n); PR.h_tile.assign(s_tile.data(), s_tile.data() + n);
+        uint32_t nt = 0;
+        for (uint32_t s = 0; s < n; s++) nt += h_npix[s] != 0;
+        used_slots.resize(nt);                       // tile slots in order (m_tiles[t].pixels.size() != 0)
+        for (uint32_t s = 0, i = 0; s < n; s++) if (h_npix[s]) used_slots[i++] = s;
+        slot_rank.assign(n, 0xffffffffu);
+        for (uint32_t i = 0; i < nt; i++) slot_rank[used_slots[i]] = i;
+        PR.num_tiles = nt; PR.n = n;
+        if (!nt) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: no tiles");
+        HC_ALLOC(d_used, (size_t)nt * 4);
+        CRN_CUDA(ctx, cudaMemcpyAsync(d_used.p, used_slots.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, st));
+        CRN_CUDA(ctx, cudaStreamSynchronize(st));
+        PR.valid = true;
+        tr.mark("hc tiles + palettize + D2H", 0);
     }
-    HC_ALLOC(d_enc, n); HC_ALLOC(d_tile, (size_t)n * 4); HC_ALLOC(d_npix, n); HC_ALLOC(d_pixofs, n); HC_ALLOC(d_vpix, (size_t)n * 64);
-    if (has_color) HC_ALLOC(d_cvec, (size_t)n * 24);
-    if (na) HC_ALLOC(d_avec, (size_t)na * n * 8);
-    CRN_LAUNCH(crn::hc_tiles_kernel, grid_for(ctx, chunks, crn::kHcTileWarps, 8), crn::kHcTileWarps * 32, 0, st, d_blocks, TP, d_enc.as<uint8_t>(), d_tile.as<uint32_t>(),
-               d_npix.as<uint8_t>(), d_pixofs.as<uint8_t>(), d_vpix.as<uint32_t>());
-    const int ncomp = (has_color ? 1 : 0) + na;
-    CRN_LAUNCH(crn::hc_palettize_kernel, (n * ncomp + 127) / 128, 128, 0, st, d_vpix.as<uint32_t>(), d_npix.as<uint8_t>(), d_pixofs.as<uint8_t>(), n, (int)has_color, na, comp0, comp1,
-               perceptual, d_cvec.as<float>(), d_avec.as<float>());
-    ctx->launches += 2;
-    CRN_CUDA(ctx, cudaGetLastError());
-    HcHost<uint8_t> h_npix(ctx, n), h_pixofs(ctx, n), h_enc(ctx, n);
-    HcHost<uint32_t> h_tile(ctx, n);
-    H->block_encodings.resize(n); H->tile_indices.resize(n);
-    CRN_CUDA(ctx, cudaMemcpyAsync(h_npix.data(), d_npix.p, n, cudaMemcpyDeviceToHost, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(h_pixofs.data(), d_pixofs.p, n, cudaMemcpyDeviceToHost, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(h_enc.data(), d_enc.p, n, cudaMemcpyDeviceToHost, st));
-    CRN_CUDA(ctx, cudaMemcpyAsync(h_tile.data(), d_tile.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    CRN_CUDA(ctx, cudaStreamSynchronize(st));
-    memcpy(H->block_encodings.data(), h_enc.data(), n);
-    memcpy(H->tile_indices.data(), h_tile.data(), (size_t)n * 4);
-    tr.mark("hc tiles + palettize + D2H", 0);
-    uint32_t num_tiles = 0;
-    for (uint32_t s = 0; s < n; s++) num_tiles += h_npix[s] != 0;
-    HcHost<uint32_t> used_slots(ctx, num_tiles);     // tile slots in order (m_tiles[t].pixels.size() != 0)
-    for (uint32_t s = 0, i = 0; s < n; s++) if (h_npix[s]) used_slots[i++] = s;
-    std::vector<uint32_t> slot_rank(n, 0xffffffffu);
-    for (uint32_t i = 0; i < num_tiles; i++) slot_rank[used_slots[i]] = i;
+    H->block_encodings = PR.h_enc; H->tile_indices = PR.h_tile;
+    const uint32_t num_tiles = PR.num_tiles;
     H->info.num_tiles = num_tiles;
-    if (!num_tiles) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "dxt_hc: no tiles");
-    HcBuf d_used;
-    HC_ALLOC(d_used, (size_t)num_tiles * 4);
-    CRN_CUDA(ctx, cudaMemcpyAsync(d_used.p, used_slots.data(), (size_t)num_tiles * 4, cudaMemcpyHostToDevice, st));
     crn::HcLevelWeights LW; memset(&LW, 0, sizeof(LW));
     LW.num_levels = prm->num_levels;
     for (uint32_t l = 0; l < prm->num_levels; l++) { LW.first_block[l] = prm->levels[l].first_block; LW.weight[l] = prm->levels[l].weight; }
@@ -425,14 +464,14 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         const uint32_t NV = (uint32_t)ncp * n;                           // virtual blocks (= member blocks in the CSR)
         // a13: training vectors -> sorted unique weighted vectors -> tree quantiser
         std::vector<float> codebook; uint32_t K = 0;
-        HcBuf d_tvec;
+        HcBuf& d_tvec = kind == 0 ? PR.ts6.d_tvec : PR.ts2.d_tvec;
         if (kind == 0) {
             HC_RC(hc_endpoint_codebook<6>(ctx, 0, d_cvec.as<float>(), d_used.as<uint32_t>(), num_tiles, d_npix.as<uint8_t>(), n, 1, LW,
-                                          std::min(num_tiles, prm->color_endpoint_codebook_size), d_tvec, codebook, H->info.vq_rounds[0], H->info.unique_vectors[0]));
+                                          std::min(num_tiles, prm->color_endpoint_codebook_size), PR.ts6, codebook, H->info.vq_rounds[0], H->info.unique_vectors[0]));
             K = (uint32_t)(codebook.size() / 6);
         } else {
             HC_RC(hc_endpoint_codebook<2>(ctx, 1, d_avec.as<float>(), d_used.as<uint32_t>(), num_tiles, d_npix.as<uint8_t>(), n, na, LW,
-                                          std::min(num_tiles, prm->alpha_endpoint_codebook_size), d_tvec, codebook, H->info.vq_rounds[1], H->info.unique_vectors[1]));
+                                          std::min(num_tiles, prm->alpha_endpoint_codebook_size), PR.ts2, codebook, H->info.vq_rounds[1], H->info.unique_vectors[1]));
             K = (uint32_t)(codebook.size() / 2);
         }
         tr.mark("hc endpoint sort + tree VQ", kind);

@@ -84,6 +84,10 @@ CRN_API uint64_t crn_gpu_launch_count(const crn_gpu_ctx* ctx);
  * clustered path (:136-146, :172-188).  Returning 0 abandons the call with CRN_GPU_ERR_CANCELLED.  fn = NULL removes it. */
 typedef int (*crn_gpu_progress_fn)(uint32_t phase_index, uint32_t total_phases, uint32_t subphase_index, uint32_t total_subphases, void* user);
 CRN_API void crn_gpu_set_progress(crn_gpu_ctx* ctx, crn_gpu_progress_fn fn, void* user);
+/* cudaMalloc calls made by the buffer pool of this context (and its per-element child contexts) since creation.  Buffers of the clustered /
+ * CRN paths are cached per context in size classes, so compressing texture after texture -- or trial after trial of a bitrate search -- stops
+ * allocating after the first few calls: the counter stands still in steady state (tests assert it). */
+CRN_API uint64_t crn_gpu_pool_mallocs(const crn_gpu_ctx* ctx);
 /* Vector-quantiser flavour of the clustered-DDS path (crn_gpu_vq_clusterize, crn_gpu_qdxt_init / _pack and everything above them).
  * 0 (default): crnlib::clusterizer<V>'s algorithm with sums in a fixed parallel order, one launch per frontier (csrc/vq_fast.cuh) -- the
  *    tolerance class BASELINE.json states for clustered output (PSNR within 0.05 dB, bitrate within 1 %).

@@ -95,3 +95,15 @@ def test_compress_mip_chain_is_the_reference_file(gpu_ctx, ref):
     want = ref_compress_mip_chain(ref, img, "DXT5", 1, 255, 1 | 2 | 8 | 32)
     got = gpu_ctx.compress_mip_chain([img], helpers.CRN_FMT["DXT5"], "dds", quality_level=255)
     assert got == want
+
+
+def test_bitrate_search_reuses_state_and_buffers(gpu_ctx):
+    """the trials of a target-bitrate search share the tile pass / training sets, and the buffer pool serves every trial
+    from its size classes -- a second search performs no cudaMalloc at all (crn_gpu_pool_mallocs stands still)."""
+    faces = [chain(256, 256, 70)]
+    a = gpu_ctx.compress_crn(faces, helpers.CRN_FMT["DXT1"], target_bitrate=1.0)
+    m0, l0 = gpu_ctx.pool_mallocs, gpu_ctx.launch_count
+    b = gpu_ctx.compress_crn(faces, helpers.CRN_FMT["DXT1"], target_bitrate=1.0)
+    assert a == b
+    assert gpu_ctx.pool_mallocs == m0, "the pool allocated during a repeated search"
+    assert gpu_ctx.launch_count > l0
