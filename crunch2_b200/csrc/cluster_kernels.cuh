@@ -16,8 +16,24 @@
 
 namespace crn {
 
+// CTA-per-cluster mode (large clusters): the owning warp runs the optimiser as always; each time it evaluates a batch of 32 candidates it
+// publishes them here and the CTA's other warps each take a slice of the unique colours (dxt1_eval_coop below).
+constexpr int kClusterCoopWarps = 8;            // warps of a cooperative CTA
+constexpr int kClusterCoopChunk = 32;           // unique colours per warp per round; the early-out test runs once a round (every 256 colours)
+constexpr uint32_t kClusterCoopMinBlocks = 128; // clusters with at least this many member blocks are optimised by a whole CTA
+struct Dxt1CoopShared {
+    unsigned lo[32], hi[32];                    // the batch: one candidate per lane of the owning warp
+    unsigned long long bound;                   // error of the best so far (the early-out bound)
+    const int4* ce;                             // evaluation colours of the cluster
+    Dxt1Cfg cfg;
+    unsigned valid_mask;
+    int alt, cmd;                               // cmd: 1 = evaluate this batch, 0 = no more batches for the helper warps
+    unsigned long long part[2][kClusterCoopWarps][2][32];   // per round (double buffered), warp, block type, candidate: partial error sums
+};
+
 struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays live in the global workspace
     int4* cw; int4* ce; uint8_t* sel;
+    Dxt1CoopShared* coop;              // non-null: this warp owns a cluster in CTA-per-cluster mode
     Dxt1Best best;
     float mean[3], axis[3], low[3], high[3];
     int U, total_w, pixels_have_alpha, stage;
@@ -29,6 +45,102 @@ struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays 
 };
 // found by dxt1_eval through argument-dependent lookup; the 4x4-block scratch type has no counters (generic no-op in dxt1_opt.cuh)
 __device__ __forceinline__ void dxt1_count_eval(Dxt1ClusterScratch* sc, int U) { sc->n_eval[lane_id()]++; sc->n_cu[lane_id()] += (unsigned)U; }
+
+__device__ __forceinline__ bool dxt1_is_coop(const Dxt1ClusterScratch* sc) { return sc->coop != nullptr; }
+
+// One batch of <= 32 candidates against the U evaluation colours, by all warps of the CTA: warp w sums colours [base + w * chunk, + chunk) of every
+// round for each candidate, the partial sums meet in shared memory, and every warp adds them up in the same (warp) order -- integer sums, so the
+// totals are the ones dxt1_eval_loop produces, and every warp sees the same totals and leaves the loop in the same round.  A candidate whose
+// totals have reached the bound is dropped from the following rounds (same rule as dxt1_eval_loop, tested every 256 colours instead of every 8).
+template <bool DO4, bool DO3>
+__device__ __forceinline__ void dxt1_coop_rounds(Dxt1CoopShared* cs, unsigned w, int U, const int4* __restrict__ ce, const int4 p0, const int4 p1, const int4 p2,
+                                                 const int4 p3, const int4 pm, bool valid, unsigned long long bound, unsigned long long& e4, unsigned long long& e3)
+{
+    const unsigned lane = lane_id();
+    e4 = 0; e3 = 0;
+    bool active = valid;
+    int buf = 0;
+    int base = 0;
+    do {                                                     // at least one round, so that the batch is not republished while a warp still reads it
+        unsigned long long s4 = 0, s3 = 0;
+        if (active) {
+            const int i0 = base + (int)w * kClusterCoopChunk, i1 = min(U, i0 + kClusterCoopChunk);
+#pragma unroll 2
+            for (int i = i0; i < i1; i++) {
+                const int4 c = ce[i];
+                const unsigned wt = (unsigned)c.w;
+                const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
+                const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
+                if (DO4) {
+                    const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
+                    s4 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                }
+                if (DO3) {
+                    const int d = min(d01, eval_dprime(cx, cy, cz, pm));
+                    s3 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                }
+            }
+        }
+        __syncwarp();
+        if (DO4) cs->part[buf][w][0][lane] = s4;
+        if (DO3) cs->part[buf][w][1][lane] = s3;
+        __syncthreads();
+#pragma unroll
+        for (int ww = 0; ww < kClusterCoopWarps; ww++) {
+            if (DO4) e4 += cs->part[buf][ww][0][lane];
+            if (DO3) e3 += cs->part[buf][ww][1][lane];
+        }
+        buf ^= 1;
+        if (active && ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound))) active = false;
+        base += kClusterCoopWarps * kClusterCoopChunk;
+    } while (__any_sync(CRN_FULL_MASK, active) && base < U);
+}
+
+// what every warp of the CTA does with a published batch; returns this lane's candidate's (err, alpha) as dxt1_eval does
+__device__ __noinline__ void dxt1_coop_batch(Dxt1CoopShared* cs, unsigned w, unsigned long long& err, int& alpha)
+{
+    const unsigned lane = lane_id();
+    const Dxt1Cfg cfg = cs->cfg;
+    const unsigned lo = cs->lo[lane], hi = cs->hi[lane];
+    const int alt = cs->alt;
+    const bool valid = (cs->valid_mask >> lane) & 1u;
+    const unsigned long long bound = cs->bound;
+    const int4* ce = cs->ce;
+    int r0, g0, b0, r1, g1, b1;
+    unpack565(lo, true, r0, g0, b0);
+    unpack565(hi, true, r1, g1, b1);
+    const int4 p0 = eval_palette(cfg, r0, g0, b0), p1 = eval_palette(cfg, r1, g1, b1);
+    const int4 p2 = eval_palette(cfg, (r0 * 2 + r1 + alt) / 3, (g0 * 2 + g1 + alt) / 3, (b0 * 2 + b1 + alt) / 3);
+    const int4 p3 = eval_palette(cfg, (r1 * 2 + r0 + alt) / 3, (g1 * 2 + g0 + alt) / 3, (b1 * 2 + b0 + alt) / 3);
+    const int4 pm = eval_palette(cfg, (r0 + r1 + alt) >> 1, (g0 + g1 + alt) >> 1, (b0 + b1 + alt) >> 1);
+    unsigned long long e4, e3;
+    if (cfg.do4 && cfg.do3) {
+        dxt1_coop_rounds<true, true>(cs, w, cfg.U, ce, p0, p1, p2, p3, pm, valid, bound, e4, e3);
+        alpha = e3 < e4; err = alpha ? e3 : e4;
+    } else if (cfg.do4) {
+        dxt1_coop_rounds<true, false>(cs, w, cfg.U, ce, p0, p1, p2, p3, pm, valid, bound, e4, e3);
+        alpha = 0; err = e4;
+    } else {
+        dxt1_coop_rounds<false, true>(cs, w, cfg.U, ce, p0, p1, p2, p3, pm, valid, bound, e4, e3);
+        alpha = 1; err = e3;
+    }
+    if (!valid) { err = ~0ull; alpha = 0; }
+}
+
+// dxt1_eval of the owning warp in CTA-per-cluster mode (found through argument-dependent lookup): publish the batch, meet the helper warps
+// at the barrier, take part as warp 0.  All 32 lanes come through here together (dxt1_eval's `valid` argument).
+__device__ __forceinline__ void dxt1_eval_coop(Dxt1ClusterScratch* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
+                                               unsigned long long& err, int& alpha, bool valid)
+{
+    Dxt1CoopShared* cs = sc->coop;
+    const unsigned lane = lane_id();
+    if (valid) dxt1_count_eval(sc, cfg.U);
+    cs->lo[lane] = lo; cs->hi[lane] = hi;
+    const unsigned m = __ballot_sync(CRN_FULL_MASK, valid);
+    if (lane == 0) { cs->bound = sc->best.err; cs->ce = sc->ce; cs->cfg = cfg; cs->valid_mask = m; cs->alt = alt; cs->cmd = 1; }
+    __syncthreads();
+    dxt1_coop_batch(cs, 0, err, alpha);
+}
 
 struct ClusterHashEntry { uint32_t key, first_inv, count, uidx; };   // first_inv = ~(index of first appearance)
 
@@ -158,6 +270,83 @@ __device__ __forceinline__ void cluster_order_eval_colours(Dxt1ClusterScratch* s
 
 struct ClusterResult { uint32_t endpoints; uint32_t flags; };      // flags: bit 0 invert, bit 1 alpha_block, bits 2-3 stage
 
+struct ClusterOptArgs {
+    const uint32_t* cluster_offsets; Dxt1Params prm; int dxt1a; ClusterWorkspace ws; const uint32_t* rank; const uint32_t* transparent;
+    ClusterResult* results; uint32_t* out_endpoints; unsigned long long* out_error; uint32_t* out_flags;
+};
+
+// one cluster, by the calling warp (with the CTA's other warps behind dxt1_eval when sc->coop is set)
+__device__ __forceinline__ void dxt1_optimize_one_cluster(Dxt1ClusterScratch* sc, const ClusterOptArgs& a, uint32_t c)
+{
+    const unsigned lane = lane_id();
+    const Dxt1Params prm = a.prm;
+    const uint32_t b0 = a.cluster_offsets[c], nb = a.cluster_offsets[c + 1] - b0;
+    const uint32_t N = nb * 16, P = b0 * 16;
+    if (!nb) return;
+    const uint32_t ntransp = a.dxt1a ? a.transparent[c] : 0u;
+    const int pha = ntransp != 0;                       // pixels_have_alpha as qdxt1 computes it
+    const unsigned opaque_cnt = N - ntransp;
+    const int U = (int)(a.rank[P + N] - a.rank[P]);
+    if (lane == 0) { sc->cw = a.ws.cw + P; sc->ce = a.ws.ce + P; sc->sel = a.ws.sel + P; }
+    __syncwarp();
+    // ---- the optimiser proper: same phases as the 4x4 block kernels, fused
+    dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, pha, U));
+    cluster_order_eval_colours(sc, dxt1_make_cfg(prm, pha, U), a.ws.ce2 + P);
+    dxt1_setup_common(sc, prm, pha, U, opaque_cnt, opaque_cnt != N);
+    dxt1_phase_median4(sc, prm);
+    dxt1_phase_passes(sc, prm);
+    dxt1_phase_post(sc, prm);
+    // ---- finish: combinatorial recovery + return_solution (crn_dxt1.cpp:1048-1056, :263-365)
+    unsigned out_lo = 0, out_hi = 0;
+    bool invert = false;
+    int alpha_block = 1;
+    const int stage = sc->stage;
+    if (stage != 2) {
+        const Dxt1Cfg cfg = dxt1_make_cfg(prm, pha, U);
+        if (stage == 0 && prm.quality == 4 && sc->best.err) dxt1_combinatorial(sc, cfg);
+        dxt1_best_selectors(sc, cfg);
+        alpha_block = sc->best.alpha_block;
+        invert = alpha_block ? (sc->best.lo > sc->best.hi) : (sc->best.lo < sc->best.hi);
+        out_lo = invert ? sc->best.hi : sc->best.lo; out_hi = invert ? sc->best.lo : sc->best.hi;
+    }
+    if (lane == 0) {
+        a.results[c].endpoints = out_lo | (out_hi << 16);
+        a.results[c].flags = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2);
+        if (a.out_endpoints) a.out_endpoints[c] = out_lo | (out_hi << 16);
+        if (a.out_error) a.out_error[c] = stage == 2 ? 0ull : sc->best.err;
+        // dxt_hc wants results::m_reordered (bit 0) and m_alternate_rounding (bit 4) (crn_dxt1.cpp:279-282)
+        if (a.out_flags) a.out_flags[c] = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2) | ((stage != 2 && sc->best.alt_round) ? 16u : 0u);
+    }
+    __syncwarp();
+}
+
+// work counters of a warp -> the two 64-bit words behind the work-stealing counter (next_cluster + 16 / + 18)
+__device__ __forceinline__ void cluster_flush_counters(Dxt1ClusterScratch* sc, unsigned int* next_cluster)
+{
+    const unsigned lane = lane_id();
+    unsigned long long ne = sc->n_eval[lane], nc = sc->n_cu[lane];
+    ne = warp_sum_u64(ne); nc = warp_sum_u64(nc);
+    if (lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 16), ne);
+        atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 18), nc);
+    }
+}
+
+// the work-stealing loop of one warp over order[first .. n_clusters) (order == nullptr: the clusters in index order)
+__device__ __forceinline__ void dxt1_cluster_warp_loop(Dxt1ClusterScratch* sc, const ClusterOptArgs& a, uint32_t first, uint32_t n_clusters,
+                                                       unsigned int* next_cluster, const uint32_t* __restrict__ order)
+{
+    const unsigned lane = lane_id();
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = first + atomicAdd(next_cluster, 1u);
+        c = __shfl_sync(CRN_FULL_MASK, c, 0);
+        if (c >= n_clusters) break;
+        if (order) c = order[c];                             // largest clusters first: the work-stealing tail is one small cluster, not one huge one
+        dxt1_optimize_one_cluster(sc, a, c);
+    }
+}
+
 __global__ void __launch_bounds__(kClusterWarpsPerCta * 32, 5)
 dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, Dxt1Params prm, int dxt1a,
                               ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
@@ -169,61 +358,56 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     Dxt1ClusterScratch* sc = &scratch[warp];
     sc->n_eval[lane] = 0; sc->n_cu[lane] = 0;
+    if (lane == 0) sc->coop = nullptr;
     __syncwarp();
-    for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(next_cluster, 1u);
-        c = __shfl_sync(CRN_FULL_MASK, c, 0);
-        if (c >= n_clusters) {
-            // work counters of this warp -> the two 64-bit words behind the work-stealing counter (next_cluster + 16 / + 18)
-            unsigned long long ne = sc->n_eval[lane], nc = sc->n_cu[lane];
-            ne = warp_sum_u64(ne); nc = warp_sum_u64(nc);
-            if (lane == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 16), ne);
-                atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 18), nc);
-            }
-            break;
-        }
-        if (order) c = order[c];                             // largest clusters first: the work-stealing tail is one small cluster, not one huge one
-        const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
-        const uint32_t N = nb * 16, P = b0 * 16;
-        if (!nb) continue;
-        const uint32_t ntransp = dxt1a ? transparent[c] : 0u;
-        const int pha = ntransp != 0;                       // pixels_have_alpha as qdxt1 computes it
-        const unsigned opaque_cnt = N - ntransp;
-        const int U = (int)(rank[P + N] - rank[P]);
-        if (lane == 0) { sc->cw = ws.cw + P; sc->ce = ws.ce + P; sc->sel = ws.sel + P; }
+    const ClusterOptArgs a = { cluster_offsets, prm, dxt1a, ws, rank, transparent, results, out_endpoints, out_error, out_flags };
+    dxt1_cluster_warp_loop(sc, a, 0, n_clusters, next_cluster, order);
+    cluster_flush_counters(sc, next_cluster);
+}
+
+// Large clusters first, a CTA each; then the same CTAs turn into kClusterCoopWarps independent warps for the small ones.
+// `order` lists the clusters by descending size, its first n_big entries are the large ones.  One warp per cluster leaves a dxt_hc pass at low
+// quality (a few hundred clusters of thousands of blocks) waiting for the single warp that owns the largest cluster; here that cluster's
+// colour loop -- >90 % of the optimiser's instructions at that size -- runs on eight warps.  Work-stealing counters: next_cluster[0] for the
+// large clusters (one fetch per CTA), next_cluster[1] for the rest.
+__global__ void __launch_bounds__(kClusterCoopWarps * 32, 2)
+dxt1_optimize_clusters_cta_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, uint32_t n_big, Dxt1Params prm, int dxt1a,
+                                  ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
+                                  unsigned int* __restrict__ next_cluster, ClusterResult* __restrict__ results,
+                                  uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags,
+                                  const uint32_t* __restrict__ order)
+{
+    __shared__ Dxt1ClusterScratch scratch[kClusterCoopWarps];
+    __shared__ Dxt1CoopShared coop;
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    Dxt1ClusterScratch* sc = &scratch[warp];
+    sc->n_eval[lane] = 0; sc->n_cu[lane] = 0;
+    if (lane == 0) sc->coop = nullptr;
+    __syncwarp();
+    const ClusterOptArgs a = { cluster_offsets, prm, dxt1a, ws, rank, transparent, results, out_endpoints, out_error, out_flags };
+    if (warp == 0) {
+        if (lane == 0) sc->coop = &coop;
         __syncwarp();
-        // ---- the optimiser proper: same phases as the 4x4 block kernels, fused
-        dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, pha, U));
-        cluster_order_eval_colours(sc, dxt1_make_cfg(prm, pha, U), ws.ce2 + P);
-        dxt1_setup_common(sc, prm, pha, U, opaque_cnt, opaque_cnt != N);
-        dxt1_phase_median4(sc, prm);
-        dxt1_phase_passes(sc, prm);
-        dxt1_phase_post(sc, prm);
-        // ---- finish: combinatorial recovery + return_solution (crn_dxt1.cpp:1048-1056, :263-365)
-        unsigned out_lo = 0, out_hi = 0;
-        bool invert = false;
-        int alpha_block = 1;
-        const int stage = sc->stage;
-        if (stage != 2) {
-            const Dxt1Cfg cfg = dxt1_make_cfg(prm, pha, U);
-            if (stage == 0 && prm.quality == 4 && sc->best.err) dxt1_combinatorial(sc, cfg);
-            dxt1_best_selectors(sc, cfg);
-            alpha_block = sc->best.alpha_block;
-            invert = alpha_block ? (sc->best.lo > sc->best.hi) : (sc->best.lo < sc->best.hi);
-            out_lo = invert ? sc->best.hi : sc->best.lo; out_hi = invert ? sc->best.lo : sc->best.hi;
+        for (;;) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(next_cluster, 1u);
+            c = __shfl_sync(CRN_FULL_MASK, c, 0);
+            if (c >= n_big) break;
+            dxt1_optimize_one_cluster(sc, a, order[c]);
         }
-        if (lane == 0) {
-            results[c].endpoints = out_lo | (out_hi << 16);
-            results[c].flags = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2);
-            if (out_endpoints) out_endpoints[c] = out_lo | (out_hi << 16);
-            if (out_error) out_error[c] = stage == 2 ? 0ull : sc->best.err;
-            // dxt_hc wants results::m_reordered (bit 0) and m_alternate_rounding (bit 4) (crn_dxt1.cpp:279-282)
-            if (out_flags) out_flags[c] = (invert ? 1u : 0u) | (alpha_block ? 2u : 0u) | ((unsigned)stage << 2) | ((stage != 2 && sc->best.alt_round) ? 16u : 0u);
-        }
+        if (lane == 0) { coop.cmd = 0; sc->coop = nullptr; }
         __syncwarp();
+        __syncthreads();                                     // releases the helpers
+    } else {
+        for (;;) {
+            __syncthreads();                                 // the owning warp has published a batch, or is done
+            if (!coop.cmd) break;
+            unsigned long long e; int al;
+            dxt1_coop_batch(&coop, warp, e, al);
+        }
     }
+    dxt1_cluster_warp_loop(sc, a, n_big, n_clusters, next_cluster + 1, order);
+    cluster_flush_counters(sc, next_cluster);
 }
 
 // selectors of every member pixel from its unique colour's selector; 16 lanes per member block

@@ -45,6 +45,7 @@ struct crn_gpu_ctx {
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
     void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
     const uint32_t* d_cluster_order;     // set by the dxt_hc pipeline: clusters in descending size, the order the work-stealing loop takes them
+    uint32_t cluster_big_count;          // how many leading entries of d_cluster_order have >= kClusterCoopMinBlocks member blocks (a CTA each)
     uint32_t* d_cluster_flags;           // set by the dxt_hc pipeline around a cluster-optimiser call: per-cluster m_reordered / m_alternate_rounding out
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
     void* d_wide; size_t d_wide_cap;     // transition tables + pair offsets of the wide transcoder
@@ -802,6 +803,15 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     CRN_LAUNCH(crn::cluster_compact_kernel, gp, 256, 0, ctx->stream, d_cluster_offsets, n_clusters, TP, ws, rank);
     const int threads = crn::kClusterWarpsPerCta * 32;
     const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, getenv("CRN_B200_CLUSTER_CTAS") ? atoi(getenv("CRN_B200_CLUSTER_CTAS")) : 5);
+    const uint32_t n_big = (ctx->d_cluster_order && dp.quality >= 3 && !getenv("CRN_B200_NO_COOP")) ? std::min(ctx->cluster_big_count, n_clusters) : 0;
+    if (n_big) {
+        // large clusters: a CTA each, then the CTAs finish the small ones warp by warp (cluster_kernels.cuh)
+        const unsigned want = n_big + (n_clusters - n_big + crn::kClusterCoopWarps - 1) / crn::kClusterCoopWarps;
+        const int cgrid = (int)std::min<unsigned>(want, (unsigned)ctx->sm_count * 2u);
+        CRN_LAUNCH(crn::dxt1_optimize_clusters_cta_kernel, cgrid, crn::kClusterCoopWarps * 32, 0, ctx->stream, d_cluster_offsets, n_clusters, n_big, dp, scan_alpha, ws, rank,
+                   transparent, reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error),
+                   ctx->d_cluster_flags, ctx->d_cluster_order);
+    } else
     CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, d_cluster_offsets, n_clusters, dp, scan_alpha, ws, rank, transparent,
                reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags, ctx->d_cluster_order);
     CRN_LAUNCH(crn::cluster_write_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent,
@@ -1460,14 +1470,19 @@ int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
     hp->adaptive_tile_color_psnr_derating = p->adaptive_tile_color_psnr_derating;
     hp->adaptive_tile_alpha_psnr_derating = p->adaptive_tile_alpha_psnr_derating;
     float color_mul = 1.0f;
-    const float alpha_mul = 1.0f;
+    float alpha_mul = 1.0f;
     switch (p->crn_format) {                                     // crn_comp.cpp:594-660
     case 0: hp->format = CRN_GPU_FMT_DXT1; break;
     case 2: hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = p->alpha_component; color_mul = .75f; break;
+    case 3:                                                      // DXT5_CCxY: luma in alpha, chroma in red / green (crn_comp.cpp:553-558, :614-625)
+        hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = 3; hp->perceptual = 0; color_mul = 3.5f; alpha_mul = .35f;
+        hp->adaptive_tile_color_psnr_derating = 5.0f; hp->adaptive_tile_color_alpha_weighting_ratio = 1.5f; break;
+    case 4: case 5: case 6:                                      // DXT5_xGxR / _xGBR / _AGBR (:626-636)
+        hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = 3; hp->perceptual = 0; break;
     case 7: hp->format = CRN_GPU_FMT_DXN_XY; hp->alpha_component_indices[0] = 0; hp->alpha_component_indices[1] = 1; hp->perceptual = 0; break;
     case 8: hp->format = CRN_GPU_FMT_DXN_YX; hp->alpha_component_indices[0] = 1; hp->alpha_component_indices[1] = 0; hp->perceptual = 0; break;
     case 9: hp->format = CRN_GPU_FMT_DXT5A; hp->alpha_component_indices[0] = p->alpha_component; hp->perceptual = 0; break;
-    default: return CRN_GPU_ERR_UNSUPPORTED;                     // DXT3 is refused by the reference too; swizzled DXT5 variants and ETC are not built
+    default: return CRN_GPU_ERR_UNSUPPORTED;                     // DXT3 is refused by the reference too; ETC is not built
     }
     auto clampu = [](uint32_t v, uint32_t lo, uint32_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
     const uint32_t kMin = 8, kMax = 8192;                        // cCRNMinPaletteSize / cCRNMaxPaletteSize
@@ -1642,6 +1657,10 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         const uint32_t per_face = hp.levels[l].num_blocks / p->faces;
         for (uint32_t f = 0; f < p->faces; f++) {
             CRN_CUDA(ctx, cudaMemcpyAsync(d_img.p, h_images[f * p->levels + l], (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+            if (p->crn_format >= 3 && p->crn_format <= 6) {      // cooked into the swizzled layout first (crn_comp.cpp:440-452)
+                rc = crn_gpu_convert_pixels(ctx, d_img.p, w, h, w * 4, 1 + 2 * (p->crn_format - 3));
+                if (rc) return rc;
+            }
             rc = crn_gpu_blockify(ctx, d_img.p, w, h, w * 4, 8, d_blocks.as<uint8_t>() + ((size_t)hp.levels[l].first_block + (size_t)f * per_face) * 64, nullptr, nullptr);
             if (rc) return rc;
             texels += (uint64_t)w * h;

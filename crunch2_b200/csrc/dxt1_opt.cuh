@@ -222,13 +222,20 @@ __device__ __noinline__ void dxt1_eval_fast(SC* sc, const Dxt1Cfg cfg, unsigned 
 }
 
 template <typename SC> __device__ __forceinline__ void dxt1_count_eval(SC*, int) {}      // work counters: only the cluster scratch has them
+// CTA-cooperative evaluation (cluster_kernels.cuh: several warps split the colours of one large cluster): only the cluster scratch can ask for it
+template <typename SC> __device__ __forceinline__ bool dxt1_is_coop(const SC*) { return false; }
+template <typename SC> __device__ __forceinline__ void dxt1_eval_coop(SC*, const Dxt1Cfg, unsigned, unsigned, int, unsigned long long&, int&, bool) {}
 
 // Lane-private evaluation of one candidate: evaluate_solution_uber / _hc_* without the bookkeeping
 // (crn_dxt1.cpp:1370-1561, :1759-1835).  err = min over allowed block types, alpha = 3-colour won.
 template <typename SC>
 __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
-                                       unsigned long long& err, int& alpha)
+                                       unsigned long long& err, int& alpha, bool valid = true)
 {
+    // `valid` = this lane holds a candidate.  Callers pass it instead of branching around the call: with a CTA per cluster the evaluation
+    // contains block-wide barriers, so every lane of every warp has to come through here the same number of times.
+    if (!cfg.fast && dxt1_is_coop(sc)) { dxt1_eval_coop(sc, cfg, lo, hi, alt, err, alpha, valid); return; }
+    if (!valid) { err = ~0ull; alpha = 0; return; }
     dxt1_count_eval(sc, cfg.U);
     if (cfg.fast) { dxt1_eval_fast(sc, cfg, lo, hi, alt, err, alpha); return; }
     int r0, g0, b0, r1, g1, b1;
@@ -278,7 +285,7 @@ __device__ __noinline__ bool dxt1_commit_static(SC* sc, const Dxt1Cfg cfg,
                                                    bool valid, unsigned lo, unsigned hi, int alt)
 {
     unsigned long long e = ~0ull; int alpha = 0;
-    if (valid) dxt1_eval(sc, cfg, lo, hi, alt, e, alpha);
+    dxt1_eval(sc, cfg, lo, hi, alt, e, alpha, valid);
     unsigned long long key = e; unsigned idx = lane_id();
     warp_argmin_u64(key, idx);
     if (key >= sc->best.err) return false;
@@ -534,7 +541,7 @@ __device__ __noinline__ void dxt1_live_neighbours(SC* sc, const Dxt1Cfg cfg, int
         if (which) { lo = sc->best.lo; hi = p; } else { lo = p; hi = sc->best.hi; }
         canon(lo, hi);
         unsigned long long e = ~0ull; int alpha = 0;
-        if (valid) dxt1_eval(sc, cfg, lo, hi, 0, e, alpha);
+        dxt1_eval(sc, cfg, lo, hi, 0, e, alpha, valid);
         const unsigned m = __ballot_sync(CRN_FULL_MASK, valid && e < sc->best.err);
         if (!m) { pos += 32; continue; }
         const int t = __ffs((int)m) - 1;
@@ -740,12 +747,14 @@ __device__ __noinline__ void dxt1_combinatorial(SC* sc, const Dxt1Cfg cfg)
         unsigned long long my_e = ~0ull; unsigned my_k = 0xffffffffu, my_lo = 0, my_hi = 0; int my_a = 0;
         unsigned i = 0, j = 1;
         for (unsigned s = 0; s < lane; s++) { if (++j >= np) { i++; j = i + 1; } }
-        for (unsigned k = lane; k < npairs; k += 32) {
+        for (unsigned k0 = 0; k0 < npairs; k0 += 32) {              // uniform trip count: see dxt1_eval
+            const unsigned k = k0 + lane;
+            const bool valid = k < npairs;
             unsigned long long e; int a;
-            const unsigned lo = sc->packed[i], hi = sc->packed[j];
-            dxt1_eval(sc, cfg, lo, hi, alt, e, a);
-            if (e < my_e) { my_e = e; my_k = k; my_lo = lo; my_hi = hi; my_a = a; }
-            for (int s = 0; s < 32; s++) { if (++j >= np) { i++; j = i + 1; if (i + 1 >= np) break; } }
+            const unsigned lo = valid ? sc->packed[i] : 0u, hi = valid ? sc->packed[j] : 0u;
+            dxt1_eval(sc, cfg, lo, hi, alt, e, a, valid);
+            if (valid && e < my_e) { my_e = e; my_k = k; my_lo = lo; my_hi = hi; my_a = a; }
+            if (valid) for (int s = 0; s < 32; s++) { if (++j >= np) { i++; j = i + 1; if (i + 1 >= np) break; } }
         }
         unsigned long long key = my_e; unsigned idx = my_k;
         warp_argmin_u64(key, idx);
@@ -1088,12 +1097,14 @@ __device__ __forceinline__ void dxt1_phase_passes(SC* sc, const Dxt1Params& prm)
             {
                 const int nl = n_probe[0], nh = n_probe[1], total = nl * nh;
                 unsigned long long my_e = ~0ull; unsigned my_k = 0xffffffffu, my_lo = 0, my_hi = 0; int my_a = 0;
-                for (int k = (int)lane; k < total; k += 32) {
-                    unsigned lo = sc->probe[0][k / nh], hi = sc->probe[1][k % nh];
+                for (int k0 = 0; k0 < total; k0 += 32) {                // uniform trip count: see dxt1_eval
+                    const int k = k0 + (int)lane;
+                    const bool valid = k < total;
+                    unsigned lo = valid ? sc->probe[0][k / nh] : 0u, hi = valid ? sc->probe[1][k % nh] : 0u;
                     canon(lo, hi);
                     unsigned long long e; int a;
-                    dxt1_eval(sc, cfg, lo, hi, 0, e, a);
-                    if (e < my_e) { my_e = e; my_k = (unsigned)k; my_lo = lo; my_hi = hi; my_a = a; }
+                    dxt1_eval(sc, cfg, lo, hi, 0, e, a, valid);
+                    if (valid && e < my_e) { my_e = e; my_k = (unsigned)k; my_lo = lo; my_hi = hi; my_a = a; }
                 }
                 unsigned long long keyv = my_e; unsigned idx = my_k;
                 warp_argmin_u64(keyv, idx);

@@ -552,6 +552,8 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         HC_ALLOC(d_order, (size_t)Kopt * 4 + 4);
         if (Kopt) CRN_CUDA(ctx, cudaMemcpyAsync(d_order.p, opt_order.data(), (size_t)Kopt * 4, cudaMemcpyHostToDevice, st));
         ctx->d_cluster_flags = d_flags.as<uint32_t>(); ctx->d_cluster_order = d_order.as<uint32_t>();
+        ctx->cluster_big_count = 0;
+        for (uint32_t j = 0; j < Kopt; j++) { const uint32_t c = opt_order[j]; if (opt_offs[c + 1] - opt_offs[c] < crn::kClusterCoopMinBlocks) break; ctx->cluster_big_count++; }
         int rc = kind == 0 ? crn_gpu_dxt1_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), Kopt, NVopt, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>())
                            : crn_gpu_dxt5_optimize_clusters(ctx, &pp, 0, d_vblocks, NV, d_offs.as<uint32_t>(), d_mem.as<uint32_t>(), Kopt, NVopt, d_elem.p, 8, 0, d_ep.as<uint32_t>(), d_err.as<uint64_t>());
         ctx->d_cluster_flags = nullptr; ctx->d_cluster_order = nullptr;

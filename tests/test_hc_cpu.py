@@ -99,3 +99,22 @@ def test_blockify_matches_crn_comp_layout(simctx):
         simctx.synchronize()
         assert (bx, by) == (((w + 7) & ~7) >> 2, ((h + 7) & ~7) >> 2) and bx == levels[0][2]
         assert np.array_equal(got, want)
+
+
+def test_hc_cta_per_cluster_equals_warp_per_cluster(simctx, monkeypatch):
+    """Large clusters (>= kClusterCoopMinBlocks member blocks) are optimised by a whole CTA (cluster_kernels.cuh, dxt1_optimize_clusters_cta_kernel):
+    the candidate errors are integer sums split over the warps, so every output must equal the one-warp-per-cluster kernel's, byte for byte."""
+    from bench import mip_chain
+    img = blockgen.smooth_image(192, 160, 5, alpha=True)
+    blocks, levels = hc_util.hc_layout([mip_chain(img)[:2]])
+    outs = []
+    for no_coop in ("", "1"):
+        if no_coop:
+            monkeypatch.setenv("CRN_B200_NO_COOP", "1")
+        outs.append(simctx.hc_compress(0, blocks, levels, codebook_sizes=(6, 64, 6, 64)))
+    monkeypatch.delenv("CRN_B200_NO_COOP")
+    g, w = outs
+    sizes = np.bincount(g["endpoint_indices"][:, 0].astype(np.int64))
+    assert sizes.max() >= 128, sizes            # the cooperative path really ran
+    for k in ("color_endpoints", "color_selectors", "endpoint_indices", "selector_indices", "block_encodings", "tile_indices"):
+        assert np.array_equal(g[k], w[k]), k

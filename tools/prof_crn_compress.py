@@ -19,3 +19,11 @@ for _ in range(2):
     t0 = time.perf_counter()
     data, rate, _ = ctx.compress_crn(faces, 0, quality_level=q)
     print("compress_crn q%d: %.1f ms, %d bytes, %.3f bpp" % (q, (time.perf_counter() - t0) * 1e3, len(data), rate), file=sys.stderr)
+m0 = ctx.pool_mallocs
+t0 = time.perf_counter()
+data, rate, ql = ctx.compress_crn(faces, 0, target_bitrate=1.25)
+print("search 1.25 bpp: %.1f ms, %d bytes, %.3f bpp, quality %d, pool mallocs during the search %d" % ((time.perf_counter() - t0) * 1e3, len(data), rate, ql, ctx.pool_mallocs - m0), file=sys.stderr)
+m0 = ctx.pool_mallocs
+t0 = time.perf_counter()
+data, rate, ql = ctx.compress_crn(faces, 0, target_bitrate=0.8)
+print("search 0.80 bpp: %.1f ms, %d bytes, %.3f bpp, quality %d, pool mallocs during the search %d" % ((time.perf_counter() - t0) * 1e3, len(data), rate, ql, ctx.pool_mallocs - m0), file=sys.stderr)
