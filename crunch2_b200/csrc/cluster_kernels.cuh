@@ -42,11 +42,23 @@ struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays 
     uint32_t hist[64], cursor[64];     // eval-colour ordering: counts / write cursors per magnitude class
     uint32_t n_eval[32];               // per lane: candidates evaluated (dxt1_eval calls) and unique colours they range over (sum of U):
     unsigned long long n_cu[32];       // the algorithmic work of SURVEY 8(d), U * (11 P + 1) integer ops per evaluation
+#ifdef CRN_B200_PHASE_CLOCKS
+    unsigned long long phase_clk[12];
+#endif
 };
 // found by dxt1_eval through argument-dependent lookup; the 4x4-block scratch type has no counters (generic no-op in dxt1_opt.cuh)
 __device__ __forceinline__ void dxt1_count_eval(Dxt1ClusterScratch* sc, int U) { sc->n_eval[lane_id()]++; sc->n_cu[lane_id()] += (unsigned)U; }
 
 __device__ __forceinline__ bool dxt1_is_coop(const Dxt1ClusterScratch* sc) { return sc->coop != nullptr; }
+#ifdef CRN_B200_PHASE_CLOCKS
+// one-warp evaluation: every lane adds its own cycles ([10]) and 1 ([11]); [10] / 32 is then a lower bound of the warp's time in dxt1_eval
+__device__ __forceinline__ long long dxt1_prof_begin(Dxt1ClusterScratch*) { return clock64(); }
+__device__ __forceinline__ void dxt1_prof_end(Dxt1ClusterScratch* sc, long long t0)
+{
+    atomicAdd(&sc->phase_clk[10], (unsigned long long)(clock64() - t0));
+    atomicAdd(&sc->phase_clk[11], 1ull);
+}
+#endif
 
 // One batch of <= 32 candidates against the U evaluation colours, by all warps of the CTA: warp w sums colours [base + w * chunk, + chunk) of every
 // round for each candidate, the partial sums meet in shared memory, and every warp adds them up in the same (warp) order -- integer sums, so the
@@ -138,8 +150,14 @@ __device__ __forceinline__ void dxt1_eval_coop(Dxt1ClusterScratch* sc, const Dxt
     cs->lo[lane] = lo; cs->hi[lane] = hi;
     const unsigned m = __ballot_sync(CRN_FULL_MASK, valid);
     if (lane == 0) { cs->bound = sc->best.err; cs->ce = sc->ce; cs->cfg = cfg; cs->valid_mask = m; cs->alt = alt; cs->cmd = 1; }
+#ifdef CRN_B200_PHASE_CLOCKS
+    const long long t0 = clock64();
+#endif
     __syncthreads();
     dxt1_coop_batch(cs, 0, err, alpha);
+#ifdef CRN_B200_PHASE_CLOCKS
+    if (lane == 0) { sc->phase_clk[8] += (unsigned long long)(clock64() - t0); sc->phase_clk[9]++; }
+#endif
 }
 
 struct ClusterHashEntry { uint32_t key, first_inv, count, uidx; };   // first_inv = ~(index of first appearance)
@@ -275,6 +293,16 @@ struct ClusterOptArgs {
     ClusterResult* results; uint32_t* out_endpoints; unsigned long long* out_error; uint32_t* out_flags;
 };
 
+// Profiling build only (-DCRN_B200_PHASE_CLOCKS, tools/prof_cluster_phases.sh): SM cycles of the owning warp per optimiser phase, summed over
+// the clusters into the 64-bit words at next_cluster + 20 + 2 * phase.
+#ifdef CRN_B200_PHASE_CLOCKS
+#define CRN_PHASE_BEGIN() long long ph_t0_ = clock64()
+#define CRN_PHASE_END(k) do { __syncwarp(); const long long t_ = clock64(); if (lane_id() == 0) sc->phase_clk[k] += (unsigned long long)(t_ - ph_t0_); ph_t0_ = t_; } while (0)
+#else
+#define CRN_PHASE_BEGIN() do { } while (0)
+#define CRN_PHASE_END(k) do { } while (0)
+#endif
+
 // one cluster, by the calling warp (with the CTA's other warps behind dxt1_eval when sc->coop is set)
 __device__ __forceinline__ void dxt1_optimize_one_cluster(Dxt1ClusterScratch* sc, const ClusterOptArgs& a, uint32_t c)
 {
@@ -290,12 +318,18 @@ __device__ __forceinline__ void dxt1_optimize_one_cluster(Dxt1ClusterScratch* sc
     if (lane == 0) { sc->cw = a.ws.cw + P; sc->ce = a.ws.ce + P; sc->sel = a.ws.sel + P; }
     __syncwarp();
     // ---- the optimiser proper: same phases as the 4x4 block kernels, fused
+    CRN_PHASE_BEGIN();
     dxt1_build_eval_colours(sc, dxt1_make_cfg(prm, pha, U));
     cluster_order_eval_colours(sc, dxt1_make_cfg(prm, pha, U), a.ws.ce2 + P);
+    CRN_PHASE_END(0);
     dxt1_setup_common(sc, prm, pha, U, opaque_cnt, opaque_cnt != N);
+    CRN_PHASE_END(1);
     dxt1_phase_median4(sc, prm);
+    CRN_PHASE_END(2);
     dxt1_phase_passes(sc, prm);
+    CRN_PHASE_END(3);
     dxt1_phase_post(sc, prm);
+    CRN_PHASE_END(4);
     // ---- finish: combinatorial recovery + return_solution (crn_dxt1.cpp:1048-1056, :263-365)
     unsigned out_lo = 0, out_hi = 0;
     bool invert = false;
@@ -304,7 +338,9 @@ __device__ __forceinline__ void dxt1_optimize_one_cluster(Dxt1ClusterScratch* sc
     if (stage != 2) {
         const Dxt1Cfg cfg = dxt1_make_cfg(prm, pha, U);
         if (stage == 0 && prm.quality == 4 && sc->best.err) dxt1_combinatorial(sc, cfg);
+        CRN_PHASE_END(5);
         dxt1_best_selectors(sc, cfg);
+        CRN_PHASE_END(6);
         alpha_block = sc->best.alpha_block;
         invert = alpha_block ? (sc->best.lo > sc->best.hi) : (sc->best.lo < sc->best.hi);
         out_lo = invert ? sc->best.hi : sc->best.lo; out_hi = invert ? sc->best.lo : sc->best.hi;
@@ -329,6 +365,9 @@ __device__ __forceinline__ void cluster_flush_counters(Dxt1ClusterScratch* sc, u
     if (lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 16), ne);
         atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 18), nc);
+#ifdef CRN_B200_PHASE_CLOCKS
+        for (int k = 0; k < 12; k++) atomicAdd(reinterpret_cast<unsigned long long*>(next_cluster + 20 + 2 * k), sc->phase_clk[k]);
+#endif
     }
 }
 
@@ -358,6 +397,9 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     Dxt1ClusterScratch* sc = &scratch[warp];
     sc->n_eval[lane] = 0; sc->n_cu[lane] = 0;
+#ifdef CRN_B200_PHASE_CLOCKS
+    if (lane < 12) sc->phase_clk[lane] = 0;
+#endif
     if (lane == 0) sc->coop = nullptr;
     __syncwarp();
     const ClusterOptArgs a = { cluster_offsets, prm, dxt1a, ws, rank, transparent, results, out_endpoints, out_error, out_flags };
@@ -382,6 +424,9 @@ dxt1_optimize_clusters_cta_kernel(const uint32_t* __restrict__ cluster_offsets, 
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     Dxt1ClusterScratch* sc = &scratch[warp];
     sc->n_eval[lane] = 0; sc->n_cu[lane] = 0;
+#ifdef CRN_B200_PHASE_CLOCKS
+    if (lane < 12) sc->phase_clk[lane] = 0;
+#endif
     if (lane == 0) sc->coop = nullptr;
     __syncwarp();
     const ClusterOptArgs a = { cluster_offsets, prm, dxt1a, ws, rank, transparent, results, out_endpoints, out_error, out_flags };

@@ -814,6 +814,17 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     } else
     CRN_LAUNCH(crn::dxt1_optimize_clusters_kernel, grid, threads, 0, ctx->stream, d_cluster_offsets, n_clusters, dp, scan_alpha, ws, rank, transparent,
                reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error), ctx->d_cluster_flags, ctx->d_cluster_order);
+#ifdef CRN_B200_PHASE_CLOCKS
+    {
+        unsigned long long clk[12];
+        CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CRN_CUDA(ctx, cudaMemcpy(clk, base + 80, sizeof(clk), cudaMemcpyDeviceToHost));
+        static const char* names[12] = { "eval colours + order", "setup_common", "median4", "passes (incl. eval)", "post (incl. eval)", "combinatorial (incl. eval)", "best_selectors", "-",
+                                         "coop eval (owner warp, inside the phases above)", "coop batches", "warp-mode eval, lane cycles summed", "warp-mode lane evals" };
+        fprintf(stderr, "[crn_b200] cluster optimiser phase clocks (%u clusters, %u a CTA each), owner-warp SM cycles summed over clusters:\n", n_clusters, n_big);
+        for (int k = 0; k < 12; k++) if (k != 7) fprintf(stderr, "[crn_b200]   %-52s %14llu\n", names[k], clk[k]);
+    }
+#endif
     CRN_LAUNCH(crn::cluster_write_kernel, gp, 256, 0, ctx->stream, blocks, d_cluster_offsets, d_cluster_blocks, n_clusters, TP, scan_alpha, dp.alpha_threshold, ws, transparent,
                results, static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes);
     ctx->launches += 6;
@@ -1476,7 +1487,7 @@ int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
     case 2: hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = p->alpha_component; color_mul = .75f; break;
     case 3:                                                      // DXT5_CCxY: luma in alpha, chroma in red / green (crn_comp.cpp:553-558, :614-625)
         hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = 3; hp->perceptual = 0; color_mul = 3.5f; alpha_mul = .35f;
-        hp->adaptive_tile_color_psnr_derating = 5.0f; hp->adaptive_tile_color_alpha_weighting_ratio = 1.5f; break;
+        hp->adaptive_tile_color_alpha_weighting_ratio = 1.5f; break;
     case 4: case 5: case 6:                                      // DXT5_xGxR / _xGBR / _AGBR (:626-636)
         hp->format = CRN_GPU_FMT_DXT5; hp->alpha_component_indices[0] = 3; hp->perceptual = 0; break;
     case 7: hp->format = CRN_GPU_FMT_DXN_XY; hp->alpha_component_indices[0] = 0; hp->alpha_component_indices[1] = 1; hp->perceptual = 0; break;
@@ -1491,6 +1502,7 @@ int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
         hp->alpha_endpoint_codebook_size = clampu(p->palette_sizes[2], kMin, kMax); hp->alpha_selector_codebook_size = clampu(p->palette_sizes[3], kMin, kMax);
     } else {                                                     // crn_comp.cpp:539-575
         const uint32_t max_entries = clampu(((p->width + 3) / 4) * ((p->height + 3) / 4), kMin, kMax);
+        if (p->crn_format == 3) hp->adaptive_tile_color_psnr_derating = 5.0f;    // only with derived palette sizes (crn_comp.cpp:553-558)
         float quality = (float)p->quality_level / 255;
         quality = quality < 0.0f ? 0.0f : (quality > 1.0f ? 1.0f : quality);
         auto size_for = [&](float floor_entries, float power) {
@@ -2246,15 +2258,21 @@ int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const
     case 7: fmt = CRN_GPU_FMT_DXN_XY; break;
     case 8: fmt = CRN_GPU_FMT_DXN_YX; break;
     case 9: fmt = CRN_GPU_FMT_DXT5A; break;
-    default: return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: swizzled DXT5 variants and ETC are not built");
+    case 3: case 4: case 5: case 6: fmt = CRN_GPU_FMT_DXT5; break;   // DXT5_CCxY / xGxR / xGBR / AGBR: DXT5 blocks of "cooked" pixels
+    default: return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: ETC formats are not built");
     }
+    const bool swizzled = p->crn_format >= 3 && p->crn_format <= 6;
+    // image_utils::get_image_conversion_type_from_crn_format (create_dds_tex, crn_dds_comp.cpp:90-104); declared beside the other DDS helpers
+    const uint32_t cook = swizzled ? 1u + 2u * (p->crn_format - 3u) : 0u;
+    crn_gpu_pack_params pack = p->pack;
+    if (swizzled) pack.perceptual = 0;                              // mip_level::pack_to_dxt (crn_mipmapped_texture.cpp:146-150), qdxt_pack_init (:2337-2347)
     std::vector<crn_gpu_level_desc> lv(count);                   // face-major: the order write_dds emits and qdxt_pack_init walks
     bool has_alpha = false;
     for (uint32_t f = 0; f < p->faces; f++)
         for (uint32_t l = 0; l < p->levels; l++) {
             const uint32_t w = std::max(1u, p->width >> l), h = std::max(1u, p->height >> l);
             lv[f * p->levels + l] = { h_images[f * p->levels + l], w, h, w * 4 };
-            if (!has_alpha && fmt == CRN_GPU_FMT_DXT1 && p->dxt1a_for_transparency) {                             // image_utils::has_alpha
+            if (!has_alpha && ((fmt == CRN_GPU_FMT_DXT1 && p->dxt1a_for_transparency) || fmt == CRN_GPU_FMT_DXT5A)) {  // image_utils::has_alpha
                 const uint8_t* px = static_cast<const uint8_t*>(h_images[f * p->levels + l]);
                 for (size_t i = 0, n = (size_t)w * h; i < n; i++) if (px[i * 4 + 3] < 255) { has_alpha = true; break; }
             }
@@ -2272,6 +2290,31 @@ int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const
     if (p->hierarchical == 0 && p->quality_level < 255 && fmt != CRN_GPU_FMT_DXT3)
         return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: the non-hierarchical clustered mode is not built");
     crn_gpu_qdxt* q = nullptr;                                                                                   // kept across the passes of a search (m_pQDXT_state)
+    // Levels whose pixels change before compression are staged in HBM and converted there (dds_kernels.cuh): the swizzled DXT5 layouts always
+    // (`cook`), and an opaque source going to DXT5A block by block, whose alpha becomes its luma (mip_level::pack_to_dxt,
+    // crn_mipmapped_texture.cpp:161-162; the clustered path packs the 255s as they are, qdxt_pack_init is called with cook = false).
+    HcBuf d_staged; std::vector<crn_gpu_level_desc> staged; uint32_t staged_conv = 0;
+    auto stage = [&](uint32_t conv) -> int {
+        if (staged_conv == conv) return CRN_GPU_OK;
+        CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+        if (!d_staged.p) {
+            size_t bytes = 0;
+            for (const crn_gpu_level_desc& d : lv) bytes += ((size_t)d.pitch_bytes * d.height + 255) & ~(size_t)255;
+            if (d_staged.alloc(ctx, bytes) != cudaSuccess) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_dds: out of device memory");
+        }
+        staged = lv;
+        size_t o = 0;
+        for (crn_gpu_level_desc& d : staged) {
+            uint8_t* dp = static_cast<uint8_t*>(d_staged.p) + o;
+            CRN_CUDA(ctx, cudaMemcpyAsync(dp, d.rgba, (size_t)d.pitch_bytes * d.height, cudaMemcpyHostToDevice, ctx->stream));
+            int r = crn_gpu_convert_pixels(ctx, dp, d.width, d.height, d.pitch_bytes, conv);
+            if (r) return r;
+            d.rgba = dp;
+            o += ((size_t)d.pitch_bytes * d.height + 255) & ~(size_t)255;
+        }
+        staged_conv = conv;
+        return CRN_GPU_OK;
+    };
     // one compress_pass: convert_to_dxt + write_dds (+ the LZMA measurement when a rate is wanted)
     auto pass = [&](uint32_t quality, void** file_out, uint32_t* size_out, float* rate) -> int {
         uint8_t* file = static_cast<uint8_t*>(malloc(128 + payload));
@@ -2281,9 +2324,22 @@ int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const
         if (quality == 255 || fmt == CRN_GPU_FMT_DXT3) {                                                         // crn_dds_comp.cpp:150-157: block by block
             uint8_t* dst = file + 128;
             uint64_t done = 0;
-            for (const crn_gpu_level_desc& d : lv) {
+            const uint32_t conv = cook ? cook : ((fmt == CRN_GPU_FMT_DXT5A && !has_alpha) ? (uint32_t)crn::kConvYtoA : 0u);
+            if (conv) r = stage(conv);
+            HcBuf d_blk;
+            if (conv && r == CRN_GPU_OK && d_blk.alloc(ctx, (size_t)((lv[0].width + 3) >> 2) * ((lv[0].height + 3) >> 2) * bpb) != cudaSuccess)
+                r = set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_compress_dds: out of device memory");
+            for (size_t li = 0; li < lv.size() && r == CRN_GPU_OK; li++) {
+                const crn_gpu_level_desc& d = conv ? staged[li] : lv[li];
                 r = progress_tick(ctx, 0, 1, (uint32_t)(payload ? done * 100 / payload : 0), 100);               // crn_dds_comp.cpp:130-134, :233-236
-                if (r == CRN_GPU_OK) r = crn_gpu_pack_image_host(ctx, fmt, &p->pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
+                if (r == CRN_GPU_OK && !conv) r = crn_gpu_pack_image_host(ctx, fmt, &pack, d.rgba, d.width, d.height, d.pitch_bytes, dst);
+                if (r == CRN_GPU_OK && conv) {
+                    r = crn_gpu_pack_image(ctx, fmt, &pack, d.rgba, d.width, d.height, d.pitch_bytes, d_blk.p);
+                    if (r == CRN_GPU_OK) {
+                        CRN_CUDA(ctx, cudaMemcpyAsync(dst, d_blk.p, (size_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb, cudaMemcpyDeviceToHost, ctx->stream));
+                        CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    }
+                }
                 if (r) break;
                 const size_t sz = (size_t)((d.width + 3) >> 2) * ((d.height + 3) >> 2) * bpb;
                 dst += sz; done += sz;
@@ -2293,7 +2349,10 @@ int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const
             const bool first = q == nullptr;
             if (first) {
                 r = progress_tick(ctx, 0, 2, 0, 100);                                                            // crn_dds_comp.cpp:136-146, :172-188
-                if (r == CRN_GPU_OK) r = crn_gpu_qdxt_init(ctx, fmt, &p->pack, lv.data(), count, 1, &q);
+                if (r == CRN_GPU_OK && cook) r = stage(cook);
+                if (r == CRN_GPU_OK) r = crn_gpu_qdxt_init(ctx, fmt, &pack, cook ? staged.data() : lv.data(), count, cook ? 0 : 1, &q);
+                // quality -> codebook size curve: deeper for the chroma of CCxY; .75 is for plain DXT5 only (crn_mipmapped_texture.cpp:2533-2542)
+                if (r == CRN_GPU_OK && swizzled) q->pow_mul = p->crn_format == 3 ? 1.5f : 1.0f;
                 if (r == CRN_GPU_OK && crn_gpu_qdxt_output_size(q) != payload) r = set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_compress_dds: payload size mismatch");
             }
             if (r == CRN_GPU_OK) r = first ? progress_tick(ctx, 1, 2, 0, 100) : progress_tick(ctx, 0, 1, 0, 100);
@@ -2424,7 +2483,7 @@ int crn_gpu_dds_get_desc(const void* h_dds, uint32_t dds_size, crn_gpu_dds_desc*
 
 int crn_gpu_convert_pixels(crn_gpu_ctx* ctx, void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t conversion)
 { return crn_guard(ctx, [&]() -> int {
-    if (!ctx || !d_rgba || !width || !height || pitch_bytes < width * 4 || (pitch_bytes & 3) || conversion < 1 || conversion > 9) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_convert_pixels: bad argument");
+    if (!ctx || !d_rgba || !width || !height || pitch_bytes < width * 4 || (pitch_bytes & 3) || conversion < 1 || conversion > 10) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_convert_pixels: bad argument");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = (uint64_t)width * height;
     CRN_LAUNCH(crn::pixel_convert_kernel, (uint32_t)((n + 255) / 256), 256, 0, ctx->stream, static_cast<uint8_t*>(d_rgba), width, height, pitch_bytes, conversion);

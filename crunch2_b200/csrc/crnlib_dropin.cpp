@@ -161,10 +161,15 @@ bool supported(const crn_comp_params& p)
     if (p.m_dxt_compressor_type != cCRNDXTCompressorCRN) return false;                       // CRNF / RYG block compressors: out of scope
     if (p.m_file_type == cCRNFileTypeCRN) {
         if (!(p.m_flags & cCRNCompFlagHierarchical)) return false;                           // dxt_hc's non-adaptive mode is not built
-        switch (p.m_format) { case cCRNFmtDXT1: case cCRNFmtDXT5: case cCRNFmtDXN_XY: case cCRNFmtDXN_YX: case cCRNFmtDXT5A: return true; default: return false; }
+        switch (p.m_format) {
+        case cCRNFmtDXT1: case cCRNFmtDXT5: case cCRNFmtDXT5_CCxY: case cCRNFmtDXT5_xGxR: case cCRNFmtDXT5_xGBR: case cCRNFmtDXT5_AGBR:
+        case cCRNFmtDXN_XY: case cCRNFmtDXN_YX: case cCRNFmtDXT5A: return true;
+        default: return false;                                                               // DXT3 is refused by the reference too; ETC: not built
+        }
     }
     switch (p.m_format) {
-    case cCRNFmtDXT1: case cCRNFmtDXT3: case cCRNFmtDXT5: case cCRNFmtDXN_XY: case cCRNFmtDXN_YX: case cCRNFmtDXT5A: return true;
+    case cCRNFmtDXT1: case cCRNFmtDXT3: case cCRNFmtDXT5: case cCRNFmtDXT5_CCxY: case cCRNFmtDXT5_xGxR: case cCRNFmtDXT5_xGBR: case cCRNFmtDXT5_AGBR:
+    case cCRNFmtDXN_XY: case cCRNFmtDXN_YX: case cCRNFmtDXT5A: return true;
     default: return false;
     }
 }

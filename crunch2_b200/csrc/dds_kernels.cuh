@@ -15,7 +15,7 @@
 namespace crn {
 
 enum PixelConversion { kConvToCCxY = 1, kConvFromCCxY = 2, kConvToxGxR = 3, kConvFromxGxR = 4, kConvToxGBR = 5, kConvFromxGBR = 6,
-                       kConvToAGBR = 7, kConvFromAGBR = 8, kConvXYtoXYZ = 9 };
+                       kConvToAGBR = 7, kConvFromAGBR = 8, kConvXYtoXYZ = 9, kConvYtoA = 10 };
 
 __device__ __forceinline__ uint32_t clamp_u8(int v) { return v < 0 ? 0u : (v > 255 ? 255u : (uint32_t)v); }
 
@@ -60,6 +60,7 @@ __device__ __forceinline__ uint32_t convert_pixel(uint32_t p, uint32_t conv)
     case kConvToAGBR: dr = a; dg = g; db = b; da = r; break;
     case kConvFromAGBR: dr = a; dg = g; db = b; da = r; break;
     case kConvXYtoXYZ: dr = r; dg = g; db = regen_z(r, g); da = 255; break;
+    case kConvYtoA: dr = r; dg = g; db = b; da = (uint32_t)((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16) & 255u; break;   // image::set_alpha_to_luma (crn_image.h:303-315)
     default: return p;
     }
     return dr | (dg << 8) | (db << 16) | (da << 24);

@@ -225,6 +225,8 @@ template <typename SC> __device__ __forceinline__ void dxt1_count_eval(SC*, int)
 // CTA-cooperative evaluation (cluster_kernels.cuh: several warps split the colours of one large cluster): only the cluster scratch can ask for it
 template <typename SC> __device__ __forceinline__ bool dxt1_is_coop(const SC*) { return false; }
 template <typename SC> __device__ __forceinline__ void dxt1_eval_coop(SC*, const Dxt1Cfg, unsigned, unsigned, int, unsigned long long&, int&, bool) {}
+template <typename SC> __device__ __forceinline__ long long dxt1_prof_begin(SC*) { return 0; }                  // profiling build of the cluster kernels only
+template <typename SC> __device__ __forceinline__ void dxt1_prof_end(SC*, long long) {}
 
 // Lane-private evaluation of one candidate: evaluate_solution_uber / _hc_* without the bookkeeping
 // (crn_dxt1.cpp:1370-1561, :1759-1835).  err = min over allowed block types, alpha = 3-colour won.
@@ -238,6 +240,7 @@ __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, u
     if (!valid) { err = ~0ull; alpha = 0; return; }
     dxt1_count_eval(sc, cfg.U);
     if (cfg.fast) { dxt1_eval_fast(sc, cfg, lo, hi, alt, err, alpha); return; }
+    const long long prof_t0 = dxt1_prof_begin(sc);
     int r0, g0, b0, r1, g1, b1;
     unpack565(lo, true, r0, g0, b0);
     unpack565(hi, true, r1, g1, b1);
@@ -257,6 +260,7 @@ __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, u
         dxt1_eval_loop<false, true>(sc, cfg.U, p0, p1, p2, p3, pm, bound, e4, e3);
         alpha = 1; err = e3;
     }
+    dxt1_prof_end(sc, prof_t0);
 }
 
 // Commit candidate (lo, hi, alt) with error e / block type alpha as the new best, applying the

@@ -452,7 +452,7 @@ CRN_API int crn_gpu_crn_to_dds(crn_gpu_ctx* ctx, const void* h_crn, uint32_t crn
  * both block types, dxt1a_for_transparency). */
 typedef struct crn_gpu_dds_params {
     uint32_t struct_size;               /* sizeof(crn_gpu_dds_params) */
-    uint32_t crn_format;                /* 0 DXT1, 1 DXT3, 2 DXT5, 7 DXN_XY, 8 DXN_YX, 9 DXT5A */
+    uint32_t crn_format;                /* crn_format: 0 DXT1, 1 DXT3, 2 DXT5, 3 DXT5_CCxY, 4 DXT5_xGxR, 5 DXT5_xGBR, 6 DXT5_AGBR, 7 DXN_XY, 8 DXN_YX, 9 DXT5A */
     uint32_t width, height, levels, faces;
     uint32_t quality_level;             /* m_quality_level */
     uint32_t dxt1a_for_transparency;    /* cCRNCompFlagDXT1AForTransparency */
