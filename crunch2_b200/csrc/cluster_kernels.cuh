@@ -18,7 +18,13 @@ namespace crn {
 
 // CTA-per-cluster mode (large clusters): the owning warp runs the optimiser as always; each time it evaluates a batch of 32 candidates it
 // publishes them here and the CTA's other warps each take a slice of the unique colours (dxt1_eval_coop below).
-constexpr int kClusterCoopWarps = 8;            // warps of a cooperative CTA
+#ifndef CRN_COOP_WARPS
+#define CRN_COOP_WARPS 8
+#endif
+#ifndef CRN_COOP_OCC
+#define CRN_COOP_OCC 2
+#endif
+constexpr int kClusterCoopWarps = CRN_COOP_WARPS;   // warps of a cooperative CTA
 constexpr int kClusterCoopChunk = 32;           // unique colours per warp per round; the early-out test runs once a round (every 256 colours)
 constexpr uint32_t kClusterCoopMinBlocks = 128; // clusters with at least this many member blocks are optimised by a whole CTA
 struct Dxt1CoopShared {
@@ -412,7 +418,7 @@ dxt1_optimize_clusters_kernel(const uint32_t* __restrict__ cluster_offsets, uint
 // quality (a few hundred clusters of thousands of blocks) waiting for the single warp that owns the largest cluster; here that cluster's
 // colour loop -- >90 % of the optimiser's instructions at that size -- runs on eight warps.  Work-stealing counters: next_cluster[0] for the
 // large clusters (one fetch per CTA), next_cluster[1] for the rest.
-__global__ void __launch_bounds__(kClusterCoopWarps * 32, 2)
+__global__ void __launch_bounds__(kClusterCoopWarps * 32, CRN_COOP_OCC)
 dxt1_optimize_clusters_cta_kernel(const uint32_t* __restrict__ cluster_offsets, uint32_t n_clusters, uint32_t n_big, Dxt1Params prm, int dxt1a,
                                   ClusterWorkspace ws, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ transparent,
                                   unsigned int* __restrict__ next_cluster, ClusterResult* __restrict__ results,

@@ -665,6 +665,7 @@ int crn_gpu_pack_image(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_par
         dp.use_alpha_blocks = (format == CRN_GPU_FMT_DXT1 || format == CRN_GPU_FMT_DXT1A) ? both : 0;
         dp.force_alpha_blocks = 0;
         dp.grayscale_sampling = params->grayscale_sampling ? 1 : 0;
+        dp.parallel_sums = 0;
         dp.alpha_threshold = params->dxt1a_alpha_threshold;
         const int dxt1a = format == CRN_GPU_FMT_DXT1A;
         // five phase kernels per chunk of blocks; the per-block state lives in ctx->d_state between them
@@ -781,6 +782,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     dp.use_alpha_blocks = params->use_both_block_types ? 1 : 0;
     dp.force_alpha_blocks = 0;
     dp.grayscale_sampling = params->grayscale_sampling ? 1 : 0;
+    dp.parallel_sums = (ctx->vq_exact || getenv("CRN_B200_ORDERED_SUMS")) ? 0 : 1;     // crn_gpu_set_vq_mode: exact keeps the reference's member order
     // qdxt1::pack (crn_qdxt1.cpp:920-923): without 3-colour blocks the alpha threshold is forced to 0
     dp.alpha_threshold = dp.use_alpha_blocks ? params->dxt1a_alpha_threshold : 0;
     const int scan_alpha = (dxt1a && dp.use_alpha_blocks) ? 1 : 0;
@@ -807,7 +809,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     if (n_big) {
         // large clusters: a CTA each, then the CTAs finish the small ones warp by warp (cluster_kernels.cuh)
         const unsigned want = n_big + (n_clusters - n_big + crn::kClusterCoopWarps - 1) / crn::kClusterCoopWarps;
-        const int cgrid = (int)std::min<unsigned>(want, (unsigned)ctx->sm_count * 2u);
+        const int cgrid = (int)std::min<unsigned>(want, (unsigned)ctx->sm_count * (unsigned)CRN_COOP_OCC);
         CRN_LAUNCH(crn::dxt1_optimize_clusters_cta_kernel, cgrid, crn::kClusterCoopWarps * 32, 0, ctx->stream, d_cluster_offsets, n_clusters, n_big, dp, scan_alpha, ws, rank,
                    transparent, reinterpret_cast<unsigned int*>(base), results, d_cluster_endpoints, reinterpret_cast<unsigned long long*>(d_cluster_error),
                    ctx->d_cluster_flags, ctx->d_cluster_order);

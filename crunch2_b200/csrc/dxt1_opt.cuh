@@ -40,7 +40,13 @@ struct Dxt1Params {
     int force_alpha_blocks;
     int grayscale_sampling;
     unsigned alpha_threshold;
+    // 1: clusters with more than kDxt1ParallelSumMinColours unique colours form their float sums (perceptual averages, mean, covariance, the
+    // 4-means of try_median4) lane-parallel instead of in the reference's member order.  The optimiser's result then depends on rounding
+    // noise of those sums -- tolerance class; set by the cluster kernels unless the context is in exact mode (crn_gpu_set_vq_mode).  The 4x4
+    // block kernels never set it.
+    int parallel_sums;
 };
+constexpr int kDxt1ParallelSumMinColours = 64;
 
 struct Dxt1Best {              // warp-uniform
     unsigned long long err;
@@ -77,6 +83,7 @@ struct Dxt1Cfg {               // warp-uniform evaluation mode
     bool hc;                   // m_evaluate_hc (:2085)
     bool fast;                 // quality < better: evaluate_solution_fast (:1594-1757) instead of _uber
     bool perc;                 // m_perceptual (perceptual && !grayscale_sampling): scales the fast evaluator's axis by 8 / 24
+    bool par;                  // Dxt1Params::parallel_sums applies to this cluster
 };
 
 __device__ __forceinline__ void unpack565(unsigned c, bool scaled, int& r, int& g, int& b)
@@ -348,7 +355,9 @@ __device__ __noinline__ bool dxt1_refine(SC* sc, const Dxt1Cfg cfg, int level)
     dxt1_best_selectors(sc, cfg);
     double akku_0 = 0, akku_1 = 0, akku_2 = 0;
     double At1_r = 0, At1_g = 0, At1_b = 0, At2_r = 0, At2_g = 0, At2_b = 0;
-    for (int i = 0; i < cfg.U; i++) {
+    // Every term is an integer (small table value x colour component x pixel count) and every partial sum stays far below 2^53, so these
+    // double sums are exact in any order: the colours are split over the lanes and the nine totals meet in a butterfly.
+    for (int i = (int)lane_id(); i < cfg.U; i += 32) {
         const int4 c = sc->cw[i];
         const double weight = (double)(unsigned)c.w;
         const double r = c.x * weight, g = c.y * weight, b = c.z * weight;
@@ -360,6 +369,9 @@ __device__ __noinline__ bool dxt1_refine(SC* sc, const Dxt1Cfg cfg, int level)
         At1_r += w1 * r; At1_g += w1 * g; At1_b += w1 * b;
         At2_r += r; At2_g += g; At2_b += b;
     }
+    akku_0 = warp_sum_f64(akku_0); akku_1 = warp_sum_f64(akku_1); akku_2 = warp_sum_f64(akku_2);
+    At1_r = warp_sum_f64(At1_r); At1_g = warp_sum_f64(At1_g); At1_b = warp_sum_f64(At1_b);
+    At2_r = warp_sum_f64(At2_r); At2_g = warp_sum_f64(At2_g); At2_b = warp_sum_f64(At2_b);
     At2_r = 3 * At2_r - At1_r; At2_g = 3 * At2_g - At1_g; At2_b = 3 * At2_b - At1_b;
     const double xx = akku_2, yy = akku_1, xy = akku_0;
     const double t = xx * yy - xy * xy;
@@ -457,8 +469,10 @@ __device__ __noinline__ bool dxt1_median4(SC* sc, const Dxt1Cfg cfg, int quality
 #pragma unroll
             for (int j = 0; j < 4; j++) { nm[j].x = nm[j].y = nm[j].z = 0.0f; nw[j] = 0.0f; }
             float total_dist = 0;
+            // cfg.par: lane l takes colours l, l + 32, ... and the 17 sums meet in a butterfly (every lane gets the same totals)
+            const int i0 = cfg.par ? (int)lane_id() : 0, istep = cfg.par ? 32 : 1;
 #pragma unroll 1
-            for (int i = 0; i < U; i++) {
+            for (int i = i0; i < U; i += istep) {
                 const V3 v = norm_color(sc, i, mean);
                 float best_dist = v3_sqdist(means[0], v);
                 int best_index = 0;
@@ -472,6 +486,11 @@ __device__ __noinline__ bool dxt1_median4(SC* sc, const Dxt1Cfg cfg, int quality
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     if (j == best_index) { nm[j].x += v.x * fw; nm[j].y += v.y * fw; nm[j].z += v.z * fw; nw[j] += fw; }
+            }
+            if (cfg.par) {
+                total_dist = warp_sum_f32(total_dist);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { nm[j].x = warp_sum_f32(nm[j].x); nm[j].y = warp_sum_f32(nm[j].y); nm[j].z = warp_sum_f32(nm[j].z); nw[j] = warp_sum_f32(nw[j]); }
             }
             unsigned highest_index = 0; float highest_weight = 0; bool empty_cell = false;
 #pragma unroll
@@ -612,7 +631,9 @@ __device__ __noinline__ void comp_moments(SC* sc, const Dxt1Cfg cfg, int comp, C
 {
 #pragma unroll
     for (int s = 0; s < 4; s++) m.W[s] = m.WP2[s] = m.WPP[s] = 0;
-    for (int i = 0; i < cfg.U; i++) {
+    const unsigned lane = lane_id();
+    // wrapping integer sums: any order gives the same words, so the colours are split over the lanes
+    for (int i = (int)lane; i < cfg.U; i += 32) {
         const int4 c = sc->cw[i];
         const unsigned long long p = (unsigned)(comp == 0 ? c.x : (comp == 1 ? c.y : c.z)), w = (unsigned)c.w;
         const int s = sc->sel[i];
@@ -620,8 +641,9 @@ __device__ __noinline__ void comp_moments(SC* sc, const Dxt1Cfg cfg, int comp, C
         for (int k = 0; k < 4; k++)
             if (k == s) { m.W[k] += w; m.WP2[k] += w * p * 2; m.WPP[k] += w * p * p; }
     }
+#pragma unroll
+    for (int s = 0; s < 4; s++) { m.W[s] = warp_sum_u64(m.W[s]); m.WP2[s] = warp_sum_u64(m.WP2[s]); m.WPP[s] = warp_sum_u64(m.WPP[s]); }
     const unsigned limit = comp == 1 ? 64 : 32;
-    const unsigned lane = lane_id();
 #pragma unroll
     for (int s = 0; s < 4; s++) {
         unsigned long long mn = ~0ull;
@@ -794,6 +816,7 @@ __device__ __forceinline__ Dxt1Cfg dxt1_make_cfg(const Dxt1Params& prm, int pixe
     cfg.gray = !perceptual && prm.grayscale_sampling;
     cfg.wr = perceptual ? 8 : 1; cfg.wg = perceptual ? 25 : 1; cfg.wb = 1;
     cfg.fast = prm.quality < 3; cfg.perc = perceptual;
+    cfg.par = prm.parallel_sums && U > kDxt1ParallelSumMinColours;
     if (pixels_have_alpha || prm.force_alpha_blocks) { cfg.do4 = false; cfg.do3 = true; }
     else if (!prm.use_alpha_blocks) { cfg.do4 = true; cfg.do3 = false; }
     else { cfg.do4 = true; cfg.do3 = true; }
@@ -817,6 +840,7 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
     const unsigned lane = lane_id();
     const Dxt1Cfg cfg = dxt1_make_cfg(prm, pixels_have_alpha, U);
     const bool perceptual = prm.perceptual && !prm.grayscale_sampling;
+    const int i0 = cfg.par ? (int)lane : 0, istep = cfg.par ? 32 : 1;       // cfg.par: each O(U) float sum below is split over the lanes
     if (lane == 0) {
         sc->best.lo = sc->best.hi = 0; sc->best.err = ~0ull; sc->best.alpha_block = 0; sc->best.alt_round = 0; sc->best.enforce = 0; sc->best.enforced_sel = 0;
     }
@@ -840,7 +864,7 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
         float pwx = 1.0f, pwy = 1.0f, pwz = 1.0f;
         if (perceptual) {
             float ave_redness = 0, ave_blueness = 0, ave_l = 0;
-            for (int i = 0; i < U; i++) {
+            for (int i = i0; i < U; i += istep) {
                 const int4 c = sc->cw[i];
                 const int l = (c.x + c.y + c.z + 1) / 3;
                 const float fl = (float)l;
@@ -849,6 +873,7 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
                 ave_blueness += scale * (float)c.z;
                 ave_l += fl;
             }
+            if (cfg.par) { ave_redness = warp_sum_f32(ave_redness); ave_blueness = warp_sum_f32(ave_blueness); ave_l = warp_sum_f32(ave_l); }
             const float ftw = (float)total_w;
             ave_redness /= ftw; ave_blueness /= ftw; ave_l /= ftw;
             ave_l = ave_l * 16.0f / 255.0f;
@@ -869,13 +894,17 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
             // compute_vectors (:155-189)
             V3 meanw;
             mean.x = mean.y = mean.z = 0.0f; meanw.x = meanw.y = meanw.z = 0.0f;
-            for (int i = 0; i < U; i++) {
+            for (int i = i0; i < U; i += istep) {
                 const int4 c = sc->cw[i];
                 const float fw = (float)(unsigned)c.w;
                 const float nx = (float)c.x * 1.0f / 255.0f, ny = (float)c.y * 1.0f / 255.0f, nz = (float)c.z * 1.0f / 255.0f;
                 const float wx = pwx * nx, wy = pwy * ny, wz = pwz * nz;
                 mean.x += nx * fw; mean.y += ny * fw; mean.z += nz * fw;
                 meanw.x += wx * fw; meanw.y += wy * fw; meanw.z += wz * fw;
+            }
+            if (cfg.par) {
+                mean.x = warp_sum_f32(mean.x); mean.y = warp_sum_f32(mean.y); mean.z = warp_sum_f32(mean.z);
+                meanw.x = warp_sum_f32(meanw.x); meanw.y = warp_sum_f32(meanw.y); meanw.z = warp_sum_f32(meanw.z);
             }
             {
                 const float inv = 1.0f / (float)total_w;
@@ -884,7 +913,7 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
             }
             // compute_pca on the weighted vectors (:192-256)
             double cov0 = 0, cov1 = 0, cov2 = 0, cov3 = 0, cov4 = 0, cov5 = 0;
-            for (int i = 0; i < U; i++) {
+            for (int i = i0; i < U; i += istep) {
                 const int4 c = sc->cw[i];
                 const float nx = (float)c.x * 1.0f / 255.0f, ny = (float)c.y * 1.0f / 255.0f, nz = (float)c.z * 1.0f / 255.0f;
                 const float r = pwx * nx - meanw.x, g = pwy * ny - meanw.y, b = pwz * nz - meanw.z;
@@ -896,6 +925,10 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
                 } else {
                     cov0 += (double)rr; cov1 += (double)rg; cov2 += (double)rb; cov3 += (double)gg; cov4 += (double)gb; cov5 += (double)bb;
                 }
+            }
+            if (cfg.par) {
+                cov0 = warp_sum_f64(cov0); cov1 = warp_sum_f64(cov1); cov2 = warp_sum_f64(cov2);
+                cov3 = warp_sum_f64(cov3); cov4 = warp_sum_f64(cov4); cov5 = warp_sum_f64(cov5);
             }
             double vfr = (double).9f, vfg = 1.0, vfb = (double).7f;
 #pragma unroll 1
@@ -930,13 +963,20 @@ __device__ __forceinline__ void dxt1_setup_common(SC* sc, const Dxt1Params& prm,
             }
         }
         float l = 1e+9f, h = -1e+9f;
-        for (int i = 0; i < U; i++) {
+        for (int i = i0; i < U; i += istep) {
             const V3 v = norm_color(sc, i, mean);
             float d = v.x * axis.x;
             d += v.y * axis.y;
             d += v.z * axis.z;
             l = l < d ? l : d;
             h = h > d ? h : d;
+        }
+        if (cfg.par) {
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) {
+                const float ol = __shfl_xor_sync(CRN_FULL_MASK, l, ofs), oh = __shfl_xor_sync(CRN_FULL_MASK, h, ofs);
+                l = fminf(l, ol); h = fmaxf(h, oh);                  // (commutative, so every lane ends with the same pair)
+            }
         }
         V3 low_color, high_color;
         low_color.x = mean.x + axis.x * l; low_color.y = mean.y + axis.y * l; low_color.z = mean.z + axis.z * l;
@@ -1149,7 +1189,11 @@ __device__ __forceinline__ void dxt1_phase_post(SC* sc, const Dxt1Params& prm)
         bool choose_solid_block = false;
         dxt1_best_selectors(sc, cfg);
         bool all_equal = true;
-        for (int i = 1; i < U; i++) all_equal = all_equal && sc->sel[i] == sc->sel[0];
+        {
+            const uint8_t s0 = sc->sel[0];
+            for (int i = 1 + (int)lane_id(); i < U; i += 32) all_equal = all_equal && sc->sel[i] == s0;
+            all_equal = __all_sync(CRN_FULL_MASK, all_equal);
+        }
         if (all_equal) choose_solid_block = dxt1_try_solid(sc, cfg, prm);
         if (!choose_solid_block && quality == 4) dxt1_optimize_comps(sc, cfg);
     }

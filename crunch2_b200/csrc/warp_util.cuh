@@ -32,6 +32,19 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     return v;
 }
 
+// butterfly sums: every lane ends with the same value (each step adds the same two numbers on both lanes of a pair)
+__device__ __forceinline__ float warp_sum_f32(float v)
+{
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(CRN_FULL_MASK, v, ofs);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(CRN_FULL_MASK, v, ofs);
+    return v;
+}
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 {
 #pragma unroll

@@ -90,7 +90,9 @@ CRN_API void crn_gpu_set_progress(crn_gpu_ctx* ctx, crn_gpu_progress_fn fn, void
 CRN_API uint64_t crn_gpu_pool_mallocs(const crn_gpu_ctx* ctx);
 /* Vector-quantiser flavour of the clustered-DDS path (crn_gpu_vq_clusterize, crn_gpu_qdxt_init / _pack and everything above them).
  * 0 (default): crnlib::clusterizer<V>'s algorithm with sums in a fixed parallel order, one launch per frontier (csrc/vq_fast.cuh) -- the
- *    tolerance class BASELINE.json states for clustered output (PSNR within 0.05 dB, bitrate within 1 %).
+ *    tolerance class BASELINE.json states for clustered output (PSNR within 0.05 dB, bitrate within 1 %).  The N-pixel colour optimiser
+ *    (crn_gpu_dxt1_optimize_clusters and its callers) likewise forms the O(U) float sums of clusters with more than 64 unique colours
+ *    (mean, covariance, try_median4's 4-means) lane-parallel; every integer error sum stays exact.
  * 1: the reference's member-order float accumulations reproduced bit for bit (csrc/vq_kernels.cuh), so that the cluster assignment EQUALS
  *    the reference's -- several times slower; kept for verification.  The environment variable CRN_B200_VQ_EXACT=1 sets it at context creation. */
 CRN_API void crn_gpu_set_vq_mode(crn_gpu_ctx* ctx, int exact_member_order);

@@ -59,9 +59,13 @@ def run_color(ctx, port, blocks, offs, members, q=4, perc=1, uab=0, dxt1a=False)
             assert (out[b] == want).all(), (c, k)
 
 
-@pytest.fixture(scope="module")
-def simctx(sim):
+@pytest.fixture(scope="module", params=["member-order sums", "lane-parallel sums"])
+def simctx(sim, request):
+    """crn_gpu_set_vq_mode(exact) keeps every float sum of the optimiser in the reference's member order -- the bit-exact contract.  The default
+    forms the O(U) sums of clusters with more than 64 unique colours lane-parallel (dxt1_opt.cuh, Dxt1Params::parallel_sums; tolerance class
+    by contract); on these inputs the rounding noise changes no decision, so the same equalities are asserted for both."""
     ctx = crn.Context(0, lib=sim)
+    ctx.set_vq_mode(request.param == "member-order sums")
     yield ctx
     ctx.close()
 
