@@ -22,7 +22,7 @@ namespace crn {
 #define CRN_COOP_WARPS 8
 #endif
 #ifndef CRN_COOP_OCC
-#define CRN_COOP_OCC 2
+#define CRN_COOP_OCC 3
 #endif
 constexpr int kClusterCoopWarps = CRN_COOP_WARPS;   // warps of a cooperative CTA
 constexpr int kClusterCoopChunk = 32;           // unique colours per warp per round; the early-out test runs once a round (every 256 colours)
@@ -504,68 +504,235 @@ struct Dxt5aClusterScratch : Dxt5aScratch {
     uint8_t uidx_of_value[256];
 };
 
-__global__ void __launch_bounds__(kClusterWarpsPerCta * 32)
+// Candidate error from prefix sums over the 8-bit value axis.  A DXT5A palette is a set of points on a line, so the value that takes palette
+// entry e_m is decided by the midpoints to its sorted neighbours, and the error over such an interval is S2 - 2 e S1 + e^2 S0 with
+// S0 / S1 / S2 = sums of w, w v, w v^2 over the interval -- the same integer the reference reaches by trying all 8 entries for every unique
+// value (crn_dxt5a.cpp:198-262; a tie between two entries contributes the same d^2 either way), in O(16) instead of O(16 U) per candidate.
+// Not valid where the reference's 32-bit product d*d*weight wraps: the kernel checks the largest weight and keeps dxt5a_eval<true> there.
+struct Dxt5aPrefix {
+    unsigned long long s1[257], s2[257];   // [x] = sum over values v < x
+    uint32_t s0[257];
+};
+__device__ __forceinline__ unsigned long long dxt5a_interval_err(const Dxt5aPrefix* pf, unsigned e, int t_prev, int t)
+{   // values in (t_prev, t] against palette entry e
+    const unsigned long long c = pf->s0[t + 1] - pf->s0[t_prev + 1], a = pf->s1[t + 1] - pf->s1[t_prev + 1], b = pf->s2[t + 1] - pf->s2[t_prev + 1];
+    return b - 2ull * e * a + (unsigned long long)(e * e) * c;
+}
+__device__ __forceinline__ void dxt5a_eval_prefix(const Dxt5aPrefix* pf, unsigned l, unsigned h, bool both, unsigned long long& err, unsigned& type)
+{
+    const unsigned lo = min(l, h), hi = max(l, h);       // both palettes are symmetric in l <-> h as sets (crn_dxt.cpp:404-430)
+    unsigned p[8];
+    dxt5a_values8(lo, hi, p);                            // ascending: p0, p2 .. p7, p1
+    unsigned long long e8 = 0;
+    {
+        int tp = -1;
+        unsigned cur = p[0];
+#pragma unroll
+        for (int m = 2; m <= 8; m++) {
+            const unsigned nxt = m == 8 ? p[1] : p[m];
+            const int t = (int)((cur + nxt) >> 1);
+            e8 += dxt5a_interval_err(pf, cur, tp, t);
+            tp = t; cur = nxt;
+        }
+        e8 += dxt5a_interval_err(pf, cur, tp, 255);
+    }
+    err = e8; type = 0;
+    if (both) {
+        dxt5a_values6(lo, hi, p);                        // ascending: 0, p0, p2 .. p5, p1, 255
+        unsigned long long e6 = 0;
+        int tp = -1;
+        unsigned cur = 0;
+#pragma unroll
+        for (int m = 0; m < 7; m++) {
+            const unsigned nxt = m == 0 ? p[0] : (m <= 4 ? p[m + 1] : (m == 5 ? p[1] : 255u));
+            const int t = (int)((cur + nxt) >> 1);
+            e6 += dxt5a_interval_err(pf, cur, tp, t);
+            tp = t; cur = nxt;
+        }
+        e6 += dxt5a_interval_err(pf, cur, tp, 255);
+        if (e6 < e8) { err = e6; type = 1; }
+    }
+}
+
+constexpr int kAlphaClusterWarps = 8;
+struct Dxt5aCtaScratch {
+    Dxt5aClusterScratch c;
+    Dxt5aPrefix pf;
+    unsigned long long red_err[kAlphaClusterWarps];
+    uint32_t red_k[kAlphaClusterWarps], red_l[kAlphaClusterWarps], red_h[kAlphaClusterWarps], red_t[kAlphaClusterWarps];
+    uint32_t cluster, max_weight, n_unique;
+};
+
+// pair number k (i-major over i < j < U) -> (i, j)
+__device__ __forceinline__ void dxt5a_pair_of(unsigned k, int U, int& i, int& j)
+{
+    // row i starts at off(i) = i (2U - i - 1) / 2; first guess from the quadratic, then corrected
+    const float fu = (float)(2 * U - 1);
+    int r = (int)((fu - sqrtf(fmaxf(fu * fu - 8.0f * (float)k, 0.0f))) * 0.5f);
+    r = max(0, min(r, U - 2));
+    while (r > 0 && (unsigned)(r * (2 * U - r - 1) / 2) > k) r--;
+    while ((unsigned)((r + 1) * (2 * U - r - 2) / 2) <= k) r++;
+    i = r; j = r + 1 + (int)(k - (unsigned)(r * (2 * U - r - 1) / 2));
+}
+
+// One CTA per cluster (qdxt5::pack_endpoints_task, crn_qdxt5.cpp:452-576 -> dxt5_endpoint_optimizer::compute): the O(N) passes (histogram of the
+// member pixels, selector write-back) and the all-pairs phase of the search run on all 256 threads; candidates are scored from prefix sums.
+// Results equal the one-warp kernel's (and the reference's): the all-pairs winner is the first minimum in pair order, reduced over
+// (error, pair number); the probe window around the live best stays on one warp, 32 speculative candidates at a time.
+__global__ void __launch_bounds__(kAlphaClusterWarps * 32)
 dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_t* __restrict__ cluster_offsets,
                               const uint32_t* __restrict__ cluster_blocks, uint32_t n_clusters, uint32_t comp, int quality, int both_types,
                               unsigned int* __restrict__ next_cluster, uint8_t* __restrict__ out, uint32_t out_stride, uint32_t out_ofs,
                               uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint32_t* __restrict__ out_flags,
                               const uint32_t* __restrict__ order)
 {
-    __shared__ Dxt5aClusterScratch scratch[kClusterWarpsPerCta];
-    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    Dxt5aClusterScratch* sc = &scratch[warp];
+    __shared__ Dxt5aCtaScratch S;
+    Dxt5aClusterScratch* sc = &S.c;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
+    constexpr unsigned T = kAlphaClusterWarps * 32;
+    const bool both = both_types != 0;
     for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(next_cluster, 1u);
-        c = __shfl_sync(CRN_FULL_MASK, c, 0);
+        __syncthreads();
+        if (tid == 0) S.cluster = atomicAdd(next_cluster, 1u);
+        __syncthreads();
+        uint32_t c = S.cluster;
         if (c >= n_clusters) break;
         if (order) c = order[c];
         const uint32_t b0 = cluster_offsets[c], nb = cluster_offsets[c + 1] - b0;
         const uint32_t* members = cluster_blocks + b0;
         const uint32_t N = nb * 16;
         if (!nb) continue;
-        for (uint32_t v = lane; v < 256; v += 32) { sc->first[v] = 0; sc->count[v] = 0; }
-        __syncwarp();
-        for (uint32_t i = lane; i < N; i += 32) {
+        sc->first[tid] = 0; sc->count[tid] = 0;
+        if (tid == 0) { S.max_weight = 0; S.n_unique = 0; }
+        __syncthreads();
+        for (uint32_t i = tid; i < N; i += T) {
             const uint32_t a = (cluster_pixel(blocks, members, i) >> (8 * comp)) & 0xffu;
             atomicMax(&sc->first[a], ~i);
             atomicAdd(&sc->count[a], 1u);
         }
-        __syncwarp();
+        __syncthreads();
         // unique values ordered by first appearance (crn_dxt5a.cpp:58-75): rank = number of present values seen earlier
-        int U = 0;
-        for (uint32_t v = lane; v < 256; v += 32) {
-            const uint32_t f = sc->first[v];
+        {
+            const uint32_t f = sc->first[tid];
             if (f) {
                 int rank = 0;
                 for (uint32_t o = 0; o < 256; o++) rank += sc->first[o] > f;     // larger ~index == earlier
-                sc->val[rank] = (uint8_t)v; sc->wgt[rank] = sc->count[v]; sc->uidx_of_value[v] = (uint8_t)rank;
+                sc->val[rank] = (uint8_t)tid; sc->wgt[rank] = sc->count[tid]; sc->uidx_of_value[tid] = (uint8_t)rank;
+                atomicMax(&S.max_weight, sc->count[tid]);
+                atomicAdd(&S.n_unique, 1u);
             }
         }
-        __syncwarp();
-        for (uint32_t v = lane; v < 256; v += 32) U += sc->first[v] != 0;
+        __syncthreads();
+        const int U = (int)S.n_unique;
+        // prefix sums over the value axis (warp 0: 8 values per lane, then a scan over the lanes)
+        if (warp == 0) {
+            unsigned long long a0 = 0, a1 = 0, a2 = 0;
+            uint32_t c0[8]; unsigned long long c1[8], c2[8];
 #pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) U += __shfl_xor_sync(CRN_FULL_MASK, U, ofs);
-        unsigned first, second;
+            for (int q = 0; q < 8; q++) {
+                const unsigned v = lane * 8 + q;
+                const unsigned long long w = sc->count[v];
+                c0[q] = (uint32_t)a0; c1[q] = a1; c2[q] = a2;
+                a0 += w; a1 += w * v; a2 += w * v * v;
+            }
+            unsigned long long x0 = a0, x1 = a1, x2 = a2;
+#pragma unroll
+            for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                const unsigned long long y0 = __shfl_up_sync(CRN_FULL_MASK, x0, ofs), y1 = __shfl_up_sync(CRN_FULL_MASK, x1, ofs), y2 = __shfl_up_sync(CRN_FULL_MASK, x2, ofs);
+                if (lane >= (unsigned)ofs) { x0 += y0; x1 += y1; x2 += y2; }
+            }
+            const unsigned long long base0 = x0 - a0, base1 = x1 - a1, base2 = x2 - a2;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const unsigned v = lane * 8 + q;
+                S.pf.s0[v] = (uint32_t)base0 + c0[q]; S.pf.s1[v] = base1 + c1[q]; S.pf.s2[v] = base2 + c2[q];
+            }
+            if (lane == 31) { S.pf.s0[256] = (uint32_t)x0; S.pf.s1[256] = x1; S.pf.s2[256] = x2; }
+        }
+        __syncthreads();
+        // d*d*weight stays below 2^31 for every value: the prefix-sum evaluator equals the reference's sum (255^2 * 33025 < 2^31)
+        const bool exact_prefix = S.max_weight <= 33025u;
+        unsigned first = 0, second = 0;
         unsigned long long err = 0;
         unsigned reordered = 0;                              // results::m_reordered (crn_dxt5a.cpp:150-182)
         if (U == 1) {
             first = second = sc->val[0];
-            if (lane == 0) sc->sel[0] = 0;
-            __syncwarp();
+            if (tid == 0) sc->sel[0] = 0;
         } else {
-            const Dxt5aBest best = N > 33025u ? dxt5a_search<true>(sc, U, quality, both_types != 0) : dxt5a_search<false>(sc, U, quality, both_types != 0);
-            err = best.error;
-            dxt5a_finish(sc, U, best, first, second);
-            reordered = (best.first != best.second && first != best.first) ? 1u : 0u;
+            // ---- phase 1: every pair (i<j) of unique values, i-major (crn_dxt5a.cpp:93-103), over all threads
+            unsigned long long my_err = ~0ull;
+            unsigned my_k = 0xffffffffu, my_type = 0, my_l = 0, my_h = 0;
+            const unsigned npairs = (unsigned)(U * (U - 1) / 2);
+            for (unsigned k = tid; k < npairs; k += T) {
+                int i, j;
+                dxt5a_pair_of(k, U, i, j);
+                unsigned long long e; unsigned ty;
+                const unsigned l = sc->val[i], h = sc->val[j];
+                if (exact_prefix) dxt5a_eval_prefix(&S.pf, l, h, both, e, ty);
+                else dxt5a_eval<true>(sc, U, l, h, both, e, ty);
+                if (e < my_err) { my_err = e; my_k = k; my_type = ty; my_l = l; my_h = h; }
+            }
+            {
+                unsigned long long key = my_err; unsigned idx = my_k;
+                warp_argmin_u64(key, idx);                   // (error, pair number): the first minimum in sequence order
+                const unsigned owner = __ballot_sync(CRN_FULL_MASK, my_err == key && my_k == idx);
+                const int src = owner ? __ffs((int)owner) - 1 : 0;
+                const unsigned wl = __shfl_sync(CRN_FULL_MASK, my_l, src), wh = __shfl_sync(CRN_FULL_MASK, my_h, src), wt = __shfl_sync(CRN_FULL_MASK, my_type, src);
+                if (lane == 0) { S.red_err[warp] = key; S.red_k[warp] = idx; S.red_l[warp] = wl; S.red_h[warp] = wh; S.red_t[warp] = wt; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                Dxt5aBest best;
+                int bw = 0;
+                for (int w = 1; w < kAlphaClusterWarps; w++)
+                    if (S.red_err[w] < S.red_err[bw] || (S.red_err[w] == S.red_err[bw] && S.red_k[w] < S.red_k[bw])) bw = w;
+                best.error = S.red_err[bw]; best.first = S.red_l[bw]; best.second = S.red_h[bw]; best.block_type = S.red_t[bw];
+                // ---- phase 2: probe window around the live best (crn_dxt5a.cpp:105-149), one warp
+                if (quality >= 3 && best.error) {
+                    const int P = (quality == 4) ? 16 : 8;
+                    const int W = 2 * P + 1;
+                    int k0 = 0, row_ld = -1000, row_l = 0;
+                    while (k0 < W * W && best.error) {
+                        const int ld0 = k0 / W - P;
+                        if (ld0 != row_ld) { row_ld = ld0; row_l = (int)best.first + ld0; }
+                        if (row_l > 255) break;                                   // :119-122
+                        const int k = k0 + (int)lane;
+                        const int ld = k / W - P, hd = k % W - P;
+                        const int l = (ld == row_ld) ? row_l : (int)best.first + ld;
+                        const int h = (int)best.second + hd;
+                        const bool valid = (k < W * W) && l >= 0 && l <= 255 && h >= 0 && h <= 255;
+                        unsigned long long e = ~0ull; unsigned ty = 0;
+                        if (valid) {
+                            if (exact_prefix) dxt5a_eval_prefix(&S.pf, (unsigned)l, (unsigned)h, both, e, ty);
+                            else dxt5a_eval<true>(sc, U, (unsigned)l, (unsigned)h, both, e, ty);
+                        }
+                        const unsigned m = __ballot_sync(CRN_FULL_MASK, valid && e < best.error);
+                        if (!m) { k0 += 32; continue; }
+                        const int t = __ffs((int)m) - 1;
+                        best.error = __shfl_sync(CRN_FULL_MASK, e, t);
+                        best.block_type = __shfl_sync(CRN_FULL_MASK, ty, t);
+                        const int wl = __shfl_sync(CRN_FULL_MASK, l, t), wh = __shfl_sync(CRN_FULL_MASK, h, t);
+                        const int wld = __shfl_sync(CRN_FULL_MASK, ld, t);
+                        best.first = (unsigned)wl; best.second = (unsigned)wh;
+                        row_ld = wld; row_l = wl;                                  // the rest of this row keeps its l
+                        k0 = k0 + t + 1;
+                    }
+                }
+                err = best.error;
+                dxt5a_finish(sc, U, best, first, second);
+                reordered = (best.first != best.second && first != best.first) ? 1u : 0u;
+                if (lane == 0) { S.red_l[0] = first; S.red_h[0] = second; }
+            }
         }
-        if (lane == 0) {
+        __syncthreads();
+        if (U != 1) { first = S.red_l[0]; second = S.red_h[0]; }
+        if (tid == 0) {
             if (out_endpoints) out_endpoints[c] = first | (second << 8);
             if (out_error) out_error[c] = err;
             if (out_flags) out_flags[c] = reordered;
         }
-        for (uint32_t base = 0; base < N; base += 32) {
-            const uint32_t i = base + lane;
+        for (uint32_t base = 0; base < N; base += T) {
+            const uint32_t i = base + tid;
             unsigned long long bits = 0;
             if (i < N) {
                 const uint32_t a = (cluster_pixel(blocks, members, i) >> (8 * comp)) & 0xffu;
@@ -577,7 +744,6 @@ dxt5_optimize_clusters_kernel(const uint32_t* __restrict__ blocks, const uint32_
                 *reinterpret_cast<unsigned long long*>(out + (size_t)members[i >> 4] * out_stride + out_ofs) =
                     (unsigned long long)first | ((unsigned long long)second << 8) | (bits << 16);
         }
-        __syncwarp();
     }
 }
 

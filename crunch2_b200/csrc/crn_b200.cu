@@ -851,8 +851,8 @@ int crn_gpu_dxt5_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
     int rc = ensure(ctx, &ctx->d_cluster_ws, &ctx->d_cluster_ws_cap, 1024);
     if (rc) return rc;
     CRN_CUDA(ctx, cudaMemsetAsync(ctx->d_cluster_ws, 0, 256, ctx->stream));
-    const int threads = crn::kClusterWarpsPerCta * 32;
-    const int grid = grid_for(ctx, n_clusters, crn::kClusterWarpsPerCta, getenv("CRN_B200_CLUSTER_CTAS") ? atoi(getenv("CRN_B200_CLUSTER_CTAS")) : 5);
+    const int threads = crn::kAlphaClusterWarps * 32;                    // a CTA per cluster, work-stealing over the size-ordered list
+    const int grid = (int)std::min<uint32_t>(n_clusters, (uint32_t)ctx->sm_count * 8u);
     CRN_LAUNCH(crn::dxt5_optimize_clusters_kernel, grid, threads, 0, ctx->stream, static_cast<const uint32_t*>(d_blocks_rgba), d_cluster_offsets,
                d_cluster_blocks, n_clusters, component, (int)params->dxt_quality, params->use_both_block_types ? 1 : 0,
                reinterpret_cast<unsigned int*>(ctx->d_cluster_ws), static_cast<uint8_t*>(d_out), out_stride_bytes, out_offset_bytes,

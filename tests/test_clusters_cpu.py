@@ -196,3 +196,32 @@ def test_color_clusters_lower_quality_levels_match_port(simctx, port, q):
     offs, members = make_clusters(60, [1, 2, 3, 5, 8, 13], 40 + q)
     run_color(simctx, port, blocks, offs, members, q=q, perc=1, uab=0)
     run_color(simctx, port, blocks, offs, members, q=q, perc=0, uab=1)
+
+
+def test_alpha_cluster_with_a_weight_that_wraps_the_reference_product(simctx, port):
+    """crn_dxt5a.cpp:225-228 forms d*d*weight in 32-bit ints: one value carried by more than 33025 pixels can wrap it.  The kernel scores
+    candidates from prefix sums only while no weight can do that and falls back to the per-value loop otherwise -- both against the port."""
+    rng = np.random.default_rng(5)
+    n_blocks = 2400
+    blocks = np.zeros((n_blocks, 16, 4), np.uint8)
+    blocks[..., 3] = 17                                         # 38400 pixels, ~36000 of them one value
+    noisy = rng.choice(n_blocks * 16, 2400, replace=False)
+    blocks.reshape(-1, 4)[noisy, 3] = rng.integers(0, 256, 2400)
+    offs = np.array([0, n_blocks], np.uint32); members = np.arange(n_blocks, dtype=np.uint32)
+    for q, both in ((4, 1), (3, 0)):
+        out = np.zeros((n_blocks, 8), np.uint8)
+        ep = np.zeros(1, np.uint32); err = np.zeros(1, np.uint64)
+        simctx.optimize_clusters("alpha", blocks.ctypes.data, n_blocks, offs.ctypes.data, members.ctypes.data, 1, n_blocks,
+                                 out.ctypes.data, 8, 0, crn.PackParams(dxt_quality=q, use_both_block_types=both), component=3,
+                                 d_endpoints=ep.ctypes.data, d_error=err.ctypes.data)
+        simctx.synchronize()
+        px = np.ascontiguousarray(blocks.reshape(-1, 4)); n = len(px)
+        f = ctypes.c_uint8(); s = ctypes.c_uint8(); e = ctypes.c_uint64(); bt = ctypes.c_uint8(); sel = np.zeros(n, np.uint8)
+        port.op_dxt5_optimize(P(px), n, 3, q, both, ctypes.byref(f), ctypes.byref(s), P(sel), ctypes.byref(e), ctypes.byref(bt))
+        assert (int(ep[0]) & 0xff, int(ep[0]) >> 8) == (f.value, s.value)
+        assert int(err[0]) == e.value
+        got_sel = np.zeros(n, np.uint8)
+        bits = out.view(np.uint64).ravel() >> np.uint64(16)
+        for i in range(16):
+            got_sel[i::16] = (bits >> np.uint64(3 * i)) & np.uint64(7)
+        assert (got_sel == sel).all()
