@@ -29,7 +29,7 @@ class _PackParams(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_uint32), ("dxt_quality", ctypes.c_uint32), ("perceptual", ctypes.c_uint32),
                 ("use_both_block_types", ctypes.c_uint32), ("dxt1a_alpha_threshold", ctypes.c_uint32),
                 ("use_transparent_indices_for_black", ctypes.c_uint32), ("grayscale_sampling", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32 * 5)]
+                ("non_hierarchical", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 4)]
 
 
 class _TextureInfo(ctypes.Structure):
@@ -554,7 +554,7 @@ class Context:
         return Qdxt(self, fmt, levels, params or PackParams())
 
     # --- CRN -> DXTn transcoding (crnd_unpack_begin / crnd_unpack_level / crnd_unpack_end) -----------
-    def compress_dds(self, images, crn_format, quality_level=255, params=None, dxt1a_for_transparency=False, target_bitrate=0.0, with_rate=False):
+    def compress_dds(self, images, crn_format, quality_level=255, params=None, dxt1a_for_transparency=False, target_bitrate=0.0, with_rate=False, hierarchical=True):
         """crn_compress to a .DDS (dds_comp, crnlib/crn_dds_comp.cpp:148-289): images[face][level] = (h, w, 4) uint8 host arrays.
         quality_level 255 packs block by block, lower values take the clustered path.  Returns the file bytes."""
         faces, levels = len(images), len(images[0])
@@ -563,6 +563,7 @@ class Context:
         self._lib.crn_gpu_default_dds_params(ctypes.byref(p))
         p.crn_format, p.width, p.height, p.levels, p.faces = int(crn_format), int(w), int(h), int(levels), int(faces)
         p.quality_level, p.dxt1a_for_transparency = int(quality_level), int(bool(dxt1a_for_transparency))
+        p.hierarchical = int(bool(hierarchical))
         if params is not None:
             p.pack = params._c()
         flat = [np.ascontiguousarray(images[f][l], np.uint8) for f in range(faces) for l in range(levels)]

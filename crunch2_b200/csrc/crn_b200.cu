@@ -264,6 +264,7 @@ struct crn_gpu_qdxt {
     crn_gpu_ctx* ctx;
     uint32_t format, n_blocks, num_levels, bytes_per_block, num_elements;
     float pow_mul;
+    int flat;                         // qdxt1_params::m_hierarchical == false: every block is its own tile (crn_qdxt1.cpp:370-403)
     crn_gpu_pack_params params;
     std::vector<crn_gpu_mip_desc> mips;
     crn_qdxt_element el[3];
@@ -376,9 +377,9 @@ int qdxt_init_element(crn_gpu_qdxt* q, crn_qdxt_element& e)
     const int threads = crn::kQdxtWarpsPerCta * 32;
     const int grid = grid_for(ctx, mt.total_chunks, crn::kQdxtWarpsPerCta, 8);
     if (e.kind == 0)
-        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, q->d_blocks, mt, 3u, e.d_vecs, e.d_wts, (uint8_t*)nullptr, e.d_keys);
+        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, q->d_blocks, mt, 3u, e.d_vecs, e.d_wts, (uint8_t*)nullptr, e.d_keys, q->flat);
     else
-        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, q->d_blocks, mt, e.comp, e.d_vecs, e.d_wts, (uint8_t*)nullptr, e.d_keys);
+        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, q->d_blocks, mt, e.comp, e.d_vecs, e.d_wts, (uint8_t*)nullptr, e.d_keys, q->flat);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     // distinct dxt_fast selector patterns (crn_qdxt1.cpp:415-438, crn_qdxt5.cpp:395-421)
@@ -874,9 +875,9 @@ int crn_gpu_qdxt_training(crn_gpu_ctx* ctx, uint32_t kind, uint32_t component, c
     const int grid = grid_for(ctx, mt.total_chunks, crn::kQdxtWarpsPerCta, 8);
     const uint32_t* blocks = static_cast<const uint32_t*>(d_blocks_rgba);
     if (kind == 0)
-        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding, (unsigned long long*)nullptr);
+        CRN_LAUNCH(crn::qdxt_training_kernel<0>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding, (unsigned long long*)nullptr, 0);
     else
-        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding, (unsigned long long*)nullptr);
+        CRN_LAUNCH(crn::qdxt_training_kernel<1>, grid, threads, 0, ctx->stream, blocks, mt, component, static_cast<uint8_t*>(d_vectors), d_weights, d_chunk_encoding, (unsigned long long*)nullptr, 0);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;
@@ -946,6 +947,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
     if (!q) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_qdxt_init: out of host memory");
     q->ctx = ctx; q->format = format; q->params = *params; q->num_levels = num_levels;
     q->bytes_per_block = crn_gpu_bytes_per_block(format);
+    q->flat = params->non_hierarchical ? 1 : 0;
     q->pow_mul = format == CRN_GPU_FMT_DXT5 ? .75f : 1.0f;           // crn_mipmapped_texture.cpp:2529-2539
     q->d_blocks = nullptr; q->d_out = nullptr; q->num_elements = 0; q->d_blocks_cap = q->d_out_cap = 0;
     // element table (crn_mipmapped_texture.cpp:2319-2366)
@@ -1589,13 +1591,13 @@ void crn_gpu_free_file(void* file) { free(file); }
 // crnlib/crn_texture_comp.cpp:120-262): same bracket updates, interpolation, acceptance rule and stop test.
 // pass(quality, &file, &size, &rate) produces a malloc'ed file; the best one is returned.
 }  // extern "C" (templates need C++ linkage)
+struct BitrateBest { float bitrate = 1e+10f; int quality = -1; void* file = nullptr; uint32_t size = 0; };   // survives the reference's second search
 template <typename Pass>
-static int bitrate_search(crn_gpu_ctx* ctx, float target, Pass pass, void** out_file, uint32_t* out_size, float* out_bitrate, int* out_quality, float* out_highest)
+static int bitrate_search(crn_gpu_ctx* ctx, float target, Pass pass, BitrateBest& best, float* out_highest)
 {
-    float best_bitrate = 1e+10f, cached[256], highest = 0.0f;
-    int best_quality = -1, low = 0, high = 255;
+    float cached[256], highest = 0.0f;
+    int low = 0, high = 255;
     for (int i = 0; i < 256; i++) cached[i] = -1.0f;
-    void* best_file = nullptr; uint32_t best_size = 0;
     uint32_t iter = 0;
     bool binary = false;
     while (low <= high) {
@@ -1620,23 +1622,20 @@ static int bitrate_search(crn_gpu_ctx* ctx, float target, Pass pass, void** out_
         }
         void* file = nullptr; uint32_t size = 0; float rate = 0.0f;
         const int rc = pass((uint32_t)trial, &file, &size, &rate);
-        if (rc) { free(best_file); return rc; }
+        if (rc) { free(best.file); best.file = nullptr; return rc; }
         cached[trial] = rate;
         if (rate > highest) highest = rate;
-        if (best_quality < 0 || (rate <= target && best_bitrate > target) ||
-            ((rate <= target || best_bitrate > target) && fabsf(rate - target) < fabsf(best_bitrate - target))) {
-            best_bitrate = rate; best_quality = trial;
-            free(best_file); best_file = file; best_size = size; file = nullptr;
-            if (best_bitrate <= target && fabsf(best_bitrate - target) < .005f) break;
+        if (best.quality < 0 || (rate <= target && best.bitrate > target) ||
+            ((rate <= target || best.bitrate > target) && fabsf(rate - target) < fabsf(best.bitrate - target))) {
+            best.bitrate = rate; best.quality = trial;
+            free(best.file); best.file = file; best.size = size; file = nullptr;
+            if (best.bitrate <= target && fabsf(best.bitrate - target) < .005f) break;
         }
         free(file);
         if (rate > target) high = trial - 1; else low = trial + 1;
         if (++iter > 8) binary = true;
     }
-    if (best_quality < 0) { free(best_file); return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "bitrate search found nothing"); }
-    *out_file = best_file; *out_size = best_size;
-    if (out_bitrate) *out_bitrate = best_bitrate;
-    if (out_quality) *out_quality = best_quality;
+    if (best.quality < 0) { free(best.file); best.file = nullptr; return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "bitrate search found nothing"); }
     if (out_highest) *out_highest = highest;
     return CRN_GPU_OK;
 }
@@ -1717,13 +1716,16 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         if (out_quality) *out_quality = p->quality_level;
         return CRN_GPU_OK;
     }
-    // (the reference retries without adaptive block sizes when even quality 255 stays under the target; dxt_hc's
-    //  non-hierarchical mode is not built, so the best hierarchical result stands)
-    int best_quality = -1; float best_bitrate = 0.0f;
-    rc = bitrate_search(ctx, p->target_bitrate, pass, out_file, out_size, &best_bitrate, &best_quality, nullptr);
+    // When even the highest bitrate stays under the target the reference clears cCRNCompFlagHierarchical and searches again
+    // (crn_texture_comp.cpp:232-250).  dxt_hc never reads m_hierarchical in this revision (crnlib/crn_dxt_hc.cpp has no use of it), so for a
+    // .crn that second search repeats the first one's passes exactly and cannot replace the best (a new best needs a strictly smaller
+    // distance to the target): it is not re-run here.
+    BitrateBest best;
+    rc = bitrate_search(ctx, p->target_bitrate, pass, best, nullptr);
     if (rc) return rc;
-    if (out_bitrate) *out_bitrate = best_bitrate;
-    if (out_quality) *out_quality = (uint32_t)best_quality;
+    *out_file = best.file; *out_size = best.size;
+    if (out_bitrate) *out_bitrate = best.bitrate;
+    if (out_quality) *out_quality = (uint32_t)best.quality;
     return CRN_GPU_OK;
 }); }
 
@@ -2289,8 +2291,7 @@ int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const
     uint8_t header[128];
     int rc = crn_gpu_dds_header(p->crn_format, p->width, p->height, p->levels, p->faces, header);
     if (rc) return set_err(ctx, rc, "crn_gpu_compress_dds: format has no DDS form");
-    if (p->hierarchical == 0 && p->quality_level < 255 && fmt != CRN_GPU_FMT_DXT3)
-        return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: the non-hierarchical clustered mode is not built");
+    if (p->hierarchical == 0) pack.non_hierarchical = 1;                                                         // m_q1_params / m_q5_params .m_hierarchical (crn_dds_comp.cpp:160-166)
     crn_gpu_qdxt* q = nullptr;                                                                                   // kept across the passes of a search (m_pQDXT_state)
     // Levels whose pixels change before compression are staged in HBM and converted there (dds_kernels.cuh): the swizzled DXT5 layouts always
     // (`cook`), and an opaque source going to DXT5A block by block, whose alpha becomes its luma (mip_level::pack_to_dxt,
@@ -2380,13 +2381,21 @@ int crn_gpu_compress_dds_ex(crn_gpu_ctx* ctx, const crn_gpu_dds_params* p, const
         return CRN_GPU_OK;
     }
     if (!lzma_packed_size("crn", 3)) { if (q) crn_gpu_qdxt_free(q); return set_err(ctx, CRN_GPU_ERR_UNSUPPORTED, "crn_gpu_compress_dds: a target bitrate needs liblzma.so.5 for the size measurement"); }
-    int best_quality = -1; float best_bitrate = 0.0f;
-    rc = bitrate_search(ctx, p->target_bitrate, pass, out_file, out_size, &best_bitrate, &best_quality, nullptr);
+    BitrateBest best;
+    float highest = 0.0f;
+    rc = bitrate_search(ctx, p->target_bitrate, pass, best, &highest);
+    if (rc == CRN_GPU_OK && !pack.non_hierarchical && highest < p->target_bitrate && fabsf(best.bitrate - p->target_bitrate) >= .005f) {
+        // "Unable to achieve desired bitrate - disabling adaptive block sizes and retrying search" (crn_texture_comp.cpp:232-250):
+        // compress_init again without cCRNCompFlagHierarchical, a second search; the best so far stands unless a pass comes closer
+        if (q) { crn_gpu_qdxt_free(q); q = nullptr; }
+        pack.non_hierarchical = 1;
+        rc = bitrate_search(ctx, p->target_bitrate, pass, best, &highest);
+    }
     if (q) crn_gpu_qdxt_free(q);
-    // (the reference's retry without adaptive block sizes, crn_texture_comp.cpp:232-250, needs the non-hierarchical mode: not built)
     if (rc) return rc;
-    if (out_bitrate) *out_bitrate = best_bitrate;
-    if (out_quality) *out_quality = (uint32_t)best_quality;
+    *out_file = best.file; *out_size = best.size;
+    if (out_bitrate) *out_bitrate = best.bitrate;
+    if (out_quality) *out_quality = (uint32_t)best.quality;
     return CRN_GPU_OK;
 }); }
 

@@ -160,7 +160,7 @@ bool supported(const crn_comp_params& p)
     // what this path implements; anything else fails like an invalid parameter would (NULL), never falls back to a CPU
     if (p.m_dxt_compressor_type != cCRNDXTCompressorCRN) return false;                       // CRNF / RYG block compressors: out of scope
     if (p.m_file_type == cCRNFileTypeCRN) {
-        if (!(p.m_flags & cCRNCompFlagHierarchical)) return false;                           // dxt_hc's non-adaptive mode is not built
+        // (cCRNCompFlagHierarchical: dxt_hc never reads m_hierarchical in this revision, crnlib/crn_dxt_hc.cpp; nothing to switch)
         switch (p.m_format) {
         case cCRNFmtDXT1: case cCRNFmtDXT5: case cCRNFmtDXT5_CCxY: case cCRNFmtDXT5_xGxR: case cCRNFmtDXT5_xGBR: case cCRNFmtDXT5_AGBR:
         case cCRNFmtDXN_XY: case cCRNFmtDXN_YX: case cCRNFmtDXT5A: return true;

@@ -294,7 +294,7 @@ template <int KIND>
 __global__ void __launch_bounds__(kQdxtWarpsPerCta * 32)
 qdxt_training_kernel(const uint32_t* __restrict__ blocks, QdxtMipTable mt, uint32_t comp,
                      uint8_t* __restrict__ out_vecs, uint32_t* __restrict__ out_weights, uint8_t* __restrict__ out_encoding,
-                     unsigned long long* __restrict__ out_sel_keys)
+                     unsigned long long* __restrict__ out_sel_keys, int flat)
 {
     const unsigned lane = lane_id();
     const uint32_t warps = gridDim.x * kQdxtWarpsPerCta;
@@ -379,6 +379,8 @@ qdxt_training_kernel(const uint32_t* __restrict__ blocks, QdxtMipTable mt, uint3
             psnr = psnr - (double)der;
             if (psnr > best) { best = psnr; best_e = e; }
         }
+        // m_hierarchical == false (crn_qdxt1.cpp:370-403, crn_qdxt5.cpp:346-382): every block stands alone = the four-4x4-tile encoding
+        if (flat) best_e = 7;
         if (out_encoding && lane == 0) out_encoding[ch] = (uint8_t)best_e;
         // training vectors of the winning encoding's tiles
         const int nt = g_enc_nt[best_e];

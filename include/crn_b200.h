@@ -59,7 +59,8 @@ typedef struct crn_gpu_pack_params {
     uint32_t dxt1a_alpha_threshold;     /* default 128 */
     uint32_t use_transparent_indices_for_black;
     uint32_t grayscale_sampling;
-    uint32_t reserved[5];
+    uint32_t non_hierarchical;          /* clustered paths: qdxt1/qdxt5_params::m_hierarchical == false -- per-block training vectors, no adaptive tiles */
+    uint32_t reserved[4];
 } crn_gpu_pack_params;
 
 typedef struct crn_gpu_ctx crn_gpu_ctx;

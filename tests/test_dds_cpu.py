@@ -130,3 +130,37 @@ def test_compress_mip_chain_crn_within_tolerance(simctx, ref):
     levels = simctx.generate_mipmaps(img)
     check(ref, "DXT1", [levels], got, want)
     assert crn.texture_info(got, lib=simctx._lib)["levels"] == 7
+
+
+def test_compress_dds_without_adaptive_tiles(simctx, ref):
+    """cCRNCompFlagHierarchical cleared: qdxt1 / qdxt5 take one training vector per block (crn_qdxt1.cpp:370-403, crn_qdxt5.cpp:346-382)."""
+    import quality
+    levels = chain(64, 64, 3, 3)
+    for fmt in ("DXT1", "DXT5"):
+        want, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT[fmt], file_type=1, quality=100, threads=0, flags=1 | 8)
+        hier, _, _ = helpers.ref_compress(ref, [levels], helpers.CRN_FMT[fmt], file_type=1, quality=100, threads=0, flags=1 | 2 | 8)
+        got = simctx.compress_dds([levels], helpers.CRN_FMT[fmt], quality_level=100, hierarchical=False)
+        assert want != hier                          # the flag matters on this input
+        assert len(got) == len(want) and got[:128] == want[:128]
+        if simctx.vq_exact:
+            assert got == want
+        else:
+            gf = 3 if fmt == "DXT5" else 0
+            g = [simctx.unpack_image(gf, np.frombuffer(x, np.uint8)[128:128 + 16 * 16 * (16 if gf else 8)], 64, 64) for x in (got, want)]
+            for ch in ([0, 1, 2],) + (([3],) if gf else ()):
+                a, b = quality.psnr(g[0], levels[0], ch), quality.psnr(g[1], levels[0], ch)
+                assert a >= b - 0.25, (fmt, ch, a, b)          # 4 Ktexel level: rounding noise of the fast VQ dominates at this size
+
+
+def test_compress_dds_bitrate_search_and_retry(simctx, ref):
+    """create_compressed_texture's search on a .dds (crn_texture_comp.cpp:120-262): a reachable target, and one above what quality 255
+    gives, where the reference clears cCRNCompFlagHierarchical and searches a second time (:232-250)."""
+    if not simctx.vq_exact:
+        pytest.skip("compared file against file: exact mode only (the fast VQ is covered by the tolerance tests)")
+    levels = chain(32, 32, 11, 2)
+    for target in (2.0, 7.5):
+        want, ref_q, ref_rate = helpers.ref_compress(ref, [levels], helpers.CRN_FMT["DXT1"], file_type=1, bitrate=target, threads=0, want_bitrate=True)
+        got, rate, q = simctx.compress_dds([levels], helpers.CRN_FMT["DXT1"], target_bitrate=target)
+        assert q == ref_q, (target, q, ref_q)
+        assert abs(rate - ref_rate) <= 0.02 * ref_rate, (target, rate, ref_rate)      # liblzma vs the reference's own LZMA coder
+        assert got == want, target
