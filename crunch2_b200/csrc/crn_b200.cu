@@ -509,6 +509,7 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
 
 #include "hc_host.h"
 #include "crn_writer.h"
+#include "writer_kernels.cuh"
 
 extern "C" {
 
@@ -1534,10 +1535,69 @@ int crn_gpu_crn_hc_params(const crn_gpu_crn_params* p, crn_gpu_hc_params* hp)
     return CRN_GPU_OK;
 }); }
 
+}  // extern "C"
+// The colour palette orderings of the writer on the device (writer_kernels.cuh): one launch, five CTAs.
+static bool order_color_on_device(void* user, const uint32_t* ep_lo, const uint32_t* ep_hi, uint32_t n, const uint32_t* row_start, const uint32_t* col, const uint32_t* cnt,
+                                  uint32_t selected, const uint32_t base[3], const uint32_t* selectors, uint32_t n_sel, uint16_t* remap4, uint16_t* sel_remap)
+{
+    crn_gpu_ctx* ctx = static_cast<crn_gpu_ctx*>(user);
+    if (!ctx || !n || !n_sel || n > (uint32_t)crn::kOrderMaxN || n_sel > (uint32_t)crn::kOrderMaxN || getenv("CRN_B200_HOST_ORDER")) return false;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
+    const uint32_t nt = row_start[n];
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_lo = 0, o_hi = o_lo + al((size_t)n * 4), o_rs = o_hi + al((size_t)n * 4), o_col = o_rs + al((size_t)(n + 1) * 4), o_cnt = o_col + al((size_t)nt * 4),
+                 o_sel = o_cnt + al((size_t)nt * 4), o_remap = o_sel + al((size_t)n_sel * 4), o_sremap = o_remap + al((size_t)4 * n * 2), total = o_sremap + al((size_t)n_sel * 2);
+    HcBuf d;
+    if (d.alloc(ctx, total) != cudaSuccess) return false;
+    uint8_t* b = static_cast<uint8_t*>(d.p);
+    cudaStream_t st = ctx->stream;
+    bool ok = true;
+    ok &= cudaMemcpyAsync(b + o_lo, ep_lo, (size_t)n * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b + o_hi, ep_hi, (size_t)n * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(b + o_rs, row_start, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (nt) {
+        ok &= cudaMemcpyAsync(b + o_col, col, (size_t)nt * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        ok &= cudaMemcpyAsync(b + o_cnt, cnt, (size_t)nt * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
+    ok &= cudaMemcpyAsync(b + o_sel, selectors, (size_t)n_sel * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (!ok) return false;
+    crn::OrderColorJob J;
+    J.ep_lo = reinterpret_cast<const uint32_t*>(b + o_lo); J.ep_hi = reinterpret_cast<const uint32_t*>(b + o_hi);
+    J.row_start = reinterpret_cast<const uint32_t*>(b + o_rs); J.col = reinterpret_cast<const uint32_t*>(b + o_col); J.cnt = reinterpret_cast<const uint32_t*>(b + o_cnt);
+    J.selectors = reinterpret_cast<const uint32_t*>(b + o_sel);
+    J.n = n; J.n_sel = n_sel; J.selected = selected;
+    J.base[0] = base[0]; J.base[1] = base[1]; J.base[2] = base[2];
+    J.remap = reinterpret_cast<uint16_t*>(b + o_remap); J.sel_remap = reinterpret_cast<uint16_t*>(b + o_sremap);
+#ifdef __CUDACC__
+    if (cudaFuncSetAttribute(crn::crn_order_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::OrderSmem)) != cudaSuccess) return false;
+#endif
+    CRN_LAUNCH(crn::crn_order_color_kernel, 5, crn::kOrderThreads, sizeof(crn::OrderSmem), st, J);
+    ctx->launches++;
+    ok &= cudaMemcpyAsync(remap4, b + o_remap, (size_t)4 * n * 2, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaMemcpyAsync(sel_remap, b + o_sremap, (size_t)n_sel * 2, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok &= cudaStreamSynchronize(st) == cudaSuccess;
+    return ok && cudaGetLastError() == cudaSuccess;
+}
+
+static int crn_write_impl(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, const uint16_t* endpoint_indices, const uint16_t* selector_indices,
+                          const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
+                          const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
+                          void** out_file, uint32_t* out_size);
+extern "C" {
 int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, const uint16_t* endpoint_indices, const uint16_t* selector_indices,
                       const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
                       const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
                       void** out_file, uint32_t* out_size)
+{
+    return crn_write_impl(nullptr, p, hp, endpoint_indices, selector_indices, color_endpoints, n_color_endpoints, alpha_endpoints, n_alpha_endpoints, color_selectors, n_color_selectors,
+                          alpha_selectors, n_alpha_selectors, out_file, out_size);
+}
+}  // extern "C"
+// ctx != nullptr: the palette orderings run on that context's device; nullptr: host loops only (the public entry point has no context)
+static int crn_write_impl(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, const uint16_t* endpoint_indices, const uint16_t* selector_indices,
+                          const uint32_t* color_endpoints, uint32_t n_color_endpoints, const uint32_t* alpha_endpoints, uint32_t n_alpha_endpoints,
+                          const uint32_t* color_selectors, uint32_t n_color_selectors, const uint64_t* alpha_selectors, uint32_t n_alpha_selectors,
+                          void** out_file, uint32_t* out_size)
 { return crn_guard(nullptr, [&]() -> int {
     if (out_file) *out_file = nullptr;
     if (out_size) *out_size = 0;
@@ -1573,6 +1633,8 @@ int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, 
             (in.has_alpha0 && (e[1] >= n_alpha_endpoints || s[1] >= n_alpha_selectors)) || (in.has_alpha1 && (e[2] >= n_alpha_endpoints || s[2] >= n_alpha_selectors)))
             return CRN_GPU_ERR_BAD_DATA;
     }
+    crnw::Input::ColorOrderHook hook = { ctx, order_color_on_device };
+    in.color_order_hook = ctx ? &hook : nullptr;
     try {
         crnw::Writer w(in);
         std::vector<uint8_t> file;
@@ -1584,6 +1646,7 @@ int crn_gpu_crn_write(const crn_gpu_crn_params* p, const crn_gpu_hc_params* hp, 
     } catch (const std::bad_alloc&) { return CRN_GPU_ERR_NO_MEMORY; }
     return CRN_GPU_OK;
 }); }
+extern "C" {
 
 void crn_gpu_free_file(void* file) { free(file); }
 
@@ -1697,9 +1760,9 @@ int crn_gpu_compress_crn(crn_gpu_ctx* ctx, const crn_gpu_crn_params* p, const vo
         r = hc_compress_prepared(ctx, &qhp, d_blocks.p, 0, &H, &prepared);
         if (r) return r;
         const double tp1 = wall_ms();
-        r = crn_gpu_crn_write(&q, &qhp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),
-                              H->alpha_endpoints.data(), (uint32_t)H->alpha_endpoints.size(), H->color_selectors.data(), (uint32_t)H->color_selectors.size(),
-                              H->alpha_selectors.data(), (uint32_t)H->alpha_selectors.size(), file, size);
+        r = crn_write_impl(ctx, &q, &qhp, H->endpoint_indices.data(), H->selector_indices.data(), H->color_endpoints.data(), (uint32_t)H->color_endpoints.size(),
+                           H->alpha_endpoints.data(), (uint32_t)H->alpha_endpoints.size(), H->color_selectors.data(), (uint32_t)H->color_selectors.size(),
+                           H->alpha_selectors.data(), (uint32_t)H->alpha_selectors.size(), file, size);
         crn_gpu_hc_free(H);
         if (r) return set_err(ctx, r, "crn_gpu_compress_crn: the writer rejected the quantiser's output");
         *bitrate = (*size * 8.0f) / (float)texels;                                                                // crn_comp.cpp:1640-1653

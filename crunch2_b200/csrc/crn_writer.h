@@ -43,6 +43,15 @@ struct Input {
     const uint32_t* color_selectors; uint32_t n_color_selectors;
     const uint64_t* alpha_selectors; uint32_t n_alpha_selectors;
     bool has_color, has_alpha0, has_alpha1;
+    // Optional: the colour palette orderings computed elsewhere (csrc/writer_kernels.cuh through crn_gpu_compress_crn).  Fills remap[0..3]
+    // (trial 0 = greedy chain, 1..3 = the weighted chains with similarity bases `base`) and sel_remap exactly as the host loops below would;
+    // returns false to decline (the host loops run).
+    struct ColorOrderHook {
+        void* user;
+        bool (*run)(void* user, const uint32_t* ep_lo, const uint32_t* ep_hi, uint32_t n, const uint32_t* row_start, const uint32_t* col, const uint32_t* cnt,
+                    uint32_t selected, const uint32_t base[3], const uint32_t* selectors, uint32_t n_sel, uint16_t* remap4, uint16_t* sel_remap);
+    };
+    const ColorOrderHook* color_order_hook;
 };
 
 // ---- bit output: MSB first, 7 zero bits of padding, whole bytes (crn_symbol_codec.cpp:1373-1412) ----------
@@ -520,12 +529,31 @@ struct Writer {
         static const float weights[4] = {0.0f, 0.0f, 1.0f / 6.0f, 0.5f};
         std::vector<uint16_t> remap[4]; std::vector<uint8_t> packed[4]; uint64_t bits[4]; bool ok[4] = {false, false, false, false};
         bool sel_ok = true;
+        bool ordered = false;                                                     // all five orderings already done by the hook
+        if (in.color_order_hook && n <= 8192 && in.n_color_selectors <= 8192) {
+            std::vector<uint32_t> lo(n), hi(n);
+            for (uint32_t i = 0; i < n; i++) {
+                lo[i] = (uint32_t)eps[i].lo[0] | ((uint32_t)eps[i].lo[1] << 8) | ((uint32_t)eps[i].lo[2] << 16);
+                hi[i] = (uint32_t)eps[i].hi[0] | ((uint32_t)eps[i].hi[1] << 8) | ((uint32_t)eps[i].hi[2] << 16);
+            }
+            const uint32_t base[3] = { (uint32_t)(4000 * (1.0f + weights[1])), (uint32_t)(4000 * (1.0f + weights[2])), (uint32_t)(4000 * (1.0f + weights[3])) };
+            std::vector<uint16_t> all((size_t)4 * n);
+            sel_remap[0].resize(in.n_color_selectors);
+            const auto th0 = std::chrono::steady_clock::now();
+            ordered = in.color_order_hook->run(in.color_order_hook->user, lo.data(), hi.data(), n, T.row_start.data(), T.col.data(), T.cnt.data(), selected, base,
+                                               in.color_selectors, in.n_color_selectors, all.data(), sel_remap[0].data());
+            if (ordered) for (int t = 0; t < 4; t++) remap[t].assign(all.begin() + (size_t)t * n, all.begin() + (size_t)(t + 1) * n);
+            if (getenv("CRN_B200_TRACE")) fprintf(stderr, "[crn_writer] colour orderings on the device: %.1f ms%s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count(), ordered ? "" : " (declined)");
+        }
         std::vector<std::thread> pool;
-        pool.emplace_back([&]() { sel_ok = order_color_selectors(); });          // independent of the endpoint order
+        pool.emplace_back([&]() {                                                 // independent of the endpoint order
+            sel_ok = ordered ? pack_selectors<uint32_t>(in.color_selectors, in.n_color_selectors, 4, sel_remap[0], packed_sel[0]) : order_color_selectors();
+        });
         for (int t = 0; t < 4; t++)
             pool.emplace_back([&, t]() {
                 const auto tt0 = std::chrono::steady_clock::now();
-                if (t) remap_color_endpoints(eps.data(), T, n, selected, weights[t], remap[t]);
+                if (ordered) { }
+                else if (t) remap_color_endpoints(eps.data(), T, n, selected, weights[t], remap[t]);
                 else {
                     ColorEp zero; memset(&zero, 0, sizeof(zero));
                     greedy_chain(eps.data(), n, zero, [](const ColorEp& a, const ColorEp& b) { return ep_dist(a, b); }, remap[0]);

@@ -107,3 +107,16 @@ def test_bitrate_search_reuses_state_and_buffers(gpu_ctx):
     assert a == b
     assert gpu_ctx.pool_mallocs == m0, "the pool allocated during a repeated search"
     assert gpu_ctx.launch_count > l0
+
+
+@pytest.mark.gpu
+def test_gpu_writer_orderings_at_full_palette_size(gpu_ctx, monkeypatch):
+    """8192-entry palettes: the device orderings (writer_kernels.cuh) against crn_writer.h's host loops, whole file"""
+    import blockgen
+    from bench import mip_chain
+    levels = [np.ascontiguousarray(l) for l in mip_chain(blockgen.smooth_image(1024, 1024, 77, alpha=False))]
+    dev, _, _ = gpu_ctx.compress_crn([levels], 0, quality_level=255)
+    monkeypatch.setenv("CRN_B200_HOST_ORDER", "1")
+    host, _, _ = gpu_ctx.compress_crn([levels], 0, quality_level=255)
+    monkeypatch.delenv("CRN_B200_HOST_ORDER")
+    assert dev == host
