@@ -35,11 +35,13 @@ struct Dxt1CoopShared {
     unsigned valid_mask;
     int alt, cmd;                               // cmd: 1 = evaluate this batch, 0 = no more batches for the helper warps
     unsigned long long part[2][kClusterCoopWarps][2][32];   // per round (double buffered), warp, block type, candidate: partial error sums
+    int4 cbuf[kClusterCoopWarps][kClusterCoopChunk];        // the colours of each warp's current slice
 };
 
 struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays live in the global workspace
     int4* cw; int4* ce; uint8_t* sel;
     Dxt1CoopShared* coop;              // non-null: this warp owns a cluster in CTA-per-cluster mode
+    int4 cbuf[32];                     // one-warp evaluation: the 32 evaluation colours being scored (coalesced load -> broadcast reads)
     Dxt1Best best;
     float mean[3], axis[3], low[3], high[3];
     int U, total_w, pixels_have_alpha, stage;
@@ -55,7 +57,7 @@ struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays 
 // found by dxt1_eval through argument-dependent lookup; the 4x4-block scratch type has no counters (generic no-op in dxt1_opt.cuh)
 __device__ __forceinline__ void dxt1_count_eval(Dxt1ClusterScratch* sc, int U) { sc->n_eval[lane_id()]++; sc->n_cu[lane_id()] += (unsigned)U; }
 
-__device__ __forceinline__ bool dxt1_is_coop(const Dxt1ClusterScratch* sc) { return sc->coop != nullptr; }
+__device__ __forceinline__ bool dxt1_is_coop(const Dxt1ClusterScratch*) { return true; }     // every evaluation of a cluster goes through dxt1_eval_coop below
 #ifdef CRN_B200_PHASE_CLOCKS
 // one-warp evaluation: every lane adds its own cycles ([10]) and 1 ([11]); [10] / 32 is then a lower bound of the warp's time in dxt1_eval
 __device__ __forceinline__ long long dxt1_prof_begin(Dxt1ClusterScratch*) { return clock64(); }
@@ -79,13 +81,25 @@ __device__ __forceinline__ void dxt1_coop_rounds(Dxt1CoopShared* cs, unsigned w,
     bool active = valid;
     int buf = 0;
     int base = 0;
+    static_assert(kClusterCoopChunk == 32, "one colour per lane per round");
+    constexpr int STEP = kClusterCoopWarps * kClusterCoopChunk;
+    int4* cbuf = cs->cbuf[w];
+    // the slice of the next round is fetched (one coalesced 512-byte load per warp) while this round's is being scored out of shared memory
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if ((int)(w * kClusterCoopChunk + lane) < U) nxt = ce[w * kClusterCoopChunk + lane];
     do {                                                     // at least one round, so that the batch is not republished while a warp still reads it
         unsigned long long s4 = 0, s3 = 0;
+        cbuf[lane] = nxt;
+        __syncwarp();
+        {
+            const int ni = base + STEP + (int)(w * kClusterCoopChunk + lane);
+            if (ni < U) nxt = ce[ni];
+        }
         if (active) {
-            const int i0 = base + (int)w * kClusterCoopChunk, i1 = min(U, i0 + kClusterCoopChunk);
-#pragma unroll 2
-            for (int i = i0; i < i1; i++) {
-                const int4 c = ce[i];
+            const int i0 = base + (int)w * kClusterCoopChunk, cnt = min(U, i0 + kClusterCoopChunk) - i0;
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                const int4 c = cbuf[j];
                 const unsigned wt = (unsigned)c.w;
                 const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
                 const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
@@ -147,10 +161,81 @@ __device__ __noinline__ void dxt1_coop_batch(Dxt1CoopShared* cs, unsigned w, uns
 
 // dxt1_eval of the owning warp in CTA-per-cluster mode (found through argument-dependent lookup): publish the batch, meet the helper warps
 // at the barrier, take part as warp 0.  All 32 lanes come through here together (dxt1_eval's `valid` argument).
+// One-warp evaluation of a cluster's candidates (one per lane): the colours go through sc->cbuf 32 at a time -- one coalesced load per chunk,
+// issued a chunk ahead -- instead of 32 lanes each walking the global array with dependent broadcast loads.  Same sums and the same early-out
+// rule as dxt1_eval_loop (a lane stops at the first multiple of 8 colours where its partial sums have reached the bound).
+template <bool DO4, bool DO3>
+__device__ __forceinline__ void dxt1_eval_loop_staged(Dxt1ClusterScratch* sc, int U, const int4 p0, const int4 p1, const int4 p2, const int4 p3, const int4 pm,
+                                                      bool valid, unsigned long long bound, unsigned long long& e4, unsigned long long& e3)
+{
+    const unsigned lane = lane_id();
+    const int4* __restrict__ ce = sc->ce;
+    e4 = 0; e3 = 0;
+    bool active = valid;
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if ((int)lane < U) nxt = ce[lane];
+    for (int base = 0; base < U; base += 32) {
+        sc->cbuf[lane] = nxt;
+        __syncwarp();
+        if (base + 32 + (int)lane < U) nxt = ce[base + 32 + lane];
+        if (active) {
+            const int cnt = min(32, U - base);
+            for (int j = 0; j < cnt;) {
+                const int stop = min(cnt, j + 8);
+#pragma unroll 2
+                for (; j < stop; j++) {
+                    const int4 c = sc->cbuf[j];
+                    const unsigned wt = (unsigned)c.w;
+                    const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
+                    const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
+                    if (DO4) {
+                        const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
+                        e4 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                    }
+                    if (DO3) {
+                        const int d = min(d01, eval_dprime(cx, cy, cz, pm));
+                        e3 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                    }
+                }
+                if ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound)) { active = false; break; }
+            }
+        }
+        if (!__any_sync(CRN_FULL_MASK, active)) break;       // (also the barrier before the stage is refilled)
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void dxt1_eval_warp(Dxt1ClusterScratch* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt, unsigned long long& err, int& alpha, bool valid)
+{
+    __syncwarp();
+    if (valid) dxt1_count_eval(sc, cfg.U);
+    int r0, g0, b0, r1, g1, b1;
+    unpack565(lo, true, r0, g0, b0);
+    unpack565(hi, true, r1, g1, b1);
+    const int4 p0 = eval_palette(cfg, r0, g0, b0), p1 = eval_palette(cfg, r1, g1, b1);
+    const int4 p2 = eval_palette(cfg, (r0 * 2 + r1 + alt) / 3, (g0 * 2 + g1 + alt) / 3, (b0 * 2 + b1 + alt) / 3);
+    const int4 p3 = eval_palette(cfg, (r1 * 2 + r0 + alt) / 3, (g1 * 2 + g0 + alt) / 3, (b1 * 2 + b0 + alt) / 3);
+    const int4 pm = eval_palette(cfg, (r0 + r1 + alt) >> 1, (g0 + g1 + alt) >> 1, (b0 + b1 + alt) >> 1);
+    unsigned long long e4, e3;
+    const unsigned long long bound = sc->best.err;
+    if (cfg.do4 && cfg.do3) {
+        dxt1_eval_loop_staged<true, true>(sc, cfg.U, p0, p1, p2, p3, pm, valid, bound, e4, e3);
+        alpha = e3 < e4; err = alpha ? e3 : e4;
+    } else if (cfg.do4) {
+        dxt1_eval_loop_staged<true, false>(sc, cfg.U, p0, p1, p2, p3, pm, valid, bound, e4, e3);
+        alpha = 0; err = e4;
+    } else {
+        dxt1_eval_loop_staged<false, true>(sc, cfg.U, p0, p1, p2, p3, pm, valid, bound, e4, e3);
+        alpha = 1; err = e3;
+    }
+    if (!valid) { err = ~0ull; alpha = 0; }
+}
+
 __device__ __forceinline__ void dxt1_eval_coop(Dxt1ClusterScratch* sc, const Dxt1Cfg cfg, unsigned lo, unsigned hi, int alt,
                                                unsigned long long& err, int& alpha, bool valid)
 {
     Dxt1CoopShared* cs = sc->coop;
+    if (!cs) { dxt1_eval_warp(sc, cfg, lo, hi, alt, err, alpha, valid); return; }     // one warp per cluster
     const unsigned lane = lane_id();
     if (valid) dxt1_count_eval(sc, cfg.U);
     cs->lo[lane] = lo; cs->hi[lane] = hi;

@@ -102,9 +102,14 @@ int ensure(crn_gpu_ctx* ctx, void** p, size_t* cap, size_t need)
     if (*cap >= need) return CRN_GPU_OK;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
-    cudaError_t ce = cudaMalloc(p, need);
+    // Grow with 1/8 headroom, in whole 2 MiB pages: a bitrate search asks for a few KB more every time the cluster count reaches a new
+    // maximum, and re-allocating a 3 GB workspace (cudaFree + cudaMalloc: several hundred ms) for that was the slowest step of a trial.
+    size_t want = need > (64u << 20) ? need + need / 8 : need;
+    want = (want + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    cudaError_t ce = cudaMalloc(p, want);
+    if (ce != cudaSuccess) { (void)cudaGetLastError(); want = need; ce = cudaMalloc(p, want); }
     if (ce != cudaSuccess) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "cudaMalloc", ce);
-    *cap = need;
+    *cap = want;
     return CRN_GPU_OK;
 }
 

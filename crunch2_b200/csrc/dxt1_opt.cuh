@@ -243,7 +243,7 @@ __device__ __noinline__ void dxt1_eval(SC* sc, const Dxt1Cfg cfg, unsigned lo, u
 {
     // `valid` = this lane holds a candidate.  Callers pass it instead of branching around the call: with a CTA per cluster the evaluation
     // contains block-wide barriers, so every lane of every warp has to come through here the same number of times.
-    if (!cfg.fast && dxt1_is_coop(sc)) { dxt1_eval_coop(sc, cfg, lo, hi, alt, err, alpha, valid); return; }
+    if (!cfg.fast && dxt1_is_coop(sc)) { dxt1_eval_coop(sc, cfg, lo, hi, alt, err, alpha, valid); return; }     // (cluster scratch: always; see cluster_kernels.cuh)
     if (!valid) { err = ~0ull; alpha = 0; return; }
     dxt1_count_eval(sc, cfg.U);
     if (cfg.fast) { dxt1_eval_fast(sc, cfg, lo, hi, alt, err, alpha); return; }

@@ -14,7 +14,7 @@ import crunch2_b200 as crn  # noqa: E402
 from crunch2_b200 import api  # noqa: E402
 from bench import mip_chain  # noqa: E402
 
-lib = api._declare(ctypes.CDLL(os.environ.get("CRN_B200_LIB") or os.path.join(ROOT, "crunch2_b200", "libcrn_b200_prof.so")))
+lib = api._declare(ctypes.CDLL(os.environ.get("CRN_B200_LIB") or os.path.join(ROOT, "crunch2_b200", "libcrn_b200_prof.so" if os.path.exists(os.path.join(ROOT, "crunch2_b200", "libcrn_b200_prof.so")) and os.environ.get("CRN_B200_PHASES") else "libcrn_b200.so")))
 ctx = crn.Context(0, lib=lib)
 faces = [[np.ascontiguousarray(l) for l in mip_chain(blockgen.smooth_image(2048, 2048, 3000 + f, alpha=False))] for f in range(6)]
 for q in [int(a) for a in sys.argv[1:]] or [128]:
