@@ -38,6 +38,7 @@ METRICS = {"c2_dxt5_q128_4096_mips": "clustered DXT5 .DDS compress throughput (-
            "c1_dxt1_2048_mips": "DXT1 block-by-block compress throughput (uber, perceptual)",
            "dxt5_2048": "DXT5 block-by-block compress throughput (uber, perceptual)"}
 UNIT = "Mtexel/s"
+C5_WORKERS = 3          # --c5-workers
 CLUSTERED = ("c2_dxt5_q128_4096_mips",)
 CRN_FMT_OF = {0: 0, 3: 2}            # dxt_format -> crn_format for the reference's crn_compress
 
@@ -434,27 +435,60 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
         img = blockgen.smooth_image(1024, 1024, 50000 + mine[0], alpha=True)
         q = ctx.qdxt_init(fmts[mine[0] % 3][0], [img]); q.pack(128); q.close()
     l0 = ctx.launch_count
-    dt = 0.0
-    # the synthetic textures come from a small pool of generator threads running ahead of the GPU (0.2 s of numpy each)
+    # A batch converter keeps several textures in flight: C5_WORKERS contexts on this GPU (each its own stream and host threads), the rank's
+    # textures dealt round-robin.  Every worker sums the wall time of its own calls (host pixels in / host blocks out); the rank's time is the
+    # slowest worker's sum.  The synthetic textures come from a small pool of generator threads running ahead (0.2 s of numpy each, not timed).
+    import crunch2_b200 as crn
     from concurrent.futures import ThreadPoolExecutor
+    nworkers = max(1, min(C5_WORKERS, len(mine)))
+    ctxs = [ctx] + [crn.Context(dev.index if dev.index is not None else 0) for _ in range(nworkers - 1)]
+    for c in ctxs[1:]:
+        img = blockgen.smooth_image(1024, 1024, 50000 + mine[0], alpha=True)
+        q = c.qdxt_init(fmts[mine[0] % 3][0], [img]); q.pack(128); q.close()
     pool = ThreadPoolExecutor(max(2, min(8, (os.cpu_count() or 2) // max(1, world))))
-    ahead, futs = 16, {}
-    for k, i in enumerate(mine):
-        for j in mine[k:k + ahead]:
-            if j not in futs:
-                futs[j] = pool.submit(blockgen.smooth_image, 1024, 1024, 50000 + j, True)
-        img = futs.pop(i).result()
-        t0 = time.perf_counter()
-        q = ctx.qdxt_init(fmts[i % 3][0], [img]); out_i = q.pack(128); q.close()
-        dt += time.perf_counter() - t0
-        if i < 12:
-            keep[i] = (img, out_i.copy())
+    ahead, futs, flock = 16, {}, threading.Lock()
+
+    def image(k):
+        with flock:
+            for j in mine[k:k + ahead]:
+                if j not in futs:
+                    futs[j] = pool.submit(blockgen.smooth_image, 1024, 1024, 50000 + j, True)
+            f = futs.pop(mine[k])
+        return f.result()
+    sums = [0.0] * nworkers
+    errors = []
+
+    def work(wi):
+        try:
+            c = ctxs[wi]
+            for k in range(wi, len(mine), nworkers):
+                i = mine[k]
+                img = image(k)
+                t0 = time.perf_counter()
+                q = c.qdxt_init(fmts[i % 3][0], [img]); out_i = q.pack(128); q.close()
+                sums[wi] += time.perf_counter() - t0
+                if i < 12:
+                    keep[i] = (img, out_i.copy())
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+    ths = [threading.Thread(target=work, args=(wi,)) for wi in range(nworkers)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
     pool.shutdown(wait=False)
+    if errors:
+        raise errors[0]
+    dt = max(sums)
+    launches = sum(c.launch_count for c in ctxs) - l0
+    for c in ctxs[1:]:
+        c.close()
     dt_all = shard.max_over_ranks(dt, dev)
     out = {"workload": "c5_batch: %d x 1024x1024 (DXT1/DXT5/DXN_XY mix), clustered DDS q128, one level each" % n_textures, "n_textures": n_textures,
            "value": n_textures * 1024 * 1024 / dt_all / 1e6, "unit": UNIT, "ms_per_texture": dt_all * 1e3 / max(1, len(mine)),
-           "timing": "host wall clock summed over the per-texture calls (host pixels in / host blocks out), slowest rank",
-           "gpu_launches_per_texture": int((ctx.launch_count - l0) // max(1, len(mine))), "partitioning": "texture -> rank (LPT), %d rank(s)" % world}
+           "timing": "host wall clock summed over each worker's per-texture calls (host pixels in / host blocks out), slowest worker of the slowest rank",
+           "gpu_launches_per_texture": int(launches // max(1, len(mine))), "partitioning": "texture -> rank (LPT), %d rank(s); %d textures in flight per GPU" % (world, nworkers),
+           "workers_per_gpu": nworkers}
     if with_reference and rank == 0:
         import helpers
         ref = helpers.load_ref()
@@ -826,6 +860,7 @@ def main():
     ap.add_argument("--no-block-pack", action="store_true")
     ap.add_argument("--no-hc", action="store_true")
     ap.add_argument("--c5-textures", type=int, default=1024, help="textures of the configs[4] batch (BASELINE: 1024)")
+    ap.add_argument("--c5-workers", type=int, default=3, help="textures in flight per GPU in the configs[4] batch (one context each)")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -887,6 +922,8 @@ def main():
     batch_c5 = None
     if clustered and not args.no_block_pack:
         try:
+            global C5_WORKERS
+            C5_WORKERS = max(1, args.c5_workers)
             batch_c5 = run_batch_c5(ctx, dev, rank, world, args.c5_textures, with_reference=not args.no_cpu_baseline)
         except Exception as e:
             batch_c5 = {"error": str(e)[:300]}
