@@ -473,8 +473,10 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
     // which goes device-to-device into d_members (see vq_leaf_offsets); only the offsets travel
     uint32_t sel_members = 0;
     if (e.kind == 0) {
+        tr.mark("pack: selector vectors", eli);
         rc = qdxt_vq<16>(e, nullptr, n, max_selector_clusters, true, sel_tree, e.d_members, false);
         if (rc) return rc;
+        tr.mark("pack: selector VQ build", eli);
         crn::vq_leaf_offsets(sel_tree, 0u, e.offsets);
         sel_members = n;
     } else {

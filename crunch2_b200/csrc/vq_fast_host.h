@@ -30,7 +30,7 @@ struct VqOrderSim {
     uint32_t total = 0;
     static uint32_t bin_of(float v) { uint32_t b; memcpy(&b, &v, 4); return b >> 16; }
     static float bin_floor(uint32_t bin) { const uint32_t b = bin << 16; float v; memcpy(&v, &b, 4); return v; }
-    void reset(const std::vector<VqHostNode>& nodes)
+    void reset(const VqNodeVec& nodes)
     {
         hist.assign(kBins, 0u); pending.clear(); done.clear(); total = 0;
         add(root, nodes[root].variance, nodes[root].count, 3.0e38f, true);
@@ -65,7 +65,7 @@ struct VqOrderSim {
     // after the last round: the budget() winners (the nodes the reference would have popped).  Everything above the histogram bin that holds
     // the budget-th key wins outright; only that bin's entries need a selection.  need_ranks: also order them as the reference pops them
     // (m_codebook_index, what retrieve_clusters(max) prunes by); a caller that keeps every leaf only needs to know WHICH nodes were split.
-    void finish(std::vector<VqHostNode>& nodes, uint32_t& split_index, bool need_ranks)
+    void finish(VqNodeVec& nodes, uint32_t& split_index, bool need_ranks)
     {
         const uint32_t b = budget();
         auto before = [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key > y.key : x.id < y.id; };
@@ -97,11 +97,33 @@ struct VqOrderSim {
 
 // Host-side arrays of a build, kept by the caller between builds: a 600 K-leaf tree needs ~100 MB of them, and fresh allocations of that size
 // come back from the OS page by page (first-touch faults cost more than the work done on the data).
+// page-locked host array that only grows: cudaMemcpyAsync to or from pageable memory blocks the caller until the copy is done, which
+// would serialise the piecewise rounds (the host could not record piece c while the device works on piece c + 1)
+template <typename T> struct VqPinned {
+    T* p = nullptr; size_t cap = 0;
+    VqPinned() = default;
+    VqPinned(const VqPinned&) = delete;
+    VqPinned& operator=(const VqPinned&) = delete;
+    ~VqPinned() { if (p) cudaFreeHost(p); }
+    bool ensure(size_t n)
+    {
+        if (n <= cap) return true;
+        size_t c = cap ? cap : 4096;
+        while (c < n) c *= 2;
+        void* q = nullptr;
+        if (cudaHostAlloc(&q, c * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        if (p) cudaFreeHost(p);                         // contents are rebuilt every round: nothing to keep
+        p = static_cast<T*>(q); cap = c;
+        return true;
+    }
+};
+
 struct VqFastScratch {
-    std::vector<uint2> slots;
-    std::vector<VqFastResult> results;
+    VqPinned<uint2> slots;
+    VqPinned<VqFastResult> results;
+    VqPinned<uint32_t> all;
     std::vector<uint32_t> lists[4];                     // node-size classes: thread-block cluster, CTA, warp, single thread
-    std::vector<uint32_t> slot_node, all, node_sim;     // node_sim: which sim (partition) a node belongs to
+    std::vector<uint32_t> slot_node, node_sim, todo;        // node_sim: which sim (partition) a node belongs to
     std::vector<VqOrderSim> sims;
     std::vector<uint32_t> parts[4];
 };
@@ -109,8 +131,11 @@ struct VqFastScratch {
 template <int D> class VqFastBuilder {
 public:
     VqFastBuilder(cudaStream_t stream, uint64_t* launch_counter, VqWorkspace* ws, int sm_count, VqFastScratch* scratch)
-        : stream_(stream), launches_(launch_counter), ws_(ws), sm_count_(sm_count), sc_(*scratch), h_slots_(scratch->slots), h_results_(scratch->results), lists_(scratch->lists),
+        : stream_(stream), launches_(launch_counter), ws_(ws), sm_count_(sm_count), sc_(*scratch), lists_(scratch->lists),
           sims_(scratch->sims), node_sim_(scratch->node_sim) {}
+    ~VqFastBuilder() { if (events_ready_) for (cudaEvent_t e : events_) cudaEventDestroy(e); }
+    VqFastBuilder(const VqFastBuilder&) = delete;
+    VqFastBuilder& operator=(const VqFastBuilder&) = delete;
 
     // Same contract as VqBuilder<D>::build (vq_host.h): d_vecs u8[][D], d_wts u32[], d_ids ascending ids (nullptr = 0..n-1);
     // threaded = threaded_clusterizer<V>::create_clusters (three PCA divisions, then one clusterizer per non-empty partition).
@@ -120,10 +145,11 @@ public:
     {
         res.nodes.clear(); res.trees.clear(); res.perm.clear(); res.rounds = 0; res.device_splits = 0;      // capacity kept (see VqFastScratch)
         if (!n) return cudaSuccess;
+        const double t_build0 = now_ms();
         n_ = n; vecs_ = d_vecs; wts_ = d_wts;
         cudaError_t ce = allocate(n, max_size);
         if (ce != cudaSuccess) return ce;
-        std::vector<VqHostNode>& nodes = res.nodes;
+        VqNodeVec& nodes = res.nodes;
         // root statistics (generate_codebook :76-93)
         const unsigned rg = std::max(1u, std::min<unsigned>((n + 8191) / 8192, 64u));
         CRN_LAUNCH(vq_fast_root_kernel<D>, rg, 512, 0, stream_, vecs_, wts_, d_ids, n, d_perm_, d_root_); count();
@@ -135,6 +161,8 @@ public:
         for (int d = 0; d < D + 2; d++) { tot[d] = 0; for (unsigned g = 0; g < rg; g++) tot[d] += part[(size_t)g * (D + 2) + d]; }
         nodes.reserve(std::min<size_t>((size_t)2 * n + 16, (size_t)4 * max_size + 64));
         nodes.resize(1);
+        nodes[0] = VqHostNode();
+        node_count_ = 1;
         nodes[0].begin = 0; nodes[0].count = n;
         {
             float c[D], dot = 0;
@@ -174,7 +202,7 @@ public:
                 t.root = p; t.max_size = (max_size + total / 2) / total;
                 res.trees.push_back(t);
             }
-            for (VqHostNode& nd : nodes) nd.processed = 0;           // the divisions are not clusterizer splits
+            for (uint32_t i = 0; i < node_count_; i++) nodes[i].processed = 0;           // the divisions are not clusterizer splits
             for (uint32_t p : parts) nodes[p].left = -1;
         } else {
             VqTreeSim t;
@@ -183,7 +211,7 @@ public:
         }
         sims_.resize(res.trees.size());
         for (size_t i = 0; i < sims_.size(); i++) { sims_[i].root = res.trees[i].root; sims_[i].max_size = res.trees[i].max_size; sims_[i].reset(nodes); }
-        node_sim_.assign(nodes.size(), 0u);
+        node_sim_.assign(node_count_, 0u);
         for (size_t i = 0; i < sims_.size(); i++) node_sim_[sims_[i].root] = (uint32_t)i;
         for (;;) {
             const double th = now_ms();
@@ -213,7 +241,7 @@ public:
             const double th = now_ms();
             bool par = false;
 #ifdef __CUDACC__
-            if (sims_.size() > 1 && sims_.size() <= 4 && nodes.size() > 65536) {
+            if (sims_.size() > 1 && sims_.size() <= 4 && node_count_ > 65536) {
                 if (!pool_) pool_.reset(new VqPool());
                 pool_->run4([&](int i) { if ((size_t)i < sims_.size()) sims_[i].finish(nodes, res.trees[i].split_index, need_ranks); });
                 par = true;
@@ -229,8 +257,8 @@ public:
         }
         ce = cudaStreamSynchronize(stream_);
         if (getenv("CRN_B200_TRACE"))
-            fprintf(stderr, "[crn_b200] vq_fast<%d> n=%u max=%u: %u rounds, %u device splits, device+copies %.1f ms (of which slot prep %.1f), scatter %.1f ms, wanted %.1f ms, finish %.1f ms\n", D, n,
-                    max_size, res.rounds, res.device_splits, t_enqueue_ + t_sync_, t_prep_, t_host_, t_wanted_, t_finish_);
+            fprintf(stderr, "[crn_b200] vq_fast<%d> n=%u max=%u: %u rounds, %u device splits, enqueue %.1f ms (of which slot prep %.1f), waiting for the device %.1f ms, recording %.1f ms, wanted %.1f ms, finish %.1f ms; whole build %.1f ms\n", D, n,
+                    max_size, res.rounds, res.device_splits, t_enqueue_, t_prep_, t_sync_, t_host_, t_wanted_, t_finish_, now_ms() - t_build0);
         return ce;
     }
 
@@ -241,7 +269,7 @@ private:
     uint64_t* launches_;
     VqWorkspace* ws_;
     int sm_count_;
-    uint32_t n_ = 0, node_cap_ = 0, slot_cap_ = 0;
+    uint32_t n_ = 0, node_cap_ = 0, slot_cap_ = 0, node_count_ = 0;
     const uint8_t* vecs_ = nullptr;
     const uint32_t* wts_ = nullptr;
     uint32_t *d_perm_ = nullptr, *d_tmp_ = nullptr, *d_list_ = nullptr;
@@ -251,8 +279,6 @@ private:
     VqFastNodes nodes_ = {};
     bool wide_ok_ = true;
     VqFastScratch& sc_;
-    std::vector<uint2>& h_slots_;
-    std::vector<VqFastResult>& h_results_;
     std::vector<uint32_t> (&lists_)[4];
 #ifdef __CUDACC__
     std::unique_ptr<VqPool> pool_;
@@ -260,6 +286,8 @@ private:
     std::vector<VqOrderSim>& sims_;
     std::vector<uint32_t>& node_sim_;
     double t_enqueue_ = 0, t_sync_ = 0, t_host_ = 0, t_wanted_ = 0, t_finish_ = 0, t_prep_ = 0;
+    cudaEvent_t events_[4] = {};
+    bool events_ready_ = false;
     static constexpr uint32_t kHugeNode = 8192, kLargeNode = 1024;
     static constexpr int kClusterCtas = 8, kWideClusterCtas = 16, kClusterThreads = 512;
     static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
@@ -342,89 +370,135 @@ private:
     }
 #endif
 
-    // split every node of `frontier` on the device and record the results; mode 1 = threaded_clusterizer's PCA division
-    cudaError_t round(const std::vector<uint32_t>& frontier, std::vector<VqHostNode>& nodes, int mode)
+    // Split every node of `frontier` on the device and record the results; mode 1 = threaded_clusterizer's PCA division.
+    // Large frontiers go in kChunks pieces, each with its own launches and its own copy back, so that the host records piece c (the node
+    // table, the order simulations) while the device is splitting piece c + 1.  Pieces are cut across the partitions: piece c holds the c-th
+    // quarter of EVERY partition's nodes, so recording a piece still spreads over the partitions' host threads.
+    static constexpr uint32_t kChunks = 4, kPipelineMin = 16384;
+    cudaError_t round(const std::vector<uint32_t>& frontier, VqNodeVec& nodes, int mode)
     {
         const double t0 = now_ms();
-        h_slots_.clear();
-        double t_prep = 0;
-        for (int k = 0; k < 4; k++) lists_[k].clear();
         std::vector<uint32_t>& slot_node = sc_.slot_node;
         slot_node.clear();
-        uint32_t next_child = (uint32_t)nodes.size();
+        std::vector<uint32_t>& todo = sc_.todo;
+        todo.clear();
         for (uint32_t id : frontier) {
             VqHostNode& nd = nodes[id];
             if (nd.count < 2 && mode == 0) { nd.processed = 1; nd.unsplittable = 1; continue; }
-            const uint32_t s = (uint32_t)h_slots_.size();
-            h_slots_.push_back(make_uint2(id, next_child));
-            slot_node.push_back(id);
-            next_child += 2;
-            const bool tiny = mode == 0 && nd.count <= kVqTinyNode;
-#ifdef __CUDACC__
-            lists_[tiny ? 3 : (nd.count >= kHugeNode ? 0 : (nd.count >= kLargeNode ? 1 : 2))].push_back(s);
-#else
-            lists_[tiny ? 3 : (nd.count >= kLargeNode ? 1 : 2)].push_back(s);      // the emulator has no thread-block clusters
-#endif
+            todo.push_back(id);
         }
-        const uint32_t F = (uint32_t)h_slots_.size();
+        const uint32_t F = (uint32_t)todo.size();
         if (!F) return cudaSuccess;
-        t_prep = now_ms() - t0; t_prep_ += t_prep;
         if (F > slot_cap_) return cudaErrorMemoryAllocation;
-        if (next_child > node_cap_) { const cudaError_t ge = ensure_nodes(next_child, nodes.size()); if (ge != cudaSuccess) return ge; }
-        cudaMemcpyAsync(d_slots_, h_slots_.data(), sizeof(uint2) * F, cudaMemcpyHostToDevice, stream_);
-        std::vector<uint32_t>& all = sc_.all;
-        all.clear();
-        for (int k = 0; k < 4; k++) all.insert(all.end(), lists_[k].begin(), lists_[k].end());
-        cudaMemcpyAsync(d_list_, all.data(), sizeof(uint32_t) * F, cudaMemcpyHostToDevice, stream_);
-        const uint32_t* dl = d_list_;
-#ifdef __CUDACC__
-        if (!lists_[0].empty()) {
-            const uint32_t cnt = (uint32_t)lists_[0].size();
-            bool launched = false;
-            if (cnt <= 8 && wide_ok_) {
-                launched = launch_cluster<kWideClusterCtas>(dl, cnt, mode);
-                if (!launched) { wide_ok_ = false; (void)cudaGetLastError(); }
+        if (!sc_.slots.ensure(F) || !sc_.results.ensure(F) || !sc_.all.ensure(F)) return cudaErrorMemoryAllocation;
+        uint2* const h_slots = sc_.slots.p;
+        VqFastResult* const h_results = sc_.results.p;
+        uint32_t* const all = sc_.all.p;
+        uint32_t nslots = 0, nall = 0;
+        // partitions: contiguous runs of one sim in the frontier (wanted() is called sim by sim)
+        uint32_t pb[5] = { 0, F, F, F, F };
+        uint32_t np = 1;
+        if (mode == 0 && sims_.size() > 1 && sims_.size() <= 4) {
+            for (uint32_t s = 1; s < F && np < 4; s++) if (node_sim_[todo[s]] != node_sim_[todo[s - 1]]) pb[np++] = s;
+            for (uint32_t k = np; k <= 4; k++) pb[k] = F;
+        }
+        uint32_t nchunks = 1;
+        {
+            const char* pm = getenv("CRN_B200_VQ_PIPELINE_MIN");          // tests lower it so that small inputs take the piecewise path too
+            const uint32_t min_f = pm ? (uint32_t)atoi(pm) : kPipelineMin;
+            if (mode == 0 && F >= min_f && F >= 2 * kChunks && !getenv("CRN_B200_VQ_NO_PIPELINE")) nchunks = kChunks;
+        }
+        // slot order: piece-major, partition inside; sub[c][p] .. sub[c][p + 1] = the slots of partition p in piece c
+        uint32_t sub[kChunks][5];
+        uint32_t next_child = node_count_;
+        for (uint32_t c = 0; c < nchunks; c++)
+            for (uint32_t p = 0; p < 4; p++) {
+                sub[c][p] = nslots;
+                if (p < np) {
+                    const uint32_t len = pb[p + 1] - pb[p];
+                    const uint32_t a = pb[p] + (uint32_t)((uint64_t)len * c / nchunks), b = pb[p] + (uint32_t)((uint64_t)len * (c + 1) / nchunks);
+                    for (uint32_t k = a; k < b; k++) { h_slots[nslots++] = make_uint2(todo[k], next_child); slot_node.push_back(todo[k]); next_child += 2; }
+                }
+                sub[c][4] = nslots;
             }
-            if (!launched && !launch_cluster<kClusterCtas>(dl, cnt, mode)) return cudaGetLastError();
-            count();
-            dl += cnt;
-        }
+        // size classes per piece, concatenated: [piece 0: cluster | cta | warp | thread][piece 1: ...]
+        uint32_t cls_cnt[kChunks][4];
+        for (uint32_t c = 0; c < nchunks; c++) {
+            for (int k = 0; k < 4; k++) lists_[k].clear();
+            for (uint32_t s = sub[c][0]; s < sub[c][4]; s++) {
+                const uint32_t cnt = nodes[slot_node[s]].count;
+                const bool tiny = mode == 0 && cnt <= kVqTinyNode;
+#ifdef __CUDACC__
+                lists_[tiny ? 3 : (cnt >= kHugeNode ? 0 : (cnt >= kLargeNode ? 1 : 2))].push_back(s);
+#else
+                lists_[tiny ? 3 : (cnt >= kLargeNode ? 1 : 2)].push_back(s);      // the emulator has no thread-block clusters
 #endif
-        if (!lists_[1].empty()) {
-            const uint32_t cnt = (uint32_t)lists_[1].size();
-            CRN_LAUNCH((vq_fast_split_kernel<D, 256, 1>), cnt, 256, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
-            dl += cnt;
+            }
+            for (int k = 0; k < 4; k++) {
+                cls_cnt[c][k] = (uint32_t)lists_[k].size();
+                if (cls_cnt[c][k]) memcpy(all + nall, lists_[k].data(), sizeof(uint32_t) * cls_cnt[c][k]);
+                nall += cls_cnt[c][k];
+            }
         }
-        if (!lists_[2].empty()) {
-            const uint32_t cnt = (uint32_t)lists_[2].size();
-            const unsigned grid = (unsigned)std::min<size_t>(cnt, (size_t)sm_count_ * 32);
-            CRN_LAUNCH((vq_fast_split_kernel<D, 32, 1>), grid, 32, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
-            dl += cnt;
+        const double t_prep = now_ms() - t0; t_prep_ += t_prep;
+        if (next_child > node_cap_) { const cudaError_t ge = ensure_nodes(next_child, node_count_); if (ge != cudaSuccess) return ge; }
+        cudaMemcpyAsync(d_slots_, h_slots, sizeof(uint2) * F, cudaMemcpyHostToDevice, stream_);
+        cudaMemcpyAsync(d_list_, all, sizeof(uint32_t) * F, cudaMemcpyHostToDevice, stream_);
+        if (nchunks > 1 && !events_ready_) {
+            for (uint32_t c = 0; c < kChunks; c++) if (cudaEventCreateWithFlags(&events_[c], cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
+            events_ready_ = true;
         }
-        if (!lists_[3].empty()) {
-            const uint32_t cnt = (uint32_t)lists_[3].size();
-            CRN_LAUNCH(vq_fast_tiny_kernel<D>, (cnt + 127) / 128, 128, 0, stream_, vecs_, wts_, d_perm_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_); count();
+        const uint32_t* dl = d_list_;
+        size_t n_cluster = 0, n_cta = 0, n_warp = 0, n_thread = 0;
+        for (uint32_t c = 0; c < nchunks; c++) {
+#ifdef __CUDACC__
+            if (cls_cnt[c][0]) {
+                const uint32_t cnt = cls_cnt[c][0];
+                bool launched = false;
+                if (cnt <= 8 && wide_ok_) {
+                    launched = launch_cluster<kWideClusterCtas>(dl, cnt, mode);
+                    if (!launched) { wide_ok_ = false; (void)cudaGetLastError(); }
+                }
+                if (!launched && !launch_cluster<kClusterCtas>(dl, cnt, mode)) return cudaGetLastError();
+                count();
+                dl += cnt; n_cluster += cnt;
+            }
+#endif
+            if (cls_cnt[c][1]) {
+                const uint32_t cnt = cls_cnt[c][1];
+                CRN_LAUNCH((vq_fast_split_kernel<D, 256, 1>), cnt, 256, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
+                dl += cnt; n_cta += cnt;
+            }
+            if (cls_cnt[c][2]) {
+                const uint32_t cnt = cls_cnt[c][2];
+                const unsigned grid = (unsigned)std::min<size_t>(cnt, (size_t)sm_count_ * 32);
+                CRN_LAUNCH((vq_fast_split_kernel<D, 32, 1>), grid, 32, 0, stream_, vecs_, wts_, d_perm_, d_tmp_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_, mode); count();
+                dl += cnt; n_warp += cnt;
+            }
+            if (cls_cnt[c][3]) {
+                const uint32_t cnt = cls_cnt[c][3];
+                CRN_LAUNCH(vq_fast_tiny_kernel<D>, (cnt + 127) / 128, 128, 0, stream_, vecs_, wts_, d_perm_, nodes_, (const uint2*)d_slots_, dl, cnt, d_results_); count();
+                dl += cnt; n_thread += cnt;
+            }
+            const uint32_t s0 = sub[c][0], s1 = sub[c][4];
+            if (s1 > s0) cudaMemcpyAsync(h_results + s0, d_results_ + s0, sizeof(VqFastResult) * (s1 - s0), cudaMemcpyDeviceToHost, stream_);
+            if (nchunks > 1) cudaEventRecord(events_[c], stream_);
         }
-        h_results_.resize(F);
-        cudaMemcpyAsync(h_results_.data(), d_results_, sizeof(VqFastResult) * F, cudaMemcpyDeviceToHost, stream_);
         const double t1 = now_ms();
-        cudaError_t ce = cudaStreamSynchronize(stream_);
-        const double t2 = now_ms();
-        if (ce != cudaSuccess) return ce;
-        ce = cudaGetLastError();
-        if (ce != cudaSuccess) return ce;
-        nodes.resize(next_child);
+        nodes.resize(next_child);                                // (no construction: VqDefaultInitAlloc; the records are assigned below)
+        node_count_ = next_child;
         if (mode == 0) node_sim_.resize(next_child, 0u);
         auto scatter = [&](uint32_t s0, uint32_t s1) {
             for (uint32_t s = s0; s < s1; s++) {
-                const VqFastResult& r = h_results_[s];
+                const VqFastResult& r = h_results[s];
                 VqHostNode& par = nodes[slot_node[s]];
                 par.processed = 1;
                 if (r.state != 1) { par.unsplittable = 1; continue; }
-                const uint32_t child = h_slots_[s].y;
+                const uint32_t child = h_slots[s].y;
                 par.left = (int32_t)child;
                 VqHostNode& l = nodes[child];
                 VqHostNode& rr = nodes[child + 1];
+                l = VqHostNode(); rr = VqHostNode();                 // (the table is reused between builds: stale records)
                 l.begin = par.begin; l.count = r.n_left; l.variance = r.lvar;
                 rr.begin = par.begin + r.n_left; rr.count = par.count - r.n_left; rr.variance = r.rvar;
                 par.child_count[0] = l.count; par.child_count[1] = rr.count;
@@ -439,26 +513,30 @@ private:
                 }
             }
         };
-        // threaded_clusterizer's partitions are independent: their slots are contiguous in the frontier (wanted() is called sim by sim),
-        // every record written belongs to one partition only, so each partition's share goes to its own host thread
-        bool done_parallel = false;
+        double t_wait = 0, t_rec = 0;
+        for (uint32_t c = 0; c < nchunks; c++) {
+            const double ta = now_ms();
+            cudaError_t ce = nchunks > 1 ? cudaEventSynchronize(events_[c]) : cudaStreamSynchronize(stream_);
+            if (ce != cudaSuccess) return ce;
+            const double tb = now_ms();
+            // every record written belongs to one partition only, so each partition's share of the piece goes to its own host thread
+            bool done_parallel = false;
 #ifdef __CUDACC__
-        if (mode == 0 && sims_.size() > 1 && sims_.size() <= 4 && F > 16384) {
-            uint32_t bounds[5] = { 0, F, F, F, F };
-            uint32_t nb = 1;
-            for (uint32_t s = 1; s < F && nb < 4; s++) if (node_sim_[slot_node[s]] != node_sim_[slot_node[s - 1]]) bounds[nb++] = s;
-            for (uint32_t k = nb; k <= 4; k++) bounds[k] = F;
-            if (!pool_) pool_.reset(new VqPool());
-            pool_->run4([&](int i) { if (bounds[i] < bounds[i + 1]) scatter(bounds[i], bounds[i + 1]); });
-            done_parallel = true;
-        }
+            if (np > 1 && sub[c][4] - sub[c][0] > 4096) {
+                if (!pool_) pool_.reset(new VqPool());
+                pool_->run4([&](int i) { if (sub[c][i] < sub[c][i + 1]) scatter(sub[c][i], sub[c][i + 1]); });
+                done_parallel = true;
+            }
 #endif
-        if (!done_parallel) scatter(0, F);
-        const double t3 = now_ms();
-        t_enqueue_ += t1 - t0; t_sync_ += t2 - t1; t_host_ += t3 - t2;
+            if (!done_parallel) scatter(sub[c][0], sub[c][4]);
+            t_wait += tb - ta; t_rec += now_ms() - tb;
+        }
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) return ce;
+        t_enqueue_ += t1 - t0; t_sync_ += t_wait; t_host_ += t_rec;
         if (getenv("CRN_B200_TRACE_ROUNDS"))
-            fprintf(stderr, "[crn_b200]   vq_fast<%d> round F=%u (cluster %zu, cta %zu, warp %zu, thread %zu): device %.2f ms, host %.2f ms\n", D, F, lists_[0].size(), lists_[1].size(), lists_[2].size(), lists_[3].size(),
-                    t2 - t0, t3 - t2);
+            fprintf(stderr, "[crn_b200]   vq_fast<%d> round F=%u in %u piece(s) (cluster %zu, cta %zu, warp %zu, thread %zu): enqueue %.2f ms, waiting for the device %.2f ms, recording %.2f ms\n",
+                    D, F, nchunks, n_cluster, n_cta, n_warp, n_thread, t1 - t0, t_wait, t_rec);
         return cudaSuccess;
     }
 };

@@ -40,6 +40,17 @@ struct VqHostNode {
     float child_var[2] = {0, 0};
 };
 
+// Node tables grow to a million records per build; a plain vector would write every new record twice (its constructor, then the split
+// result).  With this allocator resize() leaves new records uninitialised: whoever appends nodes assigns VqHostNode() or every field.
+template <typename T> struct VqDefaultInitAlloc : std::allocator<T> {
+    template <typename U> struct rebind { using other = VqDefaultInitAlloc<U>; };
+    VqDefaultInitAlloc() = default;
+    template <typename U> VqDefaultInitAlloc(const VqDefaultInitAlloc<U>&) {}
+    template <typename U> void construct(U*) noexcept {}
+    template <typename U, typename A0, typename... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+};
+typedef std::vector<VqHostNode, VqDefaultInitAlloc<VqHostNode>> VqNodeVec;
+
 struct VqHeapEntry { float variance; uint32_t id; };   // the key travels with the id: sift loops stay inside one array
 
 struct VqTreeSim {                   // one clusterizer<V> instance
@@ -58,7 +69,7 @@ struct VqTreeSim {                   // one clusterizer<V> instance
     static uint32_t bin_of(float v) { uint32_t b; memcpy(&b, &v, 4); return (b >> 19) & (kBins - 1); }
     static float bin_floor(uint32_t bin) { const uint32_t b = bin << 19; float v; memcpy(&v, &b, 4); return v; }
 
-    void reset(const std::vector<VqHostNode>& nodes)
+    void reset(const VqNodeVec& nodes)
     {
         heap.assign((size_t)max_size + 2, VqHeapEntry{0.0f, 0u});
         hist.assign(kBins, 0u);
@@ -100,7 +111,7 @@ struct VqTreeSim {                   // one clusterizer<V> instance
     }
     bool finished() const { return !(total_leaves < max_size && heap_size); }
     // advance as far as the device results allow
-    void run(std::vector<VqHostNode>& nodes)
+    void run(VqNodeVec& nodes)
     {
         while (!finished()) {
             VqHostNode& nd = nodes[heap[1].id];
@@ -142,7 +153,7 @@ struct VqTreeSim {                   // one clusterizer<V> instance
 };
 
 struct VqResult {                    // host-side outcome of one build
-    std::vector<VqHostNode> nodes;
+    VqNodeVec nodes;
     std::vector<VqTreeSim> trees;
     std::vector<uint32_t> perm;      // vector indices, grouped by node range
     uint32_t rounds = 0, device_splits = 0;
@@ -292,7 +303,7 @@ public:
         if (ce != cudaSuccess) return ce;
         n_ = n; vecs_ = d_vecs; wts_ = d_wts;
         if (kSmemCov > 48 * 1024) cudaFuncSetAttribute(vq_stream_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov);
-        std::vector<VqHostNode>& nodes = res.nodes;
+        VqNodeVec& nodes = res.nodes;
 
         // root: identity order + statistics
         launch_fill_identity(d_ids, n);
@@ -311,6 +322,7 @@ public:
         if (ce != cudaSuccess) return ce;
         nodes.reserve(std::min<size_t>((size_t)2 * n + 16, (size_t)4 * max_size + 64));
         nodes.resize(1);
+        nodes[0] = VqHostNode();
         nodes[0].begin = 0; nodes[0].count = n; nodes[0].variance = root_var;
 
         std::vector<uint32_t> frontier;
@@ -409,7 +421,7 @@ private:
     // by cache misses, so each tree gets its own host thread once the heaps are large (product build only).
     // one tree: replay, collect, and order its part of the frontier by first position (what the device kernels expect);
     // the keys are gathered first so that the sort itself runs on a contiguous array
-    static void advance_tree(VqTreeSim& t, std::vector<VqHostNode>& nodes, std::vector<uint32_t>& part, double* tm)
+    static void advance_tree(VqTreeSim& t, VqNodeVec& nodes, std::vector<uint32_t>& part, double* tm)
     {
         const double a = now_ms();
         t.run(nodes);
@@ -428,7 +440,7 @@ private:
 #ifdef __CUDACC__
     std::unique_ptr<VqPool> pool_;
 #endif
-    void advance_trees(std::vector<VqTreeSim>& trees, std::vector<VqHostNode>& nodes, std::vector<uint32_t>& frontier)
+    void advance_trees(std::vector<VqTreeSim>& trees, VqNodeVec& nodes, std::vector<uint32_t>& frontier)
     {
         // threaded_clusterizer's partitions cover ascending, disjoint position ranges, so the per-tree parts concatenate
         // into a sorted frontier
@@ -509,7 +521,7 @@ private:
 
     // split every node of `frontier` (sorted by first position) on the device and record the results
     // presplit: 0 = clusterizer split; 1 / 2 = first / second level of threaded_clusterizer's PCA divisions
-    cudaError_t round(const std::vector<uint32_t>& frontier, std::vector<VqHostNode>& nodes, int presplit)
+    cudaError_t round(const std::vector<uint32_t>& frontier, VqNodeVec& nodes, int presplit)
     {
         const unsigned F = (unsigned)frontier.size(), n = n_;
         if (!F) return cudaSuccess;
@@ -563,7 +575,7 @@ private:
         // parents and children, so the four quarters of the frontier can go in parallel)
         size_t need = nodes.size();
         for (unsigned s = 0; s < F; s++) if (h_results_[s].state == 1) need = std::max(need, (size_t)h_results_[s].child + 2);
-        if (nodes.size() < need) nodes.resize(need);
+        if (nodes.size() < need) { const size_t old = nodes.size(); nodes.resize(need); for (size_t i = old; i < need; i++) nodes[i] = VqHostNode(); }
         auto scatter = [&](unsigned s0, unsigned s1) {
             for (unsigned s = s0; s < s1; s++) {
                 const VqSlotResult& r = h_results_[s];

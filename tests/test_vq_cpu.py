@@ -157,3 +157,25 @@ def test_fast_builder_degenerate_inputs(fastctx, ref):
     co_g, k_g, cb_g = fastctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, 500, 6, 65535, 64, False)
     co_r, k_r, cb_r = ref_clusterize(ref, vecs, w, 65535, 64, False)
     assert k_g == k_r and distortion(vecs, w, co_g) <= distortion(vecs, w, co_r) + 1e-6
+
+
+def test_fast_vq_piecewise_rounds_give_a_valid_tree(sim, monkeypatch):
+    """vq_fast_host.h round(): large frontiers are split in four pieces (piece-major slot order across the partitions) so that the host records
+    one piece while the device splits the next.  Lowering the threshold makes a small input take that path; the partition must still be one:
+    every vector in exactly one cluster, cluster count as asked, distortion within the fast VQ's allowance of the one-piece result."""
+    rng = np.random.default_rng(3)
+    n = 6000
+    vecs = rng.integers(0, 256, (n, 16), dtype=np.uint8); wts = rng.integers(1, 9, n).astype(np.uint32)
+    ctx = crn.Context(0, lib=sim)
+    try:
+        res = []
+        for piecewise in (False, True):
+            if piecewise:
+                monkeypatch.setenv("CRN_B200_VQ_PIPELINE_MIN", "8")
+            idx, k, _ = ctx.vq_clusterize(vecs.ctypes.data, wts.ctypes.data, n, 16, 700, 0, True)
+            assert idx.shape == (n,) and k == 700 and len(np.unique(idx)) == 700
+            res.append(distortion(vecs, wts, idx))
+        monkeypatch.delenv("CRN_B200_VQ_PIPELINE_MIN")
+        assert res[1] <= res[0] * 1.02
+    finally:
+        ctx.close()
