@@ -42,6 +42,7 @@ struct Dxt1ClusterScratch {            // per-warp shared memory; colour arrays 
     int4* cw; int4* ce; uint8_t* sel;
     Dxt1CoopShared* coop;              // non-null: this warp owns a cluster in CTA-per-cluster mode
     int4 cbuf[32];                     // one-warp evaluation: the 32 evaluation colours being scored (coalesced load -> broadcast reads)
+    int4 pal[32][5];                   // one-warp evaluation, second phase: every candidate's palette (p0 p1 p2 p3 pm)
     Dxt1Best best;
     float mean[3], axis[3], low[3], high[3];
     int U, total_w, pixels_have_alpha, stage;
@@ -161,9 +162,13 @@ __device__ __noinline__ void dxt1_coop_batch(Dxt1CoopShared* cs, unsigned w, uns
 
 // dxt1_eval of the owning warp in CTA-per-cluster mode (found through argument-dependent lookup): publish the batch, meet the helper warps
 // at the barrier, take part as warp 0.  All 32 lanes come through here together (dxt1_eval's `valid` argument).
-// One-warp evaluation of a cluster's candidates (one per lane): the colours go through sc->cbuf 32 at a time -- one coalesced load per chunk,
-// issued a chunk ahead -- instead of 32 lanes each walking the global array with dependent broadcast loads.  Same sums and the same early-out
-// rule as dxt1_eval_loop (a lane stops at the first multiple of 8 colours where its partial sums have reached the bound).
+// One-warp evaluation of a cluster's candidates (one per lane), in two phases.
+//   1. candidate per lane over the first 32 evaluation colours (the heaviest ones, cluster_order_eval_colours), read through sc->cbuf: most
+//      candidates of a batch pass the bound here and are dropped (same rule as dxt1_eval_loop, tested every 8 colours);
+//   2. the survivors one after the other, COLOUR per lane: every lane scores its own colours of the remaining U - 32 against the survivor's
+//      palette (broadcast from sc->pal) and the partial sums meet in a butterfly -- every 8 x 32 colours for the early-out, and at the end.
+// A lane-private loop keeps the whole warp waiting for its slowest lane (13.7 of 32 lanes active on configs[1], profiles/r2n); with the roles
+// swapped the cost of a batch is proportional to the number of survivors.  The sums are integers: totals equal dxt1_eval_loop's.
 template <bool DO4, bool DO3>
 __device__ __forceinline__ void dxt1_eval_loop_staged(Dxt1ClusterScratch* sc, int U, const int4 p0, const int4 p1, const int4 p2, const int4 p3, const int4 pm,
                                                       bool valid, unsigned long long bound, unsigned long long& e4, unsigned long long& e3)
@@ -172,35 +177,77 @@ __device__ __forceinline__ void dxt1_eval_loop_staged(Dxt1ClusterScratch* sc, in
     const int4* __restrict__ ce = sc->ce;
     e4 = 0; e3 = 0;
     bool active = valid;
-    int4 nxt = make_int4(0, 0, 0, 0);
-    if ((int)lane < U) nxt = ce[lane];
-    for (int base = 0; base < U; base += 32) {
-        sc->cbuf[lane] = nxt;
-        __syncwarp();
-        if (base + 32 + (int)lane < U) nxt = ce[base + 32 + lane];
-        if (active) {
-            const int cnt = min(32, U - base);
-            for (int j = 0; j < cnt;) {
-                const int stop = min(cnt, j + 8);
+    sc->cbuf[lane] = (int)lane < U ? ce[lane] : make_int4(0, 0, 0, 0);
+    sc->pal[lane][0] = p0; sc->pal[lane][1] = p1;
+    if (DO4) { sc->pal[lane][2] = p2; sc->pal[lane][3] = p3; }
+    if (DO3) sc->pal[lane][4] = pm;
+    __syncwarp();
+    if (active) {
+        const int cnt = min(32, U);
+        for (int j = 0; j < cnt;) {
+            const int stop = min(cnt, j + 8);
 #pragma unroll 2
-                for (; j < stop; j++) {
-                    const int4 c = sc->cbuf[j];
+            for (; j < stop; j++) {
+                const int4 c = sc->cbuf[j];
+                const unsigned wt = (unsigned)c.w;
+                const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
+                const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
+                if (DO4) {
+                    const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
+                    e4 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                }
+                if (DO3) {
+                    const int d = min(d01, eval_dprime(cx, cy, cz, pm));
+                    e3 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                }
+            }
+            if ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound)) { active = false; break; }
+        }
+    }
+    unsigned mask = __ballot_sync(CRN_FULL_MASK, active);
+    if (U <= 32) mask = 0;
+#ifdef CRN_B200_PHASE_CLOCKS
+    { const unsigned vm = __ballot_sync(CRN_FULL_MASK, valid); if (lane == 0) { sc->phase_clk[8] += (unsigned)__popc(vm); } }
+    if (lane == 0) { sc->phase_clk[10] += (unsigned)__popc(mask); sc->phase_clk[11] += 1; }
+#endif
+    while (mask) {
+        const int s = __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        const int4 q0 = sc->pal[s][0], q1 = sc->pal[s][1];
+        int4 q2 = q0, q3 = q0, qm = q0;
+        if (DO4) { q2 = sc->pal[s][2]; q3 = sc->pal[s][3]; }
+        if (DO3) qm = sc->pal[s][4];
+        const unsigned long long h4 = __shfl_sync(CRN_FULL_MASK, e4, s), h3 = __shfl_sync(CRN_FULL_MASK, e3, s);      // the survivor's sums so far
+        unsigned long long t4 = 0, t3 = 0;                           // this lane's share of the rest; totals at the checks
+        unsigned long long a4 = 0, a3 = 0;
+        for (int base = 32; base < U; base += 32 * 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = base + 32 * k + (int)lane;
+                if (i < U) {
+                    const int4 c = ce[i];
                     const unsigned wt = (unsigned)c.w;
                     const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
-                    const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
+                    const int d01 = min(eval_dprime(cx, cy, cz, q0), eval_dprime(cx, cy, cz, q1));
                     if (DO4) {
-                        const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
-                        e4 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                        const int d = min(d01, min(eval_dprime(cx, cy, cz, q2), eval_dprime(cx, cy, cz, q3)));
+                        a4 += (unsigned long long)(unsigned)(d + c.z) * wt;
                     }
                     if (DO3) {
-                        const int d = min(d01, eval_dprime(cx, cy, cz, pm));
-                        e3 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                        const int d = min(d01, eval_dprime(cx, cy, cz, qm));
+                        a3 += (unsigned long long)(unsigned)(d + c.z) * wt;
                     }
                 }
-                if ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound)) { active = false; break; }
+            }
+            if (base + 32 * 8 < U) {                                 // early out: the totals so far already reach the bound
+                if (DO4) t4 = h4 + warp_sum_u64(a4);
+                if (DO3) t3 = h3 + warp_sum_u64(a3);
+                if ((DO4 && DO3) ? (t4 >= bound && t3 >= bound) : (DO4 ? t4 >= bound : t3 >= bound)) break;
             }
         }
-        if (!__any_sync(CRN_FULL_MASK, active)) break;       // (also the barrier before the stage is refilled)
+        if (DO4) t4 = warp_sum_u64(a4);
+        if (DO3) t3 = warp_sum_u64(a3);
+        if ((int)lane == s) { e4 += t4; e3 += t3; }
     }
     __syncwarp();
 }

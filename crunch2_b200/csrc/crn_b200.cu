@@ -831,7 +831,7 @@ int crn_gpu_dxt1_optimize_clusters(crn_gpu_ctx* ctx, const crn_gpu_pack_params* 
         CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         CRN_CUDA(ctx, cudaMemcpy(clk, base + 80, sizeof(clk), cudaMemcpyDeviceToHost));
         static const char* names[12] = { "eval colours + order", "setup_common", "median4", "passes (incl. eval)", "post (incl. eval)", "combinatorial (incl. eval)", "best_selectors", "-",
-                                         "coop eval (owner warp, inside the phases above)", "coop batches", "warp-mode eval, lane cycles summed", "warp-mode lane evals" };
+                                         "coop eval cycles (owner warp) | warp mode: valid candidates", "coop batches", "warp mode: candidates alive after the first 32 colours", "warp mode: batches" };
         fprintf(stderr, "[crn_b200] cluster optimiser phase clocks (%u clusters, %u a CTA each), owner-warp SM cycles summed over clusters:\n", n_clusters, n_big);
         for (int k = 0; k < 12; k++) if (k != 7) fprintf(stderr, "[crn_b200]   %-52s %14llu\n", names[k], clk[k]);
     }

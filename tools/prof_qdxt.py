@@ -27,7 +27,12 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--threads", type=int, default=max(0, min(15, (os.cpu_count() or 1) - 1)))
     a = ap.parse_args()
-    ctx = crn.Context(0)
+    if os.environ.get("CRN_B200_LIB"):                       # e.g. the phase-clock profiling build (make -C crunch2_b200/csrc prof)
+        import ctypes
+        from crunch2_b200 import api
+        ctx = crn.Context(0, lib=api._declare(ctypes.CDLL(os.environ["CRN_B200_LIB"])))
+    else:
+        ctx = crn.Context(0)
     for size in a.sizes:
         levels = mip_chain(blockgen.smooth_image(size, size, 11, alpha=True))
         texels = sum(l.shape[0] * l.shape[1] for l in levels)
