@@ -254,8 +254,9 @@ struct crn_qdxt_element {
     uint32_t* d_wts;
     uint8_t* d_cat;
     uint32_t *d_offsets, *d_members, *d_ids;
+    uint32_t* d_ep_perm;              // final permutation of the endpoint tree: every cluster pack() retrieves is a range of it
     unsigned long long* d_keys;       // per-block dxt_fast selector keys + the distinct-count table
-    size_t caps[7];                   // pool capacities of d_vecs, d_wts, d_cat, d_offsets, d_members, d_ids, d_keys
+    size_t caps[8];                   // pool capacities of d_vecs, d_wts, d_cat, d_offsets, d_members, d_ids, d_keys, d_ep_perm
     std::vector<uint32_t> cluster_of, offsets, members;
     std::vector<uint8_t> cat;
     cudaEvent_t ev_opt[2];            // brackets the endpoint optimisation of the last pack()
@@ -280,12 +281,19 @@ struct crn_gpu_qdxt {
 
 namespace {
 
+struct HcBufLite {                                // pooled device scratch, returned on scope exit
+    crn_gpu_ctx* ctx; void* p = nullptr; size_t cap = 0;
+    explicit HcBufLite(crn_gpu_ctx* c) : ctx(c) {}
+    ~HcBufLite() { if (p) pool_free(ctx, p, cap); }
+    cudaError_t alloc(size_t bytes) { return pool_alloc(ctx, &p, bytes ? bytes : 1, &cap); }
+};
+
 void qdxt_release(crn_gpu_qdxt* q)
 {
     for (uint32_t i = 0; i < q->num_elements; i++) {
         crn_qdxt_element& e = q->el[i];
-        void* ptrs[] = {e.d_vecs, e.d_wts, e.d_cat, e.d_offsets, e.d_members, e.d_ids, e.d_keys};
-        for (int k = 0; k < 7; k++) pool_free(q->ctx, ptrs[k], e.caps[k]);
+        void* ptrs[] = {e.d_vecs, e.d_wts, e.d_cat, e.d_offsets, e.d_members, e.d_ids, e.d_keys, e.d_ep_perm};
+        for (int k = 0; k < 8; k++) pool_free(q->ctx, ptrs[k], e.caps[k]);
         for (cudaEvent_t ev : e.ev_opt) if (ev) cudaEventDestroy(ev);
         // e.ctx is q->ctx->child[i]: it stays with the parent context
     }
@@ -402,7 +410,8 @@ int qdxt_init_element(crn_gpu_qdxt* q, crn_qdxt_element& e)
     e.max_selector_clusters = distinct + 128;
     tr.mark("init: tile analysis + distinct", eli);
     // endpoint codebook: generate_codebook(65535) (crn_qdxt1.cpp:405-413, crn_qdxt5.cpp:386-393)
-    const int rc = e.kind == 0 ? qdxt_vq<6>(e, nullptr, n, 65535u, false, e.endpoint_tree) : qdxt_vq<2>(e, nullptr, n, 65535u, false, e.endpoint_tree);
+    // the tree's final permutation stays on the device: retrieve_clusters() at any size is a set of ranges of it (vq_range_offsets)
+    const int rc = e.kind == 0 ? qdxt_vq<6>(e, nullptr, n, 65535u, false, e.endpoint_tree, e.d_ep_perm) : qdxt_vq<2>(e, nullptr, n, 65535u, false, e.endpoint_tree, e.d_ep_perm);
     if (tr.on) fprintf(stderr, "[crn_b200] endpoint tree: %u rounds, %u device splits\n", e.endpoint_tree.rounds, e.endpoint_tree.device_splits);
     tr.mark("init: endpoint tree", eli);
     return rc;
@@ -432,14 +441,50 @@ int qdxt_pack_element(crn_gpu_qdxt* q, crn_qdxt_element& e, uint32_t quality_lev
     crn_gpu_pack_params pp = q->params;
     if (e.kind == 0) pp.use_both_block_types = e.use_alpha_blocks ? 1u : 0u;      // qdxt5 keeps pack_params' flag (crn_qdxt5.cpp:468)
     // endpoint clusters
-    e.cluster_of.resize(n);
     uint32_t k_end;
-    if (quality >= 1.0f) { for (uint32_t i = 0; i < n; i++) e.cluster_of[i] = i; k_end = n; }
-    else k_end = e.endpoint_tree.retrieve(max_endpoint_clusters, e.cluster_of.data());
-    e.endpoint_clusters = k_end;
     e.offsets.assign(1, 0u); e.members.clear();
-    qdxt_append_csr(e, nullptr, n, k_end);
-    int rc = qdxt_upload_csr(e);
+    int rc;
+    if (quality >= 1.0f) {
+        e.cluster_of.resize(n);
+        for (uint32_t i = 0; i < n; i++) e.cluster_of[i] = i;
+        k_end = n;
+        qdxt_append_csr(e, nullptr, n, k_end);
+        rc = qdxt_upload_csr(e);
+    } else {
+        // retrieve_clusters(max_endpoint_clusters): every cluster is a contiguous, ascending range of the tree's permutation, so only the
+        // (<= 65535 + 1) offsets are built here and the member list is a device-to-device copy
+        k_end = crn::vq_range_offsets(e.endpoint_tree, max_endpoint_clusters, e.offsets);
+        rc = qdxt_upload_csr(e);                              // offsets only
+#ifdef __CUDACC__
+        if (rc == CRN_GPU_OK) {
+            // d_vecs (16 bytes per block) is free between the endpoint tree and the selector vectors: cluster_of | sorted keys | ids
+            uint32_t* d_cl = reinterpret_cast<uint32_t*>(e.d_vecs);
+            uint32_t *d_cl_sorted = d_cl + n, *d_id = d_cl + 2 * (size_t)n;
+            CRN_LAUNCH(crn::range_cluster_of_kernel, (n + 255) / 256, 256, 0, ctx->stream, e.d_ep_perm, e.d_offsets, k_end, n, d_cl, d_id);
+            int bits = 1;
+            while ((1u << bits) < k_end && bits < 32) bits++;
+            size_t temp_bytes = 0;
+            CRN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_cl, d_cl_sorted, d_id, e.d_members, (int)n, 0, bits, ctx->stream));
+            HcBufLite tmp(ctx);
+            if (tmp.alloc(temp_bytes) != cudaSuccess) return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "clustered DDS: sort scratch");
+            CRN_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, temp_bytes, d_cl, d_cl_sorted, d_id, e.d_members, (int)n, 0, bits, ctx->stream));
+            ctx->launches += 3;
+            CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // tmp goes back to the pool
+        }
+#else
+        if (rc == CRN_GPU_OK) {                               // emulation build: the same on the host
+            std::vector<uint32_t> perm(n);
+            CRN_CUDA(ctx, cudaMemcpyAsync(perm.data(), e.d_ep_perm, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            e.cluster_of.resize(n);
+            for (uint32_t c = 0; c < k_end; c++) for (uint32_t i = e.offsets[c]; i < e.offsets[c + 1]; i++) e.cluster_of[perm[i]] = c;
+            e.offsets.assign(1, 0u); e.members.clear();
+            qdxt_append_csr(e, nullptr, n, k_end);
+            rc = qdxt_upload_csr(e);
+        }
+#endif
+    }
+    e.endpoint_clusters = k_end;
     if (rc) return rc;
     if (tr.on) {
         std::vector<uint32_t> sz(k_end);
@@ -964,7 +1009,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
         crn_qdxt_element& e = q->el[ne++];
         e.kind = kind; e.comp = comp; e.offset = offset; e.use_alpha_blocks = use_alpha;
         e.max_selector_clusters = 0; e.endpoint_clusters = e.selector_clusters = 0;
-        e.ctx = nullptr; e.d_vecs = nullptr; e.d_wts = nullptr; e.d_cat = nullptr; e.d_offsets = e.d_members = e.d_ids = nullptr; e.d_keys = nullptr; e.rc = 0; e.ev_opt[0] = e.ev_opt[1] = nullptr; e.endpoint_opt_ms = 0;
+        e.ctx = nullptr; e.d_vecs = nullptr; e.d_wts = nullptr; e.d_cat = nullptr; e.d_offsets = e.d_members = e.d_ids = e.d_ep_perm = nullptr; e.d_keys = nullptr; e.rc = 0; e.ev_opt[0] = e.ev_opt[1] = nullptr; e.endpoint_opt_ms = 0;
         memset(e.caps, 0, sizeof(e.caps));
         q->num_elements = ne;
     };
@@ -1013,6 +1058,7 @@ int crn_gpu_qdxt_init(crn_gpu_ctx* ctx, uint32_t format, const crn_gpu_pack_para
         QDXT_ALLOC(e.d_members, (size_t)n * 4, e.caps[4]);
         QDXT_ALLOC(e.d_ids, (size_t)n * 4, e.caps[5]);
         QDXT_ALLOC(e.d_keys, ((size_t)n + cap + 2) * 8, e.caps[6]);
+        QDXT_ALLOC(e.d_ep_perm, (size_t)n * 4, e.caps[7]);
     }
 #undef QDXT_ALLOC
     // pixel blocks of every level (crn_mipmapped_texture.cpp:2419-2472)

@@ -509,4 +509,18 @@ __global__ void __launch_bounds__(256) blockify_padded_kernel(const uint8_t* __r
     blocks[i] = *reinterpret_cast<const uint32_t*>(rgba + (size_t)y * pitch + (size_t)x * 4);
 }
 
+// retrieve_clusters() on the device: the clusters are ranges [offsets[c], offsets[c + 1]) of the tree's final permutation; block perm[i] goes to the
+// cluster whose range holds position i.  A stable sort of the block ids by that key then lists every cluster's members in ascending order, as
+// the reference's scan over cluster indices does (crn_qdxt1.cpp:941-960).
+__global__ void __launch_bounds__(256) range_cluster_of_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ offsets, uint32_t n_clusters, uint32_t n,
+                                                               uint32_t* __restrict__ cluster_of, uint32_t* __restrict__ ids)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t lo = 0, hi = n_clusters;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid; }
+    cluster_of[perm[i]] = lo;
+    ids[i] = i;
+}
+
 }  // namespace crn

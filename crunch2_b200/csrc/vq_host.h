@@ -197,6 +197,36 @@ struct VqResult {                    // host-side outcome of one build
 // list, so with every leaf kept (retrieve_clusters(0)) cluster k is simply the k-th leaf in position order and its members
 // are perm[begin .. begin + count) -- already ascending, already on the device.  Appends the leaves' first positions
 // (+ base) to `offsets` (which ends with the running total) in the reference's retrieval order; returns the leaf count.
+// The same for retrieve_clusters(max_clusters): a node whose split came too late for the budget is kept whole -- still one range.
+// `offsets` must hold its leading 0; returns the number of clusters (numbered like VqResult::retrieve).
+inline uint32_t vq_range_offsets(const VqResult& res, uint32_t max_clusters, std::vector<uint32_t>& offsets)
+{
+    uint32_t nclusters = 0, total = 0;
+    std::vector<uint32_t> stack;
+    offsets.pop_back();
+    for (const VqTreeSim& t : res.trees) {
+        stack.clear();
+        uint32_t cur = t.root;
+        for (;;) {
+            const VqHostNode& nd = res.nodes[cur];
+            const bool leaf = nd.split_rank < 0;
+            if (leaf || (max_clusters && (uint32_t)nd.split_rank + 2 > max_clusters)) {
+                offsets.push_back(nd.begin);
+                total = nd.begin + nd.count;
+                nclusters++;
+                if (stack.empty()) break;
+                cur = stack.back();
+                stack.pop_back();
+                continue;
+            }
+            stack.push_back((uint32_t)nd.left + 1);
+            cur = (uint32_t)nd.left;
+        }
+    }
+    offsets.push_back(total);
+    return nclusters;
+}
+
 inline uint32_t vq_leaf_offsets(const VqResult& res, uint32_t base, std::vector<uint32_t>& offsets)
 {
     uint32_t leaves = 0, total = 0;

@@ -17,7 +17,7 @@ def simctx(sim):
     ctx.close()
 
 
-@pytest.mark.parametrize("fmt,size,q", [("DXT1", 96, 255), ("DXT1", 64, 60), ("DXT5", 64, 200), ("DXT1", 160, 255)])
+@pytest.mark.parametrize("fmt,size,q", [("DXT1", 64, 255), ("DXT1", 64, 60), ("DXT5", 48, 200)])
 def test_device_orderings_equal_host_orderings(simctx, monkeypatch, fmt, size, q):
     img = blockgen.smooth_image(size, size - 16, 21 + size, alpha=True)
     levels = mip_chain(img)[:3]
