@@ -1409,6 +1409,7 @@ int crn_gpu_generate_mipmaps(crn_gpu_ctx* ctx, const crn_gpu_resample_params* pa
     for (uint32_t l = 1; l < n; l++) {
         MipPlan& P = plans[l - 1];
         HC_RC(mip_plan_launch(ctx, params, P, T, d_level0, width, height, pitch_bytes, out, P.dw * 4));
+        if (params->renormalize) HC_RC(crn_gpu_convert_pixels(ctx, out, P.dw, P.dh, P.dw * 4, crn::kConvRenormNormalMap));   // :2207-2208
         out += (size_t)P.dw * P.dh * 4;
     }
     CRN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2610,7 +2611,7 @@ int crn_gpu_dds_get_desc(const void* h_dds, uint32_t dds_size, crn_gpu_dds_desc*
 
 int crn_gpu_convert_pixels(crn_gpu_ctx* ctx, void* d_rgba, uint32_t width, uint32_t height, uint32_t pitch_bytes, uint32_t conversion)
 { return crn_guard(ctx, [&]() -> int {
-    if (!ctx || !d_rgba || !width || !height || pitch_bytes < width * 4 || (pitch_bytes & 3) || conversion < 1 || conversion > 10) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_convert_pixels: bad argument");
+    if (!ctx || !d_rgba || !width || !height || pitch_bytes < width * 4 || (pitch_bytes & 3) || conversion < 1 || conversion > 11) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_convert_pixels: bad argument");
     CRN_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = (uint64_t)width * height;
     CRN_LAUNCH(crn::pixel_convert_kernel, (uint32_t)((n + 255) / 256), 256, 0, ctx->stream, static_cast<uint8_t*>(d_rgba), width, height, pitch_bytes, conversion);
@@ -2689,6 +2690,96 @@ int crn_gpu_dds_to_images(crn_gpu_ctx* ctx, const void* h_dds, uint32_t dds_size
         P.d.block_format = CRN_GPU_FMT_DXT1A; P.d.file_format = dds_cc('D', 'X', '1', 'A'); P.d.pixel_format = dds_cc('R', 'G', 'B', 'A');
     }
     if (desc) *desc = P.d;
+    return CRN_GPU_OK;
+}); }
+
+int crn_gpu_prepare_mip_source(crn_gpu_ctx* ctx, const crn_gpu_mip_source_params* sp, const crn_gpu_resample_params* mip, uint32_t faces, uint32_t width, uint32_t height,
+                               const void* const* h_level0_faces, void** out_faces, uint32_t* out_width, uint32_t* out_height, uint32_t* out_changed)
+{ return crn_guard(ctx, [&]() -> int {
+    if (!ctx) return CRN_GPU_ERR_BAD_PARAM;
+    if (!sp || sp->struct_size != sizeof(crn_gpu_mip_source_params) || !mip || mip->struct_size != sizeof(crn_gpu_resample_params) || (faces != 1 && faces != 6) || !width || !height ||
+        width > 4096 || height > 4096 || !h_level0_faces || !out_faces || !out_width || !out_height || sp->scale_mode > 5)
+        return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_prepare_mip_source: bad argument");
+    for (uint32_t f = 0; f < faces; f++) { if (!h_level0_faces[f]) return set_err(ctx, CRN_GPU_ERR_BAD_PARAM, "crn_gpu_prepare_mip_source: missing image"); out_faces[f] = nullptr; }
+    if (out_changed) *out_changed = 0;
+    // the working image of face 0 while cropping (cubemaps are never cropped): origin + size inside the source
+    uint32_t ox = 0, oy = 0, cw = width, ch = height;
+    bool cropped = false;
+    if (sp->window_right > sp->window_left && sp->window_bottom > sp->window_top && faces == 1) {          // rect::is_empty, :392-408
+        const uint32_t x = sp->window_left, y = sp->window_top;
+        if (x < cw && y < ch) { ox = x; oy = y; cw = sp->window_right - sp->window_left; ch = sp->window_bottom - sp->window_top; cropped = true; }   // image::extract_block refuses an origin outside
+    }
+    int new_w = (int)cw, new_h = (int)ch;
+    const bool clamp = sp->clamp_width && sp->clamp_height;
+    if (clamp && (new_w > (int)sp->clamp_width || new_h > (int)sp->clamp_height) && !sp->clamp_scale && faces == 1) {      // :413-433: clamp by cropping at the origin
+        new_w = (int)std::min<uint32_t>(sp->clamp_width, (uint32_t)new_w); new_h = (int)std::min<uint32_t>(sp->clamp_height, (uint32_t)new_h);
+        // mipmapped_texture::crop(0, 0, ...) of the (possibly already cropped) image
+        cw = (uint32_t)new_w; ch = (uint32_t)new_h; cropped = true;
+    }
+    auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    auto lower = [](int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; };
+    auto upper = [&](int v) { if (is_pow2(v)) return v; int r = 1; while (r < v) r *= 2; return r; };
+    if (sp->scale_mode) {                                                                                  // :435-499
+        const bool p2 = is_pow2(new_w) && is_pow2(new_h);
+        switch (sp->scale_mode) {
+        case 1: new_w = (int)(uint32_t)sp->scale_x; new_h = (int)(uint32_t)sp->scale_y; break;
+        case 2: new_w = (int)(uint32_t)(sp->scale_x * (float)new_w + .5f); new_h = (int)(uint32_t)(sp->scale_y * (float)new_h + .5f); break;
+        case 3: if (!p2) { new_w = lower(new_w); new_h = lower(new_h); } break;
+        case 4: if (!p2) {
+                    const int lw = lower(new_w), lh = lower(new_h), uw = upper(new_w), uh = upper(new_h);
+                    new_w = labs(new_w - lw) < labs(new_w - uw) ? lw : uw;
+                    new_h = labs(new_h - lh) < labs(new_h - uh) ? lh : uh;
+                }
+                break;
+        case 5: if (!p2) { new_w = upper(new_w); new_h = upper(new_h); } break;
+        }
+    }
+    if (clamp && (new_w > (int)sp->clamp_width || new_h > (int)sp->clamp_height) && sp->clamp_scale) {       // :501-511
+        new_w = (int)std::min<uint32_t>(sp->clamp_width, (uint32_t)new_w); new_h = (int)std::min<uint32_t>(sp->clamp_height, (uint32_t)new_h);
+    }
+    new_w = std::min(std::max(new_w, 1), 4096); new_h = std::min(std::max(new_h, 1), 4096);                  // cCRNMaxLevelResolution
+    const bool resize = new_w != (int)cw || new_h != (int)ch || (mip->renormalize && sp->rtopmip);
+    *out_width = (uint32_t)new_w; *out_height = (uint32_t)new_h;
+    if (!cropped && !resize) return CRN_GPU_OK;
+    if (out_changed) *out_changed = 1;
+    CRN_CUDA(ctx, cudaSetDevice(ctx->device));
+    crn_gpu_resample_params rp = *mip;
+    rp.filter_scale = 1.0f; rp.wrapping = 0;                                                                 // :522-529 (m_wrapping is cleared whenever the texture has faces, i.e. always)
+    auto release = [&]() { for (uint32_t f = 0; f < faces; f++) { free(out_faces[f]); out_faces[f] = nullptr; } };
+    for (uint32_t f = 0; f < faces; f++) {
+        // crop on the host side of the copy: rows of the window, clamped reads past the source edge (extract_block's get_clamped)
+        std::vector<uint8_t> win;
+        const uint8_t* src = static_cast<const uint8_t*>(h_level0_faces[f]);
+        const uint8_t* img = src; uint32_t iw = width, ih = height;
+        if (cropped) {
+            win.resize((size_t)cw * ch * 4);
+            for (uint32_t y = 0; y < ch; y++) {
+                const uint32_t sy = std::min(oy + y, height - 1);
+                for (uint32_t x = 0; x < cw; x++) memcpy(&win[((size_t)y * cw + x) * 4], src + ((size_t)sy * width + std::min(ox + x, width - 1)) * 4, 4);
+            }
+            img = win.data(); iw = cw; ih = ch;
+        }
+        uint8_t* dst = static_cast<uint8_t*>(malloc((size_t)new_w * new_h * 4));
+        if (!dst) { release(); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_prepare_mip_source: out of host memory"); }
+        out_faces[f] = dst;
+        if (!resize) { memcpy(dst, img, (size_t)iw * ih * 4); continue; }
+        if (!rp.num_comps) {                                                                                 // is_component_valid(3): any alpha below 255 in the source
+            bool has_alpha = false;
+            for (uint32_t g = 0; g < faces && !has_alpha; g++) {
+                const uint8_t* px = static_cast<const uint8_t*>(h_level0_faces[g]);
+                for (size_t i = 0, n = (size_t)width * height; i < n; i++) if (px[i * 4 + 3] < 255) { has_alpha = true; break; }
+            }
+            rp.num_comps = has_alpha ? 4 : 3;
+        }
+        HcBuf d_in, d_out;
+        if (d_in.alloc(ctx, (size_t)iw * ih * 4) != cudaSuccess || d_out.alloc(ctx, (size_t)new_w * new_h * 4) != cudaSuccess) { release(); return set_err(ctx, CRN_GPU_ERR_NO_MEMORY, "crn_gpu_prepare_mip_source: out of device memory"); }
+        int rc = CRN_GPU_OK;
+        if (cudaMemcpyAsync(d_in.p, img, (size_t)iw * ih * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = CRN_GPU_ERR_CUDA;
+        if (rc == CRN_GPU_OK) rc = crn_gpu_resample(ctx, &rp, d_in.p, iw, ih, iw * 4, d_out.p, (uint32_t)new_w, (uint32_t)new_h, (uint32_t)new_w * 4);
+        if (rc == CRN_GPU_OK && rp.renormalize) rc = crn_gpu_convert_pixels(ctx, d_out.p, (uint32_t)new_w, (uint32_t)new_h, (uint32_t)new_w * 4, crn::kConvRenormNormalMap);
+        if (rc == CRN_GPU_OK && (cudaMemcpyAsync(dst, d_out.p, (size_t)new_w * new_h * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = CRN_GPU_ERR_CUDA;
+        if (rc) { release(); return rc == CRN_GPU_ERR_CUDA ? set_err(ctx, rc, "crn_gpu_prepare_mip_source: copy") : rc; }
+    }
     return CRN_GPU_OK;
 }); }
 

@@ -190,10 +190,12 @@ void* compress_common(const crn_comp_params& p, const crn_mipmap_params* mip, cr
     if (crn) fill_crn_params(p, cp); else fill_dds_params(p, dp);
     // create_texture_mipmaps (crnlib/crn_texture_comp.cpp:352-575): which levels go in
     bool generate = false;
+    const void* faces[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    struct Replaced { void* p[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; ~Replaced() { for (void* q : p) if (q) crn_gpu_free_file(q); } } replaced;
+    crn_gpu_resample_params rp;
+    crn_gpu_default_resample_params(&rp);
+    bool source_changed = false;
     if (mip) {
-        if (mip->m_scale_mode != cCRNSMDisabled || mip->m_window_left || mip->m_window_top || mip->m_window_right || mip->m_window_bottom ||
-            mip->m_clamp_width || mip->m_clamp_height || mip->m_renormalize || mip->m_rtopmip)
-            return nullptr;                                                                   // crop / clamp / rescale / renormalise: not built
         switch (mip->m_mode) {
         case cCRNMipModeUseSourceOrGenerateMips: generate = p.m_levels == 1; break;
         case cCRNMipModeUseSourceMips: break;
@@ -201,15 +203,28 @@ void* compress_common(const crn_comp_params& p, const crn_mipmap_params* mip, cr
         case cCRNMipModeNoMips: if (crn) cp.levels = 1; else dp.levels = 1; break;
         default: return nullptr;
         }
+        rp.filter = (uint32_t)mip->m_filter; rp.filter_scale = mip->m_blurriness; rp.srgb = mip->m_gamma_filtering ? 1u : 0u;
+        rp.source_gamma = mip->m_gamma; rp.wrapping = mip->m_tiled ? 1u : 0u; rp.num_comps = 0; rp.renormalize = mip->m_renormalize ? 1u : 0u;
+        // crop / clamp / rescale / renormalise the top level (crnlib/crn_texture_comp.cpp:392-540); a crop or resize drops every other source level
+        crn_gpu_mip_source_params sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.struct_size = sizeof(sp);
+        sp.window_left = mip->m_window_left; sp.window_top = mip->m_window_top; sp.window_right = mip->m_window_right; sp.window_bottom = mip->m_window_bottom;
+        sp.clamp_width = mip->m_clamp_width; sp.clamp_height = mip->m_clamp_height; sp.clamp_scale = mip->m_clamp_scale ? 1u : 0u;
+        sp.scale_mode = (uint32_t)mip->m_scale_mode; sp.scale_x = mip->m_scale_x; sp.scale_y = mip->m_scale_y; sp.rtopmip = mip->m_rtopmip ? 1u : 0u;
+        const void* src[6];
+        for (crn_uint32 f = 0; f < p.m_faces; f++) { if (!p.m_pImages[f][0]) return nullptr; src[f] = p.m_pImages[f][0]; }
+        uint32_t nw = 0, nh = 0, changed = 0;
+        if (crn_gpu_prepare_mip_source(ctx, &sp, &rp, p.m_faces, p.m_width, p.m_height, src, replaced.p, &nw, &nh, &changed) != CRN_GPU_OK) return nullptr;
+        if (changed) {
+            source_changed = true;
+            for (crn_uint32 f = 0; f < p.m_faces; f++) faces[f] = replaced.p[f];
+            if (crn) { cp.width = nw; cp.height = nh; cp.levels = 1; } else { dp.width = nw; dp.height = nh; dp.levels = 1; }
+        }
     }
     std::vector<const void*> flat;
     if (generate) {
-        const void* faces[6];
-        for (crn_uint32 f = 0; f < p.m_faces; f++) { if (!p.m_pImages[f][0]) return nullptr; faces[f] = p.m_pImages[f][0]; }
-        crn_gpu_resample_params rp;
-        crn_gpu_default_resample_params(&rp);
-        rp.filter = (uint32_t)mip->m_filter; rp.filter_scale = mip->m_blurriness; rp.srgb = mip->m_gamma_filtering ? 1u : 0u;
-        rp.source_gamma = mip->m_gamma; rp.wrapping = mip->m_tiled ? 1u : 0u; rp.num_comps = 0;
+        for (crn_uint32 f = 0; f < p.m_faces; f++) if (!faces[f]) { if (!p.m_pImages[f][0]) return nullptr; faces[f] = p.m_pImages[f][0]; }
         if (crn && cp.target_bitrate > 0.0f) {}                                               // handled inside crn_gpu_compress_crn
         rc = crn_gpu_compress_mip_chain(ctx, crn ? 0u : 1u, crn ? &cp : nullptr, crn ? nullptr : &dp, &rp, mip->m_min_mip_size, mip->m_max_levels, faces, &file, &size);
         if (rc == CRN_GPU_OK && crn) {                                                        // the chain call has no rate outputs: file bits / texels (crn_comp.cpp:1640-1653)
@@ -223,7 +238,11 @@ void* compress_common(const crn_comp_params& p, const crn_mipmap_params* mip, cr
     } else {
         const crn_uint32 levels = crn ? cp.levels : dp.levels;
         for (crn_uint32 f = 0; f < p.m_faces; f++)
-            for (crn_uint32 l = 0; l < levels; l++) { if (!p.m_pImages[f][l]) return nullptr; flat.push_back(p.m_pImages[f][l]); }
+            for (crn_uint32 l = 0; l < levels; l++) {
+                const void* img = (source_changed && l == 0) ? faces[f] : p.m_pImages[f][l];
+                if (!img) return nullptr;
+                flat.push_back(img);
+            }
         if (crn) rc = crn_gpu_compress_crn(ctx, &cp, flat.data(), &file, &size, &rate, &quality);
         else rc = crn_gpu_compress_dds_ex(ctx, &dp, flat.data(), &file, &size, pb ? &rate : nullptr, &quality);
     }

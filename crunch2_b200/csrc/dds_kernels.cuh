@@ -15,7 +15,7 @@
 namespace crn {
 
 enum PixelConversion { kConvToCCxY = 1, kConvFromCCxY = 2, kConvToxGxR = 3, kConvFromxGxR = 4, kConvToxGBR = 5, kConvFromxGBR = 6,
-                       kConvToAGBR = 7, kConvFromAGBR = 8, kConvXYtoXYZ = 9, kConvYtoA = 10 };
+                       kConvToAGBR = 7, kConvFromAGBR = 8, kConvXYtoXYZ = 9, kConvYtoA = 10, kConvRenormNormalMap = 11 };
 
 __device__ __forceinline__ uint32_t clamp_u8(int v) { return v < 0 ? 0u : (v > 255 ? 255u : (uint32_t)v); }
 
@@ -33,8 +33,38 @@ __device__ __forceinline__ uint32_t regen_z(uint32_t x, uint32_t y)
     return clamp_u8((int)vz);
 }
 
+// image_utils::renorm_normal_map (crn_image_utils.cpp:369-428), one texel
+__device__ __forceinline__ uint32_t renorm_pixel(uint32_t p)
+{
+    uint32_t c[3] = { p & 255u, (p >> 8) & 255u, (p >> 16) & 255u };
+    const uint32_t a = p >> 24;
+    if (c[0] == 128 && c[1] == 128 && c[2] == 128) return p;
+    float v[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float t = (float)c[i];
+        t *= 1.0f / 255.0f; t *= 2.0f; t -= 1.0f;
+        v[i] = t < -1.0f ? -1.0f : (t > 1.0f ? 1.0f : t);
+    }
+    float n = v[0] * v[0]; n += v[1] * v[1]; n += v[2] * v[2];          // vec::norm, in component order
+    const float length = sqrtf(n);
+    if (length < .077f) { c[0] = c[1] = c[2] = 128; }
+    else if (fabsf(length - 1.0f) > .077f) {
+        if (length != 0.0f) { v[0] /= length; v[1] /= length; v[2] /= length; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            float t = floorf((v[i] + 1.0f) * .5f * 255.0f + .5f);
+            t = t < 0.0f ? 0.0f : (t > 255.0f ? 255.0f : t);
+            c[i] = (uint32_t)t;
+        }
+        if (c[0] == 128 && c[1] == 128) c[2] = c[2] < 128 ? 0u : 255u;
+    }
+    return c[0] | (c[1] << 8) | (c[2] << 16) | (a << 24);
+}
+
 __device__ __forceinline__ uint32_t convert_pixel(uint32_t p, uint32_t conv)
 {
+    if (conv == kConvRenormNormalMap) return renorm_pixel(p);
     const int r = p & 255, g = (p >> 8) & 255, b = (p >> 16) & 255, a = p >> 24;
     uint32_t dr, dg, db, da;
     switch (conv) {

@@ -39,7 +39,24 @@ class CrnCompParams(ctypes.Structure):      # crn_comp_params, inc/crnlib.h:231-
         return self
 
 
+class CrnMipmapParams(ctypes.Structure):    # crn_mipmap_params, inc/crnlib.h:471-574
+    _fields_ = [("m_size_of_obj", ctypes.c_uint32), ("m_mode", ctypes.c_uint32), ("m_filter", ctypes.c_uint32), ("m_gamma_filtering", ctypes.c_uint32),
+                ("m_gamma", ctypes.c_float), ("m_blurriness", ctypes.c_float), ("m_max_levels", ctypes.c_uint32), ("m_min_mip_size", ctypes.c_uint32),
+                ("m_renormalize", ctypes.c_uint32), ("m_rtopmip", ctypes.c_uint32), ("m_tiled", ctypes.c_uint32), ("m_scale_mode", ctypes.c_uint32),
+                ("m_scale_x", ctypes.c_float), ("m_scale_y", ctypes.c_float), ("m_window_left", ctypes.c_uint32), ("m_window_top", ctypes.c_uint32),
+                ("m_window_right", ctypes.c_uint32), ("m_window_bottom", ctypes.c_uint32), ("m_clamp_scale", ctypes.c_uint32), ("m_clamp_width", ctypes.c_uint32),
+                ("m_clamp_height", ctypes.c_uint32)]
+
+    def clear(self):                        # crn_mipmap_params::clear()
+        ctypes.memset(ctypes.byref(self), 0, ctypes.sizeof(self))
+        self.m_size_of_obj = ctypes.sizeof(self)
+        self.m_mode = 0; self.m_filter = 4; self.m_gamma_filtering = 1; self.m_gamma = 2.2; self.m_blurriness = .9
+        self.m_max_levels = MAX_LEVELS; self.m_min_mip_size = 1; self.m_scale_x = 1.0; self.m_scale_y = 1.0
+        return self
+
+
 _SYMS = {"crn_compress": "_Z12crn_compressRK15crn_comp_paramsRjPjPf",
+         "crn_compress_mip": "_Z12crn_compressRK15crn_comp_paramsRK17crn_mipmap_paramsRjPjPf",
          "crn_free_block": "_Z14crn_free_blockPv",
          "crn_decompress_crn_to_dds": "_Z25crn_decompress_crn_to_ddsPKvRj",
          "crn_get_version_number": "_Z22crn_get_version_numberv"}
@@ -62,6 +79,9 @@ def load(path=None):
     f = getattr(lib, _SYMS["crn_compress"])
     f.restype = ctypes.c_void_p
     f.argtypes = [ctypes.POINTER(CrnCompParams), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_float)]
+    fm = getattr(lib, _SYMS["crn_compress_mip"])
+    fm.restype = ctypes.c_void_p
+    fm.argtypes = [ctypes.POINTER(CrnCompParams), ctypes.POINTER(CrnMipmapParams), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_float)]
     g = getattr(lib, _SYMS["crn_free_block"]); g.restype = None; g.argtypes = [ctypes.c_void_p]
     h = getattr(lib, _SYMS["crn_decompress_crn_to_dds"]); h.restype = ctypes.c_void_p; h.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32)]
     if path is None:
@@ -70,7 +90,7 @@ def load(path=None):
 
 
 def crn_compress(images, crn_format, file_type=FILE_DDS, quality_level=255, flags=None, target_bitrate=0.0, dxt_quality=4, alpha_component=3, progress=None,
-                 want_rate=True, lib=None):
+                 want_rate=True, lib=None, mipmap_params=None):
     """crn_compress (inc/crnlib.h:609) through the drop-in.  images[face][level]: (h, w, 4) uint8, C-contiguous (pinned host memory is fine).
     Returns (file bytes, actual quality level, actual bitrate) or raises RuntimeError when the call returns NULL."""
     lib = lib or load()
@@ -94,7 +114,10 @@ def crn_compress(images, crn_format, file_type=FILE_DDS, quality_level=255, flag
         cb = PROGRESS_FN(progress)
         p.m_pProgress_func = ctypes.cast(cb, ctypes.c_void_p)
     size = ctypes.c_uint32(); q = ctypes.c_uint32(); rate = ctypes.c_float()
-    ptr = getattr(lib, _SYMS["crn_compress"])(ctypes.byref(p), ctypes.byref(size), ctypes.byref(q), ctypes.byref(rate) if want_rate else None)
+    if mipmap_params is not None:           # the crn_mipmap_params overload (inc/crnlib.h:614)
+        ptr = getattr(lib, _SYMS["crn_compress_mip"])(ctypes.byref(p), ctypes.byref(mipmap_params), ctypes.byref(size), ctypes.byref(q), ctypes.byref(rate) if want_rate else None)
+    else:
+        ptr = getattr(lib, _SYMS["crn_compress"])(ctypes.byref(p), ctypes.byref(size), ctypes.byref(q), ctypes.byref(rate) if want_rate else None)
     if not ptr:
         raise RuntimeError("crn_compress returned NULL")
     try:

@@ -277,7 +277,8 @@ typedef struct crn_gpu_resample_params {
     float source_gamma;                 /* 2.2 */
     uint32_t wrapping;                  /* m_tiled */
     uint32_t num_comps;
-    uint32_t reserved[3];
+    uint32_t renormalize;               /* m_renormalize: image_utils::renorm_normal_map on every resampled image */
+    uint32_t reserved[2];
 } crn_gpu_resample_params;
 CRN_API void crn_gpu_default_resample_params(crn_gpu_resample_params* p);
 CRN_API int crn_gpu_resample(crn_gpu_ctx* ctx, const crn_gpu_resample_params* params, const void* d_src, uint32_t src_width, uint32_t src_height, uint32_t src_pitch_bytes,
@@ -504,7 +505,23 @@ CRN_API int crn_gpu_convert_pixels(crn_gpu_ctx* ctx, void* d_rgba, uint32_t widt
  * crn_gpu_compress_crn (file_type 0, `cp`) or crn_gpu_compress_dds (file_type 1, `dp`); the params' `levels` is replaced by the
  * generated count.  mip = NULL takes crn_mipmap_params' defaults (kaiser, gamma filtering 2.2, blurriness 0.9); num_comps 0 =
  * decide like the reference (4 when any source texel has alpha < 255, else 3).  min_mip_size / max_levels 0 = 1 / 16.
- * Cropping, clamping and rescaling of the source (crn_mipmap_params::m_window_*, m_clamp_*, m_scale_mode) are not built. */
+ * Cropping, clamping and rescaling of the source (crn_mipmap_params::m_window_*, m_clamp_*, m_scale_mode): crn_gpu_prepare_mip_source first. */
+/* The source options of create_texture_mipmaps (crnlib/crn_texture_comp.cpp:392-540): crop to a window, clamp, rescale (crn_scale_mode), and
+ * the resample to the resulting size (filter scale 1, never wrapping -- the reference clears m_wrapping there -- renormalised when asked; also
+ * forced by renormalize && rtopmip at unchanged size).  Level 0 of each face in (host, tight pitch).  *out_width / *out_height = the size
+ * compression continues with; out_faces[f] = a malloc'ed replacement image (crn_gpu_free_file) or NULL when the source is used as it is.
+ * Like the reference, cropping a cubemap is skipped (with clamp_scale = 0 its clamp too) and every mip level but 0 is dropped by a crop or resize. */
+typedef struct crn_gpu_mip_source_params {
+    uint32_t struct_size;               /* sizeof(crn_gpu_mip_source_params) */
+    uint32_t window_left, window_top, window_right, window_bottom;
+    uint32_t clamp_width, clamp_height, clamp_scale;
+    uint32_t scale_mode;                /* crn_scale_mode (inc/crnlib.h:454-466): 0 disabled, 1 absolute, 2 relative, 3 lower, 4 nearest, 5 next power of two */
+    float scale_x, scale_y;
+    uint32_t rtopmip;
+    uint32_t reserved[4];
+} crn_gpu_mip_source_params;
+CRN_API int crn_gpu_prepare_mip_source(crn_gpu_ctx* ctx, const crn_gpu_mip_source_params* sp, const crn_gpu_resample_params* mip, uint32_t faces, uint32_t width, uint32_t height,
+                                       const void* const* h_level0_faces, void** out_faces, uint32_t* out_width, uint32_t* out_height, uint32_t* out_changed);
 CRN_API int crn_gpu_compress_mip_chain(crn_gpu_ctx* ctx, uint32_t file_type, const crn_gpu_crn_params* cp, const crn_gpu_dds_params* dp, const crn_gpu_resample_params* mip,
                                        uint32_t min_mip_size, uint32_t max_levels, const void* const* h_level0_faces, void** out_file, uint32_t* out_size);
 

@@ -239,6 +239,33 @@ SHIM_API void* ref_compress_mip_chain(int file_type, int format, uint32_t width,
     return q;
 }
 
+// crn_compress(comp_params, mipmap_params) with a caller-built crn_mipmap_params (same layout as inc/crnlib.h:471-574): the crop / clamp /
+// rescale / renormalise options of create_texture_mipmaps
+SHIM_API void* ref_compress_mip_params(int file_type, int format, uint32_t width, uint32_t height, uint32_t levels, const uint32_t* const* images, uint32_t flags,
+                                       uint32_t quality_level, uint32_t helper_threads, const void* mipmap_params, uint32_t* out_size)
+{
+    crn_comp_params cp;
+    cp.m_file_type = (crn_file_type)file_type;
+    cp.m_format = (crn_format)format;
+    cp.m_width = width; cp.m_height = height; cp.m_faces = 1; cp.m_levels = levels;
+    cp.m_flags = flags;
+    cp.m_quality_level = quality_level;
+    cp.m_num_helper_threads = helper_threads;
+    for (uint32_t l = 0; l < levels; l++) cp.m_pImages[0][l] = images[l];
+    crn_mipmap_params mp;
+    memcpy(&mp, mipmap_params, sizeof(mp));
+    mp.m_size_of_obj = sizeof(mp);
+    crn_uint32 size = 0;
+    void* p = crn_compress(cp, mp, size, NULL, NULL);
+    *out_size = 0;
+    if (!p) return NULL;
+    void* q = malloc(size);
+    memcpy(q, p, size);
+    crn_free_block(p);
+    *out_size = size;
+    return q;
+}
+
 SHIM_API void ref_free(void* p) { free(p); }
 
 SHIM_API void* ref_crn_to_dds(const void* crn, uint32_t crn_size, uint32_t* dds_size)
