@@ -1622,10 +1622,16 @@ static bool order_color_on_device(void* user, const uint32_t* ep_lo, const uint3
     J.n = n; J.n_sel = n_sel; J.selected = selected;
     J.base[0] = base[0]; J.base[1] = base[1]; J.base[2] = base[2];
     J.remap = reinterpret_cast<uint16_t*>(b + o_remap); J.sel_remap = reinterpret_cast<uint16_t*>(b + o_sremap);
+    int threads = crn::kOrderThreads;
+    if (const char* t = getenv("CRN_B200_ORDER_THREADS")) { const int v = atoi(t); if (v == 256 || v == 512 || v == 1024) threads = v; }
 #ifdef __CUDACC__
-    if (cudaFuncSetAttribute(crn::crn_order_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::OrderSmem)) != cudaSuccess) return false;
+    if (cudaFuncSetAttribute(crn::crn_order_color_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::OrderSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(crn::crn_order_color_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::OrderSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(crn::crn_order_color_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(crn::OrderSmem)) != cudaSuccess) return false;
 #endif
-    CRN_LAUNCH(crn::crn_order_color_kernel, 5, crn::kOrderThreads, sizeof(crn::OrderSmem), st, J);
+    if (threads == 256) CRN_LAUNCH(crn::crn_order_color_kernel<256>, 5, 256, sizeof(crn::OrderSmem), st, J);
+    else if (threads == 512) CRN_LAUNCH(crn::crn_order_color_kernel<512>, 5, 512, sizeof(crn::OrderSmem), st, J);
+    else CRN_LAUNCH(crn::crn_order_color_kernel<1024>, 5, 1024, sizeof(crn::OrderSmem), st, J);
     ctx->launches++;
     ok &= cudaMemcpyAsync(remap4, b + o_remap, (size_t)4 * n * 2, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     ok &= cudaMemcpyAsync(sel_remap, b + o_sremap, (size_t)n_sel * 2, cudaMemcpyDeviceToHost, st) == cudaSuccess;

@@ -15,9 +15,8 @@
 
 namespace crn {
 
-constexpr int kOrderThreads = 1024;
+constexpr int kOrderThreads = 1024;                     // default CTA size (CRN_B200_ORDER_THREADS = 256 / 512 picks another instantiation)
 constexpr int kOrderMaxN = 8192;
-constexpr int kOrderPer = kOrderMaxN / kOrderThreads;
 
 struct OrderColorJob {
     const uint32_t* ep_lo; const uint32_t* ep_hi;        // n endpoints, components expanded to 8 bits: r | g << 8 | b << 16
@@ -31,6 +30,7 @@ struct OrderColorJob {
 
 struct OrderSmem {
     uint32_t freq[kOrderMaxN];
+    uint32_t row_start[kOrderMaxN + 1];                  // weighted trials: the transition lists' row starts (one dependent global load less per step)
     uint32_t data_a[kOrderMaxN], data_b[kOrderMaxN];     // greedy chains: the items by id
     int16_t pos[kOrderMaxN];
     uint16_t chosen[2 * kOrderMaxN + 2];                 // weighted trials: the chain; greedy chains: id by slot
@@ -56,12 +56,14 @@ __device__ __forceinline__ unsigned long long order_block_max(OrderSmem* sm, uns
     v = order_warp_max(v);
     if (lane_id() == 0) sm->red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return order_warp_max(sm->red[lane_id()]);
+    return order_warp_max(lane_id() < (blockDim.x >> 5) ? sm->red[lane_id()] : 0ull);
 }
 
 // remap_color_endpoints of crn_writer.h (optimize_color_endpoints_task, crn_comp.cpp:800-878)
+template <int T>
 __device__ __forceinline__ void order_weighted_chain(OrderSmem* sm, const OrderColorJob& J, uint32_t base, uint16_t* __restrict__ remap)
 {
+    constexpr int kOrderThreads = T, kOrderPer = kOrderMaxN / T;
     const unsigned tid = threadIdx.x;
     const uint32_t n = J.n;
     uint32_t lo[kOrderPer], hi[kOrderPer], fs[kOrderPer], bs[kOrderPer];
@@ -72,6 +74,7 @@ __device__ __forceinline__ void order_weighted_chain(OrderSmem* sm, const OrderC
         lo[k] = hi[k] = fs[k] = bs[k] = 0;
         if (i < n) { lo[k] = J.ep_lo[i]; hi[k] = J.ep_hi[i]; alive |= 1u << k; sm->freq[i] = 0; sm->pos[i] = -1; }
     }
+    for (uint32_t i = tid; i <= n; i += kOrderThreads) sm->row_start[i] = J.row_start[i];
     uint32_t selected = J.selected;
     int front = (int)n, back = (int)n;
     uint32_t front_lo = J.ep_lo[selected], front_hi = J.ep_hi[selected], back_lo = front_lo, back_hi = front_hi;
@@ -80,7 +83,8 @@ __device__ __forceinline__ void order_weighted_chain(OrderSmem* sm, const OrderC
     __syncthreads();
     if (tid == 0) { sm->chosen[front] = (uint16_t)selected; sm->pos[selected] = (int16_t)front; }
     if ((selected % kOrderThreads) == tid) alive &= ~(1u << (selected / kOrderThreads));
-    for (uint32_t k = J.row_start[selected] + tid; k < J.row_start[selected + 1]; k += kOrderThreads) sm->freq[J.col[k]] += J.cnt[k];
+    __syncthreads();
+    for (uint32_t k = sm->row_start[selected] + tid; k < sm->row_start[selected + 1]; k += kOrderThreads) sm->freq[J.col[k]] += J.cnt[k];
     __syncthreads();
     for (uint32_t left = n - 1; left; left--) {
         // the unplaced entry of largest value; ties: the lowest index (the reference's `value == best && index < selected`)
@@ -109,7 +113,7 @@ __device__ __forceinline__ void order_weighted_chain(OrderSmem* sm, const OrderC
         // frequencies it adds to the entries still unplaced
         uint32_t pf = 0, pb = 0;
         const int L = back - front;
-        for (uint32_t k = J.row_start[selected] + tid; k < J.row_start[selected + 1]; k += kOrderThreads) {
+        for (uint32_t k = sm->row_start[selected] + tid; k < sm->row_start[selected + 1]; k += kOrderThreads) {
             const uint32_t c = J.col[k], w = J.cnt[k];
             const int at = sm->pos[c];
             if (at >= 0) {
@@ -123,7 +127,7 @@ __device__ __forceinline__ void order_weighted_chain(OrderSmem* sm, const OrderC
         for (int ofs = 16; ofs > 0; ofs >>= 1) { pf += __shfl_xor_sync(CRN_FULL_MASK, pf, ofs); pb += __shfl_xor_sync(CRN_FULL_MASK, pb, ofs); }
         if (lane_id() == 0) { sm->red_f[tid >> 5] = pf; sm->red_b[tid >> 5] = pb; }
         __syncthreads();
-        pf = sm->red_f[lane_id()]; pb = sm->red_b[lane_id()];
+        pf = lane_id() < (unsigned)(kOrderThreads >> 5) ? sm->red_f[lane_id()] : 0u; pb = lane_id() < (unsigned)(kOrderThreads >> 5) ? sm->red_b[lane_id()] : 0u;
 #pragma unroll
         for (int ofs = 16; ofs > 0; ofs >>= 1) { pf += __shfl_xor_sync(CRN_FULL_MASK, pf, ofs); pb += __shfl_xor_sync(CRN_FULL_MASK, pb, ofs); }
         const uint32_t wfs = sm->win_fs, wbs = sm->win_bs;
@@ -139,9 +143,10 @@ __device__ __forceinline__ void order_weighted_chain(OrderSmem* sm, const OrderC
 
 // greedy_chain of crn_writer.h: nearest unplaced item to the last placed one, first minimum in the reference's array order (candidates in an
 // array, the winner replaced by the last one).  DIST(a_item, b_item, a_cur, b_cur).
-template <typename Dist>
+template <int T, typename Dist>
 __device__ __forceinline__ void order_greedy_chain(OrderSmem* sm, const uint32_t* __restrict__ ga, const uint32_t* __restrict__ gb, uint32_t n, Dist dist, uint16_t* __restrict__ remap)
 {
+    constexpr int kOrderThreads = T;
     const unsigned tid = threadIdx.x;
     for (uint32_t i = tid; i < n; i += kOrderThreads) { sm->data_a[i] = ga[i]; sm->data_b[i] = gb ? gb[i] : 0u; sm->chosen[i] = (uint16_t)i; }
     uint32_t cur_a = 0, cur_b = 0;
@@ -166,16 +171,17 @@ __device__ __forceinline__ void order_greedy_chain(OrderSmem* sm, const uint32_t
 }
 
 // CTA 0: greedy chain of the endpoints (trial 0); CTAs 1..3: the weighted trials; CTA 4: greedy chain of the selectors
-__global__ void __launch_bounds__(kOrderThreads) crn_order_color_kernel(OrderColorJob J)
+template <int T>
+__global__ void __launch_bounds__(T) crn_order_color_kernel(OrderColorJob J)
 {
     CRN_DYN_SMEM(OrderSmem, sm);
     if (blockIdx.x == 0)
-        order_greedy_chain(sm, J.ep_lo, J.ep_hi, J.n, [](uint32_t alo, uint32_t ahi, uint32_t clo, uint32_t chi) { return order_dist3(alo, clo) + order_dist3(ahi, chi); }, J.remap);
+        order_greedy_chain<T>(sm, J.ep_lo, J.ep_hi, J.n, [](uint32_t alo, uint32_t ahi, uint32_t clo, uint32_t chi) { return order_dist3(alo, clo) + order_dist3(ahi, chi); }, J.remap);
     else if (blockIdx.x < 4)
-        order_weighted_chain(sm, J, J.base[blockIdx.x - 1], J.remap + (size_t)blockIdx.x * J.n);
+        order_weighted_chain<T>(sm, J, J.base[blockIdx.x - 1], J.remap + (size_t)blockIdx.x * J.n);
     else
         // per-pixel selector distance {0, 5, 14, 10} on the XOR of the 2-bit selectors (crn_comp.cpp:941-953) = 5 b0 + 14 b1 - 9 (b0 & b1)
-        order_greedy_chain(sm, J.selectors, nullptr, J.n_sel, [](uint32_t s, uint32_t, uint32_t ref, uint32_t) {
+        order_greedy_chain<T>(sm, J.selectors, nullptr, J.n_sel, [](uint32_t s, uint32_t, uint32_t ref, uint32_t) {
             const uint32_t x = s ^ ref;
             return 5u * (uint32_t)__popc(x & 0x55555555u) + 14u * (uint32_t)__popc(x & 0xAAAAAAAAu) - 9u * (uint32_t)__popc(x & (x >> 1) & 0x55555555u);
         }, J.sel_remap);
