@@ -9,6 +9,7 @@
 // at a time), the sort + dedup of training vectors, the CSR build, and the final remap.
 #pragma once
 #include <queue>
+#include <thread>
 
 namespace {
 
@@ -489,24 +490,64 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
         // cluster member lists: the tiles' 16-pixel virtual blocks, component-major then tile-slot order (:970-977, :1246-1260)
         std::vector<uint32_t> offs(K + 1, 0);
         HcHost<uint32_t> members(ctx, NV), block_cluster(ctx, NV);
-        for (int a = 0; a < ncp; a++)
-            for (uint32_t i = 0; i < num_tiles; i++) offs[tcl[(size_t)a * num_tiles + i] + 1] += h_npix[used_slots[i]] / 16;
-        for (uint32_t c = 0; c < K; c++) offs[c + 1] += offs[c];
         {
-            std::vector<uint32_t> cur(offs.begin(), offs.end() - 1);
-            for (int a = 0; a < ncp; a++)
-                for (uint32_t i = 0; i < num_tiles; i++) {
-                    const uint32_t s = used_slots[i], c = tcl[(size_t)a * num_tiles + i];
-                    const uint32_t vb0 = (uint32_t)a * n + (s & ~3u) + h_pixofs[s] / 16;
+            // a stable counting sort of the (component, tile) sequence by cluster, in chunks: every chunk counts its clusters, the counts are
+            // prefixed chunk-major inside each cluster, every chunk then writes its own slices -- the order inside a cluster stays the sequence's
+#ifdef __CUDACC__
+            const uint32_t nchunk = NT >= 65536 ? 8u : 1u;
+#else
+            const uint32_t nchunk = 1u;
+#endif
+            std::vector<std::vector<uint32_t>> cnt(nchunk, std::vector<uint32_t>(K, 0u));
+            auto chunk_range = [&](uint32_t t, uint32_t& j0, uint32_t& j1) { j0 = (uint32_t)((uint64_t)NT * t / nchunk); j1 = (uint32_t)((uint64_t)NT * (t + 1) / nchunk); };
+            auto count_chunk = [&](uint32_t t) {
+                uint32_t j0, j1; chunk_range(t, j0, j1);
+                std::vector<uint32_t>& c = cnt[t];
+                for (uint32_t j = j0; j < j1; j++) c[tcl[j]] += h_npix[used_slots[j % num_tiles]] / 16;
+            };
+            auto fill_chunk = [&](uint32_t t) {
+                uint32_t j0, j1; chunk_range(t, j0, j1);
+                std::vector<uint32_t>& cur = cnt[t];              // now: this chunk's first slot in every cluster
+                for (uint32_t j = j0; j < j1; j++) {
+                    const uint32_t a = j / num_tiles, s = used_slots[j % num_tiles], c = tcl[j];
+                    const uint32_t vb0 = a * n + (s & ~3u) + h_pixofs[s] / 16;
                     for (uint32_t k = 0; k < h_npix[s] / 16u; k++) members[cur[c]++] = vb0 + k;
                 }
-        }
-        for (int a = 0; a < ncp; a++)
-            for (uint32_t b = 0; b < n; b++) {
-                const uint32_t c = tcl[(size_t)a * num_tiles + slot_rank[H->tile_indices[b]]];
-                block_cluster[(size_t)a * n + b] = c;
-                raw_endpoint[(size_t)b * 3 + (kind ? 1 + a : 0)] = (uint16_t)c;
+            };
+            auto run_chunks = [&](auto fn) {
+                std::vector<std::thread> th;
+                for (uint32_t t = 1; t < nchunk; t++) th.emplace_back(fn, t);
+                fn(0u);
+                for (auto& x : th) x.join();
+            };
+            run_chunks(count_chunk);
+            for (uint32_t c = 0; c < K; c++) {
+                uint32_t run = offs[c];
+                for (uint32_t t = 0; t < nchunk; t++) { const uint32_t v = cnt[t][c]; cnt[t][c] = run; run += v; }
+                offs[c + 1] = run;
             }
+            run_chunks(fill_chunk);
+        }
+        {
+            auto per_block = [&](uint32_t b0, uint32_t b1) {
+                for (int a = 0; a < ncp; a++)
+                    for (uint32_t b = b0; b < b1; b++) {
+                        const uint32_t c = tcl[(size_t)a * num_tiles + slot_rank[H->tile_indices[b]]];
+                        block_cluster[(size_t)a * n + b] = c;
+                        raw_endpoint[(size_t)b * 3 + (kind ? 1 + a : 0)] = (uint16_t)c;
+                    }
+            };
+#ifdef __CUDACC__
+            if (n >= 262144) {
+                const uint32_t nt = 6;
+                std::vector<std::thread> th;
+                for (uint32_t t = 1; t < nt; t++) th.emplace_back(per_block, (uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt));
+                per_block(0, n / nt);
+                for (auto& x : th) x.join();
+            } else
+#endif
+            per_block(0, n);
+        }
         std::vector<uint32_t> poffs(K + 1);
         for (uint32_t c = 0; c <= K; c++) poffs[c] = offs[c] * 16;
         tr.mark("hc CSR build (host)", kind);
@@ -781,21 +822,37 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     dedup32(alpha_cluster_ep, alpha_cluster_used, H->alpha_endpoints, ae_remap);
     dedup32(color_sel_cb, color_sel_used, H->color_selectors, cs_remap);
     dedup64(alpha_sel_cb, alpha_sel_used, H->alpha_selectors, as_remap);
+    // every block's record depends only on the raw indices of itself and its left / upper neighbour, so the rows go to host threads
     for (uint32_t l = 0; l < prm->num_levels; l++) {
-        const uint32_t first = prm->levels[l].first_block, end = first + prm->levels[l].num_blocks, bw = prm->levels[l].block_width;
-        uint32_t b = first;
-        for (uint32_t by = 0; b < end; by++)
-            for (uint32_t bx = 0; bx < bw; bx++, b++) {
-                bool top = by != 0, left = top || bx;
-                for (int c = has_color ? 0 : 1; c < 1 + na; c++) {
-                    const uint16_t e = (c ? ae_remap : ce_remap)[raw_endpoint[(size_t)b * 3 + c]];
-                    left = left && e == H->endpoint_indices[(size_t)(b - 1) * 4 + c];
-                    top = top && e == H->endpoint_indices[(size_t)(b - bw) * 4 + c];
-                    H->endpoint_indices[(size_t)b * 4 + c] = e;
-                    H->selector_indices[(size_t)b * 4 + c] = (c ? as_remap : cs_remap)[raw_selector[(size_t)b * 3 + c]];
+        const uint32_t first = prm->levels[l].first_block, nblk = prm->levels[l].num_blocks, bw = prm->levels[l].block_width;
+        const uint32_t rows = bw ? nblk / bw : 0;
+        auto do_rows = [&](uint32_t y0, uint32_t y1) {
+            for (uint32_t by = y0; by < y1; by++)
+                for (uint32_t bx = 0; bx < bw; bx++) {
+                    const uint32_t b = first + by * bw + bx;
+                    bool top = by != 0, left = top || bx;
+                    for (int c = has_color ? 0 : 1; c < 1 + na; c++) {
+                        const std::vector<uint16_t>& er = c ? ae_remap : ce_remap;
+                        const uint16_t e = er[raw_endpoint[(size_t)b * 3 + c]];
+                        left = left && e == er[raw_endpoint[(size_t)(b - 1) * 3 + c]];      // (b - 1 / b - bw are only read when the flag is still set)
+                        top = top && e == er[raw_endpoint[(size_t)(b - bw) * 3 + c]];
+                        H->endpoint_indices[(size_t)b * 4 + c] = e;
+                        H->selector_indices[(size_t)b * 4 + c] = (c ? as_remap : cs_remap)[raw_selector[(size_t)b * 3 + c]];
+                    }
+                    H->endpoint_indices[(size_t)b * 4 + 3] = left ? 1 : (top ? 2 : 0);
                 }
-                H->endpoint_indices[(size_t)b * 4 + 3] = left ? 1 : (top ? 2 : 0);
-            }
+        };
+#ifdef __CUDACC__
+        if (nblk >= 65536) {
+            const uint32_t nt = 8;
+            std::vector<std::thread> th;
+            for (uint32_t t = 1; t < nt; t++) th.emplace_back(do_rows, (uint32_t)((uint64_t)rows * t / nt), (uint32_t)((uint64_t)rows * (t + 1) / nt));
+            do_rows(0, rows / nt);
+            for (auto& x : th) x.join();
+            continue;
+        }
+#endif
+        do_rows(0, rows);
     }
     tr.mark("hc tail (host)", 0);
     H->info.num_blocks = n;
