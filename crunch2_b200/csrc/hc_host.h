@@ -457,10 +457,36 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
     // independent; for DXT5 they run concurrently, the alpha pass on a child context (own stream, scratch and buffer pool).
     CRN_CUDA(ctx, cudaStreamSynchronize(st));                          // d_used and everything the tile pass produced is complete
     crn_gpu_ctx* const parent = ctx;
+    // Sharded calls: before the payload all-gather every rank exchanges one 16-byte status record (status, cluster count).  A rank that
+    // leaves run_kind early -- error return or exception -- sends status 1 from this guard's destructor, so the other ranks see a failure
+    // instead of waiting in the collective; a cluster-count mismatch (the ranks' tree quantisers diverged) is caught the same way.
+    struct ShardAgreement {
+        const crn_gpu_hc_params* prm; bool done;
+        explicit ShardAgreement(const crn_gpu_hc_params* p) : prm(p), done(p->shard_count <= 1) {}
+        int agree(uint32_t status, uint32_t K)
+        {
+            done = true;
+            const uint32_t SC = prm->shard_count, SR = prm->shard_rank;
+            std::vector<uint32_t> w((size_t)SC * 4, 0u);
+            w[(size_t)SR * 4] = status; w[(size_t)SR * 4 + 1] = K; w[(size_t)SR * 4 + 2] = 0x43524E53u;
+            if (prm->exchange(prm->exchange_user, w.data(), 16, SC) != 0) return -1;
+            for (uint32_t r = 0; r < SC; r++) {
+                if (w[(size_t)r * 4 + 2] != 0x43524E53u || w[(size_t)r * 4] != 0u) return 1;
+                if (w[(size_t)r * 4 + 1] != K) return 2;
+            }
+            return 0;
+        }
+        ~ShardAgreement() { if (!done) { try { agree(1u, 0u); } catch (...) {} } }
+    };
     auto run_kind = [&](crn_gpu_ctx* ctx, int kind) -> int {
         cudaStream_t st = ctx->stream;
         QdxtTrace tr(ctx);
         (void)parent;
+        ShardAgreement agreement(prm);
+        if (prm->shard_count > 1) {                                      // test hook: tests/test_shard_gloo.py makes one rank fail before the exchange
+            const char* f = getenv("CRN_B200_TEST_FAIL_RANK");
+            if (f && (uint32_t)atoi(f) == prm->shard_rank) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_hc_compress: failure injected by CRN_B200_TEST_FAIL_RANK");
+        }
         const int ncp = kind ? na : 1;                                   // components handled together
         const uint32_t NV = (uint32_t)ncp * n;                           // virtual blocks (= member blocks in the CSR)
         // a13: training vectors -> sorted unique weighted vectors -> tree quantiser
@@ -620,6 +646,12 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                 CRN_CUDA(ctx, cudaMemcpyAsync(s_rok.data(), d_rok.p, Kopt, cudaMemcpyDeviceToHost, st));
             }
             CRN_CUDA(ctx, cudaStreamSynchronize(st));
+            {
+                const int ag = agreement.agree(0u, K);
+                if (ag < 0) return set_err(ctx, CRN_GPU_ERR_CUDA, "crn_gpu_hc_compress: the exchange callback failed");
+                if (ag == 1) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_hc_compress (sharded): another rank failed before the exchange");
+                if (ag == 2) return set_err(ctx, CRN_GPU_ERR_BAD_DATA, "crn_gpu_hc_compress (sharded): the ranks disagree on the number of clusters");
+            }
             const uint32_t per = (K + SC - 1) / SC;
             std::vector<uint32_t> xbuf((size_t)SC * per * 4, 0);
             for (uint32_t j = 0; j < Kopt; j++) { uint32_t* r = &xbuf[((size_t)SR * per + j) * 4]; r[0] = s_ep[j]; r[1] = s_fl[j]; r[2] = s_rep[j]; r[3] = s_rok[j]; }

@@ -138,3 +138,45 @@ def test_gloo_sharded_crn_compress(tmp_path, sim):
     ranks = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
     assert len(ranks) == 2 and ranks[0]["same"] and ranks[1]["same"]
     assert ranks[0]["sha"] == ranks[1]["sha"] and ranks[0]["size"] > 100
+
+
+FAIL_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch, torch.distributed as dist
+import blockgen, helpers, hc_util
+import crunch2_b200 as crn
+from crunch2_b200 import shard
+from bench import mip_chain
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+os.environ["CRN_B200_TEST_FAIL_RANK"] = "1"          # rank 1 fails inside the call, before the all-gather
+ctx = crn.Context(0, lib=helpers.load_sim())
+blocks, levels = hc_util.hc_layout([mip_chain(blockgen.smooth_image(64, 48, 11, alpha=True))[:2]])
+msg = ""
+try:
+    ctx.hc_compress(0, blocks, levels, codebook_sizes=(48, 48, 24, 48), shard=(rank, world, shard.allgather_inplace))
+except crn.CrnGpuError as e:
+    msg = str(e)
+gathered = [None] * world
+dist.all_gather_object(gathered, msg)
+if rank == 0:
+    print(json.dumps(gathered))
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_sharded_failure_is_agreed_on(tmp_path, sim):
+    """A rank that fails before the exchange must not leave the others waiting in the collective: it sends a status record on its way out
+    (hc_host.h ShardAgreement), and every rank returns an error."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "fail_worker.py"
+    script.write_text(FAIL_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), helpers.ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    msgs = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    assert "injected" in msgs[1]
+    assert "another rank failed" in msgs[0]
