@@ -229,18 +229,21 @@ inline uint32_t vq_range_offsets(const VqResult& res, uint32_t max_clusters, std
 
 inline uint32_t vq_leaf_offsets(const VqResult& res, uint32_t base, std::vector<uint32_t>& offsets)
 {
-    uint32_t leaves = 0, total = 0;
-    std::vector<uint32_t> stack;
-    offsets.pop_back();                                            // the running total comes back at the end
-    for (const VqTreeSim& t : res.trees) {
-        stack.clear();
+    // one depth-first walk per tree (threaded_clusterizer: four); the trees cover disjoint, ascending position ranges, so they are walked
+    // on their own host threads and their leaf lists concatenated
+    const size_t nt = res.trees.size();
+    std::vector<std::vector<uint32_t>> part(nt);
+    std::vector<uint32_t> last(nt, 0u);
+    auto walk = [&](size_t ti) {
+        const VqTreeSim& t = res.trees[ti];
+        std::vector<uint32_t>& out = part[ti];
+        std::vector<uint32_t> stack;
         uint32_t cur = t.root;
         for (;;) {
             const VqHostNode& nd = res.nodes[cur];
             if (nd.split_rank < 0) {
-                offsets.push_back(base + nd.begin);
-                total = nd.begin + nd.count;
-                leaves++;
+                out.push_back(base + nd.begin);
+                last[ti] = nd.begin + nd.count;
                 if (stack.empty()) break;
                 cur = stack.back();
                 stack.pop_back();
@@ -249,6 +252,22 @@ inline uint32_t vq_leaf_offsets(const VqResult& res, uint32_t base, std::vector<
             stack.push_back((uint32_t)nd.left + 1);
             cur = (uint32_t)nd.left;
         }
+    };
+#ifdef __CUDACC__
+    if (nt > 1 && res.nodes.size() > 65536) {
+        std::vector<std::thread> th;
+        for (size_t ti = 1; ti < nt; ti++) th.emplace_back(walk, ti);
+        walk(0);
+        for (std::thread& x : th) x.join();
+    } else
+#endif
+    for (size_t ti = 0; ti < nt; ti++) walk(ti);
+    uint32_t leaves = 0, total = 0;
+    offsets.pop_back();                                            // the running total comes back at the end
+    for (size_t ti = 0; ti < nt; ti++) {
+        offsets.insert(offsets.end(), part[ti].begin(), part[ti].end());
+        leaves += (uint32_t)part[ti].size();
+        if (!part[ti].empty()) total = last[ti];
     }
     offsets.push_back(base + total);
     return leaves;
