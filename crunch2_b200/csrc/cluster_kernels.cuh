@@ -221,11 +221,18 @@ __device__ __forceinline__ void dxt1_eval_loop_staged(Dxt1ClusterScratch* sc, in
         unsigned long long t4 = 0, t3 = 0;                           // this lane's share of the rest; totals at the checks
         unsigned long long a4 = 0, a3 = 0;
         for (int base = 32; base < U; base += 32 * 8) {
+            // the eight loads of a group go out together (clamped index + zero weight past the end: no predicate between them)
+            int4 cbatch[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int i = base + 32 * k + (int)lane;
-                if (i < U) {
-                    const int4 c = ce[i];
+                cbatch[k] = ce[min(i, U - 1)];
+                if (i >= U) cbatch[k].w = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                {
+                    const int4 c = cbatch[k];
                     const unsigned wt = (unsigned)c.w;
                     const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
                     const int d01 = min(eval_dprime(cx, cy, cz, q0), eval_dprime(cx, cy, cz, q1));
