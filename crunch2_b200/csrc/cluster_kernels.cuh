@@ -25,7 +25,11 @@ namespace crn {
 #define CRN_COOP_OCC 3
 #endif
 constexpr int kClusterCoopWarps = CRN_COOP_WARPS;   // warps of a cooperative CTA
-constexpr int kClusterCoopChunk = 32;           // unique colours per warp per round; the early-out test runs once a round (every 256 colours)
+constexpr int kClusterCoopChunk = 32;           // unique colours per warp per slice
+#ifndef CRN_COOP_SLICES
+#define CRN_COOP_SLICES 2
+#endif
+constexpr int kClusterCoopSlices = CRN_COOP_SLICES;   // slices per warp per round; the early-out test runs once a round (every 8 x 32 x this colours)
 constexpr uint32_t kClusterCoopMinBlocks = 128; // clusters with at least this many member blocks are optimised by a whole CTA
 struct Dxt1CoopShared {
     unsigned lo[32], hi[32];                    // the batch: one candidate per lane of the owning warp
@@ -81,36 +85,42 @@ __device__ __forceinline__ void dxt1_coop_rounds(Dxt1CoopShared* cs, unsigned w,
     e4 = 0; e3 = 0;
     bool active = valid;
     int buf = 0;
-    int base = 0;
-    static_assert(kClusterCoopChunk == 32, "one colour per lane per round");
-    constexpr int STEP = kClusterCoopWarps * kClusterCoopChunk;
+    static_assert(kClusterCoopChunk == 32, "one colour per lane per slice");
+    // Slice k of warp w = colours [(k W + w) 32, + 32); a round is kClusterCoopSlices slices per warp, then one exchange of partial sums.
+    // The next slice is fetched (one coalesced 512-byte load per warp) while the current one is being scored out of shared memory.
     int4* cbuf = cs->cbuf[w];
-    // the slice of the next round is fetched (one coalesced 512-byte load per warp) while this round's is being scored out of shared memory
+    int k = 0;
     int4 nxt = make_int4(0, 0, 0, 0);
-    if ((int)(w * kClusterCoopChunk + lane) < U) nxt = ce[w * kClusterCoopChunk + lane];
+    if ((int)(w * 32 + lane) < U) nxt = ce[w * 32 + lane];
     do {                                                     // at least one round, so that the batch is not republished while a warp still reads it
         unsigned long long s4 = 0, s3 = 0;
-        cbuf[lane] = nxt;
-        __syncwarp();
-        {
-            const int ni = base + STEP + (int)(w * kClusterCoopChunk + lane);
-            if (ni < U) nxt = ce[ni];
-        }
-        if (active) {
-            const int i0 = base + (int)w * kClusterCoopChunk, cnt = min(U, i0 + kClusterCoopChunk) - i0;
+#pragma unroll 1
+        for (int sl = 0; sl < kClusterCoopSlices; sl++, k++) {
+            const int i0 = (k * kClusterCoopWarps + (int)w) * 32;
+            if (sl && i0 - (int)w * 32 >= U) { k += kClusterCoopSlices - sl; break; }    // (warp-uniform) nothing left for any warp in this round
+            __syncwarp();
+            cbuf[lane] = nxt;
+            __syncwarp();
+            {
+                const int ni = ((k + 1) * kClusterCoopWarps + (int)w) * 32 + (int)lane;
+                if (ni < U) nxt = ce[ni];
+            }
+            if (active) {
+                const int cnt = min(U, i0 + 32) - i0;
 #pragma unroll 4
-            for (int j = 0; j < cnt; j++) {
-                const int4 c = cbuf[j];
-                const unsigned wt = (unsigned)c.w;
-                const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
-                const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
-                if (DO4) {
-                    const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
-                    s4 += (unsigned long long)(unsigned)(d + c.z) * wt;
-                }
-                if (DO3) {
-                    const int d = min(d01, eval_dprime(cx, cy, cz, pm));
-                    s3 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                for (int j = 0; j < cnt; j++) {
+                    const int4 c = cbuf[j];
+                    const unsigned wt = (unsigned)c.w;
+                    const int cx = c.x & 0xffff, cy = c.x >> 16, cz = c.y;
+                    const int d01 = min(eval_dprime(cx, cy, cz, p0), eval_dprime(cx, cy, cz, p1));
+                    if (DO4) {
+                        const int d = min(d01, min(eval_dprime(cx, cy, cz, p2), eval_dprime(cx, cy, cz, p3)));
+                        s4 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                    }
+                    if (DO3) {
+                        const int d = min(d01, eval_dprime(cx, cy, cz, pm));
+                        s3 += (unsigned long long)(unsigned)(d + c.z) * wt;
+                    }
                 }
             }
         }
@@ -125,10 +135,8 @@ __device__ __forceinline__ void dxt1_coop_rounds(Dxt1CoopShared* cs, unsigned w,
         }
         buf ^= 1;
         if (active && ((DO4 && DO3) ? (e4 >= bound && e3 >= bound) : (DO4 ? e4 >= bound : e3 >= bound))) active = false;
-        base += kClusterCoopWarps * kClusterCoopChunk;
-    } while (__any_sync(CRN_FULL_MASK, active) && base < U);
+    } while (__any_sync(CRN_FULL_MASK, active) && k * kClusterCoopWarps * 32 < U);
 }
-
 // what every warp of the CTA does with a published batch; returns this lane's candidate's (err, alpha) as dxt1_eval does
 __device__ __noinline__ void dxt1_coop_batch(Dxt1CoopShared* cs, unsigned w, unsigned long long& err, int& alpha)
 {
