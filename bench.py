@@ -775,8 +775,8 @@ def run_clustered(args, ctx, ext, dev, wl, barrier, world):
     top = {"kernel": "dxt1_optimize_clusters_* (colour element, %d endpoint clusters)" % info["endpoint_clusters"][0],
            "ms": col_ms, "blocks": nblocks(levels), "bytes_per_block": 64 + 8,
            # dram__bytes_read.sum + dram__bytes_write.sum of dxt1_optimize_clusters_kernel on this exact workload, one launch
-           # (profiles/r2n_cluster_opt_c2_ncu.txt): the cluster workspace (hash table, unique colours, evaluation colours) on top of the 72 B/block
-           "traffic": 1176502000 + 1023954000,
+           # (profiles/r2z_cluster_opt_c2_ncu.txt): the cluster workspace (hash table, unique colours, evaluation colours) on top of the 72 B/block
+           "traffic": 1205408000 + 1155808000,
            "all_elements_ms": [float(x) for x in np.mean(np.array(opt_ms), axis=0)],
            "issue": {"candidates": int(info["opt_candidates"][0]), "colour_evals": int(info["opt_colour_evals"][0]), "palette_entries": int(info["opt_palette_entries"][0]),
                      "clusters": int(info["endpoint_clusters"][0])},
@@ -970,8 +970,8 @@ def main():
                          "note": "algorithmic count U*(11P+1) per evaluation, full U for every candidate: the kernel's early-outs skip about half of it and an IMAD "
                                  "counts as two operations, so this frac can exceed 1; what the hardware executed is in `ncu`",
                          # one ncu --set full capture of this kernel on this workload (profiles/r2n_cluster_opt_c2_ncu.txt): not measured by this run
-                         "ncu": {"profile": "profiles/r2n_cluster_opt_c2_ncu.txt", "issue_active_frac": 0.591, "pipe_fma_frac": 0.335, "pipe_alu_frac": 0.365,
-                                 "warp_inst_executed": 27444680859, "active_lanes_per_inst": 13.67, "lane_inst_per_s_frac_of_peak": 0.237}}
+                         "ncu": {"profile": "profiles/r2z_cluster_opt_c2_ncu.txt", "issue_active_frac": 0.635, "pipe_fma_frac": 0.323, "pipe_alu_frac": 0.412,
+                                 "warp_inst_executed": 21177907352, "active_lanes_per_inst": 31.23, "lane_inst_per_s_frac_of_peak": 0.586}}
     if "all_elements_ms" in top:
         roof["all_elements_ms"] = top["all_elements_ms"]
     out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
