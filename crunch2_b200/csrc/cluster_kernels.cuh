@@ -1,6 +1,7 @@
 // cluster_kernels.cuh -- N-pixel ("cluster") form of the endpoint optimisers and the selector re-vote
-// (SURVEY 8(a) rows a7, a9, a15/a20 core, a21): one warp per cluster, clusters given as CSR lists of
-// member blocks over a [n_blocks][16] RGBA8 block array.
+// (SURVEY 8(a) rows a7, a9, a15/a20 core, a21): clusters given as CSR lists of member blocks over a
+// [n_blocks][16] RGBA8 block array.  Colour: one warp per small cluster, one 8-warp CTA per large one
+// (dxt1_optimize_clusters_cta_kernel); alpha: one CTA per cluster, candidates scored from prefix sums.
 //
 // Replaces the bodies of qdxt1::pack_endpoints_task / qdxt5::pack_endpoints_task (reference
 // crnlib/crn_qdxt1.cpp:471-699, crnlib/crn_qdxt5.cpp:452-576: concatenate the member blocks' pixels,
