@@ -141,3 +141,20 @@ def test_mipmap_source_options_match_reference_file(lib, ref, case):
     assert want is not None
     assert got[:128] == want[:128]              # size and level count first
     assert got == want
+
+
+def test_mipmap_source_options_cubemap(lib, ref):
+    """Six faces: the window is ignored ("Can't crop cubemap textures"), a scale mode resamples every face; .dds block by block against the
+    reference's crn_compress on the faces its own resampler produces."""
+    import ctypes
+    from test_mip_cpu import ref_resample
+    faces = [blockgen.smooth_image(24, 24, 300 + f, alpha=False) for f in range(6)]
+    mp = dropin.CrnMipmapParams().clear()
+    mp.m_mode = 3                                            # cCRNMipModeNoMips
+    mp.m_window_left, mp.m_window_top, mp.m_window_right, mp.m_window_bottom = 2, 2, 10, 10
+    mp.m_scale_mode = 2; mp.m_scale_x = 0.5; mp.m_scale_y = 0.5
+    got, _, _ = dropin.crn_compress([[f] for f in faces], 0, file_type=dropin.FILE_DDS, quality_level=255, flags=1 | 2 | 8 | 32, lib=lib, mipmap_params=mp)
+    small = [ref_resample(ref, f, 12, 12, filt="kaiser", scale=1.0, srgb=True, gamma=2.2, wrap=False, comps=3, multithreaded=False) for f in faces]
+    want, _, _ = helpers.ref_compress(ref, [[f] for f in small], 0, file_type=1, quality=255, threads=0, flags=1 | 2 | 8 | 32)
+    assert got[:128] == want[:128]
+    assert got == want
