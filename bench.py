@@ -419,6 +419,26 @@ def run_mipgen(ctx, ext, dev, flush, steps, peak_gbs, with_reference=True):
     return out
 
 
+C5_BASES = 48          # distinct base images of the configs[4] batch; texture i = base i % 48 under its own cyclic shift
+
+
+def c5_texture(i, cache=None):
+    """Texture i of the configs[4] batch: 1024 x 1024 RGBA.  The first 48 are generated outright (0.2 s of numpy each); texture i >= 48 is base
+    i % 48 moved by a cyclic shift of its own, so all 1024 images differ while the generator stays out of the way of the timed calls (fully
+    generated images for every texture would keep every host core busy for 200 s and slow the calls being measured)."""
+    import blockgen
+    b = i % C5_BASES
+    base = cache.get(b) if cache is not None else None
+    if base is None:
+        base = blockgen.smooth_image(1024, 1024, 50000 + b, alpha=True)
+        if cache is not None:
+            cache[b] = base
+    k = i // C5_BASES
+    if k == 0:
+        return base
+    return np.ascontiguousarray(np.roll(base, ((k * 37) % 1024, (k * 101) % 1024), axis=(0, 1)))
+
+
 def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
     """BASELINE configs[4]: a batch of 1024 x 1024 textures, formats cycling DXT1 / DXT5 / DXN_XY (i mod 3), each clustered-compressed at
     quality 128 to DDS blocks through the public binding (host pixels in, host blocks out).  Textures are partitioned over the ranks by
@@ -432,27 +452,28 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
     mine = shard.partition_units([65536] * n_textures, world)[rank]
     keep = {}
     if mine:                                                     # warm the context's buffer pool
-        img = blockgen.smooth_image(1024, 1024, 50000 + mine[0], alpha=True)
+        img = c5_texture(mine[0])
         q = ctx.qdxt_init(fmts[mine[0] % 3][0], [img]); q.pack(128); q.close()
     l0 = ctx.launch_count
     # A batch converter keeps several textures in flight: C5_WORKERS contexts on this GPU (each its own stream and host threads), the rank's
     # textures dealt round-robin.  Every worker sums the wall time of its own calls (host pixels in / host blocks out); the rank's time is the
-    # slowest worker's sum.  The synthetic textures come from a small pool of generator threads running ahead (0.2 s of numpy each, not timed).
+    # slowest worker's sum.  The synthetic textures (c5_texture) come from two generator threads running ahead, not timed.
     import crunch2_b200 as crn
     from concurrent.futures import ThreadPoolExecutor
-    nworkers = max(1, min(C5_WORKERS, len(mine)))
+    # (each texture in flight keeps ~4 host threads busy: two element threads and their scatter pools)
+    nworkers = max(1, min(C5_WORKERS, len(mine), max(1, ((os.cpu_count() or 1) // max(1, world)) // 4)))
     ctxs = [ctx] + [crn.Context(dev.index if dev.index is not None else 0) for _ in range(nworkers - 1)]
     for c in ctxs[1:]:
-        img = blockgen.smooth_image(1024, 1024, 50000 + mine[0], alpha=True)
+        img = c5_texture(mine[0])
         q = c.qdxt_init(fmts[mine[0] % 3][0], [img]); q.pack(128); q.close()
-    pool = ThreadPoolExecutor(max(2, min(8, (os.cpu_count() or 2) // max(1, world))))
-    ahead, futs, flock = 16, {}, threading.Lock()
+    pool = ThreadPoolExecutor(2)
+    ahead, futs, flock, bases = 8, {}, threading.Lock(), {}
 
     def image(k):
         with flock:
             for j in mine[k:k + ahead]:
                 if j not in futs:
-                    futs[j] = pool.submit(blockgen.smooth_image, 1024, 1024, 50000 + j, True)
+                    futs[j] = pool.submit(c5_texture, j, bases)
             f = futs.pop(mine[k])
         return f.result()
     sums = [0.0] * nworkers
@@ -485,6 +506,7 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
         c.close()
     dt_all = shard.max_over_ranks(dt, dev)
     out = {"workload": "c5_batch: %d x 1024x1024 (DXT1/DXT5/DXN_XY mix), clustered DDS q128, one level each" % n_textures, "n_textures": n_textures,
+           "data": "synthetic: %d generated base images, every further texture a base under its own cyclic shift (all %d images differ)" % (min(C5_BASES, n_textures), n_textures),
            "value": n_textures * 1024 * 1024 / dt_all / 1e6, "unit": UNIT, "ms_per_texture": dt_all * 1e3 / max(1, len(mine)),
            "timing": "host wall clock summed over each worker's per-texture calls (host pixels in / host blocks out), slowest worker of the slowest rank",
            "gpu_launches_per_texture": int(launches // max(1, len(mine))), "partitioning": "texture -> rank (LPT), %d rank(s); %d textures in flight per GPU" % (world, nworkers),
@@ -495,7 +517,7 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
         if ref is not None:
             th, workers = cpu_threads(), cpu_workers()
             sample = [i for i in range(min(12, n_textures))]
-            imgs = {i: (keep[i][0] if i in keep else blockgen.smooth_image(1024, 1024, 50000 + i, alpha=True)) for i in sample}
+            imgs = {i: (keep[i][0] if i in keep else c5_texture(i)) for i in sample}
             ref_out = {}
 
             def one(i):
