@@ -312,6 +312,7 @@ private:
         for (;;) {
             const double t0 = now();
             while (gen_.load(std::memory_order_acquire) == seen) {
+                std::this_thread::yield();                  // several ranks may share a few cores: a spinning worker must not keep one to itself
                 if (now() - t0 > 4.0) {
                     std::unique_lock<std::mutex> l(m_);
                     cv_.wait(l, [&]() { return gen_.load() != seen; });
