@@ -445,7 +445,7 @@ private:
         cudaMemcpyAsync(d_slots_, h_slots, sizeof(uint2) * F, cudaMemcpyHostToDevice, stream_);
         cudaMemcpyAsync(d_list_, all, sizeof(uint32_t) * F, cudaMemcpyHostToDevice, stream_);
         if (nchunks > 1 && !events_ready_) {
-            for (uint32_t c = 0; c < kChunks; c++) if (cudaEventCreateWithFlags(&events_[c], cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
+            for (uint32_t c = 0; c < kChunks; c++) if (cudaEventCreateWithFlags(&events_[c], crn::event_flags()) != cudaSuccess) return cudaGetLastError();
             events_ready_ = true;
         }
         const uint32_t* dl = d_list_;
