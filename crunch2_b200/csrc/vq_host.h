@@ -283,6 +283,20 @@ struct VqWorkspace {                 // device slab reused across builds (+ the 
 // ways (spawning threads per round cost more than the work they did).
 class VqPool {
 public:
+    // How long an idle worker spins before it parks on the condition variable.  With cores to spare (>= 8 hardware threads per visible GPU)
+    // 4 ms: rounds follow each other within a millisecond or two and a parked thread takes tens of microseconds to get going.  With ranks
+    // sharing a few cores (8 GPUs on a 32-core host) the spinners compete with the threads doing the work: 0.05 ms.  CRN_B200_POOL_SPIN_MS overrides.
+    static double spin_ms()
+    {
+        static const double v = [] {
+            if (const char* e = getenv("CRN_B200_POOL_SPIN_MS")) return atof(e);
+            int ndev = 1;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+            const unsigned hc = std::thread::hardware_concurrency();
+            return (hc && hc / (unsigned)ndev < 8u) ? 0.05 : 4.0;
+        }();
+        return v;
+    }
     VqPool() { for (int i = 0; i < 3; i++) workers_[i] = std::thread([this, i]() { loop(i + 1); }); }
     ~VqPool()
     {
@@ -313,7 +327,7 @@ private:
             const double t0 = now();
             while (gen_.load(std::memory_order_acquire) == seen) {
                 std::this_thread::yield();                  // several ranks may share a few cores: a spinning worker must not keep one to itself
-                if (now() - t0 > 4.0) {
+                if (now() - t0 > spin_ms()) {
                     std::unique_lock<std::mutex> l(m_);
                     cv_.wait(l, [&]() { return gen_.load() != seen; });
                     break;
