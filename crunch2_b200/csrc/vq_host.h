@@ -289,7 +289,7 @@ public:
     static double spin_ms()
     {
         static const double v = [] {
-            if (const char* e = getenv("CRN_B200_POOL_SPIN_MS")) return atof(e);
+            if (const char* e = getenv("CRN_B200_POOL_SPIN_MS")) { if (*e) return atof(e); }
             int ndev = 1;
             if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
             const unsigned hc = std::thread::hardware_concurrency();

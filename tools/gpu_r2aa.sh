@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 N=${1:-4}
 nproc
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 3 --warmup 3 --c5-textures 256 --no-cpu-baseline > gpurun_out/r2aa_bench_${N}gpu.json 2> gpurun_out/r2aa_bench_${N}gpu.err; tail -2 gpurun_out/r2aa_bench_${N}gpu.err
+CRN_B200_POOL_SPIN_MS=${SPIN:-} timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 3 --warmup 3 --c5-textures 256 --no-cpu-baseline > gpurun_out/r2aa_bench_${N}gpu.json 2> gpurun_out/r2aa_bench_${N}gpu.err; tail -2 gpurun_out/r2aa_bench_${N}gpu.err
 python - <<PY
 import json
 d=json.load(open('gpurun_out/r2aa_bench_${N}gpu.json'))
