@@ -217,16 +217,37 @@ inline uint64_t transmit_cost(const Model& m)
     return bw.total;
 }
 
-// crc16 of crnlib/crn_checksum.cpp (the header and data checksums crnd_validate_file verifies)
+// crc16 of crnlib/crn_checksum.cpp (the header and data checksums crnd_validate_file verifies): CCITT polynomial, one dependent chain of ~8
+// operations per byte in the reference's form (13 ms for a 3.7 MB file).  Same function eight bytes at a time: the register only reaches the
+// first two bytes of a group, so the state after the group is the XOR of eight table entries, T[k][x] = state after byte x and k zero bytes.
+inline uint16_t crc16_byte(uint16_t crc, uint8_t b)
+{
+    const uint16_t q = (uint16_t)(b ^ (crc >> 8));
+    crc = (uint16_t)(crc << 8);
+    uint16_t r = (uint16_t)((q >> 4) ^ q);
+    crc ^= r; r = (uint16_t)(r << 5); crc ^= r; r = (uint16_t)(r << 7); crc ^= r;
+    return crc;
+}
+struct Crc16Tables {
+    uint16_t t[8][256];
+    Crc16Tables()
+    {
+        for (uint32_t x = 0; x < 256; x++) {
+            uint16_t c = crc16_byte(0, (uint8_t)x);
+            t[0][x] = c;
+            for (int k = 1; k < 8; k++) { c = crc16_byte(c, 0); t[k][x] = c; }
+        }
+    }
+};
 inline uint16_t crc16(const uint8_t* p, size_t n)
 {
+    static const Crc16Tables T;
     uint16_t crc = 0xFFFF;
-    for (size_t i = 0; i < n; i++) {
-        const uint16_t q = (uint16_t)(p[i] ^ (crc >> 8));
-        crc = (uint16_t)(crc << 8);
-        uint16_t r = (uint16_t)((q >> 4) ^ q);
-        crc ^= r; r = (uint16_t)(r << 5); crc ^= r; r = (uint16_t)(r << 7); crc ^= r;
-    }
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        crc = (uint16_t)(T.t[7][(uint8_t)((crc >> 8) ^ p[i])] ^ T.t[6][(uint8_t)((crc & 0xFF) ^ p[i + 1])] ^ T.t[5][p[i + 2]] ^ T.t[4][p[i + 3]] ^
+                         T.t[3][p[i + 4]] ^ T.t[2][p[i + 5]] ^ T.t[1][p[i + 6]] ^ T.t[0][p[i + 7]]);
+    for (; i < n; i++) crc = crc16_byte(crc, p[i]);
     return (uint16_t)~crc;
 }
 
