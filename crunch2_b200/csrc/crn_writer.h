@@ -370,25 +370,54 @@ struct Transitions {
     std::vector<uint32_t> row_start;     // n + 1
     std::vector<uint32_t> col, cnt;
     std::vector<uint32_t> sum;
-    // for_each(f) must call f(i, j) once per directed transition, and enumerate the same sequence each time it is called
-    template <typename Enum>
-    void build(uint32_t n, Enum&& for_each)
-    {   // bucket by row, then count each row's columns in a dense scratch table: linear in the number of transitions
+    // range(b0, b1, f) must call f(i, j) once per directed transition of blocks [b0, b1) (a block's transitions depend only on itself and its
+    // predecessor), the same ones every time it is called.  Blocks are cut into chunks that run on host threads: per-chunk row counts, a
+    // chunk-major prefix inside every row, per-chunk fills, then the rows are merged (duplicates counted, columns sorted) in parallel.
+    template <typename Range>
+    void build(uint32_t n, uint32_t num_blocks, Range&& range)
+    {
+        uint32_t nchunk = num_blocks >= (1u << 16) ? 8u : 1u;
+        if (const char* e = getenv("CRN_B200_WRITER_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64 && (uint32_t)v <= num_blocks) nchunk = (uint32_t)v; }   // tests force the chunked path on small inputs
+        auto chunk = [&](uint32_t t, uint32_t& b0, uint32_t& b1) { b0 = (uint32_t)((uint64_t)num_blocks * t / nchunk); b1 = (uint32_t)((uint64_t)num_blocks * (t + 1) / nchunk); };
+        auto run = [&](auto fn) {
+            std::vector<std::thread> th;
+            for (uint32_t t = 1; t < nchunk; t++) th.emplace_back(fn, t);
+            fn(0u);
+            for (std::thread& x : th) x.join();
+        };
+        std::vector<std::vector<uint32_t>> cnt_t(nchunk, std::vector<uint32_t>(n, 0u));
+        run([&](uint32_t t) { uint32_t b0, b1; chunk(t, b0, b1); std::vector<uint32_t>& c = cnt_t[t]; range(b0, b1, [&](uint32_t i, uint32_t) { c[i]++; }); });
         std::vector<uint32_t> start(n + 1, 0);
-        for_each([&](uint32_t i, uint32_t) { start[i + 1]++; });
-        for (uint32_t i = 0; i < n; i++) start[i + 1] += start[i];
-        std::vector<uint32_t> cols(start[n]), fill(start.begin(), start.end() - 1);
-        for_each([&](uint32_t i, uint32_t j) { cols[fill[i]++] = j; });
-        row_start.assign(n + 1, 0); col.clear(); cnt.clear(); sum.assign(n, 0);
-        std::vector<uint32_t> seen(n, 0), touched;
         for (uint32_t i = 0; i < n; i++) {
-            touched.clear();
-            for (uint32_t k = start[i]; k < start[i + 1]; k++) if (!seen[cols[k]]++) touched.push_back(cols[k]);
-            std::sort(touched.begin(), touched.end());
-            for (uint32_t j : touched) { col.push_back(j); cnt.push_back(seen[j]); seen[j] = 0; }
-            sum[i] = start[i + 1] - start[i];
-            row_start[i + 1] = (uint32_t)col.size();
+            uint32_t run_ofs = start[i];
+            for (uint32_t t = 0; t < nchunk; t++) { const uint32_t v = cnt_t[t][i]; cnt_t[t][i] = run_ofs; run_ofs += v; }     // now: the chunk's first slot in row i
+            start[i + 1] = run_ofs;
         }
+        std::vector<uint32_t> cols(start[n]);
+        run([&](uint32_t t) { uint32_t b0, b1; chunk(t, b0, b1); std::vector<uint32_t>& f = cnt_t[t]; range(b0, b1, [&](uint32_t i, uint32_t j) { cols[f[i]++] = j; }); });
+        // merge every row: rows dealt to the threads in contiguous runs of equal transition count
+        row_start.assign(n + 1, 0); sum.assign(n, 0);
+        std::vector<std::vector<uint32_t>> col_t(nchunk), cntv_t(nchunk);
+        std::vector<uint32_t> row_lo(nchunk + 1, n);
+        row_lo[0] = 0;
+        for (uint32_t t = 1, i = 0; t < nchunk; t++) { const uint64_t want = (uint64_t)start[n] * t / nchunk; while (i < n && start[i] < want) i++; row_lo[t] = i; }
+        std::vector<uint32_t> row_len(n, 0);
+        run([&](uint32_t t) {
+            std::vector<uint32_t> seen(n, 0), touched;
+            std::vector<uint32_t>& oc = col_t[t]; std::vector<uint32_t>& ov = cntv_t[t];
+            for (uint32_t i = row_lo[t]; i < row_lo[t + 1]; i++) {
+                touched.clear();
+                for (uint32_t k = start[i]; k < start[i + 1]; k++) if (!seen[cols[k]]++) touched.push_back(cols[k]);
+                std::sort(touched.begin(), touched.end());
+                for (uint32_t j : touched) { oc.push_back(j); ov.push_back(seen[j]); seen[j] = 0; }
+                sum[i] = start[i + 1] - start[i];
+                row_len[i] = (uint32_t)touched.size();
+            }
+        });
+        for (uint32_t i = 0; i < n; i++) row_start[i + 1] = row_start[i] + row_len[i];
+        col.clear(); cnt.clear();
+        col.reserve(row_start[n]); cnt.reserve(row_start[n]);
+        for (uint32_t t = 0; t < nchunk; t++) { col.insert(col.end(), col_t[t].begin(), col_t[t].end()); cnt.insert(cnt.end(), cntv_t[t].begin(), cntv_t[t].end()); }
     }
     uint16_t busiest() const
     {
@@ -535,9 +564,9 @@ struct Writer {
         const uint32_t n = in.n_color_endpoints;
         const auto tb0 = std::chrono::steady_clock::now();
         Transitions T;
-        T.build(n, [&](auto&& emit) {
-            uint32_t prev = 0;
-            for (uint32_t b = 0; b < in.num_blocks; b++) {
+        T.build(n, in.num_blocks, [&](uint32_t b0, uint32_t b1, auto&& emit) {
+            uint32_t prev = b0 ? in.endpoint_indices[(size_t)(b0 - 1) * 4] : 0u;
+            for (uint32_t b = b0; b < b1; b++) {
                 const uint32_t i = in.endpoint_indices[(size_t)b * 4];
                 if (coded(b) && i != prev) { emit(i, prev); emit(prev, i); }
                 prev = i;
@@ -631,9 +660,10 @@ struct Writer {
     {
         const uint32_t n = in.n_alpha_endpoints;
         Transitions T;
-        T.build(n, [&](auto&& emit) {
+        T.build(n, in.num_blocks, [&](uint32_t b0, uint32_t b1, auto&& emit) {
             uint32_t prev[2] = {0, 0};
-            for (uint32_t b = 0; b < in.num_blocks; b++) {
+            if (b0) { prev[0] = in.endpoint_indices[(size_t)(b0 - 1) * 4 + 1]; prev[1] = in.endpoint_indices[(size_t)(b0 - 1) * 4 + 2]; }
+            for (uint32_t b = b0; b < b1; b++) {
                 const uint32_t i0 = in.endpoint_indices[(size_t)b * 4 + 1], i1 = in.endpoint_indices[(size_t)b * 4 + 2];
                 if (coded(b)) {
                     if (in.has_alpha0 && i0 != prev[0]) { emit(i0, prev[0]); emit(prev[0], i0); }

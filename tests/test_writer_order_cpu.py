@@ -26,3 +26,16 @@ def test_device_orderings_equal_host_orderings(simctx, monkeypatch, fmt, size, q
     host, _, _ = simctx.compress_crn([levels], helpers.CRN_FMT[fmt], quality_level=q)
     monkeypatch.delenv("CRN_B200_HOST_ORDER")
     assert dev == host
+
+
+@pytest.mark.parametrize("fmt", ["DXT1", "DXT5"])
+def test_chunked_transition_lists_equal_single_chunk(simctx, monkeypatch, fmt):
+    """Transitions::build cuts the blocks into chunks for host threads at >= 65536 blocks; forced here on a small input: same file."""
+    img = blockgen.smooth_image(80, 64, 5, alpha=True)
+    levels = mip_chain(img)[:3]
+    monkeypatch.setenv("CRN_B200_WRITER_CHUNKS", "1")
+    one, _, _ = simctx.compress_crn([levels], helpers.CRN_FMT[fmt], quality_level=200)
+    monkeypatch.setenv("CRN_B200_WRITER_CHUNKS", "7")
+    many, _, _ = simctx.compress_crn([levels], helpers.CRN_FMT[fmt], quality_level=200)
+    monkeypatch.delenv("CRN_B200_WRITER_CHUNKS")
+    assert one == many
