@@ -45,6 +45,7 @@ struct crn_gpu_ctx {
     void* d_state; size_t d_state_cap;   // Dxt1BlockState scratch of the colour phase kernels
     void* d_cluster_ws; size_t d_cluster_ws_cap;   // hash / colour workspace of the cluster optimiser
     const uint32_t* d_cluster_order;     // set by the dxt_hc pipeline: clusters in descending size, the order the work-stealing loop takes them
+    int refine_parallel;                 // set by the dxt_hc pipeline outside exact mode: the refiner's least-squares sums lane-parallel (refiner_kernels.cuh)
     uint32_t cluster_big_count;          // how many leading entries of d_cluster_order have >= kClusterCoopMinBlocks member blocks (a CTA each)
     uint32_t* d_cluster_flags;           // set by the dxt_hc pipeline around a cluster-optimiser call: per-cluster m_reordered / m_alternate_rounding out
     void* d_files; size_t d_files_cap;   // TranscodeFile array of a batched transcode launch
@@ -1176,7 +1177,7 @@ int crn_gpu_refine_endpoints(crn_gpu_ctx* ctx, int dxt1_selectors, int perceptua
     const int grid = grid_for(ctx, n_clusters, crn::kRefineWarpsPerCta, 8);
     CRN_LAUNCH(crn::refine_endpoints_kernel, grid, crn::kRefineWarpsPerCta * 32, 0, ctx->stream, static_cast<const uint32_t*>(d_pixels_rgba), d_selectors, d_offsets,
                n_clusters, dxt1_selectors ? 1 : 0, perceptual ? 1 : 0, component, reinterpret_cast<const unsigned long long*>(d_error_to_beat),
-               d_endpoints, reinterpret_cast<unsigned long long*>(d_error), d_ok);
+               d_endpoints, reinterpret_cast<unsigned long long*>(d_error), d_ok, ctx->refine_parallel ? 1 : 0);
     ctx->launches++;
     CRN_CUDA(ctx, cudaGetLastError());
     return CRN_GPU_OK;

@@ -633,8 +633,13 @@ int hc_compress_impl(crn_gpu_ctx* ctx, const crn_gpu_hc_params* prm, const void*
                        d_elem.as<unsigned long long>(), d_cpix.as<uint32_t>(), d_csel.as<uint8_t>());
             ctx->launches++;
         }
-        HC_RC(crn_gpu_refine_endpoints(ctx, kind == 0 ? 1 : 0, perceptual, 0, d_cpix.p, d_csel.as<uint8_t>(), d_poffs.as<uint32_t>(), Kopt, d_err.as<uint64_t>(),
-                                       d_rep.as<uint32_t>(), d_rerr.as<uint64_t>(), d_rok.as<uint8_t>()));
+        ctx->refine_parallel = (parent->vq_exact || getenv("CRN_B200_ORDERED_SUMS")) ? 0 : 1;
+        {
+            const int rrc = crn_gpu_refine_endpoints(ctx, kind == 0 ? 1 : 0, perceptual, 0, d_cpix.p, d_csel.as<uint8_t>(), d_poffs.as<uint32_t>(), Kopt, d_err.as<uint64_t>(),
+                                                     d_rep.as<uint32_t>(), d_rerr.as<uint64_t>(), d_rok.as<uint8_t>());
+            ctx->refine_parallel = 0;
+            if (rrc) return rrc;
+        }
         std::vector<uint32_t> ep(K, 0), rep(K, 0); std::vector<uint8_t> rok(K, 0);
         if (SC > 1) {
             // this rank's results -> all ranks: one 16-byte record per cluster through the caller's all-gather

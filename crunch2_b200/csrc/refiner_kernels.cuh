@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kRefineWarpsPerCta * 32)
 refine_endpoints_kernel(const uint32_t* __restrict__ pixels, const uint8_t* __restrict__ selectors, const uint32_t* __restrict__ offsets,
                         uint32_t n_clusters, int dxt1_selectors, int perceptual, uint32_t comp,
                         const unsigned long long* __restrict__ error_to_beat,
-                        uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint8_t* __restrict__ out_ok)
+                        uint32_t* __restrict__ out_endpoints, unsigned long long* __restrict__ out_error, uint8_t* __restrict__ out_ok, int parallel_sums)
 {
     __shared__ RefineSmem smem[kRefineWarpsPerCta];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -71,7 +71,32 @@ refine_endpoints_kernel(const uint32_t* __restrict__ pixels, const uint8_t* __re
             continue;
         }
         // ---- least squares (:51-128): lane j owns sum j -- 0 alpha^2, 1 beta^2, 2 alpha beta, 3-5 alpha x, 6-8 beta x
+        // parallel_sums (the dxt_hc pipeline outside exact mode): every lane sums its own pixels of all nine sums and the totals meet in a
+        // butterfly -- the sums then depend on rounding noise, tolerance class like the quantiser that formed the cluster.  A warp spends
+        // n / 32 steps there instead of n (13 ms of a configs[2] pass were eleven ordered chains over ~14 K pixels per cluster).
         double acc = 0.0;
+        double a2, b2, ab, axs[3], bxs[3];
+        if (parallel_sums) {
+            double t0 = 0, t1 = 0, t2 = 0, tx[3] = { 0, 0, 0 }, ty[3] = { 0, 0, 0 };
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t px = pixels[p0 + i];
+                const unsigned c = selectors[p0 + i];
+                double k;
+                if (dxt1_selectors) { const unsigned lin = (0x2130u >> (4 * c)) & 3u; k = (float)lin * 1.0f / 3.0f; }
+                else { const unsigned lin = (0x65432170u >> (4 * c)) & 7u; k = (float)lin * 1.0f / 7.0f; }
+                const double alpha = 1.0f - k, beta = k;
+                t0 += alpha * alpha; t1 += beta * beta; t2 += alpha * beta;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const unsigned ch = dxt1_selectors ? (unsigned)j : comp;
+                    const float xf = dxt1_selectors ? (float)((px >> (8 * ch)) & 0xffu) * 1.0f / 255.0f : (float)((px >> (8 * ch)) & 0xffu) / 255.0f;
+                    tx[j] += alpha * (double)xf; ty[j] += beta * (double)xf;
+                }
+            }
+            a2 = warp_sum_f64(t0); b2 = warp_sum_f64(t1); ab = warp_sum_f64(t2);
+#pragma unroll
+            for (int j = 0; j < 3; j++) { axs[j] = warp_sum_f64(tx[j]); bxs[j] = warp_sum_f64(ty[j]); }
+        } else {
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t px = pixels[p0 + i];
             const unsigned c = selectors[p0 + i];
@@ -90,13 +115,16 @@ refine_endpoints_kernel(const uint32_t* __restrict__ pixels, const uint8_t* __re
             else term = beta * x;
             acc += term;
         }
-        const double a2 = __shfl_sync(CRN_FULL_MASK, acc, 0), b2 = __shfl_sync(CRN_FULL_MASK, acc, 1), ab = __shfl_sync(CRN_FULL_MASK, acc, 2);
+        a2 = __shfl_sync(CRN_FULL_MASK, acc, 0); b2 = __shfl_sync(CRN_FULL_MASK, acc, 1); ab = __shfl_sync(CRN_FULL_MASK, acc, 2);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { axs[j] = __shfl_sync(CRN_FULL_MASK, acc, 3 + j); bxs[j] = __shfl_sync(CRN_FULL_MASK, acc, 6 + j); }
+        }
         float l[3], h[3];
         {
             const uint32_t px0 = pixels[p0];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                const double ax = __shfl_sync(CRN_FULL_MASK, acc, 3 + j), bx = __shfl_sync(CRN_FULL_MASK, acc, 6 + j);
+                const double ax = axs[j], bx = bxs[j];
                 const unsigned ch = dxt1_selectors ? (unsigned)j : comp;
                 const double first = dxt1_selectors ? (double)((float)((px0 >> (8 * ch)) & 0xffu) * 1.0f / 255.0f) : (double)((float)((px0 >> (8 * ch)) & 0xffu) / 255.0f);
                 double a, b;
