@@ -478,6 +478,36 @@ template <int D> __device__ __forceinline__ void hc_load_vec(const float* __rest
         for (int q = 0; q < D / 2; q++) { const float2 x = p[q]; v[2 * q] = x.x; v[2 * q + 1] = x.y; }
     }
 }
+// Walks the members first, first + stride, ... below e, calling f(i, id, v, w) once per member in that order.  The row and weight of the NEXT member
+// are loaded before f runs on the current one and the member index after that is already in flight, so the two dependent gathers (perm -> row) overlap
+// the arithmetic instead of being paid in series every iteration: the root split ran at long_scoreboard 13.5 of 16 cycles per issue with one chain per
+// thread (profiles/r2ad_hc_tree_ncu.txt).  The order of the calls, and so every per-thread sum, is unchanged.
+template <int D, typename F>
+__device__ __forceinline__ void hc_for_members(const float* __restrict__ vecs, const uint32_t* __restrict__ wts, const uint32_t* __restrict__ perm,
+                                               uint32_t first, uint32_t e, uint32_t stride, F&& f)
+{
+    if (first >= e) return;
+    uint32_t i = first, id = perm[i];
+    uint32_t id_next = (i + stride < e) ? perm[i + stride] : 0;
+    float v[D]; hc_load_vec<D>(vecs, id, v);
+    uint32_t w = wts[id];
+    for (;;) {
+        const uint32_t in = i + stride;
+        const bool more = in < e;
+        float vn[D]; uint32_t wn = 0, id2 = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) vn[d] = 0.0f;
+        if (more) {
+            hc_load_vec<D>(vecs, id_next, vn); wn = wts[id_next];
+            if (in + stride < e) id2 = perm[in + stride];
+        }
+        f(i, id, v, w);
+        if (!more) break;
+        i = in; id = id_next; id_next = id2; w = wn;
+#pragma unroll
+        for (int d = 0; d < D; d++) v[d] = vn[d];
+    }
+}
 template <int D> __device__ __forceinline__ float hc_sqdist(const float (&a)[D], const float (&b)[D])
 {
     float s = 0;
@@ -542,12 +572,11 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             unsigned long long key = 0;
-            for (uint32_t i = sb + tid; i < se; i += T) {
-                float v[D]; hc_load_vec<D>(vecs, perm[i], v);
+            hc_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t i, uint32_t, const float (&v)[D], uint32_t) {
                 const float d2 = pass ? hc_sqdist<D>(v, seed[0]) : hc_sqdist<D>(v, centroid);
                 const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(~i);
                 key = k > key ? k : key;
-            }
+            });
             hc_group_reduce<T, G, K, false>(red, parity, nullptr, 0, &key, 1, nullptr);
             const uint32_t pos = ~(unsigned)key;
             hc_load_vec<D>(vecs, perm[pos], seed[pass]);
@@ -560,17 +589,15 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
         {
 #pragma unroll
             for (int d = 0; d <= D; d++) tot[d] = 0;
-            for (uint32_t i = sb + tid; i < se; i += T) {
-                const uint32_t id = perm[i];
-                float v[D]; hc_load_vec<D>(vecs, id, v);
-                const float w = (float)wts[id];
+            hc_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&v)[D], uint32_t wi) {
+                const float w = (float)wi;
                 float dot = v[0] * v[0];
 #pragma unroll
                 for (int d = 1; d < D; d++) dot += v[d] * v[d];
 #pragma unroll
                 for (int d = 0; d < D; d++) tot[d] += (double)(v[d] * w);
                 tot[D] += (double)(dot * w);
-            }
+            });
             hc_group_reduce<T, G, K, true>(red, parity, tot, D + 1, nullptr, 0, nullptr);
         }
         if (begin + 2 < end) {
@@ -581,16 +608,14 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
                 float acc[16];
 #pragma unroll
                 for (int y = 0; y < 16; y++) acc[y] = 0.0f;
-                for (uint32_t i = sb + ml; i < se; i += LANES) {
-                    const uint32_t id = perm[i];
-                    float v[D]; hc_load_vec<D>(vecs, id, v);
-                    const float w = (float)wts[id];
-                    float vx = 0;
+                hc_for_members<D>(vecs, wts, perm, sb + ml, se, LANES, [&](uint32_t, uint32_t, const float (&vr)[D], uint32_t wi) {
+                    const float w = (float)wi;
+                    float v[D], vx = 0;
 #pragma unroll
-                    for (int d = 0; d < D; d++) { v[d] -= centroid[d]; if (d == x) vx = v[d]; }
+                    for (int d = 0; d < D; d++) { v[d] = vr[d] - centroid[d]; if (d == x) vx = v[d]; }
 #pragma unroll
                     for (int y = 0; y < 16; y++) acc[y % D] += vx * (v[y % D] * w);
-                }
+                });
                 __syncthreads();
 #pragma unroll
                 for (int y = 0; y < 16; y++) s_cov[tid * 16 + y] = acc[y];
@@ -670,10 +695,8 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
             double sl[D + 2];
 #pragma unroll
             for (int d = 0; d < D + 2; d++) sl[d] = 0;
-            for (uint32_t i = sb + tid; i < se; i += T) {
-                const uint32_t id = perm[i];
-                float v[D]; hc_load_vec<D>(vecs, id, v);
-                const float w = (float)wts[id];
+            hc_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&v)[D], uint32_t wi) {
+                const float w = (float)wi;
                 float t = (v[0] - centroid[0]) * axis[0];
 #pragma unroll
                 for (int d = 1; d < D; d++) t += (v[d] - centroid[d]) * axis[d];
@@ -683,7 +706,7 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
                     for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
                     sl[D] += (double)w;
                 }
-            }
+            });
             hc_group_reduce<T, G, K, true>(red, parity, sl, D + 2, nullptr, 0, nullptr);
             const double lw = sl[D], rw = sl[D + 1] - sl[D];
             if (lw > 0.0 && rw > 0.0) {
@@ -705,11 +728,9 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
             for (int d = 0; d <= D; d++) sl[d] = 0;
 #pragma unroll
             for (int d = 0; d < D; d++) { used_left[d] = left[d]; used_right[d] = right[d]; }
-            for (uint32_t i = sb + tid; i < se; i += T) {
-                const uint32_t id = perm[i];
-                float v[D]; hc_load_vec<D>(vecs, id, v);
+            hc_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&v)[D], uint32_t wi) {
                 if (hc_sqdist<D>(left, v) < hc_sqdist<D>(right, v)) {
-                    const unsigned wi = wts[id]; const float w = (float)wi;
+                    const float w = (float)wi;
                     float dot = v[0] * v[0];
 #pragma unroll
                     for (int d = 1; d < D; d++) dot += v[d] * v[d];
@@ -717,7 +738,7 @@ hc_tree_split_kernel(const float* __restrict__ vecs, const uint32_t* __restrict_
                     for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
                     sl[D] += (double)(dot * w); uu[0] += wi; uu[1]++;
                 }
-            }
+            });
             hc_group_reduce<T, G, K, true>(red, parity, sl, D + 1, uu, 2, upre);
             lw = uu[0]; n_left = (uint32_t)uu[1]; left_before = (uint32_t)upre[1];
             rw = total_weight - lw;
