@@ -26,20 +26,63 @@ struct VqFastNodes {
 };
 struct VqFastResult { int state; uint32_t n_left; float lvar, rvar; };      // state: 1 split, 2 unsplittable
 
-template <int D> __device__ __forceinline__ void vqf_load(const uint8_t* __restrict__ vecs, uint32_t id, float (&v)[D])
+// A training vector as stored (D bytes), fetched first and unpacked to floats only when it is used -- so that a row can be kept in flight across an
+// iteration in 4 registers instead of 16.
+template <int D> struct VqfRaw { uint32_t w[D == 16 ? 4 : (D == 2 ? 1 : D / 2)]; };
+template <int D> __device__ __forceinline__ VqfRaw<D> vqf_load_raw(const uint8_t* __restrict__ vecs, uint32_t id)
 {
+    VqfRaw<D> r;
     if (D == 16) {
         const uint4 q = *reinterpret_cast<const uint4*>(vecs + (size_t)id * 16);
-        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k % D] = (float)((w[k >> 2] >> (8 * (k & 3))) & 255u);
+        r.w[0] = q.x; r.w[1 % (D == 16 ? 4 : 1)] = q.y; r.w[2 % (D == 16 ? 4 : 1)] = q.z; r.w[3 % (D == 16 ? 4 : 1)] = q.w;
     } else if (D == 2) {
-        const uint16_t q = *reinterpret_cast<const uint16_t*>(vecs + (size_t)id * 2);
-        v[0] = (float)(q & 255u); v[1 % D] = (float)(q >> 8);
+        r.w[0] = *reinterpret_cast<const uint16_t*>(vecs + (size_t)id * 2);
     } else {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(vecs + (size_t)id * D);      // D = 6: 2-byte aligned
 #pragma unroll
-        for (int k = 0; k < D / 2; k++) { const uint32_t q = p[k]; v[2 * k] = (float)(q & 255u); v[(2 * k + 1) % D] = (float)(q >> 8); }
+        for (int k = 0; k < D / 2; k++) r.w[k % (D == 16 ? 4 : (D == 2 ? 1 : D / 2))] = p[k];
+    }
+    return r;
+}
+template <int D> __device__ __forceinline__ void vqf_unpack(const VqfRaw<D>& r, float (&v)[D])
+{
+    if (D == 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k % D] = (float)((r.w[(k >> 2) % (D == 16 ? 4 : 1)] >> (8 * (k & 3))) & 255u);
+    } else if (D == 2) {
+        v[0] = (float)(r.w[0] & 255u); v[1 % D] = (float)(r.w[0] >> 8);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D / 2; k++) { const uint32_t q = r.w[k % (D == 16 ? 4 : (D == 2 ? 1 : D / 2))]; v[2 * k] = (float)(q & 255u); v[(2 * k + 1) % D] = (float)(q >> 8); }
+    }
+}
+template <int D> __device__ __forceinline__ void vqf_load(const uint8_t* __restrict__ vecs, uint32_t id, float (&v)[D])
+{
+    vqf_unpack<D>(vqf_load_raw<D>(vecs, id), v);
+}
+// Walks the members first, first + stride, ... below e, calling f(i, id, v, w) once per member in that order, with the next member's packed row and
+// weight and the index after that already in flight (see hc_for_members in hc_kernels.cuh: the split kernels wait on the perm -> row gather chain).
+template <int D, typename F>
+__device__ __forceinline__ void vqf_for_members(const uint8_t* __restrict__ vecs, const uint32_t* __restrict__ wts, const uint32_t* __restrict__ perm,
+                                                uint32_t first, uint32_t e, uint32_t stride, F&& f)
+{
+    if (first >= e) return;
+    uint32_t i = first, id = perm[i];
+    uint32_t id_next = (i + stride < e) ? perm[i + stride] : 0;
+    VqfRaw<D> raw = vqf_load_raw<D>(vecs, id);
+    uint32_t w = wts[id];
+    for (;;) {
+        const uint32_t in = i + stride;
+        const bool more = in < e;
+        VqfRaw<D> raw_next = raw; uint32_t wn = 0, id2 = 0;
+        if (more) {
+            raw_next = vqf_load_raw<D>(vecs, id_next); wn = wts[id_next];
+            if (in + stride < e) id2 = perm[in + stride];
+        }
+        float v[D]; vqf_unpack<D>(raw, v);
+        f(i, id, v, w);
+        if (!more) break;
+        i = in; id = id_next; id_next = id2; w = wn; raw = raw_next;
     }
 }
 
@@ -71,17 +114,15 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
         {
 #pragma unroll
             for (int d = 0; d < D + 2; d++) tot[d] = 0;
-            for (uint32_t i = sb + tid; i < se; i += T) {
-                const uint32_t id = perm[i];
-                float v[D]; vqf_load<D>(vecs, id, v);
-                const float w = (float)wts[id];
+            vqf_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&v)[D], uint32_t wi) {
+                const float w = (float)wi;
                 float dot = v[0] * v[0];
 #pragma unroll
                 for (int d = 1; d < D; d++) dot += v[d] * v[d];
 #pragma unroll
                 for (int d = 0; d < D; d++) tot[d] += (double)(v[d] * w);
                 tot[D] += (double)(dot * w); tot[D + 1] += (double)w;
-            }
+            });
             hc_group_reduce<T, G, K, true>(red, parity, tot, D + 2, nullptr, 0, nullptr);
         }
         float centroid[D];
@@ -109,16 +150,14 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
                 float acc[16];
 #pragma unroll
                 for (int y = 0; y < 16; y++) acc[y] = 0.0f;
-                for (uint32_t i = sb + ml; i < se; i += LANES) {
-                    const uint32_t id = perm[i];
-                    float v[D]; vqf_load<D>(vecs, id, v);
-                    const float w = (float)wts[id];
-                    float vx = 0;
+                vqf_for_members<D>(vecs, wts, perm, sb + ml, se, LANES, [&](uint32_t, uint32_t, const float (&vr)[D], uint32_t wi) {
+                    const float w = (float)wi;
+                    float v[D], vx = 0;
 #pragma unroll
-                    for (int d = 0; d < D; d++) { v[d] -= centroid[d]; if (d == x) vx = v[d]; }
+                    for (int d = 0; d < D; d++) { v[d] = vr[d] - centroid[d]; if (d == x) vx = v[d]; }
 #pragma unroll
                     for (int y = 0; y < 16; y++) acc[y % D] += vx * (v[y % D] * w);
-                }
+                });
                 __syncthreads();
 #pragma unroll
                 for (int y = 0; y < 16; y++) s_cov[(tid * 16 + y) % COVN] = acc[y];
@@ -142,18 +181,17 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
                 float acc[NC];
 #pragma unroll
                 for (int k = 0; k < NC; k++) acc[k] = 0.0f;
-                for (uint32_t i = sb + tid; i < se; i += T) {
-                    const uint32_t id = perm[i];
-                    float v[D]; vqf_load<D>(vecs, id, v);
-                    const float w = (float)wts[id];
+                vqf_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&vr)[D], uint32_t wi) {
+                    const float w = (float)wi;
+                    float v[D];
 #pragma unroll
-                    for (int d = 0; d < D; d++) v[d] -= centroid[d];
+                    for (int d = 0; d < D; d++) v[d] = vr[d] - centroid[d];
                     int k = 0;
 #pragma unroll
                     for (int x = 0; x < D; x++)
 #pragma unroll
                         for (int y = x; y < D; y++) acc[k++] += v[x] * (v[y] * w);
-                }
+                });
                 double dacc[NC];
 #pragma unroll
                 for (int k = 0; k < NC; k++) dacc[k] = (double)acc[k];
@@ -205,10 +243,8 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
                 double sl[D + 1];
 #pragma unroll
                 for (int d = 0; d <= D; d++) sl[d] = 0;
-                for (uint32_t i = sb + tid; i < se; i += T) {
-                    const uint32_t id = perm[i];
-                    float v[D]; vqf_load<D>(vecs, id, v);
-                    const float w = (float)wts[id];
+                vqf_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&v)[D], uint32_t wi) {
+                    const float w = (float)wi;
                     float t = (v[0] - centroid[0]) * axis[0];
 #pragma unroll
                     for (int d = 1; d < D; d++) t += (v[d] - centroid[d]) * axis[d];
@@ -217,7 +253,7 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
                         for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
                         sl[D] += (double)w;
                     }
-                }
+                });
                 hc_group_reduce<T, G, K, true>(red, parity, sl, D + 1, nullptr, 0, nullptr);
                 const double lwt = sl[D], rwt = tot[D + 1] - sl[D];
                 if (lwt > 0.0 && rwt > 0.0) {
@@ -234,12 +270,11 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
                 unsigned long long key = 0;
-                for (uint32_t i = sb + tid; i < se; i += T) {
-                    float v[D]; vqf_load<D>(vecs, perm[i], v);
+                vqf_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t i, uint32_t, const float (&v)[D], uint32_t) {
                     const float d2 = pass ? hc_sqdist<D>(v, seed[0]) : hc_sqdist<D>(v, centroid);
                     const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(~i);
                     key = k > key ? k : key;
-                }
+                });
                 hc_group_reduce<T, G, K, false>(red, parity, nullptr, 0, &key, 1, nullptr);
                 const uint32_t pos = ~(unsigned)key;
                 vqf_load<D>(vecs, perm[pos], seed[pass]);
@@ -261,9 +296,7 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
             for (int d = 0; d <= D; d++) sl[d] = 0;
 #pragma unroll
             for (int d = 0; d < D; d++) { used_left[d] = left[d]; used_right[d] = right[d]; }
-            for (uint32_t i = sb + tid; i < se; i += T) {
-                const uint32_t id = perm[i];
-                float v[D]; vqf_load<D>(vecs, id, v);
+            vqf_for_members<D>(vecs, wts, perm, sb + tid, se, T, [&](uint32_t, uint32_t, const float (&v)[D], uint32_t wi) {
                 bool is_left;
                 if (mode == 1) {
                     float t = (v[0] - right[0]) * left[0];
@@ -272,7 +305,7 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
                     is_left = t < 0.0f;
                 } else is_left = hc_sqdist<D>(left, v) < hc_sqdist<D>(right, v);
                 if (is_left) {
-                    const unsigned wi = wts[id]; const float w = (float)wi;
+                    const float w = (float)wi;
                     float dot = v[0] * v[0];
 #pragma unroll
                     for (int d = 1; d < D; d++) dot += v[d] * v[d];
@@ -280,7 +313,7 @@ vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restric
                     for (int d = 0; d < D; d++) sl[d] += (double)(v[d] * w);
                     sl[D] += (double)(dot * w); uu[0] += wi; uu[1]++;
                 }
-            }
+            });
             hc_group_reduce<T, G, K, true>(red, parity, sl, D + 1, uu, 2, upre);
             lw = uu[0]; n_left = (uint32_t)uu[1]; left_before = (uint32_t)upre[1];
             rw = (unsigned long long)tot[D + 1] - lw;
