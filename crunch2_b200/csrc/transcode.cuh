@@ -317,7 +317,7 @@ __device__ __forceinline__ void transcode_level(TranscodeSmem* sm, const Transco
         {
             const uint32_t col = bx0 + (lane < n ? lane : 0u);
             const uint32_t ref = lane < n ? bb->ref[lane] : 1u;
-            const uint2 top = rowval[col];
+            const uint2 top = lane < n ? rowval[col] : make_uint2(0u, 0u);      // idle lanes must not read the column lane 0 rewrites below
             uint32_t vce = 0, va0 = 0, va1 = 0;
             if (HAS_COLOR) { vce = resolve_indices(ref, bb->dce[lane], top.x & 0xffffu, ce, nce, n); ce = __shfl_sync(CRN_FULL_MASK, vce, (int)n - 1); }
             if (HAS_A0) { va0 = resolve_indices(ref, bb->da0[lane], top.x >> 16, a0, nae, n); a0 = __shfl_sync(CRN_FULL_MASK, va0, (int)n - 1); }

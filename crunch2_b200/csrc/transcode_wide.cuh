@@ -232,7 +232,7 @@ static inline void wide_st16(wide_addr a, uint32_t v) { *reinterpret_cast<uint16
 struct __align__(16) WideSmemB {
     uint8_t tab[2][kWideTabBytes * kWideWin];   // per window: PP[4], Gd, Gt (kWideWin bytes each), Gd2, Gt2 (2 * kWideWin each)
     uint16_t rt[kWideMaxW / 4 + 8];             // layouts of the pairs below, two pairs per entry (+ read-ahead slack)
-    uint32_t done;
+    uint32_t done[2];                           // end-of-walk flag of epoch e in done[e & 1]: the walker may be one epoch ahead of a thread still reading
 };
 
 __device__ __forceinline__ void wide_walk(WideSmemB* smp, const WideLevel& wl, int pipe)
@@ -267,7 +267,7 @@ __device__ __forceinline__ void wide_walk(WideSmemB* smp, const WideLevel& wl, i
             if (v < NV) *reinterpret_cast<uint4*>(&sm.tab[e & 1][v * 16]) = regs[k];
         }
     };
-    if (tid == 0) sm.done = 0;
+    if (tid == 0) { sm.done[0] = 0; sm.done[1] = 0; }
     if (tid >= 32) { load_window(0); store_window(0); if (pipe) load_window(1); }
     __syncthreads();
     // The walker is ONE thread: what bounds it is the number of instructions it issues per pair (a lone warp issues one
@@ -282,7 +282,7 @@ __device__ __forceinline__ void wide_walk(WideSmemB* smp, const WideLevel& wl, i
             while (outp < last) *outp++ = nbits;
             __threadfence();
             *reinterpret_cast<volatile uint32_t*>(wl.progress) = nrows;
-            sm.done = 1;
+            sm.done[e & 1] = 1;
         } else if (tid == 0) {
             const uint32_t wb = e * kWideWB, wend = wb + kWideWB;
             const wide_addr tb = wide_smem(sm.tab[e & 1]) - wb;            // tb + o = &PP[0][o - wb]
@@ -347,13 +347,13 @@ __device__ __forceinline__ void wide_walk(WideSmemB* smp, const WideLevel& wl, i
                     *reinterpret_cast<volatile uint32_t*>(wl.progress) = row;
                 }
             }
-            if (row >= nrows) sm.done = 1;
+            if (row >= nrows) sm.done[e & 1] = 1;
         } else if (tid >= 32) {
             if (pipe) { store_window(e + 1); load_window(e + 2); }
             else { load_window(e + 1); store_window(e + 1); }
         }
         __syncthreads();
-        if (sm.done) break;
+        if (sm.done[e & 1]) break;
     }
 }
 
