@@ -62,6 +62,36 @@ struct VqOrderSim {
         }
         pending.resize(keep);
     }
+    // `v` by key descending, then id ascending -- the order `before` in finish() gives -- as an LSD radix sort of 64-bit (inverted key bits, id)
+    // words: std::sort with the comparator took 4.7 ms of a 14 ms colour endpoint tree (150 K candidates).  Digits every word agrees on are skipped.
+    static void sort_cands(std::vector<Cand>& v)
+    {
+        const size_t n = v.size();
+        if (n < 4096) { std::sort(v.begin(), v.end(), [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key > y.key : x.id < y.id; }); return; }
+        std::vector<uint64_t> a(n), b(n);
+        for (size_t i = 0; i < n; i++) {
+            const float k = v[i].key == 0.0f ? 0.0f : v[i].key;                        // -0 and +0 compare equal
+            uint32_t u; memcpy(&u, &k, 4);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);                            // ascending in the float's order
+            a[i] = ((uint64_t)(~u) << 32) | v[i].id;
+        }
+        constexpr unsigned kDigit = 11, kBuckets = 1u << kDigit;
+        for (unsigned shift = 0; shift < 64; shift += kDigit) {
+            uint32_t cnt[kBuckets] = { 0 };
+            for (size_t i = 0; i < n; i++) cnt[(a[i] >> shift) & (kBuckets - 1)]++;
+            if (cnt[(a[0] >> shift) & (kBuckets - 1)] == n) continue;
+            uint32_t at = 0;
+            for (unsigned k = 0; k < kBuckets; k++) { const uint32_t c = cnt[k]; cnt[k] = at; at += c; }
+            for (size_t i = 0; i < n; i++) b[cnt[(a[i] >> shift) & (kBuckets - 1)]++] = a[i];
+            a.swap(b);
+        }
+        for (size_t i = 0; i < n; i++) {
+            uint32_t u = ~(uint32_t)(a[i] >> 32);
+            u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+            float k; memcpy(&k, &u, 4);
+            v[i] = Cand{ k, (uint32_t)a[i] };
+        }
+    }
     // after the last round: the budget() winners (the nodes the reference would have popped).  Everything above the histogram bin that holds
     // the budget-th key wins outright; only that bin's entries need a selection.  need_ranks: also order them as the reference pops them
     // (m_codebook_index, what retrieve_clusters(max) prunes by); a caller that keeps every leaf only needs to know WHICH nodes were split.
@@ -85,7 +115,7 @@ struct VqOrderSim {
             if (edge.size() > want) { std::nth_element(edge.begin(), edge.begin() + want, edge.end(), before); edge.resize(want); }
             done.insert(done.end(), edge.begin(), edge.end());
         }
-        if (need_ranks) std::sort(done.begin(), done.end(), before);
+        if (need_ranks) sort_cands(done);
         uint32_t rank = 0;
         for (const Cand& c : done) {
             VqHostNode& nd = nodes[c.id];
