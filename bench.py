@@ -38,7 +38,7 @@ METRICS = {"c2_dxt5_q128_4096_mips": "clustered DXT5 .DDS compress throughput (-
            "c1_dxt1_2048_mips": "DXT1 block-by-block compress throughput (uber, perceptual)",
            "dxt5_2048": "DXT5 block-by-block compress throughput (uber, perceptual)"}
 UNIT = "Mtexel/s"
-C5_WORKERS = 3          # --c5-workers
+C5_WORKERS = 8          # --c5-workers
 CLUSTERED = ("c2_dxt5_q128_4096_mips",)
 CRN_FMT_OF = {0: 0, 3: 2}            # dxt_format -> crn_format for the reference's crn_compress
 
@@ -496,18 +496,21 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
         q = ctx.qdxt_init(fmts[mine[0] % 3][0], [img]); q.pack(128); q.close()
     l0 = ctx.launch_count
     # A batch converter keeps several textures in flight: C5_WORKERS contexts on this GPU (each its own stream and host threads), the rank's
-    # textures dealt round-robin.  Every worker sums the wall time of its own calls (host pixels in / host blocks out); the rank's time is the
+    # textures pulled from one queue (formats cost differently: dealing them round-robin left the DXT5 worker to finish alone).  Every worker sums the wall time of its own calls (host pixels in / host blocks out); the rank's time is the
     # slowest worker's sum.  The synthetic textures (c5_texture) come from two generator threads running ahead, not timed.
     import crunch2_b200 as crn
     from concurrent.futures import ThreadPoolExecutor
-    # (each texture in flight keeps ~4 host threads busy: two element threads and their scatter pools)
-    nworkers = max(1, min(C5_WORKERS, len(mine), max(1, ((os.cpu_count() or 1) // max(1, world)) // 4)))
+    # A texture in flight has two element threads and their scatter pools, but they mostly wait for the device: measured on 16 cores, one
+    # GPU (1024 textures): 3 in flight 106 Mtexel/s (round-robin dealing, which gave every worker ONE format), 4 148, 6 156, 8 189.  So one
+    # texture in flight per two host cores, up to C5_WORKERS -- except on a rank with fewer than 8 cores, where the old one-per-four stays.
+    cores_per_rank = (os.cpu_count() or 1) // max(1, world)
+    nworkers = max(1, min(C5_WORKERS, len(mine), cores_per_rank // 2 if cores_per_rank >= 8 else cores_per_rank // 4))
     ctxs = [ctx] + [crn.Context(dev.index if dev.index is not None else 0) for _ in range(nworkers - 1)]
     for c in ctxs[1:]:
         img = c5_texture(mine[0])
         q = c.qdxt_init(fmts[mine[0] % 3][0], [img]); q.pack(128); q.close()
     pool = ThreadPoolExecutor(2)
-    ahead, futs, flock, bases = 8, {}, threading.Lock(), {}
+    ahead, futs, flock, bases = max(8, 2 * nworkers), {}, threading.Lock(), {}
 
     def image(k):
         with flock:
@@ -518,11 +521,17 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
         return f.result()
     sums = [0.0] * nworkers
     errors = []
+    next_k, klock = [0], threading.Lock()
 
     def work(wi):
         try:
             c = ctxs[wi]
-            for k in range(wi, len(mine), nworkers):
+            while True:
+                with klock:
+                    k = next_k[0]
+                    next_k[0] += 1
+                if k >= len(mine):
+                    break
                 i = mine[k]
                 img = image(k)
                 t0 = time.perf_counter()
@@ -922,7 +931,7 @@ def main():
     ap.add_argument("--no-block-pack", action="store_true")
     ap.add_argument("--no-hc", action="store_true")
     ap.add_argument("--c5-textures", type=int, default=1024, help="textures of the configs[4] batch (BASELINE: 1024)")
-    ap.add_argument("--c5-workers", type=int, default=3, help="textures in flight per GPU in the configs[4] batch (one context each)")
+    ap.add_argument("--c5-workers", type=int, default=8, help="textures in flight per GPU in the configs[4] batch (one context each)")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
