@@ -67,7 +67,8 @@ struct VqOrderSim {
     static void sort_cands(std::vector<Cand>& v)
     {
         const size_t n = v.size();
-        if (n < 4096) { std::sort(v.begin(), v.end(), [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key > y.key : x.id < y.id; }); return; }
+        static const size_t radix_min = [] { const char* e = getenv("CRN_B200_RANK_RADIX_MIN"); return e ? (size_t)atoi(e) : (size_t)4096; }();      // (tests lower it)
+        if (n < 2 || n < radix_min) { std::sort(v.begin(), v.end(), [](const Cand& x, const Cand& y) { return x.key != y.key ? x.key > y.key : x.id < y.id; }); return; }
         std::vector<uint64_t> a(n), b(n);
         for (size_t i = 0; i < n; i++) {
             const float k = v[i].key == 0.0f ? 0.0f : v[i].key;                        // -0 and +0 compare equal

@@ -179,3 +179,36 @@ def test_fast_vq_piecewise_rounds_give_a_valid_tree(sim, monkeypatch):
         assert res[1] <= res[0] * 1.02
     finally:
         ctx.close()
+
+
+_RADIX_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import helpers
+import crunch2_b200 as crn
+rng = np.random.default_rng(11)
+n = 5000
+base = rng.integers(0, 256, (900, 6)).astype(np.uint8)          # repeated vectors: equal keys, so the id tie-break is exercised
+vecs = np.ascontiguousarray(base[rng.integers(0, 900, n)]); w = rng.integers(1, 5, n).astype(np.uint32)
+ctx = crn.Context(0, lib=helpers.load_sim())
+co, k, cb = ctx.vq_clusterize(vecs.ctypes.data, w.ctypes.data, n, 6, 65535, 300, False)
+ctx.close()
+sys.stdout.write("%%d %%d %%s" %% (k, cb, co.tobytes().hex()))
+"""
+
+
+def test_fast_vq_split_ranks_radix_sort_equals_std_sort(sim):
+    """VqOrderSim::sort_cands (vq_fast_host.h): the split ranks that retrieve_clusters(max) prunes by are ordered with an LSD radix sort above
+    4096 candidates and std::sort below.  CRN_B200_RANK_RADIX_MIN is read once per process, so each setting runs in its own interpreter; the
+    pruned clustering must be the same array either way."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for radix_min in ("0", "100000000"):
+        env = dict(os.environ, CRN_B200_RANK_RADIX_MIN=radix_min)
+        r = subprocess.run([sys.executable, "-c", _RADIX_CHILD % (root, os.path.join(root, "tests"))], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and outs[0].split()[0] == "300"
