@@ -88,8 +88,16 @@ __device__ __forceinline__ void vqf_for_members(const uint8_t* __restrict__ vecs
 
 // mode: 0 = clusterizer<V>::split_node; 1 = threaded_clusterizer<V>::compute_split (own centroid, PCA division only; the children come back
 // with the root statistics generate_codebook would compute for them, crn_clusterizer.h:76-93)
+// -DCRN_VQ_WARP_MINB=n: minimum CTAs per SM of the warp-per-node instantiation (T = 32), i.e. a register cap.  Measured at the end of round 2
+// (tools/gpu_r2ai.sh, configs[1] step): 12 CTAs (168 registers, 40 B spilled) takes the <16, 32, 1> launches from 22.4 to 18.4 ms of kernel time
+// per step, 16 CTAs (128 registers) to 20.0 ms; the step's wall time did not move beyond its noise, and the change came too late for a full
+// validation run, so the default build leaves the bound off.
 template <int D, int T, int G>
+#ifdef CRN_VQ_WARP_MINB
+__global__ void __launch_bounds__(T, T == 32 ? CRN_VQ_WARP_MINB : 1)
+#else
 __global__ void __launch_bounds__(T)
+#endif
 vq_fast_split_kernel(const uint8_t* __restrict__ vecs, const uint32_t* __restrict__ wts, uint32_t* __restrict__ perm, uint32_t* __restrict__ perm_tmp,
                      VqFastNodes N, const uint2* __restrict__ slots, const uint32_t* __restrict__ slot_list, uint32_t nslots, VqFastResult* __restrict__ results, int mode)
 {
