@@ -542,10 +542,12 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
         except Exception as e:      # noqa: BLE001
             errors.append(e)
     ths = [threading.Thread(target=work, args=(wi,)) for wi in range(nworkers)]
+    t_wall0 = time.perf_counter()
     for t in ths:
         t.start()
     for t in ths:
         t.join()
+    wall_s = time.perf_counter() - t_wall0          # includes waiting for the synthetic images, which `sums` leaves out
     pool.shutdown(wait=False)
     if errors:
         raise errors[0]
@@ -559,7 +561,9 @@ def run_batch_c5(ctx, dev, rank, world, n_textures, with_reference=True):
            "value": n_textures * 1024 * 1024 / dt_all / 1e6, "unit": UNIT, "ms_per_texture": dt_all * 1e3 / max(1, len(mine)),
            "timing": "host wall clock summed over each worker's per-texture calls (host pixels in / host blocks out), slowest worker of the slowest rank",
            "gpu_launches_per_texture": int(launches // max(1, len(mine))), "partitioning": "texture -> rank (LPT), %d rank(s); %d textures in flight per GPU" % (world, nworkers),
-           "workers_per_gpu": nworkers}
+           "workers_per_gpu": nworkers,
+           "wall_s_this_rank": round(wall_s, 4),
+           "value_by_wall_this_rank": len(mine) * 1024 * 1024 / max(wall_s, 1e-9) / 1e6}
     if with_reference and rank == 0:
         import helpers
         ref = helpers.load_ref()
